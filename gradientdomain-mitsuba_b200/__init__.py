@@ -1,0 +1,9 @@
+"""gdb200 — host-side mirror of the reference's interfaces for the G-PT +
+screened-Poisson hot path, over the C ABI in ``include/gdb200.h``.
+
+Everything here calls the sm_100a CUDA library ``libgdb200.so`` through ctypes.
+There is no CPU implementation in this package: if the library is missing or no
+CUDA device is present the calls raise.
+"""
+from ._ffi import lib, Gdb200Error, Stats, library_path  # noqa: F401
+from .poisson import PoissonSolver, SolverParams, poisson_solve, PoissonPlan  # noqa: F401

@@ -1,0 +1,64 @@
+"""ctypes binding of include/gdb200.h (the C-ABI drop-in boundary)."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class Gdb200Error(RuntimeError):
+    """Raised for any non-zero status of the C ABI (the plugin shim turns the
+    same status into Log(EError), which throws — reference logger.cpp:100-148)."""
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [("device_ms", ctypes.c_double), ("h2d_ms", ctypes.c_double), ("d2h_ms", ctypes.c_double),
+                ("launches", ctypes.c_int), ("irls_iters", ctypes.c_int), ("cg_iters", ctypes.c_int),
+                ("reserved0", ctypes.c_int), ("samples", ctypes.c_double), ("rays", ctypes.c_double),
+                ("path_vertices", ctypes.c_double), ("state_bytes", ctypes.c_double)]
+
+
+class PoissonConfig(ctypes.Structure):
+    _fields_ = [("irlsIterMax", ctypes.c_int), ("irlsRegInit", ctypes.c_float), ("irlsRegIter", ctypes.c_float),
+                ("cgIterMax", ctypes.c_int), ("cgIterCheck", ctypes.c_int), ("cgTolerance", ctypes.c_float)]
+
+
+def library_path():
+    return os.path.join(_HERE, "libgdb200.so")
+
+
+_lib = None
+
+
+def lib():
+    """Load libgdb200.so (built in-tree by __graft_entry__.build()). No fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise Gdb200Error(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(gdb200 has no CPU fallback)")
+    L = ctypes.CDLL(path)
+    c_float_p = ctypes.POINTER(ctypes.c_float)
+    vp = ctypes.c_void_p
+    L.gdb200_version.restype = ctypes.c_int
+    L.gdb200_last_error.restype = ctypes.c_char_p
+    L.gdb200_device_count.argtypes = [ctypes.POINTER(ctypes.c_int)]
+    L.gdb200_set_device.argtypes = [ctypes.c_int]
+    L.gdb200_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
+    L.gdb200_host_free.argtypes = [vp]
+    L.gdb200_poisson_preset.argtypes = [ctypes.c_char_p, ctypes.POINTER(PoissonConfig)]
+    L.gdb200_poisson_plan_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]
+    L.gdb200_poisson_plan_destroy.argtypes = [vp]
+    L.gdb200_poisson_plan_destroy.restype = None
+    L.gdb200_poisson_solve_device.argtypes = [vp, vp, vp, vp, vp, ctypes.c_float, ctypes.POINTER(PoissonConfig),
+                                              vp, vp, ctypes.POINTER(Stats)]
+    L.gdb200_poisson_solve.argtypes = [vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                       ctypes.c_char_p, vp, ctypes.POINTER(Stats)]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise Gdb200Error(f"gdb200 error {rc}: {lib().gdb200_last_error().decode(errors='replace')}")

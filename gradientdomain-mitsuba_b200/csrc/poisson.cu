@@ -1,0 +1,677 @@
+// gdb200 screened-Poisson reconstruction for sm_100a: the whole IRLS-over-CG
+// solve of the reference (src/integrators/poisson_solver/Solver.cpp:374-509,
+// vector ops Backend.cpp:154-376) as ONE persistent cooperative kernel.
+//
+// Design (not a port of BackendCUDA.cu's 10 small kernels + host syncs):
+//   * planar SoA fp32 planes with a 4-pixel pitch, every access a 16-byte
+//     LDG/STG.128; interleaved RGB only at the import/export edges (fused).
+//   * 64x16-pixel thread tiles, tiles dealt round-robin to a grid of exactly the
+//     co-resident CTA count, so the 5-point stencil's halo rows are L1/L2 hits and
+//     each plane crosses HBM once per phase.
+//   * per CG iteration two phases / two grid barriers instead of three kernels:
+//       A: p = r + b*p_old (recomputed on the halo), x += a_prev*p_old,
+//          Ap = P'W2P p, pAp            (reads r,p_old,x,w2; writes p,x,Ap)
+//       B: r -= a*Ap, rz                (reads r,Ap; writes r)
+//     = 120 B/pixel against the reference's 132.
+//   * `e = b - Px` is never stored: w2 and r = P'W2 e recompute it from b and x
+//     (IRLS prologue 156 B/pixel against the reference's 336).
+//   * reductions: fp32 per thread, fp64 warp/block/grid tree in a fixed order
+//     (deterministic, independent of timing); w2 normalisation, alpha/beta and
+//     the cgIterCheck/cgTolerance early-out all stay on the device.
+// Per-pixel arithmetic keeps the reference's operation order and is compiled
+// with -fmad=false, so differences against the CPU reference come from
+// reduction order only.
+#include "common.h"
+#include <cooperative_groups.h>
+#include <cfloat>
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+
+namespace cg = cooperative_groups;
+
+namespace gdb200 {
+
+constexpr int kThreads = 256;
+constexpr int kTileGX  = 16;   // groups of 4 pixels per tile row  (64 px)
+constexpr int kTileY   = 16;   // rows per tile
+static_assert(kTileGX * kTileY == kThreads, "one thread per 4-pixel group");
+
+enum Plane {
+    B0 = 0, BX = 3, BY = 6,      // b = [alpha*throughput; dx; dy]   (Solver.cpp:321-329)
+    X = 9, R = 12, PA = 15, PB = 18, AP = 21,
+    W0 = 24, WX = 25, WY = 26,   // w2, normalised
+    V0 = 27, VX = 28, VY = 29,   // 1/(|e|+reg) before normalisation
+    kPlanes = 30
+};
+
+struct PoissonArgs {
+    int W, H, Wp, Gx, tilesX, nTiles, aosVec;
+    float alpha;
+    gdb200_poisson_config cfg;
+    float *plane[kPlanes];
+    const float *in_dx, *in_dy, *in_thr, *in_direct;
+    float *out_final;
+    double *red;      // [2][grid][3]
+    int *iters;       // [0] IRLS iterations, [1] CG iterations
+};
+
+struct F4 { float v[4]; };
+
+__device__ __forceinline__ F4 ld4(const float *p)
+{
+    float4 t = *reinterpret_cast<const float4 *>(p);
+    return F4{{t.x, t.y, t.z, t.w}};
+}
+__device__ __forceinline__ void st4(float *p, const F4 &a)
+{
+    *reinterpret_cast<float4 *>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
+}
+__device__ __forceinline__ F4 zero4() { return F4{{0.f, 0.f, 0.f, 0.f}}; }
+
+// Deterministic grid-wide sum of three per-thread doubles. Contains one grid barrier.
+__device__ void grid_sum3(cg::grid_group &grid, double *red, int &parity, double a0, double a1,
+                          double a2, float out[3])
+{
+    __shared__ double s_part[kThreads / 32][3];
+    __shared__ float s_out[3];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    if (lane == 0) { s_part[warp][0] = a0; s_part[warp][1] = a1; s_part[warp][2] = a2; }
+    __syncthreads();
+    double *slot = red + (size_t)parity * gridDim.x * 3;
+    if (threadIdx.x < 3) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; w++) s += s_part[w][threadIdx.x];
+        slot[(size_t)blockIdx.x * 3 + threadIdx.x] = s;
+    }
+    grid.sync();
+    if (warp == 0) {
+        double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+        for (int b = lane; b < (int)gridDim.x; b += 32) {
+            t0 += slot[(size_t)b * 3 + 0];
+            t1 += slot[(size_t)b * 3 + 1];
+            t2 += slot[(size_t)b * 3 + 2];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            t0 += __shfl_xor_sync(0xffffffffu, t0, o);
+            t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+            t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+        }
+        if (lane == 0) { s_out[0] = (float)t0; s_out[1] = (float)t1; s_out[2] = (float)t2; }
+    }
+    __syncthreads();
+    out[0] = s_out[0]; out[1] = s_out[1]; out[2] = s_out[2];
+    parity ^= 1;
+    __syncthreads();
+}
+
+struct TileIter {
+    int y, x0, idx;
+    bool valid;
+};
+
+__device__ __forceinline__ TileIter tile_thread(const PoissonArgs &a, int tile)
+{
+    const int tx = tile % a.tilesX, ty = tile / a.tilesX;
+    const int gx = tx * kTileGX + (threadIdx.x % kTileGX);
+    TileIter t;
+    t.y = ty * kTileY + (threadIdx.x / kTileGX);
+    t.x0 = gx * 4;
+    t.valid = gx < a.Gx && t.y < a.H;
+    t.idx = t.y * a.Wp + t.x0;
+    return t;
+}
+
+// ---- interleaved RGB <-> planar ------------------------------------------------------------
+__device__ __forceinline__ void load_rgb4(const float *aos, const PoissonArgs &a, const TileIter &t,
+                                          F4 &r, F4 &g, F4 &b)
+{
+    const size_t base = ((size_t)t.y * a.W + t.x0) * 3;
+    if (a.aosVec) {
+        F4 f0 = ld4(aos + base), f1 = ld4(aos + base + 4), f2 = ld4(aos + base + 8);
+        r = F4{{f0.v[0], f0.v[3], f1.v[2], f2.v[1]}};
+        g = F4{{f0.v[1], f1.v[0], f1.v[3], f2.v[2]}};
+        b = F4{{f0.v[2], f1.v[1], f2.v[0], f2.v[3]}};
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const bool in = t.x0 + j < a.W;
+            r.v[j] = in ? aos[base + 3 * j + 0] : 0.f;
+            g.v[j] = in ? aos[base + 3 * j + 1] : 0.f;
+            b.v[j] = in ? aos[base + 3 * j + 2] : 0.f;
+        }
+    }
+}
+
+__device__ __forceinline__ void store_rgb4(float *aos, const PoissonArgs &a, const TileIter &t,
+                                           const F4 &r, const F4 &g, const F4 &b)
+{
+    const size_t base = ((size_t)t.y * a.W + t.x0) * 3;
+    if (a.aosVec) {
+        st4(aos + base,     F4{{r.v[0], g.v[0], b.v[0], r.v[1]}});
+        st4(aos + base + 4, F4{{g.v[1], b.v[1], r.v[2], g.v[2]}});
+        st4(aos + base + 8, F4{{b.v[2], r.v[3], g.v[3], b.v[3]}});
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (t.x0 + j < a.W) {
+                aos[base + 3 * j + 0] = r.v[j];
+                aos[base + 3 * j + 1] = g.v[j];
+                aos[base + 3 * j + 2] = b.v[j];
+            }
+    }
+}
+
+// ---- phase: import  (Solver.cpp:321-337) ----------------------------------------------------
+__device__ void phase_import(const PoissonArgs &a)
+{
+    for (int tile = blockIdx.x; tile < a.nTiles; tile += gridDim.x) {
+        const TileIter t = tile_thread(a, tile);
+        if (!t.valid) continue;
+        F4 c[3];
+        if (a.in_thr) load_rgb4(a.in_thr, a, t, c[0], c[1], c[2]);
+        else c[0] = c[1] = c[2] = zero4();
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+            F4 b0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) b0.v[j] = c[ch].v[j] * a.alpha;
+            st4(a.plane[B0 + ch] + t.idx, b0);
+            st4(a.plane[X + ch] + t.idx, c[ch]);
+            st4(a.plane[PA + ch] + t.idx, zero4());
+        }
+        load_rgb4(a.in_dx, a, t, c[0], c[1], c[2]);
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) st4(a.plane[BX + ch] + t.idx, c[ch]);
+        load_rgb4(a.in_dy, a, t, c[0], c[1], c[2]);
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) st4(a.plane[BY + ch] + t.idx, c[ch]);
+    }
+}
+
+// e = b - P x at this thread's 4 pixels, one channel (Backend.cpp:165-186, :256-272 with a=-1).
+__device__ __forceinline__ void residual4(const PoissonArgs &a, const TileIter &t, int ch,
+                                          F4 &e0, F4 &ex, F4 &ey)
+{
+    const float *x = a.plane[X + ch];
+    const F4 xc = ld4(x + t.idx);
+    const F4 b0 = ld4(a.plane[B0 + ch] + t.idx);
+    const F4 bx = ld4(a.plane[BX + ch] + t.idx);
+    const F4 by = ld4(a.plane[BY + ch] + t.idx);
+    const float xr = (t.x0 + 4 < a.W) ? x[t.idx + 4] : 0.f;
+    const F4 xd = (t.y != a.H - 1) ? ld4(x + t.idx + a.Wp) : zero4();
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int xx = t.x0 + j;
+        const float xi = xc.v[j];
+        const float nx = (j == 3) ? xr : xc.v[j + 1];
+        const float p0 = xi * a.alpha;
+        const float p1 = (xx != a.W - 1) ? nx - xi : 0.f;
+        const float p2 = (t.y != a.H - 1) ? xd.v[j] - xi : 0.f;
+        e0.v[j] = b0.v[j] - p0;
+        ex.v[j] = bx.v[j] - p1;
+        ey.v[j] = by.v[j] - p2;
+    }
+}
+
+// ---- phase: w2 numerators 1/(|e|+reg) and their sum (Backend.cpp:351-366) -------------------
+__device__ void phase_weights(const PoissonArgs &a, bool first, float reg, double &sum)
+{
+    for (int tile = blockIdx.x; tile < a.nTiles; tile += gridDim.x) {
+        const TileIter t = tile_thread(a, tile);
+        if (!t.valid) continue;
+        F4 v0, vx, vy;
+        if (first) {                                   // Solver.cpp:391-392: w2 = 1
+#pragma unroll
+            for (int j = 0; j < 4; j++) v0.v[j] = vx.v[j] = vy.v[j] = (t.x0 + j < a.W) ? 1.f : 0.f;
+        } else {
+            F4 e0[3], ex[3], ey[3];
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) residual4(a, t, ch, e0[ch], ex[ch], ey[ch]);
+            float part = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const bool in = t.x0 + j < a.W;
+                const float l0 = sqrtf(e0[0].v[j] * e0[0].v[j] + e0[1].v[j] * e0[1].v[j] + e0[2].v[j] * e0[2].v[j]);
+                const float lx = sqrtf(ex[0].v[j] * ex[0].v[j] + ex[1].v[j] * ex[1].v[j] + ex[2].v[j] * ex[2].v[j]);
+                const float ly = sqrtf(ey[0].v[j] * ey[0].v[j] + ey[1].v[j] * ey[1].v[j] + ey[2].v[j] * ey[2].v[j]);
+                v0.v[j] = in ? 1.0f / (l0 + reg) : 0.f;
+                vx.v[j] = in ? 1.0f / (lx + reg) : 0.f;
+                vy.v[j] = in ? 1.0f / (ly + reg) : 0.f;
+                part += v0.v[j] + vx.v[j] + vy.v[j];
+            }
+            sum += (double)part;
+        }
+        st4(a.plane[V0] + t.idx, v0);
+        st4(a.plane[VX] + t.idx, vx);
+        st4(a.plane[VY] + t.idx, vy);
+    }
+}
+
+// ---- phase: w2 = coef*v, r = P' W2 (b - Px), rz = r.r  (Backend.cpp:368-372, :190-217) ------
+__device__ void phase_rhs(const PoissonArgs &a, float coef, double rz[3])
+{
+    float acc[3] = {0.f, 0.f, 0.f};
+    for (int tile = blockIdx.x; tile < a.nTiles; tile += gridDim.x) {
+        const TileIter t = tile_thread(a, tile);
+        if (!t.valid) continue;
+        const bool hasL = t.x0 > 0, hasU = t.y > 0;
+        F4 w0 = ld4(a.plane[V0] + t.idx), wx = ld4(a.plane[VX] + t.idx), wy = ld4(a.plane[VY] + t.idx);
+        F4 wyu = hasU ? ld4(a.plane[VY] + t.idx - a.Wp) : zero4();
+        float wxl = hasL ? a.plane[VX][t.idx - 1] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; j++) { w0.v[j] *= coef; wx.v[j] *= coef; wy.v[j] *= coef; wyu.v[j] *= coef; }
+        wxl *= coef;
+        st4(a.plane[W0] + t.idx, w0);
+        st4(a.plane[WX] + t.idx, wx);
+        st4(a.plane[WY] + t.idx, wy);
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+            const float *x = a.plane[X + ch];
+            F4 e0, ex, ey;
+            residual4(a, t, ch, e0, ex, ey);
+            const F4 xc = ld4(x + t.idx);
+            // ex at the left neighbour and ey at the upper neighbour, recomputed.
+            float exl = 0.f;
+            if (hasL) exl = a.plane[BX + ch][t.idx - 1] - (xc.v[0] - x[t.idx - 1]);
+            F4 eyu = zero4();
+            if (hasU) {
+                const F4 xu = ld4(x + t.idx - a.Wp), byu = ld4(a.plane[BY + ch] + t.idx - a.Wp);
+#pragma unroll
+                for (int j = 0; j < 4; j++) eyu.v[j] = byu.v[j] - (xc.v[j] - xu.v[j]);
+            }
+            F4 r;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int xx = t.x0 + j;
+                float v = w0.v[j] * e0.v[j] * a.alpha;
+                if (xx != 0)        v += (j == 0 ? wxl : wx.v[j - 1]) * (j == 0 ? exl : ex.v[j - 1]);
+                if (xx != a.W - 1)  v -= wx.v[j] * ex.v[j];
+                if (t.y != 0)       v += wyu.v[j] * eyu.v[j];
+                if (t.y != a.H - 1) v -= wy.v[j] * ey.v[j];
+                if (xx >= a.W) v = 0.f;
+                r.v[j] = v;
+                acc[ch] += v * v;
+            }
+            st4(a.plane[R + ch] + t.idx, r);
+        }
+    }
+    rz[0] = acc[0]; rz[1] = acc[1]; rz[2] = acc[2];
+}
+
+// ---- phase A: p = r + b*p_old; x += a_prev*p_old; Ap = A p; pAp ---------------------------
+// (Backend.cpp:325-347 of the previous iteration fused with :221-252 of this one.)
+__device__ void phase_cg_a(const PoissonArgs &a, int pOld, int pNew, const float aPrev[3],
+                           const float beta[3], double pAp[3])
+{
+    const float alphaSqr = a.alpha * a.alpha;
+    float acc[3] = {0.f, 0.f, 0.f};
+    for (int tile = blockIdx.x; tile < a.nTiles; tile += gridDim.x) {
+        const TileIter t = tile_thread(a, tile);
+        if (!t.valid) continue;
+        const bool hasL = t.x0 > 0, hasR = t.x0 + 4 < a.W, hasU = t.y > 0, hasD = t.y < a.H - 1;
+        const F4 w0 = ld4(a.plane[W0] + t.idx), wx = ld4(a.plane[WX] + t.idx), wy = ld4(a.plane[WY] + t.idx);
+        const F4 wyu = hasU ? ld4(a.plane[WY] + t.idx - a.Wp) : zero4();
+        const float wxl = hasL ? a.plane[WX][t.idx - 1] : 0.f;
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+            const float *r = a.plane[R + ch], *po = a.plane[pOld + ch];
+            const float b = beta[ch], al = aPrev[ch];
+            const F4 rc = ld4(r + t.idx), pc = ld4(po + t.idx);
+            F4 xv = ld4(a.plane[X + ch] + t.idx);
+            F4 c, u = zero4(), d = zero4();
+            float l = 0.f, rr = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                xv.v[j] += pc.v[j] * al;
+                c.v[j] = rc.v[j] + pc.v[j] * b;
+            }
+            if (hasU) {
+                const F4 r2 = ld4(r + t.idx - a.Wp), p2 = ld4(po + t.idx - a.Wp);
+#pragma unroll
+                for (int j = 0; j < 4; j++) u.v[j] = r2.v[j] + p2.v[j] * b;
+            }
+            if (hasD) {
+                const F4 r2 = ld4(r + t.idx + a.Wp), p2 = ld4(po + t.idx + a.Wp);
+#pragma unroll
+                for (int j = 0; j < 4; j++) d.v[j] = r2.v[j] + p2.v[j] * b;
+            }
+            if (hasL) l = r[t.idx - 1] + po[t.idx - 1] * b;
+            if (hasR) rr = r[t.idx + 4] + po[t.idx + 4] * b;
+            F4 Ap;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int xx = t.x0 + j;
+                const float xi = c.v[j];
+                float v = w0.v[j] * xi * alphaSqr;
+                if (xx != 0)        v += (j == 0 ? wxl : wx.v[j - 1]) * (xi - (j == 0 ? l : c.v[j - 1]));
+                if (xx != a.W - 1)  v += wx.v[j] * (xi - (j == 3 ? rr : c.v[j + 1]));
+                if (t.y != 0)       v += wyu.v[j] * (xi - u.v[j]);
+                if (t.y != a.H - 1) v += wy.v[j] * (xi - d.v[j]);
+                if (xx >= a.W) v = 0.f;
+                Ap.v[j] = v;
+                acc[ch] += xi * v;
+            }
+            st4(a.plane[X + ch] + t.idx, xv);
+            st4(a.plane[pNew + ch] + t.idx, c);
+            st4(a.plane[AP + ch] + t.idx, Ap);
+        }
+    }
+    pAp[0] = acc[0]; pAp[1] = acc[1]; pAp[2] = acc[2];
+}
+
+// ---- phase B: r -= a*Ap; rz = r.r   (Backend.cpp:296-321) ----------------------------------
+__device__ void phase_cg_b(const PoissonArgs &a, const float al[3], double rz[3])
+{
+    float acc[3] = {0.f, 0.f, 0.f};
+    for (int tile = blockIdx.x; tile < a.nTiles; tile += gridDim.x) {
+        const TileIter t = tile_thread(a, tile);
+        if (!t.valid) continue;
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+            F4 r = ld4(a.plane[R + ch] + t.idx);
+            const F4 Ap = ld4(a.plane[AP + ch] + t.idx);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float ri = r.v[j] - Ap.v[j] * al[ch];
+                r.v[j] = ri;
+                acc[ch] += ri * ri;
+            }
+            st4(a.plane[R + ch] + t.idx, r);
+        }
+    }
+    rz[0] = acc[0]; rz[1] = acc[1]; rz[2] = acc[2];
+}
+
+// ---- phase: pending x += a*p of the last CG iteration --------------------------------------
+__device__ void phase_flush_x(const PoissonArgs &a, int pCur, const float al[3])
+{
+    for (int tile = blockIdx.x; tile < a.nTiles; tile += gridDim.x) {
+        const TileIter t = tile_thread(a, tile);
+        if (!t.valid) continue;
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+            F4 x = ld4(a.plane[X + ch] + t.idx);
+            const F4 p = ld4(a.plane[pCur + ch] + t.idx);
+#pragma unroll
+            for (int j = 0; j < 4; j++) x.v[j] += p.v[j] * al[ch];
+            st4(a.plane[X + ch] + t.idx, x);
+        }
+    }
+}
+
+// ---- phase: final = 1*direct + x  (Solver.cpp:561-567), with the last x update folded in ---
+__device__ void phase_export(const PoissonArgs &a, int pCur, const float al[3])
+{
+    for (int tile = blockIdx.x; tile < a.nTiles; tile += gridDim.x) {
+        const TileIter t = tile_thread(a, tile);
+        if (!t.valid) continue;
+        F4 x[3];
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+            x[ch] = ld4(a.plane[X + ch] + t.idx);
+            const F4 p = ld4(a.plane[pCur + ch] + t.idx);
+#pragma unroll
+            for (int j = 0; j < 4; j++) x[ch].v[j] += p.v[j] * al[ch];
+        }
+        if (a.in_direct) {
+            F4 d[3];
+            load_rgb4(a.in_direct, a, t, d[0], d[1], d[2]);
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) x[ch].v[j] = 1.0f * d[ch].v[j] + x[ch].v[j];
+        }
+        store_rgb4(a.out_final, a, t, x[0], x[1], x[2]);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 2) poisson_irls_cg_kernel(const PoissonArgs a)
+{
+    cg::grid_group grid = cg::this_grid();
+    int parity = 0;
+    int cgTotal = 0, irlsDone = 0;
+    const float n3 = (float)(3 * a.W * a.H);   // (float)w2->numElems, Backend.cpp:368
+
+    phase_import(a);
+    grid.sync();
+
+    int pCur = PA;                       // plane set holding the current search direction
+    float aPrev[3] = {0.f, 0.f, 0.f};    // step of the CG iteration whose x update is pending
+
+    for (int irls = 0; irls < a.cfg.irlsIterMax; irls++) {
+        if (irls > 0) {                                   // apply the pending x update first
+            phase_flush_x(a, pCur, aPrev);
+            grid.sync();
+        }
+        aPrev[0] = aPrev[1] = aPrev[2] = 0.f;
+        float coef = 1.0f;
+        if (irls == 0) {
+            double dummy = 0.0;
+            phase_weights(a, true, 0.f, dummy);
+            grid.sync();
+        } else {
+            const float reg = a.cfg.irlsRegInit * powf(a.cfg.irlsRegIter, (float)(irls - 1));   // Solver.cpp:395
+            double s = 0.0;
+            phase_weights(a, false, reg, s);
+            float tot[3];
+            grid_sum3(grid, a.red, parity, s, 0.0, 0.0, tot);
+            coef = n3 / tot[0];
+        }
+        double part[3];
+        float rzA[3], rzB[3], pAp[3];
+        float *rz = rzA, *rz2 = rzB;
+        phase_rhs(a, coef, part);
+        grid_sum3(grid, a.red, parity, part[0], part[1], part[2], rz);
+
+        float beta[3] = {0.f, 0.f, 0.f};                  // first direction: p = r (Solver.cpp:405)
+        for (int cgi = 0;; cgi++) {
+            if (cgi % a.cfg.cgIterCheck == 0 || cgi == a.cfg.cgIterMax) {   // Solver.cpp:411-445
+                const float errL2W = rz[0] + rz[1] + rz[2];
+                if (cgi == a.cfg.cgIterMax || errL2W <= a.cfg.cgTolerance) break;
+            }
+            { float *tmp = rz; rz = rz2; rz2 = tmp; }                       // Solver.cpp:466
+            const int pNew = (pCur == PA) ? PB : PA;
+            phase_cg_a(a, pCur, pNew, aPrev, beta, part);
+            grid_sum3(grid, a.red, parity, part[0], part[1], part[2], pAp);
+            pCur = pNew;
+            float al[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) al[c] = rz2[c] / fmaxf(pAp[c], FLT_MIN);   // Backend.cpp:309
+            phase_cg_b(a, al, part);
+            grid_sum3(grid, a.red, parity, part[0], part[1], part[2], rz);
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                beta[c] = rz[c] / fmaxf(rz2[c], FLT_MIN);                          // Backend.cpp:339
+                aPrev[c] = al[c];
+            }
+            cgTotal++;
+        }
+        irlsDone++;
+    }
+    phase_export(a, pCur, aPrev);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { a.iters[0] = irlsDone; a.iters[1] = cgTotal; }
+}
+
+}  // namespace gdb200
+
+// =================================================================================== host ====
+
+struct gdb200_poisson_plan {
+    int device = 0, w = 0, h = 0, wp = 0, grid = 0;
+    float *planes = nullptr;
+    double *red = nullptr;
+    int *iters = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // staging for the host-pointer entry point
+    float *d_in[4] = {nullptr, nullptr, nullptr, nullptr};
+    float *d_out = nullptr;
+};
+
+using namespace gdb200;
+
+extern "C" {
+
+int gdb200_poisson_preset(const char *preset, gdb200_poisson_config *c)
+{
+    if (!preset || !c) return set_error(GDB200_ERR_ARGUMENT, "preset/out_cfg is NULL");
+    // Base config, Solver.cpp:92-100.
+    c->irlsIterMax = 1; c->irlsRegInit = 0.f; c->irlsRegIter = 0.f;
+    c->cgIterMax = 1; c->cgIterCheck = 100; c->cgTolerance = 0.f;
+    if (!strcmp(preset, "L1D")) { c->irlsIterMax = 20; c->irlsRegInit = 0.05f; c->irlsRegIter = 0.5f; c->cgIterMax = 50; return GDB200_OK; }
+    if (!strcmp(preset, "L1Q")) { c->irlsIterMax = 64; c->irlsRegInit = 1.0f; c->irlsRegIter = 0.7f; c->cgIterMax = 1000; return GDB200_OK; }
+    if (!strcmp(preset, "L1L")) { c->irlsIterMax = 7; c->irlsRegInit = 1.0e-4f; c->irlsRegIter = 1.0e-1f; c->cgIterMax = 20000; c->cgTolerance = 1.0e-20f; return GDB200_OK; }
+    if (!strcmp(preset, "L2D")) { c->cgIterMax = 50; return GDB200_OK; }
+    if (!strcmp(preset, "L2Q")) { c->cgIterMax = 500; return GDB200_OK; }
+    return set_error(GDB200_ERR_ARGUMENT, "unknown solver preset '%s' (expected L1D, L1Q, L1L, L2D or L2Q)", preset);
+}
+
+void gdb200_poisson_plan_destroy(gdb200_poisson_plan *p)
+{
+    if (!p) return;
+    cudaFree(p->planes); cudaFree(p->red); cudaFree(p->iters);
+    for (float *d : p->d_in) cudaFree(d);
+    cudaFree(p->d_out);
+    if (p->ev0) cudaEventDestroy(p->ev0);
+    if (p->ev1) cudaEventDestroy(p->ev1);
+    delete p;
+}
+
+int gdb200_poisson_plan_create(int w, int h, gdb200_poisson_plan **out)
+{
+    if (!out) return set_error(GDB200_ERR_ARGUMENT, "out_plan is NULL");
+    *out = nullptr;
+    if (w <= 0 || h <= 0 || (long long)w * h > (1LL << 29))
+        return set_error(GDB200_ERR_ARGUMENT, "invalid image size %dx%d", w, h);
+    DeviceInfo di;
+    if (int rc = device_info(&di)) return rc;
+    gdb200_poisson_plan *p = new gdb200_poisson_plan;
+    p->device = di.device; p->w = w; p->h = h; p->wp = (w + 3) & ~3;
+    const size_t planeElems = (size_t)p->wp * h;
+    int occ = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, poisson_irls_cg_kernel, kThreads, 0);
+    if (e != cudaSuccess || occ < 1) {
+        delete p;
+        return set_error(GDB200_ERR_CUDA, "poisson kernel not launchable on this device: %s "
+                         "(library is built for sm_100a only)", cudaGetErrorString(e));
+    }
+    const int tilesX = (p->wp / 4 + kTileGX - 1) / kTileGX, tilesY = (h + kTileY - 1) / kTileY;
+    const long long nTiles = (long long)tilesX * tilesY;
+    p->grid = (int)std::min<long long>(nTiles, (long long)occ * di.sms);
+#define PLAN_CUDA(call) do { cudaError_t e2 = (call); if (e2 != cudaSuccess) { gdb200_poisson_plan_destroy(p); \
+        return set_error(GDB200_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e2)); } } while (0)
+    PLAN_CUDA(cudaMalloc(&p->planes, planeElems * kPlanes * sizeof(float)));
+    PLAN_CUDA(cudaMemset(p->planes, 0, planeElems * kPlanes * sizeof(float)));
+    PLAN_CUDA(cudaMalloc(&p->red, sizeof(double) * 2 * 3 * p->grid));
+    PLAN_CUDA(cudaMalloc(&p->iters, sizeof(int) * 2));
+    PLAN_CUDA(cudaEventCreate(&p->ev0));
+    PLAN_CUDA(cudaEventCreate(&p->ev1));
+#undef PLAN_CUDA
+    *out = p;
+    return GDB200_OK;
+}
+
+int gdb200_poisson_solve_device(gdb200_poisson_plan *p, const float *d_dx, const float *d_dy,
+                                const float *d_thr, const float *d_direct, float alpha,
+                                const gdb200_poisson_config *cfg, float *d_out, void *stream,
+                                gdb200_stats *stats)
+{
+    if (!p || !d_dx || !d_dy || !cfg || !d_out)
+        return set_error(GDB200_ERR_ARGUMENT, "plan, dx, dy, cfg and out_final are required");
+    PoissonArgs a;
+    memset(&a, 0, sizeof(a));
+    a.W = p->w; a.H = p->h; a.Wp = p->wp; a.Gx = p->wp / 4;
+    a.tilesX = (a.Gx + kTileGX - 1) / kTileGX;
+    a.nTiles = a.tilesX * ((p->h + kTileY - 1) / kTileY);
+    a.aosVec = (p->w % 4 == 0) &&
+               ((((uintptr_t)d_dx | (uintptr_t)d_dy | (uintptr_t)d_thr | (uintptr_t)d_direct | (uintptr_t)d_out) & 15) == 0);
+    // Params::sanitize (Solver.cpp:168-178) and m_P.alpha (Solver.cpp:319).
+    a.alpha = d_thr ? fmaxf(alpha, 0.f) : 0.f;
+    a.cfg = *cfg;
+    a.cfg.irlsIterMax = std::max(cfg->irlsIterMax, 1);
+    a.cfg.irlsRegInit = fmaxf(cfg->irlsRegInit, 0.f);
+    a.cfg.irlsRegIter = fmaxf(cfg->irlsRegIter, 0.f);
+    a.cfg.cgIterMax = std::max(cfg->cgIterMax, 1);
+    a.cfg.cgIterCheck = std::max(cfg->cgIterCheck, 1);
+    a.cfg.cgTolerance = fmaxf(cfg->cgTolerance, 0.f);
+    const size_t planeElems = (size_t)p->wp * p->h;
+    for (int i = 0; i < kPlanes; i++) a.plane[i] = p->planes + planeElems * i;
+    a.in_dx = d_dx; a.in_dy = d_dy; a.in_thr = d_thr; a.in_direct = d_direct; a.out_final = d_out;
+    a.red = p->red; a.iters = p->iters;
+
+    cudaStream_t s = (cudaStream_t)stream;
+    if (stats) GDB_CUDA(cudaEventRecord(p->ev0, s));
+    void *kargs[] = {&a};
+    GDB_CUDA(cudaLaunchCooperativeKernel((void *)poisson_irls_cg_kernel, dim3(p->grid), dim3(kThreads), kargs, 0, s));
+    if (stats) {
+        GDB_CUDA(cudaEventRecord(p->ev1, s));
+        GDB_CUDA(cudaEventSynchronize(p->ev1));
+        float ms = 0.f;
+        GDB_CUDA(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
+        int it[2];
+        GDB_CUDA(cudaMemcpy(it, p->iters, sizeof(it), cudaMemcpyDeviceToHost));
+        stats->device_ms = ms; stats->launches = 1; stats->irls_iters = it[0]; stats->cg_iters = it[1];
+    }
+    return GDB200_OK;
+}
+
+int gdb200_poisson_solve(const float *dx, const float *dy, const float *throughput,
+                         const float *direct, int w, int h, float alpha, const char *preset,
+                         float *out_final, gdb200_stats *stats)
+{
+    if (!dx || !dy || !out_final) return set_error(GDB200_ERR_ARGUMENT, "dx, dy and out_final are required");
+    gdb200_poisson_config cfg;
+    if (int rc = gdb200_poisson_preset(preset, &cfg)) return rc;
+    // One cached plan per thread: Mitsuba calls this once per render, benches call it in a loop.
+    static thread_local gdb200_poisson_plan *cached = nullptr;
+    int dev = -1;
+    if (int rc = require_device()) return rc;
+    GDB_CUDA(cudaGetDevice(&dev));
+    if (cached && (cached->w != w || cached->h != h || cached->device != dev)) {
+        gdb200_poisson_plan_destroy(cached);
+        cached = nullptr;
+    }
+    if (!cached) if (int rc = gdb200_poisson_plan_create(w, h, &cached)) return rc;
+    gdb200_poisson_plan *p = cached;
+    const size_t bytes = (size_t)w * h * 3 * sizeof(float);
+    const float *src[4] = {dx, dy, throughput, direct};
+    for (int i = 0; i < 4; i++)
+        if (src[i] && !p->d_in[i]) GDB_CUDA(cudaMalloc(&p->d_in[i], bytes));
+    if (!p->d_out) GDB_CUDA(cudaMalloc(&p->d_out, bytes));
+
+    cudaEvent_t e[4];
+    for (auto &ev : e) GDB_CUDA(cudaEventCreate(&ev));
+    cudaStream_t s = 0;
+    GDB_CUDA(cudaEventRecord(e[0], s));
+    for (int i = 0; i < 4; i++)
+        if (src[i]) GDB_CUDA(cudaMemcpyAsync(p->d_in[i], src[i], bytes, cudaMemcpyHostToDevice, s));
+    GDB_CUDA(cudaEventRecord(e[1], s));
+    gdb200_stats local;
+    memset(&local, 0, sizeof(local));
+    int rc = gdb200_poisson_solve_device(p, p->d_in[0], p->d_in[1], throughput ? p->d_in[2] : nullptr,
+                                         direct ? p->d_in[3] : nullptr, alpha, &cfg, p->d_out, s, &local);
+    if (rc) return rc;
+    GDB_CUDA(cudaEventRecord(e[2], s));
+    GDB_CUDA(cudaMemcpyAsync(out_final, p->d_out, bytes, cudaMemcpyDeviceToHost, s));
+    GDB_CUDA(cudaEventRecord(e[3], s));
+    GDB_CUDA(cudaEventSynchronize(e[3]));
+    if (stats) {
+        float a = 0.f, b = 0.f;
+        GDB_CUDA(cudaEventElapsedTime(&a, e[0], e[1]));
+        GDB_CUDA(cudaEventElapsedTime(&b, e[2], e[3]));
+        *stats = local;
+        stats->h2d_ms = a; stats->d2h_ms = b;
+    }
+    for (auto &ev : e) cudaEventDestroy(ev);
+    return GDB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,27 @@
+// Test infrastructure: thin extern "C" entry over the UNMODIFIED reference
+// solver (src/integrators/poisson_solver/Solver.{hpp,cpp}), built by
+// oracle/Makefile into oracle/_ref/.  Mirrors the call sequence of
+// gpt.cpp:1445-1462.  Only tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / --impl reference legs may load the resulting library.
+#include "Solver.hpp"
+#include <string>
+
+extern "C" int ref_poisson_solve(const float *dx, const float *dy, const float *throughput,
+                                 const float *direct, int w, int h, float alpha,
+                                 const char *preset, float *out_final, float *out_seconds)
+{
+    poisson::Solver::Params params;
+    if (!params.setConfigPreset(preset)) return 1;
+    params.alpha = alpha;
+    static float s_seconds; s_seconds = -1.f;
+    params.setLogFunction(poisson::Solver::Params::LogFunction([](const std::string &m) {
+        float v; if (sscanf(m.c_str(), "Execution time = %f s", &v) == 1) s_seconds = v; }));
+    poisson::Solver solver(params);
+    solver.importImagesMTS(const_cast<float*>(dx), const_cast<float*>(dy),
+                           const_cast<float*>(throughput), const_cast<float*>(direct), w, h);
+    solver.setupBackend();
+    solver.solveIndirect();
+    solver.exportImagesMTS(out_final);
+    if (out_seconds) *out_seconds = s_seconds;
+    return 0;
+}

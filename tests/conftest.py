@@ -1,0 +1,69 @@
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+REFERENCE = "/root/reference"
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+def _make(target):
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), target], check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+
+
+class Oracle:
+    """ctypes view of oracle/libgdb200_oracle.so (the CPU restatement) and, when
+    built, oracle/_ref/libref_poisson.so (the reference's own solver sources)."""
+
+    def __init__(self):
+        path = os.path.join(ROOT, "oracle", "libgdb200_oracle.so")
+        if not os.path.exists(path):
+            _make("restatement")
+        self.lib = ctypes.CDLL(path)
+        ref_path = os.path.join(ROOT, "oracle", "_ref", "libref_poisson.so")
+        if not os.path.exists(ref_path) and os.path.isdir(REFERENCE):
+            _make("ref")
+        self.ref = ctypes.CDLL(ref_path) if os.path.exists(ref_path) else None
+
+    @staticmethod
+    def _p(a):
+        return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+    def poisson(self, dx, dy, thr, direct, alpha=0.2, preset="L1D"):
+        h, w, _ = dx.shape
+        out = np.empty_like(dx)
+        rc = self.lib.gdb200_oracle_poisson_solve(self._p(dx), self._p(dy), self._p(thr), self._p(direct),
+                                                  w, h, ctypes.c_float(alpha), preset.encode(), self._p(out))
+        assert rc == 0
+        return out
+
+    def poisson_ref(self, dx, dy, thr, direct, alpha=0.2, preset="L1D"):
+        h, w, _ = dx.shape
+        out = np.empty_like(dx)
+        sec = ctypes.c_float()
+        rc = self.ref.ref_poisson_solve(self._p(dx), self._p(dy), self._p(thr), self._p(direct), w, h,
+                                        ctypes.c_float(alpha), preset.encode(), self._p(out), ctypes.byref(sec))
+        assert rc == 0
+        return out
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    return Oracle()
+
+
+def rmse(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.sqrt(np.mean((a - b) ** 2)))

@@ -1,0 +1,64 @@
+"""CPU tests: the C-ABI shared library loads and exports every symbol that
+include/gdb200.h declares; host-side mirrors validate arguments like the reference."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import gdb200
+from conftest import ROOT
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "gdb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gdb200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = ctypes.CDLL(gdb200.library_path())
+    syms = _declared_symbols()
+    assert len(syms) >= 10
+    for s in syms:
+        assert hasattr(L, s), f"{s} declared in include/gdb200.h but not exported"
+
+
+def test_version_and_error_string():
+    L = gdb200.lib()
+    assert L.gdb200_version() >= 100
+    assert isinstance(L.gdb200_last_error(), bytes)
+
+
+def test_presets_match_reference_table():
+    # Solver.cpp:105-160
+    table = {"L1D": (20, 0.05, 0.5, 50, 0.0), "L1Q": (64, 1.0, 0.7, 1000, 0.0), "L1L": (7, 1e-4, 1e-1, 20000, 1e-20),
+             "L2D": (1, 0.0, 0.0, 50, 0.0), "L2Q": (1, 0.0, 0.0, 500, 0.0)}
+    for name, (irls, r0, ri, cgmax, tol) in table.items():
+        p = gdb200.SolverParams()
+        assert p.setConfigPreset(name)
+        assert (p.cfg.irlsIterMax, p.cfg.cgIterMax, p.cfg.cgIterCheck) == (irls, cgmax, 100)
+        assert p.cfg.irlsRegInit == pytest.approx(r0) and p.cfg.irlsRegIter == pytest.approx(ri)
+        assert p.cfg.cgTolerance == pytest.approx(tol)
+    assert not gdb200.SolverParams().setConfigPreset("L3")     # Solver.cpp:163 returns false
+
+
+def test_no_cpu_fallback_without_device():
+    """Without a GPU the product path must fail loudly, never compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import numpy as np
+    z = np.zeros((4, 4, 3), np.float32)
+    with pytest.raises(gdb200.Gdb200Error):
+        gdb200.poisson_solve(z, z, z, z, 4, 4)
+
+
+def test_product_does_not_reference_oracle():
+    """Only tests/, smoke() and bench.py may touch oracle/."""
+    pkg = os.path.join(ROOT, "gradientdomain-mitsuba_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh", "Makefile")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle/" not in text and "libgdb200_oracle" not in text and "libref_poisson" not in text, f
