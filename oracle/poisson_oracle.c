@@ -48,6 +48,16 @@ static int oracle_preset_lookup(const char *name, oracle_preset *p)
 
 static float maxf(float a, float b) { return a > b ? a : b; }
 
+/* Reduction accumulators.  Faithful mode (default) rounds to fp32 after every add =
+ * the reference's sequential `float` sums.  acc64 mode keeps fp64 sums and exists only so
+ * tests can measure how far reduction order alone moves the result (the parity noise floor). */
+static int g_acc64 = 0;
+static inline void acc_add(double *acc, float v)
+{
+    if (g_acc64) *acc += (double)v;
+    else *acc = (double)(float)((float)*acc + v);
+}
+
 /* e = b - P*x   (Backend.cpp:165-186 then :256-272 with a = -1) */
 static void residual(float *e, const float *b, const float *x, int w, int h, float alpha)
 {
@@ -70,15 +80,15 @@ static void residual(float *e, const float *b, const float *x, int w, int h, flo
 /* Backend.cpp:351-376 */
 static void calc_w2(float *w2, const float *e, size_t n3, float reg)
 {
-    float sum = 0.0f;
+    double sum = 0.0;
     for (size_t i = 0; i < n3; i++) {
         const float *v = e + 3 * i;
         float len = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
         float wi = 1.0f / (len + reg);
         w2[i] = wi;
-        sum += wi;
+        acc_add(&sum, wi);
     }
-    float coef = (float)(int)n3 / sum;
+    float coef = (float)(int)n3 / (float)sum;
     for (size_t i = 0; i < n3; i++) w2[i] *= coef;
 }
 
@@ -101,11 +111,11 @@ static void calc_PTW2x(float *r, const float *w2, const float *e, int w, int h, 
 }
 
 /* Ap = P' W2 P p ; pAp = sum p*Ap   (Backend.cpp:221-252) */
-static void calc_Ax_xAx(float *Ap, float pAp[3], const float *w2, const float *p, int w, int h, float alpha)
+static void calc_Ax_xAx(float *Ap, float pAp_out[3], const float *w2, const float *p, int w, int h, float alpha)
 {
     size_t n = (size_t)w * h;
     float alphaSqr = alpha * alpha;
-    pAp[0] = pAp[1] = pAp[2] = 0.0f;
+    double pAp[3] = {0.0, 0.0, 0.0};
     for (int yy = 0; yy < h; yy++)
         for (int xx = 0; xx < w; xx++) {
             size_t i = (size_t)yy * w + xx;
@@ -117,9 +127,10 @@ static void calc_Ax_xAx(float *Ap, float pAp[3], const float *w2, const float *p
                 if (yy != 0)     v += w2[2 * n + i - w] * (xi - p[3 * (i - w) + c]);
                 if (yy != h - 1) v += w2[2 * n + i]     * (xi - p[3 * (i + w) + c]);
                 Ap[3 * i + c] = v;
-                pAp[c] += xi * v;
+                acc_add(&pAp[c], xi * v);
             }
         }
+    for (int c = 0; c < 3; c++) pAp_out[c] = (float)pAp[c];
 }
 
 int gdb200_oracle_poisson_solve(const float *dx, const float *dy, const float *throughput,
@@ -160,9 +171,10 @@ int gdb200_oracle_poisson_solve(const float *dx, const float *dy, const float *t
         float rzA[3], rzB[3], pAp[3];
         float *rz = rzA, *rz2 = rzB;
         calc_PTW2x(r, w2, e, w, h, alpha);                                /* :403 */
-        rz[0] = rz[1] = rz[2] = 0.0f;                                     /* :404 */
+        double acc[3] = {0.0, 0.0, 0.0};                                  /* :404 */
         for (size_t i = 0; i < n; i++)
-            for (int c = 0; c < 3; c++) rz[c] += r[3 * i + c] * r[3 * i + c];
+            for (int c = 0; c < 3; c++) acc_add(&acc[c], r[3 * i + c] * r[3 * i + c]);
+        for (int c = 0; c < 3; c++) rz[c] = (float)acc[c];
         memcpy(p, r, sizeof(float) * n3);                                 /* :405 */
 
         for (int cg = 0;; cg++) {
@@ -174,13 +186,14 @@ int gdb200_oracle_poisson_solve(const float *dx, const float *dy, const float *t
             calc_Ax_xAx(Ap, pAp, w2, p, w, h, alpha);                     /* :467 */
             float a[3], bb[3];
             for (int c = 0; c < 3; c++) a[c] = rz2[c] / maxf(pAp[c], FLT_MIN);
-            rz[0] = rz[1] = rz[2] = 0.0f;                                 /* :468, Backend.cpp:296-321 */
+            acc[0] = acc[1] = acc[2] = 0.0;                               /* :468, Backend.cpp:296-321 */
             for (size_t i = 0; i < n; i++)
                 for (int c = 0; c < 3; c++) {
                     float ri = r[3 * i + c] - Ap[3 * i + c] * a[c];
                     r[3 * i + c] = ri;
-                    rz[c] += ri * ri;
+                    acc_add(&acc[c], ri * ri);
                 }
+            for (int c = 0; c < 3; c++) rz[c] = (float)acc[c];
             for (int c = 0; c < 3; c++) bb[c] = rz[c] / maxf(rz2[c], FLT_MIN);
             for (size_t i = 0; i < n; i++)                                /* :469, Backend.cpp:325-347 */
                 for (int c = 0; c < 3; c++) {
@@ -197,6 +210,18 @@ int gdb200_oracle_poisson_solve(const float *dx, const float *dy, const float *t
 
     free(b); free(e); free(w2); free(x); free(r); free(p); free(Ap);
     return 0;
+}
+
+/* Same algorithm with exact (fp64) reduction sums: NOT the reference's arithmetic, only a
+ * yardstick for reduction-order sensitivity. */
+int gdb200_oracle_poisson_solve_acc64(const float *dx, const float *dy, const float *throughput,
+                                      const float *direct, int w, int h, float alpha,
+                                      const char *preset, float *out_final)
+{
+    g_acc64 = 1;
+    int rc = gdb200_oracle_poisson_solve(dx, dy, throughput, direct, w, h, alpha, preset, out_final);
+    g_acc64 = 0;
+    return rc;
 }
 
 #ifdef __cplusplus

@@ -48,6 +48,16 @@ class Oracle:
         assert rc == 0
         return out
 
+    def poisson_acc64(self, dx, dy, thr, direct, alpha=0.2, preset="L1D"):
+        """Same algorithm with exact fp64 reduction sums: a yardstick for how far reduction
+        order alone moves the result (not the reference's arithmetic)."""
+        h, w, _ = dx.shape
+        out = np.empty_like(dx)
+        rc = self.lib.gdb200_oracle_poisson_solve_acc64(self._p(dx), self._p(dy), self._p(thr), self._p(direct),
+                                                        w, h, ctypes.c_float(alpha), preset.encode(), self._p(out))
+        assert rc == 0
+        return out
+
     def poisson_ref(self, dx, dy, thr, direct, alpha=0.2, preset="L1D"):
         h, w, _ = dx.shape
         out = np.empty_like(dx)

@@ -18,19 +18,31 @@ pytestmark = pytest.mark.gpu
 TOL = {"L2D": 1e-6, "L1D": 1e-5, "L2Q": 5e-6}
 
 
+def check_parity(oracle, d, w, h, alpha, preset, got, scale=1.0):
+    """got must match the faithful oracle within TOL, or — on tiny images, where IRLS
+    amplifies reduction-order noise beyond TOL — within 2x the distance that reduction
+    order alone moves the oracle itself (faithful fp32 sums vs exact sums)."""
+    ref = oracle.poisson(d["dx"], d["dy"], d["throughput"], d["direct"], alpha=alpha, preset=preset)
+    exact = oracle.poisson_acc64(d["dx"], d["dy"], d["throughput"], d["direct"], alpha=alpha, preset=preset)
+    floor = rmse(ref, exact)
+    err = rmse(got, ref)
+    assert err <= max(TOL[preset] * scale, 2.0 * floor), (err, floor, float(np.abs(got - ref).max()))
+    # the kernel's tree sums are near-exact, so it must sit at least as close to the exact-sum oracle
+    assert rmse(got, exact) <= max(TOL[preset] * scale, 2.0 * floor), (rmse(got, exact), floor)
+
+
 @pytest.mark.parametrize("size", [(512, 512), (64, 48), (33, 17), (130, 70), (257, 65)])
 @pytest.mark.parametrize("preset", ["L2D", "L1D"])
 def test_parity_vs_oracle(oracle, size, preset):
     w, h = size
     d = synth.solver_inputs(w, h, seed=1234, last_col_nonzero=True)
-    ref = oracle.poisson(d["dx"], d["dy"], d["throughput"], d["direct"], alpha=0.2, preset=preset)
     st = gdb200.Stats()
     got = gdb200.poisson_solve(d["dx"], d["dy"], d["throughput"], d["direct"], w, h, 0.2, preset, stats=st)
     assert st.launches == 1
     assert st.irls_iters == (20 if preset == "L1D" else 1)
     assert st.cg_iters == st.irls_iters * 50
     assert np.isfinite(got).all()
-    assert rmse(got, ref) <= TOL[preset], (rmse(got, ref), np.abs(got - ref).max())
+    check_parity(oracle, d, w, h, 0.2, preset, got)
 
 
 @pytest.mark.parametrize("size", [(1, 1), (2, 1), (1, 5), (3, 3), (4, 4), (5, 2), (67, 3)])
@@ -38,9 +50,8 @@ def test_tiny_and_ragged_sizes(oracle, size):
     w, h = size
     d = synth.solver_inputs(w, h, seed=9, last_col_nonzero=True)
     for preset in ("L2D", "L1D"):
-        ref = oracle.poisson(d["dx"], d["dy"], d["throughput"], d["direct"], preset=preset)
         got = gdb200.poisson_solve(d["dx"], d["dy"], d["throughput"], d["direct"], w, h, 0.2, preset)
-        assert rmse(got, ref) <= TOL[preset] * 5
+        check_parity(oracle, d, w, h, 0.2, preset, got)
 
 
 def test_null_direct_and_null_throughput(oracle):
@@ -58,9 +69,8 @@ def test_null_direct_and_null_throughput(oracle):
 def test_alpha_sweep(oracle, alpha):
     w, h = 160, 96
     d = synth.solver_inputs(w, h, seed=21)
-    ref = oracle.poisson(d["dx"], d["dy"], d["throughput"], d["direct"], alpha=alpha, preset="L1D")
     got = gdb200.poisson_solve(d["dx"], d["dy"], d["throughput"], d["direct"], w, h, alpha, "L1D")
-    assert rmse(got, ref) <= 1e-5
+    check_parity(oracle, d, w, h, alpha, "L1D", got)
 
 
 @pytest.mark.parametrize("preset", ["L2D", "L1D"])
