@@ -93,6 +93,116 @@ int gdb200_poisson_solve(const float *dx, const float *dy, const float *throughp
                          const float *direct, int w, int h, float alpha,
                          const char *preset, float *out_final, gdb200_stats *stats);
 
+
+/* ------------------------------------------------------ flattened scene */
+
+/* The plugin shim flattens Mitsuba's Scene into these plain structs once per
+ * render.  All reals are fp64 (the reference requires a
+ * DOUBLE_PRECISION build, README.txt:115-118).  Matrices are row-major 4x4. */
+
+enum { GDB200_SHAPE_RECTANGLE = 0,   /* src/shapes/rectangle.cpp: unit square [-1,1]^2 in z=0 under to_world */
+       GDB200_SHAPE_SPHERE    = 1,   /* src/shapes/sphere.cpp: centre + radius (no rotation)               */
+       GDB200_SHAPE_MESH      = 2 }; /* TriMesh without vertex normals: triangles [first_tri, first_tri+tri_count) */
+
+enum { GDB200_BSDF_DIFFUSE        = 0,   /* src/bsdfs/diffuse.cpp        */
+       GDB200_BSDF_ROUGHCONDUCTOR = 1,   /* src/bsdfs/roughconductor.cpp (sampleVisible = true) */
+       GDB200_BSDF_CONDUCTOR      = 2,   /* src/bsdfs/conductor.cpp      */
+       GDB200_BSDF_DIELECTRIC     = 3 }; /* src/bsdfs/dielectric.cpp     */
+
+enum { GDB200_MICROFACET_BECKMANN = 0, GDB200_MICROFACET_GGX = 1 };   /* src/bsdfs/microfacet.h */
+
+typedef struct gdb200_camera {          /* src/sensors/perspective.cpp:126-180,271-298 */
+    double sample_to_camera[16];        /* m_sampleToCamera (projective)               */
+    double camera_to_world[16];         /* m_worldTransform at shutter open            */
+    double near_clip, far_clip;
+    int    width, height;               /* film / crop size                            */
+} gdb200_camera;
+
+typedef struct gdb200_shape {
+    int    type;                        /* GDB200_SHAPE_*                              */
+    int    material;                    /* index into materials (every shape has one; shape.cpp:48-72) */
+    int    emitter;                     /* index into emitters or -1                   */
+    int    flip_normals;                /* sphere only                                 */
+    double to_world[16], to_object[16]; /* rectangle                                   */
+    double center[3], radius;           /* sphere                                      */
+    int    first_tri, tri_count;        /* mesh                                        */
+} gdb200_shape;
+
+typedef struct gdb200_material {
+    int    type;                        /* GDB200_BSDF_*                               */
+    int    distribution;                /* GDB200_MICROFACET_* (roughconductor)        */
+    double reflectance[3];              /* diffuse                                     */
+    double specular_reflectance[3];     /* conductors, dielectric                      */
+    double specular_transmittance[3];   /* dielectric                                  */
+    double eta[3], k[3];                /* conductors: complex IOR per channel         */
+    double alpha;                       /* roughconductor                              */
+    double ior_ratio;                   /* dielectric: intIOR / extIOR                 */
+} gdb200_material;
+
+typedef struct gdb200_emitter {         /* src/emitters/area.cpp                       */
+    int    shape;                       /* the (rectangle) shape that emits            */
+    int    reserved;
+    double radiance[3];
+    double sampling_weight;             /* emitter.cpp:103, default 1                  */
+} gdb200_emitter;
+
+typedef struct gdb200_scene_desc {
+    gdb200_camera          camera;
+    double                 rfilter_radius;   /* box filter radius incl. its +1e-5 (box.cpp:38) */
+    int                    n_shapes, n_materials, n_emitters, n_vertices, n_triangles;
+    const gdb200_shape    *shapes;
+    const gdb200_material *materials;
+    const gdb200_emitter  *emitters;
+    const double          *vertices;         /* n_vertices * 3                          */
+    const int             *triangles;        /* n_triangles * 3 vertex indices          */
+} gdb200_scene_desc;
+
+/* ------------------------------------------------------- G-PT integrator */
+
+/* Same names, defaults and validation as the reference's XML parameters
+ * (gpt.cpp:1194-1210, integrator.cpp:190-225, docs.xml:537-559). */
+typedef struct gdb200_gpt_params {
+    int      max_depth;          /* maxDepth, -1 = infinite                         */
+    int      rr_depth;           /* rrDepth (5)                                     */
+    int      strict_normals;     /* strictNormals (false)                           */
+    double   shift_threshold;    /* shiftThreshold (0.001)                          */
+    int      spp;                /* sampler sampleCount                             */
+    int      reserved;
+    uint64_t seed;               /* gdb200_counter sampler seed                     */
+    int      y_begin, y_end;     /* rows of base pixels this call renders (tile sharding); 0,0 = all */
+} gdb200_gpt_params;
+
+/* Host output buffers, each width*height*3 fp64, interleaved RGB; any may be NULL.
+ * Developed like MultiFilm::developMulti (value * 1/weight, fmtconv.cpp:1036-1045). */
+typedef struct gdb200_buffers {
+    double *throughput, *dx, *dy, *direct, *preview_final;
+} gdb200_buffers;
+
+typedef struct gdb200_scene gdb200_scene;
+
+int  gdb200_scene_create(const gdb200_scene_desc *desc, gdb200_scene **out_scene);
+void gdb200_scene_destroy(gdb200_scene *scene);
+
+/* Renders the five G-PT buffers (replaces GradientPathIntegrator::render's
+ * scheduling of renderBlock, gpt.cpp:1397-1410 / 1220-1355).  Accumulators stay
+ * resident on the device inside `scene`; `out` (optional) receives developed copies. */
+int  gdb200_gpt_render(gdb200_scene *scene, const gdb200_gpt_params *params,
+                       gdb200_buffers *out, gdb200_stats *stats);
+
+/* Device pointers (fp32, w*h*3 interleaved) of the developed throughput, dx, dy
+ * and direct buffers after gdb200_gpt_render: the solver inputs of gpt.cpp:1439-1442. */
+int  gdb200_gpt_solver_inputs(gdb200_scene *scene, const float **d_dx, const float **d_dy,
+                              const float **d_throughput, const float **d_direct);
+
+/* Raw accumulators (value RGB + weight) for multi-GPU tile merging: 5 buffers
+ * [final,throughput,dx,dy,direct] x height x width x 4 fp64, device pointer. */
+int  gdb200_gpt_accumulators(gdb200_scene *scene, double **d_accum, size_t *bytes);
+/* Re-develop after the accumulators were modified externally (tile merge). */
+int  gdb200_gpt_develop(gdb200_scene *scene, gdb200_buffers *out);
+
+/* Asynchronous cancel (Integrator::cancel, integrator.h:77-84). */
+void gdb200_cancel(gdb200_scene *scene);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,1300 @@
+// TEST INFRASTRUCTURE — CPU oracle for the G-PT tracer (fp64, scalar, OpenMP over row bands).
+//
+// A restatement of the reference's algorithm for the hot path, each function citing the
+// reference file:line it follows:
+//   src/integrators/gpt/gpt.cpp:84-114,176-231,242-369,397-436,439-463,468-1180,1220-1355
+// plus the slice of Mitsuba the BASELINE scenes exercise: perspective sensor, rectangle /
+// sphere / flat triangle shapes, nearest-hit and shadow-ray epsilons of the kd-tree front end,
+// area emitters on rectangles, diffuse / roughconductor / conductor / dielectric BSDFs,
+// box reconstruction filter, ImageBlock::put and MultiFilm::developMulti semantics.
+//
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+// may load this.  The product (libgdb200.so) never links or calls it.
+//
+// PARITY UNPINNED: the reference ships no test, scene or golden image for gpt, and Mitsuba
+// itself cannot be built in this environment (Boost/Xerces/OpenEXR/Eigen absent), so this
+// restatement is checked only by its own invariants (tests/test_gpt_oracle.py): agreement of
+// throughput+direct with a restated plain MIS path tracer (gpt.cpp:1489-1662), gradient
+// antisymmetry, weight bookkeeping.  Known deliberate deviation: gpt.cpp:957 leaves
+// shiftedDRec.measure uninitialised; the intended ESolidAngle is used here.
+//
+// Random numbers: the `gdb200_counter` sampler.  Sampler::generate(pixel) (gpt.cpp:1250-1251)
+// re-keys a splitmix64 stream from (seed, pixel.x, pixel.y); next1D/next2D then consume that
+// stream sequentially over all spp samples of the pixel (gpt never calls advance()).
+#include "../include/gdb200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+namespace {
+
+typedef double Float;
+const Float Epsilon = 1e-7, ShadowEpsilon = 1e-5;          // constants.h:25-26 (DOUBLE_PRECISION)
+const Float DeltaEpsilon = (Float)1e-3f;                   // constants.h:31 (a float literal)
+const Float D_EPSILON = 1e-14;                             // gpt.cpp:63
+const Float PI = 3.14159265358979323846, INV_PI = 0.31830988618379067154;
+const Float INF = std::numeric_limits<Float>::infinity();
+
+// ---------------------------------------------------------------- vectors / spectra
+struct V3 { Float x, y, z; };
+inline V3 v3(Float x, Float y, Float z) { V3 r = {x, y, z}; return r; }
+inline V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+inline V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+inline V3 operator-(V3 a) { return v3(-a.x, -a.y, -a.z); }
+inline V3 operator*(V3 a, Float f) { return v3(a.x * f, a.y * f, a.z * f); }
+inline V3 operator*(Float f, V3 a) { return v3(a.x * f, a.y * f, a.z * f); }
+inline V3 operator*(V3 a, V3 b) { return v3(a.x * b.x, a.y * b.y, a.z * b.z); }   // spectra
+inline V3 operator/(V3 a, Float f) { Float r = (Float)1 / f; return v3(a.x * r, a.y * r, a.z * r); }  // vector.h:535-542
+inline Float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline V3 cross(V3 a, V3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+inline Float lengthSquared(V3 a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
+inline Float length(V3 a) { return std::sqrt(lengthSquared(a)); }
+inline V3 normalize(V3 a) { return a / length(a); }                               // vector.h:625-627
+inline bool isZero(V3 a) { return a.x == 0 && a.y == 0 && a.z == 0; }
+inline Float maxComp(V3 a) { return std::max(a.x, std::max(a.y, a.z)); }
+typedef V3 Spec;
+inline Spec spec(Float v) { return v3(v, v, v); }
+inline Spec specOf(const double *p) { return v3(p[0], p[1], p[2]); }
+inline Spec safeSqrt(Spec s) { return v3(std::sqrt(std::max(0.0, s.x)), std::sqrt(std::max(0.0, s.y)), std::sqrt(std::max(0.0, s.z))); }
+inline Spec operator/(Spec a, Spec b) { return v3(a.x / b.x, a.y / b.y, a.z / b.z); }
+
+struct Frame { V3 s, t, n; };
+inline V3 toLocal(const Frame &f, V3 v) { return v3(dot(v, f.s), dot(v, f.t), dot(v, f.n)); }     // frame.h:74-80
+inline V3 toWorld(const Frame &f, V3 v) { return f.s * v.x + f.t * v.y + f.n * v.z; }             // frame.h:83-85
+
+// transform.h:108-125 (points, projective), :128-137 (affine), :175-183 (vectors), :203-211 (normals)
+inline V3 xfPoint(const double *m, V3 p)
+{
+    Float x = m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3];
+    Float y = m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7];
+    Float z = m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11];
+    Float w = m[12] * p.x + m[13] * p.y + m[14] * p.z + m[15];
+    if (w == 1.0) return v3(x, y, z);
+    return v3(x, y, z) / w;
+}
+inline V3 xfAffine(const double *m, V3 p)
+{
+    return v3(m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3], m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7],
+              m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11]);
+}
+inline V3 xfVector(const double *m, V3 v)
+{
+    return v3(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[4] * v.x + m[5] * v.y + m[6] * v.z,
+              m[8] * v.x + m[9] * v.y + m[10] * v.z);
+}
+inline V3 xfNormal(const double *inv, V3 v)
+{
+    return v3(inv[0] * v.x + inv[4] * v.y + inv[8] * v.z, inv[1] * v.x + inv[5] * v.y + inv[9] * v.z,
+              inv[2] * v.x + inv[6] * v.y + inv[10] * v.z);
+}
+
+// util.cpp:592-601
+inline void coordinateSystem(V3 a, V3 &b, V3 &c)
+{
+    if (std::abs(a.x) > std::abs(a.y)) {
+        Float invLen = 1.0 / std::sqrt(a.x * a.x + a.z * a.z);
+        c = v3(a.z * invLen, 0.0, -a.x * invLen);
+    } else {
+        Float invLen = 1.0 / std::sqrt(a.y * a.y + a.z * a.z);
+        c = v3(0.0, a.z * invLen, -a.y * invLen);
+    }
+    b = cross(c, a);
+}
+// util.cpp:603-608
+inline void computeShadingFrame(V3 n, V3 dpdu, Frame &f)
+{
+    f.n = n;
+    f.s = normalize(dpdu - f.n * dot(f.n, dpdu));
+    f.t = cross(f.n, f.s);
+}
+
+// ---------------------------------------------------------------- sampler (gdb200_counter)
+struct Sampler {
+    uint64_t key, n;
+    static uint64_t mix(uint64_t z)
+    {
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+        return z ^ (z >> 31);
+    }
+    void generate(uint64_t seed, int px, int py)   // Sampler::generate(const Point2i&)
+    {
+        key = mix(mix(seed + 0x9E3779B97F4A7C15ULL) ^ ((uint64_t)(uint32_t)px | ((uint64_t)(uint32_t)py << 32)));
+        n = 0;
+    }
+    Float next1D()
+    {
+        n++;
+        return (Float)(mix(key + n * 0x9E3779B97F4A7C15ULL) >> 11) * (1.0 / 9007199254740992.0);
+    }
+    void next2D(Float &x, Float &y) { x = next1D(); y = next1D(); }
+};
+
+// ---------------------------------------------------------------- scene
+enum { EDiffuseReflection = 0x1, EGlossyReflection = 0x4, EDeltaReflection = 0x10, EDeltaTransmission = 0x20,
+       ESmooth = 0xF, EDelta = 0x30, ETransmissionBits = 0x2 | 0x8 | 0x20, EBackSide = 0x20000, EFrontSide = 0x10000 };
+enum Measure { ESolidAngle, EDiscrete };
+
+struct Tri { V3 p0, p1, p2; int k; Float n_u, n_v, n_d, a_u, a_v, b_nu, b_nv, c_nu, c_nv; int shape; };
+
+struct Shape {
+    gdb200_shape d;
+    V3 dpdu, dpdv; Frame frame; Float invArea;     // rectangle.cpp:100-110
+};
+
+struct Scene {
+    gdb200_camera cam;
+    Float invResX, invResY, filterRadius;
+    std::vector<Shape> shapes;
+    std::vector<gdb200_material> mats;
+    std::vector<gdb200_emitter> ems;
+    std::vector<Tri> tris;
+    std::vector<Float> emCdf;      // DiscreteDistribution over samplingWeight (scene.cpp:357-380)
+    Float emNormalization;
+};
+
+struct Its {
+    Float t; V3 p; V3 geoN; Frame sh; V3 wi; int shape;
+    bool valid() const { return t != INF; }
+};
+
+struct Ray { V3 o, d; Float mint, maxt; };
+inline V3 at(const Ray &r, Float t) { return r.o + r.d * t; }
+
+// triaccel.h:61-95
+bool triLoad(Tri &T, V3 A, V3 B, V3 C)
+{
+    static const int waldModulo[4] = {1, 2, 0, 1};
+    V3 b = C - A, c = B - A, N = cross(c, b);
+    const Float Nv[3] = {N.x, N.y, N.z}, bv[3] = {b.x, b.y, b.z}, cv[3] = {c.x, c.y, c.z}, Av[3] = {A.x, A.y, A.z};
+    int k = 0;
+    for (int j = 0; j < 3; j++) if (std::abs(Nv[j]) > std::abs(Nv[k])) k = j;
+    int u = waldModulo[k], v = waldModulo[k + 1];
+    const Float n_k = Nv[k], denom = bv[u] * cv[v] - bv[v] * cv[u];
+    T.p0 = A; T.p1 = B; T.p2 = C;
+    if (denom == 0) { T.k = 3; return false; }
+    T.k = k;
+    T.n_u = Nv[u] / n_k; T.n_v = Nv[v] / n_k; T.n_d = dot(A, N) / n_k;
+    T.b_nu = bv[u] / denom; T.b_nv = -bv[v] / denom; T.a_u = Av[u]; T.a_v = Av[v];
+    T.c_nu = cv[v] / denom; T.c_nv = -cv[u] / denom;
+    return true;
+}
+// triaccel.h:97-158
+inline bool triIntersect(const Tri &T, const Ray &ray, Float mint, Float maxt, Float &u, Float &v, Float &t)
+{
+    Float o_u, o_v, o_k, d_u, d_v, d_k;
+    switch (T.k) {
+        case 0: o_u = ray.o.y; o_v = ray.o.z; o_k = ray.o.x; d_u = ray.d.y; d_v = ray.d.z; d_k = ray.d.x; break;
+        case 1: o_u = ray.o.z; o_v = ray.o.x; o_k = ray.o.y; d_u = ray.d.z; d_v = ray.d.x; d_k = ray.d.y; break;
+        case 2: o_u = ray.o.x; o_v = ray.o.y; o_k = ray.o.z; d_u = ray.d.x; d_v = ray.d.y; d_k = ray.d.z; break;
+        default: return false;
+    }
+    t = (T.n_d - o_u * T.n_u - o_v * T.n_v - o_k) / (d_u * T.n_u + d_v * T.n_v + d_k);
+    if (t < mint || t > maxt) return false;
+    const Float hu = o_u + t * d_u - T.a_u, hv = o_v + t * d_v - T.a_v;
+    u = hv * T.b_nu + hu * T.b_nv;
+    v = hu * T.c_nu + hv * T.c_nv;
+    return u >= 0 && v >= 0 && u + v <= 1.0;
+}
+
+// rectangle.cpp:125-151
+inline bool rectIntersect(const Shape &s, const Ray &r, Float mint, Float maxt, Float &t)
+{
+    V3 o = xfAffine(s.d.to_object, r.o), d = xfVector(s.d.to_object, r.d);
+    Float hit = -o.z / d.z;
+    if (!(hit >= mint && hit <= maxt)) return false;
+    V3 local = o + d * hit;
+    if (std::abs(local.x) <= 1 && std::abs(local.y) <= 1) { t = hit; return true; }
+    return false;
+}
+
+// util.cpp:487-525
+inline bool solveQuadratic(double a, double b, double c, double &x0, double &x1)
+{
+    if (a == 0) { if (b != 0) { x0 = x1 = -c / b; return true; } return false; }
+    double discrim = b * b - 4.0 * a * c;
+    if (discrim < 0) return false;
+    double temp, sqrtDiscrim = std::sqrt(discrim);
+    if (b < 0) temp = -0.5 * (b - sqrtDiscrim); else temp = -0.5 * (b + sqrtDiscrim);
+    x0 = temp / a; x1 = c / temp;
+    if (x0 > x1) std::swap(x0, x1);
+    return true;
+}
+// sphere.cpp:163-187
+inline bool sphereIntersect(const Shape &s, const Ray &r, Float mint, Float maxt, Float &t)
+{
+    V3 o = r.o - specOf(s.d.center), d = r.d;
+    double A = lengthSquared(d), B = 2 * dot(o, d), C = lengthSquared(o) - s.d.radius * s.d.radius;
+    double nearT, farT;
+    if (!solveQuadratic(A, B, C, nearT, farT)) return false;
+    if (!(nearT <= maxt && farT >= mint)) return false;
+    if (nearT < mint) { if (farT > maxt) return false; t = farT; } else t = nearT;
+    return true;
+}
+
+// Nearest hit in [mint, maxt] over all primitives = what the kd-tree traversal returns
+// (sahkdtree3.h:179-308: every candidate is tested against the shrinking [mint,maxt]).
+// Returns primitive kind/index through (shape, tri, u, v).
+bool nearestHit(const Scene &sc, const Ray &ray, Float mint, Float maxt, bool anyHit, Float &tOut, int &shapeOut,
+                int &triOut, Float &uOut, Float &vOut)
+{
+    bool found = false;
+    for (size_t i = 0; i < sc.shapes.size(); i++) {
+        const Shape &s = sc.shapes[i];
+        Float t;
+        if (s.d.type == GDB200_SHAPE_RECTANGLE) {
+            if (rectIntersect(s, ray, mint, maxt, t)) { if (anyHit) return true; maxt = t; found = true; shapeOut = (int)i; triOut = -1; }
+        } else if (s.d.type == GDB200_SHAPE_SPHERE) {
+            if (sphereIntersect(s, ray, mint, maxt, t)) { if (anyHit) return true; maxt = t; found = true; shapeOut = (int)i; triOut = -1; }
+        }
+    }
+    for (size_t i = 0; i < sc.tris.size(); i++) {
+        Float t, u, v;
+        if (triIntersect(sc.tris[i], ray, mint, maxt, u, v, t)) {
+            if (anyHit) return true;
+            maxt = t; found = true; shapeOut = sc.tris[i].shape; triOut = (int)i; uOut = u; vOut = v;
+        }
+    }
+    tOut = maxt;
+    return found;
+}
+
+inline Float maxAbs(V3 o) { return std::max(std::max(std::abs(o.x), std::abs(o.y)), std::abs(o.z)); }
+
+// ShapeKDTree::rayIntersect(ray, its): skdtree.cpp:112-147 + skdtree.h:343-428
+bool rayIntersect(const Scene &sc, const Ray &ray, Its &its)
+{
+    its.t = INF;
+    Float rayMinT = ray.mint;
+    if (rayMinT == Epsilon) rayMinT *= std::max(maxAbs(ray.o), Epsilon);
+    if (!(ray.maxt > rayMinT)) return false;
+    Float t, u = 0, v = 0; int shape = -1, tri = -1;
+    if (!nearestHit(sc, ray, rayMinT, ray.maxt, false, t, shape, tri, u, v)) return false;
+    const Shape &s = sc.shapes[shape];
+    its.t = t; its.shape = shape;
+    V3 dpdu;
+    if (tri >= 0) {                                            // skdtree.h:348-419, BarycentricPos = true
+        const Tri &T = sc.tris[tri];
+        const V3 b = v3(1 - u - v, u, v);
+        its.p = T.p0 * b.x + T.p1 * b.y + T.p2 * b.z;
+        V3 side1 = T.p1 - T.p0, side2 = T.p2 - T.p0, faceNormal = cross(side1, side2);
+        Float len = length(faceNormal);
+        if (!isZero(faceNormal)) faceNormal = faceNormal / len;
+        dpdu = side1;
+        its.sh.n = faceNormal;
+        its.geoN = faceNormal;
+    } else if (s.d.type == GDB200_SHAPE_RECTANGLE) {           // rectangle.cpp:158-171
+        its.geoN = s.frame.n;
+        its.sh.n = s.frame.n;
+        dpdu = s.dpdu;
+        its.p = at(ray, its.t);
+    } else {                                                   // sphere.cpp:197-240 (identity rotation)
+        its.p = at(ray, its.t);
+        V3 c = specOf(s.d.center), local = its.p - c;
+        dpdu = v3(-local.y, local.x, 0) * (2 * PI);
+        its.geoN = normalize(its.p - c);
+        if (s.d.flip_normals) its.geoN = its.geoN * -1.0;
+        its.sh.n = its.geoN;
+    }
+    computeShadingFrame(its.sh.n, dpdu, its.sh);               // skdtree.h:425
+    its.wi = toLocal(its.sh, -ray.d);                          // skdtree.h:426
+    return true;
+}
+
+// ShapeKDTree::rayIntersect(ray) — shadow rays: skdtree.cpp:206-226 (no Epsilon floor on the scale)
+bool rayOccluded(const Scene &sc, const Ray &ray)
+{
+    Float rayMinT = ray.mint;
+    if (rayMinT == Epsilon) rayMinT *= maxAbs(ray.o);
+    if (!(ray.maxt > rayMinT)) return false;
+    Float t, u, v; int a, b;
+    return nearestHit(sc, ray, rayMinT, ray.maxt, true, t, a, b, u, v);
+}
+
+// ---------------------------------------------------------------- BSDFs
+inline unsigned bsdfType(const gdb200_material &m)
+{
+    switch (m.type) {
+        case GDB200_BSDF_DIFFUSE:   // diffuse.cpp:97-101: no component at all when the reflectance is black
+            return (std::max(m.reflectance[0], std::max(m.reflectance[1], m.reflectance[2])) > 0) ? (EDiffuseReflection | EFrontSide) : 0;
+        case GDB200_BSDF_ROUGHCONDUCTOR: return EGlossyReflection | EFrontSide;
+        case GDB200_BSDF_CONDUCTOR: return EDeltaReflection | EFrontSide;
+        default: return EDeltaReflection | EDeltaTransmission | EFrontSide | EBackSide;
+    }
+}
+inline int bsdfComponentCount(const gdb200_material &m)
+{
+    if (m.type == GDB200_BSDF_DIELECTRIC) return 2;
+    if (m.type == GDB200_BSDF_DIFFUSE) return bsdfType(m) ? 1 : 0;
+    return 1;
+}
+inline Float bsdfRoughness(const gdb200_material &m, int)
+{
+    switch (m.type) {
+        case GDB200_BSDF_DIFFUSE: return INF;                               // diffuse.cpp:167-169
+        case GDB200_BSDF_ROUGHCONDUCTOR: return 0.5 * (m.alpha + m.alpha);  // roughconductor.cpp:437-440
+        default: return 0.0;                                                // conductor.cpp:287, dielectric.cpp:393
+    }
+}
+inline Float bsdfEta(const gdb200_material &m) { return m.type == GDB200_BSDF_DIELECTRIC ? m.ior_ratio : 1.0; }  // bsdf.cpp:62-64, dielectric.cpp:389
+
+// warp.cpp:81-102
+inline void squareToUniformDiskConcentric(Float sx, Float sy, Float &ox, Float &oy)
+{
+    Float r1 = 2.0 * sx - 1.0, r2 = 2.0 * sy - 1.0, phi, r;
+    if (r1 == 0 && r2 == 0) { r = phi = 0; }
+    else if (r1 * r1 > r2 * r2) { r = r1; phi = (PI / 4.0) * (r2 / r1); }
+    else { r = r2; phi = (PI / 2.0) - (r1 / r2) * (PI / 4.0); }
+    ox = r * std::cos(phi); oy = r * std::sin(phi);
+}
+// warp.cpp:43-52
+inline V3 squareToCosineHemisphere(Float sx, Float sy)
+{
+    Float px, py;
+    squareToUniformDiskConcentric(sx, sy, px, py);
+    Float z = std::sqrt(std::max(0.0, 1.0 - px * px - py * py));
+    if (z == 0) z = (Float)1e-10f;
+    return v3(px, py, z);
+}
+
+// ---- microfacet.h (isotropic, sampleVisible = true)
+struct Microfacet {
+    int type; Float alpha;
+    Microfacet(int t, Float a) : type(t), alpha(std::max(a, (Float)1e-4f)) {}        // microfacet.h:67-71
+    Float eval(V3 m) const                                                            // :191-235
+    {
+        if (m.z <= 0) return 0.0;
+        Float cosTheta2 = m.z * m.z;
+        Float beckmannExponent = ((m.x * m.x) / (alpha * alpha) + (m.y * m.y) / (alpha * alpha)) / cosTheta2;
+        Float result;
+        if (type == GDB200_MICROFACET_BECKMANN)
+            result = std::exp(-beckmannExponent) / (PI * alpha * alpha * cosTheta2 * cosTheta2);
+        else {
+            Float root = ((Float)1 + beckmannExponent) * cosTheta2;
+            result = (Float)1 / (PI * alpha * alpha * root * root);
+        }
+        if (result * m.z < (Float)1e-20f) result = 0;
+        return result;
+    }
+    Float smithG1(V3 v, V3 m) const                                                   // :470-508
+    {
+        if (dot(v, m) * v.z <= 0) return 0.0;
+        Float temp = 1 - v.z * v.z;
+        Float tanTheta = temp <= 0.0 ? 0.0 : std::abs(std::sqrt(temp) / v.z);         // frame.h tanTheta
+        if (tanTheta == 0.0) return 1.0;
+        if (type == GDB200_MICROFACET_BECKMANN) {
+            Float a = 1.0 / (alpha * tanTheta);
+            if (a >= (Float)1.6f) return 1.0;
+            Float aSqr = a * a;
+            return ((Float)3.535f * a + (Float)2.181f * aSqr) / (1.0 + (Float)2.276f * a + (Float)2.577f * aSqr);
+        }
+        Float root = alpha * tanTheta, r;                                             // math.cpp:89-101 hypot2(1, root)
+        if (1.0 > std::abs(root)) { r = root / 1.0; r = 1.0 * std::sqrt(1.0 + r * r); }
+        else if (root != 0.0) { r = 1.0 / root; r = std::abs(root) * std::sqrt(1.0 + r * r); }
+        else r = 0.0;
+        return 2.0 / (1.0 + r);
+    }
+    Float G(V3 wi, V3 wo, V3 m) const { return smithG1(wi, m) * smithG1(wo, m); }     // :514-516
+    Float pdfVisible(V3 wi, V3 m) const                                               // :455-459
+    {
+        if (wi.z == 0) return 0.0;
+        return smithG1(wi, m) * std::abs(dot(wi, m)) * eval(m) / std::abs(wi.z);
+    }
+    void sampleVisible11(Float thetaI, Float sx, Float sy, Float &slopeX, Float &slopeY) const   // :573-696
+    {
+        const Float SQRT_PI_INV = 1 / std::sqrt(PI);
+        if (type == GDB200_MICROFACET_BECKMANN) {
+            if (thetaI < (Float)1e-4f) {
+                Float r = std::sqrt(-std::log(1.0 - sx));
+                Float sinPhi = std::sin(2 * PI * sy), cosPhi = std::cos(2 * PI * sy);
+                slopeX = r * cosPhi; slopeY = r * sinPhi; return;
+            }
+            Float tanThetaI = std::tan(thetaI), cotThetaI = 1 / tanThetaI;
+            Float a = -1, c = mtsErf(cotThetaI);
+            Float sample_x = std::max(sx, (Float)1e-6f);
+            Float fit = 1 + thetaI * ((Float)-0.876f + thetaI * ((Float)0.4265f - (Float)0.0594f * thetaI));
+            Float b = c - (1 + c) * std::pow(1 - sample_x, fit);
+            Float normalization = 1 / (1 + c + SQRT_PI_INV * tanThetaI * std::exp(-cotThetaI * cotThetaI));
+            int it = 0;
+            while (++it < 10) {
+                if (!(b >= a && b <= c)) b = 0.5 * (a + c);
+                Float invErf = erfinv(b);
+                Float value = normalization * (1 + b + SQRT_PI_INV * tanThetaI * std::exp(-invErf * invErf)) - sample_x;
+                Float derivative = normalization * (1 - invErf * tanThetaI);
+                if (std::abs(value) < (Float)1e-5f) break;
+                if (value > 0) c = b; else a = b;
+                b -= value / derivative;
+            }
+            slopeX = erfinv(b);
+            slopeY = erfinv(2.0 * std::max(sy, (Float)1e-6f) - 1.0);
+            return;
+        }
+        if (thetaI < (Float)1e-4f) {
+            Float r = std::sqrt(std::max(0.0, sx / (1 - sx)));
+            Float sinPhi = std::sin(2 * PI * sy), cosPhi = std::cos(2 * PI * sy);
+            slopeX = r * cosPhi; slopeY = r * sinPhi; return;
+        }
+        Float tanThetaI = std::tan(thetaI);
+        Float a = 1 / tanThetaI;
+        Float G1 = 2.0 / (1.0 + std::sqrt(std::max(0.0, 1.0 + 1.0 / (a * a))));
+        Float A = 2.0 * sx / G1 - 1.0;
+        if (std::abs(A) == 1) A -= std::copysign(1.0, A) * Epsilon;
+        Float tmp = 1.0 / (A * A - 1.0);
+        Float B = tanThetaI;
+        Float D = std::sqrt(std::max(0.0, B * B * tmp * tmp - (A * A - B * B) * tmp));
+        Float slope_x_1 = B * tmp - D, slope_x_2 = B * tmp + D;
+        slopeX = (A < 0.0 || slope_x_2 > 1.0 / tanThetaI) ? slope_x_1 : slope_x_2;
+        Float S;
+        if (sy > 0.5) { S = 1.0; sy = 2.0 * (sy - 0.5); } else { S = -1.0; sy = 2.0 * (0.5 - sy); }
+        Float z = (sy * (sy * (sy * (-(Float)0.365728915865723) + (Float)0.790235037209296) - (Float)0.424965825137544) + (Float)0.000152998850436920) /
+                  (sy * (sy * (sy * (sy * (Float)0.169507819808272 - (Float)0.397203533833404) - (Float)0.232500544458471) + (Float)1) - (Float)0.539825872510702);
+        slopeY = S * z * std::sqrt(1.0 + slopeX * slopeX);
+    }
+    // math.cpp:55-72 math::erf (Abramowitz & Stegun 7.1.26, not libm's erf)
+    static Float mtsErf(Float x)
+    {
+        const Float a1 = 0.254829592, a2 = -0.284496736, a3 = 1.421413741, a4 = -1.453152027, a5 = 1.061405429, p = 0.3275911;
+        Float sign = std::copysign(1.0, x);
+        x = std::abs(x);
+        Float t = 1.0 / (1.0 + p * x);
+        Float y = 1.0 - (((((a5 * t + a4) * t) + a3) * t + a2) * t + a1) * t * std::exp(-x * x);
+        return sign * y;
+    }
+    // math.cpp:25-53 math::erfinv (Giles' polynomial)
+    static Float erfinv(Float x)
+    {
+        Float w = -std::log(((Float)1 - x) * ((Float)1 + x)), p;
+        if (w < (Float)5) {
+            w = w - (Float)2.5;
+            p = (Float)2.81022636e-08; p = (Float)3.43273939e-07 + p * w; p = (Float)-3.5233877e-06 + p * w;
+            p = (Float)-4.39150654e-06 + p * w; p = (Float)0.00021858087 + p * w; p = (Float)-0.00125372503 + p * w;
+            p = (Float)-0.00417768164 + p * w; p = (Float)0.246640727 + p * w; p = (Float)1.50140941 + p * w;
+        } else {
+            w = std::sqrt(w) - (Float)3;
+            p = (Float)-0.000200214257; p = (Float)0.000100950558 + p * w; p = (Float)0.00134934322 + p * w;
+            p = (Float)-0.00367342844 + p * w; p = (Float)0.00573950773 + p * w; p = (Float)-0.0076224613 + p * w;
+            p = (Float)0.00943887047 + p * w; p = (Float)1.00167406 + p * w; p = (Float)2.83297682 + p * w;
+        }
+        return p * x;
+    }
+    V3 sampleVisible(V3 _wi, Float sx, Float sy) const                                // :421-452
+    {
+        V3 wi = normalize(v3(alpha * _wi.x, alpha * _wi.y, _wi.z));
+        Float theta = 0, phi = 0;
+        if (wi.z < (Float)0.99999) { theta = std::acos(wi.z); phi = std::atan2(wi.y, wi.x); }
+        Float sinPhi = std::sin(phi), cosPhi = std::cos(phi);
+        Float slx, sly;
+        sampleVisible11(theta, sx, sy, slx, sly);
+        Float rx = cosPhi * slx - sinPhi * sly, ry = sinPhi * slx + cosPhi * sly;
+        rx *= alpha; ry *= alpha;
+        Float normalization = (Float)1 / std::sqrt(rx * rx + ry * ry + (Float)1.0);
+        return v3(-rx * normalization, -ry * normalization, normalization);
+    }
+};
+
+// util.cpp:739-761
+inline Spec fresnelConductorExact(Float cosThetaI, Spec eta, Spec k)
+{
+    Float cosThetaI2 = cosThetaI * cosThetaI, sinThetaI2 = 1 - cosThetaI2, sinThetaI4 = sinThetaI2 * sinThetaI2;
+    Spec temp1 = eta * eta - k * k - spec(sinThetaI2);
+    Spec a2pb2 = safeSqrt(temp1 * temp1 + k * k * eta * eta * 4.0);
+    Spec a = safeSqrt((a2pb2 + temp1) * 0.5);
+    Spec term1 = a2pb2 + spec(cosThetaI2), term2 = a * (2 * cosThetaI);
+    Spec Rs2 = (term1 - term2) / (term1 + term2);
+    Spec term3 = a2pb2 * cosThetaI2 + spec(sinThetaI4), term4 = term2 * sinThetaI2;
+    Spec Rp2 = Rs2 * (term3 - term4) / (term3 + term4);
+    return 0.5 * (Rp2 + Rs2);
+}
+// util.cpp:651-681
+inline Float fresnelDielectricExt(Float cosThetaI_, Float &cosThetaT_, Float eta)
+{
+    if (eta == 1) { cosThetaT_ = -cosThetaI_; return 0.0; }
+    Float scale = (cosThetaI_ > 0) ? 1 / eta : eta, cosThetaTSqr = 1 - (1 - cosThetaI_ * cosThetaI_) * (scale * scale);
+    if (cosThetaTSqr <= 0.0) { cosThetaT_ = 0.0; return 1.0; }
+    Float cosThetaI = std::abs(cosThetaI_), cosThetaT = std::sqrt(cosThetaTSqr);
+    Float Rs = (cosThetaI - eta * cosThetaT) / (cosThetaI + eta * cosThetaT);
+    Float Rp = (eta * cosThetaI - cosThetaT) / (eta * cosThetaI + cosThetaT);
+    cosThetaT_ = (cosThetaI_ > 0) ? -cosThetaT : cosThetaT;
+    return 0.5 * (Rs * Rs + Rp * Rp);
+}
+inline V3 reflectLocal(V3 wi) { return v3(-wi.x, -wi.y, wi.z); }
+inline V3 refractLocal(const gdb200_material &m, V3 wi, Float cosThetaT)              // dielectric.cpp:223-226
+{
+    Float scale = -(cosThetaT < 0 ? 1.0 / m.ior_ratio : m.ior_ratio);
+    return v3(scale * wi.x, scale * wi.y, cosThetaT);
+}
+
+Spec bsdfEval(const gdb200_material &m, V3 wi, V3 wo, Measure measure)
+{
+    switch (m.type) {
+    case GDB200_BSDF_DIFFUSE:                                                          // diffuse.cpp:110-119
+        if (measure != ESolidAngle || wi.z <= 0 || wo.z <= 0) return spec(0);
+        return specOf(m.reflectance) * (INV_PI * wo.z);
+    case GDB200_BSDF_ROUGHCONDUCTOR: {                                                 // roughconductor.cpp:256-292
+        if (measure != ESolidAngle || wi.z <= 0 || wo.z <= 0) return spec(0);
+        V3 H = normalize(wo + wi);
+        Microfacet distr(m.distribution, m.alpha);
+        const Float D = distr.eval(H);
+        if (D == 0) return spec(0);
+        const Spec F = fresnelConductorExact(dot(wi, H), specOf(m.eta), specOf(m.k)) * specOf(m.specular_reflectance);
+        const Float G = distr.G(wi, wo, H);
+        Float model = D * G / (4.0 * wi.z);
+        return F * model;
+    }
+    case GDB200_BSDF_CONDUCTOR:                                                        // conductor.cpp:221-235
+        if (measure != EDiscrete || wi.z <= 0 || wo.z <= 0 || std::abs(dot(reflectLocal(wi), wo) - 1) > DeltaEpsilon) return spec(0);
+        return specOf(m.specular_reflectance) * fresnelConductorExact(wi.z, specOf(m.eta), specOf(m.k));
+    default: {                                                                         // dielectric.cpp:228-254
+        bool discrete = measure == EDiscrete;
+        Float cosThetaT, F = fresnelDielectricExt(wi.z, cosThetaT, m.ior_ratio);
+        if (wi.z * wo.z >= 0) {
+            if (!discrete || std::abs(dot(reflectLocal(wi), wo) - 1) > DeltaEpsilon) return spec(0);
+            return specOf(m.specular_reflectance) * F;
+        }
+        if (!discrete || std::abs(dot(refractLocal(m, wi, cosThetaT), wo) - 1) > DeltaEpsilon) return spec(0);
+        Float factor = cosThetaT < 0 ? 1.0 / m.ior_ratio : m.ior_ratio;
+        return specOf(m.specular_transmittance) * factor * factor * (1 - F);
+    }
+    }
+}
+
+Float bsdfPdf(const gdb200_material &m, V3 wi, V3 wo, Measure measure)
+{
+    switch (m.type) {
+    case GDB200_BSDF_DIFFUSE:                                                          // diffuse.cpp:121-129
+        if (measure != ESolidAngle || wi.z <= 0 || wo.z <= 0) return 0.0;
+        return INV_PI * wo.z;
+    case GDB200_BSDF_ROUGHCONDUCTOR: {                                                 // roughconductor.cpp:294-320
+        if (measure != ESolidAngle || wi.z <= 0 || wo.z <= 0) return 0.0;
+        V3 H = normalize(wo + wi);
+        Microfacet distr(m.distribution, m.alpha);
+        return distr.eval(H) * distr.smithG1(wi, H) / (4.0 * wi.z);
+    }
+    case GDB200_BSDF_CONDUCTOR:                                                        // conductor.cpp:237-250
+        if (measure != EDiscrete || wi.z <= 0 || wo.z <= 0 || std::abs(dot(reflectLocal(wi), wo) - 1) > DeltaEpsilon) return 0.0;
+        return 1.0;
+    default: {                                                                         // dielectric.cpp:256-275
+        bool discrete = measure == EDiscrete;
+        Float cosThetaT, F = fresnelDielectricExt(wi.z, cosThetaT, m.ior_ratio);
+        if (wi.z * wo.z >= 0) {
+            if (!discrete || std::abs(dot(reflectLocal(wi), wo) - 1) > DeltaEpsilon) return 0.0;
+            return F;
+        }
+        if (!discrete || std::abs(dot(refractLocal(m, wi, cosThetaT), wo) - 1) > DeltaEpsilon) return 0.0;
+        return 1 - F;
+    }
+    }
+}
+
+struct BSDFSample { V3 wi, wo; Float eta; unsigned sampledType; Spec weight; Float pdf; };
+
+// BSDF::sample(bRec, pdf, sample) with pdf pre-set to 0 by the caller (gpt.cpp:450-457)
+void bsdfSample(const gdb200_material &m, BSDFSample &r, Float sx, Float sy)
+{
+    r.weight = spec(0); r.pdf = 0; r.eta = 1.0; r.sampledType = 0; r.wo = v3(0, 0, 0);
+    switch (m.type) {
+    case GDB200_BSDF_DIFFUSE:                                                          // diffuse.cpp:143-153
+        if (r.wi.z <= 0) return;
+        r.wo = squareToCosineHemisphere(sx, sy);
+        r.sampledType = EDiffuseReflection;
+        r.pdf = INV_PI * r.wo.z;
+        r.weight = specOf(m.reflectance);
+        return;
+    case GDB200_BSDF_ROUGHCONDUCTOR: {                                                 // roughconductor.cpp:369-419
+        if (r.wi.z < 0) return;
+        Microfacet distr(m.distribution, m.alpha);
+        V3 mm = distr.sampleVisible(r.wi, sx, sy);
+        Float temporaryPdf = distr.pdfVisible(r.wi, mm);
+        if (temporaryPdf == 0) return;
+        r.wo = 2 * dot(r.wi, mm) * mm - r.wi;
+        r.sampledType = EGlossyReflection;
+        if (r.wo.z <= 0) return;
+        Spec F = fresnelConductorExact(dot(r.wi, mm), specOf(m.eta), specOf(m.k)) * specOf(m.specular_reflectance);
+        Float weight = distr.smithG1(r.wo, mm);
+        if (weight > 0) { r.pdf = temporaryPdf / (4.0 * dot(r.wo, mm)); r.weight = F * weight; }
+        return;
+    }
+    case GDB200_BSDF_CONDUCTOR:                                                        // conductor.cpp:268-285
+        if (r.wi.z <= 0) return;
+        r.sampledType = EDeltaReflection;
+        r.wo = reflectLocal(r.wi);
+        r.pdf = 1;
+        r.weight = specOf(m.specular_reflectance) * fresnelConductorExact(r.wi.z, specOf(m.eta), specOf(m.k));
+        return;
+    default: {                                                                         // dielectric.cpp:277-305
+        Float cosThetaT, F = fresnelDielectricExt(r.wi.z, cosThetaT, m.ior_ratio);
+        if (sx <= F) {
+            r.sampledType = EDeltaReflection; r.wo = reflectLocal(r.wi); r.eta = 1.0; r.pdf = F;
+            r.weight = specOf(m.specular_reflectance);
+        } else {
+            r.sampledType = EDeltaTransmission; r.wo = refractLocal(m, r.wi, cosThetaT);
+            r.eta = cosThetaT < 0 ? m.ior_ratio : 1.0 / m.ior_ratio; r.pdf = 1 - F;
+            Float factor = cosThetaT < 0 ? 1.0 / m.ior_ratio : m.ior_ratio;
+            r.weight = specOf(m.specular_transmittance) * (factor * factor);
+        }
+        return;
+    }
+    }
+}
+
+// ---------------------------------------------------------------- emitters
+struct DRec { V3 ref, refN, p, n, d; Float dist, pdf; int emitter; };   // DirectSamplingRecord (measure: solid angle)
+
+inline const gdb200_material &matOf(const Scene &sc, const Its &its) { return sc.mats[sc.shapes[its.shape].d.material]; }
+inline bool isEmitter(const Scene &sc, const Its &its) { return sc.shapes[its.shape].d.emitter >= 0; }
+// Intersection::Le -> AreaLight::eval, area.cpp:104-109
+inline Spec emittedLe(const Scene &sc, const Its &its, V3 d)
+{
+    if (dot(its.sh.n, d) <= 0) return spec(0);
+    return specOf(sc.ems[sc.shapes[its.shape].d.emitter].radiance);
+}
+// records.inl:160-165
+inline void initDRec(const Scene &sc, const Its &ref, DRec &r)
+{
+    r.ref = ref.p;
+    r.refN = v3(0, 0, 0);
+    if ((bsdfType(matOf(sc, ref)) & (ETransmissionBits | EBackSide)) == 0) r.refN = ref.sh.n;
+}
+
+// Scene::sampleEmitterDirectVisible, scene.cpp:855-879 (+ pmf.h:124-188, area.cpp:158-176,
+// shape.cpp:102-114, rectangle.cpp:210-216).  Returns value = Le/pdf (0 when occluded).
+Spec sampleEmitterDirectVisible(const Scene &sc, DRec &dRec, Float sx, Float sy, bool &visible)
+{
+    // DiscreteDistribution::sampleReuse
+    size_t nE = sc.ems.size();
+    size_t entry = std::lower_bound(sc.emCdf.begin(), sc.emCdf.end(), sx) - sc.emCdf.begin();
+    size_t index = std::min(nE - 1, (size_t)std::max((ptrdiff_t)0, (ptrdiff_t)entry - 1));
+    while (sc.emCdf[index + 1] - sc.emCdf[index] == 0 && index < nE) ++index;
+    Float emPdf = sc.emCdf[index + 1] - sc.emCdf[index];
+    sx = (sx - sc.emCdf[index]) / (sc.emCdf[index + 1] - sc.emCdf[index]);
+
+    const gdb200_emitter &em = sc.ems[index];
+    const Shape &s = sc.shapes[em.shape];
+    dRec.p = xfPoint(s.d.to_world, v3(sx * 2 - 1, sy * 2 - 1, 0));
+    dRec.n = s.frame.n;
+    dRec.pdf = s.invArea;
+    dRec.d = dRec.p - dRec.ref;
+    Float distSquared = lengthSquared(dRec.d);
+    dRec.dist = std::sqrt(distSquared);
+    dRec.d = dRec.d / dRec.dist;
+    Float dp = std::abs(dot(dRec.d, dRec.n));
+    dRec.pdf *= dp != 0 ? (distSquared / dp) : 0.0;
+    Spec value;
+    if (dot(dRec.d, dRec.refN) >= 0 && dot(dRec.d, dRec.n) < 0 && dRec.pdf != 0) value = specOf(em.radiance) / dRec.pdf;
+    else { dRec.pdf = 0.0; value = spec(0); }
+    dRec.emitter = (int)index;
+    dRec.pdf *= emPdf;
+    value = value / emPdf;
+    Ray ray = {dRec.ref, dRec.d, Epsilon, dRec.dist * (1 - ShadowEpsilon)};
+    if (rayOccluded(sc, ray)) { visible = false; return spec(0); }
+    visible = true;
+    return value;
+}
+
+// Scene::pdfEmitterDirect, scene.cpp:976-979 + area.cpp:178-186 + shape.cpp:116-126
+Float pdfEmitterDirect(const Scene &sc, const DRec &dRec)
+{
+    const gdb200_emitter &em = sc.ems[dRec.emitter];
+    Float pdf = 0.0;
+    if (dot(dRec.d, dRec.refN) >= 0 && dot(dRec.d, dRec.n) < 0)
+        pdf = sc.shapes[em.shape].invArea * (dRec.dist * dRec.dist) / std::abs(dot(dRec.d, dRec.n));
+    return pdf * (em.sampling_weight * sc.emNormalization);
+}
+
+// ---------------------------------------------------------------- G-PT
+enum VertexType { VERTEX_TYPE_GLOSSY, VERTEX_TYPE_DIFFUSE };
+enum RayConnection { RAY_NOT_CONNECTED, RAY_RECENTLY_CONNECTED, RAY_CONNECTED };
+
+struct Config { int maxDepth, minDepth, rrDepth; bool strictNormals; Float shiftThreshold; };
+
+struct RayState {                      // gpt.cpp:135-173
+    Ray ray; Spec throughput; Float pdf; Spec radiance, gradient; Its its; Float eta; bool alive; RayConnection connection_status;
+    RayState() : throughput(spec(0)), pdf(1.0), radiance(spec(0)), gradient(spec(0)), eta(1.0), alive(true), connection_status(RAY_NOT_CONNECTED) {}
+    void addRadiance(Spec c, Float w) { radiance = radiance + c * w; }
+    void addGradient(Spec c, Float w) { gradient = gradient + c * w; }
+};
+
+// gpt.cpp:176-226
+VertexType getVertexType(const gdb200_material &m, const Config &cfg, unsigned bsdfTypeMask)
+{
+    Float lowest = INF;
+    bool found_smooth = false, found_dirac = false;
+    for (int i = 0, n = bsdfComponentCount(m); i < n; ++i) {
+        Float r = bsdfRoughness(m, i);
+        if (r == 0) { found_dirac = true; if (!(bsdfTypeMask & EDelta)) continue; } else found_smooth = true;
+        if (r < lowest) lowest = r;
+    }
+    if (!found_smooth && found_dirac && !(bsdfTypeMask & EDelta)) lowest = 0;
+    return lowest <= cfg.shiftThreshold ? VERTEX_TYPE_GLOSSY : VERTEX_TYPE_DIFFUSE;
+}
+
+// util.cpp:763-765, :774-792
+inline V3 reflectAbout(V3 wi, V3 n) { return 2 * dot(wi, n) * n - wi; }
+inline V3 refractAbout(V3 wi, V3 n, Float eta)
+{
+    if (eta == 1) return -wi;
+    Float cosThetaI = dot(wi, n);
+    if (cosThetaI > 0) eta = 1 / eta;
+    Float cosThetaTSqr = 1 - (1 - cosThetaI * cosThetaI) * (eta * eta);
+    if (cosThetaTSqr <= 0.0) return v3(0, 0, 0);
+    return n * (cosThetaI * eta - std::copysign(1.0, cosThetaI) * std::sqrt(cosThetaTSqr)) - wi * eta;
+}
+
+struct ShiftResult { bool success; Float jacobian; V3 wo; };
+
+// gpt.cpp:242-305
+ShiftResult halfVectorShift(V3 mainWi, V3 mainWo, V3 shiftedWi, Float mainEta, Float shiftedEta)
+{
+    ShiftResult result; result.success = false; result.jacobian = 0; result.wo = v3(0, 0, 0);
+    if (mainWi.z * mainWo.z < 0) {
+        if (mainEta == 1 || shiftedEta == 1) return result;
+        V3 hMain = (mainWi.z < 0) ? -(mainWi * mainEta + mainWo) : -(mainWi + mainWo * mainEta);
+        V3 h = normalize(hMain);
+        V3 shiftedWo = refractAbout(shiftedWi, h, shiftedEta);
+        if (isZero(shiftedWo)) return result;
+        V3 hShifted = (shiftedWi.z < 0) ? -(shiftedWi * shiftedEta + shiftedWo) : -(shiftedWi + shiftedWo * shiftedEta);
+        Float hLengthSquared = lengthSquared(hShifted) / (D_EPSILON + lengthSquared(hMain));
+        Float WoDotH = std::abs(dot(mainWo, h)) / (D_EPSILON + std::abs(dot(shiftedWo, h)));
+        result.success = true; result.wo = shiftedWo; result.jacobian = hLengthSquared * WoDotH;
+    } else {
+        V3 h = normalize(mainWi + mainWo);
+        V3 shiftedWo = reflectAbout(shiftedWi, h);
+        Float WoDotH = dot(shiftedWo, h) / dot(mainWo, h);
+        result.success = true; result.wo = shiftedWo; result.jacobian = std::abs(WoDotH);
+    }
+    return result;
+}
+
+// gpt.cpp:84-93
+bool testVisibility(const Scene &sc, V3 p1, V3 p2)
+{
+    Ray r = {p1, p2 - p1, Epsilon, 1.0 - ShadowEpsilon};
+    return !rayOccluded(sc, r);
+}
+// gpt.cpp:316-345
+ShiftResult reconnectShift(const Scene &sc, V3 mainSource, V3 target, V3 shiftSource, V3 targetNormal)
+{
+    ShiftResult result; result.success = false; result.jacobian = 0; result.wo = v3(0, 0, 0);
+    if (!testVisibility(sc, shiftSource, target)) return result;
+    V3 mainEdge = mainSource - target, shiftedEdge = shiftSource - target;
+    Float mainL2 = lengthSquared(mainEdge), shiftedL2 = lengthSquared(shiftedEdge);
+    V3 shiftedWo = -shiftedEdge / std::sqrt(shiftedL2);
+    Float mainOpposingCosine = dot(mainEdge, targetNormal) / std::sqrt(mainL2);
+    Float shiftedOpposingCosine = dot(shiftedWo, targetNormal);
+    result.jacobian = std::abs(shiftedOpposingCosine * mainL2) / (D_EPSILON + std::abs(mainOpposingCosine * shiftedL2));
+    result.success = true; result.wo = shiftedWo;
+    return result;
+}
+
+struct Counters { double rays, vertices; };
+
+// perspective.cpp:271-298 (ray differentials are unused by the textures-free material subset)
+void sampleCameraRay(const Scene &sc, Float px, Float py, Ray &ray)
+{
+    V3 nearP = xfPoint(sc.cam.sample_to_camera, v3(px * sc.invResX, py * sc.invResY, 0.0));
+    V3 d = normalize(nearP);
+    Float invZ = 1.0 / d.z;
+    ray.mint = sc.cam.near_clip * invZ;
+    ray.maxt = sc.cam.far_clip * invZ;
+    ray.o = xfAffine(sc.cam.camera_to_world, v3(0, 0, 0));
+    ray.d = xfVector(sc.cam.camera_to_world, d);
+}
+
+// gpt.cpp:468-1180.  No environment emitter, no subsurface in this subset: those branches
+// (gpt.cpp:486-488,501-504,786-803,908-915,1053-1074) reduce to "path leaves the scene".
+void evaluate(const Scene &sc, const Config &cfg, Sampler &sampler, RayState &main, RayState *shiftedRays,
+              int secondaryCount, Spec &out_veryDirect, Counters &cnt)
+{
+    rayIntersect(sc, main.ray, main.its); cnt.rays++;                               // :472
+    main.ray.mint = Epsilon;
+    for (int i = 0; i < secondaryCount; ++i) {
+        rayIntersect(sc, shiftedRays[i].ray, shiftedRays[i].its); cnt.rays++;       // :476-480
+        shiftedRays[i].ray.mint = Epsilon;
+    }
+    if (!main.its.valid()) return;                                                  // :482-492 (no environment)
+    if (isEmitter(sc, main.its)) out_veryDirect = out_veryDirect + main.throughput * emittedLe(sc, main.its, -main.ray.d);  // :497-499
+    for (int i = 0; i < secondaryCount; ++i) if (!shiftedRays[i].its.valid()) shiftedRays[i].alive = false;              // :508-513
+    if (cfg.strictNormals) {                                                        // :516-531
+        if (dot(main.ray.d, main.its.geoN) * main.its.wi.z >= 0) return;
+        for (int i = 0; i < secondaryCount; ++i) {
+            RayState &s = shiftedRays[i];
+            if (dot(s.ray.d, s.its.geoN) * s.its.wi.z >= 0) s.alive = false;
+        }
+    }
+
+    int depth = 1;                                                                  // :535
+    while (depth < cfg.maxDepth || cfg.maxDepth < 0) {                              // :537
+        if (cfg.strictNormals) {                                                    // :541-555
+            if (dot(main.ray.d, main.its.geoN) * main.its.wi.z >= 0) break;
+            for (int i = 0; i < secondaryCount; ++i) {
+                RayState &s = shiftedRays[i];
+                if (dot(s.ray.d, s.its.geoN) * s.its.wi.z >= 0) s.alive = false;
+            }
+        }
+        const bool lastSegment = (depth + 1 == cfg.maxDepth);                       // :558
+        const gdb200_material &mainBSDF = matOf(sc, main.its);
+
+        // ---- direct illumination sampling, :565-730
+        if ((bsdfType(mainBSDF) & ESmooth) && depth + 1 >= cfg.minDepth) {          // :568
+            DRec dRec; initDRec(sc, main.its, dRec);
+            Float lsx, lsy; sampler.next2D(lsx, lsy);                               // :572
+            bool mainEmitterVisible;
+            Spec value = sampleEmitterDirectVisible(sc, dRec, lsx, lsy, mainEmitterVisible); cnt.rays++;
+            Spec mainEmitterRadiance = value * dRec.pdf;                            // :575
+            V3 mainWoLocal = toLocal(main.its.sh, dRec.d);
+            Spec mainBSDFValue = bsdfEval(mainBSDF, main.its.wi, mainWoLocal, ESolidAngle);                  // :588
+            Float mainBsdfPdf = mainEmitterVisible ? bsdfPdf(mainBSDF, main.its.wi, mainWoLocal, ESolidAngle) : 0;  // :592
+            Float mainDistanceSquared = lengthSquared(main.its.p - dRec.p);         // :595-596
+            Float mainOpposingCosine = dot(dRec.n, (main.its.p - dRec.p)) / std::sqrt(mainDistanceSquared);
+            Float mainWeightNumerator = main.pdf * dRec.pdf;                        // :599-600
+            Float mainWeightDenominator = (main.pdf * main.pdf) * ((dRec.pdf * dRec.pdf) + (mainBsdfPdf * mainBsdfPdf));
+            if (!cfg.strictNormals || dot(main.its.geoN, dRec.d) * mainWoLocal.z > 0) {                      // :607
+                for (int i = 0; i < secondaryCount; ++i) {
+                    RayState &shifted = shiftedRays[i];
+                    Spec mainContribution = spec(0), shiftedContribution = spec(0);
+                    Float weight = 0;
+                    bool shiftSuccessful = shifted.alive;
+                    if (shiftSuccessful) {
+                        if (shifted.connection_status == RAY_CONNECTED) {           // :622-637
+                            Float shiftedBsdfPdf = mainBsdfPdf, shiftedDRecPdf = dRec.pdf, jacobian = 1;
+                            Float den = (jacobian * shifted.pdf) * (jacobian * shifted.pdf) * ((shiftedDRecPdf * shiftedDRecPdf) + (shiftedBsdfPdf * shiftedBsdfPdf));
+                            weight = mainWeightNumerator / (D_EPSILON + den + mainWeightDenominator);
+                            mainContribution = main.throughput * (mainBSDFValue * mainEmitterRadiance);
+                            shiftedContribution = jacobian * shifted.throughput * (mainBSDFValue * mainEmitterRadiance);
+                        } else if (shifted.connection_status == RAY_RECENTLY_CONNECTED) {   // :638-658
+                            V3 incoming = normalize(shifted.its.p - main.its.p);
+                            V3 wiL = toLocal(main.its.sh, incoming);
+                            Float shiftedBsdfPdf = mainEmitterVisible ? bsdfPdf(mainBSDF, wiL, mainWoLocal, ESolidAngle) : 0;
+                            Float shiftedDRecPdf = dRec.pdf;
+                            Spec shiftedBsdfValue = bsdfEval(mainBSDF, wiL, mainWoLocal, ESolidAngle);
+                            Float jacobian = 1;
+                            Float den = (jacobian * shifted.pdf) * (jacobian * shifted.pdf) * ((shiftedDRecPdf * shiftedDRecPdf) + (shiftedBsdfPdf * shiftedBsdfPdf));
+                            weight = mainWeightNumerator / (D_EPSILON + den + mainWeightDenominator);
+                            mainContribution = main.throughput * (mainBSDFValue * mainEmitterRadiance);
+                            shiftedContribution = jacobian * shifted.throughput * (shiftedBsdfValue * mainEmitterRadiance);
+                        } else {                                                    // :659-705
+                            const gdb200_material &shiftedBSDF = matOf(sc, shifted.its);
+                            VertexType mainVT = getVertexType(mainBSDF, cfg, ESmooth), shiftedVT = getVertexType(shiftedBSDF, cfg, ESmooth);
+                            if (mainVT == VERTEX_TYPE_DIFFUSE && shiftedVT == VERTEX_TYPE_DIFFUSE) {   // :672 (no point lights here)
+                                DRec sRec; initDRec(sc, shifted.its, sRec);
+                                bool shiftedEmitterVisible;
+                                Spec sv = sampleEmitterDirectVisible(sc, sRec, lsx, lsy, shiftedEmitterVisible); cnt.rays++;
+                                Spec shiftedEmitterRadiance = sv * sRec.pdf;
+                                Float shiftedDRecPdf = sRec.pdf;
+                                Float shiftedDistanceSquared = lengthSquared(dRec.p - shifted.its.p);
+                                V3 emitterDirection = (dRec.p - shifted.its.p) / std::sqrt(shiftedDistanceSquared);
+                                Float shiftedOpposingCosine = -dot(dRec.n, emitterDirection);
+                                V3 woL = toLocal(shifted.its.sh, emitterDirection);
+                                if (cfg.strictNormals && dot(shifted.its.geoN, emitterDirection) * woL.z < 0) {
+                                    shiftSuccessful = false;
+                                } else {
+                                    Spec shiftedBsdfValue = bsdfEval(shiftedBSDF, shifted.its.wi, woL, ESolidAngle);
+                                    Float shiftedBsdfPdf = shiftedEmitterVisible ? bsdfPdf(shiftedBSDF, shifted.its.wi, woL, ESolidAngle) : 0;
+                                    Float jacobian = std::abs(shiftedOpposingCosine * mainDistanceSquared) / (Epsilon + std::abs(mainOpposingCosine * shiftedDistanceSquared));   // :695
+                                    Float den = (jacobian * shifted.pdf) * (jacobian * shifted.pdf) * ((shiftedDRecPdf * shiftedDRecPdf) + (shiftedBsdfPdf * shiftedBsdfPdf));
+                                    weight = mainWeightNumerator / (D_EPSILON + den + mainWeightDenominator);
+                                    mainContribution = main.throughput * (mainBSDFValue * mainEmitterRadiance);
+                                    shiftedContribution = jacobian * shifted.throughput * (shiftedBsdfValue * shiftedEmitterRadiance);
+                                }
+                            }
+                        }
+                    }
+                    if (!shiftSuccessful) {                                         // :708-717
+                        weight = mainWeightNumerator / (D_EPSILON + mainWeightDenominator);
+                        mainContribution = main.throughput * (mainBSDFValue * mainEmitterRadiance);
+                        shiftedContribution = spec(0);
+                    }
+                    main.addRadiance(mainContribution, weight);                     // :723-726
+                    shifted.addRadiance(shiftedContribution, weight);
+                    shifted.addGradient(shiftedContribution - mainContribution, weight);
+                }
+            }
+        }
+
+        // ---- BSDF sampling and emitter hits, :737-826
+        BSDFSample bs; bs.wi = main.its.wi;
+        { Float sx, sy; sampler.next2D(sx, sy); bsdfSample(mainBSDF, bs, sx, sy); }  // :456-457
+        if (bs.pdf <= 0.0) break;                                                   // :739
+        const V3 mainWo = toWorld(main.its.sh, bs.wo);
+        Float mainWoDotGeoN = dot(main.its.geoN, mainWo);
+        if (cfg.strictNormals && mainWoDotGeoN * bs.wo.z <= 0) break;               // :748
+        Its previousMainIts = main.its;                                             // :753
+        bool mainHitEmitter = false;
+        Spec mainEmitterRadiance = spec(0);
+        DRec mainDRec; initDRec(sc, main.its, mainDRec);                            // :759
+        VertexType mainVertexType = getVertexType(mainBSDF, cfg, bs.sampledType);   // :764
+        VertexType mainNextVertexType;
+        main.ray.o = main.its.p; main.ray.d = mainWo; main.ray.mint = Epsilon; main.ray.maxt = INF;   // :767
+        cnt.rays++;
+        if (rayIntersect(sc, main.ray, main.its)) {                                 // :769-784
+            if (isEmitter(sc, main.its)) {
+                mainEmitterRadiance = emittedLe(sc, main.its, -main.ray.d);
+                mainDRec.p = main.its.p; mainDRec.n = main.its.sh.n; mainDRec.d = main.ray.d; mainDRec.dist = main.its.t;   // setQuery, records.inl:167-175
+                mainDRec.emitter = sc.shapes[main.its.shape].d.emitter;
+                mainHitEmitter = true;
+            }
+            mainNextVertexType = getVertexType(matOf(sc, main.its), cfg, bs.sampledType);
+        } else {
+            break;                                                                  // :800-803 (no environment emitter)
+        }
+        Float mainBsdfPdf = bs.pdf, mainPreviousPdf = main.pdf;                     // :807-812
+        main.throughput = main.throughput * (bs.weight * bs.pdf);
+        main.pdf *= bs.pdf;
+        main.eta *= bs.eta;
+        const Float mainLumPdf = (mainHitEmitter && depth + 1 >= cfg.minDepth && !(bs.sampledType & EDelta)) ? pdfEmitterDirect(sc, mainDRec) : 0;   // :815-816
+        Float mainWeightNumerator = mainPreviousPdf * bs.pdf;                       // :819-820
+        Float mainWeightDenominator = (mainPreviousPdf * mainPreviousPdf) * ((mainLumPdf * mainLumPdf) + (mainBsdfPdf * mainBsdfPdf));
+
+        for (int i = 0; i < secondaryCount; ++i) {                                  // :830-1151
+            RayState &shifted = shiftedRays[i];
+            Spec mainContribution = spec(0), shiftedContribution = spec(0);
+            Float weight = 0;
+            bool postponedShiftEnd = false;
+            if (shifted.alive) {
+                Float shiftedPreviousPdf = shifted.pdf;
+                if (shifted.connection_status == RAY_CONNECTED) {                   // :844-861
+                    Spec shiftedBsdfValue = bs.weight * bs.pdf;
+                    shifted.throughput = shifted.throughput * shiftedBsdfValue;
+                    shifted.pdf *= mainBsdfPdf;
+                    Float den = (shiftedPreviousPdf * shiftedPreviousPdf) * ((mainLumPdf * mainLumPdf) + (mainBsdfPdf * mainBsdfPdf));
+                    weight = mainWeightNumerator / (D_EPSILON + den + mainWeightDenominator);
+                    mainContribution = main.throughput * mainEmitterRadiance;
+                    shiftedContribution = shifted.throughput * mainEmitterRadiance;
+                } else if (shifted.connection_status == RAY_RECENTLY_CONNECTED) {   // :862-888
+                    V3 incoming = normalize(shifted.its.p - main.ray.o);
+                    V3 wiL = toLocal(previousMainIts.sh, incoming), woL = toLocal(previousMainIts.sh, main.ray.d);
+                    Measure measure = (bs.sampledType & EDelta) ? EDiscrete : ESolidAngle;
+                    Spec shiftedBsdfValue = bsdfEval(mainBSDF, wiL, woL, measure);
+                    Float shiftedBsdfPdf = bsdfPdf(mainBSDF, wiL, woL, measure);
+                    shifted.throughput = shifted.throughput * shiftedBsdfValue;
+                    shifted.pdf *= shiftedBsdfPdf;
+                    shifted.connection_status = RAY_CONNECTED;
+                    Float den = (shiftedPreviousPdf * shiftedPreviousPdf) * ((mainLumPdf * mainLumPdf) + (shiftedBsdfPdf * shiftedBsdfPdf));
+                    weight = mainWeightNumerator / (D_EPSILON + den + mainWeightDenominator);
+                    mainContribution = main.throughput * mainEmitterRadiance;
+                    shiftedContribution = shifted.throughput * mainEmitterRadiance;
+                } else {                                                            // :889-1126
+                    const gdb200_material &shiftedBSDF = matOf(sc, shifted.its);
+                    VertexType shiftedVertexType = getVertexType(shiftedBSDF, cfg, bs.sampledType);
+                    if (mainVertexType == VERTEX_TYPE_DIFFUSE && mainNextVertexType == VERTEX_TYPE_DIFFUSE && shiftedVertexType == VERTEX_TYPE_DIFFUSE) {
+                        if (!lastSegment || mainHitEmitter) {                       // :901
+                            ShiftResult sr = reconnectShift(sc, main.ray.o, main.its.p, shifted.its.p, main.its.geoN); cnt.rays++;   // :907
+                            if (!sr.success) { shifted.alive = false; goto shift_failed; }
+                            V3 incomingDirection = -shifted.ray.d, outgoingDirection = sr.wo;
+                            V3 wiL = toLocal(shifted.its.sh, incomingDirection), woL = toLocal(shifted.its.sh, outgoingDirection);
+                            if (cfg.strictNormals && dot(outgoingDirection, shifted.its.geoN) * woL.z <= 0) { shifted.alive = false; goto shift_failed; }
+                            Spec shiftedBsdfValue = bsdfEval(shiftedBSDF, wiL, woL, ESolidAngle);    // :935-936
+                            Float shiftedBsdfPdf = bsdfPdf(shiftedBSDF, wiL, woL, ESolidAngle);
+                            shifted.throughput = shifted.throughput * (shiftedBsdfValue * sr.jacobian);
+                            shifted.pdf *= shiftedBsdfPdf * sr.jacobian;
+                            shifted.connection_status = RAY_RECENTLY_CONNECTED;
+                            if (mainHitEmitter) {                                   // :944-985
+                                Spec shiftedEmitterRadiance = emittedLe(sc, main.its, -outgoingDirection);
+                                DRec sd;                                            // :957-964
+                                sd.p = mainDRec.p; sd.n = mainDRec.n;
+                                sd.dist = length(mainDRec.p - shifted.its.p);
+                                sd.d = (mainDRec.p - shifted.its.p) / sd.dist;
+                                sd.ref = mainDRec.ref; sd.refN = shifted.its.sh.n; sd.emitter = mainDRec.emitter;
+                                Float shiftedLumPdf = pdfEmitterDirect(sc, sd);
+                                Float den = (shiftedPreviousPdf * shiftedPreviousPdf) * ((shiftedLumPdf * shiftedLumPdf) + (shiftedBsdfPdf * shiftedBsdfPdf));
+                                weight = mainWeightNumerator / (D_EPSILON + den + mainWeightDenominator);
+                                mainContribution = main.throughput * mainEmitterRadiance;
+                                shiftedContribution = shifted.throughput * shiftedEmitterRadiance;
+                            }
+                        }
+                    } else {                                                        // half-vector shift, :987-1126
+                        V3 tangentSpaceIncomingDirection = toLocal(shifted.its.sh, -shifted.ray.d);
+                        V3 tangentSpaceOutgoingDirection = v3(0, 0, 0);
+                        Spec shiftedEmitterRadiance = spec(0);
+                        bool bothDelta = (bs.sampledType & EDelta) && (bsdfType(shiftedBSDF) & EDelta);
+                        bool bothSmooth = (bs.sampledType & ESmooth) && (bsdfType(shiftedBSDF) & ESmooth);
+                        if (!(bothDelta || bothSmooth)) { shifted.alive = false; goto half_vector_shift_failed; }
+                        {
+                            ShiftResult sr = halfVectorShift(bs.wi, bs.wo, toLocal(shifted.its.sh, -shifted.ray.d), bsdfEta(mainBSDF), bsdfEta(shiftedBSDF));   // :1006
+                            if (bs.sampledType & EDelta) sr.jacobian = 1;           // :1008-1011
+                            if (sr.success) {
+                                shifted.throughput = shifted.throughput * sr.jacobian;
+                                shifted.pdf *= sr.jacobian;
+                                tangentSpaceOutgoingDirection = sr.wo;
+                            } else { shifted.alive = false; goto half_vector_shift_failed; }
+                            V3 outgoingDirection = toWorld(shifted.its.sh, tangentSpaceOutgoingDirection);
+                            Measure measure = (bs.sampledType & EDelta) ? EDiscrete : ESolidAngle;
+                            shifted.throughput = shifted.throughput * bsdfEval(shiftedBSDF, tangentSpaceIncomingDirection, tangentSpaceOutgoingDirection, measure);   // :1030-1031
+                            shifted.pdf *= bsdfPdf(shiftedBSDF, tangentSpaceIncomingDirection, tangentSpaceOutgoingDirection, measure);
+                            if (shifted.pdf == 0) { shifted.alive = false; goto half_vector_shift_failed; }
+                            if (cfg.strictNormals && dot(outgoingDirection, shifted.its.geoN) * tangentSpaceOutgoingDirection.z <= 0) { shifted.alive = false; goto half_vector_shift_failed; }
+                            VertexType shiftedVertexType2 = getVertexType(shiftedBSDF, cfg, bs.sampledType);   // :1047
+                            shifted.ray.o = shifted.its.p; shifted.ray.d = outgoingDirection; shifted.ray.mint = Epsilon; shifted.ray.maxt = INF;   // :1050
+                            cnt.rays++;
+                            if (!rayIntersect(sc, shifted.ray, shifted.its)) {      // :1052-1058 (no environment)
+                                shifted.alive = false; goto half_vector_shift_failed;
+                            } else {
+                                VertexType shiftedNextVertexType = getVertexType(matOf(sc, shifted.its), cfg, bs.sampledType);
+                                if (mainVertexType == VERTEX_TYPE_DIFFUSE && shiftedVertexType2 == VERTEX_TYPE_DIFFUSE && shiftedNextVertexType == VERTEX_TYPE_DIFFUSE) {   // :1089-1093
+                                    shifted.alive = false; goto half_vector_shift_failed;
+                                }
+                                if (isEmitter(sc, shifted.its)) shiftedEmitterRadiance = emittedLe(sc, shifted.its, -shifted.ray.d);   // :1095-1098
+                            }
+                        }
+half_vector_shift_failed:
+                        if (shifted.alive) {                                        // :1107-1112
+                            weight = main.pdf / (shifted.pdf * shifted.pdf + main.pdf * main.pdf);
+                            mainContribution = main.throughput * mainEmitterRadiance;
+                            shiftedContribution = shifted.throughput * shiftedEmitterRadiance;
+                        } else {                                                    // :1113-1125
+                            weight = (Float)1 / main.pdf;
+                            mainContribution = main.throughput * mainEmitterRadiance;
+                            shiftedContribution = spec(0);
+                            shifted.alive = true;
+                            postponedShiftEnd = true;
+                        }
+                    }
+                }
+            }
+shift_failed:
+            if (!shifted.alive) {                                                   // :1131-1136
+                weight = mainWeightNumerator / (D_EPSILON + mainWeightDenominator);
+                mainContribution = main.throughput * mainEmitterRadiance;
+                shiftedContribution = spec(0);
+            }
+            if (depth + 1 >= cfg.minDepth) {                                        // :1140-1146
+                main.addRadiance(mainContribution, weight);
+                shifted.addRadiance(shiftedContribution, weight);
+                shifted.addGradient(shiftedContribution - mainContribution, weight);
+            }
+            if (postponedShiftEnd) shifted.alive = false;                           // :1148-1150
+        }
+
+        // :1154-1157: the base path always has a valid hit here (no environment emitter)
+        if (depth++ >= cfg.rrDepth) {                                               // :1159-1174
+            Float q = std::min(maxComp(main.throughput / main.pdf) * main.eta * main.eta, (Float)0.95f);
+            if (sampler.next1D() >= q) break;
+            main.pdf *= q;
+            for (int i = 0; i < secondaryCount; ++i) shiftedRays[i].pdf *= q;
+        }
+    }
+    cnt.vertices += depth;                                                          // :1178-1179
+}
+
+// ---------------------------------------------------------------- film
+struct Film {
+    int w, h; Float radius, tap;           // tap = discretised box weight 1/(2r) (rfilter.cpp:37-55, box.cpp:45-47)
+    std::vector<Float> acc;                // [5][h][w][4]: R,G,B,weight   (the alpha channel of gpt_wr.h:60 is dropped)
+    Float *px(int buf, int x, int y) { return &acc[(((size_t)buf * h + y) * w + x) * 4]; }
+    // rfilter.h:76-77 with MTS_FILTER_RESOLUTION = 31
+    Float evalDiscretized(Float x) const
+    {
+        int idx = std::min((int)std::abs(x * (31 / radius)), 31);
+        return idx < 31 ? tap : 0.0;
+    }
+    // GPTWorkResult::put (gpt_wr.h:56-64) -> ImageBlock::put (imageblock.h:150-195), in image coordinates
+    void put(Float sx, Float sy, Spec v, Float weight, int buf, bool allowNegative)
+    {
+        const Float value[4] = {v.x, v.y, v.z, weight};
+        for (int i = 0; i < 4; i++)
+            if (!std::isfinite(value[i]) || (!allowNegative && value[i] < 0)) return;   // sample dropped with its weight
+        const Float posx = sx - 0.5, posy = sy - 0.5;
+        const int minx = std::max((int)std::ceil(posx - radius), 0), miny = std::max((int)std::ceil(posy - radius), 0);
+        const int maxx = std::min((int)std::floor(posx + radius), w - 1), maxy = std::min((int)std::floor(posy + radius), h - 1);
+        for (int y = miny; y <= maxy; ++y) {
+            const Float weightY = evalDiscretized(y - posy);
+            for (int x = minx; x <= maxx; ++x) {
+                const Float wgt = evalDiscretized(x - posx) * weightY;
+                Float *dst = px(buf, x, y);
+                for (int k = 0; k < 4; k++) dst[k] += wgt * value[k];
+            }
+        }
+    }
+};
+
+enum { BUF_FINAL = 0, BUF_THROUGHPUT = 1, BUF_DX = 2, BUF_DY = 3, BUF_DIRECT = 4 };
+
+void buildScene(const gdb200_scene_desc *d, Scene &sc)
+{
+    sc.cam = d->camera;
+    sc.invResX = 1.0 / d->camera.width; sc.invResY = 1.0 / d->camera.height;   // sensor.cpp: m_invResolution
+    sc.filterRadius = d->rfilter_radius;
+    sc.mats.assign(d->materials, d->materials + d->n_materials);
+    sc.ems.assign(d->emitters, d->emitters + d->n_emitters);
+    for (int i = 0; i < d->n_shapes; i++) {
+        Shape s; s.d = d->shapes[i];
+        if (s.d.type == GDB200_SHAPE_RECTANGLE) {                               // rectangle.cpp:100-110
+            s.dpdu = xfVector(s.d.to_world, v3(2, 0, 0));
+            s.dpdv = xfVector(s.d.to_world, v3(0, 2, 0));
+            V3 normal = normalize(xfNormal(s.d.to_object, v3(0, 0, 1)));
+            s.frame.s = normalize(s.dpdu); s.frame.t = normalize(s.dpdv); s.frame.n = normal;
+            s.invArea = 1.0 / (length(s.dpdu) * length(s.dpdv));
+        } else if (s.d.type == GDB200_SHAPE_MESH) {
+            for (int t = s.d.first_tri; t < s.d.first_tri + s.d.tri_count; t++) {
+                const int *ix = d->triangles + 3 * t;
+                Tri T; T.shape = i;
+                triLoad(T, specOf(d->vertices + 3 * ix[0]), specOf(d->vertices + 3 * ix[1]), specOf(d->vertices + 3 * ix[2]));
+                sc.tris.push_back(T);
+            }
+        }
+        sc.shapes.push_back(s);
+    }
+    // scene.cpp:357-380 + pmf.h:100-114: CDF over samplingWeight, normalised
+    sc.emCdf.assign(1, 0.0);
+    for (size_t i = 0; i < sc.ems.size(); i++) sc.emCdf.push_back(sc.emCdf.back() + sc.ems[i].sampling_weight);
+    Float sum = sc.emCdf.back();
+    sc.emNormalization = sum > 0 ? 1.0 / sum : 0.0;
+    if (sum > 0) { for (size_t i = 1; i < sc.emCdf.size(); i++) sc.emCdf[i] *= sc.emNormalization; sc.emCdf.back() = 1.0; }
+}
+
+}  // namespace
+
+extern "C" {
+
+// renderBlock (gpt.cpp:1220-1355) over the whole image + developMulti (multifilm.cpp:366-416).
+// out buffers: width*height*3 doubles each (any may be NULL); out_weights (optional): 5*h*w weights.
+// counters (optional): [0] samples, [1] rays, [2] sum of base path depths.
+int gdb200_oracle_gpt_render(const gdb200_scene_desc *desc, const gdb200_gpt_params *prm, gdb200_buffers *out,
+                             double *out_weights, double *counters, int num_threads)
+{
+    if (!desc || !prm || desc->n_emitters < 1) return 1;
+    Scene sc; buildScene(desc, sc);
+    Config cfg; cfg.maxDepth = prm->max_depth; cfg.minDepth = 1; cfg.rrDepth = prm->rr_depth;   // gpt.cpp:1368-1371
+    cfg.strictNormals = prm->strict_normals != 0; cfg.shiftThreshold = prm->shift_threshold;
+    const int W = sc.cam.width, H = sc.cam.height;
+    Film film; film.w = W; film.h = H; film.radius = sc.filterRadius; film.tap = 1.0 / (2 * film.radius);
+    film.acc.assign((size_t)5 * W * H * 4, 0.0);
+    const int y0 = (prm->y_begin == 0 && prm->y_end == 0) ? 0 : prm->y_begin, y1 = (prm->y_begin == 0 && prm->y_end == 0) ? H : prm->y_end;
+    double totRays = 0, totVerts = 0;
+    // Row bands of 4: a sample in row y writes rows y-2..y+2 at most, so bands of equal parity
+    // never touch the same film rows and can run concurrently without atomics.
+    const int band = 4, nBands = (y1 - y0 + band - 1) / band;
+    for (int parity = 0; parity < 2; parity++) {
+#pragma omp parallel for schedule(dynamic, 1) num_threads(num_threads > 0 ? num_threads : 1) reduction(+ : totRays, totVerts)
+        for (int b = parity; b < nBands; b += 2) {
+            Counters cnt = {0, 0};
+            Sampler sampler;
+            for (int y = y0 + b * band; y < std::min(y1, y0 + (b + 1) * band); y++)
+                for (int x = 0; x < W; x++) {
+                    sampler.generate(prm->seed, x, y);                              // gpt.cpp:1250-1251
+                    for (int j = 0; j < prm->spp; j++) {
+                        Float u, v; sampler.next2D(u, v);                           // :1261
+                        const Float spx = x + u, spy = y + v;
+                        RayState main, shifted[4];
+                        static const Float shiftX[4] = {1, 0, -1, 0}, shiftY[4] = {0, 1, 0, -1};   // :410-415
+                        sampleCameraRay(sc, spx, spy, main.ray); main.throughput = spec(1);
+                        for (int i = 0; i < 4; i++) { sampleCameraRay(sc, spx + shiftX[i], spy + shiftY[i], shifted[i].ray); shifted[i].throughput = spec(1); }
+                        Spec veryDirect = spec(0);
+                        evaluate(sc, cfg, sampler, main, shifted, 4, veryDirect, cnt);
+                        const int RIGHT = 0, BOTTOM = 1, LEFT = 2, TOP = 3;         // :1283-1286
+                        const Spec C = main.radiance;
+                        // :1319-1324 preview/final
+                        film.put(spx, spy, (8 * veryDirect) + (2 * C), 4.0, BUF_FINAL, false);
+                        film.put(spx - 1, spy, 2 * shifted[LEFT].radiance, 1.0, BUF_FINAL, false);
+                        film.put(spx + 1, spy, 2 * shifted[RIGHT].radiance, 1.0, BUF_FINAL, false);
+                        film.put(spx, spy - 1, 2 * shifted[TOP].radiance, 1.0, BUF_FINAL, false);
+                        film.put(spx, spy + 1, 2 * shifted[BOTTOM].radiance, 1.0, BUF_FINAL, false);
+                        // :1334-1339 throughput
+                        film.put(spx, spy, 2 * C, 4.0, BUF_THROUGHPUT, false);
+                        film.put(spx - 1, spy, 2 * shifted[LEFT].radiance, 1.0, BUF_THROUGHPUT, false);
+                        film.put(spx + 1, spy, 2 * shifted[RIGHT].radiance, 1.0, BUF_THROUGHPUT, false);
+                        film.put(spx, spy - 1, 2 * shifted[TOP].radiance, 1.0, BUF_THROUGHPUT, false);
+                        film.put(spx, spy + 1, 2 * shifted[BOTTOM].radiance, 1.0, BUF_THROUGHPUT, false);
+                        // :1345-1348 gradients
+                        film.put(spx - 1, spy, -(2 * shifted[LEFT].gradient), 1.0, BUF_DX, true);
+                        film.put(spx, spy, 2 * shifted[RIGHT].gradient, 1.0, BUF_DX, true);
+                        film.put(spx, spy - 1, -(2 * shifted[TOP].gradient), 1.0, BUF_DY, true);
+                        film.put(spx, spy, 2 * shifted[BOTTOM].gradient, 1.0, BUF_DY, true);
+                        // :1352 very direct
+                        film.put(spx, spy, veryDirect, 1.0, BUF_DIRECT, false);
+                    }
+                }
+            totRays += cnt.rays; totVerts += cnt.vertices;
+        }
+    }
+    // develop: value * (1/weight), 0 where weight == 0 (fmtconv.cpp:1036-1045)
+    double *dst[5] = {out ? out->preview_final : 0, out ? out->throughput : 0, out ? out->dx : 0, out ? out->dy : 0, out ? out->direct : 0};
+    for (int buf = 0; buf < 5; buf++)
+        for (int y = 0; y < H; y++)
+            for (int x = 0; x < W; x++) {
+                const Float *p = film.px(buf, x, y);
+                const Float wgt = p[3], inv = (wgt != 0) ? 1 / wgt : wgt;
+                if (dst[buf]) for (int c = 0; c < 3; c++) dst[buf][((size_t)y * W + x) * 3 + c] = p[c] * inv;
+                if (out_weights) out_weights[((size_t)buf * H + y) * W + x] = wgt;
+            }
+    if (counters) { counters[0] = (double)W * (y1 - y0) * prm->spp; counters[1] = totRays; counters[2] = totVerts; }
+    return 0;
+}
+
+// Plain MIS path tracer = GradientPathIntegrator::Li (gpt.cpp:1489-1662, a copy of
+// src/integrators/path/path.cpp) driven by the same sampler; used only to cross-check the
+// G-PT restatement (E[throughput + direct] == E[Li]).  out: width*height*3 doubles.
+int gdb200_oracle_path_render(const gdb200_scene_desc *desc, const gdb200_gpt_params *prm, double *out, int num_threads)
+{
+    if (!desc || !prm || !out) return 1;
+    Scene sc; buildScene(desc, sc);
+    const int W = sc.cam.width, H = sc.cam.height;
+#pragma omp parallel for schedule(dynamic, 4) num_threads(num_threads > 0 ? num_threads : 1)
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            Sampler sampler; sampler.generate(prm->seed ^ 0x5bd1e995u, x, y);
+            Spec sum = spec(0);
+            for (int j = 0; j < prm->spp; j++) {
+                Float u, v; sampler.next2D(u, v);
+                Ray ray; sampleCameraRay(sc, x + u, y + v, ray);
+                Its its; rayIntersect(sc, ray, its);
+                ray.mint = Epsilon;
+                Spec Li = spec(0), throughput = spec(1);
+                Float eta = 1.0; bool scattered = false; int depth = 1;
+                while (depth <= prm->max_depth || prm->max_depth < 0) {
+                    if (!its.valid()) break;
+                    const gdb200_material &bsdf = matOf(sc, its);
+                    if (isEmitter(sc, its) && !scattered) Li = Li + throughput * emittedLe(sc, its, -ray.d);   // :1527-1529 (EEmittedRadiance only on the first vertex)
+                    if (depth >= prm->max_depth && prm->max_depth > 0) break;
+                    DRec dRec; initDRec(sc, its, dRec);
+                    if (bsdfType(bsdf) & ESmooth) {                                                             // :1553-1585
+                        Float sx, sy; sampler.next2D(sx, sy);
+                        bool vis; Spec value = sampleEmitterDirectVisible(sc, dRec, sx, sy, vis);
+                        if (vis && !(value.x == 0 && value.y == 0 && value.z == 0)) {
+                            V3 woL = toLocal(its.sh, dRec.d);
+                            Spec bsdfVal = bsdfEval(bsdf, its.wi, woL, ESolidAngle);
+                            if (!(bsdfVal.x == 0 && bsdfVal.y == 0 && bsdfVal.z == 0)) {
+                                Float bsdfPdfV = bsdfPdf(bsdf, its.wi, woL, ESolidAngle);
+                                Float a = dRec.pdf * dRec.pdf, b = bsdfPdfV * bsdfPdfV;
+                                Li = Li + throughput * value * bsdfVal * (a / (a + b));
+                            }
+                        }
+                    }
+                    BSDFSample bs; bs.wi = its.wi;
+                    { Float sx, sy; sampler.next2D(sx, sy); bsdfSample(bsdf, bs, sx, sy); }
+                    if (bs.pdf <= 0 || (bs.weight.x == 0 && bs.weight.y == 0 && bs.weight.z == 0)) break;
+                    scattered = true;
+                    const V3 wo = toWorld(its.sh, bs.wo);
+                    Ray next = {its.p, wo, Epsilon, INF};
+                    Its prev = its;
+                    bool hit = rayIntersect(sc, next, its);
+                    throughput = throughput * bs.weight;
+                    eta *= bs.eta;
+                    if (!hit) break;
+                    if (isEmitter(sc, its)) {                                                                   // :1611-1645
+                        Spec value = emittedLe(sc, its, -next.d);
+                        DRec q; initDRec(sc, prev, q);
+                        q.p = its.p; q.n = its.sh.n; q.d = next.d; q.dist = its.t; q.emitter = sc.shapes[its.shape].d.emitter;
+                        const Float lumPdf = !(bs.sampledType & EDelta) ? pdfEmitterDirect(sc, q) : 0;
+                        Float a = bs.pdf * bs.pdf, b = lumPdf * lumPdf;
+                        Li = Li + throughput * value * (a / (a + b));
+                    }
+                    ray = next;
+                    if (depth++ >= prm->rr_depth) {                                                             // :1649-1660
+                        Float q = std::min(maxComp(throughput) * eta * eta, (Float)0.95f);
+                        if (sampler.next1D() >= q) break;
+                        throughput = throughput / q;
+                    }
+                }
+                sum = sum + Li;
+            }
+            for (int c = 0; c < 3; c++) out[((size_t)y * W + x) * 3 + c] = (&sum.x)[c] / prm->spp;
+        }
+    return 0;
+}
+
+}  // extern "C"
