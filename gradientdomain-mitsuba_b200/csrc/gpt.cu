@@ -1,0 +1,893 @@
+// gdb200 G-PT wavefront tracer for sm_100a (fp64).
+//
+// Replaces GradientPathIntegrator::render's block scheduler + renderBlock + evaluatePoint +
+// evaluate (reference src/integrators/gpt/gpt.cpp:397-436, 468-1180, 1220-1355) with a
+// wavefront over persistent per-pixel path slots:
+//
+//   * one slot per base pixel owns that pixel's sample stream (the gdb200_counter sampler is
+//     re-keyed per pixel exactly where the reference calls Sampler::generate, gpt.cpp:1250, and
+//     the spp samples of a pixel consume it sequentially, so results do not depend on scheduling);
+//   * state lives in HBM as struct-of-arrays [field][slot] (146 fp64 + 14 int32 fields): every
+//     state access of a warp is one coalesced 256-byte row per field;
+//   * each wavefront step launches
+//       gpt_generate_kernel : slots whose path ended splat its 15 film contributions
+//                             (gpt.cpp:1319-1352) and start their next sample: 5 camera rays +
+//                             primary hits, very-direct emission;
+//       gpt_bounce_kernel   : one iteration of the reference's bounce loop (NEE with the
+//                             4-strategy MIS, BSDF sample, extension ray, the reconnection /
+//                             half-vector shift of the 4 offset paths, Russian roulette) for every
+//                             live slot;
+//   * both kernels append their survivors to the next step's queues with warp-aggregated
+//     (match_any + popc + one atomic per warp and bucket) stream compaction, bucketed by the
+//     material id of the base vertex, so a warp of the bounce kernel shades one BSDF type;
+//   * film accumulators are fp64 value+weight planes updated with red.global.add.f64.
+//
+// Arithmetic follows the reference's operation order (compiled with -fmad=false) so that the
+// fp64 buffers match the CPU oracle to rounding of the transcendental functions.
+#include "common.h"
+#include "gpt_device.cuh"
+#include <math_constants.h>
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+namespace gdb200 {
+
+
+// ------------------------------------------------------------------ state layout
+enum BaseField { BF_RAYD = 0, BF_P = 3, BF_GN = 6, BF_S = 9, BF_T = 12, BF_N = 15, BF_WI = 18, BF_THR = 21, BF_PDF = 24,
+                 BF_ETA = 25, BF_RAD = 26, BF_VD = 29, BF_SPX = 32, BF_SPY = 33, BF_COUNT = 34 };
+enum OffField { OF_THR = 0, OF_PDF = 3, OF_RAD = 4, OF_GRAD = 7, OF_P = 10, OF_GN = 13, OF_S = 16, OF_T = 19, OF_N = 22,
+                OF_WI = 25, OF_COUNT = 28 };
+constexpr int kDoubleFields = BF_COUNT + 4 * OF_COUNT;   // 146
+enum IntField { IF_STATUS = 0, IF_MAT, IF_EMI, IF_DEPTH, IF_SAMPLE, IF_RNGN, IF_OFLAGS, IF_OMAT0, IF_OMAT1, IF_OMAT2, IF_OMAT3,
+                IF_COUNT };
+enum SlotStatus { ST_FRESH = 0, ST_LIVE = 1, ST_FINISHED = 2, ST_DONE = 3 };
+enum { RAY_NOT_CONNECTED = 0, RAY_RECENTLY_CONNECTED = 1, RAY_CONNECTED = 2 };
+enum { BUF_FINAL = 0, BUF_THROUGHPUT = 1, BUF_DX = 2, BUF_DY = 3, BUF_DIRECT = 4 };
+
+constexpr int kBounceThreads = 128, kGenThreads = 128;
+
+struct GptArgs {
+    double *sd;            // [kDoubleFields][nSlots]
+    int *si;               // [IF_COUNT][nSlots]
+    uint64_t *key;         // [nSlots]
+    int nSlots, width, height, yBegin;
+    int spp, nBuckets;
+    uint64_t seed;
+    Config cfg;
+    double *film;          // [5][H][W][4]
+    int *liveList;         // [2][nBuckets][nSlots]
+    int *genList;          // [2][nSlots]
+    int *liveCount;        // [2][kMaxMaterials]
+    int *genCount;         // [2]
+    unsigned long long *counters;   // [0] done slots, [1] rays, [2] path vertices, [3] samples
+};
+
+GDB_D double &SD(const GptArgs &a, int field, int slot) { return a.sd[(size_t)field * a.nSlots + slot]; }
+GDB_D int &SI(const GptArgs &a, int field, int slot) { return a.si[(size_t)field * a.nSlots + slot]; }
+GDB_D V3 ld3(const GptArgs &a, int field, int slot) { return mk(SD(a, field, slot), SD(a, field + 1, slot), SD(a, field + 2, slot)); }
+GDB_D void st3(const GptArgs &a, int field, int slot, V3 v) { SD(a, field, slot) = v.x; SD(a, field + 1, slot) = v.y; SD(a, field + 2, slot) = v.z; }
+
+GDB_D void storeBaseIts(const GptArgs &a, int slot, const Its &its)
+{
+    st3(a, BF_P, slot, its.p); st3(a, BF_GN, slot, its.geoN); st3(a, BF_S, slot, its.sh.s); st3(a, BF_T, slot, its.sh.t);
+    st3(a, BF_N, slot, its.sh.n); st3(a, BF_WI, slot, its.wi);
+    SI(a, IF_MAT, slot) = its.material; SI(a, IF_EMI, slot) = its.emitter;
+}
+GDB_D void loadBaseIts(const GptArgs &a, int slot, Its &its)
+{
+    its.t = 0; its.p = ld3(a, BF_P, slot); its.geoN = ld3(a, BF_GN, slot); its.sh.s = ld3(a, BF_S, slot); its.sh.t = ld3(a, BF_T, slot);
+    its.sh.n = ld3(a, BF_N, slot); its.wi = ld3(a, BF_WI, slot);
+    its.material = SI(a, IF_MAT, slot); its.emitter = SI(a, IF_EMI, slot);
+}
+GDB_D void storeOffIts(const GptArgs &a, int slot, int i, const Its &its)
+{
+    const int o = BF_COUNT + i * OF_COUNT;
+    st3(a, o + OF_P, slot, its.p); st3(a, o + OF_GN, slot, its.geoN); st3(a, o + OF_S, slot, its.sh.s); st3(a, o + OF_T, slot, its.sh.t);
+    st3(a, o + OF_N, slot, its.sh.n); st3(a, o + OF_WI, slot, its.wi);
+    SI(a, IF_OMAT0 + i, slot) = its.material;
+}
+GDB_D void loadOffIts(const GptArgs &a, int slot, int i, Its &its)
+{
+    const int o = BF_COUNT + i * OF_COUNT;
+    its.t = 0; its.p = ld3(a, o + OF_P, slot); its.geoN = ld3(a, o + OF_GN, slot); its.sh.s = ld3(a, o + OF_S, slot); its.sh.t = ld3(a, o + OF_T, slot);
+    its.sh.n = ld3(a, o + OF_N, slot); its.wi = ld3(a, o + OF_WI, slot);
+    its.material = SI(a, IF_OMAT0 + i, slot); its.emitter = -1;
+}
+
+// Warp-aggregated append of `slot` to queue `bucket` (active lanes only).
+GDB_D void appendBucketed(int *lists, int *counts, int nSlots, int bucket, int slot)
+{
+    const unsigned peers = __match_any_sync(__activemask(), bucket);
+    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1, rank = __popc(peers & ((1u << lane) - 1));
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&counts[bucket], __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    lists[(size_t)bucket * nSlots + base + rank] = slot;
+}
+// One atomic per warp for statistics counters.
+GDB_D void countWarp(unsigned long long *ctr, unsigned v)
+{
+    const unsigned m = __activemask();
+    const unsigned s = __reduce_add_sync(m, v);
+    if ((int)(threadIdx.x & 31) == __ffs(m) - 1 && s) atomicAdd(ctr, (unsigned long long)s);
+}
+
+// ------------------------------------------------------------------ film (ImageBlock::put, imageblock.h:150-195)
+GDB_D Float evalDiscretized(Float x)      // rfilter.h:76-77, MTS_FILTER_RESOLUTION = 31; box taps = 1/(2r) (rfilter.cpp:37-55)
+{
+    const int idx = min((int)fabs(x * c_scene.filterScale), 31);
+    return idx < 31 ? c_scene.filterTap : 0.0;
+}
+GDB_D void filmPut(const GptArgs &a, Float sx, Float sy, Spec v, Float weight, int buf, bool allowNegative)
+{
+    const Float value[4] = {v.x, v.y, v.z, weight};
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        if (!isfinite(value[i]) || (!allowNegative && value[i] < 0)) return;       // dropped together with its weight
+    const Float radius = c_scene.filterRadius, posx = sx - 0.5, posy = sy - 0.5;
+    const int W = a.width, H = a.height;
+    const int minx = max((int)ceil(posx - radius), 0), miny = max((int)ceil(posy - radius), 0);
+    const int maxx = min((int)floor(posx + radius), W - 1), maxy = min((int)floor(posy + radius), H - 1);
+    for (int y = miny; y <= maxy; ++y) {
+        const Float weightY = evalDiscretized(y - posy);
+        for (int x = minx; x <= maxx; ++x) {
+            const Float wgt = evalDiscretized(x - posx) * weightY;
+            double *dst = a.film + ((((size_t)buf * H + y) * W + x) << 2);
+#pragma unroll
+            for (int k = 0; k < 4; k++) atomicAdd(dst + k, wgt * value[k]);
+        }
+    }
+}
+
+// The 15 puts of renderBlock (gpt.cpp:1319-1352).
+GDB_D void splatSample(const GptArgs &a, Float spx, Float spy, Spec veryDirect, Spec C, const Spec rad[4], const Spec grad[4])
+{
+    const int RIGHT = 0, BOTTOM = 1, LEFT = 2, TOP = 3;
+    filmPut(a, spx, spy, (8 * veryDirect) + (2 * C), 4.0, BUF_FINAL, false);
+    filmPut(a, spx - 1, spy, 2 * rad[LEFT], 1.0, BUF_FINAL, false);
+    filmPut(a, spx + 1, spy, 2 * rad[RIGHT], 1.0, BUF_FINAL, false);
+    filmPut(a, spx, spy - 1, 2 * rad[TOP], 1.0, BUF_FINAL, false);
+    filmPut(a, spx, spy + 1, 2 * rad[BOTTOM], 1.0, BUF_FINAL, false);
+    filmPut(a, spx, spy, 2 * C, 4.0, BUF_THROUGHPUT, false);
+    filmPut(a, spx - 1, spy, 2 * rad[LEFT], 1.0, BUF_THROUGHPUT, false);
+    filmPut(a, spx + 1, spy, 2 * rad[RIGHT], 1.0, BUF_THROUGHPUT, false);
+    filmPut(a, spx, spy - 1, 2 * rad[TOP], 1.0, BUF_THROUGHPUT, false);
+    filmPut(a, spx, spy + 1, 2 * rad[BOTTOM], 1.0, BUF_THROUGHPUT, false);
+    filmPut(a, spx - 1, spy, -(2 * grad[LEFT]), 1.0, BUF_DX, true);
+    filmPut(a, spx, spy, 2 * grad[RIGHT], 1.0, BUF_DX, true);
+    filmPut(a, spx, spy - 1, -(2 * grad[TOP]), 1.0, BUF_DY, true);
+    filmPut(a, spx, spy, 2 * grad[BOTTOM], 1.0, BUF_DY, true);
+    filmPut(a, spx, spy, veryDirect, 1.0, BUF_DIRECT, false);
+}
+
+GDB_D unsigned packFlag(int i, bool alive, int conn) { return ((alive ? 1u : 0u) | ((unsigned)conn << 1)) << (3 * i); }
+GDB_D bool flagAlive(unsigned f, int i) { return (f >> (3 * i)) & 1u; }
+GDB_D int flagConn(unsigned f, int i) { return (f >> (3 * i + 1)) & 3u; }
+GDB_D unsigned setFlag(unsigned f, int i, bool alive, int conn) { return (f & ~(7u << (3 * i))) | packFlag(i, alive, conn); }
+
+// ------------------------------------------------------------------ generate: splat finished paths, start next samples
+__global__ void __launch_bounds__(kGenThreads) gpt_generate_kernel(const GptArgs a, int parity)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= a.genCount[parity]) return;
+    const int slot = a.genList[(size_t)parity * a.nSlots + g];
+    const int px = slot % a.width, py = a.yBegin + slot / a.width;
+
+    if (SI(a, IF_STATUS, slot) == ST_FINISHED) {
+        Spec rad[4], grad[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { const int o = BF_COUNT + i * OF_COUNT; rad[i] = ld3(a, o + OF_RAD, slot); grad[i] = ld3(a, o + OF_GRAD, slot); }
+        splatSample(a, SD(a, BF_SPX, slot), SD(a, BF_SPY, slot), ld3(a, BF_VD, slot), ld3(a, BF_RAD, slot), rad, grad);
+    }
+
+    Sampler smp; smp.key = a.key[slot]; smp.n = (uint32_t)SI(a, IF_RNGN, slot);
+    int j = SI(a, IF_SAMPLE, slot);
+    unsigned long long rays = 0, samples = 0;
+    int status = ST_DONE;
+    while (j < a.spp) {
+        j++; samples++;
+        const Float u = smp.next1D(), v = smp.next1D();                              // gpt.cpp:1261
+        const Float spx = px + u, spy = py + v;
+        Ray ray; Its mits;
+        sampleCameraRay(spx, spy, ray);                                              // gpt.cpp:402
+        const bool mainValid = rayIntersect(ray, mits); rays += 5;                   // gpt.cpp:472
+        Spec veryDirect = splat(0);
+        unsigned flags = 0;
+        bool early = !mainValid;                                                     // gpt.cpp:482-492 (no environment emitter)
+        if (mainValid && mits.emitter >= 0) veryDirect = veryDirect + splat(1.0) * emittedLe(mits, -ray.d);   // gpt.cpp:497-499
+        if (mainValid && a.cfg.strictNormals && dot(ray.d, mits.geoN) * mits.wi.z >= 0) early = true;          // gpt.cpp:518-521
+        const Float shiftX[4] = {1, 0, -1, 0}, shiftY[4] = {0, 1, 0, -1};            // gpt.cpp:410-415
+#pragma unroll 1
+        for (int i = 0; i < 4; i++) {
+            Ray sray; Its sits;
+            sampleCameraRay(spx + shiftX[i], spy + shiftY[i], sray);                 // gpt.cpp:418
+            bool alive = rayIntersect(sray, sits);                                   // gpt.cpp:476-480, 508-513
+            if (alive && a.cfg.strictNormals && dot(sray.d, sits.geoN) * sits.wi.z >= 0) alive = false;   // gpt.cpp:523-530
+            flags |= packFlag(i, alive, RAY_NOT_CONNECTED);
+            if (!early) {
+                const int o = BF_COUNT + i * OF_COUNT;
+                st3(a, o + OF_THR, slot, splat(1.0)); SD(a, o + OF_PDF, slot) = 1.0;
+                st3(a, o + OF_RAD, slot, splat(0)); st3(a, o + OF_GRAD, slot, splat(0));
+                if (alive) storeOffIts(a, slot, i, sits);
+            }
+        }
+        if (early || !(1 < a.cfg.maxDepth || a.cfg.maxDepth < 0)) {                  // bounce loop never entered (gpt.cpp:537)
+            const Spec zero[4] = {splat(0), splat(0), splat(0), splat(0)};
+            splatSample(a, spx, spy, veryDirect, splat(0), zero, zero);
+            if (!early) atomicAdd(&a.counters[2], 1ULL);                             // avgPathLength += depth (1), gpt.cpp:1178-1179
+            continue;
+        }
+        st3(a, BF_RAYD, slot, ray.d); storeBaseIts(a, slot, mits);
+        st3(a, BF_THR, slot, splat(1.0)); SD(a, BF_PDF, slot) = 1.0; SD(a, BF_ETA, slot) = 1.0;
+        st3(a, BF_RAD, slot, splat(0)); st3(a, BF_VD, slot, veryDirect);
+        SD(a, BF_SPX, slot) = spx; SD(a, BF_SPY, slot) = spy;
+        SI(a, IF_DEPTH, slot) = 1; SI(a, IF_OFLAGS, slot) = (int)flags;
+        status = ST_LIVE;
+        appendBucketed(a.liveList + (size_t)parity * a.nBuckets * a.nSlots, a.liveCount + parity * kMaxMaterials, a.nSlots, mits.material, slot);
+        break;
+    }
+    SI(a, IF_STATUS, slot) = status; SI(a, IF_SAMPLE, slot) = j; SI(a, IF_RNGN, slot) = (int)smp.n;
+    countWarp(&a.counters[0], status == ST_DONE ? 1u : 0u);
+    countWarp(&a.counters[1], (unsigned)rays);
+    countWarp(&a.counters[3], (unsigned)samples);
+}
+
+// ------------------------------------------------------------------ bounce: one iteration of gpt.cpp:537-1175
+__global__ void __launch_bounds__(kBounceThreads) gpt_bounce_kernel(const GptArgs a, int parity)
+{
+    // thread -> (material bucket, index): buckets are padded to whole warps so a warp shades one BSDF
+    __shared__ int s_begin[kMaxMaterials + 1], s_count[kMaxMaterials];
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int b = 0; b < a.nBuckets; b++) { const int c = a.liveCount[parity * kMaxMaterials + b]; s_begin[b] = acc; s_count[b] = c; acc += (c + 31) & ~31; }
+        s_begin[a.nBuckets] = acc;
+    }
+    __syncthreads();
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= s_begin[a.nBuckets]) return;
+    int b = 0;
+    while (g >= s_begin[b + 1]) b++;
+    const int idx = g - s_begin[b];
+    if (idx >= s_count[b]) return;
+    const int slot = a.liveList[((size_t)parity * a.nBuckets + b) * a.nSlots + idx];
+    const int next = parity ^ 1;
+    const Config cfg = a.cfg;
+
+    Its mits; loadBaseIts(a, slot, mits);
+    V3 mrayD = ld3(a, BF_RAYD, slot);
+    Spec mthr = ld3(a, BF_THR, slot), mrad = ld3(a, BF_RAD, slot);
+    Float mpdf = SD(a, BF_PDF, slot), meta = SD(a, BF_ETA, slot);
+    int depth = SI(a, IF_DEPTH, slot);
+    unsigned flags = (unsigned)SI(a, IF_OFLAGS, slot);
+    Sampler smp; smp.key = a.key[slot]; smp.n = (uint32_t)SI(a, IF_RNGN, slot);
+    unsigned long long rays = 0;
+    bool ended = false;
+
+    do {
+        if (cfg.strictNormals) {                                                     // gpt.cpp:541-555
+            if (dot(mrayD, mits.geoN) * mits.wi.z >= 0) { ended = true; break; }
+            // offsets: their ray direction equals toWorld(-wi) of the stored vertex
+            for (int i = 0; i < 4; i++) {
+                if (!flagAlive(flags, i) || flagConn(flags, i) != RAY_NOT_CONNECTED) continue;
+                Its sits; loadOffIts(a, slot, i, sits);
+                const V3 sd = -toWorld(sits.sh, sits.wi);
+                if (dot(sd, sits.geoN) * sits.wi.z >= 0) flags = setFlag(flags, i, false, flagConn(flags, i));
+            }
+        }
+        const bool lastSegment = (depth + 1 == cfg.maxDepth);                        // gpt.cpp:558
+        const DMaterial &mainBSDF = c_scene.materials[mits.material];
+
+        // ---------------- next event estimation, gpt.cpp:565-730
+        if ((mainBSDF.flags & ESmooth) && depth + 1 >= cfg.minDepth) {
+            DRec dRec; initDRec(mits, dRec);
+            const Float lsx = smp.next1D(), lsy = smp.next1D();                      // gpt.cpp:572
+            bool mainEmitterVisible;
+            const Spec value = sampleEmitterDirectVisible(dRec, lsx, lsy, mainEmitterVisible); rays++;
+            const Spec mainEmitterRadiance = value * dRec.pdf;                       // gpt.cpp:575
+            const V3 mainWoLocal = toLocal(mits.sh, dRec.d);
+            Spec mainBSDFValue; Float mainBsdfPdf;
+            bsdfEvalPdf(mainBSDF, mits.wi, mainWoLocal, ESolidAngle, mainBSDFValue, mainBsdfPdf);   // gpt.cpp:588
+            if (!mainEmitterVisible) mainBsdfPdf = 0;                                // gpt.cpp:592
+            const Float mainDistanceSquared = len2(mits.p - dRec.p);                 // gpt.cpp:595-596
+            const Float mainOpposingCosine = dot(dRec.n, (mits.p - dRec.p)) / sqrt(mainDistanceSquared);
+            const Float mainWeightNumerator = mpdf * dRec.pdf;                       // gpt.cpp:599-600
+            const Float mainWeightDenominator = (mpdf * mpdf) * ((dRec.pdf * dRec.pdf) + (mainBsdfPdf * mainBsdfPdf));
+            if (!cfg.strictNormals || dot(mits.geoN, dRec.d) * mainWoLocal.z > 0) {  // gpt.cpp:607
+                const Spec mainContributionAll = mthr * (mainBSDFValue * mainEmitterRadiance);
+#pragma unroll 1
+                for (int i = 0; i < 4; ++i) {
+                    const int o = BF_COUNT + i * OF_COUNT;
+                    Spec mainContribution = splat(0), shiftedContribution = splat(0);
+                    Float weight = 0;
+                    bool shiftSuccessful = flagAlive(flags, i);
+                    const int conn = flagConn(flags, i);
+                    if (shiftSuccessful) {
+                        const Spec sthr = ld3(a, o + OF_THR, slot);
+                        const Float spdf = SD(a, o + OF_PDF, slot);
+                        if (conn == RAY_CONNECTED) {                                 // gpt.cpp:622-637
+                            const Float jacobian = 1;
+                            const Float den = (jacobian * spdf) * (jacobian * spdf) * ((dRec.pdf * dRec.pdf) + (mainBsdfPdf * mainBsdfPdf));
+                            weight = mainWeightNumerator / (kDEps + den + mainWeightDenominator);
+                            mainContribution = mainContributionAll;
+                            shiftedContribution = jacobian * sthr * (mainBSDFValue * mainEmitterRadiance);
+                        } else if (conn == RAY_RECENTLY_CONNECTED) {                 // gpt.cpp:638-658
+                            const V3 incoming = normalize(ld3(a, o + OF_P, slot) - mits.p);
+                            const V3 wiL = toLocal(mits.sh, incoming);
+                            Spec shiftedBsdfValue; Float shiftedBsdfPdf;
+                            bsdfEvalPdf(mainBSDF, wiL, mainWoLocal, ESolidAngle, shiftedBsdfValue, shiftedBsdfPdf);
+                            if (!mainEmitterVisible) shiftedBsdfPdf = 0;
+                            const Float jacobian = 1;
+                            const Float den = (jacobian * spdf) * (jacobian * spdf) * ((dRec.pdf * dRec.pdf) + (shiftedBsdfPdf * shiftedBsdfPdf));
+                            weight = mainWeightNumerator / (kDEps + den + mainWeightDenominator);
+                            mainContribution = mainContributionAll;
+                            shiftedContribution = jacobian * sthr * (shiftedBsdfValue * mainEmitterRadiance);
+                        } else {                                                     // gpt.cpp:659-705
+                            Its sits; loadOffIts(a, slot, i, sits);
+                            const DMaterial &shiftedBSDF = c_scene.materials[sits.material];
+                            if (vertexType(mainBSDF, ESmooth) == VERTEX_TYPE_DIFFUSE && vertexType(shiftedBSDF, ESmooth) == VERTEX_TYPE_DIFFUSE) {   // gpt.cpp:672
+                                DRec sRec; initDRec(sits, sRec);
+                                bool shiftedEmitterVisible;
+                                const Spec sv = sampleEmitterDirectVisible(sRec, lsx, lsy, shiftedEmitterVisible); rays++;
+                                const Spec shiftedEmitterRadiance = sv * sRec.pdf;
+                                const Float shiftedDRecPdf = sRec.pdf;
+                                const Float shiftedDistanceSquared = len2(dRec.p - sits.p);
+                                const V3 emitterDirection = (dRec.p - sits.p) / sqrt(shiftedDistanceSquared);
+                                const Float shiftedOpposingCosine = -dot(dRec.n, emitterDirection);
+                                const V3 woL = toLocal(sits.sh, emitterDirection);
+                                if (cfg.strictNormals && dot(sits.geoN, emitterDirection) * woL.z < 0) {
+                                    shiftSuccessful = false;
+                                } else {
+                                    Spec shiftedBsdfValue; Float shiftedBsdfPdf;
+                                    bsdfEvalPdf(shiftedBSDF, sits.wi, woL, ESolidAngle, shiftedBsdfValue, shiftedBsdfPdf);
+                                    if (!shiftedEmitterVisible) shiftedBsdfPdf = 0;
+                                    const Float jacobian = fabs(shiftedOpposingCosine * mainDistanceSquared) / (kEpsilon + fabs(mainOpposingCosine * shiftedDistanceSquared));   // gpt.cpp:695
+                                    const Float den = (jacobian * spdf) * (jacobian * spdf) * ((shiftedDRecPdf * shiftedDRecPdf) + (shiftedBsdfPdf * shiftedBsdfPdf));
+                                    weight = mainWeightNumerator / (kDEps + den + mainWeightDenominator);
+                                    mainContribution = mainContributionAll;
+                                    shiftedContribution = jacobian * sthr * (shiftedBsdfValue * shiftedEmitterRadiance);
+                                }
+                            }   // else: weight and both contributions stay 0 (gpt.cpp:613-615)
+                        }
+                    }
+                    if (!shiftSuccessful) {                                          // gpt.cpp:708-717
+                        weight = mainWeightNumerator / (kDEps + mainWeightDenominator);
+                        mainContribution = mainContributionAll;
+                        shiftedContribution = splat(0);
+                    }
+                    mrad = mrad + mainContribution * weight;                         // gpt.cpp:723-726
+                    st3(a, o + OF_RAD, slot, ld3(a, o + OF_RAD, slot) + shiftedContribution * weight);
+                    st3(a, o + OF_GRAD, slot, ld3(a, o + OF_GRAD, slot) + (shiftedContribution - mainContribution) * weight);
+                }
+            }
+        }
+
+        // ---------------- BSDF sampling and emitter hits, gpt.cpp:737-826
+        BSDFSample bs;
+        { const Float sx = smp.next1D(), sy = smp.next1D(); bsdfSample(mainBSDF, mits.wi, sx, sy, bs); }   // gpt.cpp:456-457
+        if (bs.pdf <= 0.0) { ended = true; break; }                                  // gpt.cpp:739
+        const V3 mainWo = toWorld(mits.sh, bs.wo);
+        if (cfg.strictNormals && dot(mits.geoN, mainWo) * bs.wo.z <= 0) { ended = true; break; }   // gpt.cpp:748
+        const Frame prevSh = mits.sh; const V3 prevWi = mits.wi;                // previousMainIts, gpt.cpp:753
+        bool mainHitEmitter = false;
+        Spec mainEmitterRadiance = splat(0);
+        DRec mainDRec; initDRec(mits, mainDRec);                                     // gpt.cpp:759
+        const int mainVertexType = vertexType(mainBSDF, bs.sampledType);             // gpt.cpp:764
+        Ray mray; mray.o = mits.p; mray.d = mainWo; mray.mint = kEpsilon; mray.maxt = CUDART_INF;   // gpt.cpp:767
+        rays++;
+        if (!rayIntersect(mray, mits)) { ended = true; break; }                      // gpt.cpp:800-803 (no environment emitter)
+        mrayD = mainWo;
+        if (mits.emitter >= 0) {                                                     // gpt.cpp:771-776
+            mainEmitterRadiance = emittedLe(mits, -mray.d);
+            mainDRec.p = mits.p; mainDRec.n = mits.sh.n; mainDRec.d = mray.d; mainDRec.dist = mits.t; mainDRec.emitter = mits.emitter;
+            mainHitEmitter = true;
+        }
+        const int mainNextVertexType = vertexType(c_scene.materials[mits.material], bs.sampledType);   // gpt.cpp:784
+        const Float mainBsdfPdf = bs.pdf, mainPreviousPdf = mpdf;                    // gpt.cpp:807-812
+        mthr = mthr * (bs.weight * bs.pdf);
+        mpdf *= bs.pdf;
+        meta *= bs.eta;
+        const Float mainLumPdf = (mainHitEmitter && depth + 1 >= cfg.minDepth && !(bs.sampledType & EDelta)) ? pdfEmitterDirect(mainDRec) : 0;   // gpt.cpp:815-816
+        const Float mainWeightNumerator = mainPreviousPdf * bs.pdf;                  // gpt.cpp:819-820
+        const Float mainWeightDenominator = (mainPreviousPdf * mainPreviousPdf) * ((mainLumPdf * mainLumPdf) + (mainBsdfPdf * mainBsdfPdf));
+        const Spec mainContributionAll = mthr * mainEmitterRadiance;
+
+#pragma unroll 1
+        for (int i = 0; i < 4; ++i) {                                                // gpt.cpp:830-1151
+            const int o = BF_COUNT + i * OF_COUNT;
+            Spec mainContribution = splat(0), shiftedContribution = splat(0);
+            Float weight = 0;
+            bool postponedShiftEnd = false, alive = flagAlive(flags, i);
+            int conn = flagConn(flags, i);
+            if (alive) {
+                Spec sthr = ld3(a, o + OF_THR, slot);
+                Float spdf = SD(a, o + OF_PDF, slot);
+                const Float shiftedPreviousPdf = spdf;
+                if (conn == RAY_CONNECTED) {                                         // gpt.cpp:844-861
+                    sthr = sthr * (bs.weight * bs.pdf);
+                    spdf *= mainBsdfPdf;
+                    const Float den = (shiftedPreviousPdf * shiftedPreviousPdf) * ((mainLumPdf * mainLumPdf) + (mainBsdfPdf * mainBsdfPdf));
+                    weight = mainWeightNumerator / (kDEps + den + mainWeightDenominator);
+                    mainContribution = mainContributionAll;
+                    shiftedContribution = sthr * mainEmitterRadiance;
+                } else if (conn == RAY_RECENTLY_CONNECTED) {                         // gpt.cpp:862-888
+                    const V3 incoming = normalize(ld3(a, o + OF_P, slot) - mray.o);
+                    const V3 wiL = toLocal(prevSh, incoming), woL = toLocal(prevSh, mray.d);
+                    const int measure = (bs.sampledType & EDelta) ? EDiscrete : ESolidAngle;
+                    Spec shiftedBsdfValue; Float shiftedBsdfPdf;
+                    bsdfEvalPdf(mainBSDF, wiL, woL, measure, shiftedBsdfValue, shiftedBsdfPdf);
+                    sthr = sthr * shiftedBsdfValue;
+                    spdf *= shiftedBsdfPdf;
+                    conn = RAY_CONNECTED;
+                    const Float den = (shiftedPreviousPdf * shiftedPreviousPdf) * ((mainLumPdf * mainLumPdf) + (shiftedBsdfPdf * shiftedBsdfPdf));
+                    weight = mainWeightNumerator / (kDEps + den + mainWeightDenominator);
+                    mainContribution = mainContributionAll;
+                    shiftedContribution = sthr * mainEmitterRadiance;
+                } else {                                                             // gpt.cpp:889-1126
+                    Its sits; loadOffIts(a, slot, i, sits);
+                    const DMaterial &shiftedBSDF = c_scene.materials[sits.material];
+                    const int shiftedVertexType = vertexType(shiftedBSDF, bs.sampledType);
+                    if (mainVertexType == VERTEX_TYPE_DIFFUSE && mainNextVertexType == VERTEX_TYPE_DIFFUSE && shiftedVertexType == VERTEX_TYPE_DIFFUSE) {
+                        if (!lastSegment || mainHitEmitter) {                        // gpt.cpp:901
+                            const ShiftResult sr = reconnectShift(mray.o, mits.p, sits.p, mits.geoN); rays++;   // gpt.cpp:907
+                            if (!sr.success) { alive = false; }
+                            else {
+                                const V3 outgoingDirection = sr.wo;
+                                const V3 wiL = sits.wi, woL = toLocal(sits.sh, outgoingDirection);
+                                if (cfg.strictNormals && dot(outgoingDirection, sits.geoN) * woL.z <= 0) { alive = false; }
+                                else {
+                                    Spec shiftedBsdfValue; Float shiftedBsdfPdf;
+                                    bsdfEvalPdf(shiftedBSDF, wiL, woL, ESolidAngle, shiftedBsdfValue, shiftedBsdfPdf);   // gpt.cpp:935-936
+                                    sthr = sthr * (shiftedBsdfValue * sr.jacobian);
+                                    spdf *= shiftedBsdfPdf * sr.jacobian;
+                                    conn = RAY_RECENTLY_CONNECTED;
+                                    if (mainHitEmitter) {                            // gpt.cpp:944-985
+                                        const Spec shiftedEmitterRadiance = emittedLe(mits, -outgoingDirection);
+                                        DRec sd;                                     // gpt.cpp:957-964 (measure: solid angle)
+                                        sd.p = mainDRec.p; sd.n = mainDRec.n;
+                                        sd.dist = len(mainDRec.p - sits.p);
+                                        sd.d = (mainDRec.p - sits.p) / sd.dist;
+                                        sd.ref = mainDRec.ref; sd.refN = sits.sh.n; sd.emitter = mainDRec.emitter;
+                                        const Float shiftedLumPdf = pdfEmitterDirect(sd);
+                                        const Float den = (shiftedPreviousPdf * shiftedPreviousPdf) * ((shiftedLumPdf * shiftedLumPdf) + (shiftedBsdfPdf * shiftedBsdfPdf));
+                                        weight = mainWeightNumerator / (kDEps + den + mainWeightDenominator);
+                                        mainContribution = mainContributionAll;
+                                        shiftedContribution = sthr * shiftedEmitterRadiance;
+                                    }   // else weight and contributions stay 0 (gpt.cpp:833-836)
+                                }
+                            }
+                        }
+                    } else {                                                         // half-vector shift, gpt.cpp:987-1126
+                        Spec shiftedEmitterRadiance = splat(0);
+                        const bool bothDelta = (bs.sampledType & EDelta) && (shiftedBSDF.flags & EDelta);
+                        const bool bothSmooth = (bs.sampledType & ESmooth) && (shiftedBSDF.flags & ESmooth);
+                        bool ok = bothDelta || bothSmooth;
+                        if (ok) {
+                            ShiftResult sr = halfVectorShift(prevWi, bs.wo, sits.wi, mainBSDF.bsdfEta, shiftedBSDF.bsdfEta);   // gpt.cpp:1006
+                            if (bs.sampledType & EDelta) sr.jacobian = 1;            // gpt.cpp:1008-1011
+                            ok = sr.success;
+                            if (ok) {
+                                sthr = sthr * sr.jacobian;
+                                spdf *= sr.jacobian;
+                                const V3 tangentSpaceOutgoingDirection = sr.wo;
+                                const V3 outgoingDirection = toWorld(sits.sh, tangentSpaceOutgoingDirection);
+                                const int measure = (bs.sampledType & EDelta) ? EDiscrete : ESolidAngle;
+                                Spec ev; Float pv;
+                                bsdfEvalPdf(shiftedBSDF, sits.wi, tangentSpaceOutgoingDirection, measure, ev, pv);   // gpt.cpp:1030-1031
+                                sthr = sthr * ev;
+                                spdf *= pv;
+                                if (spdf == 0) ok = false;                           // gpt.cpp:1033-1037
+                                if (ok && cfg.strictNormals && dot(outgoingDirection, sits.geoN) * tangentSpaceOutgoingDirection.z <= 0) ok = false;
+                                if (ok) {
+                                    const int shiftedVertexType2 = vertexType(shiftedBSDF, bs.sampledType);   // gpt.cpp:1047
+                                    Ray sray; sray.o = sits.p; sray.d = outgoingDirection; sray.mint = kEpsilon; sray.maxt = CUDART_INF;   // gpt.cpp:1050
+                                    rays++;
+                                    if (!rayIntersect(sray, sits)) ok = false;       // gpt.cpp:1052-1058 (no environment emitter)
+                                    else {
+                                        const int shiftedNextVertexType = vertexType(c_scene.materials[sits.material], bs.sampledType);
+                                        if (mainVertexType == VERTEX_TYPE_DIFFUSE && shiftedVertexType2 == VERTEX_TYPE_DIFFUSE && shiftedNextVertexType == VERTEX_TYPE_DIFFUSE) ok = false;   // gpt.cpp:1089-1093
+                                        else {
+                                            if (sits.emitter >= 0) shiftedEmitterRadiance = emittedLe(sits, -sray.d);   // gpt.cpp:1095-1098
+                                            storeOffIts(a, slot, i, sits);
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                        if (ok) {                                                    // gpt.cpp:1107-1112
+                            weight = mpdf / (spdf * spdf + mpdf * mpdf);
+                            mainContribution = mainContributionAll;
+                            shiftedContribution = sthr * shiftedEmitterRadiance;
+                        } else {                                                     // gpt.cpp:1113-1125
+                            weight = (Float)1 / mpdf;
+                            mainContribution = mainContributionAll;
+                            shiftedContribution = splat(0);
+                            postponedShiftEnd = true;
+                        }
+                    }
+                }
+                st3(a, o + OF_THR, slot, sthr); SD(a, o + OF_PDF, slot) = spdf;
+            }
+            if (!alive) {                                                            // gpt.cpp:1131-1136
+                weight = mainWeightNumerator / (kDEps + mainWeightDenominator);
+                mainContribution = mainContributionAll;
+                shiftedContribution = splat(0);
+            }
+            if (depth + 1 >= cfg.minDepth) {                                         // gpt.cpp:1140-1146
+                mrad = mrad + mainContribution * weight;
+                st3(a, o + OF_RAD, slot, ld3(a, o + OF_RAD, slot) + shiftedContribution * weight);
+                st3(a, o + OF_GRAD, slot, ld3(a, o + OF_GRAD, slot) + (shiftedContribution - mainContribution) * weight);
+            }
+            if (postponedShiftEnd) alive = false;                                    // gpt.cpp:1148-1150
+            flags = setFlag(flags, i, alive, conn);
+        }
+
+        if (depth++ >= cfg.rrDepth) {                                                // gpt.cpp:1159-1174
+            const Float q = fmin(maxComp(mthr / mpdf) * meta * meta, (Float)0.95f);
+            if (smp.next1D() >= q) { ended = true; break; }
+            mpdf *= q;
+            for (int i = 0; i < 4; ++i) SD(a, BF_COUNT + i * OF_COUNT + OF_PDF, slot) *= q;
+        }
+        if (!(depth < cfg.maxDepth || cfg.maxDepth < 0)) ended = true;               // gpt.cpp:537
+    } while (false);
+
+    st3(a, BF_RAD, slot, mrad);
+    SI(a, IF_RNGN, slot) = (int)smp.n;
+    countWarp(&a.counters[1], (unsigned)rays);
+    countWarp(&a.counters[2], ended ? (unsigned)depth : 0u);                         // gpt.cpp:1178-1179
+    if (ended) {
+        SI(a, IF_STATUS, slot) = ST_FINISHED;
+        appendBucketed(a.genList + (size_t)next * a.nSlots, a.genCount + next, a.nSlots, 0, slot);
+    } else {
+        st3(a, BF_RAYD, slot, mrayD); storeBaseIts(a, slot, mits);
+        st3(a, BF_THR, slot, mthr); SD(a, BF_PDF, slot) = mpdf; SD(a, BF_ETA, slot) = meta;
+        SI(a, IF_DEPTH, slot) = depth; SI(a, IF_OFLAGS, slot) = (int)flags;
+        appendBucketed(a.liveList + (size_t)next * a.nBuckets * a.nSlots, a.liveCount + next * kMaxMaterials, a.nSlots, mits.material, slot);
+    }
+}
+
+__global__ void gpt_init_kernel(const GptArgs a)
+{
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= a.nSlots) return;
+    const int px = slot % a.width, py = a.yBegin + slot / a.width;
+    a.key[slot] = samplerKey(a.seed, px, py);                                        // Sampler::generate, gpt.cpp:1250-1251
+    SI(a, IF_STATUS, slot) = ST_FRESH; SI(a, IF_SAMPLE, slot) = 0; SI(a, IF_RNGN, slot) = 0;
+    a.genList[slot] = slot;
+    if (slot == 0) { a.genCount[0] = a.nSlots; a.genCount[1] = 0; }
+    if (slot < 2 * kMaxMaterials) a.liveCount[slot] = 0;
+}
+
+__global__ void gpt_reset_counts_kernel(const GptArgs a, int parity)
+{
+    if (threadIdx.x < kMaxMaterials) a.liveCount[parity * kMaxMaterials + threadIdx.x] = 0;
+    if (threadIdx.x == 0) a.genCount[parity] = 0;
+}
+
+// MultiFilm::developMulti (multifilm.cpp:366-416, fmtconv.cpp:1036-1045): value * (1/weight), plus the
+// Float -> float conversion of gpt.cpp:1439-1442 for the solver inputs.
+__global__ void gpt_develop_kernel(const double *film, int n, double *dev64 /*[5][n][3]*/, float *dev32 /*[5][n][3]*/)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 5 * n) return;
+    const double *p = film + (size_t)i * 4;
+    const double wgt = p[3], inv = (wgt != 0) ? 1 / wgt : wgt;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const double v = p[c] * inv;
+        dev64[(size_t)i * 3 + c] = v;
+        dev32[(size_t)i * 3 + c] = (float)v;
+    }
+}
+
+}  // namespace gdb200
+
+// ======================================================================================= host ==
+
+using namespace gdb200;
+
+struct gdb200_scene {
+    int device = 0;
+    DScene host;                       // flattened tables (vertex classification filled per render)
+    std::vector<gdb200_material> mats;
+    int width = 0, height = 0;
+    // device buffers
+    double *film = nullptr, *dev64 = nullptr; float *dev32 = nullptr;
+    double *sd = nullptr; int *si = nullptr; uint64_t *key = nullptr;
+    int *liveList = nullptr, *genList = nullptr, *liveCount = nullptr, *genCount = nullptr;
+    unsigned long long *counters = nullptr;
+    int slotCapacity = 0, bucketCapacity = 0;
+    volatile int cancel = 0;
+};
+
+static std::mutex g_constMutex;    // c_scene is one per device: serialise renders that share a device
+
+namespace {
+
+int flattenScene(const gdb200_scene_desc *d, gdb200_scene *s)
+{
+    DScene &h = s->host;
+    memset(&h, 0, sizeof(h));
+    const gdb200_camera &c = d->camera;
+    if (c.width <= 0 || c.height <= 0) return set_error(GDB200_ERR_ARGUMENT, "invalid film size %dx%d", c.width, c.height);
+    if (d->n_emitters < 1) return set_error(GDB200_ERR_ARGUMENT, "scene has no emitter");
+    if (d->n_materials > kMaxMaterials || d->n_emitters > kMaxEmitters)
+        return set_error(GDB200_ERR_ARGUMENT, "too many materials/emitters (%d/%d, limits %d/%d)", d->n_materials, d->n_emitters, kMaxMaterials, kMaxEmitters);
+    memcpy(h.sampleToCamera, c.sample_to_camera, sizeof(h.sampleToCamera));
+    memcpy(h.cameraToWorld, c.camera_to_world, sizeof(h.cameraToWorld));
+    h.nearClip = c.near_clip; h.farClip = c.far_clip; h.width = c.width; h.height = c.height;
+    h.invResX = 1.0 / c.width; h.invResY = 1.0 / c.height;
+    h.filterRadius = d->rfilter_radius; h.filterTap = 1.0 / (2 * d->rfilter_radius); h.filterScale = 31 / d->rfilter_radius;
+    s->width = c.width; s->height = c.height;
+    s->mats.assign(d->materials, d->materials + d->n_materials);
+    h.nMaterials = d->n_materials;
+    std::vector<int> rectOfShape(d->n_shapes, -1);
+    for (int i = 0; i < d->n_shapes; i++) {
+        const gdb200_shape &sh = d->shapes[i];
+        if (sh.material < 0 || sh.material >= d->n_materials) return set_error(GDB200_ERR_ARGUMENT, "shape %d: bad material index", i);
+        if (sh.type == GDB200_SHAPE_RECTANGLE) {                                     // rectangle.cpp:100-110
+            if (h.nRects >= kMaxRects) return set_error(GDB200_ERR_ARGUMENT, "too many rectangles (limit %d)", kMaxRects);
+            if (sh.to_world[12] != 0 || sh.to_world[13] != 0 || sh.to_world[14] != 0 || sh.to_world[15] != 1)
+                return set_error(GDB200_ERR_ARGUMENT, "shape %d: toWorld must be affine", i);
+            DRect &r = h.rects[h.nRects];
+            memcpy(r.toObject, sh.to_object, sizeof(r.toObject)); memcpy(r.toWorld, sh.to_world, sizeof(r.toWorld));
+            r.dpdu = xfVector(sh.to_world, mk(2, 0, 0));
+            const V3 dpdv = xfVector(sh.to_world, mk(0, 2, 0));
+            r.n = normalize(xfNormal(sh.to_object, mk(0, 0, 1)));
+            r.invArea = 1.0 / (len(r.dpdu) * len(dpdv));
+            r.material = sh.material; r.emitter = sh.emitter;
+            rectOfShape[i] = h.nRects++;
+        } else if (sh.type == GDB200_SHAPE_SPHERE) {
+            if (h.nSpheres >= kMaxSpheres) return set_error(GDB200_ERR_ARGUMENT, "too many spheres (limit %d)", kMaxSpheres);
+            if (sh.emitter >= 0) return set_error(GDB200_ERR_ARGUMENT, "shape %d: sphere emitters are not supported yet", i);
+            DSphere &sp = h.spheres[h.nSpheres++];
+            sp.center = mk(sh.center[0], sh.center[1], sh.center[2]); sp.radius = sh.radius; sp.flip = sh.flip_normals;
+            sp.material = sh.material; sp.emitter = -1;
+        } else if (sh.type == GDB200_SHAPE_MESH) {
+            if (sh.emitter >= 0) return set_error(GDB200_ERR_ARGUMENT, "shape %d: mesh emitters are not supported yet", i);
+            for (int t = sh.first_tri; t < sh.first_tri + sh.tri_count; t++) {
+                if (h.nTris >= kMaxTris) return set_error(GDB200_ERR_ARGUMENT, "too many triangles for the constant-memory scene table (limit %d); the BVH path is not built yet", kMaxTris);
+                if (t < 0 || t >= d->n_triangles) return set_error(GDB200_ERR_ARGUMENT, "shape %d: triangle range out of bounds", i);
+                const int *ix = d->triangles + 3 * t;
+                const double *va = d->vertices + 3 * ix[0], *vb = d->vertices + 3 * ix[1], *vc = d->vertices + 3 * ix[2];
+                const V3 A = mk(va[0], va[1], va[2]), B = mk(vb[0], vb[1], vb[2]), C = mk(vc[0], vc[1], vc[2]);
+                DTri &T = h.tris[h.nTris++];                                         // TriAccel::load, triaccel.h:61-95
+                static const int waldModulo[4] = {1, 2, 0, 1};
+                const V3 b = C - A, cc = B - A, N = cross(cc, b);
+                const double Nv[3] = {N.x, N.y, N.z}, bv[3] = {b.x, b.y, b.z}, cv[3] = {cc.x, cc.y, cc.z}, Av[3] = {A.x, A.y, A.z};
+                int k = 0;
+                for (int j = 0; j < 3; j++) if (std::abs(Nv[j]) > std::abs(Nv[k])) k = j;
+                const int u = waldModulo[k], v = waldModulo[k + 1];
+                const double n_k = Nv[k], denom = bv[u] * cv[v] - bv[v] * cv[u];
+                T.p0 = A; T.p1 = B; T.p2 = C; T.material = sh.material; T.emitter = -1;
+                if (denom == 0) { T.k = 3; continue; }
+                T.k = k;
+                T.n_u = Nv[u] / n_k; T.n_v = Nv[v] / n_k; T.n_d = dot(A, N) / n_k;
+                T.b_nu = bv[u] / denom; T.b_nv = -bv[v] / denom; T.a_u = Av[u]; T.a_v = Av[v];
+                T.c_nu = cv[v] / denom; T.c_nv = -cv[u] / denom;
+                V3 faceNormal = cross(B - A, C - A);                                 // skdtree.h:367-371
+                const double l = len(faceNormal);
+                if (!isZero(faceNormal)) faceNormal = faceNormal / l;
+                T.faceNormal = faceNormal;
+            }
+        } else return set_error(GDB200_ERR_ARGUMENT, "shape %d: unknown type %d", i, sh.type);
+    }
+    // emitters: DiscreteDistribution over samplingWeight (scene.cpp:357-380, pmf.h:100-114)
+    h.nEmitters = d->n_emitters;
+    h.emCdf[0] = 0.0;
+    for (int i = 0; i < d->n_emitters; i++) h.emCdf[i + 1] = h.emCdf[i] + d->emitters[i].sampling_weight;
+    const double sum = h.emCdf[d->n_emitters], norm = sum > 0 ? 1.0 / sum : 0.0;
+    if (sum > 0) { for (int i = 1; i <= d->n_emitters; i++) h.emCdf[i] *= norm; h.emCdf[d->n_emitters] = 1.0; }
+    for (int i = 0; i < d->n_emitters; i++) {
+        const gdb200_emitter &e = d->emitters[i];
+        if (e.shape < 0 || e.shape >= d->n_shapes || rectOfShape[e.shape] < 0)
+            return set_error(GDB200_ERR_ARGUMENT, "emitter %d: only rectangle area emitters are supported", i);
+        h.emitters[i].rect = rectOfShape[e.shape];
+        h.emitters[i].radiance = mk(e.radiance[0], e.radiance[1], e.radiance[2]);
+        h.emitters[i].pdfDiscrete = e.sampling_weight * norm;
+    }
+    return GDB200_OK;
+}
+
+// Per-material facts incl. the vertex classification of gpt.cpp:176-226 for this shiftThreshold.
+void classifyMaterials(gdb200_scene *s, double shiftThreshold)
+{
+    for (size_t i = 0; i < s->mats.size(); i++) {
+        const gdb200_material &m = s->mats[i];
+        DMaterial &o = s->host.materials[i];
+        o.type = m.type; o.distribution = m.distribution;
+        o.reflectance = mk(m.reflectance[0], m.reflectance[1], m.reflectance[2]);
+        o.specR = mk(m.specular_reflectance[0], m.specular_reflectance[1], m.specular_reflectance[2]);
+        o.specT = mk(m.specular_transmittance[0], m.specular_transmittance[1], m.specular_transmittance[2]);
+        o.eta = mk(m.eta[0], m.eta[1], m.eta[2]); o.k = mk(m.k[0], m.k[1], m.k[2]);
+        o.alpha = std::max(m.alpha, (double)1e-4f);                                  // microfacet.h:67-71
+        o.iorRatio = m.ior_ratio;
+        o.bsdfEta = m.type == GDB200_BSDF_DIELECTRIC ? m.ior_ratio : 1.0;            // bsdf.cpp:62-64, dielectric.cpp:389
+        int nComp = 1; double rough[2] = {0, 0};
+        const double inf = std::numeric_limits<double>::infinity();
+        switch (m.type) {
+            case GDB200_BSDF_DIFFUSE:                                                // diffuse.cpp:97-101,167-169
+                o.flags = std::max(m.reflectance[0], std::max(m.reflectance[1], m.reflectance[2])) > 0 ? (EDiffuseReflection | EFrontSide) : 0;
+                nComp = o.flags ? 1 : 0; rough[0] = inf; break;
+            case GDB200_BSDF_ROUGHCONDUCTOR: o.flags = EGlossyReflection | EFrontSide; rough[0] = 0.5 * (m.alpha + m.alpha); break;   // roughconductor.cpp:437-440
+            case GDB200_BSDF_CONDUCTOR: o.flags = EDeltaReflection | EFrontSide; rough[0] = 0; break;
+            default: o.flags = EDeltaReflection | EDeltaTransmission | EFrontSide | EBackSide; nComp = 2; break;
+        }
+        o.refNFromShading = (o.flags & (ETransmissionBits | EBackSide)) == 0;        // records.inl:160-165
+        for (int deltaQuery = 0; deltaQuery < 2; deltaQuery++) {                     // gpt.cpp:194-226
+            double lowest = inf; bool found_smooth = false, found_dirac = false;
+            for (int c = 0; c < nComp; c++) {
+                const double r = rough[c];
+                if (r == 0) { found_dirac = true; if (!deltaQuery) continue; } else found_smooth = true;
+                if (r < lowest) lowest = r;
+            }
+            if (!found_smooth && found_dirac && !deltaQuery) lowest = 0;
+            (deltaQuery ? o.vtDelta : o.vtSmooth) = lowest <= shiftThreshold ? VERTEX_TYPE_GLOSSY : VERTEX_TYPE_DIFFUSE;
+        }
+    }
+}
+
+void freeSceneBuffers(gdb200_scene *s)
+{
+    cudaFree(s->film); cudaFree(s->dev64); cudaFree(s->dev32); cudaFree(s->sd); cudaFree(s->si); cudaFree(s->key);
+    cudaFree(s->liveList); cudaFree(s->genList); cudaFree(s->liveCount); cudaFree(s->genCount); cudaFree(s->counters);
+    s->film = s->dev64 = s->sd = nullptr; s->dev32 = nullptr; s->si = nullptr; s->key = nullptr;
+    s->liveList = s->genList = s->liveCount = s->genCount = nullptr; s->counters = nullptr; s->slotCapacity = 0;
+}
+
+int developAndCopy(gdb200_scene *s, gdb200_buffers *out)
+{
+    const int n = s->width * s->height;
+    gpt_develop_kernel<<<(5 * n + 255) / 256, 256>>>(s->film, n, s->dev64, s->dev32);
+    GDB_CUDA(cudaGetLastError());
+    if (out) {
+        double *dst[5] = {out->preview_final, out->throughput, out->dx, out->dy, out->direct};
+        for (int b = 0; b < 5; b++)
+            if (dst[b]) GDB_CUDA(cudaMemcpy(dst[b], s->dev64 + (size_t)b * n * 3, sizeof(double) * n * 3, cudaMemcpyDeviceToHost));
+    }
+    GDB_CUDA(cudaDeviceSynchronize());
+    return GDB200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gdb200_scene_create(const gdb200_scene_desc *desc, gdb200_scene **out)
+{
+    if (!desc || !out) return set_error(GDB200_ERR_ARGUMENT, "desc/out_scene is NULL");
+    *out = nullptr;
+    DeviceInfo di;
+    if (int rc = device_info(&di)) return rc;
+    gdb200_scene *s = new gdb200_scene;
+    s->device = di.device;
+    if (int rc = flattenScene(desc, s)) { delete s; return rc; }
+    const size_t n = (size_t)s->width * s->height;
+    cudaError_t e = cudaMalloc(&s->film, sizeof(double) * 5 * n * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&s->dev64, sizeof(double) * 5 * n * 3);
+    if (e == cudaSuccess) e = cudaMalloc(&s->dev32, sizeof(float) * 5 * n * 3);
+    if (e == cudaSuccess) e = cudaMalloc(&s->counters, sizeof(unsigned long long) * 8);
+    if (e == cudaSuccess) e = cudaMemset(s->film, 0, sizeof(double) * 5 * n * 4);
+    if (e != cudaSuccess) { freeSceneBuffers(s); delete s; return set_error(GDB200_ERR_CUDA, "scene allocation failed: %s", cudaGetErrorString(e)); }
+    *out = s;
+    return GDB200_OK;
+}
+
+void gdb200_scene_destroy(gdb200_scene *s)
+{
+    if (!s) return;
+    freeSceneBuffers(s);
+    delete s;
+}
+
+void gdb200_cancel(gdb200_scene *s) { if (s) s->cancel = 1; }
+
+int gdb200_gpt_render(gdb200_scene *s, const gdb200_gpt_params *p, gdb200_buffers *out, gdb200_stats *stats)
+{
+    if (!s || !p) return set_error(GDB200_ERR_ARGUMENT, "scene/params is NULL");
+    // Parameter validation of gpt.cpp:1194-1210 / integrator.cpp:190-225.
+    if (p->max_depth <= 0 && p->max_depth != -1) return set_error(GDB200_ERR_ARGUMENT, "'maxDepth' must be set to -1 (infinite) or a value greater than zero!");
+    if (p->rr_depth <= 0) return set_error(GDB200_ERR_ARGUMENT, "'rrDepth' must be set to a value greater than zero!");
+    if (p->spp <= 0) return set_error(GDB200_ERR_ARGUMENT, "sampleCount must be positive");
+    const bool all = (p->y_begin == 0 && p->y_end == 0);
+    const int y0 = all ? 0 : p->y_begin, y1 = all ? s->height : p->y_end;
+    if (y0 < 0 || y1 > s->height || y0 >= y1) return set_error(GDB200_ERR_ARGUMENT, "invalid row range [%d,%d)", y0, y1);
+    GDB_CUDA(cudaSetDevice(s->device));
+    const int nSlots = s->width * (y1 - y0), nBuckets = s->host.nMaterials;
+    if (nSlots > s->slotCapacity || nBuckets > s->bucketCapacity) {
+        cudaFree(s->sd); cudaFree(s->si); cudaFree(s->key); cudaFree(s->liveList); cudaFree(s->genList); cudaFree(s->liveCount); cudaFree(s->genCount);
+        s->sd = nullptr; s->si = nullptr; s->key = nullptr; s->liveList = s->genList = s->liveCount = s->genCount = nullptr;
+        GDB_CUDA(cudaMalloc(&s->sd, sizeof(double) * kDoubleFields * (size_t)nSlots));
+        GDB_CUDA(cudaMalloc(&s->si, sizeof(int) * IF_COUNT * (size_t)nSlots));
+        GDB_CUDA(cudaMalloc(&s->key, sizeof(uint64_t) * (size_t)nSlots));
+        GDB_CUDA(cudaMalloc(&s->liveList, sizeof(int) * 2 * (size_t)nBuckets * nSlots));
+        GDB_CUDA(cudaMalloc(&s->genList, sizeof(int) * 2 * (size_t)nSlots));
+        GDB_CUDA(cudaMalloc(&s->liveCount, sizeof(int) * 2 * kMaxMaterials));
+        GDB_CUDA(cudaMalloc(&s->genCount, sizeof(int) * 2));
+        s->slotCapacity = nSlots; s->bucketCapacity = nBuckets;
+    }
+    classifyMaterials(s, p->shift_threshold);
+
+    std::lock_guard<std::mutex> lock(g_constMutex);
+    GDB_CUDA(cudaMemcpyToSymbol(c_scene, &s->host, sizeof(DScene)));
+    GDB_CUDA(cudaMemset(s->film, 0, sizeof(double) * 5 * (size_t)s->width * s->height * 4));
+    GDB_CUDA(cudaMemset(s->counters, 0, sizeof(unsigned long long) * 8));
+
+    GptArgs a;
+    memset(&a, 0, sizeof(a));
+    a.sd = s->sd; a.si = s->si; a.key = s->key; a.nSlots = nSlots; a.width = s->width; a.height = s->height; a.yBegin = y0;
+    a.spp = p->spp; a.nBuckets = nBuckets; a.seed = p->seed;
+    a.cfg.maxDepth = p->max_depth; a.cfg.minDepth = 1; a.cfg.rrDepth = p->rr_depth;         // gpt.cpp:1368-1371
+    a.cfg.strictNormals = p->strict_normals; a.cfg.shiftThreshold = p->shift_threshold;
+    a.film = s->film; a.liveList = s->liveList; a.genList = s->genList; a.liveCount = s->liveCount; a.genCount = s->genCount;
+    a.counters = s->counters;
+
+    cudaEvent_t e0, e1;
+    GDB_CUDA(cudaEventCreate(&e0)); GDB_CUDA(cudaEventCreate(&e1));
+    GDB_CUDA(cudaEventRecord(e0));
+    s->cancel = 0;
+    gpt_init_kernel<<<(nSlots + 255) / 256, 256>>>(a);
+    int launches = 1;
+    const int genBlocks = (nSlots + kGenThreads - 1) / kGenThreads;
+    const int bounceBlocks = (nSlots + 32 * nBuckets + kBounceThreads - 1) / kBounceThreads;
+    unsigned long long hostCounters[4] = {0, 0, 0, 0};
+    int parity = 0;
+    const long long maxSteps = (long long)p->spp * 4096 + 65536;     // safety net: never spin forever on a broken queue
+    for (long long step = 0;; step++) {
+        if (step > maxSteps) { cudaEventDestroy(e0); cudaEventDestroy(e1); return set_error(GDB200_ERR_CUDA, "wavefront did not drain after %lld steps", step); }
+        gpt_generate_kernel<<<genBlocks, kGenThreads>>>(a, parity);
+        gpt_bounce_kernel<<<bounceBlocks, kBounceThreads>>>(a, parity);
+        gpt_reset_counts_kernel<<<1, 64>>>(a, parity);
+        launches += 3;
+        parity ^= 1;
+        if ((step & 31) == 31) {
+            GDB_CUDA(cudaMemcpy(hostCounters, s->counters, sizeof(hostCounters), cudaMemcpyDeviceToHost));
+            if (hostCounters[0] >= (unsigned long long)nSlots) break;
+            if (s->cancel) { cudaEventDestroy(e0); cudaEventDestroy(e1); return set_error(GDB200_ERR_CANCELLED, "render cancelled"); }
+        }
+    }
+    GDB_CUDA(cudaEventRecord(e1));
+    GDB_CUDA(cudaEventSynchronize(e1));
+    GDB_CUDA(cudaGetLastError());
+    float ms = 0.f;
+    GDB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    GDB_CUDA(cudaMemcpy(hostCounters, s->counters, sizeof(hostCounters), cudaMemcpyDeviceToHost));
+    if (int rc = developAndCopy(s, out)) return rc;
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->device_ms = ms; stats->launches = launches + 1;
+        stats->samples = (double)hostCounters[3]; stats->rays = (double)hostCounters[1]; stats->path_vertices = (double)hostCounters[2];
+    }
+    return GDB200_OK;
+}
+
+int gdb200_gpt_solver_inputs(gdb200_scene *s, const float **d_dx, const float **d_dy, const float **d_thr, const float **d_direct)
+{
+    if (!s) return set_error(GDB200_ERR_ARGUMENT, "scene is NULL");
+    const size_t n3 = (size_t)s->width * s->height * 3;
+    if (d_thr) *d_thr = s->dev32 + BUF_THROUGHPUT * n3;
+    if (d_dx) *d_dx = s->dev32 + BUF_DX * n3;
+    if (d_dy) *d_dy = s->dev32 + BUF_DY * n3;
+    if (d_direct) *d_direct = s->dev32 + BUF_DIRECT * n3;
+    return GDB200_OK;
+}
+
+int gdb200_gpt_accumulators(gdb200_scene *s, double **d_accum, size_t *bytes)
+{
+    if (!s || !d_accum) return set_error(GDB200_ERR_ARGUMENT, "scene/d_accum is NULL");
+    *d_accum = s->film;
+    if (bytes) *bytes = sizeof(double) * 5 * (size_t)s->width * s->height * 4;
+    return GDB200_OK;
+}
+
+int gdb200_gpt_develop(gdb200_scene *s, gdb200_buffers *out)
+{
+    if (!s) return set_error(GDB200_ERR_ARGUMENT, "scene is NULL");
+    GDB_CUDA(cudaSetDevice(s->device));
+    return developAndCopy(s, out);
+}
+
+}  // extern "C"

@@ -1,0 +1,649 @@
+// gdb200 G-PT tracer — device-side scene model, intersection and BSDF evaluation (fp64).
+//
+// What these functions compute is fixed by the reference (file:line cited per function);
+// how they are organised is not: the scene is a flat constant-memory table, shapes are tested
+// by an unrolled uniform loop (every lane reads the same primitive => constant-cache
+// broadcast), materials are plain structs switched on a small enum, and per-material facts
+// that the reference re-derives through virtual calls on every use (BSDF type flags, the
+// glossy/diffuse vertex classification of gpt.cpp:176-226) are precomputed at scene upload.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <math_constants.h>
+#include "../../include/gdb200.h"
+
+namespace gdb200 {
+
+typedef double Float;
+
+#define GDB_HD __host__ __device__ __forceinline__
+#define GDB_D __device__ __forceinline__
+
+constexpr Float kEpsilon = 1e-7, kShadowEpsilon = 1e-5;       // constants.h:25-26 (DOUBLE_PRECISION)
+constexpr Float kDeltaEpsilon = (Float)1e-3f;                 // constants.h:31 (float literal)
+constexpr Float kDEps = 1e-14;                                // gpt.cpp:63 D_EPSILON
+constexpr Float kPi = 3.14159265358979323846, kInvPi = 0.31830988618379067154;
+
+struct V3 { Float x, y, z; };
+GDB_HD V3 mk(Float x, Float y, Float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+GDB_HD V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+GDB_HD V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+GDB_HD V3 operator-(V3 a) { return mk(-a.x, -a.y, -a.z); }
+GDB_HD V3 operator*(V3 a, Float f) { return mk(a.x * f, a.y * f, a.z * f); }
+GDB_HD V3 operator*(Float f, V3 a) { return mk(a.x * f, a.y * f, a.z * f); }
+GDB_HD V3 operator*(V3 a, V3 b) { return mk(a.x * b.x, a.y * b.y, a.z * b.z); }
+GDB_HD V3 operator/(V3 a, Float f) { Float r = (Float)1 / f; return mk(a.x * r, a.y * r, a.z * r); }   // vector.h:535-542
+GDB_HD V3 cdiv(V3 a, V3 b) { return mk(a.x / b.x, a.y / b.y, a.z / b.z); }
+GDB_HD Float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+GDB_HD V3 cross(V3 a, V3 b) { return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+GDB_HD Float len2(V3 a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
+GDB_HD Float len(V3 a) { return sqrt(len2(a)); }
+GDB_HD V3 normalize(V3 a) { return a / len(a); }
+GDB_HD bool isZero(V3 a) { return a.x == 0 && a.y == 0 && a.z == 0; }
+GDB_HD Float maxComp(V3 a) { return fmax(a.x, fmax(a.y, a.z)); }
+GDB_HD V3 splat(Float v) { return mk(v, v, v); }
+GDB_HD V3 safeSqrt3(V3 s) { return mk(sqrt(fmax(0.0, s.x)), sqrt(fmax(0.0, s.y)), sqrt(fmax(0.0, s.z))); }
+typedef V3 Spec;
+
+struct Frame { V3 s, t, n; };
+GDB_HD V3 toLocal(const Frame &f, V3 v) { return mk(dot(v, f.s), dot(v, f.t), dot(v, f.n)); }   // frame.h:74-80
+GDB_HD V3 toWorld(const Frame &f, V3 v) { return f.s * v.x + f.t * v.y + f.n * v.z; }           // frame.h:83-85
+
+GDB_HD V3 xfAffine(const Float *m, V3 p)     // transform.h:128-137
+{
+    return mk(m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3], m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7],
+              m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11]);
+}
+GDB_HD V3 xfVector(const Float *m, V3 v)     // transform.h:175-183
+{
+    return mk(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[4] * v.x + m[5] * v.y + m[6] * v.z,
+              m[8] * v.x + m[9] * v.y + m[10] * v.z);
+}
+GDB_HD V3 xfPoint(const Float *m, V3 p)      // transform.h:108-125
+{
+    Float x = m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3];
+    Float y = m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7];
+    Float z = m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11];
+    Float w = m[12] * p.x + m[13] * p.y + m[14] * p.z + m[15];
+    if (w == 1.0) return mk(x, y, z);
+    return mk(x, y, z) / w;
+}
+GDB_HD V3 xfNormal(const Float *inv, V3 v)   // transform.h:203-211
+{
+    return mk(inv[0] * v.x + inv[4] * v.y + inv[8] * v.z, inv[1] * v.x + inv[5] * v.y + inv[9] * v.z,
+              inv[2] * v.x + inv[6] * v.y + inv[10] * v.z);
+}
+GDB_HD void computeShadingFrame(V3 n, V3 dpdu, Frame &f)    // util.cpp:603-608
+{
+    f.n = n;
+    f.s = normalize(dpdu - f.n * dot(f.n, dpdu));
+    f.t = cross(f.n, f.s);
+}
+
+// ---------------------------------------------------------------- scene tables
+enum : unsigned { EDiffuseReflection = 0x1, EGlossyReflection = 0x4, EDeltaReflection = 0x10, EDeltaTransmission = 0x20,
+                  ESmooth = 0xF, EDelta = 0x30, ETransmissionBits = 0x2 | 0x8 | 0x20, EBackSide = 0x20000, EFrontSide = 0x10000 };
+enum Measure { ESolidAngle = 0, EDiscrete = 1 };
+enum VertexType { VERTEX_TYPE_GLOSSY = 0, VERTEX_TYPE_DIFFUSE = 1 };
+
+constexpr int kMaxRects = 24, kMaxSpheres = 8, kMaxTris = 192, kMaxMaterials = 32, kMaxEmitters = 8;
+
+struct DRect   { Float toObject[12], toWorld[12]; V3 dpdu, n; Float invArea; int material, emitter; };
+struct DSphere { V3 center; Float radius; int flip, material, emitter, pad; };
+struct DTri    { Float n_u, n_v, n_d, a_u, a_v, b_nu, b_nv, c_nu, c_nv; V3 p0, p1, p2, faceNormal; int k, material, emitter, pad; };
+struct DMaterial {
+    int type, distribution; unsigned flags; int vtSmooth, vtDelta, refNFromShading, pad0, pad1;
+    Spec reflectance, specR, specT, eta, k; Float alpha, iorRatio, bsdfEta;
+};
+struct DEmitter { int rect, pad; Spec radiance; Float pdfDiscrete; };   // pdfDiscrete = samplingWeight * normalization (scene.h:855-857)
+
+struct DScene {
+    Float sampleToCamera[16], cameraToWorld[12];
+    Float nearClip, farClip, invResX, invResY, filterRadius, filterTap, filterScale;
+    int width, height, nRects, nSpheres, nTris, nMaterials, nEmitters, pad;
+    Float emCdf[kMaxEmitters + 1];
+    DRect rects[kMaxRects];
+    DSphere spheres[kMaxSpheres];
+    DMaterial materials[kMaxMaterials];
+    DEmitter emitters[kMaxEmitters];
+    DTri tris[kMaxTris];
+};
+
+__constant__ DScene c_scene;   // one per device; renders sharing a device are serialised on the host
+
+struct Config { int maxDepth, minDepth, rrDepth, strictNormals; Float shiftThreshold; };
+
+struct Its { Float t; V3 p, geoN; Frame sh; V3 wi; int material, emitter; };   // emitter: index or -1
+struct Ray { V3 o, d; Float mint, maxt; };
+
+// ---------------------------------------------------------------- intersection
+GDB_D Float maxAbs3(V3 o) { return fmax(fmax(fabs(o.x), fabs(o.y)), fabs(o.z)); }
+
+// util.cpp:487-525
+GDB_D bool solveQuadratic(double a, double b, double c, double &x0, double &x1)
+{
+    if (a == 0) { if (b != 0) { x0 = x1 = -c / b; return true; } return false; }
+    double discrim = b * b - 4.0 * a * c;
+    if (discrim < 0) return false;
+    double temp, sqrtDiscrim = sqrt(discrim);
+    if (b < 0) temp = -0.5 * (b - sqrtDiscrim); else temp = -0.5 * (b + sqrtDiscrim);
+    x0 = temp / a; x1 = c / temp;
+    if (x0 > x1) { double t = x0; x0 = x1; x1 = t; }
+    return true;
+}
+
+// Candidate tests against the shrinking [mint, maxt] = the outcome of the reference's kd-tree
+// traversal (sahkdtree3.h:179-308).  kind: 0 rect, 1 sphere, 2 triangle.
+template <bool AnyHit>
+GDB_D bool closestPrimitive(const Ray &ray, Float mint, Float maxt, Float &tOut, int &kind, int &index, Float &uOut, Float &vOut)
+{
+    bool found = false;
+    for (int i = 0; i < c_scene.nRects; i++) {                       // rectangle.cpp:125-151
+        const DRect &r = c_scene.rects[i];
+        const V3 o = xfAffine(r.toObject, ray.o), d = xfVector(r.toObject, ray.d);
+        const Float hit = -o.z / d.z;
+        if (!(hit >= mint && hit <= maxt)) continue;
+        const V3 local = o + d * hit;
+        if (fabs(local.x) <= 1 && fabs(local.y) <= 1) {
+            if (AnyHit) return true;
+            maxt = hit; found = true; kind = 0; index = i;
+        }
+    }
+    for (int i = 0; i < c_scene.nSpheres; i++) {                     // sphere.cpp:163-187
+        const DSphere &s = c_scene.spheres[i];
+        const V3 o = ray.o - s.center;
+        const double A = len2(ray.d), B = 2 * dot(o, ray.d), C = len2(o) - s.radius * s.radius;
+        double nearT, farT;
+        if (!solveQuadratic(A, B, C, nearT, farT)) continue;
+        if (!(nearT <= maxt && farT >= mint)) continue;
+        Float t;
+        if (nearT < mint) { if (farT > maxt) continue; t = farT; } else t = nearT;
+        if (AnyHit) return true;
+        maxt = t; found = true; kind = 1; index = i;
+    }
+    for (int i = 0; i < c_scene.nTris; i++) {                        // triaccel.h:97-158
+        const DTri &T = c_scene.tris[i];
+        Float o_u, o_v, o_k, d_u, d_v, d_k;
+        if (T.k == 0) { o_u = ray.o.y; o_v = ray.o.z; o_k = ray.o.x; d_u = ray.d.y; d_v = ray.d.z; d_k = ray.d.x; }
+        else if (T.k == 1) { o_u = ray.o.z; o_v = ray.o.x; o_k = ray.o.y; d_u = ray.d.z; d_v = ray.d.x; d_k = ray.d.y; }
+        else if (T.k == 2) { o_u = ray.o.x; o_v = ray.o.y; o_k = ray.o.z; d_u = ray.d.x; d_v = ray.d.y; d_k = ray.d.z; }
+        else continue;
+        const Float t = (T.n_d - o_u * T.n_u - o_v * T.n_v - o_k) / (d_u * T.n_u + d_v * T.n_v + d_k);
+        if (t < mint || t > maxt) continue;
+        const Float hu = o_u + t * d_u - T.a_u, hv = o_v + t * d_v - T.a_v;
+        const Float u = hv * T.b_nu + hu * T.b_nv, v = hu * T.c_nu + hv * T.c_nv;
+        if (u >= 0 && v >= 0 && u + v <= 1.0) {
+            if (AnyHit) return true;
+            maxt = t; found = true; kind = 2; index = i; uOut = u; vOut = v;
+        }
+    }
+    tOut = maxt;
+    return found;
+}
+
+// ShapeKDTree::rayIntersect(ray, its): skdtree.cpp:112-147, record fill skdtree.h:343-428.
+GDB_D bool rayIntersect(const Ray &ray, Its &its)
+{
+    its.t = CUDART_INF;
+    Float rayMinT = ray.mint;
+    if (rayMinT == kEpsilon) rayMinT *= fmax(maxAbs3(ray.o), kEpsilon);
+    if (!(ray.maxt > rayMinT)) return false;
+    Float t, u = 0, v = 0; int kind = 0, index = 0;
+    if (!closestPrimitive<false>(ray, rayMinT, ray.maxt, t, kind, index, u, v)) return false;
+    its.t = t;
+    V3 dpdu;
+    if (kind == 2) {                                                 // skdtree.h:348-419 (BarycentricPos)
+        const DTri &T = c_scene.tris[index];
+        const V3 b = mk(1 - u - v, u, v);
+        its.p = T.p0 * b.x + T.p1 * b.y + T.p2 * b.z;
+        dpdu = T.p1 - T.p0;
+        its.sh.n = T.faceNormal; its.geoN = T.faceNormal;
+        its.material = T.material; its.emitter = T.emitter;
+    } else if (kind == 0) {                                          // rectangle.cpp:158-171
+        const DRect &r = c_scene.rects[index];
+        its.geoN = r.n; its.sh.n = r.n; dpdu = r.dpdu;
+        its.p = ray.o + ray.d * t;
+        its.material = r.material; its.emitter = r.emitter;
+    } else {                                                         // sphere.cpp:197-240
+        const DSphere &s = c_scene.spheres[index];
+        its.p = ray.o + ray.d * t;
+        const V3 local = its.p - s.center;
+        dpdu = mk(-local.y, local.x, 0) * (2 * kPi);
+        its.geoN = normalize(its.p - s.center);
+        if (s.flip) its.geoN = its.geoN * -1.0;
+        its.sh.n = its.geoN;
+        its.material = s.material; its.emitter = s.emitter;
+    }
+    computeShadingFrame(its.sh.n, dpdu, its.sh);                     // skdtree.h:425
+    its.wi = toLocal(its.sh, -ray.d);                                // skdtree.h:426
+    return true;
+}
+
+// ShapeKDTree::rayIntersect(ray) for shadow rays: skdtree.cpp:206-226
+GDB_D bool rayOccluded(const Ray &ray)
+{
+    Float rayMinT = ray.mint;
+    if (rayMinT == kEpsilon) rayMinT *= maxAbs3(ray.o);
+    if (!(ray.maxt > rayMinT)) return false;
+    Float t, u, v; int a, b;
+    return closestPrimitive<true>(ray, rayMinT, ray.maxt, t, a, b, u, v);
+}
+
+// ---------------------------------------------------------------- sampling helpers
+GDB_D void squareToUniformDiskConcentric(Float sx, Float sy, Float &ox, Float &oy)   // warp.cpp:81-102
+{
+    Float r1 = 2.0 * sx - 1.0, r2 = 2.0 * sy - 1.0, phi, r;
+    if (r1 == 0 && r2 == 0) { r = phi = 0; }
+    else if (r1 * r1 > r2 * r2) { r = r1; phi = (kPi / 4.0) * (r2 / r1); }
+    else { r = r2; phi = (kPi / 2.0) - (r1 / r2) * (kPi / 4.0); }
+    ox = r * cos(phi); oy = r * sin(phi);
+}
+GDB_D V3 squareToCosineHemisphere(Float sx, Float sy)                                 // warp.cpp:43-52
+{
+    Float px, py;
+    squareToUniformDiskConcentric(sx, sy, px, py);
+    Float z = sqrt(fmax(0.0, 1.0 - px * px - py * py));
+    if (z == 0) z = (Float)1e-10f;
+    return mk(px, py, z);
+}
+
+// ---------------------------------------------------------------- microfacet.h (isotropic, visible normals)
+GDB_D Float mfEval(int type, Float alpha, V3 m)                                       // :191-235
+{
+    if (m.z <= 0) return 0.0;
+    const Float cosTheta2 = m.z * m.z;
+    const Float beckmannExponent = ((m.x * m.x) / (alpha * alpha) + (m.y * m.y) / (alpha * alpha)) / cosTheta2;
+    Float result;
+    if (type == GDB200_MICROFACET_BECKMANN) result = exp(-beckmannExponent) / (kPi * alpha * alpha * cosTheta2 * cosTheta2);
+    else { const Float root = ((Float)1 + beckmannExponent) * cosTheta2; result = (Float)1 / (kPi * alpha * alpha * root * root); }
+    if (result * m.z < (Float)1e-20f) result = 0;
+    return result;
+}
+GDB_D Float mfSmithG1(int type, Float alpha, V3 v, V3 m)                              // :470-508
+{
+    if (dot(v, m) * v.z <= 0) return 0.0;
+    const Float temp = 1 - v.z * v.z;
+    const Float tanTheta = temp <= 0.0 ? 0.0 : fabs(sqrt(temp) / v.z);
+    if (tanTheta == 0.0) return 1.0;
+    if (type == GDB200_MICROFACET_BECKMANN) {
+        const Float a = 1.0 / (alpha * tanTheta);
+        if (a >= (Float)1.6f) return 1.0;
+        const Float aSqr = a * a;
+        return ((Float)3.535f * a + (Float)2.181f * aSqr) / (1.0 + (Float)2.276f * a + (Float)2.577f * aSqr);
+    }
+    const Float root = alpha * tanTheta;                                             // math.cpp:89-101 hypot2(1, root)
+    Float r;
+    if (1.0 > fabs(root)) { r = root / 1.0; r = 1.0 * sqrt(1.0 + r * r); }
+    else if (root != 0.0) { r = 1.0 / root; r = fabs(root) * sqrt(1.0 + r * r); }
+    else r = 0.0;
+    return 2.0 / (1.0 + r);
+}
+GDB_D Float mfPdfVisible(int type, Float alpha, V3 wi, V3 m)                          // :455-459
+{
+    if (wi.z == 0) return 0.0;
+    return mfSmithG1(type, alpha, wi, m) * fabs(dot(wi, m)) * mfEval(type, alpha, m) / fabs(wi.z);
+}
+GDB_D Float mtsErf(Float x)                                                           // math.cpp:55-72
+{
+    const Float a1 = 0.254829592, a2 = -0.284496736, a3 = 1.421413741, a4 = -1.453152027, a5 = 1.061405429, p = 0.3275911;
+    const Float sign = copysign(1.0, x);
+    x = fabs(x);
+    const Float t = 1.0 / (1.0 + p * x);
+    const Float y = 1.0 - (((((a5 * t + a4) * t) + a3) * t + a2) * t + a1) * t * exp(-x * x);
+    return sign * y;
+}
+GDB_D Float mtsErfinv(Float x)                                                        // math.cpp:25-53
+{
+    Float w = -log(((Float)1 - x) * ((Float)1 + x)), p;
+    if (w < (Float)5) {
+        w = w - (Float)2.5;
+        p = (Float)2.81022636e-08; p = (Float)3.43273939e-07 + p * w; p = (Float)-3.5233877e-06 + p * w;
+        p = (Float)-4.39150654e-06 + p * w; p = (Float)0.00021858087 + p * w; p = (Float)-0.00125372503 + p * w;
+        p = (Float)-0.00417768164 + p * w; p = (Float)0.246640727 + p * w; p = (Float)1.50140941 + p * w;
+    } else {
+        w = sqrt(w) - (Float)3;
+        p = (Float)-0.000200214257; p = (Float)0.000100950558 + p * w; p = (Float)0.00134934322 + p * w;
+        p = (Float)-0.00367342844 + p * w; p = (Float)0.00573950773 + p * w; p = (Float)-0.0076224613 + p * w;
+        p = (Float)0.00943887047 + p * w; p = (Float)1.00167406 + p * w; p = (Float)2.83297682 + p * w;
+    }
+    return p * x;
+}
+GDB_D void mfSampleVisible11(int type, Float thetaI, Float sx, Float sy, Float &slopeX, Float &slopeY)   // :573-696
+{
+    const Float SQRT_PI_INV = 1 / sqrt(kPi);
+    if (type == GDB200_MICROFACET_BECKMANN) {
+        if (thetaI < (Float)1e-4f) {
+            const Float r = sqrt(-log(1.0 - sx));
+            const Float sinPhi = sin(2 * kPi * sy), cosPhi = cos(2 * kPi * sy);
+            slopeX = r * cosPhi; slopeY = r * sinPhi; return;
+        }
+        const Float tanThetaI = tan(thetaI), cotThetaI = 1 / tanThetaI;
+        Float a = -1, c = mtsErf(cotThetaI);
+        const Float sample_x = fmax(sx, (Float)1e-6f);
+        const Float fit = 1 + thetaI * ((Float)-0.876f + thetaI * ((Float)0.4265f - (Float)0.0594f * thetaI));
+        Float b = c - (1 + c) * pow(1 - sample_x, fit);
+        const Float normalization = 1 / (1 + c + SQRT_PI_INV * tanThetaI * exp(-cotThetaI * cotThetaI));
+        int it = 0;
+        while (++it < 10) {
+            if (!(b >= a && b <= c)) b = 0.5 * (a + c);
+            const Float invErf = mtsErfinv(b);
+            const Float value = normalization * (1 + b + SQRT_PI_INV * tanThetaI * exp(-invErf * invErf)) - sample_x;
+            const Float derivative = normalization * (1 - invErf * tanThetaI);
+            if (fabs(value) < (Float)1e-5f) break;
+            if (value > 0) c = b; else a = b;
+            b -= value / derivative;
+        }
+        slopeX = mtsErfinv(b);
+        slopeY = mtsErfinv(2.0 * fmax(sy, (Float)1e-6f) - 1.0);
+        return;
+    }
+    if (thetaI < (Float)1e-4f) {
+        const Float r = sqrt(fmax(0.0, sx / (1 - sx)));
+        const Float sinPhi = sin(2 * kPi * sy), cosPhi = cos(2 * kPi * sy);
+        slopeX = r * cosPhi; slopeY = r * sinPhi; return;
+    }
+    const Float tanThetaI = tan(thetaI);
+    const Float a = 1 / tanThetaI;
+    const Float G1 = 2.0 / (1.0 + sqrt(fmax(0.0, 1.0 + 1.0 / (a * a))));
+    Float A = 2.0 * sx / G1 - 1.0;
+    if (fabs(A) == 1) A -= copysign(1.0, A) * kEpsilon;
+    const Float tmp = 1.0 / (A * A - 1.0);
+    const Float B = tanThetaI;
+    const Float D = sqrt(fmax(0.0, B * B * tmp * tmp - (A * A - B * B) * tmp));
+    const Float slope_x_1 = B * tmp - D, slope_x_2 = B * tmp + D;
+    slopeX = (A < 0.0 || slope_x_2 > 1.0 / tanThetaI) ? slope_x_1 : slope_x_2;
+    Float S;
+    if (sy > 0.5) { S = 1.0; sy = 2.0 * (sy - 0.5); } else { S = -1.0; sy = 2.0 * (0.5 - sy); }
+    const Float z = (sy * (sy * (sy * (-(Float)0.365728915865723) + (Float)0.790235037209296) - (Float)0.424965825137544) + (Float)0.000152998850436920) /
+                    (sy * (sy * (sy * (sy * (Float)0.169507819808272 - (Float)0.397203533833404) - (Float)0.232500544458471) + (Float)1) - (Float)0.539825872510702);
+    slopeY = S * z * sqrt(1.0 + slopeX * slopeX);
+}
+GDB_D V3 mfSampleVisible(int type, Float alpha, V3 _wi, Float sx, Float sy)           // :421-452
+{
+    const V3 wi = normalize(mk(alpha * _wi.x, alpha * _wi.y, _wi.z));
+    Float theta = 0, phi = 0;
+    if (wi.z < (Float)0.99999) { theta = acos(wi.z); phi = atan2(wi.y, wi.x); }
+    const Float sinPhi = sin(phi), cosPhi = cos(phi);
+    Float slx, sly;
+    mfSampleVisible11(type, theta, sx, sy, slx, sly);
+    Float rx = cosPhi * slx - sinPhi * sly, ry = sinPhi * slx + cosPhi * sly;
+    rx *= alpha; ry *= alpha;
+    const Float normalization = (Float)1 / sqrt(rx * rx + ry * ry + (Float)1.0);
+    return mk(-rx * normalization, -ry * normalization, normalization);
+}
+
+GDB_D Spec fresnelConductorExact(Float cosThetaI, Spec eta, Spec k)                   // util.cpp:739-761
+{
+    const Float cosThetaI2 = cosThetaI * cosThetaI, sinThetaI2 = 1 - cosThetaI2, sinThetaI4 = sinThetaI2 * sinThetaI2;
+    const Spec temp1 = eta * eta - k * k - splat(sinThetaI2);
+    const Spec a2pb2 = safeSqrt3(temp1 * temp1 + k * k * eta * eta * 4.0);
+    const Spec a = safeSqrt3((a2pb2 + temp1) * 0.5);
+    const Spec term1 = a2pb2 + splat(cosThetaI2), term2 = a * (2 * cosThetaI);
+    const Spec Rs2 = cdiv(term1 - term2, term1 + term2);
+    const Spec term3 = a2pb2 * cosThetaI2 + splat(sinThetaI4), term4 = term2 * sinThetaI2;
+    const Spec Rp2 = cdiv(Rs2 * (term3 - term4), term3 + term4);
+    return 0.5 * (Rp2 + Rs2);
+}
+GDB_D Float fresnelDielectricExt(Float cosThetaI_, Float &cosThetaT_, Float eta)      // util.cpp:651-681
+{
+    if (eta == 1) { cosThetaT_ = -cosThetaI_; return 0.0; }
+    const Float scale = (cosThetaI_ > 0) ? 1 / eta : eta, cosThetaTSqr = 1 - (1 - cosThetaI_ * cosThetaI_) * (scale * scale);
+    if (cosThetaTSqr <= 0.0) { cosThetaT_ = 0.0; return 1.0; }
+    const Float cosThetaI = fabs(cosThetaI_), cosThetaT = sqrt(cosThetaTSqr);
+    const Float Rs = (cosThetaI - eta * cosThetaT) / (cosThetaI + eta * cosThetaT);
+    const Float Rp = (eta * cosThetaI - cosThetaT) / (eta * cosThetaI + cosThetaT);
+    cosThetaT_ = (cosThetaI_ > 0) ? -cosThetaT : cosThetaT;
+    return 0.5 * (Rs * Rs + Rp * Rp);
+}
+GDB_D V3 reflectLocal(V3 wi) { return mk(-wi.x, -wi.y, wi.z); }
+GDB_D V3 refractLocal(const DMaterial &m, V3 wi, Float cosThetaT)                     // dielectric.cpp:223-226
+{
+    const Float scale = -(cosThetaT < 0 ? 1.0 / m.iorRatio : m.iorRatio);
+    return mk(scale * wi.x, scale * wi.y, cosThetaT);
+}
+
+// ---------------------------------------------------------------- BSDF eval / pdf / sample
+// Evaluates f*cos and the solid-angle (or discrete) density together: every call site of the
+// reference asks for both (gpt.cpp:588-592,645-647,693-694,871-872,935-936,1030-1031).
+GDB_D void bsdfEvalPdf(const DMaterial &m, V3 wi, V3 wo, int measure, Spec &value, Float &pdf)
+{
+    value = splat(0); pdf = 0;
+    switch (m.type) {
+    case GDB200_BSDF_DIFFUSE:                                                          // diffuse.cpp:110-129
+        if (measure != ESolidAngle || wi.z <= 0 || wo.z <= 0) return;
+        value = m.reflectance * (kInvPi * wo.z);
+        pdf = kInvPi * wo.z;
+        return;
+    case GDB200_BSDF_ROUGHCONDUCTOR: {                                                 // roughconductor.cpp:256-320
+        if (measure != ESolidAngle || wi.z <= 0 || wo.z <= 0) return;
+        const V3 H = normalize(wo + wi);
+        const Float D = mfEval(m.distribution, m.alpha, H);
+        const Float G1i = mfSmithG1(m.distribution, m.alpha, wi, H);
+        pdf = D * G1i / (4.0 * wi.z);
+        if (D == 0) return;
+        const Spec F = fresnelConductorExact(dot(wi, H), m.eta, m.k) * m.specR;
+        const Float G = G1i * mfSmithG1(m.distribution, m.alpha, wo, H);
+        const Float model = D * G / (4.0 * wi.z);
+        value = F * model;
+        return;
+    }
+    case GDB200_BSDF_CONDUCTOR:                                                        // conductor.cpp:221-250
+        if (measure != EDiscrete || wi.z <= 0 || wo.z <= 0 || fabs(dot(reflectLocal(wi), wo) - 1) > kDeltaEpsilon) return;
+        value = m.specR * fresnelConductorExact(wi.z, m.eta, m.k);
+        pdf = 1.0;
+        return;
+    default: {                                                                         // dielectric.cpp:228-275
+        Float cosThetaT;
+        const Float F = fresnelDielectricExt(wi.z, cosThetaT, m.iorRatio);
+        if (wi.z * wo.z >= 0) {
+            if (measure != EDiscrete || fabs(dot(reflectLocal(wi), wo) - 1) > kDeltaEpsilon) return;
+            value = m.specR * F; pdf = F;
+        } else {
+            if (measure != EDiscrete || fabs(dot(refractLocal(m, wi, cosThetaT), wo) - 1) > kDeltaEpsilon) return;
+            const Float factor = cosThetaT < 0 ? 1.0 / m.iorRatio : m.iorRatio;
+            value = m.specT * factor * factor * (1 - F); pdf = 1 - F;
+        }
+        return;
+    }
+    }
+}
+
+struct BSDFSample { V3 wo; Float eta; unsigned sampledType; Spec weight; Float pdf; };
+
+// BSDF::sample(bRec, pdf, sample), pdf pre-set to 0 by the caller (gpt.cpp:450-457)
+GDB_D void bsdfSample(const DMaterial &m, V3 wi, Float sx, Float sy, BSDFSample &r)
+{
+    r.weight = splat(0); r.pdf = 0; r.eta = 1.0; r.sampledType = 0; r.wo = mk(0, 0, 0);
+    switch (m.type) {
+    case GDB200_BSDF_DIFFUSE:                                                          // diffuse.cpp:143-153
+        if (wi.z <= 0) return;
+        r.wo = squareToCosineHemisphere(sx, sy);
+        r.sampledType = EDiffuseReflection;
+        r.pdf = kInvPi * r.wo.z;
+        r.weight = m.reflectance;
+        return;
+    case GDB200_BSDF_ROUGHCONDUCTOR: {                                                 // roughconductor.cpp:369-419
+        if (wi.z < 0) return;
+        const V3 mm = mfSampleVisible(m.distribution, m.alpha, wi, sx, sy);
+        const Float temporaryPdf = mfPdfVisible(m.distribution, m.alpha, wi, mm);
+        if (temporaryPdf == 0) return;
+        r.wo = 2 * dot(wi, mm) * mm - wi;
+        r.sampledType = EGlossyReflection;
+        if (r.wo.z <= 0) return;
+        const Spec F = fresnelConductorExact(dot(wi, mm), m.eta, m.k) * m.specR;
+        const Float weight = mfSmithG1(m.distribution, m.alpha, r.wo, mm);
+        if (weight > 0) { r.pdf = temporaryPdf / (4.0 * dot(r.wo, mm)); r.weight = F * weight; }
+        return;
+    }
+    case GDB200_BSDF_CONDUCTOR:                                                        // conductor.cpp:268-285
+        if (wi.z <= 0) return;
+        r.sampledType = EDeltaReflection;
+        r.wo = reflectLocal(wi);
+        r.pdf = 1;
+        r.weight = m.specR * fresnelConductorExact(wi.z, m.eta, m.k);
+        return;
+    default: {                                                                         // dielectric.cpp:277-305
+        Float cosThetaT;
+        const Float F = fresnelDielectricExt(wi.z, cosThetaT, m.iorRatio);
+        if (sx <= F) {
+            r.sampledType = EDeltaReflection; r.wo = reflectLocal(wi); r.eta = 1.0; r.pdf = F;
+            r.weight = m.specR;
+        } else {
+            r.sampledType = EDeltaTransmission; r.wo = refractLocal(m, wi, cosThetaT);
+            r.eta = cosThetaT < 0 ? m.iorRatio : 1.0 / m.iorRatio; r.pdf = 1 - F;
+            const Float factor = cosThetaT < 0 ? 1.0 / m.iorRatio : m.iorRatio;
+            r.weight = m.specT * (factor * factor);
+        }
+        return;
+    }
+    }
+}
+
+GDB_D int vertexType(const DMaterial &m, unsigned bsdfTypeMask)                       // gpt.cpp:176-226, precomputed per material
+{
+    return (bsdfTypeMask & EDelta) ? m.vtDelta : m.vtSmooth;
+}
+
+// ---------------------------------------------------------------- emitters
+struct DRec { V3 ref, refN, p, n, d; Float dist, pdf; int emitter; };
+
+GDB_D Spec emittedLe(const Its &its, V3 d)                                            // area.cpp:104-109
+{
+    if (dot(its.sh.n, d) <= 0) return splat(0);
+    return c_scene.emitters[its.emitter].radiance;
+}
+GDB_D void initDRec(const Its &ref, DRec &r)                                          // records.inl:160-165
+{
+    r.ref = ref.p;
+    r.refN = c_scene.materials[ref.material].refNFromShading ? ref.sh.n : mk(0, 0, 0);
+}
+
+// Scene::sampleEmitterDirectVisible, scene.cpp:855-879 (pmf.h:124-188, area.cpp:158-176,
+// shape.cpp:102-114, rectangle.cpp:210-216)
+GDB_D Spec sampleEmitterDirectVisible(DRec &dRec, Float sx, Float sy, bool &visible)
+{
+    const int nE = c_scene.nEmitters;
+    int entry = 0;                                                                     // std::lower_bound over the CDF
+    while (entry <= nE && c_scene.emCdf[entry] < sx) entry++;
+    int index = min(nE - 1, max(0, entry - 1));
+    while (c_scene.emCdf[index + 1] - c_scene.emCdf[index] == 0 && index < nE) ++index;
+    const Float emPdf = c_scene.emCdf[index + 1] - c_scene.emCdf[index];
+    sx = (sx - c_scene.emCdf[index]) / (c_scene.emCdf[index + 1] - c_scene.emCdf[index]);
+
+    const DEmitter &em = c_scene.emitters[index];
+    const DRect &s = c_scene.rects[em.rect];
+    dRec.p = xfAffine(s.toWorld, mk(sx * 2 - 1, sy * 2 - 1, 0));
+    dRec.n = s.n;
+    dRec.pdf = s.invArea;
+    dRec.d = dRec.p - dRec.ref;
+    const Float distSquared = len2(dRec.d);
+    dRec.dist = sqrt(distSquared);
+    dRec.d = dRec.d / dRec.dist;
+    const Float dp = fabs(dot(dRec.d, dRec.n));
+    dRec.pdf *= dp != 0 ? (distSquared / dp) : 0.0;
+    Spec value;
+    if (dot(dRec.d, dRec.refN) >= 0 && dot(dRec.d, dRec.n) < 0 && dRec.pdf != 0) value = em.radiance / dRec.pdf;
+    else { dRec.pdf = 0.0; value = splat(0); }
+    dRec.emitter = index;
+    dRec.pdf *= emPdf;
+    value = value / emPdf;
+    Ray ray; ray.o = dRec.ref; ray.d = dRec.d; ray.mint = kEpsilon; ray.maxt = dRec.dist * (1 - kShadowEpsilon);
+    if (rayOccluded(ray)) { visible = false; return splat(0); }
+    visible = true;
+    return value;
+}
+
+// Scene::pdfEmitterDirect, scene.cpp:976-979 + area.cpp:178-186 + shape.cpp:116-126
+GDB_D Float pdfEmitterDirect(const DRec &dRec)
+{
+    const DEmitter &em = c_scene.emitters[dRec.emitter];
+    Float pdf = 0.0;
+    if (dot(dRec.d, dRec.refN) >= 0 && dot(dRec.d, dRec.n) < 0)
+        pdf = c_scene.rects[em.rect].invArea * (dRec.dist * dRec.dist) / fabs(dot(dRec.d, dRec.n));
+    return pdf * em.pdfDiscrete;
+}
+
+// ---------------------------------------------------------------- shifts
+GDB_D V3 reflectAbout(V3 wi, V3 n) { return 2 * dot(wi, n) * n - wi; }                // util.cpp:763-765
+GDB_D V3 refractAbout(V3 wi, V3 n, Float eta)                                         // util.cpp:774-792
+{
+    if (eta == 1) return -wi;
+    const Float cosThetaI = dot(wi, n);
+    if (cosThetaI > 0) eta = 1 / eta;
+    const Float cosThetaTSqr = 1 - (1 - cosThetaI * cosThetaI) * (eta * eta);
+    if (cosThetaTSqr <= 0.0) return mk(0, 0, 0);
+    return n * (cosThetaI * eta - copysign(1.0, cosThetaI) * sqrt(cosThetaTSqr)) - wi * eta;
+}
+
+struct ShiftResult { bool success; Float jacobian; V3 wo; };
+
+GDB_D ShiftResult halfVectorShift(V3 mainWi, V3 mainWo, V3 shiftedWi, Float mainEta, Float shiftedEta)   // gpt.cpp:242-305
+{
+    ShiftResult result; result.success = false; result.jacobian = 0; result.wo = mk(0, 0, 0);
+    if (mainWi.z * mainWo.z < 0) {
+        if (mainEta == 1 || shiftedEta == 1) return result;
+        const V3 hMain = (mainWi.z < 0) ? -(mainWi * mainEta + mainWo) : -(mainWi + mainWo * mainEta);
+        const V3 h = normalize(hMain);
+        const V3 shiftedWo = refractAbout(shiftedWi, h, shiftedEta);
+        if (isZero(shiftedWo)) return result;
+        const V3 hShifted = (shiftedWi.z < 0) ? -(shiftedWi * shiftedEta + shiftedWo) : -(shiftedWi + shiftedWo * shiftedEta);
+        const Float hLengthSquared = len2(hShifted) / (kDEps + len2(hMain));
+        const Float WoDotH = fabs(dot(mainWo, h)) / (kDEps + fabs(dot(shiftedWo, h)));
+        result.success = true; result.wo = shiftedWo; result.jacobian = hLengthSquared * WoDotH;
+    } else {
+        const V3 h = normalize(mainWi + mainWo);
+        const V3 shiftedWo = reflectAbout(shiftedWi, h);
+        const Float WoDotH = dot(shiftedWo, h) / dot(mainWo, h);
+        result.success = true; result.wo = shiftedWo; result.jacobian = fabs(WoDotH);
+    }
+    return result;
+}
+
+GDB_D ShiftResult reconnectShift(V3 mainSource, V3 target, V3 shiftSource, V3 targetNormal)   // gpt.cpp:84-93, 316-345
+{
+    ShiftResult result; result.success = false; result.jacobian = 0; result.wo = mk(0, 0, 0);
+    Ray r; r.o = shiftSource; r.d = target - shiftSource; r.mint = kEpsilon; r.maxt = 1.0 - kShadowEpsilon;
+    if (rayOccluded(r)) return result;
+    const V3 mainEdge = mainSource - target, shiftedEdge = shiftSource - target;
+    const Float mainL2 = len2(mainEdge), shiftedL2 = len2(shiftedEdge);
+    const V3 shiftedWo = -shiftedEdge / sqrt(shiftedL2);
+    const Float mainOpposingCosine = dot(mainEdge, targetNormal) / sqrt(mainL2);
+    const Float shiftedOpposingCosine = dot(shiftedWo, targetNormal);
+    result.jacobian = fabs(shiftedOpposingCosine * mainL2) / (kDEps + fabs(mainOpposingCosine * shiftedL2));
+    result.success = true; result.wo = shiftedWo;
+    return result;
+}
+
+// perspective.cpp:271-298
+GDB_D void sampleCameraRay(Float px, Float py, Ray &ray)
+{
+    const V3 nearP = xfPoint(c_scene.sampleToCamera, mk(px * c_scene.invResX, py * c_scene.invResY, 0.0));
+    const V3 d = normalize(nearP);
+    const Float invZ = 1.0 / d.z;
+    ray.mint = c_scene.nearClip * invZ;
+    ray.maxt = c_scene.farClip * invZ;
+    ray.o = xfAffine(c_scene.cameraToWorld, mk(0, 0, 0));
+    ray.d = xfVector(c_scene.cameraToWorld, d);
+}
+
+// ---------------------------------------------------------------- sampler (gdb200_counter)
+GDB_HD uint64_t mix64(uint64_t z)
+{
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+GDB_HD uint64_t samplerKey(uint64_t seed, int px, int py)
+{
+    return mix64(mix64(seed + 0x9E3779B97F4A7C15ULL) ^ ((uint64_t)(uint32_t)px | ((uint64_t)(uint32_t)py << 32)));
+}
+struct Sampler {
+    uint64_t key; uint32_t n;
+    GDB_D Float next1D()
+    {
+        n++;
+        return (Float)(mix64(key + (uint64_t)n * 0x9E3779B97F4A7C15ULL) >> 11) * (1.0 / 9007199254740992.0);
+    }
+};
+
+}  // namespace gdb200

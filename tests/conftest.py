@@ -58,6 +58,27 @@ class Oracle:
         assert rc == 0
         return out
 
+    def gpt(self, desc, params, threads=8):
+        """CPU oracle of the G-PT tracer. Returns (buffers dict like the integrator's, weights[5,h,w], counters[3])."""
+        from gdb200 import scenes
+        w, h = desc.camera.width, desc.camera.height
+        names = (("throughput", "-throughput"), ("dx", "-dx"), ("dy", "-dy"), ("direct", "-direct"), ("preview_final", "-final"))
+        out = {n: np.zeros((h, w, 3)) for _, n in names}
+        B = scenes.Buffers()
+        for field, n in names:
+            setattr(B, field, out[n].ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+        wts, cnt = np.zeros((5, h, w)), np.zeros(3)
+        rc = self.lib.gdb200_oracle_gpt_render(ctypes.byref(desc), ctypes.byref(params), ctypes.byref(B),
+                                               self._p(wts), self._p(cnt), threads)
+        assert rc == 0
+        return out, wts, cnt
+
+    def path(self, desc, params, threads=8):
+        w, h = desc.camera.width, desc.camera.height
+        out = np.zeros((h, w, 3))
+        assert self.lib.gdb200_oracle_path_render(ctypes.byref(desc), ctypes.byref(params), self._p(out), threads) == 0
+        return out
+
     def poisson_ref(self, dx, dy, thr, direct, alpha=0.2, preset="L1D"):
         h, w, _ = dx.shape
         out = np.empty_like(dx)
