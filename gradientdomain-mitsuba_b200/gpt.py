@@ -35,6 +35,15 @@ def _bind(L):
     L._gpt_bound = True
 
 
+def device_view(ptr, shape, typestr="<f8"):
+    """Zero-copy torch view of a raw device pointer owned by libgdb200 (plumbing for NCCL)."""
+    import torch
+
+    class _Dev:
+        __cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+    return torch.as_tensor(_Dev(), device="cuda")
+
+
 class Scene:
     """Device-resident flattened scene (gdb200_scene)."""
 
@@ -45,6 +54,23 @@ class Scene:
         self.width, self.height = desc.camera.width, desc.camera.height
         self._h = ctypes.c_void_p()
         check(L.gdb200_scene_create(ctypes.byref(desc), ctypes.byref(self._h)))
+
+    def accumulators(self):
+        """torch view [5, h, w, 4] (fp64: R,G,B,weight) of the raw film accumulators."""
+        ptr, nbytes = ctypes.c_void_p(), ctypes.c_size_t()
+        check(lib().gdb200_gpt_accumulators(self._h, ctypes.byref(ptr), ctypes.byref(nbytes)))
+        return device_view(ptr.value, (5, self.height, self.width, 4))
+
+    def develop(self, download=True):
+        """Re-develop after the accumulators were merged across GPUs (gdb200_gpt_develop)."""
+        out, B = {}, _scenes.Buffers()
+        if download:
+            for field, name in (("preview_final", "-final"), ("throughput", "-throughput"), ("dx", "-dx"),
+                                ("dy", "-dy"), ("direct", "-direct")):
+                out[name] = np.empty((self.height, self.width, 3), dtype=np.float64)
+                setattr(B, field, out[name].ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+        check(lib().gdb200_gpt_develop(self._h, ctypes.byref(B)))
+        return out
 
     def close(self):
         if self._h:

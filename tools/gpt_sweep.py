@@ -1,0 +1,23 @@
+"""Tracer throughput probe: Msamples/s of gdb200_gpt_render (device time, CUDA events inside the library)."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import gdb200  # noqa: E402
+from gdb200 import scenes  # noqa: E402
+
+cases = [("cbox_diffuse", 512, 16), ("cbox_diffuse", 512, 64), ("cbox_glossy", 1024, 16), ("cbox_glossy", 1024, 64)]
+if len(sys.argv) > 1:
+    cases = [(a.split(":")[0], int(a.split(":")[1]), int(a.split(":")[2])) for a in sys.argv[1:]]
+for name, n, spp in cases:
+    desc = getattr(scenes, name)(n, n)
+    scene = gdb200.Scene(desc)
+    integ = gdb200.GPTIntegrator(reconstructL1=False, reconstructL2=False)
+    for rep in range(2):
+        integ.trace(scene, spp=spp, seed=0, download=False)
+    st = integ.stats
+    print(json.dumps({"scene": name, "size": n, "spp": spp, "ms": round(st.device_ms, 2), "launches": st.launches,
+                      "Msamples_s": round(st.samples / st.device_ms / 1e3, 2), "rays_per_sample": round(st.rays / st.samples, 2),
+                      "avg_depth": round(st.path_vertices / st.samples, 3), "Grays_s": round(st.rays / st.device_ms / 1e6, 2)}), flush=True)
+    scene.close()
