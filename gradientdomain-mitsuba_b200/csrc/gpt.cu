@@ -17,7 +17,7 @@
 //                             4-strategy MIS, BSDF sample, extension ray, the reconnection /
 //                             half-vector shift of the 4 offset paths, Russian roulette) for every
 //                             live slot;
-//   * both kernels append their survivors to the next step's queues with warp-aggregated
+//   * gpt_compact_kernel rebuilds the live queues every step with ballot/popc stream compaction,
 //     (match_any + popc + one atomic per warp and bucket) stream compaction, bucketed by the
 //     material id of the base vertex, so a warp of the bounce kernel shades one BSDF type;
 //   * film accumulators are fp64 value+weight planes updated with red.global.add.f64.
@@ -48,20 +48,19 @@ enum { RAY_NOT_CONNECTED = 0, RAY_RECENTLY_CONNECTED = 1, RAY_CONNECTED = 2 };
 enum { BUF_FINAL = 0, BUF_THROUGHPUT = 1, BUF_DX = 2, BUF_DY = 3, BUF_DIRECT = 4 };
 
 constexpr int kBounceThreads = 128, kGenThreads = 128;
+constexpr int kBuckets = 12;  // one queue per (BSDF type of the base vertex) x (shift stage of the offset paths)
 
 struct GptArgs {
     double *sd;            // [kDoubleFields][nSlots]
     int *si;               // [IF_COUNT][nSlots]
     uint64_t *key;         // [nSlots]
     int nSlots, width, height, yBegin;
-    int spp, nBuckets;
+    int spp, pad0;
     uint64_t seed;
     Config cfg;
     double *film;          // [5][H][W][4]
-    int *liveList;         // [2][nBuckets][nSlots]
-    int *genList;          // [2][nSlots]
-    int *liveCount;        // [2][kMaxMaterials]
-    int *genCount;         // [2]
+    int *liveList;         // [2][kBuckets][nSlots]
+    int *liveCount;        // [2][kBuckets]
     unsigned long long *counters;   // [0] done slots, [1] rays, [2] path vertices, [3] samples
 };
 
@@ -97,16 +96,6 @@ GDB_D void loadOffIts(const GptArgs &a, int slot, int i, Its &its)
     its.material = SI(a, IF_OMAT0 + i, slot); its.emitter = -1;
 }
 
-// Warp-aggregated append of `slot` to queue `bucket` (active lanes only).
-GDB_D void appendBucketed(int *lists, int *counts, int nSlots, int bucket, int slot)
-{
-    const unsigned peers = __match_any_sync(__activemask(), bucket);
-    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1, rank = __popc(peers & ((1u << lane) - 1));
-    int base = 0;
-    if (lane == leader) base = atomicAdd(&counts[bucket], __popc(peers));
-    base = __shfl_sync(peers, base, leader);
-    lists[(size_t)bucket * nSlots + base + rank] = slot;
-}
 // One atomic per warp for statistics counters.
 GDB_D void countWarp(unsigned long long *ctr, unsigned v)
 {
@@ -121,7 +110,7 @@ GDB_D Float evalDiscretized(Float x)      // rfilter.h:76-77, MTS_FILTER_RESOLUT
     const int idx = min((int)fabs(x * c_scene.filterScale), 31);
     return idx < 31 ? c_scene.filterTap : 0.0;
 }
-GDB_D void filmPut(const GptArgs &a, Float sx, Float sy, Spec v, Float weight, int buf, bool allowNegative)
+GDB_CALL void filmPut(const GptArgs &a, Float sx, Float sy, Spec v, Float weight, int buf, bool allowNegative)
 {
     const Float value[4] = {v.x, v.y, v.z, weight};
 #pragma unroll
@@ -169,11 +158,11 @@ GDB_D int flagConn(unsigned f, int i) { return (f >> (3 * i + 1)) & 3u; }
 GDB_D unsigned setFlag(unsigned f, int i, bool alive, int conn) { return (f & ~(7u << (3 * i))) | packFlag(i, alive, conn); }
 
 // ------------------------------------------------------------------ generate: splat finished paths, start next samples
-__global__ void __launch_bounds__(kGenThreads) gpt_generate_kernel(const GptArgs a, int parity)
+__global__ void __launch_bounds__(kGenThreads) gpt_generate_kernel(const GptArgs a)
 {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= a.genCount[parity]) return;
-    const int slot = a.genList[(size_t)parity * a.nSlots + g];
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= a.nSlots) return;
+    { const int st = SI(a, IF_STATUS, slot); if (st != ST_FRESH && st != ST_FINISHED) return; }
     const int px = slot % a.width, py = a.yBegin + slot / a.width;
 
     if (SI(a, IF_STATUS, slot) == ST_FINISHED) {
@@ -226,7 +215,6 @@ __global__ void __launch_bounds__(kGenThreads) gpt_generate_kernel(const GptArgs
         SD(a, BF_SPX, slot) = spx; SD(a, BF_SPY, slot) = spy;
         SI(a, IF_DEPTH, slot) = 1; SI(a, IF_OFLAGS, slot) = (int)flags;
         status = ST_LIVE;
-        appendBucketed(a.liveList + (size_t)parity * a.nBuckets * a.nSlots, a.liveCount + parity * kMaxMaterials, a.nSlots, mits.material, slot);
         break;
     }
     SI(a, IF_STATUS, slot) = status; SI(a, IF_SAMPLE, slot) = j; SI(a, IF_RNGN, slot) = (int)smp.n;
@@ -236,24 +224,31 @@ __global__ void __launch_bounds__(kGenThreads) gpt_generate_kernel(const GptArgs
 }
 
 // ------------------------------------------------------------------ bounce: one iteration of gpt.cpp:537-1175
+// The reference runs two loops over the offset paths per bounce (NEE, then BSDF-sample stage).
+// Here the base path's NEE, BSDF sample and extension ray are computed first and ONE loop then
+// performs both stages per offset path, so each offset's state crosses HBM once per bounce; the
+// base path's radiance is still accumulated in the reference's order (all NEE terms, then all
+// BSDF-stage terms).
 __global__ void __launch_bounds__(kBounceThreads) gpt_bounce_kernel(const GptArgs a, int parity)
 {
-    // thread -> (material bucket, index): buckets are padded to whole warps so a warp shades one BSDF
-    __shared__ int s_begin[kMaxMaterials + 1], s_count[kMaxMaterials];
+    // thread -> (BSDF-type bucket, index).  Buckets are padded to whole warps so a warp shades one BSDF
+    // type; inside a bucket the slots are in ascending pixel order (gpt_compact_kernel), so the
+    // struct-of-arrays state rows are still read as (near-)contiguous sectors.
+    __shared__ int s_begin[kBuckets + 1], s_count[kBuckets];
     if (threadIdx.x == 0) {
         int acc = 0;
-        for (int b = 0; b < a.nBuckets; b++) { const int c = a.liveCount[parity * kMaxMaterials + b]; s_begin[b] = acc; s_count[b] = c; acc += (c + 31) & ~31; }
-        s_begin[a.nBuckets] = acc;
+        for (int b = 0; b < kBuckets; b++) { const int c = a.liveCount[parity * kBuckets + b]; s_begin[b] = acc; s_count[b] = c; acc += (c + 31) & ~31; }
+        s_begin[kBuckets] = acc;
+        if (blockIdx.x == 0) for (int b = 0; b < kBuckets; b++) a.liveCount[(parity ^ 1) * kBuckets + b] = 0;   // for the next step's compaction
     }
     __syncthreads();
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= s_begin[a.nBuckets]) return;
+    if (g >= s_begin[kBuckets]) return;
     int b = 0;
     while (g >= s_begin[b + 1]) b++;
     const int idx = g - s_begin[b];
     if (idx >= s_count[b]) return;
-    const int slot = a.liveList[((size_t)parity * a.nBuckets + b) * a.nSlots + idx];
-    const int next = parity ^ 1;
+    const int slot = a.liveList[((size_t)parity * kBuckets + b) * a.nSlots + idx];
     const Config cfg = a.cfg;
 
     Its mits; loadBaseIts(a, slot, mits);
@@ -263,307 +258,365 @@ __global__ void __launch_bounds__(kBounceThreads) gpt_bounce_kernel(const GptArg
     int depth = SI(a, IF_DEPTH, slot);
     unsigned flags = (unsigned)SI(a, IF_OFLAGS, slot);
     Sampler smp; smp.key = a.key[slot]; smp.n = (uint32_t)SI(a, IF_RNGN, slot);
-    unsigned long long rays = 0;
+    unsigned rays = 0;
     bool ended = false;
 
-    do {
-        if (cfg.strictNormals) {                                                     // gpt.cpp:541-555
-            if (dot(mrayD, mits.geoN) * mits.wi.z >= 0) { ended = true; break; }
-            // offsets: their ray direction equals toWorld(-wi) of the stored vertex
-            for (int i = 0; i < 4; i++) {
+    if (cfg.strictNormals) {                                                         // gpt.cpp:541-555
+        if (dot(mrayD, mits.geoN) * mits.wi.z >= 0) ended = true;
+        else
+            for (int i = 0; i < 4; i++) {       // an unconnected offset's ray direction is -toWorld(wi) of its stored vertex
                 if (!flagAlive(flags, i) || flagConn(flags, i) != RAY_NOT_CONNECTED) continue;
                 Its sits; loadOffIts(a, slot, i, sits);
                 const V3 sd = -toWorld(sits.sh, sits.wi);
                 if (dot(sd, sits.geoN) * sits.wi.z >= 0) flags = setFlag(flags, i, false, flagConn(flags, i));
             }
-        }
+    }
+
+    if (!ended) {
         const bool lastSegment = (depth + 1 == cfg.maxDepth);                        // gpt.cpp:558
         const DMaterial &mainBSDF = c_scene.materials[mits.material];
+        const Frame prevSh = mits.sh; const V3 prevP = mits.p, prevWi = mits.wi;     // the vertex both stages shade (previousMainIts, gpt.cpp:753)
 
-        // ---------------- next event estimation, gpt.cpp:565-730
-        if ((mainBSDF.flags & ESmooth) && depth + 1 >= cfg.minDepth) {
+        // ---------------- base path: next event estimation, gpt.cpp:565-607
+        bool neeActive = false, neeVisible = false;
+        Float lsx = 0, lsy = 0, neeBsdfPdf = 0, neeDistSq = 0, neeOppCos = 0, neeWNum = 0, neeWDen = 0, neeLightPdf = 0;
+        V3 neeWoLocal = mk(0, 0, 0), neeLightP = mk(0, 0, 0), neeLightN = mk(0, 0, 0);
+        Spec neeBsdfValue = splat(0), neeEmitterRadiance = splat(0), neeContributionAll = splat(0);
+        if ((mainBSDF.flags & ESmooth) && depth + 1 >= cfg.minDepth) {               // gpt.cpp:568
             DRec dRec; initDRec(mits, dRec);
-            const Float lsx = smp.next1D(), lsy = smp.next1D();                      // gpt.cpp:572
-            bool mainEmitterVisible;
-            const Spec value = sampleEmitterDirectVisible(dRec, lsx, lsy, mainEmitterVisible); rays++;
-            const Spec mainEmitterRadiance = value * dRec.pdf;                       // gpt.cpp:575
-            const V3 mainWoLocal = toLocal(mits.sh, dRec.d);
-            Spec mainBSDFValue; Float mainBsdfPdf;
-            bsdfEvalPdf(mainBSDF, mits.wi, mainWoLocal, ESolidAngle, mainBSDFValue, mainBsdfPdf);   // gpt.cpp:588
-            if (!mainEmitterVisible) mainBsdfPdf = 0;                                // gpt.cpp:592
-            const Float mainDistanceSquared = len2(mits.p - dRec.p);                 // gpt.cpp:595-596
-            const Float mainOpposingCosine = dot(dRec.n, (mits.p - dRec.p)) / sqrt(mainDistanceSquared);
-            const Float mainWeightNumerator = mpdf * dRec.pdf;                       // gpt.cpp:599-600
-            const Float mainWeightDenominator = (mpdf * mpdf) * ((dRec.pdf * dRec.pdf) + (mainBsdfPdf * mainBsdfPdf));
-            if (!cfg.strictNormals || dot(mits.geoN, dRec.d) * mainWoLocal.z > 0) {  // gpt.cpp:607
-                const Spec mainContributionAll = mthr * (mainBSDFValue * mainEmitterRadiance);
-#pragma unroll 1
-                for (int i = 0; i < 4; ++i) {
-                    const int o = BF_COUNT + i * OF_COUNT;
-                    Spec mainContribution = splat(0), shiftedContribution = splat(0);
-                    Float weight = 0;
-                    bool shiftSuccessful = flagAlive(flags, i);
-                    const int conn = flagConn(flags, i);
-                    if (shiftSuccessful) {
-                        const Spec sthr = ld3(a, o + OF_THR, slot);
-                        const Float spdf = SD(a, o + OF_PDF, slot);
-                        if (conn == RAY_CONNECTED) {                                 // gpt.cpp:622-637
-                            const Float jacobian = 1;
-                            const Float den = (jacobian * spdf) * (jacobian * spdf) * ((dRec.pdf * dRec.pdf) + (mainBsdfPdf * mainBsdfPdf));
-                            weight = mainWeightNumerator / (kDEps + den + mainWeightDenominator);
-                            mainContribution = mainContributionAll;
-                            shiftedContribution = jacobian * sthr * (mainBSDFValue * mainEmitterRadiance);
-                        } else if (conn == RAY_RECENTLY_CONNECTED) {                 // gpt.cpp:638-658
-                            const V3 incoming = normalize(ld3(a, o + OF_P, slot) - mits.p);
-                            const V3 wiL = toLocal(mits.sh, incoming);
-                            Spec shiftedBsdfValue; Float shiftedBsdfPdf;
-                            bsdfEvalPdf(mainBSDF, wiL, mainWoLocal, ESolidAngle, shiftedBsdfValue, shiftedBsdfPdf);
-                            if (!mainEmitterVisible) shiftedBsdfPdf = 0;
-                            const Float jacobian = 1;
-                            const Float den = (jacobian * spdf) * (jacobian * spdf) * ((dRec.pdf * dRec.pdf) + (shiftedBsdfPdf * shiftedBsdfPdf));
-                            weight = mainWeightNumerator / (kDEps + den + mainWeightDenominator);
-                            mainContribution = mainContributionAll;
-                            shiftedContribution = jacobian * sthr * (shiftedBsdfValue * mainEmitterRadiance);
-                        } else {                                                     // gpt.cpp:659-705
-                            Its sits; loadOffIts(a, slot, i, sits);
-                            const DMaterial &shiftedBSDF = c_scene.materials[sits.material];
-                            if (vertexType(mainBSDF, ESmooth) == VERTEX_TYPE_DIFFUSE && vertexType(shiftedBSDF, ESmooth) == VERTEX_TYPE_DIFFUSE) {   // gpt.cpp:672
-                                DRec sRec; initDRec(sits, sRec);
-                                bool shiftedEmitterVisible;
-                                const Spec sv = sampleEmitterDirectVisible(sRec, lsx, lsy, shiftedEmitterVisible); rays++;
-                                const Spec shiftedEmitterRadiance = sv * sRec.pdf;
-                                const Float shiftedDRecPdf = sRec.pdf;
-                                const Float shiftedDistanceSquared = len2(dRec.p - sits.p);
-                                const V3 emitterDirection = (dRec.p - sits.p) / sqrt(shiftedDistanceSquared);
-                                const Float shiftedOpposingCosine = -dot(dRec.n, emitterDirection);
-                                const V3 woL = toLocal(sits.sh, emitterDirection);
-                                if (cfg.strictNormals && dot(sits.geoN, emitterDirection) * woL.z < 0) {
-                                    shiftSuccessful = false;
-                                } else {
-                                    Spec shiftedBsdfValue; Float shiftedBsdfPdf;
-                                    bsdfEvalPdf(shiftedBSDF, sits.wi, woL, ESolidAngle, shiftedBsdfValue, shiftedBsdfPdf);
-                                    if (!shiftedEmitterVisible) shiftedBsdfPdf = 0;
-                                    const Float jacobian = fabs(shiftedOpposingCosine * mainDistanceSquared) / (kEpsilon + fabs(mainOpposingCosine * shiftedDistanceSquared));   // gpt.cpp:695
-                                    const Float den = (jacobian * spdf) * (jacobian * spdf) * ((shiftedDRecPdf * shiftedDRecPdf) + (shiftedBsdfPdf * shiftedBsdfPdf));
-                                    weight = mainWeightNumerator / (kDEps + den + mainWeightDenominator);
-                                    mainContribution = mainContributionAll;
-                                    shiftedContribution = jacobian * sthr * (shiftedBsdfValue * shiftedEmitterRadiance);
-                                }
-                            }   // else: weight and both contributions stay 0 (gpt.cpp:613-615)
-                        }
+            lsx = smp.next1D(); lsy = smp.next1D();                                  // gpt.cpp:572
+            const Spec value = sampleEmitterDirectVisible(dRec, lsx, lsy, neeVisible); rays++;
+            neeEmitterRadiance = value * dRec.pdf;                                   // gpt.cpp:575
+            neeWoLocal = toLocal(mits.sh, dRec.d);
+            bsdfEvalPdf(mainBSDF, mits.wi, neeWoLocal, ESolidAngle, neeBsdfValue, neeBsdfPdf);   // gpt.cpp:588
+            if (!neeVisible) neeBsdfPdf = 0;                                         // gpt.cpp:592
+            neeDistSq = len2(mits.p - dRec.p);                                       // gpt.cpp:595-596
+            neeOppCos = dot(dRec.n, (mits.p - dRec.p)) / sqrt(neeDistSq);
+            neeWNum = mpdf * dRec.pdf;                                               // gpt.cpp:599-600
+            neeWDen = (mpdf * mpdf) * ((dRec.pdf * dRec.pdf) + (neeBsdfPdf * neeBsdfPdf));
+            neeLightP = dRec.p; neeLightN = dRec.n; neeLightPdf = dRec.pdf;
+            neeActive = !cfg.strictNormals || dot(mits.geoN, dRec.d) * neeWoLocal.z > 0;   // gpt.cpp:607
+            neeContributionAll = mthr * (neeBsdfValue * neeEmitterRadiance);
+        }
+
+        // ---------------- base path: BSDF sample + extension, gpt.cpp:737-820
+        bool bsdfStage = false, mainHitEmitter = false;
+        BSDFSample bs;
+        { const Float sx = smp.next1D(), sy = smp.next1D(); bsdfSample(mainBSDF, mits.wi, sx, sy, bs); }   // gpt.cpp:456-457
+        Spec mainEmitterRadiance = splat(0), mainContributionAll = splat(0);
+        DRec mainDRec; initDRec(mits, mainDRec);                                     // gpt.cpp:759
+        int mainVertexType = 0, mainNextVertexType = 0;
+        Float mainLumPdf = 0, mainWeightNumerator = 0, mainWeightDenominator = 0;
+        if (bs.pdf <= 0.0) ended = true;                                             // gpt.cpp:739
+        else {
+            const V3 mainWo = toWorld(mits.sh, bs.wo);
+            if (cfg.strictNormals && dot(mits.geoN, mainWo) * bs.wo.z <= 0) ended = true;   // gpt.cpp:748
+            else {
+                mainVertexType = vertexType(mainBSDF, bs.sampledType);               // gpt.cpp:764
+                Ray mray; mray.o = mits.p; mray.d = mainWo; mray.mint = kEpsilon; mray.maxt = CUDART_INF;   // gpt.cpp:767
+                rays++;
+                if (!rayIntersect(mray, mits)) ended = true;                         // gpt.cpp:800-803 (no environment emitter)
+                else {
+                    bsdfStage = true;
+                    mrayD = mainWo;
+                    if (mits.emitter >= 0) {                                         // gpt.cpp:771-776
+                        mainEmitterRadiance = emittedLe(mits, -mainWo);
+                        mainDRec.p = mits.p; mainDRec.n = mits.sh.n; mainDRec.d = mainWo; mainDRec.dist = mits.t; mainDRec.emitter = mits.emitter;
+                        mainHitEmitter = true;
                     }
-                    if (!shiftSuccessful) {                                          // gpt.cpp:708-717
-                        weight = mainWeightNumerator / (kDEps + mainWeightDenominator);
-                        mainContribution = mainContributionAll;
-                        shiftedContribution = splat(0);
-                    }
-                    mrad = mrad + mainContribution * weight;                         // gpt.cpp:723-726
-                    st3(a, o + OF_RAD, slot, ld3(a, o + OF_RAD, slot) + shiftedContribution * weight);
-                    st3(a, o + OF_GRAD, slot, ld3(a, o + OF_GRAD, slot) + (shiftedContribution - mainContribution) * weight);
+                    mainNextVertexType = vertexType(c_scene.materials[mits.material], bs.sampledType);   // gpt.cpp:784
+                    const Float mainPreviousPdf = mpdf;                              // gpt.cpp:807-812
+                    mthr = mthr * (bs.weight * bs.pdf);
+                    mpdf *= bs.pdf;
+                    meta *= bs.eta;
+                    mainLumPdf = (mainHitEmitter && depth + 1 >= cfg.minDepth && !(bs.sampledType & EDelta)) ? pdfEmitterDirect(mainDRec) : 0;   // gpt.cpp:815-816
+                    mainWeightNumerator = mainPreviousPdf * bs.pdf;                  // gpt.cpp:819-820
+                    mainWeightDenominator = (mainPreviousPdf * mainPreviousPdf) * ((mainLumPdf * mainLumPdf) + (bs.pdf * bs.pdf));
+                    mainContributionAll = mthr * mainEmitterRadiance;
                 }
             }
         }
+        const Float mainBsdfPdf = bs.pdf;
+        const bool addBsdfStage = bsdfStage && depth + 1 >= cfg.minDepth;            // gpt.cpp:1140
 
-        // ---------------- BSDF sampling and emitter hits, gpt.cpp:737-826
-        BSDFSample bs;
-        { const Float sx = smp.next1D(), sy = smp.next1D(); bsdfSample(mainBSDF, mits.wi, sx, sy, bs); }   // gpt.cpp:456-457
-        if (bs.pdf <= 0.0) { ended = true; break; }                                  // gpt.cpp:739
-        const V3 mainWo = toWorld(mits.sh, bs.wo);
-        if (cfg.strictNormals && dot(mits.geoN, mainWo) * bs.wo.z <= 0) { ended = true; break; }   // gpt.cpp:748
-        const Frame prevSh = mits.sh; const V3 prevWi = mits.wi;                // previousMainIts, gpt.cpp:753
-        bool mainHitEmitter = false;
-        Spec mainEmitterRadiance = splat(0);
-        DRec mainDRec; initDRec(mits, mainDRec);                                     // gpt.cpp:759
-        const int mainVertexType = vertexType(mainBSDF, bs.sampledType);             // gpt.cpp:764
-        Ray mray; mray.o = mits.p; mray.d = mainWo; mray.mint = kEpsilon; mray.maxt = CUDART_INF;   // gpt.cpp:767
-        rays++;
-        if (!rayIntersect(mray, mits)) { ended = true; break; }                      // gpt.cpp:800-803 (no environment emitter)
-        mrayD = mainWo;
-        if (mits.emitter >= 0) {                                                     // gpt.cpp:771-776
-            mainEmitterRadiance = emittedLe(mits, -mray.d);
-            mainDRec.p = mits.p; mainDRec.n = mits.sh.n; mainDRec.d = mray.d; mainDRec.dist = mits.t; mainDRec.emitter = mits.emitter;
-            mainHitEmitter = true;
-        }
-        const int mainNextVertexType = vertexType(c_scene.materials[mits.material], bs.sampledType);   // gpt.cpp:784
-        const Float mainBsdfPdf = bs.pdf, mainPreviousPdf = mpdf;                    // gpt.cpp:807-812
-        mthr = mthr * (bs.weight * bs.pdf);
-        mpdf *= bs.pdf;
-        meta *= bs.eta;
-        const Float mainLumPdf = (mainHitEmitter && depth + 1 >= cfg.minDepth && !(bs.sampledType & EDelta)) ? pdfEmitterDirect(mainDRec) : 0;   // gpt.cpp:815-816
-        const Float mainWeightNumerator = mainPreviousPdf * bs.pdf;                  // gpt.cpp:819-820
-        const Float mainWeightDenominator = (mainPreviousPdf * mainPreviousPdf) * ((mainLumPdf * mainLumPdf) + (mainBsdfPdf * mainBsdfPdf));
-        const Spec mainContributionAll = mthr * mainEmitterRadiance;
-
+        // ---------------- the four offset paths: gpt.cpp:609-727 and 830-1151 in one pass
+        Float bw0 = 0, bw1 = 0, bw2 = 0, bw3 = 0; unsigned bHas = 0;                 // BSDF-stage weights of the base contribution
 #pragma unroll 1
-        for (int i = 0; i < 4; ++i) {                                                // gpt.cpp:830-1151
+        for (int i = 0; i < 4; ++i) {
             const int o = BF_COUNT + i * OF_COUNT;
-            Spec mainContribution = splat(0), shiftedContribution = splat(0);
-            Float weight = 0;
-            bool postponedShiftEnd = false, alive = flagAlive(flags, i);
+            bool alive = flagAlive(flags, i);
             int conn = flagConn(flags, i);
-            if (alive) {
-                Spec sthr = ld3(a, o + OF_THR, slot);
-                Float spdf = SD(a, o + OF_PDF, slot);
-                const Float shiftedPreviousPdf = spdf;
-                if (conn == RAY_CONNECTED) {                                         // gpt.cpp:844-861
-                    sthr = sthr * (bs.weight * bs.pdf);
-                    spdf *= mainBsdfPdf;
-                    const Float den = (shiftedPreviousPdf * shiftedPreviousPdf) * ((mainLumPdf * mainLumPdf) + (mainBsdfPdf * mainBsdfPdf));
-                    weight = mainWeightNumerator / (kDEps + den + mainWeightDenominator);
-                    mainContribution = mainContributionAll;
-                    shiftedContribution = sthr * mainEmitterRadiance;
-                } else if (conn == RAY_RECENTLY_CONNECTED) {                         // gpt.cpp:862-888
-                    const V3 incoming = normalize(ld3(a, o + OF_P, slot) - mray.o);
-                    const V3 wiL = toLocal(prevSh, incoming), woL = toLocal(prevSh, mray.d);
-                    const int measure = (bs.sampledType & EDelta) ? EDiscrete : ESolidAngle;
-                    Spec shiftedBsdfValue; Float shiftedBsdfPdf;
-                    bsdfEvalPdf(mainBSDF, wiL, woL, measure, shiftedBsdfValue, shiftedBsdfPdf);
-                    sthr = sthr * shiftedBsdfValue;
-                    spdf *= shiftedBsdfPdf;
-                    conn = RAY_CONNECTED;
-                    const Float den = (shiftedPreviousPdf * shiftedPreviousPdf) * ((mainLumPdf * mainLumPdf) + (shiftedBsdfPdf * shiftedBsdfPdf));
-                    weight = mainWeightNumerator / (kDEps + den + mainWeightDenominator);
-                    mainContribution = mainContributionAll;
-                    shiftedContribution = sthr * mainEmitterRadiance;
-                } else {                                                             // gpt.cpp:889-1126
-                    Its sits; loadOffIts(a, slot, i, sits);
-                    const DMaterial &shiftedBSDF = c_scene.materials[sits.material];
-                    const int shiftedVertexType = vertexType(shiftedBSDF, bs.sampledType);
-                    if (mainVertexType == VERTEX_TYPE_DIFFUSE && mainNextVertexType == VERTEX_TYPE_DIFFUSE && shiftedVertexType == VERTEX_TYPE_DIFFUSE) {
-                        if (!lastSegment || mainHitEmitter) {                        // gpt.cpp:901
-                            const ShiftResult sr = reconnectShift(mray.o, mits.p, sits.p, mits.geoN); rays++;   // gpt.cpp:907
-                            if (!sr.success) { alive = false; }
-                            else {
-                                const V3 outgoingDirection = sr.wo;
-                                const V3 wiL = sits.wi, woL = toLocal(sits.sh, outgoingDirection);
-                                if (cfg.strictNormals && dot(outgoingDirection, sits.geoN) * woL.z <= 0) { alive = false; }
+            Spec sthr = splat(0); Float spdf = 0;
+            if (alive) { sthr = ld3(a, o + OF_THR, slot); spdf = SD(a, o + OF_PDF, slot); }
+            Spec srad = ld3(a, o + OF_RAD, slot), sgrad = ld3(a, o + OF_GRAD, slot);
+            Its sits;
+            if (alive && conn == RAY_NOT_CONNECTED) loadOffIts(a, slot, i, sits);
+            V3 recentWiL = mk(0, 0, 0);
+            if (alive && conn == RAY_RECENTLY_CONNECTED) recentWiL = toLocal(prevSh, normalize(ld3(a, o + OF_P, slot) - prevP));   // gpt.cpp:640, 864
+
+            if (neeActive) {                                                         // ---- NEE stage, gpt.cpp:609-727
+                Spec mainContribution = splat(0), shiftedContribution = splat(0);
+                Float weight = 0;
+                bool shiftSuccessful = alive;
+                if (shiftSuccessful) {
+                    if (conn == RAY_CONNECTED) {                                     // gpt.cpp:622-637
+                        const Float jacobian = 1;
+                        const Float den = (jacobian * spdf) * (jacobian * spdf) * ((neeLightPdf * neeLightPdf) + (neeBsdfPdf * neeBsdfPdf));
+                        weight = neeWNum / (kDEps + den + neeWDen);
+                        mainContribution = neeContributionAll;
+                        shiftedContribution = jacobian * sthr * (neeBsdfValue * neeEmitterRadiance);
+                    } else if (conn == RAY_RECENTLY_CONNECTED) {                     // gpt.cpp:638-658
+                        Spec shiftedBsdfValue; Float shiftedBsdfPdf;
+                        bsdfEvalPdf(mainBSDF, recentWiL, neeWoLocal, ESolidAngle, shiftedBsdfValue, shiftedBsdfPdf);
+                        if (!neeVisible) shiftedBsdfPdf = 0;
+                        const Float jacobian = 1;
+                        const Float den = (jacobian * spdf) * (jacobian * spdf) * ((neeLightPdf * neeLightPdf) + (shiftedBsdfPdf * shiftedBsdfPdf));
+                        weight = neeWNum / (kDEps + den + neeWDen);
+                        mainContribution = neeContributionAll;
+                        shiftedContribution = jacobian * sthr * (shiftedBsdfValue * neeEmitterRadiance);
+                    } else {                                                         // gpt.cpp:659-705
+                        const DMaterial &shiftedBSDF = c_scene.materials[sits.material];
+                        if (vertexType(mainBSDF, ESmooth) == VERTEX_TYPE_DIFFUSE && vertexType(shiftedBSDF, ESmooth) == VERTEX_TYPE_DIFFUSE) {   // gpt.cpp:672
+                            DRec sRec; initDRec(sits, sRec);
+                            bool shiftedEmitterVisible;
+                            const Spec sv = sampleEmitterDirectVisible(sRec, lsx, lsy, shiftedEmitterVisible); rays++;
+                            const Spec shiftedEmitterRadiance = sv * sRec.pdf;
+                            const Float shiftedDRecPdf = sRec.pdf;
+                            const Float shiftedDistanceSquared = len2(neeLightP - sits.p);
+                            const V3 emitterDirection = (neeLightP - sits.p) / sqrt(shiftedDistanceSquared);
+                            const Float shiftedOpposingCosine = -dot(neeLightN, emitterDirection);
+                            const V3 woL = toLocal(sits.sh, emitterDirection);
+                            if (cfg.strictNormals && dot(sits.geoN, emitterDirection) * woL.z < 0) {
+                                shiftSuccessful = false;
+                            } else {
+                                Spec shiftedBsdfValue; Float shiftedBsdfPdf;
+                                bsdfEvalPdf(shiftedBSDF, sits.wi, woL, ESolidAngle, shiftedBsdfValue, shiftedBsdfPdf);
+                                if (!shiftedEmitterVisible) shiftedBsdfPdf = 0;
+                                const Float jacobian = fabs(shiftedOpposingCosine * neeDistSq) / (kEpsilon + fabs(neeOppCos * shiftedDistanceSquared));   // gpt.cpp:695
+                                const Float den = (jacobian * spdf) * (jacobian * spdf) * ((shiftedDRecPdf * shiftedDRecPdf) + (shiftedBsdfPdf * shiftedBsdfPdf));
+                                weight = neeWNum / (kDEps + den + neeWDen);
+                                mainContribution = neeContributionAll;
+                                shiftedContribution = jacobian * sthr * (shiftedBsdfValue * shiftedEmitterRadiance);
+                            }
+                        }   // else: weight and both contributions stay 0 (gpt.cpp:613-615)
+                    }
+                }
+                if (!shiftSuccessful) {                                              // gpt.cpp:708-717
+                    weight = neeWNum / (kDEps + neeWDen);
+                    mainContribution = neeContributionAll;
+                    shiftedContribution = splat(0);
+                }
+                mrad = mrad + mainContribution * weight;                             // gpt.cpp:723-726
+                srad = srad + shiftedContribution * weight;
+                sgrad = sgrad + (shiftedContribution - mainContribution) * weight;
+            }
+
+            if (bsdfStage) {                                                         // ---- BSDF-sample stage, gpt.cpp:830-1151
+                Spec mainContribution = splat(0), shiftedContribution = splat(0);
+                Float weight = 0;
+                bool postponedShiftEnd = false;
+                if (alive) {
+                    const Float shiftedPreviousPdf = spdf;
+                    if (conn == RAY_CONNECTED) {                                     // gpt.cpp:844-861
+                        sthr = sthr * (bs.weight * bs.pdf);
+                        spdf *= mainBsdfPdf;
+                        const Float den = (shiftedPreviousPdf * shiftedPreviousPdf) * ((mainLumPdf * mainLumPdf) + (mainBsdfPdf * mainBsdfPdf));
+                        weight = mainWeightNumerator / (kDEps + den + mainWeightDenominator);
+                        mainContribution = mainContributionAll;
+                        shiftedContribution = sthr * mainEmitterRadiance;
+                    } else if (conn == RAY_RECENTLY_CONNECTED) {                     // gpt.cpp:862-888
+                        const V3 woL = toLocal(prevSh, mrayD);
+                        const int measure = (bs.sampledType & EDelta) ? EDiscrete : ESolidAngle;
+                        Spec shiftedBsdfValue; Float shiftedBsdfPdf;
+                        bsdfEvalPdf(mainBSDF, recentWiL, woL, measure, shiftedBsdfValue, shiftedBsdfPdf);
+                        sthr = sthr * shiftedBsdfValue;
+                        spdf *= shiftedBsdfPdf;
+                        conn = RAY_CONNECTED;
+                        const Float den = (shiftedPreviousPdf * shiftedPreviousPdf) * ((mainLumPdf * mainLumPdf) + (shiftedBsdfPdf * shiftedBsdfPdf));
+                        weight = mainWeightNumerator / (kDEps + den + mainWeightDenominator);
+                        mainContribution = mainContributionAll;
+                        shiftedContribution = sthr * mainEmitterRadiance;
+                    } else {                                                         // gpt.cpp:889-1126
+                        const DMaterial &shiftedBSDF = c_scene.materials[sits.material];
+                        const int shiftedVertexType = vertexType(shiftedBSDF, bs.sampledType);
+                        if (mainVertexType == VERTEX_TYPE_DIFFUSE && mainNextVertexType == VERTEX_TYPE_DIFFUSE && shiftedVertexType == VERTEX_TYPE_DIFFUSE) {
+                            if (!lastSegment || mainHitEmitter) {                    // gpt.cpp:901
+                                const ShiftResult sr = reconnectShift(prevP, mits.p, sits.p, mits.geoN); rays++;   // gpt.cpp:907
+                                if (!sr.success) alive = false;
                                 else {
-                                    Spec shiftedBsdfValue; Float shiftedBsdfPdf;
-                                    bsdfEvalPdf(shiftedBSDF, wiL, woL, ESolidAngle, shiftedBsdfValue, shiftedBsdfPdf);   // gpt.cpp:935-936
-                                    sthr = sthr * (shiftedBsdfValue * sr.jacobian);
-                                    spdf *= shiftedBsdfPdf * sr.jacobian;
-                                    conn = RAY_RECENTLY_CONNECTED;
-                                    if (mainHitEmitter) {                            // gpt.cpp:944-985
-                                        const Spec shiftedEmitterRadiance = emittedLe(mits, -outgoingDirection);
-                                        DRec sd;                                     // gpt.cpp:957-964 (measure: solid angle)
-                                        sd.p = mainDRec.p; sd.n = mainDRec.n;
-                                        sd.dist = len(mainDRec.p - sits.p);
-                                        sd.d = (mainDRec.p - sits.p) / sd.dist;
-                                        sd.ref = mainDRec.ref; sd.refN = sits.sh.n; sd.emitter = mainDRec.emitter;
-                                        const Float shiftedLumPdf = pdfEmitterDirect(sd);
-                                        const Float den = (shiftedPreviousPdf * shiftedPreviousPdf) * ((shiftedLumPdf * shiftedLumPdf) + (shiftedBsdfPdf * shiftedBsdfPdf));
-                                        weight = mainWeightNumerator / (kDEps + den + mainWeightDenominator);
-                                        mainContribution = mainContributionAll;
-                                        shiftedContribution = sthr * shiftedEmitterRadiance;
-                                    }   // else weight and contributions stay 0 (gpt.cpp:833-836)
+                                    const V3 outgoingDirection = sr.wo;
+                                    const V3 woL = toLocal(sits.sh, outgoingDirection);
+                                    if (cfg.strictNormals && dot(outgoingDirection, sits.geoN) * woL.z <= 0) alive = false;
+                                    else {
+                                        Spec shiftedBsdfValue; Float shiftedBsdfPdf;
+                                        bsdfEvalPdf(shiftedBSDF, sits.wi, woL, ESolidAngle, shiftedBsdfValue, shiftedBsdfPdf);   // gpt.cpp:935-936
+                                        sthr = sthr * (shiftedBsdfValue * sr.jacobian);
+                                        spdf *= shiftedBsdfPdf * sr.jacobian;
+                                        conn = RAY_RECENTLY_CONNECTED;
+                                        if (mainHitEmitter) {                        // gpt.cpp:944-985
+                                            const Spec shiftedEmitterRadiance = emittedLe(mits, -outgoingDirection);
+                                            DRec sd;                                 // gpt.cpp:957-964 (measure: solid angle)
+                                            sd.p = mainDRec.p; sd.n = mainDRec.n;
+                                            sd.dist = len(mainDRec.p - sits.p);
+                                            sd.d = (mainDRec.p - sits.p) / sd.dist;
+                                            sd.ref = mainDRec.ref; sd.refN = sits.sh.n; sd.emitter = mainDRec.emitter;
+                                            const Float shiftedLumPdf = pdfEmitterDirect(sd);
+                                            const Float den = (shiftedPreviousPdf * shiftedPreviousPdf) * ((shiftedLumPdf * shiftedLumPdf) + (shiftedBsdfPdf * shiftedBsdfPdf));
+                                            weight = mainWeightNumerator / (kDEps + den + mainWeightDenominator);
+                                            mainContribution = mainContributionAll;
+                                            shiftedContribution = sthr * shiftedEmitterRadiance;
+                                        }   // else weight and contributions stay 0 (gpt.cpp:833-836)
+                                    }
                                 }
                             }
-                        }
-                    } else {                                                         // half-vector shift, gpt.cpp:987-1126
-                        Spec shiftedEmitterRadiance = splat(0);
-                        const bool bothDelta = (bs.sampledType & EDelta) && (shiftedBSDF.flags & EDelta);
-                        const bool bothSmooth = (bs.sampledType & ESmooth) && (shiftedBSDF.flags & ESmooth);
-                        bool ok = bothDelta || bothSmooth;
-                        if (ok) {
-                            ShiftResult sr = halfVectorShift(prevWi, bs.wo, sits.wi, mainBSDF.bsdfEta, shiftedBSDF.bsdfEta);   // gpt.cpp:1006
-                            if (bs.sampledType & EDelta) sr.jacobian = 1;            // gpt.cpp:1008-1011
-                            ok = sr.success;
+                        } else {                                                     // half-vector shift, gpt.cpp:987-1126
+                            Spec shiftedEmitterRadiance = splat(0);
+                            const bool bothDelta = (bs.sampledType & EDelta) && (shiftedBSDF.flags & EDelta);
+                            const bool bothSmooth = (bs.sampledType & ESmooth) && (shiftedBSDF.flags & ESmooth);
+                            bool ok = bothDelta || bothSmooth;
                             if (ok) {
-                                sthr = sthr * sr.jacobian;
-                                spdf *= sr.jacobian;
-                                const V3 tangentSpaceOutgoingDirection = sr.wo;
-                                const V3 outgoingDirection = toWorld(sits.sh, tangentSpaceOutgoingDirection);
-                                const int measure = (bs.sampledType & EDelta) ? EDiscrete : ESolidAngle;
-                                Spec ev; Float pv;
-                                bsdfEvalPdf(shiftedBSDF, sits.wi, tangentSpaceOutgoingDirection, measure, ev, pv);   // gpt.cpp:1030-1031
-                                sthr = sthr * ev;
-                                spdf *= pv;
-                                if (spdf == 0) ok = false;                           // gpt.cpp:1033-1037
-                                if (ok && cfg.strictNormals && dot(outgoingDirection, sits.geoN) * tangentSpaceOutgoingDirection.z <= 0) ok = false;
+                                ShiftResult sr = halfVectorShift(prevWi, bs.wo, sits.wi, mainBSDF.bsdfEta, shiftedBSDF.bsdfEta);   // gpt.cpp:1006
+                                if (bs.sampledType & EDelta) sr.jacobian = 1;        // gpt.cpp:1008-1011
+                                ok = sr.success;
                                 if (ok) {
-                                    const int shiftedVertexType2 = vertexType(shiftedBSDF, bs.sampledType);   // gpt.cpp:1047
-                                    Ray sray; sray.o = sits.p; sray.d = outgoingDirection; sray.mint = kEpsilon; sray.maxt = CUDART_INF;   // gpt.cpp:1050
-                                    rays++;
-                                    if (!rayIntersect(sray, sits)) ok = false;       // gpt.cpp:1052-1058 (no environment emitter)
-                                    else {
-                                        const int shiftedNextVertexType = vertexType(c_scene.materials[sits.material], bs.sampledType);
-                                        if (mainVertexType == VERTEX_TYPE_DIFFUSE && shiftedVertexType2 == VERTEX_TYPE_DIFFUSE && shiftedNextVertexType == VERTEX_TYPE_DIFFUSE) ok = false;   // gpt.cpp:1089-1093
+                                    sthr = sthr * sr.jacobian;
+                                    spdf *= sr.jacobian;
+                                    const V3 tangentSpaceOutgoingDirection = sr.wo;
+                                    const V3 outgoingDirection = toWorld(sits.sh, tangentSpaceOutgoingDirection);
+                                    const int measure = (bs.sampledType & EDelta) ? EDiscrete : ESolidAngle;
+                                    Spec ev; Float pv;
+                                    bsdfEvalPdf(shiftedBSDF, sits.wi, tangentSpaceOutgoingDirection, measure, ev, pv);   // gpt.cpp:1030-1031
+                                    sthr = sthr * ev;
+                                    spdf *= pv;
+                                    if (spdf == 0) ok = false;                       // gpt.cpp:1033-1037
+                                    if (ok && cfg.strictNormals && dot(outgoingDirection, sits.geoN) * tangentSpaceOutgoingDirection.z <= 0) ok = false;
+                                    if (ok) {
+                                        const int shiftedVertexType2 = vertexType(shiftedBSDF, bs.sampledType);   // gpt.cpp:1047
+                                        Ray sray; sray.o = sits.p; sray.d = outgoingDirection; sray.mint = kEpsilon; sray.maxt = CUDART_INF;   // gpt.cpp:1050
+                                        rays++;
+                                        if (!rayIntersect(sray, sits)) ok = false;   // gpt.cpp:1052-1058 (no environment emitter)
                                         else {
-                                            if (sits.emitter >= 0) shiftedEmitterRadiance = emittedLe(sits, -sray.d);   // gpt.cpp:1095-1098
-                                            storeOffIts(a, slot, i, sits);
+                                            const int shiftedNextVertexType = vertexType(c_scene.materials[sits.material], bs.sampledType);
+                                            if (mainVertexType == VERTEX_TYPE_DIFFUSE && shiftedVertexType2 == VERTEX_TYPE_DIFFUSE && shiftedNextVertexType == VERTEX_TYPE_DIFFUSE) ok = false;   // gpt.cpp:1089-1093
+                                            else {
+                                                if (sits.emitter >= 0) shiftedEmitterRadiance = emittedLe(sits, -sray.d);   // gpt.cpp:1095-1098
+                                                storeOffIts(a, slot, i, sits);
+                                            }
                                         }
                                     }
                                 }
                             }
-                        }
-                        if (ok) {                                                    // gpt.cpp:1107-1112
-                            weight = mpdf / (spdf * spdf + mpdf * mpdf);
-                            mainContribution = mainContributionAll;
-                            shiftedContribution = sthr * shiftedEmitterRadiance;
-                        } else {                                                     // gpt.cpp:1113-1125
-                            weight = (Float)1 / mpdf;
-                            mainContribution = mainContributionAll;
-                            shiftedContribution = splat(0);
-                            postponedShiftEnd = true;
+                            if (ok) {                                                // gpt.cpp:1107-1112
+                                weight = mpdf / (spdf * spdf + mpdf * mpdf);
+                                mainContribution = mainContributionAll;
+                                shiftedContribution = sthr * shiftedEmitterRadiance;
+                            } else {                                                 // gpt.cpp:1113-1125
+                                weight = (Float)1 / mpdf;
+                                mainContribution = mainContributionAll;
+                                shiftedContribution = splat(0);
+                                postponedShiftEnd = true;
+                            }
                         }
                     }
                 }
-                st3(a, o + OF_THR, slot, sthr); SD(a, o + OF_PDF, slot) = spdf;
+                if (!alive) {                                                        // gpt.cpp:1131-1136
+                    weight = mainWeightNumerator / (kDEps + mainWeightDenominator);
+                    mainContribution = mainContributionAll;
+                    shiftedContribution = splat(0);
+                }
+                if (addBsdfStage) {                                                  // gpt.cpp:1140-1146
+                    const bool has = !(mainContribution.x == 0 && mainContribution.y == 0 && mainContribution.z == 0 && weight == 0);
+                    if (has) {
+                        bHas |= 1u << i;
+                        if (i == 0) bw0 = weight; else if (i == 1) bw1 = weight; else if (i == 2) bw2 = weight; else bw3 = weight;
+                    }
+                    srad = srad + shiftedContribution * weight;
+                    sgrad = sgrad + (shiftedContribution - mainContribution) * weight;
+                }
+                if (postponedShiftEnd) alive = false;                                // gpt.cpp:1148-1150
+                flags = setFlag(flags, i, alive, conn);
             }
-            if (!alive) {                                                            // gpt.cpp:1131-1136
-                weight = mainWeightNumerator / (kDEps + mainWeightDenominator);
-                mainContribution = mainContributionAll;
-                shiftedContribution = splat(0);
-            }
-            if (depth + 1 >= cfg.minDepth) {                                         // gpt.cpp:1140-1146
-                mrad = mrad + mainContribution * weight;
-                st3(a, o + OF_RAD, slot, ld3(a, o + OF_RAD, slot) + shiftedContribution * weight);
-                st3(a, o + OF_GRAD, slot, ld3(a, o + OF_GRAD, slot) + (shiftedContribution - mainContribution) * weight);
-            }
-            if (postponedShiftEnd) alive = false;                                    // gpt.cpp:1148-1150
-            flags = setFlag(flags, i, alive, conn);
+            if (flagAlive(flags, i) || alive) { st3(a, o + OF_THR, slot, sthr); SD(a, o + OF_PDF, slot) = spdf; }
+            st3(a, o + OF_RAD, slot, srad); st3(a, o + OF_GRAD, slot, sgrad);
         }
+        // base radiance: BSDF-stage terms after all NEE terms, in offset order (gpt.cpp:1142)
+        if (bHas & 1u) mrad = mrad + mainContributionAll * bw0;
+        if (bHas & 2u) mrad = mrad + mainContributionAll * bw1;
+        if (bHas & 4u) mrad = mrad + mainContributionAll * bw2;
+        if (bHas & 8u) mrad = mrad + mainContributionAll * bw3;
 
-        if (depth++ >= cfg.rrDepth) {                                                // gpt.cpp:1159-1174
-            const Float q = fmin(maxComp(mthr / mpdf) * meta * meta, (Float)0.95f);
-            if (smp.next1D() >= q) { ended = true; break; }
-            mpdf *= q;
-            for (int i = 0; i < 4; ++i) SD(a, BF_COUNT + i * OF_COUNT + OF_PDF, slot) *= q;
+        if (!ended) {
+            if (depth++ >= cfg.rrDepth) {                                            // gpt.cpp:1159-1174
+                const Float q = fmin(maxComp(mthr / mpdf) * meta * meta, (Float)0.95f);
+                if (smp.next1D() >= q) ended = true;
+                else {
+                    mpdf *= q;
+                    for (int i = 0; i < 4; ++i) SD(a, BF_COUNT + i * OF_COUNT + OF_PDF, slot) *= q;
+                }
+            }
+            if (!ended && !(depth < cfg.maxDepth || cfg.maxDepth < 0)) ended = true; // gpt.cpp:537
         }
-        if (!(depth < cfg.maxDepth || cfg.maxDepth < 0)) ended = true;               // gpt.cpp:537
-    } while (false);
+    }
 
     st3(a, BF_RAD, slot, mrad);
     SI(a, IF_RNGN, slot) = (int)smp.n;
-    countWarp(&a.counters[1], (unsigned)rays);
+    countWarp(&a.counters[1], rays);
     countWarp(&a.counters[2], ended ? (unsigned)depth : 0u);                         // gpt.cpp:1178-1179
     if (ended) {
         SI(a, IF_STATUS, slot) = ST_FINISHED;
-        appendBucketed(a.genList + (size_t)next * a.nSlots, a.genCount + next, a.nSlots, 0, slot);
     } else {
         st3(a, BF_RAYD, slot, mrayD); storeBaseIts(a, slot, mits);
         st3(a, BF_THR, slot, mthr); SD(a, BF_PDF, slot) = mpdf; SD(a, BF_ETA, slot) = meta;
         SI(a, IF_DEPTH, slot) = depth; SI(a, IF_OFLAGS, slot) = (int)flags;
-        appendBucketed(a.liveList + (size_t)next * a.nBuckets * a.nSlots, a.liveCount + next * kMaxMaterials, a.nSlots, mits.material, slot);
     }
+}
+
+// Stream compaction of the live slots, bucketed by the BSDF type of the base vertex.  Order-preserving
+// inside each 256-slot chunk (warp ballots + popc ranks, a shared-memory prefix over the 8 warps, one
+// atomic per chunk and bucket), so bucket lists stay sorted by pixel up to chunk granularity.
+__global__ void __launch_bounds__(256) gpt_compact_kernel(const GptArgs a, int parity)
+{
+    __shared__ int s_warp[8][kBuckets], s_base[kBuckets];
+    const int slot = blockIdx.x * 256 + threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int bucket = -1;
+    if (slot < a.nSlots && SI(a, IF_STATUS, slot) == ST_LIVE) {
+        // stage 0: some offset path is still unconnected (shadow + reconnection / half-vector rays ahead),
+        // stage 1: some offset was connected on the previous bounce (extra BSDF evaluations), stage 2: all
+        // offsets ride along with the base path or are dead.  Lanes of one warp then run the same branches.
+        const unsigned f = (unsigned)SI(a, IF_OFLAGS, slot);
+        int stage = 2;
+        for (int i = 0; i < 4; i++) {
+            if (!flagAlive(f, i)) continue;
+            const int c = flagConn(f, i);
+            if (c == RAY_NOT_CONNECTED) stage = 0; else if (c == RAY_RECENTLY_CONNECTED && stage == 2) stage = 1;
+        }
+        bucket = c_scene.materials[SI(a, IF_MAT, slot)].type * 3 + stage;
+    }
+    int rank = 0;
+#pragma unroll
+    for (int b = 0; b < kBuckets; b++) {
+        const unsigned m = __ballot_sync(0xffffffffu, bucket == b);
+        if (bucket == b) rank = __popc(m & ((1u << lane) - 1));
+        if (lane == 0) s_warp[warp][b] = __popc(m);
+    }
+    __syncthreads();
+    if (threadIdx.x < kBuckets) {
+        int tot = 0;
+        for (int w = 0; w < 8; w++) { const int c = s_warp[w][threadIdx.x]; s_warp[w][threadIdx.x] = tot; tot += c; }
+        s_base[threadIdx.x] = tot ? atomicAdd(&a.liveCount[parity * kBuckets + threadIdx.x], tot) : 0;
+    }
+    __syncthreads();
+    if (bucket >= 0) a.liveList[((size_t)parity * kBuckets + bucket) * a.nSlots + s_base[bucket] + s_warp[warp][bucket] + rank] = slot;
 }
 
 __global__ void gpt_init_kernel(const GptArgs a)
 {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot < 2 * kBuckets) a.liveCount[slot] = 0;
     if (slot >= a.nSlots) return;
     const int px = slot % a.width, py = a.yBegin + slot / a.width;
     a.key[slot] = samplerKey(a.seed, px, py);                                        // Sampler::generate, gpt.cpp:1250-1251
     SI(a, IF_STATUS, slot) = ST_FRESH; SI(a, IF_SAMPLE, slot) = 0; SI(a, IF_RNGN, slot) = 0;
-    a.genList[slot] = slot;
-    if (slot == 0) { a.genCount[0] = a.nSlots; a.genCount[1] = 0; }
-    if (slot < 2 * kMaxMaterials) a.liveCount[slot] = 0;
-}
-
-__global__ void gpt_reset_counts_kernel(const GptArgs a, int parity)
-{
-    if (threadIdx.x < kMaxMaterials) a.liveCount[parity * kMaxMaterials + threadIdx.x] = 0;
-    if (threadIdx.x == 0) a.genCount[parity] = 0;
 }
 
 // MultiFilm::developMulti (multifilm.cpp:366-416, fmtconv.cpp:1036-1045): value * (1/weight), plus the
@@ -596,9 +649,9 @@ struct gdb200_scene {
     // device buffers
     double *film = nullptr, *dev64 = nullptr; float *dev32 = nullptr;
     double *sd = nullptr; int *si = nullptr; uint64_t *key = nullptr;
-    int *liveList = nullptr, *genList = nullptr, *liveCount = nullptr, *genCount = nullptr;
+    int *liveList = nullptr, *liveCount = nullptr;
     unsigned long long *counters = nullptr;
-    int slotCapacity = 0, bucketCapacity = 0;
+    int slotCapacity = 0;
     volatile int cancel = 0;
 };
 
@@ -647,12 +700,22 @@ int flattenScene(const gdb200_scene_desc *d, gdb200_scene *s)
             sp.material = sh.material; sp.emitter = -1;
         } else if (sh.type == GDB200_SHAPE_MESH) {
             if (sh.emitter >= 0) return set_error(GDB200_ERR_ARGUMENT, "shape %d: mesh emitters are not supported yet", i);
+            if (h.nMeshes >= kMaxMeshes) return set_error(GDB200_ERR_ARGUMENT, "too many meshes (limit %d)", kMaxMeshes);
+            DMesh &M = h.meshes[h.nMeshes++];
+            M.first = h.nTris; M.count = 0;
+            const double big = std::numeric_limits<double>::infinity();
+            M.lo = mk(big, big, big); M.hi = mk(-big, -big, -big);
             for (int t = sh.first_tri; t < sh.first_tri + sh.tri_count; t++) {
                 if (h.nTris >= kMaxTris) return set_error(GDB200_ERR_ARGUMENT, "too many triangles for the constant-memory scene table (limit %d); the BVH path is not built yet", kMaxTris);
                 if (t < 0 || t >= d->n_triangles) return set_error(GDB200_ERR_ARGUMENT, "shape %d: triangle range out of bounds", i);
                 const int *ix = d->triangles + 3 * t;
                 const double *va = d->vertices + 3 * ix[0], *vb = d->vertices + 3 * ix[1], *vc = d->vertices + 3 * ix[2];
                 const V3 A = mk(va[0], va[1], va[2]), B = mk(vb[0], vb[1], vb[2]), C = mk(vc[0], vc[1], vc[2]);
+                for (const V3 &P : {A, B, C}) {
+                    M.lo = mk(std::min(M.lo.x, P.x), std::min(M.lo.y, P.y), std::min(M.lo.z, P.z));
+                    M.hi = mk(std::max(M.hi.x, P.x), std::max(M.hi.y, P.y), std::max(M.hi.z, P.z));
+                }
+                M.count++;
                 DTri &T = h.tris[h.nTris++];                                         // TriAccel::load, triaccel.h:61-95
                 static const int waldModulo[4] = {1, 2, 0, 1};
                 const V3 b = C - A, cc = B - A, N = cross(cc, b);
@@ -673,6 +736,12 @@ int flattenScene(const gdb200_scene_desc *d, gdb200_scene *s)
                 T.faceNormal = faceNormal;
             }
         } else return set_error(GDB200_ERR_ARGUMENT, "shape %d: unknown type %d", i, sh.type);
+    }
+    for (int mi = 0; mi < h.nMeshes; mi++) {   // enlarge the skip-bounds far beyond any rounding of the slab test
+        DMesh &M = h.meshes[mi];
+        const V3 ext = M.hi - M.lo;
+        const double pad = 1e-6 * std::max(1.0, std::max(ext.x, std::max(ext.y, ext.z))) + 1e-9 * std::max(maxComp(M.hi), -std::min(M.lo.x, std::min(M.lo.y, M.lo.z)));
+        M.lo = M.lo - splat(pad); M.hi = M.hi + splat(pad);
     }
     // emitters: DiscreteDistribution over samplingWeight (scene.cpp:357-380, pmf.h:100-114)
     h.nEmitters = d->n_emitters;
@@ -732,9 +801,9 @@ void classifyMaterials(gdb200_scene *s, double shiftThreshold)
 void freeSceneBuffers(gdb200_scene *s)
 {
     cudaFree(s->film); cudaFree(s->dev64); cudaFree(s->dev32); cudaFree(s->sd); cudaFree(s->si); cudaFree(s->key);
-    cudaFree(s->liveList); cudaFree(s->genList); cudaFree(s->liveCount); cudaFree(s->genCount); cudaFree(s->counters);
+    cudaFree(s->liveList); cudaFree(s->liveCount); cudaFree(s->counters);
     s->film = s->dev64 = s->sd = nullptr; s->dev32 = nullptr; s->si = nullptr; s->key = nullptr;
-    s->liveList = s->genList = s->liveCount = s->genCount = nullptr; s->counters = nullptr; s->slotCapacity = 0;
+    s->liveList = s->liveCount = nullptr; s->counters = nullptr; s->slotCapacity = 0;
 }
 
 int developAndCopy(gdb200_scene *s, gdb200_buffers *out)
@@ -795,18 +864,16 @@ int gdb200_gpt_render(gdb200_scene *s, const gdb200_gpt_params *p, gdb200_buffer
     const int y0 = all ? 0 : p->y_begin, y1 = all ? s->height : p->y_end;
     if (y0 < 0 || y1 > s->height || y0 >= y1) return set_error(GDB200_ERR_ARGUMENT, "invalid row range [%d,%d)", y0, y1);
     GDB_CUDA(cudaSetDevice(s->device));
-    const int nSlots = s->width * (y1 - y0), nBuckets = s->host.nMaterials;
-    if (nSlots > s->slotCapacity || nBuckets > s->bucketCapacity) {
-        cudaFree(s->sd); cudaFree(s->si); cudaFree(s->key); cudaFree(s->liveList); cudaFree(s->genList); cudaFree(s->liveCount); cudaFree(s->genCount);
-        s->sd = nullptr; s->si = nullptr; s->key = nullptr; s->liveList = s->genList = s->liveCount = s->genCount = nullptr;
+    const int nSlots = s->width * (y1 - y0);
+    if (nSlots > s->slotCapacity) {
+        cudaFree(s->sd); cudaFree(s->si); cudaFree(s->key); cudaFree(s->liveList); cudaFree(s->liveCount);
+        s->sd = nullptr; s->si = nullptr; s->key = nullptr; s->liveList = s->liveCount = nullptr;
         GDB_CUDA(cudaMalloc(&s->sd, sizeof(double) * kDoubleFields * (size_t)nSlots));
         GDB_CUDA(cudaMalloc(&s->si, sizeof(int) * IF_COUNT * (size_t)nSlots));
         GDB_CUDA(cudaMalloc(&s->key, sizeof(uint64_t) * (size_t)nSlots));
-        GDB_CUDA(cudaMalloc(&s->liveList, sizeof(int) * 2 * (size_t)nBuckets * nSlots));
-        GDB_CUDA(cudaMalloc(&s->genList, sizeof(int) * 2 * (size_t)nSlots));
-        GDB_CUDA(cudaMalloc(&s->liveCount, sizeof(int) * 2 * kMaxMaterials));
-        GDB_CUDA(cudaMalloc(&s->genCount, sizeof(int) * 2));
-        s->slotCapacity = nSlots; s->bucketCapacity = nBuckets;
+        GDB_CUDA(cudaMalloc(&s->liveList, sizeof(int) * 2 * (size_t)kBuckets * nSlots));
+        GDB_CUDA(cudaMalloc(&s->liveCount, sizeof(int) * 2 * kBuckets));
+        s->slotCapacity = nSlots;
     }
     classifyMaterials(s, p->shift_threshold);
 
@@ -818,10 +885,10 @@ int gdb200_gpt_render(gdb200_scene *s, const gdb200_gpt_params *p, gdb200_buffer
     GptArgs a;
     memset(&a, 0, sizeof(a));
     a.sd = s->sd; a.si = s->si; a.key = s->key; a.nSlots = nSlots; a.width = s->width; a.height = s->height; a.yBegin = y0;
-    a.spp = p->spp; a.nBuckets = nBuckets; a.seed = p->seed;
+    a.spp = p->spp; a.seed = p->seed;
     a.cfg.maxDepth = p->max_depth; a.cfg.minDepth = 1; a.cfg.rrDepth = p->rr_depth;         // gpt.cpp:1368-1371
     a.cfg.strictNormals = p->strict_normals; a.cfg.shiftThreshold = p->shift_threshold;
-    a.film = s->film; a.liveList = s->liveList; a.genList = s->genList; a.liveCount = s->liveCount; a.genCount = s->genCount;
+    a.film = s->film; a.liveList = s->liveList; a.liveCount = s->liveCount;
     a.counters = s->counters;
 
     cudaEvent_t e0, e1;
@@ -831,18 +898,18 @@ int gdb200_gpt_render(gdb200_scene *s, const gdb200_gpt_params *p, gdb200_buffer
     gpt_init_kernel<<<(nSlots + 255) / 256, 256>>>(a);
     int launches = 1;
     const int genBlocks = (nSlots + kGenThreads - 1) / kGenThreads;
-    const int bounceBlocks = (nSlots + 32 * nBuckets + kBounceThreads - 1) / kBounceThreads;
+    const int bounceBlocks = (nSlots + 32 * kBuckets + kBounceThreads - 1) / kBounceThreads;
     unsigned long long hostCounters[4] = {0, 0, 0, 0};
     int parity = 0;
-    const long long maxSteps = (long long)p->spp * 4096 + 65536;     // safety net: never spin forever on a broken queue
+    const long long maxSteps = (long long)p->spp * 4096 + 65536;     // safety net: never spin forever
     for (long long step = 0;; step++) {
         if (step > maxSteps) { cudaEventDestroy(e0); cudaEventDestroy(e1); return set_error(GDB200_ERR_CUDA, "wavefront did not drain after %lld steps", step); }
-        gpt_generate_kernel<<<genBlocks, kGenThreads>>>(a, parity);
+        gpt_generate_kernel<<<genBlocks, kGenThreads>>>(a);
+        gpt_compact_kernel<<<(nSlots + 255) / 256, 256>>>(a, parity);
         gpt_bounce_kernel<<<bounceBlocks, kBounceThreads>>>(a, parity);
-        gpt_reset_counts_kernel<<<1, 64>>>(a, parity);
         launches += 3;
         parity ^= 1;
-        if ((step & 31) == 31) {
+        if ((step & 15) == 15) {
             GDB_CUDA(cudaMemcpy(hostCounters, s->counters, sizeof(hostCounters), cudaMemcpyDeviceToHost));
             if (hostCounters[0] >= (unsigned long long)nSlots) break;
             if (s->cancel) { cudaEventDestroy(e0); cudaEventDestroy(e1); return set_error(GDB200_ERR_CANCELLED, "render cancelled"); }

@@ -18,6 +18,7 @@ typedef double Float;
 
 #define GDB_HD __host__ __device__ __forceinline__
 #define GDB_D __device__ __forceinline__
+#define GDB_CALL __device__ __noinline__     // big shared routines: keep one copy so the kernels fit the instruction cache
 
 constexpr Float kEpsilon = 1e-7, kShadowEpsilon = 1e-5;       // constants.h:25-26 (DOUBLE_PRECISION)
 constexpr Float kDeltaEpsilon = (Float)1e-3f;                 // constants.h:31 (float literal)
@@ -86,11 +87,12 @@ enum : unsigned { EDiffuseReflection = 0x1, EGlossyReflection = 0x4, EDeltaRefle
 enum Measure { ESolidAngle = 0, EDiscrete = 1 };
 enum VertexType { VERTEX_TYPE_GLOSSY = 0, VERTEX_TYPE_DIFFUSE = 1 };
 
-constexpr int kMaxRects = 24, kMaxSpheres = 8, kMaxTris = 192, kMaxMaterials = 32, kMaxEmitters = 8;
+constexpr int kMaxRects = 24, kMaxSpheres = 8, kMaxTris = 192, kMaxMeshes = 16, kMaxMaterials = 32, kMaxEmitters = 8;
 
 struct DRect   { Float toObject[12], toWorld[12]; V3 dpdu, n; Float invArea; int material, emitter; };
 struct DSphere { V3 center; Float radius; int flip, material, emitter, pad; };
 struct DTri    { Float n_u, n_v, n_d, a_u, a_v, b_nu, b_nv, c_nu, c_nv; V3 p0, p1, p2, faceNormal; int k, material, emitter, pad; };
+struct DMesh   { V3 lo, hi; int first, count; };   // conservative (enlarged) bounds of one TriMesh, used only to skip its triangles
 struct DMaterial {
     int type, distribution; unsigned flags; int vtSmooth, vtDelta, refNFromShading, pad0, pad1;
     Spec reflectance, specR, specT, eta, k; Float alpha, iorRatio, bsdfEta;
@@ -100,12 +102,13 @@ struct DEmitter { int rect, pad; Spec radiance; Float pdfDiscrete; };   // pdfDi
 struct DScene {
     Float sampleToCamera[16], cameraToWorld[12];
     Float nearClip, farClip, invResX, invResY, filterRadius, filterTap, filterScale;
-    int width, height, nRects, nSpheres, nTris, nMaterials, nEmitters, pad;
+    int width, height, nRects, nSpheres, nTris, nMaterials, nEmitters, nMeshes;
     Float emCdf[kMaxEmitters + 1];
     DRect rects[kMaxRects];
     DSphere spheres[kMaxSpheres];
     DMaterial materials[kMaxMaterials];
     DEmitter emitters[kMaxEmitters];
+    DMesh meshes[kMaxMeshes];
     DTri tris[kMaxTris];
 };
 
@@ -140,11 +143,16 @@ GDB_D bool closestPrimitive(const Ray &ray, Float mint, Float maxt, Float &tOut,
     bool found = false;
     for (int i = 0; i < c_scene.nRects; i++) {                       // rectangle.cpp:125-151
         const DRect &r = c_scene.rects[i];
-        const V3 o = xfAffine(r.toObject, ray.o), d = xfVector(r.toObject, ray.d);
-        const Float hit = -o.z / d.z;
+        const Float *m = r.toObject;
+        const Float oz = m[8] * ray.o.x + m[9] * ray.o.y + m[10] * ray.o.z + m[11];
+        const Float dz = m[8] * ray.d.x + m[9] * ray.d.y + m[10] * ray.d.z;
+        // -oz/dz can only land in [mint, maxt] (mint > 0) when oz and dz have opposite signs: skip the divide otherwise
+        if (mint > 0 && !((oz < 0 && dz > 0) || (oz > 0 && dz < 0))) continue;
+        const Float hit = -oz / dz;
         if (!(hit >= mint && hit <= maxt)) continue;
-        const V3 local = o + d * hit;
-        if (fabs(local.x) <= 1 && fabs(local.y) <= 1) {
+        const Float lx = (m[0] * ray.o.x + m[1] * ray.o.y + m[2] * ray.o.z + m[3]) + (m[0] * ray.d.x + m[1] * ray.d.y + m[2] * ray.d.z) * hit;
+        const Float ly = (m[4] * ray.o.x + m[5] * ray.o.y + m[6] * ray.o.z + m[7]) + (m[4] * ray.d.x + m[5] * ray.d.y + m[6] * ray.d.z) * hit;
+        if (fabs(lx) <= 1 && fabs(ly) <= 1) {
             if (AnyHit) return true;
             maxt = hit; found = true; kind = 0; index = i;
         }
@@ -161,20 +169,33 @@ GDB_D bool closestPrimitive(const Ray &ray, Float mint, Float maxt, Float &tOut,
         if (AnyHit) return true;
         maxt = t; found = true; kind = 1; index = i;
     }
-    for (int i = 0; i < c_scene.nTris; i++) {                        // triaccel.h:97-158
-        const DTri &T = c_scene.tris[i];
-        Float o_u, o_v, o_k, d_u, d_v, d_k;
-        if (T.k == 0) { o_u = ray.o.y; o_v = ray.o.z; o_k = ray.o.x; d_u = ray.d.y; d_v = ray.d.z; d_k = ray.d.x; }
-        else if (T.k == 1) { o_u = ray.o.z; o_v = ray.o.x; o_k = ray.o.y; d_u = ray.d.z; d_v = ray.d.x; d_k = ray.d.y; }
-        else if (T.k == 2) { o_u = ray.o.x; o_v = ray.o.y; o_k = ray.o.z; d_u = ray.d.x; d_v = ray.d.y; d_k = ray.d.z; }
-        else continue;
-        const Float t = (T.n_d - o_u * T.n_u - o_v * T.n_v - o_k) / (d_u * T.n_u + d_v * T.n_v + d_k);
-        if (t < mint || t > maxt) continue;
-        const Float hu = o_u + t * d_u - T.a_u, hv = o_v + t * d_v - T.a_v;
-        const Float u = hv * T.b_nu + hu * T.b_nv, v = hu * T.c_nu + hv * T.c_nv;
-        if (u >= 0 && v >= 0 && u + v <= 1.0) {
-            if (AnyHit) return true;
-            maxt = t; found = true; kind = 2; index = i; uOut = u; vOut = v;
+    if (c_scene.nMeshes > 0) {
+        const V3 inv = mk(1.0 / ray.d.x, 1.0 / ray.d.y, 1.0 / ray.d.z);
+        for (int mi = 0; mi < c_scene.nMeshes; mi++) {
+            const DMesh &M = c_scene.meshes[mi];
+            // slab test against the enlarged bounds: purely a skip of triangles that cannot be hit in [mint, maxt]
+            const Float ax = (M.lo.x - ray.o.x) * inv.x, bx = (M.hi.x - ray.o.x) * inv.x;
+            const Float ay = (M.lo.y - ray.o.y) * inv.y, by = (M.hi.y - ray.o.y) * inv.y;
+            const Float az = (M.lo.z - ray.o.z) * inv.z, bz = (M.hi.z - ray.o.z) * inv.z;
+            const Float tn = fmax(fmax(fmin(ax, bx), fmin(ay, by)), fmin(az, bz));
+            const Float tf = fmin(fmin(fmax(ax, bx), fmax(ay, by)), fmax(az, bz));
+            if (tn > tf || tf < mint || tn > maxt) continue;
+            for (int i = M.first; i < M.first + M.count; i++) {          // triaccel.h:97-158
+                const DTri &T = c_scene.tris[i];
+                Float o_u, o_v, o_k, d_u, d_v, d_k;
+                if (T.k == 0) { o_u = ray.o.y; o_v = ray.o.z; o_k = ray.o.x; d_u = ray.d.y; d_v = ray.d.z; d_k = ray.d.x; }
+                else if (T.k == 1) { o_u = ray.o.z; o_v = ray.o.x; o_k = ray.o.y; d_u = ray.d.z; d_v = ray.d.x; d_k = ray.d.y; }
+                else if (T.k == 2) { o_u = ray.o.x; o_v = ray.o.y; o_k = ray.o.z; d_u = ray.d.x; d_v = ray.d.y; d_k = ray.d.z; }
+                else continue;
+                const Float t = (T.n_d - o_u * T.n_u - o_v * T.n_v - o_k) / (d_u * T.n_u + d_v * T.n_v + d_k);
+                if (t < mint || t > maxt) continue;
+                const Float hu = o_u + t * d_u - T.a_u, hv = o_v + t * d_v - T.a_v;
+                const Float u = hv * T.b_nu + hu * T.b_nv, v = hu * T.c_nu + hv * T.c_nv;
+                if (u >= 0 && v >= 0 && u + v <= 1.0) {
+                    if (AnyHit) return true;
+                    maxt = t; found = true; kind = 2; index = i; uOut = u; vOut = v;
+                }
+            }
         }
     }
     tOut = maxt;
@@ -182,7 +203,7 @@ GDB_D bool closestPrimitive(const Ray &ray, Float mint, Float maxt, Float &tOut,
 }
 
 // ShapeKDTree::rayIntersect(ray, its): skdtree.cpp:112-147, record fill skdtree.h:343-428.
-GDB_D bool rayIntersect(const Ray &ray, Its &its)
+GDB_CALL bool rayIntersect(const Ray &ray, Its &its)
 {
     its.t = CUDART_INF;
     Float rayMinT = ray.mint;
@@ -220,7 +241,7 @@ GDB_D bool rayIntersect(const Ray &ray, Its &its)
 }
 
 // ShapeKDTree::rayIntersect(ray) for shadow rays: skdtree.cpp:206-226
-GDB_D bool rayOccluded(const Ray &ray)
+GDB_CALL bool rayOccluded(const Ray &ray)
 {
     Float rayMinT = ray.mint;
     if (rayMinT == kEpsilon) rayMinT *= maxAbs3(ray.o);
@@ -405,7 +426,7 @@ GDB_D V3 refractLocal(const DMaterial &m, V3 wi, Float cosThetaT)               
 // ---------------------------------------------------------------- BSDF eval / pdf / sample
 // Evaluates f*cos and the solid-angle (or discrete) density together: every call site of the
 // reference asks for both (gpt.cpp:588-592,645-647,693-694,871-872,935-936,1030-1031).
-GDB_D void bsdfEvalPdf(const DMaterial &m, V3 wi, V3 wo, int measure, Spec &value, Float &pdf)
+GDB_CALL void bsdfEvalPdf(const DMaterial &m, V3 wi, V3 wo, int measure, Spec &value, Float &pdf)
 {
     value = splat(0); pdf = 0;
     switch (m.type) {
@@ -451,7 +472,7 @@ GDB_D void bsdfEvalPdf(const DMaterial &m, V3 wi, V3 wo, int measure, Spec &valu
 struct BSDFSample { V3 wo; Float eta; unsigned sampledType; Spec weight; Float pdf; };
 
 // BSDF::sample(bRec, pdf, sample), pdf pre-set to 0 by the caller (gpt.cpp:450-457)
-GDB_D void bsdfSample(const DMaterial &m, V3 wi, Float sx, Float sy, BSDFSample &r)
+GDB_CALL void bsdfSample(const DMaterial &m, V3 wi, Float sx, Float sy, BSDFSample &r)
 {
     r.weight = splat(0); r.pdf = 0; r.eta = 1.0; r.sampledType = 0; r.wo = mk(0, 0, 0);
     switch (m.type) {
@@ -520,7 +541,7 @@ GDB_D void initDRec(const Its &ref, DRec &r)                                    
 
 // Scene::sampleEmitterDirectVisible, scene.cpp:855-879 (pmf.h:124-188, area.cpp:158-176,
 // shape.cpp:102-114, rectangle.cpp:210-216)
-GDB_D Spec sampleEmitterDirectVisible(DRec &dRec, Float sx, Float sy, bool &visible)
+GDB_CALL Spec sampleEmitterDirectVisible(DRec &dRec, Float sx, Float sy, bool &visible)
 {
     const int nE = c_scene.nEmitters;
     int entry = 0;                                                                     // std::lower_bound over the CDF
