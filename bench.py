@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py — G-PT Msamples/s (+ Poisson-solve ms) of the gdb200 hot path on N B200s.
+
+Contract: `python bench.py --gpus N --steps K --warmup W [--impl reference]` prints ONE JSON line.
+A "step" is one pass of the hot path over the BASELINE workload: trace the five G-PT buffers of the
+configured scene at its full sample count, merge image strips across ranks (N>1), develop the film
+and run the screened-Poisson reconstruction — everything GradientPathIntegrator::render does after
+scene loading (reference gpt.cpp:1358-1480).
+
+Workload at every N: BASELINE.json configs[1] — "Cornell box + glossy sphere, 1024x1024, 256 spp,
+G-PT L1" (synthetic scene gdb200.scenes.cbox_glossy; the reference ships no scenes).  N>1 shards the
+image into row strips (strong scaling: the image is fixed).
+
+value : whole-job Msamples/s, scene + accumulators resident in HBM, no host copies in the timed region.
+e2e   : the same through the public API (gdb200.Scene + GPTIntegrator.render) with host buffers:
+        scene upload, trace, develop, 5 fp64 buffers + the reconstructed image copied back.
+--impl reference: the CPU restatement of the reference tracer (oracle/, all host cores) on a bounded
+        sample of the same workload, plus the reference's own solver (oracle/_ref) for the solve time.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (scene builder, width, height, spp, reconstruction)
+    "gpt-c2": ("cbox_glossy", 1024, 1024, 256, "L1"),
+    "gpt-c1": ("cbox_diffuse", 512, 512, 64, "L2"),
+}
+# algorithmic bytes of one reconstruction per pixel
+SOLVER_BYTES = {"L1": 138684, "L2": 6900}
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        super().__init__(daemon=True)
+        self.device, self.rows, self.proc = device, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(int(r[1]) for r in self.rows if len(r) > 2 and r[1].isdigit())
+        mx = [int(r[2]) for r in self.rows if len(r) > 2 and r[2].isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def load_oracle():
+    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "libgdb200_oracle.so"))
+    ref_path = os.path.join(ROOT, "oracle", "_ref", "libref_poisson_mt.so")
+    ref = ctypes.CDLL(ref_path) if os.path.exists(ref_path) else None
+    return lib, ref
+
+
+def cpu_tracer_rate(desc, params_fn, spp, threads):
+    """Msamples/s of the CPU restatement (oracle/gpt_oracle.cpp, OpenMP) on desc at `spp`."""
+    lib, _ = load_oracle()
+    from gdb200 import scenes
+    prm = params_fn(spp)
+    B = scenes.Buffers()
+    cnt = (ctypes.c_double * 3)()
+    t0 = time.perf_counter()
+    rc = lib.gdb200_oracle_gpt_render(ctypes.byref(desc), ctypes.byref(prm), ctypes.byref(B), None, cnt, threads)
+    dt = time.perf_counter() - t0
+    assert rc == 0
+    return cnt[0] / dt / 1e6, dt
+
+
+def cpu_solver_seconds(w, h, preset):
+    """The reference's own solver sources (oracle/_ref, all cores via OMP_NUM_THREADS) on synthetic buffers."""
+    import numpy as np
+    from gdb200 import synth
+    _, ref = load_oracle()
+    if ref is None:
+        return None
+    d = synth.solver_inputs(w, h, seed=1234)
+    out = np.empty_like(d["dx"])
+    sec = ctypes.c_float()
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    t0 = time.perf_counter()
+    ref.ref_poisson_solve(p(d["dx"]), p(d["dy"]), p(d["throughput"]), p(d["direct"]), w, h, ctypes.c_float(0.2),
+                          preset.encode(), p(out), ctypes.byref(sec))
+    return time.perf_counter() - t0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gdb200", choices=["gdb200", "reference"])
+    ap.add_argument("--workload", default="gpt-c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--spp", type=int, default=0, help="override the workload's sample count (invalidates the headline)")
+    ap.add_argument("--cpu-spp", type=int, default=8, help="samples/pixel of the bounded CPU-baseline sample")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    scene_name, W, H, spp, recon = WORKLOADS[args.workload]
+    if args.spp:
+        spp = args.spp
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+
+    import gdb200
+    from gdb200 import scenes, tiles
+    desc = getattr(scenes, scene_name)(W, H)
+    integ = gdb200.GPTIntegrator(reconstructL1=(recon == "L1"), reconstructL2=(recon == "L2"), reconstructAlpha=0.2)
+    config = {"workload": f"{scene_name} {W}x{H} @ {spp} spp, G-PT {recon} reconstruction (BASELINE configs[1])"
+                          if args.workload == "gpt-c2" else f"{scene_name} {W}x{H} @ {spp} spp, G-PT {recon}",
+              "scene": "synthetic Cornell box + GGX spheres (gdb200.scenes)", "sampler": "gdb200_counter seed 0",
+              "maxDepth": -1, "rrDepth": 5, "shiftThreshold": 0.001, "alpha": 0.2,
+              "parallelism": f"row strips x{world}" if world > 1 else "1 GPU",
+              "l2_flush": "per-step working set (1.2 GB wavefront state + 168 MB film) exceeds the 126 MB L2"}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        cpu_spp = max(1, args.cpu_spp // 4)
+        rates = []
+        for i in range(args.warmup + args.steps):
+            r, dt = cpu_tracer_rate(desc, lambda s: integ.params(s, 0), cpu_spp, cores)
+            if i >= args.warmup:
+                rates.append((r, dt))
+        val = sum(r for r, _ in rates) / len(rates)
+        solve_s = cpu_solver_seconds(W, H, recon + "D")
+        line = {"impl": "reference", "metric": "gpt_msamples_per_s", "value": round(val, 4), "unit": "Msamples/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": round(1e3 * sum(dt for _, dt in rates) / len(rates), 2), "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "poisson_solve_ms": round(solve_s * 1e3, 1) if solve_s else None,
+                "cpu_baseline": {"value": round(val, 4), "unit": "Msamples/s", "cores": cores, "kind": "port",
+                                 "sample": f"{scene_name} {W}x{H} @ {cpu_spp} spp per step (of {spp}); tracer = CPU restatement "
+                                           "oracle/gpt_oracle.cpp (Mitsuba itself cannot be built here), solver = reference sources"},
+                "e2e": {"value": round(val, 4), "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ gdb200 arm (GPU)
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    gdb200.lib().gdb200_set_device(local_rank)
+    scene = gdb200.Scene(desc)
+    plan = gdb200.PoissonPlan(W, H) if rank == 0 else None
+    rows = tiles.strip_rows(H, rank, world) if world > 1 else None
+    acc = scene.accumulators() if world > 1 else None
+    agg = {"bounce_ms": 0.0, "generate_ms": 0.0, "compact_ms": 0.0, "state_bytes": 0.0, "bounce_launches": 0, "trace_ms": 0.0,
+           "solve_ms": 0.0, "launches": 0, "samples": 0.0, "rays": 0.0, "exchange_bytes": 0}
+
+    def step(timed):
+        integ.trace(scene, spp=spp, seed=0, rows=rows, download=False)
+        if world > 1:
+            nb = tiles.exchange_boundaries(acc, world)
+            tiles.gather_strips(acc, rank, world)
+            if rank == 0:
+                scene.develop(download=False)
+        if rank == 0:
+            integ.reconstruct(scene, plan, download=False)
+        if timed:
+            st = integ.stats
+            for k in ("bounce_ms", "generate_ms", "compact_ms", "state_bytes", "bounce_launches", "samples", "rays"):
+                agg[k] += getattr(st, k)
+            agg["trace_ms"] += st.device_ms
+            agg["launches"] += st.launches + 1 + (1 if rank == 0 else 0)
+            if rank == 0:
+                agg["solve_ms"] += integ.solver_stats.device_ms
+            if world > 1:
+                agg["exchange_bytes"] += nb
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(False)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(True)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    samples = torch.tensor([agg["samples"]], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(samples, op=dist.ReduceOp.SUM)
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms, total_samples = float(ms.item()), float(samples.item())
+
+    # ------------------------------------------------------------------ end to end through the public API
+    h2d = ctypes.sizeof(scenes.SceneDesc) + desc.n_shapes * ctypes.sizeof(scenes.Shape) + desc.n_materials * ctypes.sizeof(scenes.Material) \
+        + desc.n_emitters * ctypes.sizeof(scenes.Emitter) + desc.n_vertices * 24 + desc.n_triangles * 12
+    d2h = 5 * W * H * 3 * 8 + W * H * 3 * 4
+    e2e_steps = max(1, min(2, args.steps))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        if world == 1:
+            sc = gdb200.Scene(desc)                      # scene upload (H2D) is part of the user-visible call
+            out = integ.render(sc, spp=spp, seed=0)      # trace + develop + D2H of 5 buffers + solve + D2H of final
+            sc.close()
+        else:
+            integ.trace(scene, spp=spp, seed=0, rows=rows, download=False)
+            tiles.exchange_boundaries(acc, world)
+            tiles.gather_strips(acc, rank, world)
+            if rank == 0:
+                out = scene.develop(download=True)
+                out["-final"] = integ.reconstruct(scene, plan, download=True)
+        barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_val = W * H * spp * e2e_steps / float(e2e_s.item()) / 1e6
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        bounce_avg_ms = agg["bounce_ms"] / max(1, agg["bounce_launches"])
+        achieved = agg["state_bytes"] / max(agg["bounce_ms"], 1e-9) / 1e6          # GB/s
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_gpt_bounce_summary.json")))["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        solve_ms = agg["solve_ms"] / args.steps
+        line = {"metric": "gpt_msamples_per_s", "value": round(total_samples / total_ms / 1e3, 3), "unit": "Msamples/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 2),
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config,
+                "tracer_msamples_per_s": round(agg["samples"] * world / max(agg["trace_ms"], 1e-9) / 1e3, 3) if world == 1
+                else round(total_samples / max(agg["trace_ms"], 1e-9) / 1e3, 3),
+                "poisson_solve_ms": round(solve_ms, 3), "poisson_preset": recon + "D",
+                "poisson_roofline": {"bound": "hbm", "achieved": round(SOLVER_BYTES[recon] * W * H / max(solve_ms, 1e-9) / 1e6, 1),
+                                     "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                     "frac": round(SOLVER_BYTES[recon] * W * H / max(solve_ms, 1e-9) / 1e6 / peaks["hbm_gbs"], 3),
+                                     "note": "working set fits the 126 MB L2 at this size; grade the solver roofline on tools/solver_sweep.py 4K/8K"},
+                "rays_per_sample": round(agg["rays"] / max(agg["samples"], 1), 2),
+                "e2e": {"value": round(e2e_val, 3), "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": int(agg["launches"]),
+                "clocks": clocks,
+                "roofline": {"bound": "hbm", "kernel": "gpt_bounce_kernel", "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"],
+                             "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": traffic,
+                             "peak_source": peak_src, "avg_launch_ms": round(bounce_avg_ms, 4),
+                             "share_of_step": round(agg["bounce_ms"] / max(agg["trace_ms"], 1e-9), 3),
+                             "note": "algorithmic bytes = SURVEY §8d wavefront record sizes counted on device; the kernel is "
+                                     "fp64-issue/latency bound, not HBM bound (see profiles/)"}}
+        if world > 1:
+            line["exchange_bytes_per_step"] = int(agg["exchange_bytes"] / args.steps)
+        if world == 1:
+            rate, dt = cpu_tracer_rate(desc, lambda s: integ.params(s, 0), args.cpu_spp, cores)
+            line["cpu_baseline"] = {"value": round(rate, 4), "unit": "Msamples/s", "cores": cores, "kind": "port",
+                                    "sample": f"{scene_name} {W}x{H} @ {args.cpu_spp} spp (of {spp}), {dt:.1f} s, CPU restatement "
+                                              "oracle/gpt_oracle.cpp with OpenMP over row bands"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

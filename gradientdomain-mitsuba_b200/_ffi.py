@@ -14,7 +14,9 @@ class Stats(ctypes.Structure):
     _fields_ = [("device_ms", ctypes.c_double), ("h2d_ms", ctypes.c_double), ("d2h_ms", ctypes.c_double),
                 ("launches", ctypes.c_int), ("irls_iters", ctypes.c_int), ("cg_iters", ctypes.c_int),
                 ("reserved0", ctypes.c_int), ("samples", ctypes.c_double), ("rays", ctypes.c_double),
-                ("path_vertices", ctypes.c_double), ("state_bytes", ctypes.c_double)]
+                ("path_vertices", ctypes.c_double), ("state_bytes", ctypes.c_double), ("bounce_ms", ctypes.c_double),
+                ("generate_ms", ctypes.c_double), ("compact_ms", ctypes.c_double), ("path_bounces", ctypes.c_double),
+                ("bounce_launches", ctypes.c_int), ("reserved1", ctypes.c_int)]
 
 
 class PoissonConfig(ctypes.Structure):
@@ -23,7 +25,8 @@ class PoissonConfig(ctypes.Structure):
 
 
 def library_path():
-    return os.path.join(_HERE, "libgdb200.so")
+    # GDB200_LIBRARY: developer switch to A/B-test another build of the same CUDA library
+    return os.environ.get("GDB200_LIBRARY") or os.path.join(_HERE, "libgdb200.so")
 
 
 _lib = None

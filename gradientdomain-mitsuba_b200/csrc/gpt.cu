@@ -61,7 +61,7 @@ struct GptArgs {
     double *film;          // [5][H][W][4]
     int *liveList;         // [2][kBuckets][nSlots]
     int *liveCount;        // [2][kBuckets]
-    unsigned long long *counters;   // [0] done slots, [1] rays, [2] path vertices, [3] samples
+    unsigned long long *counters;   // [0] done slots, [1] rays, [2] path vertices, [3] samples, [4] state bytes, [5] path bounces
 };
 
 GDB_D double &SD(const GptArgs &a, int field, int slot) { return a.sd[(size_t)field * a.nSlots + slot]; }
@@ -260,6 +260,13 @@ __global__ void __launch_bounds__(kBounceThreads) gpt_bounce_kernel(const GptArg
     Sampler smp; smp.key = a.key[slot]; smp.n = (uint32_t)SI(a, IF_RNGN, slot);
     unsigned rays = 0;
     bool ended = false;
+    {   // algorithmic state traffic of this path-bounce (record sizes of SURVEY.md §8d: base 320 B,
+        // unconnected offset 304 B, connected offset 88 B; read + write)
+        unsigned bytes = 320;
+        for (int i = 0; i < 4; i++) if (flagAlive(flags, i)) bytes += flagConn(flags, i) == RAY_CONNECTED ? 88 : 304;
+        countWarp(&a.counters[4], 2 * bytes);
+        countWarp(&a.counters[5], 1u);
+    }
 
     if (cfg.strictNormals) {                                                         // gpt.cpp:541-555
         if (dot(mrayD, mits.geoN) * mits.wi.z >= 0) ended = true;
@@ -899,14 +906,20 @@ int gdb200_gpt_render(gdb200_scene *s, const gdb200_gpt_params *p, gdb200_buffer
     int launches = 1;
     const int genBlocks = (nSlots + kGenThreads - 1) / kGenThreads;
     const int bounceBlocks = (nSlots + 32 * kBuckets + kBounceThreads - 1) / kBounceThreads;
-    unsigned long long hostCounters[4] = {0, 0, 0, 0};
+    unsigned long long hostCounters[6] = {0, 0, 0, 0, 0, 0};
     int parity = 0;
+    std::vector<cudaEvent_t> marks;   // per-kernel timing (only when the caller asked for stats)
     const long long maxSteps = (long long)p->spp * 4096 + 65536;     // safety net: never spin forever
     for (long long step = 0;; step++) {
         if (step > maxSteps) { cudaEventDestroy(e0); cudaEventDestroy(e1); return set_error(GDB200_ERR_CUDA, "wavefront did not drain after %lld steps", step); }
+        auto mark = [&]() { if (stats) { cudaEvent_t ev; cudaEventCreate(&ev); cudaEventRecord(ev); marks.push_back(ev); } };
+        mark();
         gpt_generate_kernel<<<genBlocks, kGenThreads>>>(a);
+        mark();
         gpt_compact_kernel<<<(nSlots + 255) / 256, 256>>>(a, parity);
+        mark();
         gpt_bounce_kernel<<<bounceBlocks, kBounceThreads>>>(a, parity);
+        mark();
         launches += 3;
         parity ^= 1;
         if ((step & 15) == 15) {
@@ -927,7 +940,14 @@ int gdb200_gpt_render(gdb200_scene *s, const gdb200_gpt_params *p, gdb200_buffer
         memset(stats, 0, sizeof(*stats));
         stats->device_ms = ms; stats->launches = launches + 1;
         stats->samples = (double)hostCounters[3]; stats->rays = (double)hostCounters[1]; stats->path_vertices = (double)hostCounters[2];
+        stats->state_bytes = (double)hostCounters[4]; stats->path_bounces = (double)hostCounters[5];
+        for (size_t i = 0; i + 3 < marks.size(); i += 4) {
+            float g = 0, c = 0, b = 0;
+            cudaEventElapsedTime(&g, marks[i], marks[i + 1]); cudaEventElapsedTime(&c, marks[i + 1], marks[i + 2]); cudaEventElapsedTime(&b, marks[i + 2], marks[i + 3]);
+            stats->generate_ms += g; stats->compact_ms += c; stats->bounce_ms += b; stats->bounce_launches++;
+        }
     }
+    for (cudaEvent_t ev : marks) cudaEventDestroy(ev);
     return GDB200_OK;
 }
 

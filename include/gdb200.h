@@ -52,7 +52,13 @@ typedef struct gdb200_stats {
     double samples;         /* evaluatePoint() samples traced (tracer)           */
     double rays;            /* rays cast (tracer)                                */
     double path_vertices;   /* sum of base-path depths (tracer; "Average path length", gpt.cpp:1178-1179) */
-    double state_bytes;     /* wavefront state bytes moved through HBM (tracer)  */
+    double state_bytes;     /* algorithmic wavefront state bytes of the bounce kernel, SURVEY.md §8d record sizes (tracer) */
+    double bounce_ms;       /* summed CUDA-event time of the gpt_bounce_kernel launches   */
+    double generate_ms;     /* ... of the gpt_generate_kernel launches                    */
+    double compact_ms;      /* ... of the gpt_compact_kernel launches                     */
+    double path_bounces;    /* base-path bounce iterations executed (tracer)              */
+    int    bounce_launches; /* wavefront steps                                            */
+    int    reserved1;
 } gdb200_stats;
 
 /* ------------------------------------------------ screened Poisson solver */

@@ -1,0 +1,66 @@
+"""CPU test (world_size 2, gloo): strip sharding + boundary all-reduce + gather reproduce the
+single-process accumulator film.  The per-rank "tracer" is the CPU oracle restricted to its rows,
+so this also checks the oracle's y_begin/y_end path."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import gdb200  # noqa: F401
+from gdb200 import scenes, tiles
+from conftest import Oracle
+
+
+def test_strip_partition_covers_image():
+    for h in (1, 7, 64, 1080):
+        for world in (1, 2, 3, 8):
+            rows = [tiles.strip_rows(h, r, world) for r in range(world)]
+            assert rows[0][0] == 0 and rows[-1][1] == h
+            assert all(rows[i][1] == rows[i + 1][0] for i in range(world - 1))
+    assert tiles.boundary_rows(64, 2) == [30, 31, 32, 33]
+    assert tiles.boundary_rows(64, 1) == []
+
+
+def _oracle_acc(orc, desc, prm):
+    """Raw accumulators [5,h,w,4] from the oracle: developed value * weight, weight."""
+    out, wts, _ = orc.gpt(desc, prm, threads=2)
+    h, w = desc.camera.height, desc.camera.width
+    acc = np.zeros((5, h, w, 4))
+    for i, name in enumerate(("-final", "-throughput", "-dx", "-dy", "-direct")):
+        acc[i, ..., :3] = out[name] * wts[i][..., None]
+        acc[i, ..., 3] = wts[i]
+    return acc
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        orc = Oracle()
+        w = h = 24
+        desc = scenes.cbox_diffuse(w, h)
+        prm = scenes.default_params(spp=2, seed=9)
+        prm.y_begin, prm.y_end = tiles.strip_rows(h, rank, world)
+        acc = torch.from_numpy(_oracle_acc(orc, desc, prm))
+        tiles.exchange_boundaries(acc, world)
+        tiles.gather_strips(acc, rank, world)
+        if rank == 0:
+            ret["acc"] = acc.numpy().copy()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_strips_match_single_process():
+    world, port = 2, 29611
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+        merged = ret["acc"]
+    orc = Oracle()
+    desc = scenes.cbox_diffuse(24, 24)
+    full = _oracle_acc(orc, desc, scenes.default_params(spp=2, seed=9))
+    np.testing.assert_allclose(merged, full, rtol=1e-12, atol=1e-13)
