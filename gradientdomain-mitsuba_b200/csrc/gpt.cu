@@ -229,6 +229,10 @@ __global__ void __launch_bounds__(kGenThreads) gpt_generate_kernel(const GptArgs
 // performs both stages per offset path, so each offset's state crosses HBM once per bounce; the
 // base path's radiance is still accumulated in the reference's order (all NEE terms, then all
 // BSDF-stage terms).
+// PHASE 0 = next-event estimation of the base path and of its four offset paths (gpt.cpp:565-730);
+// PHASE 1 = BSDF sample, extension ray, shifts, Russian roulette (gpt.cpp:737-1175).  Two launches per
+// step over the same queues: each phase's hot code fits the instruction cache and needs fewer registers.
+template <int PHASE>
 __global__ void __launch_bounds__(kBounceThreads) gpt_bounce_kernel(const GptArgs a, int parity)
 {
     // thread -> (BSDF-type bucket, index).  Buckets are padded to whole warps so a warp shades one BSDF
@@ -239,7 +243,7 @@ __global__ void __launch_bounds__(kBounceThreads) gpt_bounce_kernel(const GptArg
         int acc = 0;
         for (int b = 0; b < kBuckets; b++) { const int c = a.liveCount[parity * kBuckets + b]; s_begin[b] = acc; s_count[b] = c; acc += (c + 31) & ~31; }
         s_begin[kBuckets] = acc;
-        if (blockIdx.x == 0) for (int b = 0; b < kBuckets; b++) a.liveCount[(parity ^ 1) * kBuckets + b] = 0;   // for the next step's compaction
+        if (PHASE == 1 && blockIdx.x == 0) for (int b = 0; b < kBuckets; b++) a.liveCount[(parity ^ 1) * kBuckets + b] = 0;   // for the next step's compaction
     }
     __syncthreads();
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -249,6 +253,7 @@ __global__ void __launch_bounds__(kBounceThreads) gpt_bounce_kernel(const GptArg
     const int idx = g - s_begin[b];
     if (idx >= s_count[b]) return;
     const int slot = a.liveList[((size_t)parity * kBuckets + b) * a.nSlots + idx];
+    if (PHASE == 1 && SI(a, IF_STATUS, slot) != ST_LIVE) return;      // ended in phase 0 (strictNormals)
     const Config cfg = a.cfg;
 
     Its mits; loadBaseIts(a, slot, mits);
@@ -260,7 +265,7 @@ __global__ void __launch_bounds__(kBounceThreads) gpt_bounce_kernel(const GptArg
     Sampler smp; smp.key = a.key[slot]; smp.n = (uint32_t)SI(a, IF_RNGN, slot);
     unsigned rays = 0;
     bool ended = false;
-    {   // algorithmic state traffic of this path-bounce (record sizes of SURVEY.md §8d: base 320 B,
+    if (PHASE == 0) {   // algorithmic state traffic of this path-bounce (record sizes of SURVEY.md §8d: base 320 B,
         // unconnected offset 304 B, connected offset 88 B; read + write)
         unsigned bytes = 320;
         for (int i = 0; i < 4; i++) if (flagAlive(flags, i)) bytes += flagConn(flags, i) == RAY_CONNECTED ? 88 : 304;
@@ -268,7 +273,7 @@ __global__ void __launch_bounds__(kBounceThreads) gpt_bounce_kernel(const GptArg
         countWarp(&a.counters[5], 1u);
     }
 
-    if (cfg.strictNormals) {                                                         // gpt.cpp:541-555
+    if (PHASE == 0 && cfg.strictNormals) {                                           // gpt.cpp:541-555
         if (dot(mrayD, mits.geoN) * mits.wi.z >= 0) ended = true;
         else
             for (int i = 0; i < 4; i++) {       // an unconnected offset's ray direction is -toWorld(wi) of its stored vertex
@@ -289,7 +294,7 @@ __global__ void __launch_bounds__(kBounceThreads) gpt_bounce_kernel(const GptArg
         Float lsx = 0, lsy = 0, neeBsdfPdf = 0, neeDistSq = 0, neeOppCos = 0, neeWNum = 0, neeWDen = 0, neeLightPdf = 0;
         V3 neeWoLocal = mk(0, 0, 0), neeLightP = mk(0, 0, 0), neeLightN = mk(0, 0, 0);
         Spec neeBsdfValue = splat(0), neeEmitterRadiance = splat(0), neeContributionAll = splat(0);
-        if ((mainBSDF.flags & ESmooth) && depth + 1 >= cfg.minDepth) {               // gpt.cpp:568
+        if (PHASE == 0 && (mainBSDF.flags & ESmooth) && depth + 1 >= cfg.minDepth) { // gpt.cpp:568
             DRec dRec; initDRec(mits, dRec);
             lsx = smp.next1D(); lsy = smp.next1D();                                  // gpt.cpp:572
             const Spec value = sampleEmitterDirectVisible(dRec, lsx, lsy, neeVisible); rays++;
@@ -309,12 +314,14 @@ __global__ void __launch_bounds__(kBounceThreads) gpt_bounce_kernel(const GptArg
         // ---------------- base path: BSDF sample + extension, gpt.cpp:737-820
         bool bsdfStage = false, mainHitEmitter = false;
         BSDFSample bs;
-        { const Float sx = smp.next1D(), sy = smp.next1D(); bsdfSample(mainBSDF, mits.wi, sx, sy, bs); }   // gpt.cpp:456-457
+        bs.weight = splat(0); bs.pdf = 0; bs.eta = 1.0; bs.sampledType = 0; bs.wo = mk(0, 0, 0);
+        if (PHASE == 1) { const Float sx = smp.next1D(), sy = smp.next1D(); bsdfSample(mainBSDF, mits.wi, sx, sy, bs); }   // gpt.cpp:456-457
         Spec mainEmitterRadiance = splat(0), mainContributionAll = splat(0);
         DRec mainDRec; initDRec(mits, mainDRec);                                     // gpt.cpp:759
         int mainVertexType = 0, mainNextVertexType = 0;
         Float mainLumPdf = 0, mainWeightNumerator = 0, mainWeightDenominator = 0;
-        if (bs.pdf <= 0.0) ended = true;                                             // gpt.cpp:739
+        if (PHASE == 0) { }
+        else if (bs.pdf <= 0.0) ended = true;                                        // gpt.cpp:739
         else {
             const V3 mainWo = toWorld(mits.sh, bs.wo);
             if (cfg.strictNormals && dot(mits.geoN, mainWo) * bs.wo.z <= 0) ended = true;   // gpt.cpp:748
@@ -361,7 +368,7 @@ __global__ void __launch_bounds__(kBounceThreads) gpt_bounce_kernel(const GptArg
             V3 recentWiL = mk(0, 0, 0);
             if (alive && conn == RAY_RECENTLY_CONNECTED) recentWiL = toLocal(prevSh, normalize(ld3(a, o + OF_P, slot) - prevP));   // gpt.cpp:640, 864
 
-            if (neeActive) {                                                         // ---- NEE stage, gpt.cpp:609-727
+            if (PHASE == 0 && neeActive) {                                           // ---- NEE stage, gpt.cpp:609-727
                 Spec mainContribution = splat(0), shiftedContribution = splat(0);
                 Float weight = 0;
                 bool shiftSuccessful = alive;
@@ -418,7 +425,7 @@ __global__ void __launch_bounds__(kBounceThreads) gpt_bounce_kernel(const GptArg
                 sgrad = sgrad + (shiftedContribution - mainContribution) * weight;
             }
 
-            if (bsdfStage) {                                                         // ---- BSDF-sample stage, gpt.cpp:830-1151
+            if (PHASE == 1 && bsdfStage) {                                           // ---- BSDF-sample stage, gpt.cpp:830-1151
                 Spec mainContribution = splat(0), shiftedContribution = splat(0);
                 Float weight = 0;
                 bool postponedShiftEnd = false;
@@ -543,7 +550,7 @@ __global__ void __launch_bounds__(kBounceThreads) gpt_bounce_kernel(const GptArg
                 if (postponedShiftEnd) alive = false;                                // gpt.cpp:1148-1150
                 flags = setFlag(flags, i, alive, conn);
             }
-            if (flagAlive(flags, i) || alive) { st3(a, o + OF_THR, slot, sthr); SD(a, o + OF_PDF, slot) = spdf; }
+            if (PHASE == 1 && (flagAlive(flags, i) || alive)) { st3(a, o + OF_THR, slot, sthr); SD(a, o + OF_PDF, slot) = spdf; }
             st3(a, o + OF_RAD, slot, srad); st3(a, o + OF_GRAD, slot, sgrad);
         }
         // base radiance: BSDF-stage terms after all NEE terms, in offset order (gpt.cpp:1142)
@@ -552,7 +559,7 @@ __global__ void __launch_bounds__(kBounceThreads) gpt_bounce_kernel(const GptArg
         if (bHas & 4u) mrad = mrad + mainContributionAll * bw2;
         if (bHas & 8u) mrad = mrad + mainContributionAll * bw3;
 
-        if (!ended) {
+        if (PHASE == 1 && !ended) {
             if (depth++ >= cfg.rrDepth) {                                            // gpt.cpp:1159-1174
                 const Float q = fmin(maxComp(mthr / mpdf) * meta * meta, (Float)0.95f);
                 if (smp.next1D() >= q) ended = true;
@@ -571,6 +578,8 @@ __global__ void __launch_bounds__(kBounceThreads) gpt_bounce_kernel(const GptArg
     countWarp(&a.counters[2], ended ? (unsigned)depth : 0u);                         // gpt.cpp:1178-1179
     if (ended) {
         SI(a, IF_STATUS, slot) = ST_FINISHED;
+    } else if (PHASE == 0) {
+        if (cfg.strictNormals) SI(a, IF_OFLAGS, slot) = (int)flags;
     } else {
         st3(a, BF_RAYD, slot, mrayD); storeBaseIts(a, slot, mits);
         st3(a, BF_THR, slot, mthr); SD(a, BF_PDF, slot) = mpdf; SD(a, BF_ETA, slot) = meta;
@@ -712,8 +721,9 @@ int flattenScene(const gdb200_scene_desc *d, gdb200_scene *s)
             M.first = h.nTris; M.count = 0;
             const double big = std::numeric_limits<double>::infinity();
             M.lo = mk(big, big, big); M.hi = mk(-big, -big, -big);
+            std::vector<DTri> meshTris;
             for (int t = sh.first_tri; t < sh.first_tri + sh.tri_count; t++) {
-                if (h.nTris >= kMaxTris) return set_error(GDB200_ERR_ARGUMENT, "too many triangles for the constant-memory scene table (limit %d); the BVH path is not built yet", kMaxTris);
+                if (h.nTris + (int)meshTris.size() >= kMaxTris) return set_error(GDB200_ERR_ARGUMENT, "too many triangles for the constant-memory scene table (limit %d); the BVH path is not built yet", kMaxTris);
                 if (t < 0 || t >= d->n_triangles) return set_error(GDB200_ERR_ARGUMENT, "shape %d: triangle range out of bounds", i);
                 const int *ix = d->triangles + 3 * t;
                 const double *va = d->vertices + 3 * ix[0], *vb = d->vertices + 3 * ix[1], *vc = d->vertices + 3 * ix[2];
@@ -722,8 +732,8 @@ int flattenScene(const gdb200_scene_desc *d, gdb200_scene *s)
                     M.lo = mk(std::min(M.lo.x, P.x), std::min(M.lo.y, P.y), std::min(M.lo.z, P.z));
                     M.hi = mk(std::max(M.hi.x, P.x), std::max(M.hi.y, P.y), std::max(M.hi.z, P.z));
                 }
-                M.count++;
-                DTri &T = h.tris[h.nTris++];                                         // TriAccel::load, triaccel.h:61-95
+                DTri T;                                                              // TriAccel::load, triaccel.h:61-95
+                memset(&T, 0, sizeof(T));
                 static const int waldModulo[4] = {1, 2, 0, 1};
                 const V3 b = C - A, cc = B - A, N = cross(cc, b);
                 const double Nv[3] = {N.x, N.y, N.z}, bv[3] = {b.x, b.y, b.z}, cv[3] = {cc.x, cc.y, cc.z}, Av[3] = {A.x, A.y, A.z};
@@ -732,7 +742,7 @@ int flattenScene(const gdb200_scene_desc *d, gdb200_scene *s)
                 const int u = waldModulo[k], v = waldModulo[k + 1];
                 const double n_k = Nv[k], denom = bv[u] * cv[v] - bv[v] * cv[u];
                 T.p0 = A; T.p1 = B; T.p2 = C; T.material = sh.material; T.emitter = -1;
-                if (denom == 0) { T.k = 3; continue; }
+                if (denom == 0) continue;                                            // degenerate: k = 3, never hit (triaccel.h:75-78)
                 T.k = k;
                 T.n_u = Nv[u] / n_k; T.n_v = Nv[v] / n_k; T.n_d = dot(A, N) / n_k;
                 T.b_nu = bv[u] / denom; T.b_nv = -bv[v] / denom; T.a_u = Av[u]; T.a_v = Av[v];
@@ -741,7 +751,13 @@ int flattenScene(const gdb200_scene_desc *d, gdb200_scene *s)
                 const double l = len(faceNormal);
                 if (!isZero(faceNormal)) faceNormal = faceNormal / l;
                 T.faceNormal = faceNormal;
+                meshTris.push_back(T);
             }
+            for (int k = 0; k < 3; k++) {          // store grouped by projection axis (order inside a group is kept)
+                for (const DTri &T : meshTris) if (T.k == k) h.tris[h.nTris++] = T;
+                M.kEnd[k] = h.nTris;
+            }
+            M.count = h.nTris - M.first;
         } else return set_error(GDB200_ERR_ARGUMENT, "shape %d: unknown type %d", i, sh.type);
     }
     for (int mi = 0; mi < h.nMeshes; mi++) {   // enlarge the skip-bounds far beyond any rounding of the slab test
@@ -918,9 +934,10 @@ int gdb200_gpt_render(gdb200_scene *s, const gdb200_gpt_params *p, gdb200_buffer
         mark();
         gpt_compact_kernel<<<(nSlots + 255) / 256, 256>>>(a, parity);
         mark();
-        gpt_bounce_kernel<<<bounceBlocks, kBounceThreads>>>(a, parity);
+        gpt_bounce_kernel<0><<<bounceBlocks, kBounceThreads>>>(a, parity);
+        gpt_bounce_kernel<1><<<bounceBlocks, kBounceThreads>>>(a, parity);
         mark();
-        launches += 3;
+        launches += 4;
         parity ^= 1;
         if ((step & 15) == 15) {
             GDB_CUDA(cudaMemcpy(hostCounters, s->counters, sizeof(hostCounters), cudaMemcpyDeviceToHost));

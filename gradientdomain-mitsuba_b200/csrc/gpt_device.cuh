@@ -92,7 +92,7 @@ constexpr int kMaxRects = 24, kMaxSpheres = 8, kMaxTris = 192, kMaxMeshes = 16, 
 struct DRect   { Float toObject[12], toWorld[12]; V3 dpdu, n; Float invArea; int material, emitter; };
 struct DSphere { V3 center; Float radius; int flip, material, emitter, pad; };
 struct DTri    { Float n_u, n_v, n_d, a_u, a_v, b_nu, b_nv, c_nu, c_nv; V3 p0, p1, p2, faceNormal; int k, material, emitter, pad; };
-struct DMesh   { V3 lo, hi; int first, count; };   // conservative (enlarged) bounds of one TriMesh, used only to skip its triangles
+struct DMesh   { V3 lo, hi; int first, count; int kEnd[3], pad; };   // triangles of a mesh are stored grouped by projection axis k: [first,kEnd[0]) k=0, [kEnd[0],kEnd[1]) k=1, [kEnd[1],kEnd[2]) k=2   // conservative (enlarged) bounds of one TriMesh, used only to skip its triangles
 struct DMaterial {
     int type, distribution; unsigned flags; int vtSmooth, vtDelta, refNFromShading, pad0, pad1;
     Spec reflectance, specR, specT, eta, k; Float alpha, iorRatio, bsdfEta;
@@ -180,20 +180,26 @@ GDB_D bool closestPrimitive(const Ray &ray, Float mint, Float maxt, Float &tOut,
             const Float tn = fmax(fmax(fmin(ax, bx), fmin(ay, by)), fmin(az, bz));
             const Float tf = fmin(fmin(fmax(ax, bx), fmax(ay, by)), fmax(az, bz));
             if (tn > tf || tf < mint || tn > maxt) continue;
-            for (int i = M.first; i < M.first + M.count; i++) {          // triaccel.h:97-158
-                const DTri &T = c_scene.tris[i];
+            // triaccel.h:97-158; the triangles are grouped by their projection axis k, so the ray's
+            // (u,v,k) component permutation is done once per group instead of once per triangle
+            int i = M.first;
+#pragma unroll 1
+            for (int k = 0; k < 3; k++) {
                 Float o_u, o_v, o_k, d_u, d_v, d_k;
-                if (T.k == 0) { o_u = ray.o.y; o_v = ray.o.z; o_k = ray.o.x; d_u = ray.d.y; d_v = ray.d.z; d_k = ray.d.x; }
-                else if (T.k == 1) { o_u = ray.o.z; o_v = ray.o.x; o_k = ray.o.y; d_u = ray.d.z; d_v = ray.d.x; d_k = ray.d.y; }
-                else if (T.k == 2) { o_u = ray.o.x; o_v = ray.o.y; o_k = ray.o.z; d_u = ray.d.x; d_v = ray.d.y; d_k = ray.d.z; }
-                else continue;
-                const Float t = (T.n_d - o_u * T.n_u - o_v * T.n_v - o_k) / (d_u * T.n_u + d_v * T.n_v + d_k);
-                if (t < mint || t > maxt) continue;
-                const Float hu = o_u + t * d_u - T.a_u, hv = o_v + t * d_v - T.a_v;
-                const Float u = hv * T.b_nu + hu * T.b_nv, v = hu * T.c_nu + hv * T.c_nv;
-                if (u >= 0 && v >= 0 && u + v <= 1.0) {
-                    if (AnyHit) return true;
-                    maxt = t; found = true; kind = 2; index = i; uOut = u; vOut = v;
+                if (k == 0) { o_u = ray.o.y; o_v = ray.o.z; o_k = ray.o.x; d_u = ray.d.y; d_v = ray.d.z; d_k = ray.d.x; }
+                else if (k == 1) { o_u = ray.o.z; o_v = ray.o.x; o_k = ray.o.y; d_u = ray.d.z; d_v = ray.d.x; d_k = ray.d.y; }
+                else { o_u = ray.o.x; o_v = ray.o.y; o_k = ray.o.z; d_u = ray.d.x; d_v = ray.d.y; d_k = ray.d.z; }
+                const int end = M.kEnd[k];
+                for (; i < end; i++) {
+                    const DTri &T = c_scene.tris[i];
+                    const Float t = (T.n_d - o_u * T.n_u - o_v * T.n_v - o_k) / (d_u * T.n_u + d_v * T.n_v + d_k);
+                    if (t < mint || t > maxt) continue;
+                    const Float hu = o_u + t * d_u - T.a_u, hv = o_v + t * d_v - T.a_v;
+                    const Float u = hv * T.b_nu + hu * T.b_nv, v = hu * T.c_nu + hv * T.c_nv;
+                    if (u >= 0 && v >= 0 && u + v <= 1.0) {
+                        if (AnyHit) return true;
+                        maxt = t; found = true; kind = 2; index = i; uOut = u; vOut = v;
+                    }
                 }
             }
         }
