@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(kBounceThreads) gpt_bounce_kernel(const GptArg
 
     if (!ended) {
         const bool lastSegment = (depth + 1 == cfg.maxDepth);                        // gpt.cpp:558
-        const DMaterial &mainBSDF = c_scene.materials[mits.material];
+        const DMaterial &mainBSDF = c_sceneG->materials[mits.material];
         const Frame prevSh = mits.sh; const V3 prevP = mits.p, prevWi = mits.wi;     // the vertex both stages shade (previousMainIts, gpt.cpp:753)
 
         // ---------------- base path: next event estimation, gpt.cpp:565-607
@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(kBounceThreads) gpt_bounce_kernel(const GptArg
                         mainDRec.p = mits.p; mainDRec.n = mits.sh.n; mainDRec.d = mainWo; mainDRec.dist = mits.t; mainDRec.emitter = mits.emitter;
                         mainHitEmitter = true;
                     }
-                    mainNextVertexType = vertexType(c_scene.materials[mits.material], bs.sampledType);   // gpt.cpp:784
+                    mainNextVertexType = vertexType(c_sceneG->materials[mits.material], bs.sampledType);   // gpt.cpp:784
                     const Float mainPreviousPdf = mpdf;                              // gpt.cpp:807-812
                     mthr = mthr * (bs.weight * bs.pdf);
                     mpdf *= bs.pdf;
@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(kBounceThreads) gpt_bounce_kernel(const GptArg
                         mainContribution = neeContributionAll;
                         shiftedContribution = jacobian * sthr * (shiftedBsdfValue * neeEmitterRadiance);
                     } else {                                                         // gpt.cpp:659-705
-                        const DMaterial &shiftedBSDF = c_scene.materials[sits.material];
+                        const DMaterial &shiftedBSDF = c_sceneG->materials[sits.material];
                         if (vertexType(mainBSDF, ESmooth) == VERTEX_TYPE_DIFFUSE && vertexType(shiftedBSDF, ESmooth) == VERTEX_TYPE_DIFFUSE) {   // gpt.cpp:672
                             DRec sRec; initDRec(sits, sRec);
                             bool shiftedEmitterVisible;
@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(kBounceThreads) gpt_bounce_kernel(const GptArg
                         mainContribution = mainContributionAll;
                         shiftedContribution = sthr * mainEmitterRadiance;
                     } else {                                                         // gpt.cpp:889-1126
-                        const DMaterial &shiftedBSDF = c_scene.materials[sits.material];
+                        const DMaterial &shiftedBSDF = c_sceneG->materials[sits.material];
                         const int shiftedVertexType = vertexType(shiftedBSDF, bs.sampledType);
                         if (mainVertexType == VERTEX_TYPE_DIFFUSE && mainNextVertexType == VERTEX_TYPE_DIFFUSE && shiftedVertexType == VERTEX_TYPE_DIFFUSE) {
                             if (!lastSegment || mainHitEmitter) {                    // gpt.cpp:901
@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(kBounceThreads) gpt_bounce_kernel(const GptArg
                                         rays++;
                                         if (!rayIntersect(sray, sits)) ok = false;   // gpt.cpp:1052-1058 (no environment emitter)
                                         else {
-                                            const int shiftedNextVertexType = vertexType(c_scene.materials[sits.material], bs.sampledType);
+                                            const int shiftedNextVertexType = vertexType(c_sceneG->materials[sits.material], bs.sampledType);
                                             if (mainVertexType == VERTEX_TYPE_DIFFUSE && shiftedVertexType2 == VERTEX_TYPE_DIFFUSE && shiftedNextVertexType == VERTEX_TYPE_DIFFUSE) ok = false;   // gpt.cpp:1089-1093
                                             else {
                                                 if (sits.emitter >= 0) shiftedEmitterRadiance = emittedLe(sits, -sray.d);   // gpt.cpp:1095-1098
@@ -606,7 +606,7 @@ __global__ void __launch_bounds__(256) gpt_compact_kernel(const GptArgs a, int p
             const int c = flagConn(f, i);
             if (c == RAY_NOT_CONNECTED) stage = 0; else if (c == RAY_RECENTLY_CONNECTED && stage == 2) stage = 1;
         }
-        bucket = c_scene.materials[SI(a, IF_MAT, slot)].type * 3 + stage;
+        bucket = c_sceneG->materials[SI(a, IF_MAT, slot)].type * 3 + stage;
     }
     int rank = 0;
 #pragma unroll
@@ -635,6 +635,50 @@ __global__ void gpt_init_kernel(const GptArgs a)
     SI(a, IF_STATUS, slot) = ST_FRESH; SI(a, IF_SAMPLE, slot) = 0; SI(a, IF_RNGN, slot) = 0;
 }
 
+// Self-check of the candidate selection in closestPrimitive: random nearest-hit and shadow rays (from
+// surface points, between surface points, from free space) must give bit-identical answers with and
+// without the bounds pass.
+__global__ void gpt_check_culling_kernel(unsigned long long seed, int nRays, unsigned long long *mismatch)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nRays) return;
+    Sampler smp; smp.key = samplerKey(seed, g, 12345); smp.n = 0;
+    auto surfacePoint = [&]() {
+        const int nR = c_scene.nRects, nT = c_scene.nTris, nS = c_scene.nSpheres;
+        const int pick = min(nR + nT + nS - 1, (int)(smp.next1D() * (nR + nT + nS)));
+        const Float u = smp.next1D(), v = smp.next1D();
+        if (pick < nR) return xfAffine(c_sceneG->rects[pick].toWorld, mk(2 * u - 1, 2 * v - 1, 0));
+        if (pick < nR + nT) { const DTri &T = c_sceneG->tris[pick - nR]; const Float a = sqrt(u); return T.p0 * (1 - a) + T.p1 * (a * (1 - v)) + T.p2 * (a * v); }
+        const DSphere &sp = c_sceneG->spheres[pick - nR - nT];
+        const Float z = 1 - 2 * u, r = sqrt(fmax(0.0, 1 - z * z)), phi = 2 * kPi * v;
+        return sp.center + mk(r * cos(phi), r * sin(phi), z) * sp.radius;
+    };
+    Ray ray;
+    const int flavour = g % 3;
+    if (flavour == 0) {            // extension ray from a surface point
+        ray.o = surfacePoint();
+        const Float z = 1 - 2 * smp.next1D(), r = sqrt(fmax(0.0, 1 - z * z)), phi = 2 * kPi * smp.next1D();
+        ray.d = mk(r * cos(phi), r * sin(phi), z); ray.mint = kEpsilon; ray.maxt = CUDART_INF;
+    } else if (flavour == 1) {     // visibility segment between two surface points (gpt.cpp:84-93)
+        ray.o = surfacePoint(); ray.d = surfacePoint() - ray.o; ray.mint = kEpsilon; ray.maxt = 1.0 - kShadowEpsilon;
+    } else {                       // camera-like ray from free space
+        ray.o = mk((2 * smp.next1D() - 1) * 2, (2 * smp.next1D() - 1) * 2, (2 * smp.next1D() - 1) * 5);
+        ray.d = normalize(surfacePoint() - ray.o); ray.mint = 1e-2; ray.maxt = 1e4;
+    }
+    Float rayMinT = ray.mint;
+    if (rayMinT == kEpsilon) rayMinT *= fmax(maxAbs3(ray.o), kEpsilon);
+    Float t1 = 0, t2 = 0, u1 = 0, v1 = 0, u2 = 0, v2 = 0; int k1 = -1, i1 = -1, k2 = -1, i2 = -1;
+    const bool h1 = closestPrimitive<false>(ray, rayMinT, ray.maxt, t1, k1, i1, u1, v1);
+    const bool h2 = closestPrimitiveExhaustive<false>(ray, rayMinT, ray.maxt, t2, k2, i2, u2, v2);
+    Float tt = 0, uu = 0, vv = 0; int kk = -1, ii = -1;
+    const bool a1 = closestPrimitive<true>(ray, rayMinT, ray.maxt, tt, kk, ii, uu, vv);
+    const bool a2 = closestPrimitiveExhaustive<true>(ray, rayMinT, ray.maxt, tt, kk, ii, uu, vv);
+    bool bad = (h1 != h2) || (a1 != a2) || (h1 != a1);
+    if (h1 && h2) bad = bad || t1 != t2 || k1 != k2 || i1 != i2 || (k1 == 2 && (u1 != u2 || v1 != v2));
+    if (bad) atomicAdd(mismatch, 1ULL);
+    if (h1) atomicAdd(mismatch + 1, 1ULL);
+}
+
 // MultiFilm::developMulti (multifilm.cpp:366-416, fmtconv.cpp:1036-1045): value * (1/weight), plus the
 // Float -> float conversion of gpt.cpp:1439-1442 for the solver inputs.
 __global__ void gpt_develop_kernel(const double *film, int n, double *dev64 /*[5][n][3]*/, float *dev32 /*[5][n][3]*/)
@@ -660,6 +704,8 @@ using namespace gdb200;
 struct gdb200_scene {
     int device = 0;
     DScene host;                       // flattened tables (vertex classification filled per render)
+    DBounds bounds[kMaxPrims];         // padded per-primitive bounds (candidate selection)
+    DScene *dScene = nullptr;          // global-memory copy of `host` for per-lane indexed reads
     std::vector<gdb200_material> mats;
     int width = 0, height = 0;
     // device buffers
@@ -766,6 +812,34 @@ int flattenScene(const gdb200_scene_desc *d, gdb200_scene *s)
         const double pad = 1e-6 * std::max(1.0, std::max(ext.x, std::max(ext.y, ext.z))) + 1e-9 * std::max(maxComp(M.hi), -std::min(M.lo.x, std::min(M.lo.y, M.lo.z)));
         M.lo = M.lo - splat(pad); M.hi = M.hi + splat(pad);
     }
+    // padded bounds of every primitive for the candidate pass of closestPrimitive
+    {
+        double scale = 0;
+        for (int k = 0; k < 3; k++) scale = std::max(scale, std::abs(c.camera_to_world[4 * k + 3]));
+        int np = 0;
+        auto grow = [&](DBounds &B, V3 P) {
+            const double v[3] = {P.x, P.y, P.z};
+            for (int k = 0; k < 3; k++) { B.lo[k] = std::min(B.lo[k], (float)v[k]); B.hi[k] = std::max(B.hi[k], (float)v[k]); scale = std::max(scale, std::abs(v[k])); }
+        };
+        auto reset = [](DBounds &B) { for (int k = 0; k < 3; k++) { B.lo[k] = std::numeric_limits<float>::infinity(); B.hi[k] = -B.lo[k]; } };
+        for (int i = 0; i < h.nRects; i++) {
+            DBounds &B = s->bounds[np++]; reset(B);
+            for (int sx = -1; sx <= 1; sx += 2) for (int sy = -1; sy <= 1; sy += 2) grow(B, xfAffine(h.rects[i].toWorld, mk(sx, sy, 0)));
+        }
+        for (int i = 0; i < h.nSpheres; i++) {
+            DBounds &B = s->bounds[np++]; reset(B);
+            grow(B, h.spheres[i].center - splat(h.spheres[i].radius)); grow(B, h.spheres[i].center + splat(h.spheres[i].radius));
+        }
+        for (int i = 0; i < h.nTris; i++) {
+            DBounds &B = s->bounds[np++]; reset(B);
+            grow(B, h.tris[i].p0); grow(B, h.tris[i].p1); grow(B, h.tris[i].p2);
+        }
+        for (int i = 0; i < np; i++)        // pad by 1e-4 of the scene scale: >100x the fp32 rounding of the slab test (errors and
+            for (int k = 0; k < 3; k++) {   // padding both scale with |1/d| per axis, so the margin holds for any ray direction)
+                const float pad = (float)(1e-4 * (scale + (s->bounds[i].hi[k] - s->bounds[i].lo[k])) + 1e-6);
+                s->bounds[i].lo[k] -= pad; s->bounds[i].hi[k] += pad;
+            }
+    }
     // emitters: DiscreteDistribution over samplingWeight (scene.cpp:357-380, pmf.h:100-114)
     h.nEmitters = d->n_emitters;
     h.emCdf[0] = 0.0;
@@ -824,9 +898,19 @@ void classifyMaterials(gdb200_scene *s, double shiftThreshold)
 void freeSceneBuffers(gdb200_scene *s)
 {
     cudaFree(s->film); cudaFree(s->dev64); cudaFree(s->dev32); cudaFree(s->sd); cudaFree(s->si); cudaFree(s->key);
-    cudaFree(s->liveList); cudaFree(s->liveCount); cudaFree(s->counters);
+    cudaFree(s->liveList); cudaFree(s->liveCount); cudaFree(s->counters); cudaFree(s->dScene); s->dScene = nullptr;
     s->film = s->dev64 = s->sd = nullptr; s->dev32 = nullptr; s->si = nullptr; s->key = nullptr;
     s->liveList = s->liveCount = nullptr; s->counters = nullptr; s->slotCapacity = 0;
+}
+
+int uploadScene(gdb200_scene *s)
+{
+    GDB_CUDA(cudaMemcpyToSymbol(c_scene, &s->host, sizeof(DScene)));
+    GDB_CUDA(cudaMemcpyToSymbol(c_bounds, s->bounds, sizeof(s->bounds)));
+    if (!s->dScene) GDB_CUDA(cudaMalloc(&s->dScene, sizeof(DScene)));
+    GDB_CUDA(cudaMemcpy(s->dScene, &s->host, sizeof(DScene), cudaMemcpyHostToDevice));
+    GDB_CUDA(cudaMemcpyToSymbol(c_sceneG, &s->dScene, sizeof(s->dScene)));
+    return GDB200_OK;
 }
 
 int developAndCopy(gdb200_scene *s, gdb200_buffers *out)
@@ -901,7 +985,7 @@ int gdb200_gpt_render(gdb200_scene *s, const gdb200_gpt_params *p, gdb200_buffer
     classifyMaterials(s, p->shift_threshold);
 
     std::lock_guard<std::mutex> lock(g_constMutex);
-    GDB_CUDA(cudaMemcpyToSymbol(c_scene, &s->host, sizeof(DScene)));
+    if (int rc = uploadScene(s)) return rc;
     GDB_CUDA(cudaMemset(s->film, 0, sizeof(double) * 5 * (size_t)s->width * s->height * 4));
     GDB_CUDA(cudaMemset(s->counters, 0, sizeof(unsigned long long) * 8));
 
@@ -965,6 +1049,23 @@ int gdb200_gpt_render(gdb200_scene *s, const gdb200_gpt_params *p, gdb200_buffer
         }
     }
     for (cudaEvent_t ev : marks) cudaEventDestroy(ev);
+    return GDB200_OK;
+}
+
+int gdb200_debug_check_culling(gdb200_scene *s, int n_rays, unsigned long long seed, unsigned long long *out_mismatches, unsigned long long *out_hits)
+{
+    if (!s || !out_mismatches || n_rays <= 0) return set_error(GDB200_ERR_ARGUMENT, "scene/out is NULL");
+    GDB_CUDA(cudaSetDevice(s->device));
+    classifyMaterials(s, 0.001);
+    std::lock_guard<std::mutex> lock(g_constMutex);
+    if (int rc = uploadScene(s)) return rc;
+    GDB_CUDA(cudaMemset(s->counters, 0, sizeof(unsigned long long) * 8));
+    gpt_check_culling_kernel<<<(n_rays + 127) / 128, 128>>>(seed, n_rays, s->counters);
+    GDB_CUDA(cudaGetLastError());
+    unsigned long long h[2];
+    GDB_CUDA(cudaMemcpy(h, s->counters, sizeof(h), cudaMemcpyDeviceToHost));
+    *out_mismatches = h[0];
+    if (out_hits) *out_hits = h[1];
     return GDB200_OK;
 }
 

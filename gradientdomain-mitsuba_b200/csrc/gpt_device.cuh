@@ -114,6 +114,16 @@ struct DScene {
 
 __constant__ DScene c_scene;   // one per device; renders sharing a device are serialised on the host
 
+// The same tables in global memory.  Constant memory serialises a warp whose lanes read different
+// entries, so every access with a per-lane index (the hit primitive, the material of a vertex, a lane's
+// candidate primitive) goes through this copy (L1-cached); c_scene serves the warp-uniform loops.
+__constant__ const DScene *c_sceneG;
+
+// Padded world-space bounds of every primitive, in test order: rectangles, spheres, triangles.
+constexpr int kMaxPrims = kMaxRects + kMaxSpheres + kMaxTris;
+struct DBounds { float lo[3], hi[3]; };   // single precision is enough for a conservative (padded) slab test
+__constant__ DBounds c_bounds[kMaxPrims];
+
 struct Config { int maxDepth, minDepth, rrDepth, strictNormals; Float shiftThreshold; };
 
 struct Its { Float t; V3 p, geoN; Frame sh; V3 wi; int material, emitter; };   // emitter: index or -1
@@ -135,75 +145,108 @@ GDB_D bool solveQuadratic(double a, double b, double c, double &x0, double &x1)
     return true;
 }
 
-// Candidate tests against the shrinking [mint, maxt] = the outcome of the reference's kd-tree
-// traversal (sahkdtree3.h:179-308).  kind: 0 rect, 1 sphere, 2 triangle.
+// Exact fp64 tests of the reference, one primitive each.
+GDB_D bool rectHit(const DRect &r, const Ray &ray, Float mint, Float maxt, Float &t)          // rectangle.cpp:125-151
+{
+    const Float *m = r.toObject;
+    const Float oz = m[8] * ray.o.x + m[9] * ray.o.y + m[10] * ray.o.z + m[11];
+    const Float dz = m[8] * ray.d.x + m[9] * ray.d.y + m[10] * ray.d.z;
+    const Float hit = -oz / dz;
+    if (!(hit >= mint && hit <= maxt)) return false;
+    const Float lx = (m[0] * ray.o.x + m[1] * ray.o.y + m[2] * ray.o.z + m[3]) + (m[0] * ray.d.x + m[1] * ray.d.y + m[2] * ray.d.z) * hit;
+    const Float ly = (m[4] * ray.o.x + m[5] * ray.o.y + m[6] * ray.o.z + m[7]) + (m[4] * ray.d.x + m[5] * ray.d.y + m[6] * ray.d.z) * hit;
+    if (fabs(lx) <= 1 && fabs(ly) <= 1) { t = hit; return true; }
+    return false;
+}
+GDB_D bool sphereHit(const DSphere &s, const Ray &ray, Float mint, Float maxt, Float &t)      // sphere.cpp:163-187
+{
+    const V3 o = ray.o - s.center;
+    const double A = len2(ray.d), B = 2 * dot(o, ray.d), C = len2(o) - s.radius * s.radius;
+    double nearT, farT;
+    if (!solveQuadratic(A, B, C, nearT, farT)) return false;
+    if (!(nearT <= maxt && farT >= mint)) return false;
+    if (nearT < mint) { if (farT > maxt) return false; t = farT; } else t = nearT;
+    return true;
+}
+GDB_D bool triHit(const DTri &T, const Ray &ray, Float mint, Float maxt, Float &t, Float &u, Float &v)   // triaccel.h:97-158
+{
+    const int k = T.k;
+    if (k > 2) return false;
+    const Float o_u = k == 0 ? ray.o.y : (k == 1 ? ray.o.z : ray.o.x), o_v = k == 0 ? ray.o.z : (k == 1 ? ray.o.x : ray.o.y);
+    const Float o_k = k == 0 ? ray.o.x : (k == 1 ? ray.o.y : ray.o.z);
+    const Float d_u = k == 0 ? ray.d.y : (k == 1 ? ray.d.z : ray.d.x), d_v = k == 0 ? ray.d.z : (k == 1 ? ray.d.x : ray.d.y);
+    const Float d_k = k == 0 ? ray.d.x : (k == 1 ? ray.d.y : ray.d.z);
+    t = (T.n_d - o_u * T.n_u - o_v * T.n_v - o_k) / (d_u * T.n_u + d_v * T.n_v + d_k);
+    if (t < mint || t > maxt) return false;
+    const Float hu = o_u + t * d_u - T.a_u, hv = o_v + t * d_v - T.a_v;
+    u = hv * T.b_nu + hu * T.b_nv;
+    v = hu * T.c_nu + hv * T.c_nv;
+    return u >= 0 && v >= 0 && u + v <= 1.0;
+}
+
+// Nearest (or any) hit in [mint, maxt] = the outcome of the reference's kd-tree traversal
+// (sahkdtree3.h:179-308: every candidate is tested against the shrinking interval).
+//   pass 1: a division-free slab test of the ray against the padded bounds of every primitive, as a
+//           warp-uniform loop over constant memory, yields a per-lane candidate mask;
+//   pass 2: each lane walks ITS OWN candidates (typically 2-4 of 32) through the reference's exact
+//           fp64 test, in primitive order.  All lanes run the same test code on different primitives,
+//           so incoherent rays no longer pay for the union of everything any lane might hit.
+// The bounds are conservative, so the answers are those of testing every primitive.
 template <bool AnyHit>
 GDB_D bool closestPrimitive(const Ray &ray, Float mint, Float maxt, Float &tOut, int &kind, int &index, Float &uOut, Float &vOut)
 {
+    const DScene *g = c_sceneG;
+    const int nR = c_scene.nRects, nS = c_scene.nSpheres, nP = nR + nS + c_scene.nTris;
+    const float ox = (float)ray.o.x, oy = (float)ray.o.y, oz = (float)ray.o.z;
+    const float ix = 1.0f / (float)ray.d.x, iy = 1.0f / (float)ray.d.y, iz = 1.0f / (float)ray.d.z;
+    const float tlo = (float)mint * 0.999f, thi0 = (float)maxt * 1.001f;      // (+inf stays +inf)
     bool found = false;
-    for (int i = 0; i < c_scene.nRects; i++) {                       // rectangle.cpp:125-151
-        const DRect &r = c_scene.rects[i];
-        const Float *m = r.toObject;
-        const Float oz = m[8] * ray.o.x + m[9] * ray.o.y + m[10] * ray.o.z + m[11];
-        const Float dz = m[8] * ray.d.x + m[9] * ray.d.y + m[10] * ray.d.z;
-        // -oz/dz can only land in [mint, maxt] (mint > 0) when oz and dz have opposite signs: skip the divide otherwise
-        if (mint > 0 && !((oz < 0 && dz > 0) || (oz > 0 && dz < 0))) continue;
-        const Float hit = -oz / dz;
-        if (!(hit >= mint && hit <= maxt)) continue;
-        const Float lx = (m[0] * ray.o.x + m[1] * ray.o.y + m[2] * ray.o.z + m[3]) + (m[0] * ray.d.x + m[1] * ray.d.y + m[2] * ray.d.z) * hit;
-        const Float ly = (m[4] * ray.o.x + m[5] * ray.o.y + m[6] * ray.o.z + m[7]) + (m[4] * ray.d.x + m[5] * ray.d.y + m[6] * ray.d.z) * hit;
-        if (fabs(lx) <= 1 && fabs(ly) <= 1) {
-            if (AnyHit) return true;
-            maxt = hit; found = true; kind = 0; index = i;
+    for (int base = 0; base < nP; base += 32) {
+        const int cnt = min(32, nP - base);
+        const float thi = found ? (float)maxt * 1.001f : thi0;
+        unsigned mask = 0;
+        for (int j = 0; j < cnt; j++) {
+            const DBounds &B = c_bounds[base + j];
+            const float ax = (B.lo[0] - ox) * ix, bx = (B.hi[0] - ox) * ix;
+            const float ay = (B.lo[1] - oy) * iy, by = (B.hi[1] - oy) * iy;
+            const float az = (B.lo[2] - oz) * iz, bz = (B.hi[2] - oz) * iz;
+            const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+            const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+            if (tn <= tf && tf >= tlo && tn <= thi) mask |= 1u << j;
+        }
+        // rectangles
+        const int rEnd = min(max(nR - base, 0), 32), sEnd = min(max(nR + nS - base, 0), 32);
+        unsigned m = mask & (rEnd >= 32 ? 0xffffffffu : ((1u << rEnd) - 1));
+        while (m) {
+            const int p = base + __ffs(m) - 1; m &= m - 1;
+            Float t;
+            if (rectHit(g->rects[p], ray, mint, maxt, t)) { if (AnyHit) return true; maxt = t; found = true; kind = 0; index = p; }
+        }
+        m = mask & (sEnd >= 32 ? 0xffffffffu : ((1u << sEnd) - 1)) & ~(rEnd >= 32 ? 0xffffffffu : ((1u << rEnd) - 1));
+        while (m) {
+            const int p = base + __ffs(m) - 1; m &= m - 1;
+            Float t;
+            if (sphereHit(g->spheres[p - nR], ray, mint, maxt, t)) { if (AnyHit) return true; maxt = t; found = true; kind = 1; index = p - nR; }
+        }
+        m = mask & ~(sEnd >= 32 ? 0xffffffffu : ((1u << sEnd) - 1));
+        while (m) {
+            const int p = base + __ffs(m) - 1; m &= m - 1;
+            Float t, u, v;
+            if (triHit(g->tris[p - nR - nS], ray, mint, maxt, t, u, v)) { if (AnyHit) return true; maxt = t; found = true; kind = 2; index = p - nR - nS; uOut = u; vOut = v; }
         }
     }
-    for (int i = 0; i < c_scene.nSpheres; i++) {                     // sphere.cpp:163-187
-        const DSphere &s = c_scene.spheres[i];
-        const V3 o = ray.o - s.center;
-        const double A = len2(ray.d), B = 2 * dot(o, ray.d), C = len2(o) - s.radius * s.radius;
-        double nearT, farT;
-        if (!solveQuadratic(A, B, C, nearT, farT)) continue;
-        if (!(nearT <= maxt && farT >= mint)) continue;
-        Float t;
-        if (nearT < mint) { if (farT > maxt) continue; t = farT; } else t = nearT;
-        if (AnyHit) return true;
-        maxt = t; found = true; kind = 1; index = i;
-    }
-    if (c_scene.nMeshes > 0) {
-        const V3 inv = mk(1.0 / ray.d.x, 1.0 / ray.d.y, 1.0 / ray.d.z);
-        for (int mi = 0; mi < c_scene.nMeshes; mi++) {
-            const DMesh &M = c_scene.meshes[mi];
-            // slab test against the enlarged bounds: purely a skip of triangles that cannot be hit in [mint, maxt]
-            const Float ax = (M.lo.x - ray.o.x) * inv.x, bx = (M.hi.x - ray.o.x) * inv.x;
-            const Float ay = (M.lo.y - ray.o.y) * inv.y, by = (M.hi.y - ray.o.y) * inv.y;
-            const Float az = (M.lo.z - ray.o.z) * inv.z, bz = (M.hi.z - ray.o.z) * inv.z;
-            const Float tn = fmax(fmax(fmin(ax, bx), fmin(ay, by)), fmin(az, bz));
-            const Float tf = fmin(fmin(fmax(ax, bx), fmax(ay, by)), fmax(az, bz));
-            if (tn > tf || tf < mint || tn > maxt) continue;
-            // triaccel.h:97-158; the triangles are grouped by their projection axis k, so the ray's
-            // (u,v,k) component permutation is done once per group instead of once per triangle
-            int i = M.first;
-#pragma unroll 1
-            for (int k = 0; k < 3; k++) {
-                Float o_u, o_v, o_k, d_u, d_v, d_k;
-                if (k == 0) { o_u = ray.o.y; o_v = ray.o.z; o_k = ray.o.x; d_u = ray.d.y; d_v = ray.d.z; d_k = ray.d.x; }
-                else if (k == 1) { o_u = ray.o.z; o_v = ray.o.x; o_k = ray.o.y; d_u = ray.d.z; d_v = ray.d.x; d_k = ray.d.y; }
-                else { o_u = ray.o.x; o_v = ray.o.y; o_k = ray.o.z; d_u = ray.d.x; d_v = ray.d.y; d_k = ray.d.z; }
-                const int end = M.kEnd[k];
-                for (; i < end; i++) {
-                    const DTri &T = c_scene.tris[i];
-                    const Float t = (T.n_d - o_u * T.n_u - o_v * T.n_v - o_k) / (d_u * T.n_u + d_v * T.n_v + d_k);
-                    if (t < mint || t > maxt) continue;
-                    const Float hu = o_u + t * d_u - T.a_u, hv = o_v + t * d_v - T.a_v;
-                    const Float u = hv * T.b_nu + hu * T.b_nv, v = hu * T.c_nu + hv * T.c_nv;
-                    if (u >= 0 && v >= 0 && u + v <= 1.0) {
-                        if (AnyHit) return true;
-                        maxt = t; found = true; kind = 2; index = i; uOut = u; vOut = v;
-                    }
-                }
-            }
-        }
-    }
+    tOut = maxt;
+    return found;
+}
+
+// Reference-order brute force over every primitive: used by the self-check kernel only.
+template <bool AnyHit>
+GDB_D bool closestPrimitiveExhaustive(const Ray &ray, Float mint, Float maxt, Float &tOut, int &kind, int &index, Float &uOut, Float &vOut)
+{
+    bool found = false;
+    for (int i = 0; i < c_scene.nRects; i++) { Float t; if (rectHit(c_scene.rects[i], ray, mint, maxt, t)) { if (AnyHit) return true; maxt = t; found = true; kind = 0; index = i; } }
+    for (int i = 0; i < c_scene.nSpheres; i++) { Float t; if (sphereHit(c_scene.spheres[i], ray, mint, maxt, t)) { if (AnyHit) return true; maxt = t; found = true; kind = 1; index = i; } }
+    for (int i = 0; i < c_scene.nTris; i++) { Float t, u, v; if (triHit(c_scene.tris[i], ray, mint, maxt, t, u, v)) { if (AnyHit) return true; maxt = t; found = true; kind = 2; index = i; uOut = u; vOut = v; } }
     tOut = maxt;
     return found;
 }
@@ -220,19 +263,19 @@ GDB_CALL bool rayIntersect(const Ray &ray, Its &its)
     its.t = t;
     V3 dpdu;
     if (kind == 2) {                                                 // skdtree.h:348-419 (BarycentricPos)
-        const DTri &T = c_scene.tris[index];
+        const DTri &T = c_sceneG->tris[index];
         const V3 b = mk(1 - u - v, u, v);
         its.p = T.p0 * b.x + T.p1 * b.y + T.p2 * b.z;
         dpdu = T.p1 - T.p0;
         its.sh.n = T.faceNormal; its.geoN = T.faceNormal;
         its.material = T.material; its.emitter = T.emitter;
     } else if (kind == 0) {                                          // rectangle.cpp:158-171
-        const DRect &r = c_scene.rects[index];
+        const DRect &r = c_sceneG->rects[index];
         its.geoN = r.n; its.sh.n = r.n; dpdu = r.dpdu;
         its.p = ray.o + ray.d * t;
         its.material = r.material; its.emitter = r.emitter;
     } else {                                                         // sphere.cpp:197-240
-        const DSphere &s = c_scene.spheres[index];
+        const DSphere &s = c_sceneG->spheres[index];
         its.p = ray.o + ray.d * t;
         const V3 local = its.p - s.center;
         dpdu = mk(-local.y, local.x, 0) * (2 * kPi);
@@ -537,12 +580,12 @@ struct DRec { V3 ref, refN, p, n, d; Float dist, pdf; int emitter; };
 GDB_D Spec emittedLe(const Its &its, V3 d)                                            // area.cpp:104-109
 {
     if (dot(its.sh.n, d) <= 0) return splat(0);
-    return c_scene.emitters[its.emitter].radiance;
+    return c_sceneG->emitters[its.emitter].radiance;
 }
 GDB_D void initDRec(const Its &ref, DRec &r)                                          // records.inl:160-165
 {
     r.ref = ref.p;
-    r.refN = c_scene.materials[ref.material].refNFromShading ? ref.sh.n : mk(0, 0, 0);
+    r.refN = c_sceneG->materials[ref.material].refNFromShading ? ref.sh.n : mk(0, 0, 0);
 }
 
 // Scene::sampleEmitterDirectVisible, scene.cpp:855-879 (pmf.h:124-188, area.cpp:158-176,

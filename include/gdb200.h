@@ -206,6 +206,11 @@ int  gdb200_gpt_accumulators(gdb200_scene *scene, double **d_accum, size_t *byte
 /* Re-develop after the accumulators were modified externally (tile merge). */
 int  gdb200_gpt_develop(gdb200_scene *scene, gdb200_buffers *out);
 
+/* Self-check: traces n_rays random rays through `scene` with and without the bounds-based candidate
+ * selection of the intersection routine and counts answers that differ (must be 0). */
+int  gdb200_debug_check_culling(gdb200_scene *scene, int n_rays, unsigned long long seed,
+                                unsigned long long *out_mismatches, unsigned long long *out_hits);
+
 /* Asynchronous cancel (Integrator::cancel, integrator.h:77-84). */
 void gdb200_cancel(gdb200_scene *scene);
 

@@ -105,3 +105,20 @@ def test_end_to_end_render_with_reconstruction(oracle):
     ref_final = oracle.poisson(f32["-dx"], f32["-dy"], f32["-throughput"], f32["-direct"], alpha=0.2, preset="L2D")
     rm = float(np.sqrt(np.mean((out["-final"] - ref_final) ** 2)))
     assert rm <= 1e-5, rm          # BASELINE: final-image RMSE within 1e-5 of the reference
+
+
+@pytest.mark.parametrize("scene_name", ["cbox_diffuse", "cbox_glossy"])
+def test_candidate_selection_never_changes_a_hit(scene_name):
+    """The bounds-based candidate pass of the intersection routine must be invisible:
+    3M random rays (extension, visibility-segment and camera-like), 0 differing answers."""
+    import ctypes
+    desc = getattr(scenes, scene_name)(64, 64)
+    scene = gdb200.Scene(desc)
+    L = gdb200.lib()
+    L.gdb200_debug_check_culling.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_ulonglong,
+                                             ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(ctypes.c_ulonglong)]
+    bad, hits = ctypes.c_ulonglong(), ctypes.c_ulonglong()
+    for seed in range(3):
+        assert L.gdb200_debug_check_culling(scene._h, 1_000_000, seed, ctypes.byref(bad), ctypes.byref(hits)) == 0
+        assert bad.value == 0, (seed, bad.value)
+        assert hits.value > 500_000
