@@ -36,11 +36,13 @@ namespace gdb200 {
 
 
 // ------------------------------------------------------------------ state layout
-enum BaseField { BF_RAYD = 0, BF_P = 3, BF_GN = 6, BF_S = 9, BF_T = 12, BF_N = 15, BF_WI = 18, BF_THR = 21, BF_PDF = 24,
-                 BF_ETA = 25, BF_RAD = 26, BF_VD = 29, BF_SPX = 32, BF_SPY = 33, BF_COUNT = 34 };
-enum OffField { OF_THR = 0, OF_PDF = 3, OF_RAD = 4, OF_GRAD = 7, OF_P = 10, OF_GN = 13, OF_S = 16, OF_T = 19, OF_N = 22,
-                OF_WI = 25, OF_COUNT = 28 };
-constexpr int kDoubleFields = BF_COUNT + 4 * OF_COUNT;   // 146
+// fp64 state is stored as 32-byte records [record][slot][4]: one vector (and one scalar riding in its 4th
+// lane) per record.  A record is exactly one DRAM sector, so a lane always consumes every byte it
+// fetches, however scattered the slots of a material/stage queue are.
+enum BaseRec { BR_RAYD = 0 /* w: path pdf */, BR_P /* w: eta */, BR_GN /* w: sample x */, BR_S /* w: sample y */, BR_T, BR_N, BR_WI,
+               BR_THR, BR_RAD, BR_VD, BR_COUNT };
+enum OffRec { OR_THR = 0 /* w: path pdf */, OR_RAD, OR_GRAD, OR_P, OR_GN, OR_S, OR_T, OR_N, OR_WI, OR_COUNT };
+constexpr int kRecords = BR_COUNT + 4 * OR_COUNT;   // 46 records = 1472 B per slot
 enum IntField { IF_STATUS = 0, IF_MAT, IF_EMI, IF_DEPTH, IF_SAMPLE, IF_RNGN, IF_OFLAGS, IF_OMAT0, IF_OMAT1, IF_OMAT2, IF_OMAT3,
                 IF_COUNT };
 enum SlotStatus { ST_FRESH = 0, ST_LIVE = 1, ST_FINISHED = 2, ST_DONE = 3 };
@@ -51,7 +53,7 @@ constexpr int kBounceThreads = 128, kGenThreads = 128;
 constexpr int kBuckets = 12;  // one queue per (BSDF type of the base vertex) x (shift stage of the offset paths)
 
 struct GptArgs {
-    double *sd;            // [kDoubleFields][nSlots]
+    double *sd;            // [kRecords][nSlots][4]
     int *si;               // [IF_COUNT][nSlots]
     uint64_t *key;         // [nSlots]
     int nSlots, width, height, yBegin;
@@ -61,39 +63,74 @@ struct GptArgs {
     double *film;          // [5][H][W][4]
     int *liveList;         // [2][kBuckets][nSlots]
     int *liveCount;        // [2][kBuckets]
+    int *genList;          // [2][nSlots]: slots whose path ended (to splat + regenerate)
+    int *genCount;         // [2]
     unsigned long long *counters;   // [0] done slots, [1] rays, [2] path vertices, [3] samples, [4] state bytes, [5] path bounces
 };
 
-GDB_D double &SD(const GptArgs &a, int field, int slot) { return a.sd[(size_t)field * a.nSlots + slot]; }
+GDB_D double *REC(const GptArgs &a, int rec, int slot) { return a.sd + (((size_t)rec * a.nSlots + slot) << 2); }
+GDB_D double &W(const GptArgs &a, int rec, int slot) { return REC(a, rec, slot)[3]; }
 GDB_D int &SI(const GptArgs &a, int field, int slot) { return a.si[(size_t)field * a.nSlots + slot]; }
-GDB_D V3 ld3(const GptArgs &a, int field, int slot) { return mk(SD(a, field, slot), SD(a, field + 1, slot), SD(a, field + 2, slot)); }
-GDB_D void st3(const GptArgs &a, int field, int slot, V3 v) { SD(a, field, slot) = v.x; SD(a, field + 1, slot) = v.y; SD(a, field + 2, slot) = v.z; }
+GDB_D V3 ldv(const GptArgs &a, int rec, int slot)
+{
+    const double2 *p = reinterpret_cast<const double2 *>(REC(a, rec, slot));
+    const double2 lo = p[0], hi = p[1];
+    return mk(lo.x, lo.y, hi.x);
+}
+GDB_D void ldvw(const GptArgs &a, int rec, int slot, V3 &v, Float &w)
+{
+    const double2 *p = reinterpret_cast<const double2 *>(REC(a, rec, slot));
+    const double2 lo = p[0], hi = p[1];
+    v = mk(lo.x, lo.y, hi.x); w = hi.y;
+}
+GDB_D void stv(const GptArgs &a, int rec, int slot, V3 v)
+{
+    double *p = REC(a, rec, slot);
+    *reinterpret_cast<double2 *>(p) = make_double2(v.x, v.y);
+    p[2] = v.z;
+}
+GDB_D void stvw(const GptArgs &a, int rec, int slot, V3 v, Float w)
+{
+    double2 *p = reinterpret_cast<double2 *>(REC(a, rec, slot));
+    p[0] = make_double2(v.x, v.y); p[1] = make_double2(v.z, w);
+}
 
 GDB_D void storeBaseIts(const GptArgs &a, int slot, const Its &its)
 {
-    st3(a, BF_P, slot, its.p); st3(a, BF_GN, slot, its.geoN); st3(a, BF_S, slot, its.sh.s); st3(a, BF_T, slot, its.sh.t);
-    st3(a, BF_N, slot, its.sh.n); st3(a, BF_WI, slot, its.wi);
+    stv(a, BR_P, slot, its.p); stv(a, BR_GN, slot, its.geoN); stv(a, BR_S, slot, its.sh.s); stv(a, BR_T, slot, its.sh.t);
+    stv(a, BR_N, slot, its.sh.n); stv(a, BR_WI, slot, its.wi);
     SI(a, IF_MAT, slot) = its.material; SI(a, IF_EMI, slot) = its.emitter;
 }
 GDB_D void loadBaseIts(const GptArgs &a, int slot, Its &its)
 {
-    its.t = 0; its.p = ld3(a, BF_P, slot); its.geoN = ld3(a, BF_GN, slot); its.sh.s = ld3(a, BF_S, slot); its.sh.t = ld3(a, BF_T, slot);
-    its.sh.n = ld3(a, BF_N, slot); its.wi = ld3(a, BF_WI, slot);
+    its.t = 0; its.p = ldv(a, BR_P, slot); its.geoN = ldv(a, BR_GN, slot); its.sh.s = ldv(a, BR_S, slot); its.sh.t = ldv(a, BR_T, slot);
+    its.sh.n = ldv(a, BR_N, slot); its.wi = ldv(a, BR_WI, slot);
     its.material = SI(a, IF_MAT, slot); its.emitter = SI(a, IF_EMI, slot);
 }
 GDB_D void storeOffIts(const GptArgs &a, int slot, int i, const Its &its)
 {
-    const int o = BF_COUNT + i * OF_COUNT;
-    st3(a, o + OF_P, slot, its.p); st3(a, o + OF_GN, slot, its.geoN); st3(a, o + OF_S, slot, its.sh.s); st3(a, o + OF_T, slot, its.sh.t);
-    st3(a, o + OF_N, slot, its.sh.n); st3(a, o + OF_WI, slot, its.wi);
+    const int o = BR_COUNT + i * OR_COUNT;
+    stv(a, o + OR_P, slot, its.p); stv(a, o + OR_GN, slot, its.geoN); stv(a, o + OR_S, slot, its.sh.s); stv(a, o + OR_T, slot, its.sh.t);
+    stv(a, o + OR_N, slot, its.sh.n); stv(a, o + OR_WI, slot, its.wi);
     SI(a, IF_OMAT0 + i, slot) = its.material;
 }
 GDB_D void loadOffIts(const GptArgs &a, int slot, int i, Its &its)
 {
-    const int o = BF_COUNT + i * OF_COUNT;
-    its.t = 0; its.p = ld3(a, o + OF_P, slot); its.geoN = ld3(a, o + OF_GN, slot); its.sh.s = ld3(a, o + OF_S, slot); its.sh.t = ld3(a, o + OF_T, slot);
-    its.sh.n = ld3(a, o + OF_N, slot); its.wi = ld3(a, o + OF_WI, slot);
+    const int o = BR_COUNT + i * OR_COUNT;
+    its.t = 0; its.p = ldv(a, o + OR_P, slot); its.geoN = ldv(a, o + OR_GN, slot); its.sh.s = ldv(a, o + OR_S, slot); its.sh.t = ldv(a, o + OR_T, slot);
+    its.sh.n = ldv(a, o + OR_N, slot); its.wi = ldv(a, o + OR_WI, slot);
     its.material = SI(a, IF_OMAT0 + i, slot); its.emitter = -1;
+}
+
+// Warp-aggregated append of an ended slot to the next step's regeneration queue.
+GDB_D void appendGen(const GptArgs &a, int parity, int slot)
+{
+    const unsigned m = __activemask();
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&a.genCount[parity], __popc(m));
+    base = __shfl_sync(m, base, leader);
+    a.genList[(size_t)parity * a.nSlots + base + __popc(m & ((1u << lane) - 1))] = slot;
 }
 
 // One atomic per warp for statistics counters.
@@ -158,18 +195,18 @@ GDB_D int flagConn(unsigned f, int i) { return (f >> (3 * i + 1)) & 3u; }
 GDB_D unsigned setFlag(unsigned f, int i, bool alive, int conn) { return (f & ~(7u << (3 * i))) | packFlag(i, alive, conn); }
 
 // ------------------------------------------------------------------ generate: splat finished paths, start next samples
-__global__ void __launch_bounds__(kGenThreads) gpt_generate_kernel(const GptArgs a)
+__global__ void __launch_bounds__(kGenThreads) gpt_generate_kernel(const GptArgs a, int parity)
 {
-    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= a.nSlots) return;
-    { const int st = SI(a, IF_STATUS, slot); if (st != ST_FRESH && st != ST_FINISHED) return; }
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= a.genCount[parity]) return;
+    const int slot = a.genList[(size_t)parity * a.nSlots + g];
     const int px = slot % a.width, py = a.yBegin + slot / a.width;
 
     if (SI(a, IF_STATUS, slot) == ST_FINISHED) {
         Spec rad[4], grad[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) { const int o = BF_COUNT + i * OF_COUNT; rad[i] = ld3(a, o + OF_RAD, slot); grad[i] = ld3(a, o + OF_GRAD, slot); }
-        splatSample(a, SD(a, BF_SPX, slot), SD(a, BF_SPY, slot), ld3(a, BF_VD, slot), ld3(a, BF_RAD, slot), rad, grad);
+        for (int i = 0; i < 4; i++) { const int o = BR_COUNT + i * OR_COUNT; rad[i] = ldv(a, o + OR_RAD, slot); grad[i] = ldv(a, o + OR_GRAD, slot); }
+        splatSample(a, W(a, BR_GN, slot), W(a, BR_S, slot), ldv(a, BR_VD, slot), ldv(a, BR_RAD, slot), rad, grad);
     }
 
     Sampler smp; smp.key = a.key[slot]; smp.n = (uint32_t)SI(a, IF_RNGN, slot);
@@ -197,9 +234,9 @@ __global__ void __launch_bounds__(kGenThreads) gpt_generate_kernel(const GptArgs
             if (alive && a.cfg.strictNormals && dot(sray.d, sits.geoN) * sits.wi.z >= 0) alive = false;   // gpt.cpp:523-530
             flags |= packFlag(i, alive, RAY_NOT_CONNECTED);
             if (!early) {
-                const int o = BF_COUNT + i * OF_COUNT;
-                st3(a, o + OF_THR, slot, splat(1.0)); SD(a, o + OF_PDF, slot) = 1.0;
-                st3(a, o + OF_RAD, slot, splat(0)); st3(a, o + OF_GRAD, slot, splat(0));
+                const int o = BR_COUNT + i * OR_COUNT;
+                stvw(a, o + OR_THR, slot, splat(1.0), 1.0);
+                stv(a, o + OR_RAD, slot, splat(0)); stv(a, o + OR_GRAD, slot, splat(0));
                 if (alive) storeOffIts(a, slot, i, sits);
             }
         }
@@ -209,10 +246,11 @@ __global__ void __launch_bounds__(kGenThreads) gpt_generate_kernel(const GptArgs
             if (!early) atomicAdd(&a.counters[2], 1ULL);                             // avgPathLength += depth (1), gpt.cpp:1178-1179
             continue;
         }
-        st3(a, BF_RAYD, slot, ray.d); storeBaseIts(a, slot, mits);
-        st3(a, BF_THR, slot, splat(1.0)); SD(a, BF_PDF, slot) = 1.0; SD(a, BF_ETA, slot) = 1.0;
-        st3(a, BF_RAD, slot, splat(0)); st3(a, BF_VD, slot, veryDirect);
-        SD(a, BF_SPX, slot) = spx; SD(a, BF_SPY, slot) = spy;
+        storeBaseIts(a, slot, mits);
+        stvw(a, BR_RAYD, slot, ray.d, 1.0); W(a, BR_P, slot) = 1.0;          // pdf = 1, eta = 1
+        stv(a, BR_THR, slot, splat(1.0));
+        stv(a, BR_RAD, slot, splat(0)); stv(a, BR_VD, slot, veryDirect);
+        W(a, BR_GN, slot) = spx; W(a, BR_S, slot) = spy;
         SI(a, IF_DEPTH, slot) = 1; SI(a, IF_OFLAGS, slot) = (int)flags;
         status = ST_LIVE;
         break;
@@ -244,6 +282,7 @@ __global__ void __launch_bounds__(kBounceThreads) gpt_bounce_kernel(const GptArg
         for (int b = 0; b < kBuckets; b++) { const int c = a.liveCount[parity * kBuckets + b]; s_begin[b] = acc; s_count[b] = c; acc += (c + 31) & ~31; }
         s_begin[kBuckets] = acc;
         if (PHASE == 1 && blockIdx.x == 0) for (int b = 0; b < kBuckets; b++) a.liveCount[(parity ^ 1) * kBuckets + b] = 0;   // for the next step's compaction
+        if (PHASE == 0 && blockIdx.x == 0) a.genCount[parity] = 0;          // this step's regeneration queue has been consumed
     }
     __syncthreads();
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -257,9 +296,10 @@ __global__ void __launch_bounds__(kBounceThreads) gpt_bounce_kernel(const GptArg
     const Config cfg = a.cfg;
 
     Its mits; loadBaseIts(a, slot, mits);
-    V3 mrayD = ld3(a, BF_RAYD, slot);
-    Spec mthr = ld3(a, BF_THR, slot), mrad = ld3(a, BF_RAD, slot);
-    Float mpdf = SD(a, BF_PDF, slot), meta = SD(a, BF_ETA, slot);
+    V3 mrayD; Float mpdf;
+    ldvw(a, BR_RAYD, slot, mrayD, mpdf);
+    Spec mthr = ldv(a, BR_THR, slot), mrad = ldv(a, BR_RAD, slot);
+    Float meta = W(a, BR_P, slot);
     int depth = SI(a, IF_DEPTH, slot);
     unsigned flags = (unsigned)SI(a, IF_OFLAGS, slot);
     Sampler smp; smp.key = a.key[slot]; smp.n = (uint32_t)SI(a, IF_RNGN, slot);
@@ -357,16 +397,16 @@ __global__ void __launch_bounds__(kBounceThreads) gpt_bounce_kernel(const GptArg
         Float bw0 = 0, bw1 = 0, bw2 = 0, bw3 = 0; unsigned bHas = 0;                 // BSDF-stage weights of the base contribution
 #pragma unroll 1
         for (int i = 0; i < 4; ++i) {
-            const int o = BF_COUNT + i * OF_COUNT;
+            const int o = BR_COUNT + i * OR_COUNT;
             bool alive = flagAlive(flags, i);
             int conn = flagConn(flags, i);
             Spec sthr = splat(0); Float spdf = 0;
-            if (alive) { sthr = ld3(a, o + OF_THR, slot); spdf = SD(a, o + OF_PDF, slot); }
-            Spec srad = ld3(a, o + OF_RAD, slot), sgrad = ld3(a, o + OF_GRAD, slot);
+            if (alive) ldvw(a, o + OR_THR, slot, sthr, spdf);
+            Spec srad = ldv(a, o + OR_RAD, slot), sgrad = ldv(a, o + OR_GRAD, slot);
             Its sits;
             if (alive && conn == RAY_NOT_CONNECTED) loadOffIts(a, slot, i, sits);
             V3 recentWiL = mk(0, 0, 0);
-            if (alive && conn == RAY_RECENTLY_CONNECTED) recentWiL = toLocal(prevSh, normalize(ld3(a, o + OF_P, slot) - prevP));   // gpt.cpp:640, 864
+            if (alive && conn == RAY_RECENTLY_CONNECTED) recentWiL = toLocal(prevSh, normalize(ldv(a, o + OR_P, slot) - prevP));   // gpt.cpp:640, 864
 
             if (PHASE == 0 && neeActive) {                                           // ---- NEE stage, gpt.cpp:609-727
                 Spec mainContribution = splat(0), shiftedContribution = splat(0);
@@ -550,8 +590,8 @@ __global__ void __launch_bounds__(kBounceThreads) gpt_bounce_kernel(const GptArg
                 if (postponedShiftEnd) alive = false;                                // gpt.cpp:1148-1150
                 flags = setFlag(flags, i, alive, conn);
             }
-            if (PHASE == 1 && (flagAlive(flags, i) || alive)) { st3(a, o + OF_THR, slot, sthr); SD(a, o + OF_PDF, slot) = spdf; }
-            st3(a, o + OF_RAD, slot, srad); st3(a, o + OF_GRAD, slot, sgrad);
+            if (PHASE == 1 && (flagAlive(flags, i) || alive)) stvw(a, o + OR_THR, slot, sthr, spdf);
+            stv(a, o + OR_RAD, slot, srad); stv(a, o + OR_GRAD, slot, sgrad);
         }
         // base radiance: BSDF-stage terms after all NEE terms, in offset order (gpt.cpp:1142)
         if (bHas & 1u) mrad = mrad + mainContributionAll * bw0;
@@ -565,24 +605,26 @@ __global__ void __launch_bounds__(kBounceThreads) gpt_bounce_kernel(const GptArg
                 if (smp.next1D() >= q) ended = true;
                 else {
                     mpdf *= q;
-                    for (int i = 0; i < 4; ++i) SD(a, BF_COUNT + i * OF_COUNT + OF_PDF, slot) *= q;
+                    for (int i = 0; i < 4; ++i) W(a, BR_COUNT + i * OR_COUNT + OR_THR, slot) *= q;
                 }
             }
             if (!ended && !(depth < cfg.maxDepth || cfg.maxDepth < 0)) ended = true; // gpt.cpp:537
         }
     }
 
-    st3(a, BF_RAD, slot, mrad);
+    stv(a, BR_RAD, slot, mrad);
     SI(a, IF_RNGN, slot) = (int)smp.n;
     countWarp(&a.counters[1], rays);
     countWarp(&a.counters[2], ended ? (unsigned)depth : 0u);                         // gpt.cpp:1178-1179
     if (ended) {
         SI(a, IF_STATUS, slot) = ST_FINISHED;
+        appendGen(a, parity ^ 1, slot);
     } else if (PHASE == 0) {
         if (cfg.strictNormals) SI(a, IF_OFLAGS, slot) = (int)flags;
     } else {
-        st3(a, BF_RAYD, slot, mrayD); storeBaseIts(a, slot, mits);
-        st3(a, BF_THR, slot, mthr); SD(a, BF_PDF, slot) = mpdf; SD(a, BF_ETA, slot) = meta;
+        storeBaseIts(a, slot, mits);
+        stvw(a, BR_RAYD, slot, mrayD, mpdf); W(a, BR_P, slot) = meta;
+        stv(a, BR_THR, slot, mthr);
         SI(a, IF_DEPTH, slot) = depth; SI(a, IF_OFLAGS, slot) = (int)flags;
     }
 }
@@ -629,7 +671,9 @@ __global__ void gpt_init_kernel(const GptArgs a)
 {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot < 2 * kBuckets) a.liveCount[slot] = 0;
+    if (slot == 0) { a.genCount[0] = a.nSlots; a.genCount[1] = 0; }
     if (slot >= a.nSlots) return;
+    a.genList[slot] = slot;
     const int px = slot % a.width, py = a.yBegin + slot / a.width;
     a.key[slot] = samplerKey(a.seed, px, py);                                        // Sampler::generate, gpt.cpp:1250-1251
     SI(a, IF_STATUS, slot) = ST_FRESH; SI(a, IF_SAMPLE, slot) = 0; SI(a, IF_RNGN, slot) = 0;
@@ -711,7 +755,7 @@ struct gdb200_scene {
     // device buffers
     double *film = nullptr, *dev64 = nullptr; float *dev32 = nullptr;
     double *sd = nullptr; int *si = nullptr; uint64_t *key = nullptr;
-    int *liveList = nullptr, *liveCount = nullptr;
+    int *liveList = nullptr, *liveCount = nullptr, *genList = nullptr, *genCount = nullptr;
     unsigned long long *counters = nullptr;
     int slotCapacity = 0;
     volatile int cancel = 0;
@@ -898,9 +942,9 @@ void classifyMaterials(gdb200_scene *s, double shiftThreshold)
 void freeSceneBuffers(gdb200_scene *s)
 {
     cudaFree(s->film); cudaFree(s->dev64); cudaFree(s->dev32); cudaFree(s->sd); cudaFree(s->si); cudaFree(s->key);
-    cudaFree(s->liveList); cudaFree(s->liveCount); cudaFree(s->counters); cudaFree(s->dScene); s->dScene = nullptr;
+    cudaFree(s->liveList); cudaFree(s->liveCount); cudaFree(s->genList); cudaFree(s->genCount); cudaFree(s->counters); cudaFree(s->dScene); s->dScene = nullptr;
     s->film = s->dev64 = s->sd = nullptr; s->dev32 = nullptr; s->si = nullptr; s->key = nullptr;
-    s->liveList = s->liveCount = nullptr; s->counters = nullptr; s->slotCapacity = 0;
+    s->liveList = s->liveCount = s->genList = s->genCount = nullptr; s->counters = nullptr; s->slotCapacity = 0;
 }
 
 int uploadScene(gdb200_scene *s)
@@ -973,13 +1017,15 @@ int gdb200_gpt_render(gdb200_scene *s, const gdb200_gpt_params *p, gdb200_buffer
     GDB_CUDA(cudaSetDevice(s->device));
     const int nSlots = s->width * (y1 - y0);
     if (nSlots > s->slotCapacity) {
-        cudaFree(s->sd); cudaFree(s->si); cudaFree(s->key); cudaFree(s->liveList); cudaFree(s->liveCount);
-        s->sd = nullptr; s->si = nullptr; s->key = nullptr; s->liveList = s->liveCount = nullptr;
-        GDB_CUDA(cudaMalloc(&s->sd, sizeof(double) * kDoubleFields * (size_t)nSlots));
+        cudaFree(s->sd); cudaFree(s->si); cudaFree(s->key); cudaFree(s->liveList); cudaFree(s->liveCount); cudaFree(s->genList); cudaFree(s->genCount);
+        s->sd = nullptr; s->si = nullptr; s->key = nullptr; s->liveList = s->liveCount = s->genList = s->genCount = nullptr;
+        GDB_CUDA(cudaMalloc(&s->sd, sizeof(double) * 4 * kRecords * (size_t)nSlots));
         GDB_CUDA(cudaMalloc(&s->si, sizeof(int) * IF_COUNT * (size_t)nSlots));
         GDB_CUDA(cudaMalloc(&s->key, sizeof(uint64_t) * (size_t)nSlots));
         GDB_CUDA(cudaMalloc(&s->liveList, sizeof(int) * 2 * (size_t)kBuckets * nSlots));
         GDB_CUDA(cudaMalloc(&s->liveCount, sizeof(int) * 2 * kBuckets));
+        GDB_CUDA(cudaMalloc(&s->genList, sizeof(int) * 2 * (size_t)nSlots));
+        GDB_CUDA(cudaMalloc(&s->genCount, sizeof(int) * 2));
         s->slotCapacity = nSlots;
     }
     classifyMaterials(s, p->shift_threshold);
@@ -995,7 +1041,7 @@ int gdb200_gpt_render(gdb200_scene *s, const gdb200_gpt_params *p, gdb200_buffer
     a.spp = p->spp; a.seed = p->seed;
     a.cfg.maxDepth = p->max_depth; a.cfg.minDepth = 1; a.cfg.rrDepth = p->rr_depth;         // gpt.cpp:1368-1371
     a.cfg.strictNormals = p->strict_normals; a.cfg.shiftThreshold = p->shift_threshold;
-    a.film = s->film; a.liveList = s->liveList; a.liveCount = s->liveCount;
+    a.film = s->film; a.liveList = s->liveList; a.liveCount = s->liveCount; a.genList = s->genList; a.genCount = s->genCount;
     a.counters = s->counters;
 
     cudaEvent_t e0, e1;
@@ -1014,7 +1060,7 @@ int gdb200_gpt_render(gdb200_scene *s, const gdb200_gpt_params *p, gdb200_buffer
         if (step > maxSteps) { cudaEventDestroy(e0); cudaEventDestroy(e1); return set_error(GDB200_ERR_CUDA, "wavefront did not drain after %lld steps", step); }
         auto mark = [&]() { if (stats) { cudaEvent_t ev; cudaEventCreate(&ev); cudaEventRecord(ev); marks.push_back(ev); } };
         mark();
-        gpt_generate_kernel<<<genBlocks, kGenThreads>>>(a);
+        gpt_generate_kernel<<<genBlocks, kGenThreads>>>(a, parity);
         mark();
         gpt_compact_kernel<<<(nSlots + 255) / 256, 256>>>(a, parity);
         mark();
