@@ -81,4 +81,26 @@ int gdb200_host_free(void *ptr)
     return GDB200_OK;
 }
 
+int gdb200_device_alloc(void **out_ptr, size_t bytes)
+{
+    if (!out_ptr) return gdb200::set_error(GDB200_ERR_ARGUMENT, "out_ptr is NULL");
+    if (int rc = gdb200::require_device()) return rc;
+    GDB_CUDA(cudaMalloc(out_ptr, bytes));
+    return GDB200_OK;
+}
+
+int gdb200_device_free(void *ptr)
+{
+    if (!ptr) return GDB200_OK;
+    GDB_CUDA(cudaFree(ptr));
+    return GDB200_OK;
+}
+
+int gdb200_device_download(void *host_dst, const void *device_src, size_t bytes)
+{
+    if (!host_dst || !device_src) return gdb200::set_error(GDB200_ERR_ARGUMENT, "NULL pointer");
+    GDB_CUDA(cudaMemcpy(host_dst, device_src, bytes, cudaMemcpyDeviceToHost));
+    return GDB200_OK;
+}
+
 }  // extern "C"

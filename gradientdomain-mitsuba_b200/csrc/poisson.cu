@@ -434,7 +434,7 @@ __device__ void phase_export(const PoissonArgs &a, int pCur, const float al[3])
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 2) poisson_irls_cg_kernel(const PoissonArgs a)
+__global__ void __launch_bounds__(kThreads, 4) poisson_irls_cg_kernel(const PoissonArgs a)
 {
     cg::grid_group grid = cg::this_grid();
     int parity = 0;

@@ -1,0 +1,321 @@
+// Mitsuba 0.5 integrator plugin shim: loads as plugins/gpt.so and hands the G-PT hot path to libgdb200.
+//
+// Drop-in for the reference's src/integrators/gpt/{gpt.cpp,gpt_proc.cpp,gpt_wr.cpp} + poisson_solver/:
+// same plugin name, same XML parameters / defaults / error messages (gpt.cpp:1191-1211), same five
+// multifilm buffers (gpt.cpp:1380), same render() contract (integrator.h:49-130).  It is built inside a
+// Mitsuba tree; here it is only syntax-checked against plugin/stub/mitsuba_stub.h
+// because Mitsuba's dependencies are not installed in this environment.
+#if defined(GDB200_STUB_HEADERS)
+#include "stub/mitsuba_stub.h"
+#else
+#include <mitsuba/render/scene.h>
+#include <mitsuba/render/integrator.h>
+#include <mitsuba/render/renderjob.h>
+#include <mitsuba/render/trimesh.h>
+#include <mitsuba/core/plugin.h>
+#include <mitsuba/core/bitmap.h>
+#endif
+#include <vector>
+#include <string>
+#include <cstring>
+#include "../../include/gdb200.h"
+
+MTS_NAMESPACE_BEGIN
+
+namespace {
+
+void copyMatrix(const Matrix4x4 &m, double *dst) {
+	for (int r = 0; r < 4; ++r)
+		for (int c = 0; c < 4; ++c)
+			dst[4 * r + c] = (double) m(r, c);
+}
+
+void copySpectrum(const Spectrum &s, double *dst) {
+	for (int i = 0; i < 3; ++i)        /* gpt.cpp:1432 already assumes SPECTRUM_SAMPLES == 3 */
+		dst[i] = (double) s[i];
+}
+
+/// Flattened copy of the parts of a Scene the hot path reads (SURVEY.md §8b "What it calls back into")
+struct FlatScene {
+	gdb200_scene_desc desc;
+	std::vector<gdb200_shape> shapes;
+	std::vector<gdb200_material> materials;
+	std::vector<gdb200_emitter> emitters;
+	std::vector<double> vertices;
+	std::vector<int> triangles;
+
+	int addMaterial(const BSDF *bsdf, bool isEmitterShape) {
+		gdb200_material m;
+		memset(&m, 0, sizeof(m));
+		for (int i = 0; i < 3; ++i) { m.specular_reflectance[i] = 1; m.specular_transmittance[i] = 1; m.k[i] = 1; }
+		const std::string cls = bsdf ? bsdf->getClass()->getName() : "";
+		const Properties &p = bsdf ? bsdf->getProperties() : Properties();
+		if (!bsdf) {
+			/* shape.cpp:48-72: emitters get an absorbing diffuse BSDF, everything else diffuse 0.5 */
+			m.type = GDB200_BSDF_DIFFUSE;
+			for (int i = 0; i < 3; ++i) m.reflectance[i] = isEmitterShape ? 0.0 : 0.5;
+		} else if (cls == "SmoothDiffuse") {
+			m.type = GDB200_BSDF_DIFFUSE;
+			copySpectrum(p.getSpectrum(p.hasProperty("reflectance") ? "reflectance" : "diffuseReflectance", Spectrum(.5f)), m.reflectance);
+		} else if (cls == "RoughConductor" || cls == "SmoothConductor") {
+			m.type = cls == "RoughConductor" ? GDB200_BSDF_ROUGHCONDUCTOR : GDB200_BSDF_CONDUCTOR;
+			copySpectrum(p.getSpectrum("eta", Spectrum(0.0f)), m.eta);
+			copySpectrum(p.getSpectrum("k", Spectrum(1.0f)), m.k);
+			copySpectrum(p.getSpectrum("specularReflectance", Spectrum(1.0f)), m.specular_reflectance);
+			m.alpha = p.getFloat("alpha", 0.1f);
+			const std::string distr = p.getString("distribution", "beckmann");
+			if (distr == "ggx") m.distribution = GDB200_MICROFACET_GGX;
+			else if (distr == "beckmann") m.distribution = GDB200_MICROFACET_BECKMANN;
+			else SLog(EError, "gdb200: microfacet distribution \"%s\" is not supported", distr.c_str());
+			if (p.hasProperty("alphaU") || p.hasProperty("alphaV") || !p.getBoolean("sampleVisible", true))
+				SLog(EError, "gdb200: anisotropic / non-visible-normal roughconductor is not supported");
+		} else if (cls == "SmoothDielectric") {
+			m.type = GDB200_BSDF_DIELECTRIC;
+			m.ior_ratio = bsdf->getEta();        /* dielectric.cpp:389-391 */
+			copySpectrum(p.getSpectrum("specularReflectance", Spectrum(1.0f)), m.specular_reflectance);
+			copySpectrum(p.getSpectrum("specularTransmittance", Spectrum(1.0f)), m.specular_transmittance);
+		} else {
+			SLog(EError, "gdb200: BSDF class \"%s\" is outside the supported hot-path subset", cls.c_str());
+		}
+		materials.push_back(m);
+		return (int) materials.size() - 1;
+	}
+
+	void build(const Scene *scene, const Sensor *sensor) {
+		memset(&desc, 0, sizeof(desc));
+		const Film *film = sensor->getFilm();
+		const Vector2i size = film->getCropSize();
+		if (film->getCropSize() != film->getSize())
+			SLog(EError, "gdb200: crop windows are not supported yet");
+		const PerspectiveCamera *cam = dynamic_cast<const PerspectiveCamera *>(sensor);
+		if (!cam || sensor->needsApertureSample() || sensor->needsTimeSample())
+			SLog(EError, "gdb200: only the pinhole 'perspective' sensor is supported");
+		/* perspective.cpp:126-160 with Mitsuba's own Transform algebra (so the numerically inverted
+		   m_sampleToCamera is bit-identical to the reference's) */
+		const Float aspect = cam->getAspect();
+		const Transform cameraToSample =
+			  Transform::scale(Vector(-0.5f, -0.5f*aspect, 1.0f))
+			* Transform::translate(Vector(-1.0f, -1.0f/aspect, 0.0f))
+			* Transform::perspective(cam->getXFov(), cam->getNearClip(), cam->getFarClip());
+		copyMatrix(cameraToSample.inverse().getMatrix(), desc.camera.sample_to_camera);
+		copyMatrix(cam->getWorldTransform()->eval(0).getMatrix(), desc.camera.camera_to_world);
+		desc.camera.near_clip = cam->getNearClip();
+		desc.camera.far_clip = cam->getFarClip();
+		desc.camera.width = size.x;
+		desc.camera.height = size.y;
+
+		const ReconstructionFilter *rf = film->getReconstructionFilter();
+		if (rf->getClass()->getName() != "BoxFilter")
+			SLog(EError, "gdb200: only the 'box' reconstruction filter is supported (the default is gaussian, film.cpp:89-95)");
+		desc.rfilter_radius = rf->getRadius();     /* 0.5 + 1e-5, box.cpp:38 */
+
+		const ref_vector<Shape> &list = scene->getShapes();
+		for (size_t i = 0; i < list.size(); ++i) {
+			const Shape *shape = list[i].get();
+			gdb200_shape s;
+			memset(&s, 0, sizeof(s));
+			s.emitter = -1;
+			s.material = addMaterial(shape->getBSDF(), shape->isEmitter());
+			const std::string cls = shape->getClass()->getName();
+			const Properties &p = shape->getProperties();
+			if (cls == "Rectangle") {
+				Transform toWorld = p.getTransform("toWorld", Transform());
+				if (p.getBoolean("flipNormals", false))
+					toWorld = toWorld * Transform::scale(Vector(1, 1, -1));     /* rectangle.cpp:82-84 */
+				s.type = GDB200_SHAPE_RECTANGLE;
+				copyMatrix(toWorld.getMatrix(), s.to_world);
+				copyMatrix(toWorld.inverse().getMatrix(), s.to_object);
+			} else if (cls == "Sphere") {
+				const Transform toWorld = p.getTransform("toWorld", Transform());
+				const Point center = toWorld(p.getPoint("center", Point(0.0f)));
+				s.type = GDB200_SHAPE_SPHERE;
+				s.center[0] = center.x; s.center[1] = center.y; s.center[2] = center.z;
+				s.radius = p.getFloat("radius", 1.0f) * toWorld(Vector(1, 0, 0)).length();
+				s.flip_normals = p.getBoolean("flipNormals", false);
+			} else if (shape->getClass()->derivesFrom(MTS_CLASS(TriMesh))) {
+				const TriMesh *mesh = static_cast<const TriMesh *>(shape);
+				if (mesh->hasVertexNormals())
+					SLog(EError, "gdb200: meshes with vertex normals are not supported yet");
+				s.type = GDB200_SHAPE_MESH;
+				s.first_tri = (int) triangles.size() / 3;
+				s.tri_count = (int) mesh->getTriangleCount();
+				const int base = (int) vertices.size() / 3;
+				for (size_t v = 0; v < mesh->getVertexCount(); ++v)
+					for (int k = 0; k < 3; ++k)
+						vertices.push_back(mesh->getVertexPositions()[v][k]);
+				for (size_t t = 0; t < mesh->getTriangleCount(); ++t)
+					for (int k = 0; k < 3; ++k)
+						triangles.push_back(base + (int) mesh->getTriangles()[t].idx[k]);
+			} else {
+				SLog(EError, "gdb200: shape class \"%s\" is outside the supported hot-path subset", cls.c_str());
+			}
+			if (shape->isEmitter()) {
+				const Emitter *e = shape->getEmitter();
+				if (e->getClass()->getName() != "AreaLight" || s.type != GDB200_SHAPE_RECTANGLE)
+					SLog(EError, "gdb200: only 'area' emitters on rectangles are supported");
+				gdb200_emitter em;
+				memset(&em, 0, sizeof(em));
+				em.shape = (int) shapes.size();
+				copySpectrum(e->getProperties().getSpectrum("radiance", Spectrum(1.0f)), em.radiance);
+				em.sampling_weight = e->getSamplingWeight();
+				s.emitter = (int) emitters.size();
+				emitters.push_back(em);
+			}
+			shapes.push_back(s);
+		}
+		if (scene->getEnvironmentEmitter())
+			SLog(EError, "gdb200: environment emitters are not supported yet");
+		desc.n_shapes = (int) shapes.size();       desc.shapes = shapes.data();
+		desc.n_materials = (int) materials.size(); desc.materials = materials.data();
+		desc.n_emitters = (int) emitters.size();   desc.emitters = emitters.data();
+		desc.n_vertices = (int) vertices.size() / 3;   desc.vertices = vertices.data();
+		desc.n_triangles = (int) triangles.size() / 3; desc.triangles = triangles.data();
+	}
+};
+
+} // namespace
+
+class GDB200GradientPathIntegrator : public MonteCarloIntegrator {
+public:
+	GDB200GradientPathIntegrator(const Properties &props) : MonteCarloIntegrator(props), m_scene(NULL) {
+		/* identical to gpt.cpp:1194-1210 */
+		m_shiftThreshold = props.getFloat("shiftThreshold", Float(0.001));
+		m_reconstructL1 = props.getBoolean("reconstructL1", true);
+		m_reconstructL2 = props.getBoolean("reconstructL2", false);
+		m_reconstructAlpha = (Float) props.getFloat("reconstructAlpha", Float(0.2));
+		m_seed = (uint64_t) props.getSize("seed", 0);
+		if (m_reconstructL1 && m_reconstructL2)
+			Log(EError, "Disable 'reconstructL1' or 'reconstructL2': Cannot display two reconstructions at a time!");
+		if (m_reconstructAlpha <= 0.0f)
+			Log(EError, "'reconstructAlpha' must be set to a value greater than zero!");
+		if (m_maxDepth <= 0 && m_maxDepth != -1)
+			Log(EError, "'maxDepth' must be set to -1 (infinite) or a value greater than zero!");
+	}
+
+	GDB200GradientPathIntegrator(Stream *stream, InstanceManager *manager)
+		: MonteCarloIntegrator(stream, manager), m_scene(NULL) {
+		/* wire order of GradientPathTracerConfig::serialize, gpt.h:47-67 */
+		m_shiftThreshold = stream->readFloat();
+		m_reconstructL1 = stream->readBool();
+		m_reconstructL2 = stream->readBool();
+		m_reconstructAlpha = stream->readFloat();
+		m_seed = 0;
+	}
+
+	void serialize(Stream *stream, InstanceManager *manager) const {
+		MonteCarloIntegrator::serialize(stream, manager);
+		stream->writeFloat(m_shiftThreshold);
+		stream->writeBool(m_reconstructL1);
+		stream->writeBool(m_reconstructL2);
+		stream->writeFloat(m_reconstructAlpha);
+	}
+
+	bool render(Scene *scene, RenderQueue *queue, const RenderJob *job,
+			int sceneResID, int sensorResID, int samplerResID) {
+		if (m_hideEmitters)      /* gpt.cpp:1362-1365 */
+			Log(EError, "Option 'hideEmitters' not implemented for Gradient-Domain Path Tracing!");
+
+		ref<Scheduler> sched = Scheduler::getInstance();
+		ref<Sensor> sensor = static_cast<Sensor *>(sched->getResource(sensorResID));
+		ref<Film> film = sensor->getFilm();
+		const Sampler *sampler = static_cast<const Sampler *>(sched->getResource(samplerResID, 0));
+
+		std::vector<std::string> outNames = {"-final", "-throughput", "-dx", "-dy", "-direct"};   /* gpt.cpp:1380 */
+		if (!film->setBuffers(outNames)) {
+			Log(EError, "Cannot render image! G-PT has been called without MultiFilm.");
+			return false;
+		}
+
+		FlatScene flat;
+		flat.build(scene, sensor.get());
+		if (gdb200_scene_create(&flat.desc, &m_scene) != GDB200_OK)
+			Log(EError, "gdb200: %s", gdb200_last_error());
+
+		gdb200_gpt_params params;
+		memset(&params, 0, sizeof(params));
+		params.max_depth = m_maxDepth;
+		params.rr_depth = m_rrDepth;
+		params.strict_normals = m_strictNormals;
+		params.shift_threshold = m_shiftThreshold;
+		params.spp = (int) sampler->getSampleCount();
+		params.seed = m_seed;
+
+		const Vector2i size = film->getCropSize();
+		const size_t n3 = (size_t) size.x * size.y * 3;
+		std::vector<double> buf[5];
+		for (int i = 0; i < 5; ++i) buf[i].resize(n3);
+		gdb200_buffers out = { buf[1].data(), buf[2].data(), buf[3].data(), buf[4].data(), buf[0].data() };
+		gdb200_stats stats;
+		int rc = gdb200_gpt_render(m_scene, &params, &out, &stats);
+		if (rc == GDB200_ERR_CANCELLED) { release(); return false; }
+		if (rc != GDB200_OK) { std::string msg = gdb200_last_error(); release(); Log(EError, "gdb200: %s", msg.c_str()); }
+		Log(EInfo, "gdb200: traced %.0f samples in %.1f ms (%.1f Msamples/s)", stats.samples, stats.device_ms,
+			stats.samples / stats.device_ms * 1e-3);
+
+		/* Reconstruct (gpt.cpp:1415-1477): solver inputs are the developed buffers cast to float, on the device */
+		if (m_reconstructL1 || m_reconstructL2) {
+			const float *d_dx, *d_dy, *d_tp, *d_direct;
+			gdb200_poisson_plan *plan = NULL;
+			gdb200_poisson_config cfg;
+			std::vector<float> rec(n3);
+			rc = gdb200_gpt_solver_inputs(m_scene, &d_dx, &d_dy, &d_tp, &d_direct);
+			if (rc == GDB200_OK) rc = gdb200_poisson_preset(m_reconstructL1 ? "L1D" : "L2D", &cfg);
+			if (rc == GDB200_OK) rc = gdb200_poisson_plan_create(size.x, size.y, &plan);
+			float *d_final = NULL;
+			if (rc == GDB200_OK) rc = gdb200_device_alloc((void **) &d_final, n3 * sizeof(float));
+			if (rc == GDB200_OK) rc = gdb200_poisson_solve_device(plan, d_dx, d_dy, d_tp, d_direct, (float) m_reconstructAlpha, &cfg, d_final, NULL, &stats);
+			if (rc == GDB200_OK) rc = gdb200_device_download(rec.data(), d_final, n3 * sizeof(float));
+			gdb200_device_free(d_final);
+			gdb200_poisson_plan_destroy(plan);
+			if (rc != GDB200_OK) { std::string msg = gdb200_last_error(); release(); Log(EError, "gdb200: %s", msg.c_str()); }
+			Log(EInfo, "Execution time = %.2f s", stats.device_ms * 1e-3);     /* Solver.cpp:500 */
+			for (size_t i = 0; i < n3; ++i) buf[0][i] = (double) rec[i];
+		}
+
+		/* Hand the five buffers to the MultiFilm (gpt.cpp:1464-1475) */
+		for (int b = 0; b < 5; ++b) {
+			ref<Bitmap> bitmap = new Bitmap(Bitmap::ESpectrum, Bitmap::EFloat, size);
+			Float *dst = bitmap->getFloatData();
+			for (size_t i = 0; i < n3; ++i) dst[i] = (Float) buf[b][i];
+			film->setBitmapMulti(bitmap, 1, b);
+		}
+		release();
+		return true;
+	}
+
+	void cancel() {
+		if (m_scene) gdb200_cancel(m_scene);     /* asynchronous, integrator.h:77-84 */
+	}
+
+	Spectrum Li(const RayDifferential &ray, RadianceQueryRecord &rRec) const {
+		/* only reached by the SSS irradiance preprocess, which G-PT does not support (README.txt:64-67) */
+		Log(EError, "gdb200: Li() is not available; subsurface preprocessing is out of scope");
+		return Spectrum(0.0f);
+	}
+
+	std::string toString() const {
+		std::ostringstream oss;
+		oss << "GradientPathIntegrator[gdb200," << endl
+			<< "  maxDepth = " << m_maxDepth << "," << endl
+			<< "  rrDepth = " << m_rrDepth << "," << endl
+			<< "  shiftThreshold = " << m_shiftThreshold << "," << endl
+			<< "  reconstructL1 = " << m_reconstructL1 << "," << endl
+			<< "  reconstructL2 = " << m_reconstructL2 << "," << endl
+			<< "  reconstructAlpha = " << m_reconstructAlpha << endl
+			<< "]";
+		return oss.str();
+	}
+
+	MTS_DECLARE_CLASS()
+private:
+	void release() { if (m_scene) { gdb200_scene_destroy(m_scene); m_scene = NULL; } }
+
+	Float m_shiftThreshold, m_reconstructAlpha;
+	bool m_reconstructL1, m_reconstructL2;
+	uint64_t m_seed;
+	gdb200_scene *m_scene;
+};
+
+MTS_IMPLEMENT_CLASS_S(GDB200GradientPathIntegrator, false, MonteCarloIntegrator)
+MTS_EXPORT_PLUGIN(GDB200GradientPathIntegrator, "Gradient Path Integrator (gdb200, B200)");
+MTS_NAMESPACE_END

@@ -41,6 +41,10 @@ int         gdb200_set_device(int device);
  * PCIe/NVLink-C2C copy bandwidth. */
 int         gdb200_host_alloc(void **out_ptr, size_t bytes);
 int         gdb200_host_free(void *ptr);
+/* Plain device buffers for callers without their own CUDA runtime (the Mitsuba shim). */
+int         gdb200_device_alloc(void **out_ptr, size_t bytes);
+int         gdb200_device_free(void *ptr);
+int         gdb200_device_download(void *host_dst, const void *device_src, size_t bytes);
 
 typedef struct gdb200_stats {
     double device_ms;       /* CUDA-event time of the device work of this call   */

@@ -62,3 +62,24 @@ def test_product_does_not_reference_oracle():
             if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh", "Makefile")):
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "oracle/" not in text and "libgdb200_oracle" not in text and "libref_poisson" not in text, f
+
+
+def test_plugin_shim_compiles():
+    """The Mitsuba plugin shim must at least be valid C++ against the (stubbed) Mitsuba interfaces it uses."""
+    import subprocess
+    src = os.path.join(ROOT, "gradientdomain-mitsuba_b200", "plugin", "gpt_plugin.cpp")
+    r = subprocess.run(["/usr/bin/g++", "-std=c++11", "-fsyntax-only", "-DGDB200_STUB_HEADERS", "-Wall", src],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+
+
+def test_integrator_parameter_validation_matches_reference_messages():
+    # gpt.cpp:1203-1210
+    for kw, msg in ((dict(reconstructL1=True, reconstructL2=True), "Cannot display two reconstructions"),
+                    (dict(reconstructAlpha=-1.0), "'reconstructAlpha' must be set to a value greater than zero!"),
+                    (dict(maxDepth=0), "'maxDepth' must be set to -1 (infinite) or a value greater than zero!"),
+                    (dict(maxDepth=-2), "'maxDepth'")):
+        with pytest.raises(gdb200.Gdb200Error, match=msg.replace("(", r"\(").replace(")", r"\)")):
+            gdb200.GPTIntegrator(**kw)
+    g = gdb200.GPTIntegrator(minDepth=7)
+    assert g.minDepth == 1 and g.rrDepth == 5 and g.maxDepth == -1 and g.shiftThreshold == 0.001   # gpt.cpp:1194-1201,1369
