@@ -144,7 +144,7 @@ def main():
                           if args.workload == "gpt-c2" else f"{scene_name} {W}x{H} @ {spp} spp, G-PT {recon}",
               "scene": "synthetic Cornell box + GGX spheres (gdb200.scenes)", "sampler": "gdb200_counter seed 0",
               "maxDepth": -1, "rrDepth": 5, "shiftThreshold": 0.001, "alpha": 0.2,
-              "parallelism": f"row strips x{world}" if world > 1 else "1 GPU",
+              "parallelism": f"interleaved 16-row bands x{world}, one NCCL all-reduce of the film accumulators" if world > 1 else "1 GPU",
               "l2_flush": "per-step working set (1.2 GB wavefront state + 168 MB film) exceeds the 126 MB L2"}
 
     # ------------------------------------------------------------------ reference arm (CPU)
@@ -180,16 +180,15 @@ def main():
     gdb200.lib().gdb200_set_device(local_rank)
     scene = gdb200.Scene(desc)
     plan = gdb200.PoissonPlan(W, H) if rank == 0 else None
-    rows = tiles.strip_rows(H, rank, world) if world > 1 else None
+    bands = tiles.band_spec(rank, world, 16) if world > 1 else None    # interleaved 16-row bands: balanced strong scaling
     acc = scene.accumulators() if world > 1 else None
     agg = {"bounce_ms": 0.0, "generate_ms": 0.0, "compact_ms": 0.0, "state_bytes": 0.0, "bounce_launches": 0, "trace_ms": 0.0,
            "solve_ms": 0.0, "launches": 0, "samples": 0.0, "rays": 0.0, "exchange_bytes": 0}
 
     def step(timed):
-        integ.trace(scene, spp=spp, seed=0, rows=rows, download=False)
+        integ.trace(scene, spp=spp, seed=0, bands=bands, download=False)
         if world > 1:
-            nb = tiles.exchange_boundaries(acc, world)
-            tiles.gather_strips(acc, rank, world)
+            nb = tiles.exchange_all(acc, world)
             if rank == 0:
                 scene.develop(download=False)
         if rank == 0:
@@ -243,9 +242,8 @@ def main():
             out = integ.render(sc, spp=spp, seed=0)      # trace + develop + D2H of 5 buffers + solve + D2H of final
             sc.close()
         else:
-            integ.trace(scene, spp=spp, seed=0, rows=rows, download=False)
-            tiles.exchange_boundaries(acc, world)
-            tiles.gather_strips(acc, rank, world)
+            integ.trace(scene, spp=spp, seed=0, bands=bands, download=False)
+            tiles.exchange_all(acc, world)
             if rank == 0:
                 out = scene.develop(download=True)
                 out["-final"] = integ.reconstruct(scene, plan, download=True)

@@ -57,6 +57,7 @@ struct GptArgs {
     int *si;               // [IF_COUNT][nSlots]
     uint64_t *key;         // [nSlots]
     int nSlots, width, height, yBegin;
+    int bandRows, bandCount, bandIndex, pad1;   // interleaved row bands (bandCount > 1) instead of one strip
     int spp, pad0;
     uint64_t seed;
     Config cfg;
@@ -133,6 +134,14 @@ GDB_D void appendGen(const GptArgs &a, int parity, int slot)
     a.genList[(size_t)parity * a.nSlots + base + __popc(m & ((1u << lane) - 1))] = slot;
 }
 
+// Image row of a slot: one contiguous strip, or interleaved bands of bandRows rows dealt round-robin to bandCount ranks.
+GDB_D int slotRow(const GptArgs &a, int slot)
+{
+    const int lr = slot / a.width;
+    if (a.bandCount <= 1) return a.yBegin + lr;
+    return ((lr / a.bandRows) * a.bandCount + a.bandIndex) * a.bandRows + lr % a.bandRows;
+}
+
 // One atomic per warp for statistics counters.
 GDB_D void countWarp(unsigned long long *ctr, unsigned v)
 {
@@ -200,7 +209,7 @@ __global__ void __launch_bounds__(kGenThreads) gpt_generate_kernel(const GptArgs
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= a.genCount[parity]) return;
     const int slot = a.genList[(size_t)parity * a.nSlots + g];
-    const int px = slot % a.width, py = a.yBegin + slot / a.width;
+    const int px = slot % a.width, py = slotRow(a, slot);
 
     if (SI(a, IF_STATUS, slot) == ST_FINISHED) {
         Spec rad[4], grad[4];
@@ -674,7 +683,7 @@ __global__ void gpt_init_kernel(const GptArgs a)
     if (slot == 0) { a.genCount[0] = a.nSlots; a.genCount[1] = 0; }
     if (slot >= a.nSlots) return;
     a.genList[slot] = slot;
-    const int px = slot % a.width, py = a.yBegin + slot / a.width;
+    const int px = slot % a.width, py = slotRow(a, slot);
     a.key[slot] = samplerKey(a.seed, px, py);                                        // Sampler::generate, gpt.cpp:1250-1251
     SI(a, IF_STATUS, slot) = ST_FRESH; SI(a, IF_SAMPLE, slot) = 0; SI(a, IF_RNGN, slot) = 0;
 }
@@ -1011,11 +1020,20 @@ int gdb200_gpt_render(gdb200_scene *s, const gdb200_gpt_params *p, gdb200_buffer
     if (p->max_depth <= 0 && p->max_depth != -1) return set_error(GDB200_ERR_ARGUMENT, "'maxDepth' must be set to -1 (infinite) or a value greater than zero!");
     if (p->rr_depth <= 0) return set_error(GDB200_ERR_ARGUMENT, "'rrDepth' must be set to a value greater than zero!");
     if (p->spp <= 0) return set_error(GDB200_ERR_ARGUMENT, "sampleCount must be positive");
-    const bool all = (p->y_begin == 0 && p->y_end == 0);
+    const bool banded = p->band_count > 1;
+    const bool all = banded || (p->y_begin == 0 && p->y_end == 0);
     const int y0 = all ? 0 : p->y_begin, y1 = all ? s->height : p->y_end;
     if (y0 < 0 || y1 > s->height || y0 >= y1) return set_error(GDB200_ERR_ARGUMENT, "invalid row range [%d,%d)", y0, y1);
+    int ownedRows = y1 - y0;
+    if (banded) {
+        if (p->band_rows <= 0 || p->band_index < 0 || p->band_index >= p->band_count)
+            return set_error(GDB200_ERR_ARGUMENT, "invalid band sharding (%d rows, index %d of %d)", p->band_rows, p->band_index, p->band_count);
+        ownedRows = 0;
+        for (int y = 0; y < s->height; y++) ownedRows += ((y / p->band_rows) % p->band_count) == p->band_index;
+        if (ownedRows == 0) return set_error(GDB200_ERR_ARGUMENT, "band sharding leaves rank %d without rows", p->band_index);
+    }
     GDB_CUDA(cudaSetDevice(s->device));
-    const int nSlots = s->width * (y1 - y0);
+    const int nSlots = s->width * ownedRows;
     if (nSlots > s->slotCapacity) {
         cudaFree(s->sd); cudaFree(s->si); cudaFree(s->key); cudaFree(s->liveList); cudaFree(s->liveCount); cudaFree(s->genList); cudaFree(s->genCount);
         s->sd = nullptr; s->si = nullptr; s->key = nullptr; s->liveList = s->liveCount = s->genList = s->genCount = nullptr;
@@ -1039,6 +1057,7 @@ int gdb200_gpt_render(gdb200_scene *s, const gdb200_gpt_params *p, gdb200_buffer
     memset(&a, 0, sizeof(a));
     a.sd = s->sd; a.si = s->si; a.key = s->key; a.nSlots = nSlots; a.width = s->width; a.height = s->height; a.yBegin = y0;
     a.spp = p->spp; a.seed = p->seed;
+    a.bandRows = banded ? p->band_rows : 0; a.bandCount = banded ? p->band_count : 0; a.bandIndex = banded ? p->band_index : 0;
     a.cfg.maxDepth = p->max_depth; a.cfg.minDepth = 1; a.cfg.rrDepth = p->rr_depth;         // gpt.cpp:1368-1371
     a.cfg.strictNormals = p->strict_normals; a.cfg.shiftThreshold = p->shift_threshold;
     a.film = s->film; a.liveList = s->liveList; a.liveCount = s->liveCount; a.genList = s->genList; a.genCount = s->genCount;

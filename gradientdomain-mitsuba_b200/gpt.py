@@ -105,14 +105,16 @@ class GPTIntegrator:
         self.reconstructL1, self.reconstructL2, self.reconstructAlpha = reconstructL1, reconstructL2, reconstructAlpha
         self.stats, self.solver_stats = Stats(), Stats()
 
-    def params(self, spp, seed=0, rows=None):
+    def params(self, spp, seed=0, rows=None, bands=None):
         p = _scenes.default_params(spp=spp, seed=seed, max_depth=self.maxDepth, rr_depth=self.rrDepth,
                                    shift_threshold=self.shiftThreshold, strict_normals=self.strictNormals)
         if rows is not None:
             p.y_begin, p.y_end = rows
+        if bands is not None:                      # (band_rows, band_count, band_index)
+            p.band_rows, p.band_count, p.band_index = bands
         return p
 
-    def trace(self, scene, spp, seed=0, rows=None, download=True):
+    def trace(self, scene, spp, seed=0, rows=None, download=True, bands=None):
         """The sampling part of render(): returns the developed fp64 buffers (h,w,3)."""
         if self.hideEmitters:   # gpt.cpp:1362-1365
             raise Gdb200Error("Option 'hideEmitters' not implemented for Gradient-Domain Path Tracing!")
@@ -124,7 +126,7 @@ class GPTIntegrator:
                                 ("dy", "-dy"), ("direct", "-direct")):
                 out[name] = np.empty((h, w, 3), dtype=np.float64)
                 setattr(B, field, out[name].ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
-        p = self.params(spp, seed, rows)
+        p = self.params(spp, seed, rows, bands)
         check(lib().gdb200_gpt_render(scene._h, ctypes.byref(p), ctypes.byref(B), ctypes.byref(self.stats)))
         return out
 

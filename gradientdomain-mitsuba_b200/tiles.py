@@ -67,3 +67,22 @@ def gather_strips(acc, rank, world, group=None):
         return 0
     dist.gather(mine, None, dst=0, group=group)
     return mine.numel() * mine.element_size()
+
+
+def band_spec(rank, world, band_rows=16):
+    """(band_rows, band_count, band_index) for gdb200_gpt_params: interleaved row bands balance the
+    per-strip cost differences of contiguous strips (paths under the light are short, floor paths long)."""
+    return (band_rows, world, rank)
+
+
+def band_owned_rows(height, rank, world, band_rows=16):
+    return [y for y in range(height) if (y // band_rows) % world == rank]
+
+
+def exchange_all(acc, world, group=None):
+    """Interleaved bands put a strip boundary every band_rows rows, so the halo rows are a large part of
+    the film: sum the whole accumulator film with ONE all-reduce; every rank then holds the full image."""
+    if world <= 1:
+        return 0
+    dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
+    return acc.numel() * acc.element_size()

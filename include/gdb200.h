@@ -180,6 +180,9 @@ typedef struct gdb200_gpt_params {
     int      reserved;
     uint64_t seed;               /* gdb200_counter sampler seed                     */
     int      y_begin, y_end;     /* rows of base pixels this call renders (tile sharding); 0,0 = all */
+    /* Interleaved row bands (load-balanced tile sharding): when band_count > 1 this call renders the
+     * rows y with (y / band_rows) % band_count == band_index, and y_begin/y_end are ignored. */
+    int      band_rows, band_count, band_index, reserved2;
 } gdb200_gpt_params;
 
 /* Host output buffers, each width*height*3 fp64, interleaved RGB; any may be NULL.

@@ -122,3 +122,22 @@ def test_candidate_selection_never_changes_a_hit(scene_name):
         assert L.gdb200_debug_check_culling(scene._h, 1_000_000, seed, ctypes.byref(bad), ctypes.byref(hits)) == 0
         assert bad.value == 0, (seed, bad.value)
         assert hits.value > 500_000
+
+
+def test_interleaved_bands_sum_to_full_image():
+    """Band sharding used by the multi-GPU bench: 3 'ranks' render interleaved 8-row bands; the summed
+    accumulators equal the single-GPU film."""
+    w, h = 64, 50
+    desc = scenes.cbox_glossy(w, h)
+    integ = gdb200.GPTIntegrator(reconstructL1=False, reconstructL2=False)
+    scene = gdb200.Scene(desc)
+    full = integ.trace(scene, spp=4, seed=5)
+    acc = None
+    for r in range(3):
+        integ.trace(scene, spp=4, seed=5, bands=(8, 3, r), download=False)
+        part = scene.accumulators().clone()
+        acc = part if acc is None else acc + part
+    scene.accumulators().copy_(acc)
+    merged = scene.develop()
+    for name in ("-final", "-throughput", "-dx", "-dy", "-direct"):
+        np.testing.assert_allclose(merged[name], full[name], rtol=1e-12, atol=1e-14)
