@@ -204,11 +204,8 @@ GDB_D int flagConn(unsigned f, int i) { return (f >> (3 * i + 1)) & 3u; }
 GDB_D unsigned setFlag(unsigned f, int i, bool alive, int conn) { return (f & ~(7u << (3 * i))) | packFlag(i, alive, conn); }
 
 // ------------------------------------------------------------------ generate: splat finished paths, start next samples
-__global__ void __launch_bounds__(kGenThreads) gpt_generate_kernel(const GptArgs a, int parity)
+GDB_D void generateBody(const GptArgs &a, int slot)
 {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= a.genCount[parity]) return;
-    const int slot = a.genList[(size_t)parity * a.nSlots + g];
     const int px = slot % a.width, py = slotRow(a, slot);
 
     if (SI(a, IF_STATUS, slot) == ST_FINISHED) {
@@ -270,6 +267,13 @@ __global__ void __launch_bounds__(kGenThreads) gpt_generate_kernel(const GptArgs
     countWarp(&a.counters[3], (unsigned)samples);
 }
 
+__global__ void __launch_bounds__(kGenThreads) gpt_generate_kernel(const GptArgs a, int parity)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= a.genCount[parity]) return;
+    generateBody(a, a.genList[(size_t)parity * a.nSlots + g]);
+}
+
 // ------------------------------------------------------------------ bounce: one iteration of gpt.cpp:537-1175
 // The reference runs two loops over the offset paths per bounce (NEE, then BSDF-sample stage).
 // Here the base path's NEE, BSDF sample and extension ray are computed first and ONE loop then
@@ -279,28 +283,11 @@ __global__ void __launch_bounds__(kGenThreads) gpt_generate_kernel(const GptArgs
 // PHASE 0 = next-event estimation of the base path and of its four offset paths (gpt.cpp:565-730);
 // PHASE 1 = BSDF sample, extension ray, shifts, Russian roulette (gpt.cpp:737-1175).  Two launches per
 // step over the same queues: each phase's hot code fits the instruction cache and needs fewer registers.
-template <int PHASE>
-__global__ void __launch_bounds__(kBounceThreads) gpt_bounce_kernel(const GptArgs a, int parity)
+// QUEUED: the step-synchronous wavefront (ended slots are appended to the regeneration queue);
+// !QUEUED: the tail kernel, where a thread runs its slot to completion.
+template <int PHASE, bool QUEUED>
+GDB_D void bounceBody(const GptArgs &a, int slot, int parity)
 {
-    // thread -> (BSDF-type bucket, index).  Buckets are padded to whole warps so a warp shades one BSDF
-    // type; inside a bucket the slots are in ascending pixel order (gpt_compact_kernel), so the
-    // struct-of-arrays state rows are still read as (near-)contiguous sectors.
-    __shared__ int s_begin[kBuckets + 1], s_count[kBuckets];
-    if (threadIdx.x == 0) {
-        int acc = 0;
-        for (int b = 0; b < kBuckets; b++) { const int c = a.liveCount[parity * kBuckets + b]; s_begin[b] = acc; s_count[b] = c; acc += (c + 31) & ~31; }
-        s_begin[kBuckets] = acc;
-        if (PHASE == 1 && blockIdx.x == 0) for (int b = 0; b < kBuckets; b++) a.liveCount[(parity ^ 1) * kBuckets + b] = 0;   // for the next step's compaction
-        if (PHASE == 0 && blockIdx.x == 0) a.genCount[parity] = 0;          // this step's regeneration queue has been consumed
-    }
-    __syncthreads();
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= s_begin[kBuckets]) return;
-    int b = 0;
-    while (g >= s_begin[b + 1]) b++;
-    const int idx = g - s_begin[b];
-    if (idx >= s_count[b]) return;
-    const int slot = a.liveList[((size_t)parity * kBuckets + b) * a.nSlots + idx];
     if (PHASE == 1 && SI(a, IF_STATUS, slot) != ST_LIVE) return;      // ended in phase 0 (strictNormals)
     const Config cfg = a.cfg;
 
@@ -627,7 +614,7 @@ __global__ void __launch_bounds__(kBounceThreads) gpt_bounce_kernel(const GptArg
     countWarp(&a.counters[2], ended ? (unsigned)depth : 0u);                         // gpt.cpp:1178-1179
     if (ended) {
         SI(a, IF_STATUS, slot) = ST_FINISHED;
-        appendGen(a, parity ^ 1, slot);
+        if (QUEUED) appendGen(a, parity ^ 1, slot);
     } else if (PHASE == 0) {
         if (cfg.strictNormals) SI(a, IF_OFLAGS, slot) = (int)flags;
     } else {
@@ -635,6 +622,47 @@ __global__ void __launch_bounds__(kBounceThreads) gpt_bounce_kernel(const GptArg
         stvw(a, BR_RAYD, slot, mrayD, mpdf); W(a, BR_P, slot) = meta;
         stv(a, BR_THR, slot, mthr);
         SI(a, IF_DEPTH, slot) = depth; SI(a, IF_OFLAGS, slot) = (int)flags;
+    }
+}
+
+template <int PHASE>
+__global__ void __launch_bounds__(kBounceThreads) gpt_bounce_kernel(const GptArgs a, int parity)
+{
+    // thread -> (BSDF-type bucket, index).  Buckets are padded to whole warps so a warp shades one BSDF
+    // type; inside a bucket the slots are in ascending pixel order (gpt_compact_kernel), so the
+    // struct-of-arrays state rows are still read as (near-)contiguous sectors.
+    __shared__ int s_begin[kBuckets + 1], s_count[kBuckets];
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int b = 0; b < kBuckets; b++) { const int c = a.liveCount[parity * kBuckets + b]; s_begin[b] = acc; s_count[b] = c; acc += (c + 31) & ~31; }
+        s_begin[kBuckets] = acc;
+        if (PHASE == 1 && blockIdx.x == 0) for (int b = 0; b < kBuckets; b++) a.liveCount[(parity ^ 1) * kBuckets + b] = 0;   // for the next step's compaction
+        if (PHASE == 0 && blockIdx.x == 0) a.genCount[parity] = 0;          // this step's regeneration queue has been consumed
+    }
+    __syncthreads();
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= s_begin[kBuckets]) return;
+    int b = 0;
+    while (g >= s_begin[b + 1]) b++;
+    const int idx = g - s_begin[b];
+    if (idx >= s_count[b]) return;
+    const int slot = a.liveList[((size_t)parity * kBuckets + b) * a.nSlots + idx];
+    bounceBody<PHASE, true>(a, slot, parity);
+}
+
+// Tail of the render: once few pixel streams are still running, stepping the whole wavefront costs four
+// launches per bounce for a handful of warps.  Here every remaining slot is simply run to completion by
+// one thread (generate -> NEE phase -> BSDF phase -> ... until its pixel's samples are exhausted).
+__global__ void __launch_bounds__(kBounceThreads) gpt_tail_kernel(const GptArgs a)
+{
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= a.nSlots) return;
+    for (;;) {
+        const int st = SI(a, IF_STATUS, slot);
+        if (st == ST_DONE) break;
+        if (st != ST_LIVE) { generateBody(a, slot); continue; }
+        bounceBody<0, false>(a, slot, 0);
+        if (SI(a, IF_STATUS, slot) == ST_LIVE) bounceBody<1, false>(a, slot, 0);
     }
 }
 
@@ -1092,6 +1120,13 @@ int gdb200_gpt_render(gdb200_scene *s, const gdb200_gpt_params *p, gdb200_buffer
             GDB_CUDA(cudaMemcpy(hostCounters, s->counters, sizeof(hostCounters), cudaMemcpyDeviceToHost));
             if (hostCounters[0] >= (unsigned long long)nSlots) break;
             if (s->cancel) { cudaEventDestroy(e0); cudaEventDestroy(e1); return set_error(GDB200_ERR_CANCELLED, "render cancelled"); }
+            // tail: few pixel streams left => finish them in one launch instead of 4 launches per bounce
+            const unsigned long long remaining = (unsigned long long)nSlots - hostCounters[0];
+            if (remaining <= (unsigned long long)std::max(nSlots / 16, std::min(nSlots, 16384))) {
+                gpt_tail_kernel<<<(nSlots + kBounceThreads - 1) / kBounceThreads, kBounceThreads>>>(a);
+                launches++;
+                break;
+            }
         }
     }
     GDB_CUDA(cudaEventRecord(e1));
