@@ -1102,6 +1102,8 @@ int gdb200_gpt_render(gdb200_scene *s, const gdb200_gpt_params *p, gdb200_buffer
     unsigned long long hostCounters[6] = {0, 0, 0, 0, 0, 0};
     int parity = 0;
     std::vector<cudaEvent_t> marks;   // per-kernel timing (only when the caller asked for stats)
+    unsigned long long tailThreshold = (unsigned long long)std::max(nSlots / 16, std::min(nSlots, 16384));
+    if (getenv("GDB200_TAIL_ALL")) tailThreshold = (unsigned long long)nSlots;     // experiment: megakernel for the whole render
     const long long maxSteps = (long long)p->spp * 4096 + 65536;     // safety net: never spin forever
     for (long long step = 0;; step++) {
         if (step > maxSteps) { cudaEventDestroy(e0); cudaEventDestroy(e1); return set_error(GDB200_ERR_CUDA, "wavefront did not drain after %lld steps", step); }
@@ -1122,7 +1124,7 @@ int gdb200_gpt_render(gdb200_scene *s, const gdb200_gpt_params *p, gdb200_buffer
             if (s->cancel) { cudaEventDestroy(e0); cudaEventDestroy(e1); return set_error(GDB200_ERR_CANCELLED, "render cancelled"); }
             // tail: few pixel streams left => finish them in one launch instead of 4 launches per bounce
             const unsigned long long remaining = (unsigned long long)nSlots - hostCounters[0];
-            if (remaining <= (unsigned long long)std::max(nSlots / 16, std::min(nSlots, 16384))) {
+            if (remaining <= tailThreshold) {
                 gpt_tail_kernel<<<(nSlots + kBounceThreads - 1) / kBounceThreads, kBounceThreads>>>(a);
                 launches++;
                 break;
