@@ -10,16 +10,19 @@
 //   * state lives in HBM as struct-of-arrays [field][slot] (146 fp64 + 14 int32 fields): every
 //     state access of a warp is one coalesced 256-byte row per field;
 //   * each wavefront step launches
-//       gpt_generate_kernel : slots whose path ended splat its 15 film contributions
-//                             (gpt.cpp:1319-1352) and start their next sample: 5 camera rays +
-//                             primary hits, very-direct emission;
-//       gpt_bounce_kernel   : one iteration of the reference's bounce loop (NEE with the
-//                             4-strategy MIS, BSDF sample, extension ray, the reconnection /
-//                             half-vector shift of the 4 offset paths, Russian roulette) for every
-//                             live slot;
-//   * gpt_compact_kernel rebuilds the live queues every step with ballot/popc stream compaction,
-//     (match_any + popc + one atomic per warp and bucket) stream compaction, bucketed by the
-//     material id of the base vertex, so a warp of the bounce kernel shades one BSDF type;
+//       gpt_generate_kernel : the slots of the regeneration queue splat the 15 film contributions of
+//                             their finished path (gpt.cpp:1319-1352) and start their next sample:
+//                             5 camera rays + primary hits, very-direct emission;
+//       gpt_compact_kernel  : ballot/popc stream compaction of the live slots into 12 queues =
+//                             BSDF type of the base vertex x shift stage of the offset paths
+//                             (order-preserving per 256-slot chunk), so a warp shades one BSDF type with
+//                             its offset paths in the same connection state;
+//       gpt_bounce_kernel   : one iteration of the reference's bounce loop for every queued slot: NEE
+//                             with the 4-strategy MIS, BSDF sample, extension ray, reconnection /
+//                             half-vector shift of the 4 offset paths, Russian roulette;
+//     the last few pixel streams are run to completion by gpt_tail_kernel in one launch;
+//   * state lives in HBM as 32-byte records [record][slot][4 fp64] (one DRAM sector each), so queues
+//     of scattered slots never over-fetch;
 //   * film accumulators are fp64 value+weight planes updated with red.global.add.f64.
 //
 // Arithmetic follows the reference's operation order (compiled with -fmad=false) so that the
@@ -39,17 +42,12 @@ namespace gdb200 {
 // fp64 state is stored as 32-byte records [record][slot][4]: one vector (and one scalar riding in its 4th
 // lane) per record.  A record is exactly one DRAM sector, so a lane always consumes every byte it
 // fetches, however scattered the slots of a material/stage queue are.
-enum VertexRec { VS_RAYD = 0, VS_P, VS_GN, VS_S, VS_T, VS_N, VS_WI, VS_COUNT };       // base-path vertex, double-buffered (IF_VSEL)
-enum BaseRec { BR_THR = 2 * VS_COUNT, BR_RAD, BR_VD, BR_SCAL /* pdf, eta, sample x, sample y */, BR_END };
+enum BaseRec { BR_RAYD = 0 /* w: path pdf */, BR_P /* w: eta */, BR_GN /* w: sample x */, BR_S /* w: sample y */, BR_T, BR_N, BR_WI,
+               BR_THR, BR_RAD, BR_VD, BR_COUNT };
 enum OffRec { OR_THR = 0 /* w: path pdf */, OR_RAD, OR_GRAD, OR_P, OR_GN, OR_S, OR_T, OR_N, OR_WI, OR_COUNT };
-constexpr int kOffBase = BR_END;
-// per-bounce context written by the base-path kernels and read by the per-offset-path kernels
-enum CtxRec { NC_LP = kOffBase + 4 * OR_COUNT /* w: light pdf */, NC_LN /* w: bsdf pdf */, NC_WO /* w: dist^2 */, NC_FV /* w: opposing cosine */,
-              NC_LE /* w: weight numerator */, NC_CA /* w: weight denominator */, NC_LS /* light sample x,y */, NW_TERMS /* base-path NEE weights per offset */,
-              BC_WO /* w: bsdf pdf */, BC_WT /* w: hit distance */, BC_LE /* w: light pdf of the bsdf sample */, BC_CA /* w: weight numerator */,
-              BC_DEN /* x: weight denominator */, BW_TERMS /* base-path BSDF-stage weights per offset */, kRecords };
-enum IntField { IF_STATUS = 0, IF_VSEL, IF_MAT0, IF_MAT1, IF_EMI0, IF_EMI1, IF_DEPTH, IF_SAMPLE, IF_RNGN, IF_OFLAG0, IF_OFLAG1, IF_OFLAG2, IF_OFLAG3,
-                IF_OMAT0, IF_OMAT1, IF_OMAT2, IF_OMAT3, IF_NEEFLAGS, IF_BSDFFLAGS, IF_COUNT };
+constexpr int kRecords = BR_COUNT + 4 * OR_COUNT;   // 46 records = 1472 B per slot
+enum IntField { IF_STATUS = 0, IF_MAT, IF_EMI, IF_DEPTH, IF_SAMPLE, IF_RNGN, IF_OFLAGS, IF_OMAT0, IF_OMAT1, IF_OMAT2, IF_OMAT3,
+                IF_COUNT };
 enum SlotStatus { ST_FRESH = 0, ST_LIVE = 1, ST_FINISHED = 2, ST_DONE = 3 };
 enum { RAY_NOT_CONNECTED = 0, RAY_RECENTLY_CONNECTED = 1, RAY_CONNECTED = 2 };
 enum { BUF_FINAL = 0, BUF_THROUGHPUT = 1, BUF_DX = 2, BUF_DY = 3, BUF_DIRECT = 4 };
@@ -101,41 +99,31 @@ GDB_D void stvw(const GptArgs &a, int rec, int slot, V3 v, Float w)
     p[0] = make_double2(v.x, v.y); p[1] = make_double2(v.z, w);
 }
 
-GDB_D void storeBaseIts(const GptArgs &a, int slot, int sel, const Its &its)
+GDB_D void storeBaseIts(const GptArgs &a, int slot, const Its &its)
 {
-    const int v = sel * VS_COUNT;
-    stv(a, v + VS_P, slot, its.p); stv(a, v + VS_GN, slot, its.geoN); stv(a, v + VS_S, slot, its.sh.s); stv(a, v + VS_T, slot, its.sh.t);
-    stv(a, v + VS_N, slot, its.sh.n); stv(a, v + VS_WI, slot, its.wi);
-    SI(a, IF_MAT0 + sel, slot) = its.material; SI(a, IF_EMI0 + sel, slot) = its.emitter;
+    stv(a, BR_P, slot, its.p); stv(a, BR_GN, slot, its.geoN); stv(a, BR_S, slot, its.sh.s); stv(a, BR_T, slot, its.sh.t);
+    stv(a, BR_N, slot, its.sh.n); stv(a, BR_WI, slot, its.wi);
+    SI(a, IF_MAT, slot) = its.material; SI(a, IF_EMI, slot) = its.emitter;
 }
-GDB_D void loadBaseIts(const GptArgs &a, int slot, int sel, Its &its)
+GDB_D void loadBaseIts(const GptArgs &a, int slot, Its &its)
 {
-    const int v = sel * VS_COUNT;
-    its.t = 0; its.p = ldv(a, v + VS_P, slot); its.geoN = ldv(a, v + VS_GN, slot); its.sh.s = ldv(a, v + VS_S, slot); its.sh.t = ldv(a, v + VS_T, slot);
-    its.sh.n = ldv(a, v + VS_N, slot); its.wi = ldv(a, v + VS_WI, slot);
-    its.material = SI(a, IF_MAT0 + sel, slot); its.emitter = SI(a, IF_EMI0 + sel, slot);
+    its.t = 0; its.p = ldv(a, BR_P, slot); its.geoN = ldv(a, BR_GN, slot); its.sh.s = ldv(a, BR_S, slot); its.sh.t = ldv(a, BR_T, slot);
+    its.sh.n = ldv(a, BR_N, slot); its.wi = ldv(a, BR_WI, slot);
+    its.material = SI(a, IF_MAT, slot); its.emitter = SI(a, IF_EMI, slot);
 }
 GDB_D void storeOffIts(const GptArgs &a, int slot, int i, const Its &its)
 {
-    const int o = kOffBase + i * OR_COUNT;
+    const int o = BR_COUNT + i * OR_COUNT;
     stv(a, o + OR_P, slot, its.p); stv(a, o + OR_GN, slot, its.geoN); stv(a, o + OR_S, slot, its.sh.s); stv(a, o + OR_T, slot, its.sh.t);
     stv(a, o + OR_N, slot, its.sh.n); stv(a, o + OR_WI, slot, its.wi);
     SI(a, IF_OMAT0 + i, slot) = its.material;
 }
 GDB_D void loadOffIts(const GptArgs &a, int slot, int i, Its &its)
 {
-    const int o = kOffBase + i * OR_COUNT;
+    const int o = BR_COUNT + i * OR_COUNT;
     its.t = 0; its.p = ldv(a, o + OR_P, slot); its.geoN = ldv(a, o + OR_GN, slot); its.sh.s = ldv(a, o + OR_S, slot); its.sh.t = ldv(a, o + OR_T, slot);
     its.sh.n = ldv(a, o + OR_N, slot); its.wi = ldv(a, o + OR_WI, slot);
     its.material = SI(a, IF_OMAT0 + i, slot); its.emitter = -1;
-}
-
-// shifted.addRadiance / addGradient (gpt.cpp:147-156).  Most bounces add exact zeros (light sample occluded, no
-// emitter hit); x + 0 == x bit for bit, so those skip the read-modify-write of the two accumulator records.
-GDB_D void accumulateOffset(const GptArgs &a, int o, int slot, Spec dRad, Spec dGrad)
-{
-    if (!(dRad.x == 0 && dRad.y == 0 && dRad.z == 0)) stv(a, o + OR_RAD, slot, ldv(a, o + OR_RAD, slot) + dRad);
-    if (!(dGrad.x == 0 && dGrad.y == 0 && dGrad.z == 0)) stv(a, o + OR_GRAD, slot, ldv(a, o + OR_GRAD, slot) + dGrad);
 }
 
 // Warp-aggregated append of an ended slot to the next step's regeneration queue.
@@ -213,10 +201,10 @@ GDB_D void splatSample(const GptArgs &a, Float spx, Float spy, Spec veryDirect, 
     filmPut(a, spx, spy, veryDirect, 1.0, BUF_DIRECT, false);
 }
 
-// offset-path flag word (one int per offset path): bit 0 alive, bits 1-2 connection status
-GDB_D bool flagAlive(int f) { return f & 1; }
-GDB_D int flagConn(int f) { return (f >> 1) & 3; }
-GDB_D int makeFlag(bool alive, int conn) { return (alive ? 1 : 0) | (conn << 1); }
+GDB_D unsigned packFlag(int i, bool alive, int conn) { return ((alive ? 1u : 0u) | ((unsigned)conn << 1)) << (3 * i); }
+GDB_D bool flagAlive(unsigned f, int i) { return (f >> (3 * i)) & 1u; }
+GDB_D int flagConn(unsigned f, int i) { return (f >> (3 * i + 1)) & 3u; }
+GDB_D unsigned setFlag(unsigned f, int i, bool alive, int conn) { return (f & ~(7u << (3 * i))) | packFlag(i, alive, conn); }
 
 // ------------------------------------------------------------------ generate: splat finished paths, start next samples
 GDB_D void generateBody(const GptArgs &a, int slot)
@@ -226,8 +214,8 @@ GDB_D void generateBody(const GptArgs &a, int slot)
     if (SI(a, IF_STATUS, slot) == ST_FINISHED) {
         Spec rad[4], grad[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) { const int o = kOffBase + i * OR_COUNT; rad[i] = ldv(a, o + OR_RAD, slot); grad[i] = ldv(a, o + OR_GRAD, slot); }
-        splatSample(a, REC(a, BR_SCAL, slot)[2], REC(a, BR_SCAL, slot)[3], ldv(a, BR_VD, slot), ldv(a, BR_RAD, slot), rad, grad);
+        for (int i = 0; i < 4; i++) { const int o = BR_COUNT + i * OR_COUNT; rad[i] = ldv(a, o + OR_RAD, slot); grad[i] = ldv(a, o + OR_GRAD, slot); }
+        splatSample(a, W(a, BR_GN, slot), W(a, BR_S, slot), ldv(a, BR_VD, slot), ldv(a, BR_RAD, slot), rad, grad);
     }
 
     Sampler smp; smp.key = a.key[slot]; smp.n = (uint32_t)SI(a, IF_RNGN, slot);
@@ -242,7 +230,7 @@ GDB_D void generateBody(const GptArgs &a, int slot)
         sampleCameraRay(spx, spy, ray);                                              // gpt.cpp:402
         const bool mainValid = rayIntersect(ray, mits); rays += 5;                   // gpt.cpp:472
         Spec veryDirect = splat(0);
-        int oflag[4];
+        unsigned flags = 0;
         bool early = !mainValid;                                                     // gpt.cpp:482-492 (no environment emitter)
         if (mainValid && mits.emitter >= 0) veryDirect = veryDirect + splat(1.0) * emittedLe(mits, -ray.d);   // gpt.cpp:497-499
         if (mainValid && a.cfg.strictNormals && dot(ray.d, mits.geoN) * mits.wi.z >= 0) early = true;          // gpt.cpp:518-521
@@ -253,9 +241,9 @@ GDB_D void generateBody(const GptArgs &a, int slot)
             sampleCameraRay(spx + shiftX[i], spy + shiftY[i], sray);                 // gpt.cpp:418
             bool alive = rayIntersect(sray, sits);                                   // gpt.cpp:476-480, 508-513
             if (alive && a.cfg.strictNormals && dot(sray.d, sits.geoN) * sits.wi.z >= 0) alive = false;   // gpt.cpp:523-530
-            oflag[i] = makeFlag(alive, RAY_NOT_CONNECTED);
+            flags |= packFlag(i, alive, RAY_NOT_CONNECTED);
             if (!early) {
-                const int o = kOffBase + i * OR_COUNT;
+                const int o = BR_COUNT + i * OR_COUNT;
                 stvw(a, o + OR_THR, slot, splat(1.0), 1.0);
                 stv(a, o + OR_RAD, slot, splat(0)); stv(a, o + OR_GRAD, slot, splat(0));
                 if (alive) storeOffIts(a, slot, i, sits);
@@ -267,13 +255,12 @@ GDB_D void generateBody(const GptArgs &a, int slot)
             if (!early) atomicAdd(&a.counters[2], 1ULL);                             // avgPathLength += depth (1), gpt.cpp:1178-1179
             continue;
         }
-        storeBaseIts(a, slot, 0, mits);
-        stv(a, VS_RAYD, slot, ray.d);
+        storeBaseIts(a, slot, mits);
+        stvw(a, BR_RAYD, slot, ray.d, 1.0); W(a, BR_P, slot) = 1.0;          // pdf = 1, eta = 1
         stv(a, BR_THR, slot, splat(1.0));
         stv(a, BR_RAD, slot, splat(0)); stv(a, BR_VD, slot, veryDirect);
-        { double2 *sc = reinterpret_cast<double2 *>(REC(a, BR_SCAL, slot)); sc[0] = make_double2(1.0, 1.0); sc[1] = make_double2(spx, spy); }   // pdf, eta, sample position
-        SI(a, IF_DEPTH, slot) = 1; SI(a, IF_VSEL, slot) = 0;
-        for (int i = 0; i < 4; i++) SI(a, IF_OFLAG0 + i, slot) = oflag[i];
+        W(a, BR_GN, slot) = spx; W(a, BR_S, slot) = spy;
+        SI(a, IF_DEPTH, slot) = 1; SI(a, IF_OFLAGS, slot) = (int)flags;
         status = ST_LIVE;
         break;
     }
@@ -291,498 +278,385 @@ __global__ void __launch_bounds__(kGenThreads) gpt_generate_kernel(const GptArgs
 }
 
 // ------------------------------------------------------------------ bounce: one iteration of gpt.cpp:537-1175
-// The reference processes the base path and then loops over its four offset paths, twice per bounce (NEE,
-// then the BSDF-sample stage).  Here each stage is a base-path kernel (one thread per slot) that leaves a small
-// context record, followed by an offset-path kernel with one thread per (slot, offset path): four times the
-// parallelism, a quarter of the serial work and far fewer live registers per thread.  The base path's
-// radiance still receives its terms in the reference's order: the offset kernels store one weight per offset,
-// the next base-path kernel adds them for offset 0..3 (all NEE terms, then all BSDF-stage terms).
-//
-//   gpt_nee_base_kernel    gpt.cpp:565-607   light sample, shadow ray, BSDF value of the base path
-//   gpt_nee_offset_kernel  gpt.cpp:609-727   the three connection cases per offset path
-//   gpt_bsdf_base_kernel   gpt.cpp:737-820   BSDF sample, extension ray, emitter hit, MIS denominators
-//   gpt_bsdf_offset_kernel gpt.cpp:830-1151  connected / recently connected / reconnection / half-vector shift
-//   gpt_bsdf_finish_kernel gpt.cpp:1140-1175 base radiance, Russian roulette, commit of the new base vertex
-
-enum { NEE_ACTIVE = 1, NEE_VISIBLE = 2 };
-enum { BF_TYPE_MASK = 0xff, BF_HIT_EMITTER = 0x100, BF_VT_DIFFUSE = 0x200, BF_NEXT_VT_DIFFUSE = 0x400, BF_STAGE = 0x800 };
-
-// thread -> (bucket, index) over the compacted queues; buckets are padded to whole warps (times `per` threads per slot)
-GDB_D int queuedSlot(const GptArgs &a, int parity, int per, int &sub)
+// The reference runs two loops over the offset paths per bounce (NEE, then BSDF-sample stage).
+// Here the base path's NEE, BSDF sample and extension ray are computed first and ONE loop then
+// performs both stages per offset path, so each offset's state crosses HBM once per bounce; the
+// base path's radiance is still accumulated in the reference's order (all NEE terms, then all
+// BSDF-stage terms).
+// PHASE 0 = next-event estimation of the base path and of its four offset paths (gpt.cpp:565-730);
+// PHASE 1 = BSDF sample, extension ray, shifts, Russian roulette (gpt.cpp:737-1175).  Two launches per
+// step over the same queues: each phase's hot code fits the instruction cache and needs fewer registers.
+// QUEUED: the step-synchronous wavefront (ended slots are appended to the regeneration queue);
+// !QUEUED: the tail kernel, where a thread runs its slot to completion.
+template <int PHASE, bool QUEUED>
+GDB_D void bounceBody(const GptArgs &a, int slot, int parity)
 {
-    __shared__ int s_begin[kBuckets + 1], s_count[kBuckets];
-    if (threadIdx.x == 0) {
-        int acc = 0;
-        for (int b = 0; b < kBuckets; b++) { const int c = a.liveCount[parity * kBuckets + b]; s_begin[b] = acc; s_count[b] = c; acc += (c * per + 31) & ~31; }
-        s_begin[kBuckets] = acc;
-    }
-    __syncthreads();
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= s_begin[kBuckets]) return -1;
-    int b = 0;
-    while (g >= s_begin[b + 1]) b++;
-    const int idx = g - s_begin[b];
-    if (idx >= s_count[b] * per) return -1;
-    sub = idx % per;
-    return a.liveList[((size_t)parity * kBuckets + b) * a.nSlots + idx / per];
-}
-
-GDB_D void endPath(const GptArgs &a, int slot, int depth, bool queued, int parity)
-{
-    SI(a, IF_STATUS, slot) = ST_FINISHED;
-    if (queued) appendGen(a, parity ^ 1, slot);
-    (void)depth;
-}
-
-// ---- NEE, base path --------------------------------------------------------------------------------------
-GDB_D void neeBase(const GptArgs &a, int slot, bool queued, int parity)
-{
+    constexpr bool kNee = PHASE != 1, kBsdf = PHASE != 0;   // PHASE 2 runs both stages in one pass over the state
+    if (PHASE == 1 && SI(a, IF_STATUS, slot) != ST_LIVE) return;      // ended in phase 0 (strictNormals)
     const Config cfg = a.cfg;
-    const int sel = SI(a, IF_VSEL, slot);
-    Its mits; loadBaseIts(a, slot, sel, mits);
-    const int depth = SI(a, IF_DEPTH, slot);
-    {   // algorithmic state traffic of this path-bounce (record sizes of SURVEY.md §8d: base 320 B,
-        // unconnected offset 304 B, connected offset 88 B; read + write)
-        unsigned bytes = 320;
-        for (int i = 0; i < 4; i++) { const int f = SI(a, IF_OFLAG0 + i, slot); if (flagAlive(f)) bytes += flagConn(f) == RAY_CONNECTED ? 88 : 304; }
-        countWarp(&a.counters[4], 2 * bytes);
-        countWarp(&a.counters[5], 1u);
-    }
-    int flags = 0;
-    unsigned rays = 0;
-    bool ended = false;
-    if (cfg.strictNormals) {                                                         // gpt.cpp:541-546 (offsets: neeOffset)
-        const V3 mrayD = ldv(a, sel * VS_COUNT + VS_RAYD, slot);
-        if (dot(mrayD, mits.geoN) * mits.wi.z >= 0) ended = true;
-    }
-    const DMaterial &mainBSDF = c_sceneG->materials[mits.material];
-    if (!ended && (mainBSDF.flags & ESmooth) && depth + 1 >= cfg.minDepth) {         // gpt.cpp:568
-        Sampler smp; smp.key = a.key[slot]; smp.n = (uint32_t)SI(a, IF_RNGN, slot);
-        const double2 *sc = reinterpret_cast<const double2 *>(REC(a, BR_SCAL, slot));
-        const Float mpdf = sc[0].x;
-        const Spec mthr = ldv(a, BR_THR, slot);
-        DRec dRec; initDRec(mits, dRec);
-        const Float lsx = smp.next1D(), lsy = smp.next1D();                          // gpt.cpp:572
-        bool visible;
-        const Spec value = sampleEmitterDirectVisible(dRec, lsx, lsy, visible); rays++;
-        const Spec emitterRadiance = value * dRec.pdf;                               // gpt.cpp:575
-        const V3 woLocal = toLocal(mits.sh, dRec.d);
-        Spec bsdfValue; Float bsdfPdf;
-        bsdfEvalPdf(mainBSDF, mits.wi, woLocal, ESolidAngle, bsdfValue, bsdfPdf);    // gpt.cpp:588
-        if (!visible) bsdfPdf = 0;                                                   // gpt.cpp:592
-        const Float distSq = len2(mits.p - dRec.p);                                  // gpt.cpp:595-596
-        const Float oppCos = dot(dRec.n, (mits.p - dRec.p)) / sqrt(distSq);
-        const Float wNum = mpdf * dRec.pdf;                                          // gpt.cpp:599-600
-        const Float wDen = (mpdf * mpdf) * ((dRec.pdf * dRec.pdf) + (bsdfPdf * bsdfPdf));
-        const bool active = !cfg.strictNormals || dot(mits.geoN, dRec.d) * woLocal.z > 0;   // gpt.cpp:607
-        flags = (active ? NEE_ACTIVE : 0) | (visible ? NEE_VISIBLE : 0);
-        if (active) {
-            stvw(a, NC_LP, slot, dRec.p, dRec.pdf); stvw(a, NC_LN, slot, dRec.n, bsdfPdf); stvw(a, NC_WO, slot, woLocal, distSq);
-            stvw(a, NC_FV, slot, bsdfValue, oppCos); stvw(a, NC_LE, slot, emitterRadiance, wNum);
-            stvw(a, NC_CA, slot, mthr * (bsdfValue * emitterRadiance), wDen);
-            *reinterpret_cast<double2 *>(REC(a, NC_LS, slot)) = make_double2(lsx, lsy);
-        }
-        SI(a, IF_RNGN, slot) = (int)smp.n;
-    }
-    SI(a, IF_NEEFLAGS, slot) = flags;
-    countWarp(&a.counters[1], rays);
-    countWarp(&a.counters[2], ended ? (unsigned)depth : 0u);                         // gpt.cpp:1178-1179
-    if (ended) endPath(a, slot, depth, queued, parity);
-}
 
-// ---- NEE, one offset path (gpt.cpp:609-727) ---------------------------------------------------------------
-GDB_D void neeOffset(const GptArgs &a, int slot, int i)
-{
-    if (SI(a, IF_STATUS, slot) != ST_LIVE) return;
-    const Config cfg = a.cfg;
-    const int o = kOffBase + i * OR_COUNT;
-    int flag = SI(a, IF_OFLAG0 + i, slot);
-    unsigned rays = 0;
-    Its sits;
-    const bool unconnected = flagAlive(flag) && flagConn(flag) == RAY_NOT_CONNECTED;
-    if (unconnected) loadOffIts(a, slot, i, sits);
-    if (cfg.strictNormals && unconnected) {          // gpt.cpp:547-554: an unconnected offset's ray direction is -toWorld(wi) of its vertex
-        const V3 sd = -toWorld(sits.sh, sits.wi);
-        if (dot(sd, sits.geoN) * sits.wi.z >= 0) { flag = makeFlag(false, flagConn(flag)); SI(a, IF_OFLAG0 + i, slot) = flag; }
-    }
-    const int nee = SI(a, IF_NEEFLAGS, slot);
-    Float termWeight = -1.0;                         // "no term": the reference adds a zero contribution with zero weight
-    if (nee & NEE_ACTIVE) {
-        V3 lightP, lightN, woLocal; Spec bsdfValue, emitterRadiance, contributionAll;
-        Float lightPdf, mainBsdfPdf, distSq, oppCos, wNum, wDen;
-        ldvw(a, NC_LP, slot, lightP, lightPdf); ldvw(a, NC_LE, slot, emitterRadiance, wNum); ldvw(a, NC_CA, slot, contributionAll, wDen);
-        ldvw(a, NC_FV, slot, bsdfValue, oppCos); ldvw(a, NC_LN, slot, lightN, mainBsdfPdf);
-        const bool alive = flagAlive(flag);
-        const int conn = flagConn(flag);
-        Spec mainContribution = splat(0), shiftedContribution = splat(0);
-        Float weight = 0;
-        bool shiftSuccessful = alive;
-        if (shiftSuccessful) {
-            Spec sthr; Float spdf;
-            ldvw(a, o + OR_THR, slot, sthr, spdf);
-            if (conn == RAY_CONNECTED) {                                             // gpt.cpp:622-637
-                const Float jacobian = 1;
-                const Float den = (jacobian * spdf) * (jacobian * spdf) * ((lightPdf * lightPdf) + (mainBsdfPdf * mainBsdfPdf));
-                weight = wNum / (kDEps + den + wDen);
-                mainContribution = contributionAll;
-                shiftedContribution = jacobian * sthr * (bsdfValue * emitterRadiance);
-            } else if (conn == RAY_RECENTLY_CONNECTED) {                             // gpt.cpp:638-658
-                const int sel = SI(a, IF_VSEL, slot), v = sel * VS_COUNT;
-                Frame sh; sh.s = ldv(a, v + VS_S, slot); sh.t = ldv(a, v + VS_T, slot); sh.n = ldv(a, v + VS_N, slot);
-                const V3 wiL = toLocal(sh, normalize(ldv(a, o + OR_P, slot) - ldv(a, v + VS_P, slot)));
-                Float dummy; ldvw(a, NC_WO, slot, woLocal, dummy);
-                Spec shiftedBsdfValue; Float shiftedBsdfPdf;
-                bsdfEvalPdf(c_sceneG->materials[SI(a, IF_MAT0 + sel, slot)], wiL, woLocal, ESolidAngle, shiftedBsdfValue, shiftedBsdfPdf);
-                if (!(nee & NEE_VISIBLE)) shiftedBsdfPdf = 0;
-                const Float jacobian = 1;
-                const Float den = (jacobian * spdf) * (jacobian * spdf) * ((lightPdf * lightPdf) + (shiftedBsdfPdf * shiftedBsdfPdf));
-                weight = wNum / (kDEps + den + wDen);
-                mainContribution = contributionAll;
-                shiftedContribution = jacobian * sthr * (shiftedBsdfValue * emitterRadiance);
-            } else {                                                                 // gpt.cpp:659-705
-                const DMaterial &mainBSDF = c_sceneG->materials[SI(a, IF_MAT0 + SI(a, IF_VSEL, slot), slot)];
-                const DMaterial &shiftedBSDF = c_sceneG->materials[sits.material];
-                if (vertexType(mainBSDF, ESmooth) == VERTEX_TYPE_DIFFUSE && vertexType(shiftedBSDF, ESmooth) == VERTEX_TYPE_DIFFUSE) {   // gpt.cpp:672
-                    ldvw(a, NC_WO, slot, woLocal, distSq);
-                    const double2 ls = *reinterpret_cast<const double2 *>(REC(a, NC_LS, slot));
-                    DRec sRec; initDRec(sits, sRec);
-                    bool shiftedEmitterVisible;
-                    const Spec sv = sampleEmitterDirectVisible(sRec, ls.x, ls.y, shiftedEmitterVisible); rays++;
-                    const Spec shiftedEmitterRadiance = sv * sRec.pdf;
-                    const Float shiftedDRecPdf = sRec.pdf;
-                    const Float shiftedDistanceSquared = len2(lightP - sits.p);
-                    const V3 emitterDirection = (lightP - sits.p) / sqrt(shiftedDistanceSquared);
-                    const Float shiftedOpposingCosine = -dot(lightN, emitterDirection);
-                    const V3 woL = toLocal(sits.sh, emitterDirection);
-                    if (cfg.strictNormals && dot(sits.geoN, emitterDirection) * woL.z < 0) {
-                        shiftSuccessful = false;
-                    } else {
-                        Spec shiftedBsdfValue; Float shiftedBsdfPdf;
-                        bsdfEvalPdf(shiftedBSDF, sits.wi, woL, ESolidAngle, shiftedBsdfValue, shiftedBsdfPdf);
-                        if (!shiftedEmitterVisible) shiftedBsdfPdf = 0;
-                        const Float jacobian = fabs(shiftedOpposingCosine * distSq) / (kEpsilon + fabs(oppCos * shiftedDistanceSquared));   // gpt.cpp:695
-                        const Float den = (jacobian * spdf) * (jacobian * spdf) * ((shiftedDRecPdf * shiftedDRecPdf) + (shiftedBsdfPdf * shiftedBsdfPdf));
-                        weight = wNum / (kDEps + den + wDen);
-                        mainContribution = contributionAll;
-                        shiftedContribution = jacobian * sthr * (shiftedBsdfValue * shiftedEmitterRadiance);
-                    }
-                }   // else: weight and both contributions stay 0 (gpt.cpp:613-615)
-            }
-        }
-        if (!shiftSuccessful) {                                                      // gpt.cpp:708-717
-            weight = wNum / (kDEps + wDen);
-            mainContribution = contributionAll;
-            shiftedContribution = splat(0);
-        }
-        if (!(mainContribution.x == 0 && mainContribution.y == 0 && mainContribution.z == 0 && weight == 0)) termWeight = weight;   // gpt.cpp:723
-        accumulateOffset(a, o, slot, shiftedContribution * weight, (shiftedContribution - mainContribution) * weight);             // gpt.cpp:724-726
-    }
-    REC(a, NW_TERMS, slot)[i] = termWeight;
-    countWarp(&a.counters[1], rays);
-}
-
-// ---- BSDF stage, base path (gpt.cpp:737-820) ----------------------------------------------------------------
-GDB_D void bsdfBase(const GptArgs &a, int slot, bool queued, int parity)
-{
-    if (SI(a, IF_STATUS, slot) != ST_LIVE) return;       // ended in neeBase (strictNormals)
-    const Config cfg = a.cfg;
-    const int sel = SI(a, IF_VSEL, slot), nsel = sel ^ 1;
-    Its mits; loadBaseIts(a, slot, sel, mits);
-    const int depth = SI(a, IF_DEPTH, slot);
+    Its mits; loadBaseIts(a, slot, mits);
+    V3 mrayD; Float mpdf;
+    ldvw(a, BR_RAYD, slot, mrayD, mpdf);
     Spec mthr = ldv(a, BR_THR, slot), mrad = ldv(a, BR_RAD, slot);
-    double2 *sc = reinterpret_cast<double2 *>(REC(a, BR_SCAL, slot));
-    Float mpdf = sc[0].x, meta = sc[0].y;
+    Float meta = W(a, BR_P, slot);
+    int depth = SI(a, IF_DEPTH, slot);
+    unsigned flags = (unsigned)SI(a, IF_OFLAGS, slot);
     Sampler smp; smp.key = a.key[slot]; smp.n = (uint32_t)SI(a, IF_RNGN, slot);
     unsigned rays = 0;
     bool ended = false;
-
-    if (SI(a, IF_NEEFLAGS, slot) & NEE_ACTIVE) {         // base radiance: the NEE terms of offsets 0..3, in order (gpt.cpp:723)
-        const Spec contributionAll = ldv(a, NC_CA, slot);
-        const double *w = REC(a, NW_TERMS, slot);
-#pragma unroll
-        for (int i = 0; i < 4; i++) if (w[i] >= 0) mrad = mrad + contributionAll * w[i];
+    if (kNee) {   // algorithmic state traffic of this path-bounce (record sizes of SURVEY.md §8d: base 320 B,
+        // unconnected offset 304 B, connected offset 88 B; read + write)
+        unsigned bytes = 320;
+        for (int i = 0; i < 4; i++) if (flagAlive(flags, i)) bytes += flagConn(flags, i) == RAY_CONNECTED ? 88 : 304;
+        countWarp(&a.counters[4], 2 * bytes);
+        countWarp(&a.counters[5], 1u);
     }
 
-    const DMaterial &mainBSDF = c_sceneG->materials[mits.material];
-    BSDFSample bs;
-    { const Float sx = smp.next1D(), sy = smp.next1D(); bsdfSample(mainBSDF, mits.wi, sx, sy, bs); }   // gpt.cpp:456-457
-    int bflags = 0;
-    if (bs.pdf <= 0.0) ended = true;                                                 // gpt.cpp:739
-    else {
-        const V3 mainWo = toWorld(mits.sh, bs.wo);
-        if (cfg.strictNormals && dot(mits.geoN, mainWo) * bs.wo.z <= 0) ended = true;       // gpt.cpp:748
+    if (kNee && cfg.strictNormals) {                                           // gpt.cpp:541-555
+        if (dot(mrayD, mits.geoN) * mits.wi.z >= 0) ended = true;
+        else
+            for (int i = 0; i < 4; i++) {       // an unconnected offset's ray direction is -toWorld(wi) of its stored vertex
+                if (!flagAlive(flags, i) || flagConn(flags, i) != RAY_NOT_CONNECTED) continue;
+                Its sits; loadOffIts(a, slot, i, sits);
+                const V3 sd = -toWorld(sits.sh, sits.wi);
+                if (dot(sd, sits.geoN) * sits.wi.z >= 0) flags = setFlag(flags, i, false, flagConn(flags, i));
+            }
+    }
+
+    if (!ended) {
+        const bool lastSegment = (depth + 1 == cfg.maxDepth);                        // gpt.cpp:558
+        const DMaterial &mainBSDF = c_sceneG->materials[mits.material];
+        const Frame prevSh = mits.sh; const V3 prevP = mits.p, prevWi = mits.wi;     // the vertex both stages shade (previousMainIts, gpt.cpp:753)
+
+        // ---------------- base path: next event estimation, gpt.cpp:565-607
+        bool neeActive = false, neeVisible = false;
+        Float lsx = 0, lsy = 0, neeBsdfPdf = 0, neeDistSq = 0, neeOppCos = 0, neeWNum = 0, neeWDen = 0, neeLightPdf = 0;
+        V3 neeWoLocal = mk(0, 0, 0), neeLightP = mk(0, 0, 0), neeLightN = mk(0, 0, 0);
+        Spec neeBsdfValue = splat(0), neeEmitterRadiance = splat(0), neeContributionAll = splat(0);
+        if (kNee && (mainBSDF.flags & ESmooth) && depth + 1 >= cfg.minDepth) {       // gpt.cpp:568
+            DRec dRec; initDRec(mits, dRec);
+            lsx = smp.next1D(); lsy = smp.next1D();                                  // gpt.cpp:572
+            const Spec value = sampleEmitterDirectVisible(dRec, lsx, lsy, neeVisible); rays++;
+            neeEmitterRadiance = value * dRec.pdf;                                   // gpt.cpp:575
+            neeWoLocal = toLocal(mits.sh, dRec.d);
+            bsdfEvalPdf(mainBSDF, mits.wi, neeWoLocal, ESolidAngle, neeBsdfValue, neeBsdfPdf);   // gpt.cpp:588
+            if (!neeVisible) neeBsdfPdf = 0;                                         // gpt.cpp:592
+            neeDistSq = len2(mits.p - dRec.p);                                       // gpt.cpp:595-596
+            neeOppCos = dot(dRec.n, (mits.p - dRec.p)) / sqrt(neeDistSq);
+            neeWNum = mpdf * dRec.pdf;                                               // gpt.cpp:599-600
+            neeWDen = (mpdf * mpdf) * ((dRec.pdf * dRec.pdf) + (neeBsdfPdf * neeBsdfPdf));
+            neeLightP = dRec.p; neeLightN = dRec.n; neeLightPdf = dRec.pdf;
+            neeActive = !cfg.strictNormals || dot(mits.geoN, dRec.d) * neeWoLocal.z > 0;   // gpt.cpp:607
+            neeContributionAll = mthr * (neeBsdfValue * neeEmitterRadiance);
+        }
+
+        // ---------------- base path: BSDF sample + extension, gpt.cpp:737-820
+        bool bsdfStage = false, mainHitEmitter = false;
+        BSDFSample bs;
+        bs.weight = splat(0); bs.pdf = 0; bs.eta = 1.0; bs.sampledType = 0; bs.wo = mk(0, 0, 0);
+        if (kBsdf) { const Float sx = smp.next1D(), sy = smp.next1D(); bsdfSample(mainBSDF, mits.wi, sx, sy, bs); }   // gpt.cpp:456-457
+        Spec mainEmitterRadiance = splat(0), mainContributionAll = splat(0);
+        DRec mainDRec; initDRec(mits, mainDRec);                                     // gpt.cpp:759
+        int mainVertexType = 0, mainNextVertexType = 0;
+        Float mainLumPdf = 0, mainWeightNumerator = 0, mainWeightDenominator = 0;
+        if (!kBsdf) { }
+        else if (bs.pdf <= 0.0) ended = true;                                        // gpt.cpp:739
         else {
-            const int mainVertexType = vertexType(mainBSDF, bs.sampledType);         // gpt.cpp:764
-            DRec mainDRec; initDRec(mits, mainDRec);                                 // gpt.cpp:759
-            Ray mray; mray.o = mits.p; mray.d = mainWo; mray.mint = kEpsilon; mray.maxt = CUDART_INF;   // gpt.cpp:767
-            rays++;
-            Its nits;
-            if (!rayIntersect(mray, nits)) ended = true;                             // gpt.cpp:800-803 (no environment emitter)
+            const V3 mainWo = toWorld(mits.sh, bs.wo);
+            if (cfg.strictNormals && dot(mits.geoN, mainWo) * bs.wo.z <= 0) ended = true;   // gpt.cpp:748
             else {
-                Spec mainEmitterRadiance = splat(0);
-                bool mainHitEmitter = false;
-                if (nits.emitter >= 0) {                                             // gpt.cpp:771-776
-                    mainEmitterRadiance = emittedLe(nits, -mainWo);
-                    mainDRec.p = nits.p; mainDRec.n = nits.sh.n; mainDRec.d = mainWo; mainDRec.dist = nits.t; mainDRec.emitter = nits.emitter;
-                    mainHitEmitter = true;
+                mainVertexType = vertexType(mainBSDF, bs.sampledType);               // gpt.cpp:764
+                Ray mray; mray.o = mits.p; mray.d = mainWo; mray.mint = kEpsilon; mray.maxt = CUDART_INF;   // gpt.cpp:767
+                rays++;
+                if (!rayIntersect(mray, mits)) ended = true;                         // gpt.cpp:800-803 (no environment emitter)
+                else {
+                    bsdfStage = true;
+                    mrayD = mainWo;
+                    if (mits.emitter >= 0) {                                         // gpt.cpp:771-776
+                        mainEmitterRadiance = emittedLe(mits, -mainWo);
+                        mainDRec.p = mits.p; mainDRec.n = mits.sh.n; mainDRec.d = mainWo; mainDRec.dist = mits.t; mainDRec.emitter = mits.emitter;
+                        mainHitEmitter = true;
+                    }
+                    mainNextVertexType = vertexType(c_sceneG->materials[mits.material], bs.sampledType);   // gpt.cpp:784
+                    const Float mainPreviousPdf = mpdf;                              // gpt.cpp:807-812
+                    mthr = mthr * (bs.weight * bs.pdf);
+                    mpdf *= bs.pdf;
+                    meta *= bs.eta;
+                    mainLumPdf = (mainHitEmitter && depth + 1 >= cfg.minDepth && !(bs.sampledType & EDelta)) ? pdfEmitterDirect(mainDRec) : 0;   // gpt.cpp:815-816
+                    mainWeightNumerator = mainPreviousPdf * bs.pdf;                  // gpt.cpp:819-820
+                    mainWeightDenominator = (mainPreviousPdf * mainPreviousPdf) * ((mainLumPdf * mainLumPdf) + (bs.pdf * bs.pdf));
+                    mainContributionAll = mthr * mainEmitterRadiance;
                 }
-                const int mainNextVertexType = vertexType(c_sceneG->materials[nits.material], bs.sampledType);   // gpt.cpp:784
-                const Float mainPreviousPdf = mpdf;                                  // gpt.cpp:807-812
-                mthr = mthr * (bs.weight * bs.pdf);
-                mpdf *= bs.pdf;
-                meta *= bs.eta;
-                const Float mainLumPdf = (mainHitEmitter && depth + 1 >= cfg.minDepth && !(bs.sampledType & EDelta)) ? pdfEmitterDirect(mainDRec) : 0;   // gpt.cpp:815-816
-                const Float wNum = mainPreviousPdf * bs.pdf;                         // gpt.cpp:819-820
-                const Float wDen = (mainPreviousPdf * mainPreviousPdf) * ((mainLumPdf * mainLumPdf) + (bs.pdf * bs.pdf));
-                bflags = BF_STAGE | (int)(bs.sampledType & BF_TYPE_MASK) | (mainHitEmitter ? BF_HIT_EMITTER : 0)
-                       | (mainVertexType == VERTEX_TYPE_DIFFUSE ? BF_VT_DIFFUSE : 0) | (mainNextVertexType == VERTEX_TYPE_DIFFUSE ? BF_NEXT_VT_DIFFUSE : 0);
-                stvw(a, BC_WO, slot, bs.wo, bs.pdf); stvw(a, BC_WT, slot, bs.weight, nits.t); stvw(a, BC_LE, slot, mainEmitterRadiance, mainLumPdf);
-                stvw(a, BC_CA, slot, mthr * mainEmitterRadiance, wNum); REC(a, BC_DEN, slot)[0] = wDen;
-                storeBaseIts(a, slot, nsel, nits);                                   // the new vertex goes to the other buffer; committed by bsdfFinish
-                stv(a, nsel * VS_COUNT + VS_RAYD, slot, mainWo);
-                stv(a, BR_THR, slot, mthr);
-                sc[0] = make_double2(mpdf, meta);
             }
         }
-    }
-    SI(a, IF_BSDFFLAGS, slot) = bflags;
-    stv(a, BR_RAD, slot, mrad);
-    SI(a, IF_RNGN, slot) = (int)smp.n;
-    countWarp(&a.counters[1], rays);
-    countWarp(&a.counters[2], ended ? (unsigned)depth : 0u);                         // gpt.cpp:1178-1179
-    if (ended) endPath(a, slot, depth, queued, parity);
-}
+        const Float mainBsdfPdf = bs.pdf;
+        const bool addBsdfStage = bsdfStage && depth + 1 >= cfg.minDepth;            // gpt.cpp:1140
 
-// ---- BSDF stage, one offset path (gpt.cpp:830-1151) ---------------------------------------------------------
-GDB_D void bsdfOffset(const GptArgs &a, int slot, int i)
-{
-    if (SI(a, IF_STATUS, slot) != ST_LIVE) return;
-    const int bflags = SI(a, IF_BSDFFLAGS, slot);
-    if (!(bflags & BF_STAGE)) return;
-    const Config cfg = a.cfg;
-    const int o = kOffBase + i * OR_COUNT;
-    const int sel = SI(a, IF_VSEL, slot), pv = sel * VS_COUNT, nv = (sel ^ 1) * VS_COUNT;
-    const int flag = SI(a, IF_OFLAG0 + i, slot);
-    bool alive = flagAlive(flag);
-    int conn = flagConn(flag);
-    const unsigned sampledType = (unsigned)(bflags & BF_TYPE_MASK);
-    const bool mainHitEmitter = bflags & BF_HIT_EMITTER;
-    const int mainVertexType = (bflags & BF_VT_DIFFUSE) ? VERTEX_TYPE_DIFFUSE : VERTEX_TYPE_GLOSSY;
-    const int mainNextVertexType = (bflags & BF_NEXT_VT_DIFFUSE) ? VERTEX_TYPE_DIFFUSE : VERTEX_TYPE_GLOSSY;
-    const int depth = SI(a, IF_DEPTH, slot);
-    const bool lastSegment = (depth + 1 == cfg.maxDepth);                            // gpt.cpp:558
-    unsigned rays = 0;
+        // ---------------- the four offset paths: gpt.cpp:609-727 and 830-1151 in one pass
+        Float bw0 = 0, bw1 = 0, bw2 = 0, bw3 = 0; unsigned bHas = 0;                 // BSDF-stage weights of the base contribution
+#pragma unroll 1
+        for (int i = 0; i < 4; ++i) {
+            const int o = BR_COUNT + i * OR_COUNT;
+            bool alive = flagAlive(flags, i);
+            int conn = flagConn(flags, i);
+            Spec sthr = splat(0); Float spdf = 0;
+            if (alive) ldvw(a, o + OR_THR, slot, sthr, spdf);
+            Spec srad = ldv(a, o + OR_RAD, slot), sgrad = ldv(a, o + OR_GRAD, slot);
+            Its sits;
+            if (alive && conn == RAY_NOT_CONNECTED) loadOffIts(a, slot, i, sits);
+            V3 recentWiL = mk(0, 0, 0);
+            if (alive && conn == RAY_RECENTLY_CONNECTED) recentWiL = toLocal(prevSh, normalize(ldv(a, o + OR_P, slot) - prevP));   // gpt.cpp:640, 864
 
-    Spec mainEmitterRadiance, mainContributionAll; Float mainLumPdf, mainWeightNumerator;
-    ldvw(a, BC_LE, slot, mainEmitterRadiance, mainLumPdf); ldvw(a, BC_CA, slot, mainContributionAll, mainWeightNumerator);
-    const Float mainWeightDenominator = REC(a, BC_DEN, slot)[0];
-    Spec mainContribution = splat(0), shiftedContribution = splat(0);
-    Float weight = 0;
-    bool postponedShiftEnd = false;
-    if (alive) {
-        Spec sthr; Float spdf;
-        ldvw(a, o + OR_THR, slot, sthr, spdf);
-        const Float shiftedPreviousPdf = spdf;
-        V3 bsWo, bsWeight; Float mainBsdfPdf, hitDist;
-        ldvw(a, BC_WO, slot, bsWo, mainBsdfPdf);
-        if (conn == RAY_CONNECTED) {                                                 // gpt.cpp:844-861
-            ldvw(a, BC_WT, slot, bsWeight, hitDist);
-            sthr = sthr * (bsWeight * mainBsdfPdf);
-            spdf *= mainBsdfPdf;
-            const Float den = (shiftedPreviousPdf * shiftedPreviousPdf) * ((mainLumPdf * mainLumPdf) + (mainBsdfPdf * mainBsdfPdf));
-            weight = mainWeightNumerator / (kDEps + den + mainWeightDenominator);
-            mainContribution = mainContributionAll;
-            shiftedContribution = sthr * mainEmitterRadiance;
-        } else if (conn == RAY_RECENTLY_CONNECTED) {                                 // gpt.cpp:862-888
-            Frame prevSh; prevSh.s = ldv(a, pv + VS_S, slot); prevSh.t = ldv(a, pv + VS_T, slot); prevSh.n = ldv(a, pv + VS_N, slot);
-            const V3 wiL = toLocal(prevSh, normalize(ldv(a, o + OR_P, slot) - ldv(a, pv + VS_P, slot)));
-            const V3 woL = toLocal(prevSh, ldv(a, nv + VS_RAYD, slot));
-            const int measure = (sampledType & EDelta) ? EDiscrete : ESolidAngle;
-            Spec shiftedBsdfValue; Float shiftedBsdfPdf;
-            bsdfEvalPdf(c_sceneG->materials[SI(a, IF_MAT0 + sel, slot)], wiL, woL, measure, shiftedBsdfValue, shiftedBsdfPdf);
-            sthr = sthr * shiftedBsdfValue;
-            spdf *= shiftedBsdfPdf;
-            conn = RAY_CONNECTED;
-            const Float den = (shiftedPreviousPdf * shiftedPreviousPdf) * ((mainLumPdf * mainLumPdf) + (shiftedBsdfPdf * shiftedBsdfPdf));
-            weight = mainWeightNumerator / (kDEps + den + mainWeightDenominator);
-            mainContribution = mainContributionAll;
-            shiftedContribution = sthr * mainEmitterRadiance;
-        } else {                                                                     // gpt.cpp:889-1126
-            Its sits; loadOffIts(a, slot, i, sits);
-            const DMaterial &mainBSDF = c_sceneG->materials[SI(a, IF_MAT0 + sel, slot)];
-            const DMaterial &shiftedBSDF = c_sceneG->materials[sits.material];
-            const int shiftedVertexType = vertexType(shiftedBSDF, sampledType);
-            if (mainVertexType == VERTEX_TYPE_DIFFUSE && mainNextVertexType == VERTEX_TYPE_DIFFUSE && shiftedVertexType == VERTEX_TYPE_DIFFUSE) {
-                if (!lastSegment || mainHitEmitter) {                                // gpt.cpp:901
-                    const V3 prevP = ldv(a, pv + VS_P, slot), newP = ldv(a, nv + VS_P, slot), newGeoN = ldv(a, nv + VS_GN, slot);
-                    const ShiftResult sr = reconnectShift(prevP, newP, sits.p, newGeoN); rays++;   // gpt.cpp:907
-                    if (!sr.success) alive = false;
-                    else {
-                        const V3 outgoingDirection = sr.wo;
-                        const V3 woL = toLocal(sits.sh, outgoingDirection);
-                        if (cfg.strictNormals && dot(outgoingDirection, sits.geoN) * woL.z <= 0) alive = false;
-                        else {
-                            Spec shiftedBsdfValue; Float shiftedBsdfPdf;
-                            bsdfEvalPdf(shiftedBSDF, sits.wi, woL, ESolidAngle, shiftedBsdfValue, shiftedBsdfPdf);   // gpt.cpp:935-936
-                            sthr = sthr * (shiftedBsdfValue * sr.jacobian);
-                            spdf *= shiftedBsdfPdf * sr.jacobian;
-                            conn = RAY_RECENTLY_CONNECTED;
-                            if (mainHitEmitter) {                                    // gpt.cpp:944-985
-                                Its nits; nits.sh.n = ldv(a, nv + VS_N, slot); nits.emitter = SI(a, IF_EMI0 + (sel ^ 1), slot);
-                                const Spec shiftedEmitterRadiance = emittedLe(nits, -outgoingDirection);
-                                DRec sd;                                             // gpt.cpp:957-964 (measure: solid angle)
-                                sd.p = newP; sd.n = nits.sh.n;
-                                sd.dist = len(newP - sits.p);
-                                sd.d = (newP - sits.p) / sd.dist;
-                                sd.ref = prevP; sd.refN = sits.sh.n; sd.emitter = nits.emitter;
-                                const Float shiftedLumPdf = pdfEmitterDirect(sd);
-                                const Float den = (shiftedPreviousPdf * shiftedPreviousPdf) * ((shiftedLumPdf * shiftedLumPdf) + (shiftedBsdfPdf * shiftedBsdfPdf));
-                                weight = mainWeightNumerator / (kDEps + den + mainWeightDenominator);
-                                mainContribution = mainContributionAll;
-                                shiftedContribution = sthr * shiftedEmitterRadiance;
-                            }   // else weight and contributions stay 0 (gpt.cpp:833-836)
-                        }
+            if (kNee && neeActive) {                                           // ---- NEE stage, gpt.cpp:609-727
+                Spec mainContribution = splat(0), shiftedContribution = splat(0);
+                Float weight = 0;
+                bool shiftSuccessful = alive;
+                if (shiftSuccessful) {
+                    if (conn == RAY_CONNECTED) {                                     // gpt.cpp:622-637
+                        const Float jacobian = 1;
+                        const Float den = (jacobian * spdf) * (jacobian * spdf) * ((neeLightPdf * neeLightPdf) + (neeBsdfPdf * neeBsdfPdf));
+                        weight = neeWNum / (kDEps + den + neeWDen);
+                        mainContribution = neeContributionAll;
+                        shiftedContribution = jacobian * sthr * (neeBsdfValue * neeEmitterRadiance);
+                    } else if (conn == RAY_RECENTLY_CONNECTED) {                     // gpt.cpp:638-658
+                        Spec shiftedBsdfValue; Float shiftedBsdfPdf;
+                        bsdfEvalPdf(mainBSDF, recentWiL, neeWoLocal, ESolidAngle, shiftedBsdfValue, shiftedBsdfPdf);
+                        if (!neeVisible) shiftedBsdfPdf = 0;
+                        const Float jacobian = 1;
+                        const Float den = (jacobian * spdf) * (jacobian * spdf) * ((neeLightPdf * neeLightPdf) + (shiftedBsdfPdf * shiftedBsdfPdf));
+                        weight = neeWNum / (kDEps + den + neeWDen);
+                        mainContribution = neeContributionAll;
+                        shiftedContribution = jacobian * sthr * (shiftedBsdfValue * neeEmitterRadiance);
+                    } else {                                                         // gpt.cpp:659-705
+                        const DMaterial &shiftedBSDF = c_sceneG->materials[sits.material];
+                        if (vertexType(mainBSDF, ESmooth) == VERTEX_TYPE_DIFFUSE && vertexType(shiftedBSDF, ESmooth) == VERTEX_TYPE_DIFFUSE) {   // gpt.cpp:672
+                            DRec sRec; initDRec(sits, sRec);
+                            bool shiftedEmitterVisible;
+                            const Spec sv = sampleEmitterDirectVisible(sRec, lsx, lsy, shiftedEmitterVisible); rays++;
+                            const Spec shiftedEmitterRadiance = sv * sRec.pdf;
+                            const Float shiftedDRecPdf = sRec.pdf;
+                            const Float shiftedDistanceSquared = len2(neeLightP - sits.p);
+                            const V3 emitterDirection = (neeLightP - sits.p) / sqrt(shiftedDistanceSquared);
+                            const Float shiftedOpposingCosine = -dot(neeLightN, emitterDirection);
+                            const V3 woL = toLocal(sits.sh, emitterDirection);
+                            if (cfg.strictNormals && dot(sits.geoN, emitterDirection) * woL.z < 0) {
+                                shiftSuccessful = false;
+                            } else {
+                                Spec shiftedBsdfValue; Float shiftedBsdfPdf;
+                                bsdfEvalPdf(shiftedBSDF, sits.wi, woL, ESolidAngle, shiftedBsdfValue, shiftedBsdfPdf);
+                                if (!shiftedEmitterVisible) shiftedBsdfPdf = 0;
+                                const Float jacobian = fabs(shiftedOpposingCosine * neeDistSq) / (kEpsilon + fabs(neeOppCos * shiftedDistanceSquared));   // gpt.cpp:695
+                                const Float den = (jacobian * spdf) * (jacobian * spdf) * ((shiftedDRecPdf * shiftedDRecPdf) + (shiftedBsdfPdf * shiftedBsdfPdf));
+                                weight = neeWNum / (kDEps + den + neeWDen);
+                                mainContribution = neeContributionAll;
+                                shiftedContribution = jacobian * sthr * (shiftedBsdfValue * shiftedEmitterRadiance);
+                            }
+                        }   // else: weight and both contributions stay 0 (gpt.cpp:613-615)
                     }
                 }
-            } else {                                                                 // half-vector shift, gpt.cpp:987-1126
-                Spec shiftedEmitterRadiance = splat(0);
-                const bool bothDelta = (sampledType & EDelta) && (shiftedBSDF.flags & EDelta);
-                const bool bothSmooth = (sampledType & ESmooth) && (shiftedBSDF.flags & ESmooth);
-                bool ok = bothDelta || bothSmooth;
-                const Float mpdf = REC(a, BR_SCAL, slot)[0];                         // main.pdf after this bounce (gpt.cpp:811)
-                if (ok) {
-                    ShiftResult sr = halfVectorShift(ldv(a, pv + VS_WI, slot), bsWo, sits.wi, mainBSDF.bsdfEta, shiftedBSDF.bsdfEta);   // gpt.cpp:1006
-                    if (sampledType & EDelta) sr.jacobian = 1;                       // gpt.cpp:1008-1011
-                    ok = sr.success;
-                    if (ok) {
-                        sthr = sthr * sr.jacobian;
-                        spdf *= sr.jacobian;
-                        const V3 tangentSpaceOutgoingDirection = sr.wo;
-                        const V3 outgoingDirection = toWorld(sits.sh, tangentSpaceOutgoingDirection);
-                        const int measure = (sampledType & EDelta) ? EDiscrete : ESolidAngle;
-                        Spec ev; Float pv2;
-                        bsdfEvalPdf(shiftedBSDF, sits.wi, tangentSpaceOutgoingDirection, measure, ev, pv2);   // gpt.cpp:1030-1031
-                        sthr = sthr * ev;
-                        spdf *= pv2;
-                        if (spdf == 0) ok = false;                                   // gpt.cpp:1033-1037
-                        if (ok && cfg.strictNormals && dot(outgoingDirection, sits.geoN) * tangentSpaceOutgoingDirection.z <= 0) ok = false;
-                        if (ok) {
-                            const int shiftedVertexType2 = vertexType(shiftedBSDF, sampledType);   // gpt.cpp:1047
-                            Ray sray; sray.o = sits.p; sray.d = outgoingDirection; sray.mint = kEpsilon; sray.maxt = CUDART_INF;   // gpt.cpp:1050
-                            rays++;
-                            if (!rayIntersect(sray, sits)) ok = false;               // gpt.cpp:1052-1058 (no environment emitter)
-                            else {
-                                const int shiftedNextVertexType = vertexType(c_sceneG->materials[sits.material], sampledType);
-                                if (mainVertexType == VERTEX_TYPE_DIFFUSE && shiftedVertexType2 == VERTEX_TYPE_DIFFUSE && shiftedNextVertexType == VERTEX_TYPE_DIFFUSE) ok = false;   // gpt.cpp:1089-1093
+                if (!shiftSuccessful) {                                              // gpt.cpp:708-717
+                    weight = neeWNum / (kDEps + neeWDen);
+                    mainContribution = neeContributionAll;
+                    shiftedContribution = splat(0);
+                }
+                mrad = mrad + mainContribution * weight;                             // gpt.cpp:723-726
+                srad = srad + shiftedContribution * weight;
+                sgrad = sgrad + (shiftedContribution - mainContribution) * weight;
+            }
+
+            if (kBsdf && bsdfStage) {                                           // ---- BSDF-sample stage, gpt.cpp:830-1151
+                Spec mainContribution = splat(0), shiftedContribution = splat(0);
+                Float weight = 0;
+                bool postponedShiftEnd = false;
+                if (alive) {
+                    const Float shiftedPreviousPdf = spdf;
+                    if (conn == RAY_CONNECTED) {                                     // gpt.cpp:844-861
+                        sthr = sthr * (bs.weight * bs.pdf);
+                        spdf *= mainBsdfPdf;
+                        const Float den = (shiftedPreviousPdf * shiftedPreviousPdf) * ((mainLumPdf * mainLumPdf) + (mainBsdfPdf * mainBsdfPdf));
+                        weight = mainWeightNumerator / (kDEps + den + mainWeightDenominator);
+                        mainContribution = mainContributionAll;
+                        shiftedContribution = sthr * mainEmitterRadiance;
+                    } else if (conn == RAY_RECENTLY_CONNECTED) {                     // gpt.cpp:862-888
+                        const V3 woL = toLocal(prevSh, mrayD);
+                        const int measure = (bs.sampledType & EDelta) ? EDiscrete : ESolidAngle;
+                        Spec shiftedBsdfValue; Float shiftedBsdfPdf;
+                        bsdfEvalPdf(mainBSDF, recentWiL, woL, measure, shiftedBsdfValue, shiftedBsdfPdf);
+                        sthr = sthr * shiftedBsdfValue;
+                        spdf *= shiftedBsdfPdf;
+                        conn = RAY_CONNECTED;
+                        const Float den = (shiftedPreviousPdf * shiftedPreviousPdf) * ((mainLumPdf * mainLumPdf) + (shiftedBsdfPdf * shiftedBsdfPdf));
+                        weight = mainWeightNumerator / (kDEps + den + mainWeightDenominator);
+                        mainContribution = mainContributionAll;
+                        shiftedContribution = sthr * mainEmitterRadiance;
+                    } else {                                                         // gpt.cpp:889-1126
+                        const DMaterial &shiftedBSDF = c_sceneG->materials[sits.material];
+                        const int shiftedVertexType = vertexType(shiftedBSDF, bs.sampledType);
+                        if (mainVertexType == VERTEX_TYPE_DIFFUSE && mainNextVertexType == VERTEX_TYPE_DIFFUSE && shiftedVertexType == VERTEX_TYPE_DIFFUSE) {
+                            if (!lastSegment || mainHitEmitter) {                    // gpt.cpp:901
+                                const ShiftResult sr = reconnectShift(prevP, mits.p, sits.p, mits.geoN); rays++;   // gpt.cpp:907
+                                if (!sr.success) alive = false;
                                 else {
-                                    if (sits.emitter >= 0) shiftedEmitterRadiance = emittedLe(sits, -sray.d);   // gpt.cpp:1095-1098
-                                    storeOffIts(a, slot, i, sits);
+                                    const V3 outgoingDirection = sr.wo;
+                                    const V3 woL = toLocal(sits.sh, outgoingDirection);
+                                    if (cfg.strictNormals && dot(outgoingDirection, sits.geoN) * woL.z <= 0) alive = false;
+                                    else {
+                                        Spec shiftedBsdfValue; Float shiftedBsdfPdf;
+                                        bsdfEvalPdf(shiftedBSDF, sits.wi, woL, ESolidAngle, shiftedBsdfValue, shiftedBsdfPdf);   // gpt.cpp:935-936
+                                        sthr = sthr * (shiftedBsdfValue * sr.jacobian);
+                                        spdf *= shiftedBsdfPdf * sr.jacobian;
+                                        conn = RAY_RECENTLY_CONNECTED;
+                                        if (mainHitEmitter) {                        // gpt.cpp:944-985
+                                            const Spec shiftedEmitterRadiance = emittedLe(mits, -outgoingDirection);
+                                            DRec sd;                                 // gpt.cpp:957-964 (measure: solid angle)
+                                            sd.p = mainDRec.p; sd.n = mainDRec.n;
+                                            sd.dist = len(mainDRec.p - sits.p);
+                                            sd.d = (mainDRec.p - sits.p) / sd.dist;
+                                            sd.ref = mainDRec.ref; sd.refN = sits.sh.n; sd.emitter = mainDRec.emitter;
+                                            const Float shiftedLumPdf = pdfEmitterDirect(sd);
+                                            const Float den = (shiftedPreviousPdf * shiftedPreviousPdf) * ((shiftedLumPdf * shiftedLumPdf) + (shiftedBsdfPdf * shiftedBsdfPdf));
+                                            weight = mainWeightNumerator / (kDEps + den + mainWeightDenominator);
+                                            mainContribution = mainContributionAll;
+                                            shiftedContribution = sthr * shiftedEmitterRadiance;
+                                        }   // else weight and contributions stay 0 (gpt.cpp:833-836)
+                                    }
                                 }
+                            }
+                        } else {                                                     // half-vector shift, gpt.cpp:987-1126
+                            Spec shiftedEmitterRadiance = splat(0);
+                            const bool bothDelta = (bs.sampledType & EDelta) && (shiftedBSDF.flags & EDelta);
+                            const bool bothSmooth = (bs.sampledType & ESmooth) && (shiftedBSDF.flags & ESmooth);
+                            bool ok = bothDelta || bothSmooth;
+                            if (ok) {
+                                ShiftResult sr = halfVectorShift(prevWi, bs.wo, sits.wi, mainBSDF.bsdfEta, shiftedBSDF.bsdfEta);   // gpt.cpp:1006
+                                if (bs.sampledType & EDelta) sr.jacobian = 1;        // gpt.cpp:1008-1011
+                                ok = sr.success;
+                                if (ok) {
+                                    sthr = sthr * sr.jacobian;
+                                    spdf *= sr.jacobian;
+                                    const V3 tangentSpaceOutgoingDirection = sr.wo;
+                                    const V3 outgoingDirection = toWorld(sits.sh, tangentSpaceOutgoingDirection);
+                                    const int measure = (bs.sampledType & EDelta) ? EDiscrete : ESolidAngle;
+                                    Spec ev; Float pv;
+                                    bsdfEvalPdf(shiftedBSDF, sits.wi, tangentSpaceOutgoingDirection, measure, ev, pv);   // gpt.cpp:1030-1031
+                                    sthr = sthr * ev;
+                                    spdf *= pv;
+                                    if (spdf == 0) ok = false;                       // gpt.cpp:1033-1037
+                                    if (ok && cfg.strictNormals && dot(outgoingDirection, sits.geoN) * tangentSpaceOutgoingDirection.z <= 0) ok = false;
+                                    if (ok) {
+                                        const int shiftedVertexType2 = vertexType(shiftedBSDF, bs.sampledType);   // gpt.cpp:1047
+                                        Ray sray; sray.o = sits.p; sray.d = outgoingDirection; sray.mint = kEpsilon; sray.maxt = CUDART_INF;   // gpt.cpp:1050
+                                        rays++;
+                                        if (!rayIntersect(sray, sits)) ok = false;   // gpt.cpp:1052-1058 (no environment emitter)
+                                        else {
+                                            const int shiftedNextVertexType = vertexType(c_sceneG->materials[sits.material], bs.sampledType);
+                                            if (mainVertexType == VERTEX_TYPE_DIFFUSE && shiftedVertexType2 == VERTEX_TYPE_DIFFUSE && shiftedNextVertexType == VERTEX_TYPE_DIFFUSE) ok = false;   // gpt.cpp:1089-1093
+                                            else {
+                                                if (sits.emitter >= 0) shiftedEmitterRadiance = emittedLe(sits, -sray.d);   // gpt.cpp:1095-1098
+                                                storeOffIts(a, slot, i, sits);
+                                            }
+                                        }
+                                    }
+                                }
+                            }
+                            if (ok) {                                                // gpt.cpp:1107-1112
+                                weight = mpdf / (spdf * spdf + mpdf * mpdf);
+                                mainContribution = mainContributionAll;
+                                shiftedContribution = sthr * shiftedEmitterRadiance;
+                            } else {                                                 // gpt.cpp:1113-1125
+                                weight = (Float)1 / mpdf;
+                                mainContribution = mainContributionAll;
+                                shiftedContribution = splat(0);
+                                postponedShiftEnd = true;
                             }
                         }
                     }
                 }
-                if (ok) {                                                            // gpt.cpp:1107-1112
-                    weight = mpdf / (spdf * spdf + mpdf * mpdf);
-                    mainContribution = mainContributionAll;
-                    shiftedContribution = sthr * shiftedEmitterRadiance;
-                } else {                                                             // gpt.cpp:1113-1125
-                    weight = (Float)1 / mpdf;
+                if (!alive) {                                                        // gpt.cpp:1131-1136
+                    weight = mainWeightNumerator / (kDEps + mainWeightDenominator);
                     mainContribution = mainContributionAll;
                     shiftedContribution = splat(0);
-                    postponedShiftEnd = true;
+                }
+                if (addBsdfStage) {                                                  // gpt.cpp:1140-1146
+                    const bool has = !(mainContribution.x == 0 && mainContribution.y == 0 && mainContribution.z == 0 && weight == 0);
+                    if (has) {
+                        bHas |= 1u << i;
+                        if (i == 0) bw0 = weight; else if (i == 1) bw1 = weight; else if (i == 2) bw2 = weight; else bw3 = weight;
+                    }
+                    srad = srad + shiftedContribution * weight;
+                    sgrad = sgrad + (shiftedContribution - mainContribution) * weight;
+                }
+                if (postponedShiftEnd) alive = false;                                // gpt.cpp:1148-1150
+                flags = setFlag(flags, i, alive, conn);
+            }
+            if (kBsdf && (flagAlive(flags, i) || alive)) stvw(a, o + OR_THR, slot, sthr, spdf);
+            stv(a, o + OR_RAD, slot, srad); stv(a, o + OR_GRAD, slot, sgrad);
+        }
+        // base radiance: BSDF-stage terms after all NEE terms, in offset order (gpt.cpp:1142)
+        if (bHas & 1u) mrad = mrad + mainContributionAll * bw0;
+        if (bHas & 2u) mrad = mrad + mainContributionAll * bw1;
+        if (bHas & 4u) mrad = mrad + mainContributionAll * bw2;
+        if (bHas & 8u) mrad = mrad + mainContributionAll * bw3;
+
+        if (kBsdf && !ended) {
+            if (depth++ >= cfg.rrDepth) {                                            // gpt.cpp:1159-1174
+                const Float q = fmin(maxComp(mthr / mpdf) * meta * meta, (Float)0.95f);
+                if (smp.next1D() >= q) ended = true;
+                else {
+                    mpdf *= q;
+                    for (int i = 0; i < 4; ++i) W(a, BR_COUNT + i * OR_COUNT + OR_THR, slot) *= q;
                 }
             }
+            if (!ended && !(depth < cfg.maxDepth || cfg.maxDepth < 0)) ended = true; // gpt.cpp:537
         }
-        stvw(a, o + OR_THR, slot, sthr, spdf);
     }
-    if (!alive) {                                                                    // gpt.cpp:1131-1136
-        weight = mainWeightNumerator / (kDEps + mainWeightDenominator);
-        mainContribution = mainContributionAll;
-        shiftedContribution = splat(0);
-    }
-    Float termWeight = -1.0;
-    if (depth + 1 >= cfg.minDepth) {                                                 // gpt.cpp:1140-1146
-        if (!(mainContribution.x == 0 && mainContribution.y == 0 && mainContribution.z == 0 && weight == 0)) termWeight = weight;
-        accumulateOffset(a, o, slot, shiftedContribution * weight, (shiftedContribution - mainContribution) * weight);
-    }
-    REC(a, BW_TERMS, slot)[i] = termWeight;
-    if (postponedShiftEnd) alive = false;                                            // gpt.cpp:1148-1150
-    SI(a, IF_OFLAG0 + i, slot) = makeFlag(alive, conn);
-    countWarp(&a.counters[1], rays);
-}
 
-// ---- BSDF stage, finish (gpt.cpp:1142, 1159-1175) -----------------------------------------------------------
-GDB_D void bsdfFinish(const GptArgs &a, int slot, bool queued, int parity)
-{
-    if (SI(a, IF_STATUS, slot) != ST_LIVE) return;
-    const Config cfg = a.cfg;
-    Spec mrad = ldv(a, BR_RAD, slot);
-    {   // base radiance: the BSDF-stage terms of offsets 0..3, in order
-        const Spec contributionAll = ldv(a, BC_CA, slot);
-        const double *w = REC(a, BW_TERMS, slot);
-#pragma unroll
-        for (int i = 0; i < 4; i++) if (w[i] >= 0) mrad = mrad + contributionAll * w[i];
-    }
     stv(a, BR_RAD, slot, mrad);
-    int depth = SI(a, IF_DEPTH, slot);
-    bool ended = false;
-    if (depth++ >= cfg.rrDepth) {                                                    // gpt.cpp:1159-1174
-        double2 *sc = reinterpret_cast<double2 *>(REC(a, BR_SCAL, slot));
-        const Float mpdf = sc[0].x, meta = sc[0].y;
-        const Spec mthr = ldv(a, BR_THR, slot);
-        Sampler smp; smp.key = a.key[slot]; smp.n = (uint32_t)SI(a, IF_RNGN, slot);
-        const Float q = fmin(maxComp(mthr / mpdf) * meta * meta, (Float)0.95f);
-        if (smp.next1D() >= q) ended = true;
-        else {
-            sc[0] = make_double2(mpdf * q, meta);
-            for (int i = 0; i < 4; ++i) W(a, kOffBase + i * OR_COUNT + OR_THR, slot) *= q;
-        }
-        SI(a, IF_RNGN, slot) = (int)smp.n;
-    }
-    if (!ended && !(depth < cfg.maxDepth || cfg.maxDepth < 0)) ended = true;         // gpt.cpp:537
+    SI(a, IF_RNGN, slot) = (int)smp.n;
+    countWarp(&a.counters[1], rays);
     countWarp(&a.counters[2], ended ? (unsigned)depth : 0u);                         // gpt.cpp:1178-1179
-    if (ended) endPath(a, slot, depth, queued, parity);
-    else { SI(a, IF_DEPTH, slot) = depth; SI(a, IF_VSEL, slot) = SI(a, IF_VSEL, slot) ^ 1; }   // commit the new base vertex
+    if (ended) {
+        SI(a, IF_STATUS, slot) = ST_FINISHED;
+        if (QUEUED) appendGen(a, parity ^ 1, slot);
+    } else if (!kBsdf) {
+        if (cfg.strictNormals) SI(a, IF_OFLAGS, slot) = (int)flags;
+    } else {
+        storeBaseIts(a, slot, mits);
+        stvw(a, BR_RAYD, slot, mrayD, mpdf); W(a, BR_P, slot) = meta;
+        stv(a, BR_THR, slot, mthr);
+        SI(a, IF_DEPTH, slot) = depth; SI(a, IF_OFLAGS, slot) = (int)flags;
+    }
 }
 
-// ---- kernels -----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBounceThreads) gpt_nee_base_kernel(const GptArgs a, int parity)
+template <int PHASE>
+__global__ void __launch_bounds__(kBounceThreads) gpt_bounce_kernel(const GptArgs a, int parity)
 {
-    int sub;
-    if (blockIdx.x == 0 && threadIdx.x == 0) a.genCount[parity] = 0;        // this step's regeneration queue has been consumed
-    const int slot = queuedSlot(a, parity, 1, sub);
-    if (slot >= 0) neeBase(a, slot, true, parity);
-}
-__global__ void __launch_bounds__(kBounceThreads) gpt_nee_offset_kernel(const GptArgs a, int parity)
-{
-    int sub;
-    const int slot = queuedSlot(a, parity, 4, sub);
-    if (slot >= 0) neeOffset(a, slot, sub);
-}
-__global__ void __launch_bounds__(kBounceThreads) gpt_bsdf_base_kernel(const GptArgs a, int parity)
-{
-    int sub;
-    const int slot = queuedSlot(a, parity, 1, sub);
-    if (slot >= 0) bsdfBase(a, slot, true, parity);
-}
-__global__ void __launch_bounds__(kBounceThreads) gpt_bsdf_offset_kernel(const GptArgs a, int parity)
-{
-    int sub;
-    const int slot = queuedSlot(a, parity, 4, sub);
-    if (slot >= 0) bsdfOffset(a, slot, sub);
-}
-__global__ void __launch_bounds__(kBounceThreads) gpt_bsdf_finish_kernel(const GptArgs a, int parity)
-{
-    int sub;
-    if (blockIdx.x == 0 && threadIdx.x == 0) for (int b = 0; b < kBuckets; b++) a.liveCount[(parity ^ 1) * kBuckets + b] = 0;   // for the next step's compaction
-    const int slot = queuedSlot(a, parity, 1, sub);
-    if (slot >= 0) bsdfFinish(a, slot, true, parity);
+    // thread -> (BSDF-type bucket, index).  Buckets are padded to whole warps so a warp shades one BSDF
+    // type; inside a bucket the slots are in ascending pixel order (gpt_compact_kernel), so the
+    // struct-of-arrays state rows are still read as (near-)contiguous sectors.
+    __shared__ int s_begin[kBuckets + 1], s_count[kBuckets];
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int b = 0; b < kBuckets; b++) { const int c = a.liveCount[parity * kBuckets + b]; s_begin[b] = acc; s_count[b] = c; acc += (c + 31) & ~31; }
+        s_begin[kBuckets] = acc;
+        if (PHASE != 0 && blockIdx.x == 0) for (int b = 0; b < kBuckets; b++) a.liveCount[(parity ^ 1) * kBuckets + b] = 0;   // for the next step's compaction
+        if (PHASE != 1 && blockIdx.x == 0) a.genCount[parity] = 0;          // this step's regeneration queue has been consumed
+    }
+    __syncthreads();
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= s_begin[kBuckets]) return;
+    int b = 0;
+    while (g >= s_begin[b + 1]) b++;
+    const int idx = g - s_begin[b];
+    if (idx >= s_count[b]) return;
+    const int slot = a.liveList[((size_t)parity * kBuckets + b) * a.nSlots + idx];
+    bounceBody<PHASE, true>(a, slot, parity);
 }
 
-// Tail of the render: once few pixel streams are still running, stepping the whole wavefront costs seven
+// Tail of the render: once few pixel streams are still running, stepping the whole wavefront costs four
 // launches per bounce for a handful of warps.  Here every remaining slot is simply run to completion by
-// one thread (generate -> NEE -> BSDF stage -> ... until its pixel's samples are exhausted).
+// one thread (generate -> NEE phase -> BSDF phase -> ... until its pixel's samples are exhausted).
 __global__ void __launch_bounds__(kBounceThreads) gpt_tail_kernel(const GptArgs a)
 {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
@@ -791,11 +665,8 @@ __global__ void __launch_bounds__(kBounceThreads) gpt_tail_kernel(const GptArgs 
         const int st = SI(a, IF_STATUS, slot);
         if (st == ST_DONE) break;
         if (st != ST_LIVE) { generateBody(a, slot); continue; }
-        neeBase(a, slot, false, 0);
-        for (int i = 0; i < 4; i++) neeOffset(a, slot, i);
-        bsdfBase(a, slot, false, 0);
-        for (int i = 0; i < 4; i++) bsdfOffset(a, slot, i);
-        bsdfFinish(a, slot, false, 0);
+        bounceBody<0, false>(a, slot, 0);
+        if (SI(a, IF_STATUS, slot) == ST_LIVE) bounceBody<1, false>(a, slot, 0);
     }
 }
 
@@ -811,14 +682,14 @@ __global__ void __launch_bounds__(256) gpt_compact_kernel(const GptArgs a, int p
         // stage 0: some offset path is still unconnected (shadow + reconnection / half-vector rays ahead),
         // stage 1: some offset was connected on the previous bounce (extra BSDF evaluations), stage 2: all
         // offsets ride along with the base path or are dead.  Lanes of one warp then run the same branches.
+        const unsigned f = (unsigned)SI(a, IF_OFLAGS, slot);
         int stage = 2;
         for (int i = 0; i < 4; i++) {
-            const int f = SI(a, IF_OFLAG0 + i, slot);
-            if (!flagAlive(f)) continue;
-            const int c = flagConn(f);
+            if (!flagAlive(f, i)) continue;
+            const int c = flagConn(f, i);
             if (c == RAY_NOT_CONNECTED) stage = 0; else if (c == RAY_RECENTLY_CONNECTED && stage == 2) stage = 1;
         }
-        bucket = c_sceneG->materials[SI(a, IF_MAT0 + SI(a, IF_VSEL, slot), slot)].type * 3 + stage;
+        bucket = c_sceneG->materials[SI(a, IF_MAT, slot)].type * 3 + stage;
     }
     int rank = 0;
 #pragma unroll
@@ -1236,7 +1107,9 @@ int gdb200_gpt_render(gdb200_scene *s, const gdb200_gpt_params *p, gdb200_buffer
     int parity = 0;
     std::vector<cudaEvent_t> marks;   // per-kernel timing (only when the caller asked for stats)
     unsigned long long tailThreshold = (unsigned long long)std::max(nSlots / 16, std::min(nSlots, 16384));
-    if (getenv("GDB200_TAIL_ALL")) tailThreshold = (unsigned long long)nSlots;     // experiment: megakernel for the whole render
+    // Default: both stages of a bounce in ONE pass over the state (least HBM traffic, fewest launches).
+    // GDB200_SPLIT_PHASES=1 runs them as two kernels (smaller hot code per kernel) for A/B measurements.
+    const bool fused = getenv("GDB200_SPLIT_PHASES") == nullptr;
     const long long maxSteps = (long long)p->spp * 4096 + 65536;     // safety net: never spin forever
     for (long long step = 0;; step++) {
         if (step > maxSteps) { cudaEventDestroy(e0); cudaEventDestroy(e1); return set_error(GDB200_ERR_CUDA, "wavefront did not drain after %lld steps", step); }
@@ -1246,13 +1119,13 @@ int gdb200_gpt_render(gdb200_scene *s, const gdb200_gpt_params *p, gdb200_buffer
         mark();
         gpt_compact_kernel<<<(nSlots + 255) / 256, 256>>>(a, parity);
         mark();
-        gpt_nee_base_kernel<<<bounceBlocks, kBounceThreads>>>(a, parity);
-        gpt_nee_offset_kernel<<<4 * bounceBlocks, kBounceThreads>>>(a, parity);
-        gpt_bsdf_base_kernel<<<bounceBlocks, kBounceThreads>>>(a, parity);
-        gpt_bsdf_offset_kernel<<<4 * bounceBlocks, kBounceThreads>>>(a, parity);
-        gpt_bsdf_finish_kernel<<<bounceBlocks, kBounceThreads>>>(a, parity);
+        if (fused) { gpt_bounce_kernel<2><<<bounceBlocks, kBounceThreads>>>(a, parity); launches += 3; }
+        else {
+            gpt_bounce_kernel<0><<<bounceBlocks, kBounceThreads>>>(a, parity);
+            gpt_bounce_kernel<1><<<bounceBlocks, kBounceThreads>>>(a, parity);
+            launches += 4;
+        }
         mark();
-        launches += 7;
         parity ^= 1;
         if ((step & 15) == 15) {
             GDB_CUDA(cudaMemcpy(hostCounters, s->counters, sizeof(hostCounters), cudaMemcpyDeviceToHost));
