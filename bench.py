@@ -186,7 +186,7 @@ def main():
            "solve_ms": 0.0, "launches": 0, "samples": 0.0, "rays": 0.0, "exchange_bytes": 0}
 
     def step(timed):
-        integ.trace(scene, spp=spp, seed=0, bands=bands, download=False)
+        integ.trace(scene, spp=spp, seed=0, bands=bands, download=False, preview=False)   # "-final" comes from the reconstruction
         if world > 1:
             nb = tiles.exchange_all(acc, world)
             if rank == 0:
@@ -242,7 +242,7 @@ def main():
             out = integ.render(sc, spp=spp, seed=0)      # trace + develop + D2H of 5 buffers + solve + D2H of final
             sc.close()
         else:
-            integ.trace(scene, spp=spp, seed=0, bands=bands, download=False)
+            integ.trace(scene, spp=spp, seed=0, bands=bands, download=False, preview=False)
             tiles.exchange_all(acc, world)
             if rank == 0:
                 out = scene.develop(download=True)

@@ -7,8 +7,6 @@
 //   * one slot per base pixel owns that pixel's sample stream (the gdb200_counter sampler is
 //     re-keyed per pixel exactly where the reference calls Sampler::generate, gpt.cpp:1250, and
 //     the spp samples of a pixel consume it sequentially, so results do not depend on scheduling);
-//   * state lives in HBM as struct-of-arrays [field][slot] (146 fp64 + 14 int32 fields): every
-//     state access of a warp is one coalesced 256-byte row per field;
 //   * each wavefront step launches
 //       gpt_generate_kernel : the slots of the regeneration queue splat the 15 film contributions of
 //                             their finished path (gpt.cpp:1319-1352) and start their next sample:
@@ -61,7 +59,7 @@ struct GptArgs {
     uint64_t *key;         // [nSlots]
     int nSlots, width, height, yBegin;
     int bandRows, bandCount, bandIndex, pad1;   // interleaved row bands (bandCount > 1) instead of one strip
-    int spp, pad0;
+    int spp, skipPreview;   // skipPreview: the "-final" preview puts (gpt.cpp:1319-1324) are not needed when a reconstruction overwrites that buffer
     uint64_t seed;
     Config cfg;
     double *film;          // [5][H][W][4]
@@ -126,6 +124,14 @@ GDB_D void loadOffIts(const GptArgs &a, int slot, int i, Its &its)
     its.material = SI(a, IF_OMAT0 + i, slot); its.emitter = -1;
 }
 
+// shifted.addRadiance / addGradient (gpt.cpp:147-156).  Most bounces add exact zeros (light sample occluded, no
+// emitter hit); x + 0 == x bit for bit, so those skip the read-modify-write of the two accumulator records.
+GDB_D void accumulateOffset(const GptArgs &a, int o, int slot, Spec dRad, Spec dGrad)
+{
+    if (!(dRad.x == 0 && dRad.y == 0 && dRad.z == 0)) stv(a, o + OR_RAD, slot, ldv(a, o + OR_RAD, slot) + dRad);
+    if (!(dGrad.x == 0 && dGrad.y == 0 && dGrad.z == 0)) stv(a, o + OR_GRAD, slot, ldv(a, o + OR_GRAD, slot) + dGrad);
+}
+
 // Warp-aggregated append of an ended slot to the next step's regeneration queue.
 GDB_D void appendGen(const GptArgs &a, int parity, int slot)
 {
@@ -184,11 +190,13 @@ GDB_CALL void filmPut(const GptArgs &a, Float sx, Float sy, Spec v, Float weight
 GDB_D void splatSample(const GptArgs &a, Float spx, Float spy, Spec veryDirect, Spec C, const Spec rad[4], const Spec grad[4])
 {
     const int RIGHT = 0, BOTTOM = 1, LEFT = 2, TOP = 3;
-    filmPut(a, spx, spy, (8 * veryDirect) + (2 * C), 4.0, BUF_FINAL, false);
-    filmPut(a, spx - 1, spy, 2 * rad[LEFT], 1.0, BUF_FINAL, false);
-    filmPut(a, spx + 1, spy, 2 * rad[RIGHT], 1.0, BUF_FINAL, false);
-    filmPut(a, spx, spy - 1, 2 * rad[TOP], 1.0, BUF_FINAL, false);
-    filmPut(a, spx, spy + 1, 2 * rad[BOTTOM], 1.0, BUF_FINAL, false);
+    if (!a.skipPreview) {
+        filmPut(a, spx, spy, (8 * veryDirect) + (2 * C), 4.0, BUF_FINAL, false);
+        filmPut(a, spx - 1, spy, 2 * rad[LEFT], 1.0, BUF_FINAL, false);
+        filmPut(a, spx + 1, spy, 2 * rad[RIGHT], 1.0, BUF_FINAL, false);
+        filmPut(a, spx, spy - 1, 2 * rad[TOP], 1.0, BUF_FINAL, false);
+        filmPut(a, spx, spy + 1, 2 * rad[BOTTOM], 1.0, BUF_FINAL, false);
+    }
     filmPut(a, spx, spy, 2 * C, 4.0, BUF_THROUGHPUT, false);
     filmPut(a, spx - 1, spy, 2 * rad[LEFT], 1.0, BUF_THROUGHPUT, false);
     filmPut(a, spx + 1, spy, 2 * rad[RIGHT], 1.0, BUF_THROUGHPUT, false);
@@ -402,7 +410,6 @@ GDB_D void bounceBody(const GptArgs &a, int slot, int parity)
             int conn = flagConn(flags, i);
             Spec sthr = splat(0); Float spdf = 0;
             if (alive) ldvw(a, o + OR_THR, slot, sthr, spdf);
-            Spec srad = ldv(a, o + OR_RAD, slot), sgrad = ldv(a, o + OR_GRAD, slot);
             Its sits;
             if (alive && conn == RAY_NOT_CONNECTED) loadOffIts(a, slot, i, sits);
             V3 recentWiL = mk(0, 0, 0);
@@ -461,8 +468,7 @@ GDB_D void bounceBody(const GptArgs &a, int slot, int parity)
                     shiftedContribution = splat(0);
                 }
                 mrad = mrad + mainContribution * weight;                             // gpt.cpp:723-726
-                srad = srad + shiftedContribution * weight;
-                sgrad = sgrad + (shiftedContribution - mainContribution) * weight;
+                accumulateOffset(a, o, slot, shiftedContribution * weight, (shiftedContribution - mainContribution) * weight);
             }
 
             if (kBsdf && bsdfStage) {                                           // ---- BSDF-sample stage, gpt.cpp:830-1151
@@ -584,14 +590,12 @@ GDB_D void bounceBody(const GptArgs &a, int slot, int parity)
                         bHas |= 1u << i;
                         if (i == 0) bw0 = weight; else if (i == 1) bw1 = weight; else if (i == 2) bw2 = weight; else bw3 = weight;
                     }
-                    srad = srad + shiftedContribution * weight;
-                    sgrad = sgrad + (shiftedContribution - mainContribution) * weight;
+                    accumulateOffset(a, o, slot, shiftedContribution * weight, (shiftedContribution - mainContribution) * weight);
                 }
                 if (postponedShiftEnd) alive = false;                                // gpt.cpp:1148-1150
                 flags = setFlag(flags, i, alive, conn);
             }
             if (kBsdf && (flagAlive(flags, i) || alive)) stvw(a, o + OR_THR, slot, sthr, spdf);
-            stv(a, o + OR_RAD, slot, srad); stv(a, o + OR_GRAD, slot, sgrad);
         }
         // base radiance: BSDF-stage terms after all NEE terms, in offset order (gpt.cpp:1142)
         if (bHas & 1u) mrad = mrad + mainContributionAll * bw0;
@@ -1088,7 +1092,7 @@ int gdb200_gpt_render(gdb200_scene *s, const gdb200_gpt_params *p, gdb200_buffer
     GptArgs a;
     memset(&a, 0, sizeof(a));
     a.sd = s->sd; a.si = s->si; a.key = s->key; a.nSlots = nSlots; a.width = s->width; a.height = s->height; a.yBegin = y0;
-    a.spp = p->spp; a.seed = p->seed;
+    a.spp = p->spp; a.seed = p->seed; a.skipPreview = p->skip_preview != 0;
     a.bandRows = banded ? p->band_rows : 0; a.bandCount = banded ? p->band_count : 0; a.bandIndex = banded ? p->band_index : 0;
     a.cfg.maxDepth = p->max_depth; a.cfg.minDepth = 1; a.cfg.rrDepth = p->rr_depth;         // gpt.cpp:1368-1371
     a.cfg.strictNormals = p->strict_normals; a.cfg.shiftThreshold = p->shift_threshold;

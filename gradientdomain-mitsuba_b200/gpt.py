@@ -105,16 +105,17 @@ class GPTIntegrator:
         self.reconstructL1, self.reconstructL2, self.reconstructAlpha = reconstructL1, reconstructL2, reconstructAlpha
         self.stats, self.solver_stats = Stats(), Stats()
 
-    def params(self, spp, seed=0, rows=None, bands=None):
+    def params(self, spp, seed=0, rows=None, bands=None, preview=True):
         p = _scenes.default_params(spp=spp, seed=seed, max_depth=self.maxDepth, rr_depth=self.rrDepth,
                                    shift_threshold=self.shiftThreshold, strict_normals=self.strictNormals)
         if rows is not None:
             p.y_begin, p.y_end = rows
+        p.skip_preview = 0 if preview else 1
         if bands is not None:                      # (band_rows, band_count, band_index)
             p.band_rows, p.band_count, p.band_index = bands
         return p
 
-    def trace(self, scene, spp, seed=0, rows=None, download=True, bands=None):
+    def trace(self, scene, spp, seed=0, rows=None, download=True, bands=None, preview=True):
         """The sampling part of render(): returns the developed fp64 buffers (h,w,3)."""
         if self.hideEmitters:   # gpt.cpp:1362-1365
             raise Gdb200Error("Option 'hideEmitters' not implemented for Gradient-Domain Path Tracing!")
@@ -126,7 +127,7 @@ class GPTIntegrator:
                                 ("dy", "-dy"), ("direct", "-direct")):
                 out[name] = np.empty((h, w, 3), dtype=np.float64)
                 setattr(B, field, out[name].ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
-        p = self.params(spp, seed, rows, bands)
+        p = self.params(spp, seed, rows, bands, preview)
         check(lib().gdb200_gpt_render(scene._h, ctypes.byref(p), ctypes.byref(B), ctypes.byref(self.stats)))
         return out
 
@@ -153,7 +154,7 @@ class GPTIntegrator:
 
     def render(self, scene, spp, seed=0):
         """Returns {"-final","-throughput","-dx","-dy","-direct"} like the five multifilm buffers."""
-        out = self.trace(scene, spp, seed)
+        out = self.trace(scene, spp, seed, preview=not (self.reconstructL1 or self.reconstructL2))
         final = self.reconstruct(scene)
         if final is not None:
             out["-final"] = final.astype(np.float64)     # setBitmapMulti(reconstruction, BUFFER_FINAL), gpt.cpp:1468-1475

@@ -239,6 +239,7 @@ public:
 		params.shift_threshold = m_shiftThreshold;
 		params.spp = (int) sampler->getSampleCount();
 		params.seed = m_seed;
+		params.skip_preview = (m_reconstructL1 || m_reconstructL2) ? 1 : 0;   /* "-final" is replaced by the reconstruction */
 
 		const Vector2i size = film->getCropSize();
 		const size_t n3 = (size_t) size.x * size.y * 3;

@@ -177,7 +177,7 @@ typedef struct gdb200_gpt_params {
     int      strict_normals;     /* strictNormals (false)                           */
     double   shift_threshold;    /* shiftThreshold (0.001)                          */
     int      spp;                /* sampler sampleCount                             */
-    int      reserved;
+    int      skip_preview;       /* 1: do not accumulate the "-final" preview (gpt.cpp:1319-1324); use when a reconstruction will overwrite it */
     uint64_t seed;               /* gdb200_counter sampler seed                     */
     int      y_begin, y_end;     /* rows of base pixels this call renders (tile sharding); 0,0 = all */
     /* Interleaved row bands (load-balanced tile sharding): when band_count > 1 this call renders the
