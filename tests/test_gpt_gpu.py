@@ -141,3 +141,47 @@ def test_interleaved_bands_sum_to_full_image():
     merged = scene.develop()
     for name in ("-final", "-throughput", "-dx", "-dy", "-direct"):
         np.testing.assert_allclose(merged[name], full[name], rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.parametrize("size,spp", [((1, 1), 8), ((3, 2), 5), ((17, 9), 3), ((64, 64), 1)])
+def test_tiny_and_ragged_images(oracle, size, spp):
+    w, h = size
+    desc = scenes.cbox_glossy(w, h)
+    integ = gdb200.GPTIntegrator(reconstructL1=False, reconstructL2=False)
+    got = integ.trace(gdb200.Scene(desc), spp=spp, seed=2)
+    ref, wts, cnt = oracle.gpt(desc, integ.params(spp, 2))
+    compare(got, ref, max_flip_frac=0.0 if w * h < 100 else 2e-3)
+    assert integ.stats.samples == w * h * spp
+
+
+def test_renders_are_reproducible_and_seed_dependent():
+    desc = scenes.cbox_diffuse(48, 48)
+    integ = gdb200.GPTIntegrator(reconstructL1=False, reconstructL2=False)
+    scene = gdb200.Scene(desc)
+    a = integ.trace(scene, spp=8, seed=7)
+    b = integ.trace(scene, spp=8, seed=7)
+    c = integ.trace(scene, spp=8, seed=8)
+    for k in a:      # film atomics commute up to fp64 rounding of the sum order
+        np.testing.assert_allclose(a[k], b[k], rtol=1e-12, atol=1e-15)
+    assert not np.allclose(a["-throughput"], c["-throughput"])
+
+
+def test_preview_skip_leaves_other_buffers_untouched():
+    desc = scenes.cbox_diffuse(40, 40)
+    integ = gdb200.GPTIntegrator(reconstructL1=False, reconstructL2=False)
+    scene = gdb200.Scene(desc)
+    a = integ.trace(scene, spp=4, seed=1, preview=True)
+    b = integ.trace(scene, spp=4, seed=1, preview=False)
+    for k in ("-throughput", "-dx", "-dy", "-direct"):
+        np.testing.assert_allclose(a[k], b[k], rtol=1e-12, atol=1e-15)
+    assert np.all(b["-final"] == 0) and a["-final"].max() > 0
+
+
+def test_scene_outside_supported_subset_fails_loudly():
+    import ctypes
+    b = scenes._cornell(16, 16)
+    glass = b.material(type=scenes.BSDF_DIELECTRIC, ior_ratio=1.5)
+    idx = b.sphere((0, 0, 0), 0.2, glass)
+    b.shapes[idx].emitter = 0                       # sphere emitters are not in the supported subset
+    with pytest.raises(gdb200.Gdb200Error, match="sphere emitters"):
+        gdb200.Scene(b.build())
