@@ -44,7 +44,7 @@ enum BaseRec { BR_RAYD = 0 /* w: path pdf */, BR_P /* w: eta */, BR_GN /* w: sam
                BR_THR, BR_RAD, BR_VD, BR_COUNT };
 enum OffRec { OR_THR = 0 /* w: path pdf */, OR_RAD, OR_GRAD, OR_P, OR_GN, OR_S, OR_T, OR_N, OR_WI, OR_COUNT };
 constexpr int kRecords = BR_COUNT + 4 * OR_COUNT;   // 46 records = 1472 B per slot
-enum IntField { IF_STATUS = 0, IF_MAT, IF_EMI, IF_DEPTH, IF_SAMPLE, IF_RNGN, IF_OFLAGS, IF_OMAT0, IF_OMAT1, IF_OMAT2, IF_OMAT3,
+enum IntField { IF_STATUS = 0, IF_MAT, IF_EMI, IF_DEPTH, IF_SAMPLE, IF_RNGN, IF_OFLAGS, IF_PAD, IF_OMAT0, IF_OMAT1, IF_OMAT2, IF_OMAT3,
                 IF_COUNT };
 enum SlotStatus { ST_FRESH = 0, ST_LIVE = 1, ST_FINISHED = 2, ST_DONE = 3 };
 enum { RAY_NOT_CONNECTED = 0, RAY_RECENTLY_CONNECTED = 1, RAY_CONNECTED = 2 };
@@ -55,8 +55,7 @@ constexpr int kBuckets = 12;  // one queue per (BSDF type of the base vertex) x 
 
 struct GptArgs {
     double *sd;            // [kRecords][nSlots][4]
-    int *si;               // [IF_COUNT][nSlots]
-    uint64_t *key;         // [nSlots]
+    int *si;               // [nSlots][16]
     int nSlots, width, height, yBegin;
     int bandRows, bandCount, bandIndex, pad1;   // interleaved row bands (bandCount > 1) instead of one strip
     int spp, skipPreview;   // skipPreview: the "-final" preview puts (gpt.cpp:1319-1324) are not needed when a reconstruction overwrites that buffer
@@ -72,7 +71,9 @@ struct GptArgs {
 
 GDB_D double *REC(const GptArgs &a, int rec, int slot) { return a.sd + (((size_t)rec * a.nSlots + slot) << 2); }
 GDB_D double &W(const GptArgs &a, int rec, int slot) { return REC(a, rec, slot)[3]; }
-GDB_D int &SI(const GptArgs &a, int field, int slot) { return a.si[(size_t)field * a.nSlots + slot]; }
+// int fields of a slot share one 64-byte line [slot][16] (fields 0-7 in its first sector), so a kernel pulls one
+// sector per slot instead of one per field; the per-pixel sampler key is recomputed, not stored.
+GDB_D int &SI(const GptArgs &a, int field, int slot) { return a.si[((size_t)slot << 4) + field]; }
 GDB_D V3 ldv(const GptArgs &a, int rec, int slot)
 {
     const double2 *p = reinterpret_cast<const double2 *>(REC(a, rec, slot));
@@ -226,7 +227,7 @@ GDB_D void generateBody(const GptArgs &a, int slot)
         splatSample(a, W(a, BR_GN, slot), W(a, BR_S, slot), ldv(a, BR_VD, slot), ldv(a, BR_RAD, slot), rad, grad);
     }
 
-    Sampler smp; smp.key = a.key[slot]; smp.n = (uint32_t)SI(a, IF_RNGN, slot);
+    Sampler smp; smp.key = samplerKey(a.seed, px, py); smp.n = (uint32_t)SI(a, IF_RNGN, slot);    // Sampler::generate, gpt.cpp:1250-1251
     int j = SI(a, IF_SAMPLE, slot);
     unsigned long long rays = 0, samples = 0;
     int status = ST_DONE;
@@ -310,7 +311,7 @@ GDB_D void bounceBody(const GptArgs &a, int slot, int parity)
     Float meta = W(a, BR_P, slot);
     int depth = SI(a, IF_DEPTH, slot);
     unsigned flags = (unsigned)SI(a, IF_OFLAGS, slot);
-    Sampler smp; smp.key = a.key[slot]; smp.n = (uint32_t)SI(a, IF_RNGN, slot);
+    Sampler smp; smp.key = samplerKey(a.seed, slot % a.width, slotRow(a, slot)); smp.n = (uint32_t)SI(a, IF_RNGN, slot);
     unsigned rays = 0;
     bool ended = false;
     if (kNee) {   // algorithmic state traffic of this path-bounce (record sizes of SURVEY.md §8d: base 320 B,
@@ -719,8 +720,6 @@ __global__ void gpt_init_kernel(const GptArgs a)
     if (slot == 0) { a.genCount[0] = a.nSlots; a.genCount[1] = 0; }
     if (slot >= a.nSlots) return;
     a.genList[slot] = slot;
-    const int px = slot % a.width, py = slotRow(a, slot);
-    a.key[slot] = samplerKey(a.seed, px, py);                                        // Sampler::generate, gpt.cpp:1250-1251
     SI(a, IF_STATUS, slot) = ST_FRESH; SI(a, IF_SAMPLE, slot) = 0; SI(a, IF_RNGN, slot) = 0;
 }
 
@@ -799,7 +798,7 @@ struct gdb200_scene {
     int width = 0, height = 0;
     // device buffers
     double *film = nullptr, *dev64 = nullptr; float *dev32 = nullptr;
-    double *sd = nullptr; int *si = nullptr; uint64_t *key = nullptr;
+    double *sd = nullptr; int *si = nullptr;
     int *liveList = nullptr, *liveCount = nullptr, *genList = nullptr, *genCount = nullptr;
     unsigned long long *counters = nullptr;
     int slotCapacity = 0;
@@ -986,9 +985,9 @@ void classifyMaterials(gdb200_scene *s, double shiftThreshold)
 
 void freeSceneBuffers(gdb200_scene *s)
 {
-    cudaFree(s->film); cudaFree(s->dev64); cudaFree(s->dev32); cudaFree(s->sd); cudaFree(s->si); cudaFree(s->key);
+    cudaFree(s->film); cudaFree(s->dev64); cudaFree(s->dev32); cudaFree(s->sd); cudaFree(s->si);
     cudaFree(s->liveList); cudaFree(s->liveCount); cudaFree(s->genList); cudaFree(s->genCount); cudaFree(s->counters); cudaFree(s->dScene); s->dScene = nullptr;
-    s->film = s->dev64 = s->sd = nullptr; s->dev32 = nullptr; s->si = nullptr; s->key = nullptr;
+    s->film = s->dev64 = s->sd = nullptr; s->dev32 = nullptr; s->si = nullptr;
     s->liveList = s->liveCount = s->genList = s->genCount = nullptr; s->counters = nullptr; s->slotCapacity = 0;
 }
 
@@ -1071,11 +1070,11 @@ int gdb200_gpt_render(gdb200_scene *s, const gdb200_gpt_params *p, gdb200_buffer
     GDB_CUDA(cudaSetDevice(s->device));
     const int nSlots = s->width * ownedRows;
     if (nSlots > s->slotCapacity) {
-        cudaFree(s->sd); cudaFree(s->si); cudaFree(s->key); cudaFree(s->liveList); cudaFree(s->liveCount); cudaFree(s->genList); cudaFree(s->genCount);
-        s->sd = nullptr; s->si = nullptr; s->key = nullptr; s->liveList = s->liveCount = s->genList = s->genCount = nullptr;
+        cudaFree(s->sd); cudaFree(s->si); cudaFree(s->liveList); cudaFree(s->liveCount); cudaFree(s->genList); cudaFree(s->genCount);
+        s->sd = nullptr; s->si = nullptr; s->liveList = s->liveCount = s->genList = s->genCount = nullptr;
         GDB_CUDA(cudaMalloc(&s->sd, sizeof(double) * 4 * kRecords * (size_t)nSlots));
-        GDB_CUDA(cudaMalloc(&s->si, sizeof(int) * IF_COUNT * (size_t)nSlots));
-        GDB_CUDA(cudaMalloc(&s->key, sizeof(uint64_t) * (size_t)nSlots));
+        static_assert(IF_COUNT <= 16, "int fields must fit the 16-int slot line");
+        GDB_CUDA(cudaMalloc(&s->si, sizeof(int) * 16 * (size_t)nSlots));
         GDB_CUDA(cudaMalloc(&s->liveList, sizeof(int) * 2 * (size_t)kBuckets * nSlots));
         GDB_CUDA(cudaMalloc(&s->liveCount, sizeof(int) * 2 * kBuckets));
         GDB_CUDA(cudaMalloc(&s->genList, sizeof(int) * 2 * (size_t)nSlots));
@@ -1091,7 +1090,7 @@ int gdb200_gpt_render(gdb200_scene *s, const gdb200_gpt_params *p, gdb200_buffer
 
     GptArgs a;
     memset(&a, 0, sizeof(a));
-    a.sd = s->sd; a.si = s->si; a.key = s->key; a.nSlots = nSlots; a.width = s->width; a.height = s->height; a.yBegin = y0;
+    a.sd = s->sd; a.si = s->si; a.nSlots = nSlots; a.width = s->width; a.height = s->height; a.yBegin = y0;
     a.spp = p->spp; a.seed = p->seed; a.skipPreview = p->skip_preview != 0;
     a.bandRows = banded ? p->band_rows : 0; a.bandCount = banded ? p->band_count : 0; a.bandIndex = banded ? p->band_index : 0;
     a.cfg.maxDepth = p->max_depth; a.cfg.minDepth = 1; a.cfg.rrDepth = p->rr_depth;         // gpt.cpp:1368-1371
