@@ -222,6 +222,20 @@ def cbox_diffuse(width=512, height=512):
     return _cornell(width, height).build()
 
 
+def cbox_materials(width=256, height=256):
+    """Coverage scene for the remaining BSDF branches: a Beckmann rough conductor (alpha 0.15, DIFFUSE class),
+    a smooth `conductor` mirror (delta reflection => half-vector shift with J := 1) and a `dielectric` sphere."""
+    b = _cornell(width, height, boxes=False)
+    beck = b.material(type=BSDF_ROUGHCONDUCTOR, alpha=0.15, eta=CU_ETA, k=CU_K, distribution=MICROFACET_BECKMANN)
+    mirror = b.material(type=BSDF_CONDUCTOR, eta=AL_ETA, k=AL_K)
+    glass = b.material(type=BSDF_DIELECTRIC, ior_ratio=1.5)
+    b.sphere((-0.55, -0.7, -0.2), 0.3, beck)
+    b.sphere((0.1, -0.65, 0.45), 0.35, mirror)
+    b.sphere((0.6, -0.75, -0.3), 0.25, glass)
+    b.box((0.0, 0.55, -0.6), (0.5, 0.05, 0.2), 0.0, b.material(reflectance=WHITE))     # a shelf: more occlusion for the shifts
+    return b.build()
+
+
 def cbox_glossy(width=1024, height=1024, delta_variant=False):
     """C2 "cbox-glossy": C1 plus two spheres — roughconductor GGX alpha=0.05 (DIFFUSE under the
     default shiftThreshold => reconnection shift) and alpha=0.0005 (GLOSSY => half-vector shift);

@@ -34,11 +34,12 @@ def compare(got, ref, max_flip_frac=2e-3):
     return report
 
 
-@pytest.mark.parametrize("scene_name", ["cbox_diffuse", "cbox_glossy", "cbox_glossy_delta"])
+@pytest.mark.parametrize("scene_name", ["cbox_diffuse", "cbox_glossy", "cbox_glossy_delta", "cbox_materials"])
 def test_tracer_matches_oracle(oracle, scene_name):
     w = h = 96
     desc = {"cbox_diffuse": lambda: scenes.cbox_diffuse(w, h), "cbox_glossy": lambda: scenes.cbox_glossy(w, h),
-            "cbox_glossy_delta": lambda: scenes.cbox_glossy(w, h, delta_variant=True)}[scene_name]()
+            "cbox_glossy_delta": lambda: scenes.cbox_glossy(w, h, delta_variant=True),
+            "cbox_materials": lambda: scenes.cbox_materials(w, h)}[scene_name]()
     integ = gdb200.GPTIntegrator(reconstructL1=False, reconstructL2=False)
     scene = gdb200.Scene(desc)
     got = integ.trace(scene, spp=16, seed=3)

@@ -19,5 +19,6 @@ for name, n, spp in cases:
     st = integ.stats
     print(json.dumps({"scene": name, "size": n, "spp": spp, "ms": round(st.device_ms, 2), "launches": st.launches,
                       "Msamples_s": round(st.samples / st.device_ms / 1e3, 2), "rays_per_sample": round(st.rays / st.samples, 2),
-                      "avg_depth": round(st.path_vertices / st.samples, 3), "Grays_s": round(st.rays / st.device_ms / 1e6, 2)}), flush=True)
+                      "avg_depth": round(st.path_vertices / st.samples, 3), "Grays_s": round(st.rays / st.device_ms / 1e6, 2), "steps": st.bounce_launches,
+                      "gen_ms": round(st.generate_ms, 1), "compact_ms": round(st.compact_ms, 1), "bounce_ms": round(st.bounce_ms, 1)}), flush=True)
     scene.close()
