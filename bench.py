@@ -124,6 +124,8 @@ def main():
     ap.add_argument("--impl", default="gdb200", choices=["gdb200", "reference"])
     ap.add_argument("--workload", default="gpt-c2", choices=sorted(WORKLOADS))
     ap.add_argument("--spp", type=int, default=0, help="override the workload's sample count (invalidates the headline)")
+    ap.add_argument("--streams", type=int, default=8, help="sample streams per pixel (gdb200_gpt_params.streams_per_pixel); "
+                    "fixed for every N so the film does not depend on the GPU count")
     ap.add_argument("--cpu-spp", type=int, default=8, help="samples/pixel of the bounded CPU-baseline sample")
     args = ap.parse_args()
 
@@ -142,7 +144,7 @@ def main():
     integ = gdb200.GPTIntegrator(reconstructL1=(recon == "L1"), reconstructL2=(recon == "L2"), reconstructAlpha=0.2)
     config = {"workload": f"{scene_name} {W}x{H} @ {spp} spp, G-PT {recon} reconstruction (BASELINE configs[1])"
                           if args.workload == "gpt-c2" else f"{scene_name} {W}x{H} @ {spp} spp, G-PT {recon}",
-              "scene": "synthetic Cornell box + GGX spheres (gdb200.scenes)", "sampler": "gdb200_counter seed 0",
+              "scene": "synthetic Cornell box + GGX spheres (gdb200.scenes)", "sampler": f"gdb200_counter seed 0, {args.streams} sample streams per pixel",
               "maxDepth": -1, "rrDepth": 5, "shiftThreshold": 0.001, "alpha": 0.2,
               "parallelism": f"interleaved 16-row bands x{world}, one NCCL all-reduce of the film accumulators" if world > 1 else "1 GPU",
               "l2_flush": "per-step working set (1.2 GB wavefront state + 168 MB film) exceeds the 126 MB L2"}
@@ -154,7 +156,7 @@ def main():
         cpu_spp = max(1, args.cpu_spp // 4)
         rates = []
         for i in range(args.warmup + args.steps):
-            r, dt = cpu_tracer_rate(desc, lambda s: integ.params(s, 0), cpu_spp, cores)
+            r, dt = cpu_tracer_rate(desc, lambda s: integ.params(s, 0, streams=min(args.streams, s)), cpu_spp, cores)
             if i >= args.warmup:
                 rates.append((r, dt))
         val = sum(r for r, _ in rates) / len(rates)
@@ -186,7 +188,7 @@ def main():
            "solve_ms": 0.0, "launches": 0, "samples": 0.0, "rays": 0.0, "exchange_bytes": 0}
 
     def step(timed):
-        integ.trace(scene, spp=spp, seed=0, bands=bands, download=False, preview=False)   # "-final" comes from the reconstruction
+        integ.trace(scene, spp=spp, seed=0, bands=bands, download=False, preview=False, streams=args.streams)   # "-final" comes from the reconstruction
         if world > 1:
             nb = tiles.exchange_all(acc, world)
             if rank == 0:
@@ -239,10 +241,10 @@ def main():
     for _ in range(e2e_steps):
         if world == 1:
             sc = gdb200.Scene(desc)                      # scene upload (H2D) is part of the user-visible call
-            out = integ.render(sc, spp=spp, seed=0)      # trace + develop + D2H of 5 buffers + solve + D2H of final
+            out = integ.render(sc, spp=spp, seed=0, streams=args.streams)      # trace + develop + D2H of 5 buffers + solve + D2H of final
             sc.close()
         else:
-            integ.trace(scene, spp=spp, seed=0, bands=bands, download=False, preview=False)
+            integ.trace(scene, spp=spp, seed=0, bands=bands, download=False, preview=False, streams=args.streams)
             tiles.exchange_all(acc, world)
             if rank == 0:
                 out = scene.develop(download=True)
@@ -287,7 +289,7 @@ def main():
         if world > 1:
             line["exchange_bytes_per_step"] = int(agg["exchange_bytes"] / args.steps)
         if world == 1:
-            rate, dt = cpu_tracer_rate(desc, lambda s: integ.params(s, 0), args.cpu_spp, cores)
+            rate, dt = cpu_tracer_rate(desc, lambda s: integ.params(s, 0, streams=min(args.streams, s)), args.cpu_spp, cores)
             line["cpu_baseline"] = {"value": round(rate, 4), "unit": "Msamples/s", "cores": cores, "kind": "port",
                                     "sample": f"{scene_name} {W}x{H} @ {args.cpu_spp} spp (of {spp}), {dt:.1f} s, CPU restatement "
                                               "oracle/gpt_oracle.cpp with OpenMP over row bands"}

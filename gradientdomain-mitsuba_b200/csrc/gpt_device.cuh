@@ -7,9 +7,11 @@
 // that the reference re-derives through virtual calls on every use (BSDF type flags, the
 // glossy/diffuse vertex classification of gpt.cpp:176-226) are precomputed at scene upload.
 #pragma once
+#ifndef GDB200_EMU          // tests/emu/ compiles this source for the host through a shim (test infrastructure)
 #include <cuda_runtime.h>
-#include <cstdint>
 #include <math_constants.h>
+#endif
+#include <cstdint>
 #include "../../include/gdb200.h"
 
 namespace gdb200 {

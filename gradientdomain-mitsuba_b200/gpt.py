@@ -105,7 +105,7 @@ class GPTIntegrator:
         self.reconstructL1, self.reconstructL2, self.reconstructAlpha = reconstructL1, reconstructL2, reconstructAlpha
         self.stats, self.solver_stats = Stats(), Stats()
 
-    def params(self, spp, seed=0, rows=None, bands=None, preview=True):
+    def params(self, spp, seed=0, rows=None, bands=None, preview=True, streams=1):
         p = _scenes.default_params(spp=spp, seed=seed, max_depth=self.maxDepth, rr_depth=self.rrDepth,
                                    shift_threshold=self.shiftThreshold, strict_normals=self.strictNormals)
         if rows is not None:
@@ -113,9 +113,10 @@ class GPTIntegrator:
         p.skip_preview = 0 if preview else 1
         if bands is not None:                      # (band_rows, band_count, band_index)
             p.band_rows, p.band_count, p.band_index = bands
+        p.streams_per_pixel = streams              # sample streams per pixel (gdb200_gpt_params.streams_per_pixel)
         return p
 
-    def trace(self, scene, spp, seed=0, rows=None, download=True, bands=None, preview=True):
+    def trace(self, scene, spp, seed=0, rows=None, download=True, bands=None, preview=True, streams=1):
         """The sampling part of render(): returns the developed fp64 buffers (h,w,3)."""
         if self.hideEmitters:   # gpt.cpp:1362-1365
             raise Gdb200Error("Option 'hideEmitters' not implemented for Gradient-Domain Path Tracing!")
@@ -127,7 +128,7 @@ class GPTIntegrator:
                                 ("dy", "-dy"), ("direct", "-direct")):
                 out[name] = np.empty((h, w, 3), dtype=np.float64)
                 setattr(B, field, out[name].ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
-        p = self.params(spp, seed, rows, bands, preview)
+        p = self.params(spp, seed, rows, bands, preview, streams)
         check(lib().gdb200_gpt_render(scene._h, ctypes.byref(p), ctypes.byref(B), ctypes.byref(self.stats)))
         return out
 
@@ -152,9 +153,9 @@ class GPTIntegrator:
             plan.close()
         return res
 
-    def render(self, scene, spp, seed=0):
+    def render(self, scene, spp, seed=0, streams=1):
         """Returns {"-final","-throughput","-dx","-dy","-direct"} like the five multifilm buffers."""
-        out = self.trace(scene, spp, seed, preview=not (self.reconstructL1 or self.reconstructL2))
+        out = self.trace(scene, spp, seed, preview=not (self.reconstructL1 or self.reconstructL2), streams=streams)
         final = self.reconstruct(scene)
         if final is not None:
             out["-final"] = final.astype(np.float64)     # setBitmapMulti(reconstruction, BUFFER_FINAL), gpt.cpp:1468-1475

@@ -52,7 +52,7 @@ class GPTParams(ctypes.Structure):
     _fields_ = [("max_depth", ctypes.c_int), ("rr_depth", ctypes.c_int), ("strict_normals", ctypes.c_int),
                 ("shift_threshold", ctypes.c_double), ("spp", ctypes.c_int), ("skip_preview", ctypes.c_int),
                 ("seed", ctypes.c_uint64), ("y_begin", ctypes.c_int), ("y_end", ctypes.c_int),
-                ("band_rows", ctypes.c_int), ("band_count", ctypes.c_int), ("band_index", ctypes.c_int), ("reserved2", ctypes.c_int)]
+                ("band_rows", ctypes.c_int), ("band_count", ctypes.c_int), ("band_index", ctypes.c_int), ("streams_per_pixel", ctypes.c_int)]
 
 
 class Buffers(ctypes.Structure):

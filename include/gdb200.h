@@ -182,7 +182,13 @@ typedef struct gdb200_gpt_params {
     int      y_begin, y_end;     /* rows of base pixels this call renders (tile sharding); 0,0 = all */
     /* Interleaved row bands (load-balanced tile sharding): when band_count > 1 this call renders the
      * rows y with (y / band_rows) % band_count == band_index, and y_begin/y_end are ignored. */
-    int      band_rows, band_count, band_index, reserved2;
+    int      band_rows, band_count, band_index;
+    /* Sample streams per pixel (0 or 1 = one).  The gdb200_counter sampler gives every pixel ONE stream that
+     * its spp samples consume sequentially (Sampler::generate(pixel), gpt.cpp:1250-1251), which caps the
+     * parallelism at one path per pixel.  With C > 1 the spp samples of a pixel are split into C chunks
+     * (chunk c gets spp/C samples, +1 for c < spp%C), chunk 0 on the pixel's stream and chunk c > 0 on an
+     * independently re-keyed one: the same film as C reference passes with sampleCount spp/C summed. */
+    int      streams_per_pixel;
 } gdb200_gpt_params;
 
 /* Host output buffers, each width*height*3 fp64, interleaved RGB; any may be NULL.

@@ -1165,6 +1165,7 @@ int gdb200_oracle_gpt_render(const gdb200_scene_desc *desc, const gdb200_gpt_par
     film.acc.assign((size_t)5 * W * H * 4, 0.0);
     const int y0 = (prm->y_begin == 0 && prm->y_end == 0) ? 0 : prm->y_begin, y1 = (prm->y_begin == 0 && prm->y_end == 0) ? H : prm->y_end;
     double totRays = 0, totVerts = 0;
+    const int nChunks = std::max(1, prm->streams_per_pixel);
     // Row bands of 4: a sample in row y writes rows y-2..y+2 at most, so bands of equal parity
     // never touch the same film rows and can run concurrently without atomics.
     const int band = 4, nBands = (y1 - y0 + band - 1) / band;
@@ -1175,8 +1176,11 @@ int gdb200_oracle_gpt_render(const gdb200_scene_desc *desc, const gdb200_gpt_par
             Sampler sampler;
             for (int y = y0 + b * band; y < std::min(y1, y0 + (b + 1) * band); y++)
                 for (int x = 0; x < W; x++) {
+                  for (int chunk = 0; chunk < nChunks; chunk++) {                     // gdb200_gpt_params.streams_per_pixel (1 = the reference's single stream)
                     sampler.generate(prm->seed, x, y);                              // gpt.cpp:1250-1251
-                    for (int j = 0; j < prm->spp; j++) {
+                    if (chunk > 0) sampler.key = Sampler::mix(sampler.key ^ ((uint64_t)chunk * 0xD1B54A32D192ED03ULL));
+                    const int chunkSpp = prm->spp / nChunks + (chunk < prm->spp % nChunks ? 1 : 0);
+                    for (int j = 0; j < chunkSpp; j++) {
                         Float u, v; sampler.next2D(u, v);                           // :1261
                         const Float spx = x + u, spy = y + v;
                         RayState main, shifted[4];
@@ -1207,6 +1211,7 @@ int gdb200_oracle_gpt_render(const gdb200_scene_desc *desc, const gdb200_gpt_par
                         // :1352 very direct
                         film.put(spx, spy, veryDirect, 1.0, BUF_DIRECT, false);
                     }
+                  }
                 }
             totRays += cnt.rays; totVerts += cnt.vertices;
         }

@@ -98,3 +98,35 @@ def rmse(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return float(np.sqrt(np.mean((a - b) ** 2)))
+
+
+class Emu:
+    """ctypes view of tests/emu/libgdb200_emu.so: the tracer's per-slot *device* routines compiled for the
+    host (test infrastructure, see tests/emu/gpt_emu.cpp), so device code can be checked against the oracle
+    without a GPU."""
+
+    def __init__(self):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "emu")], check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+        self.lib = ctypes.CDLL(os.path.join(ROOT, "tests", "emu", "libgdb200_emu.so"))
+        self.lib.gdb200_emu_last_error.restype = ctypes.c_char_p
+
+    def gpt(self, desc, params):
+        from gdb200 import scenes
+        w, h = desc.camera.width, desc.camera.height
+        names = (("throughput", "-throughput"), ("dx", "-dx"), ("dy", "-dy"), ("direct", "-direct"), ("preview_final", "-final"))
+        out = {n: np.zeros((h, w, 3)) for _, n in names}
+        B = scenes.Buffers()
+        for field, n in names:
+            setattr(B, field, out[n].ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+        cnt = np.zeros(6)
+        rc = self.lib.gdb200_emu_gpt_render(ctypes.byref(desc), ctypes.byref(params), ctypes.byref(B),
+                                            cnt.ctypes.data_as(ctypes.c_void_p))
+        if rc != 0:
+            raise RuntimeError(self.lib.gdb200_emu_last_error().decode())
+        return out, cnt     # cnt: done slots, rays, path vertices, samples, state bytes, path bounces
+
+
+@pytest.fixture(scope="session")
+def emu():
+    return Emu()

@@ -1,0 +1,53 @@
+// TEST INFRASTRUCTURE — a minimal host shim for the CUDA constructs used by the tracer's per-slot
+// device routines (gradientdomain-mitsuba_b200/csrc/gpt_device.cuh, gpt_kernels.cuh), so that
+// tests/emu/gpt_emu.cpp can run the *same source* serially on the CPU, one "thread" at a time, and
+// compare it with the oracle when no GPU is present (this container has none).  It is not a CPU
+// backend: nothing in the product loads it, libgdb200.so fails loudly without a device.
+#pragma once
+#define GDB200_EMU 1
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+
+#define __host__
+#define __device__
+#define __global__
+#define __forceinline__ inline
+#define __noinline__
+#define __constant__ static
+#define __shared__ static
+#define __launch_bounds__(...)
+#define __restrict__
+#define CUDART_INF (std::numeric_limits<double>::infinity())
+
+struct double2 { double x, y; };
+inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
+struct float4 { float x, y, z, w; };
+struct int4 { int x, y, z, w; };
+struct int2 { int x, y; };
+struct EmuDim3 { unsigned x, y, z; };
+static EmuDim3 threadIdx = {0, 0, 0}, blockIdx = {0, 0, 0}, blockDim = {1, 1, 1}, gridDim = {1, 1, 1};
+
+using std::min;
+using std::max;
+using std::isfinite;
+inline double atomicAdd(double *p, double v) { double o = *p; *p = o + v; return o; }
+inline int atomicAdd(int *p, int v) { int o = *p; *p = o + v; return o; }
+inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
+inline unsigned __activemask() { return 1u; }
+inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+template <class T> inline T __shfl_sync(unsigned, T v, int) { return v; }
+inline unsigned __reduce_add_sync(unsigned, unsigned v) { return v; }
+inline unsigned __ballot_sync(unsigned, bool p) { return p ? 1u : 0u; }
+inline bool __any_sync(unsigned, bool p) { return p; }
+inline void __syncthreads() {}
+inline void __syncwarp(unsigned = 0xffffffffu) {}
+inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
+inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
+inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
+inline double __ldg(const double *p) { return *p; }
+inline float __ldg(const float *p) { return *p; }
+inline int __ldg(const int *p) { return *p; }

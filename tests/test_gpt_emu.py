@@ -1,0 +1,71 @@
+"""The tracer's device routines (gpt_device.cuh / gpt_kernels.cuh), compiled for the host through
+tests/emu/cuda_emu.h, against the fp64 CPU oracle on identical scene bytes and sample streams.
+
+This is the CPU-side net under the GPU parity tests (tests/test_gpt_gpu.py): same source as the CUDA
+kernels' per-slot bodies, same libm as the oracle, so agreement is expected to the last few ulps
+(sum-order of the film accumulation only).  The wavefront scheduling (queues, compaction) is not
+covered here; it needs the GPU."""
+import os
+
+import numpy as np
+import pytest
+
+from gdb200 import scenes
+
+TOL = 1e-12
+
+
+def close(got, ref):
+    for name in ("-throughput", "-dx", "-dy", "-direct", "-final"):
+        scale = max(float(np.abs(ref[name]).mean()), 1e-12)
+        assert np.abs(got[name] - ref[name]).max() <= TOL * max(scale, 1.0) * 100, name
+
+
+SCENES = {"cbox_diffuse": lambda w, h: scenes.cbox_diffuse(w, h), "cbox_glossy": lambda w, h: scenes.cbox_glossy(w, h),
+          "cbox_glossy_delta": lambda w, h: scenes.cbox_glossy(w, h, delta_variant=True),
+          "cbox_materials": lambda w, h: scenes.cbox_materials(w, h)}
+
+
+@pytest.mark.parametrize("scene_name", sorted(SCENES))
+def test_device_routines_match_oracle(oracle, emu, scene_name):
+    desc = SCENES[scene_name](40, 32)
+    p = scenes.default_params(spp=6, seed=3)
+    got, cnt = emu.gpt(desc, p)
+    ref, _, c2 = oracle.gpt(desc, p)
+    close(got, ref)
+    assert cnt[3] == c2[0] == 40 * 32 * 6 and cnt[1] == c2[1] and cnt[2] == c2[2]     # samples, rays, path vertices
+
+
+@pytest.mark.parametrize("kw", [dict(max_depth=2), dict(max_depth=1), dict(rr_depth=2), dict(strict_normals=True),
+                                dict(shift_threshold=0.1)])
+def test_device_routines_parameters(oracle, emu, kw):
+    desc = scenes.cbox_glossy(24, 24)
+    p = scenes.default_params(spp=5, seed=11, **kw)
+    got, _ = emu.gpt(desc, p)
+    ref, _, _ = oracle.gpt(desc, p)
+    close(got, ref)
+
+
+@pytest.mark.parametrize("streams,spp", [(2, 8), (3, 7), (8, 5)])
+def test_streams_per_pixel(oracle, emu, streams, spp):
+    """Chunked sample streams (gdb200_gpt_params.streams_per_pixel): same film as the oracle's chunk loop,
+    every sample accounted for, also when fewer slots than streams are resident (streams dealt dynamically)."""
+    desc = scenes.cbox_glossy(20, 16)
+    p = scenes.default_params(spp=spp, seed=5)
+    p.streams_per_pixel = streams
+    ref, _, c2 = oracle.gpt(desc, p)
+    for cap in (None, 97):
+        if cap is None:
+            os.environ.pop("GDB200_MAX_SLOTS", None)
+        else:
+            os.environ["GDB200_MAX_SLOTS"] = str(cap)
+        try:
+            got, cnt = emu.gpt(desc, p)
+        finally:
+            os.environ.pop("GDB200_MAX_SLOTS", None)
+        close(got, ref)
+        assert cnt[3] == 20 * 16 * spp == c2[0]
+        assert cnt[0] == (97 if cap else 20 * 16 * streams)
+    one = scenes.default_params(spp=spp, seed=5)
+    ref1, _, _ = oracle.gpt(desc, one)
+    assert not np.allclose(ref1["-throughput"], ref["-throughput"])     # chunks > 0 really use other streams

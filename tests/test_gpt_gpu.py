@@ -186,3 +186,19 @@ def test_scene_outside_supported_subset_fails_loudly():
     b.shapes[idx].emitter = 0                       # sphere emitters are not in the supported subset
     with pytest.raises(gdb200.Gdb200Error, match="sphere emitters"):
         gdb200.Scene(b.build())
+
+
+@pytest.mark.parametrize("streams,cap", [(4, None), (3, 1000), (8, 4096)])
+def test_streams_per_pixel_match_oracle(oracle, streams, cap, monkeypatch):
+    """Chunked sample streams: the wavefront deals (pixel, chunk) streams to its slots dynamically (also with
+    fewer resident slots than streams) and still reproduces the oracle's chunk loop."""
+    w, h = 80, 64
+    desc = scenes.cbox_glossy(w, h)
+    if cap:
+        monkeypatch.setenv("GDB200_MAX_SLOTS", str(cap))
+    integ = gdb200.GPTIntegrator(reconstructL1=False, reconstructL2=False)
+    got = integ.trace(gdb200.Scene(desc), spp=10, seed=4, streams=streams)
+    ref, _, cnt = oracle.gpt(desc, integ.params(10, 4, streams=streams))
+    compare(got, ref)
+    assert integ.stats.samples == w * h * 10 == cnt[0]
+    assert abs(integ.stats.rays - cnt[1]) <= 1e-3 * cnt[1]
