@@ -58,8 +58,22 @@ def lib():
                                               vp, vp, ctypes.POINTER(Stats)]
     L.gdb200_poisson_solve.argtypes = [vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                        ctypes.c_char_p, vp, ctypes.POINTER(Stats)]
+    _check_abi(L, path)
     _lib = L
     return L
+
+
+def _check_abi(L, path):
+    """The ctypes mirrors in this package must have the layout the library was compiled with."""
+    from . import scenes
+    mine = [ctypes.sizeof(t) for t in (Stats, PoissonConfig, scenes.Camera, scenes.Shape, scenes.Material, scenes.Emitter,
+                                        scenes.EnvMap, scenes.SceneDesc, scenes.GPTParams, scenes.Buffers)]
+    if not hasattr(L, "gdb200_abi_sizes"):
+        raise Gdb200Error(f"{path} predates gdb200_abi_sizes(): rebuild it (python -c 'import __graft_entry__ as g; g.build()')")
+    theirs = (ctypes.c_int * 16)()
+    n = L.gdb200_abi_sizes(theirs, 16)
+    if n != len(mine) or list(theirs[:n]) != mine:
+        raise Gdb200Error(f"{path} was built from another include/gdb200.h (struct sizes {list(theirs[:n])} vs {mine}): rebuild it")
 
 
 def check(rc):

@@ -45,7 +45,17 @@ int device_info(DeviceInfo *out)
 
 extern "C" {
 
-int gdb200_version(void) { return 100; }
+int gdb200_version(void) { return 101; }
+
+int gdb200_abi_sizes(int *out, int capacity)
+{
+    const int sizes[] = {(int)sizeof(gdb200_stats), (int)sizeof(gdb200_poisson_config), (int)sizeof(gdb200_camera), (int)sizeof(gdb200_shape),
+                         (int)sizeof(gdb200_material), (int)sizeof(gdb200_emitter), (int)sizeof(gdb200_envmap), (int)sizeof(gdb200_scene_desc),
+                         (int)sizeof(gdb200_gpt_params), (int)sizeof(gdb200_buffers)};
+    const int n = (int)(sizeof(sizes) / sizeof(sizes[0]));
+    for (int i = 0; i < n && i < capacity; i++) out[i] = sizes[i];
+    return n;
+}
 
 const char *gdb200_last_error(void) { return gdb200::last_error().c_str(); }
 

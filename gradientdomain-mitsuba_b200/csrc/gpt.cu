@@ -40,6 +40,7 @@ using namespace gdb200;
 struct gdb200_scene : gdb200::HostScene {
     int device = 0;
     DScene *dScene = nullptr;          // global-memory copy of `host` for per-lane indexed reads
+    void *dTables = nullptr;           // one allocation holding the variable-size tables (env map + CDFs, emitter triangles, BVH)
     // device buffers
     double *film = nullptr, *dev64 = nullptr; float *dev32 = nullptr;
     double *sd = nullptr; int *si = nullptr;
@@ -56,13 +57,39 @@ namespace {
 void freeSceneBuffers(gdb200_scene *s)
 {
     cudaFree(s->film); cudaFree(s->dev64); cudaFree(s->dev32); cudaFree(s->sd); cudaFree(s->si);
-    cudaFree(s->liveList); cudaFree(s->liveCount); cudaFree(s->genList); cudaFree(s->genCount); cudaFree(s->counters); cudaFree(s->dScene); s->dScene = nullptr;
+    cudaFree(s->liveList); cudaFree(s->liveCount); cudaFree(s->genList); cudaFree(s->genCount); cudaFree(s->counters); cudaFree(s->dScene); s->dScene = nullptr; cudaFree(s->dTables); s->dTables = nullptr;
     s->film = s->dev64 = s->sd = nullptr; s->dev32 = nullptr; s->si = nullptr;
     s->liveList = s->liveCount = s->genList = s->genCount = nullptr; s->counters = nullptr; s->slotCapacity = 0;
 }
 
+// Variable-size tables go to one device allocation (once per scene); their device addresses are patched into the
+// DScene copies that the kernels read.
+int uploadTables(gdb200_scene *s)
+{
+    if (s->dTables) return GDB200_OK;
+    struct Part { const void *src; size_t bytes; size_t offset; };
+    std::vector<Part> parts = {
+        {s->envTexels.data(), s->envTexels.size() * sizeof(Float), 0}, {s->envRowWeights.data(), s->envRowWeights.size() * sizeof(Float), 0},
+        {s->emTriCdf.data(), s->emTriCdf.size() * sizeof(Float), 0}, {s->envCdfRows.data(), s->envCdfRows.size() * sizeof(float), 0},
+        {s->envCdfCols.data(), s->envCdfCols.size() * sizeof(float), 0}, {s->emTris.data(), s->emTris.size() * sizeof(DEmTri), 0},
+        {s->bvh.data(), s->bvh.size() * sizeof(BvhNode), 0}, {s->bvhTris.data(), s->bvhTris.size() * sizeof(DTri), 0}};
+    size_t total = 0;
+    for (Part &p : parts) { p.offset = total; total += (p.bytes + 255) & ~(size_t)255; }
+    if (total == 0) return GDB200_OK;
+    GDB_CUDA(cudaMalloc(&s->dTables, total));
+    char *base = (char *)s->dTables;
+    for (const Part &p : parts) if (p.bytes) GDB_CUDA(cudaMemcpy(base + p.offset, p.src, p.bytes, cudaMemcpyHostToDevice));
+    DScene &h = s->host;
+    h.env.texels = (const Float *)(base + parts[0].offset); h.env.rowWeights = (const Float *)(base + parts[1].offset);
+    h.emTriCdf = (const Float *)(base + parts[2].offset); h.env.cdfRows = (const float *)(base + parts[3].offset);
+    h.env.cdfCols = (const float *)(base + parts[4].offset); h.emTris = (const DEmTri *)(base + parts[5].offset);
+    h.bvh = (const BvhNode *)(base + parts[6].offset); h.bvhTris = (const DTri *)(base + parts[7].offset);
+    return GDB200_OK;
+}
+
 int uploadScene(gdb200_scene *s)
 {
+    if (int rc = uploadTables(s)) return rc;
     GDB_CUDA(cudaMemcpyToSymbol(c_scene, &s->host, sizeof(DScene)));
     GDB_CUDA(cudaMemcpyToSymbol(c_bounds, s->bounds, sizeof(s->bounds)));
     if (!s->dScene) GDB_CUDA(cudaMalloc(&s->dScene, sizeof(DScene)));

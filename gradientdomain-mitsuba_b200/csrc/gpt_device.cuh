@@ -25,7 +25,7 @@ typedef double Float;
 constexpr Float kEpsilon = 1e-7, kShadowEpsilon = 1e-5;       // constants.h:25-26 (DOUBLE_PRECISION)
 constexpr Float kDeltaEpsilon = (Float)1e-3f;                 // constants.h:31 (float literal)
 constexpr Float kDEps = 1e-14;                                // gpt.cpp:63 D_EPSILON
-constexpr Float kPi = 3.14159265358979323846, kInvPi = 0.31830988618379067154;
+constexpr Float kPi = 3.14159265358979323846, kInvPi = 0.31830988618379067154, kInvTwoPi = 0.15915494309189533577;
 
 struct V3 { Float x, y, z; };
 GDB_HD V3 mk(Float x, Float y, Float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
@@ -96,10 +96,24 @@ struct DSphere { V3 center; Float radius; int flip, material, emitter, pad; };
 struct DTri    { Float n_u, n_v, n_d, a_u, a_v, b_nu, b_nv, c_nu, c_nv; V3 p0, p1, p2, faceNormal; int k, material, emitter, pad; };
 struct DMesh   { V3 lo, hi; int first, count; int kEnd[3], pad; };   // triangles of a mesh are stored grouped by projection axis k: [first,kEnd[0]) k=0, [kEnd[0],kEnd[1]) k=1, [kEnd[1],kEnd[2]) k=2   // conservative (enlarged) bounds of one TriMesh, used only to skip its triangles
 struct DMaterial {
-    int type, distribution; unsigned flags; int vtSmooth, vtDelta, refNFromShading, pad0, pad1;
+    int type, distribution; unsigned flags; int vtSmooth, vtDelta, refNFromShading, twosided, nonlinear;
     Spec reflectance, specR, specT, eta, k; Float alpha, iorRatio, bsdfEta;
+    Float fdrInt, fdrExt, specSamplingWeight, invEta2;       // plastic.cpp:188-206
 };
-struct DEmitter { int rect, pad; Spec radiance; Float pdfDiscrete; };   // pdfDiscrete = samplingWeight * normalization (scene.h:855-857)
+enum { EM_RECT = 0, EM_MESH = 1, EM_ENV = 2 };
+// pdfDiscrete = samplingWeight * normalization (scene.h:855-857).  Mesh emitters: triangles [triFirst, triFirst+triCount) of
+// emTris in the mesh's own order, area CDF (triCount+1 entries) at emTriCdf[cdfFirst], invArea = 1 / surface area.
+struct DEmitter { int kind, rect, triFirst, triCount, cdfFirst, pad; Spec radiance; Float pdfDiscrete, invArea; };
+struct DEmTri { V3 p0, p1, p2; };
+// Environment map (envmap.cpp): top-level texels as Float RGB, the float CDF tables of envmap.cpp:263-311.
+struct DEnv {
+    int present, width, height, emitter;
+    Float toWorld[12], toObject[12]; V3 center; Float radius, scale, normalization, pixelSizeX, pixelSizeY;
+    const float *cdfRows, *cdfCols; const Float *rowWeights, *texels;
+};
+// BVH2 over the triangles of large meshes (scenes beyond the constant-memory table).  Bounds are single precision and
+// padded like DBounds (conservative); inner: a/b = children; leaf: a = first triangle, b = -count.
+struct BvhNode { float lo[3]; int a; float hi[3]; int b; };
 
 struct DScene {
     Float sampleToCamera[16], cameraToWorld[12];
@@ -112,6 +126,9 @@ struct DScene {
     DEmitter emitters[kMaxEmitters];
     DMesh meshes[kMaxMeshes];
     DTri tris[kMaxTris];
+    DEnv env;
+    const DEmTri *emTris; const Float *emTriCdf;
+    const BvhNode *bvh; const DTri *bvhTris; int nBvhNodes, nBvhTris;
 };
 
 __constant__ DScene c_scene;   // one per device; renders sharing a device are serialised on the host
@@ -200,7 +217,16 @@ GDB_D bool closestPrimitive(const Ray &ray, Float mint, Float maxt, Float &tOut,
     const DScene *g = c_sceneG;
     const int nR = c_scene.nRects, nS = c_scene.nSpheres, nP = nR + nS + c_scene.nTris;
     const float ox = (float)ray.o.x, oy = (float)ray.o.y, oz = (float)ray.o.z;
+#ifdef GDB_SLAB_FMA
+    // (B - o) * i as one FFMA per plane: B * i + (-o * i).  1/d is clamped to +-1e30 so an axis-parallel ray gives
+    // huge finite plane distances instead of inf - inf; the rounding of o*i (<= 2^-24 |o| |i|) is far inside the
+    // padding of the bounds (1e-4 of the scene scale, times |i|).
+    const float ix = fminf(fmaxf(1.0f / (float)ray.d.x, -1e30f), 1e30f), iy = fminf(fmaxf(1.0f / (float)ray.d.y, -1e30f), 1e30f),
+                iz = fminf(fmaxf(1.0f / (float)ray.d.z, -1e30f), 1e30f);
+    const float nx = -(ox * ix), ny = -(oy * iy), nz = -(oz * iz);
+#else
     const float ix = 1.0f / (float)ray.d.x, iy = 1.0f / (float)ray.d.y, iz = 1.0f / (float)ray.d.z;
+#endif
     const float tlo = (float)mint * 0.999f, thi0 = (float)maxt * 1.001f;      // (+inf stays +inf)
     bool found = false;
     for (int base = 0; base < nP; base += 32) {
@@ -209,12 +235,21 @@ GDB_D bool closestPrimitive(const Ray &ray, Float mint, Float maxt, Float &tOut,
         unsigned mask = 0;
         for (int j = 0; j < cnt; j++) {
             const DBounds &B = c_bounds[base + j];
+#ifdef GDB_SLAB_FMA
+            const float ax = __fmaf_rn(B.lo[0], ix, nx), bx = __fmaf_rn(B.hi[0], ix, nx);
+            const float ay = __fmaf_rn(B.lo[1], iy, ny), by = __fmaf_rn(B.hi[1], iy, ny);
+            const float az = __fmaf_rn(B.lo[2], iz, nz), bz = __fmaf_rn(B.hi[2], iz, nz);
+            const float tn = fmaxf(fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz)), tlo);
+            const float tf = fminf(fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)), thi);
+            if (tn <= tf) mask |= 1u << j;
+#else
             const float ax = (B.lo[0] - ox) * ix, bx = (B.hi[0] - ox) * ix;
             const float ay = (B.lo[1] - oy) * iy, by = (B.hi[1] - oy) * iy;
             const float az = (B.lo[2] - oz) * iz, bz = (B.hi[2] - oz) * iz;
             const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
             const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
             if (tn <= tf && tf >= tlo && tn <= thi) mask |= 1u << j;
+#endif
         }
         // rectangles
         const int rEnd = min(max(nR - base, 0), 32), sEnd = min(max(nR + nS - base, 0), 32);
@@ -237,6 +272,51 @@ GDB_D bool closestPrimitive(const Ray &ray, Float mint, Float maxt, Float &tOut,
             if (triHit(g->tris[p - nR - nS], ray, mint, maxt, t, u, v)) { if (AnyHit) return true; maxt = t; found = true; kind = 2; index = p - nR - nS; uOut = u; vOut = v; }
         }
     }
+    if (c_scene.nBvhNodes > 0) {
+        // Large meshes: per-lane BVH2 walk (fp32 padded node bounds, children visited near to far), exact fp64
+        // triangle tests in the leaves.  Same answers as testing every triangle: the bounds are conservative.
+        const BvhNode *nodes = c_scene.bvh;
+#ifndef GDB_SLAB_FMA
+        const float nx = 0, ny = 0, nz = 0;
+#endif
+        auto slab = [&](const BvhNode &N, float thi, float &tnear) {
+#ifdef GDB_SLAB_FMA
+            const float ax = __fmaf_rn(N.lo[0], ix, nx), bx = __fmaf_rn(N.hi[0], ix, nx);
+            const float ay = __fmaf_rn(N.lo[1], iy, ny), by = __fmaf_rn(N.hi[1], iy, ny);
+            const float az = __fmaf_rn(N.lo[2], iz, nz), bz = __fmaf_rn(N.hi[2], iz, nz);
+#else
+            (void)nx; (void)ny; (void)nz;
+            const float ax = (N.lo[0] - ox) * ix, bx = (N.hi[0] - ox) * ix;
+            const float ay = (N.lo[1] - oy) * iy, by = (N.hi[1] - oy) * iy;
+            const float az = (N.lo[2] - oz) * iz, bz = (N.hi[2] - oz) * iz;
+#endif
+            const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+            const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+            tnear = tn;
+            return tn <= tf && tf >= tlo && tn <= thi;
+        };
+        int stack[64], sp = 0;
+        float t0;
+        if (slab(nodes[0], found ? (float)maxt * 1.001f : thi0, t0)) stack[sp++] = 0;
+        while (sp > 0) {
+            const BvhNode N = nodes[stack[--sp]];
+            const float thi = found ? (float)maxt * 1.001f : thi0;
+            if (N.b < 0) {
+                for (int p = N.a; p < N.a - N.b; p++) {
+                    Float t, u, v;
+                    if (triHit(c_scene.bvhTris[p], ray, mint, maxt, t, u, v)) { if (AnyHit) return true; maxt = t; found = true; kind = 3; index = p; uOut = u; vOut = v; }
+                }
+            } else {
+                float ta, tb;
+                const bool ha = slab(nodes[N.a], thi, ta), hb = slab(nodes[N.b], thi, tb);
+                if (ha && hb) {
+                    const bool aFirst = ta <= tb;
+                    if (sp + 2 <= 64) { stack[sp++] = aFirst ? N.b : N.a; stack[sp++] = aFirst ? N.a : N.b; }
+                } else if (ha) { if (sp < 64) stack[sp++] = N.a; }
+                else if (hb) { if (sp < 64) stack[sp++] = N.b; }
+            }
+        }
+    }
     tOut = maxt;
     return found;
 }
@@ -249,6 +329,7 @@ GDB_D bool closestPrimitiveExhaustive(const Ray &ray, Float mint, Float maxt, Fl
     for (int i = 0; i < c_scene.nRects; i++) { Float t; if (rectHit(c_scene.rects[i], ray, mint, maxt, t)) { if (AnyHit) return true; maxt = t; found = true; kind = 0; index = i; } }
     for (int i = 0; i < c_scene.nSpheres; i++) { Float t; if (sphereHit(c_scene.spheres[i], ray, mint, maxt, t)) { if (AnyHit) return true; maxt = t; found = true; kind = 1; index = i; } }
     for (int i = 0; i < c_scene.nTris; i++) { Float t, u, v; if (triHit(c_scene.tris[i], ray, mint, maxt, t, u, v)) { if (AnyHit) return true; maxt = t; found = true; kind = 2; index = i; uOut = u; vOut = v; } }
+    for (int i = 0; i < c_scene.nBvhTris; i++) { Float t, u, v; if (triHit(c_scene.bvhTris[i], ray, mint, maxt, t, u, v)) { if (AnyHit) return true; maxt = t; found = true; kind = 3; index = i; uOut = u; vOut = v; } }
     tOut = maxt;
     return found;
 }
@@ -264,8 +345,8 @@ GDB_CALL bool rayIntersect(const Ray &ray, Its &its)
     if (!closestPrimitive<false>(ray, rayMinT, ray.maxt, t, kind, index, u, v)) return false;
     its.t = t;
     V3 dpdu;
-    if (kind == 2) {                                                 // skdtree.h:348-419 (BarycentricPos)
-        const DTri &T = c_sceneG->tris[index];
+    if (kind >= 2) {                                                 // skdtree.h:348-419 (BarycentricPos)
+        const DTri &T = kind == 2 ? c_sceneG->tris[index] : c_scene.bvhTris[index];
         const V3 b = mk(1 - u - v, u, v);
         its.p = T.p0 * b.x + T.p1 * b.y + T.p2 * b.z;
         dpdu = T.p1 - T.p0;
@@ -480,6 +561,7 @@ GDB_D V3 refractLocal(const DMaterial &m, V3 wi, Float cosThetaT)               
 GDB_CALL void bsdfEvalPdf(const DMaterial &m, V3 wi, V3 wo, int measure, Spec &value, Float &pdf)
 {
     value = splat(0); pdf = 0;
+    if (m.twosided && !(wi.z > 0)) { wi.z *= -1; wo.z *= -1; }                         // twosided.cpp:109-135
     switch (m.type) {
     case GDB200_BSDF_DIFFUSE:                                                          // diffuse.cpp:110-129
         if (measure != ESolidAngle || wi.z <= 0 || wo.z <= 0) return;
@@ -504,6 +586,22 @@ GDB_CALL void bsdfEvalPdf(const DMaterial &m, V3 wi, V3 wo, int measure, Spec &v
         value = m.specR * fresnelConductorExact(wi.z, m.eta, m.k);
         pdf = 1.0;
         return;
+    case GDB200_BSDF_PLASTIC: {                                                        // plastic.cpp:243-302 (typeMask = EAll, component = -1)
+        if (wo.z <= 0 || wi.z <= 0) return;
+        Float dummy;
+        const Float Fi = fresnelDielectricExt(wi.z, dummy, m.iorRatio);
+        const Float probSpecular = (Fi * m.specSamplingWeight) / (Fi * m.specSamplingWeight + (1 - Fi) * (1 - m.specSamplingWeight));
+        if (measure == EDiscrete) {
+            if (fabs(dot(reflectLocal(wi), wo) - 1) < kDeltaEpsilon) { value = m.specR * Fi; pdf = probSpecular; }
+        } else {
+            const Float Fo = fresnelDielectricExt(wo.z, dummy, m.iorRatio);
+            Spec diff = m.reflectance;
+            if (m.nonlinear) diff = cdiv(diff, splat(1.0) - diff * m.fdrInt); else diff = diff / (1 - m.fdrInt);
+            value = diff * ((kInvPi * wo.z) * m.invEta2 * (1 - Fi) * (1 - Fo));
+            pdf = (kInvPi * wo.z) * (1 - probSpecular);
+        }
+        return;
+    }
     default: {                                                                         // dielectric.cpp:228-275
         Float cosThetaT;
         const Float F = fresnelDielectricExt(wi.z, cosThetaT, m.iorRatio);
@@ -523,7 +621,15 @@ GDB_CALL void bsdfEvalPdf(const DMaterial &m, V3 wi, V3 wo, int measure, Spec &v
 struct BSDFSample { V3 wo; Float eta; unsigned sampledType; Spec weight; Float pdf; };
 
 // BSDF::sample(bRec, pdf, sample), pdf pre-set to 0 by the caller (gpt.cpp:450-457)
+GDB_D void bsdfSampleOneSided(const DMaterial &m, V3 wi, Float sx, Float sy, BSDFSample &r);
 GDB_CALL void bsdfSample(const DMaterial &m, V3 wi, Float sx, Float sy, BSDFSample &r)
+{
+    const bool flipped = m.twosided && wi.z < 0;                                       // twosided.cpp:160-183
+    if (flipped) wi.z *= -1;
+    bsdfSampleOneSided(m, wi, sx, sy, r);
+    if (flipped && !isZero(r.weight) && r.pdf != 0) r.wo.z *= -1;
+}
+GDB_D void bsdfSampleOneSided(const DMaterial &m, V3 wi, Float sx, Float sy, BSDFSample &r)
 {
     r.weight = splat(0); r.pdf = 0; r.eta = 1.0; r.sampledType = 0; r.wo = mk(0, 0, 0);
     switch (m.type) {
@@ -554,6 +660,25 @@ GDB_CALL void bsdfSample(const DMaterial &m, V3 wi, Float sx, Float sy, BSDFSamp
         r.pdf = 1;
         r.weight = m.specR * fresnelConductorExact(wi.z, m.eta, m.k);
         return;
+    case GDB200_BSDF_PLASTIC: {                                                        // plastic.cpp:372-414
+        if (wi.z <= 0) return;
+        Float dummy;
+        const Float Fi = fresnelDielectricExt(wi.z, dummy, m.iorRatio);
+        const Float probSpecular = (Fi * m.specSamplingWeight) / (Fi * m.specSamplingWeight + (1 - Fi) * (1 - m.specSamplingWeight));
+        if (sx < probSpecular) {
+            r.sampledType = EDeltaReflection; r.wo = reflectLocal(wi); r.pdf = probSpecular;
+            r.weight = m.specR * Fi / probSpecular;
+        } else {
+            r.sampledType = EDiffuseReflection;
+            r.wo = squareToCosineHemisphere((sx - probSpecular) / (1 - probSpecular), sy);
+            const Float Fo = fresnelDielectricExt(r.wo.z, dummy, m.iorRatio);
+            Spec diff = m.reflectance;
+            if (m.nonlinear) diff = cdiv(diff, splat(1.0) - diff * m.fdrInt); else diff = diff / (1 - m.fdrInt);
+            r.pdf = (1 - probSpecular) * (kInvPi * r.wo.z);
+            r.weight = diff * (m.invEta2 * (1 - Fi) * (1 - Fo) / (1 - probSpecular));
+        }
+        return;
+    }
     default: {                                                                         // dielectric.cpp:277-305
         Float cosThetaT;
         const Float F = fresnelDielectricExt(wi.z, cosThetaT, m.iorRatio);
@@ -590,33 +715,160 @@ GDB_D void initDRec(const Its &ref, DRec &r)                                    
     r.refN = c_sceneG->materials[ref.material].refNFromShading ? ref.sh.n : mk(0, 0, 0);
 }
 
-// Scene::sampleEmitterDirectVisible, scene.cpp:855-879 (pmf.h:124-188, area.cpp:158-176,
-// shape.cpp:102-114, rectangle.cpp:210-216)
+// DiscreteDistribution::sampleReuse (pmf.h:124-188): std::lower_bound over the n+1 CDF entries, zero-probability
+// entries skipped, the sample rescaled into the chosen bin.
+GDB_D int cdfSampleReuse(const Float *cdf, int n, Float &s, Float &pdf)
+{
+    int lo = 0, len = n + 1;                                                           // first entry with !(cdf[i] < s)
+    while (len > 0) { const int half = len >> 1; if (cdf[lo + half] < s) { lo += half + 1; len -= half + 1; } else len = half; }
+    int index = min(n - 1, max(0, lo - 1));
+    while (cdf[index + 1] - cdf[index] == 0 && index < n) ++index;
+    pdf = cdf[index + 1] - cdf[index];
+    s = (s - cdf[index]) / (cdf[index + 1] - cdf[index]);
+    return index;
+}
+
+// ---- environment map (envmap.cpp); lookups on the top MIP level, u repeats / v clamps (mipmap.h:503-566)
+GDB_D Spec envTexel(int x, int y)
+{
+    const DEnv &e = c_scene.env;
+    if (x < 0 || x >= e.width) { x = x % e.width; if (x < 0) x += e.width; }
+    y = min(max(y, 0), e.height - 1);
+    const Float *t = e.texels + ((size_t)y * e.width + x) * 3;
+    return mk(t[0], t[1], t[2]);
+}
+GDB_HD Float luminance(Spec s) { return s.x * (Float)0.212671f + s.y * (Float)0.715160f + s.z * (Float)0.072169f; }   // spectrum.h:725-727
+GDB_D Float safeAcos(Float v) { return acos(fmin(1.0, fmax(-1.0, v))); }
+// EnvironmentMap::evalEnvironment without ray differentials (envmap.cpp:385-409, mipmap.h:575-596)
+GDB_CALL Spec envEval(V3 dWorld)
+{
+    const DEnv &e = c_scene.env;
+    const V3 v = xfVector(e.toObject, dWorld);
+    const Float uvx = atan2(v.x, -v.z) * kInvTwoPi, uvy = safeAcos(v.y) * kInvPi;
+    if (!isfinite(uvx) || !isfinite(uvy)) return splat(0);
+    const Float u = uvx * e.width - (Float)0.5f, w = uvy * e.height - (Float)0.5f;
+    const int xPos = (int)floor(u), yPos = (int)floor(w);
+    const Float dx1 = u - xPos, dx2 = (Float)1.0f - dx1, dy1 = w - yPos, dy2 = (Float)1.0f - dy1;
+    const Spec value = envTexel(xPos, yPos) * dx2 * dy2 + envTexel(xPos, yPos + 1) * dx2 * dy1
+                     + envTexel(xPos + 1, yPos) * dx1 * dy2 + envTexel(xPos + 1, yPos + 1) * dx1 * dy1;
+    return value * e.scale;
+}
+// envmap.cpp:611-642
+GDB_D Float envPdfDirection(V3 d)
+{
+    const DEnv &e = c_scene.env;
+    const Float uvx = atan2(d.x, -d.z) * kInvTwoPi, uvy = safeAcos(d.y) * kInvPi;
+    if (!isfinite(uvx) || !isfinite(uvy)) return 0.0;
+    const Float u = uvx * e.width - (Float)0.5f, v = uvy * e.height - (Float)0.5f;
+    const int xPos = (int)floor(u), yPos = (int)floor(v);
+    const Float dx1 = u - xPos, dx2 = (Float)1.0f - dx1, dy1 = v - yPos, dy2 = (Float)1.0f - dy1;
+    const Spec value1 = envTexel(xPos, yPos) * dx2 * dy2 + envTexel(xPos + 1, yPos) * dx1 * dy2;
+    const Spec value2 = envTexel(xPos, yPos + 1) * dx2 * dy1 + envTexel(xPos + 1, yPos + 1) * dx1 * dy1;
+    const Float sinTheta = sqrt(fmax(0.0, 1 - d.y * d.y));
+    return (luminance(value1) * e.rowWeights[min(max(yPos, 0), e.height - 1)] + luminance(value2) * e.rowWeights[min(max(yPos + 1, 0), e.height - 1)])
+           * e.normalization / fmax(fabs(sinTheta), kEpsilon);
+}
+// sampleReuse over a float CDF (envmap.cpp:660-665): the comparison is made in single precision
+GDB_D int envSampleReuse(const float *cdf, int size, Float &sample)
+{
+    const float key = (float)sample;
+    int lo = 0, len = size + 1;
+    while (len > 0) { const int half = len >> 1; if (cdf[lo + half] < key) { lo += half + 1; len -= half + 1; } else len = half; }
+    const int index = min(max(0, lo - 1), size - 1);
+    sample = (sample - (Float)cdf[index]) / (Float)(cdf[index + 1] - cdf[index]);
+    return index;
+}
+GDB_D Float intervalToTent(Float sample)                                              // warp.cpp:143-155
+{
+    Float sign;
+    if (sample < (Float)0.5f) { sign = 1; sample *= 2; } else { sign = -1; sample = 2 * (sample - (Float)0.5f); }
+    return sign * (1 - sqrt(sample));
+}
+// envmap.cpp:571-608
+GDB_D void envSampleDirection(Float sx, Float sy, V3 &d, Spec &value, Float &pdf)
+{
+    const DEnv &e = c_scene.env;
+    const int row = envSampleReuse(e.cdfRows, e.height, sy);
+    const int col = envSampleReuse(e.cdfCols + (size_t)row * (e.width + 1), e.width, sx);
+    const Float posx = (Float)col + intervalToTent(sx), posy = (Float)row + intervalToTent(sy);
+    const int xPos = (int)floor(posx), yPos = (int)floor(posy);
+    const Float dx1 = posx - xPos, dx2 = (Float)1.0f - dx1, dy1 = posy - yPos, dy2 = (Float)1.0f - dy1;
+    const Spec value1 = envTexel(xPos, yPos) * dx2 * dy2 + envTexel(xPos + 1, yPos) * dx1 * dy2;
+    const Spec value2 = envTexel(xPos, yPos + 1) * dx2 * dy1 + envTexel(xPos + 1, yPos + 1) * dx1 * dy1;
+    value = (value1 + value2) * e.scale;
+    pdf = (luminance(value1) * e.rowWeights[min(max(yPos, 0), e.height - 1)] + luminance(value2) * e.rowWeights[min(max(yPos + 1, 0), e.height - 1)]) * e.normalization;
+    const Float phi = e.pixelSizeX * (posx + (Float)0.5f), theta = e.pixelSizeY * (posy + (Float)0.5f);
+    const Float sinPhi = sin(phi), cosPhi = cos(phi), sinTheta = sin(theta), cosTheta = cos(theta);
+    d = mk(sinPhi * sinTheta, cosTheta, -cosPhi * sinTheta);
+    pdf /= fmax(fabs(sinTheta), kEpsilon);
+}
+// BSphere::rayIntersect (bsphere.h:88-95)
+GDB_D bool envSphereIntersect(V3 o, V3 d, Float &nearT, Float &farT)
+{
+    const V3 oc = o - c_scene.env.center;
+    return solveQuadratic(len2(d), 2 * dot(oc, d), len2(oc) - c_scene.env.radius * c_scene.env.radius, nearT, farT);
+}
+// EnvironmentMap::fillDirectSamplingRecord (envmap.cpp:358-374)
+GDB_D bool envFillDRec(DRec &dRec, V3 o, V3 d)
+{
+    Float nearT, farT;
+    if (!envSphereIntersect(o, d, nearT, farT) || nearT > 0 || farT < 0) return false;
+    dRec.p = o + d * farT;
+    dRec.n = normalize(c_scene.env.center - dRec.p);
+    dRec.d = d; dRec.dist = farT; dRec.emitter = c_scene.env.emitter;
+    return true;
+}
+
+// Scene::sampleEmitterDirectVisible, scene.cpp:855-879: emitter pick (pmf.h:124-188), Emitter::sampleDirect
+// (area.cpp:158-176 over shape.cpp:102-114 with rectangle.cpp:210-216 / trimesh.cpp:412-423 + triangle.cpp:24-50;
+// envmap.cpp:516-544), then the shadow ray.
 GDB_CALL Spec sampleEmitterDirectVisible(DRec &dRec, Float sx, Float sy, bool &visible)
 {
-    const int nE = c_scene.nEmitters;
-    int entry = 0;                                                                     // std::lower_bound over the CDF
-    while (entry <= nE && c_scene.emCdf[entry] < sx) entry++;
-    int index = min(nE - 1, max(0, entry - 1));
-    while (c_scene.emCdf[index + 1] - c_scene.emCdf[index] == 0 && index < nE) ++index;
-    const Float emPdf = c_scene.emCdf[index + 1] - c_scene.emCdf[index];
-    sx = (sx - c_scene.emCdf[index]) / (c_scene.emCdf[index + 1] - c_scene.emCdf[index]);
-
-    const DEmitter &em = c_scene.emitters[index];
-    const DRect &s = c_scene.rects[em.rect];
-    dRec.p = xfAffine(s.toWorld, mk(sx * 2 - 1, sy * 2 - 1, 0));
-    dRec.n = s.n;
-    dRec.pdf = s.invArea;
-    dRec.d = dRec.p - dRec.ref;
-    const Float distSquared = len2(dRec.d);
-    dRec.dist = sqrt(distSquared);
-    dRec.d = dRec.d / dRec.dist;
-    const Float dp = fabs(dot(dRec.d, dRec.n));
-    dRec.pdf *= dp != 0 ? (distSquared / dp) : 0.0;
+    Float emPdf;
+    const int index = cdfSampleReuse(c_scene.emCdf, c_scene.nEmitters, sx, emPdf);
+    const DEmitter &em = c_sceneG->emitters[index];
     Spec value;
-    if (dot(dRec.d, dRec.refN) >= 0 && dot(dRec.d, dRec.n) < 0 && dRec.pdf != 0) value = em.radiance / dRec.pdf;
-    else { dRec.pdf = 0.0; value = splat(0); }
     dRec.emitter = index;
+    if (em.kind == EM_ENV) {
+        V3 dl; Float pdf; Spec v;
+        envSampleDirection(sx, sy, dl, v, pdf);
+        const V3 dw = xfVector(c_scene.env.toWorld, dl);
+        Float nearT = 0, farT = 0;
+        if (isZero(v) || pdf == 0 || !envSphereIntersect(dRec.ref, dw, nearT, farT) || nearT >= 0 || farT <= 0) {
+            // The reference leaves p/d/dist unset here and still traces its shadow ray with them; unreachable for
+            // maps without black texels seen from inside the bounding sphere.  Defined as: no contribution.
+            dRec.pdf = 0.0; dRec.p = dRec.ref; dRec.n = mk(0, 0, 0); dRec.d = mk(0, 0, 1); dRec.dist = 0;
+            visible = true;
+            return splat(0);
+        }
+        dRec.pdf = pdf; dRec.p = dRec.ref + dw * farT; dRec.n = normalize(c_scene.env.center - dRec.p); dRec.dist = farT; dRec.d = dw;
+        value = v / pdf;
+    } else {
+        if (em.kind == EM_RECT) {
+            const DRect &s = c_sceneG->rects[em.rect];
+            dRec.p = xfAffine(s.toWorld, mk(sx * 2 - 1, sy * 2 - 1, 0));
+            dRec.n = s.n;
+            dRec.pdf = s.invArea;
+        } else {                                                                     // trimesh.cpp:412-423
+            Float triPdf;
+            const int tri = cdfSampleReuse(c_scene.emTriCdf + em.cdfFirst, em.triCount, sy, triPdf);
+            const DEmTri &T = c_scene.emTris[em.triFirst + tri];
+            const Float a = sqrt(fmax(0.0, (Float)1.0f - sx));                           // warp.cpp:76-79
+            const Float bx = 1 - a, by = a * sy;
+            const V3 sideA = T.p1 - T.p0, sideB = T.p2 - T.p0;
+            dRec.p = T.p0 + (sideA * bx) + (sideB * by);
+            dRec.n = normalize(cross(sideA, sideB));
+            dRec.pdf = em.invArea;
+        }
+        dRec.d = dRec.p - dRec.ref;                                                  // shape.cpp:102-114
+        const Float distSquared = len2(dRec.d);
+        dRec.dist = sqrt(distSquared);
+        dRec.d = dRec.d / dRec.dist;
+        const Float dp = fabs(dot(dRec.d, dRec.n));
+        dRec.pdf *= dp != 0 ? (distSquared / dp) : 0.0;
+        if (dot(dRec.d, dRec.refN) >= 0 && dot(dRec.d, dRec.n) < 0 && dRec.pdf != 0) value = em.radiance / dRec.pdf;   // area.cpp:158-176
+        else { dRec.pdf = 0.0; value = splat(0); }
+    }
     dRec.pdf *= emPdf;
     value = value / emPdf;
     Ray ray; ray.o = dRec.ref; ray.d = dRec.d; ray.mint = kEpsilon; ray.maxt = dRec.dist * (1 - kShadowEpsilon);
@@ -625,13 +877,16 @@ GDB_CALL Spec sampleEmitterDirectVisible(DRec &dRec, Float sx, Float sy, bool &v
     return value;
 }
 
-// Scene::pdfEmitterDirect, scene.cpp:976-979 + area.cpp:178-186 + shape.cpp:116-126
+// Scene::pdfEmitterDirect, scene.cpp:976-979 + area.cpp:178-186 + shape.cpp:116-126 / envmap.cpp:546-556
 GDB_D Float pdfEmitterDirect(const DRec &dRec)
 {
-    const DEmitter &em = c_scene.emitters[dRec.emitter];
+    const DEmitter &em = c_sceneG->emitters[dRec.emitter];
     Float pdf = 0.0;
-    if (dot(dRec.d, dRec.refN) >= 0 && dot(dRec.d, dRec.n) < 0)
-        pdf = c_scene.rects[em.rect].invArea * (dRec.dist * dRec.dist) / fabs(dot(dRec.d, dRec.n));
+    if (em.kind == EM_ENV) pdf = envPdfDirection(xfVector(c_scene.env.toObject, dRec.d));
+    else if (dot(dRec.d, dRec.refN) >= 0 && dot(dRec.d, dRec.n) < 0) {
+        const Float invArea = em.kind == EM_RECT ? c_sceneG->rects[em.rect].invArea : em.invArea;
+        pdf = invArea * (dRec.dist * dRec.dist) / fabs(dot(dRec.d, dRec.n));
+    }
     return pdf * em.pdfDiscrete;
 }
 
@@ -683,6 +938,19 @@ GDB_D ShiftResult reconnectShift(V3 mainSource, V3 target, V3 shiftSource, V3 ta
     const Float shiftedOpposingCosine = dot(shiftedWo, targetNormal);
     result.jacobian = fabs(shiftedOpposingCosine * mainL2) / (kDEps + fabs(mainOpposingCosine * shiftedL2));
     result.success = true; result.wo = shiftedWo;
+    return result;
+}
+
+// environmentShift + testEnvironmentVisibility (gpt.cpp:96-114, 348-369): the offset vertex must see the environment
+// in the base path's direction; J = 1.
+GDB_D ShiftResult environmentShift(V3 mainD, V3 shiftSource)
+{
+    ShiftResult result; result.success = false; result.jacobian = 0; result.wo = mk(0, 0, 0);
+    DRec dr; dr.dist = 0;
+    envFillDRec(dr, shiftSource, mainD);
+    Ray r; r.o = shiftSource; r.d = mainD; r.mint = kEpsilon; r.maxt = (1.0 - kShadowEpsilon) * dr.dist;
+    if (rayOccluded(r)) return result;
+    result.success = true; result.jacobian = 1; result.wo = mainD;
     return result;
 }
 

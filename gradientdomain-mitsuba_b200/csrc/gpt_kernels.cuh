@@ -46,6 +46,12 @@ GDB_D double &W(const GptArgs &a, int rec, int slot) { return REC(a, rec, slot)[
 // int fields of a slot share one 64-byte line [slot][16] (fields 0-7 in its first sector), so a kernel pulls one
 // sector per slot instead of one per field; the per-pixel sampler key is recomputed, not stored.
 GDB_D int &SI(const GptArgs &a, int field, int slot) { return a.si[((size_t)slot << 4) + field]; }
+GDB_D void prefetchL2(const void *p)
+{
+#ifndef GDB200_EMU
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
 GDB_D V3 ldv(const GptArgs &a, int rec, int slot)
 {
     const double2 *p = reinterpret_cast<const double2 *>(REC(a, rec, slot));
@@ -232,7 +238,8 @@ GDB_D void generateBody(const GptArgs &a, int slot)
         const bool mainValid = rayIntersect(ray, mits); rays += 5;                   // gpt.cpp:472
         Spec veryDirect = splat(0);
         unsigned flags = 0;
-        bool early = !mainValid;                                                     // gpt.cpp:482-492 (no environment emitter)
+        bool early = !mainValid;                                                     // gpt.cpp:482-492
+        if (!mainValid && c_scene.env.present) veryDirect = veryDirect + splat(1.0) * envEval(ray.d);   // gpt.cpp:486-488 (looked up without ray differentials)
         if (mainValid && mits.emitter >= 0) veryDirect = veryDirect + splat(1.0) * emittedLe(mits, -ray.d);   // gpt.cpp:497-499
         if (mainValid && a.cfg.strictNormals && dot(ray.d, mits.geoN) * mits.wi.z >= 0) early = true;          // gpt.cpp:518-521
         const Float shiftX[4] = {1, 0, -1, 0}, shiftY[4] = {0, 1, 0, -1};            // gpt.cpp:410-415
@@ -296,6 +303,24 @@ GDB_D void bounceBody(const GptArgs &a, int slot, int parity)
     if (PHASE == 1 && SI(a, IF_STATUS, slot) != ST_LIVE) return;      // ended in phase 0 (strictNormals)
     const Config cfg = a.cfg;
 
+#ifdef GDB_PREFETCH
+    // The offset paths' records are read one offset at a time further down (each read a full DRAM round trip on
+    // the critical path of this thread): request their sectors now so those reads hit L2.
+    {
+        const unsigned f0 = (unsigned)SI(a, IF_OFLAGS, slot);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (!flagAlive(f0, i)) continue;
+            const int o = BR_COUNT + i * OR_COUNT;
+            prefetchL2(REC(a, o + OR_THR, slot)); prefetchL2(REC(a, o + OR_RAD, slot)); prefetchL2(REC(a, o + OR_GRAD, slot));
+            if (flagConn(f0, i) != RAY_CONNECTED) prefetchL2(REC(a, o + OR_P, slot));
+            if (flagConn(f0, i) == RAY_NOT_CONNECTED) {
+                prefetchL2(REC(a, o + OR_GN, slot)); prefetchL2(REC(a, o + OR_S, slot)); prefetchL2(REC(a, o + OR_T, slot));
+                prefetchL2(REC(a, o + OR_N, slot)); prefetchL2(REC(a, o + OR_WI, slot));
+            }
+        }
+    }
+#endif
     Its mits; loadBaseIts(a, slot, mits);
     V3 mrayD; Float mpdf;
     ldvw(a, BR_RAYD, slot, mrayD, mpdf);
@@ -353,7 +378,7 @@ GDB_D void bounceBody(const GptArgs &a, int slot, int parity)
         }
 
         // ---------------- base path: BSDF sample + extension, gpt.cpp:737-820
-        bool bsdfStage = false, mainHitEmitter = false;
+        bool bsdfStage = false, mainHitEmitter = false, escaped = false;
         BSDFSample bs;
         bs.weight = splat(0); bs.pdf = 0; bs.eta = 1.0; bs.sampledType = 0; bs.wo = mk(0, 0, 0);
         if (kBsdf) { const Float sx = smp.next1D(), sy = smp.next1D(); bsdfSample(mainBSDF, mits.wi, sx, sy, bs); }   // gpt.cpp:456-457
@@ -370,16 +395,23 @@ GDB_D void bounceBody(const GptArgs &a, int slot, int parity)
                 mainVertexType = vertexType(mainBSDF, bs.sampledType);               // gpt.cpp:764
                 Ray mray; mray.o = mits.p; mray.d = mainWo; mray.mint = kEpsilon; mray.maxt = CUDART_INF;   // gpt.cpp:767
                 rays++;
-                if (!rayIntersect(mray, mits)) ended = true;                         // gpt.cpp:800-803 (no environment emitter)
-                else {
+                if (rayIntersect(mray, mits)) {
                     bsdfStage = true;
-                    mrayD = mainWo;
                     if (mits.emitter >= 0) {                                         // gpt.cpp:771-776
                         mainEmitterRadiance = emittedLe(mits, -mainWo);
                         mainDRec.p = mits.p; mainDRec.n = mits.sh.n; mainDRec.d = mainWo; mainDRec.dist = mits.t; mainDRec.emitter = mits.emitter;
                         mainHitEmitter = true;
                     }
                     mainNextVertexType = vertexType(c_sceneG->materials[mits.material], bs.sampledType);   // gpt.cpp:784
+                } else if (c_scene.env.present) {                                    // gpt.cpp:786-799: the base path left the scene
+                    mainEmitterRadiance = envEval(mainWo);
+                    if (envFillDRec(mainDRec, mray.o, mainWo)) {
+                        bsdfStage = true; escaped = true; mainHitEmitter = true;
+                        mainNextVertexType = VERTEX_TYPE_DIFFUSE;                    // "environment connection as diffuse"
+                    } else ended = true;
+                } else ended = true;                                                 // gpt.cpp:800-803
+                if (bsdfStage) {
+                    mrayD = mainWo;
                     const Float mainPreviousPdf = mpdf;                              // gpt.cpp:807-812
                     mthr = mthr * (bs.weight * bs.pdf);
                     mpdf *= bs.pdf;
@@ -494,7 +526,9 @@ GDB_D void bounceBody(const GptArgs &a, int slot, int parity)
                         const int shiftedVertexType = vertexType(shiftedBSDF, bs.sampledType);
                         if (mainVertexType == VERTEX_TYPE_DIFFUSE && mainNextVertexType == VERTEX_TYPE_DIFFUSE && shiftedVertexType == VERTEX_TYPE_DIFFUSE) {
                             if (!lastSegment || mainHitEmitter) {                    // gpt.cpp:901
-                                const ShiftResult sr = reconnectShift(prevP, mits.p, sits.p, mits.geoN); rays++;   // gpt.cpp:907
+                                const ShiftResult sr = escaped ? environmentShift(mrayD, sits.p)                   // gpt.cpp:908-915
+                                                               : reconnectShift(prevP, mits.p, sits.p, mits.geoN); // gpt.cpp:907
+                                rays++;
                                 if (!sr.success) alive = false;
                                 else {
                                     const V3 outgoingDirection = sr.wo;
@@ -507,13 +541,16 @@ GDB_D void bounceBody(const GptArgs &a, int slot, int parity)
                                         spdf *= shiftedBsdfPdf * sr.jacobian;
                                         conn = RAY_RECENTLY_CONNECTED;
                                         if (mainHitEmitter) {                        // gpt.cpp:944-985
-                                            const Spec shiftedEmitterRadiance = emittedLe(mits, -outgoingDirection);
-                                            DRec sd;                                 // gpt.cpp:957-964 (measure: solid angle)
-                                            sd.p = mainDRec.p; sd.n = mainDRec.n;
-                                            sd.dist = len(mainDRec.p - sits.p);
-                                            sd.d = (mainDRec.p - sits.p) / sd.dist;
-                                            sd.ref = mainDRec.ref; sd.refN = sits.sh.n; sd.emitter = mainDRec.emitter;
-                                            const Float shiftedLumPdf = pdfEmitterDirect(sd);
+                                            Spec shiftedEmitterRadiance; Float shiftedLumPdf;
+                                            if (!escaped) {
+                                                shiftedEmitterRadiance = emittedLe(mits, -outgoingDirection);
+                                                DRec sd;                             // gpt.cpp:957-964 (measure: solid angle)
+                                                sd.p = mainDRec.p; sd.n = mainDRec.n;
+                                                sd.dist = len(mainDRec.p - sits.p);
+                                                sd.d = (mainDRec.p - sits.p) / sd.dist;
+                                                sd.ref = mainDRec.ref; sd.refN = sits.sh.n; sd.emitter = mainDRec.emitter;
+                                                shiftedLumPdf = pdfEmitterDirect(sd);
+                                            } else { shiftedEmitterRadiance = mainEmitterRadiance; shiftedLumPdf = mainLumPdf; }   // gpt.cpp:973-977
                                             const Float den = (shiftedPreviousPdf * shiftedPreviousPdf) * ((shiftedLumPdf * shiftedLumPdf) + (shiftedBsdfPdf * shiftedBsdfPdf));
                                             weight = mainWeightNumerator / (kDEps + den + mainWeightDenominator);
                                             mainContribution = mainContributionAll;
@@ -547,7 +584,11 @@ GDB_D void bounceBody(const GptArgs &a, int slot, int parity)
                                         const int shiftedVertexType2 = vertexType(shiftedBSDF, bs.sampledType);   // gpt.cpp:1047
                                         Ray sray; sray.o = sits.p; sray.d = outgoingDirection; sray.mint = kEpsilon; sray.maxt = CUDART_INF;   // gpt.cpp:1050
                                         rays++;
-                                        if (!rayIntersect(sray, sits)) ok = false;   // gpt.cpp:1052-1058 (no environment emitter)
+                                        if (!rayIntersect(sray, sits)) {             // gpt.cpp:1052-1074
+                                            if (!c_scene.env.present || !escaped) ok = false;                      // no env, or env vs non-env
+                                            else if (mainVertexType == VERTEX_TYPE_DIFFUSE && shiftedVertexType2 == VERTEX_TYPE_DIFFUSE) ok = false;
+                                            else { shiftedEmitterRadiance = envEval(sray.d); postponedShiftEnd = true; }
+                                        } else if (escaped) ok = false;               // gpt.cpp:1078-1082
                                         else {
                                             const int shiftedNextVertexType = vertexType(c_sceneG->materials[sits.material], bs.sampledType);
                                             if (mainVertexType == VERTEX_TYPE_DIFFUSE && shiftedVertexType2 == VERTEX_TYPE_DIFFUSE && shiftedNextVertexType == VERTEX_TYPE_DIFFUSE) ok = false;   // gpt.cpp:1089-1093
@@ -596,6 +637,7 @@ GDB_D void bounceBody(const GptArgs &a, int slot, int parity)
         if (bHas & 4u) mrad = mrad + mainContributionAll * bw2;
         if (bHas & 8u) mrad = mrad + mainContributionAll * bw3;
 
+        if (kBsdf && escaped) ended = true;                                          // gpt.cpp:1153-1157
         if (kBsdf && !ended) {
             if (depth++ >= cfg.rrDepth) {                                            // gpt.cpp:1159-1174
                 const Float q = fmin(maxComp(mthr / mpdf) * meta * meta, (Float)0.95f);
@@ -626,8 +668,11 @@ GDB_D void bounceBody(const GptArgs &a, int slot, int parity)
     }
 }
 
+#ifndef GDB_BOUNCE_MINBLOCKS
+#define GDB_BOUNCE_MINBLOCKS 2      // resident CTAs/SM the register allocation is sized for (2 => 255 registers)
+#endif
 template <int PHASE>
-__global__ void __launch_bounds__(kBounceThreads) gpt_bounce_kernel(const GptArgs a, int parity)
+__global__ void __launch_bounds__(kBounceThreads, GDB_BOUNCE_MINBLOCKS) gpt_bounce_kernel(const GptArgs a, int parity)
 {
     // thread -> (BSDF-type bucket, index).  Buckets are padded to whole warps so a warp shades one BSDF
     // type; inside a bucket the slots are in ascending pixel order (gpt_compact_kernel), so the
@@ -728,11 +773,12 @@ __global__ void gpt_check_culling_kernel(unsigned long long seed, int nRays, uns
     if (g >= nRays) return;
     Sampler smp; smp.key = samplerKey(seed, g, 12345); smp.n = 0;
     auto surfacePoint = [&]() {
-        const int nR = c_scene.nRects, nT = c_scene.nTris, nS = c_scene.nSpheres;
-        const int pick = min(nR + nT + nS - 1, (int)(smp.next1D() * (nR + nT + nS)));
+        const int nR = c_scene.nRects, nT = c_scene.nTris, nS = c_scene.nSpheres, nB = c_scene.nBvhTris;
+        const int pick = min(nR + nT + nS + nB - 1, (int)(smp.next1D() * (nR + nT + nS + nB)));
         const Float u = smp.next1D(), v = smp.next1D();
         if (pick < nR) return xfAffine(c_sceneG->rects[pick].toWorld, mk(2 * u - 1, 2 * v - 1, 0));
         if (pick < nR + nT) { const DTri &T = c_sceneG->tris[pick - nR]; const Float a = sqrt(u); return T.p0 * (1 - a) + T.p1 * (a * (1 - v)) + T.p2 * (a * v); }
+        if (pick >= nR + nT + nS) { const DTri &T = c_scene.bvhTris[pick - nR - nT - nS]; const Float a = sqrt(u); return T.p0 * (1 - a) + T.p1 * (a * (1 - v)) + T.p2 * (a * v); }
         const DSphere &sp = c_sceneG->spheres[pick - nR - nT];
         const Float z = 1 - 2 * u, r = sqrt(fmax(0.0, 1 - z * z)), phi = 2 * kPi * v;
         return sp.center + mk(r * cos(phi), r * sin(phi), z) * sp.radius;
@@ -758,7 +804,7 @@ __global__ void gpt_check_culling_kernel(unsigned long long seed, int nRays, uns
     const bool a1 = closestPrimitive<true>(ray, rayMinT, ray.maxt, tt, kk, ii, uu, vv);
     const bool a2 = closestPrimitiveExhaustive<true>(ray, rayMinT, ray.maxt, tt, kk, ii, uu, vv);
     bool bad = (h1 != h2) || (a1 != a2) || (h1 != a1);
-    if (h1 && h2) bad = bad || t1 != t2 || k1 != k2 || i1 != i2 || (k1 == 2 && (u1 != u2 || v1 != v2));
+    if (h1 && h2) bad = bad || t1 != t2 || k1 != k2 || i1 != i2 || (k1 >= 2 && (u1 != u2 || v1 != v2));
     if (bad) atomicAdd(mismatch, 1ULL);
     if (h1) atomicAdd(mismatch + 1, 1ULL);
 }

@@ -11,7 +11,8 @@ import math
 import numpy as np
 
 SHAPE_RECTANGLE, SHAPE_SPHERE, SHAPE_MESH = 0, 1, 2
-BSDF_DIFFUSE, BSDF_ROUGHCONDUCTOR, BSDF_CONDUCTOR, BSDF_DIELECTRIC = 0, 1, 2, 3
+BSDF_DIFFUSE, BSDF_ROUGHCONDUCTOR, BSDF_CONDUCTOR, BSDF_DIELECTRIC, BSDF_PLASTIC = 0, 1, 2, 3, 4
+EMITTER_AREA, EMITTER_ENVMAP = 0, 1
 MICROFACET_BECKMANN, MICROFACET_GGX = 0, 1
 
 D16 = ctypes.c_double * 16
@@ -32,12 +33,19 @@ class Shape(ctypes.Structure):
 class Material(ctypes.Structure):
     _fields_ = [("type", ctypes.c_int), ("distribution", ctypes.c_int), ("reflectance", D3),
                 ("specular_reflectance", D3), ("specular_transmittance", D3), ("eta", D3), ("k", D3),
-                ("alpha", ctypes.c_double), ("ior_ratio", ctypes.c_double)]
+                ("alpha", ctypes.c_double), ("ior_ratio", ctypes.c_double), ("twosided", ctypes.c_int),
+                ("nonlinear", ctypes.c_int)]
 
 
 class Emitter(ctypes.Structure):
-    _fields_ = [("shape", ctypes.c_int), ("reserved", ctypes.c_int), ("radiance", D3),
+    _fields_ = [("shape", ctypes.c_int), ("type", ctypes.c_int), ("radiance", D3),
                 ("sampling_weight", ctypes.c_double)]
+
+
+class EnvMap(ctypes.Structure):
+    _fields_ = [("width", ctypes.c_int), ("height", ctypes.c_int), ("rgb", ctypes.POINTER(ctypes.c_float)),
+                ("scale", ctypes.c_double), ("to_world", D16), ("to_object", D16), ("bsphere_center", D3),
+                ("bsphere_radius", ctypes.c_double)]
 
 
 class SceneDesc(ctypes.Structure):
@@ -45,7 +53,8 @@ class SceneDesc(ctypes.Structure):
                 ("n_materials", ctypes.c_int), ("n_emitters", ctypes.c_int), ("n_vertices", ctypes.c_int),
                 ("n_triangles", ctypes.c_int), ("shapes", ctypes.POINTER(Shape)),
                 ("materials", ctypes.POINTER(Material)), ("emitters", ctypes.POINTER(Emitter)),
-                ("vertices", ctypes.POINTER(ctypes.c_double)), ("triangles", ctypes.POINTER(ctypes.c_int))]
+                ("vertices", ctypes.POINTER(ctypes.c_double)), ("triangles", ctypes.POINTER(ctypes.c_int)),
+                ("envmap", ctypes.POINTER(EnvMap))]
 
 
 class GPTParams(ctypes.Structure):
@@ -116,6 +125,29 @@ class SceneBuilder:
         self.rfilter_radius = rfilter_radius + 1e-5      # box.cpp:38
         self.shapes, self.materials, self.emitters, self.vertices, self.triangles = [], [], [], [], []
 
+    def envmap(self, rgb, scale=1.0, to_world=None, sampling_weight=1.0):
+        """Environment emitter (envmap.cpp) from a float32 lat-long image [h, w, 3] (row 0 = +y pole)."""
+        self._env_rgb = np.ascontiguousarray(rgb, dtype=np.float32)
+        self._env_scale, self._env_to_world = float(scale), (np.eye(4) if to_world is None else np.asarray(to_world, float))
+        e = Emitter()
+        e.shape, e.type, e.radiance, e.sampling_weight = -1, EMITTER_ENVMAP, D3(0, 0, 0), sampling_weight
+        self.emitters.append(e)
+        return len(self.emitters) - 1
+
+    def _bounds(self):
+        """Scene::getAABB as EnvironmentMap::createShape sees it (scene.cpp:386-396): all shapes + the camera position."""
+        pts = [np.array(self.camera.camera_to_world[3:12:4])]
+        for sh in self.shapes:
+            if sh.type == SHAPE_RECTANGLE:
+                m = np.array(sh.to_world).reshape(4, 4)
+                pts += [(m @ np.array([sx, sy, 0, 1.0]))[:3] for sx in (-1, 1) for sy in (-1, 1)]
+            elif sh.type == SHAPE_SPHERE:
+                c = np.array(sh.center)
+                pts += [c - sh.radius, c + sh.radius]
+        pts += [np.asarray(v, float) for v in self.vertices]
+        pts = np.array(pts)
+        return pts.min(axis=0), pts.max(axis=0)
+
     def material(self, **kw):
         m = Material()
         m.type = kw.get("type", BSDF_DIFFUSE)
@@ -127,6 +159,7 @@ class SceneBuilder:
         m.k = D3(*kw.get("k", (1.0, 1.0, 1.0)))
         m.alpha = kw.get("alpha", 0.1)
         m.ior_ratio = kw.get("ior_ratio", 1.5046 / 1.000277)
+        m.twosided, m.nonlinear = int(kw.get("twosided", False)), int(kw.get("nonlinear", False))
         self.materials.append(m)
         return len(self.materials) - 1
 
@@ -155,6 +188,22 @@ class SceneBuilder:
         sh.type, sh.material, sh.emitter, sh.flip_normals = SHAPE_SPHERE, material, -1, int(flip_normals)
         sh.center, sh.radius = D3(*center), radius
         self.shapes.append(sh)
+        return len(self.shapes) - 1
+
+    def mesh(self, vertices, triangles, material, radiance=None):
+        """Flat-shaded TriMesh (no vertex normals); with `radiance` it carries an area emitter (area.cpp on a TriMesh)."""
+        base, first = len(self.vertices), len(self.triangles)
+        self.vertices.extend(np.asarray(v, float) for v in vertices)
+        self.triangles.extend((base + a, base + b, base + c) for a, b, c in triangles)
+        sh = Shape()
+        sh.type, sh.material, sh.emitter = SHAPE_MESH, material, -1
+        sh.first_tri, sh.tri_count = first, len(self.triangles) - first
+        self.shapes.append(sh)
+        if radiance is not None:
+            e = Emitter()
+            e.shape, e.type, e.radiance, e.sampling_weight = len(self.shapes) - 1, EMITTER_AREA, D3(*radiance), 1.0
+            self.emitters.append(e)
+            sh.emitter = len(self.emitters) - 1
         return len(self.shapes) - 1
 
     def box(self, center, half, rot_y_deg, material):
@@ -191,6 +240,18 @@ class SceneBuilder:
         d.shapes, d.materials, d.emitters = self._keep[0], self._keep[1], self._keep[2]
         d.vertices = ctypes.cast(self._keep[3], ctypes.POINTER(ctypes.c_double))
         d.triangles = ctypes.cast(self._keep[4], ctypes.POINTER(ctypes.c_int))
+        if getattr(self, "_env_rgb", None) is not None:
+            env = EnvMap()
+            env.height, env.width = self._env_rgb.shape[:2]
+            env.rgb = self._env_rgb.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+            env.scale = self._env_scale
+            env.to_world = D16(*self._env_to_world.reshape(-1))
+            env.to_object = D16(*np.linalg.inv(self._env_to_world).reshape(-1))
+            lo, hi = self._bounds()
+            center = (lo + hi) / 2                                   # AABB::getBSphere (aabb.cpp:44-47), radius * 1.5 (envmap.cpp:327)
+            env.bsphere_center, env.bsphere_radius = D3(*center), max(1e-7, float(np.linalg.norm(center - hi)) * 1.5)
+            self._env = env
+            d.envmap = ctypes.pointer(env)
         d._owner = self      # keep the arrays alive as long as the descriptor
         return d
 
@@ -248,6 +309,101 @@ def cbox_glossy(width=1024, height=1024, delta_variant=False):
         shiny = b.material(type=BSDF_ROUGHCONDUCTOR, alpha=0.0005, eta=AL_ETA, k=AL_K)
     b.sphere((0.33, -0.1, 0.35), 0.3, rough)
     b.sphere((-0.5, -0.7, 0.55), 0.3, shiny)
+    return b.build()
+
+
+def sky_envmap(width=64, height=32, sun=(0.35, 0.8, 0.5), sun_radiance=60.0):
+    """Procedural lat-long environment map (strictly positive): gradient sky + a soft sun disc, float32 [h, w, 3]."""
+    v, u = np.meshgrid((np.arange(height) + 0.5) / height, (np.arange(width) + 0.5) / width, indexing="ij")
+    theta, phi = v * math.pi, u * 2 * math.pi
+    d = np.stack([np.sin(phi) * np.sin(theta), np.cos(theta), -np.cos(phi) * np.sin(theta)], axis=-1)   # envmap.cpp:604
+    up = np.clip(d[..., 1], -1, 1)
+    sky = np.stack([0.35 + 0.25 * (1 - up), 0.5 + 0.2 * (1 - up), 0.9 + 0.0 * up], axis=-1) * (0.35 + 0.65 * np.clip(up + 0.2, 0, 1))[..., None]
+    ground = np.array([0.12, 0.1, 0.08])
+    img = np.where((up < 0)[..., None], ground * (1 + up[..., None] * 0.5), sky)
+    s = np.asarray(sun, float) / np.linalg.norm(sun)
+    img = img + sun_radiance * np.exp(-((1 - d @ s) / 0.02))[..., None] * np.array([1.0, 0.9, 0.7])
+    return np.ascontiguousarray(np.maximum(img, 1e-3), dtype=np.float32)
+
+
+def cbox_env(width=256, height=256):
+    """Environment-lit coverage scene (environmentShift, gpt.cpp:348-369): the Cornell box without its ceiling and
+    front, lit by a sky map plus the small area light; a near-mirror GGX sphere and a smooth conductor so that
+    half-vector-shifted offset paths leave the scene too, a glass sphere, one diffuse box."""
+    cam = make_camera(width, height, origin=(0, 0.2, 3.9), target=(0, -0.1, 0), up=(0, 1, 0), fov_deg=39.3077)
+    b = SceneBuilder(cam)
+    white, red, green = b.material(reflectance=WHITE), b.material(reflectance=RED), b.material(reflectance=GREEN)
+    black = b.material(reflectance=(0, 0, 0))
+    b.rectangle((0, -1, 0), (1, 0, 0), (0, 0, -1), white)
+    b.rectangle((0, 0, -1), (1, 0, 0), (0, 1, 0), white)
+    b.rectangle((-1, 0, 0), (0, 0, -1), (0, 1, 0), red)
+    b.rectangle((1, 0, 0), (0, 0, 1), (0, 1, 0), green)
+    b.rectangle((0.3, 0.6, -0.5), (0.2, 0, 0), (0, 0, 0.2), black, radiance=(9.0, 7.0, 3.0))
+    b.envmap(sky_envmap(), scale=1.0, to_world=rotate_y(25.0))
+    shiny = b.material(type=BSDF_ROUGHCONDUCTOR, alpha=0.0005, eta=AL_ETA, k=AL_K)
+    mirror = b.material(type=BSDF_CONDUCTOR, eta=CU_ETA, k=CU_K)
+    glass = b.material(type=BSDF_DIELECTRIC, ior_ratio=1.5)
+    b.sphere((-0.5, -0.7, 0.3), 0.3, shiny)
+    b.sphere((0.55, -0.72, 0.45), 0.28, mirror)
+    b.sphere((0.05, -0.75, 0.7), 0.25, glass)
+    b.box((-0.1, -0.7, -0.4), (0.3, 0.3, 0.3), 20.0, white)
+    return b.build()
+
+
+def cbox_mesh_lights(width=256, height=256):
+    """Mesh area emitters (area.cpp on a TriMesh: trimesh.cpp:388-423, two lights => emitter CDF of two), `plastic`
+    (delta + diffuse lobes: the two-component case of getVertexType, gpt.cpp:194-226) and `twosided` diffuse sheets."""
+    b = _cornell(width, height, boxes=False)
+    b.emitters.clear()
+    b.shapes[5].emitter = -1                                        # the rectangle light of _cornell becomes a black patch
+    y = 0.985
+    b.mesh([(-0.3, y, -0.25), (0.1, y, -0.25), (0.1, y, 0.2), (-0.3, y, 0.2), (-0.1, y, 0.35)],
+           [(0, 1, 2), (0, 2, 3), (3, 2, 4)], b.material(reflectance=(0, 0, 0)), radiance=(15.0, 11.0, 4.5))     # faces down
+    b.mesh([(0.55, -0.2, -0.6), (0.75, -0.2, -0.6), (0.65, 0.0, -0.6), (0.65, -0.1, -0.45)],
+           [(0, 2, 1), (0, 1, 3), (1, 2, 3), (2, 0, 3)], b.material(reflectance=(0, 0, 0)), radiance=(3.0, 5.0, 9.0))   # small tetrahedron
+    plastic = b.material(type=BSDF_PLASTIC, reflectance=(0.1, 0.27, 0.36), specular_reflectance=(1, 1, 1), ior_ratio=1.49 / 1.000277)
+    plastic_nl = b.material(type=BSDF_PLASTIC, reflectance=(0.5, 0.2, 0.15), ior_ratio=1.9, nonlinear=True)
+    sheet = b.material(reflectance=(0.6, 0.6, 0.2), twosided=True)
+    sheet_rc = b.material(type=BSDF_ROUGHCONDUCTOR, alpha=0.2, eta=CU_ETA, k=CU_K, twosided=True)
+    b.sphere((-0.45, -0.65, 0.2), 0.35, plastic)
+    b.box((0.45, -0.75, 0.3), (0.25, 0.25, 0.25), -25.0, plastic_nl)
+    b.rectangle((0.0, -0.2, -0.5), (0.35, 0.1, 0), (0, 0.1, 0.3), sheet)         # free-floating sheets seen from both sides
+    b.rectangle((-0.55, 0.35, -0.3), (0.2, 0, 0.1), (0, 0.25, 0), sheet_rc)
+    return b.build()
+
+
+def atrium(width=256, height=144, columns=6, segments=24, rings=10):
+    """C3-class procedural scene for the BVH path: an open courtyard of `columns`^2 faceted columns (one TriMesh of
+    ~columns^2 * segments * rings * 2 triangles) on a floor, lit by the sky map; materials mix diffuse / plastic / conductor."""
+    cam = make_camera(width, height, origin=(0.0, 2.2, 9.0), target=(0, 1.2, 0), up=(0, 1, 0), fov_deg=50.0)
+    b = SceneBuilder(cam)
+    stone = b.material(reflectance=(0.55, 0.5, 0.45), twosided=True)
+    marble = b.material(type=BSDF_PLASTIC, reflectance=(0.6, 0.58, 0.55), ior_ratio=1.5)
+    metal = b.material(type=BSDF_CONDUCTOR, eta=CU_ETA, k=CU_K)
+    b.mesh([(-8, 0, -8), (8, 0, -8), (8, 0, 8), (-8, 0, 8)], [(0, 2, 1), (0, 3, 2)], stone)      # floor, normal +y
+    for mat_i, mat in enumerate((stone, marble, metal)):
+        verts, tris = [], []
+        for cx in range(columns):
+            for cz in range(columns):
+                if (cx + cz) % 3 != mat_i:
+                    continue
+                x0, z0 = (cx - (columns - 1) / 2) * 2.2, (cz - (columns - 1) / 2) * 2.2 - 1.0
+                base = len(verts)
+                for r in range(rings + 1):
+                    yy = 3.0 * r / rings
+                    rad = 0.35 * (1.0 + 0.15 * math.sin(5.0 * yy)) * (1.25 if r in (0, rings) else 1.0)
+                    for k in range(segments):
+                        a = 2 * math.pi * k / segments
+                        verts.append((x0 + rad * math.cos(a), yy, z0 + rad * math.sin(a)))
+                for r in range(rings):
+                    for k in range(segments):
+                        k2 = (k + 1) % segments
+                        v00, v01 = base + r * segments + k, base + r * segments + k2
+                        v10, v11 = base + (r + 1) * segments + k, base + (r + 1) * segments + k2
+                        tris += [(v00, v10, v11), (v00, v11, v01)]              # outward-facing
+        if tris:
+            b.mesh(verts, tris, mat)
+    b.envmap(sky_envmap(128, 64), scale=1.0)
     return b.build()
 
 

@@ -117,7 +117,8 @@ enum { GDB200_SHAPE_RECTANGLE = 0,   /* src/shapes/rectangle.cpp: unit square [-
 enum { GDB200_BSDF_DIFFUSE        = 0,   /* src/bsdfs/diffuse.cpp        */
        GDB200_BSDF_ROUGHCONDUCTOR = 1,   /* src/bsdfs/roughconductor.cpp (sampleVisible = true) */
        GDB200_BSDF_CONDUCTOR      = 2,   /* src/bsdfs/conductor.cpp      */
-       GDB200_BSDF_DIELECTRIC     = 3 }; /* src/bsdfs/dielectric.cpp     */
+       GDB200_BSDF_DIELECTRIC     = 3,   /* src/bsdfs/dielectric.cpp     */
+       GDB200_BSDF_PLASTIC        = 4 }; /* src/bsdfs/plastic.cpp: delta reflection + diffuse lobe (the two-component case of gpt.cpp:194-226) */
 
 enum { GDB200_MICROFACET_BECKMANN = 0, GDB200_MICROFACET_GGX = 1 };   /* src/bsdfs/microfacet.h */
 
@@ -141,20 +142,37 @@ typedef struct gdb200_shape {
 typedef struct gdb200_material {
     int    type;                        /* GDB200_BSDF_*                               */
     int    distribution;                /* GDB200_MICROFACET_* (roughconductor)        */
-    double reflectance[3];              /* diffuse                                     */
-    double specular_reflectance[3];     /* conductors, dielectric                      */
+    double reflectance[3];              /* diffuse; plastic: diffuseReflectance        */
+    double specular_reflectance[3];     /* conductors, dielectric, plastic             */
     double specular_transmittance[3];   /* dielectric                                  */
     double eta[3], k[3];                /* conductors: complex IOR per channel         */
     double alpha;                       /* roughconductor                              */
-    double ior_ratio;                   /* dielectric: intIOR / extIOR                 */
+    double ior_ratio;                   /* dielectric, plastic: intIOR / extIOR        */
+    int    twosided;                    /* wrapped in <bsdf type="twosided"> (same BRDF on both sides, src/bsdfs/twosided.cpp); reflection-only BSDFs */
+    int    nonlinear;                   /* plastic: nonlinear colour shifts (plastic.cpp:176)                       */
 } gdb200_material;
 
-typedef struct gdb200_emitter {         /* src/emitters/area.cpp                       */
-    int    shape;                       /* the (rectangle) shape that emits            */
-    int    reserved;
-    double radiance[3];
+enum { GDB200_EMITTER_AREA   = 0,     /* src/emitters/area.cpp on a rectangle or a triangle mesh                */
+       GDB200_EMITTER_ENVMAP = 1 };   /* src/emitters/envmap.cpp: the scene's environment emitter (at most one) */
+
+typedef struct gdb200_emitter {
+    int    shape;                       /* area: the rectangle / mesh shape that emits; envmap: -1 */
+    int    type;                        /* GDB200_EMITTER_*                            */
+    double radiance[3];                 /* area                                        */
     double sampling_weight;             /* emitter.cpp:103, default 1                  */
 } gdb200_emitter;
+
+/* Latitude-longitude environment map (envmap.cpp).  Texels are the top MIP level as the reference holds it
+ * (RGB converted to Float); lookups are bilinear on that level, u repeats, v clamps (envmap.cpp:392-396,
+ * mipmap.h:503-596).  The bounding sphere is what EnvironmentMap::createShape derives from the scene:
+ * scene->getAABB().getBSphere() with its radius * 1.5 (envmap.cpp:325-329). */
+typedef struct gdb200_envmap {
+    int          width, height;
+    const float *rgb;                   /* height * width * 3, row 0 = +y pole         */
+    double       scale;                 /* 'scale' parameter                           */
+    double       to_world[16], to_object[16];
+    double       bsphere_center[3], bsphere_radius;
+} gdb200_envmap;
 
 typedef struct gdb200_scene_desc {
     gdb200_camera          camera;
@@ -165,6 +183,7 @@ typedef struct gdb200_scene_desc {
     const gdb200_emitter  *emitters;
     const double          *vertices;         /* n_vertices * 3                          */
     const int             *triangles;        /* n_triangles * 3 vertex indices          */
+    const gdb200_envmap   *envmap;           /* NULL, or the map of the emitter whose type is GDB200_EMITTER_ENVMAP */
 } gdb200_scene_desc;
 
 /* ------------------------------------------------------- G-PT integrator */
@@ -223,6 +242,11 @@ int  gdb200_gpt_develop(gdb200_scene *scene, gdb200_buffers *out);
  * selection of the intersection routine and counts answers that differ (must be 0). */
 int  gdb200_debug_check_culling(gdb200_scene *scene, int n_rays, unsigned long long seed,
                                 unsigned long long *out_mismatches, unsigned long long *out_hits);
+
+/* sizeof() of the structs of this header as the library was compiled, in declaration order: stats, poisson_config,
+ * camera, shape, material, emitter, envmap, scene_desc, gpt_params, buffers.  Bindings compare them with their own
+ * layout at load time so that a stale library fails loudly instead of reading shifted fields.  Returns the count. */
+int  gdb200_abi_sizes(int *out_sizes, int capacity);
 
 /* Asynchronous cancel (Integrator::cancel, integrator.h:77-84). */
 void gdb200_cancel(gdb200_scene *scene);

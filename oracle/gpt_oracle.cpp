@@ -146,6 +146,19 @@ struct Shape {
     V3 dpdu, dpdv; Frame frame; Float invArea;     // rectangle.cpp:100-110
 };
 
+// EnvironmentMap (envmap.cpp): top MIP level + the sampling tables of configure(), envmap.cpp:263-320
+struct EnvMap {
+    bool present; int w, h, emitter;
+    std::vector<Float> texels;                 // Spectrum per texel (RGB -> Float)
+    std::vector<float> cdfRows, cdfCols; std::vector<Float> rowWeights;
+    Float scale, normalization, pixelSizeX, pixelSizeY;
+    double toWorld[16], toObject[16];
+    V3 center; Float radius;                   // m_sceneBSphere
+    EnvMap() : present(false) {}
+};
+// TriMesh area sampling table (trimesh.cpp:388-403): per emitting mesh shape
+struct MeshSampling { std::vector<Float> cdf; std::vector<V3> verts; Float invSurfaceArea; };
+
 struct Scene {
     gdb200_camera cam;
     Float invResX, invResY, filterRadius;
@@ -155,6 +168,9 @@ struct Scene {
     std::vector<Tri> tris;
     std::vector<Float> emCdf;      // DiscreteDistribution over samplingWeight (scene.cpp:357-380)
     Float emNormalization;
+    EnvMap env;
+    std::vector<MeshSampling> meshSampling;    // indexed by shape (empty for non-emitting shapes)
+    std::vector<Float> fdrInt, fdrExt;         // per material: plastic.cpp:188-190
 };
 
 struct Its {
@@ -316,31 +332,46 @@ bool rayOccluded(const Scene &sc, const Ray &ray)
 }
 
 // ---------------------------------------------------------------- BSDFs
-inline unsigned bsdfType(const gdb200_material &m)
+inline unsigned nestedType(const gdb200_material &m)
 {
     switch (m.type) {
         case GDB200_BSDF_DIFFUSE:   // diffuse.cpp:97-101: no component at all when the reflectance is black
             return (std::max(m.reflectance[0], std::max(m.reflectance[1], m.reflectance[2])) > 0) ? (EDiffuseReflection | EFrontSide) : 0;
         case GDB200_BSDF_ROUGHCONDUCTOR: return EGlossyReflection | EFrontSide;
         case GDB200_BSDF_CONDUCTOR: return EDeltaReflection | EFrontSide;
+        case GDB200_BSDF_PLASTIC: return EDeltaReflection | EDiffuseReflection | EFrontSide;     // plastic.cpp:210-214
         default: return EDeltaReflection | EDeltaTransmission | EFrontSide | EBackSide;
     }
 }
-inline int bsdfComponentCount(const gdb200_material &m)
+inline int nestedComponentCount(const gdb200_material &m)
 {
-    if (m.type == GDB200_BSDF_DIELECTRIC) return 2;
-    if (m.type == GDB200_BSDF_DIFFUSE) return bsdfType(m) ? 1 : 0;
+    if (m.type == GDB200_BSDF_DIELECTRIC || m.type == GDB200_BSDF_PLASTIC) return 2;
+    if (m.type == GDB200_BSDF_DIFFUSE) return nestedType(m) ? 1 : 0;
     return 1;
 }
-inline Float bsdfRoughness(const gdb200_material &m, int)
+inline Float nestedRoughness(const gdb200_material &m, int component)
 {
     switch (m.type) {
         case GDB200_BSDF_DIFFUSE: return INF;                               // diffuse.cpp:167-169
         case GDB200_BSDF_ROUGHCONDUCTOR: return 0.5 * (m.alpha + m.alpha);  // roughconductor.cpp:437-440
+        case GDB200_BSDF_PLASTIC: return component == 0 ? 0.0 : INF;        // plastic.cpp:442-449
         default: return 0.0;                                                // conductor.cpp:287, dielectric.cpp:393
     }
 }
-inline Float bsdfEta(const gdb200_material &m) { return m.type == GDB200_BSDF_DIELECTRIC ? m.ior_ratio : 1.0; }  // bsdf.cpp:62-64, dielectric.cpp:389
+// twosided.cpp:85-101,205-210: the nested BRDF's components once as front-side and once as back-side components
+inline unsigned bsdfType(const gdb200_material &m)
+{
+    unsigned t = nestedType(m);
+    if (m.twosided && t) t |= EBackSide;
+    return t;
+}
+inline int bsdfComponentCount(const gdb200_material &m) { return nestedComponentCount(m) * (m.twosided ? 2 : 1); }
+inline Float bsdfRoughness(const gdb200_material &m, int component)
+{
+    const int n = nestedComponentCount(m);
+    return nestedRoughness(m, component < n ? component : component - n);
+}
+inline Float bsdfEta(const gdb200_material &m) { return m.type == GDB200_BSDF_DIELECTRIC ? m.ior_ratio : 1.0; }  // bsdf.cpp:62-64 (plastic, twosided), dielectric.cpp:389
 
 // warp.cpp:81-102
 inline void squareToUniformDiskConcentric(Float sx, Float sy, Float &ox, Float &oy)
@@ -528,7 +559,29 @@ inline V3 refractLocal(const gdb200_material &m, V3 wi, Float cosThetaT)        
     return v3(scale * wi.x, scale * wi.y, cosThetaT);
 }
 
-Spec bsdfEval(const gdb200_material &m, V3 wi, V3 wo, Measure measure)
+struct PlasticTerms { Float fdrInt, specularSamplingWeight, invEta2; };
+// plastic.cpp:186-206 (fdrInt by the adaptive quadrature of util.cpp:855-859, tabulated per material at scene build)
+const std::vector<Float> *g_fdrInt = 0;   // set by the render entry points before tracing (index = material pointer offset)
+const gdb200_material *g_matBase = 0;
+inline PlasticTerms plasticTerms(const gdb200_material &m)
+{
+    PlasticTerms t;
+    t.fdrInt = (*g_fdrInt)[&m - g_matBase];
+    const Float dAvg = m.reflectance[0] * 0.212671f + m.reflectance[1] * 0.715160f + m.reflectance[2] * 0.072169f;
+    const Float sAvg = m.specular_reflectance[0] * 0.212671f + m.specular_reflectance[1] * 0.715160f + m.specular_reflectance[2] * 0.072169f;
+    t.specularSamplingWeight = sAvg / (dAvg + sAvg);
+    t.invEta2 = 1 / (m.ior_ratio * m.ior_ratio);
+    return t;
+}
+inline Spec plasticDiffuse(const gdb200_material &m, const PlasticTerms &t)         // plastic.cpp:266-271
+{
+    Spec diff = specOf(m.reflectance);
+    if (m.nonlinear) diff = diff / (spec(1.0f) - diff * t.fdrInt);
+    else diff = diff / (1 - t.fdrInt);
+    return diff;
+}
+
+Spec nestedEval(const gdb200_material &m, V3 wi, V3 wo, Measure measure)
 {
     switch (m.type) {
     case GDB200_BSDF_DIFFUSE:                                                          // diffuse.cpp:110-119
@@ -548,6 +601,19 @@ Spec bsdfEval(const gdb200_material &m, V3 wi, V3 wo, Measure measure)
     case GDB200_BSDF_CONDUCTOR:                                                        // conductor.cpp:221-235
         if (measure != EDiscrete || wi.z <= 0 || wo.z <= 0 || std::abs(dot(reflectLocal(wi), wo) - 1) > DeltaEpsilon) return spec(0);
         return specOf(m.specular_reflectance) * fresnelConductorExact(wi.z, specOf(m.eta), specOf(m.k));
+    case GDB200_BSDF_PLASTIC: {                                                        // plastic.cpp:243-275 (typeMask EAll, component -1)
+        const bool hasSpecular = measure == EDiscrete, hasDiffuse = measure == ESolidAngle;
+        if (wo.z <= 0 || wi.z <= 0) return spec(0);
+        Float unused; const Float Fi = fresnelDielectricExt(wi.z, unused, m.ior_ratio);
+        const PlasticTerms t = plasticTerms(m);
+        if (hasSpecular) {
+            if (std::abs(dot(reflectLocal(wi), wo) - 1) < DeltaEpsilon) return specOf(m.specular_reflectance) * Fi;
+        } else if (hasDiffuse) {
+            const Float Fo = fresnelDielectricExt(wo.z, unused, m.ior_ratio);
+            return plasticDiffuse(m, t) * ((INV_PI * wo.z) * t.invEta2 * (1 - Fi) * (1 - Fo));
+        }
+        return spec(0);
+    }
     default: {                                                                         // dielectric.cpp:228-254
         bool discrete = measure == EDiscrete;
         Float cosThetaT, F = fresnelDielectricExt(wi.z, cosThetaT, m.ior_ratio);
@@ -562,7 +628,7 @@ Spec bsdfEval(const gdb200_material &m, V3 wi, V3 wo, Measure measure)
     }
 }
 
-Float bsdfPdf(const gdb200_material &m, V3 wi, V3 wo, Measure measure)
+Float nestedPdf(const gdb200_material &m, V3 wi, V3 wo, Measure measure)
 {
     switch (m.type) {
     case GDB200_BSDF_DIFFUSE:                                                          // diffuse.cpp:121-129
@@ -577,6 +643,16 @@ Float bsdfPdf(const gdb200_material &m, V3 wi, V3 wo, Measure measure)
     case GDB200_BSDF_CONDUCTOR:                                                        // conductor.cpp:237-250
         if (measure != EDiscrete || wi.z <= 0 || wo.z <= 0 || std::abs(dot(reflectLocal(wi), wo) - 1) > DeltaEpsilon) return 0.0;
         return 1.0;
+    case GDB200_BSDF_PLASTIC: {                                                        // plastic.cpp:277-302
+        if (wo.z <= 0 || wi.z <= 0) return 0.0;
+        Float unused; const Float Fi = fresnelDielectricExt(wi.z, unused, m.ior_ratio);
+        const PlasticTerms t = plasticTerms(m);
+        const Float probSpecular = (Fi * t.specularSamplingWeight) / (Fi * t.specularSamplingWeight + (1 - Fi) * (1 - t.specularSamplingWeight));
+        if (measure == EDiscrete) {
+            if (std::abs(dot(reflectLocal(wi), wo) - 1) < DeltaEpsilon) return probSpecular;
+        } else if (measure == ESolidAngle) return (INV_PI * wo.z) * (1 - probSpecular);
+        return 0.0;
+    }
     default: {                                                                         // dielectric.cpp:256-275
         bool discrete = measure == EDiscrete;
         Float cosThetaT, F = fresnelDielectricExt(wi.z, cosThetaT, m.ior_ratio);
@@ -593,7 +669,7 @@ Float bsdfPdf(const gdb200_material &m, V3 wi, V3 wo, Measure measure)
 struct BSDFSample { V3 wi, wo; Float eta; unsigned sampledType; Spec weight; Float pdf; };
 
 // BSDF::sample(bRec, pdf, sample) with pdf pre-set to 0 by the caller (gpt.cpp:450-457)
-void bsdfSample(const gdb200_material &m, BSDFSample &r, Float sx, Float sy)
+void nestedSample(const gdb200_material &m, BSDFSample &r, Float sx, Float sy)
 {
     r.weight = spec(0); r.pdf = 0; r.eta = 1.0; r.sampledType = 0; r.wo = v3(0, 0, 0);
     switch (m.type) {
@@ -625,6 +701,24 @@ void bsdfSample(const gdb200_material &m, BSDFSample &r, Float sx, Float sy)
         r.pdf = 1;
         r.weight = specOf(m.specular_reflectance) * fresnelConductorExact(r.wi.z, specOf(m.eta), specOf(m.k));
         return;
+    case GDB200_BSDF_PLASTIC: {                                                        // plastic.cpp:372-414 (both components requested)
+        if (r.wi.z <= 0) return;
+        Float unused; const Float Fi = fresnelDielectricExt(r.wi.z, unused, m.ior_ratio);
+        const PlasticTerms t = plasticTerms(m);
+        const Float probSpecular = (Fi * t.specularSamplingWeight) / (Fi * t.specularSamplingWeight + (1 - Fi) * (1 - t.specularSamplingWeight));
+        if (sx < probSpecular) {
+            r.sampledType = EDeltaReflection; r.wo = reflectLocal(r.wi);
+            r.pdf = probSpecular;
+            r.weight = specOf(m.specular_reflectance) * Fi / probSpecular;
+        } else {
+            r.sampledType = EDiffuseReflection;
+            r.wo = squareToCosineHemisphere((sx - probSpecular) / (1 - probSpecular), sy);
+            const Float Fo = fresnelDielectricExt(r.wo.z, unused, m.ior_ratio);
+            r.pdf = (1 - probSpecular) * (INV_PI * r.wo.z);
+            r.weight = plasticDiffuse(m, t) * (t.invEta2 * (1 - Fi) * (1 - Fo) / (1 - probSpecular));
+        }
+        return;
+    }
     default: {                                                                         // dielectric.cpp:277-305
         Float cosThetaT, F = fresnelDielectricExt(r.wi.z, cosThetaT, m.ior_ratio);
         if (sx <= F) {
@@ -638,6 +732,30 @@ void bsdfSample(const gdb200_material &m, BSDFSample &r, Float sx, Float sy)
         }
         return;
     }
+    }
+}
+
+// TwoSidedBRDF::eval / pdf / sample (twosided.cpp:109-183) around the nested BRDF (same BRDF on both sides)
+Spec bsdfEval(const gdb200_material &m, V3 wi, V3 wo, Measure measure)
+{
+    if (!m.twosided || wi.z > 0) return nestedEval(m, wi, wo, measure);
+    wi.z *= -1; wo.z *= -1;
+    return nestedEval(m, wi, wo, measure);
+}
+Float bsdfPdf(const gdb200_material &m, V3 wi, V3 wo, Measure measure)
+{
+    if (!m.twosided || wi.z > 0) return nestedPdf(m, wi, wo, measure);
+    wi.z *= -1; wo.z *= -1;
+    return nestedPdf(m, wi, wo, measure);
+}
+void bsdfSample(const gdb200_material &m, BSDFSample &r, Float sx, Float sy)
+{
+    bool flipped = false;
+    if (m.twosided && r.wi.z < 0) { r.wi.z *= -1; flipped = true; }
+    nestedSample(m, r, sx, sy);
+    if (flipped) {
+        r.wi.z *= -1;
+        if (!isZero(r.weight) && r.pdf != 0) r.wo.z *= -1;
     }
 }
 
@@ -660,33 +778,161 @@ inline void initDRec(const Scene &sc, const Its &ref, DRec &r)
     if ((bsdfType(matOf(sc, ref)) & (ETransmissionBits | EBackSide)) == 0) r.refN = ref.sh.n;
 }
 
-// Scene::sampleEmitterDirectVisible, scene.cpp:855-879 (+ pmf.h:124-188, area.cpp:158-176,
-// shape.cpp:102-114, rectangle.cpp:210-216).  Returns value = Le/pdf (0 when occluded).
+// DiscreteDistribution::sampleReuse, pmf.h:124-188
+inline size_t pmfSampleReuse(const Float *cdf, size_t n, Float &sampleValue, Float &pdf)
+{
+    size_t entry = std::lower_bound(cdf, cdf + n + 1, sampleValue) - cdf;
+    size_t index = std::min(n - 1, (size_t)std::max((ptrdiff_t)0, (ptrdiff_t)entry - 1));
+    while (cdf[index + 1] - cdf[index] == 0 && index < n) ++index;
+    pdf = cdf[index + 1] - cdf[index];
+    sampleValue = (sampleValue - cdf[index]) / (cdf[index + 1] - cdf[index]);
+    return index;
+}
+
+// ---- EnvironmentMap, envmap.cpp
+const Float INV_TWOPI = 0.15915494309189533577;
+inline Float luminance(Spec s) { return s.x * 0.212671f + s.y * 0.715160f + s.z * 0.072169f; }   // spectrum.h:725-727
+inline Float safe_acos(Float v) { return std::acos(std::min(1.0, std::max(-1.0, v))); }
+inline int floorToInt(Float v) { return (int)std::floor(v); }
+inline int modulo(int a, int b) { int r = a % b; return (r < 0) ? r + b : r; }
+// MIPMap::evalTexel(0, x, y) with ERepeat in u and EClamp in v (mipmap.h:503-566, envmap.cpp:178-179)
+inline Spec envTexel(const EnvMap &e, int x, int y)
+{
+    if (x < 0 || x >= e.w) x = modulo(x, e.w);
+    if (y < 0 || y >= e.h) y = std::min(std::max(y, 0), e.h - 1);
+    const Float *t = &e.texels[((size_t)y * e.w + x) * 3];
+    return v3(t[0], t[1], t[2]);
+}
+// MIPMap::evalBilinear(0, uv), mipmap.h:575-596
+inline Spec envBilinear(const EnvMap &e, Float uvx, Float uvy)
+{
+    if (!std::isfinite(uvx) || !std::isfinite(uvy)) return spec(0);
+    Float u = uvx * e.w - 0.5f, v = uvy * e.h - 0.5f;
+    int xPos = floorToInt(u), yPos = floorToInt(v);
+    Float dx1 = u - xPos, dx2 = 1.0f - dx1, dy1 = v - yPos, dy2 = 1.0f - dy1;
+    return envTexel(e, xPos, yPos) * dx2 * dy2 + envTexel(e, xPos, yPos + 1) * dx2 * dy1
+         + envTexel(e, xPos + 1, yPos) * dx1 * dy2 + envTexel(e, xPos + 1, yPos + 1) * dx1 * dy1;
+}
+// EnvironmentMap::evalEnvironment, envmap.cpp:385-409.  DEVIATION: the reference filters primary-ray lookups with
+// ray differentials (EWA over the MIP pyramid); every lookup here is the differential-free branch (:393-396).
+Spec evalEnvironment(const Scene &sc, V3 d)
+{
+    const EnvMap &e = sc.env;
+    V3 v = xfVector(e.toObject, d);
+    return envBilinear(e, std::atan2(v.x, -v.z) * INV_TWOPI, safe_acos(v.y) * INV_PI) * e.scale;
+}
+// envmap.cpp:660-665
+inline uint32_t envSampleReuse(const float *cdf, uint32_t size, Float &sample)
+{
+    const float *entry = std::lower_bound(cdf, cdf + size + 1, (float)sample);
+    uint32_t index = std::min((uint32_t)std::max((ptrdiff_t)0, entry - cdf - 1), size - 1);
+    sample = (sample - (Float)cdf[index]) / (Float)(cdf[index + 1] - cdf[index]);
+    return index;
+}
+inline Float intervalToTent(Float sample)                                            // warp.cpp:143-155
+{
+    Float sign;
+    if (sample < 0.5f) { sign = 1; sample *= 2; } else { sign = -1; sample = 2 * (sample - 0.5f); }
+    return sign * (1 - std::sqrt(sample));
+}
+// envmap.cpp:571-608
+void envSampleDirection(const EnvMap &e, Float sx, Float sy, V3 &d, Spec &value, Float &pdf)
+{
+    uint32_t row = envSampleReuse(&e.cdfRows[0], e.h, sy), col = envSampleReuse(&e.cdfCols[(size_t)row * (e.w + 1)], e.w, sx);
+    Float posx = (Float)col + intervalToTent(sx), posy = (Float)row + intervalToTent(sy);
+    int xPos = floorToInt(posx), yPos = floorToInt(posy);
+    Float dx1 = posx - xPos, dx2 = 1.0f - dx1, dy1 = posy - yPos, dy2 = 1.0f - dy1;
+    Spec value1 = envTexel(e, xPos, yPos) * dx2 * dy2 + envTexel(e, xPos + 1, yPos) * dx1 * dy2;
+    Spec value2 = envTexel(e, xPos, yPos + 1) * dx2 * dy1 + envTexel(e, xPos + 1, yPos + 1) * dx1 * dy1;
+    value = (value1 + value2) * e.scale;
+    pdf = (luminance(value1) * e.rowWeights[std::min(std::max(yPos, 0), e.h - 1)] + luminance(value2) * e.rowWeights[std::min(std::max(yPos + 1, 0), e.h - 1)]) * e.normalization;
+    Float sinPhi = std::sin(e.pixelSizeX * (posx + 0.5f)), cosPhi = std::cos(e.pixelSizeX * (posx + 0.5f));
+    Float sinTheta = std::sin(e.pixelSizeY * (posy + 0.5f)), cosTheta = std::cos(e.pixelSizeY * (posy + 0.5f));
+    d = v3(sinPhi * sinTheta, cosTheta, -cosPhi * sinTheta);
+    pdf /= std::max(std::abs(sinTheta), Epsilon);
+}
+// envmap.cpp:611-642
+Float envPdfDirection(const EnvMap &e, V3 d)
+{
+    Float uvx = std::atan2(d.x, -d.z) * INV_TWOPI, uvy = safe_acos(d.y) * INV_PI;
+    if (!std::isfinite(uvx) || !std::isfinite(uvy)) return 0.0;
+    Float u = uvx * e.w - 0.5f, v = uvy * e.h - 0.5f;
+    int xPos = floorToInt(u), yPos = floorToInt(v);
+    Float dx1 = u - xPos, dx2 = 1.0f - dx1, dy1 = v - yPos, dy2 = 1.0f - dy1;
+    Spec value1 = envTexel(e, xPos, yPos) * dx2 * dy2 + envTexel(e, xPos + 1, yPos) * dx1 * dy2;
+    Spec value2 = envTexel(e, xPos, yPos + 1) * dx2 * dy1 + envTexel(e, xPos + 1, yPos + 1) * dx1 * dy1;
+    Float sinTheta = std::sqrt(std::max(0.0, 1 - d.y * d.y));
+    return (luminance(value1) * e.rowWeights[std::min(std::max(yPos, 0), e.h - 1)] + luminance(value2) * e.rowWeights[std::min(std::max(yPos + 1, 0), e.h - 1)])
+        * e.normalization / std::max(std::abs(sinTheta), Epsilon);
+}
+// BSphere::rayIntersect, bsphere.h:88-95
+inline bool bsphereIntersect(const EnvMap &e, V3 o, V3 d, Float &nearHit, Float &farHit)
+{
+    V3 oc = o - e.center;
+    return solveQuadratic(lengthSquared(d), 2 * dot(oc, d), lengthSquared(oc) - e.radius * e.radius, nearHit, farHit);
+}
+// EnvironmentMap::fillDirectSamplingRecord, envmap.cpp:358-374
+bool envFillDirectSamplingRecord(const Scene &sc, DRec &dRec, V3 o, V3 d)
+{
+    Float nearT, farT;
+    if (!bsphereIntersect(sc.env, o, d, nearT, farT) || nearT > 0 || farT < 0) return false;
+    dRec.p = o + d * farT;
+    dRec.n = normalize(sc.env.center - dRec.p);
+    dRec.d = d; dRec.dist = farT; dRec.emitter = sc.env.emitter;
+    return true;
+}
+
+// Scene::sampleEmitterDirectVisible, scene.cpp:855-879 (+ pmf.h:124-188; area.cpp:158-176 over shape.cpp:102-114 with
+// rectangle.cpp:210-216 or trimesh.cpp:412-423 / triangle.cpp:24-50; envmap.cpp:516-544).  Returns value = Le/pdf
+// (0 when occluded).
 Spec sampleEmitterDirectVisible(const Scene &sc, DRec &dRec, Float sx, Float sy, bool &visible)
 {
-    // DiscreteDistribution::sampleReuse
-    size_t nE = sc.ems.size();
-    size_t entry = std::lower_bound(sc.emCdf.begin(), sc.emCdf.end(), sx) - sc.emCdf.begin();
-    size_t index = std::min(nE - 1, (size_t)std::max((ptrdiff_t)0, (ptrdiff_t)entry - 1));
-    while (sc.emCdf[index + 1] - sc.emCdf[index] == 0 && index < nE) ++index;
-    Float emPdf = sc.emCdf[index + 1] - sc.emCdf[index];
-    sx = (sx - sc.emCdf[index]) / (sc.emCdf[index + 1] - sc.emCdf[index]);
-
+    Float emPdf;
+    size_t index = pmfSampleReuse(&sc.emCdf[0], sc.ems.size(), sx, emPdf);
     const gdb200_emitter &em = sc.ems[index];
-    const Shape &s = sc.shapes[em.shape];
-    dRec.p = xfPoint(s.d.to_world, v3(sx * 2 - 1, sy * 2 - 1, 0));
-    dRec.n = s.frame.n;
-    dRec.pdf = s.invArea;
-    dRec.d = dRec.p - dRec.ref;
-    Float distSquared = lengthSquared(dRec.d);
-    dRec.dist = std::sqrt(distSquared);
-    dRec.d = dRec.d / dRec.dist;
-    Float dp = std::abs(dot(dRec.d, dRec.n));
-    dRec.pdf *= dp != 0 ? (distSquared / dp) : 0.0;
     Spec value;
-    if (dot(dRec.d, dRec.refN) >= 0 && dot(dRec.d, dRec.n) < 0 && dRec.pdf != 0) value = specOf(em.radiance) / dRec.pdf;
-    else { dRec.pdf = 0.0; value = spec(0); }
     dRec.emitter = (int)index;
+    if (em.type == GDB200_EMITTER_ENVMAP) {                                         // envmap.cpp:516-544
+        Spec v; V3 d; Float pdf;
+        envSampleDirection(sc.env, sx, sy, d, v, pdf);
+        V3 dw = xfVector(sc.env.toWorld, d);
+        Float nearT = 0, farT = 0;
+        if (isZero(v) || pdf == 0 || !bsphereIntersect(sc.env, dRec.ref, dw, nearT, farT) || nearT >= 0 || farT <= 0) {
+            // the reference returns with p/d/dist unset and its caller still traces a shadow ray from them;
+            // defined here as "no contribution" (unreachable for strictly positive maps seen from inside the sphere)
+            dRec.pdf = 0.0; dRec.p = dRec.ref; dRec.n = v3(0, 0, 0); dRec.d = v3(0, 0, 1); dRec.dist = 0;
+            visible = true;
+            return spec(0);
+        }
+        dRec.pdf = pdf; dRec.p = dRec.ref + dw * farT; dRec.n = normalize(sc.env.center - dRec.p); dRec.dist = farT; dRec.d = dw;
+        value = v / pdf;
+    } else {
+        const Shape &s = sc.shapes[em.shape];
+        if (s.d.type == GDB200_SHAPE_RECTANGLE) {                                   // rectangle.cpp:210-216
+            dRec.p = xfPoint(s.d.to_world, v3(sx * 2 - 1, sy * 2 - 1, 0));
+            dRec.n = s.frame.n;
+            dRec.pdf = s.invArea;
+        } else {                                                                    // trimesh.cpp:412-423, triangle.cpp:24-50
+            const MeshSampling &ms = sc.meshSampling[em.shape];
+            Float triPdf;
+            size_t tri = pmfSampleReuse(&ms.cdf[0], ms.cdf.size() - 1, sy, triPdf);
+            const V3 p0 = ms.verts[3 * tri], p1 = ms.verts[3 * tri + 1], p2 = ms.verts[3 * tri + 2];
+            Float a = std::sqrt(std::max(0.0, 1.0f - sx));                           // warp.cpp:76-79
+            Float bx = 1 - a, by = a * sy;
+            V3 sideA = p1 - p0, sideB = p2 - p0;
+            dRec.p = p0 + (sideA * bx) + (sideB * by);
+            dRec.n = normalize(cross(sideA, sideB));
+            dRec.pdf = ms.invSurfaceArea;
+        }
+        dRec.d = dRec.p - dRec.ref;                                                 // shape.cpp:102-114
+        Float distSquared = lengthSquared(dRec.d);
+        dRec.dist = std::sqrt(distSquared);
+        dRec.d = dRec.d / dRec.dist;
+        Float dp = std::abs(dot(dRec.d, dRec.n));
+        dRec.pdf *= dp != 0 ? (distSquared / dp) : 0.0;
+        if (dot(dRec.d, dRec.refN) >= 0 && dot(dRec.d, dRec.n) < 0 && dRec.pdf != 0) value = specOf(em.radiance) / dRec.pdf;   // area.cpp:158-176
+        else { dRec.pdf = 0.0; value = spec(0); }
+    }
     dRec.pdf *= emPdf;
     value = value / emPdf;
     Ray ray = {dRec.ref, dRec.d, Epsilon, dRec.dist * (1 - ShadowEpsilon)};
@@ -695,13 +941,17 @@ Spec sampleEmitterDirectVisible(const Scene &sc, DRec &dRec, Float sx, Float sy,
     return value;
 }
 
-// Scene::pdfEmitterDirect, scene.cpp:976-979 + area.cpp:178-186 + shape.cpp:116-126
+// Scene::pdfEmitterDirect, scene.cpp:976-979 + area.cpp:178-186 + shape.cpp:116-126 / envmap.cpp:546-556
 Float pdfEmitterDirect(const Scene &sc, const DRec &dRec)
 {
     const gdb200_emitter &em = sc.ems[dRec.emitter];
     Float pdf = 0.0;
-    if (dot(dRec.d, dRec.refN) >= 0 && dot(dRec.d, dRec.n) < 0)
-        pdf = sc.shapes[em.shape].invArea * (dRec.dist * dRec.dist) / std::abs(dot(dRec.d, dRec.n));
+    if (em.type == GDB200_EMITTER_ENVMAP) pdf = envPdfDirection(sc.env, xfVector(sc.env.toObject, dRec.d));
+    else if (dot(dRec.d, dRec.refN) >= 0 && dot(dRec.d, dRec.n) < 0) {
+        const Shape &s = sc.shapes[em.shape];
+        const Float pdfPos = s.d.type == GDB200_SHAPE_RECTANGLE ? s.invArea : sc.meshSampling[em.shape].invSurfaceArea;
+        pdf = pdfPos * (dRec.dist * dRec.dist) / std::abs(dot(dRec.d, dRec.n));
+    }
     return pdf * (em.sampling_weight * sc.emNormalization);
 }
 
@@ -790,6 +1040,25 @@ ShiftResult reconnectShift(const Scene &sc, V3 mainSource, V3 target, V3 shiftSo
     return result;
 }
 
+// gpt.cpp:96-114
+bool testEnvironmentVisibility(const Scene &sc, const Ray &ray)
+{
+    if (!sc.env.present) return false;
+    DRec dr; dr.dist = 0;
+    envFillDirectSamplingRecord(sc, dr, ray.o, ray.d);
+    Ray shadowRay = {ray.o, ray.d, Epsilon, ((Float)1.0 - ShadowEpsilon) * dr.dist};
+    return !rayOccluded(sc, shadowRay);
+}
+// gpt.cpp:348-369
+ShiftResult environmentShift(const Scene &sc, const Ray &mainRay, V3 shiftSourceVertex)
+{
+    ShiftResult result; result.success = false; result.jacobian = 0; result.wo = v3(0, 0, 0);
+    Ray offsetRay = mainRay; offsetRay.o = shiftSourceVertex;
+    if (!testEnvironmentVisibility(sc, offsetRay)) return result;
+    result.success = true; result.jacobian = 1; result.wo = mainRay.d;
+    return result;
+}
+
 struct Counters { double rays, vertices; };
 
 // perspective.cpp:271-298 (ray differentials are unused by the textures-free material subset)
@@ -815,7 +1084,10 @@ void evaluate(const Scene &sc, const Config &cfg, Sampler &sampler, RayState &ma
         rayIntersect(sc, shiftedRays[i].ray, shiftedRays[i].its); cnt.rays++;       // :476-480
         shiftedRays[i].ray.mint = Epsilon;
     }
-    if (!main.its.valid()) return;                                                  // :482-492 (no environment)
+    if (!main.its.valid()) {                                                        // :482-492
+        if (sc.env.present) out_veryDirect = out_veryDirect + main.throughput * evalEnvironment(sc, main.ray.d);
+        return;
+    }
     if (isEmitter(sc, main.its)) out_veryDirect = out_veryDirect + main.throughput * emittedLe(sc, main.its, -main.ray.d);  // :497-499
     for (int i = 0; i < secondaryCount; ++i) if (!shiftedRays[i].its.valid()) shiftedRays[i].alive = false;              // :508-513
     if (cfg.strictNormals) {                                                        // :516-531
@@ -938,8 +1210,13 @@ void evaluate(const Scene &sc, const Config &cfg, Sampler &sampler, RayState &ma
                 mainHitEmitter = true;
             }
             mainNextVertexType = getVertexType(matOf(sc, main.its), cfg, bs.sampledType);
-        } else {
-            break;                                                                  // :800-803 (no environment emitter)
+        } else {                                                                    // :786-803
+            if (sc.env.present) {
+                mainEmitterRadiance = evalEnvironment(sc, main.ray.d);
+                if (!envFillDirectSamplingRecord(sc, mainDRec, main.ray.o, main.ray.d)) break;
+                mainHitEmitter = true;
+                mainNextVertexType = VERTEX_TYPE_DIFFUSE;
+            } else break;
         }
         Float mainBsdfPdf = bs.pdf, mainPreviousPdf = main.pdf;                     // :807-812
         main.throughput = main.throughput * (bs.weight * bs.pdf);
@@ -982,7 +1259,9 @@ void evaluate(const Scene &sc, const Config &cfg, Sampler &sampler, RayState &ma
                     VertexType shiftedVertexType = getVertexType(shiftedBSDF, cfg, bs.sampledType);
                     if (mainVertexType == VERTEX_TYPE_DIFFUSE && mainNextVertexType == VERTEX_TYPE_DIFFUSE && shiftedVertexType == VERTEX_TYPE_DIFFUSE) {
                         if (!lastSegment || mainHitEmitter) {                       // :901
-                            ShiftResult sr = reconnectShift(sc, main.ray.o, main.its.p, shifted.its.p, main.its.geoN); cnt.rays++;   // :907
+                            ShiftResult sr = main.its.valid() ? reconnectShift(sc, main.ray.o, main.its.p, shifted.its.p, main.its.geoN)   // :907
+                                                              : environmentShift(sc, main.ray, shifted.its.p);                               // :908-915
+                            cnt.rays++;
                             if (!sr.success) { shifted.alive = false; goto shift_failed; }
                             V3 incomingDirection = -shifted.ray.d, outgoingDirection = sr.wo;
                             V3 wiL = toLocal(shifted.its.sh, incomingDirection), woL = toLocal(shifted.its.sh, outgoingDirection);
@@ -993,13 +1272,16 @@ void evaluate(const Scene &sc, const Config &cfg, Sampler &sampler, RayState &ma
                             shifted.pdf *= shiftedBsdfPdf * sr.jacobian;
                             shifted.connection_status = RAY_RECENTLY_CONNECTED;
                             if (mainHitEmitter) {                                   // :944-985
-                                Spec shiftedEmitterRadiance = emittedLe(sc, main.its, -outgoingDirection);
-                                DRec sd;                                            // :957-964
-                                sd.p = mainDRec.p; sd.n = mainDRec.n;
-                                sd.dist = length(mainDRec.p - shifted.its.p);
-                                sd.d = (mainDRec.p - shifted.its.p) / sd.dist;
-                                sd.ref = mainDRec.ref; sd.refN = shifted.its.sh.n; sd.emitter = mainDRec.emitter;
-                                Float shiftedLumPdf = pdfEmitterDirect(sc, sd);
+                                Spec shiftedEmitterRadiance = spec(0); Float shiftedLumPdf = 0;
+                                if (main.its.valid()) {
+                                    shiftedEmitterRadiance = emittedLe(sc, main.its, -outgoingDirection);
+                                    DRec sd;                                        // :957-964
+                                    sd.p = mainDRec.p; sd.n = mainDRec.n;
+                                    sd.dist = length(mainDRec.p - shifted.its.p);
+                                    sd.d = (mainDRec.p - shifted.its.p) / sd.dist;
+                                    sd.ref = mainDRec.ref; sd.refN = shifted.its.sh.n; sd.emitter = mainDRec.emitter;
+                                    shiftedLumPdf = pdfEmitterDirect(sc, sd);
+                                } else { shiftedEmitterRadiance = mainEmitterRadiance; shiftedLumPdf = mainLumPdf; }   // :973-977
                                 Float den = (shiftedPreviousPdf * shiftedPreviousPdf) * ((shiftedLumPdf * shiftedLumPdf) + (shiftedBsdfPdf * shiftedBsdfPdf));
                                 weight = mainWeightNumerator / (D_EPSILON + den + mainWeightDenominator);
                                 mainContribution = main.throughput * mainEmitterRadiance;
@@ -1030,9 +1312,14 @@ void evaluate(const Scene &sc, const Config &cfg, Sampler &sampler, RayState &ma
                             VertexType shiftedVertexType2 = getVertexType(shiftedBSDF, cfg, bs.sampledType);   // :1047
                             shifted.ray.o = shifted.its.p; shifted.ray.d = outgoingDirection; shifted.ray.mint = Epsilon; shifted.ray.maxt = INF;   // :1050
                             cnt.rays++;
-                            if (!rayIntersect(sc, shifted.ray, shifted.its)) {      // :1052-1058 (no environment)
-                                shifted.alive = false; goto half_vector_shift_failed;
+                            if (!rayIntersect(sc, shifted.ray, shifted.its)) {      // :1052-1074
+                                if (!sc.env.present) { shifted.alive = false; goto half_vector_shift_failed; }
+                                if (main.its.valid()) { shifted.alive = false; goto half_vector_shift_failed; }
+                                if (mainVertexType == VERTEX_TYPE_DIFFUSE && shiftedVertexType2 == VERTEX_TYPE_DIFFUSE) { shifted.alive = false; goto half_vector_shift_failed; }
+                                shiftedEmitterRadiance = evalEnvironment(sc, shifted.ray.d);
+                                postponedShiftEnd = true;
                             } else {
+                                if (!main.its.valid()) { shifted.alive = false; goto half_vector_shift_failed; }   // :1078-1082
                                 VertexType shiftedNextVertexType = getVertexType(matOf(sc, shifted.its), cfg, bs.sampledType);
                                 if (mainVertexType == VERTEX_TYPE_DIFFUSE && shiftedVertexType2 == VERTEX_TYPE_DIFFUSE && shiftedNextVertexType == VERTEX_TYPE_DIFFUSE) {   // :1089-1093
                                     shifted.alive = false; goto half_vector_shift_failed;
@@ -1069,7 +1356,7 @@ shift_failed:
             if (postponedShiftEnd) shifted.alive = false;                           // :1148-1150
         }
 
-        // :1154-1157: the base path always has a valid hit here (no environment emitter)
+        if (!main.its.valid()) break;                                               // :1154-1157: the base path hit the environment
         if (depth++ >= cfg.rrDepth) {                                               // :1159-1174
             Float q = std::min(maxComp(main.throughput / main.pdf) * main.eta * main.eta, (Float)0.95f);
             if (sampler.next1D() >= q) break;
@@ -1113,6 +1400,47 @@ struct Film {
 
 enum { BUF_FINAL = 0, BUF_THROUGHPUT = 1, BUF_DX = 2, BUF_DY = 3, BUF_DIRECT = 4 };
 
+// GaussLobattoIntegrator (quad.cpp:287-403) as fresnelDiffuseReflectance(eta, false) uses it (util.cpp:855-859):
+// maxEvals 1024, absError 0, relError 1e-5, useConvergenceEstimate = false.
+struct GaussLobatto {
+    Float eta; size_t maxEvals, evals;
+    Float f(Float xi) const { Float unused; return fresnelDielectricExt(std::sqrt(xi), unused, eta); }   // util.cpp:808-811
+    Float adaptiveStep(Float a, Float b, Float fa, Float fb, Float acc)
+    {
+        const Float m_alpha = (Float)std::sqrt(2.0 / 3.0), m_beta = (Float)(1.0 / std::sqrt(5.0));
+        const Float h = (b - a) / 2, m = (a + b) / 2;
+        const Float mll = m - m_alpha * h, ml = m - m_beta * h, mr = m + m_beta * h, mrr = m + m_alpha * h;
+        const Float fmll = f(mll), fml = f(ml), fm = f(m), fmr = f(mr), fmrr = f(mrr);
+        const Float integral2 = (h / 6) * (fa + fb + 5 * (fml + fmr));
+        const Float integral1 = (h / 1470) * (77 * (fa + fb) + 432 * (fmll + fmrr) + 625 * (fml + fmr) + 672 * fm);
+        evals += 5;
+        if (evals >= maxEvals) return integral1;
+        Float dist = acc + (integral1 - integral2);
+        if (dist == acc || mll <= a || b <= mrr) return integral1;
+        return adaptiveStep(a, mll, fa, fmll, acc) + adaptiveStep(mll, ml, fmll, fml, acc) + adaptiveStep(ml, m, fml, fm, acc)
+             + adaptiveStep(m, mr, fm, fmr, acc) + adaptiveStep(mr, mrr, fmr, fmrr, acc) + adaptiveStep(mrr, b, fmrr, fb, acc);
+    }
+    Float integrate(Float a, Float b)
+    {
+        const Float m_alpha = (Float)std::sqrt(2.0 / 3.0), m_beta = (Float)(1.0 / std::sqrt(5.0));
+        const Float m_x1 = (Float)0.94288241569547971906, m_x2 = (Float)0.64185334234578130578, m_x3 = (Float)0.23638319966214988028;
+        evals = 0;
+        const Float m = (a + b) / 2, h = (b - a) / 2;
+        const Float y1 = f(a), y3 = f(m - m_alpha * h), y5 = f(m - m_beta * h), y7 = f(m), y9 = f(m + m_beta * h), y11 = f(m + m_alpha * h), y13 = f(b);
+        Float acc = h * ((Float)0.0158271919734801831 * (y1 + y13) + (Float)0.0942738402188500455 * (f(m - m_x1 * h) + f(m + m_x1 * h))
+                         + (Float)0.1550719873365853963 * (y3 + y11) + (Float)0.1888215739601824544 * (f(m - m_x2 * h) + f(m + m_x2 * h))
+                         + (Float)0.1997734052268585268 * (y5 + y9) + (Float)0.2249264653333395270 * (f(m - m_x3 * h) + f(m + m_x3 * h))
+                         + (Float)0.2426110719014077338 * y7);
+        evals += 13;
+        const Float r = 1.0, relError = 1e-5f;
+        Float absTolerance = std::numeric_limits<Float>::infinity();
+        if (acc != 0) absTolerance = acc * std::max(relError, std::numeric_limits<Float>::epsilon()) / (r * std::numeric_limits<Float>::epsilon());
+        evals += 2;
+        return adaptiveStep(a, b, f(a), f(b), absTolerance);
+    }
+};
+inline Float fresnelDiffuseReflectance(Float eta) { GaussLobatto q; q.eta = eta; q.maxEvals = 1024; return q.integrate(0, 1); }
+
 void buildScene(const gdb200_scene_desc *d, Scene &sc)
 {
     sc.cam = d->camera;
@@ -1138,6 +1466,71 @@ void buildScene(const gdb200_scene_desc *d, Scene &sc)
         }
         sc.shapes.push_back(s);
     }
+    // TriMesh::prepareSamplingTable (trimesh.cpp:388-403) for emitting meshes
+    sc.meshSampling.resize(d->n_shapes);
+    for (int i = 0; i < d->n_shapes; i++) {
+        const gdb200_shape &sh = d->shapes[i];
+        if (sh.type != GDB200_SHAPE_MESH || sh.emitter < 0) continue;
+        MeshSampling &ms = sc.meshSampling[i];
+        ms.cdf.assign(1, 0.0);
+        for (int t = sh.first_tri; t < sh.first_tri + sh.tri_count; t++) {
+            const int *ix = d->triangles + 3 * t;
+            V3 p0 = specOf(d->vertices + 3 * ix[0]), p1 = specOf(d->vertices + 3 * ix[1]), p2 = specOf(d->vertices + 3 * ix[2]);
+            ms.verts.push_back(p0); ms.verts.push_back(p1); ms.verts.push_back(p2);
+            ms.cdf.push_back(ms.cdf.back() + 0.5f * length(cross(p1 - p0, p2 - p0)));   // triangle.cpp:61-67, pmf.h:62-71
+        }
+        Float surfaceArea = ms.cdf.back();                                       // DiscreteDistribution::normalize, pmf.h:101-114
+        if (surfaceArea > 0) {
+            Float normalization = 1.0f / surfaceArea;
+            for (size_t k = 1; k < ms.cdf.size(); ++k) ms.cdf[k] *= normalization;
+            ms.cdf.back() = 1.0f;
+        }
+        ms.invSurfaceArea = 1.0f / surfaceArea;
+    }
+    // plastic.cpp:188-190
+    sc.fdrInt.assign(d->n_materials, 0.0); sc.fdrExt.assign(d->n_materials, 0.0);
+    for (int i = 0; i < d->n_materials; i++)
+        if (d->materials[i].type == GDB200_BSDF_PLASTIC) {
+            sc.fdrInt[i] = fresnelDiffuseReflectance(1 / d->materials[i].ior_ratio);
+            sc.fdrExt[i] = fresnelDiffuseReflectance(d->materials[i].ior_ratio);
+        }
+    // EnvironmentMap::configure, envmap.cpp:263-320
+    sc.env = EnvMap();
+    for (int i = 0; i < d->n_emitters; i++) {
+        if (d->emitters[i].type != GDB200_EMITTER_ENVMAP || !d->envmap) continue;
+        const gdb200_envmap &src = *d->envmap;
+        EnvMap &e = sc.env;
+        e.present = true; e.emitter = i; e.w = src.width; e.h = src.height; e.scale = src.scale;
+        memcpy(e.toWorld, src.to_world, sizeof(e.toWorld)); memcpy(e.toObject, src.to_object, sizeof(e.toObject));
+        e.center = specOf(src.bsphere_center); e.radius = src.bsphere_radius;
+        e.texels.resize((size_t)e.w * e.h * 3);
+        for (size_t k = 0; k < e.texels.size(); k++) e.texels[k] = (Float)src.rgb[k];
+        size_t nEntries = (size_t)(e.w + 1) * (size_t)e.h;
+        e.cdfCols.assign(nEntries, 0.f); e.cdfRows.assign(e.h + 1, 0.f); e.rowWeights.assign(e.h, 0.0);
+        size_t colPos = 0, rowPos = 0;
+        Float rowSum = 0.0f;
+        e.cdfRows[rowPos++] = 0;
+        for (int y = 0; y < e.h; ++y) {
+            Float colSum = 0;
+            e.cdfCols[colPos++] = 0;
+            for (int x = 0; x < e.w; ++x) {
+                colSum += luminance(envTexel(e, x, y));
+                e.cdfCols[colPos++] = (float)colSum;
+            }
+            float normalization = 1.0f / (float)colSum;
+            for (int x = 1; x < e.w; ++x) e.cdfCols[colPos - x - 1] *= normalization;
+            e.cdfCols[colPos - 1] = 1.0f;
+            Float weight = std::sin((y + 0.5f) * PI / e.h);
+            e.rowWeights[y] = weight;
+            rowSum += colSum * weight;
+            e.cdfRows[rowPos++] = (float)rowSum;
+        }
+        float normalization = 1.0f / (float)rowSum;
+        for (int y = 1; y < e.h; ++y) e.cdfRows[rowPos - y - 1] *= normalization;
+        e.cdfRows[rowPos - 1] = 1.0f;
+        e.normalization = 1.0f / (rowSum * (2 * PI / e.w) * (PI / e.h));
+        e.pixelSizeX = 2 * PI / e.w; e.pixelSizeY = PI / e.h;
+    }
     // scene.cpp:357-380 + pmf.h:100-114: CDF over samplingWeight, normalised
     sc.emCdf.assign(1, 0.0);
     for (size_t i = 0; i < sc.ems.size(); i++) sc.emCdf.push_back(sc.emCdf.back() + sc.ems[i].sampling_weight);
@@ -1158,6 +1551,7 @@ int gdb200_oracle_gpt_render(const gdb200_scene_desc *desc, const gdb200_gpt_par
 {
     if (!desc || !prm || desc->n_emitters < 1) return 1;
     Scene sc; buildScene(desc, sc);
+    g_fdrInt = &sc.fdrInt; g_matBase = &sc.mats[0];
     Config cfg; cfg.maxDepth = prm->max_depth; cfg.minDepth = 1; cfg.rrDepth = prm->rr_depth;   // gpt.cpp:1368-1371
     cfg.strictNormals = prm->strict_normals != 0; cfg.shiftThreshold = prm->shift_threshold;
     const int W = sc.cam.width, H = sc.cam.height;
@@ -1237,6 +1631,7 @@ int gdb200_oracle_path_render(const gdb200_scene_desc *desc, const gdb200_gpt_pa
 {
     if (!desc || !prm || !out) return 1;
     Scene sc; buildScene(desc, sc);
+    g_fdrInt = &sc.fdrInt; g_matBase = &sc.mats[0];
     const int W = sc.cam.width, H = sc.cam.height;
 #pragma omp parallel for schedule(dynamic, 4) num_threads(num_threads > 0 ? num_threads : 1)
     for (int y = 0; y < H; y++)
@@ -1251,7 +1646,10 @@ int gdb200_oracle_path_render(const gdb200_scene_desc *desc, const gdb200_gpt_pa
                 Spec Li = spec(0), throughput = spec(1);
                 Float eta = 1.0; bool scattered = false; int depth = 1;
                 while (depth <= prm->max_depth || prm->max_depth < 0) {
-                    if (!its.valid()) break;
+                    if (!its.valid()) {                                                                         // :1515-1521
+                        if (!scattered && sc.env.present) Li = Li + throughput * evalEnvironment(sc, ray.d);
+                        break;
+                    }
                     const gdb200_material &bsdf = matOf(sc, its);
                     if (isEmitter(sc, its) && !scattered) Li = Li + throughput * emittedLe(sc, its, -ray.d);   // :1527-1529 (EEmittedRadiance only on the first vertex)
                     if (depth >= prm->max_depth && prm->max_depth > 0) break;
@@ -1279,7 +1677,18 @@ int gdb200_oracle_path_render(const gdb200_scene_desc *desc, const gdb200_gpt_pa
                     bool hit = rayIntersect(sc, next, its);
                     throughput = throughput * bs.weight;
                     eta *= bs.eta;
-                    if (!hit) break;
+                    if (!hit) {                                                                                 // :1618-1630
+                        if (sc.env.present) {
+                            Spec value = evalEnvironment(sc, next.d);
+                            DRec q; initDRec(sc, prev, q);
+                            if (envFillDirectSamplingRecord(sc, q, next.o, next.d)) {
+                                const Float lumPdf = !(bs.sampledType & EDelta) ? pdfEmitterDirect(sc, q) : 0;
+                                Float a = bs.pdf * bs.pdf, b = lumPdf * lumPdf;
+                                Li = Li + throughput * value * (a / (a + b));
+                            }
+                        }
+                        break;
+                    }
                     if (isEmitter(sc, its)) {                                                                   // :1611-1645
                         Spec value = emittedLe(sc, its, -next.d);
                         DRec q; initDRec(sc, prev, q);

@@ -23,7 +23,10 @@ def close(got, ref):
 
 SCENES = {"cbox_diffuse": lambda w, h: scenes.cbox_diffuse(w, h), "cbox_glossy": lambda w, h: scenes.cbox_glossy(w, h),
           "cbox_glossy_delta": lambda w, h: scenes.cbox_glossy(w, h, delta_variant=True),
-          "cbox_materials": lambda w, h: scenes.cbox_materials(w, h)}
+          "cbox_materials": lambda w, h: scenes.cbox_materials(w, h),
+          "cbox_env": lambda w, h: scenes.cbox_env(w, h),                  # environment emitter + environmentShift
+          "cbox_mesh_lights": lambda w, h: scenes.cbox_mesh_lights(w, h),  # mesh emitters, plastic, twosided
+          "atrium": lambda w, h: scenes.atrium(w, h, columns=3, segments=8, rings=4)}   # > table size: BVH path
 
 
 @pytest.mark.parametrize("scene_name", sorted(SCENES))
@@ -69,3 +72,40 @@ def test_streams_per_pixel(oracle, emu, streams, spp):
     one = scenes.default_params(spp=spp, seed=5)
     ref1, _, _ = oracle.gpt(desc, one)
     assert not np.allclose(ref1["-throughput"], ref["-throughput"])     # chunks > 0 really use other streams
+
+
+@pytest.mark.parametrize("scene_name", ["cbox_glossy", "cbox_mesh_lights"])
+def test_bvh_path_gives_the_same_film(oracle, emu, scene_name, monkeypatch):
+    """GDB200_FORCE_BVH routes every mesh triangle through the BVH instead of the constant-memory table; the
+    oracle tests every triangle, so any traversal or bounds error shows up as a changed hit."""
+    monkeypatch.setenv("GDB200_FORCE_BVH", "1")
+    desc = SCENES[scene_name](36, 28)
+    p = scenes.default_params(spp=5, seed=8)
+    got, cnt = emu.gpt(desc, p)
+    ref, _, c2 = oracle.gpt(desc, p)
+    close(got, ref)
+    assert cnt[1] == c2[1] and cnt[2] == c2[2]
+
+
+@pytest.mark.parametrize("kw", [dict(max_depth=2), dict(max_depth=3, rr_depth=1), dict(strict_normals=True), dict(shift_threshold=0.1)])
+def test_environment_scene_parameters(oracle, emu, kw):
+    desc = scenes.cbox_env(28, 24)
+    p = scenes.default_params(spp=5, seed=2, **kw)
+    got, _ = emu.gpt(desc, p)
+    ref, _, _ = oracle.gpt(desc, p)
+    close(got, ref)
+
+
+def test_unsupported_scenes_fail_loudly(emu):
+    b = scenes._cornell(8, 8)
+    b.shapes[b.sphere((0, 0, 0), 0.2, 0)].emitter = 0
+    with pytest.raises(RuntimeError, match="sphere emitters"):
+        emu.gpt(b.build(), scenes.default_params(spp=1))
+    b = scenes._cornell(8, 8)
+    b.material(type=scenes.BSDF_DIELECTRIC, twosided=True)
+    with pytest.raises(RuntimeError, match="transmission component"):
+        emu.gpt(b.build(), scenes.default_params(spp=1))
+    b = scenes._cornell(8, 8)
+    b.envmap(scenes.sky_envmap(8, 4) * 0)
+    with pytest.raises(RuntimeError, match="completely black"):
+        emu.gpt(b.build(), scenes.default_params(spp=1))
