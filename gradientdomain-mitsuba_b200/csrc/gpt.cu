@@ -188,6 +188,7 @@ int gdb200_gpt_render(gdb200_scene *s, const gdb200_gpt_params *p, gdb200_buffer
     int parity = 0;
     std::vector<cudaEvent_t> marks;   // per-kernel timing (only when the caller asked for stats)
     unsigned long long tailThreshold = (unsigned long long)std::max(nSlots / 16, std::min(nSlots, 16384));
+    if (getenv("GDB200_NO_TAIL")) tailThreshold = 0;        // test knob: drain the wavefront through its queues to the last path
     // Default: both stages of a bounce in ONE pass over the state (least HBM traffic, fewest launches).
     // GDB200_SPLIT_PHASES=1 runs them as two kernels (smaller hot code per kernel) for A/B measurements.
     const bool fused = getenv("GDB200_SPLIT_PHASES") == nullptr;

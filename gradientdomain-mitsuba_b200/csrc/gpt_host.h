@@ -194,7 +194,8 @@ inline int flattenScene(const gdb200_scene_desc *d, HostScene *s)
     h.nMaterials = d->n_materials;
     for (int i = 0; i < d->n_materials; i++) {
         const gdb200_material &m = d->materials[i];
-        if (m.type < GDB200_BSDF_DIFFUSE || m.type > GDB200_BSDF_PLASTIC) return set_error(GDB200_ERR_ARGUMENT, "material %d: unknown BSDF type %d", i, m.type);
+        static_assert(kBsdfTypes == GDB200_BSDF_PLASTIC + 1, "the compaction queues are keyed by BSDF type");
+        if (m.type < GDB200_BSDF_DIFFUSE || m.type >= kBsdfTypes) return set_error(GDB200_ERR_ARGUMENT, "material %d: unknown BSDF type %d", i, m.type);
         if (m.twosided && m.type == GDB200_BSDF_DIELECTRIC)
             return set_error(GDB200_ERR_ARGUMENT, "material %d: Only materials without a transmission component can be nested!", i);   // twosided.cpp:103-105
     }

@@ -22,7 +22,8 @@ enum { RAY_NOT_CONNECTED = 0, RAY_RECENTLY_CONNECTED = 1, RAY_CONNECTED = 2 };
 enum { BUF_FINAL = 0, BUF_THROUGHPUT = 1, BUF_DX = 2, BUF_DY = 3, BUF_DIRECT = 4 };
 
 constexpr int kBounceThreads = 128, kGenThreads = 128;
-constexpr int kBuckets = 12;  // one queue per (BSDF type of the base vertex) x (shift stage of the offset paths)
+constexpr int kBsdfTypes = GDB200_BSDF_PLASTIC + 1;
+constexpr int kBuckets = 3 * kBsdfTypes;  // one queue per (BSDF type of the base vertex) x (shift stage of the offset paths)
 
 struct GptArgs {
     double *sd;            // [kRecords][nSlots][4]
@@ -46,6 +47,44 @@ GDB_D double &W(const GptArgs &a, int rec, int slot) { return REC(a, rec, slot)[
 // int fields of a slot share one 64-byte line [slot][16] (fields 0-7 in its first sector), so a kernel pulls one
 // sector per slot instead of one per field; the per-pixel sampler key is recomputed, not stored.
 GDB_D int &SI(const GptArgs &a, int field, int slot) { return a.si[((size_t)slot << 4) + field]; }
+// Fire-and-forget fp64 accumulation into global memory: one RED.E.ADD.F64 (plain atomicAdd on a generic pointer
+// compiles to an address-space dispatch with CAS loops for the shared/local cases).
+GDB_D void redAdd(double *p, double v)
+{
+#ifdef GDB200_EMU
+    *p += v;
+#else
+    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "d"(v) : "memory");
+#endif
+}
+GDB_D void redAdd(unsigned long long *p, unsigned long long v)
+{
+#ifdef GDB200_EMU
+    *p += v;
+#else
+    asm volatile("red.global.add.u64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "l"(v) : "memory");
+#endif
+}
+GDB_D unsigned long long atomAdd(unsigned long long *p, unsigned long long v)
+{
+#ifdef GDB200_EMU
+    const unsigned long long o = *p; *p = o + v; return o;
+#else
+    unsigned long long o;
+    asm volatile("atom.global.add.u64 %0, [%1], %2;" : "=l"(o) : "l"(__cvta_generic_to_global(p)), "l"(v) : "memory");
+    return o;
+#endif
+}
+GDB_D int atomAdd(int *p, int v)
+{
+#ifdef GDB200_EMU
+    const int o = *p; *p = o + v; return o;
+#else
+    int o;
+    asm volatile("atom.global.add.s32 %0, [%1], %2;" : "=r"(o) : "l"(__cvta_generic_to_global(p)), "r"(v) : "memory");
+    return o;
+#endif
+}
 GDB_D void prefetchL2(const void *p)
 {
 #ifndef GDB200_EMU
@@ -57,6 +96,18 @@ GDB_D V3 ldv(const GptArgs &a, int rec, int slot)
     const double2 *p = reinterpret_cast<const double2 *>(REC(a, rec, slot));
     const double2 lo = p[0], hi = p[1];
     return mk(lo.x, lo.y, hi.x);
+}
+// Read of a record that was updated with redAdd (performed at L2): bypass L1, which may hold the line from before
+// the reductions when the same thread reads it back inside one launch (gpt_tail_kernel).
+GDB_D V3 ldvL2(const GptArgs &a, int rec, int slot)
+{
+#ifdef GDB200_EMU
+    return ldv(a, rec, slot);
+#else
+    const double2 *p = reinterpret_cast<const double2 *>(REC(a, rec, slot));
+    const double2 lo = __ldcg(p), hi = __ldcg(p + 1);
+    return mk(lo.x, lo.y, hi.x);
+#endif
 }
 GDB_D void ldvw(const GptArgs &a, int rec, int slot, V3 &v, Float &w)
 {
@@ -105,10 +156,17 @@ GDB_D void loadOffIts(const GptArgs &a, int slot, int i, Its &its)
 
 // shifted.addRadiance / addGradient (gpt.cpp:147-156).  Most bounces add exact zeros (light sample occluded, no
 // emitter hit); x + 0 == x bit for bit, so those skip the read-modify-write of the two accumulator records.
+// The accumulators are only ever added to, so the update is a fire-and-forget reduction (RED.ADD.F64: same x + d
+// arithmetic as load-add-store, but no load whose latency this thread would have to wait out).
 GDB_D void accumulateOffset(const GptArgs &a, int o, int slot, Spec dRad, Spec dGrad)
 {
+#ifdef GDB_RMW_ACCUM
     if (!(dRad.x == 0 && dRad.y == 0 && dRad.z == 0)) stv(a, o + OR_RAD, slot, ldv(a, o + OR_RAD, slot) + dRad);
     if (!(dGrad.x == 0 && dGrad.y == 0 && dGrad.z == 0)) stv(a, o + OR_GRAD, slot, ldv(a, o + OR_GRAD, slot) + dGrad);
+#else
+    if (!(dRad.x == 0 && dRad.y == 0 && dRad.z == 0)) { double *p = REC(a, o + OR_RAD, slot); redAdd(p, dRad.x); redAdd(p + 1, dRad.y); redAdd(p + 2, dRad.z); }
+    if (!(dGrad.x == 0 && dGrad.y == 0 && dGrad.z == 0)) { double *p = REC(a, o + OR_GRAD, slot); redAdd(p, dGrad.x); redAdd(p + 1, dGrad.y); redAdd(p + 2, dGrad.z); }
+#endif
 }
 
 // Warp-aggregated append of an ended slot to the next step's regeneration queue.
@@ -117,7 +175,7 @@ GDB_D void appendGen(const GptArgs &a, int parity, int slot)
     const unsigned m = __activemask();
     const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
     int base = 0;
-    if (lane == leader) base = atomicAdd(&a.genCount[parity], __popc(m));
+    if (lane == leader) base = atomAdd(&a.genCount[parity], __popc(m));
     base = __shfl_sync(m, base, leader);
     a.genList[(size_t)parity * a.nSlots + base + __popc(m & ((1u << lane) - 1))] = slot;
 }
@@ -149,7 +207,7 @@ GDB_D void countWarp(unsigned long long *ctr, unsigned v)
 {
     const unsigned m = __activemask();
     const unsigned s = __reduce_add_sync(m, v);
-    if ((int)(threadIdx.x & 31) == __ffs(m) - 1 && s) atomicAdd(ctr, (unsigned long long)s);
+    if ((int)(threadIdx.x & 31) == __ffs(m) - 1 && s) redAdd(ctr, (unsigned long long)s);
 }
 
 // ------------------------------------------------------------------ film (ImageBlock::put, imageblock.h:150-195)
@@ -174,7 +232,7 @@ GDB_CALL void filmPut(const GptArgs &a, Float sx, Float sy, Spec v, Float weight
             const Float wgt = evalDiscretized(x - posx) * weightY;
             double *dst = a.film + ((((size_t)buf * H + y) * W + x) << 2);
 #pragma unroll
-            for (int k = 0; k < 4; k++) atomicAdd(dst + k, wgt * value[k]);
+            for (int k = 0; k < 4; k++) redAdd(dst + k, wgt * value[k]);
         }
     }
 }
@@ -213,7 +271,7 @@ GDB_D void generateBody(const GptArgs &a, int slot)
     if (SI(a, IF_STATUS, slot) == ST_FINISHED) {
         Spec rad[4], grad[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) { const int o = BR_COUNT + i * OR_COUNT; rad[i] = ldv(a, o + OR_RAD, slot); grad[i] = ldv(a, o + OR_GRAD, slot); }
+        for (int i = 0; i < 4; i++) { const int o = BR_COUNT + i * OR_COUNT; rad[i] = ldvL2(a, o + OR_RAD, slot); grad[i] = ldvL2(a, o + OR_GRAD, slot); }
         splatSample(a, W(a, BR_GN, slot), W(a, BR_S, slot), ldv(a, BR_VD, slot), ldv(a, BR_RAD, slot), rad, grad);
     }
 
@@ -225,7 +283,7 @@ GDB_D void generateBody(const GptArgs &a, int slot)
     int status = ST_DONE;
     for (;;) {
         if (j >= si.count) {                                                         // stream exhausted: take the next one
-            stream = (int)atomicAdd(&a.counters[6], 1ULL);
+            stream = (int)atomAdd(&a.counters[6], 1ULL);
             if (stream >= a.nStreams) break;
             si = streamInfo(a, stream); smp.key = si.key; smp.n = 0; j = 0;
             continue;
@@ -260,7 +318,7 @@ GDB_D void generateBody(const GptArgs &a, int slot)
         if (early || !(1 < a.cfg.maxDepth || a.cfg.maxDepth < 0)) {                  // bounce loop never entered (gpt.cpp:537)
             const Spec zero[4] = {splat(0), splat(0), splat(0), splat(0)};
             splatSample(a, spx, spy, veryDirect, splat(0), zero, zero);
-            if (!early) atomicAdd(&a.counters[2], 1ULL);                             // avgPathLength += depth (1), gpt.cpp:1178-1179
+            if (!early) redAdd(&a.counters[2], 1ULL);                             // avgPathLength += depth (1), gpt.cpp:1178-1179
             continue;
         }
         storeBaseIts(a, slot, mits);
@@ -748,7 +806,7 @@ __global__ void __launch_bounds__(256) gpt_compact_kernel(const GptArgs a, int p
     if (threadIdx.x < kBuckets) {
         int tot = 0;
         for (int w = 0; w < 8; w++) { const int c = s_warp[w][threadIdx.x]; s_warp[w][threadIdx.x] = tot; tot += c; }
-        s_base[threadIdx.x] = tot ? atomicAdd(&a.liveCount[parity * kBuckets + threadIdx.x], tot) : 0;
+        s_base[threadIdx.x] = tot ? atomAdd(&a.liveCount[parity * kBuckets + threadIdx.x], tot) : 0;
     }
     __syncthreads();
     if (bucket >= 0) a.liveList[((size_t)parity * kBuckets + bucket) * a.nSlots + s_base[bucket] + s_warp[warp][bucket] + rank] = slot;
@@ -805,8 +863,8 @@ __global__ void gpt_check_culling_kernel(unsigned long long seed, int nRays, uns
     const bool a2 = closestPrimitiveExhaustive<true>(ray, rayMinT, ray.maxt, tt, kk, ii, uu, vv);
     bool bad = (h1 != h2) || (a1 != a2) || (h1 != a1);
     if (h1 && h2) bad = bad || t1 != t2 || k1 != k2 || i1 != i2 || (k1 >= 2 && (u1 != u2 || v1 != v2));
-    if (bad) atomicAdd(mismatch, 1ULL);
-    if (h1) atomicAdd(mismatch + 1, 1ULL);
+    if (bad) redAdd(mismatch, 1ULL);
+    if (h1) redAdd(mismatch + 1, 1ULL);
 }
 
 // MultiFilm::developMulti (multifilm.cpp:366-416, fmtconv.cpp:1036-1045): value * (1/weight), plus the

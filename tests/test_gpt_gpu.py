@@ -50,7 +50,7 @@ def test_tracer_matches_oracle(oracle, scene_name):
     ref, wts, cnt = oracle.gpt(desc, integ.params(16, 3))
     rep = compare(got, ref)
     print(scene_name, rep)
-    assert integ.stats.samples == w * h * 16 == cnt[0]
+    assert integ.stats.samples == desc.camera.width * desc.camera.height * 16 == cnt[0]
     # same number of rays and path vertices unless a branch flipped
     assert abs(integ.stats.rays - cnt[1]) <= 1e-3 * cnt[1]
     assert abs(integ.stats.path_vertices - cnt[2]) <= 1e-3 * cnt[2]
@@ -228,3 +228,17 @@ def test_large_mesh_scene_renders(oracle):
     for k in out:
         assert np.isfinite(out[k]).all(), k
     assert out["-throughput"].mean() > 0.01 and integ.stats.samples == 160 * 90 * 8
+
+
+@pytest.mark.parametrize("scene_name", ["cbox_mesh_lights", "cbox_env"])
+def test_wavefront_without_tail_kernel(oracle, scene_name, monkeypatch):
+    """Small images finish in gpt_tail_kernel after the first 16 wavefront steps; GDB200_NO_TAIL keeps every path on
+    the queued wavefront (generate -> compact -> bounce) to the end, for every BSDF-type bucket."""
+    monkeypatch.setenv("GDB200_NO_TAIL", "1")
+    w, h = 72, 56
+    desc = getattr(scenes, scene_name)(w, h)
+    integ = gdb200.GPTIntegrator(reconstructL1=False, reconstructL2=False)
+    got = integ.trace(gdb200.Scene(desc), spp=6, seed=12, streams=2)
+    ref, _, cnt = oracle.gpt(desc, integ.params(6, 12, streams=2))
+    compare(got, ref)
+    assert integ.stats.samples == w * h * 6 == cnt[0]
