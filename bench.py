@@ -147,7 +147,7 @@ def main():
               "scene": "synthetic Cornell box + GGX spheres (gdb200.scenes)", "sampler": f"gdb200_counter seed 0, {args.streams} sample streams per pixel",
               "maxDepth": -1, "rrDepth": 5, "shiftThreshold": 0.001, "alpha": 0.2,
               "parallelism": f"interleaved 16-row bands x{world}, one NCCL all-reduce of the film accumulators" if world > 1 else "1 GPU",
-              "l2_flush": "per-step working set (1.2 GB wavefront state + 168 MB film) exceeds the 126 MB L2"}
+              "l2_flush": "per-step working set (>= 1.5 GB of wavefront state per million resident path slots + 168 MB film) exceeds the 126 MB L2"}
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
@@ -184,7 +184,7 @@ def main():
     plan = gdb200.PoissonPlan(W, H) if rank == 0 else None
     bands = tiles.band_spec(rank, world, 16) if world > 1 else None    # interleaved 16-row bands: balanced strong scaling
     acc = scene.accumulators() if world > 1 else None
-    agg = {"bounce_ms": 0.0, "generate_ms": 0.0, "compact_ms": 0.0, "state_bytes": 0.0, "bounce_launches": 0, "trace_ms": 0.0,
+    agg = {"bounce_ms": 0.0, "generate_ms": 0.0, "compact_ms": 0.0, "state_bytes": 0.0, "bounce_launches": 0, "trace_ms": 0.0, "path_bounces": 0.0,
            "solve_ms": 0.0, "launches": 0, "samples": 0.0, "rays": 0.0, "exchange_bytes": 0}
 
     def step(timed):
@@ -197,7 +197,7 @@ def main():
             integ.reconstruct(scene, plan, download=False)
         if timed:
             st = integ.stats
-            for k in ("bounce_ms", "generate_ms", "compact_ms", "state_bytes", "bounce_launches", "samples", "rays"):
+            for k in ("bounce_ms", "generate_ms", "compact_ms", "state_bytes", "bounce_launches", "samples", "rays", "path_bounces"):
                 agg[k] += getattr(st, k)
             agg["trace_ms"] += st.device_ms
             agg["launches"] += st.launches + 1 + (1 if rank == 0 else 0)
@@ -259,9 +259,10 @@ def main():
         peaks, peak_src = measured_peaks()
         bounce_avg_ms = agg["bounce_ms"] / max(1, agg["bounce_launches"])
         achieved = agg["state_bytes"] / max(agg["bounce_ms"], 1e-9) / 1e6          # GB/s
-        traffic = None
+        traffic = None          # DRAM bytes per launch: ncu's per-thread figure for this kernel (profiles/) x this run's threads per launch
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_gpt_bounce_summary.json")))["dram_bytes_per_launch"]
+            per_thread = json.load(open(os.path.join(ROOT, "profiles", "r01_gpt_bounce_summary.json")))["dram_bytes_per_thread"]
+            traffic = round(per_thread * agg["path_bounces"] / max(1, agg["bounce_launches"]))
         except Exception:
             pass
         solve_ms = agg["solve_ms"] / args.steps

@@ -8,4 +8,4 @@ CUDA device is present the calls raise.
 from ._ffi import lib, Gdb200Error, Stats, library_path  # noqa: F401
 from .poisson import PoissonSolver, SolverParams, poisson_solve, PoissonPlan  # noqa: F401
 from .gpt import GPTIntegrator, Scene, BUFFER_NAMES  # noqa: F401
-from . import scenes, synth  # noqa: F401
+from . import scenes, synth, pfm  # noqa: F401

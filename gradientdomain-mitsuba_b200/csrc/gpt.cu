@@ -150,7 +150,7 @@ int gdb200_gpt_render(gdb200_scene *s, const gdb200_gpt_params *p, gdb200_buffer
     if (!s || !p) return set_error(GDB200_ERR_ARGUMENT, "scene/params is NULL");
     GptArgs a;
     const char *capEnv = getenv("GDB200_MAX_SLOTS");        // resident path slots (tuning knob; streams beyond it are dealt out as slots drain)
-    if (int rc = setupArgs(*s, p, a, capEnv ? atoi(capEnv) : (1 << 20))) return rc;
+    if (int rc = setupArgs(*s, p, a, capEnv ? atoi(capEnv) : (1 << 23))) return rc;
     GDB_CUDA(cudaSetDevice(s->device));
     const int nSlots = a.nSlots;
     if (nSlots > s->slotCapacity) {

@@ -335,7 +335,7 @@ GDB_D bool closestPrimitiveExhaustive(const Ray &ray, Float mint, Float maxt, Fl
 }
 
 // ShapeKDTree::rayIntersect(ray, its): skdtree.cpp:112-147, record fill skdtree.h:343-428.
-GDB_CALL bool rayIntersect(const Ray &ray, Its &its)
+GDB_D bool rayIntersectImpl(const Ray &ray, Its &its)
 {
     its.t = CUDART_INF;
     Float rayMinT = ray.mint;
@@ -373,7 +373,7 @@ GDB_CALL bool rayIntersect(const Ray &ray, Its &its)
 }
 
 // ShapeKDTree::rayIntersect(ray) for shadow rays: skdtree.cpp:206-226
-GDB_CALL bool rayOccluded(const Ray &ray)
+GDB_D bool rayOccludedImpl(const Ray &ray)
 {
     Float rayMinT = ray.mint;
     if (rayMinT == kEpsilon) rayMinT *= maxAbs3(ray.o);
@@ -381,6 +381,32 @@ GDB_CALL bool rayOccluded(const Ray &ray)
     Float t, u, v; int a, b;
     return closestPrimitive<true>(ray, rayMinT, ray.maxt, t, a, b, u, v);
 }
+
+// The out-of-line entry points take and return their structs BY VALUE: the device ABI then passes them in registers,
+// whereas a `const Ray &` / `Its &` parameter forces the caller's struct into local memory (stack traffic through
+// L1/L2 on every call: 44 % of the bounce kernel's L2 sectors before this change, profiles/r01b_*).
+// Measured (profiles/r01_gpt_history.md, rows 17-18): by-value pays in gpt_generate_kernel (five back-to-back
+// intersections per sample, -13 % kernel time) and costs in gpt_bounce_kernel (the returned record raises the register
+// pressure around the call, +7 %), so both forms of rayIntersect exist and each kernel calls the one that suits it.
+// GDB_BYVAL switches the remaining routines for A/B builds (bit 1 rayOccluded, 2 bsdfEvalPdf, 3 bsdfSample, 4 sampleEmitterDirectVisible).
+#ifndef GDB_BYVAL
+#define GDB_BYVAL 0
+#endif
+GDB_CALL Its rayIntersectV(Ray ray) { Its its; rayIntersectImpl(ray, its); return its; }
+GDB_D bool rayIntersectByValue(const Ray &ray, Its &its)
+{
+    const Its r = rayIntersectV(ray);
+    if (r.t == CUDART_INF) { its.t = CUDART_INF; return false; }
+    its = r;
+    return true;
+}
+GDB_CALL bool rayIntersect(const Ray &ray, Its &its) { return rayIntersectImpl(ray, its); }
+#if GDB_BYVAL & 2
+GDB_CALL bool rayOccludedV(Ray ray) { return rayOccludedImpl(ray); }
+GDB_D bool rayOccluded(const Ray &ray) { return rayOccludedV(ray); }
+#else
+GDB_CALL bool rayOccluded(const Ray &ray) { return rayOccludedImpl(ray); }
+#endif
 
 // ---------------------------------------------------------------- sampling helpers
 GDB_D void squareToUniformDiskConcentric(Float sx, Float sy, Float &ox, Float &oy)   // warp.cpp:81-102
@@ -558,7 +584,7 @@ GDB_D V3 refractLocal(const DMaterial &m, V3 wi, Float cosThetaT)               
 // ---------------------------------------------------------------- BSDF eval / pdf / sample
 // Evaluates f*cos and the solid-angle (or discrete) density together: every call site of the
 // reference asks for both (gpt.cpp:588-592,645-647,693-694,871-872,935-936,1030-1031).
-GDB_CALL void bsdfEvalPdf(const DMaterial &m, V3 wi, V3 wo, int measure, Spec &value, Float &pdf)
+GDB_D void bsdfEvalPdfImpl(const DMaterial &m, V3 wi, V3 wo, int measure, Spec &value, Float &pdf)
 {
     value = splat(0); pdf = 0;
     if (m.twosided && !(wi.z > 0)) { wi.z *= -1; wo.z *= -1; }                         // twosided.cpp:109-135
@@ -618,17 +644,41 @@ GDB_CALL void bsdfEvalPdf(const DMaterial &m, V3 wi, V3 wo, int measure, Spec &v
     }
 }
 
+struct EvalPdf { Spec value; Float pdf; };
+#if GDB_BYVAL & 4
+GDB_CALL EvalPdf bsdfEvalPdfV(const DMaterial &m, V3 wi, V3 wo, int measure) { EvalPdf r; bsdfEvalPdfImpl(m, wi, wo, measure, r.value, r.pdf); return r; }
+GDB_D void bsdfEvalPdf(const DMaterial &m, V3 wi, V3 wo, int measure, Spec &value, Float &pdf)
+{
+    const EvalPdf r = bsdfEvalPdfV(m, wi, wo, measure);
+    value = r.value; pdf = r.pdf;
+}
+#else
+GDB_CALL void bsdfEvalPdf(const DMaterial &m, V3 wi, V3 wo, int measure, Spec &value, Float &pdf) { bsdfEvalPdfImpl(m, wi, wo, measure, value, pdf); }
+#endif
+
 struct BSDFSample { V3 wo; Float eta; unsigned sampledType; Spec weight; Float pdf; };
 
 // BSDF::sample(bRec, pdf, sample), pdf pre-set to 0 by the caller (gpt.cpp:450-457)
 GDB_D void bsdfSampleOneSided(const DMaterial &m, V3 wi, Float sx, Float sy, BSDFSample &r);
-GDB_CALL void bsdfSample(const DMaterial &m, V3 wi, Float sx, Float sy, BSDFSample &r)
+#if GDB_BYVAL & 8
+GDB_CALL
+#else
+GDB_D
+#endif
+BSDFSample bsdfSampleV(const DMaterial &m, V3 wi, Float sx, Float sy)
 {
+    BSDFSample r;
     const bool flipped = m.twosided && wi.z < 0;                                       // twosided.cpp:160-183
     if (flipped) wi.z *= -1;
     bsdfSampleOneSided(m, wi, sx, sy, r);
     if (flipped && !isZero(r.weight) && r.pdf != 0) r.wo.z *= -1;
+    return r;
 }
+#if GDB_BYVAL & 8
+GDB_D void bsdfSample(const DMaterial &m, V3 wi, Float sx, Float sy, BSDFSample &r) { r = bsdfSampleV(m, wi, sx, sy); }
+#else
+GDB_CALL void bsdfSample(const DMaterial &m, V3 wi, Float sx, Float sy, BSDFSample &r) { r = bsdfSampleV(m, wi, sx, sy); }
+#endif
 GDB_D void bsdfSampleOneSided(const DMaterial &m, V3 wi, Float sx, Float sy, BSDFSample &r)
 {
     r.weight = splat(0); r.pdf = 0; r.eta = 1.0; r.sampledType = 0; r.wo = mk(0, 0, 0);
@@ -822,7 +872,7 @@ GDB_D bool envFillDRec(DRec &dRec, V3 o, V3 d)
 // Scene::sampleEmitterDirectVisible, scene.cpp:855-879: emitter pick (pmf.h:124-188), Emitter::sampleDirect
 // (area.cpp:158-176 over shape.cpp:102-114 with rectangle.cpp:210-216 / trimesh.cpp:412-423 + triangle.cpp:24-50;
 // envmap.cpp:516-544), then the shadow ray.
-GDB_CALL Spec sampleEmitterDirectVisible(DRec &dRec, Float sx, Float sy, bool &visible)
+GDB_D Spec sampleEmitterDirectVisibleImpl(DRec &dRec, Float sx, Float sy, bool &visible)
 {
     Float emPdf;
     const int index = cdfSampleReuse(c_scene.emCdf, c_scene.nEmitters, sx, emPdf);
@@ -876,6 +926,26 @@ GDB_CALL Spec sampleEmitterDirectVisible(DRec &dRec, Float sx, Float sy, bool &v
     visible = true;
     return value;
 }
+
+struct EmitterSample { DRec dRec; Spec value; int visible; };
+#if GDB_BYVAL & 16
+GDB_CALL EmitterSample sampleEmitterDirectVisibleV(V3 ref, V3 refN, Float sx, Float sy)
+{
+    EmitterSample r; bool vis;
+    r.dRec.ref = ref; r.dRec.refN = refN;
+    r.value = sampleEmitterDirectVisibleImpl(r.dRec, sx, sy, vis);
+    r.visible = vis;
+    return r;
+}
+GDB_D Spec sampleEmitterDirectVisible(DRec &dRec, Float sx, Float sy, bool &visible)
+{
+    const EmitterSample r = sampleEmitterDirectVisibleV(dRec.ref, dRec.refN, sx, sy);
+    dRec = r.dRec; visible = r.visible != 0;
+    return r.value;
+}
+#else
+GDB_CALL Spec sampleEmitterDirectVisible(DRec &dRec, Float sx, Float sy, bool &visible) { return sampleEmitterDirectVisibleImpl(dRec, sx, sy, visible); }
+#endif
 
 // Scene::pdfEmitterDirect, scene.cpp:976-979 + area.cpp:178-186 + shape.cpp:116-126 / envmap.cpp:546-556
 GDB_D Float pdfEmitterDirect(const DRec &dRec)

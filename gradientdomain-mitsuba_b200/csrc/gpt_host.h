@@ -452,7 +452,7 @@ inline void classifyMaterials(HostScene *s, double shiftThreshold)
 // Parameter validation of gpt.cpp:1194-1210 / integrator.cpp:190-225 and the launch geometry of one render:
 // which pixels this call owns (row strip or interleaved bands), how many sample streams they form and how
 // many path slots are resident.  Fills every non-pointer field of GptArgs.
-inline int setupArgs(const HostScene &s, const gdb200_gpt_params *p, GptArgs &a, int maxSlots = 1 << 20)
+inline int setupArgs(const HostScene &s, const gdb200_gpt_params *p, GptArgs &a, int maxSlots = 1 << 23)
 {
     if (p->max_depth <= 0 && p->max_depth != -1) return set_error(GDB200_ERR_ARGUMENT, "'maxDepth' must be set to -1 (infinite) or a value greater than zero!");
     if (p->rr_depth <= 0) return set_error(GDB200_ERR_ARGUMENT, "'rrDepth' must be set to a value greater than zero!");

@@ -293,7 +293,7 @@ GDB_D void generateBody(const GptArgs &a, int slot)
         const Float spx = si.px + u, spy = si.py + v;
         Ray ray; Its mits;
         sampleCameraRay(spx, spy, ray);                                              // gpt.cpp:402
-        const bool mainValid = rayIntersect(ray, mits); rays += 5;                   // gpt.cpp:472
+        const bool mainValid = rayIntersectByValue(ray, mits); rays += 5;                   // gpt.cpp:472
         Spec veryDirect = splat(0);
         unsigned flags = 0;
         bool early = !mainValid;                                                     // gpt.cpp:482-492
@@ -305,7 +305,7 @@ GDB_D void generateBody(const GptArgs &a, int slot)
         for (int i = 0; i < 4; i++) {
             Ray sray; Its sits;
             sampleCameraRay(spx + shiftX[i], spy + shiftY[i], sray);                 // gpt.cpp:418
-            bool alive = rayIntersect(sray, sits);                                   // gpt.cpp:476-480, 508-513
+            bool alive = rayIntersectByValue(sray, sits);                            // gpt.cpp:476-480, 508-513
             if (alive && a.cfg.strictNormals && dot(sray.d, sits.geoN) * sits.wi.z >= 0) alive = false;   // gpt.cpp:523-530
             flags |= packFlag(i, alive, RAY_NOT_CONNECTED);
             if (!early) {
@@ -336,7 +336,10 @@ GDB_D void generateBody(const GptArgs &a, int slot)
     countWarp(&a.counters[3], (unsigned)samples);
 }
 
-__global__ void __launch_bounds__(kGenThreads) gpt_generate_kernel(const GptArgs a, int parity)
+#ifndef GDB_GEN_MINBLOCKS
+#define GDB_GEN_MINBLOCKS 2         // resident CTAs/SM the generate kernel's register allocation is sized for (2 => up to 255 registers)
+#endif
+__global__ void __launch_bounds__(kGenThreads, GDB_GEN_MINBLOCKS) gpt_generate_kernel(const GptArgs a, int parity)
 {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= a.genCount[parity]) return;

@@ -160,3 +160,9 @@ class GPTIntegrator:
         if final is not None:
             out["-final"] = final.astype(np.float64)     # setBitmapMulti(reconstruction, BUFFER_FINAL), gpt.cpp:1468-1475
         return out
+
+    def save(self, dest, buffers):
+        """MultiFilm::develop for fileFormat "pfm" (multifilm.cpp:423-516): writes <dest>-final.pfm, -throughput.pfm,
+        -dx.pfm, -dy.pfm, -direct.pfm (float32 RGB, bottom-up scanlines) and returns the paths."""
+        from . import pfm
+        return pfm.save_multifilm(dest, buffers)

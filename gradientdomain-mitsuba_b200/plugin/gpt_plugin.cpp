@@ -18,6 +18,7 @@
 #include <vector>
 #include <string>
 #include <cstring>
+#include <algorithm>
 #include "../../include/gdb200.h"
 
 MTS_NAMESPACE_BEGIN
@@ -44,6 +45,14 @@ struct FlatScene {
 	std::vector<double> vertices;
 	std::vector<int> triangles;
 
+	std::vector<float> envRGB;
+	gdb200_envmap env;
+
+	/* lookupIOR (src/bsdfs/ior.h) accepts a number or a material name; the shim takes numbers only */
+	static double lookupIORValue(const Properties &p, const std::string &name, double def) {
+		return p.hasProperty(name) ? (double) p.getFloat(name, (Float) def) : def;
+	}
+
 	int addMaterial(const BSDF *bsdf, bool isEmitterShape) {
 		gdb200_material m;
 		memset(&m, 0, sizeof(m));
@@ -69,6 +78,13 @@ struct FlatScene {
 			else SLog(EError, "gdb200: microfacet distribution \"%s\" is not supported", distr.c_str());
 			if (p.hasProperty("alphaU") || p.hasProperty("alphaV") || !p.getBoolean("sampleVisible", true))
 				SLog(EError, "gdb200: anisotropic / non-visible-normal roughconductor is not supported");
+		} else if (cls == "SmoothPlastic") {
+			m.type = GDB200_BSDF_PLASTIC;                 /* plastic.cpp:143-165 */
+			m.ior_ratio = p.hasProperty("intIOR") || p.hasProperty("extIOR")
+				? lookupIORValue(p, "intIOR", 1.49) / lookupIORValue(p, "extIOR", 1.000277) : 1.49 / 1.000277;
+			copySpectrum(p.getSpectrum("specularReflectance", Spectrum(1.0f)), m.specular_reflectance);
+			copySpectrum(p.getSpectrum("diffuseReflectance", Spectrum(0.5f)), m.reflectance);
+			m.nonlinear = p.getBoolean("nonlinear", false);
 		} else if (cls == "SmoothDielectric") {
 			m.type = GDB200_BSDF_DIELECTRIC;
 			m.ior_ratio = bsdf->getEta();        /* dielectric.cpp:389-391 */
@@ -151,10 +167,11 @@ struct FlatScene {
 			}
 			if (shape->isEmitter()) {
 				const Emitter *e = shape->getEmitter();
-				if (e->getClass()->getName() != "AreaLight" || s.type != GDB200_SHAPE_RECTANGLE)
-					SLog(EError, "gdb200: only 'area' emitters on rectangles are supported");
+				if (e->getClass()->getName() != "AreaLight" || (s.type != GDB200_SHAPE_RECTANGLE && s.type != GDB200_SHAPE_MESH))
+					SLog(EError, "gdb200: 'area' emitters are supported on rectangles and triangle meshes");
 				gdb200_emitter em;
 				memset(&em, 0, sizeof(em));
+				em.type = GDB200_EMITTER_AREA;
 				em.shape = (int) shapes.size();
 				copySpectrum(e->getProperties().getSpectrum("radiance", Spectrum(1.0f)), em.radiance);
 				em.sampling_weight = e->getSamplingWeight();
@@ -163,8 +180,42 @@ struct FlatScene {
 			}
 			shapes.push_back(s);
 		}
-		if (scene->getEnvironmentEmitter())
-			SLog(EError, "gdb200: environment emitters are not supported yet");
+		if (const Emitter *e = scene->getEnvironmentEmitter()) {
+			/* envmap.cpp: the top MIP level as a float RGB bitmap (Emitter::getBitmap, envmap.cpp:644-646), the
+			   emitter-to-world transform and the bounding sphere EnvironmentMap::createShape derives (envmap.cpp:322-329) */
+			if (e->getClass()->getName() != "EnvironmentMap")
+				SLog(EError, "gdb200: environment emitter class \"%s\" is outside the supported hot-path subset", e->getClass()->getName().c_str());
+			ref<Bitmap> bitmap = e->getBitmap(Vector2i());
+			ref<Bitmap> rgb = bitmap->convert(Bitmap::ERGB, Bitmap::EFloat32);
+			memset(&env, 0, sizeof(env));
+			env.width = rgb->getWidth(); env.height = rgb->getHeight();
+			envRGB.assign(rgb->getFloat32Data(), rgb->getFloat32Data() + (size_t) env.width * env.height * 3);
+			env.rgb = envRGB.data();
+			env.scale = e->getProperties().getFloat("scale", 1.0f);
+			const Transform toWorld = e->getWorldTransform()->eval(0);
+			copyMatrix(toWorld.getMatrix(), env.to_world);
+			copyMatrix(toWorld.inverse().getMatrix(), env.to_object);
+			AABB aabb = scene->getKDTree()->getAABB();                       /* = scene->getAABB() at createShape time, scene.cpp:386-396 */
+			aabb.expandBy(sensor->getAABB());
+			BSphere bs = aabb.getBSphere();
+			env.bsphere_center[0] = bs.center.x; env.bsphere_center[1] = bs.center.y; env.bsphere_center[2] = bs.center.z;
+			env.bsphere_radius = std::max((double) Epsilon, (double) bs.radius * 1.5);
+			gdb200_emitter em;
+			memset(&em, 0, sizeof(em));
+			em.type = GDB200_EMITTER_ENVMAP; em.shape = -1;
+			em.sampling_weight = e->getSamplingWeight();
+			/* Scene::m_emitters order decides the emitter CDF: the environment emitter sits where the scene lists it */
+			size_t envIndex = 0;
+			const ref_vector<Emitter> &all = scene->getEmitters();
+			while (envIndex < all.size() && all[envIndex].get() != e) ++envIndex;
+			envIndex = std::min(envIndex, emitters.size());
+			emitters.insert(emitters.begin() + envIndex, em);
+			for (size_t i = 0; i < shapes.size(); ++i)
+				if (shapes[i].emitter >= (int) envIndex) shapes[i].emitter++;
+			for (size_t i = 0; i < emitters.size(); ++i)
+				if (emitters[i].type == GDB200_EMITTER_AREA) for (size_t k = 0; k < shapes.size(); ++k) if (shapes[k].emitter == (int) i) emitters[i].shape = (int) k;
+			desc.envmap = &env;
+		}
 		desc.n_shapes = (int) shapes.size();       desc.shapes = shapes.data();
 		desc.n_materials = (int) materials.size(); desc.materials = materials.data();
 		desc.n_emitters = (int) emitters.size();   desc.emitters = emitters.data();
@@ -184,6 +235,8 @@ public:
 		m_reconstructL2 = props.getBoolean("reconstructL2", false);
 		m_reconstructAlpha = (Float) props.getFloat("reconstructAlpha", Float(0.2));
 		m_seed = (uint64_t) props.getSize("seed", 0);
+		/* gdb200 extension: sample streams per pixel (include/gdb200.h: gdb200_gpt_params.streams_per_pixel); 1 = the reference's single stream */
+		m_streamsPerPixel = (int) props.getSize("streamsPerPixel", 1);
 		if (m_reconstructL1 && m_reconstructL2)
 			Log(EError, "Disable 'reconstructL1' or 'reconstructL2': Cannot display two reconstructions at a time!");
 		if (m_reconstructAlpha <= 0.0f)
@@ -200,6 +253,7 @@ public:
 		m_reconstructL2 = stream->readBool();
 		m_reconstructAlpha = stream->readFloat();
 		m_seed = 0;
+		m_streamsPerPixel = 1;
 	}
 
 	void serialize(Stream *stream, InstanceManager *manager) const {
@@ -239,6 +293,7 @@ public:
 		params.shift_threshold = m_shiftThreshold;
 		params.spp = (int) sampler->getSampleCount();
 		params.seed = m_seed;
+		params.streams_per_pixel = m_streamsPerPixel;
 		params.skip_preview = (m_reconstructL1 || m_reconstructL2) ? 1 : 0;   /* "-final" is replaced by the reconstruction */
 
 		const Vector2i size = film->getCropSize();
@@ -314,6 +369,7 @@ private:
 	Float m_shiftThreshold, m_reconstructAlpha;
 	bool m_reconstructL1, m_reconstructL2;
 	uint64_t m_seed;
+	int m_streamsPerPixel;
 	gdb200_scene *m_scene;
 };
 

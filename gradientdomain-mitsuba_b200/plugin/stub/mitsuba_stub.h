@@ -24,7 +24,7 @@ typedef double Float;
 enum ELogLevel { EInfo, EWarn, EError };
 void stubLog(ELogLevel, const char *, ...);
 struct Class { std::string getName() const; bool derivesFrom(const Class *) const; };
-struct Vector2i { int x, y; bool operator!=(const Vector2i &) const; };
+struct Vector2i { int x, y; Vector2i(int = 0, int = 0); bool operator!=(const Vector2i &) const; };
 struct Vector { Float x, y, z; Vector(Float = 0, Float = 0, Float = 0); Float length() const; };
 struct Point { Float x, y, z; Point(Float = 0, Float = 0, Float = 0); Float operator[](int) const; };
 struct Spectrum { Spectrum(Float = 0); Float operator[](int) const; };
@@ -42,6 +42,7 @@ struct Transform {
 };
 struct AnimatedTransform { const Transform &eval(Float) const; };
 struct Properties {
+	Properties(const std::string & = "");
 	bool hasProperty(const std::string &) const;
 	Float getFloat(const std::string &, Float) const;
 	bool getBoolean(const std::string &, bool) const;
@@ -53,24 +54,41 @@ struct Properties {
 };
 template <typename T> struct ref { ref(T * = 0); T *operator->() const; T *get() const; operator T *() const; };
 template <typename T> struct ref_vector { size_t size() const; const ref<T> &operator[](size_t) const; };
-struct Stream { Float readFloat(); bool readBool(); void writeFloat(Float); void writeBool(bool); };
+struct Stream { Float readFloat(); bool readBool(); void writeFloat(Float); void writeBool(bool); uint64_t readULong(); void writeULong(uint64_t); };
 struct InstanceManager;
 struct ConfigurableObject { virtual ~ConfigurableObject(); virtual const Class *getClass() const; const Properties &getProperties() const; };
 struct BSDF : ConfigurableObject { Float getEta() const; static Class *m_theClass; };
-struct Emitter : ConfigurableObject { Float getSamplingWeight() const; };
+struct Bitmap;
+struct AnimatedTransform;
+struct Emitter : ConfigurableObject { Float getSamplingWeight() const; ref<Bitmap> getBitmap(const Vector2i &) const; const AnimatedTransform *getWorldTransform() const; };
 struct Shape : ConfigurableObject { const BSDF *getBSDF() const; bool isEmitter() const; const Emitter *getEmitter() const; };
 struct Triangle { uint32_t idx[3]; };
 struct TriMesh : Shape { static Class *m_theClass; bool hasVertexNormals() const; size_t getTriangleCount() const; size_t getVertexCount() const;
 	const Point *getVertexPositions() const; const Triangle *getTriangles() const; };
 struct ReconstructionFilter : ConfigurableObject { Float getRadius() const; };
-struct Bitmap { enum EPixelFormat { ESpectrum }; enum EComponentFormat { EFloat }; Bitmap(EPixelFormat, EComponentFormat, const Vector2i &); Float *getFloatData(); };
+struct Bitmap { enum EPixelFormat { ESpectrum, ERGB }; enum EComponentFormat { EFloat, EFloat32 }; Bitmap(EPixelFormat, EComponentFormat, const Vector2i &); Float *getFloatData();
+	ref<Bitmap> convert(EPixelFormat, EComponentFormat) const; int getWidth() const; int getHeight() const; const float *getFloat32Data() const; };
+struct BSphere { Point center; Float radius; };
+struct AABB { BSphere getBSphere() const; void expandBy(const AABB &); };
+static const Float Epsilon = 1e-7;
 struct Film : ConfigurableObject { Vector2i getCropSize() const; Vector2i getSize() const; const ReconstructionFilter *getReconstructionFilter() const;
 	bool setBuffers(const std::vector<std::string> &); bool setBitmapMulti(const Bitmap *, Float, int); };
 struct Sensor : ConfigurableObject { Film *getFilm(); const Film *getFilm() const; bool needsApertureSample() const; bool needsTimeSample() const;
-	const AnimatedTransform *getWorldTransform() const; };
+	const AnimatedTransform *getWorldTransform() const; AABB getAABB() const; };
 struct PerspectiveCamera : Sensor { Float getAspect() const; Float getXFov() const; Float getNearClip() const; Float getFarClip() const; };
-struct Sampler : ConfigurableObject { size_t getSampleCount() const; };
-struct Scene : ConfigurableObject { const ref_vector<Shape> &getShapes() const; const Emitter *getEnvironmentEmitter() const; };
+struct Point2i { int x, y; };
+struct Point2 { Float x, y; Point2(Float = 0, Float = 0); };
+struct Sampler : ConfigurableObject {
+	Sampler(const Properties &); Sampler(Stream *, InstanceManager *);
+	virtual void serialize(Stream *, InstanceManager *) const;
+	size_t getSampleCount() const; void request1DArray(size_t); void request2DArray(size_t);
+	static Class *m_theClass;
+	size_t m_sampleCount, m_sampleIndex; std::vector<size_t> m_req1D, m_req2D;
+	std::vector<Float *> m_sampleArrays1D; std::vector<Point2 *> m_sampleArrays2D; int m_dimension1DArray, m_dimension2DArray;
+};
+struct ShapeKDTree { const AABB &getAABB() const; };
+struct Scene : ConfigurableObject { const ref_vector<Shape> &getShapes() const; const Emitter *getEnvironmentEmitter() const;
+	const ShapeKDTree *getKDTree() const; const ref_vector<Emitter> &getEmitters() const; };
 struct RenderQueue; struct RenderJob; struct RayDifferential; struct RadianceQueryRecord;
 struct Scheduler { static Scheduler *getInstance(); ConfigurableObject *getResource(int, int = -1); };
 struct MonteCarloIntegrator : ConfigurableObject {

@@ -39,7 +39,7 @@ extern "C" int gdb200_emu_gpt_render(const gdb200_scene_desc *desc, const gdb200
     GptArgs a;
     std::vector<double> sd, film; std::vector<int> si; std::vector<unsigned long long> ctr(8, 0);
     const char *capEnv = getenv("GDB200_MAX_SLOTS");
-    if (int rc = setupArgs(hs, p, a, capEnv ? atoi(capEnv) : (1 << 20))) return rc;
+    if (int rc = setupArgs(hs, p, a, capEnv ? atoi(capEnv) : (1 << 23))) return rc;
     hs.host.env.texels = hs.envTexels.data(); hs.host.env.rowWeights = hs.envRowWeights.data(); hs.host.emTriCdf = hs.emTriCdf.data();
     hs.host.env.cdfRows = hs.envCdfRows.data(); hs.host.env.cdfCols = hs.envCdfCols.data(); hs.host.emTris = hs.emTris.data();
     hs.host.bvh = hs.bvh.data(); hs.host.bvhTris = hs.bvhTris.data();
