@@ -286,7 +286,7 @@ def main():
                              "peak_source": peak_src, "avg_launch_ms": round(bounce_avg_ms, 4),
                              "share_of_step": round(agg["bounce_ms"] / max(agg["trace_ms"], 1e-9), 3),
                              "note": "algorithmic bytes = SURVEY §8d wavefront record sizes counted on device; the kernel is "
-                                     "fp64-issue/latency bound, not HBM bound (see profiles/)"}}
+                                     "latency bound at 8 warps/SM, not HBM bound (profiles/r01b_gpt_kernels_ncu.txt)"}}
         if world > 1:
             line["exchange_bytes_per_step"] = int(agg["exchange_bytes"] / args.steps)
         if world == 1:

@@ -4,7 +4,7 @@
 //
 //   <sampler type="gdb200_counter"> <integer name="sampleCount" value="64"/> <integer name="seed" value="0"/> </sampler>
 //
-// Contract (mirrors gdb200::Sampler in csrc/gpt_device.cuh and oracle/gpt_oracle.cpp):
+// Contract (mirrors gdb200::Sampler in csrc/gpt_device.cuh; the test suite's CPU restatement uses the same generator):
 //   * generate(pixel) re-keys a splitmix64 stream from (seed, pixel.x, pixel.y) — the reference's renderBlock calls it
 //     exactly once per pixel before that pixel's samples (gpt.cpp:1250-1251), so the stream of a pixel does not depend
 //     on which worker thread renders it or in which order (the `independent` sampler's does, independent.cpp:42-45);

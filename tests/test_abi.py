@@ -83,3 +83,13 @@ def test_integrator_parameter_validation_matches_reference_messages():
             gdb200.GPTIntegrator(**kw)
     g = gdb200.GPTIntegrator(minDepth=7)
     assert g.minDepth == 1 and g.rrDepth == 5 and g.maxDepth == -1 and g.shiftThreshold == 0.001   # gpt.cpp:1194-1201,1369
+
+
+def test_sampler_plugin_source_compiles():
+    """samplers/gdb200_counter.cpp (the Mitsuba-side sampler that reproduces the tracer's per-pixel streams) is valid C++
+    against the stubbed Sampler interface."""
+    import subprocess
+    src = os.path.join(ROOT, "gradientdomain-mitsuba_b200", "plugin", "samplers", "gdb200_counter.cpp")
+    r = subprocess.run(["/usr/bin/g++", "-std=c++11", "-fsyntax-only", "-DGDB200_STUB_HEADERS", "-Wall", src],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
