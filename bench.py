@@ -33,6 +33,7 @@ WORKLOADS = {
     # name: (scene builder, width, height, spp, reconstruction)
     "gpt-c2": ("cbox_glossy", 1024, 1024, 256, "L1"),
     "gpt-c1": ("cbox_diffuse", 512, 512, 64, "L2"),
+    "gpt-c3": ("atrium_c3", 1920, 1080, 512, "L1"),     # BASELINE configs[2] stand-in: 258 k triangles (BVH path), sky-map lit
 }
 # algorithmic bytes of one reconstruction per pixel
 SOLVER_BYTES = {"L1": 138684, "L2": 6900}

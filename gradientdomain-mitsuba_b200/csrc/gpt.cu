@@ -72,7 +72,8 @@ int uploadTables(gdb200_scene *s)
         {s->envTexels.data(), s->envTexels.size() * sizeof(Float), 0}, {s->envRowWeights.data(), s->envRowWeights.size() * sizeof(Float), 0},
         {s->emTriCdf.data(), s->emTriCdf.size() * sizeof(Float), 0}, {s->envCdfRows.data(), s->envCdfRows.size() * sizeof(float), 0},
         {s->envCdfCols.data(), s->envCdfCols.size() * sizeof(float), 0}, {s->emTris.data(), s->emTris.size() * sizeof(DEmTri), 0},
-        {s->bvh.data(), s->bvh.size() * sizeof(BvhNode), 0}, {s->bvhTris.data(), s->bvhTris.size() * sizeof(DTri), 0}};
+        {s->bvh.data(), s->bvh.size() * sizeof(BvhNode), 0}, {s->bvhTris.data(), s->bvhTris.size() * sizeof(DTri), 0},
+        {s->triNormals.data(), s->triNormals.size() * sizeof(V3), 0}};
     size_t total = 0;
     for (Part &p : parts) { p.offset = total; total += (p.bytes + 255) & ~(size_t)255; }
     if (total == 0) return GDB200_OK;
@@ -84,6 +85,7 @@ int uploadTables(gdb200_scene *s)
     h.emTriCdf = (const Float *)(base + parts[2].offset); h.env.cdfRows = (const float *)(base + parts[3].offset);
     h.env.cdfCols = (const float *)(base + parts[4].offset); h.emTris = (const DEmTri *)(base + parts[5].offset);
     h.bvh = (const BvhNode *)(base + parts[6].offset); h.bvhTris = (const DTri *)(base + parts[7].offset);
+    h.triNormals = (const V3 *)(base + parts[8].offset);
     return GDB200_OK;
 }
 

@@ -93,7 +93,7 @@ constexpr int kMaxRects = 24, kMaxSpheres = 8, kMaxTris = 192, kMaxMeshes = 16, 
 
 struct DRect   { Float toObject[12], toWorld[12]; V3 dpdu, n; Float invArea; int material, emitter; };
 struct DSphere { V3 center; Float radius; int flip, material, emitter, pad; };
-struct DTri    { Float n_u, n_v, n_d, a_u, a_v, b_nu, b_nv, c_nu, c_nv; V3 p0, p1, p2, faceNormal; int k, material, emitter, pad; };
+struct DTri    { Float n_u, n_v, n_d, a_u, a_v, b_nu, b_nv, c_nu, c_nv; V3 p0, p1, p2, faceNormal; int k, material, emitter, normals; };   // normals: first of 3 vertex normals in triNormals, or -1 (flat)
 struct DMesh   { V3 lo, hi; int first, count; int kEnd[3], pad; };   // triangles of a mesh are stored grouped by projection axis k: [first,kEnd[0]) k=0, [kEnd[0],kEnd[1]) k=1, [kEnd[1],kEnd[2]) k=2   // conservative (enlarged) bounds of one TriMesh, used only to skip its triangles
 struct DMaterial {
     int type, distribution; unsigned flags; int vtSmooth, vtDelta, refNFromShading, twosided, nonlinear;
@@ -104,7 +104,7 @@ enum { EM_RECT = 0, EM_MESH = 1, EM_ENV = 2 };
 // pdfDiscrete = samplingWeight * normalization (scene.h:855-857).  Mesh emitters: triangles [triFirst, triFirst+triCount) of
 // emTris in the mesh's own order, area CDF (triCount+1 entries) at emTriCdf[cdfFirst], invArea = 1 / surface area.
 struct DEmitter { int kind, rect, triFirst, triCount, cdfFirst, pad; Spec radiance; Float pdfDiscrete, invArea; };
-struct DEmTri { V3 p0, p1, p2; };
+struct DEmTri { V3 p0, p1, p2; int normals, pad; };   // normals: as DTri
 // Environment map (envmap.cpp): top-level texels as Float RGB, the float CDF tables of envmap.cpp:263-311.
 struct DEnv {
     int present, width, height, emitter;
@@ -128,6 +128,7 @@ struct DScene {
     DTri tris[kMaxTris];
     DEnv env;
     const DEmTri *emTris; const Float *emTriCdf;
+    const V3 *triNormals;              // vertex normals of smooth-shaded triangles, 3 per triangle
     const BvhNode *bvh; const DTri *bvhTris; int nBvhNodes, nBvhTris;
 };
 
@@ -351,6 +352,11 @@ GDB_D bool rayIntersectImpl(const Ray &ray, Its &its)
         its.p = T.p0 * b.x + T.p1 * b.y + T.p2 * b.z;
         dpdu = T.p1 - T.p0;
         its.sh.n = T.faceNormal; its.geoN = T.faceNormal;
+        if (T.normals >= 0) {                                         // skdtree.h:383-394
+            const V3 *vn = c_scene.triNormals + T.normals;
+            its.sh.n = normalize(vn[0] * b.x + vn[1] * b.y + vn[2] * b.z);
+            if (dot(its.geoN, its.sh.n) < 0) its.geoN = -its.geoN;
+        }
         its.material = T.material; its.emitter = T.emitter;
     } else if (kind == 0) {                                          // rectangle.cpp:158-171
         const DRect &r = c_sceneG->rects[index];
@@ -907,7 +913,10 @@ GDB_D Spec sampleEmitterDirectVisibleImpl(DRec &dRec, Float sx, Float sy, bool &
             const Float bx = 1 - a, by = a * sy;
             const V3 sideA = T.p1 - T.p0, sideB = T.p2 - T.p0;
             dRec.p = T.p0 + (sideA * bx) + (sideB * by);
-            dRec.n = normalize(cross(sideA, sideB));
+            if (T.normals >= 0) {                                                     // triangle.cpp:33-42
+                const V3 *vn = c_scene.triNormals + T.normals;
+                dRec.n = normalize(vn[0] * ((Float)1.0f - bx - by) + vn[1] * bx + vn[2] * by);
+            } else dRec.n = normalize(cross(sideA, sideB));
             dRec.pdf = em.invArea;
         }
         dRec.d = dRec.p - dRec.ref;                                                  // shape.cpp:102-114

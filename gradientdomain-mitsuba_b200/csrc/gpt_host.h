@@ -21,6 +21,7 @@ struct HostScene {
     std::vector<Float> envTexels, envRowWeights, emTriCdf;
     std::vector<float> envCdfRows, envCdfCols;
     std::vector<DEmTri> emTris;
+    std::vector<V3> triNormals;
     std::vector<BvhNode> bvh;
     std::vector<DTri> bvhTris;
 };
@@ -30,6 +31,7 @@ struct HostScene {
 inline bool makeTri(V3 A, V3 B, V3 C, int material, int emitter, DTri &T)
 {
     memset(&T, 0, sizeof(T));
+    T.normals = -1;
     static const int waldModulo[4] = {1, 2, 0, 1};
     const V3 b = C - A, cc = B - A, N = cross(cc, b);
     const double Nv[3] = {N.x, N.y, N.z}, bv[3] = {b.x, b.y, b.z}, cv[3] = {cc.x, cc.y, cc.z}, Av[3] = {A.x, A.y, A.z};
@@ -178,7 +180,7 @@ inline int flattenScene(const gdb200_scene_desc *d, HostScene *s)
     DScene &h = s->host;
     memset(&h, 0, sizeof(h));
     s->envTexels.clear(); s->envRowWeights.clear(); s->emTriCdf.clear(); s->envCdfRows.clear(); s->envCdfCols.clear();
-    s->emTris.clear(); s->bvh.clear(); s->bvhTris.clear();
+    s->emTris.clear(); s->bvh.clear(); s->bvhTris.clear(); s->triNormals.clear();
     const gdb200_camera &c = d->camera;
     if (c.width <= 0 || c.height <= 0) return set_error(GDB200_ERR_ARGUMENT, "invalid film size %dx%d", c.width, c.height);
     if (d->n_emitters < 1) return set_error(GDB200_ERR_ARGUMENT, "scene has no emitter");
@@ -247,13 +249,20 @@ inline int flattenScene(const gdb200_scene_desc *d, HostScene *s)
                     hi = mk(std::max(hi.x, P.x), std::max(hi.y, P.y), std::max(hi.z, P.z));
                     scale = std::max(scale, std::max(std::abs(P.x), std::max(std::abs(P.y), std::abs(P.z))));
                 }
+                int normalIndex = -1;
+                if (sh.has_vertex_normals) {
+                    if (!d->normals) return set_error(GDB200_ERR_ARGUMENT, "shape %d: has_vertex_normals without gdb200_scene_desc.normals", i);
+                    normalIndex = (int)s->triNormals.size();
+                    for (int k = 0; k < 3; k++) { const double *vn = d->normals + 3 * ix[k]; s->triNormals.push_back(mk(vn[0], vn[1], vn[2])); }
+                }
                 if (sh.emitter >= 0) {                                               // trimesh.cpp:388-403, triangle.cpp:61-67
-                    DEmTri E; E.p0 = A; E.p1 = B; E.p2 = C;
+                    DEmTri E; E.p0 = A; E.p1 = B; E.p2 = C; E.normals = normalIndex; E.pad = 0;
                     s->emTris.push_back(E);
                     areaOfShape[i] += (Float)0.5f * len(cross(B - A, C - A));
                 }
                 DTri T;
                 if (!makeTri(A, B, C, sh.material, sh.emitter, T)) continue;
+                T.normals = normalIndex;
                 meshTris.push_back(T);
             }
             if (useBvh) s->bvhTris.insert(s->bvhTris.end(), meshTris.begin(), meshTris.end());

@@ -42,7 +42,7 @@ struct FlatScene {
 	std::vector<gdb200_shape> shapes;
 	std::vector<gdb200_material> materials;
 	std::vector<gdb200_emitter> emitters;
-	std::vector<double> vertices;
+	std::vector<double> vertices, normals;
 	std::vector<int> triangles;
 
 	std::vector<float> envRGB;
@@ -150,9 +150,13 @@ struct FlatScene {
 				s.flip_normals = p.getBoolean("flipNormals", false);
 			} else if (shape->getClass()->derivesFrom(MTS_CLASS(TriMesh))) {
 				const TriMesh *mesh = static_cast<const TriMesh *>(shape);
-				if (mesh->hasVertexNormals())
-					SLog(EError, "gdb200: meshes with vertex normals are not supported yet");
 				s.type = GDB200_SHAPE_MESH;
+				s.has_vertex_normals = mesh->hasVertexNormals() ? 1 : 0;
+				normals.resize(vertices.size(), 0.0);                   /* keep `normals` parallel to `vertices` */
+				if (mesh->hasVertexNormals())
+					for (size_t v = 0; v < mesh->getVertexCount(); ++v)
+						for (int k = 0; k < 3; ++k)
+							normals.push_back(mesh->getVertexNormals()[v][k]);
 				s.first_tri = (int) triangles.size() / 3;
 				s.tri_count = (int) mesh->getTriangleCount();
 				const int base = (int) vertices.size() / 3;
@@ -221,6 +225,8 @@ struct FlatScene {
 		desc.n_emitters = (int) emitters.size();   desc.emitters = emitters.data();
 		desc.n_vertices = (int) vertices.size() / 3;   desc.vertices = vertices.data();
 		desc.n_triangles = (int) triangles.size() / 3; desc.triangles = triangles.data();
+		normals.resize(vertices.size(), 0.0);
+		desc.normals = normals.data();
 	}
 };
 

@@ -27,7 +27,8 @@ class Camera(ctypes.Structure):
 class Shape(ctypes.Structure):
     _fields_ = [("type", ctypes.c_int), ("material", ctypes.c_int), ("emitter", ctypes.c_int),
                 ("flip_normals", ctypes.c_int), ("to_world", D16), ("to_object", D16), ("center", D3),
-                ("radius", ctypes.c_double), ("first_tri", ctypes.c_int), ("tri_count", ctypes.c_int)]
+                ("radius", ctypes.c_double), ("first_tri", ctypes.c_int), ("tri_count", ctypes.c_int),
+                ("has_vertex_normals", ctypes.c_int), ("reserved", ctypes.c_int)]
 
 
 class Material(ctypes.Structure):
@@ -54,7 +55,7 @@ class SceneDesc(ctypes.Structure):
                 ("n_triangles", ctypes.c_int), ("shapes", ctypes.POINTER(Shape)),
                 ("materials", ctypes.POINTER(Material)), ("emitters", ctypes.POINTER(Emitter)),
                 ("vertices", ctypes.POINTER(ctypes.c_double)), ("triangles", ctypes.POINTER(ctypes.c_int)),
-                ("envmap", ctypes.POINTER(EnvMap))]
+                ("envmap", ctypes.POINTER(EnvMap)), ("normals", ctypes.POINTER(ctypes.c_double))]
 
 
 class GPTParams(ctypes.Structure):
@@ -190,14 +191,22 @@ class SceneBuilder:
         self.shapes.append(sh)
         return len(self.shapes) - 1
 
-    def mesh(self, vertices, triangles, material, radiance=None):
-        """Flat-shaded TriMesh (no vertex normals); with `radiance` it carries an area emitter (area.cpp on a TriMesh)."""
+    def mesh(self, vertices, triangles, material, radiance=None, normals=None):
+        """TriMesh, flat-shaded or (with per-vertex `normals`) smooth-shaded; with `radiance` it carries an area
+        emitter (area.cpp on a TriMesh)."""
         base, first = len(self.vertices), len(self.triangles)
         self.vertices.extend(np.asarray(v, float) for v in vertices)
+        if not hasattr(self, "normals"):
+            self.normals = []
+        self.normals.extend([np.zeros(3)] * (base - len(self.normals)))          # earlier meshes without normals
+        if normals is not None:
+            assert len(normals) == len(vertices)
+            self.normals.extend(np.asarray(n, float) for n in normals)
         self.triangles.extend((base + a, base + b, base + c) for a, b, c in triangles)
         sh = Shape()
         sh.type, sh.material, sh.emitter = SHAPE_MESH, material, -1
         sh.first_tri, sh.tri_count = first, len(self.triangles) - first
+        sh.has_vertex_normals = int(normals is not None)
         self.shapes.append(sh)
         if radiance is not None:
             e = Emitter()
@@ -240,6 +249,11 @@ class SceneBuilder:
         d.shapes, d.materials, d.emitters = self._keep[0], self._keep[1], self._keep[2]
         d.vertices = ctypes.cast(self._keep[3], ctypes.POINTER(ctypes.c_double))
         d.triangles = ctypes.cast(self._keep[4], ctypes.POINTER(ctypes.c_int))
+        if any(sh.has_vertex_normals for sh in self.shapes):
+            nrm = list(getattr(self, "normals", []))
+            nrm.extend([np.zeros(3)] * (len(self.vertices) - len(nrm)))
+            self._keep_normals = (ctypes.c_double * (3 * len(nrm)))(*[float(c) for n in nrm for c in n])
+            d.normals = ctypes.cast(self._keep_normals, ctypes.POINTER(ctypes.c_double))
         if getattr(self, "_env_rgb", None) is not None:
             env = EnvMap()
             env.height, env.width = self._env_rgb.shape[:2]
@@ -405,6 +419,52 @@ def atrium(width=256, height=144, columns=6, segments=24, rings=10):
             b.mesh(verts, tris, mat)
     b.envmap(sky_envmap(128, 64), scale=1.0)
     return b.build()
+
+
+def uv_sphere_mesh(center, radius, segments=16, rings=8, squash=(1.0, 1.0, 1.0)):
+    """Latitude-longitude triangle mesh of an ellipsoid with analytic vertex normals: (vertices, triangles, normals)."""
+    c, q = np.asarray(center, float), np.asarray(squash, float)
+    verts, nrms, tris = [], [], []
+    for r in range(rings + 1):
+        th = math.pi * r / rings
+        for k in range(segments):
+            ph = 2 * math.pi * k / segments
+            d = np.array([math.sin(th) * math.cos(ph), math.cos(th), math.sin(th) * math.sin(ph)])
+            verts.append(c + radius * q * d)
+            n = d / q
+            nrms.append(n / np.linalg.norm(n))
+    for r in range(rings):
+        for k in range(segments):
+            k2 = (k + 1) % segments
+            v00, v01, v10, v11 = r * segments + k, r * segments + k2, (r + 1) * segments + k, (r + 1) * segments + k2
+            if r > 0:
+                tris.append((v00, v01, v11))
+            if r < rings - 1:
+                tris.append((v00, v11, v10))
+    return verts, tris, nrms
+
+
+def cbox_smooth(width=256, height=256):
+    """Smooth-shaded meshes (vertex normals, skdtree.h:383-394): shading normal != geometric normal, which is what the
+    strictNormals branches of gpt.cpp (:518-531, 541-555, 607, 685, 748, 926, 1040) exist for; one of them emits."""
+    b = _cornell(width, height, boxes=False)
+    rough = b.material(type=BSDF_ROUGHCONDUCTOR, alpha=0.08, eta=CU_ETA, k=CU_K)
+    white = b.material(reflectance=WHITE)
+    mirror = b.material(type=BSDF_CONDUCTOR, eta=AL_ETA, k=AL_K)
+    v, t, n = uv_sphere_mesh((-0.45, -0.62, 0.1), 0.38, 10, 6, squash=(1.0, 1.0, 0.8))
+    b.mesh(v, t, white, normals=n)
+    v, t, n = uv_sphere_mesh((0.45, -0.68, 0.35), 0.32, 9, 5)
+    b.mesh(v, t, rough, normals=n)
+    v, t, n = uv_sphere_mesh((0.05, -0.8, 0.7), 0.2, 8, 4)
+    b.mesh(v, t, mirror, normals=n)
+    v, t, n = uv_sphere_mesh((0.0, 0.55, -0.3), 0.12, 6, 4)
+    b.mesh(v, t, b.material(reflectance=(0, 0, 0)), radiance=(6.0, 8.0, 10.0), normals=n)     # smooth-shaded mesh emitter
+    return b.build()
+
+
+def atrium_c3(width=1920, height=1080):
+    """BASELINE configs[2] stand-in ("Sponza-class, env-map lit, mixed diffuse/specular"): 258 k triangles behind the BVH."""
+    return atrium(width, height, columns=12, segments=64, rings=14)
 
 
 def default_params(spp=64, seed=0, max_depth=-1, rr_depth=5, shift_threshold=0.001, strict_normals=False):

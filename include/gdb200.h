@@ -112,7 +112,7 @@ int gdb200_poisson_solve(const float *dx, const float *dy, const float *throughp
 
 enum { GDB200_SHAPE_RECTANGLE = 0,   /* src/shapes/rectangle.cpp: unit square [-1,1]^2 in z=0 under to_world */
        GDB200_SHAPE_SPHERE    = 1,   /* src/shapes/sphere.cpp: centre + radius (no rotation)               */
-       GDB200_SHAPE_MESH      = 2 }; /* TriMesh without vertex normals: triangles [first_tri, first_tri+tri_count) */
+       GDB200_SHAPE_MESH      = 2 }; /* TriMesh: triangles [first_tri, first_tri+tri_count), flat or with vertex normals */
 
 enum { GDB200_BSDF_DIFFUSE        = 0,   /* src/bsdfs/diffuse.cpp        */
        GDB200_BSDF_ROUGHCONDUCTOR = 1,   /* src/bsdfs/roughconductor.cpp (sampleVisible = true) */
@@ -137,6 +137,8 @@ typedef struct gdb200_shape {
     double to_world[16], to_object[16]; /* rectangle                                   */
     double center[3], radius;           /* sphere                                      */
     int    first_tri, tri_count;        /* mesh                                        */
+    int    has_vertex_normals;          /* mesh: shading normals interpolated from gdb200_scene_desc.normals (skdtree.h:383-394) */
+    int    reserved;
 } gdb200_shape;
 
 typedef struct gdb200_material {
@@ -184,6 +186,7 @@ typedef struct gdb200_scene_desc {
     const double          *vertices;         /* n_vertices * 3                          */
     const int             *triangles;        /* n_triangles * 3 vertex indices          */
     const gdb200_envmap   *envmap;           /* NULL, or the map of the emitter whose type is GDB200_EMITTER_ENVMAP */
+    const double          *normals;          /* NULL, or n_vertices * 3 vertex normals (read for shapes with has_vertex_normals) */
 } gdb200_scene_desc;
 
 /* ------------------------------------------------------- G-PT integrator */

@@ -139,7 +139,7 @@ enum { EDiffuseReflection = 0x1, EGlossyReflection = 0x4, EDeltaReflection = 0x1
        ESmooth = 0xF, EDelta = 0x30, ETransmissionBits = 0x2 | 0x8 | 0x20, EBackSide = 0x20000, EFrontSide = 0x10000 };
 enum Measure { ESolidAngle, EDiscrete };
 
-struct Tri { V3 p0, p1, p2; int k; Float n_u, n_v, n_d, a_u, a_v, b_nu, b_nv, c_nu, c_nv; int shape; };
+struct Tri { V3 p0, p1, p2; int k; Float n_u, n_v, n_d, a_u, a_v, b_nu, b_nv, c_nu, c_nv; int shape; bool hasNormals; V3 n0, n1, n2; };
 
 struct Shape {
     gdb200_shape d;
@@ -157,7 +157,7 @@ struct EnvMap {
     EnvMap() : present(false) {}
 };
 // TriMesh area sampling table (trimesh.cpp:388-403): per emitting mesh shape
-struct MeshSampling { std::vector<Float> cdf; std::vector<V3> verts; Float invSurfaceArea; };
+struct MeshSampling { std::vector<Float> cdf; std::vector<V3> verts, normals; Float invSurfaceArea; };
 
 struct Scene {
     gdb200_camera cam;
@@ -301,7 +301,10 @@ bool rayIntersect(const Scene &sc, const Ray &ray, Its &its)
         Float len = length(faceNormal);
         if (!isZero(faceNormal)) faceNormal = faceNormal / len;
         dpdu = side1;
-        its.sh.n = faceNormal;
+        if (T.hasNormals) {                                        // skdtree.h:383-394
+            its.sh.n = normalize(T.n0 * b.x + T.n1 * b.y + T.n2 * b.z);
+            if (dot(faceNormal, its.sh.n) < 0) faceNormal = -faceNormal;
+        } else its.sh.n = faceNormal;
         its.geoN = faceNormal;
     } else if (s.d.type == GDB200_SHAPE_RECTANGLE) {           // rectangle.cpp:158-171
         its.geoN = s.frame.n;
@@ -921,7 +924,9 @@ Spec sampleEmitterDirectVisible(const Scene &sc, DRec &dRec, Float sx, Float sy,
             Float bx = 1 - a, by = a * sy;
             V3 sideA = p1 - p0, sideB = p2 - p0;
             dRec.p = p0 + (sideA * bx) + (sideB * by);
-            dRec.n = normalize(cross(sideA, sideB));
+            if (!ms.normals.empty())                                                 // triangle.cpp:33-42
+                dRec.n = normalize(ms.normals[3 * tri] * (1.0f - bx - by) + ms.normals[3 * tri + 1] * bx + ms.normals[3 * tri + 2] * by);
+            else dRec.n = normalize(cross(sideA, sideB));
             dRec.pdf = ms.invSurfaceArea;
         }
         dRec.d = dRec.p - dRec.ref;                                                 // shape.cpp:102-114
@@ -1461,6 +1466,8 @@ void buildScene(const gdb200_scene_desc *d, Scene &sc)
                 const int *ix = d->triangles + 3 * t;
                 Tri T; T.shape = i;
                 triLoad(T, specOf(d->vertices + 3 * ix[0]), specOf(d->vertices + 3 * ix[1]), specOf(d->vertices + 3 * ix[2]));
+                T.hasNormals = s.d.has_vertex_normals && d->normals;
+                if (T.hasNormals) { T.n0 = specOf(d->normals + 3 * ix[0]); T.n1 = specOf(d->normals + 3 * ix[1]); T.n2 = specOf(d->normals + 3 * ix[2]); }
                 sc.tris.push_back(T);
             }
         }
@@ -1477,6 +1484,7 @@ void buildScene(const gdb200_scene_desc *d, Scene &sc)
             const int *ix = d->triangles + 3 * t;
             V3 p0 = specOf(d->vertices + 3 * ix[0]), p1 = specOf(d->vertices + 3 * ix[1]), p2 = specOf(d->vertices + 3 * ix[2]);
             ms.verts.push_back(p0); ms.verts.push_back(p1); ms.verts.push_back(p2);
+            if (sh.has_vertex_normals && d->normals) for (int k = 0; k < 3; k++) ms.normals.push_back(specOf(d->normals + 3 * ix[k]));
             ms.cdf.push_back(ms.cdf.back() + 0.5f * length(cross(p1 - p0, p2 - p0)));   // triangle.cpp:61-67, pmf.h:62-71
         }
         Float surfaceArea = ms.cdf.back();                                       // DiscreteDistribution::normalize, pmf.h:101-114

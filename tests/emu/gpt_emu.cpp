@@ -42,7 +42,7 @@ extern "C" int gdb200_emu_gpt_render(const gdb200_scene_desc *desc, const gdb200
     if (int rc = setupArgs(hs, p, a, capEnv ? atoi(capEnv) : (1 << 23))) return rc;
     hs.host.env.texels = hs.envTexels.data(); hs.host.env.rowWeights = hs.envRowWeights.data(); hs.host.emTriCdf = hs.emTriCdf.data();
     hs.host.env.cdfRows = hs.envCdfRows.data(); hs.host.env.cdfCols = hs.envCdfCols.data(); hs.host.emTris = hs.emTris.data();
-    hs.host.bvh = hs.bvh.data(); hs.host.bvhTris = hs.bvhTris.data();
+    hs.host.bvh = hs.bvh.data(); hs.host.bvhTris = hs.bvhTris.data(); hs.host.triNormals = hs.triNormals.data();
     c_scene = hs.host; static DScene sceneCopy; sceneCopy = hs.host; c_sceneG = &sceneCopy;
     memcpy(c_bounds, hs.bounds, sizeof(hs.bounds));
     const size_t n = (size_t)hs.width * hs.height;

@@ -26,7 +26,8 @@ SCENES = {"cbox_diffuse": lambda w, h: scenes.cbox_diffuse(w, h), "cbox_glossy":
           "cbox_materials": lambda w, h: scenes.cbox_materials(w, h),
           "cbox_env": lambda w, h: scenes.cbox_env(w, h),                  # environment emitter + environmentShift
           "cbox_mesh_lights": lambda w, h: scenes.cbox_mesh_lights(w, h),  # mesh emitters, plastic, twosided
-          "atrium": lambda w, h: scenes.atrium(w, h, columns=3, segments=8, rings=4)}   # > table size: BVH path
+          "atrium": lambda w, h: scenes.atrium(w, h, columns=3, segments=8, rings=4),   # > table size: BVH path
+          "cbox_smooth": lambda w, h: scenes.cbox_smooth(w, h)}             # vertex normals (shading != geometric normal), smooth mesh emitter
 
 
 @pytest.mark.parametrize("scene_name", sorted(SCENES))
@@ -85,6 +86,18 @@ def test_bvh_path_gives_the_same_film(oracle, emu, scene_name, monkeypatch):
     ref, _, c2 = oracle.gpt(desc, p)
     close(got, ref)
     assert cnt[1] == c2[1] and cnt[2] == c2[2]
+
+
+@pytest.mark.parametrize("kw", [dict(strict_normals=True), dict(strict_normals=True, max_depth=3), dict(strict_normals=True, shift_threshold=0.2)])
+def test_strict_normals_with_shading_normals(oracle, emu, kw):
+    """strictNormals only bites when shading and geometric normals differ (smooth-shaded meshes)."""
+    desc = scenes.cbox_smooth(30, 26)
+    p = scenes.default_params(spp=5, seed=6, **kw)
+    got, _ = emu.gpt(desc, p)
+    ref, _, _ = oracle.gpt(desc, p)
+    close(got, ref)
+    loose, _, _ = oracle.gpt(desc, scenes.default_params(spp=5, seed=6, **{**kw, "strict_normals": False}))
+    assert np.abs(loose["-throughput"] - ref["-throughput"]).max() > 1e-6
 
 
 @pytest.mark.parametrize("kw", [dict(max_depth=2), dict(max_depth=3, rr_depth=1), dict(strict_normals=True), dict(shift_threshold=0.1)])

@@ -35,7 +35,7 @@ def compare(got, ref, max_flip_frac=2e-3):
 
 
 @pytest.mark.parametrize("scene_name", ["cbox_diffuse", "cbox_glossy", "cbox_glossy_delta", "cbox_materials", "cbox_env",
-                                        "cbox_mesh_lights", "atrium"])
+                                        "cbox_mesh_lights", "atrium", "cbox_smooth"])
 def test_tracer_matches_oracle(oracle, scene_name):
     w = h = 96
     desc = {"cbox_diffuse": lambda: scenes.cbox_diffuse(w, h), "cbox_glossy": lambda: scenes.cbox_glossy(w, h),
@@ -43,7 +43,8 @@ def test_tracer_matches_oracle(oracle, scene_name):
             "cbox_materials": lambda: scenes.cbox_materials(w, h),
             "cbox_env": lambda: scenes.cbox_env(w, h),                     # environment emitter, environmentShift (gpt.cpp:348-369)
             "cbox_mesh_lights": lambda: scenes.cbox_mesh_lights(w, h),     # TriMesh emitters, plastic, twosided
-            "atrium": lambda: scenes.atrium(w, 54, columns=4, segments=12, rings=6)}[scene_name]()   # 1.2k triangles: BVH path
+            "atrium": lambda: scenes.atrium(w, 54, columns=4, segments=12, rings=6),   # 1.2k triangles: BVH path
+            "cbox_smooth": lambda: scenes.cbox_smooth(w, h)}[scene_name]()      # vertex normals, smooth mesh emitter
     integ = gdb200.GPTIntegrator(reconstructL1=False, reconstructL2=False)
     scene = gdb200.Scene(desc)
     got = integ.trace(scene, spp=16, seed=3)
@@ -57,10 +58,12 @@ def test_tracer_matches_oracle(oracle, scene_name):
 
 
 @pytest.mark.parametrize("kw", [dict(maxDepth=2), dict(maxDepth=1), dict(rrDepth=2), dict(strictNormals=True),
-                                dict(shiftThreshold=0.1), dict(maxDepth=5, rrDepth=3)])
+                                dict(shiftThreshold=0.1), dict(maxDepth=5, rrDepth=3), dict(strictNormals=True, scene="cbox_smooth"),
+                                dict(strictNormals=True, scene="cbox_env"), dict(maxDepth=3, scene="cbox_mesh_lights")])
 def test_tracer_parameters(oracle, kw):
     w, h = 64, 48
-    desc = scenes.cbox_glossy(w, h)
+    kw = dict(kw)
+    desc = getattr(scenes, kw.pop("scene", "cbox_glossy"))(w, h)
     integ = gdb200.GPTIntegrator(reconstructL1=False, reconstructL2=False, **kw)
     scene = gdb200.Scene(desc)
     got = integ.trace(scene, spp=8, seed=11)
