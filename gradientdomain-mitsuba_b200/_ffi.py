@@ -79,3 +79,18 @@ def _check_abi(L, path):
 def check(rc):
     if rc != 0:
         raise Gdb200Error(f"gdb200 error {rc}: {lib().gdb200_last_error().decode(errors='replace')}")
+
+
+def pinned_empty(shape, dtype):
+    """numpy array on page-locked host memory (gdb200_host_alloc) so device<->host copies of film buffers run at full
+    PCIe / NVLink-C2C bandwidth; freed when the array is garbage-collected."""
+    import weakref
+    import numpy as np
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    ptr = ctypes.c_void_p()
+    check(lib().gdb200_host_alloc(ctypes.byref(ptr), max(nbytes, 1)))
+    buf = (ctypes.c_char * max(nbytes, 1)).from_address(ptr.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    weakref.finalize(buf, lib().gdb200_host_free, ctypes.c_void_p(ptr.value))
+    return arr

@@ -117,7 +117,8 @@ struct BvhNode { float lo[3]; int a; float hi[3]; int b; };
 
 struct DScene {
     Float sampleToCamera[16], cameraToWorld[12];
-    Float nearClip, farClip, invResX, invResY, filterRadius, filterTap, filterScale;
+    Float nearClip, farClip, invResX, invResY, filterRadius, filterScale;
+    Float filterTable[32];             // ReconstructionFilter::m_values (rfilter.cpp:37-55)
     int width, height, nRects, nSpheres, nTris, nMaterials, nEmitters, nMeshes;
     Float emCdf[kMaxEmitters + 1];
     DRect rects[kMaxRects];

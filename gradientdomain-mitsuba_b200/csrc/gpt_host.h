@@ -190,7 +190,11 @@ inline int flattenScene(const gdb200_scene_desc *d, HostScene *s)
     memcpy(h.cameraToWorld, c.camera_to_world, sizeof(h.cameraToWorld));
     h.nearClip = c.near_clip; h.farClip = c.far_clip; h.width = c.width; h.height = c.height;
     h.invResX = 1.0 / c.width; h.invResY = 1.0 / c.height;
-    h.filterRadius = d->rfilter_radius; h.filterTap = 1.0 / (2 * d->rfilter_radius); h.filterScale = 31 / d->rfilter_radius;
+    if (!(d->rfilter_radius > 0)) return set_error(GDB200_ERR_ARGUMENT, "invalid reconstruction filter radius %g", d->rfilter_radius);
+    h.filterRadius = d->rfilter_radius; h.filterScale = 31 / d->rfilter_radius;
+    bool boxFilter = true;
+    for (int i = 0; i < 32; i++) { h.filterTable[i] = d->rfilter_table[i]; if (d->rfilter_table[i] != 0) boxFilter = false; }
+    if (boxFilter) { for (int i = 0; i < 31; i++) h.filterTable[i] = 1.0 / (2 * d->rfilter_radius); h.filterTable[31] = 0; }   // box.cpp:45-47 through rfilter.cpp:37-55
     s->width = c.width; s->height = c.height;
     s->mats.assign(d->materials, d->materials + d->n_materials);
     h.nMaterials = d->n_materials;

@@ -61,13 +61,14 @@ class Scene:
         check(lib().gdb200_gpt_accumulators(self._h, ctypes.byref(ptr), ctypes.byref(nbytes)))
         return device_view(ptr.value, (5, self.height, self.width, 4))
 
-    def develop(self, download=True):
+    def develop(self, download=True, out=None):
         """Re-develop after the accumulators were merged across GPUs (gdb200_gpt_develop)."""
-        out, B = {}, _scenes.Buffers()
+        out, B = ({} if out is None else out), _scenes.Buffers()
         if download:
             for field, name in (("preview_final", "-final"), ("throughput", "-throughput"), ("dx", "-dx"),
                                 ("dy", "-dy"), ("direct", "-direct")):
-                out[name] = np.empty((self.height, self.width, 3), dtype=np.float64)
+                if name not in out:
+                    out[name] = np.empty((self.height, self.width, 3), dtype=np.float64)
                 setattr(B, field, out[name].ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
         check(lib().gdb200_gpt_develop(self._h, ctypes.byref(B)))
         return out
@@ -116,18 +117,23 @@ class GPTIntegrator:
         p.streams_per_pixel = streams              # sample streams per pixel (gdb200_gpt_params.streams_per_pixel)
         return p
 
-    def trace(self, scene, spp, seed=0, rows=None, download=True, bands=None, preview=True, streams=1):
-        """The sampling part of render(): returns the developed fp64 buffers (h,w,3)."""
+    def trace(self, scene, spp, seed=0, rows=None, download=True, bands=None, preview=True, streams=1, out=None):
+        """The sampling part of render(): returns the developed fp64 buffers (h,w,3).  `out`: optional dict of
+        preallocated (h,w,3) float64 arrays to download into (e.g. gdb200.pinned_empty buffers reused across renders)."""
         if self.hideEmitters:   # gpt.cpp:1362-1365
             raise Gdb200Error("Option 'hideEmitters' not implemented for Gradient-Domain Path Tracing!")
         h, w = scene.height, scene.width
-        out = {}
+        out = {} if out is None else out
         B = _scenes.Buffers()
         if download:
             for field, name in (("preview_final", "-final"), ("throughput", "-throughput"), ("dx", "-dx"),
                                 ("dy", "-dy"), ("direct", "-direct")):
-                out[name] = np.empty((h, w, 3), dtype=np.float64)
-                setattr(B, field, out[name].ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+                if name not in out:
+                    out[name] = np.empty((h, w, 3), dtype=np.float64)
+                a = out[name]
+                if a.shape != (h, w, 3) or a.dtype != np.float64 or not a.flags["C_CONTIGUOUS"]:
+                    raise Gdb200Error(f"output buffer {name} must be a C-contiguous float64 array of shape {(h, w, 3)}")
+                setattr(B, field, a.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
         p = self.params(spp, seed, rows, bands, preview, streams)
         check(lib().gdb200_gpt_render(scene._h, ctypes.byref(p), ctypes.byref(B), ctypes.byref(self.stats)))
         return out
@@ -153,12 +159,13 @@ class GPTIntegrator:
             plan.close()
         return res
 
-    def render(self, scene, spp, seed=0, streams=1):
-        """Returns {"-final","-throughput","-dx","-dy","-direct"} like the five multifilm buffers."""
-        out = self.trace(scene, spp, seed, preview=not (self.reconstructL1 or self.reconstructL2), streams=streams)
-        final = self.reconstruct(scene)
+    def render(self, scene, spp, seed=0, streams=1, out=None, plan=None):
+        """Returns {"-final","-throughput","-dx","-dy","-direct"} like the five multifilm buffers.  `out` / `plan`:
+        optional preallocated host buffers (see trace) and solver workspace to reuse across renders."""
+        out = self.trace(scene, spp, seed, preview=not (self.reconstructL1 or self.reconstructL2), streams=streams, out=out)
+        final = self.reconstruct(scene, plan)
         if final is not None:
-            out["-final"] = final.astype(np.float64)     # setBitmapMulti(reconstruction, BUFFER_FINAL), gpt.cpp:1468-1475
+            out["-final"][...] = final                   # setBitmapMulti(reconstruction, BUFFER_FINAL), gpt.cpp:1468-1475
         return out
 
     def save(self, dest, buffers):

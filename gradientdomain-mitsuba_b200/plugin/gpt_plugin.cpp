@@ -121,9 +121,9 @@ struct FlatScene {
 		desc.camera.height = size.y;
 
 		const ReconstructionFilter *rf = film->getReconstructionFilter();
-		if (rf->getClass()->getName() != "BoxFilter")
-			SLog(EError, "gdb200: only the 'box' reconstruction filter is supported (the default is gaussian, film.cpp:89-95)");
-		desc.rfilter_radius = rf->getRadius();     /* 0.5 + 1e-5, box.cpp:38 */
+		desc.rfilter_radius = rf->getRadius();     /* box: 0.5 + 1e-5 (box.cpp:38); the film's default is gaussian (film.cpp:89-95) */
+		for (int i = 0; i < 32; ++i)               /* m_values[i] through evalDiscretized (rfilter.h:76-77): index = (int) |x * 31 / radius| */
+			desc.rfilter_table[i] = rf->evalDiscretized((i + (Float) 0.5) * rf->getRadius() / 31);
 
 		const ref_vector<Shape> &list = scene->getShapes();
 		for (size_t i = 0; i < list.size(); ++i) {

@@ -65,7 +65,7 @@ struct Shape : ConfigurableObject { const BSDF *getBSDF() const; bool isEmitter(
 struct Triangle { uint32_t idx[3]; };
 struct TriMesh : Shape { static Class *m_theClass; bool hasVertexNormals() const; size_t getTriangleCount() const; size_t getVertexCount() const;
 	const Point *getVertexPositions() const; const Point *getVertexNormals() const; const Triangle *getTriangles() const; };
-struct ReconstructionFilter : ConfigurableObject { Float getRadius() const; };
+struct ReconstructionFilter : ConfigurableObject { Float getRadius() const; Float evalDiscretized(Float) const; };
 struct Bitmap { enum EPixelFormat { ESpectrum, ERGB }; enum EComponentFormat { EFloat, EFloat32 }; Bitmap(EPixelFormat, EComponentFormat, const Vector2i &); Float *getFloatData();
 	ref<Bitmap> convert(EPixelFormat, EComponentFormat) const; int getWidth() const; int getHeight() const; const float *getFloat32Data() const; };
 struct BSphere { Point center; Float radius; };

@@ -55,7 +55,8 @@ class SceneDesc(ctypes.Structure):
                 ("n_triangles", ctypes.c_int), ("shapes", ctypes.POINTER(Shape)),
                 ("materials", ctypes.POINTER(Material)), ("emitters", ctypes.POINTER(Emitter)),
                 ("vertices", ctypes.POINTER(ctypes.c_double)), ("triangles", ctypes.POINTER(ctypes.c_int)),
-                ("envmap", ctypes.POINTER(EnvMap)), ("normals", ctypes.POINTER(ctypes.c_double))]
+                ("envmap", ctypes.POINTER(EnvMap)), ("normals", ctypes.POINTER(ctypes.c_double)),
+                ("rfilter_table", ctypes.c_double * 32)]
 
 
 class GPTParams(ctypes.Structure):
@@ -119,11 +120,29 @@ def make_camera(width, height, origin, target, up, fov_deg, near=1e-2, far=1e4):
     return cam
 
 
+def discretize_filter(f, radius, resolution=31):
+    """ReconstructionFilter::configure (rfilter.cpp:37-55): `resolution` taps over [0, radius], normalised, + a trailing 0."""
+    vals = [f(radius * i / resolution) for i in range(resolution)]
+    norm = 1.0 / (sum(vals) * 2 * radius / resolution)
+    return [v * norm for v in vals] + [0.0]
+
+
 # ------------------------------------------------------------------ builders
 class SceneBuilder:
-    def __init__(self, camera, rfilter_radius=0.5):
+    def __init__(self, camera, rfilter_radius=0.5, rfilter="box", stddev=0.5):
         self.camera = camera
         self.rfilter_radius = rfilter_radius + 1e-5      # box.cpp:38
+        self.rfilter_table = None                        # None = box
+        if rfilter == "gaussian":                        # gaussian.cpp:32-58 (Mitsuba's default film filter, film.cpp:89-95)
+            self.rfilter_radius = 4 * stddev
+            alpha = -1.0 / (2.0 * stddev * stddev)
+            self.rfilter_table = discretize_filter(
+                lambda x: max(0.0, math.exp(alpha * x * x) - math.exp(alpha * self.rfilter_radius ** 2)), self.rfilter_radius)
+        elif rfilter == "tent":                          # tent.cpp: max(0, 1 - |x / radius|), radius 1
+            self.rfilter_radius = 1.0
+            self.rfilter_table = discretize_filter(lambda x: max(0.0, 1.0 - abs(x / 1.0)), 1.0)
+        elif rfilter != "box":
+            raise ValueError(rfilter)
         self.shapes, self.materials, self.emitters, self.vertices, self.triangles = [], [], [], [], []
 
     def envmap(self, rgb, scale=1.0, to_world=None, sampling_weight=1.0):
@@ -240,6 +259,8 @@ class SceneBuilder:
     def build(self):
         d = SceneDesc()
         d.camera, d.rfilter_radius = self.camera, self.rfilter_radius
+        if self.rfilter_table is not None:
+            d.rfilter_table = (ctypes.c_double * 32)(*self.rfilter_table)
         self._keep = ((Shape * len(self.shapes))(*self.shapes), (Material * len(self.materials))(*self.materials),
                       (Emitter * max(1, len(self.emitters)))(*self.emitters),
                       (ctypes.c_double * max(1, 3 * len(self.vertices)))(*[float(c) for v in self.vertices for c in v]),
@@ -275,9 +296,9 @@ CU_ETA, CU_K = (0.2004, 0.9240, 1.1022), (3.9129, 2.4528, 2.1421)
 AL_ETA, AL_K = (1.6574, 0.8803, 0.5212), (9.2238, 6.2695, 4.8370)
 
 
-def _cornell(width, height, boxes=True):
+def _cornell(width, height, boxes=True, rfilter="box"):
     cam = make_camera(width, height, origin=(0, 0, 3.9), target=(0, 0, 0), up=(0, 1, 0), fov_deg=39.3077)
-    b = SceneBuilder(cam)
+    b = SceneBuilder(cam, rfilter=rfilter)
     white, red, green = b.material(reflectance=WHITE), b.material(reflectance=RED), b.material(reflectance=GREEN)
     black = b.material(reflectance=(0, 0, 0))            # emitter shape without a BSDF (shape.cpp:48-72)
     b.rectangle((0, -1, 0), (1, 0, 0), (0, 0, -1), white)            # floor, normal +y
@@ -292,9 +313,9 @@ def _cornell(width, height, boxes=True):
     return b
 
 
-def cbox_diffuse(width=512, height=512):
+def cbox_diffuse(width=512, height=512, rfilter="box"):
     """C1 "cbox-diffuse": all-diffuse Cornell box with two boxes and one rectangular area light."""
-    return _cornell(width, height).build()
+    return _cornell(width, height, rfilter=rfilter).build()
 
 
 def cbox_materials(width=256, height=256):

@@ -15,7 +15,14 @@ tests); the arithmetic stays in libgdb200.
 import torch
 import torch.distributed as dist
 
-HALO = 2   # rows a sample can reach above/below its base pixel row
+HALO = 2   # rows a sample can reach above/below its base pixel row with the box filter (radius 0.5 + 1e-5)
+
+
+def halo_rows(rfilter_radius):
+    """Rows a sample can reach above/below its base pixel row: the neighbour splat lands one pixel away and the filter
+    footprint spans floor(radius + 0.5) more (ImageBlock::put, imageblock.h:167-176).  Box: 2, gaussian (radius 2): 3."""
+    import math
+    return 1 + int(math.floor(rfilter_radius + 0.5))
 
 
 def strip_rows(height, rank, world):
@@ -25,21 +32,21 @@ def strip_rows(height, rank, world):
     return y0, y0 + base + (1 if rank < rem else 0)
 
 
-def boundary_rows(height, world):
-    """Row indices touched by more than one rank: +-HALO around every strip boundary."""
+def boundary_rows(height, world, halo=HALO):
+    """Row indices touched by more than one rank: +-halo around every strip boundary."""
     rows = []
     for r in range(1, world):
         y = strip_rows(height, r, world)[0]
-        rows.extend(range(max(0, y - HALO), min(height, y + HALO)))
+        rows.extend(range(max(0, y - halo), min(height, y + halo)))
     return sorted(set(rows))
 
 
-def exchange_boundaries(acc, world, group=None):
+def exchange_boundaries(acc, world, group=None, halo=HALO):
     """acc: [5, H, W, 4] accumulator film of this rank. Sums the boundary rows over all ranks
-    in place with a single all-reduce of the packed rows."""
+    in place with a single all-reduce of the packed rows (halo = halo_rows(filter radius))."""
     if world <= 1:
         return 0
-    rows = boundary_rows(acc.shape[1], world)
+    rows = boundary_rows(acc.shape[1], world, halo)
     if not rows:
         return 0
     idx = torch.as_tensor(rows, device=acc.device)

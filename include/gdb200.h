@@ -187,6 +187,10 @@ typedef struct gdb200_scene_desc {
     const int             *triangles;        /* n_triangles * 3 vertex indices          */
     const gdb200_envmap   *envmap;           /* NULL, or the map of the emitter whose type is GDB200_EMITTER_ENVMAP */
     const double          *normals;          /* NULL, or n_vertices * 3 vertex normals (read for shapes with has_vertex_normals) */
+    /* The film's reconstruction filter as ImageBlock::put uses it: ReconstructionFilter::m_values (rfilter.cpp:37-55,
+     * MTS_FILTER_RESOLUTION = 31 taps over [0, radius] + a trailing 0), looked up with evalDiscretized (rfilter.h:76-77).
+     * All zeros = the box filter: taps 1/(2*rfilter_radius). */
+    double                 rfilter_table[32];
 } gdb200_scene_desc;
 
 /* ------------------------------------------------------- G-PT integrator */

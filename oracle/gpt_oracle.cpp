@@ -1374,14 +1374,13 @@ shift_failed:
 
 // ---------------------------------------------------------------- film
 struct Film {
-    int w, h; Float radius, tap;           // tap = discretised box weight 1/(2r) (rfilter.cpp:37-55, box.cpp:45-47)
+    int w, h; Float radius, values[32];    // ReconstructionFilter::m_values (rfilter.cpp:37-55); box: 1/(2r) (box.cpp:45-47)
     std::vector<Float> acc;                // [5][h][w][4]: R,G,B,weight   (the alpha channel of gpt_wr.h:60 is dropped)
     Float *px(int buf, int x, int y) { return &acc[(((size_t)buf * h + y) * w + x) * 4]; }
     // rfilter.h:76-77 with MTS_FILTER_RESOLUTION = 31
     Float evalDiscretized(Float x) const
     {
-        int idx = std::min((int)std::abs(x * (31 / radius)), 31);
-        return idx < 31 ? tap : 0.0;
+        return values[std::min((int)std::abs(x * (31 / radius)), 31)];
     }
     // GPTWorkResult::put (gpt_wr.h:56-64) -> ImageBlock::put (imageblock.h:150-195), in image coordinates
     void put(Float sx, Float sy, Spec v, Float weight, int buf, bool allowNegative)
@@ -1563,14 +1562,18 @@ int gdb200_oracle_gpt_render(const gdb200_scene_desc *desc, const gdb200_gpt_par
     Config cfg; cfg.maxDepth = prm->max_depth; cfg.minDepth = 1; cfg.rrDepth = prm->rr_depth;   // gpt.cpp:1368-1371
     cfg.strictNormals = prm->strict_normals != 0; cfg.shiftThreshold = prm->shift_threshold;
     const int W = sc.cam.width, H = sc.cam.height;
-    Film film; film.w = W; film.h = H; film.radius = sc.filterRadius; film.tap = 1.0 / (2 * film.radius);
+    Film film; film.w = W; film.h = H; film.radius = sc.filterRadius;
+    bool box = true;
+    for (int i = 0; i < 32; i++) { film.values[i] = desc->rfilter_table[i]; if (film.values[i] != 0) box = false; }
+    if (box) { for (int i = 0; i < 31; i++) film.values[i] = 1.0 / (2 * film.radius); film.values[31] = 0; }
     film.acc.assign((size_t)5 * W * H * 4, 0.0);
     const int y0 = (prm->y_begin == 0 && prm->y_end == 0) ? 0 : prm->y_begin, y1 = (prm->y_begin == 0 && prm->y_end == 0) ? H : prm->y_end;
     double totRays = 0, totVerts = 0;
     const int nChunks = std::max(1, prm->streams_per_pixel);
-    // Row bands of 4: a sample in row y writes rows y-2..y+2 at most, so bands of equal parity
+    // Row bands of 2*reach rows (4 for the box filter): a sample in row y writes rows y-reach..y+reach at most, so bands of equal parity
     // never touch the same film rows and can run concurrently without atomics.
-    const int band = 4, nBands = (y1 - y0 + band - 1) / band;
+    const int reach = 1 + (int)std::floor(film.radius + 0.5);        // rows a sample can touch above/below its pixel row
+    const int band = 2 * reach, nBands = (y1 - y0 + band - 1) / band;
     for (int parity = 0; parity < 2; parity++) {
 #pragma omp parallel for schedule(dynamic, 1) num_threads(num_threads > 0 ? num_threads : 1) reduction(+ : totRays, totVerts)
         for (int b = parity; b < nBands; b += 2) {

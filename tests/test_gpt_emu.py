@@ -122,3 +122,20 @@ def test_unsupported_scenes_fail_loudly(emu):
     b.envmap(scenes.sky_envmap(8, 4) * 0)
     with pytest.raises(RuntimeError, match="completely black"):
         emu.gpt(b.build(), scenes.default_params(spp=1))
+
+
+@pytest.mark.parametrize("rfilter", ["gaussian", "tent"])
+def test_reconstruction_filters(oracle, emu, rfilter):
+    """Film filters other than box (gaussian is Mitsuba's default, film.cpp:89-95): the discretised table of
+    rfilter.cpp:37-55 drives the splat footprint and weights of ImageBlock::put."""
+    desc = scenes.cbox_diffuse(26, 22, rfilter=rfilter)
+    p = scenes.default_params(spp=5, seed=4)
+    got, _ = emu.gpt(desc, p)
+    ref, wts, _ = oracle.gpt(desc, p)
+    close(got, ref)
+    box, _, _ = oracle.gpt(scenes.cbox_diffuse(26, 22), p)
+    assert np.abs(box["-throughput"] - ref["-throughput"]).max() > 1e-4          # the filter matters
+    assert abs(box["-throughput"].mean() - ref["-throughput"].mean()) < 0.05 * box["-throughput"].mean()   # but keeps the energy
+    one, _, _ = oracle.gpt(desc, p, threads=1)                                  # oracle band parallelism is safe for the wider footprint
+    for k in ref:
+        assert np.array_equal(one[k], ref[k])

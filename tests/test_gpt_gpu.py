@@ -245,3 +245,27 @@ def test_wavefront_without_tail_kernel(oracle, scene_name, monkeypatch):
     ref, _, cnt = oracle.gpt(desc, integ.params(6, 12, streams=2))
     compare(got, ref)
     assert integ.stats.samples == w * h * 6 == cnt[0]
+
+
+@pytest.mark.parametrize("rfilter", ["gaussian", "tent"])
+def test_reconstruction_filters_on_gpu(oracle, rfilter):
+    desc = scenes.cbox_diffuse(72, 64, rfilter=rfilter)
+    integ = gdb200.GPTIntegrator(reconstructL1=False, reconstructL2=False)
+    got = integ.trace(gdb200.Scene(desc), spp=8, seed=4, streams=2)
+    ref, _, _ = oracle.gpt(desc, integ.params(8, 4, streams=2))
+    compare(got, ref)
+
+
+def test_download_into_pinned_buffers(oracle):
+    """trace(out=...) fills caller-provided page-locked buffers (gdb200.pinned_empty) and rejects wrong shapes."""
+    desc = scenes.cbox_glossy(40, 32)
+    integ = gdb200.GPTIntegrator(reconstructL1=False, reconstructL2=True)
+    host = {n: gdb200.pinned_empty((32, 40, 3), "float64") for n in gdb200.BUFFER_NAMES}
+    scene = gdb200.Scene(desc)
+    a = integ.render(scene, spp=4, seed=2, out=host)
+    b = integ.render(scene, spp=4, seed=2)
+    assert all(a[n] is host[n] for n in host)
+    for n in host:
+        np.testing.assert_allclose(a[n], b[n], rtol=1e-12, atol=1e-15)
+    with pytest.raises(gdb200.Gdb200Error, match="output buffer"):
+        integ.trace(scene, spp=1, out={"-dx": np.zeros((3, 3, 3))})

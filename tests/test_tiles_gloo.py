@@ -36,17 +36,17 @@ def _oracle_acc(orc, desc, prm):
     return acc
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, rfilter="box"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         orc = Oracle()
         w = h = 24
-        desc = scenes.cbox_diffuse(w, h)
+        desc = scenes.cbox_diffuse(w, h, rfilter=rfilter)
         prm = scenes.default_params(spp=2, seed=9)
         prm.y_begin, prm.y_end = tiles.strip_rows(h, rank, world)
         acc = torch.from_numpy(_oracle_acc(orc, desc, prm))
-        tiles.exchange_boundaries(acc, world)
+        tiles.exchange_boundaries(acc, world, halo=tiles.halo_rows(desc.rfilter_radius))
         tiles.gather_strips(acc, rank, world)
         if rank == 0:
             ret["acc"] = acc.numpy().copy()
@@ -54,13 +54,16 @@ def _worker(rank, world, port, ret):
         dist.destroy_process_group()
 
 
-def test_two_rank_strips_match_single_process():
-    world, port = 2, 29611
+@pytest.mark.parametrize("rfilter,port", [("box", 29611), ("gaussian", 29612)])
+def test_two_rank_strips_match_single_process(rfilter, port):
+    """The gaussian film filter (Mitsuba's default, radius 2) widens the halo to 3 rows (tiles.halo_rows)."""
+    world = 2
+    assert tiles.halo_rows(0.50001) == 2 and tiles.halo_rows(2.0) == 3
     with mp.Manager() as mgr:
         ret = mgr.dict()
-        mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, port, ret, rfilter), nprocs=world, join=True)
         merged = ret["acc"]
     orc = Oracle()
-    desc = scenes.cbox_diffuse(24, 24)
+    desc = scenes.cbox_diffuse(24, 24, rfilter=rfilter)
     full = _oracle_acc(orc, desc, scenes.default_params(spp=2, seed=9))
     np.testing.assert_allclose(merged, full, rtol=1e-12, atol=1e-13)
