@@ -100,10 +100,10 @@ struct DMaterial {
     Spec reflectance, specR, specT, eta, k; Float alpha, iorRatio, bsdfEta;
     Float fdrInt, fdrExt, specSamplingWeight, invEta2;       // plastic.cpp:188-206
 };
-enum { EM_RECT = 0, EM_MESH = 1, EM_ENV = 2 };
+enum { EM_RECT = 0, EM_MESH = 1, EM_ENV = 2, EM_POINT = 3 };
 // pdfDiscrete = samplingWeight * normalization (scene.h:855-857).  Mesh emitters: triangles [triFirst, triFirst+triCount) of
 // emTris in the mesh's own order, area CDF (triCount+1 entries) at emTriCdf[cdfFirst], invArea = 1 / surface area.
-struct DEmitter { int kind, rect, triFirst, triCount, cdfFirst, pad; Spec radiance; Float pdfDiscrete, invArea; };
+struct DEmitter { int kind, rect, triFirst, triCount, cdfFirst, pad; Spec radiance; Float pdfDiscrete, invArea; V3 position; };
 struct DEmTri { V3 p0, p1, p2; int normals, pad; };   // normals: as DTri
 // Environment map (envmap.cpp): top-level texels as Float RGB, the float CDF tables of envmap.cpp:263-311.
 struct DEnv {
@@ -900,6 +900,14 @@ GDB_D Spec sampleEmitterDirectVisibleImpl(DRec &dRec, Float sx, Float sy, bool &
         }
         dRec.pdf = pdf; dRec.p = dRec.ref + dw * farT; dRec.n = normalize(c_scene.env.center - dRec.p); dRec.dist = farT; dRec.d = dw;
         value = v / pdf;
+    } else if (em.kind == EM_POINT) {                                                // point.cpp:131-147 (measure: discrete)
+        dRec.p = em.position; dRec.n = mk(0, 0, 0);
+        dRec.d = dRec.p - dRec.ref;
+        dRec.dist = len(dRec.d);
+        const Float invDist = (Float)1.0f / dRec.dist;
+        dRec.d = dRec.d * invDist;
+        dRec.pdf = 1;
+        value = em.radiance * (invDist * invDist);
     } else {
         if (em.kind == EM_RECT) {
             const DRect &s = c_sceneG->rects[em.rect];
@@ -963,6 +971,7 @@ GDB_D Float pdfEmitterDirect(const DRec &dRec)
     const DEmitter &em = c_sceneG->emitters[dRec.emitter];
     Float pdf = 0.0;
     if (em.kind == EM_ENV) pdf = envPdfDirection(xfVector(c_scene.env.toObject, dRec.d));
+    else if (em.kind == EM_POINT) pdf = 0.0;                                         // point.cpp:149-151 for a solid-angle query
     else if (dot(dRec.d, dRec.refN) >= 0 && dot(dRec.d, dRec.n) < 0) {
         const Float invArea = em.kind == EM_RECT ? c_sceneG->rects[em.rect].invArea : em.invArea;
         pdf = invArea * (dRec.dist * dRec.dist) / fabs(dot(dRec.d, dRec.n));

@@ -338,6 +338,10 @@ inline int flattenScene(const gdb200_scene_desc *d, HostScene *s)
             if (int rc = buildEnvTables(d->envmap, i, s)) return rc;
             continue;
         }
+        if (e.type == GDB200_EMITTER_POINT) {
+            o.kind = EM_POINT; o.rect = -1; o.position = mk(e.position[0], e.position[1], e.position[2]);
+            continue;
+        }
         if (e.type != GDB200_EMITTER_AREA) return set_error(GDB200_ERR_ARGUMENT, "emitter %d: unknown type %d", i, e.type);
         if (e.shape < 0 || e.shape >= d->n_shapes || d->shapes[e.shape].emitter != i)
             return set_error(GDB200_ERR_ARGUMENT, "emitter %d: area emitter and its shape must reference each other", i);

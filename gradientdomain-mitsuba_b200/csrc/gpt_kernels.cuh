@@ -416,7 +416,7 @@ GDB_D void bounceBody(const GptArgs &a, int slot, int parity)
         const Frame prevSh = mits.sh; const V3 prevP = mits.p, prevWi = mits.wi;     // the vertex both stages shade (previousMainIts, gpt.cpp:753)
 
         // ---------------- base path: next event estimation, gpt.cpp:565-607
-        bool neeActive = false, neeVisible = false;
+        bool neeActive = false, neeVisible = false, atPointLight = false;
         Float lsx = 0, lsy = 0, neeBsdfPdf = 0, neeDistSq = 0, neeOppCos = 0, neeWNum = 0, neeWDen = 0, neeLightPdf = 0;
         V3 neeWoLocal = mk(0, 0, 0), neeLightP = mk(0, 0, 0), neeLightN = mk(0, 0, 0);
         Spec neeBsdfValue = splat(0), neeEmitterRadiance = splat(0), neeContributionAll = splat(0);
@@ -427,7 +427,8 @@ GDB_D void bounceBody(const GptArgs &a, int slot, int parity)
             neeEmitterRadiance = value * dRec.pdf;                                   // gpt.cpp:575
             neeWoLocal = toLocal(mits.sh, dRec.d);
             bsdfEvalPdf(mainBSDF, mits.wi, neeWoLocal, ESolidAngle, neeBsdfValue, neeBsdfPdf);   // gpt.cpp:588
-            if (!neeVisible) neeBsdfPdf = 0;                                         // gpt.cpp:592
+            atPointLight = c_sceneG->emitters[dRec.emitter].kind == EM_POINT;        // dRec.measure == EDiscrete; such an emitter is not "on a surface"
+            if (!neeVisible || atPointLight) neeBsdfPdf = 0;                         // gpt.cpp:592
             neeDistSq = len2(mits.p - dRec.p);                                       // gpt.cpp:595-596
             neeOppCos = dot(dRec.n, (mits.p - dRec.p)) / sqrt(neeDistSq);
             neeWNum = mpdf * dRec.pdf;                                               // gpt.cpp:599-600
@@ -514,7 +515,7 @@ GDB_D void bounceBody(const GptArgs &a, int slot, int parity)
                     } else if (conn == RAY_RECENTLY_CONNECTED) {                     // gpt.cpp:638-658
                         Spec shiftedBsdfValue; Float shiftedBsdfPdf;
                         bsdfEvalPdf(mainBSDF, recentWiL, neeWoLocal, ESolidAngle, shiftedBsdfValue, shiftedBsdfPdf);
-                        if (!neeVisible) shiftedBsdfPdf = 0;
+                        if (!neeVisible || atPointLight) shiftedBsdfPdf = 0;
                         const Float jacobian = 1;
                         const Float den = (jacobian * spdf) * (jacobian * spdf) * ((neeLightPdf * neeLightPdf) + (shiftedBsdfPdf * shiftedBsdfPdf));
                         weight = neeWNum / (kDEps + den + neeWDen);
@@ -522,7 +523,7 @@ GDB_D void bounceBody(const GptArgs &a, int slot, int parity)
                         shiftedContribution = jacobian * sthr * (shiftedBsdfValue * neeEmitterRadiance);
                     } else {                                                         // gpt.cpp:659-705
                         const DMaterial &shiftedBSDF = c_sceneG->materials[sits.material];
-                        if (vertexType(mainBSDF, ESmooth) == VERTEX_TYPE_DIFFUSE && vertexType(shiftedBSDF, ESmooth) == VERTEX_TYPE_DIFFUSE) {   // gpt.cpp:672
+                        if (atPointLight || (vertexType(mainBSDF, ESmooth) == VERTEX_TYPE_DIFFUSE && vertexType(shiftedBSDF, ESmooth) == VERTEX_TYPE_DIFFUSE)) {   // gpt.cpp:668-672
                             DRec sRec; initDRec(sits, sRec);
                             bool shiftedEmitterVisible;
                             const Spec sv = sampleEmitterDirectVisible(sRec, lsx, lsy, shiftedEmitterVisible); rays++;
@@ -537,7 +538,7 @@ GDB_D void bounceBody(const GptArgs &a, int slot, int parity)
                             } else {
                                 Spec shiftedBsdfValue; Float shiftedBsdfPdf;
                                 bsdfEvalPdf(shiftedBSDF, sits.wi, woL, ESolidAngle, shiftedBsdfValue, shiftedBsdfPdf);
-                                if (!shiftedEmitterVisible) shiftedBsdfPdf = 0;
+                                if (!shiftedEmitterVisible || atPointLight) shiftedBsdfPdf = 0;
                                 const Float jacobian = fabs(shiftedOpposingCosine * neeDistSq) / (kEpsilon + fabs(neeOppCos * shiftedDistanceSquared));   // gpt.cpp:695
                                 const Float den = (jacobian * spdf) * (jacobian * spdf) * ((shiftedDRecPdf * shiftedDRecPdf) + (shiftedBsdfPdf * shiftedBsdfPdf));
                                 weight = neeWNum / (kDEps + den + neeWDen);

@@ -184,6 +184,29 @@ struct FlatScene {
 			}
 			shapes.push_back(s);
 		}
+		{	/* emitters that are not attached to a shape: point lights (point.cpp); anything else is outside the subset */
+			const ref_vector<Emitter> &all = scene->getEmitters();
+			for (size_t i = 0; i < all.size(); ++i) {
+				const Emitter *e = all[i].get();
+				const std::string cls = e->getClass()->getName();
+				if (cls == "AreaLight" || cls == "EnvironmentMap") continue;
+				if (cls != "PointEmitter")
+					SLog(EError, "gdb200: emitter class \"%s\" is outside the supported hot-path subset", cls.c_str());
+				gdb200_emitter em;
+				memset(&em, 0, sizeof(em));
+				em.type = GDB200_EMITTER_POINT; em.shape = -1;
+				copySpectrum(e->getProperties().getSpectrum("intensity", Spectrum(1.0f)), em.radiance);
+				const Point pos = e->getWorldTransform()->eval(0)(Point(0.0f));
+				em.position[0] = pos.x; em.position[1] = pos.y; em.position[2] = pos.z;
+				em.sampling_weight = e->getSamplingWeight();
+				const size_t at = std::min(i, emitters.size());       /* keep Scene::m_emitters order: it defines the emitter CDF */
+				emitters.insert(emitters.begin() + at, em);
+				for (size_t k = 0; k < shapes.size(); ++k)
+					if (shapes[k].emitter >= (int) at) shapes[k].emitter++;
+				for (size_t j = 0; j < emitters.size(); ++j)
+					if (emitters[j].type == GDB200_EMITTER_AREA) for (size_t k = 0; k < shapes.size(); ++k) if (shapes[k].emitter == (int) j) emitters[j].shape = (int) k;
+			}
+		}
 		if (const Emitter *e = scene->getEnvironmentEmitter()) {
 			/* envmap.cpp: the top MIP level as a float RGB bitmap (Emitter::getBitmap, envmap.cpp:644-646), the
 			   emitter-to-world transform and the bounding sphere EnvironmentMap::createShape derives (envmap.cpp:322-329) */

@@ -12,7 +12,7 @@ import numpy as np
 
 SHAPE_RECTANGLE, SHAPE_SPHERE, SHAPE_MESH = 0, 1, 2
 BSDF_DIFFUSE, BSDF_ROUGHCONDUCTOR, BSDF_CONDUCTOR, BSDF_DIELECTRIC, BSDF_PLASTIC = 0, 1, 2, 3, 4
-EMITTER_AREA, EMITTER_ENVMAP = 0, 1
+EMITTER_AREA, EMITTER_ENVMAP, EMITTER_POINT = 0, 1, 2
 MICROFACET_BECKMANN, MICROFACET_GGX = 0, 1
 
 D16 = ctypes.c_double * 16
@@ -40,7 +40,7 @@ class Material(ctypes.Structure):
 
 class Emitter(ctypes.Structure):
     _fields_ = [("shape", ctypes.c_int), ("type", ctypes.c_int), ("radiance", D3),
-                ("sampling_weight", ctypes.c_double)]
+                ("sampling_weight", ctypes.c_double), ("position", D3)]
 
 
 class EnvMap(ctypes.Structure):
@@ -151,6 +151,13 @@ class SceneBuilder:
         self._env_scale, self._env_to_world = float(scale), (np.eye(4) if to_world is None else np.asarray(to_world, float))
         e = Emitter()
         e.shape, e.type, e.radiance, e.sampling_weight = -1, EMITTER_ENVMAP, D3(0, 0, 0), sampling_weight
+        self.emitters.append(e)
+        return len(self.emitters) - 1
+
+    def point_light(self, position, intensity, sampling_weight=1.0):
+        """Isotropic point emitter (point.cpp)."""
+        e = Emitter()
+        e.shape, e.type, e.radiance, e.sampling_weight, e.position = -1, EMITTER_POINT, D3(*intensity), sampling_weight, D3(*position)
         self.emitters.append(e)
         return len(self.emitters) - 1
 
@@ -486,6 +493,19 @@ def cbox_smooth(width=256, height=256):
 def atrium_c3(width=1920, height=1080):
     """BASELINE configs[2] stand-in ("Sponza-class, env-map lit, mixed diffuse/specular"): 258 k triangles behind the BVH."""
     return atrium(width, height, columns=12, segments=64, rings=14)
+
+
+def cbox_point(width=256, height=256):
+    """Point-light coverage (gpt.cpp:668-672: `mainAtPointLight` lets the light-sample shift run at glossy vertices
+    too; the BSDF-sampling strategy has zero density towards a Dirac emitter): the glossy Cornell box lit by a point
+    emitter next to its area light."""
+    b = _cornell(width, height)
+    rough = b.material(type=BSDF_ROUGHCONDUCTOR, alpha=0.05, eta=CU_ETA, k=CU_K)
+    shiny = b.material(type=BSDF_ROUGHCONDUCTOR, alpha=0.0005, eta=AL_ETA, k=AL_K)
+    b.sphere((0.33, -0.1, 0.35), 0.3, rough)
+    b.sphere((-0.5, -0.7, 0.55), 0.3, shiny)
+    b.point_light((-0.3, 0.5, 0.4), (1.5, 1.2, 0.9))
+    return b.build()
 
 
 def default_params(spp=64, seed=0, max_depth=-1, rr_depth=5, shift_threshold=0.001, strict_normals=False):

@@ -763,7 +763,7 @@ void bsdfSample(const gdb200_material &m, BSDFSample &r, Float sx, Float sy)
 }
 
 // ---------------------------------------------------------------- emitters
-struct DRec { V3 ref, refN, p, n, d; Float dist, pdf; int emitter; };   // DirectSamplingRecord (measure: solid angle)
+struct DRec { V3 ref, refN, p, n, d; Float dist, pdf; int emitter; bool discrete; };   // DirectSamplingRecord (measure: solid angle unless `discrete`)
 
 inline const gdb200_material &matOf(const Scene &sc, const Its &its) { return sc.mats[sc.shapes[its.shape].d.material]; }
 inline bool isEmitter(const Scene &sc, const Its &its) { return sc.shapes[its.shape].d.emitter >= 0; }
@@ -895,6 +895,7 @@ Spec sampleEmitterDirectVisible(const Scene &sc, DRec &dRec, Float sx, Float sy,
     const gdb200_emitter &em = sc.ems[index];
     Spec value;
     dRec.emitter = (int)index;
+    dRec.discrete = false;
     if (em.type == GDB200_EMITTER_ENVMAP) {                                         // envmap.cpp:516-544
         Spec v; V3 d; Float pdf;
         envSampleDirection(sc.env, sx, sy, d, v, pdf);
@@ -909,6 +910,16 @@ Spec sampleEmitterDirectVisible(const Scene &sc, DRec &dRec, Float sx, Float sy,
         }
         dRec.pdf = pdf; dRec.p = dRec.ref + dw * farT; dRec.n = normalize(sc.env.center - dRec.p); dRec.dist = farT; dRec.d = dw;
         value = v / pdf;
+    } else if (em.type == GDB200_EMITTER_POINT) {                                   // point.cpp:131-147
+        dRec.p = specOf(em.position);
+        dRec.pdf = 1.0f;
+        dRec.d = dRec.p - dRec.ref;
+        dRec.dist = length(dRec.d);
+        Float invDist = 1.0f / dRec.dist;
+        dRec.d = dRec.d * invDist;
+        dRec.n = v3(0, 0, 0);
+        dRec.discrete = true;
+        value = specOf(em.radiance) * (invDist * invDist);
     } else {
         const Shape &s = sc.shapes[em.shape];
         if (s.d.type == GDB200_SHAPE_RECTANGLE) {                                   // rectangle.cpp:210-216
@@ -952,6 +963,7 @@ Float pdfEmitterDirect(const Scene &sc, const DRec &dRec)
     const gdb200_emitter &em = sc.ems[dRec.emitter];
     Float pdf = 0.0;
     if (em.type == GDB200_EMITTER_ENVMAP) pdf = envPdfDirection(sc.env, xfVector(sc.env.toObject, dRec.d));
+    else if (em.type == GDB200_EMITTER_POINT) pdf = 0.0;                           // point.cpp:149-151, solid-angle query
     else if (dot(dRec.d, dRec.refN) >= 0 && dot(dRec.d, dRec.n) < 0) {
         const Shape &s = sc.shapes[em.shape];
         const Float pdfPos = s.d.type == GDB200_SHAPE_RECTANGLE ? s.invArea : sc.meshSampling[em.shape].invSurfaceArea;
@@ -1124,7 +1136,9 @@ void evaluate(const Scene &sc, const Config &cfg, Sampler &sampler, RayState &ma
             Spec mainEmitterRadiance = value * dRec.pdf;                            // :575
             V3 mainWoLocal = toLocal(main.its.sh, dRec.d);
             Spec mainBSDFValue = bsdfEval(mainBSDF, main.its.wi, mainWoLocal, ESolidAngle);                  // :588
-            Float mainBsdfPdf = mainEmitterVisible ? bsdfPdf(mainBSDF, main.its.wi, mainWoLocal, ESolidAngle) : 0;  // :592
+            const bool onSurfaceSolidAngle = sc.ems[dRec.emitter].type != GDB200_EMITTER_POINT && !dRec.discrete;   // emitter->isOnSurface() && dRec.measure == ESolidAngle
+            const bool mainAtPointLight = dRec.discrete;                            // :670
+            Float mainBsdfPdf = (onSurfaceSolidAngle && mainEmitterVisible) ? bsdfPdf(mainBSDF, main.its.wi, mainWoLocal, ESolidAngle) : 0;  // :592
             Float mainDistanceSquared = lengthSquared(main.its.p - dRec.p);         // :595-596
             Float mainOpposingCosine = dot(dRec.n, (main.its.p - dRec.p)) / std::sqrt(mainDistanceSquared);
             Float mainWeightNumerator = main.pdf * dRec.pdf;                        // :599-600
@@ -1145,7 +1159,7 @@ void evaluate(const Scene &sc, const Config &cfg, Sampler &sampler, RayState &ma
                         } else if (shifted.connection_status == RAY_RECENTLY_CONNECTED) {   // :638-658
                             V3 incoming = normalize(shifted.its.p - main.its.p);
                             V3 wiL = toLocal(main.its.sh, incoming);
-                            Float shiftedBsdfPdf = mainEmitterVisible ? bsdfPdf(mainBSDF, wiL, mainWoLocal, ESolidAngle) : 0;
+                            Float shiftedBsdfPdf = (onSurfaceSolidAngle && mainEmitterVisible) ? bsdfPdf(mainBSDF, wiL, mainWoLocal, ESolidAngle) : 0;
                             Float shiftedDRecPdf = dRec.pdf;
                             Spec shiftedBsdfValue = bsdfEval(mainBSDF, wiL, mainWoLocal, ESolidAngle);
                             Float jacobian = 1;
@@ -1156,7 +1170,7 @@ void evaluate(const Scene &sc, const Config &cfg, Sampler &sampler, RayState &ma
                         } else {                                                    // :659-705
                             const gdb200_material &shiftedBSDF = matOf(sc, shifted.its);
                             VertexType mainVT = getVertexType(mainBSDF, cfg, ESmooth), shiftedVT = getVertexType(shiftedBSDF, cfg, ESmooth);
-                            if (mainVT == VERTEX_TYPE_DIFFUSE && shiftedVT == VERTEX_TYPE_DIFFUSE) {   // :672 (no point lights here)
+                            if (mainAtPointLight || (mainVT == VERTEX_TYPE_DIFFUSE && shiftedVT == VERTEX_TYPE_DIFFUSE)) {   // :672
                                 DRec sRec; initDRec(sc, shifted.its, sRec);
                                 bool shiftedEmitterVisible;
                                 Spec sv = sampleEmitterDirectVisible(sc, sRec, lsx, lsy, shiftedEmitterVisible); cnt.rays++;
@@ -1170,7 +1184,7 @@ void evaluate(const Scene &sc, const Config &cfg, Sampler &sampler, RayState &ma
                                     shiftSuccessful = false;
                                 } else {
                                     Spec shiftedBsdfValue = bsdfEval(shiftedBSDF, shifted.its.wi, woL, ESolidAngle);
-                                    Float shiftedBsdfPdf = shiftedEmitterVisible ? bsdfPdf(shiftedBSDF, shifted.its.wi, woL, ESolidAngle) : 0;
+                                    Float shiftedBsdfPdf = (onSurfaceSolidAngle && shiftedEmitterVisible) ? bsdfPdf(shiftedBSDF, shifted.its.wi, woL, ESolidAngle) : 0;
                                     Float jacobian = std::abs(shiftedOpposingCosine * mainDistanceSquared) / (Epsilon + std::abs(mainOpposingCosine * shiftedDistanceSquared));   // :695
                                     Float den = (jacobian * shifted.pdf) * (jacobian * shifted.pdf) * ((shiftedDRecPdf * shiftedDRecPdf) + (shiftedBsdfPdf * shiftedBsdfPdf));
                                     weight = mainWeightNumerator / (D_EPSILON + den + mainWeightDenominator);
@@ -1672,7 +1686,7 @@ int gdb200_oracle_path_render(const gdb200_scene_desc *desc, const gdb200_gpt_pa
                             V3 woL = toLocal(its.sh, dRec.d);
                             Spec bsdfVal = bsdfEval(bsdf, its.wi, woL, ESolidAngle);
                             if (!(bsdfVal.x == 0 && bsdfVal.y == 0 && bsdfVal.z == 0)) {
-                                Float bsdfPdfV = bsdfPdf(bsdf, its.wi, woL, ESolidAngle);
+                                Float bsdfPdfV = dRec.discrete ? 0.0 : bsdfPdf(bsdf, its.wi, woL, ESolidAngle);   // emitter->isOnSurface() && measure == ESolidAngle, :1571-1572
                                 Float a = dRec.pdf * dRec.pdf, b = bsdfPdfV * bsdfPdfV;
                                 Li = Li + throughput * value * bsdfVal * (a / (a + b));
                             }
