@@ -117,7 +117,7 @@ struct BvhNode { float lo[3]; int a; float hi[3]; int b; };
 
 struct DScene {
     Float sampleToCamera[16], cameraToWorld[12];
-    Float nearClip, farClip, invResX, invResY, filterRadius, filterScale;
+    Float nearClip, farClip, invResX, invResY, filterRadius, filterScale, apertureRadius, focusDistance;
     Float filterTable[32];             // ReconstructionFilter::m_values (rfilter.cpp:37-55)
     int width, height, nRects, nSpheres, nTris, nMaterials, nEmitters, nMeshes;
     Float emCdf[kMaxEmitters + 1];
@@ -1043,10 +1043,23 @@ GDB_D ShiftResult environmentShift(V3 mainD, V3 shiftSource)
     return result;
 }
 
-// perspective.cpp:271-298
-GDB_D void sampleCameraRay(Float px, Float py, Ray &ray)
+// perspective.cpp:271-298; with an aperture (apertureRadius > 0) thinlens.cpp:289-318
+GDB_D void sampleCameraRay(Float px, Float py, Float ax, Float ay, Ray &ray)
 {
     const V3 nearP = xfPoint(c_scene.sampleToCamera, mk(px * c_scene.invResX, py * c_scene.invResY, 0.0));
+    if (c_scene.apertureRadius > 0) {
+        Float tx, ty;
+        squareToUniformDiskConcentric(ax, ay, tx, ty);
+        const V3 apertureP = mk(tx * c_scene.apertureRadius, ty * c_scene.apertureRadius, 0.0);
+        const V3 focusP = nearP * (c_scene.focusDistance / nearP.z);
+        const V3 d = normalize(focusP - apertureP);
+        const Float invZ = 1.0 / d.z;
+        ray.mint = c_scene.nearClip * invZ;
+        ray.maxt = c_scene.farClip * invZ;
+        ray.o = xfAffine(c_scene.cameraToWorld, apertureP);
+        ray.d = xfVector(c_scene.cameraToWorld, d);
+        return;
+    }
     const V3 d = normalize(nearP);
     const Float invZ = 1.0 / d.z;
     ray.mint = c_scene.nearClip * invZ;

@@ -189,6 +189,8 @@ inline int flattenScene(const gdb200_scene_desc *d, HostScene *s)
     memcpy(h.sampleToCamera, c.sample_to_camera, sizeof(h.sampleToCamera));
     memcpy(h.cameraToWorld, c.camera_to_world, sizeof(h.cameraToWorld));
     h.nearClip = c.near_clip; h.farClip = c.far_clip; h.width = c.width; h.height = c.height;
+    if (c.aperture_radius < 0 || (c.aperture_radius > 0 && !(c.focus_distance > 0))) return set_error(GDB200_ERR_ARGUMENT, "invalid aperture radius / focus distance");
+    h.apertureRadius = c.aperture_radius; h.focusDistance = c.focus_distance;
     h.invResX = 1.0 / c.width; h.invResY = 1.0 / c.height;
     if (!(d->rfilter_radius > 0)) return set_error(GDB200_ERR_ARGUMENT, "invalid reconstruction filter radius %g", d->rfilter_radius);
     h.filterRadius = d->rfilter_radius; h.filterScale = 31 / d->rfilter_radius;

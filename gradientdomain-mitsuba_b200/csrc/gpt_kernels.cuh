@@ -290,8 +290,10 @@ GDB_D void generateBody(const GptArgs &a, int slot)
         j++; samples++;
         const Float u = smp.next1D(), v = smp.next1D();                              // gpt.cpp:1261
         const Float spx = si.px + u, spy = si.py + v;
+        Float apx = 0.5, apy = 0.5;                                                  // gpt.cpp:1235
+        if (c_scene.apertureRadius > 0) { apx = smp.next1D(); apy = smp.next1D(); }  // needsApertureSample, gpt.cpp:1263-1265
         Ray ray; Its mits;
-        sampleCameraRay(spx, spy, ray);                                              // gpt.cpp:402
+        sampleCameraRay(spx, spy, apx, apy, ray);                                    // gpt.cpp:402
         const bool mainValid = rayIntersectByValue(ray, mits); rays += 5;                   // gpt.cpp:472
         Spec veryDirect = splat(0);
         unsigned flags = 0;
@@ -303,7 +305,7 @@ GDB_D void generateBody(const GptArgs &a, int slot)
 #pragma unroll 1
         for (int i = 0; i < 4; i++) {
             Ray sray; Its sits;
-            sampleCameraRay(spx + shiftX[i], spy + shiftY[i], sray);                 // gpt.cpp:418
+            sampleCameraRay(spx + shiftX[i], spy + shiftY[i], apx, apy, sray);       // gpt.cpp:418
             bool alive = rayIntersectByValue(sray, sits);                            // gpt.cpp:476-480, 508-513
             if (alive && a.cfg.strictNormals && dot(sray.d, sits.geoN) * sits.wi.z >= 0) alive = false;   // gpt.cpp:523-530
             flags |= packFlag(i, alive, RAY_NOT_CONNECTED);

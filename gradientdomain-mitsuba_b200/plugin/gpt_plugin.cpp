@@ -104,8 +104,13 @@ struct FlatScene {
 		if (film->getCropSize() != film->getSize())
 			SLog(EError, "gdb200: crop windows are not supported yet");
 		const PerspectiveCamera *cam = dynamic_cast<const PerspectiveCamera *>(sensor);
-		if (!cam || sensor->needsApertureSample() || sensor->needsTimeSample())
-			SLog(EError, "gdb200: only the pinhole 'perspective' sensor is supported");
+		if (!cam || sensor->needsTimeSample())
+			SLog(EError, "gdb200: only the 'perspective' and 'thinlens' sensors without motion blur are supported");
+		if (sensor->needsApertureSample()) {           /* ThinLensCamera derives from PerspectiveCamera (thinlens.cpp:118,132-137) */
+			desc.camera.aperture_radius = sensor->getProperties().getFloat("apertureRadius", 0.0f);
+			if (desc.camera.aperture_radius == 0) desc.camera.aperture_radius = Epsilon;
+			desc.camera.focus_distance = sensor->getProperties().getFloat("focusDistance", 0.0f);
+		}
 		/* perspective.cpp:126-160 with Mitsuba's own Transform algebra (so the numerically inverted
 		   m_sampleToCamera is bit-identical to the reference's) */
 		const Float aspect = cam->getAspect();

@@ -21,7 +21,8 @@ D3 = ctypes.c_double * 3
 
 class Camera(ctypes.Structure):
     _fields_ = [("sample_to_camera", D16), ("camera_to_world", D16), ("near_clip", ctypes.c_double),
-                ("far_clip", ctypes.c_double), ("width", ctypes.c_int), ("height", ctypes.c_int)]
+                ("far_clip", ctypes.c_double), ("width", ctypes.c_int), ("height", ctypes.c_int),
+                ("aperture_radius", ctypes.c_double), ("focus_distance", ctypes.c_double)]
 
 
 class Shape(ctypes.Structure):
@@ -108,7 +109,7 @@ def perspective(fov_deg, near, far):
                     dtype=np.float64)
 
 
-def make_camera(width, height, origin, target, up, fov_deg, near=1e-2, far=1e4):
+def make_camera(width, height, origin, target, up, fov_deg, near=1e-2, far=1e4, aperture_radius=0.0, focus_distance=0.0):
     """PerspectiveCamera::configure (perspective.cpp:126-160), no crop window, fovAxis = x."""
     aspect = width / height
     cam_to_sample = (scale((-0.5, -0.5 * aspect, 1.0)) @ translate((-1.0, -1.0 / aspect, 0.0))
@@ -117,6 +118,7 @@ def make_camera(width, height, origin, target, up, fov_deg, near=1e-2, far=1e4):
     cam.sample_to_camera = D16(*np.linalg.inv(cam_to_sample).reshape(-1))
     cam.camera_to_world = D16(*look_at(origin, target, up).reshape(-1))
     cam.near_clip, cam.far_clip, cam.width, cam.height = near, far, width, height
+    cam.aperture_radius, cam.focus_distance = aperture_radius, focus_distance        # thinlens.cpp; 0 = pinhole
     return cam
 
 
@@ -303,8 +305,9 @@ CU_ETA, CU_K = (0.2004, 0.9240, 1.1022), (3.9129, 2.4528, 2.1421)
 AL_ETA, AL_K = (1.6574, 0.8803, 0.5212), (9.2238, 6.2695, 4.8370)
 
 
-def _cornell(width, height, boxes=True, rfilter="box"):
-    cam = make_camera(width, height, origin=(0, 0, 3.9), target=(0, 0, 0), up=(0, 1, 0), fov_deg=39.3077)
+def _cornell(width, height, boxes=True, rfilter="box", aperture_radius=0.0, focus_distance=0.0):
+    cam = make_camera(width, height, origin=(0, 0, 3.9), target=(0, 0, 0), up=(0, 1, 0), fov_deg=39.3077,
+                      aperture_radius=aperture_radius, focus_distance=focus_distance)
     b = SceneBuilder(cam, rfilter=rfilter)
     white, red, green = b.material(reflectance=WHITE), b.material(reflectance=RED), b.material(reflectance=GREEN)
     black = b.material(reflectance=(0, 0, 0))            # emitter shape without a BSDF (shape.cpp:48-72)
@@ -336,6 +339,14 @@ def cbox_materials(width=256, height=256):
     b.sphere((0.1, -0.65, 0.45), 0.35, mirror)
     b.sphere((0.6, -0.75, -0.3), 0.25, glass)
     b.box((0.0, 0.55, -0.6), (0.5, 0.05, 0.2), 0.0, b.material(reflectance=WHITE))     # a shelf: more occlusion for the shifts
+    return b.build()
+
+
+def cbox_dof(width=256, height=256):
+    """Depth of field (`thinlens` sensor): aperture radius 0.08 focused on the tall box; every camera sample draws one
+    aperture sample that its four offset rays share."""
+    b = _cornell(width, height, aperture_radius=0.08, focus_distance=4.2)
+    b.sphere((0.33, -0.1, 0.35), 0.3, b.material(type=BSDF_ROUGHCONDUCTOR, alpha=0.05, eta=CU_ETA, k=CU_K))
     return b.build()
 
 

@@ -127,6 +127,8 @@ typedef struct gdb200_camera {          /* src/sensors/perspective.cpp:126-180,2
     double camera_to_world[16];         /* m_worldTransform at shutter open            */
     double near_clip, far_clip;
     int    width, height;               /* film / crop size                            */
+    double aperture_radius;             /* 0 = pinhole `perspective`; > 0 = `thinlens` (src/sensors/thinlens.cpp:289-318): one */
+    double focus_distance;              /* aperture sample per camera sample, shared by the base and the four offset rays (gpt.cpp:1263-1265) */
 } gdb200_camera;
 
 typedef struct gdb200_shape {

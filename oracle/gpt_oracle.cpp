@@ -1078,15 +1078,23 @@ ShiftResult environmentShift(const Scene &sc, const Ray &mainRay, V3 shiftSource
 
 struct Counters { double rays, vertices; };
 
-// perspective.cpp:271-298 (ray differentials are unused by the textures-free material subset)
-void sampleCameraRay(const Scene &sc, Float px, Float py, Ray &ray)
+// PerspectiveCamera::sampleRayDifferential, perspective.cpp:271-298 / ThinLensCamera, thinlens.cpp:289-318 (aperture_radius > 0);
+// ray differentials are unused by the texture-free material subset
+void sampleCameraRay(const Scene &sc, Float px, Float py, Float ax, Float ay, Ray &ray)
 {
     V3 nearP = xfPoint(sc.cam.sample_to_camera, v3(px * sc.invResX, py * sc.invResY, 0.0));
-    V3 d = normalize(nearP);
+    V3 d, origin = v3(0, 0, 0);
+    if (sc.cam.aperture_radius > 0) {
+        Float tx, ty; squareToUniformDiskConcentric(ax, ay, tx, ty);
+        V3 apertureP = v3(tx * sc.cam.aperture_radius, ty * sc.cam.aperture_radius, 0.0);
+        V3 focusP = nearP * (sc.cam.focus_distance / nearP.z);
+        d = normalize(focusP - apertureP);
+        origin = apertureP;
+    } else d = normalize(nearP);
     Float invZ = 1.0 / d.z;
     ray.mint = sc.cam.near_clip * invZ;
     ray.maxt = sc.cam.far_clip * invZ;
-    ray.o = xfAffine(sc.cam.camera_to_world, v3(0, 0, 0));
+    ray.o = xfAffine(sc.cam.camera_to_world, origin);
     ray.d = xfVector(sc.cam.camera_to_world, d);
 }
 
@@ -1602,10 +1610,12 @@ int gdb200_oracle_gpt_render(const gdb200_scene_desc *desc, const gdb200_gpt_par
                     for (int j = 0; j < chunkSpp; j++) {
                         Float u, v; sampler.next2D(u, v);                           // :1261
                         const Float spx = x + u, spy = y + v;
+                        Float apx = 0.5f, apy = 0.5f;                               // :1235
+                        if (sc.cam.aperture_radius > 0) sampler.next2D(apx, apy);   // needsApertureSample, :1263-1265
                         RayState main, shifted[4];
                         static const Float shiftX[4] = {1, 0, -1, 0}, shiftY[4] = {0, 1, 0, -1};   // :410-415
-                        sampleCameraRay(sc, spx, spy, main.ray); main.throughput = spec(1);
-                        for (int i = 0; i < 4; i++) { sampleCameraRay(sc, spx + shiftX[i], spy + shiftY[i], shifted[i].ray); shifted[i].throughput = spec(1); }
+                        sampleCameraRay(sc, spx, spy, apx, apy, main.ray); main.throughput = spec(1);
+                        for (int i = 0; i < 4; i++) { sampleCameraRay(sc, spx + shiftX[i], spy + shiftY[i], apx, apy, shifted[i].ray); shifted[i].throughput = spec(1); }
                         Spec veryDirect = spec(0);
                         evaluate(sc, cfg, sampler, main, shifted, 4, veryDirect, cnt);
                         const int RIGHT = 0, BOTTOM = 1, LEFT = 2, TOP = 3;         // :1283-1286
@@ -1665,7 +1675,9 @@ int gdb200_oracle_path_render(const gdb200_scene_desc *desc, const gdb200_gpt_pa
             Spec sum = spec(0);
             for (int j = 0; j < prm->spp; j++) {
                 Float u, v; sampler.next2D(u, v);
-                Ray ray; sampleCameraRay(sc, x + u, y + v, ray);
+                Float apx = 0.5f, apy = 0.5f;
+                if (sc.cam.aperture_radius > 0) sampler.next2D(apx, apy);
+                Ray ray; sampleCameraRay(sc, x + u, y + v, apx, apy, ray);
                 Its its; rayIntersect(sc, ray, its);
                 ray.mint = Epsilon;
                 Spec Li = spec(0), throughput = spec(1);

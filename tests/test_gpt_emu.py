@@ -28,6 +28,7 @@ SCENES = {"cbox_diffuse": lambda w, h: scenes.cbox_diffuse(w, h), "cbox_glossy":
           "cbox_mesh_lights": lambda w, h: scenes.cbox_mesh_lights(w, h),  # mesh emitters, plastic, twosided
           "atrium": lambda w, h: scenes.atrium(w, h, columns=3, segments=8, rings=4),   # > table size: BVH path
           "cbox_point": lambda w, h: scenes.cbox_point(w, h),               # point emitter: the EDiscrete branches of the NEE shift
+          "cbox_dof": lambda w, h: scenes.cbox_dof(w, h),                   # thinlens sensor: aperture samples
           "cbox_smooth": lambda w, h: scenes.cbox_smooth(w, h)}             # vertex normals (shading != geometric normal), smooth mesh emitter
 
 

@@ -19,14 +19,14 @@ def render(oracle):
                     "delta": lambda w, h: scenes.cbox_glossy(w, h, delta_variant=True),
                     "materials": scenes.cbox_materials, "env": scenes.cbox_env,
                     "mesh_lights": scenes.cbox_mesh_lights, "smooth": scenes.cbox_smooth,
-                    "point": scenes.cbox_point}[name](n, n)
+                    "point": scenes.cbox_point, "dof": scenes.cbox_dof}[name](n, n)
             prm = scenes.default_params(spp=spp, seed=seed, **kw)
             cache[key] = (desc, prm) + oracle.gpt(desc, prm, threads=8)
         return cache[key]
     return run
 
 
-@pytest.mark.parametrize("name", ["diffuse", "glossy", "delta", "materials", "env", "mesh_lights", "smooth", "point"])
+@pytest.mark.parametrize("name", ["diffuse", "glossy", "delta", "materials", "env", "mesh_lights", "smooth", "point", "dof"])
 def test_primal_matches_plain_path_tracer(oracle, render, name):
     """E[throughput + direct] == E[Li] (gpt.cpp:1489-1662 = path/path.cpp) for any shift strategy."""
     desc, prm, out, _, _ = render(name, n=40, spp=64)
