@@ -81,6 +81,13 @@ def check(rc):
         raise Gdb200Error(f"gdb200 error {rc}: {lib().gdb200_last_error().decode(errors='replace')}")
 
 
+def release_workspace():
+    """gdb200_release_workspace(): frees the per-device wavefront scratch memory that renders keep between calls."""
+    L = lib()
+    L.gdb200_release_workspace.restype = None
+    L.gdb200_release_workspace()
+
+
 def pinned_empty(shape, dtype):
     """numpy array on page-locked host memory (gdb200_host_alloc) so device<->host copies of film buffers run at full
     PCIe / NVLink-C2C bandwidth; freed when the array is garbage-collected."""

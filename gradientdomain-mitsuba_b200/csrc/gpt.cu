@@ -43,23 +43,36 @@ struct gdb200_scene : gdb200::HostScene {
     void *dTables = nullptr;           // one allocation holding the variable-size tables (env map + CDFs, emitter triangles, BVH)
     // device buffers
     double *film = nullptr, *dev64 = nullptr; float *dev32 = nullptr;
-    double *sd = nullptr; int *si = nullptr;
-    int *liveList = nullptr, *liveCount = nullptr, *genList = nullptr, *genCount = nullptr;
     unsigned long long *counters = nullptr;
-    int slotCapacity = 0;
     volatile int cancel = 0;
 };
 
 static std::mutex g_constMutex;    // c_scene is one per device: serialise renders that share a device
 
+// Wavefront workspace (path-slot state + queues): scratch memory that holds nothing between renders, so it is kept per
+// device and reused by every scene instead of being allocated and freed with each one (12 GB for 8 M slots: the
+// cudaMalloc/cudaFree pair cost more than 100 ms of every end-to-end render).  Guarded by g_constMutex, which already
+// serialises the renders of a device.  gdb200_release_workspace() frees it.
+struct Workspace {
+    double *sd = nullptr; int *si = nullptr;
+    int *liveList = nullptr, *liveCount = nullptr, *genList = nullptr, *genCount = nullptr;
+    int slotCapacity = 0;
+};
+static Workspace g_workspace[64];
+
+static void freeWorkspace(Workspace &w)
+{
+    cudaFree(w.sd); cudaFree(w.si); cudaFree(w.liveList); cudaFree(w.liveCount); cudaFree(w.genList); cudaFree(w.genCount);
+    w = Workspace();
+}
+
 namespace {
 
 void freeSceneBuffers(gdb200_scene *s)
 {
-    cudaFree(s->film); cudaFree(s->dev64); cudaFree(s->dev32); cudaFree(s->sd); cudaFree(s->si);
-    cudaFree(s->liveList); cudaFree(s->liveCount); cudaFree(s->genList); cudaFree(s->genCount); cudaFree(s->counters); cudaFree(s->dScene); s->dScene = nullptr; cudaFree(s->dTables); s->dTables = nullptr;
-    s->film = s->dev64 = s->sd = nullptr; s->dev32 = nullptr; s->si = nullptr;
-    s->liveList = s->liveCount = s->genList = s->genCount = nullptr; s->counters = nullptr; s->slotCapacity = 0;
+    cudaFree(s->film); cudaFree(s->dev64); cudaFree(s->dev32);
+    cudaFree(s->counters); cudaFree(s->dScene); s->dScene = nullptr; cudaFree(s->dTables); s->dTables = nullptr;
+    s->film = s->dev64 = nullptr; s->dev32 = nullptr; s->counters = nullptr;
 }
 
 // Variable-size tables go to one device allocation (once per scene); their device addresses are patched into the
@@ -147,6 +160,16 @@ void gdb200_scene_destroy(gdb200_scene *s)
 
 void gdb200_cancel(gdb200_scene *s) { if (s) s->cancel = 1; }
 
+void gdb200_release_workspace(void)
+{
+    std::lock_guard<std::mutex> lock(g_constMutex);
+    int current = 0, n = 0;
+    if (cudaGetDevice(&current) != cudaSuccess || cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return; }
+    for (int d = 0; d < n && d < 64; d++)
+        if (g_workspace[d].slotCapacity) { cudaSetDevice(d); freeWorkspace(g_workspace[d]); }
+    cudaSetDevice(current);
+}
+
 int gdb200_gpt_render(gdb200_scene *s, const gdb200_gpt_params *p, gdb200_buffers *out, gdb200_stats *stats)
 {
     if (!s || !p) return set_error(GDB200_ERR_ARGUMENT, "scene/params is NULL");
@@ -155,27 +178,29 @@ int gdb200_gpt_render(gdb200_scene *s, const gdb200_gpt_params *p, gdb200_buffer
     if (int rc = setupArgs(*s, p, a, capEnv ? atoi(capEnv) : (1 << 23))) return rc;
     GDB_CUDA(cudaSetDevice(s->device));
     const int nSlots = a.nSlots;
-    if (nSlots > s->slotCapacity) {
-        cudaFree(s->sd); cudaFree(s->si); cudaFree(s->liveList); cudaFree(s->liveCount); cudaFree(s->genList); cudaFree(s->genCount);
-        s->sd = nullptr; s->si = nullptr; s->liveList = s->liveCount = s->genList = s->genCount = nullptr;
-        GDB_CUDA(cudaMalloc(&s->sd, sizeof(double) * 4 * kRecords * (size_t)nSlots));
-        static_assert(IF_COUNT <= 16, "int fields must fit the 16-int slot line");
-        GDB_CUDA(cudaMalloc(&s->si, sizeof(int) * 16 * (size_t)nSlots));
-        GDB_CUDA(cudaMalloc(&s->liveList, sizeof(int) * 2 * (size_t)kBuckets * nSlots));
-        GDB_CUDA(cudaMalloc(&s->liveCount, sizeof(int) * 2 * kBuckets));
-        GDB_CUDA(cudaMalloc(&s->genList, sizeof(int) * 2 * (size_t)nSlots));
-        GDB_CUDA(cudaMalloc(&s->genCount, sizeof(int) * 2));
-        s->slotCapacity = nSlots;
-    }
+    if (s->device < 0 || s->device >= 64) return set_error(GDB200_ERR_ARGUMENT, "device index %d out of range", s->device);
     classifyMaterials(s, p->shift_threshold);
 
     std::lock_guard<std::mutex> lock(g_constMutex);
+    Workspace &ws = g_workspace[s->device];
+    if (nSlots > ws.slotCapacity) {
+        freeWorkspace(ws);
+        static_assert(IF_COUNT <= 16, "int fields must fit the 16-int slot line");
+        cudaError_t e = cudaMalloc(&ws.sd, sizeof(double) * 4 * kRecords * (size_t)nSlots);
+        if (e == cudaSuccess) e = cudaMalloc(&ws.si, sizeof(int) * 16 * (size_t)nSlots);
+        if (e == cudaSuccess) e = cudaMalloc(&ws.liveList, sizeof(int) * 2 * (size_t)kBuckets * nSlots);
+        if (e == cudaSuccess) e = cudaMalloc(&ws.liveCount, sizeof(int) * 2 * kBuckets);
+        if (e == cudaSuccess) e = cudaMalloc(&ws.genList, sizeof(int) * 2 * (size_t)nSlots);
+        if (e == cudaSuccess) e = cudaMalloc(&ws.genCount, sizeof(int) * 2);
+        if (e != cudaSuccess) { freeWorkspace(ws); cudaGetLastError(); return set_error(GDB200_ERR_CUDA, "wavefront workspace for %d path slots: %s", nSlots, cudaGetErrorString(e)); }
+        ws.slotCapacity = nSlots;
+    }
     if (int rc = uploadScene(s)) return rc;
     GDB_CUDA(cudaMemset(s->film, 0, sizeof(double) * 5 * (size_t)s->width * s->height * 4));
     GDB_CUDA(cudaMemset(s->counters, 0, sizeof(unsigned long long) * 8));
 
-    a.sd = s->sd; a.si = s->si;
-    a.film = s->film; a.liveList = s->liveList; a.liveCount = s->liveCount; a.genList = s->genList; a.genCount = s->genCount;
+    a.sd = ws.sd; a.si = ws.si;
+    a.film = s->film; a.liveList = ws.liveList; a.liveCount = ws.liveCount; a.genList = ws.genList; a.genCount = ws.genCount;
     a.counters = s->counters;
 
     cudaEvent_t e0, e1;

@@ -119,6 +119,7 @@ struct DScene {
     Float sampleToCamera[16], cameraToWorld[12];
     Float nearClip, farClip, invResX, invResY, filterRadius, filterScale, apertureRadius, focusDistance;
     Float filterTable[32];             // ReconstructionFilter::m_values (rfilter.cpp:37-55)
+    int filterIsBox, padFilter;        // box: every tap below index 31 is filterTable[0] (no per-lane table read)
     int width, height, nRects, nSpheres, nTris, nMaterials, nEmitters, nMeshes;
     Float emCdf[kMaxEmitters + 1];
     DRect rects[kMaxRects];

@@ -197,6 +197,8 @@ inline int flattenScene(const gdb200_scene_desc *d, HostScene *s)
     bool boxFilter = true;
     for (int i = 0; i < 32; i++) { h.filterTable[i] = d->rfilter_table[i]; if (d->rfilter_table[i] != 0) boxFilter = false; }
     if (boxFilter) { for (int i = 0; i < 31; i++) h.filterTable[i] = 1.0 / (2 * d->rfilter_radius); h.filterTable[31] = 0; }   // box.cpp:45-47 through rfilter.cpp:37-55
+    h.filterIsBox = h.filterTable[31] == 0;                 // also when the caller passed the box filter's own table
+    for (int i = 1; i < 31; i++) if (h.filterTable[i] != h.filterTable[0]) h.filterIsBox = 0;
     s->width = c.width; s->height = c.height;
     s->mats.assign(d->materials, d->materials + d->n_materials);
     h.nMaterials = d->n_materials;

@@ -213,7 +213,9 @@ GDB_D void countWarp(unsigned long long *ctr, unsigned v)
 // ------------------------------------------------------------------ film (ImageBlock::put, imageblock.h:150-195)
 GDB_D Float evalDiscretized(Float x)      // rfilter.h:76-77, MTS_FILTER_RESOLUTION = 31
 {
-    return c_sceneG->filterTable[min((int)fabs(x * c_scene.filterScale), 31)];       // per-lane index: global-memory copy
+    const int idx = min((int)fabs(x * c_scene.filterScale), 31);
+    if (c_scene.filterIsBox) return idx < 31 ? c_scene.filterTable[0] : 0.0;
+    return c_sceneG->filterTable[idx];                                               // per-lane index: global-memory copy
 }
 GDB_CALL void filmPut(const GptArgs &a, Float sx, Float sy, Spec v, Float weight, int buf, bool allowNegative)
 {

@@ -259,6 +259,10 @@ int  gdb200_debug_check_culling(gdb200_scene *scene, int n_rays, unsigned long l
  * layout at load time so that a stale library fails loudly instead of reading shifted fields.  Returns the count. */
 int  gdb200_abi_sizes(int *out_sizes, int capacity);
 
+/* The wavefront workspace (path-slot state and queues, ~1.6 KB per resident path) is scratch memory kept per device
+ * and reused across scenes and renders; this frees it on every device (e.g. before handing the GPU to another library). */
+void gdb200_release_workspace(void);
+
 /* Asynchronous cancel (Integrator::cancel, integrator.h:77-84). */
 void gdb200_cancel(gdb200_scene *scene);
 

@@ -271,3 +271,19 @@ def test_download_into_pinned_buffers(oracle):
         np.testing.assert_allclose(a[n], b[n], rtol=1e-12, atol=1e-15)
     with pytest.raises(gdb200.Gdb200Error, match="output buffer"):
         integ.trace(scene, spp=1, out={"-dx": np.zeros((3, 3, 3))})
+
+
+def test_workspace_is_reused_and_can_be_released():
+    """The wavefront scratch memory lives per device, not per scene: a second scene renders into it, and
+    gdb200_release_workspace gives it back without disturbing later renders."""
+    import torch
+    integ = gdb200.GPTIntegrator(reconstructL1=False, reconstructL2=False)
+    a = integ.trace(gdb200.Scene(scenes.cbox_diffuse(48, 48)), spp=4, seed=1)
+    free_before = torch.cuda.mem_get_info()[0]
+    b = integ.trace(gdb200.Scene(scenes.cbox_diffuse(48, 48)), spp=4, seed=1)
+    assert torch.cuda.mem_get_info()[0] >= free_before - (8 << 20)          # no new workspace for the second scene
+    gdb200.release_workspace()
+    c = integ.trace(gdb200.Scene(scenes.cbox_diffuse(48, 48)), spp=4, seed=1)
+    for k in a:
+        np.testing.assert_allclose(a[k], b[k], rtol=1e-12, atol=1e-15)
+        np.testing.assert_allclose(a[k], c[k], rtol=1e-12, atol=1e-15)

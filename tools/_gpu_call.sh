@@ -1,3 +1,4 @@
 mkdir -p gpurun_out
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --steps 2 --warmup 1 > gpurun_out/c11_bench_n8.json 2> gpurun_out/c11_bench_n8.err
-cat gpurun_out/c11_bench_n8.json; tail -5 gpurun_out/c11_bench_n8.err
+timeout 300 python -m pytest tests/test_gpt_gpu.py -m gpu -x -q > gpurun_out/c12_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/c12_pytest.log
+timeout 300 python bench.py > gpurun_out/c12_bench_n1.json 2> gpurun_out/c12_bench_n1.err
+tail -4 gpurun_out/c12_pytest.log; cat gpurun_out/c12_bench_n1.json; tail -3 gpurun_out/c12_bench_n1.err
