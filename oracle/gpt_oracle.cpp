@@ -1748,4 +1748,60 @@ int gdb200_oracle_path_render(const gdb200_scene_desc *desc, const gdb200_gpt_pa
     return 0;
 }
 
+
+// ---- batched single-plugin entry points for the chi-square tests (tests/test_chisquare.py), which restate the
+// reference's own consistency test of these plugins (src/tests/test_chisquare.cpp on data/tests/test_bsdf.xml /
+// test_emitter.xml): BSDF::sample / eval / pdf and Emitter::sampleDirect / pdfDirect.
+int gdb200_oracle_bsdf_sample_batch(const gdb200_material *m, const double *wi, int n, const double *samples,
+                                    double *wo, double *weight, double *pdf, int *sampledType)
+{
+    std::vector<Float> fdr(1, m->type == GDB200_BSDF_PLASTIC ? fresnelDiffuseReflectance(1 / m->ior_ratio) : 0.0);
+    g_fdrInt = &fdr; g_matBase = m;
+    for (int i = 0; i < n; i++) {
+        BSDFSample bs; bs.wi = v3(wi[0], wi[1], wi[2]);
+        bsdfSample(*m, bs, samples[2 * i], samples[2 * i + 1]);
+        wo[3 * i] = bs.wo.x; wo[3 * i + 1] = bs.wo.y; wo[3 * i + 2] = bs.wo.z;
+        weight[3 * i] = bs.weight.x; weight[3 * i + 1] = bs.weight.y; weight[3 * i + 2] = bs.weight.z;
+        pdf[i] = bs.pdf; sampledType[i] = (int)bs.sampledType;
+    }
+    return 0;
+}
+int gdb200_oracle_bsdf_eval_batch(const gdb200_material *m, const double *wi, int n, const double *wo, int measure,
+                                  double *value, double *pdf)
+{
+    std::vector<Float> fdr(1, m->type == GDB200_BSDF_PLASTIC ? fresnelDiffuseReflectance(1 / m->ior_ratio) : 0.0);
+    g_fdrInt = &fdr; g_matBase = m;
+    const V3 w = v3(wi[0], wi[1], wi[2]);
+    for (int i = 0; i < n; i++) {
+        const V3 o = v3(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]);
+        const Spec f = bsdfEval(*m, w, o, measure ? EDiscrete : ESolidAngle);
+        value[3 * i] = f.x; value[3 * i + 1] = f.y; value[3 * i + 2] = f.z;
+        pdf[i] = bsdfPdf(*m, w, o, measure ? EDiscrete : ESolidAngle);
+    }
+    return 0;
+}
+// EnvironmentMap::sampleDirect from the reference point `ref` (EmitterAdapter of test_chisquare.cpp:341-389): world
+// direction and solid-angle density per sample; gdb200_oracle_envmap_pdf_batch is the matching pdfDirect.
+int gdb200_oracle_envmap_sample_batch(const gdb200_scene_desc *desc, const double *ref, int n, const double *samples, double *d, double *pdf)
+{
+    Scene sc; buildScene(desc, sc);
+    if (!sc.env.present) return 1;
+    const gdb200_emitter env = sc.ems[sc.env.emitter];
+    sc.ems.assign(1, env); sc.emCdf.assign(2, 0.0); sc.emCdf[1] = 1.0; sc.emNormalization = 1.0 / env.sampling_weight; sc.env.emitter = 0;
+    for (int i = 0; i < n; i++) {
+        DRec r; r.ref = v3(ref[0], ref[1], ref[2]); r.refN = v3(0, 0, 0);
+        bool vis;
+        sampleEmitterDirectVisible(sc, r, samples[2 * i], samples[2 * i + 1], vis);   // d and pdf do not depend on the visibility
+        d[3 * i] = r.d.x; d[3 * i + 1] = r.d.y; d[3 * i + 2] = r.d.z; pdf[i] = r.pdf;
+    }
+    return 0;
+}
+int gdb200_oracle_envmap_pdf_batch(const gdb200_scene_desc *desc, int n, const double *d, double *pdf)
+{
+    Scene sc; buildScene(desc, sc);
+    if (!sc.env.present) return 1;
+    for (int i = 0; i < n; i++) pdf[i] = envPdfDirection(sc.env, xfVector(sc.env.toObject, v3(d[3 * i], d[3 * i + 1], d[3 * i + 2])));
+    return 0;
+}
+
 }  // extern "C"

@@ -62,3 +62,71 @@ extern "C" int gdb200_emu_gpt_render(const gdb200_scene_desc *desc, const gdb200
     if (counters) for (int i = 0; i < 6; i++) counters[i] = (double)ctr[i];
     return 0;
 }
+
+// ---- single-plugin entry points of the DEVICE routines for tests/test_chisquare.py (the reference's own consistency
+// test of BSDF::sample/eval/pdf and Emitter::sampleDirect/pdfDirect, src/tests/test_chisquare.cpp)
+static void emuMaterial(const gdb200_material *m, HostScene &hs)
+{
+    memset(&hs.host, 0, sizeof(hs.host));
+    hs.mats.assign(1, *m);
+    classifyMaterials(&hs, 0.001);
+}
+extern "C" int gdb200_emu_bsdf_sample_batch(const gdb200_material *m, const double *wi, int n, const double *samples,
+                                            double *wo, double *weight, double *pdf, int *sampledType)
+{
+    static HostScene hs; emuMaterial(m, hs);
+    for (int i = 0; i < n; i++) {
+        BSDFSample bs;
+        bsdfSample(hs.host.materials[0], mk(wi[0], wi[1], wi[2]), samples[2 * i], samples[2 * i + 1], bs);
+        wo[3 * i] = bs.wo.x; wo[3 * i + 1] = bs.wo.y; wo[3 * i + 2] = bs.wo.z;
+        weight[3 * i] = bs.weight.x; weight[3 * i + 1] = bs.weight.y; weight[3 * i + 2] = bs.weight.z;
+        pdf[i] = bs.pdf; sampledType[i] = (int)bs.sampledType;
+    }
+    return 0;
+}
+extern "C" int gdb200_emu_bsdf_eval_batch(const gdb200_material *m, const double *wi, int n, const double *wo, int measure,
+                                          double *value, double *pdf)
+{
+    static HostScene hs; emuMaterial(m, hs);
+    for (int i = 0; i < n; i++) {
+        Spec f; Float p;
+        bsdfEvalPdf(hs.host.materials[0], mk(wi[0], wi[1], wi[2]), mk(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]), measure ? EDiscrete : ESolidAngle, f, p);
+        value[3 * i] = f.x; value[3 * i + 1] = f.y; value[3 * i + 2] = f.z; pdf[i] = p;
+    }
+    return 0;
+}
+static int emuEnvScene(const gdb200_scene_desc *desc, HostScene &hs)
+{
+    if (int rc = flattenScene(desc, &hs)) return rc;
+    if (!hs.host.env.present) return set_error(GDB200_ERR_ARGUMENT, "scene has no environment emitter");
+    classifyMaterials(&hs, 0.001);
+    // isolate the environment emitter: one-entry selection CDF
+    hs.host.emitters[0] = hs.host.emitters[hs.host.env.emitter]; hs.host.emitters[0].pdfDiscrete = 1.0;
+    hs.host.nEmitters = 1; hs.host.emCdf[0] = 0; hs.host.emCdf[1] = 1; hs.host.env.emitter = 0;
+    hs.host.env.texels = hs.envTexels.data(); hs.host.env.rowWeights = hs.envRowWeights.data();
+    hs.host.env.cdfRows = hs.envCdfRows.data(); hs.host.env.cdfCols = hs.envCdfCols.data();
+    hs.host.emTris = hs.emTris.data(); hs.host.emTriCdf = hs.emTriCdf.data(); hs.host.triNormals = hs.triNormals.data();
+    hs.host.bvh = hs.bvh.data(); hs.host.bvhTris = hs.bvhTris.data();
+    c_scene = hs.host; static DScene sceneCopy; sceneCopy = hs.host; c_sceneG = &sceneCopy;
+    memcpy(c_bounds, hs.bounds, sizeof(hs.bounds));
+    return 0;
+}
+extern "C" int gdb200_emu_envmap_sample_batch(const gdb200_scene_desc *desc, const double *ref, int n, const double *samples, double *d, double *pdf)
+{
+    static HostScene hs;
+    if (int rc = emuEnvScene(desc, hs)) return rc;
+    for (int i = 0; i < n; i++) {
+        DRec r; r.ref = mk(ref[0], ref[1], ref[2]); r.refN = mk(0, 0, 0);
+        bool vis;
+        sampleEmitterDirectVisible(r, samples[2 * i], samples[2 * i + 1], vis);
+        d[3 * i] = r.d.x; d[3 * i + 1] = r.d.y; d[3 * i + 2] = r.d.z; pdf[i] = r.pdf;
+    }
+    return 0;
+}
+extern "C" int gdb200_emu_envmap_pdf_batch(const gdb200_scene_desc *desc, int n, const double *d, double *pdf)
+{
+    static HostScene hs;
+    if (int rc = emuEnvScene(desc, hs)) return rc;
+    for (int i = 0; i < n; i++) pdf[i] = envPdfDirection(xfVector(c_scene.env.toObject, mk(d[3 * i], d[3 * i + 1], d[3 * i + 2])));
+    return 0;
+}

@@ -1,0 +1,160 @@
+"""The reference's own consistency test for the plugins on the G-PT hot path — src/tests/test_chisquare.cpp — applied to
+the oracle's restatements AND to the device routines (host build, tests/emu): for every BSDF of the supported subset that
+data/tests/test_bsdf.xml lists (plastic, diffuse, twosided diffuse, conductor, dielectric water/air, roughconductor
+Beckmann/GGX) BSDF::sample must agree with eval/pdf (ERROR_REQ 1e-5, test_chisquare.cpp:33-38,171-201) and the sampled
+directions must pass the chi-square test against the claimed density (thetaBins 10, significance 0.25 % with Sidak
+correction over the incident directions); same for EnvironmentMap::sampleDirect vs pdfDirect on a rotated map
+(data/tests/test_emitter.xml).  This pins the plugin slice of the tracer by the reference's own test method."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from gdb200 import scenes
+from chisquare import ChiSquare
+
+ERROR_REQ = 1e-5
+EDELTA = 0x10 | 0x20
+WI_SAMPLES = 6          # the reference uses 20 incident directions; 6 keeps the CPU suite in its time budget
+
+
+def _material(**kw):
+    b = scenes.SceneBuilder(scenes.make_camera(4, 4, (0, 0, 4), (0, 0, 0), (0, 1, 0), 40))
+    return b.materials[b.material(**kw)]
+
+
+BSDFS = {
+    "plastic": dict(type=scenes.BSDF_PLASTIC, reflectance=(0.5, 0.5, 0.5), ior_ratio=1.49 / 1.000277),
+    "plastic_nonlinear": dict(type=scenes.BSDF_PLASTIC, reflectance=(0.6, 0.3, 0.2), ior_ratio=1.49 / 1.000277, nonlinear=True),
+    "diffuse": dict(reflectance=(0.5, 0.5, 0.5)),
+    "twosided_diffuse": dict(reflectance=(0.5, 0.5, 0.5), twosided=True),
+    "conductor": dict(type=scenes.BSDF_CONDUCTOR, eta=scenes.CU_ETA, k=scenes.CU_K),
+    "dielectric_water": dict(type=scenes.BSDF_DIELECTRIC, ior_ratio=1.3330 / 1.000277),
+    "roughconductor_beckmann": dict(type=scenes.BSDF_ROUGHCONDUCTOR, alpha=0.1, eta=scenes.CU_ETA, k=scenes.CU_K,
+                                    distribution=scenes.MICROFACET_BECKMANN),
+    "roughconductor_ggx": dict(type=scenes.BSDF_ROUGHCONDUCTOR, alpha=0.3, eta=scenes.AL_ETA, k=scenes.AL_K),
+    "twosided_roughconductor": dict(type=scenes.BSDF_ROUGHCONDUCTOR, alpha=0.2, eta=scenes.CU_ETA, k=scenes.CU_K, twosided=True),
+}
+
+
+class Plugin:
+    """BSDF::sample / eval / pdf of one implementation (prefix gdb200_oracle_ or gdb200_emu_)."""
+
+    def __init__(self, lib, prefix, material):
+        self.lib, self.prefix, self.m = lib, prefix, material
+
+    def sample(self, wi, u):
+        n = len(u)
+        wo, weight, pdf, typ = np.zeros((n, 3)), np.zeros((n, 3)), np.zeros(n), np.zeros(n, dtype=np.int32)
+        p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+        rc = getattr(self.lib, self.prefix + "bsdf_sample_batch")(ctypes.byref(self.m), p(wi), n, p(u), p(wo), p(weight), p(pdf), p(typ))
+        assert rc == 0
+        return wo, weight, pdf, typ
+
+    def eval(self, wi, wo, discrete):
+        wo = np.ascontiguousarray(wo)
+        n = len(wo)
+        value, pdf = np.zeros((n, 3)), np.zeros(n)
+        p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+        rc = getattr(self.lib, self.prefix + "bsdf_eval_batch")(ctypes.byref(self.m), p(wi), n, p(wo), int(discrete), p(value), p(pdf))
+        assert rc == 0
+        return value, pdf
+
+
+def _close(a, b):
+    lo, err = np.minimum(a, b), np.abs(a - b)
+    return np.where(lo < ERROR_REQ, err <= ERROR_REQ, err / np.maximum(lo, 1e-300) <= ERROR_REQ)
+
+
+@pytest.mark.parametrize("impl", ["oracle", "device"])
+@pytest.mark.parametrize("name", sorted(BSDFS))
+def test_bsdf_sampling_is_consistent(oracle, emu, impl, name):
+    m = _material(**BSDFS[name])
+    plug = Plugin(oracle.lib, "gdb200_oracle_", m) if impl == "oracle" else Plugin(emu.lib, "gdb200_emu_", m)
+    backside = BSDFS[name].get("twosided") or BSDFS[name].get("type") == scenes.BSDF_DIELECTRIC
+    rng = np.random.default_rng(hash(name) % 2 ** 31)
+    for j in range(WI_SAMPLES):
+        u0 = rng.random(2)
+        if backside:                                           # squareToUniformSphere, test_chisquare.cpp:420-421
+            z = 1 - 2 * u0[1]; r = np.sqrt(max(0.0, 1 - z * z)); wi = np.array([r * np.cos(2 * np.pi * u0[0]), r * np.sin(2 * np.pi * u0[0]), z])
+        else:                                                  # squareToCosineHemisphere
+            r, ph = np.sqrt(u0[0]), 2 * np.pi * u0[1]; wi = np.array([r * np.cos(ph), r * np.sin(ph), np.sqrt(max(0.0, 1 - u0[0]))])
+        wi = np.ascontiguousarray(wi)
+        chi = ChiSquare(10, 20, WI_SAMPLES)
+        u = rng.random((chi.sample_count, 2))
+        wo, weight, pdf_s, typ = plug.sample(wi, u)
+        ok = (weight != 0).any(axis=1)
+        discrete = (typ & EDELTA) != 0
+        # sample() against eval()/pdf() for the sampled direction and measure (test_chisquare.cpp:130-201)
+        for disc in (False, True):
+            sel = ok & (discrete == disc)
+            if not sel.any():
+                continue
+            f, pdf_e = plug.eval(wi, wo[sel], disc)
+            assert (pdf_e > 0).all(), (name, j, disc)
+            assert _close(pdf_e, pdf_s[sel]).all(), (name, j, disc)
+            manual = f / pdf_e[:, None]
+            assert _close(manual, weight[sel]).all(), (name, j, disc, np.abs(manual - weight[sel]).max())
+        # chi-square of the sampled directions against the density (pdf is reported 0 where eval is 0, test_chisquare.cpp:218-226)
+        def pdf_fn(dirs, disc):
+            f, p = plug.eval(wi, dirs, disc)
+            return np.where((f == 0).all(axis=1), 0.0, p)
+        chi.fill(wo, ok.astype(float), discrete, pdf_fn)
+        result, pval = chi.run_test()
+        assert result != "reject", (name, impl, j, wi, pval, chi.integral)
+
+
+def _env_scene():
+    b = scenes._cornell(8, 8, boxes=False)
+    rot = np.eye(4)                                            # <rotate x="1" angle="40"/>, data/tests/test_emitter.xml
+    c, s = np.cos(np.radians(40.0)), np.sin(np.radians(40.0))
+    rot[1, 1], rot[1, 2], rot[2, 1], rot[2, 2] = c, -s, s, c
+    b.envmap(scenes.sky_envmap(64, 32), scale=1.0, to_world=rot)
+    return b.build()
+
+
+@pytest.mark.parametrize("impl", ["oracle", "device"])
+def test_envmap_direct_sampling_is_consistent(oracle, emu, impl):
+    """EnvironmentMap::sampleDirect vs pdfDirect (EmitterAdapter, test_chisquare.cpp:341-389; the reference runs it with
+    thetaBins 10 on a rotated map)."""
+    desc = _env_scene()
+    lib, prefix = (oracle.lib, "gdb200_oracle_") if impl == "oracle" else (emu.lib, "gdb200_emu_")
+    chi = ChiSquare(10, 20, 1)
+    rng = np.random.default_rng(5)
+    u = rng.random((chi.sample_count, 2))
+    n = len(u)
+    d, pdf_s = np.zeros((n, 3)), np.zeros(n)
+    ref = np.zeros(3)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    assert getattr(lib, prefix + "envmap_sample_batch")(ctypes.byref(desc), p(ref), n, p(u), p(d), p(pdf_s)) == 0
+    assert np.allclose(np.linalg.norm(d, axis=1), 1.0, atol=1e-12) and (pdf_s > 0).all()
+
+    def pdf_fn(dirs, disc):
+        dirs = np.ascontiguousarray(dirs)
+        out = np.zeros(len(dirs))
+        assert getattr(lib, prefix + "envmap_pdf_batch")(ctypes.byref(desc), len(dirs), p(dirs), p(out)) == 0
+        return np.zeros(len(dirs)) if disc else out
+    assert _close(pdf_fn(d[:2000], False), pdf_s[:2000]).all()      # the density returned with the sample is pdfDirect of its direction
+    chi.fill(d, np.ones(n), np.zeros(n, dtype=bool), pdf_fn)
+    result, pval = chi.run_test()
+    assert abs(chi.integral - 1.0) < 2e-2, chi.integral              # the claimed density integrates to one over the sphere
+    assert result != "reject", (impl, pval, chi.integral)
+
+
+def test_chisquare_harness_rejects_a_wrong_density(oracle):
+    """Negative control: cosine-distributed directions against a uniform-hemisphere density must be rejected, and an
+    8 % error in a GGX density as well."""
+    m = _material(reflectance=(0.5, 0.5, 0.5))
+    plug = Plugin(oracle.lib, "gdb200_oracle_", m)
+    wi = np.ascontiguousarray([0.3, 0.2, np.sqrt(1 - 0.13)])
+    chi = ChiSquare(10, 20, 1)
+    u = np.random.default_rng(1).random((chi.sample_count, 2))
+    wo, weight, _, _ = plug.sample(wi, u)
+    chi.fill(wo, np.ones(len(wo)), np.zeros(len(wo), dtype=bool), lambda d, disc: np.where(d[:, 2] > 0, 1 / (2 * np.pi), 0.0) * (not disc))
+    assert chi.run_test()[0] == "reject"
+    m2 = _material(**BSDFS["roughconductor_ggx"])
+    plug2 = Plugin(oracle.lib, "gdb200_oracle_", m2)
+    wo2, w2, _, _ = plug2.sample(wi, u)
+    ok = (w2 != 0).any(axis=1).astype(float)
+    chi.fill(wo2, ok, np.zeros(len(wo2), dtype=bool), lambda d, disc: plug2.eval(wi, d, disc)[1] * np.where(d[:, 0] > 0, 1.08, 0.92))
+    assert chi.run_test()[0] == "reject"
