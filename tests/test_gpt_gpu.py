@@ -287,3 +287,20 @@ def test_workspace_is_reused_and_can_be_released():
     for k in a:
         np.testing.assert_allclose(a[k], b[k], rtol=1e-12, atol=1e-15)
         np.testing.assert_allclose(a[k], c[k], rtol=1e-12, atol=1e-15)
+
+
+def test_scene_file_renders_on_the_gpu(oracle, tmp_path):
+    """A Mitsuba scene file selecting `gpt` (gdb200.xmlscene) through render() and MultiFilm-style PFM output."""
+    from test_xmlscene import CBOX_XML
+    parsed = gdb200.load_scene(CBOX_XML, {"spp": "8"})
+    integ = parsed.integrator()                                  # reconstructL2 = true in the file
+    out = integ.render(gdb200.Scene(parsed.desc), spp=parsed.spp, seed=parsed.seed, streams=parsed.streams)
+    ref, _, _ = oracle.gpt(parsed.desc, integ.params(parsed.spp, parsed.seed))
+    for name in ("-throughput", "-dx", "-dy", "-direct"):
+        scale = max(float(np.abs(ref[name]).mean()), 1e-12)
+        bad = np.abs(out[name] - ref[name]).max(axis=2) > 1e-5 * scale
+        assert bad.mean() <= 2e-3, name
+        assert np.sqrt(np.mean((out[name] - ref[name])[~bad] ** 2)) <= REL * scale, name
+    paths = integ.save(str(tmp_path / "cbox.exr"), out)
+    back = gdb200.pfm.load_multifilm(str(tmp_path / "cbox"))
+    assert len(paths) == 5 and np.array_equal(back["-final"], out["-final"].astype(np.float32))

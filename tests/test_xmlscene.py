@@ -1,0 +1,195 @@
+"""Scene-file front end (gdb200.xmlscene): a Mitsuba 0.5 XML that selects the reference's `gpt` path
+flattens to the same C-ABI scene as the programmatic builder — checked by rendering both with the CPU oracle — and the
+host-side semantics of scenehandler.cpp / sensor.cpp (transform order, fov axes, $parameters, references, errors)."""
+import math
+
+import numpy as np
+import pytest
+
+import gdb200
+from gdb200 import scenes, xmlscene
+
+
+def _mat(m):
+    return " ".join(repr(float(x)) for x in np.asarray(m).reshape(-1))
+
+
+def _rect(center, s_axis, t_axis):
+    s_axis, t_axis = np.asarray(s_axis, float), np.asarray(t_axis, float)
+    n = np.cross(s_axis, t_axis)
+    n /= np.linalg.norm(n)
+    m = np.eye(4)
+    m[:3, 0], m[:3, 1], m[:3, 2], m[:3, 3] = s_axis, t_axis, n, center
+    return _mat(m)
+
+
+CBOX_XML = f"""
+<scene version="0.5.0">
+  <default name="spp" value="6"/>
+  <integrator type="gpt">
+    <integer name="maxDepth" value="-1"/> <integer name="rrDepth" value="5"/>
+    <boolean name="strictNormals" value="false"/> <float name="shiftThreshold" value="0.001"/>
+    <boolean name="reconstructL1" value="false"/> <boolean name="reconstructL2" value="true"/>
+    <float name="reconstructAlpha" value="0.2"/>
+  </integrator>
+  <sensor type="perspective">
+    <float name="fov" value="39.3077"/>
+    <transform name="toWorld"><lookat origin="0, 0, 3.9" target="0, 0, 0" up="0, 1, 0"/></transform>
+    <sampler type="independent"><integer name="sampleCount" value="$spp"/></sampler>
+    <film type="multifilm">
+      <integer name="width" value="40"/> <integer name="height" value="32"/>
+      <string name="fileFormat" value="pfm"/> <rfilter type="box"/>
+    </film>
+  </sensor>
+  <bsdf type="diffuse" id="white"><rgb name="reflectance" value="0.725, 0.71, 0.68"/></bsdf>
+  <bsdf type="diffuse" id="red"><rgb name="reflectance" value="0.63 0.065 0.05"/></bsdf>
+  <bsdf type="diffuse" id="green"><rgb name="reflectance" value="0.14, 0.45, 0.091"/></bsdf>
+  <bsdf type="diffuse" id="black"><spectrum name="reflectance" value="0"/></bsdf>
+  <shape type="rectangle"><transform name="toWorld"><matrix value="{_rect((0, -1, 0), (1, 0, 0), (0, 0, -1))}"/></transform><ref id="white"/></shape>
+  <shape type="rectangle"><transform name="toWorld"><matrix value="{_rect((0, 1, 0), (1, 0, 0), (0, 0, 1))}"/></transform><ref id="white"/></shape>
+  <shape type="rectangle"><transform name="toWorld"><matrix value="{_rect((0, 0, -1), (1, 0, 0), (0, 1, 0))}"/></transform><ref id="white"/></shape>
+  <shape type="rectangle"><transform name="toWorld"><matrix value="{_rect((-1, 0, 0), (0, 0, -1), (0, 1, 0))}"/></transform><ref id="red"/></shape>
+  <shape type="rectangle"><transform name="toWorld"><matrix value="{_rect((1, 0, 0), (0, 0, 1), (0, 1, 0))}"/></transform><ref id="green"/></shape>
+  <shape type="rectangle"><transform name="toWorld"><matrix value="{_rect((0, 0.99, 0), (0.25, 0, 0), (0, 0, 0.25))}"/></transform>
+    <ref id="black"/> <emitter type="area"><rgb name="radiance" value="17, 12, 4"/></emitter></shape>
+  <shape type="sphere"><point name="center" x="-0.55" y="-0.7" z="-0.2"/><float name="radius" value="0.3"/>
+    <bsdf type="roughconductor"><string name="distribution" value="beckmann"/><float name="alpha" value="0.15"/>
+      <rgb name="eta" value="0.2004, 0.9240, 1.1022"/><rgb name="k" value="3.9129, 2.4528, 2.1421"/><float name="extEta" value="1"/></bsdf></shape>
+  <shape type="sphere"><point name="center" x="0.1" y="-0.65" z="0.45"/><float name="radius" value="0.35"/>
+    <bsdf type="conductor"><rgb name="eta" value="1.6574, 0.8803, 0.5212"/><rgb name="k" value="9.2238, 6.2695, 4.8370"/><float name="extEta" value="1"/></bsdf></shape>
+  <shape type="sphere"><point name="center" x="0.6" y="-0.75" z="-0.3"/><float name="radius" value="0.25"/>
+    <bsdf type="dielectric"><float name="intIOR" value="1.5"/><float name="extIOR" value="1"/></bsdf></shape>
+</scene>
+"""
+
+
+def _builder_equivalent(w, h):
+    b = scenes._cornell(w, h, boxes=False)
+    beck = b.material(type=scenes.BSDF_ROUGHCONDUCTOR, alpha=0.15, eta=scenes.CU_ETA, k=scenes.CU_K, distribution=scenes.MICROFACET_BECKMANN)
+    mirror = b.material(type=scenes.BSDF_CONDUCTOR, eta=scenes.AL_ETA, k=scenes.AL_K)
+    glass = b.material(type=scenes.BSDF_DIELECTRIC, ior_ratio=1.5)
+    b.sphere((-0.55, -0.7, -0.2), 0.3, beck)
+    b.sphere((0.1, -0.65, 0.45), 0.35, mirror)
+    b.sphere((0.6, -0.75, -0.3), 0.25, glass)
+    return b.build()
+
+
+def test_xml_scene_renders_like_the_builder_scene(oracle):
+    parsed = gdb200.load_scene(CBOX_XML)
+    assert parsed.spp == 6 and parsed.seed == 0
+    assert parsed.integrator_kwargs == dict(maxDepth=-1, rrDepth=5, strictNormals=False, shiftThreshold=0.001, reconstructL1=False,
+                                            reconstructL2=True, reconstructAlpha=0.2)
+    integ = parsed.integrator()
+    ref_desc = _builder_equivalent(40, 32)
+    a, _, _ = oracle.gpt(parsed.desc, integ.params(parsed.spp, parsed.seed))
+    b, _, _ = oracle.gpt(ref_desc, integ.params(6, 0))
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    assert gdb200.load_scene(CBOX_XML, {"spp": "9"}).spp == 9                    # -D spp=9
+
+
+def test_transform_operations_compose_in_document_order():
+    import xml.etree.ElementTree as ET
+    el = ET.fromstring('<transform name="toWorld"><scale x="2" y="3" z="4"/><rotate y="1" angle="90"/><translate x="1" y="2" z="3"/></transform>')
+    m = xmlscene.parse_transform(el)
+    p = m @ np.array([1.0, 1.0, 1.0, 1.0])                                        # scale first, then rotate about y, then translate
+    assert np.allclose(p[:3], [4 + 1, 3 + 2, -2 + 3])
+    el = ET.fromstring('<transform name="toWorld"><lookat origin="1,2,3" target="1,2,0"/></transform>')   # no 'up': an arbitrary axis is chosen
+    m = xmlscene.parse_transform(el)
+    assert np.allclose(m[:3, 2], [0, 0, -1]) and np.allclose(m[:3, 3], [1, 2, 3]) and abs(np.linalg.det(m[:3, :3])) > 0.99
+    assert np.allclose(xmlscene.rotate((0, 0, 2), 90) @ np.array([1, 0, 0, 1.0]), [0, 1, 0, 1])
+
+
+@pytest.mark.parametrize("props,expect_xfov", [
+    ('<float name="fov" value="40"/>', 40.0),
+    ('<float name="fov" value="40"/><string name="fovAxis" value="y"/>', math.degrees(2 * math.atan(math.tan(math.radians(20)) * 1.5))),
+    ('<float name="fov" value="40"/><string name="fovAxis" value="smaller"/>', math.degrees(2 * math.atan(math.tan(math.radians(20)) * 1.5))),
+    ('<float name="fov" value="40"/><string name="fovAxis" value="larger"/>', 40.0),
+    ('<string name="focalLength" value="50mm"/>', math.degrees(2 * math.atan((2 * math.tan(0.5 * 2 * math.atan(math.sqrt(36 * 36 + 24 * 24) / 100)) / math.sqrt(1 + 1 / 2.25)) * 0.5))),
+])
+def test_field_of_view_axes(props, expect_xfov):
+    xml = f"""<scene version="0.5.0"><integrator type="gpt"/><sensor type="perspective">{props}
+      <film type="multifilm"><integer name="width" value="30"/><integer name="height" value="20"/></film></sensor>
+      <emitter type="point"><point name="position" x="0" y="1" z="0"/><rgb name="intensity" value="1,1,1"/></emitter></scene>"""
+    parsed = gdb200.load_scene(xml)
+    s2c = np.array(parsed.desc.camera.sample_to_camera).reshape(4, 4)
+    near = s2c @ np.array([0.0, 0.5, 0.0, 1.0])                                     # left edge of the film, mid height
+    near = near[:3] / near[3]
+    assert math.isclose(math.degrees(2 * math.atan(abs(near[0]) / near[2])), expect_xfov, rel_tol=1e-9)
+    assert parsed.desc.rfilter_radius == 2.0                                        # film default: gaussian (film.cpp:89-95)
+    assert parsed.spp == 4 and parsed.integrator_kwargs == {}
+
+
+def test_shapes_and_emitters(tmp_path, oracle):
+    obj = tmp_path / "quad.obj"
+    obj.write_text("v -1 0 -1\nv 1 0 -1\nv 1 0 1\nv -1 0 1\nvn 0 1 0\nf 1//1 4//1 3//1 2//1\n")
+    env = tmp_path / "sky.pfm"
+    gdb200.pfm.write_pfm(env, scenes.sky_envmap(16, 8))
+    xml = f"""<scene version="0.5.0"><integrator type="gpt"><integer name="streamsPerPixel" value="2"/><integer name="seed" value="7"/></integrator>
+      <sensor type="thinlens"><float name="apertureRadius" value="0.05"/><float name="focusDistance" value="4"/><float name="fov" value="45"/>
+        <transform name="toWorld"><lookat origin="0,1.5,5" target="0,0.5,0" up="0,1,0"/></transform>
+        <sampler type="independent"><integer name="sampleCount" value="3"/></sampler>
+        <film type="multifilm"><integer name="width" value="20"/><integer name="height" value="16"/><rfilter type="tent"/></film></sensor>
+      <bsdf type="twosided" id="sheet"><bsdf type="plastic"><rgb name="diffuseReflectance" value=".3,.4,.5"/></bsdf></bsdf>
+      <shape type="obj"><string name="filename" value="quad.obj"/><ref id="sheet"/></shape>
+      <shape type="obj"><string name="filename" value="quad.obj"/><boolean name="faceNormals" value="true"/>
+        <transform name="toWorld"><scale value="0.2"/><rotate x="1" angle="180"/><translate y="2"/></transform>
+        <emitter type="area"><rgb name="radiance" value="10,10,10"/></emitter></shape>
+      <shape type="cube"><transform name="toWorld"><scale value="0.3"/><translate x="0.5" y="0.3"/></transform><bsdf type="diffuse"/></shape>
+      <shape type="sphere"><transform name="toWorld"><scale value="0.25"/><translate x="-0.6" y="0.25"/></transform><bsdf type="dielectric"/></shape>
+      <emitter type="point"><transform name="toWorld"><translate x="1" y="2" z="1"/></transform><spectrum name="intensity" value="3"/></emitter>
+      <emitter type="envmap"><string name="filename" value="sky.pfm"/><float name="scale" value="0.5"/></emitter></scene>"""
+    path = tmp_path / "scene.xml"
+    path.write_text(xml)
+    parsed = gdb200.load_scene(str(path))
+    d = parsed.desc
+    assert (parsed.spp, parsed.seed, parsed.streams) == (3, 7, 2)
+    assert d.camera.aperture_radius == 0.05 and d.camera.focus_distance == 4 and d.rfilter_radius == 1.0
+    assert d.n_shapes == 4 and d.n_emitters == 3 and d.n_triangles == 2 + 2 + 12 and d.n_vertices == 4 + 4 + 24
+    assert [d.emitters[i].type for i in range(3)] == [scenes.EMITTER_AREA, scenes.EMITTER_POINT, scenes.EMITTER_ENVMAP]   # document order
+    assert d.shapes[0].has_vertex_normals == 1 and d.shapes[1].has_vertex_normals == 0 and d.shapes[2].has_vertex_normals == 1
+    assert d.materials[d.shapes[0].material].twosided == 1 and d.materials[d.shapes[0].material].type == scenes.BSDF_PLASTIC
+    assert math.isclose(d.shapes[3].radius, 0.25) and np.allclose(list(d.shapes[3].center), [-0.6, 0.25, 0])
+    assert math.isclose(d.materials[d.shapes[3].material].ior_ratio, 1.5046 / 1.00028)
+    assert d.envmap.contents.width == 16 and d.envmap.contents.scale == 0.5
+    out, _, cnt = oracle.gpt(d, parsed.integrator().params(parsed.spp, parsed.seed, streams=parsed.streams))   # and it renders
+    assert cnt[0] == 20 * 16 * 3 and np.isfinite(out["-throughput"]).all() and out["-throughput"].mean() > 0
+
+
+@pytest.mark.parametrize("fragment,message", [
+    ('<film type="hdrfilm"/>', "without MultiFilm"),
+    ('<film type="multifilm"/><bogus/>', None),
+])
+def test_film_must_be_multifilm(fragment, message):
+    xml = f"""<scene version="0.5.0"><integrator type="gpt"/><sensor type="perspective"><float name="fov" value="40"/>{fragment}</sensor>
+      <emitter type="point"><point name="position" x="0" y="1" z="0"/><rgb name="intensity" value="1,1,1"/></emitter></scene>"""
+    if message:
+        with pytest.raises(gdb200.Gdb200Error, match=message):
+            gdb200.load_scene(xml)
+    else:
+        assert gdb200.load_scene(xml).desc.camera.width == 1          # multifilm's default size (film.cpp:31-32)
+
+
+@pytest.mark.parametrize("body,message", [
+    ('<integrator type="path"/>', 'only "gpt"'),
+    ('<integrator type="gpt"><float name="bogus" value="1"/></integrator>', "Unqueried property"),
+    ('<integrator type="gpt"/><shape type="hair"/>', 'shape plugin "hair"'),
+    ('<integrator type="gpt"/><bsdf type="roughplastic"/>', 'BSDF plugin "roughplastic"'),
+    ('<integrator type="gpt"/><bsdf type="conductor"/>', "spectral data files"),
+    ('<integrator type="gpt"/><emitter type="spot"/>', 'emitter plugin "spot"'),
+    ('<integrator type="gpt"/><shape type="sphere"><ref id="nope"/></shape>', "not found"),
+    ('<integrator type="gpt"><integer name="maxDepth" value="$depth"/></integrator>', r'"\$depth" was not specified'),
+])
+def test_outside_the_subset_fails_loudly(body, message):
+    xml = f"""<scene version="0.5.0">{body}<sensor type="perspective"><float name="fov" value="40"/><film type="multifilm"/></sensor>
+      <emitter type="point"><point name="position" x="0" y="1" z="0"/><rgb name="intensity" value="1,1,1"/></emitter></scene>"""
+    with pytest.raises(gdb200.Gdb200Error, match=message):
+        gdb200.load_scene(xml)
+
+
+def test_integrator_validation_applies_to_scene_files():
+    xml = """<scene version="0.5.0"><integrator type="gpt"><boolean name="reconstructL1" value="true"/><boolean name="reconstructL2" value="true"/></integrator>
+      <sensor type="perspective"><float name="fov" value="40"/><film type="multifilm"/></sensor>
+      <emitter type="point"><point name="position" x="0" y="1" z="0"/><rgb name="intensity" value="1,1,1"/></emitter></scene>"""
+    with pytest.raises(gdb200.Gdb200Error, match="Cannot display two reconstructions"):
+        gdb200.load_scene(xml).integrator()

@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-SPP=64 timeout 60 python tools/e2e_phases.py > gpurun_out/c14_e2e_phases.log 2>&1
-cat gpurun_out/c14_e2e_phases.log
+timeout 35 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/c15_smoke.log 2>&1; echo "rc=$?" >> gpurun_out/c15_smoke.log
+tail -3 gpurun_out/c15_smoke.log
