@@ -304,3 +304,15 @@ def test_scene_file_renders_on_the_gpu(oracle, tmp_path):
     paths = integ.save(str(tmp_path / "cbox.exr"), out)
     back = gdb200.pfm.load_multifilm(str(tmp_path / "cbox"))
     assert len(paths) == 5 and np.array_equal(back["-final"], out["-final"].astype(np.float32))
+
+
+def test_gpu_reproduces_committed_golden_buffers():
+    """tests/golden/gpt_golden.npz (oracle output, committed): every scene at 20x16, 4 spp, 2 streams per pixel."""
+    from test_gpt_golden import GOLDEN, SCENES, params
+    integ = gdb200.GPTIntegrator(reconstructL1=False, reconstructL2=False)
+    p = params()
+    for name in sorted(SCENES):
+        got = integ.trace(gdb200.Scene(SCENES[name]()), spp=p.spp, seed=p.seed, streams=p.streams_per_pixel)
+        ref = {b: GOLDEN[name + b] for b in ("-throughput", "-dx", "-dy", "-direct", "-final")}
+        compare(got, ref, max_flip_frac=0.01)          # 320 pixels: at most 3 may contain a branch-flipped sample
+        assert integ.stats.samples == GOLDEN[name + "/counters"][0]
