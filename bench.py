@@ -241,6 +241,11 @@ def main():
     # host side of the end-to-end call: page-locked result buffers and the solver workspace are allocated once, like a
     # renderer that keeps its film between frames; scene upload, tracing, develop, solve and every D2H copy are timed
     host_out = {n: gdb200.pinned_empty((H, W, 3), "float64") for n in gdb200.BUFFER_NAMES} if rank == 0 else None
+    # the end-to-end leg starts after ~15 s of sustained load: sample the clocks again so that a power/thermal drop between
+    # the two legs is visible next to the number it affects ("clocks_e2e")
+    sampler_e2e = ClockSampler(local_rank)
+    if rank == 0:
+        sampler_e2e.start()
     for it in range(e2e_steps + 1):               # iteration 0 is the end-to-end warm-up (first-use allocations), not timed
         if it == 1:
             barrier()
@@ -260,6 +265,7 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_val = W * H * spp * e2e_steps / float(e2e_s.item()) / 1e6
+    clocks_e2e = sampler_e2e.stop() if rank == 0 else None
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
@@ -286,7 +292,7 @@ def main():
                 "rays_per_sample": round(agg["rays"] / max(agg["samples"], 1), 2),
                 "e2e": {"value": round(e2e_val, 3), "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(agg["launches"]),
-                "clocks": clocks,
+                "clocks": clocks, "clocks_e2e": clocks_e2e,
                 "roofline": {"bound": "hbm", "kernel": "gpt_bounce_kernel", "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"],
                              "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": traffic,
                              "peak_source": peak_src, "avg_launch_ms": round(bounce_avg_ms, 4),
