@@ -68,3 +68,16 @@ def test_oracle_denoises(oracle):
     for preset in ("L2D", "L1D"):
         fin = oracle.poisson(d["dx"], d["dy"], d["throughput"], None, preset=preset)
         assert rmse(fin, d["clean"]) < 0.25 * rmse(d["throughput"], d["clean"])
+
+
+@pytest.mark.parametrize("preset", ["L1Q", "L1L"])
+def test_oracle_bit_exact_vs_compiled_reference_slow_presets(oracle, preset):
+    """The two remaining presets of Solver::Params::setConfigPreset (Solver.cpp:117-147): L1Q = 64 IRLS x 1000 CG,
+    L1L = 7 IRLS x 20000 CG with cgTolerance 1e-20 — pinned on a small image where they finish in a second."""
+    if oracle.ref is None:
+        pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
+    d = synth.solver_inputs(24, 16, seed=7, last_col_nonzero=True)
+    a = oracle.poisson(d["dx"], d["dy"], d["throughput"], d["direct"], preset=preset)
+    b = oracle.poisson_ref(d["dx"], d["dy"], d["throughput"], d["direct"], preset=preset)
+    assert np.array_equal(a, b)
+    assert rmse(a, d["clean"]) < rmse(d["throughput"], d["clean"])
