@@ -52,7 +52,7 @@ GDB_D int &SI(const GptArgs &a, int field, int slot) { return a.si[((size_t)slot
 GDB_D void redAdd(double *p, double v)
 {
 #ifdef GDB200_EMU
-    *p += v;
+    atomicAdd(p, v);
 #else
     asm volatile("red.global.add.f64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "d"(v) : "memory");
 #endif
@@ -60,7 +60,7 @@ GDB_D void redAdd(double *p, double v)
 GDB_D void redAdd(unsigned long long *p, unsigned long long v)
 {
 #ifdef GDB200_EMU
-    *p += v;
+    atomicAdd(p, v);
 #else
     asm volatile("red.global.add.u64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "l"(v) : "memory");
 #endif
@@ -68,7 +68,7 @@ GDB_D void redAdd(unsigned long long *p, unsigned long long v)
 GDB_D unsigned long long atomAdd(unsigned long long *p, unsigned long long v)
 {
 #ifdef GDB200_EMU
-    const unsigned long long o = *p; *p = o + v; return o;
+    return atomicAdd(p, v);
 #else
     unsigned long long o;
     asm volatile("atom.global.add.u64 %0, [%1], %2;" : "=l"(o) : "l"(__cvta_generic_to_global(p)), "l"(v) : "memory");
@@ -78,7 +78,7 @@ GDB_D unsigned long long atomAdd(unsigned long long *p, unsigned long long v)
 GDB_D int atomAdd(int *p, int v)
 {
 #ifdef GDB200_EMU
-    const int o = *p; *p = o + v; return o;
+    return atomicAdd(p, v);
 #else
     int o;
     asm volatile("atom.global.add.s32 %0, [%1], %2;" : "=r"(o) : "l"(__cvta_generic_to_global(p)), "r"(v) : "memory");

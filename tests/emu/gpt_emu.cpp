@@ -130,3 +130,85 @@ extern "C" int gdb200_emu_envmap_pdf_batch(const gdb200_scene_desc *desc, int n,
     for (int i = 0; i < n; i++) pdf[i] = envPdfDirection(xfVector(c_scene.env.toObject, mk(d[3 * i], d[3 * i + 1], d[3 * i + 2])));
     return 0;
 }
+
+// ---- block mode: the queued wavefront (gpt_generate_kernel -> gpt_compact_kernel -> gpt_bounce_kernel<2> per step, then
+// gpt_tail_kernel) with every CTA run by OS threads, so that the kernels' shared-memory prologues, __syncthreads and
+// ballots execute as written.  The step loop below mirrors the host loop of gdb200_gpt_render (csrc/gpt.cu): it is a
+// restatement for the test, the kernels are the real source.
+#include <functional>
+#include <thread>
+
+static void emuLaunch(int blocks, int threads, const std::function<void()> &kernel)
+{
+    EmuBlock blk; blk.nThreads = threads;
+    blockDim.x = (unsigned)threads; gridDim.x = (unsigned)blocks;
+    for (int b = 0; b < blocks; b++) {
+        pthread_barrier_init(&blk.bar, nullptr, (unsigned)threads);
+        emu_block = &blk;
+        std::vector<std::thread> pool;
+        for (int t = 0; t < threads; t++)
+            pool.emplace_back([&, b, t]() { blockIdx.x = (unsigned)b; threadIdx.x = (unsigned)t; kernel(); });
+        for (std::thread &th : pool) th.join();
+        emu_block = nullptr;
+        pthread_barrier_destroy(&blk.bar);
+    }
+    blockDim.x = 1; gridDim.x = 1; blockIdx.x = 0; threadIdx.x = 0;
+}
+
+extern "C" int gdb200_emu_gpt_render_wavefront(const gdb200_scene_desc *desc, const gdb200_gpt_params *p, gdb200_buffers *out, double *counters)
+{
+    static HostScene hs;
+    if (int rc = flattenScene(desc, &hs)) return rc;
+    classifyMaterials(&hs, p->shift_threshold);
+    GptArgs a;
+    const char *capEnv = getenv("GDB200_MAX_SLOTS");
+    if (int rc = setupArgs(hs, p, a, capEnv ? atoi(capEnv) : (1 << 23))) return rc;
+    hs.host.env.texels = hs.envTexels.data(); hs.host.env.rowWeights = hs.envRowWeights.data(); hs.host.emTriCdf = hs.emTriCdf.data();
+    hs.host.env.cdfRows = hs.envCdfRows.data(); hs.host.env.cdfCols = hs.envCdfCols.data(); hs.host.emTris = hs.emTris.data();
+    hs.host.bvh = hs.bvh.data(); hs.host.bvhTris = hs.bvhTris.data(); hs.host.triNormals = hs.triNormals.data();
+    c_scene = hs.host; static DScene sceneCopy; sceneCopy = hs.host; c_sceneG = &sceneCopy;
+    memcpy(c_bounds, hs.bounds, sizeof(hs.bounds));
+    const size_t n = (size_t)hs.width * hs.height;
+    const int nSlots = a.nSlots;
+    std::vector<double> sd((size_t)4 * kRecords * nSlots, 0.0), film(5 * n * 4, 0.0);
+    std::vector<int> si((size_t)16 * nSlots, 0), liveList((size_t)2 * kBuckets * nSlots, -1), liveCount(2 * kBuckets, 0), genList((size_t)2 * nSlots, -1), genCount(2, 0);
+    std::vector<unsigned long long> ctr(8, 0);
+    a.sd = sd.data(); a.si = si.data(); a.film = film.data(); a.counters = ctr.data();
+    a.liveList = liveList.data(); a.liveCount = liveCount.data(); a.genList = genList.data(); a.genCount = genCount.data();
+
+    emuLaunch((nSlots + 255) / 256, 256, [&]() { gpt_init_kernel(a); });
+    const int genBlocks = (nSlots + kGenThreads - 1) / kGenThreads;
+    const int bounceBlocks = (nSlots + 32 * kBuckets + kBounceThreads - 1) / kBounceThreads;
+    unsigned long long tailThreshold = (unsigned long long)std::max(nSlots / 16, std::min(nSlots, 16384));
+    if (getenv("GDB200_NO_TAIL")) tailThreshold = 0;
+    int parity = 0;
+    const long long maxSteps = (long long)p->spp * 4096 + 65536;
+    for (long long step = 0;; step++) {
+        if (step > maxSteps) return set_error(GDB200_ERR_CUDA, "wavefront did not drain after %lld steps", step);
+        emuLaunch(genBlocks, kGenThreads, [&]() { gpt_generate_kernel(a, parity); });
+        emuLaunch((nSlots + 255) / 256, 256, [&]() { gpt_compact_kernel(a, parity); });
+        for (int b = 0; b < kBuckets; b++)                       // every queue entry must be a valid slot of the right bucket
+            for (int i = 0; i < liveCount[parity * kBuckets + b]; i++) {
+                const int slot = liveList[((size_t)parity * kBuckets + b) * nSlots + i];
+                if (slot < 0 || slot >= nSlots || si[(size_t)slot * 16 + IF_STATUS] != ST_LIVE) return set_error(GDB200_ERR_CUDA, "step %lld: bad entry %d in queue %d", step, slot, b);
+            }
+        emuLaunch(bounceBlocks, kBounceThreads, [&]() { gpt_bounce_kernel<2>(a, parity); });
+        parity ^= 1;
+        if ((step & 15) == 15) {
+            if (ctr[0] >= (unsigned long long)nSlots) break;
+            if ((unsigned long long)nSlots - ctr[0] <= tailThreshold) {
+                emuLaunch((nSlots + kBounceThreads - 1) / kBounceThreads, kBounceThreads, [&]() { gpt_tail_kernel(a); });
+                break;
+            }
+        }
+    }
+    std::vector<double> dev64(5 * n * 3); std::vector<float> dev32(5 * n * 3);
+    blockDim.x = 1; threadIdx.x = 0;
+    for (size_t i = 0; i < 5 * n; i++) { blockIdx.x = (unsigned)i; gpt_develop_kernel(film.data(), (int)n, dev64.data(), dev32.data()); }
+    if (out) {
+        double *dst[5] = {out->preview_final, out->throughput, out->dx, out->dy, out->direct};
+        for (int b = 0; b < 5; b++) if (dst[b]) memcpy(dst[b], dev64.data() + (size_t)b * n * 3, sizeof(double) * n * 3);
+    }
+    if (counters) for (int i = 0; i < 6; i++) counters[i] = (double)ctr[i];
+    return 0;
+}

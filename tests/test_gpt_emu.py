@@ -141,3 +141,24 @@ def test_reconstruction_filters(oracle, emu, rfilter):
     one, _, _ = oracle.gpt(desc, p, threads=1)                                  # oracle band parallelism is safe for the wider footprint
     for k in ref:
         assert np.array_equal(one[k], ref[k])
+
+
+@pytest.mark.parametrize("scene_name,no_tail,cap", [("cbox_glossy", False, None), ("cbox_mesh_lights", True, None),
+                                                    ("cbox_env", True, 100), ("cbox_point", True, None)])
+def test_queued_wavefront_kernels(oracle, emu, scene_name, no_tail, cap, monkeypatch):
+    """Block mode of the emulation: gpt_generate_kernel / gpt_compact_kernel / gpt_bounce_kernel<2> / gpt_tail_kernel as
+    written (shared-memory prologues, __syncthreads, ballots, queue appends), CTAs run by OS threads, with the step loop of
+    gdb200_gpt_render restated around them.  Every queue entry is checked each step; GDB200_NO_TAIL keeps all paths on the
+    queues to the end (every BSDF-type x shift-stage bucket, incl. plastic), a slot cap deals streams dynamically."""
+    if no_tail:
+        monkeypatch.setenv("GDB200_NO_TAIL", "1")
+    if cap:
+        monkeypatch.setenv("GDB200_MAX_SLOTS", str(cap))
+    desc = SCENES[scene_name](14, 10)
+    p = scenes.default_params(spp=3, seed=3)
+    p.streams_per_pixel = 2
+    got, cnt = emu.gpt_wavefront(desc, p)
+    ref, _, c2 = oracle.gpt(desc, p)
+    close(got, ref)
+    assert cnt[3] == c2[0] == 14 * 10 * 3 and cnt[1] == c2[1] and cnt[2] == c2[2]
+    assert cnt[0] == (cap if cap else 14 * 10 * 2)
