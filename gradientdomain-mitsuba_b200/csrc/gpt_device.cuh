@@ -84,7 +84,7 @@ GDB_HD void computeShadingFrame(V3 n, V3 dpdu, Frame &f)    // util.cpp:603-608
 }
 
 // ---------------------------------------------------------------- scene tables
-enum : unsigned { EDiffuseReflection = 0x1, EGlossyReflection = 0x4, EDeltaReflection = 0x10, EDeltaTransmission = 0x20,
+enum : unsigned { EDiffuseReflection = 0x1, EGlossyReflection = 0x4, EGlossyTransmission = 0x8, EDeltaReflection = 0x10, EDeltaTransmission = 0x20,
                   ESmooth = 0xF, EDelta = 0x30, ETransmissionBits = 0x2 | 0x8 | 0x20, EBackSide = 0x20000, EFrontSide = 0x10000 };
 enum Measure { ESolidAngle = 0, EDiscrete = 1 };
 enum VertexType { VERTEX_TYPE_GLOSSY = 0, VERTEX_TYPE_DIFFUSE = 1 };
@@ -582,6 +582,8 @@ GDB_D Float fresnelDielectricExt(Float cosThetaI_, Float &cosThetaT_, Float eta)
     cosThetaT_ = (cosThetaI_ > 0) ? -cosThetaT : cosThetaT;
     return 0.5 * (Rs * Rs + Rp * Rp);
 }
+GDB_D Float fresnelDielectricExt(Float cosThetaI, Float eta) { Float cosThetaT; return fresnelDielectricExt(cosThetaI, cosThetaT, eta); }
+GDB_D V3 reflectAboutLocal(V3 wi, V3 n) { return 2 * dot(wi, n) * n - wi; }                // util.cpp:763-765
 GDB_D V3 reflectLocal(V3 wi) { return mk(-wi.x, -wi.y, wi.z); }
 GDB_D V3 refractLocal(const DMaterial &m, V3 wi, Float cosThetaT)                     // dielectric.cpp:223-226
 {
@@ -620,6 +622,33 @@ GDB_D void bsdfEvalPdfImpl(const DMaterial &m, V3 wi, V3 wo, int measure, Spec &
         value = m.specR * fresnelConductorExact(wi.z, m.eta, m.k);
         pdf = 1.0;
         return;
+    case GDB200_BSDF_ROUGHDIELECTRIC: {                                                // roughdielectric.cpp:277-422 (mode ERadiance)
+        if (measure != ESolidAngle || wi.z == 0) return;
+        const bool reflect = wi.z * wo.z > 0;
+        const Float eta = wi.z > 0 ? m.iorRatio : 1 / m.iorRatio;
+        V3 H = reflect ? normalize(wo + wi) : normalize(wi + wo * eta);
+        Float dwh_dwo;
+        if (reflect) dwh_dwo = 1.0 / (4.0 * dot(wo, H));
+        else { const Float sd = dot(wi, H) + eta * dot(wo, H); dwh_dwo = (eta * eta * dot(wo, H)) / (sd * sd); }
+        H = H * copysign(1.0, H.z);
+        const Float D = mfEval(m.distribution, m.alpha, H);
+        const Float F = fresnelDielectricExt(dot(wi, H), m.iorRatio);
+        Float prob = mfPdfVisible(m.distribution, m.alpha, wi * copysign(1.0, wi.z), H);
+        prob *= reflect ? F : (1 - F);
+        pdf = fabs(prob * dwh_dwo);
+        if (D == 0) return;
+        const Float G = mfSmithG1(m.distribution, m.alpha, wi, H) * mfSmithG1(m.distribution, m.alpha, wo, H);
+        if (reflect) {
+            const Float v = F * D * G / (4.0 * fabs(wi.z));
+            value = m.specR * v;
+        } else {
+            const Float sqrtDenom = dot(wi, H) + eta * dot(wo, H);
+            const Float v = ((1 - F) * D * G * eta * eta * dot(wi, H) * dot(wo, H)) / (wi.z * sqrtDenom * sqrtDenom);
+            const Float factor = wi.z > 0 ? 1 / m.iorRatio : m.iorRatio;
+            value = m.specT * fabs(v * factor * factor);
+        }
+        return;
+    }
     case GDB200_BSDF_PLASTIC: {                                                        // plastic.cpp:243-302 (typeMask = EAll, component = -1)
         if (wo.z <= 0 || wi.z <= 0) return;
         Float dummy;
@@ -664,32 +693,34 @@ GDB_D void bsdfEvalPdf(const DMaterial &m, V3 wi, V3 wo, int measure, Spec &valu
 GDB_CALL void bsdfEvalPdf(const DMaterial &m, V3 wi, V3 wo, int measure, Spec &value, Float &pdf) { bsdfEvalPdfImpl(m, wi, wo, measure, value, pdf); }
 #endif
 
-struct BSDFSample { V3 wo; Float eta; unsigned sampledType; Spec weight; Float pdf; };
+struct BSDFSample { V3 wo; Float eta; unsigned sampledType; Spec weight; Float pdf; int extraDraws; };   // extraDraws: sampler values consumed inside sample() (EUsesSampler)
 
 // BSDF::sample(bRec, pdf, sample), pdf pre-set to 0 by the caller (gpt.cpp:450-457)
-GDB_D void bsdfSampleOneSided(const DMaterial &m, V3 wi, Float sx, Float sy, BSDFSample &r);
+GDB_D void bsdfSampleOneSided(const DMaterial &m, V3 wi, Float sx, Float sy, Float s3, BSDFSample &r);
 #if GDB_BYVAL & 8
 GDB_CALL
 #else
 GDB_D
 #endif
-BSDFSample bsdfSampleV(const DMaterial &m, V3 wi, Float sx, Float sy)
+BSDFSample bsdfSampleV(const DMaterial &m, V3 wi, Float sx, Float sy, Float s3)
 {
     BSDFSample r;
     const bool flipped = m.twosided && wi.z < 0;                                       // twosided.cpp:160-183
     if (flipped) wi.z *= -1;
-    bsdfSampleOneSided(m, wi, sx, sy, r);
+    bsdfSampleOneSided(m, wi, sx, sy, s3, r);
     if (flipped && !isZero(r.weight) && r.pdf != 0) r.wo.z *= -1;
     return r;
 }
 #if GDB_BYVAL & 8
-GDB_D void bsdfSample(const DMaterial &m, V3 wi, Float sx, Float sy, BSDFSample &r) { r = bsdfSampleV(m, wi, sx, sy); }
+// s3: the NEXT value of the pixel's sample stream, peeked by the caller; a BSDF that draws from the sampler inside
+// sample() (EUsesSampler: roughdielectric.cpp:524-531) consumes it and reports r.extraDraws = 1 so the caller advances.
+GDB_D void bsdfSample(const DMaterial &m, V3 wi, Float sx, Float sy, Float s3, BSDFSample &r) { r = bsdfSampleV(m, wi, sx, sy, s3); }
 #else
-GDB_CALL void bsdfSample(const DMaterial &m, V3 wi, Float sx, Float sy, BSDFSample &r) { r = bsdfSampleV(m, wi, sx, sy); }
+GDB_CALL void bsdfSample(const DMaterial &m, V3 wi, Float sx, Float sy, Float s3, BSDFSample &r) { r = bsdfSampleV(m, wi, sx, sy, s3); }
 #endif
-GDB_D void bsdfSampleOneSided(const DMaterial &m, V3 wi, Float sx, Float sy, BSDFSample &r)
+GDB_D void bsdfSampleOneSided(const DMaterial &m, V3 wi, Float sx, Float sy, Float s3, BSDFSample &r)
 {
-    r.weight = splat(0); r.pdf = 0; r.eta = 1.0; r.sampledType = 0; r.wo = mk(0, 0, 0);
+    r.weight = splat(0); r.pdf = 0; r.eta = 1.0; r.sampledType = 0; r.wo = mk(0, 0, 0); r.extraDraws = 0;
     switch (m.type) {
     case GDB200_BSDF_DIFFUSE:                                                          // diffuse.cpp:143-153
         if (wi.z <= 0) return;
@@ -718,6 +749,40 @@ GDB_D void bsdfSampleOneSided(const DMaterial &m, V3 wi, Float sx, Float sy, BSD
         r.pdf = 1;
         r.weight = m.specR * fresnelConductorExact(wi.z, m.eta, m.k);
         return;
+    case GDB200_BSDF_ROUGHDIELECTRIC: {                                                // roughdielectric.cpp:505-614 (both components, sampleVisible)
+        const V3 wiS = wi * copysign(1.0, wi.z);                                       // math::signum = copysign(1, x), math.h:269-278
+        const V3 mm = mfSampleVisible(m.distribution, m.alpha, wiS, sx, sy);
+        const Float microfacetPDF = mfPdfVisible(m.distribution, m.alpha, wiS, mm);
+        if (microfacetPDF == 0) return;
+        float temporaryPdf = (float)microfacetPDF;                                     // a `float` in the reference (:533)
+        Float cosThetaT;
+        const Float F = fresnelDielectricExt(dot(wi, mm), cosThetaT, m.iorRatio);
+        r.extraDraws = 1;                                                              // bRec.sampler->next1D()
+        const bool sampleReflection = !(s3 > F);
+        temporaryPdf = (float)((Float)temporaryPdf * (sampleReflection ? F : 1 - F));
+        Spec weight = splat(1.0);
+        Float dwh_dwo;
+        if (sampleReflection) {
+            r.wo = reflectAboutLocal(wi, mm); r.eta = 1.0; r.sampledType = EGlossyReflection;
+            if (wi.z * r.wo.z <= 0) return;
+            weight = weight * m.specR;
+            dwh_dwo = 1.0 / (4.0 * dot(r.wo, mm));
+        } else {
+            if (cosThetaT == 0) return;
+            const Float e = cosThetaT < 0 ? 1 / m.iorRatio : m.iorRatio;               // util.cpp:767-772
+            r.wo = mm * (dot(wi, mm) * e + cosThetaT) - wi * e;
+            r.eta = cosThetaT < 0 ? m.iorRatio : 1 / m.iorRatio; r.sampledType = EGlossyTransmission;
+            if (wi.z * r.wo.z >= 0) return;
+            const Float factor = cosThetaT < 0 ? 1 / m.iorRatio : m.iorRatio;
+            weight = weight * (m.specT * (factor * factor));
+            const Float sqrtDenom = dot(wi, mm) + r.eta * dot(r.wo, mm);
+            dwh_dwo = (r.eta * r.eta * dot(r.wo, mm)) / (sqrtDenom * sqrtDenom);
+        }
+        weight = weight * mfSmithG1(m.distribution, m.alpha, r.wo, mm);
+        temporaryPdf = (float)((Float)temporaryPdf * fabs(dwh_dwo));
+        r.pdf = temporaryPdf; r.weight = weight;
+        return;
+    }
     case GDB200_BSDF_PLASTIC: {                                                        // plastic.cpp:372-414
         if (wi.z <= 0) return;
         Float dummy;
@@ -1086,6 +1151,10 @@ struct Sampler {
     {
         n++;
         return (Float)(mix64(key + (uint64_t)n * 0x9E3779B97F4A7C15ULL) >> 11) * (1.0 / 9007199254740992.0);
+    }
+    GDB_D Float peek1D() const     // the value next1D() would return, without consuming it
+    {
+        return (Float)(mix64(key + (uint64_t)(n + 1) * 0x9E3779B97F4A7C15ULL) >> 11) * (1.0 / 9007199254740992.0);
     }
 };
 

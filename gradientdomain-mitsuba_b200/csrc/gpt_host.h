@@ -204,9 +204,9 @@ inline int flattenScene(const gdb200_scene_desc *d, HostScene *s)
     h.nMaterials = d->n_materials;
     for (int i = 0; i < d->n_materials; i++) {
         const gdb200_material &m = d->materials[i];
-        static_assert(kBsdfTypes == GDB200_BSDF_PLASTIC + 1, "the compaction queues are keyed by BSDF type");
+        static_assert(kBsdfTypes == GDB200_BSDF_ROUGHDIELECTRIC + 1, "the compaction queues are keyed by BSDF type");
         if (m.type < GDB200_BSDF_DIFFUSE || m.type >= kBsdfTypes) return set_error(GDB200_ERR_ARGUMENT, "material %d: unknown BSDF type %d", i, m.type);
-        if (m.twosided && m.type == GDB200_BSDF_DIELECTRIC)
+        if (m.twosided && (m.type == GDB200_BSDF_DIELECTRIC || m.type == GDB200_BSDF_ROUGHDIELECTRIC))
             return set_error(GDB200_ERR_ARGUMENT, "material %d: Only materials without a transmission component can be nested!", i);   // twosided.cpp:103-105
     }
     // Triangles of all meshes: in the constant-memory table while they fit, else (or with GDB200_FORCE_BVH) behind a BVH.
@@ -435,7 +435,7 @@ inline void classifyMaterials(HostScene *s, double shiftThreshold)
         o.eta = mk(m.eta[0], m.eta[1], m.eta[2]); o.k = mk(m.k[0], m.k[1], m.k[2]);
         o.alpha = std::max(m.alpha, (double)1e-4f);                                  // microfacet.h:67-71
         o.iorRatio = m.ior_ratio;
-        o.bsdfEta = m.type == GDB200_BSDF_DIELECTRIC ? m.ior_ratio : 1.0;            // bsdf.cpp:62-64, dielectric.cpp:389; plastic and twosided inherit 1
+        o.bsdfEta = (m.type == GDB200_BSDF_DIELECTRIC || m.type == GDB200_BSDF_ROUGHDIELECTRIC) ? m.ior_ratio : 1.0;   // bsdf.cpp:62-64, dielectric.cpp:389, roughdielectric.cpp:631; plastic and twosided inherit 1
         o.twosided = m.twosided != 0; o.nonlinear = m.nonlinear != 0;
         int nComp = 1; double rough[2] = {0, 0};
         const double inf = std::numeric_limits<double>::infinity();
@@ -445,6 +445,8 @@ inline void classifyMaterials(HostScene *s, double shiftThreshold)
                 nComp = o.flags ? 1 : 0; rough[0] = inf; break;
             case GDB200_BSDF_ROUGHCONDUCTOR: o.flags = EGlossyReflection | EFrontSide; rough[0] = 0.5 * (m.alpha + m.alpha); break;   // roughconductor.cpp:437-440
             case GDB200_BSDF_CONDUCTOR: o.flags = EDeltaReflection | EFrontSide; rough[0] = 0; break;
+            case GDB200_BSDF_ROUGHDIELECTRIC:                                        // roughdielectric.cpp:246-252,642-645
+                o.flags = EGlossyReflection | EGlossyTransmission | EFrontSide | EBackSide; nComp = 2; rough[0] = rough[1] = 0.5 * (m.alpha + m.alpha); break;
             case GDB200_BSDF_PLASTIC: {                                              // plastic.cpp:186-217,442-449
                 o.flags = EDeltaReflection | EDiffuseReflection | EFrontSide; nComp = 2; rough[0] = 0; rough[1] = inf;
                 o.fdrInt = fresnelDiffuseReflectance(1 / m.ior_ratio); o.fdrExt = fresnelDiffuseReflectance(m.ior_ratio);

@@ -22,7 +22,7 @@ enum { RAY_NOT_CONNECTED = 0, RAY_RECENTLY_CONNECTED = 1, RAY_CONNECTED = 2 };
 enum { BUF_FINAL = 0, BUF_THROUGHPUT = 1, BUF_DX = 2, BUF_DY = 3, BUF_DIRECT = 4 };
 
 constexpr int kBounceThreads = 128, kGenThreads = 128;
-constexpr int kBsdfTypes = GDB200_BSDF_PLASTIC + 1;
+constexpr int kBsdfTypes = GDB200_BSDF_ROUGHDIELECTRIC + 1;
 constexpr int kBuckets = 3 * kBsdfTypes;  // one queue per (BSDF type of the base vertex) x (shift stage of the offset paths)
 
 struct GptArgs {
@@ -446,7 +446,13 @@ GDB_D void bounceBody(const GptArgs &a, int slot, int parity)
         bool bsdfStage = false, mainHitEmitter = false, escaped = false;
         BSDFSample bs;
         bs.weight = splat(0); bs.pdf = 0; bs.eta = 1.0; bs.sampledType = 0; bs.wo = mk(0, 0, 0);
-        if (kBsdf) { const Float sx = smp.next1D(), sy = smp.next1D(); bsdfSample(mainBSDF, mits.wi, sx, sy, bs); }   // gpt.cpp:456-457
+        bs.extraDraws = 0;
+        if (kBsdf) {                                                                 // gpt.cpp:456-457
+            const Float sx = smp.next1D(), sy = smp.next1D();
+            const Float s3 = mainBSDF.type == GDB200_BSDF_ROUGHDIELECTRIC ? smp.peek1D() : 0.0;   // EUsesSampler: drawn inside BSDF::sample
+            bsdfSample(mainBSDF, mits.wi, sx, sy, s3, bs);
+            smp.n += (uint32_t)bs.extraDraws;
+        }
         Spec mainEmitterRadiance = splat(0), mainContributionAll = splat(0);
         DRec mainDRec; initDRec(mits, mainDRec);                                     // gpt.cpp:759
         int mainVertexType = 0, mainNextVertexType = 0;

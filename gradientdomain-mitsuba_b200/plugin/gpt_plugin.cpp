@@ -85,6 +85,18 @@ struct FlatScene {
 			copySpectrum(p.getSpectrum("specularReflectance", Spectrum(1.0f)), m.specular_reflectance);
 			copySpectrum(p.getSpectrum("diffuseReflectance", Spectrum(0.5f)), m.reflectance);
 			m.nonlinear = p.getBoolean("nonlinear", false);
+		} else if (cls == "RoughDielectric") {
+			m.type = GDB200_BSDF_ROUGHDIELECTRIC;
+			m.ior_ratio = bsdf->getEta();        /* roughdielectric.cpp:630-632 */
+			m.alpha = p.getFloat("alpha", 0.1f);
+			copySpectrum(p.getSpectrum("specularReflectance", Spectrum(1.0f)), m.specular_reflectance);
+			copySpectrum(p.getSpectrum("specularTransmittance", Spectrum(1.0f)), m.specular_transmittance);
+			const std::string distr = p.getString("distribution", "beckmann");
+			if (distr == "ggx") m.distribution = GDB200_MICROFACET_GGX;
+			else if (distr == "beckmann") m.distribution = GDB200_MICROFACET_BECKMANN;
+			else SLog(EError, "gdb200: microfacet distribution \"%s\" is not supported", distr.c_str());
+			if (p.hasProperty("alphaU") || p.hasProperty("alphaV") || !p.getBoolean("sampleVisible", true))
+				SLog(EError, "gdb200: anisotropic / non-visible-normal roughdielectric is not supported");
 		} else if (cls == "SmoothDielectric") {
 			m.type = GDB200_BSDF_DIELECTRIC;
 			m.ior_ratio = bsdf->getEta();        /* dielectric.cpp:389-391 */

@@ -11,7 +11,7 @@ import math
 import numpy as np
 
 SHAPE_RECTANGLE, SHAPE_SPHERE, SHAPE_MESH = 0, 1, 2
-BSDF_DIFFUSE, BSDF_ROUGHCONDUCTOR, BSDF_CONDUCTOR, BSDF_DIELECTRIC, BSDF_PLASTIC = 0, 1, 2, 3, 4
+BSDF_DIFFUSE, BSDF_ROUGHCONDUCTOR, BSDF_CONDUCTOR, BSDF_DIELECTRIC, BSDF_PLASTIC, BSDF_ROUGHDIELECTRIC = 0, 1, 2, 3, 4, 5
 EMITTER_AREA, EMITTER_ENVMAP, EMITTER_POINT = 0, 1, 2
 MICROFACET_BECKMANN, MICROFACET_GGX = 0, 1
 
@@ -504,6 +504,19 @@ def cbox_smooth(width=256, height=256):
 def atrium_c3(width=1920, height=1080):
     """BASELINE configs[2] stand-in ("Sponza-class, env-map lit, mixed diffuse/specular"): 258 k triangles behind the BVH."""
     return atrium(width, height, columns=12, segments=64, rings=14)
+
+
+def cbox_roughglass(width=256, height=256):
+    """Rough glass (`roughdielectric`): glossy transmission makes the refraction branch of the half-vector shift run with
+    its real Jacobian (gpt.cpp:245-290; smooth glass overrides it with 1), for a GLOSSY-classified lobe (alpha 0.0008 <=
+    shiftThreshold) and a DIFFUSE-classified one (alpha 0.15: reconnection through the rough interface)."""
+    b = _cornell(width, height, boxes=False)
+    frosted = b.material(type=BSDF_ROUGHDIELECTRIC, alpha=0.15, ior_ratio=1.5046 / 1.000277, distribution=MICROFACET_BECKMANN)
+    clear = b.material(type=BSDF_ROUGHDIELECTRIC, alpha=0.0008, ior_ratio=1.5)
+    b.sphere((-0.45, -0.65, 0.25), 0.35, frosted)
+    b.sphere((0.5, -0.7, 0.4), 0.3, clear)
+    b.box((0.0, -0.85, -0.4), (0.35, 0.15, 0.25), 30.0, b.material(reflectance=WHITE))
+    return b.build()
 
 
 def cbox_point(width=256, height=256):

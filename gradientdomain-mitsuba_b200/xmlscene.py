@@ -4,7 +4,7 @@
 A scene that selects the reference's path loads unchanged: `<integrator type="gpt">` with the reference's
 parameter names and defaults (gpt.cpp:1194-1210), a `perspective` / `thinlens` sensor with its `sampler` and `multifilm`
 film, `rectangle` / `sphere` / `cube` / `obj` shapes, `diffuse` / `roughconductor` / `conductor` / `dielectric` /
-`plastic` / `twosided` BSDFs, `area` / `point` / `envmap` emitters, `<default>` / `$variables`, `<ref id=...>`.
+`plastic` / `roughdielectric` / `twosided` BSDFs, `area` / `point` / `envmap` emitters, `<default>` / `$variables`, `<ref id=...>`.
 Anything else raises (no silent fallback), with the element's name in the message.
 
     parsed = load_scene("scene.xml", defines={"spp": "64"})
@@ -202,6 +202,21 @@ class _Loader:
                                  distribution=S.MICROFACET_GGX if distr == "ggx" else S.MICROFACET_BECKMANN, **kw)
             else:
                 idx = b.material(type=S.BSDF_CONDUCTOR, **kw)
+        elif typ == "roughdielectric":
+            if twosided:
+                raise Gdb200Error("Only materials without a transmission component can be nested!")
+            if any(n in p.values for n in ("alphaU", "alphaV")) or p.get("sampleVisible", True) is not True:
+                raise Gdb200Error("roughdielectric: anisotropic roughness / sampleVisible=false are not supported")
+            distr = p.get("distribution", "beckmann").lower()
+            if distr not in ("beckmann", "ggx"):
+                raise Gdb200Error(f"roughdielectric: microfacet distribution \"{distr}\" is not supported")
+            int_ior, ext_ior = self.ior(p.get("intIOR", "bk7")), self.ior(p.get("extIOR", "air"))
+            if int_ior == ext_ior:
+                raise Gdb200Error("The interior and exterior indices of refraction must be positive and differ!")
+            idx = b.material(type=S.BSDF_ROUGHDIELECTRIC, alpha=p.get("alpha", 0.1), ior_ratio=int_ior / ext_ior,
+                             distribution=S.MICROFACET_GGX if distr == "ggx" else S.MICROFACET_BECKMANN,
+                             specular_reflectance=p.get("specularReflectance", (1.0, 1.0, 1.0)),
+                             specular_transmittance=p.get("specularTransmittance", (1.0, 1.0, 1.0)))
         elif typ in ("dielectric", "plastic"):
             int_ior = self.ior(p.get("intIOR", "bk7" if typ == "dielectric" else "polypropylene"))
             ext_ior = self.ior(p.get("extIOR", "air"))

@@ -118,7 +118,10 @@ enum { GDB200_BSDF_DIFFUSE        = 0,   /* src/bsdfs/diffuse.cpp        */
        GDB200_BSDF_ROUGHCONDUCTOR = 1,   /* src/bsdfs/roughconductor.cpp (sampleVisible = true) */
        GDB200_BSDF_CONDUCTOR      = 2,   /* src/bsdfs/conductor.cpp      */
        GDB200_BSDF_DIELECTRIC     = 3,   /* src/bsdfs/dielectric.cpp     */
-       GDB200_BSDF_PLASTIC        = 4 }; /* src/bsdfs/plastic.cpp: delta reflection + diffuse lobe (the two-component case of gpt.cpp:194-226) */
+       GDB200_BSDF_PLASTIC        = 4,   /* src/bsdfs/plastic.cpp: delta reflection + diffuse lobe (the two-component case of gpt.cpp:194-226) */
+       GDB200_BSDF_ROUGHDIELECTRIC = 5 }; /* src/bsdfs/roughdielectric.cpp (sampleVisible = true, isotropic alpha): glossy reflection +
+                                           * transmission, the non-delta refraction half-vector shift (gpt.cpp:245-290); draws one extra
+                                           * sampler value inside BSDF::sample (EUsesSampler) */
 
 enum { GDB200_MICROFACET_BECKMANN = 0, GDB200_MICROFACET_GGX = 1 };   /* src/bsdfs/microfacet.h */
 
@@ -150,8 +153,8 @@ typedef struct gdb200_material {
     double specular_reflectance[3];     /* conductors, dielectric, plastic             */
     double specular_transmittance[3];   /* dielectric                                  */
     double eta[3], k[3];                /* conductors: complex IOR per channel         */
-    double alpha;                       /* roughconductor                              */
-    double ior_ratio;                   /* dielectric, plastic: intIOR / extIOR        */
+    double alpha;                       /* roughconductor, roughdielectric             */
+    double ior_ratio;                   /* dielectric, plastic, roughdielectric: intIOR / extIOR */
     int    twosided;                    /* wrapped in <bsdf type="twosided"> (same BRDF on both sides, src/bsdfs/twosided.cpp); reflection-only BSDFs */
     int    nonlinear;                   /* plastic: nonlinear colour shifts (plastic.cpp:176)                       */
 } gdb200_material;

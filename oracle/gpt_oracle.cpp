@@ -115,6 +115,7 @@ inline void computeShadingFrame(V3 n, V3 dpdu, Frame &f)
 // ---------------------------------------------------------------- sampler (gdb200_counter)
 struct Sampler {
     uint64_t key, n;
+    bool useForced = false; Float forced = 0;      // chi-square harness only: next1D() returns a supplied value
     static uint64_t mix(uint64_t z)
     {
         z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
@@ -129,13 +130,14 @@ struct Sampler {
     Float next1D()
     {
         n++;
+        if (useForced) return forced;
         return (Float)(mix(key + n * 0x9E3779B97F4A7C15ULL) >> 11) * (1.0 / 9007199254740992.0);
     }
     void next2D(Float &x, Float &y) { x = next1D(); y = next1D(); }
 };
 
 // ---------------------------------------------------------------- scene
-enum { EDiffuseReflection = 0x1, EGlossyReflection = 0x4, EDeltaReflection = 0x10, EDeltaTransmission = 0x20,
+enum { EDiffuseReflection = 0x1, EGlossyReflection = 0x4, EGlossyTransmission = 0x8, EDeltaReflection = 0x10, EDeltaTransmission = 0x20,
        ESmooth = 0xF, EDelta = 0x30, ETransmissionBits = 0x2 | 0x8 | 0x20, EBackSide = 0x20000, EFrontSide = 0x10000 };
 enum Measure { ESolidAngle, EDiscrete };
 
@@ -343,12 +345,13 @@ inline unsigned nestedType(const gdb200_material &m)
         case GDB200_BSDF_ROUGHCONDUCTOR: return EGlossyReflection | EFrontSide;
         case GDB200_BSDF_CONDUCTOR: return EDeltaReflection | EFrontSide;
         case GDB200_BSDF_PLASTIC: return EDeltaReflection | EDiffuseReflection | EFrontSide;     // plastic.cpp:210-214
+        case GDB200_BSDF_ROUGHDIELECTRIC: return EGlossyReflection | EGlossyTransmission | EFrontSide | EBackSide;   // roughdielectric.cpp:246-252
         default: return EDeltaReflection | EDeltaTransmission | EFrontSide | EBackSide;
     }
 }
 inline int nestedComponentCount(const gdb200_material &m)
 {
-    if (m.type == GDB200_BSDF_DIELECTRIC || m.type == GDB200_BSDF_PLASTIC) return 2;
+    if (m.type == GDB200_BSDF_DIELECTRIC || m.type == GDB200_BSDF_PLASTIC || m.type == GDB200_BSDF_ROUGHDIELECTRIC) return 2;
     if (m.type == GDB200_BSDF_DIFFUSE) return nestedType(m) ? 1 : 0;
     return 1;
 }
@@ -357,6 +360,7 @@ inline Float nestedRoughness(const gdb200_material &m, int component)
     switch (m.type) {
         case GDB200_BSDF_DIFFUSE: return INF;                               // diffuse.cpp:167-169
         case GDB200_BSDF_ROUGHCONDUCTOR: return 0.5 * (m.alpha + m.alpha);  // roughconductor.cpp:437-440
+        case GDB200_BSDF_ROUGHDIELECTRIC: return 0.5f * (m.alpha + m.alpha); // roughdielectric.cpp:642-645
         case GDB200_BSDF_PLASTIC: return component == 0 ? 0.0 : INF;        // plastic.cpp:442-449
         default: return 0.0;                                                // conductor.cpp:287, dielectric.cpp:393
     }
@@ -374,7 +378,7 @@ inline Float bsdfRoughness(const gdb200_material &m, int component)
     const int n = nestedComponentCount(m);
     return nestedRoughness(m, component < n ? component : component - n);
 }
-inline Float bsdfEta(const gdb200_material &m) { return m.type == GDB200_BSDF_DIELECTRIC ? m.ior_ratio : 1.0; }  // bsdf.cpp:62-64 (plastic, twosided), dielectric.cpp:389
+inline Float bsdfEta(const gdb200_material &m) { return (m.type == GDB200_BSDF_DIELECTRIC || m.type == GDB200_BSDF_ROUGHDIELECTRIC) ? m.ior_ratio : 1.0; }  // bsdf.cpp:62-64 (plastic, twosided), dielectric.cpp:389
 
 // warp.cpp:81-102
 inline void squareToUniformDiskConcentric(Float sx, Float sy, Float &ox, Float &oy)
@@ -604,6 +608,30 @@ Spec nestedEval(const gdb200_material &m, V3 wi, V3 wo, Measure measure)
     case GDB200_BSDF_CONDUCTOR:                                                        // conductor.cpp:221-235
         if (measure != EDiscrete || wi.z <= 0 || wo.z <= 0 || std::abs(dot(reflectLocal(wi), wo) - 1) > DeltaEpsilon) return spec(0);
         return specOf(m.specular_reflectance) * fresnelConductorExact(wi.z, specOf(m.eta), specOf(m.k));
+    case GDB200_BSDF_ROUGHDIELECTRIC: {                                                // roughdielectric.cpp:277-351 (mode ERadiance)
+        if (measure != ESolidAngle || wi.z == 0) return spec(0);
+        const Float m_eta = m.ior_ratio, m_invEta = 1 / m.ior_ratio;
+        bool reflect = wi.z * wo.z > 0;
+        V3 H;
+        if (reflect) H = normalize(wo + wi);
+        else { Float eta = wi.z > 0 ? m_eta : m_invEta; H = normalize(wi + wo * eta); }
+        H = H * std::copysign(1.0, H.z);
+        Microfacet distr(m.distribution, m.alpha);
+        const Float D = distr.eval(H);
+        if (D == 0) return spec(0);
+        Float unused; const Float F = fresnelDielectricExt(dot(wi, H), unused, m_eta);
+        const Float G = distr.G(wi, wo, H);
+        if (reflect) {
+            Float value = F * D * G / (4.0f * std::abs(wi.z));
+            return specOf(m.specular_reflectance) * value;
+        } else {
+            Float eta = wi.z > 0.0f ? m_eta : m_invEta;
+            Float sqrtDenom = dot(wi, H) + eta * dot(wo, H);
+            Float value = ((1 - F) * D * G * eta * eta * dot(wi, H) * dot(wo, H)) / (wi.z * sqrtDenom * sqrtDenom);
+            Float factor = wi.z > 0 ? m_invEta : m_eta;
+            return specOf(m.specular_transmittance) * std::abs(value * factor * factor);
+        }
+    }
     case GDB200_BSDF_PLASTIC: {                                                        // plastic.cpp:243-275 (typeMask EAll, component -1)
         const bool hasSpecular = measure == EDiscrete, hasDiffuse = measure == ESolidAngle;
         if (wo.z <= 0 || wi.z <= 0) return spec(0);
@@ -646,6 +674,25 @@ Float nestedPdf(const gdb200_material &m, V3 wi, V3 wo, Measure measure)
     case GDB200_BSDF_CONDUCTOR:                                                        // conductor.cpp:237-250
         if (measure != EDiscrete || wi.z <= 0 || wo.z <= 0 || std::abs(dot(reflectLocal(wi), wo) - 1) > DeltaEpsilon) return 0.0;
         return 1.0;
+    case GDB200_BSDF_ROUGHDIELECTRIC: {                                                // roughdielectric.cpp:353-422
+        if (measure != ESolidAngle) return 0.0;
+        const Float m_eta = m.ior_ratio, m_invEta = 1 / m.ior_ratio;
+        bool reflect = wi.z * wo.z > 0;
+        V3 H; Float dwh_dwo;
+        if (reflect) { H = normalize(wo + wi); dwh_dwo = 1.0f / (4.0f * dot(wo, H)); }
+        else {
+            Float eta = wi.z > 0 ? m_eta : m_invEta;
+            H = normalize(wi + wo * eta);
+            Float sqrtDenom = dot(wi, H) + eta * dot(wo, H);
+            dwh_dwo = (eta * eta * dot(wo, H)) / (sqrtDenom * sqrtDenom);
+        }
+        H = H * std::copysign(1.0, H.z);
+        Microfacet sampleDistr(m.distribution, m.alpha);
+        Float prob = sampleDistr.pdfVisible(wi * std::copysign(1.0, wi.z), H);
+        Float unused; Float F = fresnelDielectricExt(dot(wi, H), unused, m_eta);
+        prob *= reflect ? F : (1 - F);
+        return std::abs(prob * dwh_dwo);
+    }
     case GDB200_BSDF_PLASTIC: {                                                        // plastic.cpp:277-302
         if (wo.z <= 0 || wi.z <= 0) return 0.0;
         Float unused; const Float Fi = fresnelDielectricExt(wi.z, unused, m.ior_ratio);
@@ -672,7 +719,7 @@ Float nestedPdf(const gdb200_material &m, V3 wi, V3 wo, Measure measure)
 struct BSDFSample { V3 wi, wo; Float eta; unsigned sampledType; Spec weight; Float pdf; };
 
 // BSDF::sample(bRec, pdf, sample) with pdf pre-set to 0 by the caller (gpt.cpp:450-457)
-void nestedSample(const gdb200_material &m, BSDFSample &r, Float sx, Float sy)
+void nestedSample(const gdb200_material &m, BSDFSample &r, Float sx, Float sy, Sampler &sampler)
 {
     r.weight = spec(0); r.pdf = 0; r.eta = 1.0; r.sampledType = 0; r.wo = v3(0, 0, 0);
     switch (m.type) {
@@ -704,6 +751,42 @@ void nestedSample(const gdb200_material &m, BSDFSample &r, Float sx, Float sy)
         r.pdf = 1;
         r.weight = specOf(m.specular_reflectance) * fresnelConductorExact(r.wi.z, specOf(m.eta), specOf(m.k));
         return;
+    case GDB200_BSDF_ROUGHDIELECTRIC: {                                                // roughdielectric.cpp:505-614 (pdf-returning overload)
+        const Float m_eta = m.ior_ratio, m_invEta = 1 / m.ior_ratio;
+        Microfacet distr(m.distribution, m.alpha);
+        const V3 wiS = r.wi * std::copysign(1.0, r.wi.z);
+        const V3 mm = distr.sampleVisible(wiS, sx, sy);
+        const Float microfacetPDF = distr.pdfVisible(wiS, mm);
+        if (microfacetPDF == 0) return;
+        float temporaryPdf = microfacetPDF;                                            // :533, a float in the reference
+        Float cosThetaT;
+        Float F = fresnelDielectricExt(dot(r.wi, mm), cosThetaT, m_eta);
+        Spec weight = spec(1.0f);
+        bool sampleReflection = true;
+        if (sampler.next1D() > F) { sampleReflection = false; temporaryPdf *= 1 - F; } else { temporaryPdf *= F; }   // EUsesSampler
+        Float dwh_dwo;
+        if (sampleReflection) {
+            r.wo = 2 * dot(r.wi, mm) * mm - r.wi;                                      // reflect(wi, m), util.cpp:763-765
+            r.eta = 1.0f; r.sampledType = EGlossyReflection;
+            if (r.wi.z * r.wo.z <= 0) return;
+            weight = weight * specOf(m.specular_reflectance);
+            dwh_dwo = 1.0f / (4.0f * dot(r.wo, mm));
+        } else {
+            if (cosThetaT == 0) return;
+            Float e = cosThetaT < 0 ? 1 / m_eta : m_eta;                               // refract(wi, m, eta, cosThetaT), util.cpp:767-772
+            r.wo = mm * (dot(r.wi, mm) * e + cosThetaT) - r.wi * e;
+            r.eta = cosThetaT < 0 ? m_eta : m_invEta; r.sampledType = EGlossyTransmission;
+            if (r.wi.z * r.wo.z >= 0) return;
+            Float factor = cosThetaT < 0 ? m_invEta : m_eta;
+            weight = weight * (specOf(m.specular_transmittance) * (factor * factor));
+            Float sqrtDenom = dot(r.wi, mm) + r.eta * dot(r.wo, mm);
+            dwh_dwo = (r.eta * r.eta * dot(r.wo, mm)) / (sqrtDenom * sqrtDenom);
+        }
+        weight = weight * distr.smithG1(r.wo, mm);
+        temporaryPdf *= std::abs(dwh_dwo);
+        r.pdf = temporaryPdf; r.weight = weight;
+        return;
+    }
     case GDB200_BSDF_PLASTIC: {                                                        // plastic.cpp:372-414 (both components requested)
         if (r.wi.z <= 0) return;
         Float unused; const Float Fi = fresnelDielectricExt(r.wi.z, unused, m.ior_ratio);
@@ -751,11 +834,11 @@ Float bsdfPdf(const gdb200_material &m, V3 wi, V3 wo, Measure measure)
     wi.z *= -1; wo.z *= -1;
     return nestedPdf(m, wi, wo, measure);
 }
-void bsdfSample(const gdb200_material &m, BSDFSample &r, Float sx, Float sy)
+void bsdfSample(const gdb200_material &m, BSDFSample &r, Float sx, Float sy, Sampler &sampler)
 {
     bool flipped = false;
     if (m.twosided && r.wi.z < 0) { r.wi.z *= -1; flipped = true; }
-    nestedSample(m, r, sx, sy);
+    nestedSample(m, r, sx, sy, sampler);
     if (flipped) {
         r.wi.z *= -1;
         if (!isZero(r.weight) && r.pdf != 0) r.wo.z *= -1;
@@ -1216,7 +1299,7 @@ void evaluate(const Scene &sc, const Config &cfg, Sampler &sampler, RayState &ma
 
         // ---- BSDF sampling and emitter hits, :737-826
         BSDFSample bs; bs.wi = main.its.wi;
-        { Float sx, sy; sampler.next2D(sx, sy); bsdfSample(mainBSDF, bs, sx, sy); }  // :456-457
+        { Float sx, sy; sampler.next2D(sx, sy); bsdfSample(mainBSDF, bs, sx, sy, sampler); }  // :456-457 (bRec.sampler = rRec.sampler)
         if (bs.pdf <= 0.0) break;                                                   // :739
         const V3 mainWo = toWorld(main.its.sh, bs.wo);
         Float mainWoDotGeoN = dot(main.its.geoN, mainWo);
@@ -1705,7 +1788,7 @@ int gdb200_oracle_path_render(const gdb200_scene_desc *desc, const gdb200_gpt_pa
                         }
                     }
                     BSDFSample bs; bs.wi = its.wi;
-                    { Float sx, sy; sampler.next2D(sx, sy); bsdfSample(bsdf, bs, sx, sy); }
+                    { Float sx, sy; sampler.next2D(sx, sy); bsdfSample(bsdf, bs, sx, sy, sampler); }
                     if (bs.pdf <= 0 || (bs.weight.x == 0 && bs.weight.y == 0 && bs.weight.z == 0)) break;
                     scattered = true;
                     const V3 wo = toWorld(its.sh, bs.wo);
@@ -1759,7 +1842,8 @@ int gdb200_oracle_bsdf_sample_batch(const gdb200_material *m, const double *wi, 
     g_fdrInt = &fdr; g_matBase = m;
     for (int i = 0; i < n; i++) {
         BSDFSample bs; bs.wi = v3(wi[0], wi[1], wi[2]);
-        bsdfSample(*m, bs, samples[2 * i], samples[2 * i + 1]);
+        Sampler fake; fake.key = 0; fake.n = 0; fake.forced = samples[3 * i + 2]; fake.useForced = true;   // FakeSampler of test_chisquare.cpp
+        bsdfSample(*m, bs, samples[3 * i], samples[3 * i + 1], fake);
         wo[3 * i] = bs.wo.x; wo[3 * i + 1] = bs.wo.y; wo[3 * i + 2] = bs.wo.z;
         weight[3 * i] = bs.weight.x; weight[3 * i + 1] = bs.weight.y; weight[3 * i + 2] = bs.weight.z;
         pdf[i] = bs.pdf; sampledType[i] = (int)bs.sampledType;

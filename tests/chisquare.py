@@ -23,12 +23,16 @@ def from_spherical(theta, phi):
 
 
 class ChiSquare:
-    def __init__(self, theta_bins=10, phi_bins=0, num_tests=1, sample_count=0, quad_nodes=24):
+    def __init__(self, theta_bins=10, phi_bins=0, num_tests=1, sample_count=0, quad_nodes=12, quad_cells=4):
         self.tb, self.pb = theta_bins, phi_bins or 2 * theta_bins
         self.num_tests = num_tests
         self.sample_count = sample_count or self.tb * self.pb * 1000
         self.tolerance = self.sample_count * 1e-4
-        self.nodes, self.weights = np.polynomial.legendre.leggauss(quad_nodes)
+        # composite Gauss-Legendre rule per bin (quad_cells sub-intervals of quad_nodes points per axis): densities with a
+        # kink or jump inside a bin (critical angle of a rough dielectric) need the subdivision
+        x, w = np.polynomial.legendre.leggauss(quad_nodes)
+        self.nodes = np.concatenate([(x + 2 * c + 1) / quad_cells - 1 for c in range(quad_cells)])
+        self.weights = np.concatenate([w / quad_cells for _ in range(quad_cells)])
 
     def fill(self, directions, weights, discrete_mask, pdf_fn):
         """directions [n,3], weights [n] (0 for failed samples), discrete_mask [n]; pdf_fn(dirs, discrete) -> [m]."""

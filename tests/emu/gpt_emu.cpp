@@ -77,7 +77,7 @@ extern "C" int gdb200_emu_bsdf_sample_batch(const gdb200_material *m, const doub
     static HostScene hs; emuMaterial(m, hs);
     for (int i = 0; i < n; i++) {
         BSDFSample bs;
-        bsdfSample(hs.host.materials[0], mk(wi[0], wi[1], wi[2]), samples[2 * i], samples[2 * i + 1], bs);
+        bsdfSample(hs.host.materials[0], mk(wi[0], wi[1], wi[2]), samples[3 * i], samples[3 * i + 1], samples[3 * i + 2], bs);
         wo[3 * i] = bs.wo.x; wo[3 * i + 1] = bs.wo.y; wo[3 * i + 2] = bs.wo.z;
         weight[3 * i] = bs.weight.x; weight[3 * i + 1] = bs.weight.y; weight[3 * i + 2] = bs.weight.z;
         pdf[i] = bs.pdf; sampledType[i] = (int)bs.sampledType;

@@ -35,7 +35,7 @@ def compare(got, ref, max_flip_frac=2e-3):
 
 
 @pytest.mark.parametrize("scene_name", ["cbox_diffuse", "cbox_glossy", "cbox_glossy_delta", "cbox_materials", "cbox_env",
-                                        "cbox_mesh_lights", "atrium", "cbox_smooth", "cbox_point", "cbox_dof"])
+                                        "cbox_mesh_lights", "atrium", "cbox_smooth", "cbox_point", "cbox_dof", "cbox_roughglass"])
 def test_tracer_matches_oracle(oracle, scene_name):
     w = h = 96
     desc = {"cbox_diffuse": lambda: scenes.cbox_diffuse(w, h), "cbox_glossy": lambda: scenes.cbox_glossy(w, h),
@@ -46,7 +46,8 @@ def test_tracer_matches_oracle(oracle, scene_name):
             "atrium": lambda: scenes.atrium(w, 54, columns=4, segments=12, rings=6),   # 1.2k triangles: BVH path
             "cbox_smooth": lambda: scenes.cbox_smooth(w, h),                    # vertex normals, smooth mesh emitter
             "cbox_point": lambda: scenes.cbox_point(w, h),                      # point emitter (EDiscrete light samples)
-            "cbox_dof": lambda: scenes.cbox_dof(w, h)}[scene_name]()            # thinlens sensor (aperture samples)
+            "cbox_dof": lambda: scenes.cbox_dof(w, h),                          # thinlens sensor (aperture samples)
+            "cbox_roughglass": lambda: scenes.cbox_roughglass(w, h)}[scene_name]()   # roughdielectric (glossy transmission)
     integ = gdb200.GPTIntegrator(reconstructL1=False, reconstructL2=False)
     scene = gdb200.Scene(desc)
     got = integ.trace(scene, spp=16, seed=3)

@@ -19,14 +19,15 @@ def render(oracle):
                     "delta": lambda w, h: scenes.cbox_glossy(w, h, delta_variant=True),
                     "materials": scenes.cbox_materials, "env": scenes.cbox_env,
                     "mesh_lights": scenes.cbox_mesh_lights, "smooth": scenes.cbox_smooth,
-                    "point": scenes.cbox_point, "dof": scenes.cbox_dof}[name](n, n)
+                    "point": scenes.cbox_point, "dof": scenes.cbox_dof,
+                    "roughglass": scenes.cbox_roughglass}[name](n, n)
             prm = scenes.default_params(spp=spp, seed=seed, **kw)
             cache[key] = (desc, prm) + oracle.gpt(desc, prm, threads=8)
         return cache[key]
     return run
 
 
-@pytest.mark.parametrize("name", ["diffuse", "glossy", "delta", "materials", "env", "mesh_lights", "smooth", "point", "dof"])
+@pytest.mark.parametrize("name", ["diffuse", "glossy", "delta", "materials", "env", "mesh_lights", "smooth", "point", "dof", "roughglass"])
 def test_primal_matches_plain_path_tracer(oracle, render, name):
     """E[throughput + direct] == E[Li] (gpt.cpp:1489-1662 = path/path.cpp) for any shift strategy."""
     desc, prm, out, _, _ = render(name, n=40, spp=64)
@@ -35,7 +36,8 @@ def test_primal_matches_plain_path_tracer(oracle, render, name):
     assert np.isfinite(prim).all() and (prim >= 0).all()
     for c in range(3):
         a, b = prim[..., c].mean(), li[..., c].mean()
-        assert abs(a - b) <= 0.03 * b, (name, c, a, b)      # two independent 64-spp estimates of the same mean
+        tol = 0.05 if name == "roughglass" else 0.03        # caustics through rough glass: heavier-tailed estimates (+-2 % at 128 spp over seeds)
+        assert abs(a - b) <= tol * b, (name, c, a, b)       # two independent 64-spp estimates of the same mean
 
 
 def test_film_weights_follow_the_accumulation_rule(render):
