@@ -76,6 +76,12 @@ GDB_HD V3 xfNormal(const Float *inv, V3 v)   // transform.h:203-211
     return mk(inv[0] * v.x + inv[4] * v.y + inv[8] * v.z, inv[1] * v.x + inv[5] * v.y + inv[9] * v.z,
               inv[2] * v.x + inv[6] * v.y + inv[10] * v.z);
 }
+GDB_HD void coordinateSystem(V3 a, V3 &b, V3 &c)            // util.cpp:592-601
+{
+    if (fabs(a.x) > fabs(a.y)) { const Float invLen = 1.0 / sqrt(a.x * a.x + a.z * a.z); c = mk(a.z * invLen, 0.0, -a.x * invLen); }
+    else { const Float invLen = 1.0 / sqrt(a.y * a.y + a.z * a.z); c = mk(0.0, a.z * invLen, -a.y * invLen); }
+    b = cross(c, a);
+}
 GDB_HD void computeShadingFrame(V3 n, V3 dpdu, Frame &f)    // util.cpp:603-608
 {
     f.n = n;
@@ -100,7 +106,7 @@ struct DMaterial {
     Spec reflectance, specR, specT, eta, k; Float alpha, iorRatio, bsdfEta;
     Float fdrInt, fdrExt, specSamplingWeight, invEta2;       // plastic.cpp:188-206
 };
-enum { EM_RECT = 0, EM_MESH = 1, EM_ENV = 2, EM_POINT = 3 };
+enum { EM_RECT = 0, EM_MESH = 1, EM_ENV = 2, EM_POINT = 3, EM_SPHERE = 4 };
 // pdfDiscrete = samplingWeight * normalization (scene.h:855-857).  Mesh emitters: triangles [triFirst, triFirst+triCount) of
 // emTris in the mesh's own order, area CDF (triCount+1 entries) at emTriCdf[cdfFirst], invArea = 1 / surface area.
 struct DEmitter { int kind, rect, triFirst, triCount, cdfFirst, pad; Spec radiance; Float pdfDiscrete, invArea; V3 position; };
@@ -974,6 +980,42 @@ GDB_D Spec sampleEmitterDirectVisibleImpl(DRec &dRec, Float sx, Float sy, bool &
         dRec.d = dRec.d * invDist;
         dRec.pdf = 1;
         value = em.radiance * (invDist * invDist);
+    } else if (em.kind == EM_SPHERE) {                                               // sphere.cpp:283-355 (Shirley et al. cone sampling), then area.cpp:158-176
+        const DSphere &sp = c_sceneG->spheres[em.rect];
+        const V3 refToCenter = sp.center - dRec.ref;
+        const Float refDist2 = len2(refToCenter), invRefDist = (Float)1 / sqrt(refDist2);
+        const Float sinAlpha = sp.radius * invRefDist;
+        if (sinAlpha < 1 - kEpsilon) {
+            const Float cosAlpha = sqrt(fmax(0.0, (Float)1.0f - sinAlpha * sinAlpha));
+            const Float cosTheta = (1 - sx) + sx * cosAlpha, sinTheta = sqrt(fmax(0.0, (Float)1.0f - cosTheta * cosTheta));   // warp.cpp:54-63
+            const Float phi = (Float)2.0f * kPi * sy, sinPhi = sin(phi), cosPhi = cos(phi);
+            Frame fr; fr.n = refToCenter * invRefDist; coordinateSystem(fr.n, fr.s, fr.t);
+            dRec.d = toWorld(fr, mk(cosPhi * sinTheta, sinPhi * sinTheta, cosTheta));
+            dRec.pdf = kInvTwoPi / (1 - cosAlpha);
+            const Float projDist = dot(refToCenter, dRec.d);
+            const Float baseT = refDist2 / projDist;
+            const V3 query = dRec.ref + dRec.d * baseT;
+            const V3 queryToCenter = sp.center - query;
+            const Float queryDist2 = len2(queryToCenter), queryProjDist = dot(queryToCenter, dRec.d);
+            double nearT, farT;
+            if (!solveQuadratic(1.0, -2 * queryProjDist, queryDist2 - sp.radius * sp.radius, nearT, farT)) nearT = queryProjDist;
+            dRec.dist = baseT + nearT;
+            dRec.n = normalize(dRec.d * nearT - queryToCenter);
+            dRec.p = sp.center + dRec.n * sp.radius;
+        } else {
+            const Float z = (Float)1.0f - (Float)2.0f * sy, r = sqrt(fmax(0.0, (Float)1.0f - z * z));                       // warp.cpp:25-31
+            const Float phi = (Float)2.0f * kPi * sx;
+            const V3 d = mk(r * cos(phi), r * sin(phi), z);
+            dRec.p = sp.center + d * sp.radius; dRec.n = d;
+            dRec.d = dRec.p - dRec.ref;
+            const Float dist2 = len2(dRec.d);
+            dRec.dist = sqrt(dist2);
+            dRec.d = dRec.d / dRec.dist;
+            dRec.pdf = em.invArea * dist2 / fabs(dot(dRec.d, dRec.n));
+        }
+        if (sp.flip) dRec.n = dRec.n * -1.0;
+        if (dot(dRec.d, dRec.refN) >= 0 && dot(dRec.d, dRec.n) < 0 && dRec.pdf != 0) value = em.radiance / dRec.pdf;   // area.cpp:158-176
+        else { dRec.pdf = 0.0; value = splat(0); }
     } else {
         if (em.kind == EM_RECT) {
             const DRect &s = c_sceneG->rects[em.rect];
@@ -1038,6 +1080,14 @@ GDB_D Float pdfEmitterDirect(const DRec &dRec)
     Float pdf = 0.0;
     if (em.kind == EM_ENV) pdf = envPdfDirection(xfVector(c_scene.env.toObject, dRec.d));
     else if (em.kind == EM_POINT) pdf = 0.0;                                         // point.cpp:149-151 for a solid-angle query
+    else if (em.kind == EM_SPHERE) {                                                 // area.cpp:178-186 + sphere.cpp:357-387
+        if (dot(dRec.d, dRec.refN) >= 0 && dot(dRec.d, dRec.n) < 0) {
+            const DSphere &sp = c_sceneG->spheres[em.rect];
+            const Float invRefDist = (Float)1.0f / len(sp.center - dRec.ref), sinAlpha = sp.radius * invRefDist;
+            if (sinAlpha < 1 - kEpsilon) pdf = kInvTwoPi / (1 - sqrt(fmax(0.0, 1 - sinAlpha * sinAlpha)));
+            else pdf = em.invArea * dRec.dist * dRec.dist / fabs(dot(dRec.d, dRec.n));
+        }
+    }
     else if (dot(dRec.d, dRec.refN) >= 0 && dot(dRec.d, dRec.n) < 0) {
         const Float invArea = em.kind == EM_RECT ? c_sceneG->rects[em.rect].invArea : em.invArea;
         pdf = invArea * (dRec.dist * dRec.dist) / fabs(dot(dRec.d, dRec.n));

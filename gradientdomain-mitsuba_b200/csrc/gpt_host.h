@@ -215,12 +215,14 @@ inline int flattenScene(const gdb200_scene_desc *d, HostScene *s)
     const bool useBvh = meshTriTotal > kMaxTris || getenv("GDB200_FORCE_BVH") != nullptr;
     double scale = 0;                                   // scene scale for the padding of the fp32 bounds
     for (int k = 0; k < 3; k++) scale = std::max(scale, std::abs(c.camera_to_world[4 * k + 3]));
-    std::vector<int> rectOfShape(d->n_shapes, -1), emTriFirstOfShape(d->n_shapes, -1);
+    std::vector<int> rectOfShape(d->n_shapes, -1), emTriFirstOfShape(d->n_shapes, -1), sphereOfShape(d->n_shapes, -1);
     std::vector<double> areaOfShape(d->n_shapes, 0.0);
     for (int i = 0; i < d->n_shapes; i++) {
         const gdb200_shape &sh = d->shapes[i];
         if (sh.material < 0 || sh.material >= d->n_materials) return set_error(GDB200_ERR_ARGUMENT, "shape %d: bad material index", i);
         if (sh.emitter >= d->n_emitters) return set_error(GDB200_ERR_ARGUMENT, "shape %d: bad emitter index", i);
+        if (sh.emitter >= 0 && (d->emitters[sh.emitter].type != GDB200_EMITTER_AREA || d->emitters[sh.emitter].shape != i))
+            return set_error(GDB200_ERR_ARGUMENT, "shape %d: emitter %d belongs to another shape", i, sh.emitter);
         if (sh.type == GDB200_SHAPE_RECTANGLE) {                                     // rectangle.cpp:100-110
             if (h.nRects >= kMaxRects) return set_error(GDB200_ERR_ARGUMENT, "too many rectangles (limit %d)", kMaxRects);
             if (sh.to_world[12] != 0 || sh.to_world[13] != 0 || sh.to_world[14] != 0 || sh.to_world[15] != 1)
@@ -235,10 +237,10 @@ inline int flattenScene(const gdb200_scene_desc *d, HostScene *s)
             rectOfShape[i] = h.nRects++;
         } else if (sh.type == GDB200_SHAPE_SPHERE) {
             if (h.nSpheres >= kMaxSpheres) return set_error(GDB200_ERR_ARGUMENT, "too many spheres (limit %d)", kMaxSpheres);
-            if (sh.emitter >= 0) return set_error(GDB200_ERR_ARGUMENT, "shape %d: sphere emitters are not supported yet", i);
+            sphereOfShape[i] = h.nSpheres;
             DSphere &sp = h.spheres[h.nSpheres++];
             sp.center = mk(sh.center[0], sh.center[1], sh.center[2]); sp.radius = sh.radius; sp.flip = sh.flip_normals;
-            sp.material = sh.material; sp.emitter = -1;
+            sp.material = sh.material; sp.emitter = sh.emitter;
         } else if (sh.type == GDB200_SHAPE_MESH) {
             if (sh.first_tri < 0 || sh.tri_count < 0 || sh.first_tri + (long long)sh.tri_count > d->n_triangles)
                 return set_error(GDB200_ERR_ARGUMENT, "shape %d: triangle range out of bounds", i);
@@ -350,6 +352,11 @@ inline int flattenScene(const gdb200_scene_desc *d, HostScene *s)
         if (e.shape < 0 || e.shape >= d->n_shapes || d->shapes[e.shape].emitter != i)
             return set_error(GDB200_ERR_ARGUMENT, "emitter %d: area emitter and its shape must reference each other", i);
         if (rectOfShape[e.shape] >= 0) { o.kind = EM_RECT; o.rect = rectOfShape[e.shape]; }
+        else if (sphereOfShape[e.shape] >= 0) {                                      // sphere.cpp:126-128: m_invSurfaceArea = 1 / (4 pi r^2)
+            o.kind = EM_SPHERE; o.rect = sphereOfShape[e.shape];
+            const double r = d->shapes[e.shape].radius;
+            o.invArea = 1 / (4 * kPi * r * r);
+        }
         else if (emTriFirstOfShape[e.shape] >= 0) {
             const gdb200_shape &sh = d->shapes[e.shape];
             if (sh.tri_count < 1) return set_error(GDB200_ERR_ARGUMENT, "emitter %d: Encountered an empty triangle mesh!", i);
@@ -367,7 +374,7 @@ inline int flattenScene(const gdb200_scene_desc *d, HostScene *s)
                 s->emTriCdf[o.cdfFirst + sh.tri_count] = 1.0;
             }
             o.invArea = (Float)1.0f / areaSum;
-        } else return set_error(GDB200_ERR_ARGUMENT, "emitter %d: area emitters are supported on rectangles and triangle meshes only", i);
+        } else return set_error(GDB200_ERR_ARGUMENT, "emitter %d: area emitters are supported on rectangles, spheres and triangle meshes only", i);
     }
     return GDB200_OK;
 }

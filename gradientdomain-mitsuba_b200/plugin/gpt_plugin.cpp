@@ -188,8 +188,8 @@ struct FlatScene {
 			}
 			if (shape->isEmitter()) {
 				const Emitter *e = shape->getEmitter();
-				if (e->getClass()->getName() != "AreaLight" || (s.type != GDB200_SHAPE_RECTANGLE && s.type != GDB200_SHAPE_MESH))
-					SLog(EError, "gdb200: 'area' emitters are supported on rectangles and triangle meshes");
+				if (e->getClass()->getName() != "AreaLight")
+					SLog(EError, "gdb200: only 'area' emitters can be attached to shapes");
 				gdb200_emitter em;
 				memset(&em, 0, sizeof(em));
 				em.type = GDB200_EMITTER_AREA;

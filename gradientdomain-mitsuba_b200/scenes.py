@@ -212,11 +212,16 @@ class SceneBuilder:
             sh.emitter = len(self.emitters) - 1
         return len(self.shapes) - 1
 
-    def sphere(self, center, radius, material, flip_normals=False):
+    def sphere(self, center, radius, material, flip_normals=False, radiance=None):
         sh = Shape()
         sh.type, sh.material, sh.emitter, sh.flip_normals = SHAPE_SPHERE, material, -1, int(flip_normals)
         sh.center, sh.radius = D3(*center), radius
         self.shapes.append(sh)
+        if radiance is not None:                       # area emitter on a sphere (sphere.cpp:283-387)
+            e = Emitter()
+            e.shape, e.type, e.radiance, e.sampling_weight = len(self.shapes) - 1, EMITTER_AREA, D3(*radiance), 1.0
+            self.emitters.append(e)
+            sh.emitter = len(self.emitters) - 1
         return len(self.shapes) - 1
 
     def mesh(self, vertices, triangles, material, radiance=None, normals=None):
@@ -516,6 +521,19 @@ def cbox_roughglass(width=256, height=256):
     b.sphere((-0.45, -0.65, 0.25), 0.35, frosted)
     b.sphere((0.5, -0.7, 0.4), 0.3, clear)
     b.box((0.0, -0.85, -0.4), (0.35, 0.15, 0.25), 30.0, b.material(reflectance=WHITE))
+    return b.build()
+
+
+def cbox_sphere_lights(width=256, height=256):
+    """Sphere area emitters (Sphere::sampleDirect cone sampling / pdfDirect, sphere.cpp:283-387): a small bulb inside the
+    box, and a big inward-facing (flipNormals) dome around everything that is sampled from inside (uniform-sphere branch)."""
+    b = _cornell(width, height, boxes=True)
+    b.emitters.clear()
+    b.shapes[5].emitter = -1
+    black = b.material(reflectance=(0, 0, 0))
+    b.sphere((0.25, 0.55, 0.1), 0.12, black, radiance=(30.0, 24.0, 14.0))
+    b.sphere((0, 0, 1.5), 4.0, black, flip_normals=True, radiance=(0.2, 0.3, 0.5))
+    b.sphere((-0.5, -0.7, 0.45), 0.3, b.material(type=BSDF_ROUGHCONDUCTOR, alpha=0.1, eta=CU_ETA, k=CU_K))
     return b.build()
 
 

@@ -284,13 +284,11 @@ class _Loader:
                 b.emitters.append(e)
                 sh.emitter = len(b.emitters) - 1
         elif typ == "sphere":
-            if radiance is not None:
-                raise Gdb200Error("sphere emitters are not supported yet")
             # sphere.cpp:107-121: objectToWorld = toWorld * scale(1/s) * translate(center), s = |toWorld(1,0,0)|, radius *= s
             s_ = np.linalg.norm(to_world[:3, 0]) if "toWorld" in p.values else 1.0
             center = (to_world @ np.array([c / s_ for c in p.get("center", (0.0, 0.0, 0.0))] + [1.0]))[:3]
             radius = p.get("radius", 1.0) * s_
-            b.sphere(center, radius, mat, flip_normals=flip)
+            b.sphere(center, radius, mat, flip_normals=flip, radiance=radiance)
         elif typ == "cube":
             verts = [(1, -1, -1), (1, -1, 1), (-1, -1, 1), (-1, -1, -1), (1, 1, -1), (-1, 1, -1), (-1, 1, 1), (1, 1, 1),
                      (1, -1, -1), (1, 1, -1), (1, 1, 1), (1, -1, 1), (1, -1, 1), (1, 1, 1), (-1, 1, 1), (-1, -1, 1),

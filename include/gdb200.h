@@ -159,12 +159,12 @@ typedef struct gdb200_material {
     int    nonlinear;                   /* plastic: nonlinear colour shifts (plastic.cpp:176)                       */
 } gdb200_material;
 
-enum { GDB200_EMITTER_AREA   = 0,     /* src/emitters/area.cpp on a rectangle or a triangle mesh                */
+enum { GDB200_EMITTER_AREA   = 0,     /* src/emitters/area.cpp on a rectangle, a sphere or a triangle mesh      */
        GDB200_EMITTER_ENVMAP = 1,     /* src/emitters/envmap.cpp: the scene's environment emitter (at most one) */
        GDB200_EMITTER_POINT  = 2 };   /* src/emitters/point.cpp: isotropic point light (the EDiscrete branch of gpt.cpp:668-672) */
 
 typedef struct gdb200_emitter {
-    int    shape;                       /* area: the rectangle / mesh shape that emits; envmap, point: -1 */
+    int    shape;                       /* area: the rectangle / sphere / mesh shape that emits; envmap, point: -1 */
     int    type;                        /* GDB200_EMITTER_*                            */
     double radiance[3];                 /* area: radiance; point: intensity            */
     double sampling_weight;             /* emitter.cpp:103, default 1                  */

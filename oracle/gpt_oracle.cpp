@@ -1005,6 +1005,42 @@ Spec sampleEmitterDirectVisible(const Scene &sc, DRec &dRec, Float sx, Float sy,
         value = specOf(em.radiance) * (invDist * invDist);
     } else {
         const Shape &s = sc.shapes[em.shape];
+        if (s.d.type == GDB200_SHAPE_SPHERE) {                                      // Sphere::sampleDirect, sphere.cpp:283-355
+            const V3 m_center = specOf(s.d.center); const Float m_radius = s.d.radius, m_invSurfaceArea = 1 / (4 * PI * m_radius * m_radius);
+            const V3 refToCenter = m_center - dRec.ref;
+            const Float refDist2 = lengthSquared(refToCenter);
+            const Float invRefDist = static_cast<Float>(1) / std::sqrt(refDist2);
+            const Float sinAlpha = m_radius * invRefDist;
+            if (sinAlpha < 1 - Epsilon) {
+                Float cosAlpha = std::sqrt(std::max(0.0, 1.0f - sinAlpha * sinAlpha));
+                Float cosTheta = (1 - sx) + sx * cosAlpha, sinTheta = std::sqrt(std::max(0.0, 1.0f - cosTheta * cosTheta));   // warp.cpp:54-63
+                Float sinPhi = std::sin(2.0f * PI * sy), cosPhi = std::cos(2.0f * PI * sy);
+                Frame fr; fr.n = refToCenter * invRefDist; coordinateSystem(fr.n, fr.s, fr.t);
+                dRec.d = toWorld(fr, v3(cosPhi * sinTheta, sinPhi * sinTheta, cosTheta));
+                dRec.pdf = INV_TWOPI / (1 - cosAlpha);
+                const Float projDist = dot(refToCenter, dRec.d);
+                const Float baseT = refDist2 / projDist;
+                const V3 query = dRec.ref + dRec.d * baseT;
+                const V3 queryToCenter = m_center - query;
+                const Float queryDist2 = lengthSquared(queryToCenter), queryProjDist = dot(queryToCenter, dRec.d);
+                Float A = 1.0f, B = -2 * queryProjDist, C = queryDist2 - m_radius * m_radius;
+                double nearT, farT;
+                if (!solveQuadratic(A, B, C, nearT, farT)) nearT = queryProjDist;
+                dRec.dist = baseT + nearT;
+                dRec.n = normalize(dRec.d * nearT - queryToCenter);
+                dRec.p = m_center + dRec.n * m_radius;
+            } else {
+                Float z = 1.0f - 2.0f * sy, r = std::sqrt(std::max(0.0, 1.0f - z * z));           // squareToUniformSphere, warp.cpp:25-31
+                V3 d = v3(r * std::cos(2.0f * PI * sx), r * std::sin(2.0f * PI * sx), z);
+                dRec.p = m_center + d * m_radius; dRec.n = d;
+                dRec.d = dRec.p - dRec.ref;
+                Float dist2 = lengthSquared(dRec.d);
+                dRec.dist = std::sqrt(dist2);
+                dRec.d = dRec.d / dRec.dist;
+                dRec.pdf = m_invSurfaceArea * dist2 / std::abs(dot(dRec.d, dRec.n));
+            }
+            if (s.d.flip_normals) dRec.n = dRec.n * -1.0;
+        } else {
         if (s.d.type == GDB200_SHAPE_RECTANGLE) {                                   // rectangle.cpp:210-216
             dRec.p = xfPoint(s.d.to_world, v3(sx * 2 - 1, sy * 2 - 1, 0));
             dRec.n = s.frame.n;
@@ -1029,6 +1065,7 @@ Spec sampleEmitterDirectVisible(const Scene &sc, DRec &dRec, Float sx, Float sy,
         dRec.d = dRec.d / dRec.dist;
         Float dp = std::abs(dot(dRec.d, dRec.n));
         dRec.pdf *= dp != 0 ? (distSquared / dp) : 0.0;
+        }
         if (dot(dRec.d, dRec.refN) >= 0 && dot(dRec.d, dRec.n) < 0 && dRec.pdf != 0) value = specOf(em.radiance) / dRec.pdf;   // area.cpp:158-176
         else { dRec.pdf = 0.0; value = spec(0); }
     }
@@ -1049,8 +1086,16 @@ Float pdfEmitterDirect(const Scene &sc, const DRec &dRec)
     else if (em.type == GDB200_EMITTER_POINT) pdf = 0.0;                           // point.cpp:149-151, solid-angle query
     else if (dot(dRec.d, dRec.refN) >= 0 && dot(dRec.d, dRec.n) < 0) {
         const Shape &s = sc.shapes[em.shape];
+        if (s.d.type == GDB200_SHAPE_SPHERE) {                                      // Sphere::pdfDirect, sphere.cpp:357-387
+            const Float m_radius = s.d.radius;
+            const V3 refToCenter = specOf(s.d.center) - dRec.ref;
+            const Float invRefDist = (Float)1.0f / length(refToCenter), sinAlpha = m_radius * invRefDist;
+            if (sinAlpha < 1 - Epsilon) pdf = INV_TWOPI / (1 - std::sqrt(std::max(0.0, 1 - sinAlpha * sinAlpha)));
+            else pdf = (1 / (4 * PI * m_radius * m_radius)) * dRec.dist * dRec.dist / std::abs(dot(dRec.d, dRec.n));
+        } else {
         const Float pdfPos = s.d.type == GDB200_SHAPE_RECTANGLE ? s.invArea : sc.meshSampling[em.shape].invSurfaceArea;
         pdf = pdfPos * (dRec.dist * dRec.dist) / std::abs(dot(dRec.d, dRec.n));
+        }
     }
     return pdf * (em.sampling_weight * sc.emNormalization);
 }

@@ -29,6 +29,7 @@ SCENES = {"cbox_diffuse": lambda w, h: scenes.cbox_diffuse(w, h), "cbox_glossy":
           "atrium": lambda w, h: scenes.atrium(w, h, columns=3, segments=8, rings=4),   # > table size: BVH path
           "cbox_point": lambda w, h: scenes.cbox_point(w, h),               # point emitter: the EDiscrete branches of the NEE shift
           "cbox_dof": lambda w, h: scenes.cbox_dof(w, h),                   # thinlens sensor: aperture samples
+          "cbox_sphere_lights": lambda w, h: scenes.cbox_sphere_lights(w, h),   # sphere area emitters (cone / uniform-sphere sampling)
           "cbox_roughglass": lambda w, h: scenes.cbox_roughglass(w, h),     # roughdielectric: refraction half-vector Jacobian, in-BSDF sampler draw
           "cbox_smooth": lambda w, h: scenes.cbox_smooth(w, h)}             # vertex normals (shading != geometric normal), smooth mesh emitter
 
@@ -115,7 +116,7 @@ def test_environment_scene_parameters(oracle, emu, kw):
 def test_unsupported_scenes_fail_loudly(emu):
     b = scenes._cornell(8, 8)
     b.shapes[b.sphere((0, 0, 0), 0.2, 0)].emitter = 0
-    with pytest.raises(RuntimeError, match="sphere emitters"):
+    with pytest.raises(RuntimeError, match="belongs to another shape"):
         emu.gpt(b.build(), scenes.default_params(spp=1))
     b = scenes._cornell(8, 8)
     b.material(type=scenes.BSDF_DIELECTRIC, twosided=True)

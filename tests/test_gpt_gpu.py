@@ -35,7 +35,7 @@ def compare(got, ref, max_flip_frac=2e-3):
 
 
 @pytest.mark.parametrize("scene_name", ["cbox_diffuse", "cbox_glossy", "cbox_glossy_delta", "cbox_materials", "cbox_env",
-                                        "cbox_mesh_lights", "atrium", "cbox_smooth", "cbox_point", "cbox_dof", "cbox_roughglass"])
+                                        "cbox_mesh_lights", "atrium", "cbox_smooth", "cbox_point", "cbox_dof", "cbox_roughglass", "cbox_sphere_lights"])
 def test_tracer_matches_oracle(oracle, scene_name):
     w = h = 96
     desc = {"cbox_diffuse": lambda: scenes.cbox_diffuse(w, h), "cbox_glossy": lambda: scenes.cbox_glossy(w, h),
@@ -47,7 +47,8 @@ def test_tracer_matches_oracle(oracle, scene_name):
             "cbox_smooth": lambda: scenes.cbox_smooth(w, h),                    # vertex normals, smooth mesh emitter
             "cbox_point": lambda: scenes.cbox_point(w, h),                      # point emitter (EDiscrete light samples)
             "cbox_dof": lambda: scenes.cbox_dof(w, h),                          # thinlens sensor (aperture samples)
-            "cbox_roughglass": lambda: scenes.cbox_roughglass(w, h)}[scene_name]()   # roughdielectric (glossy transmission)
+            "cbox_roughglass": lambda: scenes.cbox_roughglass(w, h),            # roughdielectric (glossy transmission)
+            "cbox_sphere_lights": lambda: scenes.cbox_sphere_lights(w, h)}[scene_name]()   # sphere area emitters
     integ = gdb200.GPTIntegrator(reconstructL1=False, reconstructL2=False)
     scene = gdb200.Scene(desc)
     got = integ.trace(scene, spp=16, seed=3)
@@ -193,8 +194,8 @@ def test_scene_outside_supported_subset_fails_loudly():
     b = scenes._cornell(16, 16)
     glass = b.material(type=scenes.BSDF_DIELECTRIC, ior_ratio=1.5)
     idx = b.sphere((0, 0, 0), 0.2, glass)
-    b.shapes[idx].emitter = 0                       # sphere emitters are not in the supported subset
-    with pytest.raises(gdb200.Gdb200Error, match="sphere emitters"):
+    b.shapes[idx].emitter = 0                       # an emitter can only sit on the shape it names
+    with pytest.raises(gdb200.Gdb200Error, match="belongs to another shape"):
         gdb200.Scene(b.build())
 
 
