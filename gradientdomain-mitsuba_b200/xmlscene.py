@@ -443,8 +443,8 @@ class _Loader:
 
 def load_obj(path, to_world=None, face_normals=False):
     """Wavefront OBJ subset of src/shapes/obj.cpp: `v`, `vn`, polygon `f` (fan-triangulated), negative indices.  Vertex
-    normals are used when every face vertex carries one (and faceNormals is off); a file without `vn` must ask for
-    faceNormals=true, because Mitsuba would otherwise synthesise smooth normals (TriMesh::computeNormals)."""
+    normals are used when every face vertex carries one (and faceNormals is off); a file without `vn` gets the smooth
+    normals Mitsuba synthesises (TriMesh::computeNormals) unless faceNormals=true."""
     to_world = np.eye(4) if to_world is None else to_world
     v, vn, faces = [], [], []
     with open(path) as f:
@@ -466,8 +466,6 @@ def load_obj(path, to_world=None, face_normals=False):
                 for k in range(1, len(corners) - 1):
                     faces.append((corners[0], corners[k], corners[k + 1]))
     have_normals = bool(faces) and all(c[1] is not None for f_ in faces for c in f_)
-    if not have_normals and not face_normals:
-        raise Gdb200Error(f"{path}: no vertex normals; set faceNormals=true (smooth-normal synthesis is not supported)")
     nmat = np.linalg.inv(to_world[:3, :3]).T
     verts, nrms, tris, index = [], [], [], {}
     for f_ in faces:
@@ -482,7 +480,42 @@ def load_obj(path, to_world=None, face_normals=False):
                     nrms.append(n / np.linalg.norm(n))
             tri.append(index[key])
         tris.append(tuple(tri))
-    return verts, tris, (nrms if (have_normals and not face_normals) else None)
+    if have_normals and not face_normals:
+        return verts, tris, nrms
+    if face_normals:
+        return verts, tris, None
+    return verts, tris, compute_normals(verts, tris)
+
+
+def _unit_angle(u, v):
+    """unitAngle (vector.h): numerically robust angle between two unit vectors."""
+    if float(u @ v) < 0:
+        return math.pi - 2 * math.asin(min(1.0, 0.5 * float(np.linalg.norm(v + u))))
+    return 2 * math.asin(min(1.0, 0.5 * float(np.linalg.norm(v - u))))
+
+
+def compute_normals(verts, tris):
+    """TriMesh::computeNormals (trimesh.cpp:631-672): angle-weighted vertex normals (Thuermer & Wuethrich) for a mesh that
+    comes without normals and without faceNormals=true; vertices nobody touches get the bogus (1, 0, 0)."""
+    P = [np.asarray(v, float) for v in verts]
+    N = [np.zeros(3) for _ in P]
+    for tri in tris:
+        n = None
+        for i in range(3):
+            v0, v1, v2 = P[tri[i]], P[tri[(i + 1) % 3]], P[tri[(i + 2) % 3]]
+            side_a, side_b = v1 - v0, v2 - v0
+            if i == 0:
+                n = np.cross(side_a, side_b)
+                length = np.linalg.norm(n)
+                if length == 0:
+                    break
+                n = n / length
+            N[tri[i]] = N[tri[i]] + n * _unit_angle(side_a / np.linalg.norm(side_a), side_b / np.linalg.norm(side_b))
+    out = []
+    for n in N:
+        length = np.linalg.norm(n)
+        out.append(n / length if length != 0 else np.array([1.0, 0.0, 0.0]))
+    return out
 
 
 def load_image(path):

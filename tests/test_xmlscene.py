@@ -193,3 +193,16 @@ def test_integrator_validation_applies_to_scene_files():
       <emitter type="point"><point name="position" x="0" y="1" z="0"/><rgb name="intensity" value="1,1,1"/></emitter></scene>"""
     with pytest.raises(gdb200.Gdb200Error, match="Cannot display two reconstructions"):
         gdb200.load_scene(xml).integrator()
+
+
+def test_obj_without_normals_gets_angle_weighted_vertex_normals(tmp_path):
+    """TriMesh::computeNormals (trimesh.cpp:631-672): a closed octahedron's synthesised normals point radially."""
+    obj = tmp_path / "octa.obj"
+    obj.write_text("v 1 0 0\nv -1 0 0\nv 0 1 0\nv 0 -1 0\nv 0 0 1\nv 0 0 -1\n"
+                   "f 1 3 5\nf 3 2 5\nf 2 4 5\nf 4 1 5\nf 3 1 6\nf 2 3 6\nf 4 2 6\nf 1 4 6\n")
+    verts, tris, nrms = xmlscene.load_obj(str(obj))
+    assert len(verts) == 6 and len(tris) == 8 and nrms is not None
+    for v, n in zip(verts, nrms):
+        assert np.allclose(n, np.asarray(v) / np.linalg.norm(v), atol=1e-12)
+    _, _, flat = xmlscene.load_obj(str(obj), face_normals=True)
+    assert flat is None
