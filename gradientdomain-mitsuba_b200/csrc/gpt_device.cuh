@@ -106,10 +106,13 @@ struct DMaterial {
     Spec reflectance, specR, specT, eta, k; Float alpha, iorRatio, bsdfEta;
     Float fdrInt, fdrExt, specSamplingWeight, invEta2;       // plastic.cpp:188-206
 };
-enum { EM_RECT = 0, EM_MESH = 1, EM_ENV = 2, EM_POINT = 3, EM_SPHERE = 4 };
+enum { EM_RECT = 0, EM_MESH = 1, EM_ENV = 2, EM_POINT = 3, EM_SPHERE = 4, EM_SPOT = 5 };
 // pdfDiscrete = samplingWeight * normalization (scene.h:855-857).  Mesh emitters: triangles [triFirst, triFirst+triCount) of
 // emTris in the mesh's own order, area CDF (triCount+1 entries) at emTriCdf[cdfFirst], invArea = 1 / surface area.
-struct DEmitter { int kind, rect, triFirst, triCount, cdfFirst, pad; Spec radiance; Float pdfDiscrete, invArea; V3 position; };
+struct DEmitter {
+    int kind, rect, triFirst, triCount, cdfFirst, pad; Spec radiance; Float pdfDiscrete, invArea; V3 position;
+    Float toLocal[9], cutoffAngle, cosCutoff, cosBeam, invTransition;   // spot (spot.cpp:89-94): inverse rotation rows, cone angles
+};
 struct DEmTri { V3 p0, p1, p2; int normals, pad; };   // normals: as DTri
 // Environment map (envmap.cpp): top-level texels as Float RGB, the float CDF tables of envmap.cpp:263-311.
 struct DEnv {
@@ -980,6 +983,19 @@ GDB_D Spec sampleEmitterDirectVisibleImpl(DRec &dRec, Float sx, Float sy, bool &
         dRec.d = dRec.d * invDist;
         dRec.pdf = 1;
         value = em.radiance * (invDist * invDist);
+    } else if (em.kind == EM_SPOT) {                                                 // spot.cpp:184-200 with falloffCurve :105-125 (constant texture)
+        dRec.p = em.position; dRec.n = mk(0, 0, 0);
+        dRec.d = dRec.p - dRec.ref;
+        dRec.dist = len(dRec.d);
+        const Float invDist = (Float)1.0f / dRec.dist;
+        dRec.d = dRec.d * invDist;
+        dRec.pdf = 1;
+        const V3 dw = -dRec.d;
+        const Float cosTheta = em.toLocal[6] * dw.x + em.toLocal[7] * dw.y + em.toLocal[8] * dw.z;             // Frame::cosTheta of trafo.inverse()(-d), transform.h:180-181
+        Float falloff = 1;
+        if (cosTheta <= em.cosCutoff) falloff = 0;
+        else if (cosTheta < em.cosBeam) falloff = (em.cutoffAngle - acos(cosTheta)) * em.invTransition;
+        value = em.radiance * falloff * (invDist * invDist);
     } else if (em.kind == EM_SPHERE) {                                               // sphere.cpp:283-355 (Shirley et al. cone sampling), then area.cpp:158-176
         const DSphere &sp = c_sceneG->spheres[em.rect];
         const V3 refToCenter = sp.center - dRec.ref;
@@ -1079,7 +1095,7 @@ GDB_D Float pdfEmitterDirect(const DRec &dRec)
     const DEmitter &em = c_sceneG->emitters[dRec.emitter];
     Float pdf = 0.0;
     if (em.kind == EM_ENV) pdf = envPdfDirection(xfVector(c_scene.env.toObject, dRec.d));
-    else if (em.kind == EM_POINT) pdf = 0.0;                                         // point.cpp:149-151 for a solid-angle query
+    else if (em.kind == EM_POINT || em.kind == EM_SPOT) pdf = 0.0;                   // point.cpp:149-151, spot.cpp:202-204 for a solid-angle query
     else if (em.kind == EM_SPHERE) {                                                 // area.cpp:178-186 + sphere.cpp:357-387
         if (dot(dRec.d, dRec.refN) >= 0 && dot(dRec.d, dRec.n) < 0) {
             const DSphere &sp = c_sceneG->spheres[em.rect];

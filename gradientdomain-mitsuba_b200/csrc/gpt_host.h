@@ -348,6 +348,14 @@ inline int flattenScene(const gdb200_scene_desc *d, HostScene *s)
             o.kind = EM_POINT; o.rect = -1; o.position = mk(e.position[0], e.position[1], e.position[2]);
             continue;
         }
+        if (e.type == GDB200_EMITTER_SPOT) {                                         // spot.cpp:70-94
+            if (!(e.cutoff_angle >= e.beam_width)) return set_error(GDB200_ERR_ARGUMENT, "emitter %d: spot cutoffAngle must be >= beamWidth", i);
+            o.kind = EM_SPOT; o.rect = -1; o.position = mk(e.position[0], e.position[1], e.position[2]);
+            for (int k = 0; k < 9; k++) o.toLocal[k] = e.to_local[k];
+            o.cutoffAngle = e.cutoff_angle; o.cosCutoff = std::cos(e.cutoff_angle); o.cosBeam = std::cos(e.beam_width);
+            o.invTransition = 1.0f / (e.cutoff_angle - e.beam_width);
+            continue;
+        }
         if (e.type != GDB200_EMITTER_AREA) return set_error(GDB200_ERR_ARGUMENT, "emitter %d: unknown type %d", i, e.type);
         if (e.shape < 0 || e.shape >= d->n_shapes || d->shapes[e.shape].emitter != i)
             return set_error(GDB200_ERR_ARGUMENT, "emitter %d: area emitter and its shape must reference each other", i);

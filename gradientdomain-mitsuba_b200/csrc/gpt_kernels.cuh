@@ -431,7 +431,7 @@ GDB_D void bounceBody(const GptArgs &a, int slot, int parity)
             neeEmitterRadiance = value * dRec.pdf;                                   // gpt.cpp:575
             neeWoLocal = toLocal(mits.sh, dRec.d);
             bsdfEvalPdf(mainBSDF, mits.wi, neeWoLocal, ESolidAngle, neeBsdfValue, neeBsdfPdf);   // gpt.cpp:588
-            atPointLight = c_sceneG->emitters[dRec.emitter].kind == EM_POINT;        // dRec.measure == EDiscrete; such an emitter is not "on a surface"
+            atPointLight = c_sceneG->emitters[dRec.emitter].kind == EM_POINT || c_sceneG->emitters[dRec.emitter].kind == EM_SPOT;        // dRec.measure == EDiscrete; such an emitter is not "on a surface"
             if (!neeVisible || atPointLight) neeBsdfPdf = 0;                         // gpt.cpp:592
             neeDistSq = len2(mits.p - dRec.p);                                       // gpt.cpp:595-596
             neeOppCos = dot(dRec.n, (mits.p - dRec.p)) / sqrt(neeDistSq);

@@ -207,13 +207,25 @@ struct FlatScene {
 				const Emitter *e = all[i].get();
 				const std::string cls = e->getClass()->getName();
 				if (cls == "AreaLight" || cls == "EnvironmentMap") continue;
-				if (cls != "PointEmitter")
+				if (cls != "PointEmitter" && cls != "SpotEmitter")
 					SLog(EError, "gdb200: emitter class \"%s\" is outside the supported hot-path subset", cls.c_str());
 				gdb200_emitter em;
 				memset(&em, 0, sizeof(em));
 				em.type = GDB200_EMITTER_POINT; em.shape = -1;
 				copySpectrum(e->getProperties().getSpectrum("intensity", Spectrum(1.0f)), em.radiance);
-				const Point pos = e->getWorldTransform()->eval(0)(Point(0.0f));
+				const Transform &emTrafo = e->getWorldTransform()->eval(0);
+				const Point pos = emTrafo(Point(0.0f));
+				if (cls == "SpotEmitter") {                           /* spot.cpp:70-75,199: cone angles in radians, trafo.inverse() on vectors */
+					const Properties &ep = e->getProperties();
+					if (ep.hasProperty("texture"))
+						SLog(EError, "gdb200: spot projection textures are outside the supported hot-path subset");
+					em.type = GDB200_EMITTER_SPOT;
+					const Float cutoff = ep.getFloat("cutoffAngle", 20);
+					em.cutoff_angle = degToRad(cutoff);
+					em.beam_width = degToRad(ep.getFloat("beamWidth", cutoff * 3.0f / 4.0f));
+					const Matrix4x4 &inv = emTrafo.getInverseMatrix();
+					for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) em.to_local[3 * r + c] = inv(r, c);
+				}
 				em.position[0] = pos.x; em.position[1] = pos.y; em.position[2] = pos.z;
 				em.sampling_weight = e->getSamplingWeight();
 				const size_t at = std::min(i, emitters.size());       /* keep Scene::m_emitters order: it defines the emitter CDF */

@@ -33,6 +33,7 @@ struct Transform {
 	Transform();
 	Transform inverse() const;
 	const Matrix4x4 &getMatrix() const;
+	const Matrix4x4 &getInverseMatrix() const;
 	Transform operator*(const Transform &) const;
 	Point operator()(const Point &) const;
 	Vector operator()(const Vector &) const;
@@ -40,6 +41,7 @@ struct Transform {
 	static Transform translate(const Vector &);
 	static Transform perspective(Float, Float, Float);
 };
+inline Float degToRad(Float value) { return value * (3.14159265358979323846 / 180.0f); }
 struct AnimatedTransform { const Transform &eval(Float) const; };
 struct Properties {
 	Properties(const std::string & = "");

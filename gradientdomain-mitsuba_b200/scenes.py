@@ -12,7 +12,7 @@ import numpy as np
 
 SHAPE_RECTANGLE, SHAPE_SPHERE, SHAPE_MESH = 0, 1, 2
 BSDF_DIFFUSE, BSDF_ROUGHCONDUCTOR, BSDF_CONDUCTOR, BSDF_DIELECTRIC, BSDF_PLASTIC, BSDF_ROUGHDIELECTRIC = 0, 1, 2, 3, 4, 5
-EMITTER_AREA, EMITTER_ENVMAP, EMITTER_POINT = 0, 1, 2
+EMITTER_AREA, EMITTER_ENVMAP, EMITTER_POINT, EMITTER_SPOT = 0, 1, 2, 3
 MICROFACET_BECKMANN, MICROFACET_GGX = 0, 1
 
 D16 = ctypes.c_double * 16
@@ -41,7 +41,8 @@ class Material(ctypes.Structure):
 
 class Emitter(ctypes.Structure):
     _fields_ = [("shape", ctypes.c_int), ("type", ctypes.c_int), ("radiance", D3),
-                ("sampling_weight", ctypes.c_double), ("position", D3)]
+                ("sampling_weight", ctypes.c_double), ("position", D3), ("to_local", ctypes.c_double * 9),
+                ("cutoff_angle", ctypes.c_double), ("beam_width", ctypes.c_double)]
 
 
 class EnvMap(ctypes.Structure):
@@ -160,6 +161,21 @@ class SceneBuilder:
         """Isotropic point emitter (point.cpp)."""
         e = Emitter()
         e.shape, e.type, e.radiance, e.sampling_weight, e.position = -1, EMITTER_POINT, D3(*intensity), sampling_weight, D3(*position)
+        self.emitters.append(e)
+        return len(self.emitters) - 1
+
+    def spot_light(self, to_world, intensity, cutoff_angle=20.0, beam_width=None, sampling_weight=1.0):
+        """Spot emitter (spot.cpp): at to_world's origin, shining along its +z axis; angles in degrees, beamWidth defaults to
+        3/4 of cutoffAngle (spot.cpp:71-74)."""
+        m = np.asarray(to_world, dtype=np.float64).reshape(4, 4)
+        beam_width = cutoff_angle * 3.0 / 4.0 if beam_width is None else beam_width
+        if not cutoff_angle >= beam_width:
+            raise ValueError("spot: cutoffAngle must be >= beamWidth")          # Assert at spot.cpp:75
+        e = Emitter()
+        e.shape, e.type, e.radiance, e.sampling_weight = -1, EMITTER_SPOT, D3(*intensity), sampling_weight
+        e.position = D3(*m[:3, 3])
+        e.to_local = (ctypes.c_double * 9)(*np.linalg.inv(m)[:3, :3].reshape(-1))
+        e.cutoff_angle, e.beam_width = math.radians(cutoff_angle), math.radians(beam_width)
         self.emitters.append(e)
         return len(self.emitters) - 1
 
@@ -310,7 +326,7 @@ CU_ETA, CU_K = (0.2004, 0.9240, 1.1022), (3.9129, 2.4528, 2.1421)
 AL_ETA, AL_K = (1.6574, 0.8803, 0.5212), (9.2238, 6.2695, 4.8370)
 
 
-def _cornell(width, height, boxes=True, rfilter="box", aperture_radius=0.0, focus_distance=0.0):
+def _cornell(width, height, boxes=True, rfilter="box", aperture_radius=0.0, focus_distance=0.0, light=True):
     cam = make_camera(width, height, origin=(0, 0, 3.9), target=(0, 0, 0), up=(0, 1, 0), fov_deg=39.3077,
                       aperture_radius=aperture_radius, focus_distance=focus_distance)
     b = SceneBuilder(cam, rfilter=rfilter)
@@ -321,7 +337,8 @@ def _cornell(width, height, boxes=True, rfilter="box", aperture_radius=0.0, focu
     b.rectangle((0, 0, -1), (1, 0, 0), (0, 1, 0), white)             # back wall, normal +z
     b.rectangle((-1, 0, 0), (0, 0, -1), (0, 1, 0), red)              # left wall, normal +x
     b.rectangle((1, 0, 0), (0, 0, 1), (0, 1, 0), green)              # right wall, normal -x
-    b.rectangle((0, 0.99, 0), (0.25, 0, 0), (0, 0, 0.25), black, radiance=(17.0, 12.0, 4.0))   # light, normal -y
+    if light:
+        b.rectangle((0, 0.99, 0), (0.25, 0, 0), (0, 0, 0.25), black, radiance=(17.0, 12.0, 4.0))   # light, normal -y
     if boxes:
         b.box((0.33, -0.7, 0.35), (0.3, 0.3, 0.3), -17.0, white)     # short box
         b.box((-0.35, -0.4, -0.3), (0.3, 0.6, 0.3), 17.0, white)     # tall box
@@ -547,6 +564,19 @@ def cbox_point(width=256, height=256):
     b.sphere((0.33, -0.1, 0.35), 0.3, rough)
     b.sphere((-0.5, -0.7, 0.55), 0.3, shiny)
     b.point_light((-0.3, 0.5, 0.4), (1.5, 1.2, 0.9))
+    return b.build()
+
+
+def cbox_spot(width=256, height=256):
+    """Spot-emitter coverage (spot.cpp): the glossy Cornell box lit only by two spot lights whose cones cut across the
+    walls and the spheres -- full-intensity core, linear falloff ring (the acos ramp) and the dark outside of the cone all
+    inside the image; the second light is tilted, so its inverse rotation is a general matrix."""
+    b = _cornell(width, height, boxes=False, light=False)
+    rough = b.material(type=BSDF_ROUGHCONDUCTOR, alpha=0.3, eta=CU_ETA, k=CU_K)
+    b.sphere((0.33, -0.1, 0.35), 0.3, rough)
+    b.sphere((-0.5, -0.7, 0.55), 0.3, b.material(reflectance=(0.7, 0.7, 0.3)))
+    b.spot_light(look_at((0.0, 0.9, 0.2), (0.1, -1.0, 0.3), (0, 0, 1)), (6.0, 5.0, 4.0), cutoff_angle=38.0, beam_width=20.0)
+    b.spot_light(look_at((-0.8, 0.3, -0.6), (0.4, -0.5, 0.4), (0, 1, 0)), (1.0, 1.5, 2.5), cutoff_angle=25.0)
     return b.build()
 
 

@@ -4,7 +4,7 @@
 A scene that selects the reference's path loads unchanged: `<integrator type="gpt">` with the reference's
 parameter names and defaults (gpt.cpp:1194-1210), a `perspective` / `thinlens` sensor with its `sampler` and `multifilm`
 film, `rectangle` / `sphere` / `cube` / `obj` shapes, `diffuse` / `roughconductor` / `conductor` / `dielectric` /
-`plastic` / `roughdielectric` / `twosided` BSDFs, `area` / `point` / `envmap` emitters, `<default>` / `$variables`, `<ref id=...>`.
+`plastic` / `roughdielectric` / `twosided` BSDFs, `area` / `point` / `spot` / `envmap` emitters, `<default>` / `$variables`, `<ref id=...>`.
 Anything else raises (no silent fallback), with the element's name in the message.
 
     parsed = load_scene("scene.xml", defines={"spp": "64"})
@@ -322,6 +322,14 @@ class _Loader:
             if "intensity" not in p.values:
                 raise Gdb200Error("point: the default intensity (D65) needs Mitsuba's spectral data; give 'intensity' as RGB")
             self.builder.point_light(pos, p.get("intensity"), p.get("samplingWeight", 1.0))
+        elif typ == "spot":
+            if "intensity" not in p.values:
+                raise Gdb200Error("spot: give 'intensity' as RGB")
+            if "texture" in p.values or any(c.tag == "texture" for c in el):
+                raise Gdb200Error("spot: projection textures are outside the supported hot-path subset")
+            cutoff = p.get("cutoffAngle", 20.0)
+            self.builder.spot_light(p.get("toWorld", np.eye(4)), p.get("intensity"), cutoff, p.get("beamWidth", cutoff * 3.0 / 4.0),
+                                    p.get("samplingWeight", 1.0))
         elif typ == "envmap":
             fn = p.get("filename")
             path = fn if os.path.isabs(fn) else os.path.join(self.base_dir, fn)

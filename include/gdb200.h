@@ -161,14 +161,17 @@ typedef struct gdb200_material {
 
 enum { GDB200_EMITTER_AREA   = 0,     /* src/emitters/area.cpp on a rectangle, a sphere or a triangle mesh      */
        GDB200_EMITTER_ENVMAP = 1,     /* src/emitters/envmap.cpp: the scene's environment emitter (at most one) */
-       GDB200_EMITTER_POINT  = 2 };   /* src/emitters/point.cpp: isotropic point light (the EDiscrete branch of gpt.cpp:668-672) */
+       GDB200_EMITTER_POINT  = 2,     /* src/emitters/point.cpp: isotropic point light (the EDiscrete branch of gpt.cpp:668-672) */
+       GDB200_EMITTER_SPOT   = 3 };   /* src/emitters/spot.cpp: point light with a linear cone falloff (no projection texture)  */
 
 typedef struct gdb200_emitter {
     int    shape;                       /* area: the rectangle / sphere / mesh shape that emits; envmap, point: -1 */
     int    type;                        /* GDB200_EMITTER_*                            */
-    double radiance[3];                 /* area: radiance; point: intensity            */
+    double radiance[3];                 /* area: radiance; point, spot: intensity      */
     double sampling_weight;             /* emitter.cpp:103, default 1                  */
-    double position[3];                 /* point: world position                       */
+    double position[3];                 /* point, spot: world position                 */
+    double to_local[9];                 /* spot: rows of the inverse world transform's 3x3 block (trafo.inverse() applied to a vector, spot.cpp:199); the cone axis is local +z */
+    double cutoff_angle, beam_width;    /* spot: radians (spot.cpp:71-74, defaults 20 deg and 3/4 of it); cutoff_angle >= beam_width */
 } gdb200_emitter;
 
 /* Latitude-longitude environment map (envmap.cpp).  Texels are the top MIP level as the reference holds it

@@ -968,6 +968,21 @@ bool envFillDirectSamplingRecord(const Scene &sc, DRec &dRec, V3 o, V3 d)
     return true;
 }
 
+// SpotEmitter::falloffCurve, spot.cpp:105-125, for the constant "texture" (the default): d is the world direction
+// leaving the light, brought into the light's frame by the inverse transform's 3x3 block (transform.h:175-183).
+Float spotFalloff(const gdb200_emitter &em, V3 dWorld)
+{
+    const double *m = em.to_local;
+    const V3 d = v3(m[0] * dWorld.x + m[1] * dWorld.y + m[2] * dWorld.z, m[3] * dWorld.x + m[4] * dWorld.y + m[5] * dWorld.z,
+                    m[6] * dWorld.x + m[7] * dWorld.y + m[8] * dWorld.z);
+    const Float cosTheta = d.z;
+    const Float m_cosCutoffAngle = std::cos(em.cutoff_angle), m_cosBeamWidth = std::cos(em.beam_width);     // spot.cpp:89-94
+    const Float m_invTransitionWidth = 1.0f / (em.cutoff_angle - em.beam_width);
+    if (cosTheta <= m_cosCutoffAngle) return 0.0;
+    if (cosTheta >= m_cosBeamWidth) return 1.0;
+    return (em.cutoff_angle - std::acos(cosTheta)) * m_invTransitionWidth;
+}
+
 // Scene::sampleEmitterDirectVisible, scene.cpp:855-879 (+ pmf.h:124-188; area.cpp:158-176 over shape.cpp:102-114 with
 // rectangle.cpp:210-216 or trimesh.cpp:412-423 / triangle.cpp:24-50; envmap.cpp:516-544).  Returns value = Le/pdf
 // (0 when occluded).
@@ -1003,6 +1018,16 @@ Spec sampleEmitterDirectVisible(const Scene &sc, DRec &dRec, Float sx, Float sy,
         dRec.n = v3(0, 0, 0);
         dRec.discrete = true;
         value = specOf(em.radiance) * (invDist * invDist);
+    } else if (em.type == GDB200_EMITTER_SPOT) {                                    // spot.cpp:184-200
+        dRec.p = specOf(em.position);
+        dRec.pdf = 1.0f;
+        dRec.d = dRec.p - dRec.ref;
+        dRec.dist = length(dRec.d);
+        Float invDist = 1.0f / dRec.dist;
+        dRec.d = dRec.d * invDist;
+        dRec.n = v3(0, 0, 0);
+        dRec.discrete = true;
+        value = specOf(em.radiance) * spotFalloff(em, -dRec.d) * (invDist * invDist);
     } else {
         const Shape &s = sc.shapes[em.shape];
         if (s.d.type == GDB200_SHAPE_SPHERE) {                                      // Sphere::sampleDirect, sphere.cpp:283-355
@@ -1083,7 +1108,7 @@ Float pdfEmitterDirect(const Scene &sc, const DRec &dRec)
     const gdb200_emitter &em = sc.ems[dRec.emitter];
     Float pdf = 0.0;
     if (em.type == GDB200_EMITTER_ENVMAP) pdf = envPdfDirection(sc.env, xfVector(sc.env.toObject, dRec.d));
-    else if (em.type == GDB200_EMITTER_POINT) pdf = 0.0;                           // point.cpp:149-151, solid-angle query
+    else if (em.type == GDB200_EMITTER_POINT || em.type == GDB200_EMITTER_SPOT) pdf = 0.0;   // point.cpp:149-151, spot.cpp:202-204: solid-angle query
     else if (dot(dRec.d, dRec.refN) >= 0 && dot(dRec.d, dRec.n) < 0) {
         const Shape &s = sc.shapes[em.shape];
         if (s.d.type == GDB200_SHAPE_SPHERE) {                                      // Sphere::pdfDirect, sphere.cpp:357-387
@@ -1272,7 +1297,7 @@ void evaluate(const Scene &sc, const Config &cfg, Sampler &sampler, RayState &ma
             Spec mainEmitterRadiance = value * dRec.pdf;                            // :575
             V3 mainWoLocal = toLocal(main.its.sh, dRec.d);
             Spec mainBSDFValue = bsdfEval(mainBSDF, main.its.wi, mainWoLocal, ESolidAngle);                  // :588
-            const bool onSurfaceSolidAngle = sc.ems[dRec.emitter].type != GDB200_EMITTER_POINT && !dRec.discrete;   // emitter->isOnSurface() && dRec.measure == ESolidAngle
+            const bool onSurfaceSolidAngle = sc.ems[dRec.emitter].type != GDB200_EMITTER_POINT && sc.ems[dRec.emitter].type != GDB200_EMITTER_SPOT && !dRec.discrete;   // emitter->isOnSurface() && dRec.measure == ESolidAngle
             const bool mainAtPointLight = dRec.discrete;                            // :670
             Float mainBsdfPdf = (onSurfaceSolidAngle && mainEmitterVisible) ? bsdfPdf(mainBSDF, main.its.wi, mainWoLocal, ESolidAngle) : 0;  // :592
             Float mainDistanceSquared = lengthSquared(main.its.p - dRec.p);         // :595-596

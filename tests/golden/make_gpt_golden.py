@@ -22,7 +22,7 @@ SCENES = {
     "cbox_diffuse": lambda: scenes.cbox_diffuse(W, H), "cbox_glossy": lambda: scenes.cbox_glossy(W, H),
     "cbox_glossy_delta": lambda: scenes.cbox_glossy(W, H, delta_variant=True), "cbox_materials": lambda: scenes.cbox_materials(W, H),
     "cbox_env": lambda: scenes.cbox_env(W, H), "cbox_mesh_lights": lambda: scenes.cbox_mesh_lights(W, H),
-    "cbox_smooth": lambda: scenes.cbox_smooth(W, H), "cbox_point": lambda: scenes.cbox_point(W, H), "cbox_dof": lambda: scenes.cbox_dof(W, H),
+    "cbox_smooth": lambda: scenes.cbox_smooth(W, H), "cbox_point": lambda: scenes.cbox_point(W, H), "cbox_spot": lambda: scenes.cbox_spot(W, H), "cbox_dof": lambda: scenes.cbox_dof(W, H),
     "cbox_roughglass": lambda: scenes.cbox_roughglass(W, H), "cbox_sphere_lights": lambda: scenes.cbox_sphere_lights(W, H),
     "atrium": lambda: scenes.atrium(W, H, columns=3, segments=8, rings=4), "cbox_gaussian": lambda: scenes.cbox_diffuse(W, H, rfilter="gaussian"),
 }

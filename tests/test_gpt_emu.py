@@ -28,6 +28,7 @@ SCENES = {"cbox_diffuse": lambda w, h: scenes.cbox_diffuse(w, h), "cbox_glossy":
           "cbox_mesh_lights": lambda w, h: scenes.cbox_mesh_lights(w, h),  # mesh emitters, plastic, twosided
           "atrium": lambda w, h: scenes.atrium(w, h, columns=3, segments=8, rings=4),   # > table size: BVH path
           "cbox_point": lambda w, h: scenes.cbox_point(w, h),               # point emitter: the EDiscrete branches of the NEE shift
+          "cbox_spot": lambda w, h: scenes.cbox_spot(w, h),                 # spot emitters: cone falloff, only Dirac lights in the scene
           "cbox_dof": lambda w, h: scenes.cbox_dof(w, h),                   # thinlens sensor: aperture samples
           "cbox_sphere_lights": lambda w, h: scenes.cbox_sphere_lights(w, h),   # sphere area emitters (cone / uniform-sphere sampling)
           "cbox_roughglass": lambda w, h: scenes.cbox_roughglass(w, h),     # roughdielectric: refraction half-vector Jacobian, in-BSDF sampler draw
@@ -146,7 +147,7 @@ def test_reconstruction_filters(oracle, emu, rfilter):
 
 
 @pytest.mark.parametrize("scene_name,no_tail,cap", [("cbox_glossy", False, None), ("cbox_mesh_lights", True, None),
-                                                    ("cbox_env", True, 100), ("cbox_point", True, None),
+                                                    ("cbox_env", True, 100), ("cbox_point", True, None), ("cbox_spot", False, None),
                                                     ("cbox_roughglass", True, None)])
 def test_queued_wavefront_kernels(oracle, emu, scene_name, no_tail, cap, monkeypatch):
     """Block mode of the emulation: gpt_generate_kernel / gpt_compact_kernel / gpt_bounce_kernel<2> / gpt_tail_kernel as

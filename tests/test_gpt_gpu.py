@@ -35,7 +35,7 @@ def compare(got, ref, max_flip_frac=2e-3):
 
 
 @pytest.mark.parametrize("scene_name", ["cbox_diffuse", "cbox_glossy", "cbox_glossy_delta", "cbox_materials", "cbox_env",
-                                        "cbox_mesh_lights", "atrium", "cbox_smooth", "cbox_point", "cbox_dof", "cbox_roughglass", "cbox_sphere_lights"])
+                                        "cbox_mesh_lights", "atrium", "cbox_smooth", "cbox_point", "cbox_spot", "cbox_dof", "cbox_roughglass", "cbox_sphere_lights"])
 def test_tracer_matches_oracle(oracle, scene_name):
     w = h = 96
     desc = {"cbox_diffuse": lambda: scenes.cbox_diffuse(w, h), "cbox_glossy": lambda: scenes.cbox_glossy(w, h),
@@ -45,6 +45,7 @@ def test_tracer_matches_oracle(oracle, scene_name):
             "cbox_mesh_lights": lambda: scenes.cbox_mesh_lights(w, h),     # TriMesh emitters, plastic, twosided
             "atrium": lambda: scenes.atrium(w, 54, columns=4, segments=12, rings=6),   # 1.2k triangles: BVH path
             "cbox_smooth": lambda: scenes.cbox_smooth(w, h),                    # vertex normals, smooth mesh emitter
+            "cbox_spot": lambda: scenes.cbox_spot(w, h),                        # spot emitters (cone falloff)
             "cbox_point": lambda: scenes.cbox_point(w, h),                      # point emitter (EDiscrete light samples)
             "cbox_dof": lambda: scenes.cbox_dof(w, h),                          # thinlens sensor (aperture samples)
             "cbox_roughglass": lambda: scenes.cbox_roughglass(w, h),            # roughdielectric (glossy transmission)

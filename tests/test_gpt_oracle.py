@@ -19,7 +19,7 @@ def render(oracle):
                     "delta": lambda w, h: scenes.cbox_glossy(w, h, delta_variant=True),
                     "materials": scenes.cbox_materials, "env": scenes.cbox_env,
                     "mesh_lights": scenes.cbox_mesh_lights, "smooth": scenes.cbox_smooth,
-                    "point": scenes.cbox_point, "dof": scenes.cbox_dof,
+                    "point": scenes.cbox_point, "spot": scenes.cbox_spot, "dof": scenes.cbox_dof,
                     "roughglass": scenes.cbox_roughglass, "sphere_lights": scenes.cbox_sphere_lights}[name](n, n)
             prm = scenes.default_params(spp=spp, seed=seed, **kw)
             cache[key] = (desc, prm) + oracle.gpt(desc, prm, threads=8)
@@ -27,10 +27,10 @@ def render(oracle):
     return run
 
 
-@pytest.mark.parametrize("name", ["diffuse", "glossy", "delta", "materials", "env", "mesh_lights", "smooth", "point", "dof", "roughglass", "sphere_lights"])
+@pytest.mark.parametrize("name", ["diffuse", "glossy", "delta", "materials", "env", "mesh_lights", "smooth", "point", "spot", "dof", "roughglass", "sphere_lights"])
 def test_primal_matches_plain_path_tracer(oracle, render, name):
     """E[throughput + direct] == E[Li] (gpt.cpp:1489-1662 = path/path.cpp) for any shift strategy."""
-    desc, prm, out, _, _ = render(name, n=40, spp=64)
+    desc, prm, out, _, _ = render(name, n=40, spp=256 if name == "spot" else 64)   # spot: Dirac lights only, the highlight on the copper sphere carries 13 % of the energy
     li = oracle.path(desc, prm, threads=8)
     prim = out["-throughput"] + out["-direct"]
     assert np.isfinite(prim).all() and (prim >= 0).all()
@@ -93,3 +93,44 @@ def test_seed_changes_the_estimate_but_not_its_mean(oracle):
     b, _, _ = oracle.gpt(desc, scenes.default_params(spp=32, seed=2))
     assert not np.array_equal(a["-throughput"], b["-throughput"])
     assert abs(a["-throughput"].mean() - b["-throughput"].mean()) < 0.03 * a["-throughput"].mean()
+
+
+def test_spot_emitter_matches_closed_form(oracle):
+    """spot.cpp:105-125,184-200 against the closed form: a diffuse floor lit by one spot light, direct illumination only
+    (maxDepth 2): radiance = albedo/pi * I * falloff(angle to the axis) * cos(theta_floor) / r^2, falloff = 1 inside
+    beamWidth, 0 outside cutoffAngle, linear IN THE ANGLE between them."""
+    w = h = 32
+    cam = scenes.make_camera(w, h, origin=(0, 3, 0), target=(0, 0, 0), up=(0, 0, 1), fov_deg=60.0)
+    b = scenes.SceneBuilder(cam)
+    albedo, inten = np.array([0.6, 0.5, 0.4]), np.array([3.0, 2.0, 1.0])
+    b.rectangle((0, 0, 0), (2, 0, 0), (0, 0, -2), b.material(reflectance=tuple(albedo)))
+    pos, tgt, cutoff, beam = np.array([0.3, 1.2, -0.2]), np.array([-0.2, 0.0, 0.3]), 30.0, 15.0
+    b.spot_light(scenes.look_at(pos, tgt, (0, 1, 0)), tuple(inten), cutoff_angle=cutoff, beam_width=beam)
+    desc = b.build()
+    out, _, _ = oracle.gpt(desc, scenes.default_params(spp=256, seed=5, max_depth=2), threads=8)
+
+    s2c = np.array(desc.camera.sample_to_camera).reshape(4, 4)
+    c2w = np.array(desc.camera.camera_to_world).reshape(4, 4)
+    sub = (np.arange(8) + 0.5) / 8
+    py = np.broadcast_to((np.arange(h)[:, None] + sub[None]).reshape(h, 8, 1, 1), (h, 8, w, 8))
+    px = np.broadcast_to((np.arange(w)[:, None] + sub[None]).reshape(1, 1, w, 8), (h, 8, w, 8))
+    q = np.stack([px / w, py / h, np.zeros_like(px), np.ones_like(px)], -1) @ s2c.T
+    d = q[..., :3] / q[..., 3:]
+    d = (d / np.linalg.norm(d, axis=-1, keepdims=True)) @ c2w[:3, :3].T
+    o = c2w[:3, 3]
+    p = o + d * (-o[1] / d[..., 1])[..., None]                                  # floor y = 0
+    to_light = pos - p
+    r2 = (to_light ** 2).sum(-1)
+    axis = (tgt - pos) / np.linalg.norm(tgt - pos)
+    ang = np.degrees(np.arccos(np.clip(-(to_light / np.sqrt(r2)[..., None]) @ axis, -1, 1)))
+    fall = np.clip((cutoff - ang) / (cutoff - beam), 0.0, 1.0)
+    inside = (np.abs(p[..., 0]) <= 2) & (np.abs(p[..., 2]) <= 2)
+    expect = (inside * fall * (to_light[..., 1] / np.sqrt(r2)) / r2)[..., None] * (albedo / np.pi * inten)
+    expect = expect.mean(axis=(1, 3))
+    got = out["-throughput"]
+    assert (fall == 1).mean() > 0.02 and ((fall > 0) & (fall < 1)).mean() > 0.05 and (fall == 0).mean() > 0.3   # core, ramp, outside all in view
+    err = np.abs(got - expect)
+    assert err.max() <= 0.02 * expect.max() and err.mean() <= 5e-4 * expect.max()      # pixel-jitter noise at the cone edge only
+    lit = expect[..., 0] > 0.2 * expect[..., 0].max()
+    np.testing.assert_allclose(got[lit], expect[lit], rtol=0.03)
+    assert np.abs(out["-direct"]).max() == 0                                     # a Dirac light is never seen directly

@@ -176,7 +176,7 @@ def test_film_must_be_multifilm(fragment, message):
     ('<integrator type="gpt"/><shape type="hair"/>', 'shape plugin "hair"'),
     ('<integrator type="gpt"/><bsdf type="roughplastic"/>', 'BSDF plugin "roughplastic"'),
     ('<integrator type="gpt"/><bsdf type="conductor"/>', "spectral data files"),
-    ('<integrator type="gpt"/><emitter type="spot"/>', 'emitter plugin "spot"'),
+    ('<integrator type="gpt"/><emitter type="directional"/>', 'emitter plugin "directional"'),
     ('<integrator type="gpt"/><shape type="sphere"><ref id="nope"/></shape>', "not found"),
     ('<integrator type="gpt"><integer name="maxDepth" value="$depth"/></integrator>', r'"\$depth" was not specified'),
 ])
@@ -206,3 +206,40 @@ def test_obj_without_normals_gets_angle_weighted_vertex_normals(tmp_path):
         assert np.allclose(n, np.asarray(v) / np.linalg.norm(v), atol=1e-12)
     _, _, flat = xmlscene.load_obj(str(obj), face_normals=True)
     assert flat is None
+
+
+def test_spot_emitter_from_xml(tmp_path, oracle):
+    """<emitter type="spot"> (spot.cpp:70-75): lookat toWorld, cutoffAngle / beamWidth in degrees with the 3/4 default,
+    the inverse rotation the falloff uses; rendering the parsed scene equals rendering the builder's scene."""
+    xml = """<scene version="0.5.0"><integrator type="gpt"/>
+      <sensor type="perspective"><float name="fov" value="50"/>
+        <transform name="toWorld"><lookat origin="0,2,4" target="0,0,0" up="0,1,0"/></transform>
+        <sampler type="independent"><integer name="sampleCount" value="4"/></sampler>
+        <film type="multifilm"><integer name="width" value="24"/><integer name="height" value="16"/><rfilter type="box"/></film></sensor>
+      <shape type="rectangle"><transform name="toWorld"><rotate x="1" angle="-90"/><scale value="3"/></transform><bsdf type="diffuse"/></shape>
+      <emitter type="spot"><transform name="toWorld"><lookat origin="1,2,0.5" target="0,0,0" up="0,1,0"/></transform>
+        <rgb name="intensity" value="9,8,7"/><float name="cutoffAngle" value="32"/></emitter>
+      <emitter type="spot"><transform name="toWorld"><lookat origin="-1,1.5,0" target="-0.5,0,0.5"/></transform>
+        <rgb name="intensity" value="2,3,4"/><float name="cutoffAngle" value="40"/><float name="beamWidth" value="10"/>
+        <float name="samplingWeight" value="2"/></emitter></scene>"""
+    path = tmp_path / "spot.xml"
+    path.write_text(xml)
+    parsed = gdb200.load_scene(str(path))
+    d = parsed.desc
+    assert d.n_emitters == 2 and all(d.emitters[i].type == scenes.EMITTER_SPOT for i in range(2))
+    e0, e1 = d.emitters[0], d.emitters[1]
+    assert math.isclose(e0.cutoff_angle, math.radians(32)) and math.isclose(e0.beam_width, math.radians(24))
+    assert math.isclose(e1.cutoff_angle, math.radians(40)) and math.isclose(e1.beam_width, math.radians(10)) and e1.sampling_weight == 2
+    assert np.allclose(list(e0.position), [1, 2, 0.5])
+    axis = np.array([-1, -2, -0.5]) / np.linalg.norm([1, 2, 0.5])
+    assert np.allclose(np.array(list(e0.to_local)).reshape(3, 3) @ axis, [0, 0, 1], atol=1e-12)     # the cone axis is local +z
+    out, _, cnt = oracle.gpt(d, parsed.integrator().params(parsed.spp, parsed.seed))
+    assert cnt[0] == 24 * 16 * 4 and out["-throughput"].max() > 0.1 and (out["-throughput"].sum(-1) == 0).mean() > 0.1   # lit cone, dark outside
+
+    bad = xml.replace('<float name="cutoffAngle" value="32"/>', '<float name="cutoffAngle" value="10"/><float name="beamWidth" value="20"/>')
+    path.write_text(bad)
+    with pytest.raises(Exception, match="cutoffAngle"):
+        gdb200.load_scene(str(path))
+    path.write_text(xml.replace('<float name="cutoffAngle" value="32"/>', '<texture name="texture" type="bitmap"/>'))
+    with pytest.raises(Exception, match="projection textures"):
+        gdb200.load_scene(str(path))
