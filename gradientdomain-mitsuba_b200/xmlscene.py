@@ -3,7 +3,7 @@
 
 A scene that selects the reference's path loads unchanged: `<integrator type="gpt">` with the reference's
 parameter names and defaults (gpt.cpp:1194-1210), a `perspective` / `thinlens` sensor with its `sampler` and `multifilm`
-film, `rectangle` / `sphere` / `cube` / `obj` shapes, `diffuse` / `roughconductor` / `conductor` / `dielectric` /
+film, `rectangle` / `sphere` / `cube` / `obj` / `serialized` / `ply` shapes, `diffuse` / `roughconductor` / `conductor` / `dielectric` /
 `plastic` / `roughdielectric` / `twosided` BSDFs, `area` / `point` / `spot` / `envmap` emitters, `<default>` / `$variables`, `<ref id=...>`.
 Anything else raises (no silent fallback), with the element's name in the message.
 
@@ -20,6 +20,7 @@ import xml.etree.ElementTree as ET
 
 import numpy as np
 
+from . import meshio
 from . import scenes as S
 from ._ffi import Gdb200Error
 
@@ -306,8 +307,22 @@ class _Loader:
         elif typ == "obj":
             fn = p.get("filename")
             path = fn if os.path.isabs(fn) else os.path.join(self.base_dir, fn)
-            verts, tris, nrms = load_obj(path, to_world, face_normals=p.get("faceNormals", False))
+            verts, tris, nrms = load_obj(path, to_world, face_normals=p.get("faceNormals", False), flip_normals=flip)
             b.mesh(verts, tris, mat, radiance=radiance, normals=nrms)
+        elif typ in ("serialized", "ply"):
+            fn = p.get("filename")
+            path = fn if os.path.isabs(fn) else os.path.join(self.base_dir, fn)
+            if "maxSmoothAngle" in p.values:
+                raise Gdb200Error(f"{typ}: maxSmoothAngle (TriMesh::rebuildTopology) is outside the supported hot-path subset")
+            try:
+                if typ == "serialized":
+                    verts, tris, nrms = meshio.load_serialized(path, p.get("shapeIndex", 0), to_world, p.get("faceNormals", False), flip)
+                else:
+                    verts, tris, nrms = meshio.load_ply(path, to_world, p.get("faceNormals", False), flip)
+            except meshio.MeshError as e:
+                raise Gdb200Error(str(e))
+            b.mesh([tuple(v) for v in verts], [tuple(int(i) for i in t) for t in tris], mat, radiance=radiance,
+                   normals=None if nrms is None else [tuple(n) for n in nrms])
         else:
             raise Gdb200Error(f"shape plugin \"{typ}\" is outside the supported hot-path subset")
 
@@ -449,7 +464,7 @@ class _Loader:
         return parsed
 
 
-def load_obj(path, to_world=None, face_normals=False):
+def load_obj(path, to_world=None, face_normals=False, flip_normals=False):
     """Wavefront OBJ subset of src/shapes/obj.cpp: `v`, `vn`, polygon `f` (fan-triangulated), negative indices.  Vertex
     normals are used when every face vertex carries one (and faceNormals is off); a file without `vn` gets the smooth
     normals Mitsuba synthesises (TriMesh::computeNormals) unless faceNormals=true."""
@@ -488,11 +503,10 @@ def load_obj(path, to_world=None, face_normals=False):
                     nrms.append(n / np.linalg.norm(n))
             tri.append(index[key])
         tris.append(tuple(tri))
-    if have_normals and not face_normals:
-        return verts, tris, nrms
-    if face_normals:
-        return verts, tris, None
-    return verts, tris, compute_normals(verts, tris)
+    if face_normals:                                                                  # trimesh.cpp:610-622: flipNormals swaps the winding
+        return verts, ([(b_, a_, c_) for a_, b_, c_ in tris] if flip_normals else tris), None
+    nrms = nrms if have_normals else compute_normals(verts, tris)
+    return verts, tris, ([-n for n in nrms] if flip_normals else nrms)               # trimesh.cpp:624-628,662-664
 
 
 def _unit_angle(u, v):

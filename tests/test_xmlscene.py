@@ -243,3 +243,14 @@ def test_spot_emitter_from_xml(tmp_path, oracle):
     path.write_text(xml.replace('<float name="cutoffAngle" value="32"/>', '<texture name="texture" type="bitmap"/>'))
     with pytest.raises(Exception, match="projection textures"):
         gdb200.load_scene(str(path))
+
+
+def test_obj_flip_normals(tmp_path):
+    """flipNormals on a TriMesh (trimesh.cpp:610-628,662-664): vertex normals negated, or the winding swapped with faceNormals."""
+    (tmp_path / "t.obj").write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 3\n")
+    _, tris, nrms = xmlscene.load_obj(str(tmp_path / "t.obj"))
+    assert np.allclose(nrms, [(0, 0, 1)] * 3) and tris == [(0, 1, 2)]
+    _, tris, nrms = xmlscene.load_obj(str(tmp_path / "t.obj"), flip_normals=True)
+    assert np.allclose(nrms, [(0, 0, -1)] * 3) and tris == [(0, 1, 2)]
+    _, tris, nrms = xmlscene.load_obj(str(tmp_path / "t.obj"), face_normals=True, flip_normals=True)
+    assert nrms is None and tris == [(1, 0, 2)]
