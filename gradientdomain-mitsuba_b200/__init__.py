@@ -8,5 +8,5 @@ CUDA device is present the calls raise.
 from ._ffi import lib, Gdb200Error, Stats, library_path, pinned_empty, release_workspace  # noqa: F401
 from .poisson import PoissonSolver, SolverParams, poisson_solve, PoissonPlan  # noqa: F401
 from .gpt import GPTIntegrator, Scene, BUFFER_NAMES  # noqa: F401
-from . import scenes, synth, pfm, xmlscene, meshio  # noqa: F401
+from . import scenes, synth, pfm, exr, xmlscene, meshio  # noqa: F401
 from .xmlscene import load_scene  # noqa: F401

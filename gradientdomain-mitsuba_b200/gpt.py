@@ -168,8 +168,14 @@ class GPTIntegrator:
             out["-final"][...] = final                   # setBitmapMulti(reconstruction, BUFFER_FINAL), gpt.cpp:1468-1475
         return out
 
-    def save(self, dest, buffers):
-        """MultiFilm::develop for fileFormat "pfm" (multifilm.cpp:423-516): writes <dest>-final.pfm, -throughput.pfm,
-        -dx.pfm, -dy.pfm, -direct.pfm (float32 RGB, bottom-up scanlines) and returns the paths."""
+    def save(self, dest, buffers, file_format="pfm", component_format="float16"):
+        """MultiFilm::develop (multifilm.cpp:423-516): writes <dest>-final, -throughput, -dx, -dy, -direct as ".pfm"
+        (float32 RGB, bottom-up scanlines) or, for file_format "openexr" (the film's default), ".exr" (RGB, float16 or
+        float32, ZIP) and returns the paths."""
+        if file_format == "openexr":
+            from . import exr
+            return exr.save_multifilm(dest, buffers, component_format)
+        if file_format != "pfm":
+            raise ValueError("file_format must be \"openexr\" or \"pfm\"")
         from . import pfm
         return pfm.save_multifilm(dest, buffers)

@@ -81,10 +81,14 @@ def save_multifilm(dest, buffers):
 
 
 def load_multifilm(dest):
-    """The inverse of save_multifilm: {buffer name: float32 [h, w, 3]} for the files that exist."""
+    """The inverse of save_multifilm: {buffer name: float32 [h, w, 3]} for the files that exist -- ".pfm", or the ".exr"
+    files a MultiFilm writes by default (gdb200.exr)."""
     out = {}
     for name in BUFFER_NAMES:
         p = dest + name + ".pfm"
         if os.path.exists(p):
             out[name] = read_pfm(p)
+        elif os.path.exists(dest + name + ".exr"):
+            from .exr import read_exr
+            out[name] = read_exr(dest + name + ".exr")
     return out

@@ -37,6 +37,7 @@ class ParsedScene:
         self.integrator_kwargs = {}
         self.spp, self.seed, self.streams = 4, 0, 1        # sampler sampleCount default (independent.cpp:60)
         self.dest = None
+        self.file_format, self.component_format = "openexr", "float16"        # multifilm.cpp:110-117
 
     def integrator(self):
         from .gpt import GPTIntegrator
@@ -368,6 +369,16 @@ class _Loader:
             width, height = fp.get("width", width), fp.get("height", height)
             if any(k in fp.values for k in ("cropOffsetX", "cropOffsetY", "cropWidth", "cropHeight")):
                 raise Gdb200Error("film: crop windows are not supported yet")
+            parsed.file_format = str(fp.get("fileFormat", "openexr")).lower()                                    # multifilm.cpp:110-128
+            if parsed.file_format not in ("openexr", "pfm"):
+                raise Gdb200Error("The \"fileFormat\" parameter must either be equal to \"openexr\" or \"pfm\" (rgbe is outside the subset)")
+            if str(fp.get("pixelFormat", "rgb")).lower() != "rgb":
+                raise Gdb200Error("film: only pixelFormat=\"rgb\" is supported")
+            parsed.component_format = str(fp.get("componentFormat", "float16")).lower()                          # multifilm.cpp:116-117,206-215
+            if parsed.component_format not in ("float16", "float32"):
+                raise Gdb200Error("The \"componentFormat\" parameter must either be equal to \"float16\" or \"float32\" (uint32 is outside the subset)")
+            if parsed.file_format == "pfm":
+                parsed.component_format = "float32"                                                             # multifilm.cpp:222-235
             rf = next((c for c in fp.children if c.tag == "rfilter"), None)
             if rf is not None:
                 rfilter = rf.attrib["type"]

@@ -254,3 +254,22 @@ def test_obj_flip_normals(tmp_path):
     assert np.allclose(nrms, [(0, 0, -1)] * 3) and tris == [(0, 1, 2)]
     _, tris, nrms = xmlscene.load_obj(str(tmp_path / "t.obj"), face_normals=True, flip_normals=True)
     assert nrms is None and tris == [(1, 0, 2)]
+
+
+def test_film_file_format(tmp_path):
+    """multifilm.cpp:110-128,222-235: fileFormat defaults to openexr / float16; pfm forces float32; anything else raises."""
+    xml = """<scene version="0.5.0"><integrator type="gpt"/>
+      <sensor type="perspective"><film type="multifilm"><integer name="width" value="8"/><integer name="height" value="8"/>FMT</film></sensor>
+      <shape type="rectangle"><bsdf type="diffuse"/></shape>
+      <emitter type="point"><point name="position" x="0" y="0" z="1"/><rgb name="intensity" value="1,1,1"/></emitter></scene>"""
+    path = tmp_path / "f.xml"
+    for fmt, expect in (("", ("openexr", "float16")), ('<string name="fileFormat" value="PFM"/>', ("pfm", "float32")),
+                        ('<string name="componentFormat" value="float32"/>', ("openexr", "float32"))):
+        path.write_text(xml.replace("FMT", fmt))
+        parsed = gdb200.load_scene(str(path))
+        assert (parsed.file_format, parsed.component_format) == expect
+    for fmt, msg in (('<string name="fileFormat" value="rgbe"/>', "fileFormat"), ('<string name="componentFormat" value="uint32"/>', "componentFormat"),
+                     ('<string name="pixelFormat" value="luminance"/>', "pixelFormat")):
+        path.write_text(xml.replace("FMT", fmt))
+        with pytest.raises(Exception, match=msg):
+            gdb200.load_scene(str(path))

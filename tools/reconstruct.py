@@ -4,8 +4,9 @@ and color buffers are written to disk, so ... reconstruction parameters [can be 
 
     python tools/reconstruct.py <dest> [--preset L1D|L1Q|L1L|L2D|L2Q] [--alpha 0.2] [--out <file.pfm>]
 
-reads <dest>-dx.pfm, <dest>-dy.pfm, <dest>-throughput.pfm and (if present) <dest>-direct.pfm, solves on the GPU
-through gdb200_poisson_solve (no CPU path) and writes <dest>-final.pfm.
+reads <dest>-dx, <dest>-dy, <dest>-throughput and (if present) <dest>-direct as ".pfm" or ".exr" (a MultiFilm writes
+OpenEXR by default -- files rendered by the reference load as they are), solves on the GPU through gdb200_poisson_solve
+(no CPU path) and writes <dest>-final in the inputs' format (or to --out, by its extension).
 """
 import argparse
 import os
@@ -28,13 +29,18 @@ def main():
     bufs = pfm.load_multifilm(a.dest)
     for need in ("-dx", "-dy", "-throughput"):
         if need not in bufs:
-            sys.exit(f"{a.dest}{need}.pfm not found")
+            sys.exit(f"{a.dest}{need}.pfm / .exr not found")
     h, w, _ = bufs["-dx"].shape
     c = lambda x: np.ascontiguousarray(x, dtype=np.float32)  # noqa: E731
     final = gdb200.poisson_solve(c(bufs["-dx"]), c(bufs["-dy"]), c(bufs["-throughput"]),
                                  c(bufs["-direct"]) if "-direct" in bufs else None, w, h, a.alpha, a.preset)
-    out = a.out or (a.dest + "-final.pfm")
-    pfm.write_pfm(out, final)
+    as_exr = not os.path.exists(a.dest + "-dx.pfm")
+    out = a.out or (a.dest + ("-final.exr" if as_exr else "-final.pfm"))
+    if out.lower().endswith(".exr"):
+        from gdb200 import exr
+        exr.write_exr(out, final, "float32" if a.out else "float16")
+    else:
+        pfm.write_pfm(out, final)
     print(out)
 
 

@@ -5,7 +5,8 @@ multifilm.cpp:423-516).
 
     python tools/render.py scene.xml -o out/render -D spp=64
 
-writes out/render-final.pfm, -throughput.pfm, -dx.pfm, -dy.pfm, -direct.pfm.  Scene subset: gdb200.xmlscene.
+writes out/render-final, -throughput, -dx, -dy, -direct as .exr (the film's default fileFormat "openexr", float16) or .pfm
+(fileFormat "pfm").  Scene subset: gdb200.xmlscene.
 """
 import argparse
 import os
@@ -31,7 +32,7 @@ def main():
     out = integ.render(scene, spp=parsed.spp, seed=parsed.seed, streams=a.streams or parsed.streams)
     dt = time.perf_counter() - t0
     dest = a.output or os.path.splitext(a.scene)[0]
-    paths = integ.save(dest, out)
+    paths = integ.save(dest, out, parsed.file_format, parsed.component_format)
     st = integ.stats
     print(f"Render time: {dt:.2f} s  ({st.samples / max(st.device_ms, 1e-9) / 1e3:.1f} Msamples/s traced, "
           f"reconstruction {integ.solver_stats.device_ms:.1f} ms)")
