@@ -552,11 +552,19 @@ def compute_normals(verts, tris):
 
 
 def load_image(path):
-    """Environment map pixels as float32 [h, w, 3]: PFM natively; Radiance .hdr / OpenEXR through OpenCV when it has them."""
+    """Environment map pixels as float32 [h, w, 3]: PFM and scan-line OpenEXR (NO/RLE/ZIPS/ZIP) natively; Radiance .hdr and
+    the other OpenEXR compressions through OpenCV when it has them."""
     if path.lower().endswith(".pfm"):
         from .pfm import read_pfm
         img = read_pfm(path)
         return np.repeat(img[:, :, None], 3, axis=2) if img.ndim == 2 else img
+    if path.lower().endswith(".exr"):
+        from . import exr
+        try:
+            return exr.read_exr(path)
+        except exr.ExrError as e:
+            if "not supported" not in str(e):
+                raise Gdb200Error(str(e))
     os.environ.setdefault("OPENCV_IO_ENABLE_OPENEXR", "1")
     try:
         import cv2

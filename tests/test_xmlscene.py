@@ -273,3 +273,22 @@ def test_film_file_format(tmp_path):
         path.write_text(xml.replace("FMT", fmt))
         with pytest.raises(Exception, match=msg):
             gdb200.load_scene(str(path))
+
+
+def test_envmap_from_openexr(tmp_path):
+    """envmap `filename` as .exr (the usual container for light probes) gives the same texels as the .pfm."""
+    from gdb200 import exr, pfm
+    sky = scenes.sky_envmap(16, 8)
+    pfm.write_pfm(str(tmp_path / "sky.pfm"), sky)
+    exr.write_exr(str(tmp_path / "sky.exr"), sky, "float32")
+    xml = """<scene version="0.5.0"><integrator type="gpt"/>
+      <sensor type="perspective"><film type="multifilm"><integer name="width" value="8"/><integer name="height" value="8"/></film></sensor>
+      <shape type="sphere"><bsdf type="diffuse"/></shape>
+      <emitter type="envmap"><string name="filename" value="sky.EXT"/></emitter></scene>"""
+    texels = []
+    for ext in ("pfm", "exr"):
+        (tmp_path / "s.xml").write_text(xml.replace("EXT", ext))
+        d = gdb200.load_scene(str(tmp_path / "s.xml")).desc
+        env = d.envmap.contents
+        texels.append(np.ctypeslib.as_array(env.rgb, shape=(env.height, env.width, 3)).copy())
+    assert np.array_equal(texels[0], texels[1]) and texels[0].shape == (8, 16, 3)
