@@ -4,7 +4,7 @@
 A scene that selects the reference's path loads unchanged: `<integrator type="gpt">` with the reference's
 parameter names and defaults (gpt.cpp:1194-1210), a `perspective` / `thinlens` sensor with its `sampler` and `multifilm`
 film, `rectangle` / `sphere` / `cube` / `obj` / `serialized` / `ply` shapes, `diffuse` / `roughconductor` / `conductor` / `dielectric` /
-`plastic` / `roughdielectric` / `twosided` BSDFs, `area` / `point` / `spot` / `envmap` emitters, `<default>` / `$variables`, `<ref id=...>`.
+`plastic` / `roughdielectric` / `twosided` BSDFs, `area` / `point` / `spot` / `envmap` emitters, `<default>` / `$variables`, `<ref id=...>`, `<alias>`, `<include>`.
 Anything else raises (no silent fallback), with the element's name in the message.
 
     parsed = load_scene("scene.xml", defines={"spp": "64"})
@@ -54,6 +54,37 @@ def _floats(text, n=None, what="value"):
     if n is not None and len(vals) != n:
         raise Gdb200Error(f"<{what}>: expected {n} values, got \"{text}\"")
     return vals
+
+
+def _srgb_to_linear(v):
+    """fromSRGBComponent (spectrum.cpp:400-405), with its multiply-by-reciprocal operation order."""
+    return v * (1.0 / 12.92) if v <= 0.04045 else ((v + 0.055) * (1.0 / 1.055)) ** 2.4
+
+
+def _colour(tag, name, text):
+    """<rgb> / <srgb> / <spectrum> values (scenehandler.cpp:461-545) in the RGB build: three numbers, one number, or an HTML
+    "#rrggbb" code; <srgb> goes through the sRGB transfer curve.  Wavelength-sampled or file spectra need Mitsuba's
+    CIE tables and are outside the subset."""
+    if text is None:
+        raise Gdb200Error(f"<{tag} name=\"{name}\">: spectra from files need Mitsuba's spectral data; give an RGB value")
+    toks = [t for t in re.split(r"[\s,]+", text.strip()) if t]
+    if tag != "spectrum" and len(toks) == 1 and len(toks[0]) == 7 and toks[0][0] == "#":
+        try:
+            code = int(toks[0][1:], 16)
+        except ValueError:
+            raise Gdb200Error(f"Invalid {tag} value specified (in <{name}>)")
+        vals = [((code >> 16) & 0xFF) / 255.0, ((code >> 8) & 0xFF) / 255.0, (code & 0xFF) / 255.0]
+    else:
+        if any(":" in t for t in toks):
+            raise Gdb200Error(f"<{tag} name=\"{name}\">: wavelength:value spectra need Mitsuba's CIE tables; give an RGB value")
+        vals = _floats(text, None, tag)
+        if len(vals) == 1:
+            vals = vals * 3
+        if len(vals) != 3:
+            raise Gdb200Error(f"Invalid {'RGB' if tag == 'rgb' else 'sRGB' if tag == 'srgb' else 'spectrum'} value specified")
+    if tag == "srgb":
+        vals = [_srgb_to_linear(v) for v in vals]
+    return tuple(vals)
 
 
 def _bool(text):
@@ -132,12 +163,7 @@ class _Props:
                 v = subst(c.attrib["value"])
                 self.values[name] = (float(v) if c.tag == "float" else int(v) if c.tag == "integer" else _bool(v) if c.tag == "boolean" else v)
             elif c.tag in ("rgb", "spectrum", "srgb"):
-                vals = _floats(subst(c.attrib["value"]), None, c.tag)
-                if len(vals) == 1:
-                    vals = vals * 3
-                if len(vals) != 3 or c.tag == "srgb":
-                    raise Gdb200Error(f"<{c.tag} name=\"{name}\">: only RGB triples / uniform values are supported")
-                self.values[name] = tuple(vals)
+                self.values[name] = _colour(c.tag, name, subst(c.attrib.get("value", "")) if "value" in c.attrib else None)
             elif c.tag in ("point", "vector"):
                 self.values[name] = tuple(float(subst(c.attrib.get(k, "0"))) for k in "xyz")
             elif c.tag == "transform":
@@ -153,12 +179,42 @@ class _Props:
 class _Loader:
     def __init__(self, root, base_dir, defines):
         self.root, self.base_dir = root, base_dir
-        self.vars = {}
-        for d in root.iter("default"):
-            self.vars[d.attrib["name"]] = d.attrib["value"]
-        self.vars.update(defines or {})
+        self.search = [base_dir]                # FileResolver: the scene's directory, then the directories of included files
+        self.vars = dict(defines or {})
+        self.elements = self._expand(root, base_dir, 0)
         self.named = {}                # id -> material index
         self.builder = None
+
+    def _expand(self, root, directory, depth):
+        """Top-level elements in document order with <include filename=...> replaced by the included scene's children
+        (scenehandler.cpp:658-681: the nested handler shares the named objects and parameters); <default> only sets a
+        parameter that is not defined yet (:683-687)."""
+        if depth > 16:
+            raise Gdb200Error("<include>: nesting too deep (recursive include?)")
+        out = []
+        for el in root:
+            if el.tag == "default":
+                self.vars.setdefault(el.attrib["name"], el.attrib["value"])
+            elif el.tag == "include":
+                path = self.resolve(self.subst(el.attrib["filename"]))
+                inc = ET.parse(path).getroot()
+                if inc.tag != "scene":
+                    raise Gdb200Error(f"included file \"{path}\": the root element must be <scene>")
+                sub = os.path.dirname(os.path.abspath(path))
+                if sub not in self.search:
+                    self.search.append(sub)
+                out += self._expand(inc, sub, depth + 1)
+            else:
+                out.append(el)
+        return out
+
+    def resolve(self, fn):
+        if os.path.isabs(fn):
+            return fn
+        for d in self.search:
+            if os.path.exists(os.path.join(d, fn)):
+                return os.path.join(d, fn)
+        return os.path.join(self.base_dir, fn)
 
     def subst(self, text):
         def rep(m):
@@ -307,12 +363,12 @@ class _Loader:
             b.mesh(wv, tris, mat, radiance=radiance, normals=wn)
         elif typ == "obj":
             fn = p.get("filename")
-            path = fn if os.path.isabs(fn) else os.path.join(self.base_dir, fn)
+            path = self.resolve(fn)
             verts, tris, nrms = load_obj(path, to_world, face_normals=p.get("faceNormals", False), flip_normals=flip)
             b.mesh(verts, tris, mat, radiance=radiance, normals=nrms)
         elif typ in ("serialized", "ply"):
             fn = p.get("filename")
-            path = fn if os.path.isabs(fn) else os.path.join(self.base_dir, fn)
+            path = self.resolve(fn)
             if "maxSmoothAngle" in p.values:
                 raise Gdb200Error(f"{typ}: maxSmoothAngle (TriMesh::rebuildTopology) is outside the supported hot-path subset")
             try:
@@ -348,7 +404,7 @@ class _Loader:
                                     p.get("samplingWeight", 1.0))
         elif typ == "envmap":
             fn = p.get("filename")
-            path = fn if os.path.isabs(fn) else os.path.join(self.base_dir, fn)
+            path = self.resolve(fn)
             self.builder.envmap(load_image(path), scale=p.get("scale", 1.0), to_world=p.get("toWorld", np.eye(4)),
                                 sampling_weight=p.get("samplingWeight", 1.0))
         else:
@@ -449,23 +505,29 @@ class _Loader:
 
     def load(self):
         parsed = ParsedScene()
-        sensors = self.root.findall("sensor")
+        sensors = [e for e in self.elements if e.tag == "sensor"]
         if len(sensors) != 1:
             raise Gdb200Error("exactly one <sensor> is required")
         cam, rfilter, stddev = self.sensor(sensors[0], parsed)
         self.builder = S.SceneBuilder(cam, rfilter=rfilter, stddev=stddev)
-        integ = self.root.findall("integrator")
+        integ = [e for e in self.elements if e.tag == "integrator"]
         if len(integ) != 1:
             raise Gdb200Error("exactly one <integrator> is required")
         self.integrator(integ[0], parsed)
-        for el in self.root:                                   # document order = Scene::addChild order (emitter CDF order)
+        for el in self.elements:                               # document order = Scene::addChild order (emitter CDF order)
             if el.tag == "bsdf":
                 self.material(el)
             elif el.tag == "shape":
                 self.shape(el)
             elif el.tag == "emitter":
                 self.emitter(el)
-            elif el.tag in ("sensor", "integrator", "default"):
+            elif el.tag == "alias":                              # scenehandler.cpp:646-656
+                if el.attrib["id"] not in self.named:
+                    raise Gdb200Error(f"Referenced object '{el.attrib['id']}' not found!")
+                if el.attrib["as"] in self.named:
+                    raise Gdb200Error(f"Duplicate ID '{el.attrib['as']}' used in scene description!")
+                self.named[el.attrib["as"]] = self.named[el.attrib["id"]]
+            elif el.tag in ("sensor", "integrator"):
                 pass
             else:
                 raise Gdb200Error(f"<{el.tag}> is outside the supported hot-path subset")

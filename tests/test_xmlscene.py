@@ -292,3 +292,40 @@ def test_envmap_from_openexr(tmp_path):
         env = d.envmap.contents
         texels.append(np.ctypeslib.as_array(env.rgb, shape=(env.height, env.width, 3)).copy())
     assert np.array_equal(texels[0], texels[1]) and texels[0].shape == (8, 16, 3)
+
+
+def test_include_alias_and_colour_syntax(tmp_path):
+    """<include> merges the included scene's objects in place and shares ids and parameters (scenehandler.cpp:658-681),
+    <alias> gives an object a second id (:646-656), colours may be "#rrggbb" and <srgb> applies the transfer curve
+    (:461-545, spectrum.cpp:400-419)."""
+    sub = tmp_path / "parts"
+    sub.mkdir()
+    (sub / "tri.obj").write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 3\n")
+    (sub / "mats.xml").write_text("""<scene version="0.5.0"><default name="spp" value="9"/><default name="tint" value="0.25"/>
+      <bsdf type="diffuse" id="paint"><srgb name="reflectance" value="#ff8000"/></bsdf>
+      <shape type="obj"><string name="filename" value="tri.obj"/><ref id="paint"/></shape></scene>""")
+    (tmp_path / "main.xml").write_text("""<scene version="0.5.0"><default name="spp" value="5"/><integrator type="gpt"/>
+      <sensor type="perspective"><sampler type="independent"><integer name="sampleCount" value="$spp"/></sampler>
+        <film type="multifilm"><integer name="width" value="8"/><integer name="height" value="8"/></film></sensor>
+      <include filename="parts/mats.xml"/>
+      <alias id="paint" as="wallpaint"/>
+      <shape type="rectangle"><ref id="wallpaint"/></shape>
+      <shape type="sphere"><bsdf type="diffuse"><rgb name="reflectance" value="#336699"/></bsdf></shape>
+      <shape type="sphere"><bsdf type="diffuse"><srgb name="reflectance" value="$tint"/></bsdf></shape>
+      <emitter type="point"><point name="position" x="0" y="0" z="3"/><rgb name="intensity" value="5"/></emitter></scene>""")
+    parsed = gdb200.load_scene(str(tmp_path / "main.xml"))
+    d = parsed.desc
+    assert parsed.spp == 5                                                     # the first <default> wins, the include's does not override
+    assert d.n_shapes == 4 and d.shapes[0].type == scenes.SHAPE_MESH           # the included mesh comes first (document order)
+    assert d.shapes[0].material == d.shapes[1].material                        # alias -> the same BSDF instance
+    lin = lambda v: v / 12.92 if v <= 0.04045 else ((v + 0.055) / 1.055) ** 2.4
+    assert np.allclose(list(d.materials[d.shapes[0].material].reflectance), [1.0, lin(128 / 255), 0.0])
+    assert np.allclose(list(d.materials[d.shapes[2].material].reflectance), [0x33 / 255, 0x66 / 255, 0x99 / 255])
+    assert np.allclose(list(d.materials[d.shapes[3].material].reflectance), [lin(0.25)] * 3)
+    assert list(d.emitters[0].radiance) == [5.0, 5.0, 5.0]
+    (tmp_path / "bad.xml").write_text((tmp_path / "main.xml").read_text().replace('value="#336699"', 'value="400:0.1, 700:0.9"').replace('<rgb name="reflectance"', '<spectrum name="reflectance"', 1))
+    with pytest.raises(Exception, match="CIE"):
+        gdb200.load_scene(str(tmp_path / "bad.xml"))
+    (tmp_path / "dup.xml").write_text((tmp_path / "main.xml").read_text().replace('as="wallpaint"', 'as="paint"'))
+    with pytest.raises(Exception, match="Duplicate ID"):
+        gdb200.load_scene(str(tmp_path / "dup.xml"))
