@@ -17,6 +17,20 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
 
 
+# GPU tests of features added after this round's last hardware run (checked so far against the oracle through the host
+# emulation of the device code only).  They are collected last, so that with `-x` a surprise in one of them cannot hide
+# the results of the suites that have already been green on a B200.
+NOT_YET_RUN_ON_HARDWARE = ("test_tracer_matches_oracle[cbox_spot]", "test_tracer_matches_oracle[cbox_roughglass]",
+                           "test_tracer_matches_oracle[cbox_sphere_lights]", "test_wavefront_without_tail_kernel[cbox_roughglass]",
+                           "test_scene_file_renders_on_the_gpu", "test_gpu_reproduces_committed_golden_buffers")
+
+
+def pytest_collection_modifyitems(config, items):
+    late = [it for it in items if any(tag in it.nodeid for tag in NOT_YET_RUN_ON_HARDWARE)]
+    if late:
+        items[:] = [it for it in items if it not in late] + late
+
+
 def _make(target):
     subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), target], check=True,
                    stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
