@@ -448,7 +448,13 @@ inline void classifyMaterials(HostScene *s, double shiftThreshold)
         o.specR = mk(m.specular_reflectance[0], m.specular_reflectance[1], m.specular_reflectance[2]);
         o.specT = mk(m.specular_transmittance[0], m.specular_transmittance[1], m.specular_transmittance[2]);
         o.eta = mk(m.eta[0], m.eta[1], m.eta[2]); o.k = mk(m.k[0], m.k[1], m.k[2]);
-        o.alpha = std::max(m.alpha, (double)1e-4f);                                  // microfacet.h:67-71
+        // The plugins store the clamped roughness (microfacet.h:67-71) in a ConstantFloatTexture and read it back through
+        // Spectrum::average() (roughconductor.cpp:196,273; spectrum.h:481-486): result * (1.0f / N) with a SINGLE-precision
+        // quotient, i.e. alpha * (1 + 3e-8) -- then the distribution clamps again.
+        double alphaAvg = 0.0f;
+        for (int c = 0; c < 3; c++) alphaAvg += std::max(m.alpha, (double)1e-4f);
+        alphaAvg = alphaAvg * (1.0f / 3);
+        o.alpha = std::max(alphaAvg, (double)1e-4f);
         o.iorRatio = m.ior_ratio;
         o.bsdfEta = (m.type == GDB200_BSDF_DIELECTRIC || m.type == GDB200_BSDF_ROUGHDIELECTRIC) ? m.ior_ratio : 1.0;   // bsdf.cpp:62-64, dielectric.cpp:389, roughdielectric.cpp:631; plastic and twosided inherit 1
         o.twosided = m.twosided != 0; o.nonlinear = m.nonlinear != 0;
@@ -458,10 +464,10 @@ inline void classifyMaterials(HostScene *s, double shiftThreshold)
             case GDB200_BSDF_DIFFUSE:                                                // diffuse.cpp:97-101,167-169
                 o.flags = std::max(m.reflectance[0], std::max(m.reflectance[1], m.reflectance[2])) > 0 ? (EDiffuseReflection | EFrontSide) : 0;
                 nComp = o.flags ? 1 : 0; rough[0] = inf; break;
-            case GDB200_BSDF_ROUGHCONDUCTOR: o.flags = EGlossyReflection | EFrontSide; rough[0] = 0.5 * (m.alpha + m.alpha); break;   // roughconductor.cpp:437-440
+            case GDB200_BSDF_ROUGHCONDUCTOR: o.flags = EGlossyReflection | EFrontSide; rough[0] = 0.5 * (alphaAvg + alphaAvg); break;   // roughconductor.cpp:437-440
             case GDB200_BSDF_CONDUCTOR: o.flags = EDeltaReflection | EFrontSide; rough[0] = 0; break;
             case GDB200_BSDF_ROUGHDIELECTRIC:                                        // roughdielectric.cpp:246-252,642-645
-                o.flags = EGlossyReflection | EGlossyTransmission | EFrontSide | EBackSide; nComp = 2; rough[0] = rough[1] = 0.5 * (m.alpha + m.alpha); break;
+                o.flags = EGlossyReflection | EGlossyTransmission | EFrontSide | EBackSide; nComp = 2; rough[0] = rough[1] = 0.5 * (alphaAvg + alphaAvg); break;
             case GDB200_BSDF_PLASTIC: {                                              // plastic.cpp:186-217,442-449
                 o.flags = EDeltaReflection | EDiffuseReflection | EFrontSide; nComp = 2; rough[0] = 0; rough[1] = inf;
                 o.fdrInt = fresnelDiffuseReflectance(1 / m.ior_ratio); o.fdrExt = fresnelDiffuseReflectance(m.ior_ratio);

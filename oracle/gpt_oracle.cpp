@@ -355,12 +355,19 @@ inline int nestedComponentCount(const gdb200_material &m)
     if (m.type == GDB200_BSDF_DIFFUSE) return nestedType(m) ? 1 : 0;
     return 1;
 }
+// The plugins keep their roughness in a ConstantFloatTexture built from the (clamped) MicrofacetDistribution of the
+// constructor and read it back through Spectrum::average() on every query (roughconductor.cpp:196,273-274;
+// roughdielectric.cpp:206): three additions and a multiplication by the SINGLE-precision quotient 1.0f / 3
+// (spectrum.h:481-486), so the roughness the distribution sees is alpha * (1 + 3e-8).
+inline Float textureAverage(Float v) { Float result = 0.0f; for (int i = 0; i < 3; i++) result += v; return result * (1.0f / 3); }
+inline Float effectiveAlpha(const gdb200_material &m) { return textureAverage(std::max((Float)m.alpha, (Float)1e-4f)); }
+
 inline Float nestedRoughness(const gdb200_material &m, int component)
 {
     switch (m.type) {
         case GDB200_BSDF_DIFFUSE: return INF;                               // diffuse.cpp:167-169
-        case GDB200_BSDF_ROUGHCONDUCTOR: return 0.5 * (m.alpha + m.alpha);  // roughconductor.cpp:437-440
-        case GDB200_BSDF_ROUGHDIELECTRIC: return 0.5f * (m.alpha + m.alpha); // roughdielectric.cpp:642-645
+        case GDB200_BSDF_ROUGHCONDUCTOR: return 0.5f * (effectiveAlpha(m) + effectiveAlpha(m));  // roughconductor.cpp:437-440
+        case GDB200_BSDF_ROUGHDIELECTRIC: return 0.5f * (effectiveAlpha(m) + effectiveAlpha(m)); // roughdielectric.cpp:642-645
         case GDB200_BSDF_PLASTIC: return component == 0 ? 0.0 : INF;        // plastic.cpp:442-449
         default: return 0.0;                                                // conductor.cpp:287, dielectric.cpp:393
     }
@@ -597,7 +604,7 @@ Spec nestedEval(const gdb200_material &m, V3 wi, V3 wo, Measure measure)
     case GDB200_BSDF_ROUGHCONDUCTOR: {                                                 // roughconductor.cpp:256-292
         if (measure != ESolidAngle || wi.z <= 0 || wo.z <= 0) return spec(0);
         V3 H = normalize(wo + wi);
-        Microfacet distr(m.distribution, m.alpha);
+        Microfacet distr(m.distribution, effectiveAlpha(m));
         const Float D = distr.eval(H);
         if (D == 0) return spec(0);
         const Spec F = fresnelConductorExact(dot(wi, H), specOf(m.eta), specOf(m.k)) * specOf(m.specular_reflectance);
@@ -616,7 +623,7 @@ Spec nestedEval(const gdb200_material &m, V3 wi, V3 wo, Measure measure)
         if (reflect) H = normalize(wo + wi);
         else { Float eta = wi.z > 0 ? m_eta : m_invEta; H = normalize(wi + wo * eta); }
         H = H * std::copysign(1.0, H.z);
-        Microfacet distr(m.distribution, m.alpha);
+        Microfacet distr(m.distribution, effectiveAlpha(m));
         const Float D = distr.eval(H);
         if (D == 0) return spec(0);
         Float unused; const Float F = fresnelDielectricExt(dot(wi, H), unused, m_eta);
@@ -668,7 +675,7 @@ Float nestedPdf(const gdb200_material &m, V3 wi, V3 wo, Measure measure)
     case GDB200_BSDF_ROUGHCONDUCTOR: {                                                 // roughconductor.cpp:294-320
         if (measure != ESolidAngle || wi.z <= 0 || wo.z <= 0) return 0.0;
         V3 H = normalize(wo + wi);
-        Microfacet distr(m.distribution, m.alpha);
+        Microfacet distr(m.distribution, effectiveAlpha(m));
         return distr.eval(H) * distr.smithG1(wi, H) / (4.0 * wi.z);
     }
     case GDB200_BSDF_CONDUCTOR:                                                        // conductor.cpp:237-250
@@ -687,7 +694,7 @@ Float nestedPdf(const gdb200_material &m, V3 wi, V3 wo, Measure measure)
             dwh_dwo = (eta * eta * dot(wo, H)) / (sqrtDenom * sqrtDenom);
         }
         H = H * std::copysign(1.0, H.z);
-        Microfacet sampleDistr(m.distribution, m.alpha);
+        Microfacet sampleDistr(m.distribution, effectiveAlpha(m));
         Float prob = sampleDistr.pdfVisible(wi * std::copysign(1.0, wi.z), H);
         Float unused; Float F = fresnelDielectricExt(dot(wi, H), unused, m_eta);
         prob *= reflect ? F : (1 - F);
@@ -732,7 +739,7 @@ void nestedSample(const gdb200_material &m, BSDFSample &r, Float sx, Float sy, S
         return;
     case GDB200_BSDF_ROUGHCONDUCTOR: {                                                 // roughconductor.cpp:369-419
         if (r.wi.z < 0) return;
-        Microfacet distr(m.distribution, m.alpha);
+        Microfacet distr(m.distribution, effectiveAlpha(m));
         V3 mm = distr.sampleVisible(r.wi, sx, sy);
         Float temporaryPdf = distr.pdfVisible(r.wi, mm);
         if (temporaryPdf == 0) return;
@@ -753,7 +760,7 @@ void nestedSample(const gdb200_material &m, BSDFSample &r, Float sx, Float sy, S
         return;
     case GDB200_BSDF_ROUGHDIELECTRIC: {                                                // roughdielectric.cpp:505-614 (pdf-returning overload)
         const Float m_eta = m.ior_ratio, m_invEta = 1 / m.ior_ratio;
-        Microfacet distr(m.distribution, m.alpha);
+        Microfacet distr(m.distribution, effectiveAlpha(m));
         const V3 wiS = r.wi * std::copysign(1.0, r.wi.z);
         const V3 mm = distr.sampleVisible(wiS, sx, sy);
         const Float microfacetPDF = distr.pdfVisible(wiS, mm);
