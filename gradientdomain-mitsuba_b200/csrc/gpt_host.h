@@ -233,6 +233,8 @@ inline int flattenScene(const gdb200_scene_desc *d, HostScene *s)
             const V3 dpdv = xfVector(sh.to_world, mk(0, 2, 0));
             r.n = normalize(xfNormal(sh.to_object, mk(0, 0, 1)));
             r.invArea = 1.0 / (len(r.dpdu) * len(dpdv));
+            if (std::fabs(dot(normalize(r.dpdu), normalize(dpdv))) > kEpsilon)           // rectangle.cpp:108-109
+                return set_error(GDB200_ERR_ARGUMENT, "shape %d: Error: 'toWorld' transformation contains shear!", i);
             r.material = sh.material; r.emitter = sh.emitter;
             rectOfShape[i] = h.nRects++;
         } else if (sh.type == GDB200_SHAPE_SPHERE) {

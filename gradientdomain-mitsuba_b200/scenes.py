@@ -120,6 +120,7 @@ def make_camera(width, height, origin, target, up, fov_deg, near=1e-2, far=1e4, 
     cam.camera_to_world = D16(*look_at(origin, target, up).reshape(-1))
     cam.near_clip, cam.far_clip, cam.width, cam.height = near, far, width, height
     cam.aperture_radius, cam.focus_distance = aperture_radius, focus_distance        # thinlens.cpp; 0 = pinhole
+    cam.fov_deg = fov_deg                            # not part of the C struct: what a Mitsuba <sensor> would be given (tests drive the compiled reference with it)
     return cam
 
 
@@ -134,6 +135,7 @@ def discretize_filter(f, radius, resolution=31):
 class SceneBuilder:
     def __init__(self, camera, rfilter_radius=0.5, rfilter="box", stddev=0.5):
         self.camera = camera
+        self.rfilter_name = rfilter
         self.rfilter_radius = rfilter_radius + 1e-5      # box.cpp:38
         self.rfilter_table = None                        # None = box
         if rfilter == "gaussian":                        # gaussian.cpp:32-58 (Mitsuba's default film filter, film.cpp:89-95)
@@ -286,7 +288,22 @@ class SceneBuilder:
         self.shapes.append(sh)
         return len(self.shapes) - 1
 
+    def _mitsuba_emitter_order(self):
+        """Scene::m_emitters, which the emitter-selection CDF follows (scene.cpp:190-206): emitters that are scene children
+        are appended by Scene::addChild (scene.cpp:496-516), the emitters attached to shapes only by Scene::initialize ->
+        addShape, in shape order (scene.cpp:332-337,570-571) -- free emitters first, then the area lights."""
+        free = [i for i, e in enumerate(self.emitters) if e.type != EMITTER_AREA]
+        area = sorted((i for i, e in enumerate(self.emitters) if e.type == EMITTER_AREA), key=lambda i: self.emitters[i].shape)
+        order = free + area
+        if order != list(range(len(order))):
+            new_index = {old: new for new, old in enumerate(order)}
+            self.emitters = [self.emitters[i] for i in order]
+            for sh in self.shapes:
+                if sh.emitter >= 0:
+                    sh.emitter = new_index[sh.emitter]
+
     def build(self):
+        self._mitsuba_emitter_order()
         d = SceneDesc()
         d.camera, d.rfilter_radius = self.camera, self.rfilter_radius
         if self.rfilter_table is not None:
@@ -442,7 +459,7 @@ def cbox_mesh_lights(width=256, height=256):
     sheet_rc = b.material(type=BSDF_ROUGHCONDUCTOR, alpha=0.2, eta=CU_ETA, k=CU_K, twosided=True)
     b.sphere((-0.45, -0.65, 0.2), 0.35, plastic)
     b.box((0.45, -0.75, 0.3), (0.25, 0.25, 0.25), -25.0, plastic_nl)
-    b.rectangle((0.0, -0.2, -0.5), (0.35, 0.1, 0), (0, 0.1, 0.3), sheet)         # free-floating sheets seen from both sides
+    b.rectangle((0.0, -0.2, -0.5), (0.35, 0.1, 0), (-0.03, 0.105, 0.3), sheet)         # free-floating sheets seen from both sides
     b.rectangle((-0.55, 0.35, -0.3), (0.2, 0, 0.1), (0, 0.25, 0), sheet_rc)
     return b.build()
 
@@ -578,6 +595,13 @@ def cbox_spot(width=256, height=256):
     b.spot_light(look_at((0.0, 0.9, 0.2), (0.1, -1.0, 0.3), (0, 0, 1)), (6.0, 5.0, 4.0), cutoff_angle=38.0, beam_width=20.0)
     b.spot_light(look_at((-0.8, 0.3, -0.6), (0.4, -0.5, 0.4), (0, 1, 0)), (1.0, 1.5, 2.5), cutoff_angle=25.0)
     return b.build()
+
+
+def mitsuba_sensor_args(desc):
+    """(fov in degrees, rfilter plugin name) the descriptor's camera matrices and filter table were made from -- what the
+    test suite needs to build the same sensor and film in a Mitsuba build."""
+    b = desc._owner
+    return float(b.camera.fov_deg), b.rfilter_name
 
 
 def default_params(spp=64, seed=0, max_depth=-1, rr_depth=5, shift_threshold=0.001, strict_normals=False):

@@ -514,7 +514,7 @@ class _Loader:
         if len(integ) != 1:
             raise Gdb200Error("exactly one <integrator> is required")
         self.integrator(integ[0], parsed)
-        for el in self.elements:                               # document order = Scene::addChild order (emitter CDF order)
+        for el in self.elements:                               # document order; SceneBuilder.build() puts the emitters in Scene::m_emitters order
             if el.tag == "bsdf":
                 self.material(el)
             elif el.tag == "shape":

@@ -1,0 +1,338 @@
+// Test infrastructure: the REFERENCE's G-PT integrator -- src/integrators/gpt/gpt.cpp with its evaluatePoint / shift
+// mappings / MIS and renderBlock's 15 film splats, plus the scene (kd-tree), shapes, emitters, BSDFs, perspective / thinlens
+// sensor, reconstruction filters and ImageBlock::put it runs on -- compiled from /root/reference by oracle/Makefile into
+// oracle/_ref/libref_mitsuba.so and driven from a gdb200_scene_desc, the same bytes the CUDA tracer and the CPU restatement
+// take.  Random numbers come from the repo's own sampler plugin (plugin/samplers/gdb200_counter.cpp, compiled against the
+// real headers here), so the three implementations consume identical per-pixel streams.
+//
+// What is NOT the reference here: the loop over image blocks (the reference hands blocks to its scheduler's workers,
+// gpt_proc.cpp:86-117; this file hands them to std::threads) and the construction of the scene objects from the
+// C structs instead of from XML.  Each block is rendered by GradientPathIntegrator::renderBlock (gpt.cpp:1219-1352) and
+// merged with ImageBlock::put (imageblock.h:109-113), exactly what GPTRenderProcess::processResult does
+// (gpt_proc.cpp:119-128 -> MultiFilm::put).
+#include <mitsuba/render/scene.h>
+#include <mitsuba/render/trimesh.h>
+#include <mitsuba/render/imageblock.h>
+#include <mitsuba/render/renderproc.h>
+#include <mitsuba/core/statistics.h>
+#include <mitsuba/core/sched.h>
+#include <mitsuba/core/bitmap.h>
+#include <mitsuba/core/bitmap.h>
+#include <sstream>
+#include <thread>
+#include <mutex>
+#include <atomic>
+#define private public                   /* GradientPathIntegrator::m_config is filled by render() (gpt.cpp:1365-1370), which is bypassed */
+#include "/root/reference/src/integrators/gpt/gpt.h"
+#undef private
+#include "/root/reference/src/integrators/gpt/gpt_wr.h"
+#include "../include/gdb200.h"
+
+using namespace mitsuba;
+
+extern "C" {
+void *CreateInstance_diffuse(const Properties &); void *CreateInstance_roughconductor(const Properties &);
+void *CreateInstance_conductor(const Properties &); void *CreateInstance_dielectric(const Properties &);
+void *CreateInstance_plastic(const Properties &); void *CreateInstance_roughdielectric(const Properties &);
+void *CreateInstance_twosided(const Properties &);
+void *CreateInstance_rectangle(const Properties &); void *CreateInstance_sphere(const Properties &);
+void *CreateInstance_area(const Properties &); void *CreateInstance_point(const Properties &); void *CreateInstance_spot(const Properties &);
+void *CreateInstance_perspective(const Properties &); void *CreateInstance_thinlens(const Properties &);
+void *CreateInstance_multifilm(const Properties &);
+void *CreateInstance_box(const Properties &); void *CreateInstance_gaussian(const Properties &); void *CreateInstance_tent(const Properties &);
+void *CreateInstance_gdb200_counter(const Properties &);
+void *CreateInstance_gpt(const Properties &);
+}
+
+namespace {
+std::string g_error;
+std::once_flag g_init;
+
+void staticInit()
+{                                                                                // the order of src/mitsuba/mitsuba.cpp:362-373
+    Class::staticInitialization();
+    Object::staticInitialization();
+    Statistics::staticInitialization();
+    Thread::staticInitialization();
+    Logger::staticInitialization();
+    Spectrum::staticInitialization();
+    Bitmap::staticInitialization();
+    Scheduler::staticInitialization();
+    Thread::getThread()->getLogger()->setLogLevel(EWarn);
+}
+
+template <typename T> T *make(void *(*factory)(const Properties &), const Properties &props)
+{
+    T *obj = static_cast<T *>(static_cast<ConfigurableObject *>(factory(props)));
+    obj->incRef();
+    return obj;
+}
+void attach(ConfigurableObject *parent, ConfigurableObject *child)               // scenehandler.cpp: addChild, then setParent
+{
+    parent->addChild(child);
+    child->setParent(parent);
+}
+Spectrum rgb(const double *v) { Spectrum s; s.fromLinearRGB(v[0], v[1], v[2]); return s; }
+Transform transformOf(const double *m)
+{
+    Matrix4x4 mat;
+    for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) mat.m[r][c] = m[4 * r + c];
+    return Transform(mat);
+}
+
+BSDF *makeBSDF(const gdb200_material &m)
+{
+    BSDF *bsdf = NULL;
+    const char *distr = m.distribution == GDB200_MICROFACET_BECKMANN ? "beckmann" : "ggx";
+    switch (m.type) {
+        case GDB200_BSDF_DIFFUSE: { Properties p("diffuse"); p.setSpectrum("reflectance", rgb(m.reflectance)); bsdf = make<BSDF>(CreateInstance_diffuse, p); break; }
+        case GDB200_BSDF_ROUGHCONDUCTOR: case GDB200_BSDF_CONDUCTOR: {
+            Properties p(m.type == GDB200_BSDF_CONDUCTOR ? "conductor" : "roughconductor");
+            p.setString("material", "none"); p.setSpectrum("eta", rgb(m.eta)); p.setSpectrum("k", rgb(m.k)); p.setFloat("extEta", 1.0);
+            p.setSpectrum("specularReflectance", rgb(m.specular_reflectance));
+            if (m.type == GDB200_BSDF_ROUGHCONDUCTOR) { p.setFloat("alpha", m.alpha); p.setString("distribution", distr); }
+            bsdf = make<BSDF>(m.type == GDB200_BSDF_CONDUCTOR ? CreateInstance_conductor : CreateInstance_roughconductor, p);
+            break;
+        }
+        case GDB200_BSDF_DIELECTRIC: case GDB200_BSDF_ROUGHDIELECTRIC: {
+            Properties p(m.type == GDB200_BSDF_DIELECTRIC ? "dielectric" : "roughdielectric");
+            p.setFloat("intIOR", m.ior_ratio); p.setFloat("extIOR", 1.0);
+            p.setSpectrum("specularReflectance", rgb(m.specular_reflectance)); p.setSpectrum("specularTransmittance", rgb(m.specular_transmittance));
+            if (m.type == GDB200_BSDF_ROUGHDIELECTRIC) { p.setFloat("alpha", m.alpha); p.setString("distribution", distr); }
+            bsdf = make<BSDF>(m.type == GDB200_BSDF_DIELECTRIC ? CreateInstance_dielectric : CreateInstance_roughdielectric, p);
+            break;
+        }
+        case GDB200_BSDF_PLASTIC: {
+            Properties p("plastic");
+            p.setFloat("intIOR", m.ior_ratio); p.setFloat("extIOR", 1.0); p.setBoolean("nonlinear", m.nonlinear != 0);
+            p.setSpectrum("diffuseReflectance", rgb(m.reflectance)); p.setSpectrum("specularReflectance", rgb(m.specular_reflectance));
+            bsdf = make<BSDF>(CreateInstance_plastic, p);
+            break;
+        }
+        default: throw std::runtime_error("unknown material type");
+    }
+    bsdf->configure();
+    if (m.twosided) {
+        BSDF *outer = make<BSDF>(CreateInstance_twosided, Properties("twosided"));
+        attach(outer, bsdf);
+        outer->configure();
+        bsdf = outer;
+    }
+    return bsdf;
+}
+
+struct Built {
+    ref<Scene> scene;
+    ref<GradientPathIntegrator> gpt;
+    ref<Sampler> sampler;
+};
+
+Built buildScene(const gdb200_scene_desc *d, const gdb200_gpt_params *prm, double fovX, const char *rfilterName, bool gptIntegrator)
+{
+    Built out;
+    ref<Scene> scene = new Scene(Properties("scene"));
+
+    // ---- sensor <- film <- rfilter, sampler
+    const gdb200_camera &cam = d->camera;
+    Properties sp(cam.aperture_radius > 0 ? "thinlens" : "perspective");
+    sp.setTransform("toWorld", transformOf(cam.camera_to_world));
+    sp.setFloat("fov", fovX); sp.setString("fovAxis", "x");
+    sp.setFloat("nearClip", cam.near_clip); sp.setFloat("farClip", cam.far_clip);
+    if (cam.aperture_radius > 0) { sp.setFloat("apertureRadius", cam.aperture_radius); sp.setFloat("focusDistance", cam.focus_distance); }
+    Sensor *sensor = make<Sensor>(cam.aperture_radius > 0 ? CreateInstance_thinlens : CreateInstance_perspective, sp);
+    Properties fp("multifilm");
+    fp.setInteger("width", cam.width); fp.setInteger("height", cam.height); fp.setBoolean("banner", false); fp.setString("fileFormat", "pfm");
+    Film *film = make<Film>(CreateInstance_multifilm, fp);
+    const std::string rf(rfilterName);
+    ReconstructionFilter *filter = make<ReconstructionFilter>(rf == "gaussian" ? CreateInstance_gaussian : rf == "tent" ? CreateInstance_tent : CreateInstance_box,
+                                                              Properties(rf));
+    filter->configure();
+    attach(film, filter);
+    film->configure();
+    Properties smp("gdb200_counter");
+    smp.setSize("sampleCount", (size_t) prm->spp); smp.setSize("seed", (size_t) prm->seed);
+    Sampler *sampler = make<Sampler>(CreateInstance_gdb200_counter, smp);
+    sampler->configure();
+    attach(sensor, film);
+    attach(sensor, sampler);
+    sensor->configure();
+    scene->addChild(sensor);
+    out.sampler = sampler;
+
+    // ---- integrator
+    Properties ip(gptIntegrator ? "gpt" : "path");
+    ip.setInteger("maxDepth", prm->max_depth); ip.setInteger("rrDepth", prm->rr_depth); ip.setBoolean("strictNormals", prm->strict_normals != 0);
+    if (gptIntegrator) {
+        ip.setFloat("shiftThreshold", prm->shift_threshold); ip.setBoolean("reconstructL1", false); ip.setBoolean("reconstructL2", false);
+        GradientPathIntegrator *gpt = make<GradientPathIntegrator>(CreateInstance_gpt, ip);
+        gpt->configure();
+        gpt->m_config.m_maxDepth = prm->max_depth;                               // gpt.cpp:1365-1370
+        gpt->m_config.m_minDepth = 1;
+        gpt->m_config.m_rrDepth = prm->rr_depth;
+        gpt->m_config.m_strictNormals = prm->strict_normals != 0;
+        scene->addChild(gpt);
+        out.gpt = gpt;
+    } else throw std::runtime_error("only the gpt integrator is wired");
+
+    // ---- emitters that are not attached to a shape keep their slot: Scene::m_emitters follows addChild order
+    std::vector<BSDF *> bsdfs(d->n_materials);
+    for (int i = 0; i < d->n_materials; i++) bsdfs[i] = makeBSDF(d->materials[i]);
+    std::vector<ConfigurableObject *> ordered(d->n_emitters, (ConfigurableObject *) NULL);
+    for (int i = 0; i < d->n_emitters; i++) {
+        const gdb200_emitter &e = d->emitters[i];
+        if (e.type == GDB200_EMITTER_AREA) continue;
+        if (e.type == GDB200_EMITTER_ENVMAP) throw std::runtime_error("envmap emitters are not wired into the reference driver");
+        Properties p(e.type == GDB200_EMITTER_POINT ? "point" : "spot");
+        p.setSpectrum("intensity", rgb(e.radiance)); p.setFloat("samplingWeight", e.sampling_weight);
+        if (e.type == GDB200_EMITTER_POINT) p.setPoint("position", Point(e.position[0], e.position[1], e.position[2]));
+        else {
+            Matrix4x4 inv;                                                           // to_local = rows of the inverse rotation; the world matrix is its inverse
+            inv.setIdentity();
+            for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) inv.m[r][c] = e.to_local[3 * r + c];
+            Matrix4x4 rot;
+            if (!inv.invert(rot)) throw std::runtime_error("spot: singular to_local");
+            for (int r = 0; r < 3; r++) rot.m[r][3] = e.position[r];
+            p.setTransform("toWorld", Transform(rot));
+            p.setFloat("cutoffAngle", radToDeg(e.cutoff_angle)); p.setFloat("beamWidth", radToDeg(e.beam_width));
+        }
+        Emitter *em = make<Emitter>(e.type == GDB200_EMITTER_POINT ? CreateInstance_point : CreateInstance_spot, p);
+        em->configure();
+        ordered[i] = em;
+    }
+
+    // ---- shapes (with their BSDF and area emitter)
+    std::vector<Shape *> shapes(d->n_shapes);
+    for (int i = 0; i < d->n_shapes; i++) {
+        const gdb200_shape &s = d->shapes[i];
+        Shape *shape = NULL;
+        if (s.type == GDB200_SHAPE_RECTANGLE) {
+            Properties p("rectangle"); p.setTransform("toWorld", transformOf(s.to_world));
+            shape = make<Shape>(CreateInstance_rectangle, p);
+        } else if (s.type == GDB200_SHAPE_SPHERE) {
+            Properties p("sphere"); p.setPoint("center", Point(s.center[0], s.center[1], s.center[2])); p.setFloat("radius", s.radius);
+            p.setBoolean("flipNormals", s.flip_normals != 0);
+            shape = make<Shape>(CreateInstance_sphere, p);
+        } else {
+            std::map<int, uint32_t> remap;                                         // the mesh's own vertex table, in first-use order
+            std::vector<int> verts;
+            for (int t = 0; t < s.tri_count; t++) for (int k = 0; k < 3; k++) {
+                const int v = d->triangles[3 * (s.first_tri + t) + k];
+                if (!remap.count(v)) { remap[v] = (uint32_t) verts.size(); verts.push_back(v); }
+            }
+            const bool smooth = s.has_vertex_normals != 0;
+            TriMesh *mesh = new TriMesh("mesh", (size_t) s.tri_count, verts.size(), smooth, false, false, false, !smooth);
+            mesh->incRef();
+            for (size_t v = 0; v < verts.size(); v++) {
+                mesh->getVertexPositions()[v] = Point(d->vertices[3 * verts[v]], d->vertices[3 * verts[v] + 1], d->vertices[3 * verts[v] + 2]);
+                if (smooth) mesh->getVertexNormals()[v] = Normal(d->normals[3 * verts[v]], d->normals[3 * verts[v] + 1], d->normals[3 * verts[v] + 2]);
+            }
+            for (int t = 0; t < s.tri_count; t++) for (int k = 0; k < 3; k++)
+                mesh->getTriangles()[t].idx[k] = remap[d->triangles[3 * (s.first_tri + t) + k]];
+            shape = mesh;
+        }
+        attach(shape, bsdfs[s.material]);
+        if (s.emitter >= 0) {
+            const gdb200_emitter &e = d->emitters[s.emitter];
+            Properties p("area"); p.setSpectrum("radiance", rgb(e.radiance)); p.setFloat("samplingWeight", e.sampling_weight);
+            Emitter *em = make<Emitter>(CreateInstance_area, p);
+            em->configure();
+            attach(shape, em);
+        }
+        shape->configure();
+        shapes[i] = shape;
+    }
+    // Scene::m_emitters (the emitter CDF): scene-level emitters in addChild order (scene.cpp:496-516), then the shapes' emitters
+    // in shape order when Scene::initialize() runs addShape (scene.cpp:570-571).  The desc must list them the same way.
+    for (int i = 0; i < d->n_emitters; i++) if (ordered[i]) scene->addChild(ordered[i]);
+    for (int i = 0; i < d->n_shapes; i++) scene->addChild(shapes[i]);
+
+    scene->configure();
+    scene->initialize();
+    const ref_vector<Emitter> &ems = scene->getEmitters();
+    if ((int) ems.size() != d->n_emitters) throw std::runtime_error("emitter count differs from the scene description");
+    for (int i = 0; i < d->n_emitters; i++) {
+        const Emitter *expect = ordered[i] ? static_cast<const Emitter *>(ordered[i]) : shapes[d->emitters[i].shape]->getEmitter();
+        if (ems[i].get() != expect) throw std::runtime_error("the scene description lists its emitters in an order Mitsuba cannot produce (scene-level emitters first, then the shapes' emitters in shape order)");
+    }
+    out.scene = scene;
+    return out;
+}
+
+// Block loop: 32x32 blocks (scene.cpp: blockSize default), any order (every pixel re-keys the sampler), `threads` workers.
+void renderBlocks(Built &b, int threads, double *out5)
+{
+    Scene *scene = b.scene.get();
+    Sensor *sensor = scene->getSensor();
+    Film *film = sensor->getFilm();
+    const Vector2i size = film->getCropSize();
+    const ReconstructionFilter *rfilter = film->getReconstructionFilter();
+    const int bs = 32;
+    const int nbx = (size.x + bs - 1) / bs, nby = (size.y + bs - 1) / bs;
+    ref<GPTWorkResult> total = new GPTWorkResult(rfilter, size, 1);
+    total->clear();
+    std::mutex merge;
+    std::atomic<int> next(0);
+    std::string failure;
+    auto worker = [&]() {
+        try {
+            ref<Sampler> sampler = b.sampler->clone();
+            ref<GPTWorkResult> block = new GPTWorkResult(rfilter, Vector2i(bs, bs), 1);
+            const bool stop = false;
+            for (;;) {
+                const int id = next++;
+                if (id >= nbx * nby) break;
+                const Point2i off((id % nbx) * bs, (id / nbx) * bs);
+                const Vector2i sz(std::min(bs, size.x - off.x), std::min(bs, size.y - off.y));
+                block->setOffset(off); block->setSize(sz);
+                std::vector<TPoint2<uint8_t> > points;
+                for (int y = 0; y < sz.y; y++) for (int x = 0; x < sz.x; x++) points.push_back(TPoint2<uint8_t>((uint8_t) x, (uint8_t) y));
+                b.gpt->renderBlock(scene, sensor, sampler.get(), block.get(), stop, points);
+                std::lock_guard<std::mutex> guard(merge);
+                total->put(block.get());
+            }
+        } catch (const std::exception &e) { std::lock_guard<std::mutex> guard(merge); failure = e.what(); }
+    };
+    if (threads <= 1) worker();
+    else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < threads; t++) pool.push_back(std::thread([&]() {
+            ref<Thread> self = Thread::registerUnmanagedThread("gdbref");            // Mitsuba services (logger, TLS) for a foreign thread
+            worker();
+        }));
+        for (auto &t : pool) t.join();
+    }
+    if (!failure.empty()) throw std::runtime_error(failure);
+    // develop: value / weight per pixel (Bitmap::convert of ESpectrumAlphaWeight, what MultiFilm::develop writes)
+    for (int buf = 0; buf < 5; buf++) {
+        const ImageBlock *ib = total->getImageBlock(buf);
+        const Bitmap *bmp = ib->getBitmap();
+        const int border = ib->getBorderSize(), stride = bmp->getWidth();
+        const Float *data = bmp->getFloatData();
+        for (int y = 0; y < size.y; y++) for (int x = 0; x < size.x; x++) {
+            const Float *px = data + ((size_t) (y + border) * stride + (x + border)) * (SPECTRUM_SAMPLES + 2);
+            const Float w = px[SPECTRUM_SAMPLES + 1], inv = w != 0 ? 1 / w : 0;
+            double *o = out5 + (((size_t) buf * size.y + y) * size.x + x) * 3;
+            for (int c = 0; c < 3; c++) o[c] = px[c] * inv;
+        }
+    }
+}
+}
+
+extern "C" {
+
+const char *gdbref_gpt_last_error() { return g_error.c_str(); }
+
+// The reference G-PT tracer on `desc`: out5 = [5][h][w][3] developed buffers in the order -final (preview), -throughput,
+// -dx, -dy, -direct.  fov_x_deg and rfilter are what the desc's matrices / filter table were made from.
+int gdbref_gpt_render(const gdb200_scene_desc *desc, const gdb200_gpt_params *prm, double fov_x_deg, const char *rfilter, int threads, double *out5)
+{
+    try {
+        std::call_once(g_init, staticInit);
+        if (prm->streams_per_pixel > 1) throw std::runtime_error("the reference has one sample stream per pixel");
+        Built b = buildScene(desc, prm, fov_x_deg, rfilter, true);
+        renderBlocks(b, threads, out5);
+        return 0;
+    } catch (const std::exception &e) { g_error = e.what(); return 1; }
+}
+
+}

@@ -4,6 +4,7 @@
 #include <fstream>
 #include <ostream>
 #include <sys/stat.h>
+#include <cstdio>
 namespace boost { namespace filesystem {
 class path {
     std::string s;
@@ -33,6 +34,8 @@ inline bool exists(const path &p) { struct stat st; return ::stat(p.c_str(), &st
 inline bool is_directory(const path &p) { struct stat st; return ::stat(p.c_str(), &st) == 0 && S_ISDIR(st.st_mode); }
 inline unsigned long file_size(const path &p) { struct stat st; return ::stat(p.c_str(), &st) == 0 ? (unsigned long) st.st_size : 0; }
 inline long last_write_time(const path &p) { struct stat st; return ::stat(p.c_str(), &st) == 0 ? (long) st.st_mtime : 0; }
+inline bool remove(const path &p) { return ::remove(p.c_str()) == 0; }
+inline bool create_directory(const path &p) { return ::mkdir(p.c_str(), 0777) == 0; }
 inline path absolute(const path &p) { return p; }
 inline path complete(const path &p) { return p; }
 inline path current_path() { return path("."); }

@@ -1,24 +1,37 @@
-// Test infrastructure (oracle/_ref recipe): the few Mitsuba runtime services the reference's BSDF / microfacet / warp /
-// Fresnel sources name at link time, so that THOSE sources can be compiled unmodified from /root/reference and called
-// from the tests.  Nothing here is on the rendering path of the reference code under test: logging, plugin loading,
-// serialisation streams, GPU shaders and statistics are inert; Properties is a plain typed dictionary with the
-// interface of include/mitsuba/core/properties.h (the reference's own implementation needs boost::variant).
+// Test infrastructure (oracle/_ref recipe): the Mitsuba runtime services that cannot be compiled from the reference tree
+// here because they need libraries this image lacks (boost::variant, boost::multi_index, boost::mpl, Eigen, the plugin
+// loader's dlopen machinery, fonts, GPU shaders).  Everything the G-PT path computes with -- integrator, BSDFs, emitters,
+// shapes, kd-tree, sensor, film, sampler base, scheduler, threads, streams, logging -- is compiled UNMODIFIED from
+// /root/reference by oracle/Makefile; what is here is inert or a plain container:
+//   * Properties: a typed dictionary with the interface of include/mitsuba/core/properties.h,
+//   * ConfigurableObject / NetworkedObject: the trivial bodies of properties.cpp:383-413,
+//   * AnimatedTransform: static transforms only (the bodies of track.cpp:79-83,123-128,222-223 for that case),
+//   * thread-local storage: a per-thread map,
+//   * FileResolver, PluginManager, FormatConverter, Font, Renderer: not available / no-ops.
 #include <mitsuba/mitsuba.h>
 #include <mitsuba/core/properties.h>
 #include <mitsuba/core/cobject.h>
+#include <mitsuba/core/netobject.h>
 #include <mitsuba/core/plugin.h>
-#include <mitsuba/core/statistics.h>
-#include <mitsuba/core/random.h>
 #include <mitsuba/core/bitmap.h>
 #include <mitsuba/core/fresolver.h>
-#include <mitsuba/core/fstream.h>
+#include <mitsuba/core/track.h>
+#include <mitsuba/core/tls.h>
+#include <mitsuba/core/sched.h>
 #include <mitsuba/render/common.h>
 #include <mitsuba/hw/renderer.h>
-#include <cstdarg>
-#include <cstdio>
+#include <mitsuba/hw/font.h>
+#include <thread>
+#include <mutex>
+#include <sstream>
 #include <stdexcept>
 
+extern "C" void *CreateInstance_disk(const mitsuba::Properties &);
+extern "C" void *CreateInstance_diffuse(const mitsuba::Properties &);
+
 MTS_NAMESPACE_BEGIN
+
+static void unsupported(const char *what) { throw std::runtime_error(std::string("oracle/_ref support: ") + what + " is not available"); }
 
 // ---------------------------------------------------------------- Properties
 struct PropertyElement {
@@ -27,16 +40,17 @@ struct PropertyElement {
     mutable bool queried;
     PropertyElement() : type(Properties::EBoolean), b(false), i(0), f(0), queried(false) {}
 };
+typedef std::map<std::string, PropertyElement> ElementMap;
 
-Properties::Properties() : m_elements(new std::map<std::string, PropertyElement>()), m_id("unnamed") {}
-Properties::Properties(const std::string &pluginName) : m_elements(new std::map<std::string, PropertyElement>()), m_pluginName(pluginName), m_id("unnamed") {}
-Properties::Properties(const Properties &props) : m_elements(new std::map<std::string, PropertyElement>(*props.m_elements)), m_pluginName(props.m_pluginName), m_id(props.m_id) {}
+Properties::Properties() : m_elements(new ElementMap()), m_id("unnamed") {}
+Properties::Properties(const std::string &pluginName) : m_elements(new ElementMap()), m_pluginName(pluginName), m_id("unnamed") {}
+Properties::Properties(const Properties &props) : m_elements(new ElementMap(*props.m_elements)), m_pluginName(props.m_pluginName), m_id(props.m_id) {}
 Properties::~Properties() { delete m_elements; }
 void Properties::operator=(const Properties &props) { *m_elements = *props.m_elements; m_pluginName = props.m_pluginName; m_id = props.m_id; }
 
-static const PropertyElement &lookup(const std::map<std::string, PropertyElement> *m, const std::string &name, Properties::EPropertyType type)
+static const PropertyElement &lookup(const ElementMap *m, const std::string &name, Properties::EPropertyType type)
 {
-    std::map<std::string, PropertyElement>::const_iterator it = m->find(name);
+    ElementMap::const_iterator it = m->find(name);
     if (it == m->end()) throw std::runtime_error("Property \"" + name + "\" has not been specified!");
     if (it->second.type != type) throw std::runtime_error("Property \"" + name + "\" has the wrong type!");
     it->second.queried = true;
@@ -60,77 +74,141 @@ bool Properties::hasProperty(const std::string &name) const { return m_elements-
 bool Properties::removeProperty(const std::string &name) { return m_elements->erase(name) != 0; }
 Properties::EPropertyType Properties::getType(const std::string &name) const
 {
-    std::map<std::string, PropertyElement>::const_iterator it = m_elements->find(name);
+    ElementMap::const_iterator it = m_elements->find(name);
     if (it == m_elements->end()) throw std::runtime_error("Property \"" + name + "\" has not been specified!");
     return it->second.type;
 }
-void Properties::markQueried(const std::string &name) const { std::map<std::string, PropertyElement>::const_iterator it = m_elements->find(name); if (it != m_elements->end()) it->second.queried = true; }
-bool Properties::wasQueried(const std::string &name) const { std::map<std::string, PropertyElement>::const_iterator it = m_elements->find(name); return it != m_elements->end() && it->second.queried; }
+void Properties::markQueried(const std::string &name) const { ElementMap::const_iterator it = m_elements->find(name); if (it != m_elements->end()) it->second.queried = true; }
+bool Properties::wasQueried(const std::string &name) const { ElementMap::const_iterator it = m_elements->find(name); return it != m_elements->end() && it->second.queried; }
 std::vector<std::string> Properties::getUnqueried() const
 {
     std::vector<std::string> r;
-    for (std::map<std::string, PropertyElement>::const_iterator it = m_elements->begin(); it != m_elements->end(); ++it) if (!it->second.queried) r.push_back(it->first);
+    for (ElementMap::const_iterator it = m_elements->begin(); it != m_elements->end(); ++it) if (!it->second.queried) r.push_back(it->first);
     return r;
 }
-void Properties::putPropertyNames(std::vector<std::string> &results) const { for (std::map<std::string, PropertyElement>::const_iterator it = m_elements->begin(); it != m_elements->end(); ++it) results.push_back(it->first); }
+void Properties::putPropertyNames(std::vector<std::string> &results) const { for (ElementMap::const_iterator it = m_elements->begin(); it != m_elements->end(); ++it) results.push_back(it->first); }
 std::string Properties::toString() const { return "Properties[" + m_pluginName + "]"; }
+void Properties::setAnimatedTransform(const std::string &name, const AnimatedTransform *value, bool)
+{
+    if (!value->isStatic()) unsupported("an animated transform");
+    setTransform(name, value->eval(0));
+}
+ref<const AnimatedTransform> Properties::getAnimatedTransform(const std::string &name, const Transform &defVal) const
+{
+    return new AnimatedTransform(m_elements->count(name) ? lookup(m_elements, name, ETransform).t : defVal);
+}
+ref<const AnimatedTransform> Properties::getAnimatedTransform(const std::string &name, const AnimatedTransform *defVal) const
+{
+    if (m_elements->count(name)) return new AnimatedTransform(lookup(m_elements, name, ETransform).t);
+    return defVal;
+}
+ref<const AnimatedTransform> Properties::getAnimatedTransform(const std::string &name) const { return new AnimatedTransform(lookup(m_elements, name, ETransform).t); }
+std::string Properties::getAsString(const std::string &name) const
+{
+    ElementMap::const_iterator it = m_elements->find(name);
+    if (it == m_elements->end()) throw std::runtime_error("Property \"" + name + "\" has not been specified!");
+    it->second.queried = true;
+    std::ostringstream oss;
+    switch (it->second.type) {
+        case EBoolean: oss << (it->second.b ? "true" : "false"); break;
+        case EInteger: oss << it->second.i; break;
+        case EFloat: oss << it->second.f; break;
+        case EString: oss << it->second.str; break;
+        default: oss << "(value)"; break;
+    }
+    return oss.str();
+}
+std::string Properties::getAsString(const std::string &name, const std::string &defVal) const { return m_elements->count(name) ? getAsString(name) : defVal; }
+void Properties::copyAttribute(const Properties &properties, const std::string &sourceName, const std::string &targetName)
+{
+    ElementMap::const_iterator it = properties.m_elements->find(sourceName);
+    if (it == properties.m_elements->end()) throw std::runtime_error("copyAttribute(): could not find parameter \"" + sourceName + "\"!");
+    (*m_elements)[targetName] = it->second;
+}
+void Properties::merge(const Properties &p) { for (ElementMap::const_iterator it = p.m_elements->begin(); it != p.m_elements->end(); ++it) (*m_elements)[it->first] = it->second; }
+bool Properties::operator==(const Properties &p) const { return m_pluginName == p.m_pluginName && m_id == p.m_id && m_elements->size() == p.m_elements->size(); }
 
-// ---------------------------------------------------------------- ConfigurableObject (properties.cpp:383-415 restated)
+// ---------------------------------------------------------------- ConfigurableObject, NetworkedObject (properties.cpp:383-413)
 ConfigurableObject::ConfigurableObject(Stream *stream, InstanceManager *manager) : SerializableObject(stream, manager) {}
 void ConfigurableObject::setParent(ConfigurableObject *) {}
 void ConfigurableObject::configure() {}
 void ConfigurableObject::serialize(Stream *, InstanceManager *) const {}
 void ConfigurableObject::addChild(const std::string &name, ConfigurableObject *) { throw std::runtime_error("ConfigurableObject::addChild(\"" + name + "\") not implemented"); }
 MTS_IMPLEMENT_CLASS(ConfigurableObject, true, SerializableObject)
+void NetworkedObject::serialize(Stream *stream, InstanceManager *manager) const { ConfigurableObject::serialize(stream, manager); }
+void NetworkedObject::bindUsedResources(ParallelProcess *) const {}
+void NetworkedObject::wakeup(ConfigurableObject *, std::map<std::string, SerializableObject *> &) {}
+MTS_IMPLEMENT_CLASS(NetworkedObject, true, ConfigurableObject)
 
-// ---------------------------------------------------------------- inert runtime services
-static void unsupported(const char *what) { throw std::runtime_error(std::string("oracle/_ref support: ") + what + " is not available"); }
+// ---------------------------------------------------------------- AnimatedTransform, static transforms only
+AnimatedTransform::AnimatedTransform(const AnimatedTransform *trafo) : m_transform(trafo->m_transform) { if (!trafo->m_tracks.empty()) unsupported("an animated transform"); }
+AnimatedTransform::AnimatedTransform(Stream *) { unsupported("AnimatedTransform(Stream)"); }
+AnimatedTransform::~AnimatedTransform() {}
+void AnimatedTransform::serialize(Stream *) const { unsupported("AnimatedTransform::serialize"); }
+void AnimatedTransform::prependScale(const Vector &scale) { m_transform = m_transform * Transform::scale(scale); }
+AABB AnimatedTransform::getTranslationBounds() const { Point p = m_transform(Point(0.0f)); return AABB(p, p); }
+AABB AnimatedTransform::getSpatialBounds(const AABB &aabb) const { AABB r; for (int j = 0; j < 8; ++j) r.expandBy(m_transform(aabb.getCorner(j))); return r; }
+void AnimatedTransform::TransformFunctor::operator()(const Float &, Transform &) const { unsupported("an animated transform"); }
+void AnimatedTransform::collectKeyframes(std::set<Float> &result) const { if (result.size() == 0) result.insert((Float) 0); }   // track.cpp:262-263
+std::string AnimatedTransform::toString() const { return "AnimatedTransform[static]"; }
+MTS_IMPLEMENT_CLASS(AnimatedTransform, false, Object)
 
-Thread *Thread::getThread() { static char dummy[16]; return reinterpret_cast<Thread *>(dummy); }   // never dereferenced: the members below ignore `this`
-Logger *Thread::getLogger() { return NULL; }                                                   // SLog/Log skip a NULL logger ...
-FileResolver::FileResolver() {}
-std::string FileResolver::toString() const { return "FileResolver[]"; }
-MTS_IMPLEMENT_CLASS(FileResolver, false, Object)
-FileResolver *Thread::getFileResolver() { static ref<FileResolver> resolver = new FileResolver(); return resolver.get(); }
-fs::path FileResolver::resolve(const fs::path &path) const { return path; }
-void Logger::log(ELogLevel level, const Class *, const char *file, int line, const char *fmt, ...)
-{                                                                                               // ... but Assert failures call it directly
-    char buf[2048];
-    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
-    if (level >= EError) throw std::runtime_error(std::string(buf) + " (" + file + ":" + std::to_string(line) + ")");
+// ---------------------------------------------------------------- thread-local storage
+namespace detail {
+struct ThreadLocalBase::ThreadLocalPrivate {
+    ConstructFunctor construct; DestructFunctor destruct;
+    std::mutex mutex; std::map<std::thread::id, void *> slots;
+};
+ThreadLocalBase::ThreadLocalBase(const ConstructFunctor &c, const DestructFunctor &d_) : d(new ThreadLocalPrivate()) { d->construct = c; d->destruct = d_; }
+ThreadLocalBase::~ThreadLocalBase() { for (std::map<std::thread::id, void *>::iterator it = d->slots.begin(); it != d->slots.end(); ++it) d->destruct(it->second); }
+void *ThreadLocalBase::get(bool &existed)
+{
+    std::lock_guard<std::mutex> guard(d->mutex);
+    std::map<std::thread::id, void *>::iterator it = d->slots.find(std::this_thread::get_id());
+    existed = it != d->slots.end();
+    if (existed) return it->second;
+    void *v = d->construct();
+    d->slots[std::this_thread::get_id()] = v;
+    return v;
+}
+const void *ThreadLocalBase::get(bool &existed) const { return const_cast<ThreadLocalBase *>(this)->get(existed); }
+void *ThreadLocalBase::get() { bool e; return get(e); }
+const void *ThreadLocalBase::get() const { bool e; return get(e); }
+void initializeGlobalTLS() {}
+void destroyGlobalTLS() {}
+void initializeLocalTLS() {}
+void destroyLocalTLS() {}
 }
 
-StatsCounter::StatsCounter(const std::string &, const std::string &, EStatsType, uint64_t, uint64_t) {}
-StatsCounter::~StatsCounter() {}
+// ---------------------------------------------------------------- services that are not available
+FileResolver::FileResolver() {}
+std::string FileResolver::toString() const { return "FileResolver[]"; }
+fs::path FileResolver::resolve(const fs::path &path) const { return path; }
+FileResolver *FileResolver::clone() const { return new FileResolver(); }
+MTS_IMPLEMENT_CLASS(FileResolver, false, Object)
 
 ref<PluginManager> PluginManager::m_instance;
-ConfigurableObject *PluginManager::createObject(const Class *, const Properties &) { unsupported("PluginManager::createObject"); return NULL; }
+ConfigurableObject *PluginManager::createObject(const Class *, const Properties &props)
+{                                                        // the plugins the compiled sources instantiate themselves: the aperture disk of thinlens.cpp:520-533 and its default BSDF
+    if (props.getPluginName() == "disk") return static_cast<ConfigurableObject *>(CreateInstance_disk(props));
+    if (props.getPluginName() == "diffuse") return static_cast<ConfigurableObject *>(CreateInstance_diffuse(props));   // the default BSDF of shape.cpp:48-72
+    unsupported(("PluginManager::createObject(" + props.getPluginName() + ")").c_str());
+    return NULL;
+}
+std::vector<std::string> PluginManager::getLoadedPlugins() const { return std::vector<std::string>(); }
 
-Float Random::nextFloat() { unsupported("Random"); return 0; }
-size_t Random::nextSize(size_t) { unsupported("Random"); return 0; }
+void FormatConverter::staticInitialization() {}
+void FormatConverter::staticShutdown() {}
+const FormatConverter *FormatConverter::getInstance(Conversion) { unsupported("FormatConverter"); return NULL; }
 
-Bitmap::Bitmap(EPixelFormat, EComponentFormat, const Vector2i &, uint8_t, uint8_t *) { unsupported("Bitmap"); }
-Bitmap::~Bitmap() {}
-std::string Bitmap::toString() const { return "Bitmap[]"; }
-MTS_IMPLEMENT_CLASS(Bitmap, false, Object)
-ref<Bitmap> Bitmap::arithmeticOperation(EArithmeticOperation, const Bitmap *, const Bitmap *) { unsupported("Bitmap"); return NULL; }
-
-double Stream::readDouble() { unsupported("Stream"); return 0; }
-std::string Stream::readString() { unsupported("Stream"); return ""; }
-unsigned int Stream::readUInt() { unsupported("Stream"); return 0; }
-uint64_t Stream::readULong() { unsupported("Stream"); return 0; }
-void Stream::writeULong(uint64_t) { unsupported("Stream"); }
-unsigned char Stream::readUChar() { unsupported("Stream"); return 0; }
-void Stream::readDoubleArray(double *, size_t) { unsupported("Stream"); }
-void Stream::writeUChar(unsigned char) { unsupported("Stream"); }
-void Stream::writeUInt(unsigned int) { unsupported("Stream"); }
-void Stream::writeDouble(double) { unsupported("Stream"); }
-void Stream::writeString(const std::string &) { unsupported("Stream"); }
-void Stream::writeDoubleArray(const double *, size_t) { unsupported("Stream"); }
+Font::Font(EFont) { unsupported("Font"); }
+Font::~Font() {}
+void Font::convert(Bitmap::EPixelFormat, Bitmap::EComponentFormat, Float) {}
+Vector2i Font::getSize(const std::string &) const { return Vector2i(0, 0); }
+void Font::drawText(Bitmap *, Point2i, const std::string &) const {}
+MTS_IMPLEMENT_CLASS(Font, false, Object)
 
 Shader *Renderer::registerShaderForResource(const HWResource *) { return NULL; }
 void Renderer::unregisterShaderForResource(const HWResource *) {}
-
-std::ostream &operator<<(std::ostream &os, const ETransportMode &mode) { return os << (mode == ERadiance ? "radiance" : "importance"); }
 
 MTS_NAMESPACE_END

@@ -160,3 +160,31 @@ class Emu:
 @pytest.fixture(scope="session")
 def emu():
     return Emu()
+
+
+class RefMitsuba:
+    """ctypes view of oracle/_ref/libref_mitsuba.so: the REFERENCE's own G-PT integrator (src/integrators/gpt/gpt.cpp) with
+    the scene, kd-tree, shapes, emitters, BSDFs, sensor, film and filters it runs on, compiled from /root/reference
+    (recipe: oracle/Makefile) and driven from a gdb200_scene_desc (oracle/ref_gpt_shim.cpp)."""
+    PATH = os.path.join(ROOT, "oracle", "_ref", "libref_mitsuba.so")
+
+    def __init__(self):
+        if not os.path.exists(self.PATH) and os.path.isdir(REFERENCE):
+            _make("_ref/libref_mitsuba.so")
+        self.lib = ctypes.CDLL(self.PATH)
+        self.lib.gdbref_gpt_last_error.restype = ctypes.c_char_p
+
+    @classmethod
+    def available(cls):
+        return os.path.exists(cls.PATH) or os.path.isdir(REFERENCE)
+
+    def gpt(self, desc, params, threads=1):
+        from gdb200 import scenes
+        fov, rfilter = scenes.mitsuba_sensor_args(desc)
+        h, w = desc.camera.height, desc.camera.width
+        out = np.zeros((5, h, w, 3))
+        rc = self.lib.gdbref_gpt_render(ctypes.byref(desc), ctypes.byref(params), ctypes.c_double(fov), rfilter.encode(), int(threads),
+                                        out.ctypes.data_as(ctypes.c_void_p))
+        if rc:
+            raise RuntimeError(self.lib.gdbref_gpt_last_error().decode())
+        return dict(zip(("-final", "-throughput", "-dx", "-dy", "-direct"), out))

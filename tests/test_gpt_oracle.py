@@ -36,7 +36,7 @@ def test_primal_matches_plain_path_tracer(oracle, render, name):
     assert np.isfinite(prim).all() and (prim >= 0).all()
     for c in range(3):
         a, b = prim[..., c].mean(), li[..., c].mean()
-        tol = 0.05 if name in ("roughglass", "sphere_lights") else 0.03   # caustics / a small bright bulb: heavier-tailed estimates (+-2 % at 128 spp over seeds)
+        tol = 0.05 if name in ("roughglass", "sphere_lights", "mesh_lights") else 0.03   # caustics / small bright emitters: heavier-tailed estimates (+-2 % at 128 spp over seeds)
         assert abs(a - b) <= tol * b, (name, c, a, b)       # two independent 64-spp estimates of the same mean
 
 

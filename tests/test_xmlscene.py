@@ -146,7 +146,8 @@ def test_shapes_and_emitters(tmp_path, oracle):
     assert (parsed.spp, parsed.seed, parsed.streams) == (3, 7, 2)
     assert d.camera.aperture_radius == 0.05 and d.camera.focus_distance == 4 and d.rfilter_radius == 1.0
     assert d.n_shapes == 4 and d.n_emitters == 3 and d.n_triangles == 2 + 2 + 12 and d.n_vertices == 4 + 4 + 24
-    assert [d.emitters[i].type for i in range(3)] == [scenes.EMITTER_AREA, scenes.EMITTER_POINT, scenes.EMITTER_ENVMAP]   # document order
+    # Scene::m_emitters order: scene-level emitters in document order (scene.cpp:496-516), then the shapes' area lights (scene.cpp:570-571)
+    assert [d.emitters[i].type for i in range(3)] == [scenes.EMITTER_POINT, scenes.EMITTER_ENVMAP, scenes.EMITTER_AREA]
     assert d.shapes[0].has_vertex_normals == 1 and d.shapes[1].has_vertex_normals == 0 and d.shapes[2].has_vertex_normals == 1
     assert d.materials[d.shapes[0].material].twosided == 1 and d.materials[d.shapes[0].material].type == scenes.BSDF_PLASTIC
     assert math.isclose(d.shapes[3].radius, 0.25) and np.allclose(list(d.shapes[3].center), [-0.6, 0.25, 0])
