@@ -14,8 +14,9 @@ image into row strips (strong scaling: the image is fixed).
 value : whole-job Msamples/s, scene + accumulators resident in HBM, no host copies in the timed region.
 e2e   : the same through the public API (gdb200.Scene + GPTIntegrator.render) with host buffers:
         scene upload, trace, develop, 5 fp64 buffers + the reconstructed image copied back.
---impl reference: the CPU restatement of the reference tracer (oracle/, all host cores) on a bounded
-        sample of the same workload, plus the reference's own solver (oracle/_ref) for the solve time.
+--impl reference: the reference's own tracer (gpt.cpp + the Mitsuba sources it runs on, compiled into oracle/_ref; the CPU
+        restatement under oracle/ if that build is absent) on all host cores on a bounded sample of the same workload, plus
+        the reference's own solver (oracle/_ref) for the solve time.
 """
 import argparse
 import ctypes
@@ -86,10 +87,33 @@ def load_oracle():
     return lib, ref
 
 
+REF_MITSUBA = os.path.join(ROOT, "oracle", "_ref", "libref_mitsuba.so")
+CPU_KIND_NOTE = {"reference": "tracer = the reference's gpt.cpp and the Mitsuba sources it runs on, compiled from the reference tree "
+                              "(oracle/_ref/libref_mitsuba.so), its blocks dealt to one std::thread per core",
+                 "port": "tracer = CPU restatement oracle/gpt_oracle.cpp with OpenMP over row bands (oracle/_ref/libref_mitsuba.so not built)"}
+
+
 def cpu_tracer_rate(desc, params_fn, spp, threads):
-    """Msamples/s of the CPU restatement (oracle/gpt_oracle.cpp, OpenMP) on desc at `spp`."""
-    lib, _ = load_oracle()
+    """(Msamples/s, seconds, kind) of the reference tracer on the host cores, on desc at `spp`.  kind "reference": the
+    reference's own gpt.cpp + the Mitsuba sources it runs on, compiled from the reference tree into oracle/_ref
+    (one sample stream per pixel -- the reference has no other mode); kind "port": the CPU restatement
+    oracle/gpt_oracle.cpp (OpenMP over row bands), when that library is not there."""
     from gdb200 import scenes
+    if os.path.exists(REF_MITSUBA):
+        import numpy as np
+        ref = ctypes.CDLL(REF_MITSUBA)
+        ref.gdbref_gpt_last_error.restype = ctypes.c_char_p
+        prm = params_fn(spp)
+        prm.streams_per_pixel = 1
+        fov, rfilter = scenes.mitsuba_sensor_args(desc)
+        out = np.zeros((5, desc.camera.height, desc.camera.width, 3))
+        t0 = time.perf_counter()
+        rc = ref.gdbref_gpt_render(ctypes.byref(desc), ctypes.byref(prm), ctypes.c_double(fov), rfilter.encode(), int(threads),
+                                   out.ctypes.data_as(ctypes.c_void_p))
+        dt = time.perf_counter() - t0
+        assert rc == 0, ref.gdbref_gpt_last_error()
+        return desc.camera.width * desc.camera.height * spp / dt / 1e6, dt, "reference"
+    lib, _ = load_oracle()
     prm = params_fn(spp)
     B = scenes.Buffers()
     cnt = (ctypes.c_double * 3)()
@@ -97,7 +121,7 @@ def cpu_tracer_rate(desc, params_fn, spp, threads):
     rc = lib.gdb200_oracle_gpt_render(ctypes.byref(desc), ctypes.byref(prm), ctypes.byref(B), None, cnt, threads)
     dt = time.perf_counter() - t0
     assert rc == 0
-    return cnt[0] / dt / 1e6, dt
+    return cnt[0] / dt / 1e6, dt, "port"
 
 
 def cpu_solver_seconds(w, h, preset):
@@ -157,7 +181,7 @@ def main():
         cpu_spp = max(1, args.cpu_spp // 4)
         rates = []
         for i in range(args.warmup + args.steps):
-            r, dt = cpu_tracer_rate(desc, lambda s: integ.params(s, 0, streams=min(args.streams, s)), cpu_spp, cores)
+            r, dt, kind = cpu_tracer_rate(desc, lambda s: integ.params(s, 0, streams=min(args.streams, s)), cpu_spp, cores)
             if i >= args.warmup:
                 rates.append((r, dt))
         val = sum(r for r, _ in rates) / len(rates)
@@ -167,9 +191,8 @@ def main():
                 "ms_per_step": round(1e3 * sum(dt for _, dt in rates) / len(rates), 2), "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "poisson_solve_ms": round(solve_s * 1e3, 1) if solve_s else None,
-                "cpu_baseline": {"value": round(val, 4), "unit": "Msamples/s", "cores": cores, "kind": "port",
-                                 "sample": f"{scene_name} {W}x{H} @ {cpu_spp} spp per step (of {spp}); tracer = CPU restatement "
-                                           "oracle/gpt_oracle.cpp (Mitsuba itself cannot be built here), solver = reference sources"},
+                "cpu_baseline": {"value": round(val, 4), "unit": "Msamples/s", "cores": cores, "kind": kind,
+                                 "sample": f"{scene_name} {W}x{H} @ {cpu_spp} spp per step (of {spp}); " + CPU_KIND_NOTE[kind] + ", solver = reference sources"},
                 "e2e": {"value": round(val, 4), "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
@@ -302,10 +325,9 @@ def main():
         if world > 1:
             line["exchange_bytes_per_step"] = int(agg["exchange_bytes"] / args.steps)
         if world == 1:
-            rate, dt = cpu_tracer_rate(desc, lambda s: integ.params(s, 0, streams=min(args.streams, s)), args.cpu_spp, cores)
-            line["cpu_baseline"] = {"value": round(rate, 4), "unit": "Msamples/s", "cores": cores, "kind": "port",
-                                    "sample": f"{scene_name} {W}x{H} @ {args.cpu_spp} spp (of {spp}), {dt:.1f} s, CPU restatement "
-                                              "oracle/gpt_oracle.cpp with OpenMP over row bands"}
+            rate, dt, kind = cpu_tracer_rate(desc, lambda s: integ.params(s, 0, streams=min(args.streams, s)), args.cpu_spp, cores)
+            line["cpu_baseline"] = {"value": round(rate, 4), "unit": "Msamples/s", "cores": cores, "kind": kind,
+                                    "sample": f"{scene_name} {W}x{H} @ {args.cpu_spp} spp (of {spp}), {dt:.1f} s, " + CPU_KIND_NOTE[kind]}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
