@@ -155,7 +155,7 @@ constexpr int kMaxPrims = kMaxRects + kMaxSpheres + kMaxTris;
 struct DBounds { float lo[3], hi[3]; };   // single precision is enough for a conservative (padded) slab test
 __constant__ DBounds c_bounds[kMaxPrims];
 
-struct Config { int maxDepth, minDepth, rrDepth, strictNormals; Float shiftThreshold; };
+struct Config { int maxDepth, minDepth, rrDepth, strictNormals; Float shiftThreshold; int refUninitMeasure, pad; };   // refUninitMeasure: see gpt_host.h setupArgs
 
 struct Its { Float t; V3 p, geoN; Frame sh; V3 wi; int material, emitter; };   // emitter: index or -1
 struct Ray { V3 o, d; Float mint, maxt; };

@@ -528,6 +528,11 @@ inline int setupArgs(const HostScene &s, const gdb200_gpt_params *p, GptArgs &a,
     a.bandRows = banded ? p->band_rows : 0; a.bandCount = banded ? p->band_count : 0; a.bandIndex = banded ? p->band_index : 0;
     a.cfg.maxDepth = p->max_depth; a.cfg.minDepth = 1; a.cfg.rrDepth = p->rr_depth;         // gpt.cpp:1368-1371
     a.cfg.strictNormals = p->strict_normals; a.cfg.shiftThreshold = p->shift_threshold;
+    // gpt.cpp:957 default-constructs the DirectSamplingRecord of a reconnected offset path that lands on an emitter and
+    // never sets .measure before Shape::pdfDirect (shape.cpp:116-126) reads it: undefined behaviour.  The product uses the
+    // intended ESolidAngle.  A g++ -O2 build of the reference reads a stale value that is not ESolidAngle, so area emitters
+    // report density 0 there; GDB200_REF_UNINIT_MEASURE=1 reproduces that build bit for bit (used by the parity tests).
+    { const char *e = std::getenv("GDB200_REF_UNINIT_MEASURE"); a.cfg.refUninitMeasure = (e && e[0] == '1') ? 1 : 0; a.cfg.pad = 0; }
     return GDB200_OK;
 }
 

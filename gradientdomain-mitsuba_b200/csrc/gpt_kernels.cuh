@@ -621,6 +621,7 @@ GDB_D void bounceBody(const GptArgs &a, int slot, int parity)
                                                 sd.d = (mainDRec.p - sits.p) / sd.dist;
                                                 sd.ref = mainDRec.ref; sd.refN = sits.sh.n; sd.emitter = mainDRec.emitter;
                                                 shiftedLumPdf = pdfEmitterDirect(sd);
+                                                if (cfg.refUninitMeasure && c_sceneG->emitters[sd.emitter].kind != EM_ENV) shiftedLumPdf = 0;   // gpt_host.h setupArgs
                                             } else { shiftedEmitterRadiance = mainEmitterRadiance; shiftedLumPdf = mainLumPdf; }   // gpt.cpp:973-977
                                             const Float den = (shiftedPreviousPdf * shiftedPreviousPdf) * ((shiftedLumPdf * shiftedLumPdf) + (shiftedBsdfPdf * shiftedBsdfPdf));
                                             weight = mainWeightNumerator / (kDEps + den + mainWeightDenominator);

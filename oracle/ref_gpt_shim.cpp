@@ -181,7 +181,7 @@ Built buildScene(const gdb200_scene_desc *d, const gdb200_gpt_params *prm, doubl
     for (int i = 0; i < d->n_emitters; i++) {
         const gdb200_emitter &e = d->emitters[i];
         if (e.type == GDB200_EMITTER_AREA) continue;
-        if (e.type == GDB200_EMITTER_ENVMAP) throw std::runtime_error("envmap emitters are not wired into the reference driver");
+        if (e.type == GDB200_EMITTER_ENVMAP) throw std::runtime_error("envmap emitters are not wired into the reference driver (EnvironmentMap needs Bitmap::convert, i.e. the boost::mpl format converters)");
         Properties p(e.type == GDB200_EMITTER_POINT ? "point" : "spot");
         p.setSpectrum("intensity", rgb(e.radiance)); p.setFloat("samplingWeight", e.sampling_weight);
         if (e.type == GDB200_EMITTER_POINT) p.setPoint("position", Point(e.position[0], e.position[1], e.position[2]));

@@ -5,6 +5,9 @@
 #include <ostream>
 #include <sys/stat.h>
 #include <cstdio>
+#include <stdexcept>
+#include <unistd.h>
+namespace boost { namespace system { class error_code { int v; public: error_code() : v(0) {} int value() const { return v; } void assign(int x) { v = x; } }; } }
 namespace boost { namespace filesystem {
 class path {
     std::string s;
@@ -36,6 +39,8 @@ inline unsigned long file_size(const path &p) { struct stat st; return ::stat(p.
 inline long last_write_time(const path &p) { struct stat st; return ::stat(p.c_str(), &st) == 0 ? (long) st.st_mtime : 0; }
 inline bool remove(const path &p) { return ::remove(p.c_str()) == 0; }
 inline bool create_directory(const path &p) { return ::mkdir(p.c_str(), 0777) == 0; }
+inline long last_write_time(const path &p, boost::system::error_code &ec) { struct stat st; if (::stat(p.c_str(), &st) != 0) { ec.assign(1); return 0; } return (long) st.st_mtime; }
+inline void resize_file(const path &p, unsigned long size) { if (::truncate(p.c_str(), (off_t) size) != 0) throw std::runtime_error("resize_file failed"); }
 inline path absolute(const path &p) { return p; }
 inline path complete(const path &p) { return p; }
 inline path current_path() { return path("."); }

@@ -28,6 +28,7 @@
 
 extern "C" void *CreateInstance_disk(const mitsuba::Properties &);
 extern "C" void *CreateInstance_diffuse(const mitsuba::Properties &);
+extern "C" void *CreateInstance_sphere(const mitsuba::Properties &);
 
 MTS_NAMESPACE_BEGIN
 
@@ -36,7 +37,7 @@ static void unsupported(const char *what) { throw std::runtime_error(std::string
 // ---------------------------------------------------------------- Properties
 struct PropertyElement {
     Properties::EPropertyType type;
-    bool b; int64_t i; Float f; Point p; Vector v; Transform t; Spectrum s; std::string str;
+    bool b; int64_t i; Float f; Point p; Vector v; Transform t; Spectrum s; std::string str; Properties::Data data;
     mutable bool queried;
     PropertyElement() : type(Properties::EBoolean), b(false), i(0), f(0), queried(false) {}
 };
@@ -70,6 +71,7 @@ GDB_PROP(Vector, Vector, EVector, v)
 GDB_PROP(Transform, Transform, ETransform, t)
 GDB_PROP(Spectrum, Spectrum, ESpectrum, s)
 GDB_PROP(String, std::string, EString, str)
+GDB_PROP(Data, Properties::Data, EData, data)
 bool Properties::hasProperty(const std::string &name) const { return m_elements->count(name) != 0; }
 bool Properties::removeProperty(const std::string &name) { return m_elements->erase(name) != 0; }
 Properties::EPropertyType Properties::getType(const std::string &name) const
@@ -191,6 +193,7 @@ ref<PluginManager> PluginManager::m_instance;
 ConfigurableObject *PluginManager::createObject(const Class *, const Properties &props)
 {                                                        // the plugins the compiled sources instantiate themselves: the aperture disk of thinlens.cpp:520-533 and its default BSDF
     if (props.getPluginName() == "disk") return static_cast<ConfigurableObject *>(CreateInstance_disk(props));
+    if (props.getPluginName() == "sphere") return static_cast<ConfigurableObject *>(CreateInstance_sphere(props));     // the environment map's bounding sphere, envmap.cpp:325-345
     if (props.getPluginName() == "diffuse") return static_cast<ConfigurableObject *>(CreateInstance_diffuse(props));   // the default BSDF of shape.cpp:48-72
     unsupported(("PluginManager::createObject(" + props.getPluginName() + ")").c_str());
     return NULL;

@@ -319,3 +319,19 @@ def test_gpu_reproduces_committed_golden_buffers():
         ref = {b: GOLDEN[name + b] for b in ("-throughput", "-dx", "-dy", "-direct", "-final")}
         compare(got, ref, max_flip_frac=0.01)          # 320 pixels: at most 3 may contain a branch-flipped sample
         assert integ.stats.samples == GOLDEN[name + "/counters"][0]
+
+
+def test_gpu_matches_the_reference_integrator(monkeypatch):
+    """tests/golden/ref_gpt_golden.npz holds the output of the REFERENCE's own gpt.cpp (compiled from the reference tree, see
+    tests/test_ref_gpt.py) for sixteen scene / parameter cases; the CUDA tracer must reproduce it on the same scene bytes
+    and sample streams.  GDB200_REF_UNINIT_MEASURE=1: the one place where that build's behaviour is undefined (gpt.cpp:957)."""
+    import test_ref_gpt as T
+    monkeypatch.setenv("GDB200_REF_UNINIT_MEASURE", "1")
+    golden = dict(np.load(T.GOLDEN))
+    for name in sorted(T.SCENES):
+        desc, prm = T._case(name)
+        integ = gdb200.GPTIntegrator(reconstructL1=False, reconstructL2=False, maxDepth=prm.max_depth, rrDepth=prm.rr_depth,
+                                     strictNormals=bool(prm.strict_normals), shiftThreshold=prm.shift_threshold)
+        got = integ.trace(gdb200.Scene(desc), spp=prm.spp, seed=prm.seed)
+        ref = {b: golden[name + b] for b in ("-throughput", "-dx", "-dy", "-direct", "-final")}
+        compare(got, ref, max_flip_frac=0.01)          # 320 pixels: at most 3 may contain a sample whose branch a CUDA-libm ulp flipped

@@ -10,7 +10,7 @@ per-pixel sample streams (plugin/samplers/gdb200_counter.cpp compiled against th
 Bar: every buffer agrees to 1e-11 of its mean with NO branch-flipped pixel.  One knob is set for this comparison:
 gpt.cpp:957 default-constructs a DirectSamplingRecord and never sets .measure before Shape::pdfDirect reads it
 (undefined behaviour).  Compiled with g++ -O2 the stale value is not ESolidAngle, so an area emitter reports density 0 for
-the reconnected offset path's MIS weight; GDB200_ORACLE_UNINIT_MEASURE=1 makes the restatement do the same.  Without the
+the reconnected offset path's MIS weight; GDB200_REF_UNINIT_MEASURE=1 makes the restatement do the same.  Without the
 knob (the intended ESolidAngle, which is what the product implements) only those samples differ -- also checked here.
 
 The library is a build of /root/reference and cannot be rebuilt on a box without it, so the reference's outputs are also
@@ -68,7 +68,7 @@ def _differing_pixels(got, ref):
 
 @pytest.mark.parametrize("name", sorted(SCENES))
 def test_restatement_matches_the_reference_integrator(oracle, reference, name, monkeypatch):
-    monkeypatch.setenv("GDB200_ORACLE_UNINIT_MEASURE", "1")
+    monkeypatch.setenv("GDB200_REF_UNINIT_MEASURE", "1")
     desc, prm = _case(name)
     got, _, cnt = oracle.gpt(desc, prm, threads=1)
     assert cnt[0] == W * H * SPP
@@ -105,3 +105,16 @@ def test_reference_is_thread_count_invariant():
     a, b = ref.gpt(desc, prm, threads=1), ref.gpt(desc, prm, threads=4)
     for k in BUFFERS:
         np.testing.assert_allclose(a[k], b[k], rtol=0, atol=1e-13)
+
+
+@pytest.mark.parametrize("name", sorted(SCENES))
+def test_device_code_matches_the_reference_integrator(emu, reference, name, monkeypatch):
+    """The CUDA tracer's own routines (csrc/gpt_device.cuh + gpt_kernels.cuh compiled for the host, tests/emu) against the
+    reference integrator, directly, with the same knob (read by the shared host code, csrc/gpt_host.h setupArgs)."""
+    monkeypatch.setenv("GDB200_REF_UNINIT_MEASURE", "1")
+    desc, prm = _case(name)
+    got, cnt = emu.gpt(desc, prm)
+    assert cnt[3] == W * H * SPP
+    for k in BUFFERS:
+        bad = _differing_pixels(got[k], reference[name + k])
+        assert not bad.any(), (name, k, int(bad.sum()), float(np.abs(got[k] - reference[name + k]).max()))
