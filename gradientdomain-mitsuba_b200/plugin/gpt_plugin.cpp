@@ -50,6 +50,8 @@ struct FlatScene {
 
 	/* lookupIOR (src/bsdfs/ior.h) accepts a number or a material name; the shim takes numbers only */
 	static double lookupIORValue(const Properties &p, const std::string &name, double def) {
+		if (p.hasProperty(name) && p.getType(name) != Properties::EFloat)
+			SLog(EError, "gdb200: give '%s' as a number (material names are resolved by src/bsdfs/ior.h, which a plugin cannot include)", name.c_str());
 		return p.hasProperty(name) ? (double) p.getFloat(name, (Float) def) : def;
 	}
 
@@ -68,8 +70,16 @@ struct FlatScene {
 			copySpectrum(p.getSpectrum(p.hasProperty("reflectance") ? "reflectance" : "diffuseReflectance", Spectrum(.5f)), m.reflectance);
 		} else if (cls == "RoughConductor" || cls == "SmoothConductor") {
 			m.type = cls == "RoughConductor" ? GDB200_BSDF_ROUGHCONDUCTOR : GDB200_BSDF_CONDUCTOR;
-			copySpectrum(p.getSpectrum("eta", Spectrum(0.0f)), m.eta);
-			copySpectrum(p.getSpectrum("k", Spectrum(1.0f)), m.k);
+			/* conductor.cpp:154-176, roughconductor.cpp:176-193: eta and k default to the named `material` (Cu), whose measured
+			   spectra the plugin keeps private; both are divided by extEta (a number or a name, default "air") */
+			const std::string preset = p.getString("material", "Cu");
+			if ((!p.hasProperty("eta") || !p.hasProperty("k")) && preset != "none")
+				SLog(EError, "gdb200: conductor material presets (\"%s\") are not readable from the plugin; give 'eta' and 'k' explicitly", preset.c_str());
+			if (p.hasProperty("extEta") && p.getType("extEta") != Properties::EFloat)
+				SLog(EError, "gdb200: give 'extEta' as a number");
+			const Float extEta = p.getFloat("extEta", (Float) 1.000277f);         /* ior.h:43: "air", a single-precision literal */
+			copySpectrum(p.getSpectrum("eta", Spectrum(0.0f)) / extEta, m.eta);
+			copySpectrum(p.getSpectrum("k", Spectrum(1.0f)) / extEta, m.k);
 			copySpectrum(p.getSpectrum("specularReflectance", Spectrum(1.0f)), m.specular_reflectance);
 			m.alpha = p.getFloat("alpha", 0.1f);
 			const std::string distr = p.getString("distribution", "beckmann");
@@ -80,8 +90,8 @@ struct FlatScene {
 				SLog(EError, "gdb200: anisotropic / non-visible-normal roughconductor is not supported");
 		} else if (cls == "SmoothPlastic") {
 			m.type = GDB200_BSDF_PLASTIC;                 /* plastic.cpp:143-165 */
-			m.ior_ratio = p.hasProperty("intIOR") || p.hasProperty("extIOR")
-				? lookupIORValue(p, "intIOR", 1.49) / lookupIORValue(p, "extIOR", 1.000277) : 1.49 / 1.000277;
+			/* ior.h:39-66 holds single-precision literals ("polypropylene" 1.49f, "air" 1.000277f) that lookupIOR widens to Float */
+			m.ior_ratio = lookupIORValue(p, "intIOR", (double) 1.49f) / lookupIORValue(p, "extIOR", (double) 1.000277f);
 			copySpectrum(p.getSpectrum("specularReflectance", Spectrum(1.0f)), m.specular_reflectance);
 			copySpectrum(p.getSpectrum("diffuseReflectance", Spectrum(0.5f)), m.reflectance);
 			m.nonlinear = p.getBoolean("nonlinear", false);
@@ -160,10 +170,12 @@ struct FlatScene {
 				copyMatrix(toWorld.inverse().getMatrix(), s.to_object);
 			} else if (cls == "Sphere") {
 				const Transform toWorld = p.getTransform("toWorld", Transform());
-				const Point center = toWorld(p.getPoint("center", Point(0.0f)));
+				/* sphere.cpp:107-121: objectToWorld = toWorld * scale(1/s) * translate(center), s = |toWorld(1,0,0)|, radius *= s */
+				const Float scale = p.hasProperty("toWorld") ? toWorld(Vector(1, 0, 0)).length() : (Float) 1;
+				const Point center = (toWorld * Transform::scale(Vector(1 / scale)) * Transform::translate(Vector(p.getPoint("center", Point(0.0f)))))(Point(0.0f));
 				s.type = GDB200_SHAPE_SPHERE;
 				s.center[0] = center.x; s.center[1] = center.y; s.center[2] = center.z;
-				s.radius = p.getFloat("radius", 1.0f) * toWorld(Vector(1, 0, 0)).length();
+				s.radius = p.getFloat("radius", 1.0f) * scale;
 				s.flip_normals = p.getBoolean("flipNormals", false);
 			} else if (shape->getClass()->derivesFrom(MTS_CLASS(TriMesh))) {
 				const TriMesh *mesh = static_cast<const TriMesh *>(shape);

@@ -25,9 +25,9 @@ enum ELogLevel { EInfo, EWarn, EError };
 void stubLog(ELogLevel, const char *, ...);
 struct Class { std::string getName() const; bool derivesFrom(const Class *) const; };
 struct Vector2i { int x, y; Vector2i(int = 0, int = 0); bool operator!=(const Vector2i &) const; };
-struct Vector { Float x, y, z; Vector(Float = 0, Float = 0, Float = 0); Float length() const; };
 struct Point { Float x, y, z; Point(Float = 0, Float = 0, Float = 0); Float operator[](int) const; };
-struct Spectrum { Spectrum(Float = 0); Float operator[](int) const; };
+struct Vector { Float x, y, z; Vector(Float = 0, Float = 0, Float = 0); explicit Vector(const Point &); Float length() const; };
+struct Spectrum { Spectrum(Float = 0); Float operator[](int) const; Spectrum operator/(Float) const; };
 struct Matrix4x4 { Float operator()(int, int) const; };
 struct Transform {
 	Transform();
@@ -45,6 +45,8 @@ inline Float degToRad(Float value) { return value * (3.14159265358979323846 / 18
 struct AnimatedTransform { const Transform &eval(Float) const; };
 struct Properties {
 	Properties(const std::string & = "");
+	enum EPropertyType { EBoolean, EInteger, EFloat, EPoint, EVector, ETransform, EAnimatedTransform, ESpectrum, EString, EData };
+	EPropertyType getType(const std::string &) const;
 	bool hasProperty(const std::string &) const;
 	Float getFloat(const std::string &, Float) const;
 	bool getBoolean(const std::string &, bool) const;

@@ -136,7 +136,7 @@ class SceneBuilder:
     def __init__(self, camera, rfilter_radius=0.5, rfilter="box", stddev=0.5):
         self.camera = camera
         self.rfilter_name = rfilter
-        self.rfilter_radius = rfilter_radius + 1e-5      # box.cpp:38
+        self.rfilter_radius = rfilter_radius + float(np.float32(1e-5))      # box.cpp:38: `+ 1e-5f`, a single-precision literal
         self.rfilter_table = None                        # None = box
         if rfilter == "gaussian":                        # gaussian.cpp:32-58 (Mitsuba's default film filter, film.cpp:89-95)
             self.rfilter_radius = 4 * stddev

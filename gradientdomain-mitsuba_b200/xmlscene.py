@@ -24,11 +24,14 @@ from . import meshio
 from . import scenes as S
 from ._ffi import Gdb200Error
 
-IOR_NAMES = {"vacuum": 1.0, "helium": 1.00004, "hydrogen": 1.00013, "air": 1.00028, "carbon dioxide": 1.00045, "water": 1.3330,
-             "acetone": 1.36, "ethanol": 1.361, "carbon tetrachloride": 1.461, "glycerol": 1.4729, "benzene": 1.501,
-             "silicone oil": 1.52045, "bromine": 1.661, "water ice": 1.31, "fused quartz": 1.458, "pyrex": 1.470,
-             "acrylic glass": 1.49, "polypropylene": 1.49, "bk7": 1.5046, "sodium chloride": 1.544, "amber": 1.55,
-             "pet": 1.575, "diamond": 2.419}          # src/bsdfs/ior.h
+# src/bsdfs/ior.h:39-66.  The table holds single-precision literals (`1.000277f`) that lookupIOR widens to Float, so the value
+# the plugins see is the float32 rounding of each number.
+IOR_NAMES = {k: float(np.float32(v)) for k, v in {
+    "vacuum": 1.0, "helium": 1.000036, "hydrogen": 1.000132, "air": 1.000277, "carbon dioxide": 1.00045, "water": 1.3330,
+    "acetone": 1.36, "ethanol": 1.361, "carbon tetrachloride": 1.461, "glycerol": 1.4729, "benzene": 1.501,
+    "silicone oil": 1.52045, "bromine": 1.661, "water ice": 1.31, "fused quartz": 1.458, "pyrex": 1.470,
+    "acrylic glass": 1.49, "polypropylene": 1.49, "bk7": 1.5046, "sodium chloride": 1.544, "amber": 1.55,
+    "pet": 1.5750, "diamond": 2.419}.items()}
 
 
 class ParsedScene:
@@ -245,7 +248,7 @@ class _Loader:
                 if "eta" not in p.values or "k" not in p.values:
                     raise Gdb200Error(f"{typ}: the default material \"Cu\" needs Mitsuba's spectral data files; give 'eta' and 'k' as RGB")
                 eta, k = p.get("eta"), p.get("k")
-            ext = p.get("extEta", 1.000277)
+            ext = p.get("extEta", "air")
             if isinstance(ext, str):
                 ext = self.ior(ext)
             kw = dict(eta=tuple(e / ext for e in eta), k=tuple(x / ext for x in k),

@@ -322,6 +322,19 @@ extern "C" {
 
 const char *gdbref_gpt_last_error() { return g_error.c_str(); }
 
+// The Mitsuba Scene built from `desc` (reference counted; gdbref_release_scene drops it) -- for
+// oracle/ref_plugin_roundtrip.cpp, which runs the integrator plugin's scene flattening on it.
+void *gdbref_build_scene(const gdb200_scene_desc *desc, const gdb200_gpt_params *prm, double fov_x_deg, const char *rfilter)
+{
+    try {
+        std::call_once(g_init, staticInit);
+        Built b = buildScene(desc, prm, fov_x_deg, rfilter, true);
+        b.scene->incRef();
+        return b.scene.get();
+    } catch (const std::exception &e) { g_error = e.what(); return NULL; }
+}
+void gdbref_release_scene(void *scene) { if (scene) static_cast<Scene *>(scene)->decRef(); }
+
 // The reference G-PT tracer on `desc`: out5 = [5][h][w][3] developed buffers in the order -final (preview), -throughput,
 // -dx, -dy, -direct.  fov_x_deg and rfilter are what the desc's matrices / filter table were made from.
 int gdbref_gpt_render(const gdb200_scene_desc *desc, const gdb200_gpt_params *prm, double fov_x_deg, const char *rfilter, int threads, double *out5)

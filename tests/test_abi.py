@@ -73,6 +73,20 @@ def test_plugin_shim_compiles():
     assert r.returncode == 0, r.stdout
 
 
+@pytest.mark.parametrize("source", ["gpt_plugin.cpp", "samplers/gdb200_counter.cpp"])
+def test_plugin_sources_compile_against_the_real_mitsuba_headers(source):
+    """Where the reference tree is present: the plugin sources against Mitsuba's own headers (DOUBLE_PRECISION, with the
+    stand-ins of oracle/refstubs for the boost headers they include) -- the flags of the oracle/_ref recipe."""
+    import subprocess
+    if not os.path.isdir("/root/reference/include/mitsuba"):
+        pytest.skip("needs /root/reference")
+    src = os.path.join(ROOT, "gradientdomain-mitsuba_b200", "plugin", source)
+    r = subprocess.run(["/usr/bin/g++", "-std=gnu++11", "-fsyntax-only", "-fpermissive", "-w", "-include", "unistd.h", "-include", "cassert",
+                        "-I" + os.path.join(ROOT, "oracle", "refstubs"), "-I/root/reference/include", "-I" + os.path.join(ROOT, "include"),
+                        "-DDOUBLE_PRECISION", "-DSPECTRUM_SAMPLES=3", src], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+
+
 def test_integrator_parameter_validation_matches_reference_messages():
     # gpt.cpp:1203-1210
     for kw, msg in ((dict(reconstructL1=True, reconstructL2=True), "Cannot display two reconstructions"),
