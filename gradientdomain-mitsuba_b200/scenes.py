@@ -151,8 +151,11 @@ class SceneBuilder:
         self.shapes, self.materials, self.emitters, self.vertices, self.triangles = [], [], [], [], []
 
     def envmap(self, rgb, scale=1.0, to_world=None, sampling_weight=1.0):
-        """Environment emitter (envmap.cpp) from a float32 lat-long image [h, w, 3] (row 0 = +y pole)."""
-        self._env_rgb = np.ascontiguousarray(rgb, dtype=np.float32)
+        """Environment emitter (envmap.cpp) from a float32 lat-long image [h, w, 3] (row 0 = +y pole).  The reference keeps the
+        map in a MIP pyramid of HALF-precision texels (envmap.cpp:102-103: TMIPMap<Spectrum, SpectrumHalf>), so what it samples
+        and evaluates is the float16 rounding of the file's pixels; the descriptor carries those values."""
+        with np.errstate(over="ignore"):
+            self._env_rgb = np.ascontiguousarray(np.asarray(rgb, dtype=np.float32).astype(np.float16).astype(np.float32))
         self._env_scale, self._env_to_world = float(scale), (np.eye(4) if to_world is None else np.asarray(to_world, float))
         e = Emitter()
         e.shape, e.type, e.radiance, e.sampling_weight = -1, EMITTER_ENVMAP, D3(0, 0, 0), sampling_weight
@@ -182,8 +185,10 @@ class SceneBuilder:
         return len(self.emitters) - 1
 
     def _bounds(self):
-        """Scene::getAABB as EnvironmentMap::createShape sees it (scene.cpp:386-396): all shapes + the camera position."""
-        pts = [np.array(self.camera.camera_to_world[3:12:4])]
+        """Scene::getAABB as EnvironmentMap::createShape sees it (scene.cpp:386-396): the kd-tree's bounding box -- the tight
+        box of all shapes enlarged by MTS_KD_AABB_EPSILON = 1e-3f, min first and then max from the already moved min
+        (gkdtree.h:1213-1220) -- expanded by the sensor's position."""
+        pts = []
         for sh in self.shapes:
             if sh.type == SHAPE_RECTANGLE:
                 m = np.array(sh.to_world).reshape(4, 4)
@@ -193,7 +198,12 @@ class SceneBuilder:
                 pts += [c - sh.radius, c + sh.radius]
         pts += [np.asarray(v, float) for v in self.vertices]
         pts = np.array(pts)
-        return pts.min(axis=0), pts.max(axis=0)
+        lo, hi = pts.min(axis=0), pts.max(axis=0)
+        eps = float(np.float32(1e-3))
+        lo = lo - ((hi - lo) * eps + eps)
+        hi = hi + ((hi - lo) * eps + eps)
+        cam = np.array(self.camera.camera_to_world[3:12:4])
+        return np.minimum(lo, cam), np.maximum(hi, cam)
 
     def material(self, **kw):
         m = Material()

@@ -175,7 +175,7 @@ typedef struct gdb200_emitter {
 } gdb200_emitter;
 
 /* Latitude-longitude environment map (envmap.cpp).  Texels are the top MIP level as the reference holds it
- * (RGB converted to Float); lookups are bilinear on that level, u repeats, v clamps (envmap.cpp:392-396,
+ * (Emitter::getBitmap: the pyramid stores HALF-precision texels, envmap.cpp:102-103, so these are float16-representable values); lookups are bilinear on that level, u repeats, v clamps (envmap.cpp:392-396,
  * mipmap.h:503-596).  The bounding sphere is what EnvironmentMap::createShape derives from the scene:
  * scene->getAABB().getBSphere() with its radius * 1.5 (envmap.cpp:325-329). */
 typedef struct gdb200_envmap {

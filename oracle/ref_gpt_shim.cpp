@@ -36,7 +36,7 @@ void *CreateInstance_conductor(const Properties &); void *CreateInstance_dielect
 void *CreateInstance_plastic(const Properties &); void *CreateInstance_roughdielectric(const Properties &);
 void *CreateInstance_twosided(const Properties &);
 void *CreateInstance_rectangle(const Properties &); void *CreateInstance_sphere(const Properties &);
-void *CreateInstance_area(const Properties &); void *CreateInstance_point(const Properties &); void *CreateInstance_spot(const Properties &);
+void *CreateInstance_envmap(const Properties &); void *CreateInstance_area(const Properties &); void *CreateInstance_point(const Properties &); void *CreateInstance_spot(const Properties &);
 void *CreateInstance_perspective(const Properties &); void *CreateInstance_thinlens(const Properties &);
 void *CreateInstance_multifilm(const Properties &);
 void *CreateInstance_box(const Properties &); void *CreateInstance_gaussian(const Properties &); void *CreateInstance_tent(const Properties &);
@@ -181,7 +181,22 @@ Built buildScene(const gdb200_scene_desc *d, const gdb200_gpt_params *prm, doubl
     for (int i = 0; i < d->n_emitters; i++) {
         const gdb200_emitter &e = d->emitters[i];
         if (e.type == GDB200_EMITTER_AREA) continue;
-        if (e.type == GDB200_EMITTER_ENVMAP) throw std::runtime_error("envmap emitters are not wired into the reference driver (EnvironmentMap needs Bitmap::convert, i.e. the boost::mpl format converters)");
+        if (e.type == GDB200_EMITTER_ENVMAP) {                                     // envmap.cpp:108-181: the map handed over in memory ("bitmap" data property)
+            const gdb200_envmap *env = d->envmap;
+            if (!env) throw std::runtime_error("envmap emitter without gdb200_scene_desc.envmap");
+            ref<Bitmap> bmp = new Bitmap(Bitmap::ERGB, Bitmap::EFloat32, Vector2i(env->width, env->height));
+            memcpy(bmp->getFloat32Data(), env->rgb, sizeof(float) * 3 * (size_t) env->width * env->height);
+            bmp->incRef();                                                           // the emitter keeps no reference to its input
+            Properties p("envmap");
+            Properties::Data data; data.ptr = (uint8_t *) bmp.get(); data.size = sizeof(Bitmap);
+            p.setData("bitmap", data);
+            p.setFloat("scale", env->scale); p.setTransform("toWorld", transformOf(env->to_world)); p.setFloat("samplingWeight", e.sampling_weight);
+            p.setBoolean("cache", false);
+            Emitter *em = make<Emitter>(CreateInstance_envmap, p);
+            em->configure();
+            ordered[i] = em;
+            continue;
+        }
         Properties p(e.type == GDB200_EMITTER_POINT ? "point" : "spot");
         p.setSpectrum("intensity", rgb(e.radiance)); p.setFloat("samplingWeight", e.sampling_weight);
         if (e.type == GDB200_EMITTER_POINT) p.setPoint("position", Point(e.position[0], e.position[1], e.position[2]));
@@ -334,6 +349,32 @@ void *gdbref_build_scene(const gdb200_scene_desc *desc, const gdb200_gpt_params 
     } catch (const std::exception &e) { g_error = e.what(); return NULL; }
 }
 void gdbref_release_scene(void *scene) { if (scene) static_cast<Scene *>(scene)->decRef(); }
+
+// EnvironmentMap::sampleDirect / pdfDirect / evalEnvironment of the scene's environment emitter (envmap.cpp:516-556,376-409)
+// from the reference point `ref`: per sample the world direction, the solid-angle density sampleDirect reports, the density
+// pdfDirect reports for that direction, value / pdf as returned (RGB) and evalEnvironment along the direction (RGB).
+int gdbref_envmap_sample(void *handle, const double *ref, int n, const double *samples, double *dir, double *pdfSample, double *pdfEval,
+                         double *weight, double *radiance)
+{
+    try {
+        Scene *scene = static_cast<Scene *>(handle);
+        const Emitter *env = scene->getEnvironmentEmitter();
+        if (!env) throw std::runtime_error("the scene has no environment emitter");
+        for (int i = 0; i < n; i++) {
+            DirectSamplingRecord dRec(Point(ref[0], ref[1], ref[2]), 0.0f);
+            const Spectrum w = env->sampleDirect(dRec, Point2(samples[2 * i], samples[2 * i + 1]));
+            dir[3 * i] = dRec.d.x; dir[3 * i + 1] = dRec.d.y; dir[3 * i + 2] = dRec.d.z;
+            pdfSample[i] = dRec.pdf;
+            pdfEval[i] = env->pdfDirect(dRec);
+            Float r, g, b; w.toLinearRGB(r, g, b);
+            weight[3 * i] = r; weight[3 * i + 1] = g; weight[3 * i + 2] = b;
+            const Spectrum L = env->evalEnvironment(RayDifferential(Ray(dRec.ref, dRec.d, 0.0f)));
+            L.toLinearRGB(r, g, b);
+            radiance[3 * i] = r; radiance[3 * i + 1] = g; radiance[3 * i + 2] = b;
+        }
+        return 0;
+    } catch (const std::exception &e) { g_error = e.what(); return 1; }
+}
 
 // The reference G-PT tracer on `desc`: out5 = [5][h][w][3] developed buffers in the order -final (preview), -throughput,
 // -dx, -dy, -direct.  fov_x_deg and rfilter are what the desc's matrices / filter table were made from.

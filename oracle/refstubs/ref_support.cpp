@@ -14,6 +14,7 @@
 #include <mitsuba/core/netobject.h>
 #include <mitsuba/core/plugin.h>
 #include <mitsuba/core/bitmap.h>
+#include <mitsuba/core/half.h>
 #include <mitsuba/core/fresolver.h>
 #include <mitsuba/core/track.h>
 #include <mitsuba/core/tls.h>
@@ -21,6 +22,7 @@
 #include <mitsuba/render/common.h>
 #include <mitsuba/hw/renderer.h>
 #include <mitsuba/hw/font.h>
+#include <mitsuba/hw/gputexture.h>
 #include <thread>
 #include <mutex>
 #include <sstream>
@@ -29,6 +31,7 @@
 extern "C" void *CreateInstance_disk(const mitsuba::Properties &);
 extern "C" void *CreateInstance_diffuse(const mitsuba::Properties &);
 extern "C" void *CreateInstance_sphere(const mitsuba::Properties &);
+extern "C" void *CreateInstance_lanczos(const mitsuba::Properties &);
 
 MTS_NAMESPACE_BEGIN
 
@@ -194,15 +197,65 @@ ConfigurableObject *PluginManager::createObject(const Class *, const Properties 
 {                                                        // the plugins the compiled sources instantiate themselves: the aperture disk of thinlens.cpp:520-533 and its default BSDF
     if (props.getPluginName() == "disk") return static_cast<ConfigurableObject *>(CreateInstance_disk(props));
     if (props.getPluginName() == "sphere") return static_cast<ConfigurableObject *>(CreateInstance_sphere(props));     // the environment map's bounding sphere, envmap.cpp:325-345
+    if (props.getPluginName() == "lanczos") return static_cast<ConfigurableObject *>(CreateInstance_lanczos(props));   // the MIP pyramid's filter, envmap.cpp:166-171
     if (props.getPluginName() == "diffuse") return static_cast<ConfigurableObject *>(CreateInstance_diffuse(props));   // the default BSDF of shape.cpp:48-72
     unsupported(("PluginManager::createObject(" + props.getPluginName() + ")").c_str());
     return NULL;
 }
 std::vector<std::string> PluginManager::getLoadedPlugins() const { return std::vector<std::string>(); }
 
+// Bitmap::convert goes through FormatConverter (fmtconv.cpp instantiates every pair with boost::mpl).  Stand-in: plain
+// component casts between the floating-point formats for conversions that change neither the channel layout (RGB <-> the
+// 3-sample Spectrum of this build is the identity, spectrum.h) nor the gamma nor the scale -- what EnvironmentMap /
+// MIPMap ask for with a linear RGB float map.  Anything else raises.
+namespace {
+int channelsOf(Bitmap::EPixelFormat f, int channelCount)
+{
+    switch (f) {
+        case Bitmap::ELuminance: return 1; case Bitmap::ELuminanceAlpha: return 2;
+        case Bitmap::ERGB: case Bitmap::EXYZ: case Bitmap::ESpectrum: return 3;
+        case Bitmap::ERGBA: case Bitmap::EXYZA: case Bitmap::ESpectrumAlpha: return 4;
+        case Bitmap::ESpectrumAlphaWeight: return 5;
+        default: return channelCount;
+    }
+}
+template <typename S, typename D> struct CastConverter : FormatConverter {
+    Conversion m_conv;
+    CastConverter(Format a, Format b) : m_conv(a, b) {}
+    Conversion getConversion() const { return m_conv; }
+    void convert(Bitmap::EPixelFormat sf, Float sg, const void *src, Bitmap::EPixelFormat df, Float dg, void *dst, size_t count,
+                 Float multiplier, Spectrum::EConversionIntent, int channelCount) const
+    {
+        const bool sameLayout = sf == df || ((sf == Bitmap::ERGB || sf == Bitmap::ESpectrum) && (df == Bitmap::ERGB || df == Bitmap::ESpectrum));
+        if (!sameLayout || sg != dg || multiplier != 1) unsupported("this Bitmap::convert (layout, gamma or scale change)");
+        const size_t n = count * (size_t) channelsOf(sf, channelCount);
+        const S *s = static_cast<const S *>(src); D *d = static_cast<D *>(dst);
+        for (size_t i = 0; i < n; i++) d[i] = (D) (float) s[i];
+    }
+};
+}
+FormatConverter::ConverterMap FormatConverter::m_converters;
 void FormatConverter::staticInitialization() {}
 void FormatConverter::staticShutdown() {}
-const FormatConverter *FormatConverter::getInstance(Conversion) { unsupported("FormatConverter"); return NULL; }
+const FormatConverter *FormatConverter::getInstance(Conversion c)
+{
+    static CastConverter<float, float> ff(Bitmap::EFloat32, Bitmap::EFloat32);
+    static CastConverter<float, double> fd(Bitmap::EFloat32, Bitmap::EFloat64);
+    static CastConverter<double, float> df(Bitmap::EFloat64, Bitmap::EFloat32);
+    static CastConverter<double, double> dd(Bitmap::EFloat64, Bitmap::EFloat64);
+    static CastConverter<half, float> hf(Bitmap::EFloat16, Bitmap::EFloat32);          // MIPMap::toBitmap of the half-precision pyramid
+    static CastConverter<half, double> hd(Bitmap::EFloat16, Bitmap::EFloat64);
+    static CastConverter<half, half> hh(Bitmap::EFloat16, Bitmap::EFloat16);
+    if (c.first == Bitmap::EFloat16 && c.second == Bitmap::EFloat32) return &hf;
+    if (c.first == Bitmap::EFloat16 && c.second == Bitmap::EFloat64) return &hd;
+    if (c.first == Bitmap::EFloat16 && c.second == Bitmap::EFloat16) return &hh;
+    if (c.first == Bitmap::EFloat32 && c.second == Bitmap::EFloat32) return &ff;
+    if (c.first == Bitmap::EFloat32 && c.second == Bitmap::EFloat64) return &fd;
+    if (c.first == Bitmap::EFloat64 && c.second == Bitmap::EFloat32) return &df;
+    if (c.first == Bitmap::EFloat64 && c.second == Bitmap::EFloat64) return &dd;
+    unsupported("FormatConverter for non-float components");
+    return NULL;
+}
 
 Font::Font(EFont) { unsupported("Font"); }
 Font::~Font() {}
@@ -211,6 +264,7 @@ Vector2i Font::getSize(const std::string &) const { return Vector2i(0, 0); }
 void Font::drawText(Bitmap *, Point2i, const std::string &) const {}
 MTS_IMPLEMENT_CLASS(Font, false, Object)
 
+void GPUTexture::initAndRelease() {}
 Shader *Renderer::registerShaderForResource(const HWResource *) { return NULL; }
 void Renderer::unregisterShaderForResource(const HWResource *) {}
 

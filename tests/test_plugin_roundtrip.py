@@ -39,7 +39,7 @@ def _arr(x, n=None):
 
 
 @pytest.mark.parametrize("name", ["cbox_diffuse", "cbox_glossy", "cbox_materials", "cbox_mesh_lights", "cbox_smooth", "cbox_point",
-                                  "cbox_spot", "cbox_dof", "cbox_roughglass", "cbox_sphere_lights"])
+                                  "cbox_spot", "cbox_dof", "cbox_roughglass", "cbox_sphere_lights", "cbox_env"])
 def test_flattening_a_mitsuba_scene_gives_back_the_description(flatten, oracle, name):
     desc = getattr(scenes, name)(20, 16)
     prm = scenes.default_params(spp=2, seed=4)
@@ -84,6 +84,13 @@ def test_flattening_a_mitsuba_scene_gives_back_the_description(flatten, oracle, 
             assert ma.ior_ratio == mb.ior_ratio
         if ma.type in (scenes.BSDF_DIFFUSE, scenes.BSDF_PLASTIC):
             np.testing.assert_array_equal(_arr(ma.reflectance), _arr(mb.reflectance))
+    if desc.envmap:
+        e0, e1 = desc.envmap.contents, got.envmap.contents
+        assert (e0.width, e0.height, e0.scale, e0.bsphere_radius) == (e1.width, e1.height, e1.scale, e1.bsphere_radius)
+        np.testing.assert_array_equal(_arr(e0.bsphere_center), _arr(e1.bsphere_center))          # the kd-tree's enlarged box + the sensor, scene.cpp:386-396
+        np.testing.assert_array_equal(_arr(e0.to_world), _arr(e1.to_world))
+        np.testing.assert_array_equal(np.ctypeslib.as_array(e0.rgb, shape=(e0.height, e0.width, 3)),
+                                      np.ctypeslib.as_array(e1.rgb, shape=(e1.height, e1.width, 3)))      # half-precision texels, envmap.cpp:102-103
     # the same picture: both descriptions through the CPU restatement (vertex tables may be laid out differently)
     ref, _, c1 = oracle.gpt(desc, prm, threads=1)
     out, _, c2 = oracle.gpt(got, prm, threads=1)

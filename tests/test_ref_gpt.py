@@ -34,6 +34,8 @@ SCENES = {
     "cbox_glossy_strict": dict(scene="cbox_glossy", strict_normals=True), "cbox_glossy_depth3": dict(scene="cbox_glossy", max_depth=3),
     "cbox_glossy_rr2": dict(scene="cbox_glossy", rr_depth=2), "cbox_glossy_thr": dict(scene="cbox_glossy", shift_threshold=0.1),
     "cbox_diffuse_gaussian": dict(scene="cbox_diffuse", scene_kw=dict(rfilter="gaussian")),
+    "cbox_env": dict(), "cbox_env_strict": dict(scene="cbox_env", strict_normals=True),            # environment emitter, environmentShift (gpt.cpp:348-369)
+    "atrium": dict(scene_kw=dict(columns=3, segments=8, rings=4)),                                 # sky-lit, > 192 triangles (BVH path of the product)
 }
 
 
