@@ -483,6 +483,7 @@ class _Loader:
         cam.sample_to_camera = S.D16(*np.linalg.inv(cam_to_sample).reshape(-1))
         cam.camera_to_world = S.D16(*to_world.reshape(-1))
         cam.near_clip, cam.far_clip, cam.width, cam.height = near, far, width, height
+        cam.fov_deg = xfov                                                      # not in the C struct; see scenes.make_camera
         if typ == "thinlens":                                                   # thinlens.cpp:132-137
             if "apertureRadius" not in p.values:
                 raise Gdb200Error("Property \"apertureRadius\" has not been specified!")

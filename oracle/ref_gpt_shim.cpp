@@ -350,6 +350,32 @@ void *gdbref_build_scene(const gdb200_scene_desc *desc, const gdb200_gpt_params 
 }
 void gdbref_release_scene(void *scene) { if (scene) static_cast<Scene *>(scene)->decRef(); }
 
+// PerspectiveCamera's horizontal field of view for a sensor described the way a scene file does (sensor.cpp:244-307):
+// `fov` with `fovAxis` (x, y, diagonal, smaller, larger) when fov >= 0, else `focalLength` (e.g. "50mm"); film width x height.
+double gdbref_sensor_xfov(double fov, const char *fovAxis, const char *focalLength, int width, int height)
+{
+    try {
+        std::call_once(g_init, staticInit);
+        Properties sp("perspective");
+        if (fov >= 0) { sp.setFloat("fov", fov); sp.setString("fovAxis", fovAxis); }
+        else if (focalLength && focalLength[0]) sp.setString("focalLength", focalLength);
+        Sensor *sensor = make<Sensor>(CreateInstance_perspective, sp);
+        Properties fp("multifilm");
+        fp.setInteger("width", width); fp.setInteger("height", height); fp.setBoolean("banner", false); fp.setString("fileFormat", "pfm");
+        Film *film = make<Film>(CreateInstance_multifilm, fp);
+        ReconstructionFilter *filter = make<ReconstructionFilter>(CreateInstance_box, Properties("box"));
+        filter->configure();
+        attach(film, filter);
+        film->configure();
+        Sampler *sampler = make<Sampler>(CreateInstance_gdb200_counter, Properties("gdb200_counter"));
+        sampler->configure();
+        attach(sensor, film);
+        attach(sensor, sampler);
+        sensor->configure();
+        return static_cast<PerspectiveCamera *>(sensor)->getXFov();
+    } catch (const std::exception &e) { g_error = e.what(); return -1; }
+}
+
 // EnvironmentMap::sampleDirect / pdfDirect / evalEnvironment of the scene's environment emitter (envmap.cpp:516-556,376-409)
 // from the reference point `ref`: per sample the world direction, the solid-angle density sampleDirect reports, the density
 // pdfDirect reports for that direction, value / pdf as returned (RGB) and evalEnvironment along the direction (RGB).

@@ -172,4 +172,20 @@ int gdbref_warp(int kind, double param, int n, const double *in, double *out)
     });
 }
 
+
+// src/libcore/transform.cpp: kind 0 lookAt(origin, target, up), 1 rotate(axis, angle in degrees = a[3]), 2 scale(v), 3 translate(v),
+// 4 perspective(fov = a[0], near = a[1], far = a[2]); out = the 4x4 matrix followed by the 4x4 inverse the Transform carries.
+int gdbref_transform(int kind, const double *a, double *out)
+{
+    return guarded([&] {
+        Transform t;
+        if (kind == 0) t = Transform::lookAt(Point(a[0], a[1], a[2]), Point(a[3], a[4], a[5]), Vector(a[6], a[7], a[8]));
+        else if (kind == 1) t = Transform::rotate(Vector(a[0], a[1], a[2]), a[3]);
+        else if (kind == 2) t = Transform::scale(Vector(a[0], a[1], a[2]));
+        else if (kind == 3) t = Transform::translate(Vector(a[0], a[1], a[2]));
+        else t = Transform::perspective(a[0], a[1], a[2]);
+        for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) { out[4 * r + c] = t.getMatrix()(r, c); out[16 + 4 * r + c] = t.getInverseMatrix()(r, c); }
+    });
+}
+
 }

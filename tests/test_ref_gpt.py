@@ -120,3 +120,31 @@ def test_device_code_matches_the_reference_integrator(emu, reference, name, monk
     for k in BUFFERS:
         bad = _differing_pixels(got[k], reference[name + k])
         assert not bad.any(), (name, k, int(bad.sum()), float(np.abs(got[k] - reference[name + k]).max()))
+
+
+@pytest.mark.parametrize("sensor,size", [('<float name="fov" value="45"/>', (640, 480)),
+                                         ('<float name="fov" value="45"/><string name="fovAxis" value="y"/>', (640, 480)),
+                                         ('<float name="fov" value="45"/><string name="fovAxis" value="diagonal"/>', (640, 480)),
+                                         ('<float name="fov" value="45"/><string name="fovAxis" value="smaller"/>', (640, 480)),
+                                         ('<float name="fov" value="45"/><string name="fovAxis" value="smaller"/>', (480, 640)),
+                                         ('<float name="fov" value="45"/><string name="fovAxis" value="larger"/>', (480, 640)),
+                                         ('<string name="focalLength" value="35mm"/>', (640, 480)), ('', (300, 200))])
+def test_scene_file_sensor_matches_the_reference_camera(sensor, size):
+    """gdb200.xmlscene's reading of fov / fovAxis / focalLength (sensor.cpp:244-307) against the reference's PerspectiveCamera."""
+    import ctypes
+    import re
+    if not RefMitsuba.available() or os.environ.get("GDB200_NO_REF"):
+        pytest.skip("needs the compiled reference")
+    ref = RefMitsuba()
+    ref.lib.gdbref_sensor_xfov.restype = ctypes.c_double
+    xml = f"""<scene version="0.5.0"><integrator type="gpt"/>
+      <sensor type="perspective">{sensor}<film type="multifilm"><integer name="width" value="{size[0]}"/><integer name="height" value="{size[1]}"/></film></sensor>
+      <shape type="sphere"><bsdf type="diffuse"/></shape>
+      <emitter type="point"><point name="position" x="0" y="0" z="3"/><rgb name="intensity" value="1"/></emitter></scene>"""
+    got = gdb200.load_scene(xml).desc._owner.camera.fov_deg
+    fov = re.search(r'name="fov" value="([\d.]+)"', sensor)
+    axis = re.search(r'name="fovAxis" value="(\w+)"', sensor)
+    focal = re.search(r'name="focalLength" value="(\w+)"', sensor)
+    expect = ref.lib.gdbref_sensor_xfov(ctypes.c_double(float(fov.group(1)) if fov else -1.0), (axis.group(1) if axis else "x").encode(),
+                                        (focal.group(1) if focal else "").encode(), size[0], size[1])
+    assert expect > 0 and abs(got - expect) <= 1e-12 * expect, (got, expect)

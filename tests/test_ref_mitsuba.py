@@ -177,3 +177,31 @@ def test_bsdf_matches_the_reference_plugin(oracle, emu, reference_outputs, impl,
         f, p = plug.eval(wi, R[f"{name}/{j}/s_wo"], False)
         _agree(f, R[f"{name}/{j}/es_f"], (name, j, "eval at sampled"))
         _agree(p, R[f"{name}/{j}/es_pdf"], (name, j, "pdf at sampled"))
+
+
+def test_transform_algebra_matches_the_reference():
+    """The scene front ends' lookAt / rotate / scale / translate / perspective (gdb200.scenes, gdb200.xmlscene) against
+    src/libcore/transform.cpp."""
+    from gdb200 import xmlscene
+    if not os.path.exists(REF_LIB):
+        pytest.skip("needs oracle/_ref/libref_mitsuba.so")
+    lib = ctypes.CDLL(REF_LIB)
+
+    def ref(kind, args):
+        a, out = np.array(args, dtype=float), np.zeros(32)
+        assert lib.gdbref_transform(kind, P(a), P(out)) == 0
+        return out[:16].reshape(4, 4), out[16:].reshape(4, 4)
+    rng = np.random.default_rng(5)
+    for _ in range(20):
+        o, t, up = rng.normal(size=3), rng.normal(size=3), rng.normal(size=3)
+        m, inv = ref(0, list(o) + list(t) + list(up))
+        np.testing.assert_allclose(scenes.look_at(o, t, up), m, rtol=0, atol=1e-14)
+        np.testing.assert_allclose(np.linalg.inv(scenes.look_at(o, t, up)), inv, rtol=0, atol=1e-12)
+        axis, ang = rng.normal(size=3), float(rng.uniform(-360, 360))
+        np.testing.assert_allclose(xmlscene.rotate(axis, ang), ref(1, list(axis) + [ang])[0], rtol=0, atol=1e-14)
+        v = rng.uniform(0.1, 3, size=3)
+        np.testing.assert_array_equal(scenes.scale(v), ref(2, v)[0])
+        np.testing.assert_array_equal(scenes.translate(v), ref(3, v)[0])
+        fov, near, far = float(rng.uniform(5, 150)), float(rng.uniform(1e-3, 1)), float(rng.uniform(10, 1e4))
+        np.testing.assert_allclose(scenes.perspective(fov, near, far), ref(4, [fov, near, far])[0], rtol=1e-14, atol=0)
+    np.testing.assert_allclose(scenes.rotate_y(25.0), ref(1, [0, 1, 0, 25.0])[0], rtol=0, atol=1e-15)
