@@ -337,6 +337,9 @@ extern "C" {
 
 const char *gdbref_gpt_last_error() { return g_error.c_str(); }
 
+// Mitsuba's start-up sequence, once per process (every entry point of the library calls it first).
+void gdbref_static_init() { std::call_once(g_init, staticInit); }
+
 // The Mitsuba Scene built from `desc` (reference counted; gdbref_release_scene drops it) -- for
 // oracle/ref_plugin_roundtrip.cpp, which runs the integrator plugin's scene flattening on it.
 void *gdbref_build_scene(const gdb200_scene_desc *desc, const gdb200_gpt_params *prm, double fov_x_deg, const char *rfilter)

@@ -11,6 +11,8 @@
 #include <mitsuba/core/properties.h>
 #include <mitsuba/core/warp.h>
 #include <mitsuba/core/frame.h>
+#include <mitsuba/core/bitmap.h>
+#include <mitsuba/core/fstream.h>
 #include "/root/reference/src/bsdfs/microfacet.h"
 #include <stdexcept>
 #include <string>
@@ -46,6 +48,7 @@ template <typename F> int guarded(F f)
 
 extern "C" {
 
+void gdbref_static_init();                                                     // ref_gpt_shim.cpp
 const char *gdbref_last_error() { return g_error.c_str(); }
 
 // kinds: 0 float, 1 spectrum (RGB), 2 string, 3 boolean.  `nested` (a BSDF from this function) is attached as a child
@@ -54,8 +57,7 @@ void *gdbref_bsdf_create(const char *plugin, int n, const char **keys, const int
 {
     void *result = NULL;
     guarded([&] {
-        static bool rtti = false;
-        if (!rtti) { Class::staticInitialization(); rtti = true; }            // resolves the super-class links derivesFrom() walks
+        gdbref_static_init();                                                  // incl. Class::staticInitialization: the super-class links derivesFrom() walks
         Properties props(plugin);
         for (int i = 0; i < n; i++) {
             if (kinds[i] == 0) props.setFloat(keys[i], values[3 * i]);
@@ -185,6 +187,28 @@ int gdbref_transform(int kind, const double *a, double *out)
         else if (kind == 3) t = Transform::translate(Vector(a[0], a[1], a[2]));
         else t = Transform::perspective(a[0], a[1], a[2]);
         for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) { out[4 * r + c] = t.getMatrix()(r, c); out[16 + 4 * r + c] = t.getInverseMatrix()(r, c); }
+    });
+}
+
+
+// Bitmap::write(EPFM) / the EPFM reader (src/libcore/bitmap.cpp:3745-3850): writes rgb [h][w][3] float32 to `path` with the
+// reference's writer, or reads `path` with the reference's reader into rgb (which must hold w*h*3 floats; w, h are returned).
+int gdbref_pfm(int write, const char *path, int *w, int *h, float *rgb)
+{
+    return guarded([&] {
+        gdbref_static_init();
+        if (write) {
+            ref<Bitmap> bmp = new Bitmap(Bitmap::ERGB, Bitmap::EFloat32, Vector2i(*w, *h));
+            memcpy(bmp->getFloat32Data(), rgb, sizeof(float) * 3 * (size_t) *w * *h);
+            ref<FileStream> fs = new FileStream(path, FileStream::ETruncWrite);
+            bmp->write(Bitmap::EPFM, fs);
+        } else {
+            ref<FileStream> fs = new FileStream(path, FileStream::EReadOnly);
+            ref<Bitmap> bmp = new Bitmap(Bitmap::EPFM, fs);
+            if (bmp->getChannelCount() != 3 || bmp->getComponentFormat() != Bitmap::EFloat32) throw std::runtime_error("unexpected PFM layout");
+            if (rgb && *w == bmp->getWidth() && *h == bmp->getHeight()) memcpy(rgb, bmp->getFloat32Data(), sizeof(float) * 3 * (size_t) *w * *h);
+            *w = bmp->getWidth(); *h = bmp->getHeight();
+        }
     });
 }
 

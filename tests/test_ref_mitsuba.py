@@ -205,3 +205,22 @@ def test_transform_algebra_matches_the_reference():
         fov, near, far = float(rng.uniform(5, 150)), float(rng.uniform(1e-3, 1)), float(rng.uniform(10, 1e4))
         np.testing.assert_allclose(scenes.perspective(fov, near, far), ref(4, [fov, near, far])[0], rtol=1e-14, atol=0)
     np.testing.assert_allclose(scenes.rotate_y(25.0), ref(1, [0, 1, 0, 25.0])[0], rtol=0, atol=1e-15)
+
+
+def test_pfm_files_match_the_reference_reader_and_writer(tmp_path):
+    """gdb200.pfm against Bitmap::write(EPFM) / the EPFM reader of src/libcore/bitmap.cpp: identical bytes, identical pixels."""
+    from gdb200 import pfm
+    if not os.path.exists(REF_LIB):
+        pytest.skip("needs oracle/_ref/libref_mitsuba.so")
+    lib = ctypes.CDLL(REF_LIB)
+    lib.gdbref_last_error.restype = ctypes.c_char_p
+    rng = np.random.default_rng(2)
+    img = (rng.random((13, 21, 3)) * 5).astype(np.float32)
+    w, h = ctypes.c_int(21), ctypes.c_int(13)
+    ours, theirs = str(tmp_path / "ours.pfm"), str(tmp_path / "theirs.pfm")
+    pfm.write_pfm(ours, img)
+    assert lib.gdbref_pfm(1, theirs.encode(), ctypes.byref(w), ctypes.byref(h), P(img)) == 0, lib.gdbref_last_error()
+    assert open(ours, "rb").read() == open(theirs, "rb").read()
+    back = np.zeros_like(img)
+    assert lib.gdbref_pfm(0, ours.encode(), ctypes.byref(w), ctypes.byref(h), P(back)) == 0, lib.gdbref_last_error()
+    assert (w.value, h.value) == (21, 13) and np.array_equal(back, img) and np.array_equal(pfm.read_pfm(theirs), img)
