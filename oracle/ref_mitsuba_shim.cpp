@@ -13,6 +13,7 @@
 #include <mitsuba/core/frame.h>
 #include <mitsuba/core/bitmap.h>
 #include <mitsuba/core/fstream.h>
+#include <mitsuba/render/trimesh.h>
 #include "/root/reference/src/bsdfs/microfacet.h"
 #include <stdexcept>
 #include <string>
@@ -28,6 +29,7 @@ void *CreateInstance_dielectric(const Properties &);
 void *CreateInstance_plastic(const Properties &);
 void *CreateInstance_roughdielectric(const Properties &);
 void *CreateInstance_twosided(const Properties &);
+void *CreateInstance_obj(const Properties &);
 }
 
 namespace {
@@ -209,6 +211,48 @@ int gdbref_pfm(int write, const char *path, int *w, int *h, float *rgb)
             if (rgb && *w == bmp->getWidth() && *h == bmp->getHeight()) memcpy(rgb, bmp->getFloat32Data(), sizeof(float) * 3 * (size_t) *w * *h);
             *w = bmp->getWidth(); *h = bmp->getHeight();
         }
+    });
+}
+
+
+// Triangle meshes through the reference's loaders.  kind 0: the `serialized` container (TriMesh(Stream *, index),
+// trimesh.cpp:80-86,175-252), 2: the `obj` plugin (first mesh of the file); then TriMesh::configure()
+// (computeNormals, trimesh.cpp:608-681).  Returns the counts; gdbref_mesh_copy hands out the arrays of the last mesh.
+static ref<TriMesh> g_mesh;
+int gdbref_mesh_load(int kind, const char *path, int index, int faceNormals, int flipNormals, int *counts /* vertices, triangles, has normals */)
+{
+    return guarded([&] {
+        gdbref_static_init();
+        if (kind == 0) {
+            ref<FileStream> fs = new FileStream(path, FileStream::EReadOnly);
+            fs->setByteOrder(Stream::ELittleEndian);
+            g_mesh = new TriMesh(fs, index);
+        } else {
+            if (kind == 1) throw std::runtime_error("the ply plugin needs boost::mpl (ply_parser.hpp) and is not in this build");
+            Properties p("obj");
+            p.setString("filename", path); p.setBoolean("faceNormals", faceNormals != 0); p.setBoolean("flipNormals", flipNormals != 0);
+            ConfigurableObject *obj = static_cast<ConfigurableObject *>(CreateInstance_obj(p));
+            Shape *shape = static_cast<Shape *>(obj);
+            if (kind == 2) {                                              // the obj plugin is a compound shape: its meshes are elements
+                ref<Shape> keep = shape;
+                shape->configure();
+                g_mesh = static_cast<TriMesh *>(shape->getElement(0));
+                if (g_mesh == NULL) throw std::runtime_error("obj: no mesh");
+            } else g_mesh = static_cast<TriMesh *>(shape);
+        }
+        g_mesh->configure();
+        counts[0] = (int) g_mesh->getVertexCount(); counts[1] = (int) g_mesh->getTriangleCount(); counts[2] = g_mesh->hasVertexNormals() ? 1 : 0;
+    });
+}
+int gdbref_mesh_copy(double *vertices, double *normals, int *triangles)
+{
+    return guarded([&] {
+        if (g_mesh == NULL) throw std::runtime_error("no mesh loaded");
+        for (size_t i = 0; i < g_mesh->getVertexCount(); i++) for (int k = 0; k < 3; k++) {
+            vertices[3 * i + k] = g_mesh->getVertexPositions()[i][k];
+            if (g_mesh->hasVertexNormals()) normals[3 * i + k] = g_mesh->getVertexNormals()[i][k];
+        }
+        for (size_t t = 0; t < g_mesh->getTriangleCount(); t++) for (int k = 0; k < 3; k++) triangles[3 * t + k] = (int) g_mesh->getTriangles()[t].idx[k];
     });
 }
 

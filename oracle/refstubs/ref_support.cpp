@@ -190,6 +190,8 @@ FileResolver::FileResolver() {}
 std::string FileResolver::toString() const { return "FileResolver[]"; }
 fs::path FileResolver::resolve(const fs::path &path) const { return path; }
 FileResolver *FileResolver::clone() const { return new FileResolver(); }
+void FileResolver::prependPath(const fs::path &) {}
+void FileResolver::appendPath(const fs::path &) {}
 MTS_IMPLEMENT_CLASS(FileResolver, false, Object)
 
 ref<PluginManager> PluginManager::m_instance;

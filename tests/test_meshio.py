@@ -191,3 +191,56 @@ def test_scene_with_serialized_and_ply_shapes(tmp_path, oracle):
     (tmp_path / "s2.xml").write_text(xml.replace('<integer name="shapeIndex" value="0"/>', '<float name="maxSmoothAngle" value="30"/>'))
     with pytest.raises(Exception, match="maxSmoothAngle"):
         gdb200.load_scene(str(tmp_path / "s2.xml"))
+
+
+# ---------------------------------------------------------------- against the reference's own loaders (oracle/_ref)
+def _ref_mesh(kind, path, index=0, face_normals=False, flip_normals=False):
+    import ctypes
+    from conftest import RefMitsuba
+    if not RefMitsuba.available():
+        pytest.skip("needs the compiled reference")
+    lib = RefMitsuba().lib
+    lib.gdbref_last_error.restype = ctypes.c_char_p
+    counts = (ctypes.c_int * 3)()
+    assert lib.gdbref_mesh_load(kind, str(path).encode(), index, int(face_normals), int(flip_normals), counts) == 0, lib.gdbref_last_error()
+    v, n, t = np.zeros((counts[0], 3)), np.zeros((counts[0], 3)), np.zeros((counts[1], 3), dtype=np.int32)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    assert lib.gdbref_mesh_copy(p(v), p(n), p(t)) == 0
+    return v, t, (n if counts[2] else None)
+
+
+def _bumpy_sphere(seed=0):
+    v, t, _ = scenes.uv_sphere_mesh((0.1, -0.2, 0.3), 0.8, segments=10, rings=6)
+    rng = np.random.default_rng(seed)
+    return np.asarray(v) * (1 + 0.1 * rng.random((len(v), 1))), np.asarray(t)
+
+
+@pytest.mark.parametrize("double_precision", [False, True])
+def test_serialized_files_load_like_the_reference(tmp_path, double_precision):
+    """Files written by save_serialized through TriMesh(Stream *, index) + TriMesh::configure (trimesh.cpp:80-86,175-252,
+    608-681): same vertices and triangles, and the generated smooth normals of meshio.compute_normals agree with the
+    reference's to rounding."""
+    v, t = _bumpy_sphere()
+    n = np.random.default_rng(1).normal(size=v.shape)
+    n /= np.linalg.norm(n, axis=1, keepdims=True)
+    path = tmp_path / "m.serialized"
+    meshio.save_serialized(str(path), [("plain", v, t, None), ("with normals", v, t, n)], double_precision=double_precision)
+    for index in (0, 1):
+        rv, rt, rn = _ref_mesh(0, path, index)
+        ov, ot, on = meshio.load_serialized(str(path), index)
+        assert np.array_equal(rv, ov) and np.array_equal(rt, ot)
+        np.testing.assert_allclose(on, rn, rtol=0, atol=1e-14 if index == 0 else 0)
+
+
+def test_obj_files_load_like_the_reference(tmp_path):
+    """An OBJ without normals through the reference's obj plugin: the same triangles over the same positions and the same
+    generated normals per triangle corner (the two loaders may number the vertices differently)."""
+    v, t = _bumpy_sphere(3)
+    path = tmp_path / "m.obj"
+    path.write_text("".join("v %.9g %.9g %.9g\n" % tuple(p) for p in v) + "".join("f %d %d %d\n" % tuple(i + 1 for i in tri) for tri in t))
+    rv, rt, rn = _ref_mesh(2, path)
+    ov, ot, on = xmlscene.load_obj(str(path))
+    ov, on = np.asarray(ov), np.asarray(on)
+    assert len(rt) == len(ot) and rn is not None
+    np.testing.assert_allclose(ov[np.asarray(ot)], rv[rt], rtol=0, atol=0)          # corner positions, triangle by triangle
+    np.testing.assert_allclose(on[np.asarray(ot)], rn[rt], rtol=0, atol=1e-13)      # corner normals
