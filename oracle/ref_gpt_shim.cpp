@@ -353,6 +353,44 @@ void *gdbref_build_scene(const gdb200_scene_desc *desc, const gdb200_gpt_params 
 }
 void gdbref_release_scene(void *scene) { if (scene) static_cast<Scene *>(scene)->decRef(); }
 
+// GradientPathIntegrator::Li (gpt.cpp:1489-1662, the plain MIS path tracer G-PT carries for sub-surface preprocessing) averaged
+// over the pixel's samples: out = [h][w][3].  The camera sample loop around it mirrors SamplingIntegrator::renderBlock; the
+// sampler is keyed with seed ^ 0x5bd1e995 like the restatement's gdb200_oracle_path_render.
+int gdbref_gpt_li_render(const gdb200_scene_desc *desc, const gdb200_gpt_params *prm, double fov_x_deg, const char *rfilter, double *out)
+{
+    try {
+        std::call_once(g_init, staticInit);
+        gdb200_gpt_params q = *prm;
+        q.seed = prm->seed ^ 0x5bd1e995u;
+        Built b = buildScene(desc, &q, fov_x_deg, rfilter, true);
+        Scene *scene = b.scene.get();
+        Sensor *sensor = scene->getSensor();
+        Sampler *sampler = b.sampler.get();
+        const Vector2i size = sensor->getFilm()->getCropSize();
+        const bool needsAperture = sensor->needsApertureSample();
+        RadianceQueryRecord rRec(scene, sampler);
+        for (int y = 0; y < size.y; y++) for (int x = 0; x < size.x; x++) {
+            sampler->generate(Point2i(x, y));
+            Spectrum sum(0.0f);
+            for (int j = 0; j < prm->spp; j++) {
+                rRec.newQuery(RadianceQueryRecord::ERadiance, sensor->getMedium());
+                const Point2 samplePos(Point2(Point2i(x, y)) + Vector2(rRec.nextSample2D()));
+                Point2 apertureSample(0.5f);
+                if (needsAperture) apertureSample = rRec.nextSample2D();
+                RayDifferential ray;
+                Spectrum spec = sensor->sampleRayDifferential(ray, samplePos, apertureSample, 0.5f);
+                spec *= b.gpt->Li(ray, rRec);
+                sum += spec;
+            }
+            const Spectrum mean = sum / (Float) prm->spp;
+            Float r, g, bl; mean.toLinearRGB(r, g, bl);
+            double *o = out + ((size_t) y * size.x + x) * 3;
+            o[0] = r; o[1] = g; o[2] = bl;
+        }
+        return 0;
+    } catch (const std::exception &e) { g_error = e.what(); return 1; }
+}
+
 // PerspectiveCamera's horizontal field of view for a sensor described the way a scene file does (sensor.cpp:244-307):
 // `fov` with `fovAxis` (x, y, diagonal, smaller, larger) when fov >= 0, else `focalLength` (e.g. "50mm"); film width x height.
 double gdbref_sensor_xfov(double fov, const char *fovAxis, const char *focalLength, int width, int height)

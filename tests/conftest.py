@@ -189,3 +189,14 @@ class RefMitsuba:
         if rc:
             raise RuntimeError(self.lib.gdbref_gpt_last_error().decode())
         return dict(zip(("-final", "-throughput", "-dx", "-dy", "-direct"), out))
+
+    def li(self, desc, params):
+        """GradientPathIntegrator::Li averaged per pixel (what Oracle.path restates)."""
+        from gdb200 import scenes
+        fov, rfilter = scenes.mitsuba_sensor_args(desc)
+        out = np.zeros((desc.camera.height, desc.camera.width, 3))
+        rc = self.lib.gdbref_gpt_li_render(ctypes.byref(desc), ctypes.byref(params), ctypes.c_double(fov), rfilter.encode(),
+                                           out.ctypes.data_as(ctypes.c_void_p))
+        if rc:
+            raise RuntimeError(self.lib.gdbref_gpt_last_error().decode())
+        return out

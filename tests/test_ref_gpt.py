@@ -148,3 +148,14 @@ def test_scene_file_sensor_matches_the_reference_camera(sensor, size):
     expect = ref.lib.gdbref_sensor_xfov(ctypes.c_double(float(fov.group(1)) if fov else -1.0), (axis.group(1) if axis else "x").encode(),
                                         (focal.group(1) if focal else "").encode(), size[0], size[1])
     assert expect > 0 and abs(got - expect) <= 1e-12 * expect, (got, expect)
+
+
+@pytest.mark.parametrize("name", ["cbox_diffuse", "cbox_glossy", "cbox_materials", "cbox_env", "cbox_point", "cbox_dof", "cbox_roughglass"])
+def test_plain_path_tracer_matches_the_reference(oracle, name):
+    """Oracle.path -- the yardstick of the `primal == path tracer` invariant (tests/test_gpt_oracle.py) -- against
+    GradientPathIntegrator::Li (gpt.cpp:1489-1662) itself."""
+    if not RefMitsuba.available() or os.environ.get("GDB200_NO_REF"):
+        pytest.skip("needs the compiled reference")
+    desc, prm = _case(name)
+    got, ref = oracle.path(desc, prm, threads=1), RefMitsuba().li(desc, prm)
+    assert ref.max() > 0 and not _differing_pixels(got, ref).any(), float(np.abs(got - ref).max())
