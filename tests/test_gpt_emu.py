@@ -5,6 +5,7 @@ This is the CPU-side net under the GPU parity tests (tests/test_gpt_gpu.py): sam
 kernels' per-slot bodies, same libm as the oracle, so agreement is expected to the last few ulps
 (sum-order of the film accumulation only).  The wavefront scheduling (queues, compaction) is not
 covered here; it needs the GPU."""
+import math
 import os
 
 import numpy as np
@@ -166,3 +167,19 @@ def test_queued_wavefront_kernels(oracle, emu, scene_name, no_tail, cap, monkeyp
     close(got, ref)
     assert cnt[3] == c2[0] == 14 * 10 * 3 and cnt[1] == c2[1] and cnt[2] == c2[2]
     assert cnt[0] == (cap if cap else 14 * 10 * 2)
+
+
+def test_host_validation_follows_the_reference(emu):
+    """Scene flattening (csrc/gpt_host.h, shared by the library and the emulation) rejects what the reference's plugins reject."""
+    cam = scenes.make_camera(8, 8, (0, 0, 4), (0, 0, 0), (0, 1, 0), 40)
+    b = scenes.SceneBuilder(cam)
+    b.rectangle((0, 0, 0), (1, 0.2, 0), (0, 1, 0), b.material())          # s . t != 0
+    b.point_light((0, 0, 2), (1, 1, 1))
+    with pytest.raises(RuntimeError, match="contains shear"):            # rectangle.cpp:108-109
+        emu.gpt(b.build(), scenes.default_params(spp=1))
+    b = scenes.SceneBuilder(cam)
+    b.rectangle((0, 0, 0), (1, 0, 0), (0, 1, 0), b.material())
+    e = b.spot_light(scenes.look_at((0, 0, 2), (0, 0, 0), (0, 1, 0)), (1, 1, 1), cutoff_angle=20.0, beam_width=10.0)
+    b.emitters[e].beam_width = math.radians(30.0)                         # beamWidth > cutoffAngle: the Assert of spot.cpp:75
+    with pytest.raises(RuntimeError, match="cutoffAngle"):
+        emu.gpt(b.build(), scenes.default_params(spp=1))
