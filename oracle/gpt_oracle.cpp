@@ -14,7 +14,7 @@
 // PARITY PINNED against the reference itself: oracle/_ref/libref_mitsuba.so is the reference's gpt.cpp with the scene,
 // kd-tree, shape, emitter, BSDF, sensor, film and filter sources it runs on, compiled from /root/reference as they are
 // (recipe and the stand-ins for the missing third-party headers: oracle/Makefile, oracle/refstubs).  tests/test_ref_gpt.py
-// renders nineteen scene / parameter cases with both on the same scene bytes and sample streams: every buffer agrees to
+// renders twenty-one scene / parameter cases with both on the same scene bytes and sample streams: every buffer agrees to
 // 1e-11 with no differing pixel; tests/test_ref_mitsuba.py does the same per BSDF plugin (sample / eval / pdf, 1e-12).
 // The reference ships no test, scene or golden image for gpt; the invariants of tests/test_gpt_oracle.py (primal equals a
 // plain MIS path tracer, gradients are differences of the primal, weight bookkeeping) stay as independent checks.

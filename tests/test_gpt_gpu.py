@@ -323,7 +323,7 @@ def test_gpu_reproduces_committed_golden_buffers():
 
 def test_gpu_matches_the_reference_integrator(monkeypatch):
     """tests/golden/ref_gpt_golden.npz holds the output of the REFERENCE's own gpt.cpp (compiled from the reference tree, see
-    tests/test_ref_gpt.py) for nineteen scene / parameter cases; the CUDA tracer must reproduce it on the same scene bytes
+    tests/test_ref_gpt.py) for twenty-one scene / parameter cases; the CUDA tracer must reproduce it on the same scene bytes
     and sample streams.  GDB200_REF_UNINIT_MEASURE=1: the one place where that build's behaviour is undefined (gpt.cpp:957)."""
     import test_ref_gpt as T
     monkeypatch.setenv("GDB200_REF_UNINIT_MEASURE", "1")

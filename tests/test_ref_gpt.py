@@ -34,6 +34,8 @@ SCENES = {
     "cbox_glossy_strict": dict(scene="cbox_glossy", strict_normals=True), "cbox_glossy_depth3": dict(scene="cbox_glossy", max_depth=3),
     "cbox_glossy_rr2": dict(scene="cbox_glossy", rr_depth=2), "cbox_glossy_thr": dict(scene="cbox_glossy", shift_threshold=0.1),
     "cbox_diffuse_gaussian": dict(scene="cbox_diffuse", scene_kw=dict(rfilter="gaussian")),
+    "cbox_diffuse_tent": dict(scene="cbox_diffuse", scene_kw=dict(rfilter="tent")),
+    "cbox_glossy_blocks": dict(scene="cbox_glossy", size=(72, 40), spp=1),                         # several 32x32 blocks with ragged edges, merged by ImageBlock::put
     "cbox_env": dict(), "cbox_env_strict": dict(scene="cbox_env", strict_normals=True),            # environment emitter, environmentShift (gpt.cpp:348-369)
     "atrium": dict(scene_kw=dict(columns=3, segments=8, rings=4)),                                 # sky-lit, > 192 triangles (BVH path of the product)
 }
@@ -41,8 +43,9 @@ SCENES = {
 
 def _case(name):
     kw = dict(SCENES[name])
-    desc = getattr(scenes, kw.pop("scene", name))(W, H, **kw.pop("scene_kw", {}))
-    return desc, scenes.default_params(spp=SPP, seed=SEED, **kw)
+    w, h = kw.pop("size", (W, H))
+    desc = getattr(scenes, kw.pop("scene", name))(w, h, **kw.pop("scene_kw", {}))
+    return desc, scenes.default_params(spp=kw.pop("spp", SPP), seed=SEED, **kw)
 
 
 @pytest.fixture(scope="module")
@@ -73,7 +76,7 @@ def test_restatement_matches_the_reference_integrator(oracle, reference, name, m
     monkeypatch.setenv("GDB200_REF_UNINIT_MEASURE", "1")
     desc, prm = _case(name)
     got, _, cnt = oracle.gpt(desc, prm, threads=1)
-    assert cnt[0] == W * H * SPP
+    assert cnt[0] == desc.camera.width * desc.camera.height * prm.spp
     for k in BUFFERS:
         bad = _differing_pixels(got[k], reference[name + k])
         assert not bad.any(), (name, k, int(bad.sum()), float(np.abs(got[k] - reference[name + k]).max()))
@@ -116,7 +119,7 @@ def test_device_code_matches_the_reference_integrator(emu, reference, name, monk
     monkeypatch.setenv("GDB200_REF_UNINIT_MEASURE", "1")
     desc, prm = _case(name)
     got, cnt = emu.gpt(desc, prm)
-    assert cnt[3] == W * H * SPP
+    assert cnt[3] == desc.camera.width * desc.camera.height * prm.spp
     for k in BUFFERS:
         bad = _differing_pixels(got[k], reference[name + k])
         assert not bad.any(), (name, k, int(bad.sum()), float(np.abs(got[k] - reference[name + k]).max()))
