@@ -3,8 +3,9 @@
 // Drop-in for the reference's src/integrators/gpt/{gpt.cpp,gpt_proc.cpp,gpt_wr.cpp} + poisson_solver/:
 // same plugin name, same XML parameters / defaults / error messages (gpt.cpp:1191-1211), same five
 // multifilm buffers (gpt.cpp:1380), same render() contract (integrator.h:49-130).  It is built inside a
-// Mitsuba tree; here it is only syntax-checked against plugin/stub/mitsuba_stub.h
-// because Mitsuba's dependencies are not installed in this environment.
+// Mitsuba tree.  In this repository it is compiled against the reference's real headers and its scene
+// flattening is run on real Mitsuba objects by the test suite (tests/test_plugin_roundtrip.py); plugin/stub/mitsuba_stub.h
+// is a syntax check for machines without the reference tree.
 #if defined(GDB200_STUB_HEADERS)
 #include "stub/mitsuba_stub.h"
 #else

@@ -13,7 +13,8 @@
 // Limitation: gdb200's streams_per_pixel > 1 (chunked streams) has no single-pass equivalent here because the
 // Sampler API gives no per-sample hook that gpt calls; render C passes with sampleCount/C and seeds re-keyed per chunk.
 //
-// Built inside a Mitsuba tree; syntax-checked here against plugin/stub/mitsuba_stub.h only.
+// Built inside a Mitsuba tree.  The test suite compiles it against the reference's real Sampler interface and
+// feeds the reference's own gpt.cpp with it; plugin/stub/mitsuba_stub.h is a syntax check where the reference tree is absent.
 #if defined(GDB200_STUB_HEADERS)
 #include "../stub/mitsuba_stub.h"
 #else
