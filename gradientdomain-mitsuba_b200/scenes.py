@@ -199,11 +199,18 @@ class SceneBuilder:
         pts += [np.asarray(v, float) for v in self.vertices]
         pts = np.array(pts)
         lo, hi = pts.min(axis=0), pts.max(axis=0)
+        # a DOUBLE_PRECISION build first rounds the tight box outward to single precision (gkdtree.h:1003-1008, math.h:284-310)
+        lo32, hi32 = lo.astype(np.float32), hi.astype(np.float32)
+        lo = np.where(lo32.astype(np.float64) > lo, np.nextafter(lo32, np.float32(-np.inf)), lo32).astype(np.float64)
+        hi = np.where(hi32.astype(np.float64) < hi, np.nextafter(hi32, np.float32(np.inf)), hi32).astype(np.float64)
         eps = float(np.float32(1e-3))
         lo = lo - ((hi - lo) * eps + eps)
         hi = hi + ((hi - lo) * eps + eps)
-        cam = np.array(self.camera.camera_to_world[3:12:4])
-        return np.minimum(lo, cam), np.maximum(hi, cam)
+        # the sensor's box: its position, or for `thinlens` the aperture square [-r, r]^2 x {0} in camera space (thinlens.cpp:516-520)
+        c2w = np.array(self.camera.camera_to_world).reshape(4, 4)
+        r = self.camera.aperture_radius
+        cam = np.array([(c2w @ np.array([sx * r, sy * r, 0.0, 1.0]))[:3] for sx in (-1, 1) for sy in (-1, 1)])
+        return np.minimum(lo, cam.min(axis=0)), np.maximum(hi, cam.max(axis=0))
 
     def material(self, **kw):
         m = Material()

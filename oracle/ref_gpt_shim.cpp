@@ -417,6 +417,18 @@ double gdbref_sensor_xfov(double fov, const char *fovAxis, const char *focalLeng
     } catch (const std::exception &e) { g_error = e.what(); return -1; }
 }
 
+// Scene::getAABB() as the environment emitter's createShape saw it (scene.cpp:386-396): out = min[3], max[3] of the kd-tree's
+// box, then min[3], max[3] of the sensor's box.
+int gdbref_scene_bounds(void *handle, double *out)
+{
+    try {
+        Scene *scene = static_cast<Scene *>(handle);
+        const AABB a = scene->getKDTree()->getAABB(), b = scene->getSensor()->getAABB();
+        for (int k = 0; k < 3; k++) { out[k] = a.min[k]; out[3 + k] = a.max[k]; out[6 + k] = b.min[k]; out[9 + k] = b.max[k]; }
+        return 0;
+    } catch (const std::exception &e) { g_error = e.what(); return 1; }
+}
+
 // EnvironmentMap::sampleDirect / pdfDirect / evalEnvironment of the scene's environment emitter (envmap.cpp:516-556,376-409)
 // from the reference point `ref`: per sample the world direction, the solid-angle density sampleDirect reports, the density
 // pdfDirect reports for that direction, value / pdf as returned (RGB) and evalEnvironment along the direction (RGB).
