@@ -1953,6 +1953,24 @@ int gdb200_oracle_bsdf_eval_batch(const gdb200_material *m, const double *wi, in
     }
     return 0;
 }
+// Scene::rayIntersect for n rays (origin, direction, mint = Epsilon, maxt = inf): hit distance (inf = miss), shape index,
+// geometric normal, shading frame (s, t, n) -- for the comparison with the reference's kd-tree (tests/test_ref_gpt.py).
+int gdb200_oracle_intersect_batch(const gdb200_scene_desc *desc, int n, const double *o, const double *d, double *t, int *shape,
+                                  double *geoN, double *shFrame)
+{
+    Scene sc; buildScene(desc, sc);
+    for (int i = 0; i < n; i++) {
+        Ray ray = {v3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), v3(d[3 * i], d[3 * i + 1], d[3 * i + 2]), Epsilon, INF};
+        Its its;
+        const bool hit = rayIntersect(sc, ray, its);
+        t[i] = hit ? its.t : INF; shape[i] = hit ? its.shape : -1;
+        const V3 g = hit ? its.geoN : v3(0, 0, 0), fs = hit ? its.sh.s : g, ft = hit ? its.sh.t : g, fn = hit ? its.sh.n : g;
+        geoN[3 * i] = g.x; geoN[3 * i + 1] = g.y; geoN[3 * i + 2] = g.z;
+        const V3 f[3] = {fs, ft, fn};
+        for (int k = 0; k < 3; k++) { shFrame[9 * i + 3 * k] = f[k].x; shFrame[9 * i + 3 * k + 1] = f[k].y; shFrame[9 * i + 3 * k + 2] = f[k].z; }
+    }
+    return 0;
+}
 // EnvironmentMap::sampleDirect from the reference point `ref` (EmitterAdapter of test_chisquare.cpp:341-389): world
 // direction and solid-angle density per sample; gdb200_oracle_envmap_pdf_batch is the matching pdfDirect.
 int gdb200_oracle_envmap_sample_batch(const gdb200_scene_desc *desc, const double *ref, int n, const double *samples, double *d, double *pdf)

@@ -417,6 +417,27 @@ double gdbref_sensor_xfov(double fov, const char *fovAxis, const char *focalLeng
     } catch (const std::exception &e) { g_error = e.what(); return -1; }
 }
 
+// Scene::rayIntersect (the kd-tree) for n rays with mint = Epsilon, maxt = inf: hit distance (inf = miss), index of the hit
+// shape in the description, geometric normal, shading frame (s, t, n).
+int gdbref_intersect_batch(void *handle, int n, const double *o, const double *d, double *t, int *shape, double *geoN, double *shFrame)
+{
+    try {
+        Scene *scene = static_cast<Scene *>(handle);
+        const ref_vector<Shape> &shapes = scene->getShapes();
+        for (int i = 0; i < n; i++) {
+            Ray ray(Point(o[3 * i], o[3 * i + 1], o[3 * i + 2]), Vector(d[3 * i], d[3 * i + 1], d[3 * i + 2]), Epsilon, std::numeric_limits<Float>::infinity(), 0.0f);
+            Intersection its;
+            const bool hit = scene->rayIntersect(ray, its);
+            t[i] = hit ? its.t : std::numeric_limits<Float>::infinity();
+            shape[i] = -1;
+            if (hit) for (size_t k = 0; k < shapes.size(); k++) if (shapes[k].get() == its.shape) shape[i] = (int) k;
+            const Vector f[4] = {hit ? Vector(its.geoFrame.n) : Vector(0.0f), hit ? its.shFrame.s : Vector(0.0f), hit ? its.shFrame.t : Vector(0.0f), hit ? Vector(its.shFrame.n) : Vector(0.0f)};
+            for (int c = 0; c < 3; c++) { geoN[3 * i + c] = f[0][c]; for (int k = 0; k < 3; k++) shFrame[9 * i + 3 * k + c] = f[1 + k][c]; }
+        }
+        return 0;
+    } catch (const std::exception &e) { g_error = e.what(); return 1; }
+}
+
 // Scene::getAABB() as the environment emitter's createShape saw it (scene.cpp:386-396): out = min[3], max[3] of the kd-tree's
 // box, then min[3], max[3] of the sensor's box.
 int gdbref_scene_bounds(void *handle, double *out)
