@@ -181,3 +181,22 @@ def test_reference_kdtree_loses_planar_shapes_at_unrepresentable_coordinates(ora
         (_, s_ref, _, _), (_, s_orc, _, _) = _intersections(desc, np.ascontiguousarray(org), np.ascontiguousarray(dirs), oracle)
         assert (s_orc == light).all()
         assert ((s_ref != light).mean() > 0.2) == expect_loss, (light_y, float((s_ref != light).mean()))
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_queued_wavefront_kernels_match_the_reference(emu, seed, monkeypatch):
+    """The CUDA kernels as written (generate / compact / bounce / tail, run block by block on OS threads by tests/emu) against
+    the reference integrator on random scenes; GDB200_NO_TAIL on odd seeds keeps every path on the queues to the end."""
+    if not RefMitsuba.available() or os.environ.get("GDB200_NO_REF"):
+        pytest.skip("needs the compiled reference")
+    monkeypatch.setenv("GDB200_REF_UNINIT_MEASURE", "1")
+    if seed % 2:
+        monkeypatch.setenv("GDB200_NO_TAIL", "1")
+    desc = rand_scene(seed, w=12, h=8)
+    rng = np.random.default_rng(seed + 1000)
+    prm = S.default_params(spp=2, seed=seed, max_depth=int(rng.choice([-1, -1, 3, 6])), rr_depth=int(rng.choice([5, 2])),
+                           strict_normals=bool(rng.integers(0, 2)), shift_threshold=float(rng.choice([0.001, 0.05])))
+    ref = RefMitsuba().gpt(desc, prm)
+    got, _ = emu.gpt_wavefront(desc, prm)
+    for k in ref:
+        assert np.abs(got[k] - ref[k]).max() <= 1e-10 * max(float(np.abs(ref[k]).mean()), 1e-12), (seed, k)
