@@ -200,3 +200,43 @@ def test_queued_wavefront_kernels_match_the_reference(emu, seed, monkeypatch):
     got, _ = emu.gpt_wavefront(desc, prm)
     for k in ref:
         assert np.abs(got[k] - ref[k]).max() <= 1e-10 * max(float(np.abs(ref[k]).mean()), 1e-12), (seed, k)
+
+
+def _agree_with_reference(desc, prm, oracle, emu):
+    ref = RefMitsuba().gpt(desc, prm)
+    got, _, _ = oracle.gpt(desc, prm, threads=1)
+    dev, _ = emu.gpt(desc, prm)
+    for k in ref:
+        scale = max(float(np.abs(ref[k]).mean()), 1e-12)
+        assert np.abs(got[k] - ref[k]).max() <= 1e-10 * scale and np.abs(dev[k] - ref[k]).max() <= 1e-10 * scale, k
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_mirrored_rectangles_and_flipped_spheres_match_the_reference(oracle, emu, seed, monkeypatch):
+    """flipNormals: rectangles whose toWorld mirrors (rectangle.cpp:82-84, incl. an area light shining the other way) and
+    inside-out spheres (a spherical room, flipped sphere lights)."""
+    if not RefMitsuba.available() or os.environ.get("GDB200_NO_REF"):
+        pytest.skip("needs the compiled reference")
+    monkeypatch.setenv("GDB200_REF_UNINIT_MEASURE", "1")
+    rng = np.random.default_rng(100 + seed)
+    b = S.SceneBuilder(S.make_camera(14, 10, origin=(0.2, 0.3, 2.5), target=(0, 0, 0), up=(0, 1, 0), fov_deg=50.0))
+
+    def mirror(idx):
+        sh = b.shapes[idx]
+        m = np.array(sh.to_world).reshape(4, 4).copy()
+        m[:3, 2] *= -1
+        sh.to_world, sh.to_object = S.D16(*m.reshape(-1)), S.D16(*np.linalg.inv(m).reshape(-1))
+    b.sphere((0, 0, 0), 3.5, rand_material(b, rng, False), flip_normals=True)
+    b.rectangle((0, -1, 0), (1.5, 0, 0), (0, 0, -1.5), rand_material(b, rng, False))
+    for _ in range(3):
+        b.sphere(tuple(rng.uniform(-0.7, 0.7, 3)), float(rng.uniform(0.15, 0.4)), rand_material(b, rng), flip_normals=bool(rng.integers(0, 2)))
+        R = rand_rot(rng)
+        i = b.rectangle(tuple(rng.uniform(-0.7, 0.7, 3)), tuple(R[:, 0] * 0.4), tuple(R[:, 1] * 0.3), rand_material(b, rng, False))
+        if rng.integers(0, 2):
+            mirror(i)
+    black = b.material(reflectance=(0, 0, 0))
+    b.sphere((0.2, 0.8, 0.3), 0.15, black, radiance=(9, 8, 7), flip_normals=bool(seed % 2))
+    light = b.rectangle((0.1, 0.9375, 0.0), (0.3, 0, 0), (0, 0, 0.3), black, radiance=(8, 7, 6))
+    if seed % 2 == 0:
+        mirror(light)
+    _agree_with_reference(b.build(), S.default_params(spp=2, seed=seed, strict_normals=bool(seed % 2)), oracle, emu)
