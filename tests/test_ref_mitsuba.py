@@ -224,3 +224,16 @@ def test_pfm_files_match_the_reference_reader_and_writer(tmp_path):
     back = np.zeros_like(img)
     assert lib.gdbref_pfm(0, ours.encode(), ctypes.byref(w), ctypes.byref(h), P(back)) == 0, lib.gdbref_last_error()
     assert (w.value, h.value) == (21, 13) and np.array_equal(back, img) and np.array_equal(pfm.read_pfm(theirs), img)
+
+
+def test_reference_gbdpt_builds():
+    """Round-2 scaffolding: the reference's G-BDPT integrator + libbidir compile and link against the compiled Mitsuba runtime
+    (`make -C oracle gbdpt`, with the dense-matrix stand-in for the one Eigen routine) and export the plugin entry point."""
+    from conftest import REFERENCE, _make
+    lib = os.path.join(ROOT, "oracle", "_ref", "libref_gbdpt.so")
+    if not os.path.exists(lib):
+        if not os.path.isdir(REFERENCE):
+            pytest.skip("needs /root/reference")
+        _make("gbdpt")
+    ctypes.CDLL(REF_LIB, mode=ctypes.RTLD_GLOBAL)
+    assert hasattr(ctypes.CDLL(lib), "CreateInstance_gbdpt")
