@@ -99,9 +99,14 @@ def cpu_tracer_rate(desc, params_fn, spp, threads):
     (one sample stream per pixel -- the reference has no other mode); kind "port": the CPU restatement
     oracle/gpt_oracle.cpp (OpenMP over row bands), when that library is not there."""
     from gdb200 import scenes
+    ref = None
     if os.path.exists(REF_MITSUBA):
+        try:
+            ref = ctypes.CDLL(REF_MITSUBA)
+        except OSError as e:                      # a build of another machine that does not load here: fall back to the restatement
+            print(f"bench: {REF_MITSUBA} does not load ({e}); using the CPU restatement", file=sys.stderr)
+    if ref is not None:
         import numpy as np
-        ref = ctypes.CDLL(REF_MITSUBA)
         ref.gdbref_gpt_last_error.restype = ctypes.c_char_p
         prm = params_fn(spp)
         prm.streams_per_pixel = 1

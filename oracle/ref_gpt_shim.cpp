@@ -58,7 +58,7 @@ void staticInit()
     Spectrum::staticInitialization();
     Bitmap::staticInitialization();
     Scheduler::staticInitialization();
-    Thread::getThread()->getLogger()->setLogLevel(EWarn);
+    Thread::getThread()->getLogger()->setLogLevel(EError);                      // the default appender writes to stdout, which callers (bench.py) keep for their own output
 }
 
 template <typename T> T *make(void *(*factory)(const Properties &), const Properties &props)
@@ -141,7 +141,7 @@ Built buildScene(const gdb200_scene_desc *d, const gdb200_gpt_params *prm, doubl
     if (cam.aperture_radius > 0) { sp.setFloat("apertureRadius", cam.aperture_radius); sp.setFloat("focusDistance", cam.focus_distance); }
     Sensor *sensor = make<Sensor>(cam.aperture_radius > 0 ? CreateInstance_thinlens : CreateInstance_perspective, sp);
     Properties fp("multifilm");
-    fp.setInteger("width", cam.width); fp.setInteger("height", cam.height); fp.setBoolean("banner", false); fp.setString("fileFormat", "pfm");
+    fp.setInteger("width", cam.width); fp.setInteger("height", cam.height); fp.setBoolean("banner", false); fp.setString("fileFormat", "pfm"); fp.setString("componentFormat", "float32");
     Film *film = make<Film>(CreateInstance_multifilm, fp);
     const std::string rf(rfilterName);
     ReconstructionFilter *filter = make<ReconstructionFilter>(rf == "gaussian" ? CreateInstance_gaussian : rf == "tent" ? CreateInstance_tent : CreateInstance_box,
@@ -402,7 +402,7 @@ double gdbref_sensor_xfov(double fov, const char *fovAxis, const char *focalLeng
         else if (focalLength && focalLength[0]) sp.setString("focalLength", focalLength);
         Sensor *sensor = make<Sensor>(CreateInstance_perspective, sp);
         Properties fp("multifilm");
-        fp.setInteger("width", width); fp.setInteger("height", height); fp.setBoolean("banner", false); fp.setString("fileFormat", "pfm");
+        fp.setInteger("width", width); fp.setInteger("height", height); fp.setBoolean("banner", false); fp.setString("fileFormat", "pfm"); fp.setString("componentFormat", "float32");
         Film *film = make<Film>(CreateInstance_multifilm, fp);
         ReconstructionFilter *filter = make<ReconstructionFilter>(CreateInstance_box, Properties("box"));
         filter->configure();
