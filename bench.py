@@ -330,9 +330,12 @@ def main():
         if world > 1:
             line["exchange_bytes_per_step"] = int(agg["exchange_bytes"] / args.steps)
         if world == 1:
-            rate, dt, kind = cpu_tracer_rate(desc, lambda s: integ.params(s, 0, streams=min(args.streams, s)), args.cpu_spp, cores)
-            line["cpu_baseline"] = {"value": round(rate, 4), "unit": "Msamples/s", "cores": cores, "kind": kind,
-                                    "sample": f"{scene_name} {W}x{H} @ {args.cpu_spp} spp (of {spp}), {dt:.1f} s, " + CPU_KIND_NOTE[kind]}
+            try:                                  # a reported baseline: it must never cost the measured line
+                rate, dt, kind = cpu_tracer_rate(desc, lambda s: integ.params(s, 0, streams=min(args.streams, s)), args.cpu_spp, cores)
+                line["cpu_baseline"] = {"value": round(rate, 4), "unit": "Msamples/s", "cores": cores, "kind": kind,
+                                        "sample": f"{scene_name} {W}x{H} @ {args.cpu_spp} spp (of {spp}), {dt:.1f} s, " + CPU_KIND_NOTE[kind]}
+            except Exception as e:                # noqa: BLE001
+                line["cpu_baseline"] = {"value": None, "unit": "Msamples/s", "cores": cores, "kind": "unavailable", "sample": f"failed: {e}"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
