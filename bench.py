@@ -116,8 +116,9 @@ def cpu_tracer_rate(desc, params_fn, spp, threads):
         rc = ref.gdbref_gpt_render(ctypes.byref(desc), ctypes.byref(prm), ctypes.c_double(fov), rfilter.encode(), int(threads),
                                    out.ctypes.data_as(ctypes.c_void_p))
         dt = time.perf_counter() - t0
-        assert rc == 0, ref.gdbref_gpt_last_error()
-        return desc.camera.width * desc.camera.height * spp / dt / 1e6, dt, "reference"
+        if rc == 0:
+            return desc.camera.width * desc.camera.height * spp / dt / 1e6, dt, "reference"
+        print(f"bench: the compiled reference failed ({ref.gdbref_gpt_last_error().decode()}); using the CPU restatement", file=sys.stderr)
     lib, _ = load_oracle()
     prm = params_fn(spp)
     B = scenes.Buffers()
