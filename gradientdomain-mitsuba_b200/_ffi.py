@@ -16,7 +16,9 @@ class Stats(ctypes.Structure):
                 ("reserved0", ctypes.c_int), ("samples", ctypes.c_double), ("rays", ctypes.c_double),
                 ("path_vertices", ctypes.c_double), ("state_bytes", ctypes.c_double), ("bounce_ms", ctypes.c_double),
                 ("generate_ms", ctypes.c_double), ("compact_ms", ctypes.c_double), ("path_bounces", ctypes.c_double),
-                ("bounce_launches", ctypes.c_int), ("reserved1", ctypes.c_int)]
+                ("bounce_launches", ctypes.c_int), ("reserved1", ctypes.c_int),
+                ("cast_ms", ctypes.c_double), ("prepare_ms", ctypes.c_double), ("resolve_ms", ctypes.c_double),
+                ("primary_ms", ctypes.c_double), ("rays_cast", ctypes.c_double)]
 
 
 class PoissonConfig(ctypes.Structure):

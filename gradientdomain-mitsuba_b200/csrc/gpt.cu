@@ -27,6 +27,7 @@
 // fp64 buffers match the CPU oracle to rounding of the transcendental functions.
 #include "common.h"
 #include "gpt_kernels.cuh"
+#include "gpt_stages.cuh"
 #include "gpt_host.h"
 #include <algorithm>
 #include <cstring>
@@ -47,24 +48,46 @@ struct gdb200_scene : gdb200::HostScene {
     volatile int cancel = 0;
 };
 
-static std::mutex g_constMutex;    // c_scene is one per device: serialise renders that share a device
+constexpr int kMaxDevices = 64;
+// c_scene / c_sceneG / c_bounds and the wavefront workspace exist once per device: renders that share a device are
+// serialised, renders on different devices of one process (the Mitsuba plugin driving several GPUs) run concurrently.
+static std::mutex g_deviceMutex[kMaxDevices];
 
 // Wavefront workspace (path-slot state + queues): scratch memory that holds nothing between renders, so it is kept per
-// device and reused by every scene instead of being allocated and freed with each one (12 GB for 8 M slots: the
-// cudaMalloc/cudaFree pair cost more than 100 ms of every end-to-end render).  Guarded by g_constMutex, which already
-// serialises the renders of a device.  gdb200_release_workspace() frees it.
+// device and reused by every scene instead of being allocated and freed with each one (~2.8 KB per resident path: the
+// cudaMalloc/cudaFree pair cost more than 100 ms of every end-to-end render).  Guarded by g_deviceMutex[device].
+// gdb200_release_workspace() frees it.
 struct Workspace {
     double *sd = nullptr; int *si = nullptr;
-    int *liveList = nullptr, *liveCount = nullptr, *genList = nullptr, *genCount = nullptr;
-    int slotCapacity = 0;
+    int *liveList = nullptr, *liveCount = nullptr, *genList = nullptr, *genCount = nullptr;     // fused-bounce wavefront (A/B)
+    double *rays[2] = {nullptr, nullptr}, *hits = nullptr;                                       // staged wavefront
+    int *rayOwner[2] = {nullptr, nullptr}, *rayCount = nullptr, *occluded = nullptr, *qList = nullptr, *qCount = nullptr;
+    int slotCapacity = 0; bool fused = false;
+    std::vector<cudaEvent_t> events;       // timing marks of renders that ask for stats, reused across renders
 };
-static Workspace g_workspace[64];
+static Workspace g_workspace[kMaxDevices];
 
 static void freeWorkspace(Workspace &w)
 {
     cudaFree(w.sd); cudaFree(w.si); cudaFree(w.liveList); cudaFree(w.liveCount); cudaFree(w.genList); cudaFree(w.genCount);
+    cudaFree(w.rays[0]); cudaFree(w.rays[1]); cudaFree(w.hits); cudaFree(w.rayOwner[0]); cudaFree(w.rayOwner[1]);
+    cudaFree(w.rayCount); cudaFree(w.occluded); cudaFree(w.qList); cudaFree(w.qCount);
+    for (cudaEvent_t e : w.events) cudaEventDestroy(e);
     w = Workspace();
 }
+
+// Restores the caller's current device when an entry point that binds to the scene's device returns.
+struct DeviceGuard {
+    int previous = -1;
+    ~DeviceGuard() { if (previous >= 0) cudaSetDevice(previous); }
+    int bind(int device)
+    {
+        if (device < 0 || device >= kMaxDevices) return set_error(GDB200_ERR_ARGUMENT, "device index %d out of range", device);
+        if (cudaGetDevice(&previous) != cudaSuccess) { previous = -1; cudaGetLastError(); }
+        GDB_CUDA(cudaSetDevice(device));
+        return GDB200_OK;
+    }
+};
 
 namespace {
 
@@ -129,6 +152,178 @@ int developAndCopy(gdb200_scene *s, gdb200_buffers *out)
 
 }  // namespace
 
+namespace {
+
+// Timing marks of a render that asked for stats: events come from the workspace's pool (created once, reused).
+struct Marks {
+    Workspace &ws; bool on; size_t used = 0;
+    Marks(Workspace &w, bool enabled) : ws(w), on(enabled) {}
+    void mark()
+    {
+        if (!on) return;
+        if (used == ws.events.size()) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) { on = false; return; } ws.events.push_back(e); }
+        cudaEventRecord(ws.events[used++]);
+    }
+    float between(size_t i) const { float ms = 0; cudaEventElapsedTime(&ms, ws.events[i], ws.events[i + 1]); return ms; }
+};
+
+int ensureWorkspace(Workspace &ws, int nSlots, bool fused)
+{
+    if (nSlots <= ws.slotCapacity && fused == ws.fused) return GDB200_OK;
+    std::vector<cudaEvent_t> keep; keep.swap(ws.events);
+    freeWorkspace(ws);
+    ws.events.swap(keep);
+    static_assert(IF_COUNT <= 16, "int fields must fit the 16-int slot line");
+    const size_t n = (size_t)nSlots;
+    cudaError_t e = cudaMalloc(&ws.sd, sizeof(double) * 4 * (fused ? kRecords : kRecordsStaged) * n);
+    if (e == cudaSuccess) e = cudaMalloc(&ws.si, sizeof(int) * 16 * n);
+    if (fused) {
+        if (e == cudaSuccess) e = cudaMalloc(&ws.liveList, sizeof(int) * 2 * (size_t)kBuckets * n);
+        if (e == cudaSuccess) e = cudaMalloc(&ws.liveCount, sizeof(int) * 2 * kBuckets);
+        if (e == cudaSuccess) e = cudaMalloc(&ws.genList, sizeof(int) * 2 * n);
+        if (e == cudaSuccess) e = cudaMalloc(&ws.genCount, sizeof(int) * 2);
+    } else {
+        for (int q = 0; q < 2; q++) {
+            if (e == cudaSuccess) e = cudaMalloc(&ws.rays[q], sizeof(double) * 8 * 5 * n);
+            if (e == cudaSuccess) e = cudaMalloc(&ws.rayOwner[q], sizeof(int) * 5 * n);
+        }
+        if (e == cudaSuccess) e = cudaMalloc(&ws.hits, sizeof(double) * 4 * 5 * n);
+        if (e == cudaSuccess) e = cudaMalloc(&ws.occluded, sizeof(int) * 5 * n);
+        if (e == cudaSuccess) e = cudaMalloc(&ws.rayCount, sizeof(int) * 2);
+        if (e == cudaSuccess) e = cudaMalloc(&ws.qList, sizeof(int) * (size_t)kStageBuckets * n);
+        if (e == cudaSuccess) e = cudaMalloc(&ws.qCount, sizeof(int) * kStageBuckets);
+    }
+    if (e != cudaSuccess) {
+        keep.swap(ws.events); freeWorkspace(ws); ws.events.swap(keep); cudaGetLastError();
+        return set_error(GDB200_ERR_CUDA, "wavefront workspace for %d path slots: %s", nSlots, cudaGetErrorString(e));
+    }
+    ws.slotCapacity = nSlots; ws.fused = fused;
+    return GDB200_OK;
+}
+
+// Resident CTAs of a persistent kernel on this device: SM count x occupancy (one wave, the CTAs loop over their queue).
+template <class K> int persistentGrid(K kernel, int threads, int device)
+{
+    int perSM = 0, sms = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, threads, 0) != cudaSuccess || perSM < 1) { cudaGetLastError(); perSM = 1; }
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms < 1) { cudaGetLastError(); sms = 148; }
+    return perSM * sms;
+}
+
+struct RenderCounters { unsigned long long v[8] = {0, 0, 0, 0, 0, 0, 0, 0}; };
+
+// Round-1 wavefront: generate -> compact -> ONE bounce kernel per step, tail kernel at the end (kept for A/B measurements,
+// GDB200_GPT_FUSED_BOUNCE).
+int renderFused(gdb200_scene *s, const GptArgs &a, Marks &marks, gdb200_stats *stats, int &launches, int spp, RenderCounters &hc)
+{
+    const int nSlots = a.nSlots;
+    gpt_init_kernel<<<(nSlots + 255) / 256, 256>>>(a);
+    launches = 1;
+    const int genBlocks = (nSlots + kGenThreads - 1) / kGenThreads;
+    const int bounceBlocks = (nSlots + 32 * kBuckets + kBounceThreads - 1) / kBounceThreads;
+    int parity = 0;
+    unsigned long long tailThreshold = (unsigned long long)std::max(nSlots / 16, std::min(nSlots, 16384));
+    if (getenv("GDB200_NO_TAIL")) tailThreshold = 0;        // test knob: drain the wavefront through its queues to the last path
+    const long long maxSteps = (long long)spp * 4096 + 65536;     // safety net: never spin forever
+    size_t firstMark = marks.used;
+    for (long long step = 0;; step++) {
+        if (step > maxSteps) return set_error(GDB200_ERR_CUDA, "wavefront did not drain after %lld steps", step);
+        marks.mark();
+        gpt_generate_kernel<<<genBlocks, kGenThreads>>>(a, parity);
+        marks.mark();
+        gpt_compact_kernel<<<(nSlots + 255) / 256, 256>>>(a, parity);
+        marks.mark();
+        gpt_bounce_kernel<2><<<bounceBlocks, kBounceThreads>>>(a, parity); launches += 3;
+        marks.mark();
+        parity ^= 1;
+        if ((step & 15) == 15) {
+            GDB_CUDA(cudaMemcpy(hc.v, s->counters, sizeof(hc.v), cudaMemcpyDeviceToHost));
+            if (hc.v[0] >= (unsigned long long)nSlots) break;
+            if (s->cancel) return set_error(GDB200_ERR_CANCELLED, "render cancelled");
+            // tail: few pixel streams left => finish them in one launch instead of 3 launches per bounce
+            if ((unsigned long long)nSlots - hc.v[0] <= tailThreshold) {
+                gpt_tail_kernel<<<(nSlots + kBounceThreads - 1) / kBounceThreads, kBounceThreads>>>(a);
+                launches++;
+                break;
+            }
+        }
+    }
+    GDB_CUDA(cudaDeviceSynchronize());
+    if (stats && marks.on)
+        for (size_t i = firstMark; i + 3 < marks.used; i += 4) {
+            stats->generate_ms += marks.between(i); stats->compact_ms += marks.between(i + 1); stats->bounce_ms += marks.between(i + 2);
+            stats->bounce_launches++;
+        }
+    return GDB200_OK;
+}
+
+// Staged wavefront (gpt_stages.cuh): one tick = compact(A) -> primary, shade, resolve -> compact(B) -> prepare, generate -> casts.
+int renderStaged(gdb200_scene *s, const GptArgs &a, Marks &marks, gdb200_stats *stats, int &launches, int spp, RenderCounters &hc)
+{
+    const int nSlots = a.nSlots;
+    struct Grids { int primary, shade[3], resolve, prepare, generate, castNearest, castAny; };
+    static Grids grids[kMaxDevices];                 // per device, filled on first use (guarded by the device mutex)
+    Grids &g = grids[s->device];
+    if (!g.primary) {
+        g.primary = persistentGrid(gpt_stage_kernel<SK_PRIMARY>, kStageThreads, s->device);
+        g.shade[0] = persistentGrid(gpt_stage_kernel<SK_SHADE0>, kStageThreads, s->device);
+        g.shade[1] = persistentGrid(gpt_stage_kernel<SK_SHADE1>, kStageThreads, s->device);
+        g.shade[2] = persistentGrid(gpt_stage_kernel<SK_SHADE2>, kStageThreads, s->device);
+        g.resolve = persistentGrid(gpt_stage_kernel<SK_RESOLVE>, kStageThreads, s->device);
+        g.prepare = persistentGrid(gpt_stage_kernel<SK_PREPARE>, kStageThreads, s->device);
+        g.generate = persistentGrid(gpt_stage_kernel<SK_GENERATE>, kStageThreads, s->device);
+        g.castNearest = persistentGrid(gpt_cast_kernel<false>, 128, s->device);
+        g.castAny = persistentGrid(gpt_cast_kernel<true>, 128, s->device);
+    }
+    const int compactBlocks = (nSlots + 255) / 256;
+    gpt_stage_init_kernel<<<(std::max(nSlots, kStageBuckets) + 255) / 256, 256>>>(a);
+    launches = 1;
+    // a sample takes 2 ticks + (1 or 2) per bounce; streams are consumed sequentially by their slot
+    const long long maxTicks = ((long long)spp * 8192 + 131072) * std::max(1, a.nStreams / std::max(1, nSlots) + 1);
+    size_t firstMark = marks.used;
+    for (long long tick = 0;; tick++) {
+        if (tick > maxTicks) return set_error(GDB200_ERR_CUDA, "wavefront did not drain after %lld ticks", tick);
+        marks.mark();
+        gpt_stage_compact_kernel<0><<<compactBlocks, 256>>>(a);
+        marks.mark();
+        gpt_stage_kernel<SK_PRIMARY><<<g.primary, kStageThreads>>>(a);
+        marks.mark();
+        gpt_stage_kernel<SK_SHADE0><<<g.shade[0], kStageThreads>>>(a);
+        gpt_stage_kernel<SK_SHADE1><<<g.shade[1], kStageThreads>>>(a);
+        gpt_stage_kernel<SK_SHADE2><<<g.shade[2], kStageThreads>>>(a);
+        marks.mark();
+        gpt_stage_kernel<SK_RESOLVE><<<g.resolve, kStageThreads>>>(a);
+        marks.mark();
+        gpt_stage_compact_kernel<1><<<compactBlocks, 256>>>(a);
+        marks.mark();
+        gpt_stage_kernel<SK_PREPARE><<<g.prepare, kStageThreads>>>(a);
+        marks.mark();
+        gpt_stage_kernel<SK_GENERATE><<<g.generate, kStageThreads>>>(a);
+        marks.mark();
+        gpt_cast_kernel<false><<<g.castNearest, 128>>>(a);
+        gpt_cast_kernel<true><<<g.castAny, 128>>>(a);
+        marks.mark();
+        launches += 11;
+        if ((tick & 15) == 15) {
+            GDB_CUDA(cudaMemcpy(hc.v, s->counters, sizeof(hc.v), cudaMemcpyDeviceToHost));
+            if (hc.v[7]) return set_error(GDB200_ERR_CUDA, "ray queue overflow (%llu rays dropped)", hc.v[7]);
+            if (hc.v[0] >= (unsigned long long)nSlots) break;
+            if (s->cancel) return set_error(GDB200_ERR_CANCELLED, "render cancelled");
+        }
+    }
+    GDB_CUDA(cudaDeviceSynchronize());
+    if (stats && marks.on)
+        for (size_t i = firstMark; i + 8 < marks.used; i += 9) {
+            stats->compact_ms += marks.between(i) + marks.between(i + 4);
+            stats->primary_ms += marks.between(i + 1); stats->bounce_ms += marks.between(i + 2); stats->resolve_ms += marks.between(i + 3);
+            stats->prepare_ms += marks.between(i + 5); stats->generate_ms += marks.between(i + 6); stats->cast_ms += marks.between(i + 7);
+            stats->bounce_launches++;
+        }
+    return GDB200_OK;
+}
+
+}  // namespace
+
 extern "C" {
 
 int gdb200_scene_create(const gdb200_scene_desc *desc, gdb200_scene **out)
@@ -162,11 +357,12 @@ void gdb200_cancel(gdb200_scene *s) { if (s) s->cancel = 1; }
 
 void gdb200_release_workspace(void)
 {
-    std::lock_guard<std::mutex> lock(g_constMutex);
     int current = 0, n = 0;
     if (cudaGetDevice(&current) != cudaSuccess || cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return; }
-    for (int d = 0; d < n && d < 64; d++)
-        if (g_workspace[d].slotCapacity) { cudaSetDevice(d); freeWorkspace(g_workspace[d]); }
+    for (int d = 0; d < n && d < kMaxDevices; d++) {
+        std::lock_guard<std::mutex> lock(g_deviceMutex[d]);
+        if (g_workspace[d].slotCapacity || !g_workspace[d].events.empty()) { cudaSetDevice(d); freeWorkspace(g_workspace[d]); }
+    }
     cudaSetDevice(current);
 }
 
@@ -174,27 +370,17 @@ int gdb200_gpt_render(gdb200_scene *s, const gdb200_gpt_params *p, gdb200_buffer
 {
     if (!s || !p) return set_error(GDB200_ERR_ARGUMENT, "scene/params is NULL");
     GptArgs a;
-    const char *capEnv = getenv("GDB200_MAX_SLOTS");        // resident path slots (tuning knob; streams beyond it are dealt out as slots drain)
+    const char *capEnv = getenv("GDB200_MAX_SLOTS");        // developer knob; gdb200_gpt_params.max_slots is the interface
     if (int rc = setupArgs(*s, p, a, capEnv ? atoi(capEnv) : (1 << 23))) return rc;
-    GDB_CUDA(cudaSetDevice(s->device));
+    DeviceGuard guard;
+    if (int rc = guard.bind(s->device)) return rc;
     const int nSlots = a.nSlots;
-    if (s->device < 0 || s->device >= 64) return set_error(GDB200_ERR_ARGUMENT, "device index %d out of range", s->device);
-    classifyMaterials(s, p->shift_threshold);
+    const bool fused = (p->flags & GDB200_GPT_FUSED_BOUNCE) != 0;
 
-    std::lock_guard<std::mutex> lock(g_constMutex);
+    std::lock_guard<std::mutex> lock(g_deviceMutex[s->device]);
+    classifyMaterials(s, p->shift_threshold);
     Workspace &ws = g_workspace[s->device];
-    if (nSlots > ws.slotCapacity) {
-        freeWorkspace(ws);
-        static_assert(IF_COUNT <= 16, "int fields must fit the 16-int slot line");
-        cudaError_t e = cudaMalloc(&ws.sd, sizeof(double) * 4 * kRecords * (size_t)nSlots);
-        if (e == cudaSuccess) e = cudaMalloc(&ws.si, sizeof(int) * 16 * (size_t)nSlots);
-        if (e == cudaSuccess) e = cudaMalloc(&ws.liveList, sizeof(int) * 2 * (size_t)kBuckets * nSlots);
-        if (e == cudaSuccess) e = cudaMalloc(&ws.liveCount, sizeof(int) * 2 * kBuckets);
-        if (e == cudaSuccess) e = cudaMalloc(&ws.genList, sizeof(int) * 2 * (size_t)nSlots);
-        if (e == cudaSuccess) e = cudaMalloc(&ws.genCount, sizeof(int) * 2);
-        if (e != cudaSuccess) { freeWorkspace(ws); cudaGetLastError(); return set_error(GDB200_ERR_CUDA, "wavefront workspace for %d path slots: %s", nSlots, cudaGetErrorString(e)); }
-        ws.slotCapacity = nSlots;
-    }
+    if (int rc = ensureWorkspace(ws, nSlots, fused)) return rc;
     if (int rc = uploadScene(s)) return rc;
     GDB_CUDA(cudaMemset(s->film, 0, sizeof(double) * 5 * (size_t)s->width * s->height * 4));
     GDB_CUDA(cudaMemset(s->counters, 0, sizeof(unsigned long long) * 8));
@@ -202,82 +388,43 @@ int gdb200_gpt_render(gdb200_scene *s, const gdb200_gpt_params *p, gdb200_buffer
     a.sd = ws.sd; a.si = ws.si;
     a.film = s->film; a.liveList = ws.liveList; a.liveCount = ws.liveCount; a.genList = ws.genList; a.genCount = ws.genCount;
     a.counters = s->counters;
+    a.rays[0] = ws.rays[0]; a.rays[1] = ws.rays[1]; a.rayOwner[0] = ws.rayOwner[0]; a.rayOwner[1] = ws.rayOwner[1];
+    a.rayCount = ws.rayCount; a.rayCapacity = 5 * nSlots; a.hits = ws.hits; a.occluded = ws.occluded; a.qList = ws.qList; a.qCount = ws.qCount;
 
-    cudaEvent_t e0, e1;
-    GDB_CUDA(cudaEventCreate(&e0)); GDB_CUDA(cudaEventCreate(&e1));
-    GDB_CUDA(cudaEventRecord(e0));
+    if (stats) memset(stats, 0, sizeof(*stats));
+    Marks marks(ws, stats != nullptr);
+    marks.mark();                                    // [0]: start of the device work
     s->cancel = 0;
-    gpt_init_kernel<<<(nSlots + 255) / 256, 256>>>(a);
-    int launches = 1;
-    const int genBlocks = (nSlots + kGenThreads - 1) / kGenThreads;
-    const int bounceBlocks = (nSlots + 32 * kBuckets + kBounceThreads - 1) / kBounceThreads;
-    unsigned long long hostCounters[6] = {0, 0, 0, 0, 0, 0};
-    int parity = 0;
-    std::vector<cudaEvent_t> marks;   // per-kernel timing (only when the caller asked for stats)
-    unsigned long long tailThreshold = (unsigned long long)std::max(nSlots / 16, std::min(nSlots, 16384));
-    if (getenv("GDB200_NO_TAIL")) tailThreshold = 0;        // test knob: drain the wavefront through its queues to the last path
-    // Default: both stages of a bounce in ONE pass over the state (least HBM traffic, fewest launches).
-    // GDB200_SPLIT_PHASES=1 runs them as two kernels (smaller hot code per kernel) for A/B measurements.
-    const bool fused = getenv("GDB200_SPLIT_PHASES") == nullptr;
-    const long long maxSteps = (long long)p->spp * 4096 + 65536;     // safety net: never spin forever
-    for (long long step = 0;; step++) {
-        if (step > maxSteps) { cudaEventDestroy(e0); cudaEventDestroy(e1); return set_error(GDB200_ERR_CUDA, "wavefront did not drain after %lld steps", step); }
-        auto mark = [&]() { if (stats) { cudaEvent_t ev; cudaEventCreate(&ev); cudaEventRecord(ev); marks.push_back(ev); } };
-        mark();
-        gpt_generate_kernel<<<genBlocks, kGenThreads>>>(a, parity);
-        mark();
-        gpt_compact_kernel<<<(nSlots + 255) / 256, 256>>>(a, parity);
-        mark();
-        if (fused) { gpt_bounce_kernel<2><<<bounceBlocks, kBounceThreads>>>(a, parity); launches += 3; }
-        else {
-            gpt_bounce_kernel<0><<<bounceBlocks, kBounceThreads>>>(a, parity);
-            gpt_bounce_kernel<1><<<bounceBlocks, kBounceThreads>>>(a, parity);
-            launches += 4;
-        }
-        mark();
-        parity ^= 1;
-        if ((step & 15) == 15) {
-            GDB_CUDA(cudaMemcpy(hostCounters, s->counters, sizeof(hostCounters), cudaMemcpyDeviceToHost));
-            if (hostCounters[0] >= (unsigned long long)nSlots) break;
-            if (s->cancel) { cudaEventDestroy(e0); cudaEventDestroy(e1); return set_error(GDB200_ERR_CANCELLED, "render cancelled"); }
-            // tail: few pixel streams left => finish them in one launch instead of 4 launches per bounce
-            const unsigned long long remaining = (unsigned long long)nSlots - hostCounters[0];
-            if (remaining <= tailThreshold) {
-                gpt_tail_kernel<<<(nSlots + kBounceThreads - 1) / kBounceThreads, kBounceThreads>>>(a);
-                launches++;
-                break;
-            }
-        }
+    int launches = 0;
+    RenderCounters hc;
+    if (int rc = fused ? renderFused(s, a, marks, stats, launches, p->spp, hc) : renderStaged(s, a, marks, stats, launches, p->spp, hc)) {
+        cudaDeviceSynchronize(); cudaGetLastError();
+        return rc;
     }
-    GDB_CUDA(cudaEventRecord(e1));
-    GDB_CUDA(cudaEventSynchronize(e1));
     GDB_CUDA(cudaGetLastError());
     float ms = 0.f;
-    GDB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
-    GDB_CUDA(cudaMemcpy(hostCounters, s->counters, sizeof(hostCounters), cudaMemcpyDeviceToHost));
+    if (marks.on && marks.used >= 2) {
+        marks.mark();
+        GDB_CUDA(cudaEventSynchronize(ws.events[marks.used - 1]));
+        GDB_CUDA(cudaEventElapsedTime(&ms, ws.events[0], ws.events[marks.used - 1]));
+    }
+    GDB_CUDA(cudaMemcpy(hc.v, s->counters, sizeof(hc.v), cudaMemcpyDeviceToHost));
     if (int rc = developAndCopy(s, out)) return rc;
     if (stats) {
-        memset(stats, 0, sizeof(*stats));
         stats->device_ms = ms; stats->launches = launches + 1;
-        stats->samples = (double)hostCounters[3]; stats->rays = (double)hostCounters[1]; stats->path_vertices = (double)hostCounters[2];
-        stats->state_bytes = (double)hostCounters[4]; stats->path_bounces = (double)hostCounters[5];
-        for (size_t i = 0; i + 3 < marks.size(); i += 4) {
-            float g = 0, c = 0, b = 0;
-            cudaEventElapsedTime(&g, marks[i], marks[i + 1]); cudaEventElapsedTime(&c, marks[i + 1], marks[i + 2]); cudaEventElapsedTime(&b, marks[i + 2], marks[i + 3]);
-            stats->generate_ms += g; stats->compact_ms += c; stats->bounce_ms += b; stats->bounce_launches++;
-        }
+        stats->samples = (double)hc.v[3]; stats->rays = (double)hc.v[1]; stats->path_vertices = (double)hc.v[2];
+        stats->state_bytes = (double)hc.v[4]; stats->path_bounces = (double)hc.v[5];
     }
-    for (cudaEvent_t ev : marks) cudaEventDestroy(ev);
     return GDB200_OK;
 }
 
 int gdb200_debug_check_culling(gdb200_scene *s, int n_rays, unsigned long long seed, unsigned long long *out_mismatches, unsigned long long *out_hits)
 {
     if (!s || !out_mismatches || n_rays <= 0) return set_error(GDB200_ERR_ARGUMENT, "scene/out is NULL");
-    GDB_CUDA(cudaSetDevice(s->device));
+    DeviceGuard guard;
+    if (int rc = guard.bind(s->device)) return rc;
+    std::lock_guard<std::mutex> lock(g_deviceMutex[s->device]);
     classifyMaterials(s, 0.001);
-    std::lock_guard<std::mutex> lock(g_constMutex);
     if (int rc = uploadScene(s)) return rc;
     GDB_CUDA(cudaMemset(s->counters, 0, sizeof(unsigned long long) * 8));
     gpt_check_culling_kernel<<<(n_rays + 127) / 128, 128>>>(seed, n_rays, s->counters);
@@ -311,7 +458,8 @@ int gdb200_gpt_accumulators(gdb200_scene *s, double **d_accum, size_t *bytes)
 int gdb200_gpt_develop(gdb200_scene *s, gdb200_buffers *out)
 {
     if (!s) return set_error(GDB200_ERR_ARGUMENT, "scene is NULL");
-    GDB_CUDA(cudaSetDevice(s->device));
+    DeviceGuard guard;
+    if (int rc = guard.bind(s->device)) return rc;
     return developAndCopy(s, out);
 }
 

@@ -346,15 +346,24 @@ GDB_D bool closestPrimitiveExhaustive(const Ray &ray, Float mint, Float maxt, Fl
     return found;
 }
 
-// ShapeKDTree::rayIntersect(ray, its): skdtree.cpp:112-147, record fill skdtree.h:343-428.
-GDB_D bool rayIntersectImpl(const Ray &ray, Its &its)
+// ShapeKDTree::rayIntersect(ray, its): skdtree.cpp:112-147, record fill skdtree.h:343-428.  Two halves, so that the
+// staged wavefront (gpt_stages.cuh) can run the search in its own kernel (gpt_cast_kernel) and rebuild the intersection
+// record where it is consumed: a hit travels as {t, u, v, primitive}.
+struct Hit { Float t, u, v; int kind, index; };   // kind: 0 rectangle, 1 sphere, 2 table triangle, 3 BVH triangle; t = +inf: miss
+GDB_D bool castClosest(const Ray &ray, Hit &h)
 {
-    its.t = CUDART_INF;
+    h.t = CUDART_INF; h.u = 0; h.v = 0; h.kind = 0; h.index = 0;
     Float rayMinT = ray.mint;
     if (rayMinT == kEpsilon) rayMinT *= fmax(maxAbs3(ray.o), kEpsilon);
     if (!(ray.maxt > rayMinT)) return false;
-    Float t, u = 0, v = 0; int kind = 0, index = 0;
-    if (!closestPrimitive<false>(ray, rayMinT, ray.maxt, t, kind, index, u, v)) return false;
+    Float t;
+    if (!closestPrimitive<false>(ray, rayMinT, ray.maxt, t, h.kind, h.index, h.u, h.v)) return false;
+    h.t = t;
+    return true;
+}
+GDB_D void fillIts(const Ray &ray, const Hit &h, Its &its)
+{
+    const Float t = h.t, u = h.u, v = h.v; const int kind = h.kind, index = h.index;
     its.t = t;
     V3 dpdu;
     if (kind >= 2) {                                                 // skdtree.h:348-419 (BarycentricPos)
@@ -386,6 +395,12 @@ GDB_D bool rayIntersectImpl(const Ray &ray, Its &its)
     }
     computeShadingFrame(its.sh.n, dpdu, its.sh);                     // skdtree.h:425
     its.wi = toLocal(its.sh, -ray.d);                                // skdtree.h:426
+}
+GDB_D bool rayIntersectImpl(const Ray &ray, Its &its)
+{
+    Hit h;
+    if (!castClosest(ray, h)) { its.t = CUDART_INF; return false; }
+    fillIts(ray, h, its);
     return true;
 }
 
@@ -954,8 +969,12 @@ GDB_D bool envFillDRec(DRec &dRec, V3 o, V3 d)
 // Scene::sampleEmitterDirectVisible, scene.cpp:855-879: emitter pick (pmf.h:124-188), Emitter::sampleDirect
 // (area.cpp:158-176 over shape.cpp:102-114 with rectangle.cpp:210-216 / trimesh.cpp:412-423 + triangle.cpp:24-50;
 // envmap.cpp:516-544), then the shadow ray.
-GDB_D Spec sampleEmitterDirectVisibleImpl(DRec &dRec, Float sx, Float sy, bool &visible)
+// sampleEmitterDirect: everything up to the shadow ray.  needsRay == false: the environment's early return below (the
+// sample counts as visible and nothing is traced); otherwise the caller tests `shadowRay` and, if it is blocked, the
+// sample is invisible with value 0 (scene.cpp:869-876).
+GDB_D Spec sampleEmitterDirect(DRec &dRec, Float sx, Float sy, bool &needsRay, Ray &shadowRay)
 {
+    needsRay = false;
     Float emPdf;
     const int index = cdfSampleReuse(c_scene.emCdf, c_scene.nEmitters, sx, emPdf);
     const DEmitter &em = c_sceneG->emitters[index];
@@ -970,7 +989,6 @@ GDB_D Spec sampleEmitterDirectVisibleImpl(DRec &dRec, Float sx, Float sy, bool &
             // The reference leaves p/d/dist unset here and still traces its shadow ray with them; unreachable for
             // maps without black texels seen from inside the bounding sphere.  Defined as: no contribution.
             dRec.pdf = 0.0; dRec.p = dRec.ref; dRec.n = mk(0, 0, 0); dRec.d = mk(0, 0, 1); dRec.dist = 0;
-            visible = true;
             return splat(0);
         }
         dRec.pdf = pdf; dRec.p = dRec.ref + dw * farT; dRec.n = normalize(c_scene.env.center - dRec.p); dRec.dist = farT; dRec.d = dw;
@@ -1063,9 +1081,16 @@ GDB_D Spec sampleEmitterDirectVisibleImpl(DRec &dRec, Float sx, Float sy, bool &
     }
     dRec.pdf *= emPdf;
     value = value / emPdf;
-    Ray ray; ray.o = dRec.ref; ray.d = dRec.d; ray.mint = kEpsilon; ray.maxt = dRec.dist * (1 - kShadowEpsilon);
-    if (rayOccluded(ray)) { visible = false; return splat(0); }
+    shadowRay.o = dRec.ref; shadowRay.d = dRec.d; shadowRay.mint = kEpsilon; shadowRay.maxt = dRec.dist * (1 - kShadowEpsilon);
+    needsRay = true;
+    return value;
+}
+GDB_D Spec sampleEmitterDirectVisibleImpl(DRec &dRec, Float sx, Float sy, bool &visible)
+{
+    bool needsRay; Ray ray;
+    const Spec value = sampleEmitterDirect(dRec, sx, sy, needsRay, ray);
     visible = true;
+    if (needsRay && rayOccluded(ray)) { visible = false; return splat(0); }
     return value;
 }
 
@@ -1147,11 +1172,11 @@ GDB_D ShiftResult halfVectorShift(V3 mainWi, V3 mainWo, V3 shiftedWi, Float main
     return result;
 }
 
-GDB_D ShiftResult reconnectShift(V3 mainSource, V3 target, V3 shiftSource, V3 targetNormal)   // gpt.cpp:84-93, 316-345
+// The reconnection as it comes out when `r` is unobstructed (success = true); the caller tests r (testVisibility, gpt.cpp:84-93).
+GDB_D ShiftResult reconnectShiftUnoccluded(V3 mainSource, V3 target, V3 shiftSource, V3 targetNormal, Ray &r)   // gpt.cpp:316-345
 {
     ShiftResult result; result.success = false; result.jacobian = 0; result.wo = mk(0, 0, 0);
-    Ray r; r.o = shiftSource; r.d = target - shiftSource; r.mint = kEpsilon; r.maxt = 1.0 - kShadowEpsilon;
-    if (rayOccluded(r)) return result;
+    r.o = shiftSource; r.d = target - shiftSource; r.mint = kEpsilon; r.maxt = 1.0 - kShadowEpsilon;
     const V3 mainEdge = mainSource - target, shiftedEdge = shiftSource - target;
     const Float mainL2 = len2(mainEdge), shiftedL2 = len2(shiftedEdge);
     const V3 shiftedWo = -shiftedEdge / sqrt(shiftedL2);
@@ -1161,17 +1186,30 @@ GDB_D ShiftResult reconnectShift(V3 mainSource, V3 target, V3 shiftSource, V3 ta
     result.success = true; result.wo = shiftedWo;
     return result;
 }
+GDB_D ShiftResult reconnectShift(V3 mainSource, V3 target, V3 shiftSource, V3 targetNormal)   // gpt.cpp:84-93, 316-345
+{
+    Ray r;
+    ShiftResult result = reconnectShiftUnoccluded(mainSource, target, shiftSource, targetNormal, r);
+    if (rayOccluded(r)) { result.success = false; result.jacobian = 0; result.wo = mk(0, 0, 0); }
+    return result;
+}
 
 // environmentShift + testEnvironmentVisibility (gpt.cpp:96-114, 348-369): the offset vertex must see the environment
 // in the base path's direction; J = 1.
-GDB_D ShiftResult environmentShift(V3 mainD, V3 shiftSource)
+GDB_D ShiftResult environmentShiftUnoccluded(V3 mainD, V3 shiftSource, Ray &r)
 {
-    ShiftResult result; result.success = false; result.jacobian = 0; result.wo = mk(0, 0, 0);
+    ShiftResult result;
     DRec dr; dr.dist = 0;
     envFillDRec(dr, shiftSource, mainD);
-    Ray r; r.o = shiftSource; r.d = mainD; r.mint = kEpsilon; r.maxt = (1.0 - kShadowEpsilon) * dr.dist;
-    if (rayOccluded(r)) return result;
+    r.o = shiftSource; r.d = mainD; r.mint = kEpsilon; r.maxt = (1.0 - kShadowEpsilon) * dr.dist;
     result.success = true; result.jacobian = 1; result.wo = mainD;
+    return result;
+}
+GDB_D ShiftResult environmentShift(V3 mainD, V3 shiftSource)
+{
+    Ray r;
+    ShiftResult result = environmentShiftUnoccluded(mainD, shiftSource, r);
+    if (rayOccluded(r)) { result.success = false; result.jacobian = 0; result.wo = mk(0, 0, 0); }
     return result;
 }
 

@@ -523,16 +523,16 @@ inline int setupArgs(const HostScene &s, const gdb200_gpt_params *p, GptArgs &a,
     const long long nStreams = (long long)a.nPixels * a.streamsPerPixel;
     if (nStreams > 0x7fffffffLL) return set_error(GDB200_ERR_ARGUMENT, "too many sample streams (%lld)", nStreams);
     a.nStreams = (int)nStreams;
+    if (p->max_slots < 0) return set_error(GDB200_ERR_ARGUMENT, "max_slots must not be negative");
+    if (p->max_slots > 0) maxSlots = p->max_slots;
     a.nSlots = (int)std::min<long long>(nStreams, std::max(1, maxSlots));
     a.spp = p->spp; a.seed = p->seed; a.skipPreview = p->skip_preview != 0;
     a.bandRows = banded ? p->band_rows : 0; a.bandCount = banded ? p->band_count : 0; a.bandIndex = banded ? p->band_index : 0;
     a.cfg.maxDepth = p->max_depth; a.cfg.minDepth = 1; a.cfg.rrDepth = p->rr_depth;         // gpt.cpp:1368-1371
     a.cfg.strictNormals = p->strict_normals; a.cfg.shiftThreshold = p->shift_threshold;
-    // gpt.cpp:957 default-constructs the DirectSamplingRecord of a reconnected offset path that lands on an emitter and
-    // never sets .measure before Shape::pdfDirect (shape.cpp:116-126) reads it: undefined behaviour.  The product uses the
-    // intended ESolidAngle.  A g++ -O2 build of the reference reads a stale value that is not ESolidAngle, so area emitters
-    // report density 0 there; GDB200_REF_UNINIT_MEASURE=1 reproduces that build bit for bit (used by the parity tests).
-    { const char *e = std::getenv("GDB200_REF_UNINIT_MEASURE"); a.cfg.refUninitMeasure = (e && e[0] == '1') ? 1 : 0; a.cfg.pad = 0; }
+    // gpt.cpp:957 reads an uninitialised DirectSamplingRecord::measure; GDB200_GPT_REF_UNINIT_MEASURE (include/gdb200.h)
+    // selects what a g++ -O2 build of the reference does there instead of the intended ESolidAngle.
+    a.cfg.refUninitMeasure = (p->flags & GDB200_GPT_REF_UNINIT_MEASURE) ? 1 : 0; a.cfg.pad = 0;
     return GDB200_OK;
 }
 

@@ -16,8 +16,10 @@ enum BaseRec { BR_RAYD = 0 /* w: path pdf */, BR_P /* w: eta */, BR_GN /* w: sam
 enum OffRec { OR_THR = 0 /* w: path pdf */, OR_RAD, OR_GRAD, OR_P, OR_GN, OR_S, OR_T, OR_N, OR_WI, OR_COUNT };
 constexpr int kRecords = BR_COUNT + 4 * OR_COUNT;   // 46 records = 1472 B per slot
 enum IntField { IF_STATUS = 0, IF_MAT, IF_EMI, IF_DEPTH, IF_SAMPLE, IF_RNGN, IF_OFLAGS, IF_STREAM, IF_OMAT0, IF_OMAT1, IF_OMAT2, IF_OMAT3,
+                IF_BSTYPE, IF_PEND,      // staged wavefront (gpt_stages.cuh): sampled BSDF component, bookkeeping of the offsets awaiting a ray
                 IF_COUNT };
-enum SlotStatus { ST_FRESH = 0, ST_LIVE = 1, ST_FINISHED = 2, ST_DONE = 3 };
+// ST_WAIT_*: staged wavefront only -- the slot has rays in flight and continues in the named stage once they are cast
+enum SlotStatus { ST_FRESH = 0, ST_LIVE = 1, ST_FINISHED = 2, ST_DONE = 3, ST_WAIT_PRIMARY = 4, ST_WAIT_SHADE = 5, ST_WAIT_RESOLVE = 6 };
 enum { RAY_NOT_CONNECTED = 0, RAY_RECENTLY_CONNECTED = 1, RAY_CONNECTED = 2 };
 enum { BUF_FINAL = 0, BUF_THROUGHPUT = 1, BUF_DX = 2, BUF_DY = 3, BUF_DIRECT = 4 };
 
@@ -39,7 +41,16 @@ struct GptArgs {
     int *liveCount;        // [2][kBuckets]
     int *genList;          // [2][nSlots]: slots whose path ended (to splat + regenerate)
     int *genCount;         // [2]
-    unsigned long long *counters;   // [0] done slots, [1] rays, [2] path vertices, [3] samples, [4] state bytes, [5] path bounces, [6] next stream
+    unsigned long long *counters;   // [0] done slots, [1] rays, [2] path vertices, [3] samples, [4] state bytes, [5] path bounces, [6] next stream, [7] ray-queue overflows
+    // staged wavefront (gpt_stages.cuh): ray queues + results, stage queues
+    double *rays[2];       // [0] nearest-hit rays, [1] any-hit (shadow) rays: [rayCapacity][8] = o.xyz d.xyz mint maxt
+    int *rayOwner[2];      // [rayCapacity]: slot * 8 + ray id of the slot
+    int *rayCount;         // [2]
+    int rayCapacity, pad2;
+    double *hits;          // [5][nSlots][4]: t u v primitive, answers to the nearest-hit rays 0..4 of a slot
+    int *occluded;         // [5][nSlots]: answers to the any-hit rays 0..4 of a slot
+    int *qList;            // [kStageBuckets][nSlots]: slots per stage bucket
+    int *qCount;           // [kStageBuckets]
 };
 
 GDB_D double *REC(const GptArgs &a, int rec, int slot) { return a.sd + (((size_t)rec * a.nSlots + slot) << 2); }

@@ -105,6 +105,10 @@ class GPTIntegrator:
         self.shiftThreshold = shiftThreshold
         self.reconstructL1, self.reconstructL2, self.reconstructAlpha = reconstructL1, reconstructL2, reconstructAlpha
         self.stats, self.solver_stats = Stats(), Stats()
+        # not XML parameters of the reference: gdb200_gpt_params.flags / max_slots (include/gdb200.h)
+        self.refUninitMeasure = False      # reproduce the compiled reference at gpt.cpp:957 (parity tests against it)
+        self.fusedBounce = False           # round-1 single-kernel bounce (A/B measurements)
+        self.maxSlots = 0                  # resident path slots, 0 = library default
 
     def params(self, spp, seed=0, rows=None, bands=None, preview=True, streams=1):
         p = _scenes.default_params(spp=spp, seed=seed, max_depth=self.maxDepth, rr_depth=self.rrDepth,
@@ -115,6 +119,8 @@ class GPTIntegrator:
         if bands is not None:                      # (band_rows, band_count, band_index)
             p.band_rows, p.band_count, p.band_index = bands
         p.streams_per_pixel = streams              # sample streams per pixel (gdb200_gpt_params.streams_per_pixel)
+        p.flags = (_scenes.GPT_REF_UNINIT_MEASURE if self.refUninitMeasure else 0) | (_scenes.GPT_FUSED_BOUNCE if self.fusedBounce else 0)
+        p.max_slots = self.maxSlots
         return p
 
     def trace(self, scene, spp, seed=0, rows=None, download=True, bands=None, preview=True, streams=1, out=None):

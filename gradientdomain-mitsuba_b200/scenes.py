@@ -65,7 +65,11 @@ class GPTParams(ctypes.Structure):
     _fields_ = [("max_depth", ctypes.c_int), ("rr_depth", ctypes.c_int), ("strict_normals", ctypes.c_int),
                 ("shift_threshold", ctypes.c_double), ("spp", ctypes.c_int), ("skip_preview", ctypes.c_int),
                 ("seed", ctypes.c_uint64), ("y_begin", ctypes.c_int), ("y_end", ctypes.c_int),
-                ("band_rows", ctypes.c_int), ("band_count", ctypes.c_int), ("band_index", ctypes.c_int), ("streams_per_pixel", ctypes.c_int)]
+                ("band_rows", ctypes.c_int), ("band_count", ctypes.c_int), ("band_index", ctypes.c_int), ("streams_per_pixel", ctypes.c_int),
+                ("flags", ctypes.c_int), ("max_slots", ctypes.c_int)]
+
+
+GPT_REF_UNINIT_MEASURE, GPT_FUSED_BOUNCE = 1, 2      # gdb200_gpt_params.flags (include/gdb200.h)
 
 
 class Buffers(ctypes.Structure):
@@ -621,8 +625,12 @@ def mitsuba_sensor_args(desc):
     return float(b.camera.fov_deg), b.rfilter_name
 
 
-def default_params(spp=64, seed=0, max_depth=-1, rr_depth=5, shift_threshold=0.001, strict_normals=False):
+def default_params(spp=64, seed=0, max_depth=-1, rr_depth=5, shift_threshold=0.001, strict_normals=False,
+                   ref_uninit_measure=False, max_slots=0):
+    """ref_uninit_measure: GDB200_GPT_REF_UNINIT_MEASURE (reproduce the compiled reference at gpt.cpp:957, see include/gdb200.h)."""
     p = GPTParams()
     p.max_depth, p.rr_depth, p.strict_normals, p.shift_threshold = max_depth, rr_depth, int(strict_normals), shift_threshold
     p.spp, p.seed, p.y_begin, p.y_end = spp, seed, 0, 0
+    p.flags = GPT_REF_UNINIT_MEASURE if ref_uninit_measure else 0
+    p.max_slots = max_slots
     return p

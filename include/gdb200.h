@@ -61,8 +61,14 @@ typedef struct gdb200_stats {
     double generate_ms;     /* ... of the gpt_generate_kernel launches                    */
     double compact_ms;      /* ... of the gpt_compact_kernel launches                     */
     double path_bounces;    /* base-path bounce iterations executed (tracer)              */
-    int    bounce_launches; /* wavefront steps                                            */
+    int    bounce_launches; /* wavefront steps (staged wavefront: gpt_stage_kernel<shade> launches) */
     int    reserved1;
+    /* staged wavefront (csrc/gpt_stages.cuh): summed CUDA-event times per kernel family; bounce_ms = shade stage */
+    double cast_ms;         /* gpt_cast_kernel (nearest-hit + any-hit queues)             */
+    double prepare_ms;      /* gpt_stage_kernel<prepare>                                  */
+    double resolve_ms;      /* gpt_stage_kernel<resolve>                                  */
+    double primary_ms;      /* gpt_stage_kernel<primary>                                  */
+    double rays_cast;       /* rays answered by gpt_cast_kernel                           */
 } gdb200_stats;
 
 /* ------------------------------------------------ screened Poisson solver */
@@ -225,7 +231,17 @@ typedef struct gdb200_gpt_params {
      * (chunk c gets spp/C samples, +1 for c < spp%C), chunk 0 on the pixel's stream and chunk c > 0 on an
      * independently re-keyed one: the same film as C reference passes with sampleCount spp/C summed. */
     int      streams_per_pixel;
+    /* GDB200_GPT_* bits.  REF_UNINIT_MEASURE: gpt.cpp:957 default-constructs the DirectSamplingRecord of a reconnected
+     * offset path that lands on an emitter and never sets .measure before Shape::pdfDirect (shape.cpp:116-126) reads it
+     * (undefined behaviour).  By default the intended ESolidAngle is used; with this bit the tracer reproduces what a
+     * g++ -O2 build of the reference does there (area emitters report density 0), which is how images are compared
+     * bit for bit with the compiled reference.  FUSED_BOUNCE: the single-kernel bounce of round 1 (A/B measurements). */
+    int      flags;
+    int      max_slots;          /* resident path slots; 0 = default (streams beyond it are dealt out as slots drain) */
 } gdb200_gpt_params;
+
+#define GDB200_GPT_REF_UNINIT_MEASURE 1
+#define GDB200_GPT_FUSED_BOUNCE       2
 
 /* Host output buffers, each width*height*3 fp64, interleaved RGB; any may be NULL.
  * Developed like MultiFilm::developMulti (value * 1/weight, fmtconv.cpp:1036-1045). */

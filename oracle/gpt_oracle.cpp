@@ -19,7 +19,7 @@
 // The reference ships no test, scene or golden image for gpt; the invariants of tests/test_gpt_oracle.py (primal equals a
 // plain MIS path tracer, gradients are differences of the primal, weight bookkeeping) stay as independent checks.
 // One deliberate deviation: gpt.cpp:957 leaves shiftedDRec.measure uninitialised (undefined behaviour); the intended
-// ESolidAngle is used here and in the product.  GDB200_REF_UNINIT_MEASURE=1 reproduces what the g++ build of the
+// ESolidAngle is used here and in the product.  gdb200_gpt_params.flags & GDB200_GPT_REF_UNINIT_MEASURE reproduces what the g++ build of the
 // reference does instead (see the note at the use).
 //
 // Random numbers: the `gdb200_counter` sampler.  Sampler::generate(pixel) (gpt.cpp:1250-1251)
@@ -1475,7 +1475,7 @@ void evaluate(const Scene &sc, const Config &cfg, Sampler &sampler, RayState &ma
                                     shiftedLumPdf = pdfEmitterDirect(sc, sd);
                                     // gpt.cpp:957 default-constructs shiftedDRec and never sets .measure, so Shape::pdfDirect
                                     // (shape.cpp:116-126) compares an indeterminate value with ESolidAngle.  The restatement uses
-                                    // the intended ESolidAngle; GDB200_REF_UNINIT_MEASURE=1 instead mimics a build in which
+                                    // the intended ESolidAngle; gdb200_gpt_params.flags & GDB200_GPT_REF_UNINIT_MEASURE instead mimics a build in which
                                     // the stale value is not ESolidAngle (what g++ -O2 produces from the reference sources here:
                                     // an area emitter then reports density 0), for tests/test_ref_gpt.py.
                                     if (cfg.uninitMeasureIsInvalid && sc.ems[sd.emitter].type == GDB200_EMITTER_AREA) shiftedLumPdf = 0;   // also sphere.cpp:370-387
@@ -1754,7 +1754,7 @@ int gdb200_oracle_gpt_render(const gdb200_scene_desc *desc, const gdb200_gpt_par
     g_fdrInt = &sc.fdrInt; g_matBase = &sc.mats[0];
     Config cfg; cfg.maxDepth = prm->max_depth; cfg.minDepth = 1; cfg.rrDepth = prm->rr_depth;   // gpt.cpp:1368-1371
     cfg.strictNormals = prm->strict_normals != 0; cfg.shiftThreshold = prm->shift_threshold;
-    { const char *e = std::getenv("GDB200_REF_UNINIT_MEASURE"); cfg.uninitMeasureIsInvalid = e && e[0] == '1'; }
+    cfg.uninitMeasureIsInvalid = (prm->flags & GDB200_GPT_REF_UNINIT_MEASURE) != 0;
     const int W = sc.cam.width, H = sc.cam.height;
     Film film; film.w = W; film.h = H; film.radius = sc.filterRadius;
     bool box = true;

@@ -158,6 +158,24 @@ class Emu:
         return out, cnt
 
 
+    def gpt_staged(self, desc, params, grid=3):
+        """Block mode of the STAGED wavefront (csrc/gpt_stages.cuh): stage / cast / compact kernels as written, `grid`
+        persistent CTAs per launch run by OS threads."""
+        from gdb200 import scenes
+        w, h = desc.camera.width, desc.camera.height
+        names = (("throughput", "-throughput"), ("dx", "-dx"), ("dy", "-dy"), ("direct", "-direct"), ("preview_final", "-final"))
+        out = {n: np.zeros((h, w, 3)) for _, n in names}
+        B = scenes.Buffers()
+        for field, n in names:
+            setattr(B, field, out[n].ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+        cnt = np.zeros(6)
+        rc = self.lib.gdb200_emu_gpt_render_staged(ctypes.byref(desc), ctypes.byref(params), ctypes.byref(B),
+                                                   cnt.ctypes.data_as(ctypes.c_void_p), int(grid))
+        if rc != 0:
+            raise RuntimeError(self.lib.gdb200_emu_last_error().decode())
+        return out, cnt
+
+
 @pytest.fixture(scope="session")
 def emu():
     return Emu()

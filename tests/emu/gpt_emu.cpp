@@ -23,6 +23,7 @@ int set_error(int code, const char *fmt, ...)
 }
 }
 #include "../../gradientdomain-mitsuba_b200/csrc/gpt_kernels.cuh"
+#include "../../gradientdomain-mitsuba_b200/csrc/gpt_stages.cuh"
 #include "../../gradientdomain-mitsuba_b200/csrc/gpt_host.h"
 
 using namespace gdb200;
@@ -201,6 +202,82 @@ extern "C" int gdb200_emu_gpt_render_wavefront(const gdb200_scene_desc *desc, co
                 break;
             }
         }
+    }
+    std::vector<double> dev64(5 * n * 3); std::vector<float> dev32(5 * n * 3);
+    blockDim.x = 1; threadIdx.x = 0;
+    for (size_t i = 0; i < 5 * n; i++) { blockIdx.x = (unsigned)i; gpt_develop_kernel(film.data(), (int)n, dev64.data(), dev32.data()); }
+    if (out) {
+        double *dst[5] = {out->preview_final, out->throughput, out->dx, out->dy, out->direct};
+        for (int b = 0; b < 5; b++) if (dst[b]) memcpy(dst[b], dev64.data() + (size_t)b * n * 3, sizeof(double) * n * 3);
+    }
+    if (counters) for (int i = 0; i < 6; i++) counters[i] = (double)ctr[i];
+    return 0;
+}
+
+// ---- block mode of the STAGED wavefront (csrc/gpt_stages.cuh): compact(A) -> primary, shade, resolve -> compact(B) ->
+// prepare, generate -> casts, every kernel as written (persistent CTAs looping over their queues, ballots, warp-aggregated
+// ray appends), CTAs run by OS threads.  The tick loop mirrors renderStaged() of csrc/gpt.cu.  Every queue entry is checked
+// against the status it must have.
+extern "C" int gdb200_emu_gpt_render_staged(const gdb200_scene_desc *desc, const gdb200_gpt_params *p, gdb200_buffers *out, double *counters, int grid)
+{
+    static HostScene hs;
+    if (int rc = flattenScene(desc, &hs)) return rc;
+    classifyMaterials(&hs, p->shift_threshold);
+    GptArgs a;
+    const char *capEnv = getenv("GDB200_MAX_SLOTS");
+    if (int rc = setupArgs(hs, p, a, capEnv ? atoi(capEnv) : (1 << 23))) return rc;
+    hs.host.env.texels = hs.envTexels.data(); hs.host.env.rowWeights = hs.envRowWeights.data(); hs.host.emTriCdf = hs.emTriCdf.data();
+    hs.host.env.cdfRows = hs.envCdfRows.data(); hs.host.env.cdfCols = hs.envCdfCols.data(); hs.host.emTris = hs.emTris.data();
+    hs.host.bvh = hs.bvh.data(); hs.host.bvhTris = hs.bvhTris.data(); hs.host.triNormals = hs.triNormals.data();
+    c_scene = hs.host; static DScene sceneCopy; sceneCopy = hs.host; c_sceneG = &sceneCopy;
+    memcpy(c_bounds, hs.bounds, sizeof(hs.bounds));
+    const size_t n = (size_t)hs.width * hs.height;
+    const int nSlots = a.nSlots;
+    const double nan = std::numeric_limits<double>::quiet_NaN();      // a stage that reads a record nobody wrote shows up in the film
+    std::vector<double> sd((size_t)4 * kRecordsStaged * nSlots, nan), film(5 * n * 4, 0.0), rays0((size_t)8 * 5 * nSlots, nan), rays1((size_t)8 * 5 * nSlots, nan),
+        hits((size_t)4 * 5 * nSlots, nan);
+    std::vector<int> si((size_t)16 * nSlots, 0), owner0((size_t)5 * nSlots, -1), owner1((size_t)5 * nSlots, -1), occl((size_t)5 * nSlots, -1),
+        qList((size_t)kStageBuckets * nSlots, -1), qCount(kStageBuckets, 0), rayCount(2, 0);
+    std::vector<unsigned long long> ctr(8, 0);
+    a.sd = sd.data(); a.si = si.data(); a.film = film.data(); a.counters = ctr.data();
+    a.rays[0] = rays0.data(); a.rays[1] = rays1.data(); a.rayOwner[0] = owner0.data(); a.rayOwner[1] = owner1.data();
+    a.rayCount = rayCount.data(); a.rayCapacity = 5 * nSlots; a.hits = hits.data(); a.occluded = occl.data();
+    a.qList = qList.data(); a.qCount = qCount.data();
+
+    grid = std::max(1, grid);
+    emuLaunch((std::max(nSlots, kStageBuckets) + 255) / 256, 256, [&]() { gpt_stage_init_kernel(a); });
+    const int compactBlocks = (nSlots + 255) / 256;
+    auto checkQueues = [&](int first, int count, long long tick) -> int {
+        for (int b = first; b < first + count; b++)
+            for (int i = 0; i < qCount[b]; i++) {
+                const int slot = qList[(size_t)b * nSlots + i];
+                if (slot < 0 || slot >= nSlots) return set_error(GDB200_ERR_CUDA, "tick %lld: bad entry %d in queue %d", tick, slot, b);
+                const int st = si[(size_t)slot * 16 + IF_STATUS];
+                const bool ok = b == QA_PRIMARY ? st == ST_WAIT_PRIMARY : b == QA_RESOLVE ? st == ST_WAIT_RESOLVE : b < QA_RESOLVE ? st == ST_WAIT_SHADE
+                              : b == QB_GEN ? (st == ST_FINISHED || st == ST_FRESH) : st == ST_LIVE;
+                if (!ok) return set_error(GDB200_ERR_CUDA, "tick %lld: slot %d with status %d in queue %d", tick, slot, st, b);
+            }
+        return 0;
+    };
+    const long long maxTicks = ((long long)p->spp * 8192 + 131072) * std::max(1, a.nStreams / std::max(1, nSlots) + 1);
+    for (long long tick = 0;; tick++) {
+        if (tick > maxTicks) return set_error(GDB200_ERR_CUDA, "wavefront did not drain after %lld ticks", tick);
+        emuLaunch(compactBlocks, 256, [&]() { gpt_stage_compact_kernel<0>(a); });
+        if (int rc = checkQueues(0, kQA, tick)) return rc;
+        if (rayCount[0] || rayCount[1]) return set_error(GDB200_ERR_CUDA, "tick %lld: ray queues not reset", tick);
+        emuLaunch(grid, kStageThreads, [&]() { gpt_stage_kernel<SK_PRIMARY>(a); });
+        emuLaunch(grid, kStageThreads, [&]() { gpt_stage_kernel<SK_SHADE0>(a); });
+        emuLaunch(grid, kStageThreads, [&]() { gpt_stage_kernel<SK_SHADE1>(a); });
+        emuLaunch(grid, kStageThreads, [&]() { gpt_stage_kernel<SK_SHADE2>(a); });
+        emuLaunch(grid, kStageThreads, [&]() { gpt_stage_kernel<SK_RESOLVE>(a); });
+        emuLaunch(compactBlocks, 256, [&]() { gpt_stage_compact_kernel<1>(a); });
+        if (int rc = checkQueues(kQA, kStageBuckets - kQA, tick)) return rc;
+        emuLaunch(grid, kStageThreads, [&]() { gpt_stage_kernel<SK_PREPARE>(a); });
+        emuLaunch(grid, kStageThreads, [&]() { gpt_stage_kernel<SK_GENERATE>(a); });
+        emuLaunch(grid, 128, [&]() { gpt_cast_kernel<false>(a); });
+        emuLaunch(grid, 128, [&]() { gpt_cast_kernel<true>(a); });
+        if (ctr[7]) return set_error(GDB200_ERR_CUDA, "ray queue overflow");
+        if ((tick & 15) == 15 && ctr[0] >= (unsigned long long)nSlots) break;
     }
     std::vector<double> dev64(5 * n * 3); std::vector<float> dev32(5 * n * 3);
     blockDim.x = 1; threadIdx.x = 0;

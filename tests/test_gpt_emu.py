@@ -169,6 +169,50 @@ def test_queued_wavefront_kernels(oracle, emu, scene_name, no_tail, cap, monkeyp
     assert cnt[0] == (cap if cap else 14 * 10 * 2)
 
 
+@pytest.mark.parametrize("scene_name", sorted(SCENES))
+def test_staged_wavefront_kernels(oracle, emu, scene_name):
+    """Block mode of the emulation for the STAGED wavefront (csrc/gpt_stages.cuh, the product's default path): stage
+    compaction, primary / shade<0..2> / resolve / prepare / generate and the two cast kernels as written (persistent CTAs
+    over their queues, warp-aggregated ray appends), the tick loop of renderStaged() restated around them.  Every queue
+    entry is checked against the status it must have; the film, the ray count and the path-vertex count must be the
+    oracle's."""
+    w, h = (12, 8) if scene_name == "atrium" else (14, 10)
+    desc = SCENES[scene_name](w, h)
+    p = scenes.default_params(spp=3, seed=3)
+    p.streams_per_pixel = 2
+    got, cnt = emu.gpt_staged(desc, p)
+    ref, _, c2 = oracle.gpt(desc, p)
+    close(got, ref)
+    assert cnt[3] == c2[0] == w * h * 3 and cnt[1] == c2[1] and cnt[2] == c2[2]
+    assert cnt[0] == w * h * 2
+
+
+@pytest.mark.parametrize("scene_name,kw", [("cbox_glossy", dict(max_depth=2)), ("cbox_glossy", dict(max_depth=1)), ("cbox_glossy", dict(rr_depth=2)),
+                                           ("cbox_glossy", dict(strict_normals=True)), ("cbox_glossy", dict(shift_threshold=0.1)),
+                                           ("cbox_smooth", dict(strict_normals=True)), ("cbox_smooth", dict(strict_normals=True, shift_threshold=0.2)),
+                                           ("cbox_env", dict(max_depth=3, rr_depth=1)), ("cbox_env", dict(strict_normals=True)),
+                                           ("cbox_materials", dict(shift_threshold=0.1, ref_uninit_measure=True))])
+def test_staged_wavefront_parameters(oracle, emu, scene_name, kw):
+    desc = SCENES[scene_name](14, 10)
+    p = scenes.default_params(spp=4, seed=9, **kw)
+    got, cnt = emu.gpt_staged(desc, p, grid=2)
+    ref, _, c2 = oracle.gpt(desc, p)
+    close(got, ref)
+    assert cnt[1] == c2[1] and cnt[2] == c2[2]
+
+
+@pytest.mark.parametrize("cap,grid", [(37, 1), (100, 5)])
+def test_staged_wavefront_deals_streams_to_few_slots(oracle, emu, cap, grid):
+    """max_slots below the stream count: slots take the next stream from the atomic counter as they drain."""
+    desc = scenes.cbox_glossy(14, 10)
+    p = scenes.default_params(spp=5, seed=4, max_slots=cap)
+    p.streams_per_pixel = 3
+    got, cnt = emu.gpt_staged(desc, p, grid=grid)
+    ref, _, c2 = oracle.gpt(desc, p)
+    close(got, ref)
+    assert cnt[3] == c2[0] == 14 * 10 * 5 and cnt[0] == cap
+
+
 def test_host_validation_follows_the_reference(emu):
     """Scene flattening (csrc/gpt_host.h, shared by the library and the emulation) rejects what the reference's plugins reject."""
     cam = scenes.make_camera(8, 8, (0, 0, 4), (0, 0, 0), (0, 1, 0), 40)

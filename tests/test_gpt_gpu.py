@@ -216,6 +216,24 @@ def test_streams_per_pixel_match_oracle(oracle, streams, cap, monkeypatch):
     assert abs(integ.stats.rays - cnt[1]) <= 1e-3 * cnt[1]
 
 
+@pytest.mark.parametrize("scene_name", ["cbox_glossy", "cbox_materials", "cbox_env"])
+def test_staged_and_fused_wavefronts_agree(scene_name):
+    """The default staged wavefront (csrc/gpt_stages.cuh: shading stages + cast kernels) and the round-1 single-kernel bounce
+    (GDB200_GPT_FUSED_BOUNCE) run the same per-path arithmetic in the same order: same film up to the order of the film
+    atomics, same sample / ray / path-vertex counts."""
+    desc = getattr(scenes, scene_name)(88, 72)
+    integ = gdb200.GPTIntegrator(reconstructL1=False, reconstructL2=False)
+    a = integ.trace(gdb200.Scene(desc), spp=8, seed=6, streams=2)
+    ca = (integ.stats.samples, integ.stats.rays, integ.stats.path_vertices)
+    assert integ.stats.cast_ms > 0 and integ.stats.launches > 20          # the staged kernels really ran
+    integ.fusedBounce = True
+    b = integ.trace(gdb200.Scene(desc), spp=8, seed=6, streams=2)
+    assert integ.stats.cast_ms == 0
+    assert ca == (integ.stats.samples, integ.stats.rays, integ.stats.path_vertices)
+    for k in a:
+        np.testing.assert_allclose(a[k], b[k], rtol=1e-11, atol=1e-14)
+
+
 def test_forced_bvh_matches_the_table_path(monkeypatch):
     desc = scenes.cbox_glossy(64, 64)
     integ = gdb200.GPTIntegrator(reconstructL1=False, reconstructL2=False)
@@ -324,14 +342,15 @@ def test_gpu_reproduces_committed_golden_buffers():
 def test_gpu_matches_the_reference_integrator(monkeypatch):
     """tests/golden/ref_gpt_golden.npz holds the output of the REFERENCE's own gpt.cpp (compiled from the reference tree, see
     tests/test_ref_gpt.py) for twenty-one scene / parameter cases; the CUDA tracer must reproduce it on the same scene bytes
-    and sample streams.  GDB200_REF_UNINIT_MEASURE=1: the one place where that build's behaviour is undefined (gpt.cpp:957)."""
+    and sample streams.  refUninitMeasure (GDB200_GPT_REF_UNINIT_MEASURE): the one place where that build's behaviour is
+    undefined (gpt.cpp:957)."""
     import test_ref_gpt as T
-    monkeypatch.setenv("GDB200_REF_UNINIT_MEASURE", "1")
     golden = dict(np.load(T.GOLDEN))
     for name in sorted(T.SCENES):
         desc, prm = T._case(name)
         integ = gdb200.GPTIntegrator(reconstructL1=False, reconstructL2=False, maxDepth=prm.max_depth, rrDepth=prm.rr_depth,
                                      strictNormals=bool(prm.strict_normals), shiftThreshold=prm.shift_threshold)
+        integ.refUninitMeasure = True
         got = integ.trace(gdb200.Scene(desc), spp=prm.spp, seed=prm.seed)
         ref = {b: golden[name + b] for b in ("-throughput", "-dx", "-dy", "-direct", "-final")}
         compare(got, ref, max_flip_frac=0.01)          # 320 pixels: at most 3 may contain a sample whose branch a CUDA-libm ulp flipped

@@ -63,10 +63,9 @@ def rand_scene(seed,w=16,h=12):
 def test_random_scene_matches_the_reference(oracle, emu, seed, monkeypatch):
     if not RefMitsuba.available() or os.environ.get("GDB200_NO_REF"):
         pytest.skip("needs the compiled reference")
-    monkeypatch.setenv("GDB200_REF_UNINIT_MEASURE", "1")
     desc = rand_scene(seed)
     rng = np.random.default_rng(seed + 1000)
-    prm = S.default_params(spp=2, seed=seed, max_depth=int(rng.choice([-1, -1, 3, 6])), rr_depth=int(rng.choice([5, 2])),
+    prm = S.default_params(ref_uninit_measure=True, spp=2, seed=seed, max_depth=int(rng.choice([-1, -1, 3, 6])), rr_depth=int(rng.choice([5, 2])),
                            strict_normals=bool(rng.integers(0, 2)), shift_threshold=float(rng.choice([0.001, 0.05])))
     ref = RefMitsuba().gpt(desc, prm)
     got, _, _ = oracle.gpt(desc, prm, threads=1)
@@ -111,12 +110,11 @@ def test_random_scene_with_large_meshes_matches_the_reference(oracle, emu, seed,
     sampling weights, a roughness exactly at shiftThreshold."""
     if not RefMitsuba.available() or os.environ.get("GDB200_NO_REF"):
         pytest.skip("needs the compiled reference")
-    monkeypatch.setenv("GDB200_REF_UNINIT_MEASURE", "1")
     if seed % 2:
         monkeypatch.setenv("GDB200_FORCE_BVH", "1")
     desc = rand_scene2(seed)
     rng = np.random.default_rng(seed + 7)
-    prm = S.default_params(spp=2, seed=seed, max_depth=int(rng.choice([-1, 4])), strict_normals=bool(rng.integers(0, 2)))
+    prm = S.default_params(ref_uninit_measure=True, spp=2, seed=seed, max_depth=int(rng.choice([-1, 4])), strict_normals=bool(rng.integers(0, 2)))
     ref = RefMitsuba().gpt(desc, prm)
     got, _, _ = oracle.gpt(desc, prm, threads=1)
     dev, _ = emu.gpt(desc, prm)
@@ -131,7 +129,7 @@ def _intersections(desc, org, dirs, oracle):
     ref = RefMitsuba()
     ref.lib.gdbref_build_scene.restype = ctypes.c_void_p
     fov, rfilter = S.mitsuba_sensor_args(desc)
-    prm = S.default_params(spp=1)
+    prm = S.default_params(ref_uninit_measure=True, spp=1)
     handle = ref.lib.gdbref_build_scene(ctypes.byref(desc), ctypes.byref(prm), ctypes.c_double(fov), rfilter.encode())
     assert handle
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
@@ -189,12 +187,11 @@ def test_queued_wavefront_kernels_match_the_reference(emu, seed, monkeypatch):
     the reference integrator on random scenes; GDB200_NO_TAIL on odd seeds keeps every path on the queues to the end."""
     if not RefMitsuba.available() or os.environ.get("GDB200_NO_REF"):
         pytest.skip("needs the compiled reference")
-    monkeypatch.setenv("GDB200_REF_UNINIT_MEASURE", "1")
     if seed % 2:
         monkeypatch.setenv("GDB200_NO_TAIL", "1")
     desc = rand_scene(seed, w=12, h=8)
     rng = np.random.default_rng(seed + 1000)
-    prm = S.default_params(spp=2, seed=seed, max_depth=int(rng.choice([-1, -1, 3, 6])), rr_depth=int(rng.choice([5, 2])),
+    prm = S.default_params(ref_uninit_measure=True, spp=2, seed=seed, max_depth=int(rng.choice([-1, -1, 3, 6])), rr_depth=int(rng.choice([5, 2])),
                            strict_normals=bool(rng.integers(0, 2)), shift_threshold=float(rng.choice([0.001, 0.05])))
     ref = RefMitsuba().gpt(desc, prm)
     got, _ = emu.gpt_wavefront(desc, prm)
@@ -211,13 +208,28 @@ def _agree_with_reference(desc, prm, oracle, emu):
         assert np.abs(got[k] - ref[k]).max() <= 1e-10 * scale and np.abs(dev[k] - ref[k]).max() <= 1e-10 * scale, k
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_staged_wavefront_kernels_match_the_reference(emu, seed):
+    """The product's default path — the staged wavefront of csrc/gpt_stages.cuh, kernels as written, run block by block on
+    OS threads by tests/emu — against the reference integrator on random scenes."""
+    if not RefMitsuba.available() or os.environ.get("GDB200_NO_REF"):
+        pytest.skip("needs the compiled reference")
+    desc = rand_scene(seed, w=12, h=8)
+    rng = np.random.default_rng(seed + 1000)
+    prm = S.default_params(ref_uninit_measure=True, spp=2, seed=seed, max_depth=int(rng.choice([-1, -1, 3, 6])), rr_depth=int(rng.choice([5, 2])),
+                           strict_normals=bool(rng.integers(0, 2)), shift_threshold=float(rng.choice([0.001, 0.05])))
+    ref = RefMitsuba().gpt(desc, prm)
+    got, _ = emu.gpt_staged(desc, prm, grid=2)
+    for k in ref:
+        assert np.abs(got[k] - ref[k]).max() <= 1e-10 * max(float(np.abs(ref[k]).mean()), 1e-12), (seed, k)
+
+
 @pytest.mark.parametrize("seed", range(4))
 def test_mirrored_rectangles_and_flipped_spheres_match_the_reference(oracle, emu, seed, monkeypatch):
     """flipNormals: rectangles whose toWorld mirrors (rectangle.cpp:82-84, incl. an area light shining the other way) and
     inside-out spheres (a spherical room, flipped sphere lights)."""
     if not RefMitsuba.available() or os.environ.get("GDB200_NO_REF"):
         pytest.skip("needs the compiled reference")
-    monkeypatch.setenv("GDB200_REF_UNINIT_MEASURE", "1")
     rng = np.random.default_rng(100 + seed)
     b = S.SceneBuilder(S.make_camera(14, 10, origin=(0.2, 0.3, 2.5), target=(0, 0, 0), up=(0, 1, 0), fov_deg=50.0))
 
@@ -239,4 +251,4 @@ def test_mirrored_rectangles_and_flipped_spheres_match_the_reference(oracle, emu
     light = b.rectangle((0.1, 0.9375, 0.0), (0.3, 0, 0), (0, 0, 0.3), black, radiance=(8, 7, 6))
     if seed % 2 == 0:
         mirror(light)
-    _agree_with_reference(b.build(), S.default_params(spp=2, seed=seed, strict_normals=bool(seed % 2)), oracle, emu)
+    _agree_with_reference(b.build(), S.default_params(ref_uninit_measure=True, spp=2, seed=seed, strict_normals=bool(seed % 2)), oracle, emu)

@@ -10,7 +10,7 @@ per-pixel sample streams (plugin/samplers/gdb200_counter.cpp compiled against th
 Bar: every buffer agrees to 1e-11 of its mean with NO branch-flipped pixel.  One knob is set for this comparison:
 gpt.cpp:957 default-constructs a DirectSamplingRecord and never sets .measure before Shape::pdfDirect reads it
 (undefined behaviour).  Compiled with g++ -O2 the stale value is not ESolidAngle, so an area emitter reports density 0 for
-the reconnected offset path's MIS weight; GDB200_REF_UNINIT_MEASURE=1 makes the restatement do the same.  Without the
+the reconnected offset path's MIS weight; the GDB200_GPT_REF_UNINIT_MEASURE flag of gdb200_gpt_params makes the restatement do the same.  Without the
 knob (the intended ESolidAngle, which is what the product implements) only those samples differ -- also checked here.
 
 The library is a build of /root/reference and cannot be rebuilt on a box without it, so the reference's outputs are also
@@ -45,7 +45,7 @@ def _case(name):
     kw = dict(SCENES[name])
     w, h = kw.pop("size", (W, H))
     desc = getattr(scenes, kw.pop("scene", name))(w, h, **kw.pop("scene_kw", {}))
-    return desc, scenes.default_params(spp=kw.pop("spp", SPP), seed=SEED, **kw)
+    return desc, scenes.default_params(spp=kw.pop("spp", SPP), seed=SEED, ref_uninit_measure=True, **kw)   # gpt.cpp:957, see include/gdb200.h
 
 
 @pytest.fixture(scope="module")
@@ -73,7 +73,6 @@ def _differing_pixels(got, ref):
 
 @pytest.mark.parametrize("name", sorted(SCENES))
 def test_restatement_matches_the_reference_integrator(oracle, reference, name, monkeypatch):
-    monkeypatch.setenv("GDB200_REF_UNINIT_MEASURE", "1")
     desc, prm = _case(name)
     got, _, cnt = oracle.gpt(desc, prm, threads=1)
     assert cnt[0] == desc.camera.width * desc.camera.height * prm.spp
@@ -116,7 +115,6 @@ def test_reference_is_thread_count_invariant():
 def test_device_code_matches_the_reference_integrator(emu, reference, name, monkeypatch):
     """The CUDA tracer's own routines (csrc/gpt_device.cuh + gpt_kernels.cuh compiled for the host, tests/emu) against the
     reference integrator, directly, with the same knob (read by the shared host code, csrc/gpt_host.h setupArgs)."""
-    monkeypatch.setenv("GDB200_REF_UNINIT_MEASURE", "1")
     desc, prm = _case(name)
     got, cnt = emu.gpt(desc, prm)
     assert cnt[3] == desc.camera.width * desc.camera.height * prm.spp

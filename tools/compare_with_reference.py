@@ -5,7 +5,7 @@ GPU is present, with libgdb200 on the same scene bytes and sample streams, and r
 
     python tools/compare_with_reference.py scene.xml [-D spp=16] [--write dest]
 
-GDB200_REF_UNINIT_MEASURE=1 is set for the GPU render: gpt.cpp:957 reads an uninitialised value, and this reproduces what the
+GPTIntegrator.refUninitMeasure (gdb200_gpt_params.flags) is set for the GPU render: gpt.cpp:957 reads an uninitialised value, and this reproduces what the
 g++ build of the reference does there.  One sample stream per pixel (the reference has no other mode).
 Test infrastructure: this is the only tool that loads anything under oracle/."""
 import argparse
@@ -50,6 +50,7 @@ def main():
     parsed = gdb200.load_scene(a.scene, dict(kv.split("=", 1) for kv in a.D))
     integ = parsed.integrator()
     integ.reconstructL1 = integ.reconstructL2 = False
+    integ.refUninitMeasure = True      # gpt.cpp:957: what the compiled reference does there (include/gdb200.h)
     prm = integ.params(parsed.spp, parsed.seed)
     n = parsed.desc.camera.width * parsed.desc.camera.height * parsed.spp
     ref, dt = reference_render(parsed.desc, prm, a.threads)
@@ -66,7 +67,6 @@ def main():
     if not have_gpu:
         print("no GPU: nothing to compare with")
         return
-    os.environ["GDB200_REF_UNINIT_MEASURE"] = "1"
     t0 = time.perf_counter()
     got = integ.trace(gdb200.Scene(parsed.desc), spp=parsed.spp, seed=parsed.seed)
     dt = time.perf_counter() - t0
