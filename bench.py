@@ -87,38 +87,42 @@ def load_oracle():
     return lib, ref
 
 
-REF_MITSUBA = os.path.join(ROOT, "oracle", "_ref", "libref_mitsuba.so")
+# The reference's own tracer compiled from the reference tree (oracle/Makefile): the -O3 -march=x86-64-v3 build is the CPU
+# baseline (what a user's Mitsuba would be built like); the -O2 -ffp-contract=off build exists for parity
+# and is timed only if the fast one is absent.
+REF_MITSUBA = [(os.path.join(ROOT, "oracle", "_ref", "libref_mitsuba_fast.so"), "-O3 -march=x86-64-v3"),
+               (os.path.join(ROOT, "oracle", "_ref", "libref_mitsuba.so"), "-O2 -ffp-contract=off (parity build)")]
 CPU_KIND_NOTE = {"reference": "tracer = the reference's gpt.cpp and the Mitsuba sources it runs on, compiled from the reference tree "
-                              "(oracle/_ref/libref_mitsuba.so), its blocks dealt to one std::thread per core",
-                 "port": "tracer = CPU restatement oracle/gpt_oracle.cpp with OpenMP over row bands (oracle/_ref/libref_mitsuba.so not built)"}
+                              "(oracle/_ref/{lib}, {flags}), 32x32 blocks dealt to one std::thread per core, timed over the block loop "
+                              "(Mitsuba's 'Render time'; scene / kd-tree construction and film development excluded)",
+                 "port": "tracer = CPU restatement oracle/gpt_oracle.cpp with OpenMP over row bands (oracle/_ref/libref_mitsuba*.so not built)"}
 
 
 def cpu_tracer_rate(desc, params_fn, spp, threads):
-    """(Msamples/s, seconds, kind) of the reference tracer on the host cores, on desc at `spp`.  kind "reference": the
+    """(Msamples/s, seconds, kind, note) of the reference tracer on the host cores, on desc at `spp`.  kind "reference": the
     reference's own gpt.cpp + the Mitsuba sources it runs on, compiled from the reference tree into oracle/_ref
     (one sample stream per pixel -- the reference has no other mode); kind "port": the CPU restatement
-    oracle/gpt_oracle.cpp (OpenMP over row bands), when that library is not there."""
+    oracle/gpt_oracle.cpp (OpenMP over row bands), only when no such library was built.  A library that is there but fails
+    is an error, not a reason to time something else."""
     from gdb200 import scenes
-    ref = None
-    if os.path.exists(REF_MITSUBA):
-        try:
-            ref = ctypes.CDLL(REF_MITSUBA)
-        except OSError as e:                      # a build of another machine that does not load here: fall back to the restatement
-            print(f"bench: {REF_MITSUBA} does not load ({e}); using the CPU restatement", file=sys.stderr)
-    if ref is not None:
+    for path, flags in REF_MITSUBA:
+        if not os.path.exists(path):
+            continue
         import numpy as np
+        ref = ctypes.CDLL(path)
         ref.gdbref_gpt_last_error.restype = ctypes.c_char_p
         prm = params_fn(spp)
         prm.streams_per_pixel = 1
         fov, rfilter = scenes.mitsuba_sensor_args(desc)
         out = np.zeros((5, desc.camera.height, desc.camera.width, 3))
-        t0 = time.perf_counter()
-        rc = ref.gdbref_gpt_render(ctypes.byref(desc), ctypes.byref(prm), ctypes.c_double(fov), rfilter.encode(), int(threads),
-                                   out.ctypes.data_as(ctypes.c_void_p))
-        dt = time.perf_counter() - t0
-        if rc == 0:
-            return desc.camera.width * desc.camera.height * spp / dt / 1e6, dt, "reference"
-        print(f"bench: the compiled reference failed ({ref.gdbref_gpt_last_error().decode()}); using the CPU restatement", file=sys.stderr)
+        sec = ctypes.c_double()
+        rc = ref.gdbref_gpt_render_timed(ctypes.byref(desc), ctypes.byref(prm), ctypes.c_double(fov), rfilter.encode(), int(threads),
+                                         out.ctypes.data_as(ctypes.c_void_p), ctypes.byref(sec))
+        if rc != 0:
+            raise RuntimeError(f"{path}: {ref.gdbref_gpt_last_error().decode()}")
+        dt = sec.value
+        return (desc.camera.width * desc.camera.height * spp / dt / 1e6, dt, "reference",
+                CPU_KIND_NOTE["reference"].format(lib=os.path.basename(path), flags=flags))
     lib, _ = load_oracle()
     prm = params_fn(spp)
     B = scenes.Buffers()
@@ -127,7 +131,7 @@ def cpu_tracer_rate(desc, params_fn, spp, threads):
     rc = lib.gdb200_oracle_gpt_render(ctypes.byref(desc), ctypes.byref(prm), ctypes.byref(B), None, cnt, threads)
     dt = time.perf_counter() - t0
     assert rc == 0
-    return cnt[0] / dt / 1e6, dt, "port"
+    return cnt[0] / dt / 1e6, dt, "port", CPU_KIND_NOTE["port"]
 
 
 def cpu_solver_seconds(w, h, preset):
@@ -157,7 +161,8 @@ def main():
     ap.add_argument("--spp", type=int, default=0, help="override the workload's sample count (invalidates the headline)")
     ap.add_argument("--streams", type=int, default=8, help="sample streams per pixel (gdb200_gpt_params.streams_per_pixel); "
                     "fixed for every N so the film does not depend on the GPU count")
-    ap.add_argument("--cpu-spp", type=int, default=8, help="samples/pixel of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-spp", type=int, default=16, help="samples/pixel of the bounded CPU-baseline sample (cpu_baseline leg and "
+                    "every step of --impl reference)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -184,13 +189,13 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        cpu_spp = max(1, args.cpu_spp // 4)
+        cpu_spp = max(1, args.cpu_spp)
         rates = []
         for i in range(args.warmup + args.steps):
-            r, dt, kind = cpu_tracer_rate(desc, lambda s: integ.params(s, 0, streams=min(args.streams, s)), cpu_spp, cores)
+            r, dt, kind, note = cpu_tracer_rate(desc, lambda s: integ.params(s, 0), cpu_spp, cores)
             if i >= args.warmup:
                 rates.append((r, dt))
-        val = sum(r for r, _ in rates) / len(rates)
+        val = W * H * cpu_spp * len(rates) / sum(dt for _, dt in rates) / 1e6          # samples / time over the timed steps
         solve_s = cpu_solver_seconds(W, H, recon + "D")
         line = {"impl": "reference", "metric": "gpt_msamples_per_s", "value": round(val, 4), "unit": "Msamples/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -198,7 +203,8 @@ def main():
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "poisson_solve_ms": round(solve_s * 1e3, 1) if solve_s else None,
                 "cpu_baseline": {"value": round(val, 4), "unit": "Msamples/s", "cores": cores, "kind": kind,
-                                 "sample": f"{scene_name} {W}x{H} @ {cpu_spp} spp per step (of {spp}); " + CPU_KIND_NOTE[kind] + ", solver = reference sources"},
+                                 "spp": cpu_spp,
+                                 "sample": f"{scene_name} {W}x{H} @ {cpu_spp} spp per step (of {spp}); " + note + ", solver = reference sources"},
                 "e2e": {"value": round(val, 4), "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
@@ -332,9 +338,9 @@ def main():
             line["exchange_bytes_per_step"] = int(agg["exchange_bytes"] / args.steps)
         if world == 1:
             try:                                  # a reported baseline: it must never cost the measured line
-                rate, dt, kind = cpu_tracer_rate(desc, lambda s: integ.params(s, 0, streams=min(args.streams, s)), args.cpu_spp, cores)
-                line["cpu_baseline"] = {"value": round(rate, 4), "unit": "Msamples/s", "cores": cores, "kind": kind,
-                                        "sample": f"{scene_name} {W}x{H} @ {args.cpu_spp} spp (of {spp}), {dt:.1f} s, " + CPU_KIND_NOTE[kind]}
+                rate, dt, kind, note = cpu_tracer_rate(desc, lambda s: integ.params(s, 0), args.cpu_spp, cores)
+                line["cpu_baseline"] = {"value": round(rate, 4), "unit": "Msamples/s", "cores": cores, "kind": kind, "spp": args.cpu_spp,
+                                        "sample": f"{scene_name} {W}x{H} @ {args.cpu_spp} spp (of {spp}), {dt:.1f} s, " + note}
             except Exception as e:                # noqa: BLE001
                 line["cpu_baseline"] = {"value": None, "unit": "Msamples/s", "cores": cores, "kind": "unavailable", "sample": f"failed: {e}"}
         print(json.dumps(line))

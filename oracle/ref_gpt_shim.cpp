@@ -20,6 +20,7 @@
 #include <mitsuba/core/bitmap.h>
 #include <sstream>
 #include <thread>
+#include <chrono>
 #include <mutex>
 #include <atomic>
 #define private public                   /* GradientPathIntegrator::m_config is filled by render() (gpt.cpp:1365-1370), which is bypassed */
@@ -274,7 +275,7 @@ Built buildScene(const gdb200_scene_desc *d, const gdb200_gpt_params *prm, doubl
 }
 
 // Block loop: 32x32 blocks (scene.cpp: blockSize default), any order (every pixel re-keys the sampler), `threads` workers.
-void renderBlocks(Built &b, int threads, double *out5)
+void renderBlocks(Built &b, int threads, double *out5, double *blockSeconds = nullptr)
 {
     Scene *scene = b.scene.get();
     Sensor *sensor = scene->getSensor();
@@ -307,6 +308,7 @@ void renderBlocks(Built &b, int threads, double *out5)
             }
         } catch (const std::exception &e) { std::lock_guard<std::mutex> guard(merge); failure = e.what(); }
     };
+    const auto t0 = std::chrono::steady_clock::now();
     if (threads <= 1) worker();
     else {
         std::vector<std::thread> pool;
@@ -316,6 +318,7 @@ void renderBlocks(Built &b, int threads, double *out5)
         }));
         for (auto &t : pool) t.join();
     }
+    if (blockSeconds) *blockSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (!failure.empty()) throw std::runtime_error(failure);
     // develop: value / weight per pixel (Bitmap::convert of ESpectrumAlphaWeight, what MultiFilm::develop writes)
     for (int buf = 0; buf < 5; buf++) {
@@ -485,6 +488,20 @@ int gdbref_gpt_render(const gdb200_scene_desc *desc, const gdb200_gpt_params *pr
         if (prm->streams_per_pixel > 1) throw std::runtime_error("the reference has one sample stream per pixel");
         Built b = buildScene(desc, prm, fov_x_deg, rfilter, true);
         renderBlocks(b, threads, out5);
+        return 0;
+    } catch (const std::exception &e) { g_error = e.what(); return 1; }
+}
+
+// The same, reporting the wall time of the block loop alone -- worker start to last join: what Mitsuba's "Render time" covers
+// (renderjob.cpp:108), without building the Scene / kd-tree before it or developing the film after it.  bench.py's CPU baseline.
+int gdbref_gpt_render_timed(const gdb200_scene_desc *desc, const gdb200_gpt_params *prm, double fov_x_deg, const char *rfilter, int threads,
+                            double *out5, double *render_seconds)
+{
+    try {
+        std::call_once(g_init, staticInit);
+        if (prm->streams_per_pixel > 1) throw std::runtime_error("the reference has one sample stream per pixel");
+        Built b = buildScene(desc, prm, fov_x_deg, rfilter, true);
+        renderBlocks(b, threads, out5, render_seconds);
         return 0;
     } catch (const std::exception &e) { g_error = e.what(); return 1; }
 }
