@@ -60,8 +60,8 @@ static std::mutex g_deviceMutex[kMaxDevices];
 struct Workspace {
     double *sd = nullptr; int *si = nullptr;
     int *liveList = nullptr, *liveCount = nullptr, *genList = nullptr, *genCount = nullptr;     // fused-bounce wavefront (A/B)
-    double *rays[2] = {nullptr, nullptr}, *hits = nullptr;                                       // staged wavefront
-    int *rayOwner[2] = {nullptr, nullptr}, *rayCount = nullptr, *occluded = nullptr, *qList = nullptr, *qCount = nullptr;
+    double *rays[2] = {nullptr, nullptr};                                                        // staged wavefront
+    int *rayOwner[2] = {nullptr, nullptr}, *rayCount = nullptr, *qList = nullptr, *qCount = nullptr;
     int slotCapacity = 0; bool fused = false;
     std::vector<cudaEvent_t> events;       // timing marks of renders that ask for stats, reused across renders
 };
@@ -70,8 +70,8 @@ static Workspace g_workspace[kMaxDevices];
 static void freeWorkspace(Workspace &w)
 {
     cudaFree(w.sd); cudaFree(w.si); cudaFree(w.liveList); cudaFree(w.liveCount); cudaFree(w.genList); cudaFree(w.genCount);
-    cudaFree(w.rays[0]); cudaFree(w.rays[1]); cudaFree(w.hits); cudaFree(w.rayOwner[0]); cudaFree(w.rayOwner[1]);
-    cudaFree(w.rayCount); cudaFree(w.occluded); cudaFree(w.qList); cudaFree(w.qCount);
+    cudaFree(w.rays[0]); cudaFree(w.rays[1]); cudaFree(w.rayOwner[0]); cudaFree(w.rayOwner[1]);
+    cudaFree(w.rayCount); cudaFree(w.qList); cudaFree(w.qCount);
     for (cudaEvent_t e : w.events) cudaEventDestroy(e);
     w = Workspace();
 }
@@ -175,7 +175,7 @@ int ensureWorkspace(Workspace &ws, int nSlots, bool fused)
     ws.events.swap(keep);
     static_assert(IF_COUNT <= 16, "int fields must fit the 16-int slot line");
     const size_t n = (size_t)nSlots;
-    cudaError_t e = cudaMalloc(&ws.sd, sizeof(double) * 4 * (fused ? kRecords : kRecordsStaged) * n);
+    cudaError_t e = cudaMalloc(&ws.sd, sizeof(double) * 4 * kRecPitch * n);
     if (e == cudaSuccess) e = cudaMalloc(&ws.si, sizeof(int) * 16 * n);
     if (fused) {
         if (e == cudaSuccess) e = cudaMalloc(&ws.liveList, sizeof(int) * 2 * (size_t)kBuckets * n);
@@ -187,8 +187,6 @@ int ensureWorkspace(Workspace &ws, int nSlots, bool fused)
             if (e == cudaSuccess) e = cudaMalloc(&ws.rays[q], sizeof(double) * 8 * 5 * n);
             if (e == cudaSuccess) e = cudaMalloc(&ws.rayOwner[q], sizeof(int) * 5 * n);
         }
-        if (e == cudaSuccess) e = cudaMalloc(&ws.hits, sizeof(double) * 4 * 5 * n);
-        if (e == cudaSuccess) e = cudaMalloc(&ws.occluded, sizeof(int) * 5 * n);
         if (e == cudaSuccess) e = cudaMalloc(&ws.rayCount, sizeof(int) * 2);
         if (e == cudaSuccess) e = cudaMalloc(&ws.qList, sizeof(int) * (size_t)kStageBuckets * n);
         if (e == cudaSuccess) e = cudaMalloc(&ws.qCount, sizeof(int) * kStageBuckets);
@@ -389,7 +387,7 @@ int gdb200_gpt_render(gdb200_scene *s, const gdb200_gpt_params *p, gdb200_buffer
     a.film = s->film; a.liveList = ws.liveList; a.liveCount = ws.liveCount; a.genList = ws.genList; a.genCount = ws.genCount;
     a.counters = s->counters;
     a.rays[0] = ws.rays[0]; a.rays[1] = ws.rays[1]; a.rayOwner[0] = ws.rayOwner[0]; a.rayOwner[1] = ws.rayOwner[1];
-    a.rayCount = ws.rayCount; a.rayCapacity = 5 * nSlots; a.hits = ws.hits; a.occluded = ws.occluded; a.qList = ws.qList; a.qCount = ws.qCount;
+    a.rayCount = ws.rayCount; a.rayCapacity = 5 * nSlots; a.qList = ws.qList; a.qCount = ws.qCount;
 
     if (stats) memset(stats, 0, sizeof(*stats));
     Marks marks(ws, stats != nullptr);

@@ -183,6 +183,11 @@ inline int flattenScene(const gdb200_scene_desc *d, HostScene *s)
     s->emTris.clear(); s->bvh.clear(); s->bvhTris.clear(); s->triNormals.clear();
     const gdb200_camera &c = d->camera;
     if (c.width <= 0 || c.height <= 0) return set_error(GDB200_ERR_ARGUMENT, "invalid film size %dx%d", c.width, c.height);
+    if ((long long)c.width * c.height > (1LL << 28)) return set_error(GDB200_ERR_ARGUMENT, "film size %dx%d exceeds 2^28 pixels", c.width, c.height);   // 5*n*4 accumulators are indexed with int products elsewhere
+    if (d->n_shapes < 0 || d->n_materials < 1 || d->n_vertices < 0 || d->n_triangles < 0)
+        return set_error(GDB200_ERR_ARGUMENT, "invalid scene counts (%d shapes, %d materials, %d vertices, %d triangles)", d->n_shapes, d->n_materials, d->n_vertices, d->n_triangles);
+    if ((d->n_shapes && !d->shapes) || !d->materials || !d->emitters || (d->n_triangles && (!d->triangles || !d->vertices)))
+        return set_error(GDB200_ERR_ARGUMENT, "scene description has a NULL table");
     if (d->n_emitters < 1) return set_error(GDB200_ERR_ARGUMENT, "scene has no emitter");
     if (d->n_materials > kMaxMaterials || d->n_emitters > kMaxEmitters)
         return set_error(GDB200_ERR_ARGUMENT, "too many materials/emitters (%d/%d, limits %d/%d)", d->n_materials, d->n_emitters, kMaxMaterials, kMaxEmitters);
@@ -239,6 +244,7 @@ inline int flattenScene(const gdb200_scene_desc *d, HostScene *s)
             rectOfShape[i] = h.nRects++;
         } else if (sh.type == GDB200_SHAPE_SPHERE) {
             if (h.nSpheres >= kMaxSpheres) return set_error(GDB200_ERR_ARGUMENT, "too many spheres (limit %d)", kMaxSpheres);
+            if (!(sh.radius > 0)) return set_error(GDB200_ERR_ARGUMENT, "shape %d: sphere radius must be positive", i);
             sphereOfShape[i] = h.nSpheres;
             DSphere &sp = h.spheres[h.nSpheres++];
             sp.center = mk(sh.center[0], sh.center[1], sh.center[2]); sp.radius = sh.radius; sp.flip = sh.flip_normals;

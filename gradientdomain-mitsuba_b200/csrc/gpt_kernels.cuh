@@ -8,13 +8,18 @@ namespace gdb200 {
 
 
 // ------------------------------------------------------------------ state layout
-// fp64 state is stored as 32-byte records [record][slot][4]: one vector (and one scalar riding in its 4th
-// lane) per record.  A record is exactly one DRAM sector, so a lane always consumes every byte it
-// fetches, however scattered the slots of a material/stage queue are.
+// fp64 state is stored as 32-byte records: one vector (and one scalar riding in its 4th lane) per record, one DRAM
+// sector each.  Layout [slot][kRecPitch records]: everything of a slot sits in one 2 KB block.  (Round 1 used
+// [record][slot]: perfect coalescing while a kernel walks consecutive slots, but the wavefront's queues hold every
+// third or tenth slot, so each 32-byte sector came from a different DRAM row -- every kernel then saturates at the
+// ~2.5 TB/s that HBM3e delivers for row-per-sector access, with half of each 64-byte fetch granule belonging to a slot
+// that is not in the queue (profiles/r02_stage_kernels_ncu.txt).  With the slot's records adjacent, the records a
+// thread reads back to back share lines, fetch granules and DRAM rows however scattered the queue is.)
 enum BaseRec { BR_RAYD = 0 /* w: path pdf */, BR_P /* w: eta */, BR_GN /* w: sample x */, BR_S /* w: sample y */, BR_T, BR_N, BR_WI,
                BR_THR, BR_RAD, BR_VD, BR_COUNT };
 enum OffRec { OR_THR = 0 /* w: path pdf */, OR_RAD, OR_GRAD, OR_P, OR_GN, OR_S, OR_T, OR_N, OR_WI, OR_COUNT };
 constexpr int kRecords = BR_COUNT + 4 * OR_COUNT;   // 46 records = 1472 B per slot
+constexpr int kRecPitchLog2 = 6, kRecPitch = 1 << kRecPitchLog2;   // records per slot block incl. the staged wavefront's (gpt_stages.cuh), padded to 2 KB
 enum IntField { IF_STATUS = 0, IF_MAT, IF_EMI, IF_DEPTH, IF_SAMPLE, IF_RNGN, IF_OFLAGS, IF_STREAM, IF_OMAT0, IF_OMAT1, IF_OMAT2, IF_OMAT3,
                 IF_BSTYPE, IF_PEND,      // staged wavefront (gpt_stages.cuh): sampled BSDF component, bookkeeping of the offsets awaiting a ray
                 IF_COUNT };
@@ -28,7 +33,7 @@ constexpr int kBsdfTypes = GDB200_BSDF_ROUGHDIELECTRIC + 1;
 constexpr int kBuckets = 3 * kBsdfTypes;  // one queue per (BSDF type of the base vertex) x (shift stage of the offset paths)
 
 struct GptArgs {
-    double *sd;            // [kRecords][nSlots][4]
+    double *sd;            // [nSlots][kRecPitch][4]
     int *si;               // [nSlots][16]
     int nSlots, width, height, yBegin;
     int nStreams, nPixels, streamsPerPixel, pad0;   // sample streams (pixel x chunk) are dealt to the slots: stream = chunk * nPixels + pixel
@@ -47,13 +52,11 @@ struct GptArgs {
     int *rayOwner[2];      // [rayCapacity]: slot * 8 + ray id of the slot
     int *rayCount;         // [2]
     int rayCapacity, pad2;
-    double *hits;          // [5][nSlots][4]: t u v primitive, answers to the nearest-hit rays 0..4 of a slot
-    int *occluded;         // [5][nSlots]: answers to the any-hit rays 0..4 of a slot
     int *qList;            // [kStageBuckets][nSlots]: slots per stage bucket
     int *qCount;           // [kStageBuckets]
 };
 
-GDB_D double *REC(const GptArgs &a, int rec, int slot) { return a.sd + (((size_t)rec * a.nSlots + slot) << 2); }
+GDB_D double *REC(const GptArgs &a, int rec, int slot) { return a.sd + ((((size_t)slot << kRecPitchLog2) + rec) << 2); }
 GDB_D double &W(const GptArgs &a, int rec, int slot) { return REC(a, rec, slot)[3]; }
 // int fields of a slot share one 64-byte line [slot][16] (fields 0-7 in its first sector), so a kernel pulls one
 // sector per slot instead of one per field; the per-pixel sampler key is recomputed, not stored.
@@ -132,6 +135,13 @@ GDB_D void stv(const GptArgs &a, int rec, int slot, V3 v)
     *reinterpret_cast<double2 *>(p) = make_double2(v.x, v.y);
     p[2] = v.z;
 }
+// Full-sector store (4th lane zeroed): a 24-byte store makes L2 fetch the sector from DRAM first to merge it, a 32-byte one
+// does not -- the staged wavefront writes every record whole (the fused kernels keep scalars of their own in some 4th lanes).
+GDB_D void stvf(const GptArgs &a, int rec, int slot, V3 v)
+{
+    double2 *p = reinterpret_cast<double2 *>(REC(a, rec, slot));
+    p[0] = make_double2(v.x, v.y); p[1] = make_double2(v.z, 0.0);
+}
 GDB_D void stvw(const GptArgs &a, int rec, int slot, V3 v, Float w)
 {
     double2 *p = reinterpret_cast<double2 *>(REC(a, rec, slot));
@@ -149,6 +159,20 @@ GDB_D void loadBaseIts(const GptArgs &a, int slot, Its &its)
     its.t = 0; its.p = ldv(a, BR_P, slot); its.geoN = ldv(a, BR_GN, slot); its.sh.s = ldv(a, BR_S, slot); its.sh.t = ldv(a, BR_T, slot);
     its.sh.n = ldv(a, BR_N, slot); its.wi = ldv(a, BR_WI, slot);
     its.material = SI(a, IF_MAT, slot); its.emitter = SI(a, IF_EMI, slot);
+}
+// the same with whole-sector stores; eta rides in BR_P's 4th lane
+GDB_D void storeBaseItsFull(const GptArgs &a, int slot, const Its &its, Float eta)
+{
+    stvw(a, BR_P, slot, its.p, eta); stvf(a, BR_GN, slot, its.geoN); stvf(a, BR_S, slot, its.sh.s); stvf(a, BR_T, slot, its.sh.t);
+    stvf(a, BR_N, slot, its.sh.n); stvf(a, BR_WI, slot, its.wi);
+    SI(a, IF_MAT, slot) = its.material; SI(a, IF_EMI, slot) = its.emitter;
+}
+GDB_D void storeOffItsFull(const GptArgs &a, int slot, int i, const Its &its)
+{
+    const int o = BR_COUNT + i * OR_COUNT;
+    stvf(a, o + OR_P, slot, its.p); stvf(a, o + OR_GN, slot, its.geoN); stvf(a, o + OR_S, slot, its.sh.s); stvf(a, o + OR_T, slot, its.sh.t);
+    stvf(a, o + OR_N, slot, its.sh.n); stvf(a, o + OR_WI, slot, its.wi);
+    SI(a, IF_OMAT0 + i, slot) = its.material;
 }
 GDB_D void storeOffIts(const GptArgs &a, int slot, int i, const Its &its)
 {

@@ -23,10 +23,13 @@
 
 namespace gdb200 {
 
+// The staged stages write records whole (stvf / stvw).  The sample's film position rides in BR_VD.w (x) and BR_RAD.w (y).
 enum StagedRec { XR_BS_WO = kRecords /* w: pdf */, XR_BS_WEIGHT /* w: eta */,
                  XR_PD_MAIN /* base contribution of the BSDF stage */, XR_PD_W /* x: weight if a reconnection fails, y: if a half-vector shift fails */,
                  XR_PD_BW /* BSDF-stage weights of offsets 0..3 */, XR_PD_OFF0 /* per parked offset: xyz + weight of the successful outcome */,
-                 kRecordsStaged = XR_PD_OFF0 + 4 };
+                 XR_HIT0 = XR_PD_OFF0 + 4 /* answers to the slot's nearest-hit rays 0..4: t u v primitive */,
+                 XR_OCCLUDED = XR_HIT0 + 5 /* answers to its any-hit rays 0..4, as ints */, kRecordsStaged = XR_OCCLUDED + 1 };
+static_assert(kRecordsStaged <= kRecPitch, "the slot block holds every record");
 
 // Stage queues.  A: built after the casts (continuations); B: built after those ran (slots that need new rays).
 constexpr int QA_PRIMARY = 0, QA_SHADE0 = 1, QA_RESOLVE = QA_SHADE0 + kBuckets, kQA = QA_RESOLVE + 1;
@@ -37,30 +40,54 @@ enum { PEND_NONE = 0, PEND_RECONNECT = 1, PEND_HALFVECTOR = 2 };
 // accumulated (minDepth), 13 the base path left the scene, 14 the base path ended, 15 base vertex type, 16-19 offset vertex types
 GDB_D int pendKind(unsigned p, int i) { return (p >> (2 * i)) & 3u; }
 
-template <int WHICH>
-GDB_D void emitRay(const GptArgs &a, int slot, int id, const Ray &ray)
+// Statistics of one thread over its persistent loop; flushed with one warp-aggregated atomic per counter when the kernel ends.
+struct Tally { unsigned done = 0, rays = 0, vertices = 0, samples = 0, bytes = 0, bounces = 0; };
+GDB_D void flushTally(const GptArgs &a, const Tally &t)
 {
+    countWarp(&a.counters[0], t.done); countWarp(&a.counters[1], t.rays); countWarp(&a.counters[2], t.vertices);
+    countWarp(&a.counters[3], t.samples); countWarp(&a.counters[4], t.bytes); countWarp(&a.counters[5], t.bounces);
+}
+
+// Ray queues.  A stage reserves the entries it may need for a slot with ONE warp-aggregated atomic (an atomic with a return
+// value is a ~1 us round trip: five or six of them in a row per slot were a visible part of prepare and generate), writes the
+// rays it really casts and turns the rest into holes, which the cast kernels skip.  A slot's rays are adjacent in the queue.
+template <int WHICH>
+GDB_D int reserveRays(const GptArgs &a, int count)       // count <= 7 per lane
+{
+#ifdef GDB200_EMU
+    return count ? atomAdd(&a.rayCount[WHICH], count) : 0;
+#else
     const unsigned m = __activemask();
     const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    const unsigned lt = (1u << lane) - 1;
+    int prefix = 0, total = 0;
+#pragma unroll
+    for (int b = 0; b < 3; b++) { const unsigned v = __ballot_sync(m, (count >> b) & 1); prefix += __popc(v & lt) << b; total += __popc(v) << b; }
     int base = 0;
-    if (lane == leader) base = atomAdd(&a.rayCount[WHICH], __popc(m));
-    base = __shfl_sync(m, base, leader);
-    const int idx = base + __popc(m & ((1u << lane) - 1));
+    if (lane == leader && total) base = atomAdd(&a.rayCount[WHICH], total);
+    return __shfl_sync(m, base, leader) + prefix;
+#endif
+}
+template <int WHICH>
+GDB_D void putRay(const GptArgs &a, int idx, int slot, int id, const Ray &ray)
+{
     if (idx >= a.rayCapacity) { redAdd(&a.counters[7], 1ULL); return; }          // reported by the host as an error
     double2 *p = reinterpret_cast<double2 *>(a.rays[WHICH] + ((size_t)idx << 3));
     p[0] = make_double2(ray.o.x, ray.o.y); p[1] = make_double2(ray.o.z, ray.d.x);
     p[2] = make_double2(ray.d.y, ray.d.z); p[3] = make_double2(ray.mint, ray.maxt);
     a.rayOwner[WHICH][idx] = slot * 8 + id;
 }
+template <int WHICH>
+GDB_D void putHoles(const GptArgs &a, int from, int to) { for (int i = from; i < to && i < a.rayCapacity; i++) a.rayOwner[WHICH][i] = -1; }
 GDB_D Hit loadHit(const GptArgs &a, int id, int slot)
 {
-    const double2 *p = reinterpret_cast<const double2 *>(a.hits + (((size_t)id * a.nSlots + slot) << 2));
+    const double2 *p = reinterpret_cast<const double2 *>(REC(a, XR_HIT0 + id, slot));
     const double2 lo = p[0], hi = p[1];
     Hit h; h.t = lo.x; h.u = lo.y; h.v = hi.x;
     const int prim = (int)hi.y; h.kind = prim >> 28; h.index = prim & 0x0fffffff;
     return h;
 }
-GDB_D bool loadOccluded(const GptArgs &a, int id, int slot) { return a.occluded[(size_t)id * a.nSlots + slot] != 0; }
+GDB_D bool loadOccluded(const GptArgs &a, int id, int slot) { return reinterpret_cast<const int *>(REC(a, XR_OCCLUDED, slot))[id] != 0; }
 
 // ------------------------------------------------------------------ cast: the only kernels that intersect
 template <bool Any>
@@ -68,27 +95,30 @@ __global__ void __launch_bounds__(128) gpt_cast_kernel(const GptArgs a)
 {
     const int n = min(a.rayCount[Any ? 1 : 0], a.rayCapacity);
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+        const int owner = a.rayOwner[Any ? 1 : 0][r], slot = owner >> 3, id = owner & 7;
+        if (owner < 0) continue;                                                     // reserved, not cast
         const double2 *p = reinterpret_cast<const double2 *>(a.rays[Any ? 1 : 0] + ((size_t)r << 3));
         const double2 q0 = p[0], q1 = p[1], q2 = p[2], q3 = p[3];
         Ray ray; ray.o = mk(q0.x, q0.y, q1.x); ray.d = mk(q1.y, q2.x, q2.y); ray.mint = q3.x; ray.maxt = q3.y;
-        const int owner = a.rayOwner[Any ? 1 : 0][r], slot = owner >> 3, id = owner & 7;
-        if (Any) a.occluded[(size_t)id * a.nSlots + slot] = rayOccludedImpl(ray) ? 1 : 0;
+        if (Any) reinterpret_cast<int *>(REC(a, XR_OCCLUDED, slot))[id] = rayOccludedImpl(ray) ? 1 : 0;
         else {
             Hit h; castClosest(ray, h);
-            double2 *o = reinterpret_cast<double2 *>(a.hits + (((size_t)id * a.nSlots + slot) << 2));
+            double2 *o = reinterpret_cast<double2 *>(REC(a, XR_HIT0 + id, slot));
             o[0] = make_double2(h.t, h.u); o[1] = make_double2(h.v, (Float)((h.kind << 28) | h.index));
         }
     }
 }
 
 // ------------------------------------------------------------------ generate
-GDB_D void stagedGenerateBody(const GptArgs &a, int slot)
+GDB_D void stagedGenerateBody(const GptArgs &a, int slot, Tally &tally)
 {
     if (SI(a, IF_STATUS, slot) == ST_FINISHED) {
         Spec rad[4], grad[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) { const int o = BR_COUNT + i * OR_COUNT; rad[i] = ldvL2(a, o + OR_RAD, slot); grad[i] = ldvL2(a, o + OR_GRAD, slot); }
-        splatSample(a, W(a, BR_GN, slot), W(a, BR_S, slot), ldv(a, BR_VD, slot), ldv(a, BR_RAD, slot), rad, grad);
+        Spec vd, C; Float spx, spy;
+        ldvw(a, BR_VD, slot, vd, spx); ldvw(a, BR_RAD, slot, C, spy);
+        splatSample(a, spx, spy, vd, C, rad, grad);
     }
     int stream = SI(a, IF_STREAM, slot);
     StreamInfo si = streamInfo(a, stream);
@@ -108,29 +138,28 @@ GDB_D void stagedGenerateBody(const GptArgs &a, int slot)
         const Float spx = si.px + u, spy = si.py + v;
         Float apx = 0.5, apy = 0.5;                                                  // gpt.cpp:1235
         if (c_scene.apertureRadius > 0) { apx = smp.next1D(); apy = smp.next1D(); }  // gpt.cpp:1263-1265
+        const int q = reserveRays<0>(a, 5);
         Ray ray;
         sampleCameraRay(spx, spy, apx, apy, ray);                                    // gpt.cpp:402
-        emitRay<0>(a, slot, 0, ray);
+        putRay<0>(a, q, slot, 0, ray);
         const Float shiftX[4] = {1, 0, -1, 0}, shiftY[4] = {0, 1, 0, -1};            // gpt.cpp:410-415
 #pragma unroll 1
         for (int i = 0; i < 4; i++) {
             sampleCameraRay(spx + shiftX[i], spy + shiftY[i], apx, apy, ray);        // gpt.cpp:418
-            emitRay<0>(a, slot, 1 + i, ray);
+            putRay<0>(a, q + 1 + i, slot, 1 + i, ray);
         }
-        W(a, BR_GN, slot) = spx; W(a, BR_S, slot) = spy;
+        stvw(a, BR_VD, slot, splat(0), spx); stvw(a, BR_RAD, slot, splat(0), spy);
         status = ST_WAIT_PRIMARY;
         break;
     }
     SI(a, IF_STATUS, slot) = status; SI(a, IF_SAMPLE, slot) = j; SI(a, IF_RNGN, slot) = (int)smp.n; SI(a, IF_STREAM, slot) = stream;
-    countWarp(&a.counters[0], status == ST_DONE ? 1u : 0u);
-    countWarp(&a.counters[1], 5u * samples);
-    countWarp(&a.counters[3], samples);
+    tally.done += status == ST_DONE ? 1u : 0u; tally.rays += 5u * samples; tally.samples += samples;
 }
 
 // ------------------------------------------------------------------ primary: gpt.cpp:468-534 with the camera rays' answers
-GDB_D void stagedPrimaryBody(const GptArgs &a, int slot)
+GDB_D void stagedPrimaryBody(const GptArgs &a, int slot, Tally &tally)
 {
-    const Float spx = W(a, BR_GN, slot), spy = W(a, BR_S, slot);
+    const Float spx = W(a, BR_VD, slot), spy = W(a, BR_RAD, slot);
     Float apx = 0.5, apy = 0.5;
     if (c_scene.apertureRadius > 0) {                                                // the two values drawn last by generate
         Sampler smp; smp.key = streamInfo(a, SI(a, IF_STREAM, slot)).key; smp.n = (uint32_t)SI(a, IF_RNGN, slot) - 2u;
@@ -159,18 +188,18 @@ GDB_D void stagedPrimaryBody(const GptArgs &a, int slot)
         flags |= packFlag(i, alive, RAY_NOT_CONNECTED);
         const int o = BR_COUNT + i * OR_COUNT;
         stvw(a, o + OR_THR, slot, splat(1.0), 1.0);
-        stv(a, o + OR_RAD, slot, splat(0)); stv(a, o + OR_GRAD, slot, splat(0));
-        if (!early && alive) storeOffIts(a, slot, i, sits);
+        stvf(a, o + OR_RAD, slot, splat(0)); stvf(a, o + OR_GRAD, slot, splat(0));
+        if (!early && alive) storeOffItsFull(a, slot, i, sits);
     }
-    stv(a, BR_RAD, slot, splat(0)); stv(a, BR_VD, slot, veryDirect);
+    stvw(a, BR_RAD, slot, splat(0), spy); stvw(a, BR_VD, slot, veryDirect, spx);
     if (early || !(1 < a.cfg.maxDepth || a.cfg.maxDepth < 0)) {                      // bounce loop never entered (gpt.cpp:537): the
-        if (!early) redAdd(&a.counters[2], 1ULL);                                    // sample is its very-direct term; generate splats it
+        if (!early) tally.vertices += 1u;                                            // sample is its very-direct term; generate splats it
         SI(a, IF_STATUS, slot) = ST_FINISHED;
         return;
     }
-    storeBaseIts(a, slot, mits);
-    stvw(a, BR_RAYD, slot, ray.d, 1.0); W(a, BR_P, slot) = 1.0;                      // pdf = 1, eta = 1
-    stv(a, BR_THR, slot, splat(1.0));
+    storeBaseItsFull(a, slot, mits, 1.0);                                            // eta = 1
+    stvw(a, BR_RAYD, slot, ray.d, 1.0);                                              // pdf = 1
+    stvf(a, BR_THR, slot, splat(1.0));
     SI(a, IF_DEPTH, slot) = 1; SI(a, IF_OFLAGS, slot) = (int)flags;
     SI(a, IF_STATUS, slot) = ST_LIVE;
 }
@@ -211,22 +240,28 @@ GDB_D void stagedPrepareBody(const GptArgs &a, int slot)
             const Float lsx = smp.next1D(), lsy = smp.next1D();                      // gpt.cpp:572
             bool needsRay; Ray sray;
             sampleEmitterDirect(dRec, lsx, lsy, needsRay, sray);
-            if (needsRay) emitRay<1>(a, slot, 0, sray);
             const V3 woL = toLocal(mits.sh, dRec.d);
             const bool atPointLight = emitterIsDirac(dRec.emitter);
             const bool neeActive = !cfg.strictNormals || dot(mits.geoN, dRec.d) * woL.z > 0;   // gpt.cpp:607
+            unsigned own = 0;                                                        // offsets that draw their own light sample, gpt.cpp:659-676
             if (neeActive)
+                for (int i = 0; i < 4; i++)
+                    if (flagAlive(flags, i) && flagConn(flags, i) == RAY_NOT_CONNECTED &&
+                        offsetSamplesLight(mainBSDF, c_sceneG->materials[SI(a, IF_OMAT0 + i, slot)], atPointLight)) own |= 1u << i;
+            int q = reserveRays<1>(a, 1 + __popc(own));
+            const int qEnd = q + 1 + __popc(own);
+            if (needsRay) putRay<1>(a, q++, slot, 0, sray);
 #pragma unroll 1
-                for (int i = 0; i < 4; i++) {                                        // gpt.cpp:659-676
-                    if (!flagAlive(flags, i) || flagConn(flags, i) != RAY_NOT_CONNECTED) continue;
-                    const int smat = SI(a, IF_OMAT0 + i, slot);
-                    if (!offsetSamplesLight(mainBSDF, c_sceneG->materials[smat], atPointLight)) continue;
-                    const int o = BR_COUNT + i * OR_COUNT;
-                    DRec sRec; sRec.ref = ldv(a, o + OR_P, slot);
-                    sRec.refN = c_sceneG->materials[smat].refNFromShading ? ldv(a, o + OR_N, slot) : mk(0, 0, 0);
-                    sampleEmitterDirect(sRec, lsx, lsy, needsRay, sray);
-                    if (needsRay) emitRay<1>(a, slot, 1 + i, sray);
-                }
+            for (int i = 0; i < 4; i++) {
+                if (!(own & (1u << i))) continue;
+                const int smat = SI(a, IF_OMAT0 + i, slot);
+                const int o = BR_COUNT + i * OR_COUNT;
+                DRec sRec; sRec.ref = ldv(a, o + OR_P, slot);
+                sRec.refN = c_sceneG->materials[smat].refNFromShading ? ldv(a, o + OR_N, slot) : mk(0, 0, 0);
+                sampleEmitterDirect(sRec, lsx, lsy, needsRay, sray);
+                if (needsRay) putRay<1>(a, q++, slot, 1 + i, sray);
+            }
+            putHoles<1>(a, q, qEnd);
         }
         const Float sx = smp.next1D(), sy = smp.next1D();                            // gpt.cpp:456-457
         const Float s3 = mainBSDF.type == GDB200_BSDF_ROUGHDIELECTRIC ? smp.peek1D() : 0.0;
@@ -234,13 +269,16 @@ GDB_D void stagedPrepareBody(const GptArgs &a, int slot)
         bsdfSample(mainBSDF, mits.wi, sx, sy, s3, bs);
         stvw(a, XR_BS_WO, slot, bs.wo, bs.pdf); stvw(a, XR_BS_WEIGHT, slot, bs.weight, bs.eta);
         SI(a, IF_BSTYPE, slot) = (int)(bs.sampledType | ((unsigned)bs.extraDraws << 8));
+        const int q = reserveRays<0>(a, 1);
+        bool cast = false;
         if (!(bs.pdf <= 0.0)) {                                                      // gpt.cpp:739
             const V3 mainWo = toWorld(mits.sh, bs.wo);
             if (!(cfg.strictNormals && dot(mits.geoN, mainWo) * bs.wo.z <= 0)) {     // gpt.cpp:748
                 Ray mray; mray.o = mits.p; mray.d = mainWo; mray.mint = kEpsilon; mray.maxt = CUDART_INF;   // gpt.cpp:767
-                emitRay<0>(a, slot, 0, mray);
+                putRay<0>(a, q, slot, 0, mray); cast = true;
             }
         }
+        if (!cast) putHoles<0>(a, q, q + 1);
     }
     SI(a, IF_STATUS, slot) = ST_WAIT_SHADE;
 }
@@ -249,16 +287,98 @@ GDB_D void stagedPrepareBody(const GptArgs &a, int slot)
 // STAGE = the shift stage of the slot's queue (gpt_stage_compact_kernel): 0 some offset path is unconnected, 1 none is but
 // some was connected on the previous bounce, 2 every live offset rides along with the base path.  The branches a stage
 // cannot reach are compiled out, so the later (and most frequent) stages run in a fraction of stage 0's registers.
+//
+// The bounce is evaluated as the reference orders it — next-event estimation of the base path and of its four offsets
+// (gpt.cpp:565-730), then the BSDF-sample stage of all five (gpt.cpp:737-1151) — in two passes over the offset records, so
+// that nothing of the first stage but the base path's radiance sum is live during the second (the light sample, its MIS
+// terms and the offset vertices of pass one would otherwise sit in registers next to everything pass two needs).
+
+// Pass one for offset i.  Everything it needs from the base path's light sample:
+struct NeeBase {
+    Float lsx, lsy, bsdfPdf, distSq, oppCos, wNum, wDen, lightPdf;
+    V3 woLocal, lightP, lightN;
+    Spec bsdfValue, emitterRadiance, contributionAll;
+    bool visible, atPointLight;
+};
 template <int STAGE>
-GDB_D void stagedShadeBody(const GptArgs &a, int slot)
+GDB_D void shadeOffsetNee(const GptArgs &a, int slot, int i, unsigned flags, const Config &cfg, const DMaterial &mainBSDF, const Frame &prevSh, V3 prevP,
+                          const NeeBase &n, Spec &mrad)
+{
+    constexpr bool kUnconnected = STAGE == 0, kRecent = STAGE <= 1;
+    const int o = BR_COUNT + i * OR_COUNT;
+    const bool alive = flagAlive(flags, i);
+    const int conn = flagConn(flags, i);
+    Spec sthr = splat(0); Float spdf = 0;
+    if (alive) ldvw(a, o + OR_THR, slot, sthr, spdf);
+    Spec mainContribution = splat(0), shiftedContribution = splat(0);
+    Float weight = 0;
+    bool shiftSuccessful = alive;
+    if (shiftSuccessful) {
+        if (conn == RAY_CONNECTED || !kRecent) {                                     // gpt.cpp:622-637
+            const Float jacobian = 1;
+            const Float den = (jacobian * spdf) * (jacobian * spdf) * ((n.lightPdf * n.lightPdf) + (n.bsdfPdf * n.bsdfPdf));
+            weight = n.wNum / (kDEps + den + n.wDen);
+            mainContribution = n.contributionAll;
+            shiftedContribution = jacobian * sthr * (n.bsdfValue * n.emitterRadiance);
+        } else if (conn == RAY_RECENTLY_CONNECTED || !kUnconnected) {                // gpt.cpp:638-658
+            const V3 recentWiL = toLocal(prevSh, normalize(ldv(a, o + OR_P, slot) - prevP));   // gpt.cpp:640
+            Spec shiftedBsdfValue; Float shiftedBsdfPdf;
+            bsdfEvalPdf(mainBSDF, recentWiL, n.woLocal, ESolidAngle, shiftedBsdfValue, shiftedBsdfPdf);
+            if (!n.visible || n.atPointLight) shiftedBsdfPdf = 0;
+            const Float jacobian = 1;
+            const Float den = (jacobian * spdf) * (jacobian * spdf) * ((n.lightPdf * n.lightPdf) + (shiftedBsdfPdf * shiftedBsdfPdf));
+            weight = n.wNum / (kDEps + den + n.wDen);
+            mainContribution = n.contributionAll;
+            shiftedContribution = jacobian * sthr * (shiftedBsdfValue * n.emitterRadiance);
+        } else {                                                                     // gpt.cpp:659-705
+            Its sits; loadOffIts(a, slot, i, sits);
+            const DMaterial &shiftedBSDF = c_sceneG->materials[sits.material];
+            if (offsetSamplesLight(mainBSDF, shiftedBSDF, n.atPointLight)) {          // gpt.cpp:668-672
+                DRec sRec; initDRec(sits, sRec);
+                bool needsRay; Ray sray;
+                Spec sv = sampleEmitterDirect(sRec, n.lsx, n.lsy, needsRay, sray);
+                bool shiftedEmitterVisible = true;
+                if (needsRay && loadOccluded(a, 1 + i, slot)) { shiftedEmitterVisible = false; sv = splat(0); }
+                const Spec shiftedEmitterRadiance = sv * sRec.pdf;
+                const Float shiftedDRecPdf = sRec.pdf;
+                const Float shiftedDistanceSquared = len2(n.lightP - sits.p);
+                const V3 emitterDirection = (n.lightP - sits.p) / sqrt(shiftedDistanceSquared);
+                const Float shiftedOpposingCosine = -dot(n.lightN, emitterDirection);
+                const V3 woL = toLocal(sits.sh, emitterDirection);
+                if (cfg.strictNormals && dot(sits.geoN, emitterDirection) * woL.z < 0) {
+                    shiftSuccessful = false;
+                } else {
+                    Spec shiftedBsdfValue; Float shiftedBsdfPdf;
+                    bsdfEvalPdf(shiftedBSDF, sits.wi, woL, ESolidAngle, shiftedBsdfValue, shiftedBsdfPdf);
+                    if (!shiftedEmitterVisible || n.atPointLight) shiftedBsdfPdf = 0;
+                    const Float jacobian = fabs(shiftedOpposingCosine * n.distSq) / (kEpsilon + fabs(n.oppCos * shiftedDistanceSquared));   // gpt.cpp:695
+                    const Float den = (jacobian * spdf) * (jacobian * spdf) * ((shiftedDRecPdf * shiftedDRecPdf) + (shiftedBsdfPdf * shiftedBsdfPdf));
+                    weight = n.wNum / (kDEps + den + n.wDen);
+                    mainContribution = n.contributionAll;
+                    shiftedContribution = jacobian * sthr * (shiftedBsdfValue * shiftedEmitterRadiance);
+                }
+            }   // else: weight and both contributions stay 0 (gpt.cpp:613-615)
+        }
+    }
+    if (!shiftSuccessful) {                                                          // gpt.cpp:708-717
+        weight = n.wNum / (kDEps + n.wDen);
+        mainContribution = n.contributionAll;
+        shiftedContribution = splat(0);
+    }
+    mrad = mrad + mainContribution * weight;                                         // gpt.cpp:723-726
+    accumulateOffset(a, o, slot, shiftedContribution * weight, (shiftedContribution - mainContribution) * weight);
+}
+
+template <int STAGE>
+GDB_D void stagedShadeBody(const GptArgs &a, int slot, Tally &tally)
 {
     constexpr bool kUnconnected = STAGE == 0, kRecent = STAGE <= 1;
     const Config cfg = a.cfg;
     Its mits; loadBaseIts(a, slot, mits);
     V3 mrayD; Float mpdf;
     ldvw(a, BR_RAYD, slot, mrayD, mpdf);
-    Spec mthr = ldv(a, BR_THR, slot), mrad = ldv(a, BR_RAD, slot);
-    Float meta = W(a, BR_P, slot);
+    Spec mrad; Float spy;
+    ldvw(a, BR_RAD, slot, mrad, spy);
     int depth = SI(a, IF_DEPTH, slot);
     unsigned flags = (unsigned)SI(a, IF_OFLAGS, slot);
     Sampler smp; smp.key = streamInfo(a, SI(a, IF_STREAM, slot)).key; smp.n = (uint32_t)SI(a, IF_RNGN, slot);
@@ -268,8 +388,7 @@ GDB_D void stagedShadeBody(const GptArgs &a, int slot)
         // 304 B, connected offset 88 B; read + write)
         unsigned bytes = 320;
         for (int i = 0; i < 4; i++) if (flagAlive(flags, i)) bytes += flagConn(flags, i) == RAY_CONNECTED ? 88 : 304;
-        countWarp(&a.counters[4], 2 * bytes);
-        countWarp(&a.counters[5], 1u);
+        tally.bytes += 2 * bytes; tally.bounces += 1u;
     }
     if (cfg.strictNormals) ended = !strictNormalsPrepass(a, slot, mits, mrayD, flags);            // gpt.cpp:541-555
 
@@ -282,35 +401,44 @@ GDB_D void stagedShadeBody(const GptArgs &a, int slot)
     if (!ended) {
         const bool lastSegment = (depth + 1 == cfg.maxDepth);                        // gpt.cpp:558
         const DMaterial &mainBSDF = c_sceneG->materials[mits.material];
-        const Frame prevSh = mits.sh; const V3 prevP = mits.p, prevWi = mits.wi;     // the vertex both stages shade (previousMainIts, gpt.cpp:753)
 
-        // ---------------- base path: next event estimation, gpt.cpp:565-607
-        bool neeActive = false, neeVisible = false, atPointLight = false;
-        Float lsx = 0, lsy = 0, neeBsdfPdf = 0, neeDistSq = 0, neeOppCos = 0, neeWNum = 0, neeWDen = 0, neeLightPdf = 0;
-        V3 neeWoLocal = mk(0, 0, 0), neeLightP = mk(0, 0, 0), neeLightN = mk(0, 0, 0);
-        Spec neeBsdfValue = splat(0), neeEmitterRadiance = splat(0), neeContributionAll = splat(0);
+        // ================ pass one: next event estimation, gpt.cpp:565-730
         if ((mainBSDF.flags & ESmooth) && depth + 1 >= cfg.minDepth) {               // gpt.cpp:568
+            NeeBase n;
+            const Spec mthr = ldv(a, BR_THR, slot);
             DRec dRec; initDRec(mits, dRec);
-            lsx = smp.next1D(); lsy = smp.next1D();                                  // gpt.cpp:572
+            n.lsx = smp.next1D(); n.lsy = smp.next1D();                              // gpt.cpp:572
             bool needsRay; Ray sray;
-            Spec value = sampleEmitterDirect(dRec, lsx, lsy, needsRay, sray); rays++;
-            neeVisible = true;
-            if (needsRay && loadOccluded(a, 0, slot)) { neeVisible = false; value = splat(0); }   // scene.cpp:869-876
-            neeEmitterRadiance = value * dRec.pdf;                                   // gpt.cpp:575
-            neeWoLocal = toLocal(mits.sh, dRec.d);
-            bsdfEvalPdf(mainBSDF, mits.wi, neeWoLocal, ESolidAngle, neeBsdfValue, neeBsdfPdf);   // gpt.cpp:588
-            atPointLight = emitterIsDirac(dRec.emitter);                             // dRec.measure == EDiscrete
-            if (!neeVisible || atPointLight) neeBsdfPdf = 0;                         // gpt.cpp:592
-            neeDistSq = len2(mits.p - dRec.p);                                       // gpt.cpp:595-596
-            neeOppCos = dot(dRec.n, (mits.p - dRec.p)) / sqrt(neeDistSq);
-            neeWNum = mpdf * dRec.pdf;                                               // gpt.cpp:599-600
-            neeWDen = (mpdf * mpdf) * ((dRec.pdf * dRec.pdf) + (neeBsdfPdf * neeBsdfPdf));
-            neeLightP = dRec.p; neeLightN = dRec.n; neeLightPdf = dRec.pdf;
-            neeActive = !cfg.strictNormals || dot(mits.geoN, dRec.d) * neeWoLocal.z > 0;   // gpt.cpp:607
-            neeContributionAll = mthr * (neeBsdfValue * neeEmitterRadiance);
+            Spec value = sampleEmitterDirect(dRec, n.lsx, n.lsy, needsRay, sray); rays++;
+            n.visible = true;
+            if (needsRay && loadOccluded(a, 0, slot)) { n.visible = false; value = splat(0); }   // scene.cpp:869-876
+            n.emitterRadiance = value * dRec.pdf;                                    // gpt.cpp:575
+            n.woLocal = toLocal(mits.sh, dRec.d);
+            bsdfEvalPdf(mainBSDF, mits.wi, n.woLocal, ESolidAngle, n.bsdfValue, n.bsdfPdf);   // gpt.cpp:588
+            n.atPointLight = emitterIsDirac(dRec.emitter);                           // dRec.measure == EDiscrete
+            if (!n.visible || n.atPointLight) n.bsdfPdf = 0;                         // gpt.cpp:592
+            n.distSq = len2(mits.p - dRec.p);                                        // gpt.cpp:595-596
+            n.oppCos = dot(dRec.n, (mits.p - dRec.p)) / sqrt(n.distSq);
+            n.wNum = mpdf * dRec.pdf;                                                // gpt.cpp:599-600
+            n.wDen = (mpdf * mpdf) * ((dRec.pdf * dRec.pdf) + (n.bsdfPdf * n.bsdfPdf));
+            n.lightP = dRec.p; n.lightN = dRec.n; n.lightPdf = dRec.pdf;
+            const bool neeActive = !cfg.strictNormals || dot(mits.geoN, dRec.d) * n.woLocal.z > 0;   // gpt.cpp:607
+            n.contributionAll = mthr * (n.bsdfValue * n.emitterRadiance);
+            if (neeActive) {
+                // rays the reference casts for the offsets' own light samples (statistics only)
+                if (kUnconnected)
+                    for (int i = 0; i < 4; i++)
+                        if (flagAlive(flags, i) && flagConn(flags, i) == RAY_NOT_CONNECTED &&
+                            offsetSamplesLight(mainBSDF, c_sceneG->materials[SI(a, IF_OMAT0 + i, slot)], n.atPointLight)) rays++;
+#pragma unroll 1
+                for (int i = 0; i < 4; ++i) shadeOffsetNee<STAGE>(a, slot, i, flags, cfg, mainBSDF, mits.sh, mits.p, n, mrad);
+            }
         }
 
-        // ---------------- base path: BSDF sample (drawn by prepare) + the extension ray's answer, gpt.cpp:737-820
+        // ================ pass two: BSDF sample (drawn by prepare) + the extension ray's answer, gpt.cpp:737-1151
+        const Frame prevSh = mits.sh; const V3 prevP = mits.p, prevWi = mits.wi;     // the vertex both stages shade (previousMainIts, gpt.cpp:753)
+        Spec mthr = ldv(a, BR_THR, slot);
+        Float meta = W(a, BR_P, slot);
         bool bsdfStage = false, mainHitEmitter = false;
         BSDFSample bs;
         smp.n += 2;                                                                  // the two values prepare drew, gpt.cpp:456-457
@@ -324,7 +452,6 @@ GDB_D void stagedShadeBody(const GptArgs &a, int slot)
         }
         sampledType = bs.sampledType;
         Spec mainEmitterRadiance = splat(0);
-        DRec mainDRec; initDRec(mits, mainDRec);                                     // gpt.cpp:759
         int mainNextVertexType = 0;
         Float mainLumPdf = 0, mainWeightNumerator = 0, mainWeightDenominator = 0;
         if (bs.pdf <= 0.0) ended = true;                                             // gpt.cpp:739
@@ -332,6 +459,7 @@ GDB_D void stagedShadeBody(const GptArgs &a, int slot)
             const V3 mainWo = toWorld(mits.sh, bs.wo);
             if (cfg.strictNormals && dot(mits.geoN, mainWo) * bs.wo.z <= 0) ended = true;   // gpt.cpp:748
             else {
+                DRec mainDRec; initDRec(mits, mainDRec);                             // gpt.cpp:759
                 mainVertexType = vertexType(mainBSDF, bs.sampledType);               // gpt.cpp:764
                 Ray mray; mray.o = mits.p; mray.d = mainWo; mray.mint = kEpsilon; mray.maxt = CUDART_INF;   // gpt.cpp:767
                 rays++;
@@ -369,205 +497,161 @@ GDB_D void stagedShadeBody(const GptArgs &a, int slot)
         addBsdfStage = bsdfStage && depth + 1 >= cfg.minDepth;                       // gpt.cpp:1140
         failReconnect = mainWeightNumerator / (kDEps + mainWeightDenominator);       // gpt.cpp:1131-1136
         failHalfVector = (Float)1 / mpdf;                                            // gpt.cpp:1113-1125
+        // The new base vertex is final from here on: it goes to the state now, so that only what the offsets need of it
+        // (position, normals, emitter) stays in registers through their loop.  (A path that ends below never reads it.)
+        if (bsdfStage && !escaped) storeBaseItsFull(a, slot, mits, meta);
+        // Ray-queue entries for the offsets that may need a ray of their own this bounce: a visibility ray for a reconnection
+        // (any-hit queue), an extension ray for a half-vector shift (nearest-hit queue).  Reserved at once, see reserveRays.
+        int qAny = 0, qAnyEnd = 0, qNear = 0, qNearEnd = 0;
+        if (kUnconnected && bsdfStage) {
+            int nAny = 0, nNear = 0;
+            for (int i = 0; i < 4; i++) {
+                if (!flagAlive(flags, i) || flagConn(flags, i) != RAY_NOT_CONNECTED) continue;
+                const DMaterial &sb = c_sceneG->materials[SI(a, IF_OMAT0 + i, slot)];
+                if (mainVertexType == VERTEX_TYPE_DIFFUSE && mainNextVertexType == VERTEX_TYPE_DIFFUSE && vertexType(sb, bs.sampledType) == VERTEX_TYPE_DIFFUSE) {
+                    if (!lastSegment || mainHitEmitter) nAny++;
+                } else if (((bs.sampledType & EDelta) && (sb.flags & EDelta)) || ((bs.sampledType & ESmooth) && (sb.flags & ESmooth))) nNear++;
+            }
+            qAny = reserveRays<1>(a, nAny); qAnyEnd = qAny + nAny;
+            qNear = reserveRays<0>(a, nNear); qNearEnd = qNear + nNear;
+        }
 
-        // ---------------- the four offset paths: gpt.cpp:609-727 and 830-1151 in one pass
+        if (bsdfStage)
 #pragma unroll 1
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 4; ++i) {                                           // ---- BSDF-sample stage of offset i, gpt.cpp:830-1151
             const int o = BR_COUNT + i * OR_COUNT;
             bool alive = flagAlive(flags, i);
             int conn = flagConn(flags, i);
             Spec sthr = splat(0); Float spdf = 0;
             if (alive) ldvw(a, o + OR_THR, slot, sthr, spdf);
-            Its sits;
-            if (kUnconnected && alive && conn == RAY_NOT_CONNECTED) loadOffIts(a, slot, i, sits);
-            V3 recentWiL = mk(0, 0, 0);
-            if (kRecent && alive && conn == RAY_RECENTLY_CONNECTED) recentWiL = toLocal(prevSh, normalize(ldv(a, o + OR_P, slot) - prevP));   // gpt.cpp:640, 864
-
-            if (neeActive) {                                                   // ---- NEE stage, gpt.cpp:609-727
-                Spec mainContribution = splat(0), shiftedContribution = splat(0);
-                Float weight = 0;
-                bool shiftSuccessful = alive;
-                if (shiftSuccessful) {
-                    if (conn == RAY_CONNECTED || !kRecent) {                         // gpt.cpp:622-637
-                        const Float jacobian = 1;
-                        const Float den = (jacobian * spdf) * (jacobian * spdf) * ((neeLightPdf * neeLightPdf) + (neeBsdfPdf * neeBsdfPdf));
-                        weight = neeWNum / (kDEps + den + neeWDen);
-                        mainContribution = neeContributionAll;
-                        shiftedContribution = jacobian * sthr * (neeBsdfValue * neeEmitterRadiance);
-                    } else if (conn == RAY_RECENTLY_CONNECTED || !kUnconnected) {    // gpt.cpp:638-658
-                        Spec shiftedBsdfValue; Float shiftedBsdfPdf;
-                        bsdfEvalPdf(mainBSDF, recentWiL, neeWoLocal, ESolidAngle, shiftedBsdfValue, shiftedBsdfPdf);
-                        if (!neeVisible || atPointLight) shiftedBsdfPdf = 0;
-                        const Float jacobian = 1;
-                        const Float den = (jacobian * spdf) * (jacobian * spdf) * ((neeLightPdf * neeLightPdf) + (shiftedBsdfPdf * shiftedBsdfPdf));
-                        weight = neeWNum / (kDEps + den + neeWDen);
-                        mainContribution = neeContributionAll;
-                        shiftedContribution = jacobian * sthr * (shiftedBsdfValue * neeEmitterRadiance);
-                    } else {                                                         // gpt.cpp:659-705
-                        const DMaterial &shiftedBSDF = c_sceneG->materials[sits.material];
-                        if (offsetSamplesLight(mainBSDF, shiftedBSDF, atPointLight)) {   // gpt.cpp:668-672
-                            DRec sRec; initDRec(sits, sRec);
-                            bool needsRay; Ray sray;
-                            Spec sv = sampleEmitterDirect(sRec, lsx, lsy, needsRay, sray); rays++;
-                            bool shiftedEmitterVisible = true;
-                            if (needsRay && loadOccluded(a, 1 + i, slot)) { shiftedEmitterVisible = false; sv = splat(0); }
-                            const Spec shiftedEmitterRadiance = sv * sRec.pdf;
-                            const Float shiftedDRecPdf = sRec.pdf;
-                            const Float shiftedDistanceSquared = len2(neeLightP - sits.p);
-                            const V3 emitterDirection = (neeLightP - sits.p) / sqrt(shiftedDistanceSquared);
-                            const Float shiftedOpposingCosine = -dot(neeLightN, emitterDirection);
-                            const V3 woL = toLocal(sits.sh, emitterDirection);
-                            if (cfg.strictNormals && dot(sits.geoN, emitterDirection) * woL.z < 0) {
-                                shiftSuccessful = false;
-                            } else {
+            Spec mainContribution = splat(0), shiftedContribution = splat(0);
+            Float weight = 0;
+            bool postponedShiftEnd = false;
+            int parked = PEND_NONE;
+            if (alive) {
+                const Float shiftedPreviousPdf = spdf;
+                if (conn == RAY_CONNECTED || !kRecent) {                             // gpt.cpp:844-861
+                    sthr = sthr * (bs.weight * bs.pdf);
+                    spdf *= mainBsdfPdf;
+                    const Float den = (shiftedPreviousPdf * shiftedPreviousPdf) * ((mainLumPdf * mainLumPdf) + (mainBsdfPdf * mainBsdfPdf));
+                    weight = mainWeightNumerator / (kDEps + den + mainWeightDenominator);
+                    mainContribution = mainContributionAll;
+                    shiftedContribution = sthr * mainEmitterRadiance;
+                } else if (conn == RAY_RECENTLY_CONNECTED || !kUnconnected) {        // gpt.cpp:862-888
+                    const V3 recentWiL = toLocal(prevSh, normalize(ldv(a, o + OR_P, slot) - prevP));   // gpt.cpp:864
+                    const V3 woL = toLocal(prevSh, mrayD);
+                    const int measure = (bs.sampledType & EDelta) ? EDiscrete : ESolidAngle;
+                    Spec shiftedBsdfValue; Float shiftedBsdfPdf;
+                    bsdfEvalPdf(mainBSDF, recentWiL, woL, measure, shiftedBsdfValue, shiftedBsdfPdf);
+                    sthr = sthr * shiftedBsdfValue;
+                    spdf *= shiftedBsdfPdf;
+                    conn = RAY_CONNECTED;
+                    const Float den = (shiftedPreviousPdf * shiftedPreviousPdf) * ((mainLumPdf * mainLumPdf) + (shiftedBsdfPdf * shiftedBsdfPdf));
+                    weight = mainWeightNumerator / (kDEps + den + mainWeightDenominator);
+                    mainContribution = mainContributionAll;
+                    shiftedContribution = sthr * mainEmitterRadiance;
+                } else {                                                             // gpt.cpp:889-1126
+                    Its sits; loadOffIts(a, slot, i, sits);
+                    const DMaterial &shiftedBSDF = c_sceneG->materials[sits.material];
+                    const int shiftedVertexType = vertexType(shiftedBSDF, bs.sampledType);
+                    if (shiftedVertexType == VERTEX_TYPE_DIFFUSE) offVertexTypes |= 1u << i;
+                    if (mainVertexType == VERTEX_TYPE_DIFFUSE && mainNextVertexType == VERTEX_TYPE_DIFFUSE && shiftedVertexType == VERTEX_TYPE_DIFFUSE) {
+                        if (!lastSegment || mainHitEmitter) {                        // gpt.cpp:901
+                            // The reconnection computed as if its visibility ray were free; resolve replaces the outcome by
+                            // the failed one (offset dead, base contribution with the base-only weight) when it is not.
+                            Ray vray;
+                            const ShiftResult sr = escaped ? environmentShiftUnoccluded(mrayD, sits.p, vray)                   // gpt.cpp:908-915
+                                                           : reconnectShiftUnoccluded(prevP, mits.p, sits.p, mits.geoN, vray); // gpt.cpp:907
+                            rays++;
+                            const V3 outgoingDirection = sr.wo;
+                            const V3 woL = toLocal(sits.sh, outgoingDirection);
+                            if (cfg.strictNormals && dot(outgoingDirection, sits.geoN) * woL.z <= 0) alive = false;   // fails whatever the ray says
+                            else {
+                                putRay<1>(a, qAny++, slot, 1 + i, vray);
+                                parked = PEND_RECONNECT;
                                 Spec shiftedBsdfValue; Float shiftedBsdfPdf;
-                                bsdfEvalPdf(shiftedBSDF, sits.wi, woL, ESolidAngle, shiftedBsdfValue, shiftedBsdfPdf);
-                                if (!shiftedEmitterVisible || atPointLight) shiftedBsdfPdf = 0;
-                                const Float jacobian = fabs(shiftedOpposingCosine * neeDistSq) / (kEpsilon + fabs(neeOppCos * shiftedDistanceSquared));   // gpt.cpp:695
-                                const Float den = (jacobian * spdf) * (jacobian * spdf) * ((shiftedDRecPdf * shiftedDRecPdf) + (shiftedBsdfPdf * shiftedBsdfPdf));
-                                weight = neeWNum / (kDEps + den + neeWDen);
-                                mainContribution = neeContributionAll;
-                                shiftedContribution = jacobian * sthr * (shiftedBsdfValue * shiftedEmitterRadiance);
+                                bsdfEvalPdf(shiftedBSDF, sits.wi, woL, ESolidAngle, shiftedBsdfValue, shiftedBsdfPdf);   // gpt.cpp:935-936
+                                sthr = sthr * (shiftedBsdfValue * sr.jacobian);
+                                spdf *= shiftedBsdfPdf * sr.jacobian;
+                                conn = RAY_RECENTLY_CONNECTED;
+                                if (mainHitEmitter) {                                // gpt.cpp:944-985
+                                    Spec shiftedEmitterRadiance; Float shiftedLumPdf;
+                                    if (!escaped) {
+                                        shiftedEmitterRadiance = emittedLe(mits, -outgoingDirection);
+                                        DRec sd;                                     // gpt.cpp:957-964 (measure: solid angle); the base path's
+                                        sd.p = mits.p; sd.n = mits.sh.n;             // record (gpt.cpp:771-776) holds its new vertex, seen from the old one
+                                        sd.dist = len(mits.p - sits.p);
+                                        sd.d = (mits.p - sits.p) / sd.dist;
+                                        sd.ref = prevP; sd.refN = sits.sh.n; sd.emitter = mits.emitter;
+                                        shiftedLumPdf = pdfEmitterDirect(sd);
+                                        if (cfg.refUninitMeasure && c_sceneG->emitters[sd.emitter].kind != EM_ENV) shiftedLumPdf = 0;   // gpt_host.h setupArgs
+                                    } else { shiftedEmitterRadiance = mainEmitterRadiance; shiftedLumPdf = mainLumPdf; }   // gpt.cpp:973-977
+                                    const Float den = (shiftedPreviousPdf * shiftedPreviousPdf) * ((shiftedLumPdf * shiftedLumPdf) + (shiftedBsdfPdf * shiftedBsdfPdf));
+                                    weight = mainWeightNumerator / (kDEps + den + mainWeightDenominator);
+                                    mainContribution = mainContributionAll;
+                                    shiftedContribution = sthr * shiftedEmitterRadiance;
+                                }   // else weight and contributions stay 0 (gpt.cpp:833-836)
+                                stvw(a, XR_PD_OFF0 + i, slot, shiftedContribution, weight);
                             }
-                        }   // else: weight and both contributions stay 0 (gpt.cpp:613-615)
+                        }
+                    } else {                                                         // half-vector shift, gpt.cpp:987-1126
+                        const bool bothDelta = (bs.sampledType & EDelta) && (shiftedBSDF.flags & EDelta);
+                        const bool bothSmooth = (bs.sampledType & ESmooth) && (shiftedBSDF.flags & ESmooth);
+                        bool ok = bothDelta || bothSmooth;
+                        if (ok) {
+                            ShiftResult sr = halfVectorShift(prevWi, bs.wo, sits.wi, mainBSDF.bsdfEta, shiftedBSDF.bsdfEta);   // gpt.cpp:1006
+                            if (bs.sampledType & EDelta) sr.jacobian = 1;            // gpt.cpp:1008-1011
+                            ok = sr.success;
+                            if (ok) {
+                                sthr = sthr * sr.jacobian;
+                                spdf *= sr.jacobian;
+                                const V3 tangentSpaceOutgoingDirection = sr.wo;
+                                const V3 outgoingDirection = toWorld(sits.sh, tangentSpaceOutgoingDirection);
+                                const int measure = (bs.sampledType & EDelta) ? EDiscrete : ESolidAngle;
+                                Spec ev; Float pv;
+                                bsdfEvalPdf(shiftedBSDF, sits.wi, tangentSpaceOutgoingDirection, measure, ev, pv);   // gpt.cpp:1030-1031
+                                sthr = sthr * ev;
+                                spdf *= pv;
+                                if (spdf == 0) ok = false;                           // gpt.cpp:1033-1037
+                                if (ok && cfg.strictNormals && dot(outgoingDirection, sits.geoN) * tangentSpaceOutgoingDirection.z <= 0) ok = false;
+                                if (ok) {                                            // the offset's own extension ray: resolve continues at gpt.cpp:1052
+                                    Ray sray; sray.o = sits.p; sray.d = outgoingDirection; sray.mint = kEpsilon; sray.maxt = CUDART_INF;   // gpt.cpp:1050
+                                    putRay<0>(a, qNear++, slot, 1 + i, sray); rays++;
+                                    parked = PEND_HALFVECTOR;
+                                    stvw(a, XR_PD_OFF0 + i, slot, outgoingDirection, mpdf / (spdf * spdf + mpdf * mpdf));   // weight of gpt.cpp:1107-1112
+                                }
+                            }
+                        }
+                        if (!ok) {                                                   // gpt.cpp:1113-1125
+                            weight = failHalfVector;
+                            mainContribution = mainContributionAll;
+                            shiftedContribution = splat(0);
+                            postponedShiftEnd = true;
+                        }
                     }
                 }
-                if (!shiftSuccessful) {                                              // gpt.cpp:708-717
-                    weight = neeWNum / (kDEps + neeWDen);
-                    mainContribution = neeContributionAll;
+            }
+            if (parked != PEND_NONE) pend |= (unsigned)parked << (2 * i);
+            else {
+                if (!alive) {                                                        // gpt.cpp:1131-1136
+                    weight = failReconnect;
+                    mainContribution = mainContributionAll;
                     shiftedContribution = splat(0);
                 }
-                mrad = mrad + mainContribution * weight;                             // gpt.cpp:723-726
-                accumulateOffset(a, o, slot, shiftedContribution * weight, (shiftedContribution - mainContribution) * weight);
-            }
-
-            if (bsdfStage) {                                                    // ---- BSDF-sample stage, gpt.cpp:830-1151
-                Spec mainContribution = splat(0), shiftedContribution = splat(0);
-                Float weight = 0;
-                bool postponedShiftEnd = false;
-                int parked = PEND_NONE;
-                if (alive) {
-                    const Float shiftedPreviousPdf = spdf;
-                    if (conn == RAY_CONNECTED || !kRecent) {                         // gpt.cpp:844-861
-                        sthr = sthr * (bs.weight * bs.pdf);
-                        spdf *= mainBsdfPdf;
-                        const Float den = (shiftedPreviousPdf * shiftedPreviousPdf) * ((mainLumPdf * mainLumPdf) + (mainBsdfPdf * mainBsdfPdf));
-                        weight = mainWeightNumerator / (kDEps + den + mainWeightDenominator);
-                        mainContribution = mainContributionAll;
-                        shiftedContribution = sthr * mainEmitterRadiance;
-                    } else if (conn == RAY_RECENTLY_CONNECTED || !kUnconnected) {    // gpt.cpp:862-888
-                        const V3 woL = toLocal(prevSh, mrayD);
-                        const int measure = (bs.sampledType & EDelta) ? EDiscrete : ESolidAngle;
-                        Spec shiftedBsdfValue; Float shiftedBsdfPdf;
-                        bsdfEvalPdf(mainBSDF, recentWiL, woL, measure, shiftedBsdfValue, shiftedBsdfPdf);
-                        sthr = sthr * shiftedBsdfValue;
-                        spdf *= shiftedBsdfPdf;
-                        conn = RAY_CONNECTED;
-                        const Float den = (shiftedPreviousPdf * shiftedPreviousPdf) * ((mainLumPdf * mainLumPdf) + (shiftedBsdfPdf * shiftedBsdfPdf));
-                        weight = mainWeightNumerator / (kDEps + den + mainWeightDenominator);
-                        mainContribution = mainContributionAll;
-                        shiftedContribution = sthr * mainEmitterRadiance;
-                    } else {                                                         // gpt.cpp:889-1126
-                        const DMaterial &shiftedBSDF = c_sceneG->materials[sits.material];
-                        const int shiftedVertexType = vertexType(shiftedBSDF, bs.sampledType);
-                        if (shiftedVertexType == VERTEX_TYPE_DIFFUSE) offVertexTypes |= 1u << i;
-                        if (mainVertexType == VERTEX_TYPE_DIFFUSE && mainNextVertexType == VERTEX_TYPE_DIFFUSE && shiftedVertexType == VERTEX_TYPE_DIFFUSE) {
-                            if (!lastSegment || mainHitEmitter) {                    // gpt.cpp:901
-                                // The reconnection computed as if its visibility ray were free; resolve replaces the outcome by
-                                // the failed one (offset dead, base contribution with the base-only weight) when it is not.
-                                Ray vray;
-                                const ShiftResult sr = escaped ? environmentShiftUnoccluded(mrayD, sits.p, vray)                   // gpt.cpp:908-915
-                                                               : reconnectShiftUnoccluded(prevP, mits.p, sits.p, mits.geoN, vray); // gpt.cpp:907
-                                rays++;
-                                const V3 outgoingDirection = sr.wo;
-                                const V3 woL = toLocal(sits.sh, outgoingDirection);
-                                if (cfg.strictNormals && dot(outgoingDirection, sits.geoN) * woL.z <= 0) alive = false;   // fails whatever the ray says
-                                else {
-                                    emitRay<1>(a, slot, 1 + i, vray);
-                                    parked = PEND_RECONNECT;
-                                    Spec shiftedBsdfValue; Float shiftedBsdfPdf;
-                                    bsdfEvalPdf(shiftedBSDF, sits.wi, woL, ESolidAngle, shiftedBsdfValue, shiftedBsdfPdf);   // gpt.cpp:935-936
-                                    sthr = sthr * (shiftedBsdfValue * sr.jacobian);
-                                    spdf *= shiftedBsdfPdf * sr.jacobian;
-                                    conn = RAY_RECENTLY_CONNECTED;
-                                    if (mainHitEmitter) {                            // gpt.cpp:944-985
-                                        Spec shiftedEmitterRadiance; Float shiftedLumPdf;
-                                        if (!escaped) {
-                                            shiftedEmitterRadiance = emittedLe(mits, -outgoingDirection);
-                                            DRec sd;                                 // gpt.cpp:957-964 (measure: solid angle)
-                                            sd.p = mainDRec.p; sd.n = mainDRec.n;
-                                            sd.dist = len(mainDRec.p - sits.p);
-                                            sd.d = (mainDRec.p - sits.p) / sd.dist;
-                                            sd.ref = mainDRec.ref; sd.refN = sits.sh.n; sd.emitter = mainDRec.emitter;
-                                            shiftedLumPdf = pdfEmitterDirect(sd);
-                                            if (cfg.refUninitMeasure && c_sceneG->emitters[sd.emitter].kind != EM_ENV) shiftedLumPdf = 0;   // gpt_host.h setupArgs
-                                        } else { shiftedEmitterRadiance = mainEmitterRadiance; shiftedLumPdf = mainLumPdf; }   // gpt.cpp:973-977
-                                        const Float den = (shiftedPreviousPdf * shiftedPreviousPdf) * ((shiftedLumPdf * shiftedLumPdf) + (shiftedBsdfPdf * shiftedBsdfPdf));
-                                        weight = mainWeightNumerator / (kDEps + den + mainWeightDenominator);
-                                        mainContribution = mainContributionAll;
-                                        shiftedContribution = sthr * shiftedEmitterRadiance;
-                                    }   // else weight and contributions stay 0 (gpt.cpp:833-836)
-                                    stvw(a, XR_PD_OFF0 + i, slot, shiftedContribution, weight);
-                                }
-                            }
-                        } else {                                                     // half-vector shift, gpt.cpp:987-1126
-                            const bool bothDelta = (bs.sampledType & EDelta) && (shiftedBSDF.flags & EDelta);
-                            const bool bothSmooth = (bs.sampledType & ESmooth) && (shiftedBSDF.flags & ESmooth);
-                            bool ok = bothDelta || bothSmooth;
-                            if (ok) {
-                                ShiftResult sr = halfVectorShift(prevWi, bs.wo, sits.wi, mainBSDF.bsdfEta, shiftedBSDF.bsdfEta);   // gpt.cpp:1006
-                                if (bs.sampledType & EDelta) sr.jacobian = 1;        // gpt.cpp:1008-1011
-                                ok = sr.success;
-                                if (ok) {
-                                    sthr = sthr * sr.jacobian;
-                                    spdf *= sr.jacobian;
-                                    const V3 tangentSpaceOutgoingDirection = sr.wo;
-                                    const V3 outgoingDirection = toWorld(sits.sh, tangentSpaceOutgoingDirection);
-                                    const int measure = (bs.sampledType & EDelta) ? EDiscrete : ESolidAngle;
-                                    Spec ev; Float pv;
-                                    bsdfEvalPdf(shiftedBSDF, sits.wi, tangentSpaceOutgoingDirection, measure, ev, pv);   // gpt.cpp:1030-1031
-                                    sthr = sthr * ev;
-                                    spdf *= pv;
-                                    if (spdf == 0) ok = false;                       // gpt.cpp:1033-1037
-                                    if (ok && cfg.strictNormals && dot(outgoingDirection, sits.geoN) * tangentSpaceOutgoingDirection.z <= 0) ok = false;
-                                    if (ok) {                                        // the offset's own extension ray: resolve continues at gpt.cpp:1052
-                                        Ray sray; sray.o = sits.p; sray.d = outgoingDirection; sray.mint = kEpsilon; sray.maxt = CUDART_INF;   // gpt.cpp:1050
-                                        emitRay<0>(a, slot, 1 + i, sray); rays++;
-                                        parked = PEND_HALFVECTOR;
-                                        stvw(a, XR_PD_OFF0 + i, slot, outgoingDirection, mpdf / (spdf * spdf + mpdf * mpdf));   // weight of gpt.cpp:1107-1112
-                                    }
-                                }
-                            }
-                            if (!ok) {                                               // gpt.cpp:1113-1125
-                                weight = failHalfVector;
-                                mainContribution = mainContributionAll;
-                                shiftedContribution = splat(0);
-                                postponedShiftEnd = true;
-                            }
-                        }
+                if (addBsdfStage) {                                                  // gpt.cpp:1140-1146
+                    const bool has = !(mainContribution.x == 0 && mainContribution.y == 0 && mainContribution.z == 0 && weight == 0);
+                    if (has) {
+                        bHas |= 1u << i;
+                        if (i == 0) bw0 = weight; else if (i == 1) bw1 = weight; else if (i == 2) bw2 = weight; else bw3 = weight;
                     }
+                    accumulateOffset(a, o, slot, shiftedContribution * weight, (shiftedContribution - mainContribution) * weight);
                 }
-                if (parked != PEND_NONE) pend |= (unsigned)parked << (2 * i);
-                else {
-                    if (!alive) {                                                    // gpt.cpp:1131-1136
-                        weight = failReconnect;
-                        mainContribution = mainContributionAll;
-                        shiftedContribution = splat(0);
-                    }
-                    if (addBsdfStage) {                                              // gpt.cpp:1140-1146
-                        const bool has = !(mainContribution.x == 0 && mainContribution.y == 0 && mainContribution.z == 0 && weight == 0);
-                        if (has) {
-                            bHas |= 1u << i;
-                            if (i == 0) bw0 = weight; else if (i == 1) bw1 = weight; else if (i == 2) bw2 = weight; else bw3 = weight;
-                        }
-                        accumulateOffset(a, o, slot, shiftedContribution * weight, (shiftedContribution - mainContribution) * weight);
-                    }
-                    if (postponedShiftEnd) alive = false;                            // gpt.cpp:1148-1150
-                }
-                flags = setFlag(flags, i, alive, conn);
+                if (postponedShiftEnd) alive = false;                                // gpt.cpp:1148-1150
             }
-            if (flagAlive(flags, i) || alive) stvw(a, o + OR_THR, slot, sthr, spdf);
+            flags = setFlag(flags, i, alive, conn);
+            if (alive) stvw(a, o + OR_THR, slot, sthr, spdf);
         }
+        if (kUnconnected) { putHoles<1>(a, qAny, qAnyEnd); putHoles<0>(a, qNear, qNearEnd); }
         if (!pend) {    // base radiance: BSDF-stage terms after all NEE terms, in offset order (gpt.cpp:1142)
             if (bHas & 1u) mrad = mrad + mainContributionAll * bw0;
             if (bHas & 2u) mrad = mrad + mainContributionAll * bw1;
@@ -587,21 +671,19 @@ GDB_D void stagedShadeBody(const GptArgs &a, int slot)
             }
             if (!ended && !(depth < cfg.maxDepth || cfg.maxDepth < 0)) ended = true; // gpt.cpp:537
         }
+        if (!ended) {       // the vertex itself was stored above
+            stvw(a, BR_RAYD, slot, mrayD, mpdf);
+            stvf(a, BR_THR, slot, mthr);
+            SI(a, IF_DEPTH, slot) = depth;
+        }
     }
 
-    stv(a, BR_RAD, slot, mrad);
+    stvw(a, BR_RAD, slot, mrad, spy);
     SI(a, IF_RNGN, slot) = (int)smp.n;
-    countWarp(&a.counters[1], rays);
-    countWarp(&a.counters[2], ended ? (unsigned)depth : 0u);                         // gpt.cpp:1178-1179
-    if (!ended) {
-        storeBaseIts(a, slot, mits);
-        stvw(a, BR_RAYD, slot, mrayD, mpdf); W(a, BR_P, slot) = meta;
-        stv(a, BR_THR, slot, mthr);
-        SI(a, IF_DEPTH, slot) = depth;
-    }
+    tally.rays += rays; tally.vertices += ended ? (unsigned)depth : 0u;              // gpt.cpp:1178-1179
     SI(a, IF_OFLAGS, slot) = (int)flags;
     if (pend) {
-        stv(a, XR_PD_MAIN, slot, mainContributionAll);
+        stvf(a, XR_PD_MAIN, slot, mainContributionAll);
         double2 *w = reinterpret_cast<double2 *>(REC(a, XR_PD_W, slot));
         w[0] = make_double2(failReconnect, failHalfVector);
         double2 *b = reinterpret_cast<double2 *>(REC(a, XR_PD_BW, slot));
@@ -660,7 +742,7 @@ GDB_D void stagedResolveBody(const GptArgs &a, int slot)
                 if (mainVertexType == VERTEX_TYPE_DIFFUSE && shiftedVertexType2 == VERTEX_TYPE_DIFFUSE && shiftedNextVertexType == VERTEX_TYPE_DIFFUSE) ok = false;   // gpt.cpp:1089-1093
                 else {
                     if (sits.emitter >= 0) shiftedEmitterRadiance = emittedLe(sits, -d);   // gpt.cpp:1095-1098
-                    storeOffIts(a, slot, i, sits);
+                    storeOffItsFull(a, slot, i, sits);
                 }
             }
             if (ok) shiftedContribution = ldv(a, o + OR_THR, slot) * shiftedEmitterRadiance;   // gpt.cpp:1107-1112 (weight: from shade)
@@ -677,12 +759,13 @@ GDB_D void stagedResolveBody(const GptArgs &a, int slot)
         }
         if (!alive) flags = setFlag(flags, i, false, RAY_NOT_CONNECTED);
     }
-    Spec mrad = ldv(a, BR_RAD, slot);
+    Spec mrad; Float spy;
+    ldvw(a, BR_RAD, slot, mrad, spy);
     if (bHas & 1u) mrad = mrad + mainContributionAll * bw0;
     if (bHas & 2u) mrad = mrad + mainContributionAll * bw1;
     if (bHas & 4u) mrad = mrad + mainContributionAll * bw2;
     if (bHas & 8u) mrad = mrad + mainContributionAll * bw3;
-    stv(a, BR_RAD, slot, mrad);
+    stvw(a, BR_RAD, slot, mrad, spy);
     SI(a, IF_OFLAGS, slot) = (int)flags;
     SI(a, IF_STATUS, slot) = ended ? ST_FINISHED : ST_LIVE;
 }
@@ -690,21 +773,80 @@ GDB_D void stagedResolveBody(const GptArgs &a, int slot)
 // ------------------------------------------------------------------ stage kernels: persistent CTAs over the stage's queues
 enum StageKind { SK_PRIMARY = 0, SK_SHADE0, SK_SHADE1, SK_SHADE2, SK_RESOLVE, SK_PREPARE, SK_GENERATE };
 template <int KIND> struct StageQueues;
-template <> struct StageQueues<SK_PRIMARY>  { static constexpr int first = QA_PRIMARY, count = 1; };
-template <> struct StageQueues<SK_SHADE0>   { static constexpr int first = QA_SHADE0, count = kBsdfTypes; };
-template <> struct StageQueues<SK_SHADE1>   { static constexpr int first = QA_SHADE0 + kBsdfTypes, count = kBsdfTypes; };
-template <> struct StageQueues<SK_SHADE2>   { static constexpr int first = QA_SHADE0 + 2 * kBsdfTypes, count = kBsdfTypes; };
-template <> struct StageQueues<SK_RESOLVE>  { static constexpr int first = QA_RESOLVE, count = 1; };
-template <> struct StageQueues<SK_PREPARE>  { static constexpr int first = QB_PREPARE0, count = kBsdfTypes; };
-template <> struct StageQueues<SK_GENERATE> { static constexpr int first = QB_GEN, count = 1; };
-
-#ifndef GDB_STAGE_MINBLOCKS
-#define GDB_STAGE_MINBLOCKS 2
+// minBlocks: resident CTAs per SM the register allocation is sized for (4 => 128 registers, 3 => 168, 2 => 255).  Every stage is
+// bound by memory latency at the occupancy its registers allow (profiles/r02_stage_kernels_ncu.txt), so each gets the
+// smallest allocation that does not make it spill.
+#ifndef GDB_MB_PRIMARY
+#define GDB_MB_PRIMARY 4
 #endif
+#ifndef GDB_MB_SHADE0
+#define GDB_MB_SHADE0 2
+#endif
+#ifndef GDB_MB_SHADE1
+#define GDB_MB_SHADE1 2
+#endif
+#ifndef GDB_MB_SHADE2
+#define GDB_MB_SHADE2 3
+#endif
+#ifndef GDB_MB_RESOLVE
+#define GDB_MB_RESOLVE 4
+#endif
+#ifndef GDB_MB_PREPARE
+#define GDB_MB_PREPARE 4
+#endif
+#ifndef GDB_MB_GENERATE
+#define GDB_MB_GENERATE 4
+#endif
+template <> struct StageQueues<SK_PRIMARY>  { static constexpr int first = QA_PRIMARY, count = 1, minBlocks = GDB_MB_PRIMARY; };
+template <> struct StageQueues<SK_SHADE0>   { static constexpr int first = QA_SHADE0, count = kBsdfTypes, minBlocks = GDB_MB_SHADE0; };
+template <> struct StageQueues<SK_SHADE1>   { static constexpr int first = QA_SHADE0 + kBsdfTypes, count = kBsdfTypes, minBlocks = GDB_MB_SHADE1; };
+template <> struct StageQueues<SK_SHADE2>   { static constexpr int first = QA_SHADE0 + 2 * kBsdfTypes, count = kBsdfTypes, minBlocks = GDB_MB_SHADE2; };
+template <> struct StageQueues<SK_RESOLVE>  { static constexpr int first = QA_RESOLVE, count = 1, minBlocks = GDB_MB_RESOLVE; };
+template <> struct StageQueues<SK_PREPARE>  { static constexpr int first = QB_PREPARE0, count = kBsdfTypes, minBlocks = GDB_MB_PREPARE; };
+template <> struct StageQueues<SK_GENERATE> { static constexpr int first = QB_GEN, count = 1, minBlocks = GDB_MB_GENERATE; };
+
+// What a stage reads first of a slot, requested into L2 one loop iteration ahead.  Every stage is bound by the latency of
+// its state loads at the occupancy its registers allow (profiles/r02_stage_kernels_ncu.txt: long_scoreboard is the top
+// stall of all of them, L2 hit rates 20-30 %); the queue tells a thread which slot it will process next, so those DRAM
+// round trips are started while the current slot is being shaded.
+template <int KIND>
+GDB_D void prefetchSlot(const GptArgs &a, int slot)
+{
+#ifdef GDB_STAGE_PREFETCH      // measured: -8 % (profiles/r02_tracer_history.md) -- the stages are bound by DRAM transactions, not by their latency
+    auto rec = [&](int r) { prefetchL2(REC(a, r, slot)); };
+    auto hit = [&](int id) { prefetchL2(REC(a, XR_HIT0 + id, slot)); };
+    auto occ = [&](int id) { if (id == 0) prefetchL2(REC(a, XR_OCCLUDED, slot)); };
+    prefetchL2(&SI(a, 0, slot)); prefetchL2(&SI(a, 8, slot));
+    if (KIND == SK_PRIMARY) {
+        for (int id = 0; id < 5; id++) hit(id);
+        rec(BR_VD); rec(BR_RAD);
+    } else if (KIND == SK_SHADE0 || KIND == SK_SHADE1 || KIND == SK_SHADE2) {
+        for (int r = BR_RAYD; r <= BR_RAD; r++) rec(r);
+        rec(XR_BS_WO); rec(XR_BS_WEIGHT); hit(0); occ(0);
+        for (int i = 0; i < 4; i++) {
+            const int o = BR_COUNT + i * OR_COUNT;
+            rec(o + OR_THR);
+            if (KIND != SK_SHADE2) rec(o + OR_P);
+            if (KIND == SK_SHADE0) { occ(1 + i); rec(o + OR_GN); rec(o + OR_S); rec(o + OR_T); rec(o + OR_N); rec(o + OR_WI); }
+        }
+    } else if (KIND == SK_RESOLVE) {
+        rec(XR_PD_MAIN); rec(XR_PD_W); rec(XR_PD_BW); rec(BR_RAD);
+        for (int i = 0; i < 4; i++) { rec(XR_PD_OFF0 + i); hit(1 + i); occ(1 + i); }
+    } else if (KIND == SK_PREPARE) {
+        for (int r = BR_RAYD; r <= BR_WI; r++) rec(r);
+    } else {
+        for (int i = 0; i < 4; i++) { const int o = BR_COUNT + i * OR_COUNT; rec(o + OR_RAD); rec(o + OR_GRAD); }
+        rec(BR_VD); rec(BR_RAD);
+    }
+#endif
+}
+
 // thread -> (queue, index): queues are padded to whole warps so that a warp runs one queue (one BSDF type / shift stage);
 // inside a queue the slots are in ascending order up to the compaction's chunk size, so state rows are read near-contiguously.
+// The loop is pipelined by two iterations: the slot index of iteration k+2 is loaded and the state of slot k+1 prefetched
+// while slot k is processed.
 template <int KIND>
-__global__ void __launch_bounds__(kStageThreads, GDB_STAGE_MINBLOCKS) gpt_stage_kernel(const GptArgs a)
+__global__ void __launch_bounds__(kStageThreads, StageQueues<KIND>::minBlocks) gpt_stage_kernel(const GptArgs a)
 {
     constexpr int first = StageQueues<KIND>::first, nq = StageQueues<KIND>::count;
     __shared__ int s_begin[nq + 1], s_count[nq];
@@ -714,21 +856,32 @@ __global__ void __launch_bounds__(kStageThreads, GDB_STAGE_MINBLOCKS) gpt_stage_
         s_begin[nq] = acc;
     }
     __syncthreads();
-    const int total = s_begin[nq];
-    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
+    const int total = s_begin[nq], stride = gridDim.x * blockDim.x;
+    auto slotAt = [&](int g) {          // -1: padding of a queue, or past the end
+        if (g >= total) return -1;
         int b = 0;
         while (g >= s_begin[b + 1]) b++;
         const int idx = g - s_begin[b];
-        if (idx >= s_count[b]) continue;
-        const int slot = a.qList[(size_t)(first + b) * a.nSlots + idx];
-        if (KIND == SK_PRIMARY) stagedPrimaryBody(a, slot);
-        else if (KIND == SK_SHADE0) stagedShadeBody<0>(a, slot);
-        else if (KIND == SK_SHADE1) stagedShadeBody<1>(a, slot);
-        else if (KIND == SK_SHADE2) stagedShadeBody<2>(a, slot);
-        else if (KIND == SK_RESOLVE) stagedResolveBody(a, slot);
-        else if (KIND == SK_PREPARE) stagedPrepareBody(a, slot);
-        else stagedGenerateBody(a, slot);
+        return idx < s_count[b] ? a.qList[(size_t)(first + b) * a.nSlots + idx] : -1;
+    };
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    int slot = slotAt(g), slot1 = slotAt(g + stride);
+    Tally tally;
+    for (; g < total; g += stride) {
+        const int slot2 = slotAt(g + 2 * stride);
+        if (slot1 >= 0) prefetchSlot<KIND>(a, slot1);
+        if (slot >= 0) {
+            if (KIND == SK_PRIMARY) stagedPrimaryBody(a, slot, tally);
+            else if (KIND == SK_SHADE0) stagedShadeBody<0>(a, slot, tally);
+            else if (KIND == SK_SHADE1) stagedShadeBody<1>(a, slot, tally);
+            else if (KIND == SK_SHADE2) stagedShadeBody<2>(a, slot, tally);
+            else if (KIND == SK_RESOLVE) stagedResolveBody(a, slot);
+            else if (KIND == SK_PREPARE) stagedPrepareBody(a, slot);
+            else stagedGenerateBody(a, slot, tally);
+        }
+        slot = slot1; slot1 = slot2;
     }
+    if (KIND != SK_RESOLVE && KIND != SK_PREPARE) flushTally(a, tally);
 }
 
 // Ordered stream compaction into the stage queues (ballot / popc ranks per warp, shared-memory prefix over the CTA's

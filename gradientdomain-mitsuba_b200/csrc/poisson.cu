@@ -511,6 +511,7 @@ struct gdb200_poisson_plan {
     double *red = nullptr;
     int *iters = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t evHost[4] = {nullptr, nullptr, nullptr, nullptr};   // copy timing of the host-pointer entry point (created on first use)
     // staging for the host-pointer entry point
     float *d_in[4] = {nullptr, nullptr, nullptr, nullptr};
     float *d_out = nullptr;
@@ -542,6 +543,7 @@ void gdb200_poisson_plan_destroy(gdb200_poisson_plan *p)
     cudaFree(p->d_out);
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
+    for (cudaEvent_t e : p->evHost) if (e) cudaEventDestroy(e);
     delete p;
 }
 
@@ -586,6 +588,10 @@ int gdb200_poisson_solve_device(gdb200_poisson_plan *p, const float *d_dx, const
 {
     if (!p || !d_dx || !d_dy || !cfg || !d_out)
         return set_error(GDB200_ERR_ARGUMENT, "plan, dx, dy, cfg and out_final are required");
+    // the plan's workspace lives on p->device: run there whatever the caller's current device is, and give it back
+    struct Bind { int prev = -1; ~Bind() { if (prev >= 0) cudaSetDevice(prev); } } bind;
+    if (cudaGetDevice(&bind.prev) != cudaSuccess) { bind.prev = -1; cudaGetLastError(); }
+    if (bind.prev != p->device) GDB_CUDA(cudaSetDevice(p->device)); else bind.prev = -1;
     PoissonArgs a;
     memset(&a, 0, sizeof(a));
     a.W = p->w; a.H = p->h; a.Wp = p->wp; a.Gx = p->wp / 4;
@@ -647,8 +653,8 @@ int gdb200_poisson_solve(const float *dx, const float *dy, const float *throughp
         if (src[i] && !p->d_in[i]) GDB_CUDA(cudaMalloc(&p->d_in[i], bytes));
     if (!p->d_out) GDB_CUDA(cudaMalloc(&p->d_out, bytes));
 
-    cudaEvent_t e[4];
-    for (auto &ev : e) GDB_CUDA(cudaEventCreate(&ev));
+    cudaEvent_t *e = p->evHost;
+    for (int i = 0; i < 4; i++) if (!e[i]) GDB_CUDA(cudaEventCreate(&e[i]));
     cudaStream_t s = 0;
     GDB_CUDA(cudaEventRecord(e[0], s));
     for (int i = 0; i < 4; i++)
@@ -670,7 +676,6 @@ int gdb200_poisson_solve(const float *dx, const float *dy, const float *throughp
         *stats = local;
         stats->h2d_ms = a; stats->d2h_ms = b;
     }
-    for (auto &ev : e) cudaEventDestroy(ev);
     return GDB200_OK;
 }
 

@@ -47,7 +47,7 @@ extern "C" int gdb200_emu_gpt_render(const gdb200_scene_desc *desc, const gdb200
     c_scene = hs.host; static DScene sceneCopy; sceneCopy = hs.host; c_sceneG = &sceneCopy;
     memcpy(c_bounds, hs.bounds, sizeof(hs.bounds));
     const size_t n = (size_t)hs.width * hs.height;
-    sd.assign((size_t)4 * kRecords * a.nSlots, 0.0); si.assign((size_t)16 * a.nSlots, 0); film.assign(5 * n * 4, 0.0);
+    sd.assign((size_t)4 * kRecPitch * a.nSlots, 0.0); si.assign((size_t)16 * a.nSlots, 0); film.assign(5 * n * 4, 0.0);
     std::vector<int> lists((size_t)2 * a.nSlots + 2 * kBuckets + 2, 0);
     a.sd = sd.data(); a.si = si.data(); a.film = film.data(); a.counters = ctr.data();
     a.genList = lists.data(); a.liveCount = lists.data() + 2 * (size_t)a.nSlots; a.genCount = a.liveCount + 2 * kBuckets; a.liveList = nullptr;
@@ -171,7 +171,7 @@ extern "C" int gdb200_emu_gpt_render_wavefront(const gdb200_scene_desc *desc, co
     memcpy(c_bounds, hs.bounds, sizeof(hs.bounds));
     const size_t n = (size_t)hs.width * hs.height;
     const int nSlots = a.nSlots;
-    std::vector<double> sd((size_t)4 * kRecords * nSlots, 0.0), film(5 * n * 4, 0.0);
+    std::vector<double> sd((size_t)4 * kRecPitch * nSlots, 0.0), film(5 * n * 4, 0.0);
     std::vector<int> si((size_t)16 * nSlots, 0), liveList((size_t)2 * kBuckets * nSlots, -1), liveCount(2 * kBuckets, 0), genList((size_t)2 * nSlots, -1), genCount(2, 0);
     std::vector<unsigned long long> ctr(8, 0);
     a.sd = sd.data(); a.si = si.data(); a.film = film.data(); a.counters = ctr.data();
@@ -234,14 +234,13 @@ extern "C" int gdb200_emu_gpt_render_staged(const gdb200_scene_desc *desc, const
     const size_t n = (size_t)hs.width * hs.height;
     const int nSlots = a.nSlots;
     const double nan = std::numeric_limits<double>::quiet_NaN();      // a stage that reads a record nobody wrote shows up in the film
-    std::vector<double> sd((size_t)4 * kRecordsStaged * nSlots, nan), film(5 * n * 4, 0.0), rays0((size_t)8 * 5 * nSlots, nan), rays1((size_t)8 * 5 * nSlots, nan),
-        hits((size_t)4 * 5 * nSlots, nan);
-    std::vector<int> si((size_t)16 * nSlots, 0), owner0((size_t)5 * nSlots, -1), owner1((size_t)5 * nSlots, -1), occl((size_t)5 * nSlots, -1),
+    std::vector<double> sd((size_t)4 * kRecPitch * nSlots, nan), film(5 * n * 4, 0.0), rays0((size_t)8 * 5 * nSlots, nan), rays1((size_t)8 * 5 * nSlots, nan);
+    std::vector<int> si((size_t)16 * nSlots, 0), owner0((size_t)5 * nSlots, -1), owner1((size_t)5 * nSlots, -1),
         qList((size_t)kStageBuckets * nSlots, -1), qCount(kStageBuckets, 0), rayCount(2, 0);
     std::vector<unsigned long long> ctr(8, 0);
     a.sd = sd.data(); a.si = si.data(); a.film = film.data(); a.counters = ctr.data();
     a.rays[0] = rays0.data(); a.rays[1] = rays1.data(); a.rayOwner[0] = owner0.data(); a.rayOwner[1] = owner1.data();
-    a.rayCount = rayCount.data(); a.rayCapacity = 5 * nSlots; a.hits = hits.data(); a.occluded = occl.data();
+    a.rayCount = rayCount.data(); a.rayCapacity = 5 * nSlots;
     a.qList = qList.data(); a.qCount = qCount.data();
 
     grid = std::max(1, grid);

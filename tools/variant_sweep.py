@@ -43,9 +43,12 @@ for name, n, spp in cases:
         st = integ.stats
         r = st.samples / st.device_ms / 1e3
         if best is None or r > best[0]:
-            best = (r, st.device_ms, st.bounce_ms, st.generate_ms, st.bounce_launches, st.launches)
-    res["%%s:%%d:%%d" %% (name, n, spp)] = {"Msamples_s": round(best[0], 2), "ms": round(best[1], 1), "bounce_ms": round(best[2], 1),
-                                        "gen_ms": round(best[3], 1), "steps": best[4], "launches": best[5]}
+            best = (r, st.device_ms, st.bounce_ms, st.generate_ms, st.bounce_launches, st.launches, st.cast_ms, st.prepare_ms, st.resolve_ms,
+                    st.primary_ms, st.compact_ms)
+    res["%%s:%%d:%%d" %% (name, n, spp)] = {"Msamples_s": round(best[0], 2), "ms": round(best[1], 1), "shade_ms": round(best[2], 1),
+                                        "gen_ms": round(best[3], 1), "steps": best[4], "launches": best[5], "cast_ms": round(best[6], 1),
+                                        "prepare_ms": round(best[7], 1), "resolve_ms": round(best[8], 1), "primary_ms": round(best[9], 1),
+                                        "compact_ms": round(best[10], 1)}
     sc.close()
 print(json.dumps(res), flush=True)
 """
