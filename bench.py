@@ -183,7 +183,7 @@ def main():
               "scene": "synthetic Cornell box + GGX spheres (gdb200.scenes)", "sampler": f"gdb200_counter seed 0, {args.streams} sample streams per pixel",
               "maxDepth": -1, "rrDepth": 5, "shiftThreshold": 0.001, "alpha": 0.2,
               "parallelism": f"interleaved 16-row bands x{world}, one NCCL all-reduce of the film accumulators" if world > 1 else "1 GPU",
-              "l2_flush": "per-step working set (>= 1.5 GB of wavefront state per million resident path slots + 168 MB film) exceeds the 126 MB L2"}
+              "l2_flush": "per-step working set (2 KB of wavefront state per resident path slot, 8 M slots = 16 GB, + ray queues + 168 MB film) exceeds the 126 MB L2"}
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
@@ -221,6 +221,7 @@ def main():
     bands = tiles.band_spec(rank, world, 16) if world > 1 else None    # interleaved 16-row bands: balanced strong scaling
     acc = scene.accumulators() if world > 1 else None
     agg = {"bounce_ms": 0.0, "generate_ms": 0.0, "compact_ms": 0.0, "state_bytes": 0.0, "bounce_launches": 0, "trace_ms": 0.0, "path_bounces": 0.0,
+           "cast_ms": 0.0, "prepare_ms": 0.0, "resolve_ms": 0.0, "primary_ms": 0.0,
            "solve_ms": 0.0, "launches": 0, "samples": 0.0, "rays": 0.0, "exchange_bytes": 0}
 
     def step(timed):
@@ -233,7 +234,8 @@ def main():
             integ.reconstruct(scene, plan, download=False)
         if timed:
             st = integ.stats
-            for k in ("bounce_ms", "generate_ms", "compact_ms", "state_bytes", "bounce_launches", "samples", "rays", "path_bounces"):
+            for k in ("bounce_ms", "generate_ms", "compact_ms", "state_bytes", "bounce_launches", "samples", "rays", "path_bounces",
+                      "cast_ms", "prepare_ms", "resolve_ms", "primary_ms"):
                 agg[k] += getattr(st, k)
             agg["trace_ms"] += st.device_ms
             agg["launches"] += st.launches + 1 + (1 if rank == 0 else 0)
@@ -304,12 +306,17 @@ def main():
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
-        bounce_avg_ms = agg["bounce_ms"] / max(1, agg["bounce_launches"])
+        # Dominant kernel: the shade stage of the staged wavefront = gpt_stage_kernel<SK_SHADE0|1|2>, three specialisations of one
+        # stage launched back to back every tick (csrc/gpt_stages.cuh).  Algorithmic bytes = SURVEY §8d record sizes per
+        # path-bounce (read + write), counted on the device by that stage; time = CUDA events around its launches.
+        shade_launches = 3 * max(1, agg["bounce_launches"])
+        bounce_avg_ms = agg["bounce_ms"] / shade_launches
         achieved = agg["state_bytes"] / max(agg["bounce_ms"], 1e-9) / 1e6          # GB/s
-        traffic = None          # DRAM bytes per launch: ncu's per-thread figure for this kernel (profiles/) x this run's threads per launch
+        family_ms = agg["bounce_ms"] + agg["prepare_ms"] + agg["resolve_ms"] + agg["cast_ms"]
+        traffic = None          # DRAM bytes per launch: ncu's per-path-bounce figure for this stage (profiles/) x this run's bounces per launch
         try:
-            per_thread = json.load(open(os.path.join(ROOT, "profiles", "r01_gpt_bounce_summary.json")))["dram_bytes_per_thread"]
-            traffic = round(per_thread * agg["path_bounces"] / max(1, agg["bounce_launches"]))
+            per_bounce = json.load(open(os.path.join(ROOT, "profiles", "r02_gpt_shade_summary.json")))["dram_bytes_per_path_bounce"]
+            traffic = round(per_bounce * agg["path_bounces"] / shade_launches)
         except Exception:
             pass
         solve_ms = agg["solve_ms"] / args.steps
@@ -328,12 +335,17 @@ def main():
                 "e2e": {"value": round(e2e_val, 3), "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(agg["launches"]),
                 "clocks": clocks, "clocks_e2e": clocks_e2e,
-                "roofline": {"bound": "hbm", "kernel": "gpt_bounce_kernel", "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"],
+                "roofline": {"bound": "hbm", "kernel": "gpt_stage_kernel<shade0|shade1|shade2>", "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"],
                              "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": traffic,
                              "peak_source": peak_src, "avg_launch_ms": round(bounce_avg_ms, 4),
                              "share_of_step": round(agg["bounce_ms"] / max(agg["trace_ms"], 1e-9), 3),
-                             "note": "algorithmic bytes = SURVEY §8d wavefront record sizes counted on device; the kernel is "
-                                     "latency bound at 8 warps/SM, not HBM bound (profiles/r01b_gpt_kernels_ncu.txt)"}}
+                             "bounce_family": {"kernels": "prepare + shade + resolve stages + both cast kernels",
+                                               "achieved": round(agg["state_bytes"] / max(family_ms, 1e-9) / 1e6, 1),
+                                               "frac": round(agg["state_bytes"] / max(family_ms, 1e-9) / 1e6 / peaks["hbm_gbs"], 4),
+                                               "share_of_step": round(family_ms / max(agg["trace_ms"], 1e-9), 3)},
+                             "note": "algorithmic bytes = SURVEY §8d wavefront record sizes per path-bounce, counted on device; the stages "
+                                     "move 32-byte records of scattered slots, which HBM3e serves at ~2.5-3 TB/s (profiles/r02_stage_kernels_ncu.txt)"},
+                "tracer_ms": {k: round(agg[k + "_ms"] / args.steps, 1) for k in ("bounce", "cast", "prepare", "resolve", "primary", "generate", "compact")}}
         if world > 1:
             line["exchange_bytes_per_step"] = int(agg["exchange_bytes"] / args.steps)
         if world == 1:

@@ -61,7 +61,7 @@ struct Workspace {
     double *sd = nullptr; int *si = nullptr;
     int *liveList = nullptr, *liveCount = nullptr, *genList = nullptr, *genCount = nullptr;     // fused-bounce wavefront (A/B)
     double *rays[2] = {nullptr, nullptr};                                                        // staged wavefront
-    int *rayOwner[2] = {nullptr, nullptr}, *rayCount = nullptr, *qList = nullptr, *qCount = nullptr;
+    int *rayOwner[2] = {nullptr, nullptr}, *rayCount = nullptr, *qKey = nullptr, *qList = nullptr, *qCount = nullptr;
     int slotCapacity = 0; bool fused = false;
     std::vector<cudaEvent_t> events;       // timing marks of renders that ask for stats, reused across renders
 };
@@ -71,7 +71,7 @@ static void freeWorkspace(Workspace &w)
 {
     cudaFree(w.sd); cudaFree(w.si); cudaFree(w.liveList); cudaFree(w.liveCount); cudaFree(w.genList); cudaFree(w.genCount);
     cudaFree(w.rays[0]); cudaFree(w.rays[1]); cudaFree(w.rayOwner[0]); cudaFree(w.rayOwner[1]);
-    cudaFree(w.rayCount); cudaFree(w.qList); cudaFree(w.qCount);
+    cudaFree(w.rayCount); cudaFree(w.qKey); cudaFree(w.qList); cudaFree(w.qCount);
     for (cudaEvent_t e : w.events) cudaEventDestroy(e);
     w = Workspace();
 }
@@ -188,6 +188,7 @@ int ensureWorkspace(Workspace &ws, int nSlots, bool fused)
             if (e == cudaSuccess) e = cudaMalloc(&ws.rayOwner[q], sizeof(int) * 5 * n);
         }
         if (e == cudaSuccess) e = cudaMalloc(&ws.rayCount, sizeof(int) * 2);
+        if (e == cudaSuccess) e = cudaMalloc(&ws.qKey, sizeof(int) * n);
         if (e == cudaSuccess) e = cudaMalloc(&ws.qList, sizeof(int) * (size_t)kStageBuckets * n);
         if (e == cudaSuccess) e = cudaMalloc(&ws.qCount, sizeof(int) * kStageBuckets);
     }
@@ -387,7 +388,7 @@ int gdb200_gpt_render(gdb200_scene *s, const gdb200_gpt_params *p, gdb200_buffer
     a.film = s->film; a.liveList = ws.liveList; a.liveCount = ws.liveCount; a.genList = ws.genList; a.genCount = ws.genCount;
     a.counters = s->counters;
     a.rays[0] = ws.rays[0]; a.rays[1] = ws.rays[1]; a.rayOwner[0] = ws.rayOwner[0]; a.rayOwner[1] = ws.rayOwner[1];
-    a.rayCount = ws.rayCount; a.rayCapacity = 5 * nSlots; a.qList = ws.qList; a.qCount = ws.qCount;
+    a.rayCount = ws.rayCount; a.rayCapacity = 5 * nSlots; a.qKey = ws.qKey; a.qList = ws.qList; a.qCount = ws.qCount;
 
     if (stats) memset(stats, 0, sizeof(*stats));
     Marks marks(ws, stats != nullptr);

@@ -215,6 +215,49 @@ GDB_D bool triHit(const DTri &T, const Ray &ray, Float mint, Float maxt, Float &
     return u >= 0 && v >= 0 && u + v <= 1.0;
 }
 
+// Large meshes: per-lane BVH2 walk (fp32 padded node bounds, children visited near to far), exact fp64 triangle tests in
+// the leaves.  Same answers as testing every triangle: the bounds are conservative.  Continues a search that has already
+// narrowed [mint, maxt]; returns true only for an any-hit query that found an occluder.
+template <bool AnyHit>
+GDB_D bool walkBvh(const Ray &ray, Float mint, Float &maxt, bool &found, int &kind, int &index, Float &uOut, Float &vOut)
+{
+    const float ox = (float)ray.o.x, oy = (float)ray.o.y, oz = (float)ray.o.z;
+    const float ix = 1.0f / (float)ray.d.x, iy = 1.0f / (float)ray.d.y, iz = 1.0f / (float)ray.d.z;
+    const float tlo = (float)mint * 0.999f, thi0 = (float)maxt * 1.001f;
+    const BvhNode *nodes = c_scene.bvh;
+    auto slab = [&](const BvhNode &N, float thi, float &tnear) {
+        const float ax = (N.lo[0] - ox) * ix, bx = (N.hi[0] - ox) * ix;
+        const float ay = (N.lo[1] - oy) * iy, by = (N.hi[1] - oy) * iy;
+        const float az = (N.lo[2] - oz) * iz, bz = (N.hi[2] - oz) * iz;
+        const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+        const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+        tnear = tn;
+        return tn <= tf && tf >= tlo && tn <= thi;
+    };
+    int stack[64], sp = 0;
+    float t0;
+    if (slab(nodes[0], thi0, t0)) stack[sp++] = 0;
+    while (sp > 0) {
+        const BvhNode N = nodes[stack[--sp]];
+        const float thi = (float)maxt * 1.001f;
+        if (N.b < 0) {
+            for (int p = N.a; p < N.a - N.b; p++) {
+                Float t, u, v;
+                if (triHit(c_scene.bvhTris[p], ray, mint, maxt, t, u, v)) { if (AnyHit) return true; maxt = t; found = true; kind = 3; index = p; uOut = u; vOut = v; }
+            }
+        } else {
+            float ta, tb;
+            const bool ha = slab(nodes[N.a], thi, ta), hb = slab(nodes[N.b], thi, tb);
+            if (ha && hb) {
+                const bool aFirst = ta <= tb;
+                if (sp + 2 <= 64) { stack[sp++] = aFirst ? N.b : N.a; stack[sp++] = aFirst ? N.a : N.b; }
+            } else if (ha) { if (sp < 64) stack[sp++] = N.a; }
+            else if (hb) { if (sp < 64) stack[sp++] = N.b; }
+        }
+    }
+    return false;
+}
+
 // Nearest (or any) hit in [mint, maxt] = the outcome of the reference's kd-tree traversal
 // (sahkdtree3.h:179-308: every candidate is tested against the shrinking interval).
 //   pass 1: a division-free slab test of the ray against the padded bounds of every primitive, as a
@@ -223,6 +266,9 @@ GDB_D bool triHit(const DTri &T, const Ray &ray, Float mint, Float maxt, Float &
 //           fp64 test, in primitive order.  All lanes run the same test code on different primitives,
 //           so incoherent rays no longer pay for the union of everything any lane might hit.
 // The bounds are conservative, so the answers are those of testing every primitive.
+#ifndef GDB_SLAB_NO_FMA
+#define GDB_SLAB_FMA 1      // the cast kernels are issue-bound: one FFMA per plane instead of FADD + FMUL is worth 8 % of them
+#endif
 template <bool AnyHit>
 GDB_D bool closestPrimitive(const Ray &ray, Float mint, Float maxt, Float &tOut, int &kind, int &index, Float &uOut, Float &vOut)
 {
@@ -284,51 +330,7 @@ GDB_D bool closestPrimitive(const Ray &ray, Float mint, Float maxt, Float &tOut,
             if (triHit(g->tris[p - nR - nS], ray, mint, maxt, t, u, v)) { if (AnyHit) return true; maxt = t; found = true; kind = 2; index = p - nR - nS; uOut = u; vOut = v; }
         }
     }
-    if (c_scene.nBvhNodes > 0) {
-        // Large meshes: per-lane BVH2 walk (fp32 padded node bounds, children visited near to far), exact fp64
-        // triangle tests in the leaves.  Same answers as testing every triangle: the bounds are conservative.
-        const BvhNode *nodes = c_scene.bvh;
-#ifndef GDB_SLAB_FMA
-        const float nx = 0, ny = 0, nz = 0;
-#endif
-        auto slab = [&](const BvhNode &N, float thi, float &tnear) {
-#ifdef GDB_SLAB_FMA
-            const float ax = __fmaf_rn(N.lo[0], ix, nx), bx = __fmaf_rn(N.hi[0], ix, nx);
-            const float ay = __fmaf_rn(N.lo[1], iy, ny), by = __fmaf_rn(N.hi[1], iy, ny);
-            const float az = __fmaf_rn(N.lo[2], iz, nz), bz = __fmaf_rn(N.hi[2], iz, nz);
-#else
-            (void)nx; (void)ny; (void)nz;
-            const float ax = (N.lo[0] - ox) * ix, bx = (N.hi[0] - ox) * ix;
-            const float ay = (N.lo[1] - oy) * iy, by = (N.hi[1] - oy) * iy;
-            const float az = (N.lo[2] - oz) * iz, bz = (N.hi[2] - oz) * iz;
-#endif
-            const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
-            const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
-            tnear = tn;
-            return tn <= tf && tf >= tlo && tn <= thi;
-        };
-        int stack[64], sp = 0;
-        float t0;
-        if (slab(nodes[0], found ? (float)maxt * 1.001f : thi0, t0)) stack[sp++] = 0;
-        while (sp > 0) {
-            const BvhNode N = nodes[stack[--sp]];
-            const float thi = found ? (float)maxt * 1.001f : thi0;
-            if (N.b < 0) {
-                for (int p = N.a; p < N.a - N.b; p++) {
-                    Float t, u, v;
-                    if (triHit(c_scene.bvhTris[p], ray, mint, maxt, t, u, v)) { if (AnyHit) return true; maxt = t; found = true; kind = 3; index = p; uOut = u; vOut = v; }
-                }
-            } else {
-                float ta, tb;
-                const bool ha = slab(nodes[N.a], thi, ta), hb = slab(nodes[N.b], thi, tb);
-                if (ha && hb) {
-                    const bool aFirst = ta <= tb;
-                    if (sp + 2 <= 64) { stack[sp++] = aFirst ? N.b : N.a; stack[sp++] = aFirst ? N.a : N.b; }
-                } else if (ha) { if (sp < 64) stack[sp++] = N.a; }
-                else if (hb) { if (sp < 64) stack[sp++] = N.b; }
-            }
-        }
-    }
+    if (c_scene.nBvhNodes > 0 && walkBvh<AnyHit>(ray, mint, maxt, found, kind, index, uOut, vOut)) return true;
     tOut = maxt;
     return found;
 }

@@ -15,10 +15,14 @@ namespace gdb200 {
 // ~2.5 TB/s that HBM3e delivers for row-per-sector access, with half of each 64-byte fetch granule belonging to a slot
 // that is not in the queue (profiles/r02_stage_kernels_ncu.txt).  With the slot's records adjacent, the records a
 // thread reads back to back share lines, fetch granules and DRAM rows however scattered the queue is.)
-enum BaseRec { BR_RAYD = 0 /* w: path pdf */, BR_P /* w: eta */, BR_GN /* w: sample x */, BR_S /* w: sample y */, BR_T, BR_N, BR_WI,
-               BR_THR, BR_RAD, BR_VD, BR_COUNT };
-enum OffRec { OR_THR = 0 /* w: path pdf */, OR_RAD, OR_GRAD, OR_P, OR_GN, OR_S, OR_T, OR_N, OR_WI, OR_COUNT };
-constexpr int kRecords = BR_COUNT + 4 * OR_COUNT;   // 46 records = 1472 B per slot
+// Records of the base path and of one offset path.  Both groups are padded to 12 records = three 128-byte lines, so a group
+// starts on a line boundary and records that are used together (THR|RAD, GRAD|P, ...) share DRAM's 64-byte access granule.
+// The *_X records belong to the staged wavefront (gpt_stages.cuh).
+enum BaseRec { BR_RAYD = 0 /* w: path pdf */, BR_P /* w: eta */, BR_GN /* w: sample x (fused kernels) */, BR_S /* w: sample y (fused kernels) */,
+               BR_T, BR_N, BR_WI, BR_THR, BR_RAD, BR_VD, BR_X0, BR_X1, BR_COUNT };
+enum OffRec { OR_THR = 0 /* w: path pdf */, OR_RAD, OR_GRAD, OR_P, OR_GN, OR_S, OR_T, OR_N, OR_WI, OR_X0, OR_X1, OR_X2, OR_COUNT };
+static_assert(BR_COUNT == 12 && OR_COUNT == 12, "record groups are whole cache lines");
+constexpr int kRecords = BR_COUNT + 4 * OR_COUNT;   // 60 records
 constexpr int kRecPitchLog2 = 6, kRecPitch = 1 << kRecPitchLog2;   // records per slot block incl. the staged wavefront's (gpt_stages.cuh), padded to 2 KB
 enum IntField { IF_STATUS = 0, IF_MAT, IF_EMI, IF_DEPTH, IF_SAMPLE, IF_RNGN, IF_OFLAGS, IF_STREAM, IF_OMAT0, IF_OMAT1, IF_OMAT2, IF_OMAT3,
                 IF_BSTYPE, IF_PEND,      // staged wavefront (gpt_stages.cuh): sampled BSDF component, bookkeeping of the offsets awaiting a ray
@@ -52,6 +56,7 @@ struct GptArgs {
     int *rayOwner[2];      // [rayCapacity]: slot * 8 + ray id of the slot
     int *rayCount;         // [2]
     int rayCapacity, pad2;
+    int *qKey;             // [nSlots]: the stage queue a slot belongs in next (-1: none), written by the stage that leaves it there
     int *qList;            // [kStageBuckets][nSlots]: slots per stage bucket
     int *qCount;           // [kStageBuckets]
 };

@@ -24,11 +24,13 @@
 namespace gdb200 {
 
 // The staged stages write records whole (stvf / stvw).  The sample's film position rides in BR_VD.w (x) and BR_RAD.w (y).
-enum StagedRec { XR_BS_WO = kRecords /* w: pdf */, XR_BS_WEIGHT /* w: eta */,
+enum StagedRec { XR_HIT0 = BR_X0 /* answer to the slot's nearest-hit ray 0: t u v primitive */, XR_OCCLUDED = BR_X1 /* answers to its any-hit rays 0..4, as ints */,
+                 XR_PD_BW = BR_COUNT + OR_X2 /* BSDF-stage weights of offsets 0..3 (spare record of offset 0's group) */,
+                 XR_BS_WO = kRecords /* w: pdf */, XR_BS_WEIGHT /* w: eta */,
                  XR_PD_MAIN /* base contribution of the BSDF stage */, XR_PD_W /* x: weight if a reconnection fails, y: if a half-vector shift fails */,
-                 XR_PD_BW /* BSDF-stage weights of offsets 0..3 */, XR_PD_OFF0 /* per parked offset: xyz + weight of the successful outcome */,
-                 XR_HIT0 = XR_PD_OFF0 + 4 /* answers to the slot's nearest-hit rays 0..4: t u v primitive */,
-                 XR_OCCLUDED = XR_HIT0 + 5 /* answers to its any-hit rays 0..4, as ints */, kRecordsStaged = XR_OCCLUDED + 1 };
+                 kRecordsStaged };
+GDB_D constexpr int hitRec(int id) { return id == 0 ? (int)XR_HIT0 : BR_COUNT + (id - 1) * OR_COUNT + OR_X1; }   // answer to nearest-hit ray id (1..4: in offset id-1's group)
+GDB_D constexpr int pendRec(int i) { return BR_COUNT + i * OR_COUNT + OR_X0; }   // parked offset i: xyz + weight of the successful outcome
 static_assert(kRecordsStaged <= kRecPitch, "the slot block holds every record");
 
 // Stage queues.  A: built after the casts (continuations); B: built after those ran (slots that need new rays).
@@ -39,6 +41,23 @@ enum { PEND_NONE = 0, PEND_RECONNECT = 1, PEND_HALFVECTOR = 2 };
 // IF_PEND: bits 0-7 pending kind of offsets 0..3 (2 bits each), 8-11 offsets whose BSDF-stage weight is set, 12 the stage is
 // accumulated (minDepth), 13 the base path left the scene, 14 the base path ended, 15 base vertex type, 16-19 offset vertex types
 GDB_D int pendKind(unsigned p, int i) { return (p >> (2 * i)) & 3u; }
+
+// Where a slot goes next.  The compaction kernels read only this dense array (4 B per slot) instead of the slots' state.
+GDB_D int shiftStage(unsigned flags)
+{
+    // stage 0: some offset path is still unconnected (its own light sample, a reconnection or half-vector ray ahead),
+    // stage 1: some offset was connected on the previous bounce (extra BSDF evaluations), stage 2: all offsets ride along
+    // with the base path or are dead.  Lanes of one warp then run the same branches.
+    int stage = 2;
+    for (int i = 0; i < 4; i++) {
+        if (!flagAlive(flags, i)) continue;
+        const int c = flagConn(flags, i);
+        if (c == RAY_NOT_CONNECTED) stage = 0; else if (c == RAY_RECENTLY_CONNECTED && stage == 2) stage = 1;
+    }
+    return stage;
+}
+GDB_D void setStatus(const GptArgs &a, int slot, int status, int queue) { SI(a, IF_STATUS, slot) = status; a.qKey[slot] = queue; }
+GDB_D int prepareQueue(int material) { return QB_PREPARE0 + c_sceneG->materials[material].type; }
 
 // Statistics of one thread over its persistent loop; flushed with one warp-aggregated atomic per counter when the kernel ends.
 struct Tally { unsigned done = 0, rays = 0, vertices = 0, samples = 0, bytes = 0, bounces = 0; };
@@ -81,7 +100,7 @@ template <int WHICH>
 GDB_D void putHoles(const GptArgs &a, int from, int to) { for (int i = from; i < to && i < a.rayCapacity; i++) a.rayOwner[WHICH][i] = -1; }
 GDB_D Hit loadHit(const GptArgs &a, int id, int slot)
 {
-    const double2 *p = reinterpret_cast<const double2 *>(REC(a, XR_HIT0 + id, slot));
+    const double2 *p = reinterpret_cast<const double2 *>(REC(a, hitRec(id), slot));
     const double2 lo = p[0], hi = p[1];
     Hit h; h.t = lo.x; h.u = lo.y; h.v = hi.x;
     const int prim = (int)hi.y; h.kind = prim >> 28; h.index = prim & 0x0fffffff;
@@ -103,7 +122,7 @@ __global__ void __launch_bounds__(128) gpt_cast_kernel(const GptArgs a)
         if (Any) reinterpret_cast<int *>(REC(a, XR_OCCLUDED, slot))[id] = rayOccludedImpl(ray) ? 1 : 0;
         else {
             Hit h; castClosest(ray, h);
-            double2 *o = reinterpret_cast<double2 *>(REC(a, XR_HIT0 + id, slot));
+            double2 *o = reinterpret_cast<double2 *>(REC(a, hitRec(id), slot));
             o[0] = make_double2(h.t, h.u); o[1] = make_double2(h.v, (Float)((h.kind << 28) | h.index));
         }
     }
@@ -152,7 +171,8 @@ GDB_D void stagedGenerateBody(const GptArgs &a, int slot, Tally &tally)
         status = ST_WAIT_PRIMARY;
         break;
     }
-    SI(a, IF_STATUS, slot) = status; SI(a, IF_SAMPLE, slot) = j; SI(a, IF_RNGN, slot) = (int)smp.n; SI(a, IF_STREAM, slot) = stream;
+    setStatus(a, slot, status, status == ST_DONE ? -1 : QA_PRIMARY);
+    SI(a, IF_SAMPLE, slot) = j; SI(a, IF_RNGN, slot) = (int)smp.n; SI(a, IF_STREAM, slot) = stream;
     tally.done += status == ST_DONE ? 1u : 0u; tally.rays += 5u * samples; tally.samples += samples;
 }
 
@@ -194,14 +214,14 @@ GDB_D void stagedPrimaryBody(const GptArgs &a, int slot, Tally &tally)
     stvw(a, BR_RAD, slot, splat(0), spy); stvw(a, BR_VD, slot, veryDirect, spx);
     if (early || !(1 < a.cfg.maxDepth || a.cfg.maxDepth < 0)) {                      // bounce loop never entered (gpt.cpp:537): the
         if (!early) tally.vertices += 1u;                                            // sample is its very-direct term; generate splats it
-        SI(a, IF_STATUS, slot) = ST_FINISHED;
+        setStatus(a, slot, ST_FINISHED, QB_GEN);
         return;
     }
     storeBaseItsFull(a, slot, mits, 1.0);                                            // eta = 1
     stvw(a, BR_RAYD, slot, ray.d, 1.0);                                              // pdf = 1
     stvf(a, BR_THR, slot, splat(1.0));
     SI(a, IF_DEPTH, slot) = 1; SI(a, IF_OFLAGS, slot) = (int)flags;
-    SI(a, IF_STATUS, slot) = ST_LIVE;
+    setStatus(a, slot, ST_LIVE, prepareQueue(mits.material));
 }
 
 // ------------------------------------------------------------------ prepare: the rays a bounce starts with
@@ -230,6 +250,7 @@ GDB_D void stagedPrepareBody(const GptArgs &a, int slot)
     Its mits; loadBaseIts(a, slot, mits);
     const int depth = SI(a, IF_DEPTH, slot);
     unsigned flags = (unsigned)SI(a, IF_OFLAGS, slot);
+    const int shadeQueue = QA_SHADE0 + shiftStage(flags) * kBsdfTypes + c_sceneG->materials[mits.material].type;
     Sampler smp; smp.key = streamInfo(a, SI(a, IF_STREAM, slot)).key; smp.n = (uint32_t)SI(a, IF_RNGN, slot);
     bool ended = false;
     if (cfg.strictNormals) ended = !strictNormalsPrepass(a, slot, mits, ldv(a, BR_RAYD, slot), flags);
@@ -280,7 +301,7 @@ GDB_D void stagedPrepareBody(const GptArgs &a, int slot)
         }
         if (!cast) putHoles<0>(a, q, q + 1);
     }
-    SI(a, IF_STATUS, slot) = ST_WAIT_SHADE;
+    setStatus(a, slot, ST_WAIT_SHADE, shadeQueue);
 }
 
 // ------------------------------------------------------------------ shade: bounceBody without a single ray cast
@@ -591,7 +612,7 @@ GDB_D void stagedShadeBody(const GptArgs &a, int slot, Tally &tally)
                                     mainContribution = mainContributionAll;
                                     shiftedContribution = sthr * shiftedEmitterRadiance;
                                 }   // else weight and contributions stay 0 (gpt.cpp:833-836)
-                                stvw(a, XR_PD_OFF0 + i, slot, shiftedContribution, weight);
+                                stvw(a, pendRec(i), slot, shiftedContribution, weight);
                             }
                         }
                     } else {                                                         // half-vector shift, gpt.cpp:987-1126
@@ -618,7 +639,7 @@ GDB_D void stagedShadeBody(const GptArgs &a, int slot, Tally &tally)
                                     Ray sray; sray.o = sits.p; sray.d = outgoingDirection; sray.mint = kEpsilon; sray.maxt = CUDART_INF;   // gpt.cpp:1050
                                     putRay<0>(a, qNear++, slot, 1 + i, sray); rays++;
                                     parked = PEND_HALFVECTOR;
-                                    stvw(a, XR_PD_OFF0 + i, slot, outgoingDirection, mpdf / (spdf * spdf + mpdf * mpdf));   // weight of gpt.cpp:1107-1112
+                                    stvw(a, pendRec(i), slot, outgoingDirection, mpdf / (spdf * spdf + mpdf * mpdf));   // weight of gpt.cpp:1107-1112
                                 }
                             }
                         }
@@ -696,8 +717,9 @@ GDB_D void stagedShadeBody(const GptArgs &a, int slot, Tally &tally)
         pend |= offVertexTypes << 16;
         SI(a, IF_PEND, slot) = (int)pend;
         SI(a, IF_BSTYPE, slot) = (int)sampledType;
-        SI(a, IF_STATUS, slot) = ST_WAIT_RESOLVE;
-    } else SI(a, IF_STATUS, slot) = ended ? ST_FINISHED : ST_LIVE;
+        setStatus(a, slot, ST_WAIT_RESOLVE, QA_RESOLVE);
+    } else if (ended) setStatus(a, slot, ST_FINISHED, QB_GEN);
+    else setStatus(a, slot, ST_LIVE, prepareQueue(mits.material));
 }
 
 // ------------------------------------------------------------------ resolve: the parked offsets of gpt.cpp:889-1126
@@ -718,7 +740,7 @@ GDB_D void stagedResolveBody(const GptArgs &a, int slot)
         if (kind == PEND_NONE) continue;
         const int o = BR_COUNT + i * OR_COUNT;
         V3 v; Float weight;
-        ldvw(a, XR_PD_OFF0 + i, slot, v, weight);
+        ldvw(a, pendRec(i), slot, v, weight);
         Spec shiftedContribution = splat(0);
         bool alive = true;
         if (kind == PEND_RECONNECT) {
@@ -767,17 +789,18 @@ GDB_D void stagedResolveBody(const GptArgs &a, int slot)
     if (bHas & 8u) mrad = mrad + mainContributionAll * bw3;
     stvw(a, BR_RAD, slot, mrad, spy);
     SI(a, IF_OFLAGS, slot) = (int)flags;
-    SI(a, IF_STATUS, slot) = ended ? ST_FINISHED : ST_LIVE;
+    if (ended) setStatus(a, slot, ST_FINISHED, QB_GEN);
+    else setStatus(a, slot, ST_LIVE, prepareQueue(SI(a, IF_MAT, slot)));
 }
 
 // ------------------------------------------------------------------ stage kernels: persistent CTAs over the stage's queues
 enum StageKind { SK_PRIMARY = 0, SK_SHADE0, SK_SHADE1, SK_SHADE2, SK_RESOLVE, SK_PREPARE, SK_GENERATE };
 template <int KIND> struct StageQueues;
-// minBlocks: resident CTAs per SM the register allocation is sized for (4 => 128 registers, 3 => 168, 2 => 255).  Every stage is
-// bound by memory latency at the occupancy its registers allow (profiles/r02_stage_kernels_ncu.txt), so each gets the
-// smallest allocation that does not make it spill.
+// minBlocks: resident CTAs per SM the register allocation is sized for (4 => 128 registers, 3 => 168, 2 => 255).  Measured
+// (profiles/r02_tracer_history.md): a stage gains nothing from more resident warps but loses ~8 % to a few hundred bytes of
+// spills, so each gets the largest occupancy at which it does not spill.
 #ifndef GDB_MB_PRIMARY
-#define GDB_MB_PRIMARY 4
+#define GDB_MB_PRIMARY 3
 #endif
 #ifndef GDB_MB_SHADE0
 #define GDB_MB_SHADE0 2
@@ -786,16 +809,16 @@ template <int KIND> struct StageQueues;
 #define GDB_MB_SHADE1 2
 #endif
 #ifndef GDB_MB_SHADE2
-#define GDB_MB_SHADE2 3
+#define GDB_MB_SHADE2 2
 #endif
 #ifndef GDB_MB_RESOLVE
 #define GDB_MB_RESOLVE 4
 #endif
 #ifndef GDB_MB_PREPARE
-#define GDB_MB_PREPARE 4
+#define GDB_MB_PREPARE 3
 #endif
 #ifndef GDB_MB_GENERATE
-#define GDB_MB_GENERATE 4
+#define GDB_MB_GENERATE 3
 #endif
 template <> struct StageQueues<SK_PRIMARY>  { static constexpr int first = QA_PRIMARY, count = 1, minBlocks = GDB_MB_PRIMARY; };
 template <> struct StageQueues<SK_SHADE0>   { static constexpr int first = QA_SHADE0, count = kBsdfTypes, minBlocks = GDB_MB_SHADE0; };
@@ -812,9 +835,9 @@ template <> struct StageQueues<SK_GENERATE> { static constexpr int first = QB_GE
 template <int KIND>
 GDB_D void prefetchSlot(const GptArgs &a, int slot)
 {
-#ifdef GDB_STAGE_PREFETCH      // measured: -8 % (profiles/r02_tracer_history.md) -- the stages are bound by DRAM transactions, not by their latency
+#if defined(GDB_STAGE_PREFETCH) || defined(GDB_STAGE_PREFETCH_SELF)     // measured: -8 % (profiles/r02_tracer_history.md)
     auto rec = [&](int r) { prefetchL2(REC(a, r, slot)); };
-    auto hit = [&](int id) { prefetchL2(REC(a, XR_HIT0 + id, slot)); };
+    auto hit = [&](int id) { prefetchL2(REC(a, hitRec(id), slot)); };
     auto occ = [&](int id) { if (id == 0) prefetchL2(REC(a, XR_OCCLUDED, slot)); };
     prefetchL2(&SI(a, 0, slot)); prefetchL2(&SI(a, 8, slot));
     if (KIND == SK_PRIMARY) {
@@ -831,7 +854,7 @@ GDB_D void prefetchSlot(const GptArgs &a, int slot)
         }
     } else if (KIND == SK_RESOLVE) {
         rec(XR_PD_MAIN); rec(XR_PD_W); rec(XR_PD_BW); rec(BR_RAD);
-        for (int i = 0; i < 4; i++) { rec(XR_PD_OFF0 + i); hit(1 + i); occ(1 + i); }
+        for (int i = 0; i < 4; i++) { rec(pendRec(i)); hit(1 + i); occ(1 + i); }
     } else if (KIND == SK_PREPARE) {
         for (int r = BR_RAYD; r <= BR_WI; r++) rec(r);
     } else {
@@ -869,7 +892,12 @@ __global__ void __launch_bounds__(kStageThreads, StageQueues<KIND>::minBlocks) g
     Tally tally;
     for (; g < total; g += stride) {
         const int slot2 = slotAt(g + 2 * stride);
+#ifdef GDB_STAGE_PREFETCH
         if (slot1 >= 0) prefetchSlot<KIND>(a, slot1);
+#endif
+#ifdef GDB_STAGE_PREFETCH_SELF
+        if (slot >= 0) prefetchSlot<KIND>(a, slot);
+#endif
         if (slot >= 0) {
             if (KIND == SK_PRIMARY) stagedPrimaryBody(a, slot, tally);
             else if (KIND == SK_SHADE0) stagedShadeBody<0>(a, slot, tally);
@@ -899,27 +927,8 @@ __global__ void __launch_bounds__(256) gpt_stage_compact_kernel(const GptArgs a)
     const int slot = blockIdx.x * 256 + threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int bucket = -1;
     if (slot < a.nSlots) {
-        const int st = SI(a, IF_STATUS, slot);
-        if (PHASE == 0) {
-            if (st == ST_WAIT_PRIMARY) bucket = QA_PRIMARY;
-            else if (st == ST_WAIT_RESOLVE) bucket = QA_RESOLVE;
-            else if (st == ST_WAIT_SHADE) {
-                // stage 0: some offset path is still unconnected (its own light sample, a reconnection or half-vector ray
-                // ahead), stage 1: some offset was connected on the previous bounce (extra BSDF evaluations), stage 2: all
-                // offsets ride along with the base path or are dead.  Lanes of one warp then run the same branches.
-                const unsigned f = (unsigned)SI(a, IF_OFLAGS, slot);
-                int stage = 2;
-                for (int i = 0; i < 4; i++) {
-                    if (!flagAlive(f, i)) continue;
-                    const int c = flagConn(f, i);
-                    if (c == RAY_NOT_CONNECTED) stage = 0; else if (c == RAY_RECENTLY_CONNECTED && stage == 2) stage = 1;
-                }
-                bucket = QA_SHADE0 + stage * kBsdfTypes + c_sceneG->materials[SI(a, IF_MAT, slot)].type;
-            }
-        } else {
-            if (st == ST_LIVE) bucket = QB_PREPARE0 + c_sceneG->materials[SI(a, IF_MAT, slot)].type - first;
-            else if (st == ST_FINISHED || st == ST_FRESH) bucket = QB_GEN - first;
-        }
+        const int key = a.qKey[slot] - first;
+        if (key >= 0 && key < nq) bucket = key;
     }
     int rank = 0;
 #pragma unroll
@@ -944,7 +953,8 @@ __global__ void gpt_stage_init_kernel(const GptArgs a)
     if (slot < kStageBuckets) a.qCount[slot] = 0;
     if (slot == 0) { a.rayCount[0] = 0; a.rayCount[1] = 0; a.counters[6] = (unsigned long long)a.nSlots; }
     if (slot >= a.nSlots) return;
-    SI(a, IF_STATUS, slot) = ST_FRESH; SI(a, IF_SAMPLE, slot) = 0; SI(a, IF_RNGN, slot) = 0; SI(a, IF_STREAM, slot) = slot;   // slot s starts on stream s
+    setStatus(a, slot, ST_FRESH, QB_GEN);
+    SI(a, IF_SAMPLE, slot) = 0; SI(a, IF_RNGN, slot) = 0; SI(a, IF_STREAM, slot) = slot;   // slot s starts on stream s
 }
 
 }  // namespace gdb200

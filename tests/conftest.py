@@ -158,6 +158,14 @@ class Emu:
         return out, cnt
 
 
+    def check_culling(self, desc, n_rays, seed):
+        """(mismatches, hits): candidate selection of the intersection searches vs exhaustive testing on random rays."""
+        out = (ctypes.c_ulonglong * 2)()
+        rc = self.lib.gdb200_emu_check_culling(ctypes.byref(desc), int(n_rays), ctypes.c_ulonglong(seed), out)
+        if rc != 0:
+            raise RuntimeError(self.lib.gdb200_emu_last_error().decode())
+        return int(out[0]), int(out[1])
+
     def gpt_staged(self, desc, params, grid=3):
         """Block mode of the STAGED wavefront (csrc/gpt_stages.cuh): stage / cast / compact kernels as written, `grid`
         persistent CTAs per launch run by OS threads."""

@@ -71,6 +71,8 @@ inline unsigned __ballot_sync(unsigned, bool p)
 inline bool __any_sync(unsigned, bool p) { return p; }
 inline void __syncwarp(unsigned = 0xffffffffu) {}
 inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
+inline float __frcp_rn(float x) { return 1.0f / x; }
+inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
 inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
 inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
 inline double __ldg(const double *p) { return *p; }

@@ -214,6 +214,25 @@ extern "C" int gdb200_emu_gpt_render_wavefront(const gdb200_scene_desc *desc, co
     return 0;
 }
 
+// ---- gpt_check_culling_kernel on the host: candidate selection by padded bounds (closestPrimitive, incl. the BVH walk)
+// against testing every primitive, on random rays.
+extern "C" int gdb200_emu_check_culling(const gdb200_scene_desc *desc, int nRays, unsigned long long seed, unsigned long long *out2)
+{
+    static HostScene hs;
+    if (int rc = flattenScene(desc, &hs)) return rc;
+    classifyMaterials(&hs, 0.001);
+    hs.host.env.texels = hs.envTexels.data(); hs.host.env.rowWeights = hs.envRowWeights.data(); hs.host.emTriCdf = hs.emTriCdf.data();
+    hs.host.env.cdfRows = hs.envCdfRows.data(); hs.host.env.cdfCols = hs.envCdfCols.data(); hs.host.emTris = hs.emTris.data();
+    hs.host.bvh = hs.bvh.data(); hs.host.bvhTris = hs.bvhTris.data(); hs.host.triNormals = hs.triNormals.data();
+    c_scene = hs.host; static DScene sceneCopy; sceneCopy = hs.host; c_sceneG = &sceneCopy;
+    memcpy(c_bounds, hs.bounds, sizeof(hs.bounds));
+    out2[0] = out2[1] = 0;
+    blockDim.x = 1; threadIdx.x = 0;
+    for (int g = 0; g < nRays; g++) { blockIdx.x = (unsigned)g; gpt_check_culling_kernel(seed, nRays, out2); }
+    blockIdx.x = 0;
+    return 0;
+}
+
 // ---- block mode of the STAGED wavefront (csrc/gpt_stages.cuh): compact(A) -> primary, shade, resolve -> compact(B) ->
 // prepare, generate -> casts, every kernel as written (persistent CTAs looping over their queues, ballots, warp-aggregated
 // ray appends), CTAs run by OS threads.  The tick loop mirrors renderStaged() of csrc/gpt.cu.  Every queue entry is checked
@@ -236,12 +255,12 @@ extern "C" int gdb200_emu_gpt_render_staged(const gdb200_scene_desc *desc, const
     const double nan = std::numeric_limits<double>::quiet_NaN();      // a stage that reads a record nobody wrote shows up in the film
     std::vector<double> sd((size_t)4 * kRecPitch * nSlots, nan), film(5 * n * 4, 0.0), rays0((size_t)8 * 5 * nSlots, nan), rays1((size_t)8 * 5 * nSlots, nan);
     std::vector<int> si((size_t)16 * nSlots, 0), owner0((size_t)5 * nSlots, -1), owner1((size_t)5 * nSlots, -1),
-        qList((size_t)kStageBuckets * nSlots, -1), qCount(kStageBuckets, 0), rayCount(2, 0);
+        qKey(nSlots, -1), qList((size_t)kStageBuckets * nSlots, -1), qCount(kStageBuckets, 0), rayCount(2, 0);
     std::vector<unsigned long long> ctr(8, 0);
     a.sd = sd.data(); a.si = si.data(); a.film = film.data(); a.counters = ctr.data();
     a.rays[0] = rays0.data(); a.rays[1] = rays1.data(); a.rayOwner[0] = owner0.data(); a.rayOwner[1] = owner1.data();
     a.rayCount = rayCount.data(); a.rayCapacity = 5 * nSlots;
-    a.qList = qList.data(); a.qCount = qCount.data();
+    a.qKey = qKey.data(); a.qList = qList.data(); a.qCount = qCount.data();
 
     grid = std::max(1, grid);
     emuLaunch((std::max(nSlots, kStageBuckets) + 255) / 256, 256, [&]() { gpt_stage_init_kernel(a); });

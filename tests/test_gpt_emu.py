@@ -213,6 +213,18 @@ def test_staged_wavefront_deals_streams_to_few_slots(oracle, emu, cap, grid):
     assert cnt[3] == c2[0] == 14 * 10 * 5 and cnt[0] == cap
 
 
+@pytest.mark.parametrize("scene_name", ["cbox_glossy", "cbox_diffuse", "cbox_mesh_lights", "cbox_smooth", "atrium", "cbox_sphere_lights"])
+def test_candidate_selection_never_changes_a_hit_on_the_host(emu, scene_name):
+    """gpt_check_culling_kernel on the host: the bounds-based candidate pass of closestPrimitive (table primitives and the
+    BVH walk) must give the answers of testing every primitive -- nearest hit and occlusion, for extension,
+    visibility-segment and camera-like rays."""
+    desc = SCENES[scene_name](32, 24)
+    for seed in range(2):
+        bad, hits = emu.check_culling(desc, 150_000, seed)
+        assert bad == 0, (scene_name, seed, bad)
+        assert hits > 50_000
+
+
 def test_host_validation_follows_the_reference(emu):
     """Scene flattening (csrc/gpt_host.h, shared by the library and the emulation) rejects what the reference's plugins reject."""
     cam = scenes.make_camera(8, 8, (0, 0, 4), (0, 0, 0), (0, 1, 0), 40)
