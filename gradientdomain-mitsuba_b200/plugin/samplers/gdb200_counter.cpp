@@ -10,8 +10,10 @@
 //     on which worker thread renders it or in which order (the `independent` sampler's does, independent.cpp:42-45);
 //   * next1D()/next2D() consume the stream sequentially over all spp samples of the pixel (gpt never calls advance());
 //   * sample arrays (request1DArray/request2DArray) are not used by gpt and are filled from the same stream.
-// Limitation: gdb200's streams_per_pixel > 1 (chunked streams) has no single-pass equivalent here because the
-// Sampler API gives no per-sample hook that gpt calls; render C passes with sampleCount/C and seeds re-keyed per chunk.
+//   * `chunk` (default 0) selects one of gdb200's chunked streams (gdb200_gpt_params.streams_per_pixel = C > 1): chunk 0
+//     is the pixel's stream, chunk c > 0 an independently re-keyed one (the key of streamInfo() in csrc/gpt_kernels.cuh).
+//     The Sampler API gives no per-sample hook that gpt calls, so a C-stream film is C passes of the reference, pass c with
+//     <integer name="chunk" value="c"/> and sampleCount = spp/C (+1 for c < spp%C), films summed (oracle/ref_gpt_shim.cpp).
 //
 // Built inside a Mitsuba tree.  The test suite compiles it against the reference's real Sampler interface and
 // feeds the reference's own gpt.cpp with it; plugin/stub/mitsuba_stub.h is a syntax check where the reference tree is absent.
@@ -26,26 +28,30 @@ MTS_NAMESPACE_BEGIN
 
 class GDB200CounterSampler : public Sampler {
 public:
-	GDB200CounterSampler() : Sampler(Properties()), m_seed(0), m_key(0), m_n(0) { }
+	GDB200CounterSampler() : Sampler(Properties()), m_seed(0), m_chunk(0), m_key(0), m_n(0) { }
 
 	GDB200CounterSampler(const Properties &props) : Sampler(props), m_key(0), m_n(0) {
 		m_sampleCount = props.getSize("sampleCount", 4);
 		m_seed = (uint64_t) props.getSize("seed", 0);
+		m_chunk = (uint64_t) props.getSize("chunk", 0);
 	}
 
 	GDB200CounterSampler(Stream *stream, InstanceManager *manager) : Sampler(stream, manager), m_key(0), m_n(0) {
 		m_seed = stream->readULong();
+		m_chunk = stream->readULong();
 	}
 
 	void serialize(Stream *stream, InstanceManager *manager) const {
 		Sampler::serialize(stream, manager);
 		stream->writeULong(m_seed);
+		stream->writeULong(m_chunk);
 	}
 
 	ref<Sampler> clone() {
 		ref<GDB200CounterSampler> sampler = new GDB200CounterSampler();
 		sampler->m_sampleCount = m_sampleCount;
 		sampler->m_seed = m_seed;
+		sampler->m_chunk = m_chunk;
 		for (size_t i=0; i<m_req1D.size(); ++i)
 			sampler->request1DArray(m_req1D[i]);
 		for (size_t i=0; i<m_req2D.size(); ++i)
@@ -62,6 +68,8 @@ public:
 	void generate(const Point2i &pos) {
 		m_key = mix(mix(m_seed + 0x9E3779B97F4A7C15ULL)
 			^ ((uint64_t) (uint32_t) pos.x | ((uint64_t) (uint32_t) pos.y << 32)));
+		if (m_chunk > 0)
+			m_key = mix(m_key ^ (m_chunk * 0xD1B54A32D192ED03ULL));
 		m_n = 0;
 		for (size_t i=0; i<m_req1D.size(); i++)
 			for (size_t j=0; j<m_sampleCount * m_req1D[i]; ++j)
@@ -89,14 +97,15 @@ public:
 		std::ostringstream oss;
 		oss << "GDB200CounterSampler[" << endl
 			<< "  sampleCount = " << m_sampleCount << "," << endl
-			<< "  seed = " << m_seed << endl
+			<< "  seed = " << m_seed << "," << endl
+			<< "  chunk = " << m_chunk << endl
 			<< "]";
 		return oss.str();
 	}
 
 	MTS_DECLARE_CLASS()
 private:
-	uint64_t m_seed, m_key, m_n;
+	uint64_t m_seed, m_chunk, m_key, m_n;
 };
 
 MTS_IMPLEMENT_CLASS_S(GDB200CounterSampler, false, Sampler)

@@ -126,6 +126,7 @@ struct Built {
     ref<Scene> scene;
     ref<GradientPathIntegrator> gpt;
     ref<Sampler> sampler;
+    std::vector<ref<Sampler> > chunkSamplers;   // streams_per_pixel = C > 1: one sampler per chunk (sampleCount and `chunk` set), see renderBlocks
 };
 
 Built buildScene(const gdb200_scene_desc *d, const gdb200_gpt_params *prm, double fovX, const char *rfilterName, bool gptIntegrator)
@@ -159,6 +160,18 @@ Built buildScene(const gdb200_scene_desc *d, const gdb200_gpt_params *prm, doubl
     sensor->configure();
     scene->addChild(sensor);
     out.sampler = sampler;
+    // gdb200's chunked sample streams: chunk c of a pixel holds spp/C samples (+1 for c < spp%C) and draws from the stream
+    // that the sampler plugin's `chunk` property selects.  The reference renders them as C passes into one film.
+    const int C = std::max(1, prm->streams_per_pixel);
+    for (int c = 0; c < C && C > 1; c++) {
+        const int count = prm->spp / C + (c < prm->spp % C ? 1 : 0);
+        if (count == 0) continue;
+        Properties cp("gdb200_counter");
+        cp.setSize("sampleCount", (size_t) count); cp.setSize("seed", (size_t) prm->seed); cp.setSize("chunk", (size_t) c);
+        Sampler *cs = make<Sampler>(CreateInstance_gdb200_counter, cp);
+        cs->configure();
+        out.chunkSamplers.push_back(cs);
+    }
 
     // ---- integrator
     Properties ip(gptIntegrator ? "gpt" : "path");
@@ -291,7 +304,9 @@ void renderBlocks(Built &b, int threads, double *out5, double *blockSeconds = nu
     std::string failure;
     auto worker = [&]() {
         try {
-            ref<Sampler> sampler = b.sampler->clone();
+            std::vector<ref<Sampler> > samplers;               // one pass per sample stream of a pixel (a single one for the reference's own mode)
+            if (b.chunkSamplers.empty()) samplers.push_back(b.sampler->clone());
+            else for (size_t c = 0; c < b.chunkSamplers.size(); c++) samplers.push_back(b.chunkSamplers[c]->clone());
             ref<GPTWorkResult> block = new GPTWorkResult(rfilter, Vector2i(bs, bs), 1);
             const bool stop = false;
             for (;;) {
@@ -302,9 +317,11 @@ void renderBlocks(Built &b, int threads, double *out5, double *blockSeconds = nu
                 block->setOffset(off); block->setSize(sz);
                 std::vector<TPoint2<uint8_t> > points;
                 for (int y = 0; y < sz.y; y++) for (int x = 0; x < sz.x; x++) points.push_back(TPoint2<uint8_t>((uint8_t) x, (uint8_t) y));
-                b.gpt->renderBlock(scene, sensor, sampler.get(), block.get(), stop, points);
-                std::lock_guard<std::mutex> guard(merge);
-                total->put(block.get());
+                for (size_t c = 0; c < samplers.size(); c++) {
+                    b.gpt->renderBlock(scene, sensor, samplers[c].get(), block.get(), stop, points);   // clears the block, then accumulates
+                    std::lock_guard<std::mutex> guard(merge);
+                    total->put(block.get());
+                }
             }
         } catch (const std::exception &e) { std::lock_guard<std::mutex> guard(merge); failure = e.what(); }
     };
@@ -485,7 +502,6 @@ int gdbref_gpt_render(const gdb200_scene_desc *desc, const gdb200_gpt_params *pr
 {
     try {
         std::call_once(g_init, staticInit);
-        if (prm->streams_per_pixel > 1) throw std::runtime_error("the reference has one sample stream per pixel");
         Built b = buildScene(desc, prm, fov_x_deg, rfilter, true);
         renderBlocks(b, threads, out5);
         return 0;
@@ -499,7 +515,6 @@ int gdbref_gpt_render_timed(const gdb200_scene_desc *desc, const gdb200_gpt_para
 {
     try {
         std::call_once(g_init, staticInit);
-        if (prm->streams_per_pixel > 1) throw std::runtime_error("the reference has one sample stream per pixel");
         Built b = buildScene(desc, prm, fov_x_deg, rfilter, true);
         renderBlocks(b, threads, out5, render_seconds);
         return 0;

@@ -6,13 +6,16 @@
 #include "Solver.hpp"
 #include <string>
 
-extern "C" int ref_poisson_solve(const float *dx, const float *dy, const float *throughput,
-                                 const float *direct, int w, int h, float alpha,
-                                 const char *preset, float *out_final, float *out_seconds)
+// backend: "Auto" (what gpt.cpp leaves), "OpenMP", "Naive" or -- in the build with the reference's CUDA backend compiled in
+// (oracle/_ref/libref_poisson_cuda.so) -- "CUDA" (Solver.cpp:262-294).
+extern "C" int ref_poisson_solve_backend(const float *dx, const float *dy, const float *throughput,
+                                         const float *direct, int w, int h, float alpha,
+                                         const char *preset, const char *backend, float *out_final, float *out_seconds)
 {
     poisson::Solver::Params params;
     if (!params.setConfigPreset(preset)) return 1;
     params.alpha = alpha;
+    params.backend = backend;
     static float s_seconds; s_seconds = -1.f;
     params.setLogFunction(poisson::Solver::Params::LogFunction([](const std::string &m) {
         float v; if (sscanf(m.c_str(), "Execution time = %f s", &v) == 1) s_seconds = v; }));
@@ -24,4 +27,15 @@ extern "C" int ref_poisson_solve(const float *dx, const float *dy, const float *
     solver.exportImagesMTS(out_final);
     if (out_seconds) *out_seconds = s_seconds;
     return 0;
+}
+
+extern "C" int ref_poisson_solve(const float *dx, const float *dy, const float *throughput,
+                                 const float *direct, int w, int h, float alpha,
+                                 const char *preset, float *out_final, float *out_seconds)
+{
+#ifdef REF_POISSON_HAS_CUDA
+    return ref_poisson_solve_backend(dx, dy, throughput, direct, w, h, alpha, preset, "OpenMP", out_final, out_seconds);
+#else
+    return ref_poisson_solve_backend(dx, dy, throughput, direct, w, h, alpha, preset, "Auto", out_final, out_seconds);
+#endif
 }

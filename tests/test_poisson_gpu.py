@@ -45,6 +45,36 @@ def test_parity_vs_oracle(oracle, size, preset):
     check_parity(oracle, d, w, h, 0.2, preset, got)
 
 
+@pytest.mark.parametrize("size,preset", [((1024, 1024), "L2D"), ((1024, 1024), "L1D"), ((1920, 1080), "L2D"), ((1920, 1080), "L1D")])
+def test_parity_at_the_benchmark_sizes(oracle, size, preset):
+    """BASELINE configs C2 (1024^2) and C3 (1920x1080) buffer sizes, both presets, against the pinned restatement of the
+    reference solver (bit-identical to Solver.cpp as shipped: one thread, sequential fp32 sums; ~30 s of CPU per L1D case)."""
+    w, h = size
+    d = synth.solver_inputs(w, h, seed=77)
+    st = gdb200.Stats()
+    got = gdb200.poisson_solve(d["dx"], d["dy"], d["throughput"], d["direct"], w, h, 0.2, preset, stats=st)
+    assert st.irls_iters == (20 if preset == "L1D" else 1) and st.cg_iters == st.irls_iters * 50
+    ref = oracle.poisson(d["dx"], d["dy"], d["throughput"], d["direct"], alpha=0.2, preset=preset)
+    err = rmse(got, ref)
+    print(f"{w}x{h} {preset}: RMSE vs reference {err:.3e}, max abs {float(np.abs(got - ref).max()):.3e}, solve {st.device_ms:.2f} ms")
+    assert err <= TOL[preset], err
+
+
+@pytest.mark.parametrize("preset,iters", [("L1Q", (64, 1000)), ("L1L", (7, 20000)), ("L2Q", (1, 500))])
+def test_quality_presets_match_the_oracle(oracle, preset, iters):
+    """Solver::Params::setConfigPreset (Solver.cpp:90-164): the high-quality presets L1Q / L1L / L2Q on a small image, where
+    the CPU restatement finishes in seconds.  L1L ends its CG early on cgTolerance (1e-20 of the initial residual)."""
+    w, h = 96, 64
+    d = synth.solver_inputs(w, h, seed=3)
+    st = gdb200.Stats()
+    got = gdb200.poisson_solve(d["dx"], d["dy"], d["throughput"], d["direct"], w, h, 0.2, preset, stats=st)
+    ref = oracle.poisson(d["dx"], d["dy"], d["throughput"], d["direct"], alpha=0.2, preset=preset)
+    exact = oracle.poisson_acc64(d["dx"], d["dy"], d["throughput"], d["direct"], alpha=0.2, preset=preset)
+    assert st.irls_iters == iters[0] and st.cg_iters <= iters[0] * iters[1]
+    floor = rmse(ref, exact)
+    assert rmse(got, ref) <= max(2e-5, 3.0 * floor), (rmse(got, ref), floor)
+
+
 @pytest.mark.parametrize("size", [(1, 1), (2, 1), (1, 5), (3, 3), (4, 4), (5, 2), (67, 3)])
 def test_tiny_and_ragged_sizes(oracle, size):
     w, h = size

@@ -171,3 +171,25 @@ def test_committed_reference_fixture_is_current(reference):
     assert sorted(golden) == sorted(reference)
     for k in reference:
         np.testing.assert_allclose(golden[k], reference[k], rtol=0, atol=1e-15, err_msg=k)
+
+
+@pytest.mark.parametrize("streams,spp", [(2, 4), (3, 7), (8, 8)])
+def test_chunked_sample_streams_match_the_reference(oracle, emu, streams, spp):
+    """gdb200's streams_per_pixel = C: the film of C passes of the REFERENCE integrator, pass c drawing from the `chunk` = c
+    stream of the gdb200_counter sampler plugin with sampleCount = spp/C (+1 for c < spp%C), summed in one film.  That is what
+    the bench's headline mode (8 streams per pixel) computes, so it is pinned against the reference like the one-stream mode."""
+    if not RefMitsuba.available() or os.environ.get("GDB200_NO_REF"):
+        pytest.skip("needs the compiled reference")
+    desc = scenes.cbox_glossy(W, H)
+    prm = scenes.default_params(spp=spp, seed=SEED, ref_uninit_measure=True)
+    prm.streams_per_pixel = streams
+    ref = RefMitsuba().gpt(desc, prm, threads=2)
+    got, _, cnt = oracle.gpt(desc, prm, threads=1)
+    dev, _ = emu.gpt_staged(desc, prm)
+    assert cnt[0] == W * H * spp
+    for k in ref:
+        scale = max(float(np.abs(ref[k]).mean()), 1e-12)
+        assert np.abs(got[k] - ref[k]).max() <= 1e-11 * scale, (k, "restatement")
+        assert np.abs(dev[k] - ref[k]).max() <= 1e-11 * scale, (k, "device source")
+    one = scenes.default_params(spp=spp, seed=SEED, ref_uninit_measure=True)
+    assert not np.allclose(RefMitsuba().gpt(desc, one)["-throughput"], ref["-throughput"])      # the chunks really draw other numbers
