@@ -185,7 +185,7 @@ int ensureWorkspace(Workspace &ws, int nSlots, bool fused)
     } else {
         for (int q = 0; q < 2; q++) {
             if (e == cudaSuccess) e = cudaMalloc(&ws.rays[q], sizeof(double) * 8 * 5 * n);
-            if (e == cudaSuccess) e = cudaMalloc(&ws.rayOwner[q], sizeof(int) * 5 * n);
+            if (e == cudaSuccess) e = cudaMalloc(&ws.rayOwner[q], sizeof(int) * (5 * n + 4));      // + the 16-byte rounding of a bulk copy
         }
         if (e == cudaSuccess) e = cudaMalloc(&ws.rayCount, sizeof(int) * 2);
         if (e == cudaSuccess) e = cudaMalloc(&ws.qKey, sizeof(int) * n);
@@ -271,8 +271,8 @@ int renderStaged(gdb200_scene *s, const GptArgs &a, Marks &marks, gdb200_stats *
         g.resolve = persistentGrid(gpt_stage_kernel<SK_RESOLVE>, kStageThreads, s->device);
         g.prepare = persistentGrid(gpt_stage_kernel<SK_PREPARE>, kStageThreads, s->device);
         g.generate = persistentGrid(gpt_stage_kernel<SK_GENERATE>, kStageThreads, s->device);
-        g.castNearest = persistentGrid(gpt_cast_kernel<false>, 128, s->device);
-        g.castAny = persistentGrid(gpt_cast_kernel<true>, 128, s->device);
+        g.castNearest = persistentGrid(gpt_cast_kernel<false>, kCastThreads, s->device);
+        g.castAny = persistentGrid(gpt_cast_kernel<true>, kCastThreads, s->device);
     }
     const int compactBlocks = (nSlots + 255) / 256;
     gpt_stage_init_kernel<<<(std::max(nSlots, kStageBuckets) + 255) / 256, 256>>>(a);
@@ -280,10 +280,19 @@ int renderStaged(gdb200_scene *s, const GptArgs &a, Marks &marks, gdb200_stats *
     // a sample takes 2 ticks + (1 or 2) per bounce; streams are consumed sequentially by their slot
     const long long maxTicks = ((long long)spp * 8192 + 131072) * std::max(1, a.nStreams / std::max(1, nSlots) + 1);
     size_t firstMark = marks.used;
+    const char *printTick = getenv("GDB200_PRINT_QUEUES");      // profiling aid: queue lengths of one tick on stderr (pairs an ncu capture of that tick with its work)
     for (long long tick = 0;; tick++) {
         if (tick > maxTicks) return set_error(GDB200_ERR_CUDA, "wavefront did not drain after %lld ticks", tick);
         marks.mark();
         gpt_stage_compact_kernel<0><<<compactBlocks, 256>>>(a);
+        if (printTick && tick == atoll(printTick)) {
+            int q[kStageBuckets], r[2];
+            cudaMemcpy(q, a.qCount, sizeof(q), cudaMemcpyDeviceToHost);
+            int shade[3] = {0, 0, 0};
+            for (int st = 0; st < 3; st++) for (int t = 0; t < kBsdfTypes; t++) shade[st] += q[QA_SHADE0 + st * kBsdfTypes + t];
+            fprintf(stderr, "gdb200 tick %lld: primary %d shade0 %d shade1 %d shade2 %d resolve %d (slots %d)\n", tick, q[QA_PRIMARY], shade[0], shade[1], shade[2], q[QA_RESOLVE], nSlots);
+            (void)r;
+        }
         marks.mark();
         gpt_stage_kernel<SK_PRIMARY><<<g.primary, kStageThreads>>>(a);
         marks.mark();
@@ -299,8 +308,8 @@ int renderStaged(gdb200_scene *s, const GptArgs &a, Marks &marks, gdb200_stats *
         marks.mark();
         gpt_stage_kernel<SK_GENERATE><<<g.generate, kStageThreads>>>(a);
         marks.mark();
-        gpt_cast_kernel<false><<<g.castNearest, 128>>>(a);
-        gpt_cast_kernel<true><<<g.castAny, 128>>>(a);
+        gpt_cast_kernel<false><<<g.castNearest, kCastThreads>>>(a);
+        gpt_cast_kernel<true><<<g.castAny, kCastThreads>>>(a);
         marks.mark();
         launches += 11;
         if ((tick & 15) == 15) {

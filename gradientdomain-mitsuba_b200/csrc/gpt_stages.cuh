@@ -109,23 +109,80 @@ GDB_D Hit loadHit(const GptArgs &a, int id, int slot)
 GDB_D bool loadOccluded(const GptArgs &a, int id, int slot) { return reinterpret_cast<const int *>(REC(a, XR_OCCLUDED, slot))[id] != 0; }
 
 // ------------------------------------------------------------------ cast: the only kernels that intersect
-template <bool Any>
-__global__ void __launch_bounds__(128) gpt_cast_kernel(const GptArgs a)
+// The ray queue is dense, so a CTA's batch of rays is one contiguous block of memory: it is brought into shared memory by the
+// TMA unit as a 1-D bulk copy (cp.async.bulk, completion on an mbarrier), double buffered -- thread 0 issues the copy of the
+// CTA's next batch before the threads start on the current one, so the loads of batch k+1 run under the intersection
+// arithmetic of batch k and cost the warps no load instructions and no registers.
+constexpr int kCastThreads = 128;
+#ifndef GDB200_EMU
+GDB_D unsigned smemAddr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+GDB_D void mbarInit(unsigned long long *bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count) : "memory"); }
+GDB_D void mbarExpectTx(unsigned long long *bar, unsigned bytes)
 {
-    const int n = min(a.rayCount[Any ? 1 : 0], a.rayCapacity);
-    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
-        const int owner = a.rayOwner[Any ? 1 : 0][r], slot = owner >> 3, id = owner & 7;
-        if (owner < 0) continue;                                                     // reserved, not cast
-        const double2 *p = reinterpret_cast<const double2 *>(a.rays[Any ? 1 : 0] + ((size_t)r << 3));
-        const double2 q0 = p[0], q1 = p[1], q2 = p[2], q3 = p[3];
-        Ray ray; ray.o = mk(q0.x, q0.y, q1.x); ray.d = mk(q1.y, q2.x, q2.y); ray.mint = q3.x; ray.maxt = q3.y;
-        if (Any) reinterpret_cast<int *>(REC(a, XR_OCCLUDED, slot))[id] = rayOccludedImpl(ray) ? 1 : 0;
-        else {
-            Hit h; castClosest(ray, h);
-            double2 *o = reinterpret_cast<double2 *>(REC(a, hitRec(id), slot));
-            o[0] = make_double2(h.t, h.u); o[1] = make_double2(h.v, (Float)((h.kind << 28) | h.index));
-        }
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+GDB_D void mbarWait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile("{\n .reg .pred p;\n WAIT:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE;\n bra WAIT;\n DONE:\n}" ::"r"(smemAddr(bar)), "r"(parity) : "memory");
+}
+GDB_D void bulkLoad(void *dstShared, const void *srcGlobal, unsigned bytes, unsigned long long *bar)       // bytes: multiple of 16
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smemAddr(dstShared)), "l"(__cvta_generic_to_global(srcGlobal)), "r"(bytes), "r"(smemAddr(bar)) : "memory");
+}
+#endif
+
+// One queue entry: the search, and its answer into the owner slot's block.
+template <bool Any>
+GDB_D void castOne(const GptArgs &a, int owner, const double *q)
+{
+    if (owner < 0) return;                                                           // reserved, not cast
+    const int slot = owner >> 3, id = owner & 7;
+    Ray ray; ray.o = mk(q[0], q[1], q[2]); ray.d = mk(q[3], q[4], q[5]); ray.mint = q[6]; ray.maxt = q[7];
+    if (Any) reinterpret_cast<int *>(REC(a, XR_OCCLUDED, slot))[id] = rayOccludedImpl(ray) ? 1 : 0;
+    else {
+        Hit h; castClosest(ray, h);
+        double2 *o = reinterpret_cast<double2 *>(REC(a, hitRec(id), slot));
+        o[0] = make_double2(h.t, h.u); o[1] = make_double2(h.v, (Float)((h.kind << 28) | h.index));
     }
+}
+
+template <bool Any>
+__global__ void __launch_bounds__(kCastThreads) gpt_cast_kernel(const GptArgs a)
+{
+    constexpr int Q = Any ? 1 : 0;
+    const int n = min(a.rayCount[Q], a.rayCapacity);
+#ifdef GDB200_EMU
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) castOne<Any>(a, a.rayOwner[Q][r], a.rays[Q] + ((size_t)r << 3));
+#else
+    const int nBatches = (n + kCastThreads - 1) / kCastThreads;
+    __shared__ __align__(128) double s_rays[2][kCastThreads * 8];
+    __shared__ __align__(16) int s_owner[2][kCastThreads];
+    __shared__ __align__(8) unsigned long long s_bar[2];
+    if (threadIdx.x == 0) {
+        mbarInit(&s_bar[0], 1); mbarInit(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto fetch = [&](int batch, int stage) {      // thread 0: the batch's rays (64 B each) and owners (4 B each, the copy padded to 16 B)
+        const int cnt = min(kCastThreads, n - batch * kCastThreads);
+        const unsigned rayBytes = (unsigned)cnt * 64u, ownerBytes = ((unsigned)cnt * 4u + 15u) & ~15u;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // the stage was last read through the generic proxy
+        mbarExpectTx(&s_bar[stage], rayBytes + ownerBytes);
+        bulkLoad(&s_rays[stage][0], a.rays[Q] + ((size_t)batch * kCastThreads << 3), rayBytes, &s_bar[stage]);
+        bulkLoad(&s_owner[stage][0], a.rayOwner[Q] + (size_t)batch * kCastThreads, ownerBytes, &s_bar[stage]);
+    };
+    unsigned parity[2] = {0u, 0u};
+    int stage = 0;
+    if (threadIdx.x == 0 && (int)blockIdx.x < nBatches) fetch(blockIdx.x, 0);
+    for (int batch = blockIdx.x; batch < nBatches; batch += gridDim.x, stage ^= 1) {
+        if (threadIdx.x == 0 && batch + (int)gridDim.x < nBatches) fetch(batch + gridDim.x, stage ^ 1);
+        mbarWait(&s_bar[stage], parity[stage]); parity[stage] ^= 1u;
+        const int r = batch * kCastThreads + threadIdx.x;
+        castOne<Any>(a, r < n ? s_owner[stage][threadIdx.x] : -1, &s_rays[stage][threadIdx.x << 3]);
+        __syncthreads();                          // every thread is done with the stage before the TMA unit refills it
+    }
+#endif
 }
 
 // ------------------------------------------------------------------ generate
