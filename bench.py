@@ -182,7 +182,7 @@ def main():
                           if args.workload == "gpt-c2" else f"{scene_name} {W}x{H} @ {spp} spp, G-PT {recon}",
               "scene": "synthetic Cornell box + GGX spheres (gdb200.scenes)", "sampler": f"gdb200_counter seed 0, {args.streams} sample streams per pixel",
               "maxDepth": -1, "rrDepth": 5, "shiftThreshold": 0.001, "alpha": 0.2,
-              "parallelism": f"interleaved 16-row bands x{world}, one NCCL all-reduce of the film accumulators" if world > 1 else "1 GPU",
+              "parallelism": f"{world} cost-balanced row strips, one NCCL all-reduce of the strip-boundary rows + strips sent to rank 0 (develop + solve)" if world > 1 else "1 GPU",
               "l2_flush": "per-step working set (2 KB of wavefront state per resident path slot, 8 M slots = 16 GB, + ray queues + 168 MB film) exceeds the 126 MB L2"}
 
     # ------------------------------------------------------------------ reference arm (CPU)
@@ -218,21 +218,45 @@ def main():
     gdb200.lib().gdb200_set_device(local_rank)
     scene = gdb200.Scene(desc)
     plan = gdb200.PoissonPlan(W, H) if rank == 0 else None
-    bands = tiles.band_spec(rank, world, 16) if world > 1 else None    # interleaved 16-row bands: balanced strong scaling
+    # N > 1: contiguous row strips.  A sample reaches at most halo rows beyond its strip, so ONE all-reduce of
+    # the packed rows around the strip boundaries completes the film; rank 0 then receives the strip interiors, develops and
+    # solves.  The strips are cost-balanced during the warm-up steps (tiles.rebalance): rows differ in cost, and rank 0 traces
+    # less because it alone develops and solves afterwards.
+    bounds = tiles.even_bounds(H, world)
+    halo = tiles.halo_rows(desc.rfilter_radius)
     acc = scene.accumulators() if world > 1 else None
+    phase = {"exchange_ms": 0.0, "develop_ms": 0.0, "solve_wall_ms": 0.0}
     agg = {"bounce_ms": 0.0, "generate_ms": 0.0, "compact_ms": 0.0, "state_bytes": 0.0, "bounce_launches": 0, "trace_ms": 0.0, "path_bounces": 0.0,
            "cast_ms": 0.0, "prepare_ms": 0.0, "resolve_ms": 0.0, "primary_ms": 0.0,
            "solve_ms": 0.0, "launches": 0, "samples": 0.0, "rays": 0.0, "exchange_bytes": 0}
 
-    def step(timed):
-        integ.trace(scene, spp=spp, seed=0, bands=bands, download=False, preview=False, streams=args.streams)   # "-final" comes from the reconstruction
+    def step(timed, balance=False):
+        nonlocal bounds
+        rows = (bounds[rank], bounds[rank + 1]) if world > 1 else None
+        integ.trace(scene, spp=spp, seed=0, rows=rows, download=False, preview=False, streams=args.streams)   # "-final" comes from the reconstruction
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
+        nb = 0
         if world > 1:
-            nb = tiles.exchange_all(acc, world)
-            if rank == 0:
-                scene.develop(download=False)
+            nb = tiles.exchange_boundaries(acc, world, halo=halo, bounds=bounds)
+            nb += tiles.gather_strips(acc, rank, world, bounds=bounds, first_buffer=1)
+        ev[1].record()
+        if world > 1 and rank == 0:
+            scene.develop(download=False)
+        ev[2].record()
         if rank == 0:
             integ.reconstruct(scene, plan, download=False)
+        ev[3].record()
+        if balance and world > 1:          # warm-up only: every rank learns every strip's tracing time and rank 0's tail
+            torch.cuda.synchronize()
+            mine = torch.tensor([integ.stats.device_ms, ev[1].elapsed_time(ev[3]) if rank == 0 else 0.0], device="cuda", dtype=torch.float64)
+            every = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(every, mine)
+            bounds = tiles.rebalance(bounds, [float(t[0]) for t in every], [float(t[1]) for t in every])
         if timed:
+            torch.cuda.synchronize()
+            phase["exchange_ms"] += ev[0].elapsed_time(ev[1]); phase["develop_ms"] += ev[1].elapsed_time(ev[2])
+            phase["solve_wall_ms"] += ev[2].elapsed_time(ev[3])
             st = integ.stats
             for k in ("bounce_ms", "generate_ms", "compact_ms", "state_bytes", "bounce_launches", "samples", "rays", "path_bounces",
                       "cast_ms", "prepare_ms", "resolve_ms", "primary_ms"):
@@ -250,7 +274,7 @@ def main():
         torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        step(False)
+        step(False, balance=True)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -292,8 +316,9 @@ def main():
             out = integ.render(sc, spp=spp, seed=0, streams=args.streams, out=host_out, plan=plan)   # trace + develop + D2H of 5 buffers + solve + D2H of final
             sc.close()
         else:
-            integ.trace(scene, spp=spp, seed=0, bands=bands, download=False, preview=False, streams=args.streams)
-            tiles.exchange_all(acc, world)
+            integ.trace(scene, spp=spp, seed=0, rows=(bounds[rank], bounds[rank + 1]), download=False, preview=False, streams=args.streams)
+            tiles.exchange_boundaries(acc, world, halo=halo, bounds=bounds)
+            tiles.gather_strips(acc, rank, world, bounds=bounds, first_buffer=1)
             if rank == 0:
                 out = scene.develop(download=True, out=host_out)
                 out["-final"][...] = integ.reconstruct(scene, plan, download=True)
@@ -348,6 +373,8 @@ def main():
                 "tracer_ms": {k: round(agg[k + "_ms"] / args.steps, 1) for k in ("bounce", "cast", "prepare", "resolve", "primary", "generate", "compact")}}
         if world > 1:
             line["exchange_bytes_per_step"] = int(agg["exchange_bytes"] / args.steps)
+            line["strip_bounds"] = bounds
+        line["rank0_phase_ms"] = {k: round(v / args.steps, 2) for k, v in phase.items()}
         if world == 1:
             try:                                  # a reported baseline: it must never cost the measured line
                 rate, dt, kind, note = cpu_tracer_rate(desc, lambda s: integ.params(s, 0), args.cpu_spp, cores)

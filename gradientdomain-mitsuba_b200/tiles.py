@@ -32,21 +32,55 @@ def strip_rows(height, rank, world):
     return y0, y0 + base + (1 if rank < rem else 0)
 
 
-def boundary_rows(height, world, halo=HALO):
-    """Row indices touched by more than one rank: +-halo around every strip boundary."""
+def even_bounds(height, world):
+    """Strip boundaries [y_0 = 0, y_1, ..., y_world = height] of strip_rows."""
+    return [strip_rows(height, r, world)[0] for r in range(world)] + [height]
+
+
+def boundary_rows(height, world, halo=HALO, bounds=None):
+    """Row indices touched by more than one rank: +-halo around every strip boundary (bounds: explicit strip boundaries,
+    default the even split)."""
+    bounds = even_bounds(height, world) if bounds is None else bounds
     rows = []
-    for r in range(1, world):
-        y = strip_rows(height, r, world)[0]
+    for y in bounds[1:-1]:
         rows.extend(range(max(0, y - halo), min(height, y + halo)))
     return sorted(set(rows))
 
 
-def exchange_boundaries(acc, world, group=None, halo=HALO):
+def rebalance(bounds, cost_ms, extra_ms=None, min_rows=4):
+    """Cost-balanced strip boundaries.  cost_ms[r]: measured tracing time of rank r on its current strip [bounds[r], bounds[r+1])
+    (the per-row cost is taken as constant inside a strip: floor rows cost more than rows under the light, so even strips
+    finish at different times); extra_ms[r]: work that rank r alone does after the exchange (rank 0: develop + the Poisson
+    solve) and that the other ranks would otherwise wait out.  Returns boundaries for which cost + extra is equal on all
+    ranks.  Deterministic: every rank computes the same boundaries from the all-gathered times."""
+    world = len(bounds) - 1
+    extra = [0.0] * world if extra_ms is None else [float(e) for e in extra_ms]
+    height = bounds[-1]
+    row_cost = []
+    for r in range(world):
+        n = max(1, bounds[r + 1] - bounds[r])
+        row_cost.extend([max(float(cost_ms[r]), 1e-6) / n] * (bounds[r + 1] - bounds[r]))
+    total = sum(row_cost) + sum(extra)
+    target = total / world                       # finishing time of every rank
+    new, y, acc = [0], 0, 0.0
+    for r in range(world - 1):
+        budget = max(target - extra[r], 0.0)     # tracing time rank r may spend
+        start = y
+        while y < height - (world - 1 - r) * min_rows and (acc + row_cost[y] <= budget or y - start < min_rows):
+            acc += row_cost[y]
+            y += 1
+        new.append(y)
+        acc = 0.0
+    new.append(height)
+    return new
+
+
+def exchange_boundaries(acc, world, group=None, halo=HALO, bounds=None):
     """acc: [5, H, W, 4] accumulator film of this rank. Sums the boundary rows over all ranks
     in place with a single all-reduce of the packed rows (halo = halo_rows(filter radius))."""
     if world <= 1:
         return 0
-    rows = boundary_rows(acc.shape[1], world, halo)
+    rows = boundary_rows(acc.shape[1], world, halo, bounds)
     if not rows:
         return 0
     idx = torch.as_tensor(rows, device=acc.device)
@@ -56,23 +90,28 @@ def exchange_boundaries(acc, world, group=None, halo=HALO):
     return packed.numel() * packed.element_size()
 
 
-def gather_strips(acc, rank, world, group=None):
+def gather_strips(acc, rank, world, group=None, bounds=None, first_buffer=0):
     """After exchange_boundaries: rank 0 receives every rank's strip interior so that its film is
-    the complete image. Returns the bytes this rank sent."""
+    the complete image. Returns the bytes this rank sent.  first_buffer = 1 leaves out the "-final" preview accumulator
+    (buffer 0), which stays empty when a reconstruction will overwrite it (skip_preview)."""
     if world <= 1:
         return 0
+    acc = acc[first_buffer:]
     h = acc.shape[1]
-    sizes = [strip_rows(h, r, world) for r in range(world)]
+    bounds = even_bounds(h, world) if bounds is None else bounds
+    sizes = [(bounds[r], bounds[r + 1]) for r in range(world)]
     y0, y1 = sizes[rank]
-    mine = acc[:, y0:y1].contiguous()
-    if rank == 0:
-        bufs = [torch.empty((acc.shape[0], b - a, acc.shape[2], acc.shape[3]), dtype=acc.dtype, device=acc.device)
-                for (a, b) in sizes]
-        dist.gather(mine, bufs, dst=0, group=group)
-        for (a, b), t in zip(sizes[1:], bufs[1:]):
-            acc[:, a:b].copy_(t)
+    if rank == 0:                                  # strips may differ in height (rebalance): point-to-point, batched so all are in flight at once
+        bufs = [torch.empty((acc.shape[0], b0 - a0, acc.shape[2], acc.shape[3]), dtype=acc.dtype, device=acc.device) for (a0, b0) in sizes[1:]]
+        ops = [dist.P2POp(dist.irecv, t, r, group) for r, t in zip(range(1, world), bufs)]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        for (a0, b0), t in zip(sizes[1:], bufs):
+            acc[:, a0:b0].copy_(t)
         return 0
-    dist.gather(mine, None, dst=0, group=group)
+    mine = acc[:, y0:y1].contiguous()
+    for req in dist.batch_isend_irecv([dist.P2POp(dist.isend, mine, 0, group)]):
+        req.wait()
     return mine.numel() * mine.element_size()
 
 

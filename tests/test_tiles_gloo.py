@@ -25,6 +25,24 @@ def test_strip_partition_covers_image():
     assert tiles.boundary_rows(64, 1) == []
 
 
+def test_cost_balanced_strips():
+    """tiles.rebalance: strips of equal measured cost, with the work that rank 0 does alone (develop + solve) taken off its
+    share; boundaries stay ordered, keep a minimum height and cover the image."""
+    b = tiles.even_bounds(1024, 4)
+    assert b == [0, 256, 512, 768, 1024] and tiles.boundary_rows(1024, 4, bounds=b) == tiles.boundary_rows(1024, 4)
+    nb = tiles.rebalance(b, [100.0, 100.0, 100.0, 100.0])
+    assert nb == b                                                   # already balanced
+    nb = tiles.rebalance(b, [50.0, 100.0, 100.0, 150.0])             # cheap rows at the top, expensive at the bottom
+    assert nb[0] == 0 and nb[-1] == 1024 and all(nb[i] < nb[i + 1] for i in range(4))
+    cost = lambda bb: [sum(([50.0] * 256 + [100.0] * 512 + [150.0] * 256)[bb[r]:bb[r + 1]]) / 256 for r in range(4)]  # noqa: E731
+    c = cost(nb)
+    assert max(c) - min(c) <= 0.02 * sum(c) / 4, c
+    nb0 = tiles.rebalance(b, [100.0] * 4, extra_ms=[40.0, 0, 0, 0])  # rank 0 solves afterwards: it traces less
+    assert nb0[1] < 256 and abs((nb0[1] * 100.0 / 256 + 40.0) - (nb0[2] - nb0[1]) * 100.0 / 256) <= 2.0
+    tiny = tiles.rebalance([0, 4, 8, 12], [1.0, 1000.0, 1.0])
+    assert tiny[0] == 0 and tiny[-1] == 12 and all(tiny[i + 1] - tiny[i] >= 1 for i in range(3))
+
+
 def _oracle_acc(orc, desc, prm):
     """Raw accumulators [5,h,w,4] from the oracle: developed value * weight, weight."""
     out, wts, _ = orc.gpt(desc, prm, threads=2)
@@ -44,10 +62,11 @@ def _worker(rank, world, port, ret, rfilter="box"):
         w = h = 24
         desc = scenes.cbox_diffuse(w, h, rfilter=rfilter)
         prm = scenes.default_params(spp=2, seed=9)
-        prm.y_begin, prm.y_end = tiles.strip_rows(h, rank, world)
+        bounds = tiles.even_bounds(h, world) if rfilter == "box" else [0, 9, h]      # second case: uneven (rebalanced) strips
+        prm.y_begin, prm.y_end = bounds[rank], bounds[rank + 1]
         acc = torch.from_numpy(_oracle_acc(orc, desc, prm))
-        tiles.exchange_boundaries(acc, world, halo=tiles.halo_rows(desc.rfilter_radius))
-        tiles.gather_strips(acc, rank, world)
+        tiles.exchange_boundaries(acc, world, halo=tiles.halo_rows(desc.rfilter_radius), bounds=bounds)
+        tiles.gather_strips(acc, rank, world, bounds=bounds)
         if rank == 0:
             ret["acc"] = acc.numpy().copy()
     finally:
