@@ -305,7 +305,11 @@ public:
 		m_reconstructL1 = props.getBoolean("reconstructL1", true);
 		m_reconstructL2 = props.getBoolean("reconstructL2", false);
 		m_reconstructAlpha = (Float) props.getFloat("reconstructAlpha", Float(0.2));
+		/* sampler seed: taken from the scene's gdb200_counter sampler (plugin/samplers/gdb200_counter.cpp) at render time unless given here */
+		m_hasSeed = props.hasProperty("seed");
 		m_seed = (uint64_t) props.getSize("seed", 0);
+		/* parity switch, see GDB200_GPT_REF_UNINIT_MEASURE in include/gdb200.h (gpt.cpp:957) */
+		m_refUninitMeasure = props.getBoolean("refUninitMeasure", false);
 		/* gdb200 extension: sample streams per pixel (include/gdb200.h: gdb200_gpt_params.streams_per_pixel); 1 = the reference's single stream */
 		m_streamsPerPixel = (int) props.getSize("streamsPerPixel", 1);
 		if (m_reconstructL1 && m_reconstructL2)
@@ -323,7 +327,7 @@ public:
 		m_reconstructL1 = stream->readBool();
 		m_reconstructL2 = stream->readBool();
 		m_reconstructAlpha = stream->readFloat();
-		m_seed = 0;
+		m_seed = 0; m_hasSeed = false; m_refUninitMeasure = false;
 		m_streamsPerPixel = 1;
 	}
 
@@ -364,6 +368,9 @@ public:
 		params.shift_threshold = m_shiftThreshold;
 		params.spp = (int) sampler->getSampleCount();
 		params.seed = m_seed;
+		if (!m_hasSeed && sampler->getProperties().hasProperty("seed"))       /* the gdb200_counter sampler of the scene */
+			params.seed = (uint64_t) sampler->getProperties().getSize("seed", 0);
+		params.flags = m_refUninitMeasure ? GDB200_GPT_REF_UNINIT_MEASURE : 0;
 		params.streams_per_pixel = m_streamsPerPixel;
 		params.skip_preview = (m_reconstructL1 || m_reconstructL2) ? 1 : 0;   /* "-final" is replaced by the reconstruction */
 
@@ -438,7 +445,7 @@ private:
 	void release() { if (m_scene) { gdb200_scene_destroy(m_scene); m_scene = NULL; } }
 
 	Float m_shiftThreshold, m_reconstructAlpha;
-	bool m_reconstructL1, m_reconstructL2;
+	bool m_reconstructL1, m_reconstructL2, m_hasSeed, m_refUninitMeasure;
 	uint64_t m_seed;
 	int m_streamsPerPixel;
 	gdb200_scene *m_scene;

@@ -13,7 +13,7 @@
 //   * `chunk` (default 0) selects one of gdb200's chunked streams (gdb200_gpt_params.streams_per_pixel = C > 1): chunk 0
 //     is the pixel's stream, chunk c > 0 an independently re-keyed one (the key of streamInfo() in csrc/gpt_kernels.cuh).
 //     The Sampler API gives no per-sample hook that gpt calls, so a C-stream film is C passes of the reference, pass c with
-//     <integer name="chunk" value="c"/> and sampleCount = spp/C (+1 for c < spp%C), films summed (oracle/ref_gpt_shim.cpp).
+//     <integer name="chunk" value="c"/> and sampleCount = spp/C (+1 for c < spp%C), films summed (the test suite drives the reference that way).
 //
 // Built inside a Mitsuba tree.  The test suite compiles it against the reference's real Sampler interface and
 // feeds the reference's own gpt.cpp with it; plugin/stub/mitsuba_stub.h is a syntax check where the reference tree is absent.

@@ -98,3 +98,45 @@ def test_flattening_a_mitsuba_scene_gives_back_the_description(flatten, oracle, 
     for k in ref:
         scale = max(float(np.abs(ref[k]).mean()), 1e-12)
         assert np.abs(out[k] - ref[k]).max() <= 1e-9 * scale, (name, k)
+
+
+# ------------------------------------------------------------------ render() of the plugin under Mitsuba's own host objects
+@pytest.mark.gpu
+@pytest.mark.parametrize("scene_name,recon", [("cbox_glossy", "L2"), ("cbox_mesh_lights", "L1"), ("cbox_env", None)])
+def test_plugin_render_through_mitsuba_host_objects(oracle, tmp_path, scene_name, recon):
+    """GDB200GradientPathIntegrator::render (plugin/gpt_plugin.cpp) called the way Mitsuba's RenderJob calls an integrator:
+    a real Scene with sensor, MultiFilm and the gdb200_counter sampler (the reference's own classes, built by
+    oracle/_ref/libref_mitsuba.so), registered as Scheduler resources, then MultiFilm::develop writing the five PFM files
+    (oracle/ref_plugin_roundtrip.cpp: gdbref_plugin_render).  Nothing of the Python API of this package is on that path; the
+    files are compared with the STOCK reference `gpt` integrator on the same Scene and sampler, and "-final" with the reference
+    solver on the reference's buffers."""
+    from conftest import RefMitsuba
+    from gdb200 import pfm
+    if not os.path.exists(LIB) or not os.path.exists(RefMitsuba.PATH):
+        pytest.skip("needs oracle/_ref/libref_plugin_roundtrip.so and libref_mitsuba.so (builds of /root/reference)")
+    lib = ctypes.CDLL(LIB)
+    lib.gdbref_roundtrip_last_error.restype = ctypes.c_char_p
+    w, h, spp = 48, 40, 6
+    desc = getattr(scenes, scene_name)(w, h)
+    prm = scenes.default_params(spp=spp, seed=11, ref_uninit_measure=True)
+    fov, rfilter = scenes.mitsuba_sensor_args(desc)
+    dest = str(tmp_path / "out")
+    rc = lib.gdbref_plugin_render(ctypes.byref(desc), ctypes.byref(prm), ctypes.c_double(fov), rfilter.encode(),
+                                  int(recon == "L1"), int(recon == "L2"), ctypes.c_double(0.2), dest.encode())
+    assert rc == 0, lib.gdbref_roundtrip_last_error().decode()
+    got = pfm.load_multifilm(dest)                                  # <dest>-final.pfm, -throughput, -dx, -dy, -direct
+    ref = RefMitsuba().gpt(desc, prm, threads=2)                    # the reference's own gpt.cpp on the same scene bytes
+    for name in ("-throughput", "-dx", "-dy", "-direct"):
+        r32 = ref[name].astype(np.float32)
+        scale = max(float(np.abs(r32).mean()), 1e-12)
+        assert np.abs(got[name] - r32).max() <= 2e-6 * max(scale, float(np.abs(r32).max())), name      # PFM holds float32
+    if recon:
+        f32 = {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in ref.items()}
+        want = oracle.poisson(f32["-dx"], f32["-dy"], f32["-throughput"], f32["-direct"], alpha=0.2, preset=recon + "D")
+        exact = oracle.poisson_acc64(f32["-dx"], f32["-dy"], f32["-throughput"], f32["-direct"], alpha=0.2, preset=recon + "D")
+        floor = float(np.sqrt(np.mean((want.astype(np.float64) - exact) ** 2)))
+        err = float(np.sqrt(np.mean((got["-final"].astype(np.float64) - want) ** 2)))
+        assert err <= max(1e-5, 2.0 * floor), (err, floor)
+    else:                                                           # no reconstruction: "-final" is the preview accumulated by the tracer
+        r32 = ref["-final"].astype(np.float32)
+        assert np.abs(got["-final"] - r32).max() <= 2e-6 * float(np.abs(r32).max())
