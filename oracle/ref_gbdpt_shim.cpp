@@ -11,6 +11,8 @@
 #include <mitsuba/render/renderqueue.h>
 #include <mitsuba/core/sched.h>
 #include <mitsuba/core/plugin.h>
+#include <mitsuba/core/logger.h>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 #include "../include/gdb200.h"
@@ -24,7 +26,6 @@ extern "C" const char *gdbref_gpt_last_error();
 
 namespace {
 std::string g_error;
-std::once_flag g_workers;
 }
 
 extern "C" const char *gdbref_gbdpt_last_error() { return g_error.c_str(); }
@@ -39,11 +40,12 @@ extern "C" int gdbref_gbdpt_render(const gdb200_scene_desc *desc, const gdb200_g
     Scene *scene = static_cast<Scene *>(handle);
     int rc = 0;
     try {
+        if (getenv("GDBREF_LOG")) Thread::getThread()->getLogger()->setLogLevel(EInfo);   // the library keeps Mitsuba's log at EError otherwise
         Scheduler *sched = Scheduler::getInstance();
-        std::call_once(g_workers, [&]() {
-            for (int i = 0; i < std::max(1, threads); i++) sched->registerWorker(new LocalWorker(i, formatString("wrk%i", i)));
-            sched->start();
-        });
+        std::vector<ref<Worker> > workers;                                          // started and stopped per call: no thread outlives it
+        for (int i = 0; i < std::max(1, threads); i++) { workers.push_back(new LocalWorker(i, formatString("wrk%i", i))); sched->registerWorker(workers.back()); }
+        sched->start();
+        struct StopScheduler { Scheduler *s; std::vector<ref<Worker> > &w; ~StopScheduler() { s->stop(); for (size_t i = 0; i < w.size(); i++) s->unregisterWorker(w[i]); } } stop = {sched, workers};
         Properties ip("gbdpt");
         ip.setInteger("maxDepth", prm->max_depth); ip.setInteger("rrDepth", prm->rr_depth);
         ip.setFloat("shiftThreshold", prm->shift_threshold); ip.setBoolean("lightImage", light_image != 0);

@@ -229,9 +229,33 @@ template <typename S, typename D> struct CastConverter : FormatConverter {
                  Float multiplier, Spectrum::EConversionIntent, int channelCount) const
     {
         const bool sameLayout = sf == df || ((sf == Bitmap::ERGB || sf == Bitmap::ESpectrum) && (df == Bitmap::ERGB || df == Bitmap::ESpectrum));
-        if (!sameLayout || sg != dg || multiplier != 1) unsupported("this Bitmap::convert (layout, gamma or scale change)");
-        const size_t n = count * (size_t) channelsOf(sf, channelCount);
         const S *s = static_cast<const S *>(src); D *d = static_cast<D *>(dst);
+        if (sg != dg) unsupported("this Bitmap::convert (gamma change)");
+        if (sf == Bitmap::ESpectrumAlphaWeight && (df == Bitmap::ERGB || df == Bitmap::ESpectrum)) {
+            // developing a film: value * (1 / weight), fmtconv.cpp:1036-1045 (ESpectrum) and the ERGB case above it
+            // (toLinearRGB is the identity in the SPECTRUM_SAMPLES = 3 build)
+            for (size_t i = 0; i < count; i++, s += 5, d += 3) {
+                const Float weight = (Float) s[4], invWeight = (weight != 0) ? 1 / weight : weight;
+                for (int c = 0; c < 3; c++)
+                    d[c] = df == Bitmap::ESpectrum ? (D) ((Float) s[c] * (multiplier * invWeight)) : (D) (((Float) s[c] * invWeight) * multiplier);
+            }
+            return;
+        }
+        if ((sf == Bitmap::ESpectrum || sf == Bitmap::ERGB) && df == Bitmap::ESpectrumAlphaWeight) {
+            // Film::setBitmap of a developed image: the value, alpha = weight = 1 (fmtconv.cpp, ESpectrum -> ESpectrumAlphaWeight)
+            for (size_t i = 0; i < count; i++, s += 3, d += 5) {
+                for (int c = 0; c < 3; c++) d[c] = (D) ((Float) s[c] * multiplier);
+                d[3] = (D) 1; d[4] = (D) 1;
+            }
+            return;
+        }
+        if (!sameLayout) unsupported("this Bitmap::convert (layout change)");
+        const size_t n = count * (size_t) channelsOf(sf, channelCount);
+        if (multiplier != 1) {                     // convertScalar(value, 1, NULL, multiplier, 1): value * multiplier
+            const size_t colour = (size_t) std::min(channelsOf(sf, channelCount), 3), stride = (size_t) channelsOf(sf, channelCount);
+            for (size_t i = 0; i < n; i++) d[i] = (i % stride) < colour ? (D) ((Float) s[i] * multiplier) : (D) (Float) s[i];
+            return;
+        }
         for (size_t i = 0; i < n; i++) d[i] = (D) (float) s[i];
     }
 };

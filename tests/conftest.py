@@ -226,3 +226,34 @@ class RefMitsuba:
         if rc:
             raise RuntimeError(self.lib.gdbref_gpt_last_error().decode())
         return out
+
+
+class RefGbdpt:
+    """ctypes view of oracle/_ref/libref_gbdpt.so: the REFERENCE's own G-BDPT integrator (src/integrators/gbdpt over
+    src/libbidir) rendered through a real RenderJob on Mitsuba's scheduler (oracle/ref_gbdpt_shim.cpp); returns the seven
+    buffers MultiFilm writes for it (gbdpt.cpp:164) as float32 arrays."""
+    PATH = os.path.join(ROOT, "oracle", "_ref", "libref_gbdpt.so")
+    NAMES = ("-L1", "-L2", "-gradientNegY", "-gradientNegX", "-gradientPosX", "-gradientPosY", "-primal")
+
+    def __init__(self):
+        if not os.path.exists(self.PATH) and os.path.isdir(REFERENCE):
+            _make("_ref/libref_gbdpt.so")
+        ctypes.CDLL(RefMitsuba.PATH, mode=ctypes.RTLD_GLOBAL)
+        self.lib = ctypes.CDLL(self.PATH)
+        self.lib.gdbref_gbdpt_last_error.restype = ctypes.c_char_p
+
+    @classmethod
+    def available(cls):
+        return os.path.exists(cls.PATH) or os.path.isdir(REFERENCE)
+
+    def render(self, desc, params, light_image=True, alpha=0.2, threads=4):
+        import tempfile
+        from gdb200 import scenes, pfm
+        fov, rfilter = scenes.mitsuba_sensor_args(desc)
+        with tempfile.TemporaryDirectory() as d:
+            dest = os.path.join(d, "out")
+            rc = self.lib.gdbref_gbdpt_render(ctypes.byref(desc), ctypes.byref(params), ctypes.c_double(fov), rfilter.encode(),
+                                              int(light_image), ctypes.c_double(alpha), int(threads), dest.encode())
+            if rc:
+                raise RuntimeError(self.lib.gdbref_gbdpt_last_error().decode())
+            return {n: pfm.read_pfm(dest + n + ".pfm") for n in self.NAMES}
