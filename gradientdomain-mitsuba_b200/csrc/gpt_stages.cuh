@@ -155,6 +155,13 @@ __global__ void __launch_bounds__(kCastThreads) gpt_cast_kernel(const GptArgs a)
 #ifdef GDB200_EMU
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) castOne<Any>(a, a.rayOwner[Q][r], a.rays[Q] + ((size_t)r << 3));
 #else
+    if (c_scene.nBvhNodes > 0) {
+        // Scenes behind the BVH: a ray's traversal length varies by an order of magnitude, and the barrier that hands a
+        // staged batch back to the TMA unit makes the CTA's 128 threads wait for its slowest ray (ncu: 3 of 13 stall cycles
+        // per issue on the barrier).  Plain per-thread loads here, no barrier.
+        for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) castOne<Any>(a, a.rayOwner[Q][r], a.rays[Q] + ((size_t)r << 3));
+        return;
+    }
     const int nBatches = (n + kCastThreads - 1) / kCastThreads;
     __shared__ __align__(128) double s_rays[2][kCastThreads * 8];
     __shared__ __align__(16) int s_owner[2][kCastThreads];

@@ -368,8 +368,10 @@ public:
 		params.shift_threshold = m_shiftThreshold;
 		params.spp = (int) sampler->getSampleCount();
 		params.seed = m_seed;
-		if (!m_hasSeed && sampler->getProperties().hasProperty("seed"))       /* the gdb200_counter sampler of the scene */
-			params.seed = (uint64_t) sampler->getProperties().getSize("seed", 0);
+		/* the scene's own sampler object carries the XML properties (the per-core clones registered with the scheduler do not) */
+		const Sampler *sceneSampler = scene->getSampler();
+		if (!m_hasSeed && sceneSampler && sceneSampler->getProperties().hasProperty("seed"))   /* <sampler type="gdb200_counter"> */
+			params.seed = (uint64_t) sceneSampler->getProperties().getSize("seed", 0);
 		params.flags = m_refUninitMeasure ? GDB200_GPT_REF_UNINIT_MEASURE : 0;
 		params.streams_per_pixel = m_streamsPerPixel;
 		params.skip_preview = (m_reconstructL1 || m_reconstructL2) ? 1 : 0;   /* "-final" is replaced by the reconstruction */

@@ -92,7 +92,7 @@ struct Sampler : ConfigurableObject {
 };
 struct ShapeKDTree { const AABB &getAABB() const; };
 struct Scene : ConfigurableObject { const ref_vector<Shape> &getShapes() const; const Emitter *getEnvironmentEmitter() const;
-	const ShapeKDTree *getKDTree() const; const ref_vector<Emitter> &getEmitters() const; };
+	const ShapeKDTree *getKDTree() const; const ref_vector<Emitter> &getEmitters() const; const Sampler *getSampler() const; };
 struct RenderQueue; struct RenderJob; struct RayDifferential; struct RadianceQueryRecord;
 struct Scheduler { static Scheduler *getInstance(); ConfigurableObject *getResource(int, int = -1); };
 struct MonteCarloIntegrator : ConfigurableObject {

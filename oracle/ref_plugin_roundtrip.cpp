@@ -40,7 +40,10 @@ extern "C" int gdbref_plugin_render(const gdb200_scene_desc *desc, const gdb200_
     Scene *scene = static_cast<Scene *>(handle);
     int rc = 0, sceneRes = -1, sensorRes = -1, samplerRes = -1;
     Scheduler *sched = Scheduler::getInstance();
+    ref<Worker> worker;                                  // a host has at least one local worker (mitsuba.cpp:259-262); the plugin schedules nothing on it
     try {
+        if (sched->getCoreCount() == 0) { worker = new LocalWorker(0, "wrk0"); sched->registerWorker(worker.get()); }
+        if (!sched->isRunning()) sched->start();
         Properties ip("gpt");                                                      // the XML parameters of <integrator type="gpt">
         ip.setInteger("maxDepth", prm->max_depth); ip.setInteger("rrDepth", prm->rr_depth);
         ip.setBoolean("strictNormals", prm->strict_normals != 0); ip.setFloat("shiftThreshold", prm->shift_threshold);
@@ -54,7 +57,7 @@ extern "C" int gdbref_plugin_render(const gdb200_scene_desc *desc, const gdb200_
         ref<Sampler> sampler = scene->getSampler();
         sceneRes = sched->registerResource(scene);
         sensorRes = sched->registerResource(sensor);
-        std::vector<SerializableObject *> samplers(std::max<size_t>(1, sched->getCoreCount()));
+        std::vector<SerializableObject *> samplers(sched->getCoreCount());             // one sampler per core, renderjob.cpp:60-69
         for (size_t i = 0; i < samplers.size(); ++i) { ref<Sampler> c = sampler->clone(); c->incRef(); samplers[i] = c.get(); }
         samplerRes = sched->registerMultiResource(samplers);
         for (size_t i = 0; i < samplers.size(); ++i) samplers[i]->decRef();
@@ -67,6 +70,8 @@ extern "C" int gdbref_plugin_render(const gdb200_scene_desc *desc, const gdb200_
     if (samplerRes >= 0) sched->unregisterResource(samplerRes);
     if (sensorRes >= 0) sched->unregisterResource(sensorRes);
     if (sceneRes >= 0) sched->unregisterResource(sceneRes);
+    if (sched->isRunning()) sched->stop();
+    if (worker) sched->unregisterWorker(worker.get());
     gdbref_release_scene(handle);
     return rc;
 }

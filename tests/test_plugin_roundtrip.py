@@ -100,6 +100,28 @@ def test_flattening_a_mitsuba_scene_gives_back_the_description(flatten, oracle, 
         assert np.abs(out[k] - ref[k]).max() <= 1e-9 * scale, (name, k)
 
 
+def test_plugin_render_fails_loudly_without_a_gpu(tmp_path):
+    """The same harness on a box without a GPU: scene, scheduler resources and render() are set up as on the GPU box, and the
+    plugin turns the library's "no CUDA device" status into Mitsuba's Log(EError) exception -- no CPU fallback, no silent
+    success."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("this box has a GPU")
+    if not os.path.exists(LIB):
+        pytest.skip("needs oracle/_ref/libref_plugin_roundtrip.so (a build of /root/reference)")
+    lib = ctypes.CDLL(LIB)
+    lib.gdbref_roundtrip_last_error.restype = ctypes.c_char_p
+    desc = scenes.cbox_glossy(16, 12)
+    prm = scenes.default_params(spp=2, seed=1)
+    fov, rfilter = scenes.mitsuba_sensor_args(desc)
+    rc = lib.gdbref_plugin_render(ctypes.byref(desc), ctypes.byref(prm), ctypes.c_double(fov), rfilter.encode(), 0, 1,
+                                  ctypes.c_double(0.2), str(tmp_path / "out").encode())
+    assert rc != 0
+    msg = lib.gdbref_roundtrip_last_error().decode()
+    assert "gdb200" in msg and ("CUDA" in msg or "device" in msg), msg
+    assert not list(tmp_path.iterdir())
+
+
 # ------------------------------------------------------------------ render() of the plugin under Mitsuba's own host objects
 @pytest.mark.gpu
 @pytest.mark.parametrize("scene_name,recon", [("cbox_glossy", "L2"), ("cbox_mesh_lights", "L1"), ("cbox_env", None)])
