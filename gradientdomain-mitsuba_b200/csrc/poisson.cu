@@ -421,6 +421,7 @@ __device__ void phase_export(const PoissonArgs &a, int pCur, const float al[3])
             const F4 p = ld4(a.plane[pCur + ch] + t.idx);
 #pragma unroll
             for (int j = 0; j < 4; j++) x[ch].v[j] += p.v[j] * al[ch];
+            st4(a.plane[X + ch] + t.idx, x[ch]);                  // the solved x stays in the plan (gdb200_poisson_metrics_device)
         }
         if (a.in_direct) {
             F4 d[3];
@@ -501,6 +502,35 @@ __global__ void __launch_bounds__(kThreads, 4) poisson_irls_cg_kernel(const Pois
     if (blockIdx.x == 0 && threadIdx.x == 0) { a.iters[0] = irlsDone; a.iters[1] = cgTotal; }
 }
 
+// ---- Solver::evaluateMetricsMTS (Solver.cpp:511-541) on the x a solve left in the plan: e = b - P x; the primal block of e
+// goes out as an image, sum |e_i| and sum |e_i|^2 over the 3n RGB elements of e as two doubles (the host divides by 3n).
+__global__ void __launch_bounds__(kThreads) poisson_metrics_kernel(const PoissonArgs a, float *err, double *sums)
+{
+    double s1 = 0.0, s2 = 0.0;
+    for (int tile = blockIdx.x; tile < a.nTiles; tile += gridDim.x) {
+        const TileIter t = tile_thread(a, tile);
+        if (!t.valid) continue;
+        F4 e0[3], ex[3], ey[3];
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) residual4(a, t, ch, e0[ch], ex[ch], ey[ch]);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (t.x0 + j >= a.W) continue;
+            const F4 *blk[3] = {e0, ex, ey};
+#pragma unroll
+            for (int b = 0; b < 3; b++) {
+                const float r = blk[b][0].v[j], g = blk[b][1].v[j], bl = blk[b][2].v[j];
+                const float l2 = r * r + g * g + bl * bl;
+                s1 += (double)sqrtf(l2); s2 += (double)l2;
+            }
+        }
+        store_rgb4(err, a, t, e0[0], e0[1], e0[2]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&sums[0], s1); atomicAdd(&sums[1], s2); }
+}
+
 }  // namespace gdb200
 
 // =================================================================================== host ====
@@ -512,6 +542,8 @@ struct gdb200_poisson_plan {
     int *iters = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t evHost[4] = {nullptr, nullptr, nullptr, nullptr};   // copy timing of the host-pointer entry point (created on first use)
+    gdb200::PoissonArgs last;          // geometry, alpha and planes of the last solve (gdb200_poisson_metrics_device)
+    bool solved = false;
     // staging for the host-pointer entry point
     float *d_in[4] = {nullptr, nullptr, nullptr, nullptr};
     float *d_out = nullptr;
@@ -614,6 +646,7 @@ int gdb200_poisson_solve_device(gdb200_poisson_plan *p, const float *d_dx, const
     a.red = p->red; a.iters = p->iters;
 
     cudaStream_t s = (cudaStream_t)stream;
+    p->last = a; p->solved = true;
     if (stats) GDB_CUDA(cudaEventRecord(p->ev0, s));
     void *kargs[] = {&a};
     GDB_CUDA(cudaLaunchCooperativeKernel((void *)poisson_irls_cg_kernel, dim3(p->grid), dim3(kThreads), kargs, 0, s));
@@ -629,6 +662,43 @@ int gdb200_poisson_solve_device(gdb200_poisson_plan *p, const float *d_dx, const
     return GDB200_OK;
 }
 
+static thread_local gdb200_poisson_plan *g_cachedPlan = nullptr;     // plan of this thread's host-pointer solves
+
+int gdb200_poisson_metrics_device(gdb200_poisson_plan *p, float *d_err, float *out_errL1, float *out_errL2, void *stream);
+
+/* Host-pointer form: Solver::evaluateMetricsMTS after the gdb200_poisson_solve this thread made last. */
+int gdb200_poisson_metrics(float *err, float *out_errL1, float *out_errL2)
+{
+    gdb200_poisson_plan *p = g_cachedPlan;
+    if (!p || !p->solved || !p->d_out) return set_error(GDB200_ERR_ARGUMENT, "evaluateMetrics needs a gdb200_poisson_solve on this thread first");
+    if (!err) return set_error(GDB200_ERR_ARGUMENT, "err is NULL");
+    if (int rc = gdb200_poisson_metrics_device(p, p->d_out, out_errL1, out_errL2, nullptr)) return rc;    // d_out: staging, already copied out
+    GDB_CUDA(cudaMemcpy(err, p->d_out, (size_t)p->w * p->h * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+    return GDB200_OK;
+}
+
+int gdb200_poisson_metrics_device(gdb200_poisson_plan *p, float *d_err, float *out_errL1, float *out_errL2, void *stream)
+{
+    if (!p || !d_err || !out_errL1 || !out_errL2) return set_error(GDB200_ERR_ARGUMENT, "plan, err and the two outputs are required");
+    if (!p->solved) return set_error(GDB200_ERR_ARGUMENT, "evaluateMetrics needs a solve on this plan first");
+    struct Bind { int prev = -1; ~Bind() { if (prev >= 0) cudaSetDevice(prev); } } bind;
+    if (cudaGetDevice(&bind.prev) != cudaSuccess) { bind.prev = -1; cudaGetLastError(); }
+    if (bind.prev != p->device) GDB_CUDA(cudaSetDevice(p->device)); else bind.prev = -1;
+    cudaStream_t s = (cudaStream_t)stream;
+    PoissonArgs a = p->last;
+    a.aosVec = (p->w % 4 == 0) && (((uintptr_t)d_err & 15) == 0);
+    double *sums = p->red;                       // the solve's reduction scratch is free between solves
+    GDB_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2, s));
+    poisson_metrics_kernel<<<p->grid, kThreads, 0, s>>>(a, d_err, sums);
+    GDB_CUDA(cudaGetLastError());
+    double h[2];
+    GDB_CUDA(cudaMemcpyAsync(h, sums, sizeof(h), cudaMemcpyDeviceToHost, s));
+    GDB_CUDA(cudaStreamSynchronize(s));
+    const double n3 = 3.0 * (double)p->w * (double)p->h;
+    *out_errL1 = (float)(h[0] / n3); *out_errL2 = (float)(h[1] / n3);
+    return GDB200_OK;
+}
+
 int gdb200_poisson_solve(const float *dx, const float *dy, const float *throughput,
                          const float *direct, int w, int h, float alpha, const char *preset,
                          float *out_final, gdb200_stats *stats)
@@ -637,7 +707,7 @@ int gdb200_poisson_solve(const float *dx, const float *dy, const float *throughp
     gdb200_poisson_config cfg;
     if (int rc = gdb200_poisson_preset(preset, &cfg)) return rc;
     // One cached plan per thread: Mitsuba calls this once per render, benches call it in a loop.
-    static thread_local gdb200_poisson_plan *cached = nullptr;
+    gdb200_poisson_plan *&cached = g_cachedPlan;
     int dev = -1;
     if (int rc = require_device()) return rc;
     GDB_CUDA(cudaGetDevice(&dev));

@@ -119,6 +119,19 @@ class PoissonSolver:
         if self.params.logFunc:
             self.params.logFunc("Execution time = %.2f s\n" % (self.stats.device_ms * 1e-3))  # Solver.cpp:500
 
+    def evaluateMetricsMTS(self, err):
+        """Solver::evaluateMetricsMTS (Solver.cpp:511-541): fills err (h, w, 3 float32) with the primal block of b - P*x and
+        returns (errL1, errL2), the mean |e| and mean |e|^2 over the 3*w*h RGB elements of e."""
+        if self._final is None:
+            raise Gdb200Error("evaluateMetricsMTS() before solveIndirect()")      # reference asserts m_x, Solver.cpp:513
+        L = lib()
+        L.gdb200_poisson_metrics.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]
+        out = np.empty(self._final.shape, dtype=np.float32)
+        l1, l2 = ctypes.c_float(), ctypes.c_float()
+        check(L.gdb200_poisson_metrics(out.ctypes.data_as(ctypes.c_void_p), ctypes.byref(l1), ctypes.byref(l2)))
+        np.copyto(np.asarray(err).reshape(out.shape), out)
+        return l1.value, l2.value
+
     def exportImagesMTS(self, rec):
         if self._final is None:
             raise Gdb200Error("exportImagesMTS() before solveIndirect()")

@@ -103,6 +103,13 @@ int gdb200_poisson_solve_device(gdb200_poisson_plan *plan,
                                 float alpha, const gdb200_poisson_config *cfg,
                                 float *d_out_final, void *stream, gdb200_stats *stats);
 
+/* Solver::evaluateMetricsMTS (Solver.cpp:511-541; Solver.hpp:116) on the result of the last solve of `plan`: e = b - P*x with
+ * b = [alpha*throughput; dx; dy]; d_err (device, w*h*3 floats) receives the primal block of e, *out_errL1 / *out_errL2 the mean
+ * of |e_i| and of |e_i|^2 over the 3*w*h RGB elements of e.  Synchronous. */
+int gdb200_poisson_metrics_device(gdb200_poisson_plan *plan, float *d_err, float *out_errL1, float *out_errL2, void *stream);
+/* The same after this thread's last gdb200_poisson_solve (host buffers): err = w*h*3 floats. */
+int gdb200_poisson_metrics(float *err, float *out_errL1, float *out_errL2);
+
 /* Host-pointer entry = importImagesMTS + setupBackend + solveIndirect +
  * exportImagesMTS (gpt.cpp:1456-1462) in one call.  Copies in, solves, copies out. */
 int gdb200_poisson_solve(const float *dx, const float *dy, const float *throughput,

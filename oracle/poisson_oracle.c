@@ -133,9 +133,10 @@ static void calc_Ax_xAx(float *Ap, float pAp_out[3], const float *w2, const floa
     for (int c = 0; c < 3; c++) pAp_out[c] = (float)pAp[c];
 }
 
-int gdb200_oracle_poisson_solve(const float *dx, const float *dy, const float *throughput,
-                                const float *direct, int w, int h, float alpha,
-                                const char *preset, float *out_final)
+/* out_err / out_errL: optional outputs of Solver::evaluateMetricsMTS (Solver.cpp:511-541) on the solved x */
+static int oracle_solve(const float *dx, const float *dy, const float *throughput,
+                        const float *direct, int w, int h, float alpha,
+                        const char *preset, float *out_final, float *out_err, float *out_errL)
 {
     oracle_preset ps;
     if (!oracle_preset_lookup(preset, &ps) || w <= 0 || h <= 0 || !dx || !dy) return 1;
@@ -205,11 +206,40 @@ int gdb200_oracle_poisson_solve(const float *dx, const float *dy, const float *t
     }
 
     /* Solver.cpp:561-567: final = 1*direct + x, or x when there is no direct image */
-    for (size_t i = 0; i < n3; i++)
-        out_final[i] = direct ? 1.0f * direct[i] + x[i] : x[i];
+    if (out_final)
+        for (size_t i = 0; i < n3; i++)
+            out_final[i] = direct ? 1.0f * direct[i] + x[i] : x[i];
+
+    if (out_errL) {      /* Solver::evaluateMetricsMTS, Solver.cpp:511-541: e = b - P*x, mean |e| and mean |e|^2 over its 3n RGB elements */
+        residual(e, b, x, w, h, alpha);
+        float errL1 = 0.0f, errL2 = 0.0f;
+        for (size_t i = 0; i < n3; i++) {
+            const float *v = e + 3 * i;
+            errL1 += sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);     /* length(), Defs.hpp */
+            errL2 += v[0] * v[0] + v[1] * v[1] + v[2] * v[2];            /* lenSqr() */
+        }
+        out_errL[0] = errL1 / (float)(int)n3;
+        out_errL[1] = errL2 / (float)(int)n3;
+        if (out_err) memcpy(out_err, e, sizeof(float) * n3);             /* the primal block of e */
+    }
 
     free(b); free(e); free(w2); free(x); free(r); free(p); free(Ap);
     return 0;
+}
+
+int gdb200_oracle_poisson_solve(const float *dx, const float *dy, const float *throughput,
+                                const float *direct, int w, int h, float alpha,
+                                const char *preset, float *out_final)
+{
+    return oracle_solve(dx, dy, throughput, direct, w, h, alpha, preset, out_final, NULL, NULL);
+}
+
+/* Solve, then Solver::evaluateMetricsMTS: out_err = w*h*3 (the primal block of b - P*x), out_errL = {errL1, errL2} */
+int gdb200_oracle_poisson_metrics(const float *dx, const float *dy, const float *throughput,
+                                  const float *direct, int w, int h, float alpha,
+                                  const char *preset, float *out_final, float *out_err, float *out_errL)
+{
+    return oracle_solve(dx, dy, throughput, direct, w, h, alpha, preset, out_final, out_err, out_errL);
 }
 
 /* Same algorithm with exact (fp64) reduction sums: NOT the reference's arithmetic, only a

@@ -39,3 +39,25 @@ extern "C" int ref_poisson_solve(const float *dx, const float *dy, const float *
     return ref_poisson_solve_backend(dx, dy, throughput, direct, w, h, alpha, preset, "Auto", out_final, out_seconds);
 #endif
 }
+
+// Solve, then the reference's own Solver::evaluateMetricsMTS (Solver.cpp:511-541): err = w*h*3, errL = {errL1, errL2}.
+extern "C" int ref_poisson_metrics(const float *dx, const float *dy, const float *throughput,
+                                   const float *direct, int w, int h, float alpha,
+                                   const char *preset, float *out_final, float *out_err, float *out_errL)
+{
+    poisson::Solver::Params params;
+    if (!params.setConfigPreset(preset)) return 1;
+    params.alpha = alpha;
+#ifdef REF_POISSON_HAS_CUDA
+    params.backend = "OpenMP";
+#endif
+    params.setLogFunction(poisson::Solver::Params::LogFunction([](const std::string &) {}));
+    poisson::Solver solver(params);
+    solver.importImagesMTS(const_cast<float*>(dx), const_cast<float*>(dy),
+                           const_cast<float*>(throughput), const_cast<float*>(direct), w, h);
+    solver.setupBackend();
+    solver.solveIndirect();
+    solver.evaluateMetricsMTS(out_err, out_errL[0], out_errL[1]);
+    solver.exportImagesMTS(out_final);
+    return 0;
+}

@@ -167,3 +167,24 @@ def test_solver_class_mirrors_reference_call_order(oracle):
     ref = oracle.poisson(d["dx"], d["dy"], d["throughput"], d["direct"], preset="L2D")
     assert rmse(rec, ref) <= 1e-6
     assert logs and logs[0].startswith("Execution time")
+
+
+@pytest.mark.parametrize("preset", ["L2D", "L1D"])
+def test_evaluate_metrics_matches_the_oracle(oracle, preset):
+    """Solver::evaluateMetricsMTS through the Solver look-alike: the error image and both error means of the solved x."""
+    w, h = 130, 70
+    d = synth.solver_inputs(w, h, seed=8)
+    params = gdb200.SolverParams()
+    params.setConfigPreset(preset)
+    solver = gdb200.PoissonSolver(params)
+    solver.importImagesMTS(d["dx"], d["dy"], d["throughput"], d["direct"], w, h)
+    solver.setupBackend()
+    solver.solveIndirect()
+    err = np.empty((h, w, 3), dtype=np.float32)
+    l1, l2 = solver.evaluateMetricsMTS(err)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    final, rerr, errL = np.empty_like(d["dx"]), np.empty_like(d["dx"]), (ctypes.c_float * 2)()
+    assert oracle.lib.gdb200_oracle_poisson_metrics(p(d["dx"]), p(d["dy"]), p(d["throughput"]), p(d["direct"]), w, h,
+                                                    ctypes.c_float(params.alpha), preset.encode(), p(final), p(rerr), errL) == 0
+    assert rmse(err, rerr) <= TOL[preset]
+    assert abs(l1 - errL[0]) <= 1e-4 * errL[0] + 1e-7 and abs(l2 - errL[1]) <= 1e-4 * errL[1] + 1e-9, ((l1, l2), tuple(errL))

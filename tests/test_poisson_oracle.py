@@ -81,3 +81,21 @@ def test_oracle_bit_exact_vs_compiled_reference_slow_presets(oracle, preset):
     b = oracle.poisson_ref(d["dx"], d["dy"], d["throughput"], d["direct"], preset=preset)
     assert np.array_equal(a, b)
     assert rmse(a, d["clean"]) < rmse(d["throughput"], d["clean"])
+
+
+@pytest.mark.parametrize("preset", ["L2D", "L1D"])
+def test_metrics_restatement_matches_the_reference(oracle, preset):
+    """Solver::evaluateMetricsMTS (Solver.cpp:511-541): the restatement against the reference's own method, bit for bit."""
+    import ctypes
+    if oracle.ref is None:
+        pytest.skip("needs oracle/_ref/libref_poisson.so")
+    w, h = 40, 28
+    d = synth.solver_inputs(w, h, seed=21)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    res = {}
+    for name, fn in (("port", oracle.lib.gdb200_oracle_poisson_metrics), ("ref", oracle.ref.ref_poisson_metrics)):
+        final, err, errL = np.empty_like(d["dx"]), np.empty_like(d["dx"]), (ctypes.c_float * 2)()
+        assert fn(p(d["dx"]), p(d["dy"]), p(d["throughput"]), p(d["direct"]), w, h, ctypes.c_float(0.2), preset.encode(), p(final), p(err), errL) == 0
+        res[name] = (final, err, (errL[0], errL[1]))
+    assert np.array_equal(res["port"][0], res["ref"][0]) and np.array_equal(res["port"][1], res["ref"][1])
+    assert res["port"][2] == res["ref"][2] and res["ref"][2][0] > 0
