@@ -159,7 +159,7 @@ def main():
     ap.add_argument("--impl", default="gdb200", choices=["gdb200", "reference"])
     ap.add_argument("--workload", default="gpt-c2", choices=sorted(WORKLOADS))
     ap.add_argument("--spp", type=int, default=0, help="override the workload's sample count (invalidates the headline)")
-    ap.add_argument("--streams", type=int, default=8, help="sample streams per pixel (gdb200_gpt_params.streams_per_pixel); "
+    ap.add_argument("--streams", type=int, default=16, help="sample streams per pixel (gdb200_gpt_params.streams_per_pixel); "
                     "fixed for every N so the film does not depend on the GPU count")
     ap.add_argument("--cpu-spp", type=int, default=16, help="samples/pixel of the bounded CPU-baseline sample (cpu_baseline leg and "
                     "every step of --impl reference)")

@@ -414,6 +414,6 @@ def test_c1_full_configuration_matches_the_reference(oracle):
 
 
 def test_c2_configuration_matches_the_reference(oracle):
-    """BASELINE configs[1] at its full resolution with the bench's 8 sample streams per pixel (the reference renders them as
-    8 passes, oracle/ref_gpt_shim.cpp), 16 of the 256 spp (what the reference traces here in seconds), L1 reconstruction."""
-    _reference_config_case(oracle, "cbox_glossy", 1024, 1024, 16, 8, "L1D")
+    """BASELINE configs[1] at its full resolution with the bench's 16 sample streams per pixel (the reference renders them as
+    16 passes, oracle/ref_gpt_shim.cpp), 32 of the 256 spp (what the reference traces here in seconds), L1 reconstruction."""
+    _reference_config_case(oracle, "cbox_glossy", 1024, 1024, 32, 16, "L1D")

@@ -124,7 +124,7 @@ def test_plugin_render_fails_loudly_without_a_gpu(tmp_path):
 
 # ------------------------------------------------------------------ render() of the plugin under Mitsuba's own host objects
 @pytest.mark.gpu
-@pytest.mark.parametrize("scene_name,recon", [("cbox_glossy", "L2"), ("cbox_mesh_lights", "L1"), ("cbox_env", None)])
+@pytest.mark.parametrize("scene_name,recon", [("cbox_glossy", "L2"), ("cbox_materials", "L1"), ("cbox_env", None)])
 def test_plugin_render_through_mitsuba_host_objects(oracle, tmp_path, scene_name, recon):
     """GDB200GradientPathIntegrator::render (plugin/gpt_plugin.cpp) called the way Mitsuba's RenderJob calls an integrator:
     a real Scene with sensor, MultiFilm and the gdb200_counter sampler (the reference's own classes, built by
