@@ -292,6 +292,12 @@ def main():
         dist.all_reduce(samples, op=dist.ReduceOp.SUM)
     clocks = sampler.stop() if rank == 0 else None
     total_ms, total_samples = float(ms.item()), float(samples.item())
+    rank_trace_ms = [agg["trace_ms"] / args.steps]
+    if world > 1:                                   # every rank's mean tracing time per step: names the limiting rank / phase
+        mine = torch.tensor([agg["trace_ms"] / args.steps], device="cuda", dtype=torch.float64)
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        rank_trace_ms = [round(float(t.item()), 1) for t in every]
 
     # ------------------------------------------------------------------ end to end through the public API
     h2d = ctypes.sizeof(scenes.SceneDesc) + desc.n_shapes * ctypes.sizeof(scenes.Shape) + desc.n_materials * ctypes.sizeof(scenes.Material) \
@@ -374,6 +380,7 @@ def main():
         if world > 1:
             line["exchange_bytes_per_step"] = int(agg["exchange_bytes"] / args.steps)
             line["strip_bounds"] = bounds
+            line["rank_trace_ms"] = rank_trace_ms
         line["rank0_phase_ms"] = {k: round(v / args.steps, 2) for k, v in phase.items()}
         if world == 1:
             try:                                  # a reported baseline: it must never cost the measured line
