@@ -417,3 +417,27 @@ def test_c2_configuration_matches_the_reference(oracle):
     """BASELINE configs[1] at its full resolution with the bench's 16 sample streams per pixel (the reference renders them as
     16 passes, oracle/ref_gpt_shim.cpp), 32 of the 256 spp (what the reference traces here in seconds), L1 reconstruction."""
     _reference_config_case(oracle, "cbox_glossy", 1024, 1024, 32, 16, "L1D")
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_scenes_match_oracle_on_the_gpu(oracle, seed, monkeypatch):
+    """The randomised scenes of tests/test_ref_fuzz.py (random materials of every BSDF type, rectangle / sphere / mesh shapes
+    and lights, point / spot / environment emitters, thinlens, film filters, strictNormals, depth limits) through the CUDA
+    kernels: every buffer against the oracle, which tests/test_ref_fuzz.py holds to the compiled reference on the same scenes.
+    Odd seeds use the generator with large meshes (BVH path, forced on some)."""
+    import test_ref_fuzz as F
+    if seed % 2:
+        if seed % 4 == 1:
+            monkeypatch.setenv("GDB200_FORCE_BVH", "1")
+        desc = F.rand_scene2(seed, w=40, h=30)
+    else:
+        desc = F.rand_scene(seed, w=40, h=30)
+    rng = np.random.default_rng(seed + 1000)
+    kw = dict(maxDepth=int(rng.choice([-1, -1, 3, 6])), rrDepth=int(rng.choice([5, 2])), strictNormals=bool(rng.integers(0, 2)),
+              shiftThreshold=float(rng.choice([0.001, 0.05])))
+    integ = gdb200.GPTIntegrator(reconstructL1=False, reconstructL2=False, **kw)
+    streams = int(rng.choice([1, 3]))
+    got = integ.trace(gdb200.Scene(desc), spp=6, seed=seed, streams=streams)
+    ref, _, cnt = oracle.gpt(desc, integ.params(6, seed, streams=streams))
+    compare(got, ref, max_flip_frac=5e-3)          # 1200 pixels: a handful may hold a sample whose branch a CUDA-libm ulp flipped
+    assert integ.stats.samples == cnt[0]
