@@ -7,7 +7,10 @@ into rows y-2..y+2 (4 neighbours + the box filter's 1e-5 overhang), so after tra
 
   1. ONE all-reduce(sum) over the packed rows around the strip boundaries completes the
      halo rows (throughput/dx/dy/direct/final value+weight planes), and
-  2. rank 0 gathers the strip interiors, develops the film and runs the global Poisson solve.
+  2. rank 0 receives the strip interiors, develops the film and runs the global Poisson solve.
+
+Strips need not be equal: rebalance() moves the boundaries so that every rank's tracing time plus the work it alone does
+afterwards (rank 0: develop + solve) is the same, from times measured on the previous render.
 
 Everything here is device-agnostic torch.distributed plumbing (NCCL on GPUs, gloo in the CPU
 tests); the arithmetic stays in libgdb200.
@@ -113,22 +116,3 @@ def gather_strips(acc, rank, world, group=None, bounds=None, first_buffer=0):
     for req in dist.batch_isend_irecv([dist.P2POp(dist.isend, mine, 0, group)]):
         req.wait()
     return mine.numel() * mine.element_size()
-
-
-def band_spec(rank, world, band_rows=16):
-    """(band_rows, band_count, band_index) for gdb200_gpt_params: interleaved row bands balance the
-    per-strip cost differences of contiguous strips (paths under the light are short, floor paths long)."""
-    return (band_rows, world, rank)
-
-
-def band_owned_rows(height, rank, world, band_rows=16):
-    return [y for y in range(height) if (y // band_rows) % world == rank]
-
-
-def exchange_all(acc, world, group=None):
-    """Interleaved bands put a strip boundary every band_rows rows, so the halo rows are a large part of
-    the film: sum the whole accumulator film with ONE all-reduce; every rank then holds the full image."""
-    if world <= 1:
-        return 0
-    dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
-    return acc.numel() * acc.element_size()
