@@ -36,6 +36,12 @@ constexpr int kThreads = 256;
 constexpr int kTileGX  = 16;   // groups of 4 pixels per tile row  (64 px)
 constexpr int kTileY   = 16;   // rows per tile
 static_assert(kTileGX * kTileY == kThreads, "one thread per 4-pixel group");
+// Resident variant (images of <= kResTiles tiles per CTA, e.g. 1024x1024 on 148 SMs x 4 CTAs): a CTA works on the same tiles in
+// every phase, so the CG vectors only their own thread ever touches -- x and Ap -- stay in shared memory for the whole CG loop
+// (2 tiles x 2 vectors x 3 channels x 256 threads x 16 B = 48 KB per CTA): 72 instead of 120 B of L2 traffic per pixel and CG
+// iteration, and a working set (r, p, p', w2) that fits one L2 partition.  Same arithmetic, same reduction order, same bits.
+constexpr int kResTiles = 2;
+constexpr int kResBytes = kResTiles * 2 * 3 * kThreads * 16;
 
 enum Plane {
     B0 = 0, BX = 3, BY = 6,      // b = [alpha*throughput; dx; dy]   (Solver.cpp:321-329)
@@ -69,48 +75,55 @@ __device__ __forceinline__ void st4(float *p, const F4 &a)
 }
 __device__ __forceinline__ F4 zero4() { return F4{{0.f, 0.f, 0.f, 0.f}}; }
 
-// Deterministic grid-wide sum of three per-thread doubles. Contains one grid barrier.
+// Deterministic grid-wide sum of three per-thread doubles; the result is returned to THREAD 0 of every CTA only (it derives the
+// CG scalars and publishes them in shared memory, see CgScalars).  Contains one grid barrier.  After the barrier EVERY thread fetches
+// its share of the per-CTA partials (<= 3 independent loads per component at 592 CTAs: one L2 round trip instead of a 19-step
+// loop on one warp), then a fixed-order warp / block tree.  The shared scratch is indexed by the call's parity so that a call
+// needs no trailing __syncthreads.
 __device__ void grid_sum3(cg::grid_group &grid, double *red, int &parity, double a0, double a1,
                           double a2, float out[3])
 {
-    __shared__ double s_part[kThreads / 32][3];
-    __shared__ float s_out[3];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ double s_part[2][kThreads / 32][3];
+    __shared__ double s_tot[2][kThreads / 32][3];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, par = parity;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         a0 += __shfl_xor_sync(0xffffffffu, a0, o);
         a1 += __shfl_xor_sync(0xffffffffu, a1, o);
         a2 += __shfl_xor_sync(0xffffffffu, a2, o);
     }
-    if (lane == 0) { s_part[warp][0] = a0; s_part[warp][1] = a1; s_part[warp][2] = a2; }
+    if (lane == 0) { s_part[par][warp][0] = a0; s_part[par][warp][1] = a1; s_part[par][warp][2] = a2; }
     __syncthreads();
-    double *slot = red + (size_t)parity * gridDim.x * 3;
+    const int G = (int)gridDim.x;
+    double *slot = red + (size_t)par * G * 3;      // [3][G]
     if (threadIdx.x < 3) {
         double s = 0.0;
 #pragma unroll
-        for (int w = 0; w < kThreads / 32; w++) s += s_part[w][threadIdx.x];
-        slot[(size_t)blockIdx.x * 3 + threadIdx.x] = s;
+        for (int w = 0; w < kThreads / 32; w++) s += s_part[par][w][threadIdx.x];
+        slot[(size_t)threadIdx.x * G + blockIdx.x] = s;
     }
     grid.sync();
-    if (warp == 0) {
-        double t0 = 0.0, t1 = 0.0, t2 = 0.0;
-        for (int b = lane; b < (int)gridDim.x; b += 32) {
-            t0 += slot[(size_t)b * 3 + 0];
-            t1 += slot[(size_t)b * 3 + 1];
-            t2 += slot[(size_t)b * 3 + 2];
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            t0 += __shfl_xor_sync(0xffffffffu, t0, o);
-            t1 += __shfl_xor_sync(0xffffffffu, t1, o);
-            t2 += __shfl_xor_sync(0xffffffffu, t2, o);
-        }
-        if (lane == 0) { s_out[0] = (float)t0; s_out[1] = (float)t1; s_out[2] = (float)t2; }
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+    for (int b = threadIdx.x; b < G; b += kThreads) {
+        t0 += __ldcg(slot + b);
+        t1 += __ldcg(slot + G + b);
+        t2 += __ldcg(slot + 2 * G + b);
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        t0 += __shfl_xor_sync(0xffffffffu, t0, o);
+        t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+        t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+    }
+    if (lane == 0) { s_tot[par][warp][0] = t0; s_tot[par][warp][1] = t1; s_tot[par][warp][2] = t2; }
     __syncthreads();
-    out[0] = s_out[0]; out[1] = s_out[1]; out[2] = s_out[2];
+    if (threadIdx.x == 0) {
+        t0 = t1 = t2 = 0.0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; w++) { t0 += s_tot[par][w][0]; t1 += s_tot[par][w][1]; t2 += s_tot[par][w][2]; }
+        out[0] = (float)t0; out[1] = (float)t1; out[2] = (float)t2;
+    }
     parity ^= 1;
-    __syncthreads();
 }
 
 struct TileIter {
@@ -307,6 +320,17 @@ __device__ void phase_rhs(const PoissonArgs &a, float coef, double rz[3])
     rz[0] = acc[0]; rz[1] = acc[1]; rz[2] = acc[2];
 }
 
+// Resident x (which = 0) / Ap (which = 1) of this thread's 4 pixels in the CTA's k-th tile.
+__device__ __forceinline__ F4 res_ld(const float4 *res, int k, int which, int ch)
+{
+    const float4 t = res[((k * 2 + which) * 3 + ch) * kThreads + threadIdx.x];
+    return F4{{t.x, t.y, t.z, t.w}};
+}
+__device__ __forceinline__ void res_st(float4 *res, int k, int which, int ch, const F4 &v)
+{
+    res[((k * 2 + which) * 3 + ch) * kThreads + threadIdx.x] = make_float4(v.v[0], v.v[1], v.v[2], v.v[3]);
+}
+
 // ---- phase A: p = r + b*p_old; x += a_prev*p_old; Ap = A p; pAp ---------------------------
 // (Backend.cpp:325-347 of the previous iteration fused with :221-252 of this one.)
 __device__ void phase_cg_a(const PoissonArgs &a, int pOld, int pNew, const float aPrev[3],
@@ -368,17 +392,105 @@ __device__ void phase_cg_a(const PoissonArgs &a, int pOld, int pNew, const float
     pAp[0] = acc[0]; pAp[1] = acc[1]; pAp[2] = acc[2];
 }
 
+// Phase A of the resident variant.  x and Ap live in shared memory (res); the new search direction c = r + b*p_old is handed
+// to the neighbouring threads through a shared tile (one channel at a time: 18 x 72 floats) instead of being recomputed from
+// r and p_old re-read through L1 -- with 48 KB of the CTA's shared memory taken, L1 no longer holds the tile's rows (measured:
+// hit rate 25 % instead of 48 %, more L2 traffic than the streaming variant saves).  Only the tile's outer ring is recomputed
+// from global r / p_old.  Same expressions on the same values as phase_cg_a => same bits.
+constexpr int kHaloPitch = kTileGX * 4 + 8;     // 4 floats of margin left and right keep the float4 rows 16-byte aligned
+__device__ void phase_cg_a_res(const PoissonArgs &a, int pOld, int pNew, const float aPrev[3],
+                               const float beta[3], double pAp[3], float4 *res, bool xResident)
+{
+    __shared__ __align__(16) float s_c[kTileY + 2][kHaloPitch];
+    const float alphaSqr = a.alpha * a.alpha;
+    const int lx = threadIdx.x % kTileGX, ly = threadIdx.x / kTileGX;
+    float acc[3] = {0.f, 0.f, 0.f};
+    int k = -1;
+    for (int tile = blockIdx.x; tile < a.nTiles; tile += gridDim.x) {
+        k++;
+        const TileIter t = tile_thread(a, tile);
+        const bool hasL = t.x0 > 0, hasR = t.x0 + 4 < a.W, hasU = t.y > 0, hasD = t.y < a.H - 1;
+        F4 w0 = zero4(), wx = zero4(), wy = zero4(), wyu = zero4();
+        float wxl = 0.f;
+        if (t.valid) {
+            w0 = ld4(a.plane[W0] + t.idx); wx = ld4(a.plane[WX] + t.idx); wy = ld4(a.plane[WY] + t.idx);
+            if (hasU) wyu = ld4(a.plane[WY] + t.idx - a.Wp);
+            if (hasL) wxl = a.plane[WX][t.idx - 1];
+        }
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+            const float *r = a.plane[R + ch], *po = a.plane[pOld + ch];
+            const float b = beta[ch], al = aPrev[ch];
+            F4 c = zero4();
+            if (t.valid) {
+                const F4 rc = ld4(r + t.idx), pc = ld4(po + t.idx);
+                F4 xv = xResident ? res_ld(res, k, 0, ch) : ld4(a.plane[X + ch] + t.idx);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    xv.v[j] += pc.v[j] * al;
+                    c.v[j] = rc.v[j] + pc.v[j] * b;
+                }
+                res_st(res, k, 0, ch, xv);
+                st4(a.plane[pNew + ch] + t.idx, c);
+                *reinterpret_cast<float4 *>(&s_c[ly + 1][4 + 4 * lx]) = make_float4(c.v[0], c.v[1], c.v[2], c.v[3]);
+                // the ring around the tile, from the neighbouring tiles' r and p_old
+                if (ly == 0 && hasU) {
+                    const F4 r2 = ld4(r + t.idx - a.Wp), p2 = ld4(po + t.idx - a.Wp);
+                    *reinterpret_cast<float4 *>(&s_c[0][4 + 4 * lx]) =
+                        make_float4(r2.v[0] + p2.v[0] * b, r2.v[1] + p2.v[1] * b, r2.v[2] + p2.v[2] * b, r2.v[3] + p2.v[3] * b);
+                }
+                if (ly == kTileY - 1 && hasD) {
+                    const F4 r2 = ld4(r + t.idx + a.Wp), p2 = ld4(po + t.idx + a.Wp);
+                    *reinterpret_cast<float4 *>(&s_c[kTileY + 1][4 + 4 * lx]) =
+                        make_float4(r2.v[0] + p2.v[0] * b, r2.v[1] + p2.v[1] * b, r2.v[2] + p2.v[2] * b, r2.v[3] + p2.v[3] * b);
+                }
+                if (lx == 0 && hasL) s_c[ly + 1][3] = r[t.idx - 1] + po[t.idx - 1] * b;
+                if (lx == kTileGX - 1 && hasR) s_c[ly + 1][4 + 4 * kTileGX] = r[t.idx + 4] + po[t.idx + 4] * b;
+            }
+            __syncthreads();
+            if (t.valid) {
+                F4 u = zero4(), d = zero4();
+                float l = 0.f, rr = 0.f;
+                if (hasU) { const float4 q = *reinterpret_cast<const float4 *>(&s_c[ly][4 + 4 * lx]); u = F4{{q.x, q.y, q.z, q.w}}; }
+                if (hasD) { const float4 q = *reinterpret_cast<const float4 *>(&s_c[ly + 2][4 + 4 * lx]); d = F4{{q.x, q.y, q.z, q.w}}; }
+                if (hasL) l = s_c[ly + 1][3 + 4 * lx];
+                if (hasR) rr = s_c[ly + 1][8 + 4 * lx];
+                F4 Ap;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int xx = t.x0 + j;
+                    const float xi = c.v[j];
+                    float v = w0.v[j] * xi * alphaSqr;
+                    if (xx != 0)        v += (j == 0 ? wxl : wx.v[j - 1]) * (xi - (j == 0 ? l : c.v[j - 1]));
+                    if (xx != a.W - 1)  v += wx.v[j] * (xi - (j == 3 ? rr : c.v[j + 1]));
+                    if (t.y != 0)       v += wyu.v[j] * (xi - u.v[j]);
+                    if (t.y != a.H - 1) v += wy.v[j] * (xi - d.v[j]);
+                    if (xx >= a.W) v = 0.f;
+                    Ap.v[j] = v;
+                    acc[ch] += xi * v;
+                }
+                res_st(res, k, 1, ch, Ap);
+            }
+            __syncthreads();
+        }
+    }
+    pAp[0] = acc[0]; pAp[1] = acc[1]; pAp[2] = acc[2];
+}
+
 // ---- phase B: r -= a*Ap; rz = r.r   (Backend.cpp:296-321) ----------------------------------
-__device__ void phase_cg_b(const PoissonArgs &a, const float al[3], double rz[3])
+template <bool RES>
+__device__ void phase_cg_b(const PoissonArgs &a, const float al[3], double rz[3], const float4 *res)
 {
     float acc[3] = {0.f, 0.f, 0.f};
+    int k = -1;
     for (int tile = blockIdx.x; tile < a.nTiles; tile += gridDim.x) {
+        k++;
         const TileIter t = tile_thread(a, tile);
         if (!t.valid) continue;
 #pragma unroll
         for (int ch = 0; ch < 3; ch++) {
             F4 r = ld4(a.plane[R + ch] + t.idx);
-            const F4 Ap = ld4(a.plane[AP + ch] + t.idx);
+            const F4 Ap = RES ? res_ld(res, k, 1, ch) : ld4(a.plane[AP + ch] + t.idx);
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const float ri = r.v[j] - Ap.v[j] * al[ch];
@@ -392,14 +504,16 @@ __device__ void phase_cg_b(const PoissonArgs &a, const float al[3], double rz[3]
 }
 
 // ---- phase: pending x += a*p of the last CG iteration --------------------------------------
-__device__ void phase_flush_x(const PoissonArgs &a, int pCur, const float al[3])
+__device__ void phase_flush_x(const PoissonArgs &a, int pCur, const float al[3], const float4 *res, bool xResident)
 {
+    int k = -1;
     for (int tile = blockIdx.x; tile < a.nTiles; tile += gridDim.x) {
+        k++;
         const TileIter t = tile_thread(a, tile);
         if (!t.valid) continue;
 #pragma unroll
         for (int ch = 0; ch < 3; ch++) {
-            F4 x = ld4(a.plane[X + ch] + t.idx);
+            F4 x = xResident ? res_ld(res, k, 0, ch) : ld4(a.plane[X + ch] + t.idx);
             const F4 p = ld4(a.plane[pCur + ch] + t.idx);
 #pragma unroll
             for (int j = 0; j < 4; j++) x.v[j] += p.v[j] * al[ch];
@@ -409,15 +523,17 @@ __device__ void phase_flush_x(const PoissonArgs &a, int pCur, const float al[3])
 }
 
 // ---- phase: final = 1*direct + x  (Solver.cpp:561-567), with the last x update folded in ---
-__device__ void phase_export(const PoissonArgs &a, int pCur, const float al[3])
+__device__ void phase_export(const PoissonArgs &a, int pCur, const float al[3], const float4 *res, bool xResident)
 {
+    int k = -1;
     for (int tile = blockIdx.x; tile < a.nTiles; tile += gridDim.x) {
+        k++;
         const TileIter t = tile_thread(a, tile);
         if (!t.valid) continue;
         F4 x[3];
 #pragma unroll
         for (int ch = 0; ch < 3; ch++) {
-            x[ch] = ld4(a.plane[X + ch] + t.idx);
+            x[ch] = xResident ? res_ld(res, k, 0, ch) : ld4(a.plane[X + ch] + t.idx);
             const F4 p = ld4(a.plane[pCur + ch] + t.idx);
 #pragma unroll
             for (int j = 0; j < 4; j++) x[ch].v[j] += p.v[j] * al[ch];
@@ -435,71 +551,101 @@ __device__ void phase_export(const PoissonArgs &a, int pCur, const float al[3])
     }
 }
 
+// The CG scalars are uniform over the grid: thread 0 of each CTA derives them from the grid sums (every CTA the same bits) and
+// keeps them in shared memory -- 16 registers per thread less than carrying them through the phases (the kernel is capped at
+// 64 registers for 4 CTAs/SM and was spilling in the CG loop: 80 -> 156 bytes of spills cost 3 ms of 26 at 1024x1024).
+struct CgScalars {
+    float rz[2][3];      // r.r of the last two CG iterations; [cur] is the newer one (Solver.cpp:466 swaps pointers)
+    float aPrev[3];      // step of the CG iteration whose x update is pending
+    float beta[3], al[3];
+    float coef;
+};
+
+template <bool RES>
 __global__ void __launch_bounds__(kThreads, 4) poisson_irls_cg_kernel(const PoissonArgs a)
 {
+    extern __shared__ float4 s_res[];     // RES: [tile][x | Ap][channel][thread], kResBytes
+    __shared__ CgScalars sc;
+    bool xResident = false;               // the current x is in s_res, not in the X planes (uniform over the grid)
     cg::grid_group grid = cg::this_grid();
     int parity = 0;
     int cgTotal = 0, irlsDone = 0;
-    const float n3 = (float)(3 * a.W * a.H);   // (float)w2->numElems, Backend.cpp:368
+    const bool lead = threadIdx.x == 0;
 
     phase_import(a);
+    if (lead) sc.aPrev[0] = sc.aPrev[1] = sc.aPrev[2] = 0.f;
     grid.sync();
 
     int pCur = PA;                       // plane set holding the current search direction
-    float aPrev[3] = {0.f, 0.f, 0.f};    // step of the CG iteration whose x update is pending
+    int cur = 0;                         // sc.rz[cur]: r.r of the newest residual
 
     for (int irls = 0; irls < a.cfg.irlsIterMax; irls++) {
         if (irls > 0) {                                   // apply the pending x update first
-            phase_flush_x(a, pCur, aPrev);
+            phase_flush_x(a, pCur, sc.aPrev, s_res, xResident);
+            xResident = false;
             grid.sync();
         }
-        aPrev[0] = aPrev[1] = aPrev[2] = 0.f;
-        float coef = 1.0f;
+        double part[3];
+        float tot[3];
         if (irls == 0) {
             double dummy = 0.0;
             phase_weights(a, true, 0.f, dummy);
+            if (lead) sc.coef = 1.0f;
             grid.sync();
         } else {
             const float reg = a.cfg.irlsRegInit * powf(a.cfg.irlsRegIter, (float)(irls - 1));   // Solver.cpp:395
             double s = 0.0;
             phase_weights(a, false, reg, s);
-            float tot[3];
             grid_sum3(grid, a.red, parity, s, 0.0, 0.0, tot);
-            coef = n3 / tot[0];
+            if (lead) sc.coef = (float)(3 * a.W * a.H) / tot[0];      // (float)w2->numElems, Backend.cpp:368
+            __syncthreads();
         }
-        double part[3];
-        float rzA[3], rzB[3], pAp[3];
-        float *rz = rzA, *rz2 = rzB;
-        phase_rhs(a, coef, part);
-        grid_sum3(grid, a.red, parity, part[0], part[1], part[2], rz);
-
-        float beta[3] = {0.f, 0.f, 0.f};                  // first direction: p = r (Solver.cpp:405)
-        for (int cgi = 0;; cgi++) {
-            if (cgi % a.cfg.cgIterCheck == 0 || cgi == a.cfg.cgIterMax) {   // Solver.cpp:411-445
-                const float errL2W = rz[0] + rz[1] + rz[2];
-                if (cgi == a.cfg.cgIterMax || errL2W <= a.cfg.cgTolerance) break;
-            }
-            { float *tmp = rz; rz = rz2; rz2 = tmp; }                       // Solver.cpp:466
-            const int pNew = (pCur == PA) ? PB : PA;
-            phase_cg_a(a, pCur, pNew, aPrev, beta, part);
-            grid_sum3(grid, a.red, parity, part[0], part[1], part[2], pAp);
-            pCur = pNew;
-            float al[3];
-#pragma unroll
-            for (int c = 0; c < 3; c++) al[c] = rz2[c] / fmaxf(pAp[c], FLT_MIN);   // Backend.cpp:309
-            phase_cg_b(a, al, part);
-            grid_sum3(grid, a.red, parity, part[0], part[1], part[2], rz);
+        phase_rhs(a, sc.coef, part);
+        grid_sum3(grid, a.red, parity, part[0], part[1], part[2], tot);
+        if (lead) {
 #pragma unroll
             for (int c = 0; c < 3; c++) {
-                beta[c] = rz[c] / fmaxf(rz2[c], FLT_MIN);                          // Backend.cpp:339
-                aPrev[c] = al[c];
+                sc.rz[cur][c] = tot[c];
+                sc.aPrev[c] = 0.f;
+                sc.beta[c] = 0.f;                         // first direction: p = r (Solver.cpp:405)
             }
+        }
+        __syncthreads();
+
+        for (int cgi = 0;; cgi++) {
+            if (cgi % a.cfg.cgIterCheck == 0 || cgi == a.cfg.cgIterMax) {   // Solver.cpp:411-445
+                const float errL2W = sc.rz[cur][0] + sc.rz[cur][1] + sc.rz[cur][2];
+                if (cgi == a.cfg.cgIterMax || errL2W <= a.cfg.cgTolerance) break;
+            }
+            cur ^= 1;                                                       // Solver.cpp:466: rz <-> rz2
+            const int pNew = (pCur == PA) ? PB : PA;
+            if (RES) phase_cg_a_res(a, pCur, pNew, sc.aPrev, sc.beta, part, s_res, xResident);
+            else phase_cg_a(a, pCur, pNew, sc.aPrev, sc.beta, part);
+            xResident = RES;
+            grid_sum3(grid, a.red, parity, part[0], part[1], part[2], tot);
+            pCur = pNew;
+            if (lead) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) sc.al[c] = sc.rz[cur ^ 1][c] / fmaxf(tot[c], FLT_MIN);   // Backend.cpp:309
+            }
+            __syncthreads();
+            phase_cg_b<RES>(a, sc.al, part, s_res);
+            grid_sum3(grid, a.red, parity, part[0], part[1], part[2], tot);
+            if (lead) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    sc.rz[cur][c] = tot[c];
+                    sc.beta[c] = tot[c] / fmaxf(sc.rz[cur ^ 1][c], FLT_MIN);                         // Backend.cpp:339
+                    sc.aPrev[c] = sc.al[c];
+                }
+            }
+            __syncthreads();
             cgTotal++;
         }
         irlsDone++;
     }
-    phase_export(a, pCur, aPrev);
-    if (blockIdx.x == 0 && threadIdx.x == 0) { a.iters[0] = irlsDone; a.iters[1] = cgTotal; }
+    phase_export(a, pCur, sc.aPrev, s_res, xResident);
+    if (blockIdx.x == 0 && lead) { a.iters[0] = irlsDone; a.iters[1] = cgTotal; }
 }
 
 // ---- Solver::evaluateMetricsMTS (Solver.cpp:511-541) on the x a solve left in the plan: e = b - P x; the primal block of e
@@ -544,6 +690,7 @@ struct gdb200_poisson_plan {
     cudaEvent_t evHost[4] = {nullptr, nullptr, nullptr, nullptr};   // copy timing of the host-pointer entry point (created on first use)
     gdb200::PoissonArgs last;          // geometry, alpha and planes of the last solve (gdb200_poisson_metrics_device)
     bool solved = false;
+    bool resident = false;             // x and Ap of every CTA's tiles fit its shared memory (poisson_irls_cg_kernel<true>)
     // staging for the host-pointer entry point
     float *d_in[4] = {nullptr, nullptr, nullptr, nullptr};
     float *d_out = nullptr;
@@ -590,8 +737,10 @@ int gdb200_poisson_plan_create(int w, int h, gdb200_poisson_plan **out)
     gdb200_poisson_plan *p = new gdb200_poisson_plan;
     p->device = di.device; p->w = w; p->h = h; p->wp = (w + 3) & ~3;
     const size_t planeElems = (size_t)p->wp * h;
-    int occ = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, poisson_irls_cg_kernel, kThreads, 0);
+    int occ = 0, occRes = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, poisson_irls_cg_kernel<false>, kThreads, 0);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(poisson_irls_cg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kResBytes);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occRes, poisson_irls_cg_kernel<true>, kThreads, kResBytes);
     if (e != cudaSuccess || occ < 1) {
         delete p;
         return set_error(GDB200_ERR_CUDA, "poisson kernel not launchable on this device: %s "
@@ -600,6 +749,8 @@ int gdb200_poisson_plan_create(int w, int h, gdb200_poisson_plan **out)
     const int tilesX = (p->wp / 4 + kTileGX - 1) / kTileGX, tilesY = (h + kTileY - 1) / kTileY;
     const long long nTiles = (long long)tilesX * tilesY;
     p->grid = (int)std::min<long long>(nTiles, (long long)occ * di.sms);
+    // the resident variant needs the same residency and every CTA's tiles in its shared memory
+    p->resident = occRes >= occ && nTiles <= (long long)kResTiles * p->grid;
 #define PLAN_CUDA(call) do { cudaError_t e2 = (call); if (e2 != cudaSuccess) { gdb200_poisson_plan_destroy(p); \
         return set_error(GDB200_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e2)); } } while (0)
     PLAN_CUDA(cudaMalloc(&p->planes, planeElems * kPlanes * sizeof(float)));
@@ -649,7 +800,10 @@ int gdb200_poisson_solve_device(gdb200_poisson_plan *p, const float *d_dx, const
     p->last = a; p->solved = true;
     if (stats) GDB_CUDA(cudaEventRecord(p->ev0, s));
     void *kargs[] = {&a};
-    GDB_CUDA(cudaLaunchCooperativeKernel((void *)poisson_irls_cg_kernel, dim3(p->grid), dim3(kThreads), kargs, 0, s));
+    if (p->resident)
+        GDB_CUDA(cudaLaunchCooperativeKernel((void *)poisson_irls_cg_kernel<true>, dim3(p->grid), dim3(kThreads), kargs, kResBytes, s));
+    else
+        GDB_CUDA(cudaLaunchCooperativeKernel((void *)poisson_irls_cg_kernel<false>, dim3(p->grid), dim3(kThreads), kargs, 0, s));
     if (stats) {
         GDB_CUDA(cudaEventRecord(p->ev1, s));
         GDB_CUDA(cudaEventSynchronize(p->ev1));
@@ -661,6 +815,23 @@ int gdb200_poisson_solve_device(gdb200_poisson_plan *p, const float *d_dx, const
     }
     return GDB200_OK;
 }
+
+int gdb200_poisson_plan_set_resident(gdb200_poisson_plan *p, int on)
+{
+    if (!p) return set_error(GDB200_ERR_ARGUMENT, "plan is NULL");
+    if (!on) { p->resident = false; return GDB200_OK; }
+    int occRes = 0, sms = 0;
+    GDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occRes, poisson_irls_cg_kernel<true>, kThreads, kResBytes));
+    GDB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device));
+    const long long tilesX = (p->wp / 4 + kTileGX - 1) / kTileGX, nTiles = tilesX * ((p->h + kTileY - 1) / kTileY);
+    if ((long long)occRes * sms < p->grid || nTiles > (long long)kResTiles * p->grid)
+        return set_error(GDB200_ERR_ARGUMENT, "image of %dx%d does not fit the resident variant (%lld tiles, %d CTAs x %d)", p->w, p->h,
+                         nTiles, p->grid, kResTiles);
+    p->resident = true;
+    return GDB200_OK;
+}
+
+int gdb200_poisson_plan_is_resident(const gdb200_poisson_plan *p) { return p && p->resident ? 1 : 0; }
 
 static thread_local gdb200_poisson_plan *g_cachedPlan = nullptr;     // plan of this thread's host-pointer solves
 

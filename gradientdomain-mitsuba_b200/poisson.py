@@ -57,6 +57,23 @@ class PoissonPlan:
                                                 ctypes.c_void_p(stream or 0),
                                                 ctypes.byref(stats) if stats is not None else None))
 
+    @property
+    def resident(self):
+        """True when solves on this plan run the kernel variant that keeps x and Ap in shared memory (small images)."""
+        return bool(lib().gdb200_poisson_plan_is_resident(self._h))
+
+    @resident.setter
+    def resident(self, on):
+        check(lib().gdb200_poisson_plan_set_resident(self._h, 1 if on else 0))
+
+    def metrics_device(self, err, stream=None):
+        """Solver::evaluateMetricsMTS on the x the last solve left in the plan: writes the primal residual image to the device
+        buffer ``err`` and returns (errL1, errL2)."""
+        l1, l2 = ctypes.c_float(), ctypes.c_float()
+        check(lib().gdb200_poisson_metrics_device(self._h, ctypes.c_void_p(err.data_ptr() if hasattr(err, "data_ptr") else int(err)),
+                                                  ctypes.byref(l1), ctypes.byref(l2), ctypes.c_void_p(stream or 0)))
+        return l1.value, l2.value
+
     def close(self):
         if self._h:
             lib().gdb200_poisson_plan_destroy(self._h)
@@ -125,7 +142,6 @@ class PoissonSolver:
         if self._final is None:
             raise Gdb200Error("evaluateMetricsMTS() before solveIndirect()")      # reference asserts m_x, Solver.cpp:513
         L = lib()
-        L.gdb200_poisson_metrics.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]
         out = np.empty(self._final.shape, dtype=np.float32)
         l1, l2 = ctypes.c_float(), ctypes.c_float()
         check(L.gdb200_poisson_metrics(out.ctypes.data_as(ctypes.c_void_p), ctypes.byref(l1), ctypes.byref(l2)))

@@ -93,6 +93,13 @@ typedef struct gdb200_poisson_plan gdb200_poisson_plan;
 int  gdb200_poisson_plan_create(int w, int h, gdb200_poisson_plan **out_plan);
 void gdb200_poisson_plan_destroy(gdb200_poisson_plan *plan);
 
+/* Tuning knob without a reference counterpart: images small enough for every CTA to keep the CG vectors x and Ap of its tiles
+ * in shared memory (<= ~1.2 Mpixel on a B200) are solved by the "resident" variant of the kernel; plan_create selects it when
+ * it fits.  Both variants do the same arithmetic in the same order and return the same bits (tests/test_poisson_gpu.py);
+ * set_resident(plan, 0) forces the streaming variant, (plan, 1) fails with GDB200_ERR_ARGUMENT if the image does not fit. */
+int  gdb200_poisson_plan_set_resident(gdb200_poisson_plan *plan, int on);
+int  gdb200_poisson_plan_is_resident(const gdb200_poisson_plan *plan);
+
 /* Device-pointer entry: inputs/outputs are resident in HBM (w*h*3 floats each).
  * d_throughput may be NULL (alpha := 0, x0 := 0; Solver.cpp:319,334-337) and
  * d_direct may be NULL (final := x; Solver.cpp:561-562).  `stream` is a

@@ -136,6 +136,47 @@ def test_deterministic_across_runs():
     assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("size,preset", [((1024, 1024), "L1D"), ((1024, 1024), "L2D"), ((1000, 700), "L1D"), ((333, 97), "L1D"),
+                                         ((640, 360), "L1L"), ((64, 48), "L1Q")])
+def test_resident_variant_returns_the_streaming_variants_bits(size, preset):
+    """Images of <= 2 tiles per CTA are solved with x and Ap kept in shared memory (poisson_irls_cg_kernel<true>): same
+    arithmetic, same reduction order => the very same bits as the streaming variant, incl. L1L's cgTolerance early-outs (an IRLS
+    iteration without a CG step leaves nothing resident) and the solved x the plan keeps for evaluateMetrics."""
+    import torch
+    w, h = size
+    d = synth.solver_inputs(w, h, seed=91, last_col_nonzero=True)
+    t = {k: torch.from_numpy(v).cuda() for k, v in d.items()}
+    params = gdb200.SolverParams()
+    assert params.setConfigPreset(preset)
+    plan = gdb200.PoissonPlan(w, h)
+    assert plan.resident, "a B200 keeps images up to 1184 tiles resident"
+    outs, iters, metrics = [], [], []
+    for resident in (True, False, True):
+        plan.resident = resident
+        assert plan.resident == resident
+        out = torch.empty_like(t["dx"])
+        st = gdb200.Stats()
+        plan.solve_device(t["dx"], t["dy"], t["throughput"], t["direct"], 0.2, params.cfg, out, stats=st)
+        outs.append(out.cpu().numpy())
+        iters.append((st.irls_iters, st.cg_iters))
+        err = torch.empty_like(t["dx"])
+        l1, l2 = plan.metrics_device(err)
+        metrics.append((l1, l2, err.cpu().numpy()))
+    plan.close()
+    assert iters[0] == iters[1] == iters[2], iters
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    assert metrics[0][:2] == metrics[1][:2] and np.array_equal(metrics[0][2], metrics[1][2])
+
+
+def test_resident_variant_is_refused_for_large_images():
+    plan = gdb200.PoissonPlan(1920, 1080)
+    assert not plan.resident
+    with pytest.raises(gdb200.Gdb200Error, match="does not fit the resident variant"):
+        plan.resident = True
+    plan.resident = False
+    plan.close()
+
+
 def test_device_pointer_entry_matches_host_entry():
     import torch
     w, h = 320, 200
