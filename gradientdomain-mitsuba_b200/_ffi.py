@@ -56,8 +56,8 @@ def lib():
     L.gdb200_poisson_plan_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]
     L.gdb200_poisson_plan_destroy.argtypes = [vp]
     L.gdb200_poisson_plan_destroy.restype = None
-    L.gdb200_poisson_plan_set_resident.argtypes = [vp, ctypes.c_int]
-    L.gdb200_poisson_plan_is_resident.argtypes = [vp]
+    L.gdb200_poisson_plan_set_variant.argtypes = [vp, ctypes.c_int]
+    L.gdb200_poisson_plan_variant.argtypes = [vp]
     L.gdb200_poisson_metrics_device.argtypes = [vp, vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), vp]
     L.gdb200_poisson_metrics.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]
     L.gdb200_poisson_solve_device.argtypes = [vp, vp, vp, vp, vp, ctypes.c_float, ctypes.POINTER(PoissonConfig),

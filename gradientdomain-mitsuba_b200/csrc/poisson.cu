@@ -40,8 +40,12 @@ static_assert(kTileGX * kTileY == kThreads, "one thread per 4-pixel group");
 // every phase, so the CG vectors only their own thread ever touches -- x and Ap -- stay in shared memory for the whole CG loop
 // (2 tiles x 2 vectors x 3 channels x 256 threads x 16 B = 48 KB per CTA): 72 instead of 120 B of L2 traffic per pixel and CG
 // iteration, and a working set (r, p, p', w2) that fits one L2 partition.  Same arithmetic, same reduction order, same bits.
-constexpr int kResTiles = 2;
-constexpr int kResBytes = kResTiles * 2 * 3 * kThreads * 16;
+// Kernel variants: 0 = streaming (everything through L2), 1 = x and Ap resident for <= 2 tiles per CTA, 2 = x resident for
+// <= 4 tiles per CTA (1920x1080 on a B200: 96 instead of 120 B), 3 = streaming with the shared-tile exchange of phase A.
+constexpr int kResBytes = 2 * 2 * 3 * kThreads * 16;      // 48 KB either way: 2 tiles x {x, Ap} or 4 tiles x {x}
+__host__ __device__ constexpr int res_tiles(int mode) { return mode == 1 ? 2 : mode == 2 ? 4 : 0; }
+__host__ __device__ constexpr bool res_x(int mode) { return mode == 1 || mode == 2; }
+__host__ __device__ constexpr bool res_ap(int mode) { return mode == 1; }
 
 enum Plane {
     B0 = 0, BX = 3, BY = 6,      // b = [alpha*throughput; dx; dy]   (Solver.cpp:321-329)
@@ -320,15 +324,15 @@ __device__ void phase_rhs(const PoissonArgs &a, float coef, double rz[3])
     rz[0] = acc[0]; rz[1] = acc[1]; rz[2] = acc[2];
 }
 
-// Resident x (which = 0) / Ap (which = 1) of this thread's 4 pixels in the CTA's k-th tile.
-__device__ __forceinline__ F4 res_ld(const float4 *res, int k, int which, int ch)
+// Resident x (which = 0) / Ap (which = 1) of this thread's 4 pixels in the CTA's k-th tile; T = tiles the variant holds.
+template <int T> __device__ __forceinline__ F4 res_ld(const float4 *res, int k, int which, int ch)
 {
-    const float4 t = res[((k * 2 + which) * 3 + ch) * kThreads + threadIdx.x];
+    const float4 t = res[((which * T + k) * 3 + ch) * kThreads + threadIdx.x];
     return F4{{t.x, t.y, t.z, t.w}};
 }
-__device__ __forceinline__ void res_st(float4 *res, int k, int which, int ch, const F4 &v)
+template <int T> __device__ __forceinline__ void res_st(float4 *res, int k, int which, int ch, const F4 &v)
 {
-    res[((k * 2 + which) * 3 + ch) * kThreads + threadIdx.x] = make_float4(v.v[0], v.v[1], v.v[2], v.v[3]);
+    res[((which * T + k) * 3 + ch) * kThreads + threadIdx.x] = make_float4(v.v[0], v.v[1], v.v[2], v.v[3]);
 }
 
 // ---- phase A: p = r + b*p_old; x += a_prev*p_old; Ap = A p; pAp ---------------------------
@@ -398,9 +402,11 @@ __device__ void phase_cg_a(const PoissonArgs &a, int pOld, int pNew, const float
 // hit rate 25 % instead of 48 %, more L2 traffic than the streaming variant saves).  Only the tile's outer ring is recomputed
 // from global r / p_old.  Same expressions on the same values as phase_cg_a => same bits.
 constexpr int kHaloPitch = kTileGX * 4 + 8;     // 4 floats of margin left and right keep the float4 rows 16-byte aligned
+template <int MODE>
 __device__ void phase_cg_a_res(const PoissonArgs &a, int pOld, int pNew, const float aPrev[3],
                                const float beta[3], double pAp[3], float4 *res, bool xResident)
 {
+    constexpr int T = res_tiles(MODE);
     __shared__ __align__(16) float s_c[kTileY + 2][kHaloPitch];
     const float alphaSqr = a.alpha * a.alpha;
     const int lx = threadIdx.x % kTileGX, ly = threadIdx.x / kTileGX;
@@ -424,13 +430,14 @@ __device__ void phase_cg_a_res(const PoissonArgs &a, int pOld, int pNew, const f
             F4 c = zero4();
             if (t.valid) {
                 const F4 rc = ld4(r + t.idx), pc = ld4(po + t.idx);
-                F4 xv = xResident ? res_ld(res, k, 0, ch) : ld4(a.plane[X + ch] + t.idx);
+                F4 xv = (res_x(MODE) && xResident) ? res_ld<T>(res, k, 0, ch) : ld4(a.plane[X + ch] + t.idx);
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     xv.v[j] += pc.v[j] * al;
                     c.v[j] = rc.v[j] + pc.v[j] * b;
                 }
-                res_st(res, k, 0, ch, xv);
+                if (res_x(MODE)) res_st<T>(res, k, 0, ch, xv);
+                else st4(a.plane[X + ch] + t.idx, xv);
                 st4(a.plane[pNew + ch] + t.idx, c);
                 *reinterpret_cast<float4 *>(&s_c[ly + 1][4 + 4 * lx]) = make_float4(c.v[0], c.v[1], c.v[2], c.v[3]);
                 // the ring around the tile, from the neighbouring tiles' r and p_old
@@ -469,7 +476,8 @@ __device__ void phase_cg_a_res(const PoissonArgs &a, int pOld, int pNew, const f
                     Ap.v[j] = v;
                     acc[ch] += xi * v;
                 }
-                res_st(res, k, 1, ch, Ap);
+                if (res_ap(MODE)) res_st<T>(res, k, 1, ch, Ap);
+                else st4(a.plane[AP + ch] + t.idx, Ap);
             }
             __syncthreads();
         }
@@ -478,7 +486,7 @@ __device__ void phase_cg_a_res(const PoissonArgs &a, int pOld, int pNew, const f
 }
 
 // ---- phase B: r -= a*Ap; rz = r.r   (Backend.cpp:296-321) ----------------------------------
-template <bool RES>
+template <int MODE>
 __device__ void phase_cg_b(const PoissonArgs &a, const float al[3], double rz[3], const float4 *res)
 {
     float acc[3] = {0.f, 0.f, 0.f};
@@ -490,7 +498,7 @@ __device__ void phase_cg_b(const PoissonArgs &a, const float al[3], double rz[3]
 #pragma unroll
         for (int ch = 0; ch < 3; ch++) {
             F4 r = ld4(a.plane[R + ch] + t.idx);
-            const F4 Ap = RES ? res_ld(res, k, 1, ch) : ld4(a.plane[AP + ch] + t.idx);
+            const F4 Ap = res_ap(MODE) ? res_ld<res_tiles(MODE)>(res, k, 1, ch) : ld4(a.plane[AP + ch] + t.idx);
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const float ri = r.v[j] - Ap.v[j] * al[ch];
@@ -504,6 +512,7 @@ __device__ void phase_cg_b(const PoissonArgs &a, const float al[3], double rz[3]
 }
 
 // ---- phase: pending x += a*p of the last CG iteration --------------------------------------
+template <int MODE>
 __device__ void phase_flush_x(const PoissonArgs &a, int pCur, const float al[3], const float4 *res, bool xResident)
 {
     int k = -1;
@@ -513,7 +522,7 @@ __device__ void phase_flush_x(const PoissonArgs &a, int pCur, const float al[3],
         if (!t.valid) continue;
 #pragma unroll
         for (int ch = 0; ch < 3; ch++) {
-            F4 x = xResident ? res_ld(res, k, 0, ch) : ld4(a.plane[X + ch] + t.idx);
+            F4 x = (res_x(MODE) && xResident) ? res_ld<res_tiles(MODE)>(res, k, 0, ch) : ld4(a.plane[X + ch] + t.idx);
             const F4 p = ld4(a.plane[pCur + ch] + t.idx);
 #pragma unroll
             for (int j = 0; j < 4; j++) x.v[j] += p.v[j] * al[ch];
@@ -523,6 +532,7 @@ __device__ void phase_flush_x(const PoissonArgs &a, int pCur, const float al[3],
 }
 
 // ---- phase: final = 1*direct + x  (Solver.cpp:561-567), with the last x update folded in ---
+template <int MODE>
 __device__ void phase_export(const PoissonArgs &a, int pCur, const float al[3], const float4 *res, bool xResident)
 {
     int k = -1;
@@ -533,7 +543,7 @@ __device__ void phase_export(const PoissonArgs &a, int pCur, const float al[3], 
         F4 x[3];
 #pragma unroll
         for (int ch = 0; ch < 3; ch++) {
-            x[ch] = xResident ? res_ld(res, k, 0, ch) : ld4(a.plane[X + ch] + t.idx);
+            x[ch] = (res_x(MODE) && xResident) ? res_ld<res_tiles(MODE)>(res, k, 0, ch) : ld4(a.plane[X + ch] + t.idx);
             const F4 p = ld4(a.plane[pCur + ch] + t.idx);
 #pragma unroll
             for (int j = 0; j < 4; j++) x[ch].v[j] += p.v[j] * al[ch];
@@ -561,10 +571,10 @@ struct CgScalars {
     float coef;
 };
 
-template <bool RES>
+template <int MODE>
 __global__ void __launch_bounds__(kThreads, 4) poisson_irls_cg_kernel(const PoissonArgs a)
 {
-    extern __shared__ float4 s_res[];     // RES: [tile][x | Ap][channel][thread], kResBytes
+    extern __shared__ float4 s_res[];     // variants 1, 2: [x | Ap][tile][channel][thread], kResBytes
     __shared__ CgScalars sc;
     bool xResident = false;               // the current x is in s_res, not in the X planes (uniform over the grid)
     cg::grid_group grid = cg::this_grid();
@@ -581,7 +591,7 @@ __global__ void __launch_bounds__(kThreads, 4) poisson_irls_cg_kernel(const Pois
 
     for (int irls = 0; irls < a.cfg.irlsIterMax; irls++) {
         if (irls > 0) {                                   // apply the pending x update first
-            phase_flush_x(a, pCur, sc.aPrev, s_res, xResident);
+            phase_flush_x<MODE>(a, pCur, sc.aPrev, s_res, xResident);
             xResident = false;
             grid.sync();
         }
@@ -619,9 +629,9 @@ __global__ void __launch_bounds__(kThreads, 4) poisson_irls_cg_kernel(const Pois
             }
             cur ^= 1;                                                       // Solver.cpp:466: rz <-> rz2
             const int pNew = (pCur == PA) ? PB : PA;
-            if (RES) phase_cg_a_res(a, pCur, pNew, sc.aPrev, sc.beta, part, s_res, xResident);
+            if (MODE != 0) phase_cg_a_res<MODE>(a, pCur, pNew, sc.aPrev, sc.beta, part, s_res, xResident);
             else phase_cg_a(a, pCur, pNew, sc.aPrev, sc.beta, part);
-            xResident = RES;
+            xResident = res_x(MODE);
             grid_sum3(grid, a.red, parity, part[0], part[1], part[2], tot);
             pCur = pNew;
             if (lead) {
@@ -629,7 +639,7 @@ __global__ void __launch_bounds__(kThreads, 4) poisson_irls_cg_kernel(const Pois
                 for (int c = 0; c < 3; c++) sc.al[c] = sc.rz[cur ^ 1][c] / fmaxf(tot[c], FLT_MIN);   // Backend.cpp:309
             }
             __syncthreads();
-            phase_cg_b<RES>(a, sc.al, part, s_res);
+            phase_cg_b<MODE>(a, sc.al, part, s_res);
             grid_sum3(grid, a.red, parity, part[0], part[1], part[2], tot);
             if (lead) {
 #pragma unroll
@@ -644,7 +654,7 @@ __global__ void __launch_bounds__(kThreads, 4) poisson_irls_cg_kernel(const Pois
         }
         irlsDone++;
     }
-    phase_export(a, pCur, sc.aPrev, s_res, xResident);
+    phase_export<MODE>(a, pCur, sc.aPrev, s_res, xResident);
     if (blockIdx.x == 0 && lead) { a.iters[0] = irlsDone; a.iters[1] = cgTotal; }
 }
 
@@ -690,13 +700,40 @@ struct gdb200_poisson_plan {
     cudaEvent_t evHost[4] = {nullptr, nullptr, nullptr, nullptr};   // copy timing of the host-pointer entry point (created on first use)
     gdb200::PoissonArgs last;          // geometry, alpha and planes of the last solve (gdb200_poisson_metrics_device)
     bool solved = false;
-    bool resident = false;             // x and Ap of every CTA's tiles fit its shared memory (poisson_irls_cg_kernel<true>)
+    int variant = 0;                   // kernel variant the solves of this plan run (poisson_irls_cg_kernel<variant>)
+    long long nTiles = 0;
+    int occ = 0, sms = 0;
     // staging for the host-pointer entry point
     float *d_in[4] = {nullptr, nullptr, nullptr, nullptr};
     float *d_out = nullptr;
 };
 
 using namespace gdb200;
+
+static void *variant_kernel(int v)
+{
+    switch (v) {
+    case 1: return (void *)poisson_irls_cg_kernel<1>;
+    case 2: return (void *)poisson_irls_cg_kernel<2>;
+    case 3: return (void *)poisson_irls_cg_kernel<3>;
+    default: return (void *)poisson_irls_cg_kernel<0>;
+    }
+}
+static size_t variant_smem(int v) { return res_tiles(v) ? kResBytes : 0; }
+
+// A variant fits when it keeps the streaming variant's residency (the grid was sized for it) and every CTA's tiles fit.
+static bool variant_fits(const gdb200_poisson_plan *p, int v)
+{
+    if (v == 0) return true;
+    if (variant_smem(v) && cudaFuncSetAttribute(variant_kernel(v), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)variant_smem(v)) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, variant_kernel(v), kThreads, variant_smem(v)) != cudaSuccess) { cudaGetLastError(); return false; }
+    if ((long long)occ * p->sms < p->grid) return false;
+    return res_tiles(v) == 0 || p->nTiles <= (long long)res_tiles(v) * p->grid;
+}
 
 extern "C" {
 
@@ -737,10 +774,8 @@ int gdb200_poisson_plan_create(int w, int h, gdb200_poisson_plan **out)
     gdb200_poisson_plan *p = new gdb200_poisson_plan;
     p->device = di.device; p->w = w; p->h = h; p->wp = (w + 3) & ~3;
     const size_t planeElems = (size_t)p->wp * h;
-    int occ = 0, occRes = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, poisson_irls_cg_kernel<false>, kThreads, 0);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(poisson_irls_cg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kResBytes);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occRes, poisson_irls_cg_kernel<true>, kThreads, kResBytes);
+    int occ = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, poisson_irls_cg_kernel<0>, kThreads, 0);
     if (e != cudaSuccess || occ < 1) {
         delete p;
         return set_error(GDB200_ERR_CUDA, "poisson kernel not launchable on this device: %s "
@@ -749,8 +784,12 @@ int gdb200_poisson_plan_create(int w, int h, gdb200_poisson_plan **out)
     const int tilesX = (p->wp / 4 + kTileGX - 1) / kTileGX, tilesY = (h + kTileY - 1) / kTileY;
     const long long nTiles = (long long)tilesX * tilesY;
     p->grid = (int)std::min<long long>(nTiles, (long long)occ * di.sms);
-    // the resident variant needs the same residency and every CTA's tiles in its shared memory
-    p->resident = occRes >= occ && nTiles <= (long long)kResTiles * p->grid;
+    p->nTiles = nTiles;
+    p->occ = occ; p->sms = di.sms;
+    // the fastest variant that fits: x and Ap resident, else x resident, else streaming
+    p->variant = 0;
+    for (int v = 1; v <= 2 && p->variant == 0; v++)
+        if (variant_fits(p, v)) p->variant = v;
 #define PLAN_CUDA(call) do { cudaError_t e2 = (call); if (e2 != cudaSuccess) { gdb200_poisson_plan_destroy(p); \
         return set_error(GDB200_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e2)); } } while (0)
     PLAN_CUDA(cudaMalloc(&p->planes, planeElems * kPlanes * sizeof(float)));
@@ -800,10 +839,7 @@ int gdb200_poisson_solve_device(gdb200_poisson_plan *p, const float *d_dx, const
     p->last = a; p->solved = true;
     if (stats) GDB_CUDA(cudaEventRecord(p->ev0, s));
     void *kargs[] = {&a};
-    if (p->resident)
-        GDB_CUDA(cudaLaunchCooperativeKernel((void *)poisson_irls_cg_kernel<true>, dim3(p->grid), dim3(kThreads), kargs, kResBytes, s));
-    else
-        GDB_CUDA(cudaLaunchCooperativeKernel((void *)poisson_irls_cg_kernel<false>, dim3(p->grid), dim3(kThreads), kargs, 0, s));
+    GDB_CUDA(cudaLaunchCooperativeKernel(variant_kernel(p->variant), dim3(p->grid), dim3(kThreads), kargs, variant_smem(p->variant), s));
     if (stats) {
         GDB_CUDA(cudaEventRecord(p->ev1, s));
         GDB_CUDA(cudaEventSynchronize(p->ev1));
@@ -816,22 +852,18 @@ int gdb200_poisson_solve_device(gdb200_poisson_plan *p, const float *d_dx, const
     return GDB200_OK;
 }
 
-int gdb200_poisson_plan_set_resident(gdb200_poisson_plan *p, int on)
+int gdb200_poisson_plan_set_variant(gdb200_poisson_plan *p, int variant)
 {
     if (!p) return set_error(GDB200_ERR_ARGUMENT, "plan is NULL");
-    if (!on) { p->resident = false; return GDB200_OK; }
-    int occRes = 0, sms = 0;
-    GDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occRes, poisson_irls_cg_kernel<true>, kThreads, kResBytes));
-    GDB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device));
-    const long long tilesX = (p->wp / 4 + kTileGX - 1) / kTileGX, nTiles = tilesX * ((p->h + kTileY - 1) / kTileY);
-    if ((long long)occRes * sms < p->grid || nTiles > (long long)kResTiles * p->grid)
-        return set_error(GDB200_ERR_ARGUMENT, "image of %dx%d does not fit the resident variant (%lld tiles, %d CTAs x %d)", p->w, p->h,
-                         nTiles, p->grid, kResTiles);
-    p->resident = true;
+    if (variant < 0 || variant > 3) return set_error(GDB200_ERR_ARGUMENT, "solver kernel variant %d (expected 0..3)", variant);
+    if (!variant_fits(p, variant))
+        return set_error(GDB200_ERR_ARGUMENT, "image of %dx%d does not fit solver kernel variant %d (%lld tiles, %d CTAs x %d resident tiles)",
+                         p->w, p->h, variant, p->nTiles, p->grid, res_tiles(variant));
+    p->variant = variant;
     return GDB200_OK;
 }
 
-int gdb200_poisson_plan_is_resident(const gdb200_poisson_plan *p) { return p && p->resident ? 1 : 0; }
+int gdb200_poisson_plan_variant(const gdb200_poisson_plan *p) { return p ? p->variant : -1; }
 
 static thread_local gdb200_poisson_plan *g_cachedPlan = nullptr;     // plan of this thread's host-pointer solves
 

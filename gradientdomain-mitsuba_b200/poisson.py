@@ -58,13 +58,14 @@ class PoissonPlan:
                                                 ctypes.byref(stats) if stats is not None else None))
 
     @property
-    def resident(self):
-        """True when solves on this plan run the kernel variant that keeps x and Ap in shared memory (small images)."""
-        return bool(lib().gdb200_poisson_plan_is_resident(self._h))
+    def variant(self):
+        """Kernel variant the solves of this plan run: 0 streaming, 1 x and Ap resident in shared memory (small images),
+        2 x resident, 3 streaming with the shared-tile exchange (include/gdb200.h). Same bits from all of them."""
+        return int(lib().gdb200_poisson_plan_variant(self._h))
 
-    @resident.setter
-    def resident(self, on):
-        check(lib().gdb200_poisson_plan_set_resident(self._h, 1 if on else 0))
+    @variant.setter
+    def variant(self, v):
+        check(lib().gdb200_poisson_plan_set_variant(self._h, int(v)))
 
     def metrics_device(self, err, stream=None):
         """Solver::evaluateMetricsMTS on the x the last solve left in the plan: writes the primal residual image to the device

@@ -93,12 +93,13 @@ typedef struct gdb200_poisson_plan gdb200_poisson_plan;
 int  gdb200_poisson_plan_create(int w, int h, gdb200_poisson_plan **out_plan);
 void gdb200_poisson_plan_destroy(gdb200_poisson_plan *plan);
 
-/* Tuning knob without a reference counterpart: images small enough for every CTA to keep the CG vectors x and Ap of its tiles
- * in shared memory (<= ~1.2 Mpixel on a B200) are solved by the "resident" variant of the kernel; plan_create selects it when
- * it fits.  Both variants do the same arithmetic in the same order and return the same bits (tests/test_poisson_gpu.py);
- * set_resident(plan, 0) forces the streaming variant, (plan, 1) fails with GDB200_ERR_ARGUMENT if the image does not fit. */
-int  gdb200_poisson_plan_set_resident(gdb200_poisson_plan *plan, int on);
-int  gdb200_poisson_plan_is_resident(const gdb200_poisson_plan *plan);
+/* Tuning knob without a reference counterpart: the solver kernel has variants that differ in where the CG vectors live, not in
+ * arithmetic -- 0: everything streams through L2; 1: x and Ap of every CTA's tiles stay in shared memory (images up to 2 tiles
+ * per CTA, ~1.2 Mpixel on a B200); 2: x stays in shared memory (up to 4 tiles per CTA, ~2.4 Mpixel); 3: as 0 with the search
+ * direction exchanged through a shared tile.  plan_create picks the fastest that fits (1, else 2, else 0).  All variants
+ * return the same bits (tests/test_poisson_gpu.py); set_variant fails with GDB200_ERR_ARGUMENT if the image does not fit. */
+int  gdb200_poisson_plan_set_variant(gdb200_poisson_plan *plan, int variant);
+int  gdb200_poisson_plan_variant(const gdb200_poisson_plan *plan);
 
 /* Device-pointer entry: inputs/outputs are resident in HBM (w*h*3 floats each).
  * d_throughput may be NULL (alpha := 0, x0 := 0; Solver.cpp:319,334-337) and

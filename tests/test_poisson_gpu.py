@@ -136,44 +136,57 @@ def test_deterministic_across_runs():
     assert np.array_equal(a, b)
 
 
-@pytest.mark.parametrize("size,preset", [((1024, 1024), "L1D"), ((1024, 1024), "L2D"), ((1000, 700), "L1D"), ((333, 97), "L1D"),
-                                         ((640, 360), "L1L"), ((64, 48), "L1Q")])
-def test_resident_variant_returns_the_streaming_variants_bits(size, preset):
-    """Images of <= 2 tiles per CTA are solved with x and Ap kept in shared memory (poisson_irls_cg_kernel<true>): same
-    arithmetic, same reduction order => the very same bits as the streaming variant, incl. L1L's cgTolerance early-outs (an IRLS
-    iteration without a CG step leaves nothing resident) and the solved x the plan keeps for evaluateMetrics."""
+@pytest.mark.parametrize("size,preset,auto", [((1024, 1024), "L1D", 1), ((1024, 1024), "L2D", 1), ((1000, 700), "L1D", 1),
+                                              ((333, 97), "L1D", 1), ((640, 360), "L1L", 1), ((64, 48), "L1Q", 1),
+                                              ((1920, 1080), "L1D", 2), ((1500, 1201), "L2D", 2)])
+def test_kernel_variants_return_the_same_bits(size, preset, auto):
+    """The kernel variants differ in where the CG vectors live (include/gdb200.h: 1 keeps x and Ap of <= 2 tiles per CTA in
+    shared memory, 2 keeps x of <= 4 tiles, 3 only exchanges the search direction through a shared tile, 0 streams everything):
+    same arithmetic, same reduction order => the very same bits, incl. L1L's cgTolerance early-outs (an IRLS iteration
+    without a CG step leaves nothing resident) and the solved x the plan keeps for evaluateMetrics."""
     import torch
     w, h = size
-    d = synth.solver_inputs(w, h, seed=91, last_col_nonzero=True)
-    t = {k: torch.from_numpy(v).cuda() for k, v in d.items()}
+    d = synth.solver_inputs(min(w, 1024), min(h, 1024), seed=91, last_col_nonzero=True)
+    reps = (-(-h // d["dx"].shape[0]), -(-w // d["dx"].shape[1]), 1)
+    t = {k: torch.from_numpy(np.ascontiguousarray(np.tile(v, reps)[:h, :w])).cuda() for k, v in d.items()}
     params = gdb200.SolverParams()
     assert params.setConfigPreset(preset)
     plan = gdb200.PoissonPlan(w, h)
-    assert plan.resident, "a B200 keeps images up to 1184 tiles resident"
-    outs, iters, metrics = [], [], []
-    for resident in (True, False, True):
-        plan.resident = resident
-        assert plan.resident == resident
+    assert plan.variant == auto, "choice of plan_create on a B200 (148 SMs x 4 CTAs)"
+    results = {}
+    for variant in [auto] + [v for v in (0, 1, 2, 3) if v != auto and (v in (0, 3) or v > auto)] + [auto]:
+        plan.variant = variant
+        assert plan.variant == variant
         out = torch.empty_like(t["dx"])
         st = gdb200.Stats()
         plan.solve_device(t["dx"], t["dy"], t["throughput"], t["direct"], 0.2, params.cfg, out, stats=st)
-        outs.append(out.cpu().numpy())
-        iters.append((st.irls_iters, st.cg_iters))
         err = torch.empty_like(t["dx"])
         l1, l2 = plan.metrics_device(err)
-        metrics.append((l1, l2, err.cpu().numpy()))
+        got = (out.cpu().numpy(), (st.irls_iters, st.cg_iters), (l1, l2), err.cpu().numpy())
+        if not results:
+            results["first"] = got
+            continue
+        first = results["first"]
+        assert got[1] == first[1] and got[2] == first[2], (variant, got[1:3], first[1:3])
+        assert np.array_equal(got[0], first[0]) and np.array_equal(got[3], first[3]), variant
     plan.close()
-    assert iters[0] == iters[1] == iters[2], iters
-    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
-    assert metrics[0][:2] == metrics[1][:2] and np.array_equal(metrics[0][2], metrics[1][2])
 
 
-def test_resident_variant_is_refused_for_large_images():
+def test_resident_variants_are_refused_for_large_images():
     plan = gdb200.PoissonPlan(1920, 1080)
-    assert not plan.resident
-    with pytest.raises(gdb200.Gdb200Error, match="does not fit the resident variant"):
-        plan.resident = True
-    plan.resident = False
+    assert plan.variant == 2
+    with pytest.raises(gdb200.Gdb200Error, match="does not fit solver kernel variant 1"):
+        plan.variant = 1
+    plan.close()
+    plan = gdb200.PoissonPlan(3840, 2160)
+    assert plan.variant == 0
+    for v in (1, 2):
+        with pytest.raises(gdb200.Gdb200Error, match="does not fit solver kernel variant"):
+            plan.variant = v
+    with pytest.raises(gdb200.Gdb200Error, match="expected 0..3"):
+        plan.variant = 7
+    plan.variant = 3
+    plan.variant = 0
     plan.close()
 
 
