@@ -56,6 +56,9 @@ def lib():
     L.gdb200_poisson_plan_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]
     L.gdb200_poisson_plan_destroy.argtypes = [vp]
     L.gdb200_poisson_plan_destroy.restype = None
+    L.gdb200_poisson_shard_create.argtypes = [ctypes.c_int] * 6 + [ctypes.POINTER(vp)]
+    L.gdb200_poisson_shard_export.argtypes = [vp, vp]
+    L.gdb200_poisson_shard_connect.argtypes = [vp, vp, ctypes.c_int]
     L.gdb200_poisson_plan_set_variant.argtypes = [vp, ctypes.c_int]
     L.gdb200_poisson_plan_variant.argtypes = [vp]
     L.gdb200_poisson_metrics_device.argtypes = [vp, vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), vp]

@@ -27,6 +27,7 @@
 #include <algorithm>
 #include <cstring>
 #include <mutex>
+#include <unistd.h>
 
 namespace cg = cooperative_groups;
 
@@ -55,8 +56,26 @@ enum Plane {
     kPlanes = 30
 };
 
+constexpr int kMaxRanks = 16;
+
+// One reduction message of a rank: its three partial sums and the number of the reduction they belong to.
+struct __align__(32) Mail {
+    double v[3];
+    unsigned long long epoch;
+};
+
 struct PoissonArgs {
     int W, H, Wp, Gx, tilesX, nTiles, aosVec;
+    // Row band [y0, y1) of the image this GPU solves (the whole image on one GPU).  The planes hold rows y0-1 .. y1: local row
+    // 0 and local row y1-y0+1 are halo rows, refreshed by the neighbouring GPU with peer stores (see "sharded solve").
+    int y0, y1;
+    int rank, nRanks;
+    float *peerUp, *peerDown;                 // plane arrays of the GPUs holding the bands above / below (peer memory) or NULL
+    size_t peerUpElems, peerDownElems;        // their plane sizes in floats
+    int peerUpRows;                           // rows of the band above (its lower halo is its local row peerUpRows + 1)
+    Mail *mail[kMaxRanks];                    // mail[r]: rank r's mailbox [2][nRanks] (mail[rank] is local memory)
+    unsigned long long epochBase;             // solve number << 32: mailbox epochs never repeat, no reset between solves
+    unsigned *status;                         // != 0: a peer did not arrive in time (the solve gives up instead of hanging)
     float alpha;
     gdb200_poisson_config cfg;
     float *plane[kPlanes];
@@ -79,17 +98,41 @@ __device__ __forceinline__ void st4(float *p, const F4 &a)
 }
 __device__ __forceinline__ F4 zero4() { return F4{{0.f, 0.f, 0.f, 0.f}}; }
 
-// Deterministic grid-wide sum of three per-thread doubles; the result is returned to THREAD 0 of every CTA only (it derives the
-// CG scalars and publishes them in shared memory, see CgScalars).  Contains one grid barrier.  After the barrier EVERY thread fetches
-// its share of the per-CTA partials (<= 3 independent loads per component at 592 CTAs: one L2 round trip instead of a 19-step
-// loop on one warp), then a fixed-order warp / block tree.  The shared scratch is indexed by the call's parity so that a call
-// needs no trailing __syncthreads.
-__device__ void grid_sum3(cg::grid_group &grid, double *red, int &parity, double a0, double a1,
+// Deterministic sum of three per-thread doubles over the grid -- and, in a sharded solve, over the grids of all GPUs; the result
+// is returned to THREAD 0 of every CTA only (it derives the CG scalars and publishes them in shared memory, see CgScalars).
+// Contains one grid barrier.  After the barrier EVERY thread fetches its share of the per-CTA partials (<= 3 independent loads
+// per component at 592 CTAs: one L2 round trip instead of a 19-step loop on one warp), then a fixed-order warp / block tree.
+// The shared scratch is indexed by the call's parity so that a call needs no trailing __syncthreads.
+//
+// Sharded solve (nRanks > 1): CTA 0 of every GPU then posts its GPU's sums into every GPU's mailbox with 32-byte peer stores
+// over NVLink, and thread 0 of every CTA waits for the nRanks messages of this reduction in its OWN GPU's mailbox (local
+// polling) and adds them in rank order: the same bits on every GPU, so all of them take the same branches.  The message is also
+// the barrier that publishes the halo rows pushed during the phase (push_row: data store, fence.sys, grid barrier, then the
+// release store of the epoch).  Two mailbox slots by parity: a GPU can be at most one reduction ahead of the slowest one.
+struct SyncState {
+    int parity = 0;
+    unsigned long long epoch = 0;     // number of reductions so far, + PoissonArgs::epochBase
+    bool dead = false;                // a wait timed out: stop waiting, the host reports the failure
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+template <bool SHARD>
+__device__ void grid_sum3(cg::grid_group &grid, const PoissonArgs &a, SyncState &sync, double a0, double a1,
                           double a2, float out[3])
 {
     __shared__ double s_part[2][kThreads / 32][3];
     __shared__ double s_tot[2][kThreads / 32][3];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, par = parity;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, par = sync.parity;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         a0 += __shfl_xor_sync(0xffffffffu, a0, o);
@@ -99,7 +142,7 @@ __device__ void grid_sum3(cg::grid_group &grid, double *red, int &parity, double
     if (lane == 0) { s_part[par][warp][0] = a0; s_part[par][warp][1] = a1; s_part[par][warp][2] = a2; }
     __syncthreads();
     const int G = (int)gridDim.x;
-    double *slot = red + (size_t)par * G * 3;      // [3][G]
+    double *slot = a.red + (size_t)par * G * 3;      // [3][G]
     if (threadIdx.x < 3) {
         double s = 0.0;
 #pragma unroll
@@ -121,13 +164,36 @@ __device__ void grid_sum3(cg::grid_group &grid, double *red, int &parity, double
     }
     if (lane == 0) { s_tot[par][warp][0] = t0; s_tot[par][warp][1] = t1; s_tot[par][warp][2] = t2; }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        t0 = t1 = t2 = 0.0;
+    sync.parity ^= 1;
+    sync.epoch++;
+    if (threadIdx.x != 0) return;
+    t0 = t1 = t2 = 0.0;
 #pragma unroll
-        for (int w = 0; w < kThreads / 32; w++) { t0 += s_tot[par][w][0]; t1 += s_tot[par][w][1]; t2 += s_tot[par][w][2]; }
-        out[0] = (float)t0; out[1] = (float)t1; out[2] = (float)t2;
+    for (int w = 0; w < kThreads / 32; w++) { t0 += s_tot[par][w][0]; t1 += s_tot[par][w][1]; t2 += s_tot[par][w][2]; }
+    if (SHARD) {
+        const unsigned long long epoch = a.epochBase + sync.epoch;
+        if (blockIdx.x == 0) {
+            for (int r = 0; r < a.nRanks; r++) {
+                Mail *m = a.mail[r] + par * a.nRanks + a.rank;
+                m->v[0] = t0; m->v[1] = t1; m->v[2] = t2;
+            }
+            __threadfence_system();
+            for (int r = 0; r < a.nRanks; r++) st_release_sys(&(a.mail[r] + par * a.nRanks + a.rank)->epoch, epoch);
+        }
+        t0 = t1 = t2 = 0.0;
+        const Mail *box = a.mail[a.rank] + par * a.nRanks;
+        for (int r = 0; r < a.nRanks; r++) {
+            if (!sync.dead) {
+                unsigned spins = 0;
+                while (ld_acquire_sys(&box[r].epoch) != epoch) {
+                    if (++spins > (1u << 24)) { sync.dead = true; atomicExch(a.status, 1u + (unsigned)r); break; }    // ~10 s
+                    __nanosleep(64);
+                }
+            }
+            t0 += __ldcg(&box[r].v[0]); t1 += __ldcg(&box[r].v[1]); t2 += __ldcg(&box[r].v[2]);
+        }
     }
-    parity ^= 1;
+    out[0] = (float)t0; out[1] = (float)t1; out[2] = (float)t2;
 }
 
 struct TileIter {
@@ -135,16 +201,53 @@ struct TileIter {
     bool valid;
 };
 
+template <bool SHARD = true>
 __device__ __forceinline__ TileIter tile_thread(const PoissonArgs &a, int tile)
 {
+    const int y0 = SHARD ? a.y0 : 0, y1 = SHARD ? a.y1 : a.H;     // one GPU: the band is the image
     const int tx = tile % a.tilesX, ty = tile / a.tilesX;
     const int gx = tx * kTileGX + (threadIdx.x % kTileGX);
     TileIter t;
-    t.y = ty * kTileY + (threadIdx.x / kTileGX);
+    t.y = y0 + ty * kTileY + (threadIdx.x / kTileGX);
     t.x0 = gx * 4;
-    t.valid = gx < a.Gx && t.y < a.H;
-    t.idx = t.y * a.Wp + t.x0;
+    t.valid = gx < a.Gx && t.y < y1;
+    t.idx = (t.y - y0 + 1) * a.Wp + t.x0;
     return t;
+}
+
+// The 4-pixel groups of the band's two halo rows (y0-1 if it exists, then y1 if it exists), dealt over the whole grid.
+template <bool SHARD, class F> __device__ __forceinline__ void for_halo_rows(const PoissonArgs &a, bool above, bool below, F f)
+{
+    if (!SHARD) return;
+    const int n = a.Gx * 2;
+    for (int g = blockIdx.x * kThreads + threadIdx.x; g < n; g += gridDim.x * kThreads) {
+        const bool up = g < a.Gx;
+        if (up ? !(above && a.y0 > 0) : !(below && a.y1 < a.H)) continue;
+        TileIter t;
+        t.y = up ? a.y0 - 1 : a.y1;
+        t.x0 = (up ? g : g - a.Gx) * 4;
+        t.valid = true;
+        t.idx = (t.y - a.y0 + 1) * a.Wp + t.x0;
+        f(t);
+    }
+}
+
+// Sharded solve: a value this GPU wrote into the first / last row of its band goes to the neighbour's halo row as well (a
+// 16-byte store over NVLink, fire and forget; made visible by the reduction that ends the phase, grid_sum3).
+template <bool SHARD>
+__device__ __forceinline__ bool push_row(const PoissonArgs &a, const TileIter &t, int plane, const F4 &v)
+{
+    bool pushed = false;
+    if (!SHARD) return false;
+    if (a.peerUp && t.y == a.y0) {
+        st4(a.peerUp + a.peerUpElems * plane + (size_t)(a.peerUpRows + 1) * a.Wp + t.x0, v);
+        pushed = true;
+    }
+    if (a.peerDown && t.y == a.y1 - 1) {
+        st4(a.peerDown + a.peerDownElems * plane + t.x0, v);
+        pushed = true;
+    }
+    return pushed;
 }
 
 // ---- interleaved RGB <-> planar ------------------------------------------------------------
@@ -188,11 +291,9 @@ __device__ __forceinline__ void store_rgb4(float *aos, const PoissonArgs &a, con
 }
 
 // ---- phase: import  (Solver.cpp:321-337) ----------------------------------------------------
-__device__ void phase_import(const PoissonArgs &a)
+__device__ __forceinline__ void import_group(const PoissonArgs &a, const TileIter &t)
 {
-    for (int tile = blockIdx.x; tile < a.nTiles; tile += gridDim.x) {
-        const TileIter t = tile_thread(a, tile);
-        if (!t.valid) continue;
+    {
         F4 c[3];
         if (a.in_thr) load_rgb4(a.in_thr, a, t, c[0], c[1], c[2]);
         else c[0] = c[1] = c[2] = zero4();
@@ -212,6 +313,17 @@ __device__ void phase_import(const PoissonArgs &a)
 #pragma unroll
         for (int ch = 0; ch < 3; ch++) st4(a.plane[BY + ch] + t.idx, c[ch]);
     }
+}
+
+template <bool SHARD>
+__device__ void phase_import(const PoissonArgs &a)
+{
+    for (int tile = blockIdx.x; tile < a.nTiles; tile += gridDim.x) {
+        const TileIter t = tile_thread<SHARD>(a, tile);
+        if (t.valid) import_group(a, t);
+    }
+    // sharded: the inputs are whole images on every GPU, so each one imports its own halo rows
+    for_halo_rows<SHARD>(a, true, true, [&](const TileIter &t) { import_group(a, t); });
 }
 
 // e = b - P x at this thread's 4 pixels, one channel (Backend.cpp:165-186, :256-272 with a=-1).
@@ -240,10 +352,11 @@ __device__ __forceinline__ void residual4(const PoissonArgs &a, const TileIter &
 }
 
 // ---- phase: w2 numerators 1/(|e|+reg) and their sum (Backend.cpp:351-366) -------------------
+template <bool SHARD>
 __device__ void phase_weights(const PoissonArgs &a, bool first, float reg, double &sum)
 {
     for (int tile = blockIdx.x; tile < a.nTiles; tile += gridDim.x) {
-        const TileIter t = tile_thread(a, tile);
+        const TileIter t = tile_thread<SHARD>(a, tile);
         if (!t.valid) continue;
         F4 v0, vx, vy;
         if (first) {                                   // Solver.cpp:391-392: w2 = 1
@@ -271,14 +384,35 @@ __device__ void phase_weights(const PoissonArgs &a, bool first, float reg, doubl
         st4(a.plane[VX] + t.idx, vx);
         st4(a.plane[VY] + t.idx, vy);
     }
+    // sharded: the weight of the vertical gradient in the row above the band (phase_rhs / phase A read it as "wyu"), from the
+    // x halo rows -- same expression, not part of this GPU's share of the sum
+    for_halo_rows<SHARD>(a, true, false, [&](const TileIter &t) {
+        F4 vy;
+        if (first) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) vy.v[j] = (t.x0 + j < a.W) ? 1.f : 0.f;
+        } else {
+            F4 e0[3], ex[3], ey[3];
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) residual4(a, t, ch, e0[ch], ex[ch], ey[ch]);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float ly = sqrtf(ey[0].v[j] * ey[0].v[j] + ey[1].v[j] * ey[1].v[j] + ey[2].v[j] * ey[2].v[j]);
+                vy.v[j] = (t.x0 + j < a.W) ? 1.0f / (ly + reg) : 0.f;
+            }
+        }
+        st4(a.plane[VY] + t.idx, vy);
+    });
 }
 
 // ---- phase: w2 = coef*v, r = P' W2 (b - Px), rz = r.r  (Backend.cpp:368-372, :190-217) ------
+template <bool SHARD>
 __device__ void phase_rhs(const PoissonArgs &a, float coef, double rz[3])
 {
     float acc[3] = {0.f, 0.f, 0.f};
+    bool pushed = false;
     for (int tile = blockIdx.x; tile < a.nTiles; tile += gridDim.x) {
-        const TileIter t = tile_thread(a, tile);
+        const TileIter t = tile_thread<SHARD>(a, tile);
         if (!t.valid) continue;
         const bool hasL = t.x0 > 0, hasU = t.y > 0;
         F4 w0 = ld4(a.plane[V0] + t.idx), wx = ld4(a.plane[VX] + t.idx), wy = ld4(a.plane[VY] + t.idx);
@@ -319,8 +453,16 @@ __device__ void phase_rhs(const PoissonArgs &a, float coef, double rz[3])
                 acc[ch] += v * v;
             }
             st4(a.plane[R + ch] + t.idx, r);
+            pushed |= push_row<SHARD>(a, t, R + ch, r);
         }
     }
+    for_halo_rows<SHARD>(a, true, false, [&](const TileIter &t) {
+        F4 wyu = ld4(a.plane[VY] + t.idx);
+#pragma unroll
+        for (int j = 0; j < 4; j++) wyu.v[j] *= coef;
+        st4(a.plane[WY] + t.idx, wyu);
+    });
+    if (SHARD && pushed) __threadfence_system();
     rz[0] = acc[0]; rz[1] = acc[1]; rz[2] = acc[2];
 }
 
@@ -337,13 +479,15 @@ template <int T> __device__ __forceinline__ void res_st(float4 *res, int k, int 
 
 // ---- phase A: p = r + b*p_old; x += a_prev*p_old; Ap = A p; pAp ---------------------------
 // (Backend.cpp:325-347 of the previous iteration fused with :221-252 of this one.)
+template <bool SHARD>
 __device__ void phase_cg_a(const PoissonArgs &a, int pOld, int pNew, const float aPrev[3],
                            const float beta[3], double pAp[3])
 {
     const float alphaSqr = a.alpha * a.alpha;
     float acc[3] = {0.f, 0.f, 0.f};
+    bool pushed = false;
     for (int tile = blockIdx.x; tile < a.nTiles; tile += gridDim.x) {
-        const TileIter t = tile_thread(a, tile);
+        const TileIter t = tile_thread<SHARD>(a, tile);
         if (!t.valid) continue;
         const bool hasL = t.x0 > 0, hasR = t.x0 + 4 < a.W, hasU = t.y > 0, hasD = t.y < a.H - 1;
         const F4 w0 = ld4(a.plane[W0] + t.idx), wx = ld4(a.plane[WX] + t.idx), wy = ld4(a.plane[WY] + t.idx);
@@ -391,8 +535,10 @@ __device__ void phase_cg_a(const PoissonArgs &a, int pOld, int pNew, const float
             st4(a.plane[X + ch] + t.idx, xv);
             st4(a.plane[pNew + ch] + t.idx, c);
             st4(a.plane[AP + ch] + t.idx, Ap);
+            pushed |= push_row<SHARD>(a, t, pNew + ch, c);
         }
     }
+    if (SHARD && pushed) __threadfence_system();
     pAp[0] = acc[0]; pAp[1] = acc[1]; pAp[2] = acc[2];
 }
 
@@ -402,7 +548,7 @@ __device__ void phase_cg_a(const PoissonArgs &a, int pOld, int pNew, const float
 // hit rate 25 % instead of 48 %, more L2 traffic than the streaming variant saves).  Only the tile's outer ring is recomputed
 // from global r / p_old.  Same expressions on the same values as phase_cg_a => same bits.
 constexpr int kHaloPitch = kTileGX * 4 + 8;     // 4 floats of margin left and right keep the float4 rows 16-byte aligned
-template <int MODE>
+template <int MODE, bool SHARD>
 __device__ void phase_cg_a_res(const PoissonArgs &a, int pOld, int pNew, const float aPrev[3],
                                const float beta[3], double pAp[3], float4 *res, bool xResident)
 {
@@ -411,10 +557,11 @@ __device__ void phase_cg_a_res(const PoissonArgs &a, int pOld, int pNew, const f
     const float alphaSqr = a.alpha * a.alpha;
     const int lx = threadIdx.x % kTileGX, ly = threadIdx.x / kTileGX;
     float acc[3] = {0.f, 0.f, 0.f};
+    bool pushed = false;
     int k = -1;
     for (int tile = blockIdx.x; tile < a.nTiles; tile += gridDim.x) {
         k++;
-        const TileIter t = tile_thread(a, tile);
+        const TileIter t = tile_thread<SHARD>(a, tile);
         const bool hasL = t.x0 > 0, hasR = t.x0 + 4 < a.W, hasU = t.y > 0, hasD = t.y < a.H - 1;
         F4 w0 = zero4(), wx = zero4(), wy = zero4(), wyu = zero4();
         float wxl = 0.f;
@@ -439,6 +586,7 @@ __device__ void phase_cg_a_res(const PoissonArgs &a, int pOld, int pNew, const f
                 if (res_x(MODE)) res_st<T>(res, k, 0, ch, xv);
                 else st4(a.plane[X + ch] + t.idx, xv);
                 st4(a.plane[pNew + ch] + t.idx, c);
+                pushed |= push_row<SHARD>(a, t, pNew + ch, c);
                 *reinterpret_cast<float4 *>(&s_c[ly + 1][4 + 4 * lx]) = make_float4(c.v[0], c.v[1], c.v[2], c.v[3]);
                 // the ring around the tile, from the neighbouring tiles' r and p_old
                 if (ly == 0 && hasU) {
@@ -482,18 +630,20 @@ __device__ void phase_cg_a_res(const PoissonArgs &a, int pOld, int pNew, const f
             __syncthreads();
         }
     }
+    if (SHARD && pushed) __threadfence_system();
     pAp[0] = acc[0]; pAp[1] = acc[1]; pAp[2] = acc[2];
 }
 
 // ---- phase B: r -= a*Ap; rz = r.r   (Backend.cpp:296-321) ----------------------------------
-template <int MODE>
+template <int MODE, bool SHARD>
 __device__ void phase_cg_b(const PoissonArgs &a, const float al[3], double rz[3], const float4 *res)
 {
     float acc[3] = {0.f, 0.f, 0.f};
+    bool pushed = false;
     int k = -1;
     for (int tile = blockIdx.x; tile < a.nTiles; tile += gridDim.x) {
         k++;
-        const TileIter t = tile_thread(a, tile);
+        const TileIter t = tile_thread<SHARD>(a, tile);
         if (!t.valid) continue;
 #pragma unroll
         for (int ch = 0; ch < 3; ch++) {
@@ -506,19 +656,22 @@ __device__ void phase_cg_b(const PoissonArgs &a, const float al[3], double rz[3]
                 acc[ch] += ri * ri;
             }
             st4(a.plane[R + ch] + t.idx, r);
+            pushed |= push_row<SHARD>(a, t, R + ch, r);
         }
     }
+    if (SHARD && pushed) __threadfence_system();
     rz[0] = acc[0]; rz[1] = acc[1]; rz[2] = acc[2];
 }
 
 // ---- phase: pending x += a*p of the last CG iteration --------------------------------------
-template <int MODE>
+template <int MODE, bool SHARD>
 __device__ void phase_flush_x(const PoissonArgs &a, int pCur, const float al[3], const float4 *res, bool xResident)
 {
+    bool pushed = false;
     int k = -1;
     for (int tile = blockIdx.x; tile < a.nTiles; tile += gridDim.x) {
         k++;
-        const TileIter t = tile_thread(a, tile);
+        const TileIter t = tile_thread<SHARD>(a, tile);
         if (!t.valid) continue;
 #pragma unroll
         for (int ch = 0; ch < 3; ch++) {
@@ -527,18 +680,20 @@ __device__ void phase_flush_x(const PoissonArgs &a, int pCur, const float al[3],
 #pragma unroll
             for (int j = 0; j < 4; j++) x.v[j] += p.v[j] * al[ch];
             st4(a.plane[X + ch] + t.idx, x);
+            pushed |= push_row<SHARD>(a, t, X + ch, x);
         }
     }
+    if (SHARD && pushed) __threadfence_system();
 }
 
 // ---- phase: final = 1*direct + x  (Solver.cpp:561-567), with the last x update folded in ---
-template <int MODE>
+template <int MODE, bool SHARD>
 __device__ void phase_export(const PoissonArgs &a, int pCur, const float al[3], const float4 *res, bool xResident)
 {
     int k = -1;
     for (int tile = blockIdx.x; tile < a.nTiles; tile += gridDim.x) {
         k++;
-        const TileIter t = tile_thread(a, tile);
+        const TileIter t = tile_thread<SHARD>(a, tile);
         if (!t.valid) continue;
         F4 x[3];
 #pragma unroll
@@ -571,18 +726,18 @@ struct CgScalars {
     float coef;
 };
 
-template <int MODE>
+template <int MODE, bool SHARD>
 __global__ void __launch_bounds__(kThreads, 4) poisson_irls_cg_kernel(const PoissonArgs a)
 {
     extern __shared__ float4 s_res[];     // variants 1, 2: [x | Ap][tile][channel][thread], kResBytes
     __shared__ CgScalars sc;
     bool xResident = false;               // the current x is in s_res, not in the X planes (uniform over the grid)
     cg::grid_group grid = cg::this_grid();
-    int parity = 0;
+    SyncState sync;
     int cgTotal = 0, irlsDone = 0;
     const bool lead = threadIdx.x == 0;
 
-    phase_import(a);
+    phase_import<SHARD>(a);
     if (lead) sc.aPrev[0] = sc.aPrev[1] = sc.aPrev[2] = 0.f;
     grid.sync();
 
@@ -591,27 +746,31 @@ __global__ void __launch_bounds__(kThreads, 4) poisson_irls_cg_kernel(const Pois
 
     for (int irls = 0; irls < a.cfg.irlsIterMax; irls++) {
         if (irls > 0) {                                   // apply the pending x update first
-            phase_flush_x<MODE>(a, pCur, sc.aPrev, s_res, xResident);
+            phase_flush_x<MODE, SHARD>(a, pCur, sc.aPrev, s_res, xResident);
             xResident = false;
-            grid.sync();
+            if (SHARD) {                                      // a reduction of nothing: publishes the pushed x halo rows
+                float none[3];
+                grid_sum3<SHARD>(grid, a, sync, 0.0, 0.0, 0.0, none);
+                __syncthreads();
+            } else grid.sync();
         }
         double part[3];
         float tot[3];
         if (irls == 0) {
             double dummy = 0.0;
-            phase_weights(a, true, 0.f, dummy);
+            phase_weights<SHARD>(a, true, 0.f, dummy);
             if (lead) sc.coef = 1.0f;
             grid.sync();
         } else {
             const float reg = a.cfg.irlsRegInit * powf(a.cfg.irlsRegIter, (float)(irls - 1));   // Solver.cpp:395
             double s = 0.0;
-            phase_weights(a, false, reg, s);
-            grid_sum3(grid, a.red, parity, s, 0.0, 0.0, tot);
+            phase_weights<SHARD>(a, false, reg, s);
+            grid_sum3<SHARD>(grid, a, sync, s, 0.0, 0.0, tot);
             if (lead) sc.coef = (float)(3 * a.W * a.H) / tot[0];      // (float)w2->numElems, Backend.cpp:368
             __syncthreads();
         }
-        phase_rhs(a, sc.coef, part);
-        grid_sum3(grid, a.red, parity, part[0], part[1], part[2], tot);
+        phase_rhs<SHARD>(a, sc.coef, part);
+        grid_sum3<SHARD>(grid, a, sync, part[0], part[1], part[2], tot);
         if (lead) {
 #pragma unroll
             for (int c = 0; c < 3; c++) {
@@ -629,18 +788,18 @@ __global__ void __launch_bounds__(kThreads, 4) poisson_irls_cg_kernel(const Pois
             }
             cur ^= 1;                                                       // Solver.cpp:466: rz <-> rz2
             const int pNew = (pCur == PA) ? PB : PA;
-            if (MODE != 0) phase_cg_a_res<MODE>(a, pCur, pNew, sc.aPrev, sc.beta, part, s_res, xResident);
-            else phase_cg_a(a, pCur, pNew, sc.aPrev, sc.beta, part);
+            if (MODE != 0) phase_cg_a_res<MODE, SHARD>(a, pCur, pNew, sc.aPrev, sc.beta, part, s_res, xResident);
+            else phase_cg_a<SHARD>(a, pCur, pNew, sc.aPrev, sc.beta, part);
             xResident = res_x(MODE);
-            grid_sum3(grid, a.red, parity, part[0], part[1], part[2], tot);
+            grid_sum3<SHARD>(grid, a, sync, part[0], part[1], part[2], tot);
             pCur = pNew;
             if (lead) {
 #pragma unroll
                 for (int c = 0; c < 3; c++) sc.al[c] = sc.rz[cur ^ 1][c] / fmaxf(tot[c], FLT_MIN);   // Backend.cpp:309
             }
             __syncthreads();
-            phase_cg_b<MODE>(a, sc.al, part, s_res);
-            grid_sum3(grid, a.red, parity, part[0], part[1], part[2], tot);
+            phase_cg_b<MODE, SHARD>(a, sc.al, part, s_res);
+            grid_sum3<SHARD>(grid, a, sync, part[0], part[1], part[2], tot);
             if (lead) {
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
@@ -654,7 +813,7 @@ __global__ void __launch_bounds__(kThreads, 4) poisson_irls_cg_kernel(const Pois
         }
         irlsDone++;
     }
-    phase_export<MODE>(a, pCur, sc.aPrev, s_res, xResident);
+    phase_export<MODE, SHARD>(a, pCur, sc.aPrev, s_res, xResident);
     if (blockIdx.x == 0 && lead) { a.iters[0] = irlsDone; a.iters[1] = cgTotal; }
 }
 
@@ -703,6 +862,14 @@ struct gdb200_poisson_plan {
     int variant = 0;                   // kernel variant the solves of this plan run (poisson_irls_cg_kernel<variant>)
     long long nTiles = 0;
     int occ = 0, sms = 0;
+    // sharded solve: this plan covers rows [y0, y1) of the image as rank `rank` of `nRanks`
+    int y0 = 0, y1 = 0, rank = 0, nRanks = 1;
+    size_t planeElems = 0;             // floats per plane: (y1 - y0 + 2) rows of wp
+    gdb200::Mail *mail = nullptr;      // [2][nRanks], written by the peers
+    unsigned *status = nullptr;
+    unsigned long long solves = 0;
+    struct Peer { float *planes = nullptr; gdb200::Mail *mail = nullptr; int y0 = 0, y1 = 0; bool opened[2] = {false, false}; };
+    Peer peer[gdb200::kMaxRanks];
     // staging for the host-pointer entry point
     float *d_in[4] = {nullptr, nullptr, nullptr, nullptr};
     float *d_out = nullptr;
@@ -710,13 +877,13 @@ struct gdb200_poisson_plan {
 
 using namespace gdb200;
 
-static void *variant_kernel(int v)
+static void *variant_kernel(int v, bool shard)
 {
     switch (v) {
-    case 1: return (void *)poisson_irls_cg_kernel<1>;
-    case 2: return (void *)poisson_irls_cg_kernel<2>;
-    case 3: return (void *)poisson_irls_cg_kernel<3>;
-    default: return (void *)poisson_irls_cg_kernel<0>;
+    case 1: return shard ? (void *)poisson_irls_cg_kernel<1, true> : (void *)poisson_irls_cg_kernel<1, false>;
+    case 2: return shard ? (void *)poisson_irls_cg_kernel<2, true> : (void *)poisson_irls_cg_kernel<2, false>;
+    case 3: return shard ? (void *)poisson_irls_cg_kernel<3, true> : (void *)poisson_irls_cg_kernel<3, false>;
+    default: return shard ? (void *)poisson_irls_cg_kernel<0, true> : (void *)poisson_irls_cg_kernel<0, false>;
     }
 }
 static size_t variant_smem(int v) { return res_tiles(v) ? kResBytes : 0; }
@@ -725,12 +892,12 @@ static size_t variant_smem(int v) { return res_tiles(v) ? kResBytes : 0; }
 static bool variant_fits(const gdb200_poisson_plan *p, int v)
 {
     if (v == 0) return true;
-    if (variant_smem(v) && cudaFuncSetAttribute(variant_kernel(v), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)variant_smem(v)) != cudaSuccess) {
+    if (variant_smem(v) && cudaFuncSetAttribute(variant_kernel(v, p->nRanks > 1), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)variant_smem(v)) != cudaSuccess) {
         cudaGetLastError();
         return false;
     }
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, variant_kernel(v), kThreads, variant_smem(v)) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, variant_kernel(v, p->nRanks > 1), kThreads, variant_smem(v)) != cudaSuccess) { cudaGetLastError(); return false; }
     if ((long long)occ * p->sms < p->grid) return false;
     return res_tiles(v) == 0 || p->nTiles <= (long long)res_tiles(v) * p->grid;
 }
@@ -754,7 +921,11 @@ int gdb200_poisson_preset(const char *preset, gdb200_poisson_config *c)
 void gdb200_poisson_plan_destroy(gdb200_poisson_plan *p)
 {
     if (!p) return;
-    cudaFree(p->planes); cudaFree(p->red); cudaFree(p->iters);
+    for (int r = 0; r < kMaxRanks; r++) {
+        if (p->peer[r].opened[0]) cudaIpcCloseMemHandle(p->peer[r].planes);
+        if (p->peer[r].opened[1]) cudaIpcCloseMemHandle(p->peer[r].mail);
+    }
+    cudaFree(p->planes); cudaFree(p->red); cudaFree(p->iters); cudaFree(p->mail); cudaFree(p->status);
     for (float *d : p->d_in) cudaFree(d);
     cudaFree(p->d_out);
     if (p->ev0) cudaEventDestroy(p->ev0);
@@ -765,23 +936,37 @@ void gdb200_poisson_plan_destroy(gdb200_poisson_plan *p)
 
 int gdb200_poisson_plan_create(int w, int h, gdb200_poisson_plan **out)
 {
+    return gdb200_poisson_shard_create(w, h, 0, h, 0, 1, out);
+}
+
+int gdb200_poisson_shard_create(int w, int h, int y0, int y1, int rank, int n_ranks, gdb200_poisson_plan **out)
+{
     if (!out) return set_error(GDB200_ERR_ARGUMENT, "out_plan is NULL");
     *out = nullptr;
     if (w <= 0 || h <= 0 || (long long)w * h > (1LL << 29))
         return set_error(GDB200_ERR_ARGUMENT, "invalid image size %dx%d", w, h);
+    if (n_ranks < 1 || n_ranks > kMaxRanks || rank < 0 || rank >= n_ranks)
+        return set_error(GDB200_ERR_ARGUMENT, "rank %d of %d (at most %d GPUs share a solve)", rank, n_ranks, kMaxRanks);
+    if (y0 < 0 || y1 > h || y0 >= y1)
+        return set_error(GDB200_ERR_ARGUMENT, "row band [%d, %d) of a %dx%d image", y0, y1, w, h);
+    if ((rank == 0) != (y0 == 0) || (rank == n_ranks - 1) != (y1 == h))
+        return set_error(GDB200_ERR_ARGUMENT, "bands must cover the image in rank order: rank %d of %d has rows [%d, %d) of %d",
+                         rank, n_ranks, y0, y1, h);
     DeviceInfo di;
     if (int rc = device_info(&di)) return rc;
     gdb200_poisson_plan *p = new gdb200_poisson_plan;
     p->device = di.device; p->w = w; p->h = h; p->wp = (w + 3) & ~3;
-    const size_t planeElems = (size_t)p->wp * h;
+    p->y0 = y0; p->y1 = y1; p->rank = rank; p->nRanks = n_ranks;
+    const size_t planeElems = (size_t)p->wp * (y1 - y0 + 2);          // + one halo row above and below
+    p->planeElems = planeElems;
     int occ = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, poisson_irls_cg_kernel<0>, kThreads, 0);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, variant_kernel(0, n_ranks > 1), kThreads, 0);
     if (e != cudaSuccess || occ < 1) {
         delete p;
         return set_error(GDB200_ERR_CUDA, "poisson kernel not launchable on this device: %s "
                          "(library is built for sm_100a only)", cudaGetErrorString(e));
     }
-    const int tilesX = (p->wp / 4 + kTileGX - 1) / kTileGX, tilesY = (h + kTileY - 1) / kTileY;
+    const int tilesX = (p->wp / 4 + kTileGX - 1) / kTileGX, tilesY = (y1 - y0 + kTileY - 1) / kTileY;
     const long long nTiles = (long long)tilesX * tilesY;
     p->grid = (int)std::min<long long>(nTiles, (long long)occ * di.sms);
     p->nTiles = nTiles;
@@ -796,6 +981,11 @@ int gdb200_poisson_plan_create(int w, int h, gdb200_poisson_plan **out)
     PLAN_CUDA(cudaMemset(p->planes, 0, planeElems * kPlanes * sizeof(float)));
     PLAN_CUDA(cudaMalloc(&p->red, sizeof(double) * 2 * 3 * p->grid));
     PLAN_CUDA(cudaMalloc(&p->iters, sizeof(int) * 2));
+    PLAN_CUDA(cudaMalloc(&p->mail, sizeof(Mail) * 2 * kMaxRanks));
+    PLAN_CUDA(cudaMemset(p->mail, 0, sizeof(Mail) * 2 * kMaxRanks));
+    PLAN_CUDA(cudaMalloc(&p->status, sizeof(unsigned)));
+    PLAN_CUDA(cudaMemset(p->status, 0, sizeof(unsigned)));
+    p->peer[rank].planes = p->planes; p->peer[rank].mail = p->mail; p->peer[rank].y0 = y0; p->peer[rank].y1 = y1;
     PLAN_CUDA(cudaEventCreate(&p->ev0));
     PLAN_CUDA(cudaEventCreate(&p->ev1));
 #undef PLAN_CUDA
@@ -818,7 +1008,26 @@ int gdb200_poisson_solve_device(gdb200_poisson_plan *p, const float *d_dx, const
     memset(&a, 0, sizeof(a));
     a.W = p->w; a.H = p->h; a.Wp = p->wp; a.Gx = p->wp / 4;
     a.tilesX = (a.Gx + kTileGX - 1) / kTileGX;
-    a.nTiles = a.tilesX * ((p->h + kTileY - 1) / kTileY);
+    a.nTiles = a.tilesX * ((p->y1 - p->y0 + kTileY - 1) / kTileY);
+    a.y0 = p->y0; a.y1 = p->y1; a.rank = p->rank; a.nRanks = p->nRanks;
+    if (p->nRanks > 1) {
+        for (int r = 0; r < p->nRanks; r++) {
+            if (!p->peer[r].mail) return set_error(GDB200_ERR_ARGUMENT, "sharded solve: rank %d is not connected (gdb200_poisson_shard_connect)", r);
+            a.mail[r] = p->peer[r].mail;
+        }
+        if (p->rank > 0) {
+            const gdb200_poisson_plan::Peer &up = p->peer[p->rank - 1];
+            if (up.y1 != p->y0) return set_error(GDB200_ERR_ARGUMENT, "sharded solve: rank %d ends at row %d, rank %d starts at %d", p->rank - 1, up.y1, p->rank, p->y0);
+            a.peerUp = up.planes; a.peerUpRows = up.y1 - up.y0; a.peerUpElems = (size_t)p->wp * (up.y1 - up.y0 + 2);
+        }
+        if (p->rank < p->nRanks - 1) {
+            const gdb200_poisson_plan::Peer &dn = p->peer[p->rank + 1];
+            if (dn.y0 != p->y1) return set_error(GDB200_ERR_ARGUMENT, "sharded solve: rank %d ends at row %d, rank %d starts at %d", p->rank, p->y1, p->rank + 1, dn.y0);
+            a.peerDown = dn.planes; a.peerDownElems = (size_t)p->wp * (dn.y1 - dn.y0 + 2);
+        }
+    }
+    a.epochBase = (++p->solves) << 32;
+    a.status = p->status;
     a.aosVec = (p->w % 4 == 0) &&
                ((((uintptr_t)d_dx | (uintptr_t)d_dy | (uintptr_t)d_thr | (uintptr_t)d_direct | (uintptr_t)d_out) & 15) == 0);
     // Params::sanitize (Solver.cpp:168-178) and m_P.alpha (Solver.cpp:319).
@@ -830,7 +1039,7 @@ int gdb200_poisson_solve_device(gdb200_poisson_plan *p, const float *d_dx, const
     a.cfg.cgIterMax = std::max(cfg->cgIterMax, 1);
     a.cfg.cgIterCheck = std::max(cfg->cgIterCheck, 1);
     a.cfg.cgTolerance = fmaxf(cfg->cgTolerance, 0.f);
-    const size_t planeElems = (size_t)p->wp * p->h;
+    const size_t planeElems = p->planeElems;
     for (int i = 0; i < kPlanes; i++) a.plane[i] = p->planes + planeElems * i;
     a.in_dx = d_dx; a.in_dy = d_dy; a.in_thr = d_thr; a.in_direct = d_direct; a.out_final = d_out;
     a.red = p->red; a.iters = p->iters;
@@ -839,15 +1048,84 @@ int gdb200_poisson_solve_device(gdb200_poisson_plan *p, const float *d_dx, const
     p->last = a; p->solved = true;
     if (stats) GDB_CUDA(cudaEventRecord(p->ev0, s));
     void *kargs[] = {&a};
-    GDB_CUDA(cudaLaunchCooperativeKernel(variant_kernel(p->variant), dim3(p->grid), dim3(kThreads), kargs, variant_smem(p->variant), s));
-    if (stats) {
+    GDB_CUDA(cudaLaunchCooperativeKernel(variant_kernel(p->variant, p->nRanks > 1), dim3(p->grid), dim3(kThreads), kargs, variant_smem(p->variant), s));
+    if (stats || p->nRanks > 1) {
         GDB_CUDA(cudaEventRecord(p->ev1, s));
         GDB_CUDA(cudaEventSynchronize(p->ev1));
+    }
+    if (p->nRanks > 1) {
+        unsigned st = 0;
+        GDB_CUDA(cudaMemcpy(&st, p->status, sizeof(st), cudaMemcpyDeviceToHost));
+        if (st) {
+            GDB_CUDA(cudaMemset(p->status, 0, sizeof(unsigned)));
+            return set_error(GDB200_ERR_CUDA, "sharded solve: rank %d never saw the reduction message of rank %u (peer not solving, or peer memory not reachable)",
+                             p->rank, st - 1);
+        }
+    }
+    if (stats) {
         float ms = 0.f;
         GDB_CUDA(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
         int it[2];
         GDB_CUDA(cudaMemcpy(it, p->iters, sizeof(it), cudaMemcpyDeviceToHost));
         stats->device_ms = ms; stats->launches = 1; stats->irls_iters = it[0]; stats->cg_iters = it[1];
+    }
+    return GDB200_OK;
+}
+
+/* ---- sharded solve: wiring the GPUs together ------------------------------------------------------------------------------ */
+int gdb200_poisson_shard_export(gdb200_poisson_plan *p, void *out_handle)
+{
+    if (!p || !out_handle) return set_error(GDB200_ERR_ARGUMENT, "plan and out_handle are required");
+    gdb200_shard_handle h;
+    memset(&h, 0, sizeof(h));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle layout");
+    cudaIpcMemHandle_t m;
+    GDB_CUDA(cudaIpcGetMemHandle(&m, p->planes)); memcpy(h.planes, &m, 64);
+    GDB_CUDA(cudaIpcGetMemHandle(&m, p->mail));   memcpy(h.mail, &m, 64);
+    h.y0 = p->y0; h.y1 = p->y1; h.rank = p->rank; h.w = p->w; h.h = p->h;
+    h.planes_ptr = (unsigned long long)(uintptr_t)p->planes; h.mail_ptr = (unsigned long long)(uintptr_t)p->mail;
+    h.device = p->device; h.pid = (long long)getpid();
+    memcpy(out_handle, &h, sizeof(h));
+    return GDB200_OK;
+}
+
+int gdb200_poisson_shard_connect(gdb200_poisson_plan *p, const void *handles, int n)
+{
+    if (!p || !handles) return set_error(GDB200_ERR_ARGUMENT, "plan and handles are required");
+    if (n != p->nRanks) return set_error(GDB200_ERR_ARGUMENT, "%d handles for a solve shared by %d ranks", n, p->nRanks);
+    struct Bind { int prev = -1; ~Bind() { if (prev >= 0) cudaSetDevice(prev); } } bind;
+    if (cudaGetDevice(&bind.prev) != cudaSuccess) { bind.prev = -1; cudaGetLastError(); }
+    if (bind.prev != p->device) GDB_CUDA(cudaSetDevice(p->device)); else bind.prev = -1;
+    const gdb200_shard_handle *hs = (const gdb200_shard_handle *)handles;
+    for (int r = 0; r < n; r++) {
+        const gdb200_shard_handle &h = hs[r];
+        if (h.rank != r || h.w != p->w || h.h != p->h)
+            return set_error(GDB200_ERR_ARGUMENT, "handle %d describes rank %d of a %dx%d solve (expected rank %d, %dx%d)", r, h.rank, h.w, h.h, r, p->w, p->h);
+        if (r == p->rank) continue;
+        gdb200_poisson_plan::Peer &peer = p->peer[r];
+        peer.y0 = h.y0; peer.y1 = h.y1;
+        if (h.pid == (long long)getpid()) {
+            // same process (one host thread per GPU): plain peer access
+            if (h.device != p->device) {
+                int can = 0;
+                GDB_CUDA(cudaDeviceCanAccessPeer(&can, p->device, h.device));
+                if (!can) return set_error(GDB200_ERR_CUDA, "device %d cannot access the memory of device %d", p->device, h.device);
+                cudaError_t e = cudaDeviceEnablePeerAccess(h.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                    return set_error(GDB200_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d) failed: %s", h.device, cudaGetErrorString(e));
+                cudaGetLastError();
+            }
+            peer.planes = (float *)(uintptr_t)h.planes_ptr; peer.mail = (Mail *)(uintptr_t)h.mail_ptr;
+        } else {
+            cudaIpcMemHandle_t m;
+            void *ptr = nullptr;
+            memcpy(&m, h.planes, 64);
+            GDB_CUDA(cudaIpcOpenMemHandle(&ptr, m, cudaIpcMemLazyEnablePeerAccess));
+            peer.planes = (float *)ptr; peer.opened[0] = true;
+            memcpy(&m, h.mail, 64);
+            GDB_CUDA(cudaIpcOpenMemHandle(&ptr, m, cudaIpcMemLazyEnablePeerAccess));
+            peer.mail = (Mail *)ptr; peer.opened[1] = true;
+        }
     }
     return GDB200_OK;
 }

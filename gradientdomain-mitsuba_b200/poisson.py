@@ -37,13 +37,45 @@ class SolverParams:
         self.logFunc = fn
 
 
-class PoissonPlan:
-    """Device workspace for one image size (gdb200_poisson_plan)."""
+SHARD_HANDLE_BYTES = 176          # sizeof(gdb200_shard_handle), include/gdb200.h
+SHARD_ROW_ALIGN = 16              # the kernel's tile height: bands that are multiples of it leave no partly filled tile row
 
-    def __init__(self, w, h):
+
+def shard_bounds(h, n):
+    """Row bands [b[r], b[r+1]) of an h-row image for n GPUs: equal numbers of 16-row tile rows, remainder to the first ranks."""
+    tiles = -(-h // SHARD_ROW_ALIGN)
+    if n < 1 or n > tiles:
+        raise Gdb200Error(f"cannot split {h} rows ({tiles} tile rows) over {n} GPUs")
+    cuts = [min(h, ((tiles * r) // n) * SHARD_ROW_ALIGN) for r in range(n)] + [h]
+    return cuts
+
+
+class PoissonPlan:
+    """Device workspace for one image size (gdb200_poisson_plan); with ``band`` one GPU's share of a sharded solve."""
+
+    def __init__(self, w, h, band=None, rank=0, n_ranks=1):
         self.w, self.h = int(w), int(h)
+        self.band = (0, self.h) if band is None else (int(band[0]), int(band[1]))
+        self.rank, self.n_ranks = int(rank), int(n_ranks)
         self._h = ctypes.c_void_p()
-        check(lib().gdb200_poisson_plan_create(self.w, self.h, ctypes.byref(self._h)))
+        if band is None and n_ranks == 1:
+            check(lib().gdb200_poisson_plan_create(self.w, self.h, ctypes.byref(self._h)))
+        else:
+            check(lib().gdb200_poisson_shard_create(self.w, self.h, self.band[0], self.band[1], self.rank, self.n_ranks,
+                                                    ctypes.byref(self._h)))
+
+    def export_handle(self):
+        """gdb200_poisson_shard_export: the bytes the other ranks need to reach this shard's halo rows and mailbox."""
+        buf = ctypes.create_string_buffer(SHARD_HANDLE_BYTES)
+        check(lib().gdb200_poisson_shard_export(self._h, buf))
+        return buf.raw
+
+    def connect(self, handles):
+        """gdb200_poisson_shard_connect with every rank's handle (list of bytes, rank order)."""
+        blob = b"".join(handles)
+        if len(blob) != SHARD_HANDLE_BYTES * self.n_ranks:
+            raise Gdb200Error(f"expected {self.n_ranks} handles of {SHARD_HANDLE_BYTES} bytes")
+        check(lib().gdb200_poisson_shard_connect(self._h, ctypes.c_char_p(blob), self.n_ranks))
 
     def solve_device(self, dx, dy, throughput, direct, alpha, cfg, out, stream=None, stats=None):
         """All image arguments are CUDA device pointers (ints) or objects with
@@ -106,6 +138,47 @@ def poisson_solve(dx, dy, throughput, direct, w, h, alpha=0.2, preset="L1D", out
     check(lib().gdb200_poisson_solve(p(dx), p(dy), p(throughput), p(direct), w, h, ctypes.c_float(alpha),
                                      preset.encode(), p(out), ctypes.byref(stats) if stats is not None else None))
     return out
+
+
+class ShardedPoissonSolver:
+    """All GPUs of a torch.distributed group solve ONE image together (include/gdb200.h "sharded solve"): rank r owns a band
+    of rows; inside the one persistent kernel per GPU the halo rows and the CG reductions travel over NVLink peer memory.
+    torch.distributed only carries the 176-byte handles once, at construction."""
+
+    def __init__(self, w, h, group=None, bounds=None):
+        import torch.distributed as dist
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.bounds = shard_bounds(h, self.world) if bounds is None else list(bounds)
+        self.plan = PoissonPlan(w, h, band=(self.bounds[self.rank], self.bounds[self.rank + 1]), rank=self.rank, n_ranks=self.world)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, self.plan.export_handle(), group=group)
+        self.plan.connect(handles)
+        dist.barrier(group)                      # nobody starts a solve before everybody can be reached
+
+    def solve_device(self, dx, dy, throughput, direct, alpha, cfg, out, stream=None, stats=None):
+        """Collective: every rank calls it with the WHOLE images on its own GPU; fills rows bounds[rank]:bounds[rank+1] of out."""
+        self.plan.solve_device(dx, dy, throughput, direct, alpha, cfg, out, stream=stream, stats=stats)
+
+    def gather(self, out, dst=0):
+        """Rank dst receives the other ranks' bands of ``out`` (h, w, 3 float32 on the GPU) so that its copy is the whole image."""
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:
+            return
+        if self.rank == dst:
+            bufs = {r: torch.empty_like(out[self.bounds[r]:self.bounds[r + 1]]) for r in range(self.world) if r != dst}
+            for req in dist.batch_isend_irecv([dist.P2POp(dist.irecv, t, r, self.group) for r, t in bufs.items()]):
+                req.wait()
+            for r, t in bufs.items():
+                out[self.bounds[r]:self.bounds[r + 1]].copy_(t)
+        else:
+            mine = out[self.bounds[self.rank]:self.bounds[self.rank + 1]].contiguous()
+            for req in dist.batch_isend_irecv([dist.P2POp(dist.isend, mine, dst, self.group)]):
+                req.wait()
+
+    def close(self):
+        self.plan.close()
 
 
 class PoissonSolver:

@@ -93,6 +93,26 @@ typedef struct gdb200_poisson_plan gdb200_poisson_plan;
 int  gdb200_poisson_plan_create(int w, int h, gdb200_poisson_plan **out_plan);
 void gdb200_poisson_plan_destroy(gdb200_poisson_plan *plan);
 
+/* Sharded solve (SURVEY.md §8e "row-shard >= 4K"; no reference counterpart -- the reference's solver is single-device): n_ranks
+ * GPUs, one process (or host thread) each, solve ONE image together.  Rank r owns the row band [y0, y1); bands cover the image
+ * in rank order.  Inside the one persistent kernel each GPU pushes the first / last row of the CG vectors it updates into its
+ * neighbours' halo rows with stores over NVLink peer memory, and the two reductions per CG iteration travel as 32-byte
+ * messages into every GPU's mailbox -- no host round trip, no separate collective.  Wiring: every rank creates its shard,
+ * exports a handle (CUDA IPC handles of its plane array and mailbox), the host layer all-gathers the n_ranks handles
+ * (torch.distributed in gdb200.poisson.ShardedPoissonSolver) and every rank connects.  Then all ranks call
+ * gdb200_poisson_solve_device on their shard with the WHOLE input images resident on their own GPU; each writes its band's rows
+ * of out_final.  The sums are added in rank order, so every rank takes the same branches; results differ from the one-GPU
+ * solve by reduction order only.  A rank whose peers do not show up gives up after ~10 s with GDB200_ERR_CUDA. */
+typedef struct gdb200_shard_handle {
+    unsigned char planes[64], mail[64];            /* cudaIpcMemHandle_t */
+    unsigned long long planes_ptr, mail_ptr;       /* the same allocations as plain pointers, for peers in the same process */
+    long long pid;
+    int device, rank, y0, y1, w, h;
+} gdb200_shard_handle;
+int  gdb200_poisson_shard_create(int w, int h, int y0, int y1, int rank, int n_ranks, gdb200_poisson_plan **out_plan);
+int  gdb200_poisson_shard_export(gdb200_poisson_plan *plan, void *out_handle /* gdb200_shard_handle */);
+int  gdb200_poisson_shard_connect(gdb200_poisson_plan *plan, const void *handles /* n gdb200_shard_handle, rank order */, int n);
+
 /* Tuning knob without a reference counterpart: the solver kernel has variants that differ in where the CG vectors live, not in
  * arithmetic -- 0: everything streams through L2; 1: x and Ap of every CTA's tiles stay in shared memory (images up to 2 tiles
  * per CTA, ~1.2 Mpixel on a B200); 2: x stays in shared memory (up to 4 tiles per CTA, ~2.4 Mpixel); 3: as 0 with the search

@@ -190,6 +190,139 @@ def test_resident_variants_are_refused_for_large_images():
     plan.close()
 
 
+def _sharded_solve_same_process(t, w, h, bounds, cfg, devices=None, variant=None):
+    """Runs the sharded solve with one host thread per shard (same process: the shards reach each other through plain device
+    pointers / peer access instead of CUDA IPC).  devices=None puts every shard on GPU 0 -- possible while all their CTAs fit
+    the GPU together, i.e. for small images."""
+    import threading
+    import torch
+    n = len(bounds) - 1
+    devices = devices or [0] * n
+    plans = []
+    for r in range(n):
+        torch.cuda.set_device(devices[r])
+        plans.append(gdb200.PoissonPlan(w, h, band=(bounds[r], bounds[r + 1]), rank=r, n_ranks=n))
+        if variant is not None:
+            plans[-1].variant = variant
+    handles = [p.export_handle() for p in plans]
+    for p in plans:
+        p.connect(handles)
+    ins = {}
+    for d in set(devices):
+        ins[d] = {k: v.to(f"cuda:{d}") for k, v in t.items()}
+    out_by_dev = {d: torch.zeros_like(ins[d]["dx"]) for d in set(devices)}
+    errors, stats = [None] * n, [gdb200.Stats() for _ in range(n)]
+
+    def run(r):
+        try:
+            torch.cuda.set_device(devices[r])
+            stream = torch.cuda.Stream(device=devices[r])
+            i = ins[devices[r]]
+            plans[r].solve_device(i["dx"], i["dy"], i["throughput"], i["direct"], 0.2, cfg, out_by_dev[devices[r]],
+                                  stream=stream.cuda_stream, stats=stats[r])
+        except Exception as e:       # noqa: BLE001
+            errors[r] = e
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(n)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join(120)
+    assert not any(th.is_alive() for th in threads), "sharded solve hung"
+    for e in errors:
+        if e is not None:
+            raise e
+    result = np.empty((h, w, 3), dtype=np.float32)
+    for r in range(n):
+        result[bounds[r]:bounds[r + 1]] = out_by_dev[devices[r]][bounds[r]:bounds[r + 1]].cpu().numpy()
+    for p in plans:
+        p.close()
+    torch.cuda.set_device(0)
+    return result, stats
+
+
+@pytest.mark.parametrize("size,bounds,preset", [((128, 64), [0, 32, 64], "L1D"), ((128, 64), [0, 32, 64], "L2D"),
+                                                ((100, 70), [0, 16, 48, 70], "L1D"), ((64, 41), [0, 16, 41], "L1L"),
+                                                ((130, 33), [0, 32, 33], "L1D")])
+def test_sharded_solve_matches_the_single_gpu_solve(oracle, size, bounds, preset):
+    """The sharded solver (row bands, halo rows pushed through peer pointers, reductions through mailboxes -- all inside
+    the persistent kernels) on ONE GPU: small images, so that the shards' kernels are resident together.  Same arithmetic per
+    pixel; the sums are grouped per band first, so the result equals the one-plan solve up to reduction order -- held to the
+    same bound as the kernel itself against the oracle."""
+    import torch
+    w, h = size
+    d = synth.solver_inputs(w, h, seed=17, last_col_nonzero=True)
+    t = {k: torch.from_numpy(v) for k, v in d.items()}
+    params = gdb200.SolverParams()
+    assert params.setConfigPreset(preset)
+    got, stats = _sharded_solve_same_process(t, w, h, bounds, params.cfg)
+    single = gdb200.poisson_solve(d["dx"], d["dy"], d["throughput"], d["direct"], w, h, 0.2, preset)
+    if preset in TOL:
+        check_parity(oracle, d, w, h, 0.2, preset, got)
+    assert rmse(got, single) <= 2e-5, rmse(got, single)
+    assert len({(s.irls_iters, s.cg_iters) for s in stats}) == 1, "every shard takes the same branches"
+    again, _ = _sharded_solve_same_process(t, w, h, bounds, params.cfg)
+    assert np.array_equal(got, again), "deterministic"
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+def test_sharded_solve_kernel_variants_agree(variant):
+    import torch
+    w, h = 128, 96
+    d = synth.solver_inputs(w, h, seed=23, last_col_nonzero=True)
+    t = {k: torch.from_numpy(v) for k, v in d.items()}
+    params = gdb200.SolverParams()
+    assert params.setConfigPreset("L1D")
+    base, _ = _sharded_solve_same_process(t, w, h, [0, 48, 96], params.cfg, variant=0)
+    got, _ = _sharded_solve_same_process(t, w, h, [0, 48, 96], params.cfg, variant=variant)
+    assert np.array_equal(base, got)
+
+
+def test_one_rank_shard_is_the_plain_plan():
+    import torch
+    w, h = 200, 120
+    d = synth.solver_inputs(w, h, seed=5)
+    t = {k: torch.from_numpy(v).cuda() for k, v in d.items()}
+    params = gdb200.SolverParams()
+    plan = gdb200.PoissonPlan(w, h, band=(0, h), rank=0, n_ranks=1)
+    out = torch.empty_like(t["dx"])
+    plan.solve_device(t["dx"], t["dy"], t["throughput"], t["direct"], 0.2, params.cfg, out)
+    torch.cuda.synchronize()
+    plan.close()
+    assert np.array_equal(out.cpu().numpy(), gdb200.poisson_solve(d["dx"], d["dy"], d["throughput"], d["direct"], w, h, 0.2, "L1D"))
+
+
+def test_shard_arguments_are_checked():
+    with pytest.raises(gdb200.Gdb200Error, match="bands must cover the image in rank order"):
+        gdb200.PoissonPlan(64, 64, band=(16, 64), rank=0, n_ranks=2)
+    with pytest.raises(gdb200.Gdb200Error, match="row band"):
+        gdb200.PoissonPlan(64, 64, band=(32, 32), rank=1, n_ranks=2)
+    plan = gdb200.PoissonPlan(64, 64, band=(0, 32), rank=0, n_ranks=2)
+    import torch
+    z = torch.zeros((64, 64, 3), dtype=torch.float32, device="cuda")
+    with pytest.raises(gdb200.Gdb200Error, match="is not connected"):
+        plan.solve_device(z, z, z, z, 0.2, gdb200.SolverParams().cfg, z)
+    plan.close()
+
+
+@pytest.mark.skipif("__import__('torch').cuda.device_count() < 2")
+@pytest.mark.parametrize("size,preset", [((1024, 1024), "L1D"), ((3840, 2160), "L2D")])
+def test_sharded_solve_on_all_gpus(oracle, size, preset):
+    """One band per GPU of the box (host threads of this process, peer access): against the single-GPU solve."""
+    import torch
+    w, h = size
+    n = min(torch.cuda.device_count(), 8)
+    d = synth.solver_inputs(min(w, 1024), min(h, 1024), seed=3, last_col_nonzero=True)
+    reps = (-(-h // d["dx"].shape[0]), -(-w // d["dx"].shape[1]), 1)
+    d = {k: np.ascontiguousarray(np.tile(v, reps)[:h, :w]) for k, v in d.items()}
+    t = {k: torch.from_numpy(v) for k, v in d.items()}
+    params = gdb200.SolverParams()
+    assert params.setConfigPreset(preset)
+    got, stats = _sharded_solve_same_process(t, w, h, gdb200.shard_bounds(h, n), params.cfg, devices=list(range(n)))
+    single = gdb200.poisson_solve(d["dx"], d["dy"], d["throughput"], d["direct"], w, h, 0.2, preset)
+    assert rmse(got, single) <= 2 * TOL[preset], rmse(got, single)
+
+
 def test_device_pointer_entry_matches_host_entry():
     import torch
     w, h = 320, 200
