@@ -58,10 +58,11 @@ enum Plane {
 
 constexpr int kMaxRanks = 16;
 
-// One reduction message of a rank: its three partial sums and the number of the reduction they belong to.
-struct __align__(32) Mail {
-    double v[3];
-    unsigned long long epoch;
+// One reduction message of a rank: its three partial sums, each split into two 8-byte words that carry 32 bits of the double
+// and the 32-bit number of the reduction (stores of 8 bytes are atomic, so a word is either old or complete: the receiver needs
+// no separate flag and the sender no fence between data and flag -- the "LL" idea of NCCL's low-latency protocol).
+struct __align__(64) Mail {
+    unsigned long long w[8];          // w[2c] = hi32(v_c) : number, w[2c+1] = lo32(v_c) : number; w[6], w[7] unused
 };
 
 struct PoissonArgs {
@@ -73,9 +74,10 @@ struct PoissonArgs {
     float *peerUp, *peerDown;                 // plane arrays of the GPUs holding the bands above / below (peer memory) or NULL
     size_t peerUpElems, peerDownElems;        // their plane sizes in floats
     int peerUpRows;                           // rows of the band above (its lower halo is its local row peerUpRows + 1)
-    Mail *mail[kMaxRanks];                    // mail[r]: rank r's mailbox [2][nRanks] (mail[rank] is local memory)
-    unsigned long long epochBase;             // solve number << 32: mailbox epochs never repeat, no reset between solves
-    unsigned *status;                         // != 0: a peer did not arrive in time (the solve gives up instead of hanging)
+    Mail *mail[kMaxRanks];                    // mail[r]: rank r's mailbox [2][kMaxRanks] (+ its two relay slots); mail[rank] is local
+    unsigned epochBase;                       // reductions of all earlier solves: message numbers never repeat within 2^32
+    unsigned *status;                         // [0] != 0: a peer did not arrive in time (the solve gives up instead of hanging);
+                                              // [1]: number of the last reduction (the next solve's epochBase)
     float alpha;
     gdb200_poisson_config cfg;
     float *plane[kPlanes];
@@ -107,23 +109,53 @@ __device__ __forceinline__ F4 zero4() { return F4{{0.f, 0.f, 0.f, 0.f}}; }
 // Sharded solve (nRanks > 1): CTA 0 of every GPU then posts its GPU's sums into every GPU's mailbox with 32-byte peer stores
 // over NVLink, and thread 0 of every CTA waits for the nRanks messages of this reduction in its OWN GPU's mailbox (local
 // polling) and adds them in rank order: the same bits on every GPU, so all of them take the same branches.  The message is also
-// the barrier that publishes the halo rows pushed during the phase (push_row: data store, fence.sys, grid barrier, then the
-// release store of the epoch).  Two mailbox slots by parity: a GPU can be at most one reduction ahead of the slowest one.
+// the barrier that publishes the halo rows pushed during the phase (push_row: plain peer stores; the grid barrier orders them
+// before CTA 0's system-scope fence, which orders them before the message).  Two mailbox slots by parity: a GPU can be at most
+// one reduction ahead of the slowest one.
 struct SyncState {
     int parity = 0;
-    unsigned long long epoch = 0;     // number of reductions so far, + PoissonArgs::epochBase
+    unsigned epoch = 0;               // number of reductions so far (+ PoissonArgs::epochBase = the message number)
     bool dead = false;                // a wait timed out: stop waiting, the host reports the failure
 };
 
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+template <bool SYS> __device__ __forceinline__ void post_mail(Mail *m, const double v[3], unsigned long long number)
 {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(v[c]);
+        const unsigned long long hi = (bits & 0xffffffff00000000ull) | number, lo = (bits << 32) | number;
+        if (SYS) {
+            asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(&m->w[2 * c]), "l"(hi) : "memory");
+            asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(&m->w[2 * c + 1]), "l"(lo) : "memory");
+        } else {
+            asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(&m->w[2 * c]), "l"(hi) : "memory");
+            asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(&m->w[2 * c + 1]), "l"(lo) : "memory");
+        }
+    }
 }
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+
+// Polls a message slot until all six words carry `number`; false (and dead = true) after ~10 s.  A dead solve stops waiting.
+template <bool SYS> __device__ __forceinline__ bool wait_mail(const Mail *m, unsigned long long number, double v[3], bool &dead)
 {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+    unsigned long long w[6];
+    unsigned spins = 0;
+    bool ok = true;
+    for (;;) {
+#pragma unroll
+        for (int i = 0; i < 6; i += 2) {
+            if (SYS) asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[i]), "=l"(w[i + 1]) : "l"(&m->w[i]) : "memory");
+            else     asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[i]), "=l"(w[i + 1]) : "l"(&m->w[i]) : "memory");
+        }
+        bool all = true;
+#pragma unroll
+        for (int i = 0; i < 6; i++) all = all && (w[i] & 0xffffffffull) == number;
+        if (all || dead) break;
+        if (++spins > (1u << 24)) { dead = true; ok = false; break; }
+        __nanosleep(32);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) v[c] = __longlong_as_double((long long)((w[2 * c] & 0xffffffff00000000ull) | (w[2 * c + 1] >> 32)));
+    return ok;
 }
 
 template <bool SHARD>
@@ -171,26 +203,31 @@ __device__ void grid_sum3(cg::grid_group &grid, const PoissonArgs &a, SyncState 
 #pragma unroll
     for (int w = 0; w < kThreads / 32; w++) { t0 += s_tot[par][w][0]; t1 += s_tot[par][w][1]; t2 += s_tot[par][w][2]; }
     if (SHARD) {
-        const unsigned long long epoch = a.epochBase + sync.epoch;
+        const unsigned long long number = a.epochBase + sync.epoch;        // 32 bits
+        Mail *relay = a.mail[a.rank] + (2 + par) * kMaxRanks;              // this GPU's own two relay slots, behind the mailbox
         if (blockIdx.x == 0) {
-            for (int r = 0; r < a.nRanks; r++) {
-                Mail *m = a.mail[r] + par * a.nRanks + a.rank;
-                m->v[0] = t0; m->v[1] = t1; m->v[2] = t2;
-            }
+            // Everything this GPU pushed into its neighbours' halo rows during the phase happens-before the grid barrier above;
+            // this fence orders it before the message (cumulativity: one system-scope fence after an intra-GPU barrier, the
+            // shape of cooperative groups' own multi-device barrier).
             __threadfence_system();
-            for (int r = 0; r < a.nRanks; r++) st_release_sys(&(a.mail[r] + par * a.nRanks + a.rank)->epoch, epoch);
-        }
-        t0 = t1 = t2 = 0.0;
-        const Mail *box = a.mail[a.rank] + par * a.nRanks;
-        for (int r = 0; r < a.nRanks; r++) {
-            if (!sync.dead) {
-                unsigned spins = 0;
-                while (ld_acquire_sys(&box[r].epoch) != epoch) {
-                    if (++spins > (1u << 24)) { sync.dead = true; atomicExch(a.status, 1u + (unsigned)r); break; }    // ~10 s
-                    __nanosleep(64);
-                }
+            const double tv[3] = {t0, t1, t2};
+            for (int r = 0; r < a.nRanks; r++) post_mail<true>(a.mail[r] + par * kMaxRanks + a.rank, tv, number);
+            double sum[3] = {0.0, 0.0, 0.0};
+            for (int r = 0; r < a.nRanks; r++) {
+                double v[3];
+                if (!wait_mail<true>(a.mail[a.rank] + par * kMaxRanks + r, number, v, sync.dead)) atomicExch(a.status, 1u + (unsigned)r);
+                sum[0] += v[0]; sum[1] += v[1]; sum[2] += v[2];
             }
-            t0 += __ldcg(&box[r].v[0]); t1 += __ldcg(&box[r].v[1]); t2 += __ldcg(&box[r].v[2]);
+            // ONE system-scope acquire per GPU (592 of them, one per CTA, cost 6 us per reduction: they queue up per SM), then
+            // the grid total goes to the other CTAs through a local relay slot at GPU scope.
+            __threadfence_system();
+            post_mail<false>(relay, sum, number);
+            t0 = sum[0]; t1 = sum[1]; t2 = sum[2];
+        } else {
+            double v[3];
+            wait_mail<false>(relay, number, v, sync.dead);
+            __threadfence();         // acquire at GPU scope: the halo rows read after the caller's __syncthreads are the pushed ones
+            t0 = v[0]; t1 = v[1]; t2 = v[2];
         }
     }
     out[0] = (float)t0; out[1] = (float)t1; out[2] = (float)t2;
@@ -205,7 +242,13 @@ template <bool SHARD = true>
 __device__ __forceinline__ TileIter tile_thread(const PoissonArgs &a, int tile)
 {
     const int y0 = SHARD ? a.y0 : 0, y1 = SHARD ? a.y1 : a.H;     // one GPU: the band is the image
-    const int tx = tile % a.tilesX, ty = tile / a.tilesX;
+    const int tx = tile % a.tilesX;
+    int ty = tile / a.tilesX;
+    if (SHARD) {
+        // the band's first and last tile rows first: their peer stores are long done when the phase ends
+        const int tilesY = a.nTiles / a.tilesX;
+        ty = ty == 0 ? 0 : (ty == 1 ? tilesY - 1 : ty - 1);
+    }
     const int gx = tx * kTileGX + (threadIdx.x % kTileGX);
     TileIter t;
     t.y = y0 + ty * kTileY + (threadIdx.x / kTileGX);
@@ -235,19 +278,11 @@ template <bool SHARD, class F> __device__ __forceinline__ void for_halo_rows(con
 // Sharded solve: a value this GPU wrote into the first / last row of its band goes to the neighbour's halo row as well (a
 // 16-byte store over NVLink, fire and forget; made visible by the reduction that ends the phase, grid_sum3).
 template <bool SHARD>
-__device__ __forceinline__ bool push_row(const PoissonArgs &a, const TileIter &t, int plane, const F4 &v)
+__device__ __forceinline__ void push_row(const PoissonArgs &a, const TileIter &t, int plane, const F4 &v)
 {
-    bool pushed = false;
-    if (!SHARD) return false;
-    if (a.peerUp && t.y == a.y0) {
-        st4(a.peerUp + a.peerUpElems * plane + (size_t)(a.peerUpRows + 1) * a.Wp + t.x0, v);
-        pushed = true;
-    }
-    if (a.peerDown && t.y == a.y1 - 1) {
-        st4(a.peerDown + a.peerDownElems * plane + t.x0, v);
-        pushed = true;
-    }
-    return pushed;
+    if (!SHARD) return;
+    if (a.peerUp && t.y == a.y0) st4(a.peerUp + a.peerUpElems * plane + (size_t)(a.peerUpRows + 1) * a.Wp + t.x0, v);
+    if (a.peerDown && t.y == a.y1 - 1) st4(a.peerDown + a.peerDownElems * plane + t.x0, v);
 }
 
 // ---- interleaved RGB <-> planar ------------------------------------------------------------
@@ -410,7 +445,6 @@ template <bool SHARD>
 __device__ void phase_rhs(const PoissonArgs &a, float coef, double rz[3])
 {
     float acc[3] = {0.f, 0.f, 0.f};
-    bool pushed = false;
     for (int tile = blockIdx.x; tile < a.nTiles; tile += gridDim.x) {
         const TileIter t = tile_thread<SHARD>(a, tile);
         if (!t.valid) continue;
@@ -453,7 +487,7 @@ __device__ void phase_rhs(const PoissonArgs &a, float coef, double rz[3])
                 acc[ch] += v * v;
             }
             st4(a.plane[R + ch] + t.idx, r);
-            pushed |= push_row<SHARD>(a, t, R + ch, r);
+            push_row<SHARD>(a, t, R + ch, r);
         }
     }
     for_halo_rows<SHARD>(a, true, false, [&](const TileIter &t) {
@@ -462,7 +496,6 @@ __device__ void phase_rhs(const PoissonArgs &a, float coef, double rz[3])
         for (int j = 0; j < 4; j++) wyu.v[j] *= coef;
         st4(a.plane[WY] + t.idx, wyu);
     });
-    if (SHARD && pushed) __threadfence_system();
     rz[0] = acc[0]; rz[1] = acc[1]; rz[2] = acc[2];
 }
 
@@ -485,7 +518,6 @@ __device__ void phase_cg_a(const PoissonArgs &a, int pOld, int pNew, const float
 {
     const float alphaSqr = a.alpha * a.alpha;
     float acc[3] = {0.f, 0.f, 0.f};
-    bool pushed = false;
     for (int tile = blockIdx.x; tile < a.nTiles; tile += gridDim.x) {
         const TileIter t = tile_thread<SHARD>(a, tile);
         if (!t.valid) continue;
@@ -535,10 +567,9 @@ __device__ void phase_cg_a(const PoissonArgs &a, int pOld, int pNew, const float
             st4(a.plane[X + ch] + t.idx, xv);
             st4(a.plane[pNew + ch] + t.idx, c);
             st4(a.plane[AP + ch] + t.idx, Ap);
-            pushed |= push_row<SHARD>(a, t, pNew + ch, c);
+            push_row<SHARD>(a, t, pNew + ch, c);
         }
     }
-    if (SHARD && pushed) __threadfence_system();
     pAp[0] = acc[0]; pAp[1] = acc[1]; pAp[2] = acc[2];
 }
 
@@ -557,7 +588,6 @@ __device__ void phase_cg_a_res(const PoissonArgs &a, int pOld, int pNew, const f
     const float alphaSqr = a.alpha * a.alpha;
     const int lx = threadIdx.x % kTileGX, ly = threadIdx.x / kTileGX;
     float acc[3] = {0.f, 0.f, 0.f};
-    bool pushed = false;
     int k = -1;
     for (int tile = blockIdx.x; tile < a.nTiles; tile += gridDim.x) {
         k++;
@@ -586,7 +616,7 @@ __device__ void phase_cg_a_res(const PoissonArgs &a, int pOld, int pNew, const f
                 if (res_x(MODE)) res_st<T>(res, k, 0, ch, xv);
                 else st4(a.plane[X + ch] + t.idx, xv);
                 st4(a.plane[pNew + ch] + t.idx, c);
-                pushed |= push_row<SHARD>(a, t, pNew + ch, c);
+                push_row<SHARD>(a, t, pNew + ch, c);
                 *reinterpret_cast<float4 *>(&s_c[ly + 1][4 + 4 * lx]) = make_float4(c.v[0], c.v[1], c.v[2], c.v[3]);
                 // the ring around the tile, from the neighbouring tiles' r and p_old
                 if (ly == 0 && hasU) {
@@ -630,7 +660,6 @@ __device__ void phase_cg_a_res(const PoissonArgs &a, int pOld, int pNew, const f
             __syncthreads();
         }
     }
-    if (SHARD && pushed) __threadfence_system();
     pAp[0] = acc[0]; pAp[1] = acc[1]; pAp[2] = acc[2];
 }
 
@@ -639,7 +668,6 @@ template <int MODE, bool SHARD>
 __device__ void phase_cg_b(const PoissonArgs &a, const float al[3], double rz[3], const float4 *res)
 {
     float acc[3] = {0.f, 0.f, 0.f};
-    bool pushed = false;
     int k = -1;
     for (int tile = blockIdx.x; tile < a.nTiles; tile += gridDim.x) {
         k++;
@@ -656,10 +684,9 @@ __device__ void phase_cg_b(const PoissonArgs &a, const float al[3], double rz[3]
                 acc[ch] += ri * ri;
             }
             st4(a.plane[R + ch] + t.idx, r);
-            pushed |= push_row<SHARD>(a, t, R + ch, r);
+            push_row<SHARD>(a, t, R + ch, r);
         }
     }
-    if (SHARD && pushed) __threadfence_system();
     rz[0] = acc[0]; rz[1] = acc[1]; rz[2] = acc[2];
 }
 
@@ -667,7 +694,6 @@ __device__ void phase_cg_b(const PoissonArgs &a, const float al[3], double rz[3]
 template <int MODE, bool SHARD>
 __device__ void phase_flush_x(const PoissonArgs &a, int pCur, const float al[3], const float4 *res, bool xResident)
 {
-    bool pushed = false;
     int k = -1;
     for (int tile = blockIdx.x; tile < a.nTiles; tile += gridDim.x) {
         k++;
@@ -680,10 +706,9 @@ __device__ void phase_flush_x(const PoissonArgs &a, int pCur, const float al[3],
 #pragma unroll
             for (int j = 0; j < 4; j++) x.v[j] += p.v[j] * al[ch];
             st4(a.plane[X + ch] + t.idx, x);
-            pushed |= push_row<SHARD>(a, t, X + ch, x);
+            push_row<SHARD>(a, t, X + ch, x);
         }
     }
-    if (SHARD && pushed) __threadfence_system();
 }
 
 // ---- phase: final = 1*direct + x  (Solver.cpp:561-567), with the last x update folded in ---
@@ -814,7 +839,10 @@ __global__ void __launch_bounds__(kThreads, 4) poisson_irls_cg_kernel(const Pois
         irlsDone++;
     }
     phase_export<MODE, SHARD>(a, pCur, sc.aPrev, s_res, xResident);
-    if (blockIdx.x == 0 && lead) { a.iters[0] = irlsDone; a.iters[1] = cgTotal; }
+    if (blockIdx.x == 0 && lead) {
+        a.iters[0] = irlsDone; a.iters[1] = cgTotal;
+        if (SHARD) a.status[1] = a.epochBase + sync.epoch;
+    }
 }
 
 // ---- Solver::evaluateMetricsMTS (Solver.cpp:511-541) on the x a solve left in the plan: e = b - P x; the primal block of e
@@ -865,9 +893,9 @@ struct gdb200_poisson_plan {
     // sharded solve: this plan covers rows [y0, y1) of the image as rank `rank` of `nRanks`
     int y0 = 0, y1 = 0, rank = 0, nRanks = 1;
     size_t planeElems = 0;             // floats per plane: (y1 - y0 + 2) rows of wp
-    gdb200::Mail *mail = nullptr;      // [2][nRanks], written by the peers
+    gdb200::Mail *mail = nullptr;      // [2][kMaxRanks] written by the peers, then [2][kMaxRanks] of local relay slots
     unsigned *status = nullptr;
-    unsigned long long solves = 0;
+    unsigned epochBase = 16;           // message number the next solve starts after (mailboxes start zeroed)
     struct Peer { float *planes = nullptr; gdb200::Mail *mail = nullptr; int y0 = 0, y1 = 0; bool opened[2] = {false, false}; };
     Peer peer[gdb200::kMaxRanks];
     // staging for the host-pointer entry point
@@ -981,10 +1009,10 @@ int gdb200_poisson_shard_create(int w, int h, int y0, int y1, int rank, int n_ra
     PLAN_CUDA(cudaMemset(p->planes, 0, planeElems * kPlanes * sizeof(float)));
     PLAN_CUDA(cudaMalloc(&p->red, sizeof(double) * 2 * 3 * p->grid));
     PLAN_CUDA(cudaMalloc(&p->iters, sizeof(int) * 2));
-    PLAN_CUDA(cudaMalloc(&p->mail, sizeof(Mail) * 2 * kMaxRanks));
-    PLAN_CUDA(cudaMemset(p->mail, 0, sizeof(Mail) * 2 * kMaxRanks));
-    PLAN_CUDA(cudaMalloc(&p->status, sizeof(unsigned)));
-    PLAN_CUDA(cudaMemset(p->status, 0, sizeof(unsigned)));
+    PLAN_CUDA(cudaMalloc(&p->mail, sizeof(Mail) * 4 * kMaxRanks));
+    PLAN_CUDA(cudaMemset(p->mail, 0, sizeof(Mail) * 4 * kMaxRanks));
+    PLAN_CUDA(cudaMalloc(&p->status, sizeof(unsigned) * 2));
+    PLAN_CUDA(cudaMemset(p->status, 0, sizeof(unsigned) * 2));
     p->peer[rank].planes = p->planes; p->peer[rank].mail = p->mail; p->peer[rank].y0 = y0; p->peer[rank].y1 = y1;
     PLAN_CUDA(cudaEventCreate(&p->ev0));
     PLAN_CUDA(cudaEventCreate(&p->ev1));
@@ -1026,7 +1054,7 @@ int gdb200_poisson_solve_device(gdb200_poisson_plan *p, const float *d_dx, const
             a.peerDown = dn.planes; a.peerDownElems = (size_t)p->wp * (dn.y1 - dn.y0 + 2);
         }
     }
-    a.epochBase = (++p->solves) << 32;
+    a.epochBase = p->epochBase;
     a.status = p->status;
     a.aosVec = (p->w % 4 == 0) &&
                ((((uintptr_t)d_dx | (uintptr_t)d_dy | (uintptr_t)d_thr | (uintptr_t)d_direct | (uintptr_t)d_out) & 15) == 0);
@@ -1054,8 +1082,10 @@ int gdb200_poisson_solve_device(gdb200_poisson_plan *p, const float *d_dx, const
         GDB_CUDA(cudaEventSynchronize(p->ev1));
     }
     if (p->nRanks > 1) {
-        unsigned st = 0;
-        GDB_CUDA(cudaMemcpy(&st, p->status, sizeof(st), cudaMemcpyDeviceToHost));
+        unsigned st2[2] = {0, 0};
+        GDB_CUDA(cudaMemcpy(st2, p->status, sizeof(st2), cudaMemcpyDeviceToHost));
+        const unsigned st = st2[0];
+        p->epochBase = st2[1];
         if (st) {
             GDB_CUDA(cudaMemset(p->status, 0, sizeof(unsigned)));
             return set_error(GDB200_ERR_CUDA, "sharded solve: rank %d never saw the reduction message of rank %u (peer not solving, or peer memory not reachable)",
