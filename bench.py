@@ -230,6 +230,8 @@ def main():
            "cast_ms": 0.0, "prepare_ms": 0.0, "resolve_ms": 0.0, "primary_ms": 0.0,
            "solve_ms": 0.0, "launches": 0, "samples": 0.0, "rays": 0.0, "exchange_bytes": 0}
 
+    row_cost = [1.0] * H                 # per-row tracing cost learnt over the warm-up steps (tiles.rebalance)
+
     def step(timed, balance=False):
         nonlocal bounds
         rows = (bounds[rank], bounds[rank + 1]) if world > 1 else None
@@ -252,7 +254,7 @@ def main():
             mine = torch.tensor([integ.stats.device_ms, ev[1].elapsed_time(ev[3]) if rank == 0 else 0.0], device="cuda", dtype=torch.float64)
             every = [torch.zeros_like(mine) for _ in range(world)]
             dist.all_gather(every, mine)
-            bounds = tiles.rebalance(bounds, [float(t[0]) for t in every], [float(t[1]) for t in every])
+            bounds = tiles.rebalance(bounds, [float(t[0]) for t in every], [float(t[1]) for t in every], row_cost=row_cost)
         if timed:
             torch.cuda.synchronize()
             phase["exchange_ms"] += ev[0].elapsed_time(ev[1]); phase["develop_ms"] += ev[1].elapsed_time(ev[2])

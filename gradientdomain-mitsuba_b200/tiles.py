@@ -50,30 +50,42 @@ def boundary_rows(height, world, halo=HALO, bounds=None):
     return sorted(set(rows))
 
 
-def rebalance(bounds, cost_ms, extra_ms=None, min_rows=4):
+def rebalance(bounds, cost_ms, extra_ms=None, min_rows=4, row_cost=None):
     """Cost-balanced strip boundaries.  cost_ms[r]: measured tracing time of rank r on its current strip [bounds[r], bounds[r+1])
-    (the per-row cost is taken as constant inside a strip: floor rows cost more than rows under the light, so even strips
-    finish at different times); extra_ms[r]: work that rank r alone does after the exchange (rank 0: develop + the Poisson
-    solve) and that the other ranks would otherwise wait out.  Returns boundaries for which cost + extra is equal on all
-    ranks.  Deterministic: every rank computes the same boundaries from the all-gathered times."""
+    (floor rows cost more than rows under the light, so even strips finish at different times); extra_ms[r]: work that rank r
+    alone does after the exchange (rank 0: develop + the Poisson solve) and that the other ranks would otherwise wait out.
+    Returns boundaries for which cost + extra is equal on all ranks.  Deterministic: every rank computes the same boundaries
+    from the all-gathered times.
+
+    row_cost: optional list of per-row cost estimates (length = image height) that is UPDATED IN PLACE and carried from one
+    call to the next: inside each strip the estimates are scaled so that they add up to the strip's measured time, so the
+    structure learnt from earlier, different boundaries is kept (without it the cost is taken as constant inside a strip and a
+    strip that straddles cheap and expensive rows keeps missing its target)."""
     world = len(bounds) - 1
     extra = [0.0] * world if extra_ms is None else [float(e) for e in extra_ms]
     height = bounds[-1]
-    row_cost = []
+    if row_cost is None:
+        row_cost = [1.0] * height
+    elif len(row_cost) != height:
+        raise ValueError(f"row_cost has {len(row_cost)} entries for {height} rows")
     for r in range(world):
-        n = max(1, bounds[r + 1] - bounds[r])
-        row_cost.extend([max(float(cost_ms[r]), 1e-6) / n] * (bounds[r + 1] - bounds[r]))
+        a, b = bounds[r], bounds[r + 1]
+        have = sum(row_cost[a:b])
+        scale = max(float(cost_ms[r]), 1e-6) / have if have > 0 else 0.0
+        for y in range(a, b):
+            row_cost[y] = row_cost[y] * scale if have > 0 else max(float(cost_ms[r]), 1e-6) / max(1, b - a)
     total = sum(row_cost) + sum(extra)
     target = total / world                       # finishing time of every rank
-    new, y, acc = [0], 0, 0.0
+    # boundary r where the running cost reaches the sum of the first r+1 tracing budgets, rounded to the nearer row (cutting
+    # each strip greedily below its own budget would push every strip's remainder onto the last rank)
+    new, y, run, goal = [0], 0, 0.0, 0.0
     for r in range(world - 1):
-        budget = max(target - extra[r], 0.0)     # tracing time rank r may spend
-        start = y
-        while y < height - (world - 1 - r) * min_rows and (acc + row_cost[y] <= budget or y - start < min_rows):
-            acc += row_cost[y]
+        goal += max(target - extra[r], 0.0)      # tracing time ranks 0..r may spend together
+        lo, hi = new[-1] + min_rows, height - (world - 1 - r) * min_rows
+        while y < hi and (y < lo or run + 0.5 * row_cost[y] <= goal):
+            run += row_cost[y]
             y += 1
         new.append(y)
-        acc = 0.0
     new.append(height)
     return new
 

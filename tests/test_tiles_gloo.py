@@ -39,6 +39,23 @@ def test_cost_balanced_strips():
     assert max(c) - min(c) <= 0.02 * sum(c) / 4, c
     nb0 = tiles.rebalance(b, [100.0] * 4, extra_ms=[40.0, 0, 0, 0])  # rank 0 solves afterwards: it traces less
     assert nb0[1] < 256 and abs((nb0[1] * 100.0 / 256 + 40.0) - (nb0[2] - nb0[1]) * 100.0 / 256) <= 2.0
+    # a carried per-row estimate converges on a smooth cost profile where the constant-per-strip model keeps missing
+    import math
+    h, world = 1024, 8
+    density = [1.0 + 0.8 * math.sin(3.0 * y / h) + (0.6 if y > 700 else 0.0) for y in range(h)]
+    extra = [22.0 * sum(density) / 2200.0] + [0.0] * (world - 1)
+
+    def spread(bounds):
+        t = [sum(density[bounds[r]:bounds[r + 1]]) + extra[r] for r in range(world)]
+        return (max(t) - min(t)) / (sum(t) / world)
+
+    carried, rc = tiles.even_bounds(h, world), [1.0] * h
+    for _ in range(4):
+        carried = tiles.rebalance(carried, [sum(density[carried[r]:carried[r + 1]]) for r in range(world)], extra, row_cost=rc)
+    assert spread(carried) < 0.03, (spread(carried), carried)
+    assert carried[0] == 0 and carried[-1] == h and all(carried[i] < carried[i + 1] for i in range(world))
+    with pytest.raises(ValueError):
+        tiles.rebalance([0, 4, 8], [1.0, 1.0], row_cost=[1.0] * 7)
     tiny = tiles.rebalance([0, 4, 8, 12], [1.0, 1000.0, 1.0])
     assert tiny[0] == 0 and tiny[-1] == 12 and all(tiny[i + 1] - tiny[i] >= 1 for i in range(3))
 
