@@ -15,9 +15,11 @@
 #include <mitsuba/render/trimesh.h>
 #include <mitsuba/core/plugin.h>
 #include <mitsuba/core/bitmap.h>
+#include <mitsuba/core/mstream.h>
 #endif
 #include <vector>
 #include <string>
+#include <map>
 #include <cstring>
 #include <algorithm>
 #include "../../include/gdb200.h"
@@ -56,6 +58,93 @@ struct FlatScene {
 		return p.hasProperty(name) ? (double) p.getFloat(name, (Float) def) : def;
 	}
 
+#if !defined(GDB200_STUB_HEADERS)
+	/* TwoSidedBRDF keeps its nested BRDFs in private members and unserialised copies have no Properties, so the nested
+	   material is read from Mitsuba's own wire format: the adapter is serialised into a MemoryStream and the stream is read
+	   back with the Stream calls the classes' unserialisation constructors use.  InstanceManager::serialize
+	   (serialization.cpp:73-87) writes per object an id (0 = NULL, a known id = back reference) or id + class name + the
+	   class's serialize() payload; BSDF::serialize one bool (bsdf.cpp:43-46); Texture::serialize nothing (texture.cpp:77-79). */
+	struct WireReader {
+		Stream *s;
+		std::map<unsigned int, Spectrum> spectra;
+		std::map<unsigned int, Float> floats;
+		explicit WireReader(Stream *stream) : s(stream) { }
+
+		/// id + class name of the next object ("" for a back reference or NULL)
+		unsigned int object(std::string &cls) {
+			const unsigned int id = s->readUInt();
+			cls = (id != 0 && !spectra.count(id) && !floats.count(id)) ? s->readString() : std::string();
+			return id;
+		}
+		Spectrum constantSpectrum(const char *what) {       /* basicshader.cpp:29-33 */
+			std::string cls;
+			const unsigned int id = object(cls);
+			if (spectra.count(id)) return spectra[id];
+			if (cls != "ConstantSpectrumTexture")
+				SLog(EError, "gdb200: twosided: '%s' is a \"%s\"; only constant values are supported", what, cls.c_str());
+			return spectra[id] = Spectrum(s);
+		}
+		Float constantFloat(const char *what) {             /* basicshader.cpp:46-49 */
+			std::string cls;
+			const unsigned int id = object(cls);
+			if (floats.count(id)) return floats[id];
+			if (cls != "ConstantFloatTexture")
+				SLog(EError, "gdb200: twosided: '%s' is a \"%s\"; only constant values are supported", what, cls.c_str());
+			return floats[id] = s->readFloat();
+		}
+	};
+
+	/* The BRDF nested in a `twosided` adapter (twosided.cpp:77-82: BSDF::serialize, then the two nested BRDFs) */
+	void readTwoSided(const BSDF *bsdf, gdb200_material &m) {
+		ref<MemoryStream> ms = new MemoryStream();
+		ref<InstanceManager> manager = new InstanceManager();
+		bsdf->serialize(ms, manager);
+		ms->seek(0);
+		WireReader r(ms);
+		ms->readBool();
+		std::string cls;
+		const unsigned int front = r.object(cls);
+		ms->readBool();                                      /* the nested BSDF's own BSDF::serialize */
+		if (cls == "SmoothDiffuse") {                        /* diffuse.cpp:161-165 */
+			m.type = GDB200_BSDF_DIFFUSE;
+			copySpectrum(r.constantSpectrum("reflectance"), m.reflectance);
+		} else if (cls == "RoughConductor") {                /* roughconductor.cpp:216-226; eta and k are stored divided by extEta */
+			m.type = GDB200_BSDF_ROUGHCONDUCTOR;
+			const unsigned int distr = ms->readUInt();
+			const bool sampleVisible = ms->readBool();
+			const Float alphaU = r.constantFloat("alphaU"), alphaV = r.constantFloat("alphaV");
+			copySpectrum(r.constantSpectrum("specularReflectance"), m.specular_reflectance);
+			copySpectrum(Spectrum(ms), m.eta);
+			copySpectrum(Spectrum(ms), m.k);
+			if (distr == 0) m.distribution = GDB200_MICROFACET_BECKMANN;         /* microfacet.h:48-57 */
+			else if (distr == 1) m.distribution = GDB200_MICROFACET_GGX;
+			else SLog(EError, "gdb200: twosided: microfacet distribution %u is not supported", distr);
+			if (alphaU != alphaV || !sampleVisible)
+				SLog(EError, "gdb200: anisotropic / non-visible-normal roughconductor is not supported");
+			m.alpha = alphaU;
+		} else if (cls == "SmoothConductor") {               /* conductor.cpp:202-207 */
+			m.type = GDB200_BSDF_CONDUCTOR;
+			copySpectrum(r.constantSpectrum("specularReflectance"), m.specular_reflectance);
+			copySpectrum(Spectrum(ms), m.eta);
+			copySpectrum(Spectrum(ms), m.k);
+		} else if (cls == "SmoothPlastic") {                 /* plastic.cpp:177-184 */
+			m.type = GDB200_BSDF_PLASTIC;
+			m.ior_ratio = ms->readFloat();
+			m.nonlinear = ms->readBool();
+			copySpectrum(r.constantSpectrum("specularReflectance"), m.specular_reflectance);
+			copySpectrum(r.constantSpectrum("diffuseReflectance"), m.reflectance);
+		} else {
+			SLog(EError, "gdb200: twosided around a \"%s\" is outside the supported hot-path subset", cls.c_str());
+		}
+		if (ms->readUInt() != front)                        /* twosided.cpp:85-88: one nested BRDF serves both sides */
+			SLog(EError, "gdb200: twosided with two different BRDFs is not supported");
+		if (ms->getPos() != ms->getSize())
+			SLog(EError, "gdb200: twosided: %i unread bytes in the serialised \"%s\" (a Mitsuba build with another wire format?)",
+				(int) (ms->getSize() - ms->getPos()), cls.c_str());
+		m.twosided = 1;
+	}
+#endif
+
 	int addMaterial(const BSDF *bsdf, bool isEmitterShape) {
 		gdb200_material m;
 		memset(&m, 0, sizeof(m));
@@ -66,6 +155,10 @@ struct FlatScene {
 			/* shape.cpp:48-72: emitters get an absorbing diffuse BSDF, everything else diffuse 0.5 */
 			m.type = GDB200_BSDF_DIFFUSE;
 			for (int i = 0; i < 3; ++i) m.reflectance[i] = isEmitterShape ? 0.0 : 0.5;
+#if !defined(GDB200_STUB_HEADERS)
+		} else if (cls == "TwoSidedBRDF") {
+			readTwoSided(bsdf, m);
+#endif
 		} else if (cls == "SmoothDiffuse") {
 			m.type = GDB200_BSDF_DIFFUSE;
 			copySpectrum(p.getSpectrum(p.hasProperty("reflectance") ? "reflectance" : "diffuseReflectance", Spectrum(.5f)), m.reflectance);

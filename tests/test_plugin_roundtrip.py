@@ -43,10 +43,6 @@ def _arr(x, n=None):
 def test_flattening_a_mitsuba_scene_gives_back_the_description(flatten, oracle, name):
     desc = getattr(scenes, name)(20, 16)
     prm = scenes.default_params(spp=2, seed=4)
-    if name == "cbox_mesh_lights":                       # the documented gap: TwoSidedBRDF keeps its nested BSDF private
-        with pytest.raises(RuntimeError, match="TwoSidedBRDF"):
-            flatten(desc, prm)
-        return
     got = flatten(desc, prm)
     cam, gcam = desc.camera, got.camera
     assert (gcam.width, gcam.height) == (cam.width, cam.height) and gcam.near_clip == cam.near_clip and gcam.far_clip == cam.far_clip
@@ -124,7 +120,7 @@ def test_plugin_render_fails_loudly_without_a_gpu(tmp_path):
 
 # ------------------------------------------------------------------ render() of the plugin under Mitsuba's own host objects
 @pytest.mark.gpu
-@pytest.mark.parametrize("scene_name,recon", [("cbox_glossy", "L2"), ("cbox_materials", "L1"), ("cbox_env", None)])
+@pytest.mark.parametrize("scene_name,recon", [("cbox_glossy", "L2"), ("cbox_materials", "L1"), ("cbox_env", None), ("cbox_mesh_lights", "L2")])
 def test_plugin_render_through_mitsuba_host_objects(oracle, tmp_path, scene_name, recon):
     """GDB200GradientPathIntegrator::render (plugin/gpt_plugin.cpp) called the way Mitsuba's RenderJob calls an integrator:
     a real Scene with sensor, MultiFilm and the gdb200_counter sampler (the reference's own classes, built by
