@@ -363,7 +363,8 @@ def main():
                 "poisson_roofline": {"bound": "hbm", "achieved": round(SOLVER_BYTES[recon] * W * H / max(solve_ms, 1e-9) / 1e6, 1),
                                      "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                      "frac": round(SOLVER_BYTES[recon] * W * H / max(solve_ms, 1e-9) / 1e6 / peaks["hbm_gbs"], 3),
-                                     "note": "working set fits the 126 MB L2 at this size; grade the solver roofline on tools/solver_sweep.py 4K/8K"},
+                                     "kernel_variant": plan.variant,
+                                     "note": "working set fits the 126 MB L2 at this size and x / Ap stay in shared memory (kernel variant 1): grade the solver roofline on tools/solver_sweep.py 4K/8K"},
                 "rays_per_sample": round(agg["rays"] / max(agg["samples"], 1), 2),
                 "e2e": {"value": round(e2e_val, 3), "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(agg["launches"]),

@@ -7,7 +7,7 @@ set -u
 mkdir -p gpurun_out
 {
   echo "== smoke"; timeout 120 python -c "import __graft_entry__ as g; g.smoke()"; echo "rc=$?"
-  echo "== gpu tests"; timeout 900 python -m pytest tests -q -m gpu -x 2>&1 | tail -15
+  echo "== gpu tests"; timeout 1500 python -m pytest tests -q -m gpu -x 2>&1 | tail -15
   echo "== bench N=1"; timeout 600 python bench.py --steps 3 --warmup 3
   echo "== bench reference arm"; timeout 600 python bench.py --impl reference --steps 2 --warmup 1
 } > gpurun_out/round_check.log 2>&1
