@@ -64,6 +64,10 @@ struct Workspace {
     int *rayOwner[2] = {nullptr, nullptr}, *rayCount = nullptr, *qKey = nullptr, *qList = nullptr, *qCount = nullptr;
     int slotCapacity = 0; bool fused = false;
     std::vector<cudaEvent_t> events;       // timing marks of renders that ask for stats, reused across renders
+    // Film buffers of destroyed scenes, kept for the next scene of the same size (a renderer that keeps its film between
+    // frames): cudaFree of the 168 MB film is a device-wide synchronisation that took 2 ... 600 ms on the GPU boxes.
+    struct FilmSet { double *film = nullptr, *dev64 = nullptr; float *dev32 = nullptr; unsigned long long *counters = nullptr; size_t pixels = 0; };
+    std::vector<FilmSet> spareFilms;
 };
 static Workspace g_workspace[kMaxDevices];
 
@@ -73,6 +77,7 @@ static void freeWorkspace(Workspace &w)
     cudaFree(w.rays[0]); cudaFree(w.rays[1]); cudaFree(w.rayOwner[0]); cudaFree(w.rayOwner[1]);
     cudaFree(w.rayCount); cudaFree(w.qKey); cudaFree(w.qList); cudaFree(w.qCount);
     for (cudaEvent_t e : w.events) cudaEventDestroy(e);
+    for (const Workspace::FilmSet &f : w.spareFilms) { cudaFree(f.film); cudaFree(f.dev64); cudaFree(f.dev32); cudaFree(f.counters); }
     w = Workspace();
 }
 
@@ -91,10 +96,23 @@ struct DeviceGuard {
 
 namespace {
 
+constexpr size_t kSpareFilms = 2;
+
 void freeSceneBuffers(gdb200_scene *s)
 {
-    cudaFree(s->film); cudaFree(s->dev64); cudaFree(s->dev32);
-    cudaFree(s->counters); cudaFree(s->dScene); s->dScene = nullptr; cudaFree(s->dTables); s->dTables = nullptr;
+    bool kept = false;
+    if (s->film && s->dev64 && s->dev32 && s->counters && s->device >= 0 && s->device < kMaxDevices) {
+        std::lock_guard<std::mutex> lock(g_deviceMutex[s->device]);
+        Workspace &ws = g_workspace[s->device];
+        if (ws.spareFilms.size() < kSpareFilms) {
+            Workspace::FilmSet f;
+            f.film = s->film; f.dev64 = s->dev64; f.dev32 = s->dev32; f.counters = s->counters; f.pixels = (size_t)s->width * s->height;
+            ws.spareFilms.push_back(f);
+            kept = true;
+        }
+    }
+    if (!kept) { cudaFree(s->film); cudaFree(s->dev64); cudaFree(s->dev32); cudaFree(s->counters); }
+    cudaFree(s->dScene); s->dScene = nullptr; cudaFree(s->dTables); s->dTables = nullptr;
     s->film = s->dev64 = nullptr; s->dev32 = nullptr; s->counters = nullptr;
 }
 
@@ -344,10 +362,23 @@ int gdb200_scene_create(const gdb200_scene_desc *desc, gdb200_scene **out)
     s->device = di.device;
     if (int rc = flattenScene(desc, s)) { delete s; return rc; }
     const size_t n = (size_t)s->width * s->height;
-    cudaError_t e = cudaMalloc(&s->film, sizeof(double) * 5 * n * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&s->dev64, sizeof(double) * 5 * n * 3);
-    if (e == cudaSuccess) e = cudaMalloc(&s->dev32, sizeof(float) * 5 * n * 3);
-    if (e == cudaSuccess) e = cudaMalloc(&s->counters, sizeof(unsigned long long) * 8);
+    if (s->device >= 0 && s->device < kMaxDevices) {
+        std::lock_guard<std::mutex> lock(g_deviceMutex[s->device]);
+        std::vector<Workspace::FilmSet> &spare = g_workspace[s->device].spareFilms;
+        for (size_t i = 0; i < spare.size(); i++)
+            if (spare[i].pixels == n) {
+                s->film = spare[i].film; s->dev64 = spare[i].dev64; s->dev32 = spare[i].dev32; s->counters = spare[i].counters;
+                spare.erase(spare.begin() + i);
+                break;
+            }
+    }
+    cudaError_t e = cudaSuccess;
+    if (!s->film) {
+        e = cudaMalloc(&s->film, sizeof(double) * 5 * n * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&s->dev64, sizeof(double) * 5 * n * 3);
+        if (e == cudaSuccess) e = cudaMalloc(&s->dev32, sizeof(float) * 5 * n * 3);
+        if (e == cudaSuccess) e = cudaMalloc(&s->counters, sizeof(unsigned long long) * 8);
+    }
     if (e == cudaSuccess) e = cudaMemset(s->film, 0, sizeof(double) * 5 * n * 4);
     if (e != cudaSuccess) { freeSceneBuffers(s); delete s; return set_error(GDB200_ERR_CUDA, "scene allocation failed: %s", cudaGetErrorString(e)); }
     *out = s;
@@ -369,7 +400,7 @@ void gdb200_release_workspace(void)
     if (cudaGetDevice(&current) != cudaSuccess || cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return; }
     for (int d = 0; d < n && d < kMaxDevices; d++) {
         std::lock_guard<std::mutex> lock(g_deviceMutex[d]);
-        if (g_workspace[d].slotCapacity || !g_workspace[d].events.empty()) { cudaSetDevice(d); freeWorkspace(g_workspace[d]); }
+        if (g_workspace[d].slotCapacity || !g_workspace[d].events.empty() || !g_workspace[d].spareFilms.empty()) { cudaSetDevice(d); freeWorkspace(g_workspace[d]); }
     }
     cudaSetDevice(current);
 }

@@ -134,10 +134,18 @@ template <bool SYS> __device__ __forceinline__ void post_mail(Mail *m, const dou
     }
 }
 
-// Polls a message slot until all six words carry `number`; false (and dead = true) after ~10 s.  A dead solve stops waiting.
+// Polls a message slot until all six words carry `number`; false (and dead = true) after kShardTimeoutNs.  A dead solve stops
+// waiting: it runs to its end on whatever is in the mailboxes and the host reports the failure.
+constexpr unsigned long long kShardTimeoutNs = 8000000000ull;
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 template <bool SYS> __device__ __forceinline__ bool wait_mail(const Mail *m, unsigned long long number, double v[3], bool &dead)
 {
-    unsigned long long w[6];
+    unsigned long long w[6], since = 0;
     unsigned spins = 0;
     bool ok = true;
     for (;;) {
@@ -150,7 +158,11 @@ template <bool SYS> __device__ __forceinline__ bool wait_mail(const Mail *m, uns
 #pragma unroll
         for (int i = 0; i < 6; i++) all = all && (w[i] & 0xffffffffull) == number;
         if (all || dead) break;
-        if (++spins > (1u << 24)) { dead = true; ok = false; break; }
+        if ((++spins & 1023u) == 0) {
+            const unsigned long long now = global_timer_ns();
+            if (since == 0) since = now;
+            else if (now - since > kShardTimeoutNs) { dead = true; ok = false; break; }
+        }
         __nanosleep(32);
     }
 #pragma unroll

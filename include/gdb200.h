@@ -102,7 +102,8 @@ void gdb200_poisson_plan_destroy(gdb200_poisson_plan *plan);
  * (torch.distributed in gdb200.poisson.ShardedPoissonSolver) and every rank connects.  Then all ranks call
  * gdb200_poisson_solve_device on their shard with the WHOLE input images resident on their own GPU; each writes its band's rows
  * of out_final.  The sums are added in rank order, so every rank takes the same branches; results differ from the one-GPU
- * solve by reduction order only.  A rank whose peers do not show up gives up after ~10 s with GDB200_ERR_CUDA. */
+ * solve by reduction order only.  A rank whose peers do not show up gives up after 8 s with GDB200_ERR_CUDA
+ * (the shards have lost step then: destroy and re-create them). */
 typedef struct gdb200_shard_handle {
     unsigned char planes[64], mail[64];            /* cudaIpcMemHandle_t */
     unsigned long long planes_ptr, mail_ptr;       /* the same allocations as plain pointers, for peers in the same process */

@@ -305,6 +305,25 @@ def test_shard_arguments_are_checked():
     plan.close()
 
 
+def test_sharded_solve_gives_up_when_a_peer_is_missing():
+    """Two connected shards, only one of them solves: its kernel waits for the other's first reduction message, gives up after
+    8 s and the call returns an error naming the missing rank -- no hang."""
+    import time
+    import torch
+    w, h = 64, 64
+    plans = [gdb200.PoissonPlan(w, h, band=(32 * r, 32 * r + 32), rank=r, n_ranks=2) for r in range(2)]
+    handles = [p.export_handle() for p in plans]
+    for p in plans:
+        p.connect(handles)
+    z = torch.zeros((h, w, 3), dtype=torch.float32, device="cuda")
+    t0 = time.time()
+    with pytest.raises(gdb200.Gdb200Error, match="never saw the reduction message of rank 1"):
+        plans[0].solve_device(z, z, z, z, 0.2, gdb200.SolverParams().cfg, torch.empty_like(z))
+    assert 6.0 < time.time() - t0 < 60.0
+    for p in plans:
+        p.close()
+
+
 @pytest.mark.skipif("__import__('torch').cuda.device_count() < 2")
 @pytest.mark.parametrize("size,preset", [((1024, 1024), "L1D"), ((3840, 2160), "L2D")])
 def test_sharded_solve_on_all_gpus(oracle, size, preset):
