@@ -1176,6 +1176,9 @@ int gdb200_poisson_plan_set_variant(gdb200_poisson_plan *p, int variant)
 {
     if (!p) return set_error(GDB200_ERR_ARGUMENT, "plan is NULL");
     if (variant < 0 || variant > 3) return set_error(GDB200_ERR_ARGUMENT, "solver kernel variant %d (expected 0..3)", variant);
+    struct Bind { int prev = -1; ~Bind() { if (prev >= 0) cudaSetDevice(prev); } } bind;      // function attributes are per device
+    if (cudaGetDevice(&bind.prev) != cudaSuccess) { bind.prev = -1; cudaGetLastError(); }
+    if (bind.prev != p->device) GDB_CUDA(cudaSetDevice(p->device)); else bind.prev = -1;
     if (!variant_fits(p, variant))
         return set_error(GDB200_ERR_ARGUMENT, "image of %dx%d does not fit solver kernel variant %d (%lld tiles, %d CTAs x %d resident tiles)",
                          p->w, p->h, variant, p->nTiles, p->grid, res_tiles(variant));
