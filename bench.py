@@ -225,45 +225,56 @@ def main():
     bounds = tiles.even_bounds(H, world)
     halo = tiles.halo_rows(desc.rfilter_radius)
     acc = scene.accumulators() if world > 1 else None
-    phase = {"exchange_ms": 0.0, "develop_ms": 0.0, "solve_wall_ms": 0.0}
+    phase = {"exchange_ms": 0.0, "boundary_allreduce_ms": 0.0, "gather_ms": 0.0, "develop_ms": 0.0, "solve_wall_ms": 0.0}
     agg = {"bounce_ms": 0.0, "generate_ms": 0.0, "compact_ms": 0.0, "state_bytes": 0.0, "bounce_launches": 0, "trace_ms": 0.0, "path_bounces": 0.0,
            "cast_ms": 0.0, "prepare_ms": 0.0, "resolve_ms": 0.0, "primary_ms": 0.0,
-           "solve_ms": 0.0, "launches": 0, "samples": 0.0, "rays": 0.0, "exchange_bytes": 0}
+           "solve_ms": 0.0, "trace_wall_ms": 0.0, "launches": 0, "samples": 0.0, "rays": 0.0, "exchange_bytes": 0}
 
     row_cost = [1.0] * H                 # per-row tracing cost learnt over the warm-up steps (tiles.rebalance)
 
     def step(timed, balance=False):
         nonlocal bounds
         rows = (bounds[rank], bounds[rank + 1]) if world > 1 else None
+        wall0 = time.perf_counter()
         integ.trace(scene, spp=spp, seed=0, rows=rows, download=False, preview=False, streams=args.streams)   # "-final" comes from the reconstruction
+        wall1 = time.perf_counter()          # the call returns when the strip is traced (host side of the call included)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         ev[0].record()
         nb = 0
+        evb = torch.cuda.Event(enable_timing=True)
         if world > 1:
             nb = tiles.exchange_boundaries(acc, world, halo=halo, bounds=bounds)
+            evb.record()
             nb += tiles.gather_strips(acc, rank, world, bounds=bounds, first_buffer=1)
+        else:
+            evb.record()
         ev[1].record()
+        if balance and world > 1:
+            torch.cuda.synchronize()
+        wall2 = time.perf_counter()
         if world > 1 and rank == 0:
             scene.develop(download=False)
         ev[2].record()
         if rank == 0:
             integ.reconstruct(scene, plan, download=False)
         ev[3].record()
-        if balance and world > 1:          # warm-up only: every rank learns every strip's tracing time and rank 0's tail
-            torch.cuda.synchronize()
-            mine = torch.tensor([integ.stats.device_ms, ev[1].elapsed_time(ev[3]) if rank == 0 else 0.0], device="cuda", dtype=torch.float64)
+        if balance and world > 1:          # warm-up only: every rank learns every strip's tracing time and every rank's tail
+            torch.cuda.synchronize()           # (wall clock of the calls, not device time: what decides when a rank reaches the exchange)
+            mine = torch.tensor([(wall1 - wall0) * 1e3, (time.perf_counter() - wall2) * 1e3], device="cuda", dtype=torch.float64)
             every = [torch.zeros_like(mine) for _ in range(world)]
             dist.all_gather(every, mine)
             bounds = tiles.rebalance(bounds, [float(t[0]) for t in every], [float(t[1]) for t in every], row_cost=row_cost)
         if timed:
             torch.cuda.synchronize()
             phase["exchange_ms"] += ev[0].elapsed_time(ev[1]); phase["develop_ms"] += ev[1].elapsed_time(ev[2])
+            phase["boundary_allreduce_ms"] += ev[0].elapsed_time(evb); phase["gather_ms"] += evb.elapsed_time(ev[1])
             phase["solve_wall_ms"] += ev[2].elapsed_time(ev[3])
             st = integ.stats
             for k in ("bounce_ms", "generate_ms", "compact_ms", "state_bytes", "bounce_launches", "samples", "rays", "path_bounces",
                       "cast_ms", "prepare_ms", "resolve_ms", "primary_ms"):
                 agg[k] += getattr(st, k)
             agg["trace_ms"] += st.device_ms
+            agg["trace_wall_ms"] += (wall1 - wall0) * 1e3
             agg["launches"] += st.launches + 1 + (1 if rank == 0 else 0)
             if rank == 0:
                 agg["solve_ms"] += integ.solver_stats.device_ms
@@ -295,11 +306,13 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     total_ms, total_samples = float(ms.item()), float(samples.item())
     rank_trace_ms = [agg["trace_ms"] / args.steps]
+    rank_trace_wall_ms = [agg["trace_wall_ms"] / args.steps]
     if world > 1:                                   # every rank's mean tracing time per step: names the limiting rank / phase
-        mine = torch.tensor([agg["trace_ms"] / args.steps], device="cuda", dtype=torch.float64)
+        mine = torch.tensor([agg["trace_ms"] / args.steps, agg["trace_wall_ms"] / args.steps], device="cuda", dtype=torch.float64)
         every = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(every, mine)
-        rank_trace_ms = [round(float(t.item()), 1) for t in every]
+        rank_trace_ms = [round(float(t[0].item()), 1) for t in every]
+        rank_trace_wall_ms = [round(float(t[1].item()), 1) for t in every]
 
     # ------------------------------------------------------------------ end to end through the public API
     h2d = ctypes.sizeof(scenes.SceneDesc) + desc.n_shapes * ctypes.sizeof(scenes.Shape) + desc.n_materials * ctypes.sizeof(scenes.Material) \
@@ -384,6 +397,7 @@ def main():
             line["exchange_bytes_per_step"] = int(agg["exchange_bytes"] / args.steps)
             line["strip_bounds"] = bounds
             line["rank_trace_ms"] = rank_trace_ms
+            line["rank_trace_call_wall_ms"] = rank_trace_wall_ms
         line["rank0_phase_ms"] = {k: round(v / args.steps, 2) for k, v in phase.items()}
         if world == 1:
             try:                                  # a reported baseline: it must never cost the measured line
