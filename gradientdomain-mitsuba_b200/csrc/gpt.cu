@@ -64,12 +64,15 @@ struct Workspace {
     int *rayOwner[2] = {nullptr, nullptr}, *rayCount = nullptr, *qKey = nullptr, *qList = nullptr, *qCount = nullptr;
     int slotCapacity = 0; bool fused = false;
     std::vector<cudaEvent_t> events;       // timing marks of renders that ask for stats, reused across renders
+    unsigned long long *stamps = nullptr;  // phase stamps of the staged wavefront (stampPhase), kStampCapacity entries
+    std::vector<unsigned long long> stampsHost;
     // Film buffers of destroyed scenes, kept for the next scene of the same size (a renderer that keeps its film between
     // frames): cudaFree of the 168 MB film is a device-wide synchronisation that took 2 ... 600 ms on the GPU boxes.
     struct FilmSet { double *film = nullptr, *dev64 = nullptr; float *dev32 = nullptr; unsigned long long *counters = nullptr; size_t pixels = 0; };
     std::vector<FilmSet> spareFilms;
 };
 static Workspace g_workspace[kMaxDevices];
+constexpr size_t kStampCapacity = (size_t)1 << 20;     // 8 stamps per tick: 131 072 ticks, then the phase times stop growing
 
 static void freeWorkspace(Workspace &w)
 {
@@ -77,6 +80,7 @@ static void freeWorkspace(Workspace &w)
     cudaFree(w.rays[0]); cudaFree(w.rays[1]); cudaFree(w.rayOwner[0]); cudaFree(w.rayOwner[1]);
     cudaFree(w.rayCount); cudaFree(w.qKey); cudaFree(w.qList); cudaFree(w.qCount);
     for (cudaEvent_t e : w.events) cudaEventDestroy(e);
+    cudaFree(w.stamps);
     for (const Workspace::FilmSet &f : w.spareFilms) { cudaFree(f.film); cudaFree(f.dev64); cudaFree(f.dev32); cudaFree(f.counters); }
     w = Workspace();
 }
@@ -297,12 +301,21 @@ int renderStaged(gdb200_scene *s, const GptArgs &a, Marks &marks, gdb200_stats *
     launches = 1;
     // a sample takes 2 ticks + (1 or 2) per bounce; streams are consumed sequentially by their slot
     const long long maxTicks = ((long long)spp * 8192 + 131072) * std::max(1, a.nStreams / std::max(1, nSlots) + 1);
-    size_t firstMark = marks.used;
+    // phase times: the kernel that opens a phase stamps the GPU timer (stampPhase), 8 stamps per tick + one at the end
+    Workspace &ws = g_workspace[s->device];
+    const bool timing = stats && marks.on;
+    if (timing && !ws.stamps && cudaMalloc(&ws.stamps, sizeof(unsigned long long) * kStampCapacity) != cudaSuccess) { cudaGetLastError(); ws.stamps = nullptr; }
+    size_t nStamps = 0;
+    bool stampTick = false, openPhase = false;       // openPhase: the last stamped tick's cast phase still waits for its closing stamp
+    GptArgs b = a;                                   // b.mark set: this launch opens a phase
+    auto opens = [&]() -> const GptArgs & { b.mark = stampTick ? ws.stamps + nStamps++ : nullptr; return b; };
     const char *printTick = getenv("GDB200_PRINT_QUEUES");      // profiling aid: queue lengths of one tick on stderr (pairs an ncu capture of that tick with its work)
     for (long long tick = 0;; tick++) {
         if (tick > maxTicks) return set_error(GDB200_ERR_CUDA, "wavefront did not drain after %lld ticks", tick);
-        marks.mark();
-        gpt_stage_compact_kernel<0><<<compactBlocks, 256>>>(a);
+        stampTick = timing && ws.stamps && nStamps + 9 < kStampCapacity;
+        if (!stampTick && openPhase) { b.mark = ws.stamps + nStamps++; openPhase = false; gpt_stage_compact_kernel<0><<<compactBlocks, 256>>>(b); }
+        else gpt_stage_compact_kernel<0><<<compactBlocks, 256>>>(opens());
+        if (stampTick) openPhase = true;
         if (printTick && tick == atoll(printTick)) {
             int q[kStageBuckets], r[2];
             cudaMemcpy(q, a.qCount, sizeof(q), cudaMemcpyDeviceToHost);
@@ -311,24 +324,16 @@ int renderStaged(gdb200_scene *s, const GptArgs &a, Marks &marks, gdb200_stats *
             fprintf(stderr, "gdb200 tick %lld: primary %d shade0 %d shade1 %d shade2 %d resolve %d (slots %d)\n", tick, q[QA_PRIMARY], shade[0], shade[1], shade[2], q[QA_RESOLVE], nSlots);
             (void)r;
         }
-        marks.mark();
-        gpt_stage_kernel<SK_PRIMARY><<<g.primary, kStageThreads>>>(a);
-        marks.mark();
-        gpt_stage_kernel<SK_SHADE0><<<g.shade[0], kStageThreads>>>(a);
+        gpt_stage_kernel<SK_PRIMARY><<<g.primary, kStageThreads>>>(opens());
+        gpt_stage_kernel<SK_SHADE0><<<g.shade[0], kStageThreads>>>(opens());
         gpt_stage_kernel<SK_SHADE1><<<g.shade[1], kStageThreads>>>(a);
         gpt_stage_kernel<SK_SHADE2><<<g.shade[2], kStageThreads>>>(a);
-        marks.mark();
-        gpt_stage_kernel<SK_RESOLVE><<<g.resolve, kStageThreads>>>(a);
-        marks.mark();
-        gpt_stage_compact_kernel<1><<<compactBlocks, 256>>>(a);
-        marks.mark();
-        gpt_stage_kernel<SK_PREPARE><<<g.prepare, kStageThreads>>>(a);
-        marks.mark();
-        gpt_stage_kernel<SK_GENERATE><<<g.generate, kStageThreads>>>(a);
-        marks.mark();
-        gpt_cast_kernel<false><<<g.castNearest, kCastThreads>>>(a);
+        gpt_stage_kernel<SK_RESOLVE><<<g.resolve, kStageThreads>>>(opens());
+        gpt_stage_compact_kernel<1><<<compactBlocks, 256>>>(opens());
+        gpt_stage_kernel<SK_PREPARE><<<g.prepare, kStageThreads>>>(opens());
+        gpt_stage_kernel<SK_GENERATE><<<g.generate, kStageThreads>>>(opens());
+        gpt_cast_kernel<false><<<g.castNearest, kCastThreads>>>(opens());
         gpt_cast_kernel<true><<<g.castAny, kCastThreads>>>(a);
-        marks.mark();
         launches += 11;
         if ((tick & 15) == 15) {
             GDB_CUDA(cudaMemcpy(hc.v, s->counters, sizeof(hc.v), cudaMemcpyDeviceToHost));
@@ -337,14 +342,21 @@ int renderStaged(gdb200_scene *s, const GptArgs &a, Marks &marks, gdb200_stats *
             if (s->cancel) return set_error(GDB200_ERR_CANCELLED, "render cancelled");
         }
     }
+    if (openPhase) { b.mark = ws.stamps + nStamps++; gpt_stamp_kernel<<<1, 1>>>(b); launches++; }      // closes the last tick's cast phase
     GDB_CUDA(cudaDeviceSynchronize());
-    if (stats && marks.on)
-        for (size_t i = firstMark; i + 8 < marks.used; i += 9) {
-            stats->compact_ms += marks.between(i) + marks.between(i + 4);
-            stats->primary_ms += marks.between(i + 1); stats->bounce_ms += marks.between(i + 2); stats->resolve_ms += marks.between(i + 3);
-            stats->prepare_ms += marks.between(i + 5); stats->generate_ms += marks.between(i + 6); stats->cast_ms += marks.between(i + 7);
+    if (timing && nStamps % 8 == 1) {
+        ws.stampsHost.resize(nStamps);
+        GDB_CUDA(cudaMemcpy(ws.stampsHost.data(), ws.stamps, sizeof(unsigned long long) * nStamps, cudaMemcpyDeviceToHost));
+        const unsigned long long *t = ws.stampsHost.data();
+        double ns[8] = {0, 0, 0, 0, 0, 0, 0, 0};      // compact A, primary, shade, resolve, compact B, prepare, generate, casts
+        for (size_t i = 0; i + 8 < nStamps; i += 8) {
+            for (int k = 0; k < 8; k++) ns[k] += (double)(t[i + k + 1] - t[i + k]);
             stats->bounce_launches++;
         }
+        stats->compact_ms = (ns[0] + ns[4]) * 1e-6; stats->primary_ms = ns[1] * 1e-6; stats->bounce_ms = ns[2] * 1e-6;
+        stats->resolve_ms = ns[3] * 1e-6; stats->prepare_ms = ns[5] * 1e-6; stats->generate_ms = ns[6] * 1e-6;
+        stats->cast_ms = ns[7] * 1e-6;
+    }
     return GDB200_OK;
 }
 

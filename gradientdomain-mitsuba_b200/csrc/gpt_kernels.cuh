@@ -59,7 +59,22 @@ struct GptArgs {
     int *qKey;             // [nSlots]: the stage queue a slot belongs in next (-1: none), written by the stage that leaves it there
     int *qList;            // [kStageBuckets][nSlots]: slots per stage bucket
     int *qCount;           // [kStageBuckets]
+    unsigned long long *mark;   // != NULL: the kernel stores %globaltimer here when it starts (per-phase times without host events)
 };
+
+// Phase timing of the staged wavefront: the first thread of a kernel that opens a phase stamps the GPU's nanosecond timer.
+// Kernels of one stream run back to back, so the difference of two stamps is the phase between them -- read back once per
+// render (80 KB) instead of ~10 000 cudaEventElapsedTime calls (10 ms of every render, as much as 3 % of a strip at 8 GPUs).
+GDB_D void stampPhase(const GptArgs &a)
+{
+#ifndef GDB200_EMU
+    if (a.mark && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        *a.mark = t;
+    }
+#endif
+}
 
 GDB_D double *REC(const GptArgs &a, int rec, int slot) { return a.sd + ((((size_t)slot << kRecPitchLog2) + rec) << 2); }
 GDB_D double &W(const GptArgs &a, int rec, int slot) { return REC(a, rec, slot)[3]; }

@@ -151,6 +151,7 @@ template <bool Any>
 __global__ void __launch_bounds__(kCastThreads) gpt_cast_kernel(const GptArgs a)
 {
     constexpr int Q = Any ? 1 : 0;
+    stampPhase(a);
     const int n = min(a.rayCount[Q], a.rayCapacity);
 #ifdef GDB200_EMU
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) castOne<Any>(a, a.rayOwner[Q][r], a.rays[Q] + ((size_t)r << 3));
@@ -937,6 +938,7 @@ __global__ void __launch_bounds__(kStageThreads, StageQueues<KIND>::minBlocks) g
 {
     constexpr int first = StageQueues<KIND>::first, nq = StageQueues<KIND>::count;
     __shared__ int s_begin[nq + 1], s_count[nq];
+    stampPhase(a);
     if (threadIdx.x == 0) {
         int acc = 0;
         for (int b = 0; b < nq; b++) { const int c = a.qCount[first + b]; s_begin[b] = acc; s_count[b] = c; acc += (c + 31) & ~31; }
@@ -983,6 +985,7 @@ __global__ void __launch_bounds__(256) gpt_stage_compact_kernel(const GptArgs a)
 {
     constexpr int first = PHASE == 0 ? 0 : kQA, nq = PHASE == 0 ? kQA : kStageBuckets - kQA;
     __shared__ int s_warp[8][nq], s_base[nq];
+    stampPhase(a);
     if (blockIdx.x == 0 && threadIdx.x < kStageBuckets) {      // the other phase's queues have been consumed: empty them for its next pass
         const bool mine = (int)threadIdx.x >= first && (int)threadIdx.x < first + nq;
         if (!mine) a.qCount[threadIdx.x] = 0;
@@ -1010,6 +1013,8 @@ __global__ void __launch_bounds__(256) gpt_stage_compact_kernel(const GptArgs a)
     __syncthreads();
     if (bucket >= 0) a.qList[(size_t)(first + bucket) * a.nSlots + s_base[bucket] + s_warp[warp][bucket] + rank] = slot;
 }
+
+__global__ void gpt_stamp_kernel(const GptArgs a) { stampPhase(a); }
 
 __global__ void gpt_stage_init_kernel(const GptArgs a)
 {

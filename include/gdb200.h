@@ -63,7 +63,8 @@ typedef struct gdb200_stats {
     double path_bounces;    /* base-path bounce iterations executed (tracer)              */
     int    bounce_launches; /* wavefront steps (staged wavefront: gpt_stage_kernel<shade> launches) */
     int    reserved1;
-    /* staged wavefront (csrc/gpt_stages.cuh): summed CUDA-event times per kernel family; bounce_ms = shade stage */
+    /* staged wavefront (csrc/gpt_stages.cuh): time per kernel family, summed over the render from the GPU's nanosecond timer
+     * (the kernel that opens a phase stamps %globaltimer; the fused A/B path uses CUDA events); bounce_ms = shade stage */
     double cast_ms;         /* gpt_cast_kernel (nearest-hit + any-hit queues)             */
     double prepare_ms;      /* gpt_stage_kernel<prepare>                                  */
     double resolve_ms;      /* gpt_stage_kernel<resolve>                                  */
