@@ -354,7 +354,8 @@ def main():
         peaks, peak_src = measured_peaks()
         # Dominant kernel: the shade stage of the staged wavefront = gpt_stage_kernel<SK_SHADE0|1|2>, three specialisations of one
         # stage launched back to back every tick (csrc/gpt_stages.cuh).  Algorithmic bytes = SURVEY §8d record sizes per
-        # path-bounce (read + write), counted on the device by that stage; time = CUDA events around its launches.
+        # path-bounce (read + write), counted on the device by that stage; time = the GPU's nanosecond timer, stamped by the kernels that open and close
+        # the stage's launches (gdb200_stats.bounce_ms), summed over the timed region.
         shade_launches = 3 * max(1, agg["bounce_launches"])
         bounce_avg_ms = agg["bounce_ms"] / shade_launches
         achieved = agg["state_bytes"] / max(agg["bounce_ms"], 1e-9) / 1e6          # GB/s

@@ -454,7 +454,7 @@ int gdb200_gpt_render(gdb200_scene *s, const gdb200_gpt_params *p, gdb200_buffer
     }
     GDB_CUDA(cudaGetLastError());
     float ms = 0.f;
-    if (marks.on && marks.used >= 2) {
+    if (marks.on && marks.used >= 1) {               // events[0] = start of the device work; the staged path records no others
         marks.mark();
         GDB_CUDA(cudaEventSynchronize(ws.events[marks.used - 1]));
         GDB_CUDA(cudaEventElapsedTime(&ms, ws.events[0], ws.events[marks.used - 1]));

@@ -143,7 +143,10 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-template <bool SYS> __device__ __forceinline__ bool wait_mail(const Mail *m, unsigned long long number, double v[3], bool &dead)
+// BOUNDED = false (the relay slot): only CTA 0 may give up -- it then relays whatever the mailbox holds, so that every CTA of the
+// grid still computes with the same numbers and takes the same branches.  (CTAs that timed out on their own read different
+// garbage, left the CG loop at different iterations and deadlocked the grid barrier: seen once on the GPU box.)
+template <bool SYS, bool BOUNDED> __device__ __forceinline__ bool wait_mail(const Mail *m, unsigned long long number, double v[3], bool &dead)
 {
     unsigned long long w[6], since = 0;
     unsigned spins = 0;
@@ -158,7 +161,7 @@ template <bool SYS> __device__ __forceinline__ bool wait_mail(const Mail *m, uns
 #pragma unroll
         for (int i = 0; i < 6; i++) all = all && (w[i] & 0xffffffffull) == number;
         if (all || dead) break;
-        if ((++spins & 1023u) == 0) {
+        if (BOUNDED && (++spins & 1023u) == 0) {
             const unsigned long long now = global_timer_ns();
             if (since == 0) since = now;
             else if (now - since > kShardTimeoutNs) { dead = true; ok = false; break; }
@@ -227,7 +230,7 @@ __device__ void grid_sum3(cg::grid_group &grid, const PoissonArgs &a, SyncState 
             double sum[3] = {0.0, 0.0, 0.0};
             for (int r = 0; r < a.nRanks; r++) {
                 double v[3];
-                if (!wait_mail<true>(a.mail[a.rank] + par * kMaxRanks + r, number, v, sync.dead)) atomicExch(a.status, 1u + (unsigned)r);
+                if (!wait_mail<true, true>(a.mail[a.rank] + par * kMaxRanks + r, number, v, sync.dead)) atomicExch(a.status, 1u + (unsigned)r);
                 sum[0] += v[0]; sum[1] += v[1]; sum[2] += v[2];
             }
             // ONE system-scope acquire per GPU (592 of them, one per CTA, cost 6 us per reduction: they queue up per SM), then
@@ -237,7 +240,7 @@ __device__ void grid_sum3(cg::grid_group &grid, const PoissonArgs &a, SyncState 
             t0 = sum[0]; t1 = sum[1]; t2 = sum[2];
         } else {
             double v[3];
-            wait_mail<false>(relay, number, v, sync.dead);
+            wait_mail<false, false>(relay, number, v, sync.dead);
             __threadfence();         // acquire at GPU scope: the halo rows read after the caller's __syncthreads are the pushed ones
             t0 = v[0]; t1 = v[1]; t2 = v[2];
         }
