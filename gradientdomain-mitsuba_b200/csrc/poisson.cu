@@ -1148,6 +1148,9 @@ int gdb200_poisson_shard_connect(gdb200_poisson_plan *p, const void *handles, in
             return set_error(GDB200_ERR_ARGUMENT, "handle %d describes rank %d of a %dx%d solve (expected rank %d, %dx%d)", r, h.rank, h.w, h.h, r, p->w, p->h);
         if (r == p->rank) continue;
         gdb200_poisson_plan::Peer &peer = p->peer[r];
+        if (peer.opened[0]) { cudaIpcCloseMemHandle(peer.planes); peer.opened[0] = false; }      // connecting again replaces the mappings
+        if (peer.opened[1]) { cudaIpcCloseMemHandle(peer.mail); peer.opened[1] = false; }
+        peer.planes = nullptr; peer.mail = nullptr;
         peer.y0 = h.y0; peer.y1 = h.y1;
         if (h.pid == (long long)getpid()) {
             // same process (one host thread per GPU): plain peer access
