@@ -108,7 +108,8 @@ void freeSceneBuffers(gdb200_scene *s)
     if (s->film && s->dev64 && s->dev32 && s->counters && s->device >= 0 && s->device < kMaxDevices) {
         std::lock_guard<std::mutex> lock(g_deviceMutex[s->device]);
         Workspace &ws = g_workspace[s->device];
-        if (ws.spareFilms.size() < kSpareFilms) {
+        const size_t pixels = (size_t)s->width * s->height;
+        if (ws.spareFilms.size() < kSpareFilms && pixels * 340 <= ((size_t)4 << 30)) {      // 340 B per pixel; larger films are given back
             Workspace::FilmSet f;
             f.film = s->film; f.dev64 = s->dev64; f.dev32 = s->dev32; f.counters = s->counters; f.pixels = (size_t)s->width * s->height;
             ws.spareFilms.push_back(f);
