@@ -21,8 +21,10 @@
 // Per-pixel arithmetic keeps the reference's operation order and is compiled
 // with -fmad=false, so differences against the CPU reference come from
 // reduction order only.
+#ifndef GDB200_EMU          // tests/emu/poisson_emu.cpp compiles the device part of this source for the host (test infrastructure)
 #include "common.h"
 #include <cooperative_groups.h>
+#endif
 #include <cfloat>
 #include <algorithm>
 #include <cstring>
@@ -124,6 +126,10 @@ template <bool SYS> __device__ __forceinline__ void post_mail(Mail *m, const dou
     for (int c = 0; c < 3; c++) {
         const unsigned long long bits = (unsigned long long)__double_as_longlong(v[c]);
         const unsigned long long hi = (bits & 0xffffffff00000000ull) | number, lo = (bits << 32) | number;
+#ifdef GDB200_EMU
+        __atomic_store_n(&m->w[2 * c], hi, __ATOMIC_RELAXED);
+        __atomic_store_n(&m->w[2 * c + 1], lo, __ATOMIC_RELAXED);
+#else
         if (SYS) {
             asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(&m->w[2 * c]), "l"(hi) : "memory");
             asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(&m->w[2 * c + 1]), "l"(lo) : "memory");
@@ -131,17 +137,26 @@ template <bool SYS> __device__ __forceinline__ void post_mail(Mail *m, const dou
             asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(&m->w[2 * c]), "l"(hi) : "memory");
             asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(&m->w[2 * c + 1]), "l"(lo) : "memory");
         }
+#endif
     }
 }
 
 // Polls a message slot until all six words carry `number`; false (and dead = true) after kShardTimeoutNs.  A dead solve stops
 // waiting: it runs to its end on whatever is in the mailboxes and the host reports the failure.
+#ifdef GDB200_EMU
+constexpr unsigned long long kShardTimeoutNs = 3000000000ull;       // the host emulation's peer-missing test should not take long
+#else
 constexpr unsigned long long kShardTimeoutNs = 8000000000ull;
+#endif
 __device__ __forceinline__ unsigned long long global_timer_ns()
 {
+#ifdef GDB200_EMU
+    return emu_timer_ns();
+#else
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
+#endif
 }
 // BOUNDED = false (the relay slot): only CTA 0 may give up -- it then relays whatever the mailbox holds, so that every CTA of the
 // grid still computes with the same numbers and takes the same branches.  (CTAs that timed out on their own read different
@@ -154,8 +169,12 @@ template <bool SYS, bool BOUNDED> __device__ __forceinline__ bool wait_mail(cons
     for (;;) {
 #pragma unroll
         for (int i = 0; i < 6; i += 2) {
+#ifdef GDB200_EMU
+            w[i] = __atomic_load_n(&m->w[i], __ATOMIC_RELAXED); w[i + 1] = __atomic_load_n(&m->w[i + 1], __ATOMIC_RELAXED);
+#else
             if (SYS) asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[i]), "=l"(w[i + 1]) : "l"(&m->w[i]) : "memory");
             else     asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[i]), "=l"(w[i + 1]) : "l"(&m->w[i]) : "memory");
+#endif
         }
         bool all = true;
 #pragma unroll
@@ -769,7 +788,11 @@ struct CgScalars {
 template <int MODE, bool SHARD>
 __global__ void __launch_bounds__(kThreads, 4) poisson_irls_cg_kernel(const PoissonArgs a)
 {
+#ifdef GDB200_EMU
+    float4 *s_res = emu_dynamic_shared();
+#else
     extern __shared__ float4 s_res[];     // variants 1, 2: [x | Ap][tile][channel][thread], kResBytes
+#endif
     __shared__ CgScalars sc;
     bool xResident = false;               // the current x is in s_res, not in the X planes (uniform over the grid)
     cg::grid_group grid = cg::this_grid();
@@ -891,6 +914,7 @@ __global__ void __launch_bounds__(kThreads) poisson_metrics_kernel(const Poisson
 
 }  // namespace gdb200
 
+#ifndef GDB200_EMU
 // =================================================================================== host ====
 
 struct gdb200_poisson_plan {
@@ -1282,3 +1306,4 @@ int gdb200_poisson_solve(const float *dx, const float *dy, const float *throughp
 }
 
 }  // extern "C"
+#endif  // GDB200_EMU

@@ -307,7 +307,8 @@ def test_shard_arguments_are_checked():
 
 @pytest.mark.skip(reason="passed on the GPU box in a run of this file alone, then hung once inside the full suite: CTAs that timed out "
                          "on their own diverged and deadlocked the grid barrier.  Fixed since (only CTA 0 times out and relays what it "
-                         "has, csrc/poisson.cu wait_mail) but the round's GPU budget was spent before the fix could be re-run; run by hand")
+                         "has, csrc/poisson.cu wait_mail); the host emulation of the kernels reproduces the old deadlock and passes "
+                         "with the fix (tests/test_poisson_emu.py), but the round's GPU budget was spent before a hardware re-run")
 def test_sharded_solve_gives_up_when_a_peer_is_missing():
     """Two connected shards, only one of them solves: its kernel waits for the other's first reduction message, gives up after
     8 s and the call returns an error naming the missing rank -- no hang."""
