@@ -26,11 +26,11 @@ SHORT_L1 = (3, 0.05, 0.5, 6, 100, 0.0)            # the L1D recipe with fewer it
 def emu():
     subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "emu"), "poisson_emu"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
 
-    def run(d, w, h, cfg, variant=0, bounds=None, ctas=1, skip_rank=-1, tmp=None, timeout=600):
+    def run(d, w, h, cfg, variant=0, bounds=None, ctas=1, skip_rank=-1, tmp=None, timeout=600, direct=True):
         bounds = [0, h] if bounds is None else bounds
         n = len(bounds) - 1
         head = struct.pack("<6i", w, h, variant, n, ctas, skip_rank) + struct.pack(f"<{MAX_RANKS + 1}i", *(bounds + [0] * (MAX_RANKS + 1 - len(bounds))))
-        head += struct.pack("<iffiif", *cfg) + struct.pack("<fi", 0.2, 1)
+        head += struct.pack("<iffiif", *cfg) + struct.pack("<fi", 0.2, 1 if direct else 0)
         src, dst = os.path.join(tmp, "in.bin"), os.path.join(tmp, "out.bin")
         with open(src, "wb") as f:
             f.write(head)
@@ -95,3 +95,24 @@ def test_emulated_sharded_solve_gives_up_when_a_peer_is_missing(emu, tmp_path, c
     got, tail, seconds = emu(d, w, h, SHORT_L1, bounds=[0, 32, 64], ctas=ctas, skip_rank=1, tmp=str(tmp_path), timeout=180)
     assert tail[0][2] == 1 + 1, tail            # status = 1 + the rank whose message never came
     assert 2.5 < seconds < 120, seconds
+
+
+def test_emulated_early_out_is_taken_by_every_shard_alike(emu, tmp_path):
+    """cgTolerance early-outs (the L1L preset's mechanism): the decision is taken from the all-GPU sums, which every GPU adds in
+    rank order, so all shards stop at the same CG iteration -- and at the same one as the one-GPU solve here."""
+    w, h = 64, 48
+    d = synth.solver_inputs(w, h, seed=21)
+    cfg = (3, 0.05, 0.5, 12, 2, 30.0)                # check every 2nd iteration against a tolerance that is reached on the way
+    single, tail1, _ = emu(d, w, h, cfg, tmp=str(tmp_path))
+    got, tail, _ = emu(d, w, h, cfg, bounds=[0, 16, 48], ctas=1, variant=1, tmp=str(tmp_path))
+    assert 0 < tail1[0][1] < 36, tail1               # some IRLS iteration did stop early
+    assert all(tuple(t[:2]) == tuple(tail1[0][:2]) and t[2] == 0 for t in tail), (tail, tail1)
+    assert rmse(got, single) <= 2e-6
+
+
+def test_emulated_solve_without_direct(emu, oracle, tmp_path):
+    w, h = 36, 20
+    d = synth.solver_inputs(w, h, seed=8, last_col_nonzero=True)
+    got, _, _ = emu(d, w, h, L2D, bounds=[0, 16, 20], tmp=str(tmp_path), direct=False)
+    want = oracle.poisson(d["dx"], d["dy"], d["throughput"], np.zeros_like(d["direct"]), alpha=0.2, preset="L2D")
+    assert rmse(got, want) <= 1e-6
