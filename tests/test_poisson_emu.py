@@ -67,12 +67,12 @@ def test_emulated_kernel_variants_return_the_same_bits(emu, tmp_path, size, ctas
         assert tuple(tail[0][:2]) == (3, 18)
 
 
-@pytest.mark.parametrize("bounds,ctas,variant", [([0, 16, 32], 1, 0), ([0, 16, 32], 1, 1), ([0, 32, 64], 2, 0), ([0, 32, 64], 2, 1),
-                                                 ([0, 16, 32, 41], 1, 0)])
-def test_emulated_sharded_solve(emu, tmp_path, bounds, ctas, variant):
+@pytest.mark.parametrize("w,bounds,ctas,variant", [(64, [0, 16, 32], 1, 0), (64, [0, 16, 32], 1, 1), (64, [0, 32, 64], 2, 0), (64, [0, 32, 64], 2, 1),
+                                                   (64, [0, 16, 32, 41], 1, 0), (64, [0, 16, 32, 48, 64], 1, 2), (100, [0, 16, 35], 2, 3)])
+def test_emulated_sharded_solve(emu, tmp_path, w, bounds, ctas, variant):
     """Several "GPUs" (groups of CTA processes) solve one image: equal to the one-GPU solve up to reduction order, every
     shard takes the same number of iterations, and the result does not depend on the kernel variant."""
-    w, h = 64, bounds[-1]
+    h = bounds[-1]
     d = synth.solver_inputs(w, h, seed=12, last_col_nonzero=True)
     single, _, _ = emu(d, w, h, SHORT_L1, variant=0, tmp=str(tmp_path))
     got, tail, _ = emu(d, w, h, SHORT_L1, variant=variant, bounds=bounds, ctas=ctas, tmp=str(tmp_path))
